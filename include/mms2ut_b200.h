@@ -1,0 +1,142 @@
+/* C ABI of libmms2ut_b200.so -- the sm_100a kernels behind the mm_s2ut_transformer encoder hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers + sizes + a CUDA stream handle
+ * (cudaStream_t passed as void*), launches asynchronously on that stream, never allocates or frees
+ * device memory (the caller owns every buffer incl. workspaces) and returns a cudaError_t-compatible
+ * int (0 = success; argument errors return cudaErrorInvalidValue = 1).  Re-entrant; no global state
+ * except the lazily resolved driver entry point for tensor-map encoding.
+ *
+ * The reference (whxhcj/multimodal-S2UT) is pure Python on fairseq/torchaudio; each group below names
+ * the reference call site it replaces (paths relative to the reference root).
+ */
+#ifndef MMS2UT_B200_H_
+#define MMS2UT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MM_DTYPE_BF16 0
+#define MM_DTYPE_F16 1
+
+/* Library self-description: returns the ABI version (checked by the Python loader). */
+int mm_abi_version(void);
+/* Name of the last failing CUDA call inside the library on this thread ("" if none). */
+const char* mm_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Front-end.  Replaces mm_s2ut/data/audio_utils.py:326-349 (get_fbank -> fairseq _get_torchaudio_fbank
+ * -> torchaudio.compliance.kaldi.fbank(num_mel_bins=80)) and the UtteranceCMVN feature transform
+ * applied at mm_s2ut/data/speech_to_speech_dataset.py:271-273, plus fairseq _collate_frames' zero padding.
+ *
+ * mm_fbank_f32: wav [B, wav_stride] fp32 (already x 2^15), n_samples [B] int64 ->
+ *   feats [B, max_frames, 80] fp32 raw log-mel (rows >= the utterance's frame count are NOT written),
+ *   stats [B, n_chunks, 2, 80] fp64 per-chunk (sum, sum of squares), n_chunks = ceil(max_frames / 32).
+ * mm_cmvn_apply: normalises with the utterance statistics and zero-pads; writes either/both of
+ *   out_f32 [B, max_frames, 80] and out_op [B, op_frames, 80] (16-bit operand type; row r of the utterance
+ *   lands at row r + op_row_offset; all other rows are written as 0).  With stats == NULL the input is
+ *   taken as already normalised features (the reference's 3-D src_tokens contract) and only copied/padded.
+ * --------------------------------------------------------------------------------------------- */
+int mm_fbank_f32(const float* wav, const int64_t* n_samples, int32_t batch, int64_t wav_stride, float* feats,
+                 int32_t max_frames, double* stats, const float* tables, void* stream);
+/* Constant tables of the fbank kernel (povey window, FFT twiddles, sparse mel bank): the caller allocates
+ * mm_fbank_table_floats() floats on the host, fills them with mm_fbank_build_tables() and keeps a device copy
+ * that it passes to mm_fbank_f32 (the library itself owns no device memory). */
+int mm_fbank_table_floats(void);
+int mm_fbank_build_tables(float* host_out);
+int mm_cmvn_apply(const float* feats, const double* stats, const int64_t* n_samples_or_frames,
+                  int32_t lengths_are_samples, int32_t batch, int32_t max_frames, float* out_f32, void* out_op,
+                  int32_t op_frames, int32_t op_row_offset, int32_t dtype, void* stream);
+/* out_lens[b] = conv-subsampled length of utterance b (int32): frames -> floor((L-1)/2+1) n_layers times;
+ * frames = 1 + (n - 400) / 160 when lengths_are_samples.  (fairseq Conv1dSubsampler.get_out_seq_lens_tensor) */
+int mm_seq_lens(const int64_t* n_samples_or_frames, int32_t lengths_are_samples, int32_t batch, int32_t n_layers,
+                int32_t* out_lens, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * tcgen05 GEMM with fused epilogues:  acc[r, c] = sum_k A[r, k] * W[c, k]   (fp32 accumulation in TMEM)
+ * A is 16-bit [batches][rows][K] (strides in elements; a row stride smaller than K expresses the
+ * overlapping windows of a stride-2 Conv1d over a time-major buffer), optionally split along K into two
+ * tensors (a0: first k_split columns, a1: the rest).  W is 16-bit [N][K] (PyTorch Linear layout), optionally
+ * batched.  Replaces, by epilogue mode:
+ *   MM_EPI_OP        q/k/v projections (fairseq MultiheadAttention; fuse.py:76-80) -> 16-bit out, optional
+ *                    column scale (q * head_dim^-0.5), columns >= vt_col0 stored transposed (V^T) for attention
+ *   MM_EPI_RELU_OP   fc1 + ReLU (fairseq TransformerEncoderLayer)
+ *   MM_EPI_RESID_F32 out_proj / fc2 + bias + residual on the fp32 residual stream
+ *   MM_EPI_GLU_OP    Conv1d(k5,s2)+GLU #1 of fairseq Conv1dSubsampler (reached at mm_s2s_transformer.py:464)
+ *   MM_EPI_GLU_POS_F32  Conv1d+GLU #2, x*sqrt(d) + sinusoidal position (S2TTransformerEncoder._forward)
+ *   MM_EPI_F32_OP    SelectiveAttention.proj (fuse.py:115-116): fp32 and 16-bit copies
+ *   MM_EPI_GATE      selective gate, mm_s2s_transformer.py:612-618: g = sigmoid(acc + b),
+ *                    out = (1-g)*text + g*attn, stored as T x B x C
+ *   MM_EPI_F32       plain fp32 store (attention scores q k^T, fuse.py:87)
+ * --------------------------------------------------------------------------------------------- */
+enum {
+  MM_EPI_OP = 0,
+  MM_EPI_RELU_OP = 1,
+  MM_EPI_RESID_F32 = 2,
+  MM_EPI_GLU_OP = 3,
+  MM_EPI_GLU_POS_F32 = 4,
+  MM_EPI_F32_OP = 5,
+  MM_EPI_GATE = 6,
+  MM_EPI_F32 = 7
+};
+
+typedef struct mm_gemm_args {
+  const void* a0;      /* [batches][rows][k_split] */
+  const void* a1;      /* [batches][rows][k - k_split] or NULL */
+  const void* w;       /* [w_batches][n][k] */
+  int64_t a0_ld, a0_bs, a1_ld, a1_bs, w_ld, w_bs; /* row / batch strides, elements */
+  int32_t rows, batches, n, k, k_split, w_batched;
+  int32_t dtype;       /* MM_DTYPE_* of a0/a1/w and of every "op" output */
+  int32_t mode;        /* MM_EPI_* */
+  int32_t block_n;     /* 128 or 256; 0 = library default */
+  const float* bias;   /* [n] or NULL */
+  float scale;         /* MM_EPI_OP: columns < scale_cols multiplied by scale; GLU_POS: embed scale */
+  int32_t scale_cols;
+  void* out0;          /* primary output */
+  int64_t out0_ld, out0_bs;
+  void* out1;          /* secondary output (MM_EPI_F32_OP: the 16-bit copy) */
+  int64_t out1_ld, out1_bs;
+  const float* aux0;   /* RESID: residual ; GATE: text (fp32) */
+  const float* aux1;   /* GATE: attention output (fp32) */
+  int64_t aux_ld;
+  int32_t rows_per_seq; /* >0: batches==1 and row r is (b, t) = divmod(r, rows_per_seq) */
+  int32_t out_tbc;      /* RESID/GATE: store row (b,t) at (t*n_seqs + b) */
+  int32_t n_seqs;
+  int32_t out_row_offset; /* GLU_OP: output row t lands at t + out_row_offset (leading zero frames) */
+  void* vt;             /* MM_EPI_OP: transposed output [n_seqs][vt_rows][vt_ld] for columns >= vt_col0 */
+  int32_t vt_col0, vt_rows;
+  int64_t vt_ld;
+  const float* pos;     /* GLU_POS: [>= rows+2][n/2] sinusoidal table */
+  const int32_t* seq_lens; /* GLU_POS: valid length per sequence */
+} mm_gemm_args;
+
+int mm_gemm(const mm_gemm_args* args, void* stream);
+
+/* LayerNorm over the last dim (eps 1e-5, affine), fp32 in -> 16-bit operand out and/or fp32 out.
+ * Replaces F.layer_norm in fairseq TransformerEncoderLayer / final encoder LayerNorm and
+ * image_pre_norm_module (mm_s2s_transformer.py:595).  dim in {256, 512, 768, 1024}. */
+int mm_layernorm(const float* x, const float* gamma, const float* beta, int64_t rows, int32_t dim, void* out_op,
+                 float* out_f32, int32_t dtype, float eps, void* stream);
+
+/* Multi-head self-attention core (fairseq MultiheadAttention: softmax_fp32(q k^T + key-padding mask) v).
+ * qk: [B*T, qk_ld] 16-bit, q (pre-scaled) at columns [0, d), k at [d, 2d); vt: [B][d][vt_ld] (V transposed,
+ * zero beyond T); seq_lens [B] int32 valid keys; out [B*T, d] 16-bit.  head_dim must be 64. */
+int mm_self_attention(const void* qk, int64_t qk_ld, const void* vt, int64_t vt_ld, const int32_t* seq_lens,
+                      int32_t batch, int32_t seq, int32_t heads, void* out, int64_t out_ld, int32_t dtype,
+                      void* stream);
+
+/* Row softmax for the speech->image attention (fuse.py:88-111): scores fp32 [rows, ld_in] -> probabilities
+ * 16-bit [rows, ld_out]; columns [n_keys, ld_out) written as 0.  key_mask: optional [n_seqs, n_keys] uint8
+ * (1 = padded key -> -inf); rows_per_seq maps a row to its sequence. */
+int mm_softmax_rows(const float* scores, int64_t ld_in, int64_t rows, int32_t n_keys, const uint8_t* key_mask,
+                    int32_t rows_per_seq, void* probs, int64_t ld_out, int32_t dtype, void* stream);
+
+/* fp32 -> 16-bit operand conversion (weights / image features); n elements. */
+int mm_convert_f32(const float* x, void* out, int64_t n, int32_t dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMS2UT_B200_H_ */

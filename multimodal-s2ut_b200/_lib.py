@@ -1,0 +1,149 @@
+"""Build and load ``libmms2ut_b200.so`` (the C-ABI kernel library) with ctypes.
+
+The library is compiled IN-TREE by nvcc for sm_100a only (``build()``); there is no JIT cache, no
+torch C++ extension and no CPU fallback: if the shared object is missing or fails to load, every op
+raises.  Signatures mirror ``include/mms2ut_b200.h``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+from pathlib import Path
+from typing import List, Optional
+
+_PKG = Path(__file__).resolve().parent
+CSRC = _PKG / "csrc"
+INCLUDE = _PKG.parent / "include"
+LIB_PATH = _PKG / "libmms2ut_b200.so"
+SOURCES = ["abi.cu", "gemm.cu", "rowwise.cu", "fbank.cu", "attention.cu"]
+ABI_VERSION = 1
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "--use_fast_math=false",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found: cannot build libmms2ut_b200.so")
+
+
+def _stale() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    t = LIB_PATH.stat().st_mtime
+    deps = [CSRC / s for s in SOURCES] + list(CSRC.glob("*.cuh")) + [INCLUDE / "mms2ut_b200.h"]
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every .cu for sm_100a and link the shared library (cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = _nvcc()
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    objdir = _PKG / "build"
+    objdir.mkdir(exist_ok=True)
+    procs = []
+    for s in SOURCES:
+        cmd = [nvcc, *flags, "-I", str(INCLUDE), "-c", str(CSRC / s), "-o", str(objdir / (s[:-3] + ".o"))]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for s, p in procs:
+        out, _ = p.communicate()
+        if verbose and out:
+            print(out)
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {s}:\n{out}")
+    objs = [str(objdir / (s[:-3] + ".o")) for s in SOURCES]
+    cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *objs, "-lcudart"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}")
+    return LIB_PATH
+
+
+class GemmArgs(C.Structure):
+    """``mm_gemm_args`` (include/mms2ut_b200.h)."""
+
+    _fields_ = [
+        ("a0", C.c_void_p), ("a1", C.c_void_p), ("w", C.c_void_p),
+        ("a0_ld", C.c_int64), ("a0_bs", C.c_int64), ("a1_ld", C.c_int64), ("a1_bs", C.c_int64),
+        ("w_ld", C.c_int64), ("w_bs", C.c_int64),
+        ("rows", C.c_int32), ("batches", C.c_int32), ("n", C.c_int32), ("k", C.c_int32),
+        ("k_split", C.c_int32), ("w_batched", C.c_int32),
+        ("dtype", C.c_int32), ("mode", C.c_int32), ("block_n", C.c_int32),
+        ("bias", C.c_void_p), ("scale", C.c_float), ("scale_cols", C.c_int32),
+        ("out0", C.c_void_p), ("out0_ld", C.c_int64), ("out0_bs", C.c_int64),
+        ("out1", C.c_void_p), ("out1_ld", C.c_int64), ("out1_bs", C.c_int64),
+        ("aux0", C.c_void_p), ("aux1", C.c_void_p), ("aux_ld", C.c_int64),
+        ("rows_per_seq", C.c_int32), ("out_tbc", C.c_int32), ("n_seqs", C.c_int32), ("out_row_offset", C.c_int32),
+        ("vt", C.c_void_p), ("vt_col0", C.c_int32), ("vt_rows", C.c_int32), ("vt_ld", C.c_int64),
+        ("pos", C.c_void_p), ("seq_lens", C.c_void_p),
+    ]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "mm_abi_version": (C.c_int, []),
+    "mm_last_error": (C.c_char_p, []),
+    "mm_fbank_table_floats": (C.c_int, []),
+    "mm_fbank_build_tables": (C.c_int, [C.c_void_p]),
+    "mm_fbank_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
+                               C.c_void_p, C.c_void_p]),
+    "mm_cmvn_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "mm_seq_lens": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mm_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+    "mm_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                               C.c_int32, C.c_float, C.c_void_p]),
+    "mm_self_attention": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "mm_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                  C.c_int64, C.c_int32, C.c_void_p]),
+    "mm_convert_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library and bind every symbol the header declares.  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+            "There is no CPU or PyTorch fallback for this path.")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    v = lib.mm_abi_version()
+    if v != ABI_VERSION:
+        raise RuntimeError(f"libmms2ut_b200.so ABI {v} != expected {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def header_symbols() -> List[str]:
+    """Function names declared in include/mms2ut_b200.h (used by the CPU-side export test)."""
+    import re
+
+    txt = (INCLUDE / "mms2ut_b200.h").read_text()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(mm_[a-z0-9_]+)\s*\(", txt)))
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().mm_last_error().decode(errors="replace")
+        raise RuntimeError(f"libmms2ut_b200 {what} failed (code {rc}): {msg}")

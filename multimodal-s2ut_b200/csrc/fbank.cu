@@ -1,0 +1,306 @@
+// 80-bin Kaldi-compatible log-mel filterbank (torchaudio.compliance.kaldi.fbank defaults: 25 ms povey
+// window, 10 ms shift, snip_edges, DC removal, pre-emphasis 0.97, 512-point FFT, 20 Hz .. Nyquist mel bank,
+// log floor eps) + per-chunk CMVN statistics, fp32 throughout.
+//
+// One CTA = 32 consecutive frames of one utterance.  The 5360 samples they span are staged once into shared
+// memory with 128-bit coalesced loads (frames overlap 2.5x, HBM sees each sample ~once).  Each HALF-warp
+// owns a frame: the 512-point real FFT runs as a 256-point complex FFT (16 x 16 Cooley-Tukey, one
+// 16-point DFT per lane entirely in registers, a single padded shared-memory transpose between the two
+// passes), followed by the real-FFT split, |X|^2, the sparse triangular mel projection (<= 2 filters per
+// FFT bin) and log.  Per-(utterance, chunk) sums / sums of squares for utterance CMVN are reduced in
+// registers -> shared memory -> one deterministic store (no atomics).
+#include <math.h>
+
+#include "common.cuh"
+#include "host.cuh"
+#include "../../include/mms2ut_b200.h"
+
+namespace mm {
+
+constexpr int FB_WIN = 400, FB_SHIFT = 160, FB_NFFT = 512, FB_BINS = 80;
+constexpr int FB_FRAMES_PER_CTA = 32;
+constexpr int FB_WAVE = FB_WIN + (FB_FRAMES_PER_CTA - 1) * FB_SHIFT;  // 5360 samples
+constexpr int FB_MAX_NNZ = 1024;
+// table layout (floats)
+constexpr int TB_WIN = 0;                         // [400]
+constexpr int TB_TW256 = TB_WIN + 400;            // [256][2]  exp(-2 pi i m / 256)
+constexpr int TB_TW512 = TB_TW256 + 512;          // [256][2]  exp(-2 pi i k / 512)
+constexpr int TB_MELW = TB_TW512 + 512;           // [FB_MAX_NNZ]
+constexpr int TB_K0 = TB_MELW + FB_MAX_NNZ;       // [80] int: first FFT bin of filter m
+constexpr int TB_CNT = TB_K0 + 80;                // [80] int: number of bins
+constexpr int TB_OFF = TB_CNT + 80;               // [80] int: offset into MELW
+constexpr int TB_TOTAL = TB_OFF + 80;             // 2688 floats
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
+
+// forward 4-point DFT (W4 = -i), natural order in/out
+__device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+  const float2 s02 = cadd(a0, a2), d02 = csub(a0, a2);
+  const float2 s13 = cadd(a1, a3), d13 = mul_mi(csub(a1, a3));
+  a0 = cadd(s02, s13);
+  a1 = cadd(d02, d13);
+  a2 = csub(s02, s13);
+  a3 = csub(d02, d13);
+}
+
+// forward 16-point DFT in registers: n = n1 + 4 n2, k = 4 k1 + k2
+__device__ __forceinline__ void dft16(float2 (&a)[16]) {
+  constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508978f, R2 = 0.70710678118654752f;
+  // W16^m = (cos, -sin)(2 pi m / 16)
+  const float2 W[10] = {{1.f, 0.f},  {C1, -S1}, {R2, -R2}, {S1, -C1}, {0.f, -1.f},
+                        {-S1, -C1}, {-R2, -R2}, {-C1, -S1}, {-1.f, 0.f}, {-C1, S1}};
+#pragma unroll
+  for (int n1 = 0; n1 < 4; ++n1) {
+    dft4(a[n1], a[n1 + 4], a[n1 + 8], a[n1 + 12]);  // over n2 -> k2 at slot n1 + 4 k2
+#pragma unroll
+    for (int k2 = 1; k2 < 4; ++k2)
+      if (n1 * k2 != 0) a[n1 + 4 * k2] = cmul(a[n1 + 4 * k2], W[n1 * k2]);
+  }
+  float2 t[16];
+#pragma unroll
+  for (int k2 = 0; k2 < 4; ++k2) {
+    float2 b0 = a[0 + 4 * k2], b1 = a[1 + 4 * k2], b2 = a[2 + 4 * k2], b3 = a[3 + 4 * k2];
+    dft4(b0, b1, b2, b3);  // over n1 -> k1
+    t[k2] = b0, t[4 + k2] = b1, t[8 + k2] = b2, t[12 + k2] = b3;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = t[i];
+}
+
+constexpr int FB_THREADS = 256;
+constexpr int FB_HW = FB_THREADS / 16;                 // 16 half-warps
+constexpr int FB_ZBUF = 512;                           // floats per half-warp: packed input / natural-order Z
+constexpr int FB_XBUF = 16 * 17 * 2;                   // floats per half-warp: padded 16x17 complex transpose
+constexpr int FB_SMEM_FLOATS = FB_WAVE + TB_TOTAL + FB_HW * (FB_ZBUF + FB_XBUF);
+constexpr int FB_SMEM_BYTES = FB_SMEM_FLOATS * 4;
+
+__global__ void __launch_bounds__(FB_THREADS) fbank_kernel(const float* __restrict__ wav,
+                                                           const long long* __restrict__ n_samples, long long wav_stride,
+                                                           float* __restrict__ feats, int max_frames,
+                                                           double* __restrict__ stats, int n_chunks,
+                                                           const float* __restrict__ tables) {
+  extern __shared__ __align__(16) float fsm[];
+  float* s_wave = fsm;
+  float* s_tab = s_wave + FB_WAVE;
+  float* s_work = s_tab + TB_TOTAL;
+
+  const int b = blockIdx.y;
+  const int chunk = blockIdx.x;
+  const long long n = n_samples[b];
+  int nfr = n < FB_WIN ? 0 : (int)(1 + (n - FB_WIN) / FB_SHIFT);
+  nfr = min(nfr, max_frames);
+  const int f0 = chunk * FB_FRAMES_PER_CTA;
+  if (f0 >= nfr) return;  // whole CTA out of range (uniform)
+  const int nf_here = min(FB_FRAMES_PER_CTA, nfr - f0);
+
+  // ---- stage samples + tables ----
+  const long long s0 = (long long)f0 * FB_SHIFT;
+  const int n_need = FB_WIN + (nf_here - 1) * FB_SHIFT;  // <= n - s0 by construction
+  const float* wsrc = wav + (long long)b * wav_stride + s0;
+  if ((reinterpret_cast<uintptr_t>(wsrc) & 15) == 0) {
+    for (int i = threadIdx.x * 4; i < n_need; i += FB_THREADS * 4) {
+      if (i + 3 < n_need) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(wsrc + i));
+        *reinterpret_cast<float4*>(s_wave + i) = v;
+      } else {
+        for (int j = i; j < n_need; ++j) s_wave[j] = wsrc[j];
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < n_need; i += FB_THREADS) s_wave[i] = wsrc[i];
+  }
+  for (int i = threadIdx.x; i < TB_TOTAL; i += FB_THREADS) s_tab[i] = __ldg(tables + i);
+  __syncthreads();
+
+  const float* s_win = s_tab + TB_WIN;
+  const float2* s_tw256 = reinterpret_cast<const float2*>(s_tab + TB_TW256);
+  const float2* s_tw512 = reinterpret_cast<const float2*>(s_tab + TB_TW512);
+  const float* s_melw = s_tab + TB_MELW;
+  const int* s_k0 = reinterpret_cast<const int*>(s_tab + TB_K0);
+  const int* s_cnt = reinterpret_cast<const int*>(s_tab + TB_CNT);
+  const int* s_off = reinterpret_cast<const int*>(s_tab + TB_OFF);
+
+  const int hw = threadIdx.x >> 4;       // half-warp id 0..15
+  const int l = threadIdx.x & 15;        // lane in half-warp
+  const int hsel = (threadIdx.x >> 4) & 1;
+  const unsigned hmask = 0xFFFFu << (16 * hsel);
+  float* zbuf = s_work + hw * (FB_ZBUF + FB_XBUF);
+  float* xbuf = zbuf + FB_ZBUF;
+  float2* z2 = reinterpret_cast<float2*>(zbuf);
+  float2* x2 = reinterpret_cast<float2*>(xbuf);
+
+  double acc1[5] = {0., 0., 0., 0., 0.}, acc2[5] = {0., 0., 0., 0., 0.};  // fp64: a constant utterance must give mean == x exactly
+
+  for (int fl = hw; fl < nf_here; fl += FB_HW) {
+    const float* x = s_wave + fl * FB_SHIFT;
+    // ---- DC removal: mean over the 400 samples (lanes stride 16; second half-warp rotated by 16 banks) ----
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 25; ++j) {
+      int i = l + 16 * j + 16 * hsel;
+      i = i >= FB_WIN ? i - FB_WIN : i;
+      s += x[i];
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(hmask, s, o);
+    const float mean = s * (1.0f / FB_WIN);
+    // ---- pre-emphasis (replicate-left) + povey window, packed as 256 complex; zero pad 400..511 ----
+#pragma unroll
+    for (int j = 0; j < 25; ++j) {
+      int i = l + 16 * j + 16 * hsel;
+      i = i >= FB_WIN ? i - FB_WIN : i;
+      const float a = x[i] - mean;
+      const float p = x[i > 0 ? i - 1 : 0] - mean;
+      zbuf[i] = __fmul_rn(__fsub_rn(a, __fmul_rn(0.97f, p)), s_win[i]);
+    }
+#pragma unroll
+    for (int j = 0; j < 7; ++j) zbuf[FB_WIN + l + 16 * j] = 0.f;
+    __syncwarp(hmask);
+    // ---- pass 1: lane n1 = l, 16-point DFT over n2 of z[n1 + 16 n2]; twiddle W256^(n1 k2); transpose ----
+    float2 a[16];
+#pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) a[n2] = z2[l + 16 * n2];
+    dft16(a);
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) {
+      const float2 v = (k2 == 0) ? a[0] : cmul(a[k2], s_tw256[l * k2]);
+      x2[k2 * 17 + l] = v;
+    }
+    __syncwarp(hmask);
+    // ---- pass 2: lane k2 = l, 16-point DFT over n1 -> Z[16 k1 + k2] ----
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) a[n1] = x2[l * 17 + n1];
+    dft16(a);
+    __syncwarp(hmask);
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) z2[16 * k1 + l] = a[k1];
+    __syncwarp(hmask);
+    // ---- real-FFT split + power spectrum for bins 0..255 (Nyquist has zero mel weight) ----
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int k = l + 16 * j;
+      const float2 zk = z2[k];
+      float2 zm = z2[(256 - k) & 255];
+      zm.y = -zm.y;
+      const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y + zm.y));
+      const float2 d = csub(zk, zm);
+      const float2 o = make_float2(0.5f * d.y, -0.5f * d.x);  // -i/2 * (zk - zm)
+      const float2 xk = cadd(e, cmul(s_tw512[k], o));
+      xbuf[k] = xk.x * xk.x + xk.y * xk.y;
+    }
+    __syncwarp(hmask);
+    // ---- sparse mel projection + log ----
+    float* orow = feats + ((long long)b * max_frames + (f0 + fl)) * FB_BINS;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int m = l + 16 * j;
+      const int k0 = s_k0[m], cnt = s_cnt[m], off = s_off[m];
+      float e = 0.f;
+      for (int i = 0; i < cnt; ++i) e = fmaf(s_melw[off + i], xbuf[k0 + i], e);
+      const float v = logf(fmaxf(e, 1.1920928955078125e-07f));
+      orow[m] = v;
+      acc1[j] += (double)v;
+      acc2[j] += (double)v * (double)v;
+    }
+    __syncwarp(hmask);
+  }
+
+  // ---- per-chunk CMVN partial statistics: fixed-order reduction over the 16 half-warps ----
+  __syncthreads();
+  double* red = reinterpret_cast<double*>(s_work);  // [16][160]
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    red[hw * 160 + l + 16 * j] = acc1[j];
+    red[hw * 160 + 80 + l + 16 * j] = acc2[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 160) {
+    double t = 0.;
+#pragma unroll
+    for (int h = 0; h < FB_HW; ++h) t += red[h * 160 + threadIdx.x];
+    stats[((long long)b * n_chunks + chunk) * 160 + threadIdx.x] = t;
+  }
+}
+
+}  // namespace mm
+
+using namespace mm;
+
+extern "C" int mm_fbank_table_floats(void) { return TB_TOTAL; }
+
+// Host-side table construction.  The mel bank repeats torchaudio's fp32 arithmetic (get_mel_banks) so the
+// filter weights agree with the reference to the last bits; window and twiddles are rounded from double.
+extern "C" int mm_fbank_build_tables(float* out) {
+  if (!out) return bad_arg("fbank tables: null");
+  memset(out, 0, sizeof(float) * TB_TOTAL);
+  const double PI = 3.14159265358979323846;
+  for (int i = 0; i < FB_WIN; ++i) {
+    const float hann = (float)(0.5 - 0.5 * cos(2.0 * PI * i / (FB_WIN - 1)));
+    out[TB_WIN + i] = powf(hann, 0.85f);
+  }
+  for (int m = 0; m < 256; ++m) {
+    out[TB_TW256 + 2 * m] = (float)cos(2.0 * PI * m / 256.0);
+    out[TB_TW256 + 2 * m + 1] = (float)(-sin(2.0 * PI * m / 256.0));
+    out[TB_TW512 + 2 * m] = (float)cos(2.0 * PI * m / 512.0);
+    out[TB_TW512 + 2 * m + 1] = (float)(-sin(2.0 * PI * m / 512.0));
+  }
+  const double sample_freq = 16000.0, low_freq = 20.0, high_freq = 8000.0;
+  const double fft_bin_width = sample_freq / FB_NFFT;
+  const double mel_low = 1127.0 * log(1.0 + low_freq / 700.0);
+  const double mel_high = 1127.0 * log(1.0 + high_freq / 700.0);
+  const double delta = (mel_high - mel_low) / (FB_BINS + 1);
+  int* k0 = reinterpret_cast<int*>(out + TB_K0);
+  int* cnt = reinterpret_cast<int*>(out + TB_CNT);
+  int* off = reinterpret_cast<int*>(out + TB_OFF);
+  int nnz = 0;
+  for (int m = 0; m < FB_BINS; ++m) {
+    // torch: python-float scalars are applied in the tensor dtype (fp32)
+    const float left = (float)mel_low + (float)m * (float)delta;
+    const float center = (float)mel_low + ((float)m + 1.0f) * (float)delta;
+    const float right = (float)mel_low + ((float)m + 2.0f) * (float)delta;
+    int first = -1, last = -1;
+    float w[256];
+    for (int k = 0; k < 256; ++k) {
+      const float f = (float)fft_bin_width * (float)k;
+      const float mel = 1127.0f * logf(1.0f + f / 700.0f);
+      const float up = (mel - left) / (center - left);
+      const float down = (right - mel) / (right - center);
+      const float v = fmaxf(0.0f, fminf(up, down));
+      w[k] = v;
+      if (v > 0.f) {
+        if (first < 0) first = k;
+        last = k;
+      }
+    }
+    k0[m] = first < 0 ? 0 : first;
+    cnt[m] = first < 0 ? 0 : last - first + 1;
+    off[m] = nnz;
+    if (nnz + cnt[m] > FB_MAX_NNZ) return bad_arg("fbank tables: mel bank too dense");
+    for (int i = 0; i < cnt[m]; ++i) out[TB_MELW + nnz + i] = w[first + i];
+    nnz += cnt[m];
+  }
+  return 0;
+}
+
+extern "C" int mm_fbank_f32(const float* wav, const int64_t* n_samples, int32_t batch, int64_t wav_stride, float* feats,
+                            int32_t max_frames, double* stats, const float* tables, void* stream) {
+  if (!wav || !n_samples || !feats || !stats || !tables) return bad_arg("fbank: null pointer");
+  if (batch <= 0 || max_frames <= 0) return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute(fbank)");
+    attr_set = true;
+  }
+  const int n_chunks = (max_frames + FB_FRAMES_PER_CTA - 1) / FB_FRAMES_PER_CTA;
+  dim3 grid(n_chunks, batch);
+  fbank_kernel<<<grid, FB_THREADS, FB_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
+      wav, reinterpret_cast<const long long*>(n_samples), wav_stride, feats, max_frames, stats, n_chunks, tables);
+  MM_CHECK_LAUNCH("fbank_kernel launch");
+  return 0;
+}

@@ -1,0 +1,302 @@
+// HBM-bound row-wise kernels: LayerNorm, key-softmax for the speech->image attention, fp32->16-bit
+// conversion, CMVN application / zero padding, subsampled sequence lengths.
+// All are one-warp-per-row (or grid-stride) kernels with 128-bit loads/stores and warp-shuffle reductions.
+#include "common.cuh"
+#include "host.cuh"
+#include "../../include/mms2ut_b200.h"
+
+namespace mm {
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, row held in registers (DIM/32 floats per lane), two-pass statistics.
+// ---------------------------------------------------------------------------------------------------
+template <int DIM, typename OpT>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, long long rows,
+                                                         OpT* __restrict__ out_op, float* __restrict__ out_f32,
+                                                         float eps) {
+  constexpr int V = DIM / 128;  // float4 per lane
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * DIM);
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i] = __ldcs(xr + lane + 32 * i);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / DIM);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i].x -= mean, v[i].y -= mean, v[i].z -= mean, v[i].w -= mean;
+    q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / DIM) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float4 g = __ldg(g4 + lane + 32 * i), b = __ldg(b4 + lane + 32 * i);
+    float4 y;
+    y.x = fmaf(v[i].x * rstd, g.x, b.x);
+    y.y = fmaf(v[i].y * rstd, g.y, b.y);
+    y.z = fmaf(v[i].z * rstd, g.z, b.z);
+    y.w = fmaf(v[i].w * rstd, g.w, b.w);
+    if (out_f32) reinterpret_cast<float4*>(out_f32 + row * DIM)[lane + 32 * i] = y;
+    if (out_op) {
+      uint2 pk;
+      pk.x = OpTraits<OpT>::pack2(y.x, y.y);
+      pk.y = OpTraits<OpT>::pack2(y.z, y.w);
+      reinterpret_cast<uint2*>(out_op + row * DIM)[lane + 32 * i] = pk;
+    }
+  }
+}
+
+template <typename OpT>
+static int launch_ln(const float* x, const float* g, const float* b, long long rows, int dim, void* out_op,
+                     float* out_f32, float eps, cudaStream_t s) {
+  const int rows_per_block = 8;
+  const unsigned grid = (unsigned)((rows + rows_per_block - 1) / rows_per_block);
+  OpT* o = reinterpret_cast<OpT*>(out_op);
+  switch (dim) {
+    case 256: layernorm_kernel<256, OpT><<<grid, 256, 0, s>>>(x, g, b, rows, o, out_f32, eps); break;
+    case 512: layernorm_kernel<512, OpT><<<grid, 256, 0, s>>>(x, g, b, rows, o, out_f32, eps); break;
+    case 768: layernorm_kernel<768, OpT><<<grid, 256, 0, s>>>(x, g, b, rows, o, out_f32, eps); break;
+    case 1024: layernorm_kernel<1024, OpT><<<grid, 256, 0, s>>>(x, g, b, rows, o, out_f32, eps); break;
+    default: return bad_arg("layernorm dim must be 256, 512, 768 or 1024");
+  }
+  MM_CHECK_LAUNCH("layernorm_kernel launch");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Row softmax over image keys: scores fp32 [rows, ld_in] -> probabilities 16-bit [rows, ld_out].
+// One warp per row; the row (<= 1024 keys) lives in registers.
+// ---------------------------------------------------------------------------------------------------
+template <typename OpT>
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ scores, long long ld_in,
+                                                            long long rows, int n_keys,
+                                                            const uint8_t* __restrict__ key_mask, int rows_per_seq,
+                                                            OpT* __restrict__ probs, long long ld_out) {
+  constexpr int MAXV = 32;  // up to 1024 keys
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* sr = scores + row * ld_in;
+  const uint8_t* mk = key_mask ? key_mask + (row / rows_per_seq) * (long long)n_keys : nullptr;
+  float v[MAXV];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + 32 * i;
+    float s = -INFINITY;
+    if (c < n_keys) {
+      s = __ldcs(sr + c);
+      if (mk && mk[c]) s = -INFINITY;
+    }
+    v[i] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  const float mref = (mx == -INFINITY) ? 0.f : mx;  // fully masked row -> NaN like the reference (0/0)
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    v[i] = __expf(v[i] - mref);
+    sum += v[i];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  OpT* pr = probs + row * ld_out;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < ld_out) pr[c] = OpTraits<OpT>::cvt(c < n_keys ? v[i] * inv : 0.f);
+  }
+}
+
+template <typename OpT>
+__global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ x, OpT* __restrict__ out,
+                                                       long long n) {
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(x) + i);
+    uint2 pk;
+    pk.x = OpTraits<OpT>::pack2(v.x, v.y);
+    pk.y = OpTraits<OpT>::pack2(v.z, v.w);
+    reinterpret_cast<uint2*>(out)[i] = pk;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) out[n4 * 4 + threadIdx.x] = OpTraits<OpT>::cvt(x[n4 * 4 + threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CMVN apply + zero padding.  One thread per 4 mel bins of one (utterance, output row).
+// stats: [B, n_chunks, 2, 80] partial (sum, sumsq) from the fbank kernel, reduced here in a fixed order
+// (deterministic) by the first warps of each block into shared memory.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int frames_of(long long n, int lengths_are_samples) {
+  if (!lengths_are_samples) return (int)n;
+  return n < 400 ? 0 : (int)(1 + (n - 400) / 160);
+}
+
+template <typename OpT>
+__global__ void __launch_bounds__(256) cmvn_apply_kernel(const float* __restrict__ feats,
+                                                          const double* __restrict__ stats,
+                                                          const long long* __restrict__ lens, int lengths_are_samples,
+                                                          int max_frames, int n_chunks, float* __restrict__ out_f32,
+                                                          OpT* __restrict__ out_op, int op_frames, int op_row_offset,
+                                                          int rows_per_block) {
+  __shared__ float s_mean[80], s_rstd[80];
+  const int b = blockIdx.y;
+  const int nfr = min(frames_of(lens[b], lengths_are_samples), max_frames);
+  if (threadIdx.x < 80) {
+    float mean = 0.f, rstd = 1.f;
+    if (stats != nullptr && nfr > 0) {
+      double s = 0.0, q = 0.0;
+      const double* st = stats + (long long)b * n_chunks * 160;
+      const int used = (nfr + 31) / 32;
+      for (int c = 0; c < used; ++c) {
+        s += st[c * 160 + threadIdx.x];
+        q += st[c * 160 + 80 + threadIdx.x];
+      }
+      // fairseq UtteranceCMVN: var = E[x^2] - mean^2 (population), floor 1e-10
+      const float m = (float)(s / nfr);
+      const float var = (float)(q / nfr) - m * m;
+      mean = m;
+      rstd = 1.0f / sqrtf(fmaxf(var, 1e-10f));
+    }
+    s_mean[threadIdx.x] = mean;
+    s_rstd[threadIdx.x] = rstd;
+  }
+  __syncthreads();
+  // rows handled by this block: [row0, row0 + rows_per_block) of the LARGER of the two output extents
+  const int total_rows = max(op_frames, max_frames);
+  const int row0 = blockIdx.x * rows_per_block;
+  for (int idx = threadIdx.x; idx < rows_per_block * 20; idx += blockDim.x) {
+    const int row = row0 + idx / 20;
+    const int c4 = idx % 20;
+    if (row >= total_rows) break;
+    // fp32 output row `row` <-> utterance frame `row`; operand row `row` <-> frame `row - op_row_offset`
+    if (out_f32 != nullptr && row < max_frames) {
+      float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < nfr) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(feats + ((long long)b * max_frames + row) * 80) + c4);
+        y.x = (v.x - s_mean[4 * c4 + 0]) * s_rstd[4 * c4 + 0];
+        y.y = (v.y - s_mean[4 * c4 + 1]) * s_rstd[4 * c4 + 1];
+        y.z = (v.z - s_mean[4 * c4 + 2]) * s_rstd[4 * c4 + 2];
+        y.w = (v.w - s_mean[4 * c4 + 3]) * s_rstd[4 * c4 + 3];
+      }
+      reinterpret_cast<float4*>(out_f32 + ((long long)b * max_frames + row) * 80)[c4] = y;
+    }
+    if (out_op != nullptr && row < op_frames) {
+      const int fr = row - op_row_offset;
+      float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (fr >= 0 && fr < nfr) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(feats + ((long long)b * max_frames + fr) * 80) + c4);
+        y.x = (v.x - s_mean[4 * c4 + 0]) * s_rstd[4 * c4 + 0];
+        y.y = (v.y - s_mean[4 * c4 + 1]) * s_rstd[4 * c4 + 1];
+        y.z = (v.z - s_mean[4 * c4 + 2]) * s_rstd[4 * c4 + 2];
+        y.w = (v.w - s_mean[4 * c4 + 3]) * s_rstd[4 * c4 + 3];
+      }
+      uint2 pk;
+      pk.x = OpTraits<OpT>::pack2(y.x, y.y);
+      pk.y = OpTraits<OpT>::pack2(y.z, y.w);
+      reinterpret_cast<uint2*>(out_op + ((long long)b * op_frames + row) * 80)[c4] = pk;
+    }
+  }
+}
+
+__global__ void seq_lens_kernel(const long long* __restrict__ lens, int lengths_are_samples, int batch, int n_layers,
+                                int* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  int n = frames_of(lens[b], lengths_are_samples);
+  for (int i = 0; i < n_layers; ++i) n = n <= 0 ? 0 : (n - 1) / 2 + 1;  // floor((L-1)/2 + 1)
+  out[b] = n;
+}
+
+}  // namespace mm
+
+using namespace mm;
+
+extern "C" int mm_layernorm(const float* x, const float* gamma, const float* beta, int64_t rows, int32_t dim,
+                            void* out_op, float* out_f32, int32_t dtype, float eps, void* stream) {
+  if (!x || !gamma || !beta || (!out_op && !out_f32)) return bad_arg("layernorm: null pointer");
+  if (rows <= 0) return 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return dtype == MM_DTYPE_F16 ? launch_ln<__half>(x, gamma, beta, rows, dim, out_op, out_f32, eps, s)
+                               : launch_ln<__nv_bfloat16>(x, gamma, beta, rows, dim, out_op, out_f32, eps, s);
+}
+
+extern "C" int mm_softmax_rows(const float* scores, int64_t ld_in, int64_t rows, int32_t n_keys,
+                               const uint8_t* key_mask, int32_t rows_per_seq, void* probs, int64_t ld_out,
+                               int32_t dtype, void* stream) {
+  if (!scores || !probs) return bad_arg("softmax: null pointer");
+  if (n_keys <= 0 || n_keys > 1024 || ld_out > 1024 || ld_out < n_keys) return bad_arg("softmax: 1 <= n_keys <= ld_out <= 1024");
+  if (key_mask && rows_per_seq <= 0) return bad_arg("softmax: key_mask needs rows_per_seq");
+  if (rows <= 0) return 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (dtype == MM_DTYPE_F16)
+    softmax_rows_kernel<__half><<<grid, 256, 0, s>>>(scores, ld_in, rows, n_keys, key_mask, rows_per_seq,
+                                                     reinterpret_cast<__half*>(probs), ld_out);
+  else
+    softmax_rows_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(scores, ld_in, rows, n_keys, key_mask, rows_per_seq,
+                                                            reinterpret_cast<__nv_bfloat16*>(probs), ld_out);
+  MM_CHECK_LAUNCH("softmax_rows_kernel launch");
+  return 0;
+}
+
+extern "C" int mm_convert_f32(const float* x, void* out, int64_t n, int32_t dtype, void* stream) {
+  if (!x || !out) return bad_arg("convert: null pointer");
+  if (n <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out) & 7)) return bad_arg("convert: alignment");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  if (dtype == MM_DTYPE_F16)
+    convert_kernel<__half><<<(unsigned)blocks, 256, 0, s>>>(x, reinterpret_cast<__half*>(out), n);
+  else
+    convert_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>(x, reinterpret_cast<__nv_bfloat16*>(out), n);
+  MM_CHECK_LAUNCH("convert_kernel launch");
+  return 0;
+}
+
+extern "C" int mm_cmvn_apply(const float* feats, const double* stats, const int64_t* lens, int32_t lengths_are_samples,
+                             int32_t batch, int32_t max_frames, float* out_f32, void* out_op, int32_t op_frames,
+                             int32_t op_row_offset, int32_t dtype, void* stream) {
+  if (!feats || !lens || (!out_f32 && !out_op)) return bad_arg("cmvn: null pointer");
+  if (batch <= 0 || max_frames <= 0) return 0;
+  if (!out_op) op_frames = 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int rows_per_block = 64;
+  const int total_rows = op_frames > max_frames ? op_frames : max_frames;
+  dim3 grid((total_rows + rows_per_block - 1) / rows_per_block, batch);
+  const int n_chunks = (max_frames + 31) / 32;
+  const long long* l = reinterpret_cast<const long long*>(lens);
+  if (dtype == MM_DTYPE_F16)
+    cmvn_apply_kernel<__half><<<grid, 256, 0, s>>>(feats, stats, l, lengths_are_samples, max_frames, n_chunks,
+                                                   out_f32, reinterpret_cast<__half*>(out_op), op_frames,
+                                                   op_row_offset, rows_per_block);
+  else
+    cmvn_apply_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(feats, stats, l, lengths_are_samples, max_frames, n_chunks,
+                                                          out_f32, reinterpret_cast<__nv_bfloat16*>(out_op),
+                                                          op_frames, op_row_offset, rows_per_block);
+  MM_CHECK_LAUNCH("cmvn_apply_kernel launch");
+  return 0;
+}
+
+extern "C" int mm_seq_lens(const int64_t* lens, int32_t lengths_are_samples, int32_t batch, int32_t n_layers,
+                           int32_t* out_lens, void* stream) {
+  if (!lens || !out_lens) return bad_arg("seq_lens: null pointer");
+  if (batch <= 0) return 0;
+  seq_lens_kernel<<<(batch + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(lens), lengths_are_samples, batch, n_layers, out_lens);
+  MM_CHECK_LAUNCH("seq_lens_kernel launch");
+  return 0;
+}

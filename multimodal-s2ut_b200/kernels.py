@@ -1,0 +1,165 @@
+"""Thin Python wrappers over the C-ABI kernels: shape/dtype checks, pointer passing, current stream.
+
+PyTorch is used only for device memory and the stream handle; nothing here computes with torch ops.
+Every function raises if the CUDA library is missing (``_lib.load``) or the tensors are not on a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+EPI_OP, EPI_RELU_OP, EPI_RESID_F32, EPI_GLU_OP, EPI_GLU_POS_F32, EPI_F32_OP, EPI_GATE, EPI_F32 = range(8)
+_DT = {torch.bfloat16: 0, torch.float16: 1}
+
+# Launch counter: bench.py reports how many of OUR kernels ran inside the timed region.
+launch_count = 0
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DT[dt]
+    except KeyError:
+        raise TypeError(f"operand dtype must be bfloat16 or float16, got {dt}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("kernel operands must live on a CUDA device (no CPU fallback exists)")
+    return t.data_ptr()
+
+
+def _count(n: int = 1) -> None:
+    global launch_count
+    launch_count += n
+
+
+def fbank_tables(device) -> torch.Tensor:
+    lib = _lib.load()
+    n = lib.mm_fbank_table_floats()
+    host = torch.zeros(n, dtype=torch.float32)
+    _lib.check(lib.mm_fbank_build_tables(host.data_ptr()), "mm_fbank_build_tables")
+    return host.to(device)
+
+
+def fbank(wav: torch.Tensor, n_samples: torch.Tensor, feats: torch.Tensor, stats: torch.Tensor,
+          tables: torch.Tensor) -> None:
+    """wav [B, N] fp32 (x 2**15), n_samples [B] int64 -> feats [B, m, 80] raw log-mel, stats [B, ceil(m/32), 2, 80]."""
+    assert wav.dtype == torch.float32 and wav.dim() == 2 and wav.stride(1) == 1
+    assert n_samples.dtype == torch.int64 and feats.dtype == torch.float32 and feats.is_contiguous()
+    B, m = feats.shape[0], feats.shape[1]
+    assert feats.shape[2] == 80 and stats.dtype == torch.float64 and stats.is_contiguous()
+    assert stats.numel() >= B * ((m + 31) // 32) * 160
+    lib = _lib.load()
+    _lib.check(lib.mm_fbank_f32(_ptr(wav), _ptr(n_samples), B, wav.stride(0), _ptr(feats), m, _ptr(stats),
+                                _ptr(tables), _stream()), "mm_fbank_f32")
+    _count()
+
+
+def cmvn_apply(feats: torch.Tensor, stats: Optional[torch.Tensor], lens: torch.Tensor, lengths_are_samples: bool,
+               out_f32: Optional[torch.Tensor], out_op: Optional[torch.Tensor], op_row_offset: int = 0) -> None:
+    assert feats.dtype == torch.float32 and feats.is_contiguous() and feats.shape[2] == 80
+    B, m = feats.shape[0], feats.shape[1]
+    op_frames, dt = 0, 0
+    if out_op is not None:
+        assert out_op.is_contiguous() and out_op.shape[0] == B and out_op.shape[2] == 80
+        op_frames, dt = out_op.shape[1], dtype_code(out_op.dtype)
+    if out_f32 is not None:
+        assert out_f32.is_contiguous() and out_f32.shape == feats.shape
+    lib = _lib.load()
+    _lib.check(lib.mm_cmvn_apply(_ptr(feats), _ptr(stats), _ptr(lens), int(lengths_are_samples), B, m, _ptr(out_f32),
+                                 _ptr(out_op), op_frames, op_row_offset, dt, _stream()), "mm_cmvn_apply")
+    _count()
+
+
+def seq_lens(lens: torch.Tensor, lengths_are_samples: bool, n_layers: int, out: torch.Tensor) -> None:
+    assert lens.dtype == torch.int64 and out.dtype == torch.int32
+    lib = _lib.load()
+    _lib.check(lib.mm_seq_lens(_ptr(lens), int(lengths_are_samples), lens.numel(), n_layers, _ptr(out), _stream()),
+               "mm_seq_lens")
+    _count()
+
+
+def gemm(*, a0: torch.Tensor, w: torch.Tensor, rows: int, n: int, k: int, mode: int, out0: torch.Tensor,
+         a0_ld: int, out0_ld: int, batches: int = 1, a0_bs: int = 0, a1: Optional[torch.Tensor] = None,
+         a1_ld: int = 0, a1_bs: int = 0, k_split: int = 0, w_ld: Optional[int] = None, w_bs: int = 0,
+         w_batched: bool = False, bias: Optional[torch.Tensor] = None, scale: float = 1.0, scale_cols: int = 0,
+         out0_bs: int = 0, out1: Optional[torch.Tensor] = None, out1_ld: int = 0, out1_bs: int = 0,
+         aux0: Optional[torch.Tensor] = None, aux1: Optional[torch.Tensor] = None, aux_ld: int = 0,
+         rows_per_seq: int = 0, out_tbc: bool = False, n_seqs: int = 0, out_row_offset: int = 0,
+         vt: Optional[torch.Tensor] = None, vt_col0: int = 0, vt_rows: int = 0, vt_ld: int = 0,
+         pos: Optional[torch.Tensor] = None, seq_lens: Optional[torch.Tensor] = None, block_n: int = 0) -> None:
+    """acc = A @ W^T with a fused epilogue; see ``mm_gemm_args`` in include/mms2ut_b200.h."""
+    if a0.dtype != w.dtype or (a1 is not None and a1.dtype != w.dtype):
+        raise TypeError("A and W must share the 16-bit operand dtype")
+    for t in (bias, aux0, aux1, pos):
+        if t is not None and t.dtype != torch.float32:
+            raise TypeError("bias/aux/pos must be float32")
+    if seq_lens is not None and seq_lens.dtype != torch.int32:
+        raise TypeError("seq_lens must be int32")
+    g = _lib.GemmArgs()
+    g.a0, g.a1, g.w = _ptr(a0), _ptr(a1), _ptr(w)
+    g.a0_ld, g.a0_bs, g.a1_ld, g.a1_bs = a0_ld, a0_bs, a1_ld, a1_bs
+    g.w_ld, g.w_bs = (k if w_ld is None else w_ld), w_bs
+    g.rows, g.batches, g.n, g.k, g.k_split, g.w_batched = rows, batches, n, k, k_split, int(w_batched)
+    g.dtype, g.mode, g.block_n = dtype_code(w.dtype), mode, block_n
+    g.bias, g.scale, g.scale_cols = _ptr(bias), scale, scale_cols
+    g.out0, g.out0_ld, g.out0_bs = _ptr(out0), out0_ld, out0_bs
+    g.out1, g.out1_ld, g.out1_bs = _ptr(out1), out1_ld, out1_bs
+    g.aux0, g.aux1, g.aux_ld = _ptr(aux0), _ptr(aux1), aux_ld
+    g.rows_per_seq, g.out_tbc, g.n_seqs, g.out_row_offset = rows_per_seq, int(out_tbc), n_seqs, out_row_offset
+    g.vt, g.vt_col0, g.vt_rows, g.vt_ld = _ptr(vt), vt_col0, vt_rows, vt_ld
+    g.pos, g.seq_lens = _ptr(pos), _ptr(seq_lens)
+    lib = _lib.load()
+    _lib.check(lib.mm_gemm(C.byref(g), _stream()), "mm_gemm")
+    _count()
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_op: Optional[torch.Tensor] = None,
+              out_f32: Optional[torch.Tensor] = None, eps: float = 1e-5) -> None:
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    dim = x.shape[-1]
+    rows = x.numel() // dim
+    assert gamma.dtype == torch.float32 and gamma.numel() == dim and beta.numel() == dim
+    dt = dtype_code(out_op.dtype) if out_op is not None else 0
+    lib = _lib.load()
+    _lib.check(lib.mm_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), rows, dim, _ptr(out_op), _ptr(out_f32), dt, eps,
+                                _stream()), "mm_layernorm")
+    _count()
+
+
+def self_attention(qk: torch.Tensor, vt: torch.Tensor, seq_lens_: torch.Tensor, batch: int, seq: int, heads: int,
+                   out: torch.Tensor) -> None:
+    assert qk.dtype == vt.dtype == out.dtype and seq_lens_.dtype == torch.int32
+    lib = _lib.load()
+    _lib.check(lib.mm_self_attention(_ptr(qk), qk.stride(-2), _ptr(vt), vt.stride(-2), _ptr(seq_lens_), batch, seq,
+                                     heads, _ptr(out), out.stride(-2), dtype_code(qk.dtype), _stream()),
+               "mm_self_attention")
+    _count()
+
+
+def softmax_rows(scores: torch.Tensor, ld_in: int, rows: int, n_keys: int, probs: torch.Tensor, ld_out: int,
+                 key_mask: Optional[torch.Tensor] = None, rows_per_seq: int = 0) -> None:
+    assert scores.dtype == torch.float32
+    if key_mask is not None:
+        assert key_mask.dtype == torch.uint8 and key_mask.is_contiguous()
+    lib = _lib.load()
+    _lib.check(lib.mm_softmax_rows(_ptr(scores), ld_in, rows, n_keys, _ptr(key_mask), rows_per_seq, _ptr(probs),
+                                   ld_out, dtype_code(probs.dtype), _stream()), "mm_softmax_rows")
+    _count()
+
+
+def convert(x: torch.Tensor, out: torch.Tensor) -> None:
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous() and out.numel() == x.numel()
+    lib = _lib.load()
+    _lib.check(lib.mm_convert_f32(_ptr(x), _ptr(out), x.numel(), dtype_code(out.dtype), _stream()), "mm_convert_f32")
+    _count()

@@ -1,0 +1,137 @@
+"""Row-wise kernels (LayerNorm, softmax, convert, CMVN, fbank) and the self-attention core vs references."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dim", [256, 512, 768, 1024])
+def test_layernorm(cuda, dim):
+    from mm_s2ut_b200 import kernels as K
+
+    g = torch.Generator().manual_seed(dim)
+    x = (torch.randn(1003, dim, generator=g) * 3 + 0.7).to(cuda)
+    gamma, beta = torch.randn(dim, generator=g).to(cuda), torch.randn(dim, generator=g).to(cuda)
+    o16 = torch.zeros(1003, dim, dtype=torch.bfloat16, device=cuda)
+    o32 = torch.zeros(1003, dim, dtype=torch.float32, device=cuda)
+    K.layernorm(x, gamma, beta, out_op=o16, out_f32=o32)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x, (dim,), gamma, beta, 1e-5)
+    assert (o32 - ref).abs().max().item() < 2e-5
+    assert (o16.float() - ref).abs().max().item() < 4e-2
+
+
+def test_softmax_rows(cuda):
+    from mm_s2ut_b200 import kernels as K
+
+    g = torch.Generator().manual_seed(5)
+    B, T, Tk, Tkp = 3, 50, 577, 584
+    S = (torch.randn(B * T, Tkp, generator=g) * 4).to(cuda)
+    mask = (torch.rand(B, Tk, generator=g) < 0.2).to(torch.uint8).to(cuda)
+    P = torch.full((B * T, Tkp), 3.0, dtype=torch.bfloat16, device=cuda)
+    K.softmax_rows(S, Tkp, B * T, Tk, P, Tkp, key_mask=mask, rows_per_seq=T)
+    torch.cuda.synchronize()
+    s = S[:, :Tk].view(B, T, Tk).masked_fill(mask.bool()[:, None, :], float("-inf"))
+    ref = torch.softmax(s, -1).view(B * T, Tk)
+    assert (P[:, :Tk].float() - ref).abs().max().item() < 2e-3
+    assert P[:, Tk:].abs().max().item() == 0
+
+
+def test_convert(cuda):
+    from mm_s2ut_b200 import kernels as K
+
+    x = torch.randn(12345, device=cuda)[:12343].clone()
+    for dt in (torch.bfloat16, torch.float16):
+        o = torch.zeros(12343, dtype=dt, device=cuda)
+        K.convert(x, o)
+        torch.cuda.synchronize()
+        assert torch.equal(o, x.to(dt))
+
+
+def _fbank_batch(cfg, n, dur, zero_utt=None):
+    from mm_s2ut_b200 import synth
+
+    wavs, lens = synth.synth_batch(cfg, n, dur, ragged=True, zero_utt=zero_utt)
+    return wavs, synth.pad_waveforms(wavs)
+
+
+def test_fbank_vs_torchaudio(cuda):
+    """fbank (pre-CMVN) within 1e-4 relative of torchaudio.compliance.kaldi.fbank in fp32 (north_star tolerance)."""
+    from mm_s2ut_b200 import kernels as K
+    from oracle import fbank as ofb
+
+    wavs, (wav, lens) = _fbank_batch(0, 6, 3.0, zero_utt=5)
+    wav, lens = wav.to(cuda), lens.to(cuda)
+    m = 1 + (wav.shape[1] - 400) // 160
+    feats = torch.zeros(len(wavs), m, 80, device=cuda)
+    stats = torch.zeros(len(wavs), (m + 31) // 32, 2, 80, dtype=torch.float64, device=cuda)
+    K.fbank(wav, lens, feats, stats, K.fbank_tables(cuda))
+    torch.cuda.synchronize()
+    for i, w in enumerate(wavs):
+        ref = torch.from_numpy(ofb.kaldi_fbank_ta(w))
+        got = feats[i, : ref.shape[0]].cpu()
+        rel = ((got - ref).abs() / ref.abs().clamp_min(1.0)).max().item()
+        assert rel < 1e-4, (i, rel)
+        # CMVN partial sums
+        nch = (ref.shape[0] + 31) // 32
+        s = stats[i, :nch].double().sum(0).cpu()
+        assert torch.allclose(s[0], ref.double().sum(0), rtol=1e-5, atol=1e-2)
+        assert torch.allclose(s[1], (ref.double() ** 2).sum(0), rtol=1e-5, atol=1e-1)
+
+
+def test_cmvn_apply(cuda):
+    from mm_s2ut_b200 import kernels as K
+    from oracle import fbank as ofb
+
+    wavs, (wav, lens) = _fbank_batch(0, 4, 2.0, zero_utt=3)
+    wav, lens = wav.to(cuda), lens.to(cuda)
+    B = len(wavs)
+    m = 1 + (wav.shape[1] - 400) // 160
+    feats = torch.zeros(B, m, 80, device=cuda)
+    stats = torch.zeros(B, (m + 31) // 32, 2, 80, dtype=torch.float64, device=cuda)
+    K.fbank(wav, lens, feats, stats, K.fbank_tables(cuda))
+    o32 = torch.full((B, m, 80), 9.0, device=cuda)
+    m_alloc = m + 4 + (m & 1)
+    o16 = torch.full((B, m_alloc, 80), 9.0, dtype=torch.bfloat16, device=cuda)
+    K.cmvn_apply(feats, stats, lens, True, o32, o16, op_row_offset=2)
+    torch.cuda.synchronize()
+    ref, rl = ofb.features_from_waveforms(wavs)
+    ref = torch.from_numpy(ref)
+    assert ref.shape[1] == m
+    got = o32.cpu()
+    # the all-zero utterance has var floor 1e-10 -> rstd 1e5: compare it separately (values are exactly 0 there)
+    assert (got[:3] - ref[:3]).abs().max().item() < 2e-3
+    assert got[3].abs().max().item() < 1e-2 and ref[3].abs().max().item() < 1e-2
+    assert (o16[:, 2: 2 + m].float().cpu() - got).abs().max().item() < 4e-2
+    assert o16[:, :2].abs().max().item() == 0 and o16[:, 2 + m:].abs().max().item() == 0
+    for i in range(B):
+        assert got[i, int(rl[i]):].abs().max().item() == 0 if rl[i] < m else True
+
+
+@pytest.mark.parametrize("T,lens", [(250, [250, 173, 1]), (125, [125, 80]), (300, [300, 257, 40]), (750, [750, 512])])
+def test_self_attention(cuda, T, lens):
+    from mm_s2ut_b200 import kernels as K
+
+    dt, H, hd = torch.bfloat16, 4, 64
+    B, d = len(lens), 4 * 64
+    Tp = (T + 7) // 8 * 8
+    g = torch.Generator().manual_seed(T)
+    q = torch.randn(B, T, H, hd, generator=g) * 0.8
+    k = torch.randn(B, T, H, hd, generator=g)
+    v = torch.randn(B, T, H, hd, generator=g)
+    qk = torch.cat([q.reshape(B * T, d), k.reshape(B * T, d)], 1).to(cuda).to(dt).contiguous()
+    vt = torch.zeros(B, d, Tp, dtype=dt, device=cuda)
+    vt[:, :, :T] = v.reshape(B, T, d).transpose(1, 2).to(cuda).to(dt)
+    sl = torch.tensor(lens, dtype=torch.int32, device=cuda)
+    out = torch.zeros(B * T, d, dtype=dt, device=cuda)
+    K.self_attention(qk, vt, sl, B, T, H, out)
+    torch.cuda.synchronize()
+    qf = qk[:, :d].float().view(B, T, H, hd).permute(0, 2, 1, 3)
+    kf = qk[:, d:].float().view(B, T, H, hd).permute(0, 2, 1, 3)
+    vf = vt[:, :, :T].float().view(B, H, hd, T).permute(0, 1, 3, 2)
+    s = qf @ kf.transpose(-1, -2)
+    mask = torch.arange(T, device=cuda)[None, :] >= sl[:, None]
+    s = s.masked_fill(mask[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ vf).permute(0, 2, 1, 3).reshape(B * T, d)
+    assert (out.float() - ref).abs().max().item() < 3e-2
