@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""Headline benchmark: audio-seconds encoded per second, raw waveform -> fused encoder states.
+
+Workload = BASELINE.json configs[1]: mm_s2ut_transformer base (12 enc layers, d=512, ffn 2048, 8 heads),
+bf16 operands / fp32 residual stream, encoder + SelectiveAttention fusion forward, batch 64 x 10 s of
+synthetic 16 kHz audio + N(0,1) 577x768 image features, per GPU (weak scaling: every rank encodes its own
+shard of utterances; the forward path has no collective).
+
+  python bench.py [--gpus N --steps K --warmup W]            our arm (CUDA kernels through the C ABI)
+  python bench.py --impl reference [...]                     the reference's CPU path (oracle port) on host cores
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what each key means.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+BATCH, DUR_S, SR = 64, 10.0, 16000
+IMG_TOKENS, IMG_DIM = 577, 768
+PRESET = "base"
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def algorithmic_flops(B: int, m: int, d: int, ffn: int, L: int, Tk: int, Dk: int, conv_mid: int = 1024) -> float:
+    """conv + L encoder layers + fusion, per batch."""
+    T1 = (m - 1) // 2 + 1
+    T2 = (T1 - 1) // 2 + 1
+    conv = 2 * 5 * 80 * conv_mid * T1 + 2 * 5 * (conv_mid // 2) * (2 * d) * T2
+    layer = T2 * (8 * d * d + 4 * d * ffn) + 4 * T2 * T2 * d
+    fusion = T2 * 8 * d * d + 4 * Tk * Dk * d + 4 * T2 * Tk * d
+    return float(B) * (conv + L * layer + fusion)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU path (oracle port) on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference(sample_utts: int, steps: int, warmup: int, seed: int = 0):
+    import torch
+
+    import mm_s2ut_b200  # noqa: F401
+    from mm_s2ut_b200 import synth
+    from mm_s2ut_b200.config import DEFAULT_YAML, load_mm_config, make_args
+    from mm_s2ut_b200.models.mm_s2s_transformer import MM_S2STransformerEncoder
+    from oracle import fbank as ofb, fusion as ofu
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(seed)
+    args = make_args(PRESET, multimodal_translation_config_yaml=str(DEFAULT_YAML))
+    enc = MM_S2STransformerEncoder(args, build_unused_projections=False).eval()
+    sd = {k: v.detach() for k, v in enc.state_dict().items()}
+    cfg = load_mm_config(DEFAULT_YAML)
+    wavs, _ = synth.synth_batch(1, sample_utts, DUR_S, ragged=False)
+    imgs = synth.synth_images(1, sample_utts, IMG_TOKENS, IMG_DIM)
+
+    def step():
+        feats, flens = ofb.features_from_waveforms(wavs)          # torchaudio fbank + numpy CMVN, per utterance
+        with torch.no_grad():
+            return ofu.mm_encoder_forward(sd, cfg, torch.from_numpy(feats), torch.from_numpy(flens), [imgs], [None],
+                                          args.encoder_attention_heads)
+
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    sec = sum(ts) / len(ts)
+    return {"value": sample_utts * DUR_S / sec, "unit": "audio-s/s", "cores": cores, "kind": "port",
+            "sample": f"{sample_utts} x {DUR_S:.0f} s utterances of the same workload (base model, fp32 PyTorch CPU "
+                      f"oracle: torchaudio fbank + numpy CMVN + restated fairseq encoder + fusion), mean of {steps} "
+                      f"steps after {warmup} warm-up", "ms_per_step": sec * 1e3}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 8
+    r = cpu_reference(sample, max(1, a.steps), max(1, min(a.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": "audio-sec encoded/sec (fbank->fused enc)", "value": r["value"],
+        "unit": "audio-s/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a.gpus),
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    return {"workload": f"BASELINE configs[1]: mm_s2ut_transformer base (12 enc layers, d=512, ffn=2048, 8 heads) "
+                        f"encoder + SelectiveAttention fusion forward, batch {BATCH} x {DUR_S:.0f} s 16 kHz + "
+                        f"{IMG_TOKENS}x{IMG_DIM} image features per GPU",
+            "batch_per_gpu": BATCH, "utt_seconds": DUR_S, "image_feats": [IMG_TOKENS, IMG_DIM],
+            "sharding": f"utterance batches over {n} GPU(s), no forward collective",
+            "l2_policy": "inputs_larger_than_L2 (41 MB waveform + 113 MB image features per step, two input sets alternated)"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    import mm_s2ut_b200  # noqa: F401
+    from mm_s2ut_b200 import kernels as K, synth
+    from mm_s2ut_b200.config import DEFAULT_YAML, make_args
+    from mm_s2ut_b200.graph import GraphedEncoder
+    from mm_s2ut_b200.models.mm_s2s_transformer import MM_S2STransformerEncoder
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(0)
+    args = make_args(PRESET, multimodal_translation_config_yaml=str(DEFAULT_YAML))
+    enc = MM_S2STransformerEncoder(args, build_unused_projections=False).eval().to(dev)
+    n_samples = int(DUR_S * SR)
+    m = 1 + (n_samples - 400) // 160
+
+    # two input sets per rank, pinned on the host (e2e) and resident on the device (kernel-only number)
+    host_sets = []
+    for s in range(2):
+        g = torch.Generator().manual_seed(100 + 10 * rank + s)
+        n_real = 8                                   # 8 distinct synthetic utterances tiled to the batch
+        wavs, _ = synth.synth_batch(1 + rank, n_real, DUR_S, ragged=False)
+        wav = torch.stack([torch.from_numpy(wavs[i % n_real]) for i in range(BATCH)])
+        wav = wav * (0.5 + 0.5 * torch.rand(BATCH, 1, generator=g))          # distinct gains
+        img = torch.randn(BATCH, IMG_TOKENS, IMG_DIM, generator=g)
+        lens = torch.full((BATCH,), n_samples, dtype=torch.int64)
+        host_sets.append((wav.pin_memory(), lens.pin_memory(), img.pin_memory()))
+    dev_sets = [(w.to(dev), l.to(dev), i.to(dev)) for w, l, i in host_sets]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_sets[0])
+
+    ge = [GraphedEncoder(enc, BATCH, n_samples, [(IMG_TOKENS, IMG_DIM)]) for _ in range(2)]
+    n0 = K.launch_count
+    for j, g in enumerate(ge):
+        g.load_inputs(*dev_sets[j][:2], [dev_sets[j][2]])
+        g.capture()
+    torch.cuda.synchronize()
+    launches_per_fwd = (K.launch_count - n0) // (2 * 3)        # 2 warm-up + 1 capture pass per graph
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- kernel-only: inputs already resident in HBM, graph replay ----------------
+    for i in range(a.warmup):
+        ge[i & 1].replay()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        ge[i & 1].replay()
+    e1.record()
+    barrier()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    audio_s = BATCH * DUR_S * a.steps * world
+    value = audio_s / (ms_dev * 1e-3)
+
+    # ---------------- e2e: host (pinned) inputs -> H2D -> forward -> D2H of the result checksum ----------------
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+    result_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+
+    def e2e_steps(n):
+        for j in range(2):
+            free[j].record(main)
+        for i in range(n):
+            j = i & 1
+            with torch.cuda.stream(copy_stream):          # H2D of step i overlaps the forward of step i-1
+                copy_stream.wait_event(free[j])
+                ge[j].load_inputs(host_sets[j][0], host_sets[j][1], [host_sets[j][2]])
+                ready[j].record(copy_stream)
+            main.wait_event(ready[j])
+            out = ge[j].replay()
+            chk = out["encoder_out"][0].sum()             # the step's result read back by the host
+            result_host[j:j + 1].copy_(chk.reshape(1), non_blocking=True)
+            free[j].record(main)
+        main.synchronize()
+
+    e2e_steps(max(2, a.warmup))
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps(a.steps)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_value = audio_s / (e2e_ms * 1e-3)
+
+    line = None
+    if rank == 0:
+        # ---------------- instrumented pass: per-kernel device time (CUDA events on the launch stream) ------------
+        K.timing = []
+        reps = max(3, min(a.steps, 10))
+        for i in range(reps):
+            enc(dev_sets[i & 1][0], dev_sets[i & 1][1], None, None, None, imgs_list=[dev_sets[i & 1][2]],
+                img_masks_list=[None])
+        torch.cuda.synchronize()
+        fam = {}
+        for name, s0, s1, work in K.timing:
+            f = fam.setdefault(name, [0.0, 0.0, 0])
+            f[0] += s0.elapsed_time(s1)
+            f[1] += work
+            f[2] += 1
+        K.timing = None
+        total_ms = sum(v[0] for v in fam.values())
+        peaks, peak_src = _peaks()
+        kern = {}
+        for name, (ms, work, cnt) in sorted(fam.items(), key=lambda kv: -kv[1][0]):
+            tensor = name.startswith("gemm") or name == "self_attention"
+            ach = work / (ms * 1e-3) / (1e12 if tensor else 1e9) if ms > 0 else 0.0
+            kern[name] = {"launches_per_step": cnt // reps, "ms_per_step": ms / reps, "share": ms / total_ms,
+                          "achieved": ach, "unit": "TFLOP/s" if tensor else "GB/s"}
+        gemm_ms = sum(v[0] for k, v in fam.items() if k.startswith("gemm"))
+        gemm_fl = sum(v[1] for k, v in fam.items() if k.startswith("gemm"))
+        gemm_n = sum(v[2] for k, v in fam.items() if k.startswith("gemm"))
+        ach = gemm_fl / (gemm_ms * 1e-3) / 1e12
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        roofline = {
+            "bound": "tensor", "kernel": "gemm_kernel (tcgen05/TMA persistent GEMM, all epilogues)",
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
+            "launches_per_step": gemm_n // reps, "share_of_step": gemm_ms / total_ms,
+            "how": "algorithmic FLOPs (2*M*N*K per launch) / CUDA-event time per launch, eager instrumented pass",
+        }
+        fb = kern.get("fbank")
+        if fb:
+            roofline["hbm_kernels"] = {k: {"achieved_gbs": kern[k]["achieved"],
+                                           "frac": kern[k]["achieved"] / float(peaks["hbm_gbs"])}
+                                       for k in ("fbank", "cmvn_stats", "cmvn_apply", "layernorm", "softmax_rows")
+                                       if k in kern}
+        flops = algorithmic_flops(BATCH, m, args.encoder_embed_dim, args.encoder_ffn_embed_dim, args.encoder_layers,
+                                  IMG_TOKENS, IMG_DIM)
+        cpu = None
+        if world == 1 and not a.no_cpu_baseline:
+            r = cpu_reference(4, 2, 1)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line = {
+            "metric": "audio-sec encoded/sec (fbank->fused enc)", "value": value, "unit": "audio-s/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_dev / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(world),
+            "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / a.steps,
+                    "how": "pinned host waveform + fp32 image features -> cudaMemcpyAsync on a copy stream "
+                           "(double-buffered, overlapping the previous step) -> graph replay -> checksum D2H"},
+            "gpu_launches": launches_per_fwd * a.steps,
+            "launches_per_step": launches_per_fwd,
+            "clocks": clocks,
+            "roofline": roofline,
+            "tensor_flops_per_step": flops,
+            "step_tensor_frac_of_peak": flops / (ms_dev / a.steps * 1e-3) / 1e12 / peak,
+            "kernels": kern,
+            "cpu_baseline": cpu,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -32,21 +32,25 @@ const char* mm_last_error(void);
  * applied at mm_s2ut/data/speech_to_speech_dataset.py:271-273, plus fairseq _collate_frames' zero padding.
  *
  * mm_fbank_f32: wav [B, wav_stride] fp32 (already x 2^15), n_samples [B] int64 ->
- *   feats [B, max_frames, 80] fp32 raw log-mel (rows >= the utterance's frame count are NOT written),
- *   stats [B, n_chunks, 2, 80] fp64 per-chunk (sum, sum of squares), n_chunks = ceil(max_frames / 32).
- * mm_cmvn_apply: normalises with the utterance statistics and zero-pads; writes either/both of
+ *   feats [B, max_frames, 80] fp32 raw log-mel (rows >= the utterance's frame count are NOT written).
+ * mm_cmvn_stats: per-utterance, per-bin (mean, std) -> mean_std [B, 2, 80] fp32, computed with the reference's
+ *   own arithmetic (numpy fp32, sequential accumulation over frames, var = E[x^2] - mean^2 floored at 1e-10),
+ *   so that its rounding behaviour -- part of the reference's result -- is reproduced.
+ * mm_cmvn_apply: y = (x - mean) / std and zero padding; writes either/both of
  *   out_f32 [B, max_frames, 80] and out_op [B, op_frames, 80] (16-bit operand type; row r of the utterance
- *   lands at row r + op_row_offset; all other rows are written as 0).  With stats == NULL the input is
+ *   lands at row r + op_row_offset; all other rows are written as 0).  With mean_std == NULL the input is
  *   taken as already normalised features (the reference's 3-D src_tokens contract) and only copied/padded.
  * --------------------------------------------------------------------------------------------- */
 int mm_fbank_f32(const float* wav, const int64_t* n_samples, int32_t batch, int64_t wav_stride, float* feats,
-                 int32_t max_frames, double* stats, const float* tables, void* stream);
+                 int32_t max_frames, const float* tables, void* stream);
 /* Constant tables of the fbank kernel (povey window, FFT twiddles, sparse mel bank): the caller allocates
  * mm_fbank_table_floats() floats on the host, fills them with mm_fbank_build_tables() and keeps a device copy
  * that it passes to mm_fbank_f32 (the library itself owns no device memory). */
 int mm_fbank_table_floats(void);
 int mm_fbank_build_tables(float* host_out);
-int mm_cmvn_apply(const float* feats, const double* stats, const int64_t* n_samples_or_frames,
+int mm_cmvn_stats(const float* feats, const int64_t* n_samples_or_frames, int32_t lengths_are_samples,
+                  int32_t batch, int32_t max_frames, float* mean_std, void* stream);
+int mm_cmvn_apply(const float* feats, const float* mean_std, const int64_t* n_samples_or_frames,
                   int32_t lengths_are_samples, int32_t batch, int32_t max_frames, float* out_f32, void* out_op,
                   int32_t op_frames, int32_t op_row_offset, int32_t dtype, void* stream);
 /* out_lens[b] = conv-subsampled length of utterance b (int32): frames -> floor((L-1)/2+1) n_layers times;

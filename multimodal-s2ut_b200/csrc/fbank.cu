@@ -82,7 +82,6 @@ constexpr int FB_SMEM_BYTES = FB_SMEM_FLOATS * 4;
 __global__ void __launch_bounds__(FB_THREADS) fbank_kernel(const float* __restrict__ wav,
                                                            const long long* __restrict__ n_samples, long long wav_stride,
                                                            float* __restrict__ feats, int max_frames,
-                                                           double* __restrict__ stats, int n_chunks,
                                                            const float* __restrict__ tables) {
   extern __shared__ __align__(16) float fsm[];
   float* s_wave = fsm;
@@ -133,8 +132,6 @@ __global__ void __launch_bounds__(FB_THREADS) fbank_kernel(const float* __restri
   float* xbuf = zbuf + FB_ZBUF;
   float2* z2 = reinterpret_cast<float2*>(zbuf);
   float2* x2 = reinterpret_cast<float2*>(xbuf);
-
-  double acc1[5] = {0., 0., 0., 0., 0.}, acc2[5] = {0., 0., 0., 0., 0.};  // fp64: a constant utterance must give mean == x exactly
 
   for (int fl = hw; fl < nf_here; fl += FB_HW) {
     const float* x = s_wave + fl * FB_SHIFT;
@@ -204,27 +201,51 @@ __global__ void __launch_bounds__(FB_THREADS) fbank_kernel(const float* __restri
       for (int i = 0; i < cnt; ++i) e = fmaf(s_melw[off + i], xbuf[k0 + i], e);
       const float v = logf(fmaxf(e, 1.1920928955078125e-07f));
       orow[m] = v;
-      acc1[j] += (double)v;
-      acc2[j] += (double)v * (double)v;
     }
     __syncwarp(hmask);
   }
+}
 
-  // ---- per-chunk CMVN partial statistics: fixed-order reduction over the 16 half-warps ----
-  __syncthreads();
-  double* red = reinterpret_cast<double*>(s_work);  // [16][160]
+// Utterance CMVN statistics with the REFERENCE's arithmetic: fairseq UtteranceCMVN runs numpy fp32
+// `x.mean(0)` and `(x**2).sum(0)`, which accumulate sequentially over frames in fp32; the raw-moment
+// variance E[x^2]-mean^2 cancels catastrophically, so its rounding noise (up to a few 1e-2 after
+// normalisation in low-variance bins) is part of the reference's result.  One thread per (utterance, bin)
+// replays that exact order (loads are batched 8 deep and independent; only the adds are a chain).
+__global__ void __launch_bounds__(96) cmvn_stats_kernel(const float* __restrict__ feats,
+                                                        const long long* __restrict__ lens, int lengths_are_samples,
+                                                        int max_frames, float* __restrict__ mean_std) {
+  const int b = blockIdx.x, bin = threadIdx.x;
+  if (bin >= FB_BINS) return;
+  const long long n = lens[b];
+  int nfr = lengths_are_samples ? (n < FB_WIN ? 0 : (int)(1 + (n - FB_WIN) / FB_SHIFT)) : (int)n;
+  nfr = min(nfr, max_frames);
+  const float* x = feats + (long long)b * max_frames * FB_BINS + bin;
+  float s = 0.f, q = 0.f;
+  int i = 0;
+  for (; i + 8 <= nfr; i += 8) {
+    float v[8];
 #pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    red[hw * 160 + l + 16 * j] = acc1[j];
-    red[hw * 160 + 80 + l + 16 * j] = acc2[j];
-  }
-  __syncthreads();
-  if (threadIdx.x < 160) {
-    double t = 0.;
+    for (int j = 0; j < 8; ++j) v[j] = __ldg(x + (long long)(i + j) * FB_BINS);
 #pragma unroll
-    for (int h = 0; h < FB_HW; ++h) t += red[h * 160 + threadIdx.x];
-    stats[((long long)b * n_chunks + chunk) * 160 + threadIdx.x] = t;
+    for (int j = 0; j < 8; ++j) {
+      s = __fadd_rn(s, v[j]);
+      q = __fadd_rn(q, __fmul_rn(v[j], v[j]));
+    }
   }
+  for (; i < nfr; ++i) {
+    const float v = __ldg(x + (long long)i * FB_BINS);
+    s = __fadd_rn(s, v);
+    q = __fadd_rn(q, __fmul_rn(v, v));
+  }
+  float mean = 0.f, sd = 1.f;
+  if (nfr > 0) {
+    const float T = (float)nfr;
+    mean = __fdiv_rn(s, T);
+    const float var = __fsub_rn(__fdiv_rn(q, T), __fmul_rn(mean, mean));
+    sd = __fsqrt_rn(fmaxf(var, 1e-10f));
+  }
+  mean_std[(long long)b * 160 + bin] = mean;
+  mean_std[(long long)b * 160 + 80 + bin] = sd;
 }
 
 }  // namespace mm
@@ -288,8 +309,8 @@ extern "C" int mm_fbank_build_tables(float* out) {
 }
 
 extern "C" int mm_fbank_f32(const float* wav, const int64_t* n_samples, int32_t batch, int64_t wav_stride, float* feats,
-                            int32_t max_frames, double* stats, const float* tables, void* stream) {
-  if (!wav || !n_samples || !feats || !stats || !tables) return bad_arg("fbank: null pointer");
+                            int32_t max_frames, const float* tables, void* stream) {
+  if (!wav || !n_samples || !feats || !tables) return bad_arg("fbank: null pointer");
   if (batch <= 0 || max_frames <= 0) return 0;
   static bool attr_set = false;
   if (!attr_set) {
@@ -300,7 +321,17 @@ extern "C" int mm_fbank_f32(const float* wav, const int64_t* n_samples, int32_t 
   const int n_chunks = (max_frames + FB_FRAMES_PER_CTA - 1) / FB_FRAMES_PER_CTA;
   dim3 grid(n_chunks, batch);
   fbank_kernel<<<grid, FB_THREADS, FB_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
-      wav, reinterpret_cast<const long long*>(n_samples), wav_stride, feats, max_frames, stats, n_chunks, tables);
+      wav, reinterpret_cast<const long long*>(n_samples), wav_stride, feats, max_frames, tables);
   MM_CHECK_LAUNCH("fbank_kernel launch");
+  return 0;
+}
+
+extern "C" int mm_cmvn_stats(const float* feats, const int64_t* lens, int32_t lengths_are_samples, int32_t batch,
+                             int32_t max_frames, float* mean_std, void* stream) {
+  if (!feats || !lens || !mean_std) return bad_arg("cmvn_stats: null pointer");
+  if (batch <= 0 || max_frames <= 0) return 0;
+  cmvn_stats_kernel<<<batch, 96, 0, static_cast<cudaStream_t>(stream)>>>(
+      feats, reinterpret_cast<const long long*>(lens), lengths_are_samples, max_frames, mean_std);
+  MM_CHECK_LAUNCH("cmvn_stats_kernel launch");
   return 0;
 }

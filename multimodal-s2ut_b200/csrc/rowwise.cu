@@ -135,42 +135,37 @@ __global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ 
 
 // ---------------------------------------------------------------------------------------------------
 // CMVN apply + zero padding.  One thread per 4 mel bins of one (utterance, output row).
-// stats: [B, n_chunks, 2, 80] partial (sum, sumsq) from the fbank kernel, reduced here in a fixed order
-// (deterministic) by the first warps of each block into shared memory.
+// mean_std: [B, 2, 80] fp32 (mean, std) from cmvn_stats_kernel; y = (x - mean) / std with IEEE fp32
+// subtract / divide, i.e. exactly numpy's np.subtract / np.divide in fairseq UtteranceCMVN.
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int frames_of(long long n, int lengths_are_samples) {
   if (!lengths_are_samples) return (int)n;
   return n < 400 ? 0 : (int)(1 + (n - 400) / 160);
 }
 
+__device__ __forceinline__ float4 cmvn4(const float4 v, const float* s_mean, const float* s_std, int c4) {
+  float4 y;
+  y.x = __fdiv_rn(__fsub_rn(v.x, s_mean[4 * c4 + 0]), s_std[4 * c4 + 0]);
+  y.y = __fdiv_rn(__fsub_rn(v.y, s_mean[4 * c4 + 1]), s_std[4 * c4 + 1]);
+  y.z = __fdiv_rn(__fsub_rn(v.z, s_mean[4 * c4 + 2]), s_std[4 * c4 + 2]);
+  y.w = __fdiv_rn(__fsub_rn(v.w, s_mean[4 * c4 + 3]), s_std[4 * c4 + 3]);
+  return y;
+}
+
 template <typename OpT>
 __global__ void __launch_bounds__(256) cmvn_apply_kernel(const float* __restrict__ feats,
-                                                          const double* __restrict__ stats,
+                                                          const float* __restrict__ mean_std,
                                                           const long long* __restrict__ lens, int lengths_are_samples,
-                                                          int max_frames, int n_chunks, float* __restrict__ out_f32,
+                                                          int max_frames, float* __restrict__ out_f32,
                                                           OpT* __restrict__ out_op, int op_frames, int op_row_offset,
                                                           int rows_per_block) {
-  __shared__ float s_mean[80], s_rstd[80];
+  __shared__ float s_mean[80], s_std[80];
   const int b = blockIdx.y;
   const int nfr = min(frames_of(lens[b], lengths_are_samples), max_frames);
+  const bool ident = mean_std == nullptr;   // input already normalised: copy / pad only
   if (threadIdx.x < 80) {
-    float mean = 0.f, rstd = 1.f;
-    if (stats != nullptr && nfr > 0) {
-      double s = 0.0, q = 0.0;
-      const double* st = stats + (long long)b * n_chunks * 160;
-      const int used = (nfr + 31) / 32;
-      for (int c = 0; c < used; ++c) {
-        s += st[c * 160 + threadIdx.x];
-        q += st[c * 160 + 80 + threadIdx.x];
-      }
-      // fairseq UtteranceCMVN: var = E[x^2] - mean^2 (population), floor 1e-10
-      const float m = (float)(s / nfr);
-      const float var = (float)(q / nfr) - m * m;
-      mean = m;
-      rstd = 1.0f / sqrtf(fmaxf(var, 1e-10f));
-    }
-    s_mean[threadIdx.x] = mean;
-    s_rstd[threadIdx.x] = rstd;
+    s_mean[threadIdx.x] = ident ? 0.f : mean_std[(long long)b * 160 + threadIdx.x];
+    s_std[threadIdx.x] = ident ? 1.f : mean_std[(long long)b * 160 + 80 + threadIdx.x];
   }
   __syncthreads();
   // rows handled by this block: [row0, row0 + rows_per_block) of the LARGER of the two output extents
@@ -184,11 +179,8 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const float* __restrict
     if (out_f32 != nullptr && row < max_frames) {
       float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
       if (row < nfr) {
-        const float4 v = __ldcs(reinterpret_cast<const float4*>(feats + ((long long)b * max_frames + row) * 80) + c4);
-        y.x = (v.x - s_mean[4 * c4 + 0]) * s_rstd[4 * c4 + 0];
-        y.y = (v.y - s_mean[4 * c4 + 1]) * s_rstd[4 * c4 + 1];
-        y.z = (v.z - s_mean[4 * c4 + 2]) * s_rstd[4 * c4 + 2];
-        y.w = (v.w - s_mean[4 * c4 + 3]) * s_rstd[4 * c4 + 3];
+        const float4 v = __ldg(reinterpret_cast<const float4*>(feats + ((long long)b * max_frames + row) * 80) + c4);
+        y = ident ? v : cmvn4(v, s_mean, s_std, c4);
       }
       reinterpret_cast<float4*>(out_f32 + ((long long)b * max_frames + row) * 80)[c4] = y;
     }
@@ -197,10 +189,7 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const float* __restrict
       float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
       if (fr >= 0 && fr < nfr) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(feats + ((long long)b * max_frames + fr) * 80) + c4);
-        y.x = (v.x - s_mean[4 * c4 + 0]) * s_rstd[4 * c4 + 0];
-        y.y = (v.y - s_mean[4 * c4 + 1]) * s_rstd[4 * c4 + 1];
-        y.z = (v.z - s_mean[4 * c4 + 2]) * s_rstd[4 * c4 + 2];
-        y.w = (v.w - s_mean[4 * c4 + 3]) * s_rstd[4 * c4 + 3];
+        y = ident ? v : cmvn4(v, s_mean, s_std, c4);
       }
       uint2 pk;
       pk.x = OpTraits<OpT>::pack2(y.x, y.y);
@@ -267,9 +256,9 @@ extern "C" int mm_convert_f32(const float* x, void* out, int64_t n, int32_t dtyp
   return 0;
 }
 
-extern "C" int mm_cmvn_apply(const float* feats, const double* stats, const int64_t* lens, int32_t lengths_are_samples,
-                             int32_t batch, int32_t max_frames, float* out_f32, void* out_op, int32_t op_frames,
-                             int32_t op_row_offset, int32_t dtype, void* stream) {
+extern "C" int mm_cmvn_apply(const float* feats, const float* mean_std, const int64_t* lens,
+                             int32_t lengths_are_samples, int32_t batch, int32_t max_frames, float* out_f32,
+                             void* out_op, int32_t op_frames, int32_t op_row_offset, int32_t dtype, void* stream) {
   if (!feats || !lens || (!out_f32 && !out_op)) return bad_arg("cmvn: null pointer");
   if (batch <= 0 || max_frames <= 0) return 0;
   if (!out_op) op_frames = 0;
@@ -277,14 +266,13 @@ extern "C" int mm_cmvn_apply(const float* feats, const double* stats, const int6
   const int rows_per_block = 64;
   const int total_rows = op_frames > max_frames ? op_frames : max_frames;
   dim3 grid((total_rows + rows_per_block - 1) / rows_per_block, batch);
-  const int n_chunks = (max_frames + 31) / 32;
   const long long* l = reinterpret_cast<const long long*>(lens);
   if (dtype == MM_DTYPE_F16)
-    cmvn_apply_kernel<__half><<<grid, 256, 0, s>>>(feats, stats, l, lengths_are_samples, max_frames, n_chunks,
-                                                   out_f32, reinterpret_cast<__half*>(out_op), op_frames,
-                                                   op_row_offset, rows_per_block);
+    cmvn_apply_kernel<__half><<<grid, 256, 0, s>>>(feats, mean_std, l, lengths_are_samples, max_frames, out_f32,
+                                                   reinterpret_cast<__half*>(out_op), op_frames, op_row_offset,
+                                                   rows_per_block);
   else
-    cmvn_apply_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(feats, stats, l, lengths_are_samples, max_frames, n_chunks,
+    cmvn_apply_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(feats, mean_std, l, lengths_are_samples, max_frames,
                                                           out_f32, reinterpret_cast<__nv_bfloat16*>(out_op),
                                                           op_frames, op_row_offset, rows_per_block);
   MM_CHECK_LAUNCH("cmvn_apply_kernel launch");

@@ -172,8 +172,9 @@ class EncoderEngine:
             if m <= 0:
                 raise ValueError("waveform shorter than one 25 ms frame")
             raw = self.buf("fbank_raw", (B, m, 80), torch.float32)
-            stats = self.buf("fbank_stats", (B, (m + 31) // 32, 2, 80), torch.float64)
-            K.fbank(wav, lens, raw, stats, self.fbank_tables)
+            stats = self.buf("cmvn_mean_std", (B, 2, 80), torch.float32)
+            K.fbank(wav, lens, raw, self.fbank_tables)
+            K.cmvn_stats(raw, lens, True, stats)
             is_samples = True
         elif src_tokens.dim() == 3 and src_tokens.shape[2] == 80:
             raw, stats, m, is_samples = src_tokens.float().contiguous(), None, src_tokens.shape[1], False

@@ -13,6 +13,7 @@ import torch
 from . import _lib
 
 EPI_OP, EPI_RELU_OP, EPI_RESID_F32, EPI_GLU_OP, EPI_GLU_POS_F32, EPI_F32_OP, EPI_GATE, EPI_F32 = range(8)
+EPI_NAMES = ["op", "relu_op", "resid_f32", "glu_op", "glu_pos_f32", "f32_op", "gate", "f32"]
 _DT = {torch.bfloat16: 0, torch.float16: 1}
 
 # Launch counter: bench.py reports how many of OUR kernels ran inside the timed region.
@@ -38,9 +39,31 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return t.data_ptr()
 
 
-def _count(n: int = 1) -> None:
-    global launch_count
-    launch_count += n
+# Optional per-launch device timing (bench.py's instrumented pass): when `timing` is a list, every wrapper
+# brackets its launch with CUDA events on the launching stream and appends (name, start, end, work) to it.
+timing = None
+
+
+class _Launch:
+    __slots__ = ("name", "work", "e0")
+
+    def __init__(self, name: str, work: float = 0.0):
+        self.name, self.work, self.e0 = name, work, None
+
+    def __enter__(self):
+        if timing is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        global launch_count
+        launch_count += 1
+        if timing is not None and exc[0] is None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            timing.append((self.name, self.e0, e1, self.work))
+        return False
 
 
 def fbank_tables(device) -> torch.Tensor:
@@ -51,23 +74,32 @@ def fbank_tables(device) -> torch.Tensor:
     return host.to(device)
 
 
-def fbank(wav: torch.Tensor, n_samples: torch.Tensor, feats: torch.Tensor, stats: torch.Tensor,
-          tables: torch.Tensor) -> None:
-    """wav [B, N] fp32 (x 2**15), n_samples [B] int64 -> feats [B, m, 80] raw log-mel, stats [B, ceil(m/32), 2, 80]."""
+def fbank(wav: torch.Tensor, n_samples: torch.Tensor, feats: torch.Tensor, tables: torch.Tensor) -> None:
+    """wav [B, N] fp32 (x 2**15), n_samples [B] int64 -> feats [B, m, 80] raw log-mel (valid frames only)."""
     assert wav.dtype == torch.float32 and wav.dim() == 2 and wav.stride(1) == 1
     assert n_samples.dtype == torch.int64 and feats.dtype == torch.float32 and feats.is_contiguous()
     B, m = feats.shape[0], feats.shape[1]
-    assert feats.shape[2] == 80 and stats.dtype == torch.float64 and stats.is_contiguous()
-    assert stats.numel() >= B * ((m + 31) // 32) * 160
+    assert feats.shape[2] == 80
     lib = _lib.load()
-    _lib.check(lib.mm_fbank_f32(_ptr(wav), _ptr(n_samples), B, wav.stride(0), _ptr(feats), m, _ptr(stats),
-                                _ptr(tables), _stream()), "mm_fbank_f32")
-    _count()
+    with _Launch("fbank", float(4 * wav.numel() + 4 * feats.numel())):   # algorithmic bytes
+        _lib.check(lib.mm_fbank_f32(_ptr(wav), _ptr(n_samples), B, wav.stride(0), _ptr(feats), m, _ptr(tables),
+                                    _stream()), "mm_fbank_f32")
+
+
+def cmvn_stats(feats: torch.Tensor, lens: torch.Tensor, lengths_are_samples: bool, mean_std: torch.Tensor) -> None:
+    """Per-utterance (mean, std) [B, 2, 80] with the reference's sequential fp32 arithmetic."""
+    assert feats.dtype == torch.float32 and feats.is_contiguous() and feats.shape[2] == 80
+    assert mean_std.dtype == torch.float32 and mean_std.is_contiguous() and mean_std.numel() == feats.shape[0] * 160
+    lib = _lib.load()
+    with _Launch("cmvn_stats", float(4 * feats.numel())):
+        _lib.check(lib.mm_cmvn_stats(_ptr(feats), _ptr(lens), int(lengths_are_samples), feats.shape[0],
+                                     feats.shape[1], _ptr(mean_std), _stream()), "mm_cmvn_stats")
 
 
 def cmvn_apply(feats: torch.Tensor, stats: Optional[torch.Tensor], lens: torch.Tensor, lengths_are_samples: bool,
                out_f32: Optional[torch.Tensor], out_op: Optional[torch.Tensor], op_row_offset: int = 0) -> None:
     assert feats.dtype == torch.float32 and feats.is_contiguous() and feats.shape[2] == 80
+    assert stats is None or stats.dtype == torch.float32
     B, m = feats.shape[0], feats.shape[1]
     op_frames, dt = 0, 0
     if out_op is not None:
@@ -76,17 +108,20 @@ def cmvn_apply(feats: torch.Tensor, stats: Optional[torch.Tensor], lens: torch.T
     if out_f32 is not None:
         assert out_f32.is_contiguous() and out_f32.shape == feats.shape
     lib = _lib.load()
-    _lib.check(lib.mm_cmvn_apply(_ptr(feats), _ptr(stats), _ptr(lens), int(lengths_are_samples), B, m, _ptr(out_f32),
-                                 _ptr(out_op), op_frames, op_row_offset, dt, _stream()), "mm_cmvn_apply")
-    _count()
+    work = 4.0 * feats.numel() + (4.0 * out_f32.numel() if out_f32 is not None else 0.0) + \
+        (2.0 * out_op.numel() if out_op is not None else 0.0)
+    with _Launch("cmvn_apply", work):
+        _lib.check(lib.mm_cmvn_apply(_ptr(feats), _ptr(stats), _ptr(lens), int(lengths_are_samples), B, m,
+                                     _ptr(out_f32), _ptr(out_op), op_frames, op_row_offset, dt, _stream()),
+                   "mm_cmvn_apply")
 
 
 def seq_lens(lens: torch.Tensor, lengths_are_samples: bool, n_layers: int, out: torch.Tensor) -> None:
     assert lens.dtype == torch.int64 and out.dtype == torch.int32
     lib = _lib.load()
-    _lib.check(lib.mm_seq_lens(_ptr(lens), int(lengths_are_samples), lens.numel(), n_layers, _ptr(out), _stream()),
-               "mm_seq_lens")
-    _count()
+    with _Launch("seq_lens"):
+        _lib.check(lib.mm_seq_lens(_ptr(lens), int(lengths_are_samples), lens.numel(), n_layers, _ptr(out),
+                                   _stream()), "mm_seq_lens")
 
 
 def gemm(*, a0: torch.Tensor, w: torch.Tensor, rows: int, n: int, k: int, mode: int, out0: torch.Tensor,
@@ -120,8 +155,8 @@ def gemm(*, a0: torch.Tensor, w: torch.Tensor, rows: int, n: int, k: int, mode: 
     g.vt, g.vt_col0, g.vt_rows, g.vt_ld = _ptr(vt), vt_col0, vt_rows, vt_ld
     g.pos, g.seq_lens = _ptr(pos), _ptr(seq_lens)
     lib = _lib.load()
-    _lib.check(lib.mm_gemm(C.byref(g), _stream()), "mm_gemm")
-    _count()
+    with _Launch(f"gemm[{EPI_NAMES[mode]}]", 2.0 * rows * batches * n * k):          # algorithmic FLOPs
+        _lib.check(lib.mm_gemm(C.byref(g), _stream()), "mm_gemm")
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_op: Optional[torch.Tensor] = None,
@@ -132,19 +167,21 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_op: 
     assert gamma.dtype == torch.float32 and gamma.numel() == dim and beta.numel() == dim
     dt = dtype_code(out_op.dtype) if out_op is not None else 0
     lib = _lib.load()
-    _lib.check(lib.mm_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), rows, dim, _ptr(out_op), _ptr(out_f32), dt, eps,
-                                _stream()), "mm_layernorm")
-    _count()
+    work = 4.0 * x.numel() + (2.0 * x.numel() if out_op is not None else 0.0) + \
+        (4.0 * x.numel() if out_f32 is not None else 0.0)
+    with _Launch("layernorm", work):
+        _lib.check(lib.mm_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), rows, dim, _ptr(out_op), _ptr(out_f32), dt,
+                                    eps, _stream()), "mm_layernorm")
 
 
 def self_attention(qk: torch.Tensor, vt: torch.Tensor, seq_lens_: torch.Tensor, batch: int, seq: int, heads: int,
                    out: torch.Tensor) -> None:
     assert qk.dtype == vt.dtype == out.dtype and seq_lens_.dtype == torch.int32
     lib = _lib.load()
-    _lib.check(lib.mm_self_attention(_ptr(qk), qk.stride(-2), _ptr(vt), vt.stride(-2), _ptr(seq_lens_), batch, seq,
-                                     heads, _ptr(out), out.stride(-2), dtype_code(qk.dtype), _stream()),
-               "mm_self_attention")
-    _count()
+    with _Launch("self_attention", 4.0 * batch * seq * seq * heads * 64):
+        _lib.check(lib.mm_self_attention(_ptr(qk), qk.stride(-2), _ptr(vt), vt.stride(-2), _ptr(seq_lens_), batch,
+                                         seq, heads, _ptr(out), out.stride(-2), dtype_code(qk.dtype), _stream()),
+                   "mm_self_attention")
 
 
 def softmax_rows(scores: torch.Tensor, ld_in: int, rows: int, n_keys: int, probs: torch.Tensor, ld_out: int,
@@ -153,13 +190,14 @@ def softmax_rows(scores: torch.Tensor, ld_in: int, rows: int, n_keys: int, probs
     if key_mask is not None:
         assert key_mask.dtype == torch.uint8 and key_mask.is_contiguous()
     lib = _lib.load()
-    _lib.check(lib.mm_softmax_rows(_ptr(scores), ld_in, rows, n_keys, _ptr(key_mask), rows_per_seq, _ptr(probs),
-                                   ld_out, dtype_code(probs.dtype), _stream()), "mm_softmax_rows")
-    _count()
+    with _Launch("softmax_rows", 4.0 * rows * n_keys + 2.0 * rows * ld_out):
+        _lib.check(lib.mm_softmax_rows(_ptr(scores), ld_in, rows, n_keys, _ptr(key_mask), rows_per_seq, _ptr(probs),
+                                       ld_out, dtype_code(probs.dtype), _stream()), "mm_softmax_rows")
 
 
 def convert(x: torch.Tensor, out: torch.Tensor) -> None:
     assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous() and out.numel() == x.numel()
     lib = _lib.load()
-    _lib.check(lib.mm_convert_f32(_ptr(x), _ptr(out), x.numel(), dtype_code(out.dtype), _stream()), "mm_convert_f32")
-    _count()
+    with _Launch("convert", 6.0 * x.numel()):
+        _lib.check(lib.mm_convert_f32(_ptr(x), _ptr(out), x.numel(), dtype_code(out.dtype), _stream()),
+                   "mm_convert_f32")

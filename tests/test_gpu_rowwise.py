@@ -65,48 +65,65 @@ def test_fbank_vs_torchaudio(cuda):
     wav, lens = wav.to(cuda), lens.to(cuda)
     m = 1 + (wav.shape[1] - 400) // 160
     feats = torch.zeros(len(wavs), m, 80, device=cuda)
-    stats = torch.zeros(len(wavs), (m + 31) // 32, 2, 80, dtype=torch.float64, device=cuda)
-    K.fbank(wav, lens, feats, stats, K.fbank_tables(cuda))
+    K.fbank(wav, lens, feats, K.fbank_tables(cuda))
     torch.cuda.synchronize()
     for i, w in enumerate(wavs):
         ref = torch.from_numpy(ofb.kaldi_fbank_ta(w))
         got = feats[i, : ref.shape[0]].cpu()
         rel = ((got - ref).abs() / ref.abs().clamp_min(1.0)).max().item()
         assert rel < 1e-4, (i, rel)
-        # CMVN partial sums
-        nch = (ref.shape[0] + 31) // 32
-        s = stats[i, :nch].double().sum(0).cpu()
-        assert torch.allclose(s[0], ref.double().sum(0), rtol=1e-5, atol=1e-2)
-        assert torch.allclose(s[1], (ref.double() ** 2).sum(0), rtol=1e-5, atol=1e-1)
+    # silence: every bin sits on the log(eps) floor, bit-identical to torch's value
+    assert torch.equal(feats[5, : 1 + (len(wavs[5]) - 400) // 160].cpu(), torch.from_numpy(ofb.kaldi_fbank_ta(wavs[5])))
 
 
-def test_cmvn_apply(cuda):
+def test_cmvn_matches_reference_arithmetic(cuda):
+    """CMVN statistics replay numpy's sequential fp32 accumulation: given the SAME fbank values the normalised
+    features are bit-identical to fairseq UtteranceCMVN (incl. the all-zero utterance's floor behaviour)."""
     from mm_s2ut_b200 import kernels as K
     from oracle import fbank as ofb
 
     wavs, (wav, lens) = _fbank_batch(0, 4, 2.0, zero_utt=3)
+    B = len(wavs)
+    raw = [ofb.kaldi_fbank_ta(w) for w in wavs]                      # reference fbank values as input
+    ref, rl = ofb.collate_frames([ofb.utterance_cmvn(r) for r in raw])
+    m = ref.shape[1]
+    feats = torch.zeros(B, m, 80)
+    for i, r in enumerate(raw):
+        feats[i, : r.shape[0]] = torch.from_numpy(r)
+    feats, flens = feats.to(cuda), torch.from_numpy(rl).to(cuda)
+    ms = torch.zeros(B, 2, 80, device=cuda)
+    K.cmvn_stats(feats, flens, False, ms)
+    o32 = torch.full((B, m, 80), 9.0, device=cuda)
+    m_alloc = m + 4 + (m & 1)
+    o16 = torch.full((B, m_alloc, 80), 9.0, dtype=torch.bfloat16, device=cuda)
+    K.cmvn_apply(feats, ms, flens, False, o32, o16, op_row_offset=2)
+    torch.cuda.synchronize()
+    got = o32.cpu()
+    assert torch.equal(got, torch.from_numpy(ref))
+    assert torch.equal(o16[:, 2: 2 + m].cpu(), got.to(torch.bfloat16))
+    assert o16[:, :2].abs().max().item() == 0 and o16[:, 2 + m:].abs().max().item() == 0
+
+
+def test_fbank_cmvn_end_to_end(cuda):
+    """Device fbank -> stats -> apply vs torchaudio + numpy CMVN (differences: fbank's 1e-6-level rounding only)."""
+    from mm_s2ut_b200 import kernels as K
+    from oracle import fbank as ofb
+
+    wavs, (wav, lens) = _fbank_batch(0, 4, 2.0)
     wav, lens = wav.to(cuda), lens.to(cuda)
     B = len(wavs)
     m = 1 + (wav.shape[1] - 400) // 160
     feats = torch.zeros(B, m, 80, device=cuda)
-    stats = torch.zeros(B, (m + 31) // 32, 2, 80, dtype=torch.float64, device=cuda)
-    K.fbank(wav, lens, feats, stats, K.fbank_tables(cuda))
+    K.fbank(wav, lens, feats, K.fbank_tables(cuda))
+    ms = torch.zeros(B, 2, 80, device=cuda)
+    K.cmvn_stats(feats, lens, True, ms)
     o32 = torch.full((B, m, 80), 9.0, device=cuda)
-    m_alloc = m + 4 + (m & 1)
-    o16 = torch.full((B, m_alloc, 80), 9.0, dtype=torch.bfloat16, device=cuda)
-    K.cmvn_apply(feats, stats, lens, True, o32, o16, op_row_offset=2)
+    K.cmvn_apply(feats, ms, lens, True, o32, None)
     torch.cuda.synchronize()
     ref, rl = ofb.features_from_waveforms(wavs)
-    ref = torch.from_numpy(ref)
     assert ref.shape[1] == m
-    got = o32.cpu()
-    # the all-zero utterance has var floor 1e-10 -> rstd 1e5: compare it separately (values are exactly 0 there)
-    assert (got[:3] - ref[:3]).abs().max().item() < 2e-3
-    assert got[3].abs().max().item() < 1e-2 and ref[3].abs().max().item() < 1e-2
-    assert (o16[:, 2: 2 + m].float().cpu() - got).abs().max().item() < 4e-2
-    assert o16[:, :2].abs().max().item() == 0 and o16[:, 2 + m:].abs().max().item() == 0
-    for i in range(B):
-        assert got[i, int(rl[i]):].abs().max().item() == 0 if rl[i] < m else True
+    # the raw-moment variance amplifies the 1e-6-level fbank differences in low-variance bins
+    assert (o32.cpu() - torch.from_numpy(ref)).abs().max().item() < 3e-2
 
 
 @pytest.mark.parametrize("T,lens", [(250, [250, 173, 1]), (125, [125, 80]), (300, [300, 257, 40]), (750, [750, 512])])
