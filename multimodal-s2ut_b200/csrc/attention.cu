@@ -226,6 +226,285 @@ static int launch_attn(const CUtensorMap& mqk, const CUtensorMap& mvt, const int
   return 0;
 }
 
+// ===================================================================================================
+// Persistent, warp-specialised variant for T <= 256 (utterances up to ~10 s: one key chunk per query tile).
+//
+// One CTA per SM walks a list of (utterance, head, 128-query tile) items.  Roles (320 threads):
+//   warp 8      TMA producer: Q / K / V^T of item i into a 2-stage shared-memory ring
+//   warp 9      MMA issuer:   S_i = Q K^T (SS) as soon as stage i has landed and TMEM region (i & 1) is free;
+//                             O_i = P_i V (TS: P is read from TMEM) once softmax group (i & 1) has published P_i
+//   warps 0-3   softmax group 0 (even items)      } each thread owns one query row = one TMEM lane:
+//   warps 4-7   softmax group 1 (odd items)       } row max, exp2, row sum, P written back to TMEM as packed
+//                                                   16-bit over the already-consumed S columns, then O / l -> HBM
+// The two groups ping-pong: while one waits for its MMAs the other keeps the MUFU/ALU pipes busy, and the
+// producer runs one item ahead, so TMA latency, tensor work and softmax overlap instead of serialising.
+// TMEM: region g = columns [256 g, 256 g + 256): S (fp32, 256 keys) -> P in [0,128) -> O in [128,192).
+// ===================================================================================================
+constexpr int PA_STAGE_BYTES = AT_Q_BYTES + AT_K_BYTES + AT_V_BYTES;   // 80 KB
+constexpr int PA_SMEM_BYTES = 2 * PA_STAGE_BYTES + 256 + 1024;
+constexpr int PA_THREADS = 320;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// exp2(s * log2e - m * log2e) for 32 scores -> 16 packed 16-bit pairs; returns the row-sum contribution
+template <typename OpT, bool MASKED>
+__device__ __forceinline__ float softmax_chunk(const uint32_t (&r)[32], uint32_t (&pk)[16], float mb, int valid) {
+  constexpr float L2E = 1.4426950408889634f;
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; k += 2) {
+    float p0 = ex2_approx(fmaf(__uint_as_float(r[k]), L2E, -mb));
+    float p1 = ex2_approx(fmaf(__uint_as_float(r[k + 1]), L2E, -mb));
+    if (MASKED) {
+      p0 = k < valid ? p0 : 0.f;
+      p1 = k + 1 < valid ? p1 : 0.f;
+    }
+    pk[k >> 1] = OpTraits<OpT>::pack2(p0, p1);
+    l0 += p0;
+    l1 += p1;
+  }
+  return l0 + l1;
+}
+template <bool MASKED>
+__device__ __forceinline__ float max_chunk(const uint32_t (&r)[32], int valid) {
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 32; k += 4) {
+    const float a = (!MASKED || k + 0 < valid) ? __uint_as_float(r[k + 0]) : -INFINITY;
+    const float b = (!MASKED || k + 1 < valid) ? __uint_as_float(r[k + 1]) : -INFINITY;
+    const float c = (!MASKED || k + 2 < valid) ? __uint_as_float(r[k + 2]) : -INFINITY;
+    const float d = (!MASKED || k + 3 < valid) ? __uint_as_float(r[k + 3]) : -INFINITY;
+    m0 = fmaxf(m0, a), m1 = fmaxf(m1, b), m2 = fmaxf(m2, c), m3 = fmaxf(m3, d);
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+template <typename OpT>
+__global__ void __launch_bounds__(PA_THREADS, 1)
+self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant__ CUtensorMap mapVT,
+                           const int* __restrict__ seq_lens, int T, int d_model, int H, int nqt, int n_items,
+                           OpT* __restrict__ out, long long out_ld) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * PA_STAGE_BYTES);
+  uint64_t* qk_full = bars;         // [2] TMA (Q, K) -> MMA
+  uint64_t* qk_empty = bars + 2;    // [2] S MMA done -> TMA
+  uint64_t* v_full = bars + 4;      // [2] TMA (V^T) -> MMA
+  uint64_t* v_empty = bars + 6;     // [2] PV MMA done -> TMA
+  uint64_t* s_full = bars + 8;      // [2] S MMA done -> softmax group
+  uint64_t* p_full = bars + 10;     // [2] softmax group (4 warps) -> MMA
+  uint64_t* o_full = bars + 12;     // [2] PV MMA done -> softmax group
+  uint64_t* reg_free = bars + 14;   // [2] softmax group has read O -> MMA may overwrite the TMEM region
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_local = (int)blockIdx.x < n_items ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  constexpr float L2E = 1.4426950408889634f;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&mapQK);
+    tma_prefetch_desc(&mapVT);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qk_full[i], 1);
+      mbar_init(&qk_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&reg_free[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      for (int i = 0; i < n_local; ++i) {
+        const int item = blockIdx.x + i * gridDim.x;
+        const int qt = item % nqt, h = (item / nqt) % H, b = item / (nqt * H);
+        const int s = i & 1, u = i >> 1;
+        uint8_t* sQ = smem + s * PA_STAGE_BYTES;
+        uint8_t* sK = sQ + AT_Q_BYTES;
+        uint8_t* sV = sK + AT_K_BYTES;
+        mbar_wait(&qk_empty[s], (u & 1) ^ 1);
+        mbar_expect_tx(&qk_full[s], AT_Q_BYTES + AT_K_BYTES);
+        tma_load_3d(sQ, &mapQK, &qk_full[s], h * AT_HD, qt * AT_BM, b);
+        tma_load_3d(sK, &mapQK, &qk_full[s], d_model + h * AT_HD, 0, b);
+        tma_load_3d(sK + AT_K_BYTES / 2, &mapQK, &qk_full[s], d_model + h * AT_HD, 128, b);
+        mbar_wait(&v_empty[s], (u & 1) ^ 1);
+        mbar_expect_tx(&v_full[s], AT_V_BYTES);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tma_load_3d(sV + j * (AT_V_BYTES / 4), &mapVT, &v_full[s], j * 64, h * AT_HD, b);
+      }
+    }
+  } else if (warp == 9) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc(AT_BM, AT_KC, OpTraits<OpT>::fmt);
+      constexpr uint32_t idesc_o = umma_idesc(AT_BM, AT_HD, OpTraits<OpT>::fmt);
+      auto issue_s = [&](int i) {
+        const int s = i & 1, u = i >> 1;
+        mbar_wait(&qk_full[s], u & 1);
+        mbar_wait(&reg_free[s], (u & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_sw128(smem_u32(smem + s * PA_STAGE_BYTES));
+        const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + s * PA_STAGE_BYTES + AT_Q_BYTES));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_f16(tmem_base + 256 * s, adesc + 2 * kk, bdesc + 2 * kk, idesc_s, kk != 0);
+        umma_commit(&s_full[s]);
+        umma_commit(&qk_empty[s]);
+      };
+      if (n_local > 0) issue_s(0);
+      for (int i = 0; i < n_local; ++i) {
+        if (i + 1 < n_local) issue_s(i + 1);
+        const int s = i & 1, u = i >> 1;
+        mbar_wait(&v_full[s], u & 1);
+        mbar_wait(&p_full[s], u & 1);
+        tc_fence_after();
+        const uint64_t vdesc = umma_desc_sw128(smem_u32(smem + s * PA_STAGE_BYTES + AT_Q_BYTES + AT_K_BYTES));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)   // 16 keys per step: 8 packed P columns, +32 B of the V^T row
+            umma_f16_ts(tmem_base + 256 * s + 128, tmem_base + 256 * s + 8 * (4 * j + kk),
+                        vdesc + (uint64_t)((j * (AT_V_BYTES / 4)) >> 4) + 2 * kk, idesc_o, (j | kk) != 0);
+        }
+        umma_commit(&o_full[s]);
+        umma_commit(&v_empty[s]);
+      }
+    }
+  } else {
+    // ---------------- softmax + epilogue groups ----------------
+    const int g = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t t_row = tmem_base + 256 * g + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    for (int i = g; i < n_local; i += 2) {
+      const int item = blockIdx.x + i * gridDim.x;
+      const int qt = item % nqt, h = (item / nqt) % H, b = item / (nqt * H);
+      const int u = i >> 1;
+      const int len = max(1, min(seq_lens[b], T));
+      const int nch = (len + 31) >> 5;        // chunks holding at least one valid key
+      const int nfull = len >> 5;             // chunks that need no masking
+      const int rem = len & 31;               // valid keys in chunk `nfull` when rem > 0
+      mbar_wait(&s_full[g], u & 1);
+      tc_fence_after();
+      uint32_t ra[32], rb[32];
+      // ---- sweep 1: row maximum (two TMEM loads in flight) ----
+      float m = -INFINITY;
+#pragma unroll 1
+      for (int cc = 0; cc < nch; cc += 2) {
+        tmem_ld32(t_row + cc * 32, ra);
+        if (cc + 1 < nch) tmem_ld32(t_row + (cc + 1) * 32, rb);
+        tmem_ld_wait();
+        m = fmaxf(m, cc < nfull ? max_chunk<false>(ra, 32) : max_chunk<true>(ra, rem));
+        if (cc + 1 < nch) m = fmaxf(m, cc + 1 < nfull ? max_chunk<false>(rb, 32) : max_chunk<true>(rb, rem));
+      }
+      const float mb = m * L2E;
+      // ---- sweep 2: probabilities (next chunk prefetched while the current one goes through MUFU) ----
+      float l = 0.f;
+      tmem_ld32(t_row, ra);
+      tmem_ld_wait();
+#pragma unroll 1
+      for (int cc = 0; cc < AT_KC / 32; cc += 2) {
+        uint32_t pk[16];
+        if (cc + 1 < nch) tmem_ld32(t_row + (cc + 1) * 32, rb);
+        if (cc < nch) {
+          l += cc < nfull ? softmax_chunk<OpT, false>(ra, pk, mb, 32) : softmax_chunk<OpT, true>(ra, pk, mb, rem);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) pk[k] = 0u;
+        }
+        tmem_ld_wait();
+        tmem_st16(t_row + 16 * cc, pk);       // P over S columns that have already been consumed
+        if (cc + 2 < nch) tmem_ld32(t_row + (cc + 2) * 32, ra);
+        if (cc + 1 < nch) {
+          l += cc + 1 < nfull ? softmax_chunk<OpT, false>(rb, pk, mb, 32) : softmax_chunk<OpT, true>(rb, pk, mb, rem);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) pk[k] = 0u;
+        }
+        tmem_ld_wait();
+        tmem_st16(t_row + 16 * (cc + 1), pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+
+      mbar_wait(&o_full[g], u & 1);
+      tc_fence_after();
+      {
+        const int t = qt * AT_BM + row;
+        const float inv = 1.0f / l;
+        tmem_ld32(t_row + 128, ra);
+        tmem_ld32(t_row + 160, rb);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&reg_free[g]);   // O is in registers: the TMEM region may be reused
+        if (t < T) {
+          uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * T + t) * out_ld + h * AT_HD);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint4 q;
+            q.x = OpTraits<OpT>::pack2(__uint_as_float(ra[8 * k + 0]) * inv, __uint_as_float(ra[8 * k + 1]) * inv);
+            q.y = OpTraits<OpT>::pack2(__uint_as_float(ra[8 * k + 2]) * inv, __uint_as_float(ra[8 * k + 3]) * inv);
+            q.z = OpTraits<OpT>::pack2(__uint_as_float(ra[8 * k + 4]) * inv, __uint_as_float(ra[8 * k + 5]) * inv);
+            q.w = OpTraits<OpT>::pack2(__uint_as_float(ra[8 * k + 6]) * inv, __uint_as_float(ra[8 * k + 7]) * inv);
+            dst[k] = q;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint4 q;
+            q.x = OpTraits<OpT>::pack2(__uint_as_float(rb[8 * k + 0]) * inv, __uint_as_float(rb[8 * k + 1]) * inv);
+            q.y = OpTraits<OpT>::pack2(__uint_as_float(rb[8 * k + 2]) * inv, __uint_as_float(rb[8 * k + 3]) * inv);
+            q.z = OpTraits<OpT>::pack2(__uint_as_float(rb[8 * k + 4]) * inv, __uint_as_float(rb[8 * k + 5]) * inv);
+            q.w = OpTraits<OpT>::pack2(__uint_as_float(rb[8 * k + 6]) * inv, __uint_as_float(rb[8 * k + 7]) * inv);
+            dst[4 + k] = q;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <typename OpT>
+static int launch_attn_t256(const CUtensorMap& mqk, const CUtensorMap& mvt, const int* lens, int B, int T, int H, int d,
+                            void* out, long long out_ld, cudaStream_t s) {
+  auto kern = self_attention_t256_kernel<OpT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PA_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute(self_attention_t256)");
+    attr_set = true;
+  }
+  const int nqt = (T + AT_BM - 1) / AT_BM;
+  const int n_items = B * H * nqt;
+  const int grid = n_items < kNumSMs ? n_items : kNumSMs;
+  kern<<<grid, PA_THREADS, PA_SMEM_BYTES, s>>>(mqk, mvt, lens, T, d, H, nqt, n_items, reinterpret_cast<OpT*>(out),
+                                               out_ld);
+  MM_CHECK_LAUNCH("self_attention_t256_kernel launch");
+  return 0;
+}
+
 }  // namespace mm
 
 using namespace mm;
@@ -247,6 +526,9 @@ extern "C" int mm_self_attention(const void* qk, int64_t qk_ld, const void* vt, 
                     (uint64_t)d * vt_ld, 64);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (seq <= AT_KC)   // single key chunk: persistent warp-specialised kernel
+    return f16 ? launch_attn_t256<__half>(mqk, mvt, seq_lens, batch, seq, heads, d, out, out_ld, s)
+               : launch_attn_t256<__nv_bfloat16>(mqk, mvt, seq_lens, batch, seq, heads, d, out, out_ld, s);
   return f16 ? launch_attn<__half>(mqk, mvt, seq_lens, batch, seq, heads, d, out, out_ld, s)
              : launch_attn<__nv_bfloat16>(mqk, mvt, seq_lens, batch, seq, heads, d, out, out_ld, s);
 }

@@ -1,18 +1,23 @@
-// Persistent warp-specialised tcgen05 GEMM for sm_100a with fused epilogues.
+// Persistent warp-specialised tcgen05 GEMM for sm_100a with fused epilogues, CTA-pair (cta_group::2) version.
 //
 //   acc[r, c] = sum_k A[r, k] * W[c, k]          A, W 16-bit K-major; fp32 accumulators in TMEM
 //
-// Roles (256 threads, one CTA per SM, grid = min(tiles, 148)):
-//   warp 0    TMA producer: A (128 x 64) and W (BN x 64) tiles, 128B swizzle, STAGES-deep mbarrier ring
-//   warp 1    MMA issuer: one thread issues tcgen05.mma (M=128, N=BN, K=16) x 4 per k-block;
-//             tcgen05.commit frees the smem stage / publishes the accumulator
-//   warp 2    TMEM allocator (2 accumulator stages of BN columns -> epilogue overlaps the next tile's MMAs)
-//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns, fused bias / scale / ReLU / GLU / residual /
-//             positional add / sigmoid gate, vectorised global stores
-// The A operand is addressed through a 3-D tensor map (K, rows, batch) whose row stride may be smaller
-// than K: that is how the stride-2 Conv1d layers of the subsampler run as GEMMs over a time-major buffer
-// without materialising im2col.  Rows / columns past the tensor bounds are zero-filled by TMA and masked
-// in the epilogue.
+// A cluster of two CTAs (one SM each) owns a 256 x 256 output tile: each CTA stages ITS 128 rows of A and
+// ITS 128 rows of W per k-block (32 KB instead of 48 KB per 128x256x64 MACs -> 1.5x less L2->SM traffic,
+// which is what bounds the K=512 GEMMs of the encoder), the leader CTA issues one tcgen05.mma
+// (M=256, N=256, K=16) per step for both, and each CTA drains its own 128 x 256 fp32 accumulator from TMEM.
+//
+// Roles per CTA (256 threads), grid = 2 * min(pair_tiles, 74):
+//   warp 0    TMA producer (cp.async.bulk.tensor ... cta_group::2: bytes are counted on the LEADER's mbarrier)
+//   warp 1    MMA issuer (leader CTA only); tcgen05.commit multicast frees the smem stage in BOTH CTAs and
+//             publishes the accumulator to BOTH epilogues
+//   warp 2    TMEM allocator (2 accumulator stages x 256 columns: epilogue overlaps the next tile's MMAs)
+//   warps 4-7 epilogue: tcgen05.ld -> bias / scale / ReLU / GLU / residual / position / gate -> 128-byte-swizzled
+//             16 KB slabs in shared memory -> TMA store (fully coalesced, clipped at the tensor bounds);
+//             residual / gate inputs are TMA-loaded into the same slabs two slabs ahead and updated in place.
+// The A operand is addressed through a 3-D tensor map (K, rows, batch) whose row stride may be smaller than
+// K: that is how the stride-2 Conv1d layers of the subsampler run as GEMMs over a time-major buffer without
+// materialising im2col.  Rows / columns past the tensor bounds are zero-filled by TMA on load.
 #include "common.cuh"
 #include "host.cuh"
 #include "../../include/mms2ut_b200.h"
@@ -21,18 +26,13 @@ namespace mm {
 
 struct GemmDev {
   int rows, batches, n, k, kb_split, num_kb, w_batched;
-  int m_tiles_per_batch, n_tiles, num_tiles;
+  int m_pairs_per_batch, n_tiles, num_tiles;
   const float* bias;
   float scale;
   int scale_cols;
-  void* out0;
-  long long out0_ld, out0_bs;
-  void* out1;
-  long long out1_ld, out1_bs;
-  const float* aux0;
   const float* aux1;
   long long aux_ld;
-  int rows_per_seq, out_tbc, n_seqs, out_row_offset;
+  int rows_per_seq, out_row_offset;
   void* vt;
   int vt_col0, vt_rows;
   long long vt_ld;
@@ -40,135 +40,131 @@ struct GemmDev {
   const int* seq_lens;
 };
 
-template <int BN>
 struct GemmCfg {
-  static constexpr int BM = 128, BK = 64;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int TMEM_COLS = 2 * BN;  // 256 or 512 (power of two)
+  static constexpr int BM = 128, BN = 256, BK = 64;
+  static constexpr int STAGES = 5;
+  static constexpr int NB = 4;                      // epilogue staging slabs
+  static constexpr int A_BYTES = BM * BK * 2;       // 16 KB
+  static constexpr int B_BYTES = (BN / 2) * BK * 2; // 16 KB: this CTA's half of the W tile
+  static constexpr int SLAB_BYTES = BM * 128;       // 128 rows x 128 B
+  static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int BIAS_BYTES = 2 * BN * 4;
-  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + BIAS_BYTES + 1024;  // +align slack
+  static constexpr int BIAS_BYTES = BN * 4;
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + NB * SLAB_BYTES + BAR_BYTES + BIAS_BYTES + 1024;
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
+// this thread's row inside a swizzled slab: 16-byte chunk c lives at position c ^ (row & 7)
+__device__ __forceinline__ uint4* slab_chunk(uint8_t* slab, int row, int c) {
+  return reinterpret_cast<uint4*>(slab + row * 128 + ((c ^ (row & 7)) << 4));
+}
 template <typename OpT>
-__device__ __forceinline__ void store_op(OpT* dst, const float* v, int nvalid) {
-  if (nvalid == 32) {
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
+__device__ __forceinline__ void slab_write_op32(uint8_t* slab, int row, int c0, const float* v) {  // 32 values = 4 chunks
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 q;
-      q.x = OpTraits<OpT>::pack2(v[8 * i + 0], v[8 * i + 1]);
-      q.y = OpTraits<OpT>::pack2(v[8 * i + 2], v[8 * i + 3]);
-      q.z = OpTraits<OpT>::pack2(v[8 * i + 4], v[8 * i + 5]);
-      q.w = OpTraits<OpT>::pack2(v[8 * i + 6], v[8 * i + 7]);
-      d4[i] = q;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i < nvalid) dst[i] = OpTraits<OpT>::cvt(v[i]);
+  for (int i = 0; i < 4; ++i) {
+    uint4 q;
+    q.x = OpTraits<OpT>::pack2(v[8 * i + 0], v[8 * i + 1]);
+    q.y = OpTraits<OpT>::pack2(v[8 * i + 2], v[8 * i + 3]);
+    q.z = OpTraits<OpT>::pack2(v[8 * i + 4], v[8 * i + 5]);
+    q.w = OpTraits<OpT>::pack2(v[8 * i + 6], v[8 * i + 7]);
+    *slab_chunk(slab, row, c0 + i) = q;
   }
 }
-__device__ __forceinline__ void store_f32(float* dst, const float* v, int nvalid) {
-  if (nvalid == 32) {
-    float4* d4 = reinterpret_cast<float4*>(dst);
+__device__ __forceinline__ void slab_write_f32(uint8_t* slab, int row, const float* v) {  // 32 floats = 8 chunks
 #pragma unroll
-    for (int i = 0; i < 8; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i < nvalid) dst[i] = v[i];
-  }
+  for (int i = 0; i < 8; ++i)
+    *slab_chunk(slab, row, i) = make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]),
+                                           __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
 }
-__device__ __forceinline__ void load_f32(const float* src, float* v, int nvalid) {
-  if (nvalid == 32) {
-    const float4* s4 = reinterpret_cast<const float4*>(src);
+__device__ __forceinline__ void slab_read_f32(uint8_t* slab, int row, float* v) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 q = s4[i];
-      v[4 * i] = q.x, v[4 * i + 1] = q.y, v[4 * i + 2] = q.z, v[4 * i + 3] = q.w;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = (i < nvalid) ? src[i] : 0.f;
+  for (int i = 0; i < 8; ++i) {
+    const uint4 q = *slab_chunk(slab, row, i);
+    v[4 * i] = __uint_as_float(q.x), v[4 * i + 1] = __uint_as_float(q.y);
+    v[4 * i + 2] = __uint_as_float(q.z), v[4 * i + 3] = __uint_as_float(q.w);
   }
 }
 
-template <int BN, int MODE, typename OpT>
+template <int MODE, typename OpT>
 __global__ void __launch_bounds__(256, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-            const __grid_constant__ CUtensorMap mapW, const GemmDev p) {
-  using Cfg = GemmCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
+            const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapOut0,
+            const __grid_constant__ CUtensorMap mapOut1, const __grid_constant__ CUtensorMap mapAux0,
+            const GemmDev p) {
+  using Cfg = GemmCfg;
+  constexpr int STAGES = Cfg::STAGES, NB = Cfg::NB, BN = Cfg::BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
-  uint64_t* full = bars;                 // [STAGES] TMA -> MMA
-  uint64_t* empty = bars + STAGES;       // [STAGES] MMA -> TMA
-  uint64_t* tfull = bars + 2 * STAGES;   // [2] MMA -> epilogue
-  uint64_t* tempty = tfull + 2;          // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);  // [2][BN]
+  uint8_t* sB = sA + STAGES * Cfg::A_BYTES;
+  uint8_t* sSlab = sB + STAGES * Cfg::B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sSlab + NB * Cfg::SLAB_BYTES);
+  uint64_t* full = bars;                   // [STAGES] TMA -> MMA   (leader's copy is the live one)
+  uint64_t* empty = full + STAGES;         // [STAGES] MMA -> TMA   (per CTA, multicast commit)
+  uint64_t* tfull = empty + STAGES;        // [2] MMA -> epilogue   (per CTA, multicast commit)
+  uint64_t* tempty = tfull + 2;            // [2] epilogues of both CTAs -> MMA (leader's copy)
+  uint64_t* auxfull = tempty + 2;          // [NB] TMA aux load -> epilogue (per CTA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(auxfull + NB);
+  float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);  // [BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pid = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapA0);
-    tma_prefetch_desc(&mapA1);
     tma_prefetch_desc(&mapW);
+    tma_prefetch_desc(&mapOut0);
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full[i], 1);
+      mbar_init(&full[i], 1);     // leader's expect_tx covers both CTAs' bytes; the peer only issues its TMA
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], 8);   // 4 epilogue warps x 2 CTAs
     }
+    for (int i = 0; i < NB; ++i) mbar_init(&auxfull[i], 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = pid; tile < p.num_tiles; tile += npairs) {
         const int n_tile = tile % p.n_tiles;
-        const int m_tile = tile / p.n_tiles;
-        const int bi = m_tile / p.m_tiles_per_batch;
-        const int row0 = (m_tile % p.m_tiles_per_batch) * Cfg::BM;
+        const int mp = tile / p.n_tiles;
+        const int bi = mp / p.m_pairs_per_batch;
+        const int row0 = (mp % p.m_pairs_per_batch) * (2 * Cfg::BM) + rank * Cfg::BM;
+        const int wrow0 = n_tile * BN + rank * (BN / 2);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
           if (kb < p.kb_split)
-            tma_load_3d(sA + stage * Cfg::A_BYTES, &mapA0, &full[stage], kb * Cfg::BK, row0, bi);
+            tma_load_3d_2sm(sA + stage * Cfg::A_BYTES, &mapA0, &full[stage], kb * Cfg::BK, row0, bi);
           else
-            tma_load_3d(sA + stage * Cfg::A_BYTES, &mapA1, &full[stage], (kb - p.kb_split) * Cfg::BK, row0, bi);
-          tma_load_3d(sB + stage * Cfg::B_BYTES, &mapW, &full[stage], kb * Cfg::BK, n_tile * BN,
-                      p.w_batched ? bi : 0);
+            tma_load_3d_2sm(sA + stage * Cfg::A_BYTES, &mapA1, &full[stage], (kb - p.kb_split) * Cfg::BK, row0, bi);
+          tma_load_3d_2sm(sB + stage * Cfg::B_BYTES, &mapW, &full[stage], kb * Cfg::BK, wrow0,
+                          p.w_batched ? bi : 0);
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(Cfg::BM, BN, OpTraits<OpT>::fmt);
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(2 * Cfg::BM, BN, OpTraits<OpT>::fmt);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       const int k_tail = p.k - (p.num_kb - 1) * Cfg::BK;          // valid K in the last k-block
       const int tail_steps = (k_tail + 15) >> 4;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = pid; tile < p.num_tiles; tile += npairs) {
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
@@ -179,161 +175,308 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
           const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
           const int steps = (kb == p.num_kb - 1) ? tail_steps : 4;
           for (int kk = 0; kk < steps; ++kk)  // +32 B per K=16 step inside the 128 B swizzle row
-            umma_f16(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb | kk) != 0);
-          umma_commit(&empty[stage]);
+            umma_f16_2sm(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb | kk) != 0);
+          umma_commit_2sm(&empty[stage], 3);
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
-        umma_commit(&tfull[as]);
+        umma_commit_2sm(&tfull[as], 3);
         if (++as == 2) as = 0, aphase ^= 1;
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
+    // ===================== epilogue (both CTAs) =====================
     const int ew = warp - 4;                 // == warp % 4 -> TMEM lane quadrant
     const int et = threadIdx.x - 128;        // 0..127
     const int lrow = ew * 32 + lane;         // accumulator row (TMEM lane) of this thread
-    uint32_t as = 0, aphase = 0, it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    const uint32_t tempty_leader = mapa_u32(&tempty[0], 0);
+    uint32_t as = 0, aphase = 0;
+    uint32_t slab_ctr = 0;                   // running slab counter -> staging buffer ring
+    uint32_t aux_phase = 0;                  // bit b = parity of auxfull[b]
+    constexpr bool kAux = (MODE == MM_EPI_RESID_F32 || MODE == MM_EPI_GATE);
+
+    for (int tile = pid; tile < p.num_tiles; tile += npairs) {
       const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
-      const int bi = m_tile / p.m_tiles_per_batch;
-      const int r = (m_tile % p.m_tiles_per_batch) * Cfg::BM + lrow;   // row within the batch
+      const int mp = tile / p.n_tiles;
+      const int bi = mp / p.m_pairs_per_batch;
+      const int row0 = (mp % p.m_pairs_per_batch) * (2 * Cfg::BM) + rank * Cfg::BM;
+      const int r = row0 + lrow;                                         // row within the batch
       const bool rvalid = r < p.rows;
-      int b = bi, t = r;
-      if (p.rows_per_seq > 0) b = r / p.rows_per_seq, t = r - b * p.rows_per_seq;
-      const long long arow = (p.rows_per_seq > 0) ? r : (long long)bi * p.rows + r;   // aux row
       const int col_tile = n_tile * BN;
 
-      float* sb = sBias + (it & 1) * BN;
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // every thread is done with the previous tile's bias
       for (int i = et; i < BN; i += 128) {
         const int c = col_tile + i;
-        sb[i] = (p.bias != nullptr && c < p.n) ? __ldg(p.bias + c) : 0.f;
+        sBias[i] = (p.bias != nullptr && c < p.n) ? __ldg(p.bias + c) : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if constexpr (kAux) {
+        if (et == 0) {   // residual / text slabs 0 and 1 of this tile: buffers last used 4 and 3 slabs ago
+          bulk_wait_read<2>();
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const uint32_t b = (slab_ctr + s) % NB;
+            if (col_tile + s * 32 < p.n) {
+              mbar_expect_tx(&auxfull[b], Cfg::SLAB_BYTES);
+              tma_load_3d(sSlab + b * Cfg::SLAB_BYTES, &mapAux0, &auxfull[b], col_tile + s * 32, row0, bi);
+            }
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // bias visible
 
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(ew * 32) << 16);
 
-      if constexpr (MODE == MM_EPI_GLU_OP || MODE == MM_EPI_GLU_POS_F32) {
+      if constexpr (MODE == MM_EPI_OP || MODE == MM_EPI_RELU_OP) {
+        int b = bi, t = r;
+        if (p.rows_per_seq > 0) b = r / p.rows_per_seq, t = r - b * p.rows_per_seq;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+          const int col = col_tile + c0;
+          if (col >= p.n) break;                                          // uniform
+          const bool to_vt = (MODE == MM_EPI_OP) && p.vt != nullptr && col >= p.vt_col0;   // uniform
+          uint8_t* slab = sSlab + (slab_ctr % NB) * Cfg::SLAB_BYTES;
+          if (!to_vt) {
+            if (et == 0) bulk_wait_read<NB - 1>();
+            asm volatile("bar.sync 1, 128;" ::: "memory");                // slab free
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t ra[32];
+            tmem_ld32(taddr + c0 + 32 * h, ra);
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]) + sBias[c0 + 32 * h + i];
+            if constexpr (MODE == MM_EPI_OP) {
+              if (col + 32 * h < p.scale_cols) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] *= p.scale;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            if (to_vt) {
+              // transposed store: lanes hold consecutive t -> coalesced 2-byte stores per column
+              if (rvalid) {
+                const int vc = col + 32 * h - p.vt_col0;
+                OpT* dst = reinterpret_cast<OpT*>(p.vt) + ((long long)b * p.vt_rows + vc) * p.vt_ld + t;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (col + 32 * h + i < p.n) dst[(long long)i * p.vt_ld] = OpTraits<OpT>::cvt(v[i]);
+              }
+            } else {
+              slab_write_op32<OpT>(slab, lrow, 4 * h, v);
+            }
+          }
+          if (!to_vt) {
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0) {
+              tma_store_3d(&mapOut0, slab, col, row0 + p.out_row_offset, bi);
+              bulk_commit();
+            }
+            ++slab_ctr;
+          }
+          __syncwarp();
+        }
+      } else if constexpr (MODE == MM_EPI_GLU_OP) {
+        constexpr int HALF = BN / 2;
+#pragma unroll 1
+        for (int j0 = 0; j0 < HALF; j0 += 64) {
+          uint8_t* slab = sSlab + (slab_ctr % NB) * Cfg::SLAB_BYTES;
+          if (et == 0) bulk_wait_read<NB - 1>();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t ra[32], rg[32];
+            tmem_ld32(taddr + j0 + 32 * h, ra);
+            tmem_ld32(taddr + HALF + j0 + 32 * h, rg);
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float a = __uint_as_float(ra[i]) + sBias[j0 + 32 * h + i];
+              const float g = __uint_as_float(rg[i]) + sBias[HALF + j0 + 32 * h + i];
+              v[i] = a * sigmoidf_(g);
+            }
+            slab_write_op32<OpT>(slab, lrow, 4 * h, v);
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) {
+            tma_store_3d(&mapOut0, slab, n_tile * HALF + j0, row0 + p.out_row_offset, bi);
+            bulk_commit();
+          }
+          ++slab_ctr;
+        }
+      } else if constexpr (MODE == MM_EPI_GLU_POS_F32) {
         constexpr int HALF = BN / 2;
         const int n_out = p.n >> 1;
-        int slen = 0;
-        if constexpr (MODE == MM_EPI_GLU_POS_F32) slen = (rvalid && p.seq_lens) ? p.seq_lens[b] : 0x7fffffff;
+        const int slen = (rvalid && p.seq_lens) ? p.seq_lens[bi] : 0x7fffffff;
 #pragma unroll 1
         for (int j0 = 0; j0 < HALF; j0 += 32) {
+          uint8_t* slab = sSlab + (slab_ctr % NB) * Cfg::SLAB_BYTES;
+          if (et == 0) bulk_wait_read<NB - 1>();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
           uint32_t ra[32], rg[32];
           tmem_ld32(taddr + j0, ra);
           tmem_ld32(taddr + HALF + j0, rg);
           tmem_ld_wait();
           const int oc = n_tile * HALF + j0;
-          if (rvalid && oc < n_out) {
-            float v[32];
+          float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float a = __uint_as_float(ra[i]) + sb[j0 + i];
-              const float g = __uint_as_float(rg[i]) + sb[HALF + j0 + i];
-              v[i] = a * sigmoidf_(g);
-            }
-            const int nvalid = min(32, n_out - oc);
-            if constexpr (MODE == MM_EPI_GLU_OP) {
-              OpT* dst = reinterpret_cast<OpT*>(p.out0) + b * p.out0_bs + (long long)(t + p.out_row_offset) * p.out0_ld + oc;
-              store_op<OpT>(dst, v, nvalid);
-            } else {
-              if (t < slen) {
-                float pe[32];
-                load_f32(p.pos + (long long)(t + 2) * n_out + oc, pe, nvalid);
+          for (int i = 0; i < 32; ++i) {
+            const float a = __uint_as_float(ra[i]) + sBias[j0 + i];
+            const float g = __uint_as_float(rg[i]) + sBias[HALF + j0 + i];
+            v[i] = a * sigmoidf_(g) * p.scale;
+          }
+          if (rvalid && r < slen) {   // valid position t -> sinusoidal row t + 2; padded positions get the zero row
+            const float4* pe = reinterpret_cast<const float4*>(p.pos + (long long)(r + 2) * n_out + oc);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], p.scale, pe[i]);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] *= p.scale;
-              }
-              float* dst = reinterpret_cast<float*>(p.out0) + b * p.out0_bs + (long long)t * p.out0_ld + oc;
-              store_f32(dst, v, nvalid);
+            for (int i = 0; i < 8; ++i) {
+              const float4 q = __ldg(pe + i);
+              v[4 * i] += q.x, v[4 * i + 1] += q.y, v[4 * i + 2] += q.z, v[4 * i + 3] += q.w;
             }
           }
-          __syncwarp();
+          slab_write_f32(slab, lrow, v);
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) {
+            tma_store_3d(&mapOut0, slab, oc, row0, bi);
+            bulk_commit();
+          }
+          ++slab_ctr;
         }
-      } else {
-        const long long orow = p.out_tbc ? ((long long)t * p.n_seqs + b) : -1;
+      } else if constexpr (MODE == MM_EPI_F32) {
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
+          const int col = col_tile + c0;
+          if (col >= p.n) break;                                          // uniform
+          uint8_t* slab = sSlab + (slab_ctr % NB) * Cfg::SLAB_BYTES;
+          if (et == 0) bulk_wait_read<NB - 1>();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
           uint32_t ra[32];
           tmem_ld32(taddr + c0, ra);
           tmem_ld_wait();
-          const int col = col_tile + c0;
-          if (rvalid && col < p.n) {
-          const int nvalid = min(32, p.n - col);
           float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]) + sb[c0 + i];
-
-          if constexpr (MODE == MM_EPI_OP) {
-            if (col < p.scale_cols) {
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]) + sBias[c0 + i];
+          slab_write_f32(slab, lrow, v);
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) {
+            tma_store_3d(&mapOut0, slab, col, row0, bi);
+            bulk_commit();
+          }
+          ++slab_ctr;
+        }
+      } else if constexpr (MODE == MM_EPI_F32_OP) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+          const int col = col_tile + c0;
+          if (col >= p.n) break;                                          // uniform
+          // three slabs: fp32 columns [0,32), fp32 columns [32,64), 16-bit columns [0,64)
+          uint8_t* s0 = sSlab + ((slab_ctr + 0) % NB) * Cfg::SLAB_BYTES;
+          uint8_t* s1 = sSlab + ((slab_ctr + 1) % NB) * Cfg::SLAB_BYTES;
+          uint8_t* s2 = sSlab + ((slab_ctr + 2) % NB) * Cfg::SLAB_BYTES;
+          if (et == 0) bulk_wait_read<0>();   // one group per iteration covers 3 of the 4 slabs
+          asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] *= p.scale;
-            }
-            if (p.vt != nullptr && col >= p.vt_col0) {
-              // transposed store: lanes hold consecutive t -> coalesced 2-byte stores per column
-              OpT* dst = reinterpret_cast<OpT*>(p.vt) + ((long long)b * p.vt_rows + (col - p.vt_col0)) * p.vt_ld + t;
+          for (int h = 0; h < 2; ++h) {
+            uint32_t ra[32];
+            tmem_ld32(taddr + c0 + 32 * h, ra);
+            tmem_ld_wait();
+            float v[32];
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < nvalid) dst[(long long)i * p.vt_ld] = OpTraits<OpT>::cvt(v[i]);
-            } else {
-              OpT* dst = reinterpret_cast<OpT*>(p.out0) + b * p.out0_bs + (long long)t * p.out0_ld + col;
-              store_op<OpT>(dst, v, nvalid);
-            }
-          } else if constexpr (MODE == MM_EPI_RELU_OP) {
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]) + sBias[c0 + 32 * h + i];
+            slab_write_f32(h == 0 ? s0 : s1, lrow, v);
+            slab_write_op32<OpT>(s2, lrow, 4 * h, v);
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) {
+            tma_store_3d(&mapOut0, s0, col, row0, bi);
+            if (col + 32 < p.n) tma_store_3d(&mapOut0, s1, col + 32, row0, bi);
+            tma_store_3d(&mapOut1, s2, col, row0, bi);
+            bulk_commit();
+          }
+          slab_ctr += 3;
+        }
+      } else {  // MM_EPI_RESID_F32 / MM_EPI_GATE: in-place update of TMA-loaded fp32 slabs
+        const long long arow = (long long)bi * p.rows + r;
+#pragma unroll 1
+        for (int c0 = 0, s = 0; c0 < BN; c0 += 32, ++s) {
+          const int col = col_tile + c0;
+          if (col >= p.n) break;                                          // uniform
+          const uint32_t b = slab_ctr % NB;
+          uint8_t* slab = sSlab + b * Cfg::SLAB_BYTES;
+          if (et == 0 && col + 64 < p.n && c0 + 64 < BN) {                // prefetch the slab two ahead
+            bulk_wait_read<1>();
+            const uint32_t b2 = (slab_ctr + 2) % NB;
+            mbar_expect_tx(&auxfull[b2], Cfg::SLAB_BYTES);
+            tma_load_3d(sSlab + b2 * Cfg::SLAB_BYTES, &mapAux0, &auxfull[b2], col + 64, row0, bi);
+          }
+          uint32_t ra[32];
+          tmem_ld32(taddr + c0, ra);
+          tmem_ld_wait();
+          mbar_wait(&auxfull[b], (aux_phase >> b) & 1);
+          aux_phase ^= (1u << b);
+          float v[32], x[32];
+          slab_read_f32(slab, lrow, x);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-            OpT* dst = reinterpret_cast<OpT*>(p.out0) + b * p.out0_bs + (long long)t * p.out0_ld + col;
-            store_op<OpT>(dst, v, nvalid);
-          } else if constexpr (MODE == MM_EPI_RESID_F32) {
-            float x[32];
-            load_f32(p.aux0 + arow * p.aux_ld + col, x, nvalid);
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]) + sBias[c0 + i];
+          if constexpr (MODE == MM_EPI_RESID_F32) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += x[i];
-            float* dst = reinterpret_cast<float*>(p.out0) +
-                         (p.out_tbc ? orow * p.out0_ld : b * p.out0_bs + (long long)t * p.out0_ld) + col;
-            store_f32(dst, v, nvalid);
-          } else if constexpr (MODE == MM_EPI_F32_OP) {
-            float* d0 = reinterpret_cast<float*>(p.out0) + b * p.out0_bs + (long long)t * p.out0_ld + col;
-            store_f32(d0, v, nvalid);
-            OpT* d1 = reinterpret_cast<OpT*>(p.out1) + b * p.out1_bs + (long long)t * p.out1_ld + col;
-            store_op<OpT>(d1, v, nvalid);
-          } else if constexpr (MODE == MM_EPI_GATE) {
-            float x[32], o[32];
-            load_f32(p.aux0 + arow * p.aux_ld + col, x, nvalid);
-            load_f32(p.aux1 + arow * p.aux_ld + col, o, nvalid);
+          } else {
+            float o[32];
+            if (rvalid) {
+              const float4* op = reinterpret_cast<const float4*>(p.aux1 + arow * p.aux_ld + col);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 q = __ldg(op + i);
+                o[4 * i] = q.x, o[4 * i + 1] = q.y, o[4 * i + 2] = q.z, o[4 * i + 3] = q.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = 0.f;
+            }
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const float g = sigmoidf_(v[i]);
               v[i] = (1.0f - g) * x[i] + g * o[i];
             }
-            float* dst = reinterpret_cast<float*>(p.out0) +
-                         (p.out_tbc ? orow * p.out0_ld : b * p.out0_bs + (long long)t * p.out0_ld) + col;
-            store_f32(dst, v, nvalid);
-          } else {  // MM_EPI_F32
-            float* dst = reinterpret_cast<float*>(p.out0) + b * p.out0_bs + (long long)t * p.out0_ld + col;
-            store_f32(dst, v, nvalid);
           }
+          slab_write_f32(slab, lrow, v);
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) {
+            tma_store_3d(&mapOut0, slab, col, row0, bi);
+            bulk_commit();
           }
-          __syncwarp();
+          ++slab_ctr;
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (lane == 0) {
+        if (rank == 0)
+          mbar_arrive(&tempty[as]);
+        else
+          mbar_arrive_cluster(tempty_leader + as * 8);
+      }
       if (++as == 2) as = 0, aphase ^= 1;
     }
+    if (et == 0) bulk_wait<0>();   // all TMA stores of this CTA complete before its smem goes away
   }
 
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -354,59 +497,83 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
-int make_tmap_3d(CUtensorMap* out, const void* base, int is_f16, uint64_t dim0, uint64_t dim1, uint64_t dim2,
-                 uint64_t stride1, uint64_t stride2, uint32_t box_rows) {
+int make_tmap_3d_ex(CUtensorMap* out, const void* base, int kind, uint64_t dim0, uint64_t dim1, uint64_t dim2,
+                    uint64_t stride1, uint64_t stride2, uint32_t box0, uint32_t box_rows) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return bad_arg("cuTensorMapEncodeTiled entry point not available");
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || (stride1 * 2) % 16 || (stride2 * 2) % 16)
+  const uint64_t es = kind == 2 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (stride1 * es) % 16 || (stride2 * es) % 16)
     return bad_arg("TMA operand base/strides must be 16-byte aligned");
   cuuint64_t dims[3] = {dim0, dim1, dim2};
-  cuuint64_t strides[2] = {stride1 * 2, stride2 * 2};
+  cuuint64_t strides[2] = {stride1 * es, stride2 * es};
   if (dim2 == 1 && strides[1] == 0) strides[1] = strides[0] * dim1;
-  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t box[3] = {box0, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(out, is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
-                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  const CUtensorMapDataType dt = kind == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                           : (kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                        : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  CUresult r = enc(out, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_last_error, sizeof(g_last_error),
-             "cuTensorMapEncodeTiled failed (%d): dims %llu %llu %llu strides %llu %llu box %u", (int)r,
-             (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)dim2,
-             (unsigned long long)strides[0], (unsigned long long)strides[1], box_rows);
+             "cuTensorMapEncodeTiled failed (%d): kind %d dims %llu %llu %llu strides %llu %llu box %u %u", (int)r,
+             kind, (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)dim2,
+             (unsigned long long)strides[0], (unsigned long long)strides[1], box0, box_rows);
     return static_cast<int>(cudaErrorInvalidValue);
   }
   return 0;
 }
 
-template <int BN, int MODE, typename OpT>
-static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const GemmDev& p,
-                       cudaStream_t s) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_kernel<BN, MODE, OpT>;
+int make_tmap_3d(CUtensorMap* out, const void* base, int is_f16, uint64_t dim0, uint64_t dim1, uint64_t dim2,
+                 uint64_t stride1, uint64_t stride2, uint32_t box_rows) {
+  return make_tmap_3d_ex(out, base, is_f16 ? 1 : 0, dim0, dim1, dim2, stride1, stride2, 64, box_rows);
+}
+
+struct GemmMaps {
+  CUtensorMap a0, a1, w, out0, out1, aux0;
+};
+
+template <int MODE, typename OpT>
+static int launch_gemm(const GemmMaps& m, const GemmDev& p, cudaStream_t s) {
+  using Cfg = GemmCfg;
+  auto kern = gemm_kernel<MODE, OpT>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute(gemm)");
     attr_set = true;
   }
-  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-  kern<<<grid, 256, Cfg::SMEM_BYTES, s>>>(a0, a1, w, p);
-  MM_CHECK_LAUNCH("gemm_kernel launch");
+  const int max_pairs = kNumSMs / 2;
+  const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, m.a0, m.a1, m.w, m.out0, m.out1, m.aux0, p);
+  if (e != cudaSuccess) return fail(e, "gemm_kernel launch");
   return 0;
 }
 
-template <int BN, typename OpT>
-static int dispatch_mode(int mode, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w,
-                         const GemmDev& p, cudaStream_t s) {
+template <typename OpT>
+static int dispatch_mode(int mode, const GemmMaps& m, const GemmDev& p, cudaStream_t s) {
   switch (mode) {
-    case MM_EPI_OP: return launch_gemm<BN, MM_EPI_OP, OpT>(a0, a1, w, p, s);
-    case MM_EPI_RELU_OP: return launch_gemm<BN, MM_EPI_RELU_OP, OpT>(a0, a1, w, p, s);
-    case MM_EPI_RESID_F32: return launch_gemm<BN, MM_EPI_RESID_F32, OpT>(a0, a1, w, p, s);
-    case MM_EPI_GLU_OP: return launch_gemm<BN, MM_EPI_GLU_OP, OpT>(a0, a1, w, p, s);
-    case MM_EPI_GLU_POS_F32: return launch_gemm<BN, MM_EPI_GLU_POS_F32, OpT>(a0, a1, w, p, s);
-    case MM_EPI_F32_OP: return launch_gemm<BN, MM_EPI_F32_OP, OpT>(a0, a1, w, p, s);
-    case MM_EPI_GATE: return launch_gemm<BN, MM_EPI_GATE, OpT>(a0, a1, w, p, s);
-    case MM_EPI_F32: return launch_gemm<BN, MM_EPI_F32, OpT>(a0, a1, w, p, s);
+    case MM_EPI_OP: return launch_gemm<MM_EPI_OP, OpT>(m, p, s);
+    case MM_EPI_RELU_OP: return launch_gemm<MM_EPI_RELU_OP, OpT>(m, p, s);
+    case MM_EPI_RESID_F32: return launch_gemm<MM_EPI_RESID_F32, OpT>(m, p, s);
+    case MM_EPI_GLU_OP: return launch_gemm<MM_EPI_GLU_OP, OpT>(m, p, s);
+    case MM_EPI_GLU_POS_F32: return launch_gemm<MM_EPI_GLU_POS_F32, OpT>(m, p, s);
+    case MM_EPI_F32_OP: return launch_gemm<MM_EPI_F32_OP, OpT>(m, p, s);
+    case MM_EPI_GATE: return launch_gemm<MM_EPI_GATE, OpT>(m, p, s);
+    case MM_EPI_F32: return launch_gemm<MM_EPI_F32, OpT>(m, p, s);
   }
   return bad_arg("unknown epilogue mode");
 }
@@ -421,33 +588,66 @@ extern "C" int mm_gemm(const mm_gemm_args* a, void* stream) {
   const int k0 = a->a1 ? a->k_split : a->k;
   if (a->a1 && (k0 <= 0 || k0 % 64 != 0 || k0 >= a->k)) return bad_arg("k_split must be a multiple of 64 inside (0,k)");
   if (a->rows_per_seq > 0 && a->batches != 1) return bad_arg("rows_per_seq requires batches == 1");
-  int bn = a->block_n ? a->block_n : 256;
-  if (bn != 128 && bn != 256) return bad_arg("block_n must be 128 or 256");
-  const bool glu = a->mode == MM_EPI_GLU_OP || a->mode == MM_EPI_GLU_POS_F32;
-  if (glu && (a->n % bn != 0)) return bad_arg("GLU epilogue needs n % block_n == 0");
-  if ((a->out0_ld % 8) || (a->out1 && a->out1_ld % 8) || (a->aux0 && a->aux_ld % 4))
-    return bad_arg("output leading dims must be multiples of 8 elements");
-  if (a->mode == MM_EPI_RESID_F32 && !a->aux0) return bad_arg("RESID needs aux0");
-  if (a->mode == MM_EPI_GATE && (!a->aux0 || !a->aux1)) return bad_arg("GATE needs aux0 and aux1");
-  if (a->mode == MM_EPI_F32_OP && !a->out1) return bad_arg("F32_OP needs out1");
-  if (a->mode == MM_EPI_GLU_POS_F32 && !a->pos) return bad_arg("GLU_POS needs pos");
-  if (a->out_tbc && a->n_seqs <= 0) return bad_arg("out_tbc needs n_seqs");
+  if (a->block_n != 0 && a->block_n != 256) return bad_arg("block_n must be 0 or 256");
+  const int mode = a->mode;
+  const bool glu = mode == MM_EPI_GLU_OP || mode == MM_EPI_GLU_POS_F32;
+  if (glu && (a->n % 256 != 0)) return bad_arg("GLU epilogue needs n % 256 == 0");
+  if (mode == MM_EPI_RESID_F32 && !a->aux0) return bad_arg("RESID needs aux0");
+  if (mode == MM_EPI_GATE && (!a->aux0 || !a->aux1)) return bad_arg("GATE needs aux0 and aux1");
+  if (mode == MM_EPI_F32_OP && !a->out1) return bad_arg("F32_OP needs out1");
+  if (mode == MM_EPI_GLU_POS_F32 && !a->pos) return bad_arg("GLU_POS needs pos");
+  if (a->out_tbc && (a->n_seqs <= 0 || a->batches != a->n_seqs))
+    return bad_arg("out_tbc needs batched rows (batches == n_seqs)");
+  if (a->vt && mode != MM_EPI_OP) return bad_arg("vt only with MM_EPI_OP");
+  if (a->vt && (a->vt_col0 % 64)) return bad_arg("vt_col0 must be a multiple of 64");
+  if (a->rows_per_seq > 0 && !(mode == MM_EPI_OP && a->vt)) {
+    // (b, t) decomposition of flat rows is only needed by the transposed V store
+  }
+  if ((mode == MM_EPI_RESID_F32 || mode == MM_EPI_GATE) && (a->n % 32)) return bad_arg("RESID/GATE need n % 32 == 0");
 
-  CUtensorMap mA0, mA1, mW;
+  GemmMaps m;
   const int f16 = a->dtype == MM_DTYPE_F16;
-  int rc = make_tmap_3d(&mA0, a->a0, f16, (uint64_t)k0, (uint64_t)a->rows, (uint64_t)a->batches, (uint64_t)a->a0_ld,
-                        (uint64_t)a->a0_bs, 128);
+  const uint64_t rows = (uint64_t)a->rows, nb = (uint64_t)a->batches;
+  int rc = make_tmap_3d(&m.a0, a->a0, f16, (uint64_t)k0, rows, nb, (uint64_t)a->a0_ld, (uint64_t)a->a0_bs, 128);
   if (rc) return rc;
   if (a->a1) {
-    rc = make_tmap_3d(&mA1, a->a1, f16, (uint64_t)(a->k - k0), (uint64_t)a->rows, (uint64_t)a->batches,
-                      (uint64_t)a->a1_ld, (uint64_t)a->a1_bs, 128);
+    rc = make_tmap_3d(&m.a1, a->a1, f16, (uint64_t)(a->k - k0), rows, nb, (uint64_t)a->a1_ld, (uint64_t)a->a1_bs, 128);
     if (rc) return rc;
   } else {
-    mA1 = mA0;
+    m.a1 = m.a0;
   }
-  rc = make_tmap_3d(&mW, a->w, f16, (uint64_t)a->k, (uint64_t)a->n, (uint64_t)(a->w_batched ? a->batches : 1),
-                    (uint64_t)a->w_ld, (uint64_t)a->w_bs, (uint32_t)bn);
+  rc = make_tmap_3d(&m.w, a->w, f16, (uint64_t)a->k, (uint64_t)a->n, (uint64_t)(a->w_batched ? a->batches : 1),
+                    (uint64_t)a->w_ld, (uint64_t)a->w_bs, 128);
   if (rc) return rc;
+
+  // outputs: 3-D maps (columns, rows, batch); T x B x C stores are just another stride pair
+  const bool out_op = mode == MM_EPI_OP || mode == MM_EPI_RELU_OP || mode == MM_EPI_GLU_OP;
+  uint64_t n_out = glu ? (uint64_t)a->n / 2 : (uint64_t)a->n;
+  if (mode == MM_EPI_OP && a->vt) n_out = (uint64_t)a->vt_col0;
+  const uint64_t out_rows = rows + (uint64_t)a->out_row_offset;
+  uint64_t s1 = (uint64_t)a->out0_ld, s2 = (uint64_t)a->out0_bs;
+  if (a->out_tbc) s1 = (uint64_t)a->n_seqs * a->out0_ld, s2 = (uint64_t)a->out0_ld;
+  if (n_out > 0) {
+    rc = make_tmap_3d_ex(&m.out0, a->out0, out_op ? (f16 ? 1 : 0) : 2, n_out, out_rows, nb, s1, s2, out_op ? 64 : 32,
+                         128);
+    if (rc) return rc;
+  } else {
+    m.out0 = m.a0;  // every column goes to vt; never used
+  }
+  if (mode == MM_EPI_F32_OP) {
+    rc = make_tmap_3d_ex(&m.out1, a->out1, f16 ? 1 : 0, (uint64_t)a->n, rows, nb, (uint64_t)a->out1_ld,
+                         (uint64_t)a->out1_bs, 64, 128);
+    if (rc) return rc;
+  } else {
+    m.out1 = m.out0;
+  }
+  if (mode == MM_EPI_RESID_F32 || mode == MM_EPI_GATE) {
+    rc = make_tmap_3d_ex(&m.aux0, a->aux0, 2, (uint64_t)a->n, rows, nb, (uint64_t)a->aux_ld,
+                         (uint64_t)a->rows * a->aux_ld, 32, 128);
+    if (rc) return rc;
+  } else {
+    m.aux0 = m.out0;
+  }
 
   GemmDev p;
   memset(&p, 0, sizeof(p));
@@ -455,23 +655,15 @@ extern "C" int mm_gemm(const mm_gemm_args* a, void* stream) {
   p.num_kb = (a->k + 63) / 64;
   p.kb_split = a->a1 ? k0 / 64 : p.num_kb;
   p.w_batched = a->w_batched;
-  p.m_tiles_per_batch = (a->rows + 127) / 128;
-  p.n_tiles = (a->n + bn - 1) / bn;
-  p.num_tiles = p.m_tiles_per_batch * a->batches * p.n_tiles;
+  p.m_pairs_per_batch = (a->rows + 255) / 256;
+  p.n_tiles = (a->n + 255) / 256;
+  p.num_tiles = p.m_pairs_per_batch * a->batches * p.n_tiles;
   p.bias = a->bias, p.scale = a->scale, p.scale_cols = a->scale_cols;
-  p.out0 = a->out0, p.out0_ld = a->out0_ld, p.out0_bs = a->out0_bs;
-  p.out1 = a->out1, p.out1_ld = a->out1_ld, p.out1_bs = a->out1_bs;
-  p.aux0 = a->aux0, p.aux1 = a->aux1, p.aux_ld = a->aux_ld;
-  p.rows_per_seq = a->rows_per_seq, p.out_tbc = a->out_tbc, p.n_seqs = a->n_seqs;
-  p.out_row_offset = a->out_row_offset;
+  p.aux1 = a->aux1, p.aux_ld = a->aux_ld;
+  p.rows_per_seq = a->rows_per_seq, p.out_row_offset = a->out_row_offset;
   p.vt = a->vt, p.vt_col0 = a->vt_col0, p.vt_rows = a->vt_rows, p.vt_ld = a->vt_ld;
   p.pos = a->pos, p.seq_lens = a->seq_lens;
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (bn == 256) {
-    return f16 ? dispatch_mode<256, __half>(a->mode, mA0, mA1, mW, p, s)
-               : dispatch_mode<256, __nv_bfloat16>(a->mode, mA0, mA1, mW, p, s);
-  }
-  return f16 ? dispatch_mode<128, __half>(a->mode, mA0, mA1, mW, p, s)
-             : dispatch_mode<128, __nv_bfloat16>(a->mode, mA0, mA1, mW, p, s);
+  return f16 ? dispatch_mode<__half>(mode, m, p, s) : dispatch_mode<__nv_bfloat16>(mode, m, p, s);
 }

@@ -35,4 +35,8 @@ EncodeTiledFn get_encode_tiled();
 int make_tmap_3d(CUtensorMap* out, const void* base, int is_f16, uint64_t dim0, uint64_t dim1, uint64_t dim2,
                  uint64_t stride1, uint64_t stride2, uint32_t box_rows);
 
+// General form: kind 0 = bf16, 1 = f16, 2 = f32; box = {box0, box_rows, 1} (box0 * elem size must be 128 B).
+int make_tmap_3d_ex(CUtensorMap* out, const void* base, int kind, uint64_t dim0, uint64_t dim1, uint64_t dim2,
+                    uint64_t stride1, uint64_t stride2, uint32_t box0, uint32_t box_rows);
+
 }  // namespace mm

@@ -246,9 +246,13 @@ class EncoderEngine:
             K.convert(img.view(B * Tk_img, dk), img_op)
         kbuf = self.buf(f"k{j}", (B, Tk, d), op)
         vt = self.buf(f"vt_img{j}", (B, d, Tkp), op, zero=True)
-        K.gemm(a0=img_op, a0_ld=dk, rows=B * Tk_img, w=F["wkv"], n=2 * d, k=dk, mode=K.EPI_OP, bias=F["bkv"],
-               out0=kbuf, out0_ld=d, out0_bs=Tk * d, rows_per_seq=Tk_img, vt=vt, vt_col0=d, vt_rows=d, vt_ld=Tkp,
-               block_n=bn)
+        if extra == 0:   # keys are contiguous over the batch: one flat GEMM over all B * Tk image tokens
+            K.gemm(a0=img_op, a0_ld=dk, rows=B * Tk_img, w=F["wkv"], n=2 * d, k=dk, mode=K.EPI_OP, bias=F["bkv"],
+                   out0=kbuf, out0_ld=d, rows_per_seq=Tk_img, vt=vt, vt_col0=d, vt_rows=d, vt_ld=Tkp, block_n=bn)
+        else:            # per-utterance key blocks of Tk_img + 1 rows: batched rows
+            K.gemm(a0=img_op, a0_ld=dk, a0_bs=Tk_img * dk, rows=Tk_img, batches=B, w=F["wkv"], n=2 * d, k=dk,
+                   mode=K.EPI_OP, bias=F["bkv"], out0=kbuf, out0_ld=d, out0_bs=Tk * d, vt=vt, vt_col0=d, vt_rows=d,
+                   vt_ld=Tkp, block_n=bn)
         if extra:  # learned bias_k / bias_v appended as key/value number Tk_img (nn.MultiheadAttention add_bias_kv)
             kbuf[:, Tk_img, :] = F["bias_kv"][0]
             vt[:, :, Tk_img] = F["bias_kv"][1]
@@ -274,12 +278,13 @@ class EncoderEngine:
             a_op = self.buf("attn_op", (M, d), op)
             K.gemm(a0=o, a0_ld=d, rows=M, w=F["wp"], n=d, k=d, mode=K.EPI_F32_OP, bias=F["bp"], out0=a_f32, out0_ld=d,
                    out1=a_op, out1_ld=d, block_n=bn)
-            K.gemm(a0=a_op, a0_ld=d, a1=text_op, a1_ld=d, k_split=d, rows=M, w=F["wg"], n=d, k=2 * d, mode=K.EPI_GATE,
-                   bias=F["bg"], aux0=text_f32, aux1=a_f32, aux_ld=d, out0=out_tbc, out0_ld=d, rows_per_seq=T,
-                   out_tbc=True, n_seqs=B, block_n=bn)
+            # rows batched per utterance so that a tile never straddles two utterances of the T x B x C output
+            K.gemm(a0=a_op, a0_ld=d, a0_bs=T * d, a1=text_op, a1_ld=d, a1_bs=T * d, k_split=d, rows=T, batches=B,
+                   w=F["wg"], n=d, k=2 * d, mode=K.EPI_GATE, bias=F["bg"], aux0=text_f32, aux1=a_f32, aux_ld=d,
+                   out0=out_tbc, out0_ld=d, out_tbc=True, n_seqs=B, block_n=bn)
         else:
-            K.gemm(a0=o, a0_ld=d, rows=M, w=F["wp"], n=d, k=d, mode=K.EPI_RESID_F32, bias=F["bp"], aux0=text_f32,
-                   aux_ld=d, out0=out_tbc, out0_ld=d, rows_per_seq=T, out_tbc=True, n_seqs=B, block_n=bn)
+            K.gemm(a0=o, a0_ld=d, a0_bs=T * d, rows=T, batches=B, w=F["wp"], n=d, k=d, mode=K.EPI_RESID_F32,
+                   bias=F["bp"], aux0=text_f32, aux_ld=d, out0=out_tbc, out0_ld=d, out_tbc=True, n_seqs=B, block_n=bn)
 
     # ------------------------------------------------------------------------------------------
     # full forward
