@@ -118,6 +118,15 @@ typedef struct mm_gemm_args {
 
 int mm_gemm(const mm_gemm_args* args, void* stream);
 
+/* Fused sub-layer tail of the pre-LN fairseq TransformerEncoderLayer (out_proj or fc2) plus the LayerNorm that
+ * opens the next sub-layer (self_attn_layer_norm / final_layer_norm / the encoder's last layer_norm):
+ *     x[r, :] <- x[r, :] + a[r, :] W^T + bias          (fp32 residual stream, updated in place)
+ *     h[r, :] <- LayerNorm(x[r, :]) * gamma + beta      (16-bit operand copy, optional fp32 copy)
+ * a [rows, k] and w [n, k] are 16-bit, n must be 512 (a full row lives in one TMEM accumulator). */
+int mm_gemm_resid_ln(const void* a, int64_t a_ld, const void* w, int64_t w_ld, int32_t rows, int32_t k, int32_t n,
+                     const float* bias, float* x, const float* gamma, const float* beta, float eps, void* h_op,
+                     float* h_f32, int32_t dtype, void* stream);
+
 /* LayerNorm over the last dim (eps 1e-5, affine), fp32 in -> 16-bit operand out and/or fp32 out.
  * Replaces F.layer_norm in fairseq TransformerEncoderLayer / final encoder LayerNorm and
  * image_pre_norm_module (mm_s2s_transformer.py:595).  dim in {256, 512, 768, 1024}. */

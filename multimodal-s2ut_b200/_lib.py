@@ -17,7 +17,7 @@ _PKG = Path(__file__).resolve().parent
 CSRC = _PKG / "csrc"
 INCLUDE = _PKG.parent / "include"
 LIB_PATH = _PKG / "libmms2ut_b200.so"
-SOURCES = ["abi.cu", "gemm.cu", "rowwise.cu", "fbank.cu", "attention.cu"]
+SOURCES = ["abi.cu", "gemm.cu", "gemm_ln.cu", "rowwise.cu", "fbank.cu", "attention.cu"]
 ABI_VERSION = 1
 
 NVCC_FLAGS = [
@@ -102,6 +102,9 @@ EXPORTS = {
                                 C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "mm_seq_lens": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "mm_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+    "mm_gemm_resid_ln": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
+                                   C.c_int32, C.c_void_p]),
     "mm_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                C.c_int32, C.c_float, C.c_void_p]),
     "mm_self_attention": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,

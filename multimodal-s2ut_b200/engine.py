@@ -59,6 +59,7 @@ class EncoderEngine:
         if self.d // self.heads != 64 or self.d % 128 != 0:
             raise NotImplementedError("self-attention kernel is built for head_dim 64 and d_model % 128 == 0")
         self.embed_scale = float(enc.embed_scale)
+        self.fused_ln = self.d == 512 and getattr(enc, "fuse_layernorm", True)   # mm_gemm_resid_ln needs n == 512
         self.enc = enc
         self._buf: Dict[Tuple, torch.Tensor] = {}
         self._pos: Optional[torch.Tensor] = None
@@ -206,7 +207,15 @@ class EncoderEngine:
                scale=self.embed_scale, pos=self.pos_table(T + 2), seq_lens=seq_lens, block_n=self.block_n)
         return x, T
 
-    def layer(self, L: dict, x: torch.Tensor, B: int, T: int, seq_lens: torch.Tensor) -> None:
+    def layer(self, L: dict, x: torch.Tensor, B: int, T: int, seq_lens: torch.Tensor, next_ln=None,
+              h_f32: Optional[torch.Tensor] = None, h_out: Optional[torch.Tensor] = None) -> None:
+        """One pre-LN encoder layer on the fp32 residual stream ``x`` (in place).
+
+        ``next_ln`` = (gamma, beta) of the LayerNorm that FOLLOWS this layer (next layer's self_attn_layer_norm
+        or the encoder's final layer_norm).  With d_model == 512 both LayerNorms of the layer are fused into
+        the out_proj / fc2 GEMM epilogues (``mm_gemm_resid_ln``): on entry buffer ``h`` already holds
+        LN1(x), on exit it (or ``h_out``) holds next_ln(x).  Otherwise the stand-alone LayerNorm kernel runs.
+        """
         d, M, op, bn = self.d, B * T, self.op_dtype, self.block_n
         Tp = _round_up(T, 8)
         h = self.buf("h", (M, d), op)
@@ -214,18 +223,26 @@ class EncoderEngine:
         vt = self.buf("vt", (B, d, Tp), op, zero=True)               # columns >= T stay zero
         att = self.buf("att", (M, d), op)
         f = self.buf("ffn", (M, self.ffn), op)
-        K.layernorm(x, L["ln1_g"], L["ln1_b"], out_op=h)
+        fused = self.fused_ln
+        if not fused:
+            K.layernorm(x, L["ln1_g"], L["ln1_b"], out_op=h)
         K.gemm(a0=h, a0_ld=d, rows=M, w=L["wqkv"], n=3 * d, k=d, mode=K.EPI_OP, bias=L["bqkv"], scale=64 ** -0.5,
                scale_cols=d, out0=qk, out0_ld=2 * d, rows_per_seq=T, out0_bs=T * 2 * d, vt=vt, vt_col0=2 * d,
                vt_rows=d, vt_ld=Tp, block_n=bn)
         K.self_attention(qk, vt, seq_lens, B, T, self.heads, att)
-        K.gemm(a0=att, a0_ld=d, rows=M, w=L["wo"], n=d, k=d, mode=K.EPI_RESID_F32, bias=L["bo"], aux0=x, aux_ld=d,
-               out0=x, out0_ld=d, block_n=bn)
-        K.layernorm(x, L["ln2_g"], L["ln2_b"], out_op=h)
+        if fused:
+            K.gemm_resid_ln(att, L["wo"], L["bo"], x, L["ln2_g"], L["ln2_b"], h)
+        else:
+            K.gemm(a0=att, a0_ld=d, rows=M, w=L["wo"], n=d, k=d, mode=K.EPI_RESID_F32, bias=L["bo"], aux0=x,
+                   aux_ld=d, out0=x, out0_ld=d, block_n=bn)
+            K.layernorm(x, L["ln2_g"], L["ln2_b"], out_op=h)
         K.gemm(a0=h, a0_ld=d, rows=M, w=L["w1"], n=self.ffn, k=d, mode=K.EPI_RELU_OP, bias=L["b1"], out0=f,
                out0_ld=self.ffn, block_n=bn)
-        K.gemm(a0=f, a0_ld=self.ffn, rows=M, w=L["w2"], n=d, k=self.ffn, mode=K.EPI_RESID_F32, bias=L["b2"], aux0=x,
-               aux_ld=d, out0=x, out0_ld=d, block_n=bn)
+        if fused:
+            K.gemm_resid_ln(f, L["w2"], L["b2"], x, next_ln[0], next_ln[1], h if h_out is None else h_out, h_f32)
+        else:
+            K.gemm(a0=f, a0_ld=self.ffn, rows=M, w=L["w2"], n=d, k=self.ffn, mode=K.EPI_RESID_F32, bias=L["b2"],
+                   aux0=x, aux_ld=d, out0=x, out0_ld=d, block_n=bn)
 
     def fuse(self, j: int, text_f32: torch.Tensor, text_op: torch.Tensor, img: torch.Tensor,
              img_mask: Optional[torch.Tensor], B: int, T: int, out_tbc: torch.Tensor) -> None:
@@ -303,13 +320,20 @@ class EncoderEngine:
         B = x1.shape[0]
         x, T = self.subsample(x1, m, seq_lens)
         states = []
-        for L in self.layers:
-            self.layer(L, x, B, T, seq_lens)
-            if return_all_hiddens:
-                states.append(x.view(B, T, self.d).transpose(0, 1).contiguous())
         text_f32 = self.buf("text_f32", (B * T, self.d), torch.float32)
         text_op = self.buf("text_op", (B * T, self.d), self.op_dtype)
-        K.layernorm(x, self.ln_g, self.ln_b, out_op=text_op, out_f32=text_f32)
+        if self.fused_ln:   # LN1 of layer 0 is the only stand-alone LayerNorm; the rest ride on GEMM epilogues
+            K.layernorm(x, self.layers[0]["ln1_g"], self.layers[0]["ln1_b"], out_op=self.buf("h", (B * T, self.d),
+                                                                                              self.op_dtype))
+        for i, L in enumerate(self.layers):
+            last = i + 1 == len(self.layers)
+            nxt = (self.ln_g, self.ln_b) if last else (self.layers[i + 1]["ln1_g"], self.layers[i + 1]["ln1_b"])
+            self.layer(L, x, B, T, seq_lens, next_ln=nxt, h_f32=text_f32 if last else None,
+                       h_out=text_op if last else None)
+            if return_all_hiddens:
+                states.append(x.view(B, T, self.d).transpose(0, 1).contiguous())
+        if not self.fused_ln:
+            K.layernorm(x, self.ln_g, self.ln_b, out_op=text_op, out_f32=text_f32)
         mask = torch.arange(T, device=self.device)[None, :] >= seq_lens[:, None]
         if imgs_list and self.fusion:
             if drop_audio:

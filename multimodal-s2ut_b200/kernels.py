@@ -159,6 +159,22 @@ def gemm(*, a0: torch.Tensor, w: torch.Tensor, rows: int, n: int, k: int, mode: 
         _lib.check(lib.mm_gemm(C.byref(g), _stream()), "mm_gemm")
 
 
+def gemm_resid_ln(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor,
+                  beta: torch.Tensor, h_op: torch.Tensor, h_f32: Optional[torch.Tensor] = None,
+                  eps: float = 1e-5) -> None:
+    """x += a @ w.T + bias (fp32, in place); h_op (and h_f32) = LayerNorm(x) * gamma + beta.  n = 512 only."""
+    rows, k = a.shape
+    n = w.shape[0]
+    assert a.dtype == w.dtype == h_op.dtype and a.is_contiguous() and w.is_contiguous() and w.shape[1] == k
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.shape == (rows, n) and h_op.shape == (rows, n)
+    assert all(t.dtype == torch.float32 and t.numel() == n for t in (bias, gamma, beta))
+    lib = _lib.load()
+    with _Launch("gemm_resid_ln", 2.0 * rows * n * k):
+        _lib.check(lib.mm_gemm_resid_ln(_ptr(a), k, _ptr(w), k, rows, k, n, _ptr(bias), _ptr(x), _ptr(gamma),
+                                        _ptr(beta), eps, _ptr(h_op), _ptr(h_f32), dtype_code(w.dtype), _stream()),
+                   "mm_gemm_resid_ln")
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_op: Optional[torch.Tensor] = None,
               out_f32: Optional[torch.Tensor] = None, eps: float = 1e-5) -> None:
     assert x.dtype == torch.float32 and x.is_contiguous()

@@ -203,3 +203,25 @@ def test_gemm_full_size_linearity(cuda):
     assert (out[rows].float() - ref).abs().max().item() < 3e-2
     ref_all = torch.relu(a.float() @ w.float().t())
     assert (out.float() - ref_all).abs().max().item() < 3e-2
+
+
+@pytest.mark.parametrize("M,Kd,want_f32", [(1000, 512, False), (300, 2048, True), (20000, 512, True)])
+def test_gemm_resid_ln_fused(cuda, M, Kd, want_f32):
+    """x += a W^T + b and h = LayerNorm(x) in one kernel (20000 rows -> some CTA pairs take two tiles)."""
+    from mm_s2ut_b200 import kernels as K
+
+    dt, N = torch.bfloat16, 512
+    a, w = _rand((M, Kd), cuda, dt, 1.0, 1), _rand((N, Kd), cuda, dt, Kd ** -0.5, 2)
+    bias = _rand((N,), cuda, torch.float32, 0.5, 3)
+    x = _rand((M, N), cuda, torch.float32, 2.0, 4) + 0.3
+    gamma, beta = 1 + _rand((N,), cuda, torch.float32, 0.2, 5), _rand((N,), cuda, torch.float32, 0.2, 6)
+    xref = x + a.float() @ w.float().t() + bias
+    href = torch.nn.functional.layer_norm(xref, (N,), gamma, beta, 1e-5)
+    h16 = torch.zeros(M, N, dtype=dt, device=cuda)
+    h32 = torch.zeros(M, N, dtype=torch.float32, device=cuda) if want_f32 else None
+    K.gemm_resid_ln(a, w, bias, x, gamma, beta, h16, h32)
+    torch.cuda.synchronize()
+    assert (x - xref).abs().max().item() < 2e-3
+    assert (h16.float() - href).abs().max().item() < 4e-2
+    if want_f32:
+        assert (h32 - href).abs().max().item() < 2e-3
