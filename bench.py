@@ -137,7 +137,7 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 8
+    sample = int(os.environ.get("MM_BENCH_REF_SAMPLE", "8"))
     r = cpu_reference(sample, max(1, a.steps), max(1, min(a.warmup, 2)))
     line = {
         "impl": "reference", "metric": "audio-sec encoded/sec (fbank->fused enc)", "value": r["value"],

@@ -68,8 +68,10 @@ def kaldi_fbank_np(wave: np.ndarray, num_mel_bins: int = 80) -> np.ndarray:
     fr = fr * povey_window(win)[None, :]                          # kaldi.py:201-204
     pad = np.zeros((m, nfft), dtype=np.float32)
     pad[:, :win] = fr
-    spec = np.fft.rfft(pad.astype(np.float64), axis=1)            # reference rfft is fp32; fp64 here
-    power = (np.abs(spec) ** 2).astype(np.float32)                # [m, 257]
+    import scipy.fft                                              # pocketfft in single precision, like torch's CPU rfft
+
+    spec = scipy.fft.rfft(pad, axis=1)                            # complex64: the reference's rfft is fp32
+    power = (np.abs(spec) ** np.float32(2.0)).astype(np.float32)  # [m, 257]  (kaldi.py:616-618: abs().pow(2))
     bank = np.pad(mel_banks(num_mel_bins, nfft), ((0, 0), (0, 1)))  # Nyquist column zero, kaldi.py:627
     mel = power @ bank.T
     return np.log(np.maximum(mel, EPS)).astype(np.float32)        # kaldi.py:633

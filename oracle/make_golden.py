@@ -1,0 +1,149 @@
+"""Generate the committed golden vectors under tests/golden/ (run in the BUILD container only).
+
+Three sources pin the oracle (the reference ships no tests of its own):
+  1. the reference's OWN fusion code: /root/reference/mm_s2ut/models/fuse.py is imported through a two-symbol
+     fairseq stub (its only fairseq imports are FairseqDataclass and with_incremental_state, fuse.py:13-14) and
+     SelectiveAttention / MultimodalAttention are run on seeded inputs;
+  2. the real torchaudio.compliance.kaldi.fbank (what fairseq's _get_torchaudio_fbank executes) on seeded waveforms;
+  3. HF transformers' Speech2TextEncoder -- an independent port of the same fairseq S2T encoder -- with copied weights.
+/root/reference does not exist on the GPU box: only the .npz files produced here travel.
+
+    python oracle/make_golden.py
+"""
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+OUT = ROOT / "tests" / "golden"
+REF = Path("/root/reference")
+
+
+def import_reference_fuse():
+    fs = types.ModuleType("fairseq")
+    dc = types.ModuleType("fairseq.dataclass")
+    inc = types.ModuleType("fairseq.incremental_decoding_utils")
+
+    class FairseqDataclass:  # noqa: D401 - stub
+        pass
+
+    dc.FairseqDataclass = FairseqDataclass
+    inc.with_incremental_state = lambda cls: cls
+    sys.modules.update({"fairseq": fs, "fairseq.dataclass": dc, "fairseq.incremental_decoding_utils": inc})
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ref_fuse", REF / "mm_s2ut" / "models" / "fuse.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def golden_fuse():
+    fuse = import_reference_fuse()
+    torch.manual_seed(20251018)
+    d, dk, Tq, Tk, B = 128, 192, 19, 61, 3
+    sa = fuse.SelectiveAttention(qdim=d, kdim=dk, vdim=dk, attn_dim=d, intermediate_dim=d, output_dim=d, num_heads=1,
+                                 attn_drop=0.1).eval()
+    with torch.no_grad():
+        for p in sa.parameters():          # non-zero biases so every term is pinned
+            if p.dim() == 1:
+                p.normal_(0, 0.1)
+    q = torch.randn(Tq, B, d)
+    img = torch.randn(Tk, B, dk)
+    mask = torch.zeros(B, Tk, dtype=torch.bool)
+    mask[1, 40:] = True
+    with torch.no_grad():
+        out, attn = sa(q.clone(), img, img, key_padding_mask=None)
+        out_m, attn_m = sa(q.clone(), img, img, key_padding_mask=mask)
+    np.savez_compressed(OUT / "fuse_selective_attention.npz", q=q.numpy(), img=img.numpy(), mask=mask.numpy(),
+                        out=out.numpy(), attn=attn.numpy(), out_masked=out_m.numpy(), attn_masked=attn_m.numpy(),
+                        **{"sd." + k: v.numpy() for k, v in sa.state_dict().items()})
+
+    ma = fuse.MultimodalAttention(embed_dim=d, kdim=dk, vdim=dk, num_heads=1, dropout=0.1, add_bias_kv=True).eval()
+    with torch.no_grad():
+        ma.in_proj_bias.normal_(0, 0.1)
+        ma.out_proj.bias.normal_(0, 0.1)
+        ma.bias_k.normal_(0, 0.5)
+        ma.bias_v.normal_(0, 0.5)
+        text_mask = torch.zeros(B, Tq, dtype=torch.bool)
+        o1, _ = ma(text=q, text_mask=text_mask, img=img, img_mask=None, is_merge_text_img=False)
+        o2, _ = ma(text=q, text_mask=text_mask, img=img, img_mask=mask, is_merge_text_img=False)
+    np.savez_compressed(OUT / "fuse_multimodal_attention.npz", q=q.numpy(), img=img.numpy(), mask=mask.numpy(),
+                        out=o1.numpy(), out_masked=o2.numpy(),
+                        **{"sd." + k: v.numpy() for k, v in ma.state_dict().items()})
+    print("fuse goldens written")
+
+
+def golden_fbank():
+    from mm_s2ut_b200 import synth  # noqa: E402
+    import torchaudio.compliance.kaldi as ta_kaldi
+
+    data = {}
+    for u, dur in enumerate((0.5, 1.0, 2.37)):
+        w = synth.synth_waveform(7, u, dur, ragged=False)
+        f = ta_kaldi.fbank(torch.from_numpy(w).unsqueeze(0), num_mel_bins=80, sample_frequency=16000).numpy()
+        data[f"wav{u}"] = w
+        data[f"fbank{u}"] = f
+    z = np.zeros(8000, dtype=np.float32)
+    data["wav_zero"] = z
+    data["fbank_zero"] = ta_kaldi.fbank(torch.from_numpy(z).unsqueeze(0), num_mel_bins=80,
+                                        sample_frequency=16000).numpy()
+    np.savez_compressed(OUT / "fbank_torchaudio.npz", **data)
+    print("fbank goldens written")
+
+
+def golden_hf_encoder():
+    """HF Speech2TextEncoder (port of fairseq's S2T encoder): copy weights into fairseq names, store in/out."""
+    from transformers import Speech2TextConfig
+    from transformers.models.speech_to_text.modeling_speech_to_text import Speech2TextEncoder
+
+    torch.manual_seed(7)
+    d, L, H, ffn = 64, 2, 2, 128
+    cfg = Speech2TextConfig(d_model=d, encoder_layers=L, encoder_attention_heads=H, encoder_ffn_dim=ffn,
+                            num_conv_layers=2, conv_kernel_sizes=(5, 5), conv_channels=128, input_feat_per_channel=80,
+                            input_channels=1, max_source_positions=600, dropout=0.0, attention_dropout=0.0,
+                            activation_dropout=0.0, encoder_layerdrop=0.0, activation_function="relu",
+                            scale_embedding=True)
+    enc = Speech2TextEncoder(cfg).eval()
+    with torch.no_grad():
+        for n, p in enc.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    B, T = 3, 83
+    lens = torch.tensor([83, 61, 20])
+    feats = torch.randn(B, T, 80)
+    for i, n in enumerate(lens):
+        feats[i, n:] = 0
+    attn = (torch.arange(T)[None, :] < lens[:, None]).long()
+    with torch.no_grad():
+        out = enc(feats, attention_mask=attn).last_hidden_state        # [B, T', d]
+    sd = {}
+    hs = enc.state_dict()
+    for i in range(2):
+        sd[f"subsample.conv_layers.{i}.weight"] = hs[f"conv.conv_layers.{i}.weight"]
+        sd[f"subsample.conv_layers.{i}.bias"] = hs[f"conv.conv_layers.{i}.bias"]
+    for i in range(L):
+        a, b = f"layers.{i}.", f"transformer_layers.{i}."
+        for proj in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            for t in ("weight", "bias"):
+                sd[f"{b}self_attn.{proj}.{t}"] = hs[f"{a}self_attn.{proj}.{t}"]
+        for t in ("weight", "bias"):
+            sd[f"{b}self_attn_layer_norm.{t}"] = hs[f"{a}self_attn_layer_norm.{t}"]
+            sd[f"{b}final_layer_norm.{t}"] = hs[f"{a}final_layer_norm.{t}"]
+            sd[f"{b}fc1.{t}"] = hs[f"{a}fc1.{t}"]
+            sd[f"{b}fc2.{t}"] = hs[f"{a}fc2.{t}"]
+    sd["layer_norm.weight"], sd["layer_norm.bias"] = hs["layer_norm.weight"], hs["layer_norm.bias"]
+    np.savez_compressed(OUT / "hf_speech2text_encoder.npz", feats=feats.numpy(), lens=lens.numpy(), out=out.numpy(),
+                        heads=np.array(H), **{"sd." + k: v.numpy() for k, v in sd.items()})
+    print("HF encoder golden written", tuple(out.shape))
+
+
+if __name__ == "__main__":
+    OUT.mkdir(parents=True, exist_ok=True)
+    golden_fbank()
+    golden_fuse()
+    golden_hf_encoder()

@@ -170,3 +170,30 @@ def test_fp16_operands_tighter(cuda):
     out = enc(wav.cuda(), lens.cuda(), None, None, None, imgs_list=[imgs.cuda()], img_masks_list=[None])
     torch.cuda.synchronize()
     assert _compare(out, ref) < 4e-3
+
+
+def test_decoder_unit_argmax_agreement(cuda):
+    """north_star: >= 99 % agreement of the S2UT decoder's unit arg-max when fed the CUDA path's fused states vs the
+    fp32 oracle's (same restated fairseq TransformerUnitDecoder, teacher forced on seeded units)."""
+    from mm_s2ut_b200 import synth
+    from oracle import decoder as odec
+
+    enc, args, cfg = _build("base")
+    wavs, _ = synth.synth_batch(1, 6, 6.0, ragged=True)
+    imgs = synth.synth_images(1, 6)
+    ref = _oracle(enc, args, cfg, wavs, imgs)
+    wav, lens = synth.pad_waveforms(wavs)
+    enc.cuda()
+    out = enc(wav.cuda(), lens.cuda(), None, None, None, imgs_list=[imgs.cuda()], img_masks_list=[None])
+    torch.cuda.synchronize()
+    dsd = odec.init_decoder(args.decoder_embed_dim, args.decoder_ffn_embed_dim, args.decoder_layers, seed=3)
+    g = torch.Generator().manual_seed(11)
+    prev = torch.randint(4, 1004, (6, 80), generator=g)
+    prev[:, 0] = 2
+    mask = ref["encoder_padding_mask"][0]
+    with torch.no_grad():
+        l_ref = odec.unit_decoder_forward(dsd, prev, ref["encoder_out"][0], mask, args.decoder_attention_heads)
+        l_gpu = odec.unit_decoder_forward(dsd, prev, out["encoder_out"][0].float().cpu(), mask,
+                                          args.decoder_attention_heads)
+    agree = (l_ref.argmax(-1) == l_gpu.argmax(-1)).float().mean().item()
+    assert agree >= 0.99, agree

@@ -3,6 +3,8 @@ import numpy as np
 import pytest
 import torch
 
+from _util import fbank_errors
+
 pytestmark = pytest.mark.gpu
 
 
@@ -70,8 +72,8 @@ def test_fbank_vs_torchaudio(cuda):
     for i, w in enumerate(wavs):
         ref = torch.from_numpy(ofb.kaldi_fbank_ta(w))
         got = feats[i, : ref.shape[0]].cpu()
-        rel = ((got - ref).abs() / ref.abs().clamp_min(1.0)).max().item()
-        assert rel < 1e-4, (i, rel)
+        e_main, e_all = fbank_errors(got.numpy(), ref.numpy())
+        assert e_main < 1e-4 and e_all < 5e-3, (i, e_main, e_all)
     # silence: every bin sits on the log(eps) floor, bit-identical to torch's value
     assert torch.equal(feats[5, : 1 + (len(wavs[5]) - 400) // 160].cpu(), torch.from_numpy(ofb.kaldi_fbank_ta(wavs[5])))
 

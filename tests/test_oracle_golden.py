@@ -1,0 +1,81 @@
+"""CPU: the oracle restatements against the committed golden vectors (tests/golden/, made by oracle/make_golden.py
+from the reference's own fuse.py, real torchaudio and HF's port of the fairseq S2T encoder)."""
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from _util import fbank_errors
+
+G = Path(__file__).parent / "golden"
+
+
+def _sd(z, prefix=""):
+    return {prefix + k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+
+
+def test_selective_attention_matches_reference_fuse_py():
+    from oracle import fusion
+
+    z = np.load(G / "fuse_selective_attention.npz")
+    sd = _sd(z, "sa.")
+    q, img, mask = torch.from_numpy(z["q"]), torch.from_numpy(z["img"]), torch.from_numpy(z["mask"])
+    out, attn = fusion.selective_attention(sd, "sa.", q, img, img, None)
+    assert torch.allclose(out, torch.from_numpy(z["out"]), atol=2e-6, rtol=1e-5)
+    assert torch.allclose(attn, torch.from_numpy(z["attn"]), atol=1e-7, rtol=1e-5)
+    out, attn = fusion.selective_attention(sd, "sa.", q, img, img, mask)
+    assert torch.allclose(out, torch.from_numpy(z["out_masked"]), atol=2e-6, rtol=1e-5)
+    assert torch.allclose(attn, torch.from_numpy(z["attn_masked"]), atol=1e-7, rtol=1e-5)
+    assert attn[1, :, 40:].abs().max() == 0
+
+
+def test_multimodal_attention_matches_reference_fuse_py():
+    from oracle import fusion
+
+    z = np.load(G / "fuse_multimodal_attention.npz")
+    sd = _sd(z, "ma.")
+    q, img, mask = torch.from_numpy(z["q"]), torch.from_numpy(z["img"]), torch.from_numpy(z["mask"])
+    out = fusion.multimodal_attention(sd, "ma.", q, img, None)
+    assert torch.allclose(out, torch.from_numpy(z["out"]), atol=2e-6, rtol=1e-5)
+    out = fusion.multimodal_attention(sd, "ma.", q, img, mask)
+    assert torch.allclose(out, torch.from_numpy(z["out_masked"]), atol=2e-6, rtol=1e-5)
+
+
+def test_fbank_restatement_matches_torchaudio_golden():
+    from oracle import fbank as ofb
+
+    z = np.load(G / "fbank_torchaudio.npz")
+    for u in range(3):
+        got = ofb.kaldi_fbank_np(z[f"wav{u}"])
+        ref = z[f"fbank{u}"]
+        assert got.shape == ref.shape
+        e_main, e_all = fbank_errors(got, ref)
+        assert e_main < 1e-4 and e_all < 5e-3, (e_main, e_all)
+        live = ofb.kaldi_fbank_ta(z[f"wav{u}"])         # the installed torchaudio still agrees with the fixture
+        assert np.max(np.abs(live - ref)) < 1e-4
+    assert np.array_equal(ofb.kaldi_fbank_np(z["wav_zero"]), z["fbank_zero"])   # silence: the log(eps) floor
+
+
+def test_s2t_encoder_restatement_matches_hf_port():
+    from oracle import s2t
+
+    z = np.load(G / "hf_speech2text_encoder.npz")
+    sd = _sd(z)
+    out = s2t.s2t_encoder_forward(sd, torch.from_numpy(z["feats"]), torch.from_numpy(z["lens"]), int(z["heads"]))
+    x = out["encoder_out"][0].transpose(0, 1)       # [B, T', d]
+    ref = torch.from_numpy(z["out"])
+    mask = out["encoder_padding_mask"][0]
+    assert x.shape == ref.shape
+    err = ((x - ref).abs() * (~mask).unsqueeze(-1)).max().item()
+    assert err < 1e-4, err
+
+
+def test_utterance_cmvn_semantics():
+    from oracle import fbank as ofb
+
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((57, 80)) * 3 + 11).astype(np.float32)
+    y = ofb.utterance_cmvn(x)
+    assert abs(float(y.mean())) < 1e-4 and abs(float(y.std()) - 1.0) < 1e-2
+    out, lens = ofb.collate_frames([y, y[:20]])
+    assert out.shape == (2, 57, 80) and lens.tolist() == [57, 20] and np.all(out[1, 20:] == 0)
