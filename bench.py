@@ -347,16 +347,35 @@ def run_ours(a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_ours(a)
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner, ...) go to stderr
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    buf = []
+    real_print = print
+
+    def capture(*args, **kw):
+        buf.append(" ".join(str(x) for x in args))
+
+    globals()["print"] = capture
+    try:
+        if a.impl == "reference":
+            run_reference(a)
+        else:
+            run_ours(a)
+    finally:
+        globals()["print"] = real_print
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    for line in buf:
+        real_print(line, flush=True)
 
 
 if __name__ == "__main__":
