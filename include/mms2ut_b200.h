@@ -134,11 +134,11 @@ int mm_layernorm(const float* x, const float* gamma, const float* beta, int64_t 
                  float* out_f32, int32_t dtype, float eps, void* stream);
 
 /* Multi-head self-attention core (fairseq MultiheadAttention: softmax_fp32(q k^T + key-padding mask) v).
- * qk: [B*T, qk_ld] 16-bit, q (pre-scaled) at columns [0, d), k at [d, 2d); vt: [B][d][vt_ld] (V transposed,
- * zero beyond T); seq_lens [B] int32 valid keys; out [B*T, d] 16-bit.  head_dim must be 64. */
-int mm_self_attention(const void* qk, int64_t qk_ld, const void* vt, int64_t vt_ld, const int32_t* seq_lens,
-                      int32_t batch, int32_t seq, int32_t heads, void* out, int64_t out_ld, int32_t dtype,
-                      void* stream);
+ * qkv: [B*T, qkv_ld] 16-bit, q (pre-scaled by head_dim^-0.5) at columns [0, d), k at [d, 2d), v at [2d, 3d)
+ * (exactly what the QKV projection GEMM writes); seq_lens [B] int32 valid keys; out [B*T, out_ld] 16-bit.
+ * head_dim must be 64.  T <= 256 runs the persistent warp-specialised kernel, longer sequences the chunked one. */
+int mm_self_attention(const void* qkv, int64_t qkv_ld, const int32_t* seq_lens, int32_t batch, int32_t seq,
+                      int32_t heads, void* out, int64_t out_ld, int32_t dtype, void* stream);
 
 /* Row softmax for the speech->image attention (fuse.py:88-111): scores fp32 [rows, ld_in] -> probabilities
  * 16-bit [rows, ld_out]; columns [n_keys, ld_out) written as 0.  key_mask: optional [n_seqs, n_keys] uint8

@@ -107,8 +107,8 @@ EXPORTS = {
                                    C.c_int32, C.c_void_p]),
     "mm_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                C.c_int32, C.c_float, C.c_void_p]),
-    "mm_self_attention": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
-                                    C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "mm_self_attention": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                    C.c_int64, C.c_int32, C.c_void_p]),
     "mm_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                   C.c_int64, C.c_int32, C.c_void_p]),
     "mm_convert_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),

@@ -60,7 +60,7 @@ self_attention_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_co
 
   uint32_t tma_phase = 0, mma_phase = 0;
   constexpr uint32_t idesc_s = umma_idesc(AT_BM, AT_KC, OpTraits<OpT>::fmt);
-  constexpr uint32_t idesc_o = umma_idesc(AT_BM, AT_HD, OpTraits<OpT>::fmt);
+  constexpr uint32_t idesc_o = umma_idesc(AT_BM, AT_HD, OpTraits<OpT>::fmt) | (1u << 16);  // B (= V) is MN-major
 
   auto load_and_scores = [&](int c, bool with_q, bool with_v) {
     if (tid == 0) {
@@ -68,10 +68,9 @@ self_attention_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_co
       if (with_q) tma_load_3d(sQ, &mapQK, bar_tma, h * AT_HD, qt * AT_BM, b);
       tma_load_3d(sK, &mapQK, bar_tma, d_model + h * AT_HD, c * AT_KC, b);
       tma_load_3d(sK + AT_K_BYTES / 2, &mapQK, bar_tma, d_model + h * AT_HD, c * AT_KC + 128, b);
-      if (with_v) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          tma_load_3d(sV + j * (AT_V_BYTES / 4), &mapVT, bar_tma, c * AT_KC + j * 64, h * AT_HD, b);
+      if (with_v) {   // V rows = keys, 64 values (128 B) each: MN-major B operand of the PV MMA
+        tma_load_3d(sV, &mapQK, bar_tma, 2 * d_model + h * AT_HD, c * AT_KC, b);
+        tma_load_3d(sV + AT_V_BYTES / 2, &mapQK, bar_tma, 2 * d_model + h * AT_HD, c * AT_KC + 128, b);
       }
     }
     mbar_wait(bar_tma, tma_phase);
@@ -161,7 +160,7 @@ self_attention_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_co
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           umma_f16(tmem_base + AT_O_COL, adesc + (uint64_t)((j * (AT_P_BYTES / 4)) >> 4) + 2 * kk,
-                   bdesc + (uint64_t)((j * (AT_V_BYTES / 4)) >> 4) + 2 * kk, idesc_o, (c | j | kk) != 0);
+                   bdesc + (uint64_t)(((j * 64 + kk * 16) * 128) >> 4), idesc_o, (c | j | kk) != 0);
         }
       }
       umma_commit(bar_mma);
@@ -342,16 +341,16 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
         tma_load_3d(sK, &mapQK, &qk_full[s], d_model + h * AT_HD, 0, b);
         tma_load_3d(sK + AT_K_BYTES / 2, &mapQK, &qk_full[s], d_model + h * AT_HD, 128, b);
         mbar_wait(&v_empty[s], (u & 1) ^ 1);
-        mbar_expect_tx(&v_full[s], AT_V_BYTES);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tma_load_3d(sV + j * (AT_V_BYTES / 4), &mapVT, &v_full[s], j * 64, h * AT_HD, b);
+        mbar_expect_tx(&v_full[s], AT_V_BYTES);   // V rows = keys, 64 values (128 B) each: MN-major B operand
+        tma_load_3d(sV, &mapQK, &v_full[s], 2 * d_model + h * AT_HD, 0, b);
+        tma_load_3d(sV + AT_V_BYTES / 2, &mapQK, &v_full[s], 2 * d_model + h * AT_HD, 128, b);
       }
     }
   } else if (warp == 9) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc(AT_BM, AT_KC, OpTraits<OpT>::fmt);
-      constexpr uint32_t idesc_o = umma_idesc(AT_BM, AT_HD, OpTraits<OpT>::fmt);
+      constexpr uint32_t idesc_o = umma_idesc(AT_BM, AT_HD, OpTraits<OpT>::fmt) | (1u << 16);  // B (= V) is MN-major
       auto issue_s = [&](int i) {
         const int s = i & 1, u = i >> 1;
         mbar_wait(&qk_full[s], u & 1);
@@ -376,9 +375,9 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)   // 16 keys per step: 8 packed P columns, +32 B of the V^T row
+          for (int kk = 0; kk < 4; ++kk)   // 16 keys per step: 8 packed P columns, 16 V rows of 128 B
             umma_f16_ts(tmem_base + 256 * s + 128, tmem_base + 256 * s + 8 * (4 * j + kk),
-                        vdesc + (uint64_t)((j * (AT_V_BYTES / 4)) >> 4) + 2 * kk, idesc_o, (j | kk) != 0);
+                        vdesc + (uint64_t)(((j * 64 + kk * 16) * 128) >> 4), idesc_o, (j | kk) != 0);
         }
         umma_commit(&o_full[s]);
         umma_commit(&v_empty[s]);
@@ -509,22 +508,19 @@ static int launch_attn_t256(const CUtensorMap& mqk, const CUtensorMap& mvt, cons
 
 using namespace mm;
 
-extern "C" int mm_self_attention(const void* qk, int64_t qk_ld, const void* vt, int64_t vt_ld, const int32_t* seq_lens,
-                                 int32_t batch, int32_t seq, int32_t heads, void* out, int64_t out_ld, int32_t dtype,
-                                 void* stream) {
-  if (!qk || !vt || !seq_lens || !out) return bad_arg("self_attention: null pointer");
+extern "C" int mm_self_attention(const void* qkv, int64_t qkv_ld, const int32_t* seq_lens, int32_t batch, int32_t seq,
+                                 int32_t heads, void* out, int64_t out_ld, int32_t dtype, void* stream) {
+  if (!qkv || !seq_lens || !out) return bad_arg("self_attention: null pointer");
   if (batch <= 0 || seq <= 0 || heads <= 0) return bad_arg("self_attention: extents");
   const int d = heads * AT_HD;
-  if (qk_ld < 2 * d || (qk_ld % 8) || (vt_ld % 8) || vt_ld < seq || (out_ld % 8) || out_ld < d)
+  if (qkv_ld < 3 * d || (qkv_ld % 8) || (out_ld % 8) || out_ld < d)
     return bad_arg("self_attention: leading dims (head_dim must be 64)");
   const int f16 = dtype == MM_DTYPE_F16;
-  CUtensorMap mqk, mvt;
-  int rc = make_tmap_3d(&mqk, qk, f16, (uint64_t)(2 * d), (uint64_t)seq, (uint64_t)batch, (uint64_t)qk_ld,
-                        (uint64_t)seq * qk_ld, 128);
+  CUtensorMap mqk;
+  int rc = make_tmap_3d(&mqk, qkv, f16, (uint64_t)(3 * d), (uint64_t)seq, (uint64_t)batch, (uint64_t)qkv_ld,
+                        (uint64_t)seq * qkv_ld, 128);
   if (rc) return rc;
-  rc = make_tmap_3d(&mvt, vt, f16, (uint64_t)vt_ld, (uint64_t)d, (uint64_t)batch, (uint64_t)vt_ld,
-                    (uint64_t)d * vt_ld, 64);
-  if (rc) return rc;
+  const CUtensorMap& mvt = mqk;   // V is read from the same [B*T, 3d] tensor (columns [2d, 3d)) as an MN-major operand
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (seq <= AT_KC)   // single key chunk: persistent warp-specialised kernel
     return f16 ? launch_attn_t256<__half>(mqk, mvt, seq_lens, batch, seq, heads, d, out, out_ld, s)

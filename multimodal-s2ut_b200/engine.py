@@ -217,19 +217,16 @@ class EncoderEngine:
         LN1(x), on exit it (or ``h_out``) holds next_ln(x).  Otherwise the stand-alone LayerNorm kernel runs.
         """
         d, M, op, bn = self.d, B * T, self.op_dtype, self.block_n
-        Tp = _round_up(T, 8)
         h = self.buf("h", (M, d), op)
-        qk = self.buf("qk", (M, 2 * d), op)
-        vt = self.buf("vt", (B, d, Tp), op, zero=True)               # columns >= T stay zero
+        qkv = self.buf("qkv", (M, 3 * d), op)
         att = self.buf("att", (M, d), op)
         f = self.buf("ffn", (M, self.ffn), op)
         fused = self.fused_ln
         if not fused:
             K.layernorm(x, L["ln1_g"], L["ln1_b"], out_op=h)
         K.gemm(a0=h, a0_ld=d, rows=M, w=L["wqkv"], n=3 * d, k=d, mode=K.EPI_OP, bias=L["bqkv"], scale=64 ** -0.5,
-               scale_cols=d, out0=qk, out0_ld=2 * d, rows_per_seq=T, out0_bs=T * 2 * d, vt=vt, vt_col0=2 * d,
-               vt_rows=d, vt_ld=Tp, block_n=bn)
-        K.self_attention(qk, vt, seq_lens, B, T, self.heads, att)
+               scale_cols=d, out0=qkv, out0_ld=3 * d, block_n=bn)
+        K.self_attention(qkv, seq_lens, B, T, self.heads, att)
         if fused:
             K.gemm_resid_ln(att, L["wo"], L["bo"], x, L["ln2_g"], L["ln2_b"], h)
         else:

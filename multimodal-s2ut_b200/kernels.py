@@ -190,14 +190,14 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_op: 
                                     eps, _stream()), "mm_layernorm")
 
 
-def self_attention(qk: torch.Tensor, vt: torch.Tensor, seq_lens_: torch.Tensor, batch: int, seq: int, heads: int,
+def self_attention(qkv: torch.Tensor, seq_lens_: torch.Tensor, batch: int, seq: int, heads: int,
                    out: torch.Tensor) -> None:
-    assert qk.dtype == vt.dtype == out.dtype and seq_lens_.dtype == torch.int32
+    """qkv [B*T, 3d] (q pre-scaled | k | v) -> out [B*T, d]; head_dim 64."""
+    assert qkv.dtype == out.dtype and seq_lens_.dtype == torch.int32 and qkv.stride(-1) == 1
     lib = _lib.load()
     with _Launch("self_attention", 4.0 * batch * seq * seq * heads * 64):
-        _lib.check(lib.mm_self_attention(_ptr(qk), qk.stride(-2), _ptr(vt), vt.stride(-2), _ptr(seq_lens_), batch,
-                                         seq, heads, _ptr(out), out.stride(-2), dtype_code(qk.dtype), _stream()),
-                   "mm_self_attention")
+        _lib.check(lib.mm_self_attention(_ptr(qkv), qkv.stride(-2), _ptr(seq_lens_), batch, seq, heads, _ptr(out),
+                                         out.stride(-2), dtype_code(qkv.dtype), _stream()), "mm_self_attention")
 
 
 def softmax_rows(scores: torch.Tensor, ld_in: int, rows: int, n_keys: int, probs: torch.Tensor, ld_out: int,

@@ -134,21 +134,18 @@ def test_self_attention(cuda, T, lens):
 
     dt, H, hd = torch.bfloat16, 4, 64
     B, d = len(lens), 4 * 64
-    Tp = (T + 7) // 8 * 8
     g = torch.Generator().manual_seed(T)
     q = torch.randn(B, T, H, hd, generator=g) * 0.8
     k = torch.randn(B, T, H, hd, generator=g)
     v = torch.randn(B, T, H, hd, generator=g)
-    qk = torch.cat([q.reshape(B * T, d), k.reshape(B * T, d)], 1).to(cuda).to(dt).contiguous()
-    vt = torch.zeros(B, d, Tp, dtype=dt, device=cuda)
-    vt[:, :, :T] = v.reshape(B, T, d).transpose(1, 2).to(cuda).to(dt)
+    qkv = torch.cat([q.reshape(B * T, d), k.reshape(B * T, d), v.reshape(B * T, d)], 1).to(cuda).to(dt).contiguous()
     sl = torch.tensor(lens, dtype=torch.int32, device=cuda)
     out = torch.zeros(B * T, d, dtype=dt, device=cuda)
-    K.self_attention(qk, vt, sl, B, T, H, out)
+    K.self_attention(qkv, sl, B, T, H, out)
     torch.cuda.synchronize()
-    qf = qk[:, :d].float().view(B, T, H, hd).permute(0, 2, 1, 3)
-    kf = qk[:, d:].float().view(B, T, H, hd).permute(0, 2, 1, 3)
-    vf = vt[:, :, :T].float().view(B, H, hd, T).permute(0, 1, 3, 2)
+    qf = qkv[:, :d].float().view(B, T, H, hd).permute(0, 2, 1, 3)
+    kf = qkv[:, d: 2 * d].float().view(B, T, H, hd).permute(0, 2, 1, 3)
+    vf = qkv[:, 2 * d:].float().view(B, T, H, hd).permute(0, 2, 1, 3)
     s = qf @ kf.transpose(-1, -2)
     mask = torch.arange(T, device=cuda)[None, :] >= sl[:, None]
     s = s.masked_fill(mask[:, None, None, :], float("-inf"))
