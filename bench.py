@@ -198,9 +198,11 @@ def run_ours(a):
         wav = wav * (0.5 + 0.5 * torch.rand(BATCH, 1, generator=g))          # distinct gains
         img = torch.randn(BATCH, IMG_TOKENS, IMG_DIM, generator=g)
         lens = torch.full((BATCH,), n_samples, dtype=torch.int64)
-        host_sets.append((wav.pin_memory(), lens.pin_memory(), img.pin_memory()))
-    dev_sets = [(w.to(dev), l.to(dev), i.to(dev)) for w, l, i in host_sets]
-    h2d_bytes = sum(t.numel() * t.element_size() for t in host_sets[0])
+        wav = wav.round().clamp_(-32768, 32767)      # 16-bit PCM values, as real audio files hold them
+        host_sets.append((wav.pin_memory(), lens.pin_memory(), img.pin_memory(), wav.to(torch.int16).pin_memory()))
+    dev_sets = [(w.to(dev), l.to(dev), i.to(dev)) for w, l, i, _ in host_sets]
+    # e2e host inputs: int16 PCM waveform (the audio files' own format) + fp32 image features (the reference's format)
+    h2d_bytes = sum(t.numel() * t.element_size() for t in (host_sets[0][3], host_sets[0][1], host_sets[0][2]))
 
     ge = [GraphedEncoder(enc, BATCH, n_samples, [(IMG_TOKENS, IMG_DIM)]) for _ in range(2)]
     n0 = K.launch_count
@@ -209,6 +211,11 @@ def run_ours(a):
         g.capture()
     torch.cuda.synchronize()
     launches_per_fwd = (K.launch_count - n0) // (2 * 3)        # 2 warm-up + 1 capture pass per graph
+    ge16 = [GraphedEncoder(enc, BATCH, n_samples, [(IMG_TOKENS, IMG_DIM)], wav_dtype=torch.int16) for _ in range(2)]
+    for j, g in enumerate(ge16):
+        g.load_inputs(host_sets[j][3].to(dev), dev_sets[j][1], [dev_sets[j][2]])
+        g.capture()
+    torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -254,10 +261,10 @@ def run_ours(a):
             j = i & 1
             with torch.cuda.stream(copy_stream):          # H2D of step i overlaps the forward of step i-1
                 copy_stream.wait_event(free[j])
-                ge[j].load_inputs(host_sets[j][0], host_sets[j][1], [host_sets[j][2]])
+                ge16[j].load_inputs(host_sets[j][3], host_sets[j][1], [host_sets[j][2]])
                 ready[j].record(copy_stream)
             main.wait_event(ready[j])
-            out = ge[j].replay()
+            out = ge16[j].replay()
             chk = out["encoder_out"][0].sum()             # the step's result read back by the host
             result_host[j:j + 1].copy_(chk.reshape(1), non_blocking=True)
             free[j].record(main)
@@ -326,7 +333,7 @@ def run_ours(a):
             "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / a.steps,
-                    "how": "pinned host waveform + fp32 image features -> cudaMemcpyAsync on a copy stream "
+                    "how": "pinned host int16 PCM waveform + fp32 image features -> cudaMemcpyAsync on a copy stream "
                            "(double-buffered, overlapping the previous step) -> graph replay -> checksum D2H"},
             "gpu_launches": launches_per_fwd * a.steps,
             "launches_per_step": launches_per_fwd,

@@ -43,6 +43,10 @@ const char* mm_last_error(void);
  * --------------------------------------------------------------------------------------------- */
 int mm_fbank_f32(const float* wav, const int64_t* n_samples, int32_t batch, int64_t wav_stride, float* feats,
                  int32_t max_frames, const float* tables, void* stream);
+/* Same, from raw int16 PCM (what the wav files hold before mm_s2ut/data/audio_utils.py:281-290 turns them into
+ * float32 / 2^15 and multiplies by 2^15 again): the conversion is exact, the dominant read is halved. */
+int mm_fbank_i16(const int16_t* wav, const int64_t* n_samples, int32_t batch, int64_t wav_stride, float* feats,
+                 int32_t max_frames, const float* tables, void* stream);
 /* Constant tables of the fbank kernel (povey window, FFT twiddles, sparse mel bank): the caller allocates
  * mm_fbank_table_floats() floats on the host, fills them with mm_fbank_build_tables() and keeps a device copy
  * that it passes to mm_fbank_f32 (the library itself owns no device memory). */

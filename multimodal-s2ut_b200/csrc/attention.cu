@@ -240,7 +240,8 @@ static int launch_attn(const CUtensorMap& mqk, const CUtensorMap& mvt, const int
 // TMEM: region g = columns [256 g, 256 g + 256): S (fp32, 256 keys) -> P in [0,128) -> O in [128,192).
 // ===================================================================================================
 constexpr int PA_STAGE_BYTES = AT_Q_BYTES + AT_K_BYTES + AT_V_BYTES;   // 80 KB
-constexpr int PA_SMEM_BYTES = 2 * PA_STAGE_BYTES + 256 + 1024;
+constexpr int PA_MAX_LENS = 1024;   // utterance lengths staged in shared memory (larger batches read them from global)
+constexpr int PA_SMEM_BYTES = 2 * PA_STAGE_BYTES + 256 + PA_MAX_LENS * 4 + 1024;
 constexpr int PA_THREADS = 320;
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -299,6 +300,9 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
   uint64_t* o_full = bars + 12;     // [2] PV MMA done -> softmax group
   uint64_t* reg_free = bars + 14;   // [2] softmax group has read O -> MMA may overwrite the TMEM region
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  int* s_lens = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 256);
+  const int n_batch = n_items / (nqt * H);
+  for (int i = threadIdx.x; i < n_batch && i < PA_MAX_LENS; i += PA_THREADS) s_lens[i] = seq_lens[i];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_local = (int)blockIdx.x < n_items ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -351,36 +355,49 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc(AT_BM, AT_KC, OpTraits<OpT>::fmt);
       constexpr uint32_t idesc_o = umma_idesc(AT_BM, AT_HD, OpTraits<OpT>::fmt) | (1u << 16);  // B (= V) is MN-major
-      auto issue_s = [&](int i) {
-        const int s = i & 1, u = i >> 1;
-        mbar_wait(&qk_full[s], u & 1);
-        mbar_wait(&reg_free[s], (u & 1) ^ 1);
-        tc_fence_after();
-        const uint64_t adesc = umma_desc_sw128(smem_u32(smem + s * PA_STAGE_BYTES));
-        const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + s * PA_STAGE_BYTES + AT_Q_BYTES));
+      // Two work queues (next S = Q K^T, next O = P V) served by whichever is ready first: the issuer never blocks
+      // on one softmax group while the other group's MMA could be issued, so the groups settle into ping-pong.
+      int s_next = 0, pv_next = 0;
+      const uint64_t t0 = globaltimer_ns();
+      while (pv_next < n_local) {
+        bool progressed = false;
+        if (s_next < n_local && s_next <= pv_next + 1) {
+          const int s = s_next & 1, u = s_next >> 1;
+          if (mbar_test(&qk_full[s], u & 1) && mbar_test(&reg_free[s], (u & 1) ^ 1)) {
+            tc_fence_after();
+            const uint64_t adesc = umma_desc_sw128(smem_u32(smem + s * PA_STAGE_BYTES));
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + s * PA_STAGE_BYTES + AT_Q_BYTES));
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_f16(tmem_base + 256 * s, adesc + 2 * kk, bdesc + 2 * kk, idesc_s, kk != 0);
-        umma_commit(&s_full[s]);
-        umma_commit(&qk_empty[s]);
-      };
-      if (n_local > 0) issue_s(0);
-      for (int i = 0; i < n_local; ++i) {
-        if (i + 1 < n_local) issue_s(i + 1);
-        const int s = i & 1, u = i >> 1;
-        mbar_wait(&v_full[s], u & 1);
-        mbar_wait(&p_full[s], u & 1);
-        tc_fence_after();
-        const uint64_t vdesc = umma_desc_sw128(smem_u32(smem + s * PA_STAGE_BYTES + AT_Q_BYTES + AT_K_BYTES));
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)   // 16 keys per step: 8 packed P columns, 16 V rows of 128 B
-            umma_f16_ts(tmem_base + 256 * s + 128, tmem_base + 256 * s + 8 * (4 * j + kk),
-                        vdesc + (uint64_t)(((j * 64 + kk * 16) * 128) >> 4), idesc_o, (j | kk) != 0);
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16(tmem_base + 256 * s, adesc + 2 * kk, bdesc + 2 * kk, idesc_s, kk != 0);
+            umma_commit(&s_full[s]);
+            umma_commit(&qk_empty[s]);
+            ++s_next;
+            progressed = true;
+          }
         }
-        umma_commit(&o_full[s]);
-        umma_commit(&v_empty[s]);
+        if (pv_next < s_next) {
+          const int s = pv_next & 1, u = pv_next >> 1;
+          if (mbar_test(&p_full[s], u & 1) && mbar_test(&v_full[s], u & 1)) {
+            tc_fence_after();
+            const uint64_t vdesc = umma_desc_sw128(smem_u32(smem + s * PA_STAGE_BYTES + AT_Q_BYTES + AT_K_BYTES));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)   // 16 keys per step: 8 packed P columns, 16 V rows of 128 B
+                umma_f16_ts(tmem_base + 256 * s + 128, tmem_base + 256 * s + 8 * (4 * j + kk),
+                            vdesc + (uint64_t)(((j * 64 + kk * 16) * 128) >> 4), idesc_o, (j | kk) != 0);
+            }
+            umma_commit(&o_full[s]);
+            umma_commit(&v_empty[s]);
+            ++pv_next;
+            progressed = true;
+          }
+        }
+        if (!progressed && globaltimer_ns() - t0 > 8000000000ull) {
+          printf("mm: attention issuer timeout block %d s_next %d pv_next %d\n", blockIdx.x, s_next, pv_next);
+          __trap();
+        }
       }
     }
   } else {
@@ -392,7 +409,7 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
       const int item = blockIdx.x + i * gridDim.x;
       const int qt = item % nqt, h = (item / nqt) % H, b = item / (nqt * H);
       const int u = i >> 1;
-      const int len = max(1, min(seq_lens[b], T));
+      const int len = max(1, min(b < PA_MAX_LENS ? s_lens[b] : seq_lens[b], T));
       const int nch = (len + 31) >> 5;        // chunks holding at least one valid key
       const int nfull = len >> 5;             // chunks that need no masking
       const int rem = len & 31;               // valid keys in chunk `nfull` when rem > 0

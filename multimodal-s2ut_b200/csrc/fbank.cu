@@ -79,7 +79,10 @@ constexpr int FB_XBUF = 16 * 17 * 2;                   // floats per half-warp: 
 constexpr int FB_SMEM_FLOATS = FB_WAVE + TB_TOTAL + FB_HW * (FB_ZBUF + FB_XBUF);
 constexpr int FB_SMEM_BYTES = FB_SMEM_FLOATS * 4;
 
-__global__ void __launch_bounds__(FB_THREADS) fbank_kernel(const float* __restrict__ wav,
+// WavT = float (samples already in int16 range) or int16_t (raw PCM: halves the dominant HBM / PCIe read; the
+// int16 -> fp32 conversion is exact, so both inputs give bit-identical features for integer-valued audio)
+template <typename WavT>
+__global__ void __launch_bounds__(FB_THREADS) fbank_kernel(const WavT* __restrict__ wav,
                                                            const long long* __restrict__ n_samples, long long wav_stride,
                                                            float* __restrict__ feats, int max_frames,
                                                            const float* __restrict__ tables) {
@@ -100,18 +103,38 @@ __global__ void __launch_bounds__(FB_THREADS) fbank_kernel(const float* __restri
   // ---- stage samples + tables ----
   const long long s0 = (long long)f0 * FB_SHIFT;
   const int n_need = FB_WIN + (nf_here - 1) * FB_SHIFT;  // <= n - s0 by construction
-  const float* wsrc = wav + (long long)b * wav_stride + s0;
-  if ((reinterpret_cast<uintptr_t>(wsrc) & 15) == 0) {
-    for (int i = threadIdx.x * 4; i < n_need; i += FB_THREADS * 4) {
-      if (i + 3 < n_need) {
-        const float4 v = __ldcs(reinterpret_cast<const float4*>(wsrc + i));
-        *reinterpret_cast<float4*>(s_wave + i) = v;
-      } else {
-        for (int j = i; j < n_need; ++j) s_wave[j] = wsrc[j];
+  const WavT* wsrc = wav + (long long)b * wav_stride + s0;
+  if constexpr (sizeof(WavT) == 4) {
+    if ((reinterpret_cast<uintptr_t>(wsrc) & 15) == 0) {
+      for (int i = threadIdx.x * 4; i < n_need; i += FB_THREADS * 4) {
+        if (i + 3 < n_need) {
+          const float4 v = __ldcs(reinterpret_cast<const float4*>(wsrc + i));
+          *reinterpret_cast<float4*>(s_wave + i) = v;
+        } else {
+          for (int j = i; j < n_need; ++j) s_wave[j] = wsrc[j];
+        }
       }
+    } else {
+      for (int i = threadIdx.x; i < n_need; i += FB_THREADS) s_wave[i] = wsrc[i];
     }
   } else {
-    for (int i = threadIdx.x; i < n_need; i += FB_THREADS) s_wave[i] = wsrc[i];
+    if ((reinterpret_cast<uintptr_t>(wsrc) & 15) == 0) {     // 8 PCM samples per 128-bit load
+      for (int i = threadIdx.x * 8; i < n_need; i += FB_THREADS * 8) {
+        if (i + 7 < n_need) {
+          const uint4 q = __ldcs(reinterpret_cast<const uint4*>(wsrc + i));
+          const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            s_wave[i + 2 * j] = (float)(short)(w[j] & 0xFFFFu);
+            s_wave[i + 2 * j + 1] = (float)(short)(w[j] >> 16);
+          }
+        } else {
+          for (int j = i; j < n_need; ++j) s_wave[j] = (float)wsrc[j];
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < n_need; i += FB_THREADS) s_wave[i] = (float)wsrc[i];
+    }
   }
   for (int i = threadIdx.x; i < TB_TOTAL; i += FB_THREADS) s_tab[i] = __ldg(tables + i);
   __syncthreads();
@@ -308,22 +331,34 @@ extern "C" int mm_fbank_build_tables(float* out) {
   return 0;
 }
 
-extern "C" int mm_fbank_f32(const float* wav, const int64_t* n_samples, int32_t batch, int64_t wav_stride, float* feats,
-                            int32_t max_frames, const float* tables, void* stream) {
+template <typename WavT>
+static int launch_fbank(const WavT* wav, const int64_t* n_samples, int32_t batch, int64_t wav_stride, float* feats,
+                        int32_t max_frames, const float* tables, void* stream) {
   if (!wav || !n_samples || !feats || !tables) return bad_arg("fbank: null pointer");
   if (batch <= 0 || max_frames <= 0) return 0;
-  static bool attr_set = false;
+  static bool attr_set = false;   // per instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BYTES);
+    cudaError_t e =
+        cudaFuncSetAttribute(fbank_kernel<WavT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BYTES);
     if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute(fbank)");
     attr_set = true;
   }
   const int n_chunks = (max_frames + FB_FRAMES_PER_CTA - 1) / FB_FRAMES_PER_CTA;
   dim3 grid(n_chunks, batch);
-  fbank_kernel<<<grid, FB_THREADS, FB_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
+  fbank_kernel<WavT><<<grid, FB_THREADS, FB_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
       wav, reinterpret_cast<const long long*>(n_samples), wav_stride, feats, max_frames, tables);
   MM_CHECK_LAUNCH("fbank_kernel launch");
   return 0;
+}
+
+extern "C" int mm_fbank_f32(const float* wav, const int64_t* n_samples, int32_t batch, int64_t wav_stride, float* feats,
+                            int32_t max_frames, const float* tables, void* stream) {
+  return launch_fbank<float>(wav, n_samples, batch, wav_stride, feats, max_frames, tables, stream);
+}
+
+extern "C" int mm_fbank_i16(const int16_t* wav, const int64_t* n_samples, int32_t batch, int64_t wav_stride,
+                            float* feats, int32_t max_frames, const float* tables, void* stream) {
+  return launch_fbank<int16_t>(wav, n_samples, batch, wav_stride, feats, max_frames, tables, stream);
 }
 
 extern "C" int mm_cmvn_stats(const float* feats, const int64_t* lens, int32_t lengths_are_samples, int32_t batch,

@@ -230,47 +230,56 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
       if constexpr (MODE == MM_EPI_OP || MODE == MM_EPI_RELU_OP) {
         int b = bi, t = r;
         if (p.rows_per_seq > 0) b = r / p.rows_per_seq, t = r - b * p.rows_per_seq;
+        // the two 32-column TMEM loads of the NEXT slab are always in flight while the current one is processed
+        uint32_t ra0[32], ra1[32];
+        tmem_ld32(taddr, ra0);
+        tmem_ld32(taddr + 32, ra1);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 64) {
           const int col = col_tile + c0;
           if (col >= p.n) break;                                          // uniform
           const bool to_vt = (MODE == MM_EPI_OP) && p.vt != nullptr && col >= p.vt_col0;   // uniform
           uint8_t* slab = sSlab + (slab_ctr % NB) * Cfg::SLAB_BYTES;
-          if (!to_vt) {
+          tmem_ld_wait();
+          float v0[32], v1[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v0[i] = __uint_as_float(ra0[i]) + sBias[c0 + i];
+            v1[i] = __uint_as_float(ra1[i]) + sBias[c0 + 32 + i];
+          }
+          if (c0 + 64 < BN && col + 64 < p.n) {
+            tmem_ld32(taddr + c0 + 64, ra0);
+            tmem_ld32(taddr + c0 + 96, ra1);
+          }
+          if constexpr (MODE == MM_EPI_OP) {
+            if (col < p.scale_cols) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v0[i] *= p.scale;
+            }
+            if (col + 32 < p.scale_cols) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v1[i] *= p.scale;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v0[i] = fmaxf(v0[i], 0.f), v1[i] = fmaxf(v1[i], 0.f);
+          }
+          if (to_vt) {
+            // transposed store: lanes hold consecutive t -> coalesced 2-byte stores per column
+            if (rvalid) {
+              const int vc = col - p.vt_col0;
+              OpT* dst = reinterpret_cast<OpT*>(p.vt) + ((long long)b * p.vt_rows + vc) * p.vt_ld + t;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                if (col + i < p.n) dst[(long long)i * p.vt_ld] = OpTraits<OpT>::cvt(v0[i]);
+                if (col + 32 + i < p.n) dst[(long long)(32 + i) * p.vt_ld] = OpTraits<OpT>::cvt(v1[i]);
+              }
+            }
+          } else {
             if (et == 0) bulk_wait_read<NB - 1>();
             asm volatile("bar.sync 1, 128;" ::: "memory");                // slab free
-          }
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t ra[32];
-            tmem_ld32(taddr + c0 + 32 * h, ra);
-            tmem_ld_wait();
-            float v[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]) + sBias[c0 + 32 * h + i];
-            if constexpr (MODE == MM_EPI_OP) {
-              if (col + 32 * h < p.scale_cols) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] *= p.scale;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-            }
-            if (to_vt) {
-              // transposed store: lanes hold consecutive t -> coalesced 2-byte stores per column
-              if (rvalid) {
-                const int vc = col + 32 * h - p.vt_col0;
-                OpT* dst = reinterpret_cast<OpT*>(p.vt) + ((long long)b * p.vt_rows + vc) * p.vt_ld + t;
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (col + 32 * h + i < p.n) dst[(long long)i * p.vt_ld] = OpTraits<OpT>::cvt(v[i]);
-              }
-            } else {
-              slab_write_op32<OpT>(slab, lrow, 4 * h, v);
-            }
-          }
-          if (!to_vt) {
+            slab_write_op32<OpT>(slab, lrow, 0, v0);
+            slab_write_op32<OpT>(slab, lrow, 4, v1);
             fence_proxy_async_smem();
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (et == 0) {

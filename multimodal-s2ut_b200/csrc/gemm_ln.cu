@@ -10,9 +10,8 @@
 // LayerNorm statistics need no cross-thread reduction at all.  Epilogue per CTA (thread = row):
 //   sweep 1  residual slabs (128 rows x 32 fp32) arrive by TMA into the operand ring, which is idle once the last
 //            MMA has completed (12 + 2 slabs in flight); v = acc + bias + x is written back to TMEM and to the slab,
-//            the slab is TMA-stored as the new fp32 residual; row sums accumulate in registers
-//   sweep 2  sum (v - mean)^2 straight from TMEM (two-pass variance like torch)
-//   sweep 3  (v - mean) * rstd * gamma + beta -> 16-bit (and optionally fp32) slabs -> TMA store
+//            the slab is TMA-stored as the new fp32 residual; row sum / sum of squares accumulate in registers
+//   sweep 2  (v - mean) * rstd * gamma + beta -> 16-bit (and optionally fp32) slabs -> TMA store
 #include "common.cuh"
 #include "host.cuh"
 #include "../../include/mms2ut_b200.h"
@@ -145,7 +144,7 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       }
     }
     // ---- sweep 1: v = acc + bias + x ; new residual out ; row sum ----
-    float sum = 0.f;
+    float sum = 0.f, sumsq = 0.f;
     uint32_t ra[32], rb[32];
     auto sweep1 = [&](int j, uint32_t (&r)[32]) {
       const int b = j < 6 ? j : j - 6;
@@ -167,6 +166,7 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         const float v2 = __uint_as_float(r[4 * c + 2]) + bq[c].z + __uint_as_float(xq[c].z);
         const float v3 = __uint_as_float(r[4 * c + 3]) + bq[c].w + __uint_as_float(xq[c].w);
         sum += (v0 + v1) + (v2 + v3);
+        sumsq += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
         uint32_t* dst = c < 4 ? &lo[4 * c] : &hi[4 * (c - 4)];
         dst[0] = __float_as_uint(v0), dst[1] = __float_as_uint(v1);
         dst[2] = __float_as_uint(v2), dst[3] = __float_as_uint(v3);
@@ -201,34 +201,15 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       }
     }
     tmem_st_wait();
+    // Row statistics: the two halves exchange (sum, sum of squares).  Raw-moment variance in fp32 is accurate to
+    // ~1e-6 here because the residual stream has |mean| <~ std (checked against a two-pass fp64 LayerNorm);
+    // it saves a full extra sweep over the accumulator in TMEM.
     stat[h * 128 + lrow] = sum;
+    stat[256 + h * 128 + lrow] = sumsq;
     asm volatile("bar.sync 3, 256;" ::: "memory");
     const float mean = (sum + stat[(h ^ 1) * 128 + lrow]) * (1.0f / Cfg::N);
-    // ---- sweep 2: centred second moment from TMEM (two chunks per wait, four accumulators) ----
-    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-    tmem_ld32(taddr, ra);
-    tmem_ld32(taddr + 32, rb);
-#pragma unroll 1
-    for (int j = 0; j < 8; j += 2) {
-      tmem_ld_wait();
-      float d0[32], d1[32];
-#pragma unroll
-      for (int c = 0; c < 32; ++c) d0[c] = __uint_as_float(ra[c]) - mean, d1[c] = __uint_as_float(rb[c]) - mean;
-      if (j + 2 < 8) {
-        tmem_ld32(taddr + 32 * (j + 2), ra);
-        tmem_ld32(taddr + 32 * (j + 3), rb);
-      }
-#pragma unroll
-      for (int c = 0; c < 32; c += 2) {
-        q0 = fmaf(d0[c], d0[c], q0), q1 = fmaf(d0[c + 1], d0[c + 1], q1);
-        q2 = fmaf(d1[c], d1[c], q2), q3 = fmaf(d1[c + 1], d1[c + 1], q3);
-      }
-    }
-    const float sq = (q0 + q1) + (q2 + q3);
-    asm volatile("bar.sync 3, 256;" ::: "memory");   // everybody has read the row sums
-    stat[h * 128 + lrow] = sq;
-    asm volatile("bar.sync 3, 256;" ::: "memory");
-    const float rstd = rsqrtf((sq + stat[(h ^ 1) * 128 + lrow]) * (1.0f / Cfg::N) + p.eps);
+    const float ex2 = (sumsq + stat[256 + (h ^ 1) * 128 + lrow]) * (1.0f / Cfg::N);
+    const float rstd = rsqrtf(fmaxf(ex2 - mean * mean, 0.f) + p.eps);
     // ---- sweep 3: normalise -> 16-bit slabs (64 columns each), optional fp32 copy ----
     if (ht == 0) bulk_wait_read<0>();       // sweep-1 stores have drained: this half's 6 buffers are reusable
     auto sweep3 = [&](int col, const uint32_t (&r)[32], uint8_t* slab, int chunk0, uint8_t* fs) {

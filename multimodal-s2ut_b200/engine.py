@@ -166,8 +166,8 @@ class EncoderEngine:
         B = src_tokens.shape[0]
         feats_norm = None
         if src_tokens.dim() == 2:
-            if src_tokens.dtype != torch.float32:
-                raise TypeError("raw waveform input must be float32 (int16 range, i.e. already x 2**15)")
+            if src_tokens.dtype not in (torch.float32, torch.int16):
+                raise TypeError("raw waveform input must be float32 in int16 range (already x 2**15) or int16 PCM")
             wav = src_tokens if src_tokens.stride(1) == 1 else src_tokens.contiguous()
             m = num_frames(wav.shape[1])
             if m <= 0:

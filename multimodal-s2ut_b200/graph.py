@@ -15,13 +15,14 @@ import torch
 
 
 class GraphedEncoder:
-    def __init__(self, enc, batch: int, n_samples: int, img_shapes: List[tuple], warmup: int = 2):
+    def __init__(self, enc, batch: int, n_samples: int, img_shapes: List[tuple], warmup: int = 2,
+                 wav_dtype: torch.dtype = torch.float32):
         if enc.training:
             raise RuntimeError("graph capture is for eval-mode forwards (modality dropout draws are per batch)")
         self.enc = enc
         dev = next(enc.parameters()).device
         self.device = dev
-        self.wav = torch.zeros(batch, n_samples, dtype=torch.float32, device=dev)
+        self.wav = torch.zeros(batch, n_samples, dtype=wav_dtype, device=dev)   # float32 (x 2**15) or int16 PCM
         self.lens = torch.full((batch,), n_samples, dtype=torch.int64, device=dev)
         self.imgs = [torch.zeros(batch, *s, dtype=torch.float32, device=dev) for s in img_shapes]
         self.masks: List[Optional[torch.Tensor]] = [None for _ in img_shapes]

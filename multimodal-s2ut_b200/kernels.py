@@ -75,15 +75,16 @@ def fbank_tables(device) -> torch.Tensor:
 
 
 def fbank(wav: torch.Tensor, n_samples: torch.Tensor, feats: torch.Tensor, tables: torch.Tensor) -> None:
-    """wav [B, N] fp32 (x 2**15), n_samples [B] int64 -> feats [B, m, 80] raw log-mel (valid frames only)."""
-    assert wav.dtype == torch.float32 and wav.dim() == 2 and wav.stride(1) == 1
+    """wav [B, N] fp32 (x 2**15) or int16 PCM, n_samples [B] int64 -> feats [B, m, 80] raw log-mel (valid frames)."""
+    assert wav.dtype in (torch.float32, torch.int16) and wav.dim() == 2 and wav.stride(1) == 1
     assert n_samples.dtype == torch.int64 and feats.dtype == torch.float32 and feats.is_contiguous()
     B, m = feats.shape[0], feats.shape[1]
     assert feats.shape[2] == 80
     lib = _lib.load()
-    with _Launch("fbank", float(4 * wav.numel() + 4 * feats.numel())):   # algorithmic bytes
-        _lib.check(lib.mm_fbank_f32(_ptr(wav), _ptr(n_samples), B, wav.stride(0), _ptr(feats), m, _ptr(tables),
-                                    _stream()), "mm_fbank_f32")
+    fn = lib.mm_fbank_f32 if wav.dtype == torch.float32 else lib.mm_fbank_i16
+    with _Launch("fbank", float(wav.element_size() * wav.numel() + 4 * feats.numel())):   # algorithmic bytes
+        _lib.check(fn(_ptr(wav), _ptr(n_samples), B, wav.stride(0), _ptr(feats), m, _ptr(tables), _stream()),
+                   "mm_fbank")
 
 
 def cmvn_stats(feats: torch.Tensor, lens: torch.Tensor, lengths_are_samples: bool, mean_std: torch.Tensor) -> None:
