@@ -46,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not _stale():
         return LIB_PATH
     nvcc = _nvcc()
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + os.environ.get("MM_NVCC_EXTRA", "").split()
     objdir = _PKG / "build"
     objdir.mkdir(exist_ok=True)
     procs = []

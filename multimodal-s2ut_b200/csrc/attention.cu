@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(128, 1)
 self_attention_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant__ CUtensorMap mapVT,
                       const int* __restrict__ seq_lens, int T, int d_model, OpT* __restrict__ out, long long out_ld) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + AT_Q_BYTES;
   uint8_t* sV = sK + AT_K_BYTES;
@@ -289,7 +289,7 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
                            const int* __restrict__ seq_lens, int T, int d_model, int H, int nqt, int n_items,
                            OpT* __restrict__ out, long long out_ld) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * PA_STAGE_BYTES);
   uint64_t* qk_full = bars;         // [2] TMA (Q, K) -> MMA
   uint64_t* qk_empty = bars + 2;    // [2] S MMA done -> TMA

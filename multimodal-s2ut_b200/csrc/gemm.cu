@@ -42,8 +42,14 @@ struct GemmDev {
 
 struct GemmCfg {
   static constexpr int BM = 128, BN = 256, BK = 64;
-  static constexpr int STAGES = 5;
-  static constexpr int NB = 4;                      // epilogue staging slabs
+#ifndef MM_GEMM_STAGES
+#define MM_GEMM_STAGES 5
+#endif
+#ifndef MM_GEMM_NB
+#define MM_GEMM_NB 4
+#endif
+  static constexpr int STAGES = MM_GEMM_STAGES;
+  static constexpr int NB = MM_GEMM_NB;             // epilogue staging slabs
   static constexpr int A_BYTES = BM * BK * 2;       // 16 KB
   static constexpr int B_BYTES = (BN / 2) * BK * 2; // 16 KB: this CTA's half of the W tile
   static constexpr int SLAB_BYTES = BM * 128;       // 128 rows x 128 B
@@ -95,7 +101,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
   using Cfg = GemmCfg;
   constexpr int STAGES = Cfg::STAGES, NB = Cfg::NB, BN = Cfg::BN;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sA = smem;
   uint8_t* sB = sA + STAGES * Cfg::A_BYTES;
   uint8_t* sSlab = sB + STAGES * Cfg::B_BYTES;

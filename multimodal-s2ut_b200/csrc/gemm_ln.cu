@@ -50,7 +50,7 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   using Cfg = LnCfg;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* ring = smem;                                       // STAGES x (A | B0 | B1); 12 slabs in the epilogue
   uint8_t* extra = ring + STAGES * Cfg::STAGE_BYTES;          // 2 more slabs (row statistics live here)
   uint64_t* bars = reinterpret_cast<uint64_t*>(extra + 2 * Cfg::SLAB_BYTES);
