@@ -74,22 +74,20 @@ __device__ __forceinline__ void dft16(float2 (&a)[16]) {
 
 constexpr int FB_THREADS = 256;
 constexpr int FB_HW = FB_THREADS / 16;                 // 16 half-warps
-constexpr int FB_ZBUF = 512;                           // floats per half-warp: packed input / natural-order Z
-constexpr int FB_XBUF = 16 * 17 * 2;                   // floats per half-warp: padded 16x17 complex transpose
-constexpr int FB_SMEM_FLOATS = FB_WAVE + TB_TOTAL + FB_HW * (FB_ZBUF + FB_XBUF);
-constexpr int FB_SMEM_BYTES = FB_SMEM_FLOATS * 4;
+constexpr int FB_XBUF = 16 * 17 * 2;                   // floats per half-warp: padded 16x17 complex transpose / spectrum
+constexpr int FB_SMEM_FLOATS = FB_WAVE + FB_HW * FB_XBUF;
+constexpr int FB_SMEM_BYTES = FB_SMEM_FLOATS * 4;      // 56 KB -> 3-4 CTAs per SM
 
 // WavT = float (samples already in int16 range) or int16_t (raw PCM: halves the dominant HBM / PCIe read; the
 // int16 -> fp32 conversion is exact, so both inputs give bit-identical features for integer-valued audio)
 template <typename WavT>
-__global__ void __launch_bounds__(FB_THREADS) fbank_kernel(const WavT* __restrict__ wav,
-                                                           const long long* __restrict__ n_samples, long long wav_stride,
-                                                           float* __restrict__ feats, int max_frames,
-                                                           const float* __restrict__ tables) {
+__global__ void __launch_bounds__(FB_THREADS, 3) fbank_kernel(const WavT* __restrict__ wav,
+                                                              const long long* __restrict__ n_samples,
+                                                              long long wav_stride, float* __restrict__ feats,
+                                                              int max_frames, const float* __restrict__ tables) {
   extern __shared__ __align__(16) float fsm[];
   float* s_wave = fsm;
-  float* s_tab = s_wave + FB_WAVE;
-  float* s_work = s_tab + TB_TOTAL;
+  float* s_work = s_wave + FB_WAVE;
 
   const int b = blockIdx.y;
   const int chunk = blockIdx.x;
@@ -100,7 +98,7 @@ __global__ void __launch_bounds__(FB_THREADS) fbank_kernel(const WavT* __restric
   if (f0 >= nfr) return;  // whole CTA out of range (uniform)
   const int nf_here = min(FB_FRAMES_PER_CTA, nfr - f0);
 
-  // ---- stage samples + tables ----
+  // ---- stage the samples of this CTA's 32 frames (5360 values; frames overlap 2.5x) ----
   const long long s0 = (long long)f0 * FB_SHIFT;
   const int n_need = FB_WIN + (nf_here - 1) * FB_SHIFT;  // <= n - s0 by construction
   const WavT* wsrc = wav + (long long)b * wav_stride + s0;
@@ -136,25 +134,31 @@ __global__ void __launch_bounds__(FB_THREADS) fbank_kernel(const WavT* __restric
       for (int i = threadIdx.x; i < n_need; i += FB_THREADS) s_wave[i] = (float)wsrc[i];
     }
   }
-  for (int i = threadIdx.x; i < TB_TOTAL; i += FB_THREADS) s_tab[i] = __ldg(tables + i);
   __syncthreads();
 
-  const float* s_win = s_tab + TB_WIN;
-  const float2* s_tw256 = reinterpret_cast<const float2*>(s_tab + TB_TW256);
-  const float2* s_tw512 = reinterpret_cast<const float2*>(s_tab + TB_TW512);
-  const float* s_melw = s_tab + TB_MELW;
-  const int* s_k0 = reinterpret_cast<const int*>(s_tab + TB_K0);
-  const int* s_cnt = reinterpret_cast<const int*>(s_tab + TB_CNT);
-  const int* s_off = reinterpret_cast<const int*>(s_tab + TB_OFF);
+  // constant tables stay in global memory (10.7 KB, L1/L2 resident) and are read through the read-only path
+  const float2* g_win2 = reinterpret_cast<const float2*>(tables + TB_WIN);
+  const float2* g_tw256 = reinterpret_cast<const float2*>(tables + TB_TW256);
+  const float2* g_tw512 = reinterpret_cast<const float2*>(tables + TB_TW512);
+  const float* g_melw = tables + TB_MELW;
+  const int* g_k0 = reinterpret_cast<const int*>(tables + TB_K0);
+  const int* g_cnt = reinterpret_cast<const int*>(tables + TB_CNT);
+  const int* g_off = reinterpret_cast<const int*>(tables + TB_OFF);
 
   const int hw = threadIdx.x >> 4;       // half-warp id 0..15
   const int l = threadIdx.x & 15;        // lane in half-warp
   const int hsel = (threadIdx.x >> 4) & 1;
   const unsigned hmask = 0xFFFFu << (16 * hsel);
-  float* zbuf = s_work + hw * (FB_ZBUF + FB_XBUF);
-  float* xbuf = zbuf + FB_ZBUF;
-  float2* z2 = reinterpret_cast<float2*>(zbuf);
+  float* xbuf = s_work + hw * FB_XBUF;
   float2* x2 = reinterpret_cast<float2*>(xbuf);
+  // mel filters owned by this lane (l + 16 j): start bin, length, weight offset
+  int mk0[5], mcnt[5], moff[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    mk0[j] = __ldg(g_k0 + l + 16 * j);
+    mcnt[j] = __ldg(g_cnt + l + 16 * j);
+    moff[j] = __ldg(g_off + l + 16 * j);
+  }
 
   for (int fl = hw; fl < nf_here; fl += FB_HW) {
     const float* x = s_wave + fl * FB_SHIFT;
@@ -169,61 +173,61 @@ __global__ void __launch_bounds__(FB_THREADS) fbank_kernel(const WavT* __restric
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(hmask, s, o);
     const float mean = s * (1.0f / FB_WIN);
-    // ---- pre-emphasis (replicate-left) + povey window, packed as 256 complex; zero pad 400..511 ----
-#pragma unroll
-    for (int j = 0; j < 25; ++j) {
-      int i = l + 16 * j + 16 * hsel;
-      i = i >= FB_WIN ? i - FB_WIN : i;
-      const float a = x[i] - mean;
-      const float p = x[i > 0 ? i - 1 : 0] - mean;
-      zbuf[i] = __fmul_rn(__fsub_rn(a, __fmul_rn(0.97f, p)), s_win[i]);
-    }
-#pragma unroll
-    for (int j = 0; j < 7; ++j) zbuf[FB_WIN + l + 16 * j] = 0.f;
-    __syncwarp(hmask);
-    // ---- pass 1: lane n1 = l, 16-point DFT over n2 of z[n1 + 16 n2]; twiddle W256^(n1 k2); transpose ----
+    // ---- pass 1 input straight from the sample tile: z[n] = (y[2n], y[2n+1]), n = l + 16 n2, with
+    //      y[i] = ((x[i]-mean) - 0.97 (x[max(i-1,0)]-mean)) * povey[i] for i < 400, else 0 ----
     float2 a[16];
 #pragma unroll
-    for (int n2 = 0; n2 < 16; ++n2) a[n2] = z2[l + 16 * n2];
+    for (int n2 = 0; n2 < 16; ++n2) {
+      const int nn = l + 16 * n2;              // complex index; samples 2 nn, 2 nn + 1
+      if (nn < FB_WIN / 2) {
+        const float2 xv = *reinterpret_cast<const float2*>(x + 2 * nn);
+        const float xm = x[nn > 0 ? 2 * nn - 1 : 0];
+        const float2 w = __ldg(g_win2 + nn);
+        const float c0 = xv.x - mean, c1 = xv.y - mean, cm = xm - mean;
+        a[n2].x = __fmul_rn(__fsub_rn(c0, __fmul_rn(0.97f, cm)), w.x);
+        a[n2].y = __fmul_rn(__fsub_rn(c1, __fmul_rn(0.97f, c0)), w.y);
+      } else {
+        a[n2] = make_float2(0.f, 0.f);
+      }
+    }
+    // ---- pass 1: lane n1 = l, 16-point DFT over n2; twiddle W256^(n1 k2); padded transpose through smem ----
     dft16(a);
 #pragma unroll
     for (int k2 = 0; k2 < 16; ++k2) {
-      const float2 v = (k2 == 0) ? a[0] : cmul(a[k2], s_tw256[l * k2]);
+      const float2 v = (k2 == 0) ? a[0] : cmul(a[k2], __ldg(g_tw256 + l * k2));
       x2[k2 * 17 + l] = v;
     }
     __syncwarp(hmask);
-    // ---- pass 2: lane k2 = l, 16-point DFT over n1 -> Z[16 k1 + k2] ----
+    // ---- pass 2: lane k2 = l, 16-point DFT over n1 -> a[k1] = Z[16 k1 + l] ----
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) a[n1] = x2[l * 17 + n1];
     dft16(a);
-    __syncwarp(hmask);
+    __syncwarp(hmask);   // all lanes have read the transpose: xbuf is reused for the power spectrum
+    // ---- real-FFT split: X[k] needs Z[k] and conj(Z[256-k]); 256-k = 16 (15-k1) + (16-l) lives in lane 16-l
+    //      (lane 0: own slot (16-k1) & 15) -> one shuffle pair per bin instead of a trip through smem ----
+    const int src = ((16 - l) & 15) + 16 * hsel;
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) z2[16 * k1 + l] = a[k1];
-    __syncwarp(hmask);
-    // ---- real-FFT split + power spectrum for bins 0..255 (Nyquist has zero mel weight) ----
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int k = l + 16 * j;
-      const float2 zk = z2[k];
-      float2 zm = z2[(256 - k) & 255];
-      zm.y = -zm.y;
+    for (int k1 = 0; k1 < 16; ++k1) {
+      const float px = __shfl_sync(hmask, a[15 - k1].x, src);
+      const float py = __shfl_sync(hmask, a[15 - k1].y, src);
+      const float2 zk = a[k1];
+      float2 zm;
+      zm.x = (l == 0) ? a[(16 - k1) & 15].x : px;
+      zm.y = -((l == 0) ? a[(16 - k1) & 15].y : py);
       const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y + zm.y));
       const float2 d = csub(zk, zm);
       const float2 o = make_float2(0.5f * d.y, -0.5f * d.x);  // -i/2 * (zk - zm)
-      const float2 xk = cadd(e, cmul(s_tw512[k], o));
-      xbuf[k] = xk.x * xk.x + xk.y * xk.y;
+      const float2 xk = cadd(e, cmul(__ldg(g_tw512 + 16 * k1 + l), o));
+      xbuf[16 * k1 + l] = xk.x * xk.x + xk.y * xk.y;
     }
     __syncwarp(hmask);
     // ---- sparse mel projection + log ----
     float* orow = feats + ((long long)b * max_frames + (f0 + fl)) * FB_BINS;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
-      const int m = l + 16 * j;
-      const int k0 = s_k0[m], cnt = s_cnt[m], off = s_off[m];
       float e = 0.f;
-      for (int i = 0; i < cnt; ++i) e = fmaf(s_melw[off + i], xbuf[k0 + i], e);
-      const float v = logf(fmaxf(e, 1.1920928955078125e-07f));
-      orow[m] = v;
+      for (int i = 0; i < mcnt[j]; ++i) e = fmaf(__ldg(g_melw + moff[j] + i), xbuf[mk0[j] + i], e);
+      orow[l + 16 * j] = logf(fmaxf(e, 1.1920928955078125e-07f));
     }
     __syncwarp(hmask);
   }
