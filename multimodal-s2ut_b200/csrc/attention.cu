@@ -302,7 +302,6 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   int* s_lens = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 256);
   const int n_batch = n_items / (nqt * H);
-  for (int i = threadIdx.x; i < n_batch && i < PA_MAX_LENS; i += PA_THREADS) s_lens[i] = seq_lens[i];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_local = (int)blockIdx.x < n_items ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -328,6 +327,10 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();   // the QKV projection (previous kernel) is complete and visible
+  for (int i = threadIdx.x; i < n_batch && i < PA_MAX_LENS; i += PA_THREADS) s_lens[i] = seq_lens[i];
+  __syncthreads();
 
   if (warp == 8) {
     // ---------------- TMA producer ----------------
@@ -515,9 +518,20 @@ static int launch_attn_t256(const CUtensorMap& mqk, const CUtensorMap& mvt, cons
   const int nqt = (T + AT_BM - 1) / AT_BM;
   const int n_items = B * H * nqt;
   const int grid = n_items < kNumSMs ? n_items : kNumSMs;
-  kern<<<grid, PA_THREADS, PA_SMEM_BYTES, s>>>(mqk, mvt, lens, T, d, H, nqt, n_items, reinterpret_cast<OpT*>(out),
-                                               out_ld);
-  MM_CHECK_LAUNCH("self_attention_t256_kernel launch");
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(PA_THREADS);
+  cfg.dynamicSmemBytes = PA_SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mqk, mvt, lens, T, d, H, nqt, n_items, reinterpret_cast<OpT*>(out),
+                                     out_ld);
+  if (e != cudaSuccess) return fail(e, "self_attention_t256_kernel launch");
   return 0;
 }
 

@@ -139,6 +139,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // the next kernel may start its prologue on SMs this grid no longer needs
+  pdl_wait();                // everything above overlapped the previous kernel's tail; its outputs are visible now
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -566,13 +568,15 @@ static int launch_gemm(const GemmMaps& m, const GemmDev& p, cudaStream_t s) {
   cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, m.a0, m.a1, m.w, m.out0, m.out1, m.aux0, p);
   if (e != cudaSuccess) return fail(e, "gemm_kernel launch");
   return 0;

@@ -83,6 +83,8 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // the next kernel may start its prologue on SMs this grid no longer needs
+  pdl_wait();                // everything above overlapped the previous kernel's tail; its outputs are visible now
 
   // epilogue geometry: warps w and w+4 share TMEM lane quadrant (w & 3); half h owns columns [256 h, 256 h + 256)
   const int h = warp >> 2;
@@ -300,13 +302,15 @@ static int launch_ln_gemm(const CUtensorMap& mA, const CUtensorMap& mW, const CU
   cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = LnCfg::SMEM_BYTES;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mA, mW, mX, mH, mHf, p);
   if (e != cudaSuccess) return fail(e, "gemm_resid_ln_kernel launch");
   return 0;

@@ -1,4 +1,9 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_rowwise.py tests/test_gpu_int16.py tests/test_gpu_encoder.py -q -m gpu --timeout 300 > gpurun_out/t.log 2>&1
-echo "tests exit $?"; grep -E "passed|failed|Error|timeout|assert [0-9]|^E  " gpurun_out/t.log | head
-python profiles/tools/frontend_sweep.py 2>&1 | grep -E "float32" | tee gpurun_out/frontend_sweep_v2.txt
+timeout 900 python -m pytest tests -q -m gpu --timeout 300 > gpurun_out/gpu_tests.log 2>&1
+echo "gpu tests exit $?"; tail -3 gpurun_out/gpu_tests.log
+timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench10.json 2> gpurun_out/bench10.err
+echo "bench exit $?"; tail -5 gpurun_out/bench10.err; python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench10.json'))
+print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'],'roof',d['roofline']['achieved'],d['roofline']['frac'])
+PY
