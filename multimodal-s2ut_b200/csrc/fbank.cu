@@ -238,32 +238,63 @@ __global__ void __launch_bounds__(FB_THREADS, 3) fbank_kernel(const WavT* __rest
 // variance E[x^2]-mean^2 cancels catastrophically, so its rounding noise (up to a few 1e-2 after
 // normalisation in low-variance bins) is part of the reference's result.  One thread per (utterance, bin)
 // replays that exact order (loads are batched 8 deep and independent; only the adds are a chain).
-__global__ void __launch_bounds__(96) cmvn_stats_kernel(const float* __restrict__ feats,
-                                                        const long long* __restrict__ lens, int lengths_are_samples,
-                                                        int max_frames, float* __restrict__ mean_std) {
+constexpr int CS_THREADS = 256;
+constexpr int CS_TILE = 64;                              // frames per shared-memory tile (20 KB), double buffered
+__global__ void __launch_bounds__(CS_THREADS) cmvn_stats_kernel(const float* __restrict__ feats,
+                                                                const long long* __restrict__ lens,
+                                                                int lengths_are_samples, int max_frames,
+                                                                float* __restrict__ mean_std) {
+  // All 256 threads stream [64 frames x 80 bins] tiles into shared memory with 16-byte cp.async (coalesced, next
+  // tile in flight while the current one is consumed); threads 0..79 then replay numpy's frame-sequential fp32
+  // accumulation from shared memory, so the only serial chain is two dependent adds per frame.
+  __shared__ __align__(16) float tile[2][CS_TILE * FB_BINS];
   const int b = blockIdx.x, bin = threadIdx.x;
-  if (bin >= FB_BINS) return;
   const long long n = lens[b];
   int nfr = lengths_are_samples ? (n < FB_WIN ? 0 : (int)(1 + (n - FB_WIN) / FB_SHIFT)) : (int)n;
   nfr = min(nfr, max_frames);
-  const float* x = feats + (long long)b * max_frames * FB_BINS + bin;
+  const float* base = feats + (long long)b * max_frames * FB_BINS;
+  const int n_tiles = (nfr + CS_TILE - 1) / CS_TILE;
+  auto issue = [&](int t) {
+    const int rows = min(CS_TILE, nfr - t * CS_TILE);
+    const float4* src = reinterpret_cast<const float4*>(base + (long long)t * CS_TILE * FB_BINS);
+    const uint32_t dst = smem_u32(&tile[t & 1][0]);
+    for (int i = threadIdx.x; i < rows * (FB_BINS / 4); i += CS_THREADS)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 16), "l"(src + i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   float s = 0.f, q = 0.f;
-  int i = 0;
-  for (; i + 8 <= nfr; i += 8) {
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = __ldg(x + (long long)(i + j) * FB_BINS);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s = __fadd_rn(s, v[j]);
-      q = __fadd_rn(q, __fmul_rn(v[j], v[j]));
+  if (n_tiles > 0) issue(0);
+  for (int t = 0; t < n_tiles; ++t) {
+    if (t + 1 < n_tiles) {
+      issue(t + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
+    __syncthreads();
+    if (bin < FB_BINS) {
+      const int rows = min(CS_TILE, nfr - t * CS_TILE);
+      const float* x = &tile[t & 1][bin];
+      int i = 0;
+      for (; i + 8 <= rows; i += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = x[(i + j) * FB_BINS];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s = __fadd_rn(s, v[j]);
+          q = __fadd_rn(q, __fmul_rn(v[j], v[j]));
+        }
+      }
+      for (; i < rows; ++i) {
+        const float v = x[i * FB_BINS];
+        s = __fadd_rn(s, v);
+        q = __fadd_rn(q, __fmul_rn(v, v));
+      }
+    }
+    __syncthreads();   // the tile may be overwritten by the load issued two iterations later
   }
-  for (; i < nfr; ++i) {
-    const float v = __ldg(x + (long long)i * FB_BINS);
-    s = __fadd_rn(s, v);
-    q = __fadd_rn(q, __fmul_rn(v, v));
-  }
+  if (bin >= FB_BINS) return;
   float mean = 0.f, sd = 1.f;
   if (nfr > 0) {
     const float T = (float)nfr;
@@ -369,7 +400,7 @@ extern "C" int mm_cmvn_stats(const float* feats, const int64_t* lens, int32_t le
                              int32_t max_frames, float* mean_std, void* stream) {
   if (!feats || !lens || !mean_std) return bad_arg("cmvn_stats: null pointer");
   if (batch <= 0 || max_frames <= 0) return 0;
-  cmvn_stats_kernel<<<batch, 96, 0, static_cast<cudaStream_t>(stream)>>>(
+  cmvn_stats_kernel<<<batch, CS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       feats, reinterpret_cast<const long long*>(lens), lengths_are_samples, max_frames, mean_std);
   MM_CHECK_LAUNCH("cmvn_stats_kernel launch");
   return 0;
