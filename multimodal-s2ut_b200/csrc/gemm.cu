@@ -59,7 +59,9 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + NB * SLAB_BYTES + BAR_BYTES + BIAS_BYTES + 1024;
 };
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// ex2.approx + rcp.approx (2 ulp): an IEEE division here is a ~30-instruction branchy subroutine per element, and with
+// one epilogue warp per scheduler its latency is fully exposed (the GLU / gate epilogues were 4x slower than the MMAs).
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 // this thread's row inside a swizzled slab: 16-byte chunk c lives at position c ^ (row & 7)
 __device__ __forceinline__ uint4* slab_chunk(uint8_t* slab, int row, int c) {

@@ -118,6 +118,81 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
   }
 }
 
+// Vector version for 16-byte aligned rows (ld_in, ld_out multiples of 4): each lane owns V4 groups of four adjacent
+// keys -> 128-bit score loads, 64-bit probability stores, and no work beyond ceil(ld_out / 128) groups.
+template <int V4, typename OpT>
+__global__ void __launch_bounds__(256) softmax_rows_vec_kernel(const float* __restrict__ scores, long long ld_in,
+                                                                long long rows, int n_keys,
+                                                                const uint8_t* __restrict__ key_mask, int rows_per_seq,
+                                                                OpT* __restrict__ probs, long long ld_out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* sr = reinterpret_cast<const float4*>(scores + row * ld_in);
+  const uint8_t* mk = key_mask ? key_mask + (row / rows_per_seq) * (long long)n_keys : nullptr;
+  float v[V4][4];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < V4; ++i) {
+    const int c = 4 * (lane + 32 * i);
+    float4 s = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (c < n_keys) s = __ldcs(sr + lane + 32 * i);   // c + 3 < ld_in: the pad columns are readable
+    v[i][0] = s.x, v[i][1] = s.y, v[i][2] = s.z, v[i][3] = s.w;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (c + e >= n_keys || (mk && mk[c + e])) v[i][e] = -INFINITY;
+      mx = fmaxf(mx, v[i][e]);
+    }
+  }
+  mx = warp_max(mx);
+  const float mref = (mx == -INFINITY) ? 0.f : mx;  // fully masked row -> NaN like the reference (0/0)
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < V4; ++i) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[i][e] = __expf(v[i][e] - mref);
+      sum += v[i][e];
+    }
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  uint2* pr = reinterpret_cast<uint2*>(probs + row * ld_out);
+#pragma unroll
+  for (int i = 0; i < V4; ++i) {
+    const int c = 4 * (lane + 32 * i);
+    if (c < ld_out) {
+      uint2 q;
+      q.x = OpTraits<OpT>::pack2(c < n_keys ? v[i][0] * inv : 0.f, c + 1 < n_keys ? v[i][1] * inv : 0.f);
+      q.y = OpTraits<OpT>::pack2(c + 2 < n_keys ? v[i][2] * inv : 0.f, c + 3 < n_keys ? v[i][3] * inv : 0.f);
+      pr[lane + 32 * i] = q;
+    }
+  }
+}
+
+template <int V4, typename OpT>
+static void launch_softmax_vec(const float* scores, long long ld_in, long long rows, int n_keys, const uint8_t* key_mask,
+                               int rows_per_seq, void* probs, long long ld_out, cudaStream_t s) {
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  softmax_rows_vec_kernel<V4, OpT><<<grid, 256, 0, s>>>(scores, ld_in, rows, n_keys, key_mask, rows_per_seq,
+                                                        reinterpret_cast<OpT*>(probs), ld_out);
+}
+template <typename OpT>
+static void dispatch_softmax_vec(const float* scores, long long ld_in, long long rows, int n_keys,
+                                 const uint8_t* key_mask, int rows_per_seq, void* probs, long long ld_out,
+                                 cudaStream_t s) {
+  switch ((ld_out + 127) / 128) {
+    case 1: launch_softmax_vec<1, OpT>(scores, ld_in, rows, n_keys, key_mask, rows_per_seq, probs, ld_out, s); break;
+    case 2: launch_softmax_vec<2, OpT>(scores, ld_in, rows, n_keys, key_mask, rows_per_seq, probs, ld_out, s); break;
+    case 3: launch_softmax_vec<3, OpT>(scores, ld_in, rows, n_keys, key_mask, rows_per_seq, probs, ld_out, s); break;
+    case 4: launch_softmax_vec<4, OpT>(scores, ld_in, rows, n_keys, key_mask, rows_per_seq, probs, ld_out, s); break;
+    case 5: launch_softmax_vec<5, OpT>(scores, ld_in, rows, n_keys, key_mask, rows_per_seq, probs, ld_out, s); break;
+    case 6: launch_softmax_vec<6, OpT>(scores, ld_in, rows, n_keys, key_mask, rows_per_seq, probs, ld_out, s); break;
+    case 7: launch_softmax_vec<7, OpT>(scores, ld_in, rows, n_keys, key_mask, rows_per_seq, probs, ld_out, s); break;
+    default: launch_softmax_vec<8, OpT>(scores, ld_in, rows, n_keys, key_mask, rows_per_seq, probs, ld_out, s); break;
+  }
+}
+
 template <typename OpT>
 __global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ x, OpT* __restrict__ out,
                                                        long long n) {
@@ -230,6 +305,15 @@ extern "C" int mm_softmax_rows(const float* scores, int64_t ld_in, int64_t rows,
   if (rows <= 0) return 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (ld_in % 4 == 0 && ld_out % 4 == 0 && ld_in >= ((n_keys + 3) & ~3) &&
+      (reinterpret_cast<uintptr_t>(scores) & 15) == 0 && (reinterpret_cast<uintptr_t>(probs) & 7) == 0) {
+    if (dtype == MM_DTYPE_F16)
+      mm::dispatch_softmax_vec<__half>(scores, ld_in, rows, n_keys, key_mask, rows_per_seq, probs, ld_out, s);
+    else
+      mm::dispatch_softmax_vec<__nv_bfloat16>(scores, ld_in, rows, n_keys, key_mask, rows_per_seq, probs, ld_out, s);
+    MM_CHECK_LAUNCH("softmax_rows_vec_kernel launch");
+    return 0;
+  }
   if (dtype == MM_DTYPE_F16)
     softmax_rows_kernel<__half><<<grid, 256, 0, s>>>(scores, ld_in, rows, n_keys, key_mask, rows_per_seq,
                                                      reinterpret_cast<__half*>(probs), ld_out);

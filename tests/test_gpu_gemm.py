@@ -205,9 +205,13 @@ def test_gemm_full_size_linearity(cuda):
     assert (out.float() - ref_all).abs().max().item() < 3e-2
 
 
-@pytest.mark.parametrize("M,Kd,want_f32", [(1000, 512, False), (300, 2048, True), (20000, 512, True)])
+@pytest.mark.parametrize("M,Kd,want_f32", [(1000, 512, False), (300, 2048, True), (20000, 512, True),
+                                           (16000, 512, False), (20000, 2048, False), (40000, 576, False)])
 def test_gemm_resid_ln_fused(cuda, M, Kd, want_f32):
-    """x += a W^T + b and h = LayerNorm(x) in one kernel (20000 rows -> some CTA pairs take two tiles)."""
+    """x += a W^T + b and h = LayerNorm(x) in one kernel (20000 rows -> some CTA pairs take two tiles).
+
+    Without the fp32 copy the four-CTA overlapped kernel runs (40000 rows -> up to five row blocks per cluster,
+    both accumulator stages and the slab ring wrap several times)."""
     from mm_s2ut_b200 import kernels as K
 
     dt, N = torch.bfloat16, 512

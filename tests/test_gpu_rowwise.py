@@ -24,12 +24,15 @@ def test_layernorm(cuda, dim):
     assert (o16.float() - ref).abs().max().item() < 4e-2
 
 
-def test_softmax_rows(cuda):
+@pytest.mark.parametrize("Tk,Tkp", [(577, 584), (577, 579), (50, 52), (1000, 1024), (197, 200)])
+def test_softmax_rows(cuda, Tk, Tkp):
+    """Aligned leading dimensions take the 128-bit kernel, 579 the scalar one; pad columns hold NaN on input."""
     from mm_s2ut_b200 import kernels as K
 
     g = torch.Generator().manual_seed(5)
-    B, T, Tk, Tkp = 3, 50, 577, 584
+    B, T = 3, 50
     S = (torch.randn(B * T, Tkp, generator=g) * 4).to(cuda)
+    S[:, Tk:] = float("nan")
     mask = (torch.rand(B, Tk, generator=g) < 0.2).to(torch.uint8).to(cuda)
     P = torch.full((B * T, Tkp), 3.0, dtype=torch.bfloat16, device=cuda)
     K.softmax_rows(S, Tkp, B * T, Tk, P, Tkp, key_mask=mask, rows_per_seq=T)
