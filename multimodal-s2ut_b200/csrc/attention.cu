@@ -237,11 +237,15 @@ static int launch_attn(const CUtensorMap& mqk, const CUtensorMap& mvt, const int
 //                                                   16-bit over the already-consumed S columns, then O / l -> HBM
 // The two groups ping-pong: while one waits for its MMAs the other keeps the MUFU/ALU pipes busy, and the
 // producer runs one item ahead, so TMA latency, tensor work and softmax overlap instead of serialising.
-// TMEM: region g = columns [256 g, 256 g + 256): S (fp32, 256 keys) -> P in [0,128) -> O in [128,192).
+// TMEM: region g = columns [256 g, 256 g + 256): S (fp32, 256 keys) -> P(keys 0-127) in [0,64), O in [64,128),
+// P(keys 128-255) in [128,192).  P V for the first 128 keys is issued as soon as that half of P is in TMEM, while the
+// group is still exponentiating the second half.  O leaves through a swizzled 16 KB staging tile and one TMA store
+// per item (rows beyond T are clipped by the [B][T][d] tensor map).
 // ===================================================================================================
 constexpr int PA_STAGE_BYTES = AT_Q_BYTES + AT_K_BYTES + AT_V_BYTES;   // 80 KB
 constexpr int PA_MAX_LENS = 1024;   // utterance lengths staged in shared memory (larger batches read them from global)
-constexpr int PA_SMEM_BYTES = 2 * PA_STAGE_BYTES + 256 + PA_MAX_LENS * 4 + 1024;
+constexpr int PA_OUT_BYTES = AT_BM * AT_HD * 2;   // 16 KB staging tile per softmax group
+constexpr int PA_SMEM_BYTES = 2 * PA_STAGE_BYTES + 2 * PA_OUT_BYTES + 256 + PA_MAX_LENS * 4 + 1024;
 constexpr int PA_THREADS = 320;
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -283,23 +287,34 @@ __device__ __forceinline__ float max_chunk(const uint32_t (&r)[32], int valid) {
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
+#ifdef MM_ATT_TRACE
+__device__ long long g_att_trace[148 * 2 * 8 * 6];
+#define ATT_TRACE(slot)                                                                              \
+  do {                                                                                               \
+    if ((warp & 3) == 0 && lane == 0 && (i >> 1) < 8)                                                \
+      g_att_trace[((blockIdx.x * 2 + g) * 8 + (i >> 1)) * 6 + (slot)] = clock64();                   \
+  } while (0)
+#else
+#define ATT_TRACE(slot)
+#endif
+
 template <typename OpT>
 __global__ void __launch_bounds__(PA_THREADS, 1)
-self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant__ CUtensorMap mapVT,
-                           const int* __restrict__ seq_lens, int T, int d_model, int H, int nqt, int n_items,
-                           OpT* __restrict__ out, long long out_ld) {
+self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant__ CUtensorMap mapOut,
+                           const int* __restrict__ seq_lens, int T, int d_model, int H, int nqt, int n_items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * PA_STAGE_BYTES);
+  uint8_t* sOut = smem + 2 * PA_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + 2 * PA_OUT_BYTES);
   uint64_t* qk_full = bars;         // [2] TMA (Q, K) -> MMA
   uint64_t* qk_empty = bars + 2;    // [2] S MMA done -> TMA
   uint64_t* v_full = bars + 4;      // [2] TMA (V^T) -> MMA
   uint64_t* v_empty = bars + 6;     // [2] PV MMA done -> TMA
   uint64_t* s_full = bars + 8;      // [2] S MMA done -> softmax group
-  uint64_t* p_full = bars + 10;     // [2] softmax group (4 warps) -> MMA
-  uint64_t* o_full = bars + 12;     // [2] PV MMA done -> softmax group
-  uint64_t* reg_free = bars + 14;   // [2] softmax group has read O -> MMA may overwrite the TMEM region
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* p_half = bars + 10;     // [2 groups][2 halves] softmax group (4 warps) -> MMA: 128 keys of P are in TMEM
+  uint64_t* o_full = bars + 14;     // [2] PV MMA done -> softmax group
+  uint64_t* reg_free = bars + 16;   // [2] softmax group has read O -> MMA may overwrite the TMEM region
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
   int* s_lens = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 256);
   const int n_batch = n_items / (nqt * H);
 
@@ -309,14 +324,15 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
 
   if (tid == 0) {
     tma_prefetch_desc(&mapQK);
-    tma_prefetch_desc(&mapVT);
+    tma_prefetch_desc(&mapOut);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&qk_full[i], 1);
       mbar_init(&qk_empty[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&p_half[2 * i], 4);
+      mbar_init(&p_half[2 * i + 1], 4);
       mbar_init(&o_full[i], 1);
       mbar_init(&reg_free[i], 4);
     }
@@ -360,7 +376,7 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
       constexpr uint32_t idesc_o = umma_idesc(AT_BM, AT_HD, OpTraits<OpT>::fmt) | (1u << 16);  // B (= V) is MN-major
       // Two work queues (next S = Q K^T, next O = P V) served by whichever is ready first: the issuer never blocks
       // on one softmax group while the other group's MMA could be issued, so the groups settle into ping-pong.
-      int s_next = 0, pv_next = 0;
+      int s_next = 0, pva_next = 0, pv_next = 0;   // next S, next first-half P V, next second-half P V
       const uint64_t t0 = globaltimer_ns();
       while (pv_next < n_local) {
         bool progressed = false;
@@ -379,17 +395,33 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
             progressed = true;
           }
         }
-        if (pv_next < s_next) {
-          const int s = pv_next & 1, u = pv_next >> 1;
-          if (mbar_test(&p_full[s], u & 1) && mbar_test(&v_full[s], u & 1)) {
+        if (pva_next < s_next) {
+          const int s = pva_next & 1, u = pva_next >> 1;
+          if (mbar_test(&p_half[2 * s], u & 1) && mbar_test(&v_full[s], u & 1)) {
             tc_fence_after();
             const uint64_t vdesc = umma_desc_sw128(smem_u32(smem + s * PA_STAGE_BYTES + AT_Q_BYTES + AT_K_BYTES));
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 2; ++j) {
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)   // 16 keys per step: 8 packed P columns, 16 V rows of 128 B
-                umma_f16_ts(tmem_base + 256 * s + 128, tmem_base + 256 * s + 8 * (4 * j + kk),
+                umma_f16_ts(tmem_base + 256 * s + 64, tmem_base + 256 * s + 8 * (4 * j + kk),
                             vdesc + (uint64_t)(((j * 64 + kk * 16) * 128) >> 4), idesc_o, (j | kk) != 0);
+            }
+            ++pva_next;
+            progressed = true;
+          }
+        }
+        if (pv_next < pva_next) {
+          const int s = pv_next & 1, u = pv_next >> 1;
+          if (mbar_test(&p_half[2 * s + 1], u & 1)) {
+            tc_fence_after();
+            const uint64_t vdesc = umma_desc_sw128(smem_u32(smem + s * PA_STAGE_BYTES + AT_Q_BYTES + AT_K_BYTES));
+#pragma unroll
+            for (int j = 2; j < 4; ++j) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_f16_ts(tmem_base + 256 * s + 64, tmem_base + 256 * s + 128 + 8 * (4 * (j - 2) + kk),
+                            vdesc + (uint64_t)(((j * 64 + kk * 16) * 128) >> 4), idesc_o, 1);
             }
             umma_commit(&o_full[s]);
             umma_commit(&v_empty[s]);
@@ -398,7 +430,8 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
           }
         }
         if (!progressed && globaltimer_ns() - t0 > 8000000000ull) {
-          printf("mm: attention issuer timeout block %d s_next %d pv_next %d\n", blockIdx.x, s_next, pv_next);
+          printf("mm: attention issuer timeout block %d s_next %d pva_next %d pv_next %d\n", blockIdx.x, s_next,
+                 pva_next, pv_next);
           __trap();
         }
       }
@@ -416,20 +449,30 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
       const int nch = (len + 31) >> 5;        // chunks holding at least one valid key
       const int nfull = len >> 5;             // chunks that need no masking
       const int rem = len & 31;               // valid keys in chunk `nfull` when rem > 0
+      ATT_TRACE(0);
       mbar_wait(&s_full[g], u & 1);
       tc_fence_after();
+      ATT_TRACE(1);
       uint32_t ra[32], rb[32];
-      // ---- sweep 1: row maximum (two TMEM loads in flight) ----
+      // ---- sweep 1: row maximum (four TMEM loads in flight) ----
       float m = -INFINITY;
+      {
+        uint32_t rc[32], rd[32];
 #pragma unroll 1
-      for (int cc = 0; cc < nch; cc += 2) {
-        tmem_ld32(t_row + cc * 32, ra);
-        if (cc + 1 < nch) tmem_ld32(t_row + (cc + 1) * 32, rb);
-        tmem_ld_wait();
-        m = fmaxf(m, cc < nfull ? max_chunk<false>(ra, 32) : max_chunk<true>(ra, rem));
-        if (cc + 1 < nch) m = fmaxf(m, cc + 1 < nfull ? max_chunk<false>(rb, 32) : max_chunk<true>(rb, rem));
+        for (int cc = 0; cc < nch; cc += 4) {
+          tmem_ld32(t_row + cc * 32, ra);
+          if (cc + 1 < nch) tmem_ld32(t_row + (cc + 1) * 32, rb);
+          if (cc + 2 < nch) tmem_ld32(t_row + (cc + 2) * 32, rc);
+          if (cc + 3 < nch) tmem_ld32(t_row + (cc + 3) * 32, rd);
+          tmem_ld_wait();
+          m = fmaxf(m, cc < nfull ? max_chunk<false>(ra, 32) : max_chunk<true>(ra, rem));
+          if (cc + 1 < nch) m = fmaxf(m, cc + 1 < nfull ? max_chunk<false>(rb, 32) : max_chunk<true>(rb, rem));
+          if (cc + 2 < nch) m = fmaxf(m, cc + 2 < nfull ? max_chunk<false>(rc, 32) : max_chunk<true>(rc, rem));
+          if (cc + 3 < nch) m = fmaxf(m, cc + 3 < nfull ? max_chunk<false>(rd, 32) : max_chunk<true>(rd, rem));
+        }
       }
       const float mb = m * L2E;
+      ATT_TRACE(2);
       // ---- sweep 2: probabilities (next chunk prefetched while the current one goes through MUFU) ----
       float l = 0.f;
       tmem_ld32(t_row, ra);
@@ -445,7 +488,8 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
           for (int k = 0; k < 16; ++k) pk[k] = 0u;
         }
         tmem_ld_wait();
-        tmem_st16(t_row + 16 * cc, pk);       // P over S columns that have already been consumed
+        const uint32_t p_col = t_row + (cc < 4 ? 16 * cc : 128 + 16 * (cc - 4));
+        tmem_st16(p_col, pk);                 // P over S columns that have already been consumed
         if (cc + 2 < nch) tmem_ld32(t_row + (cc + 2) * 32, ra);
         if (cc + 1 < nch) {
           l += cc + 1 < nfull ? softmax_chunk<OpT, false>(rb, pk, mb, 32) : softmax_chunk<OpT, true>(rb, pk, mb, rem);
@@ -454,47 +498,63 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
           for (int k = 0; k < 16; ++k) pk[k] = 0u;
         }
         tmem_ld_wait();
-        tmem_st16(t_row + 16 * (cc + 1), pk);
+        tmem_st16(p_col + 16, pk);
+        if (cc == 2) {                        // keys 0-127 of P are complete: their P V can start now
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_half[2 * g]);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[g]);
+      if (lane == 0) mbar_arrive(&p_half[2 * g + 1]);
+      ATT_TRACE(3);
 
       mbar_wait(&o_full[g], u & 1);
       tc_fence_after();
+      ATT_TRACE(4);
       {
-        const int t = qt * AT_BM + row;
         const float inv = 1.0f / l;
-        tmem_ld32(t_row + 128, ra);
-        tmem_ld32(t_row + 160, rb);
+        tmem_ld32(t_row + 64, ra);
+        tmem_ld32(t_row + 96, rb);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&reg_free[g]);   // O is in registers: the TMEM region may be reused
-        if (t < T) {
-          uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * T + t) * out_ld + h * AT_HD);
+        uint8_t* so = sOut + g * PA_OUT_BYTES;
+        const bool elected = (warp & 3) == 0 && lane == 0;
+        if (elected) bulk_wait_read<0>();           // the previous item's store has finished reading the tile
+        if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            uint4 q;
-            q.x = OpTraits<OpT>::pack2(__uint_as_float(ra[8 * k + 0]) * inv, __uint_as_float(ra[8 * k + 1]) * inv);
-            q.y = OpTraits<OpT>::pack2(__uint_as_float(ra[8 * k + 2]) * inv, __uint_as_float(ra[8 * k + 3]) * inv);
-            q.z = OpTraits<OpT>::pack2(__uint_as_float(ra[8 * k + 4]) * inv, __uint_as_float(ra[8 * k + 5]) * inv);
-            q.w = OpTraits<OpT>::pack2(__uint_as_float(ra[8 * k + 6]) * inv, __uint_as_float(ra[8 * k + 7]) * inv);
-            dst[k] = q;
-          }
+        for (int k = 0; k < 4; ++k) {
+          uint4 q;
+          q.x = OpTraits<OpT>::pack2(__uint_as_float(ra[8 * k + 0]) * inv, __uint_as_float(ra[8 * k + 1]) * inv);
+          q.y = OpTraits<OpT>::pack2(__uint_as_float(ra[8 * k + 2]) * inv, __uint_as_float(ra[8 * k + 3]) * inv);
+          q.z = OpTraits<OpT>::pack2(__uint_as_float(ra[8 * k + 4]) * inv, __uint_as_float(ra[8 * k + 5]) * inv);
+          q.w = OpTraits<OpT>::pack2(__uint_as_float(ra[8 * k + 6]) * inv, __uint_as_float(ra[8 * k + 7]) * inv);
+          *reinterpret_cast<uint4*>(so + row * 128 + ((k ^ (row & 7)) << 4)) = q;
+        }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            uint4 q;
-            q.x = OpTraits<OpT>::pack2(__uint_as_float(rb[8 * k + 0]) * inv, __uint_as_float(rb[8 * k + 1]) * inv);
-            q.y = OpTraits<OpT>::pack2(__uint_as_float(rb[8 * k + 2]) * inv, __uint_as_float(rb[8 * k + 3]) * inv);
-            q.z = OpTraits<OpT>::pack2(__uint_as_float(rb[8 * k + 4]) * inv, __uint_as_float(rb[8 * k + 5]) * inv);
-            q.w = OpTraits<OpT>::pack2(__uint_as_float(rb[8 * k + 6]) * inv, __uint_as_float(rb[8 * k + 7]) * inv);
-            dst[4 + k] = q;
-          }
+        for (int k = 0; k < 4; ++k) {
+          uint4 q;
+          q.x = OpTraits<OpT>::pack2(__uint_as_float(rb[8 * k + 0]) * inv, __uint_as_float(rb[8 * k + 1]) * inv);
+          q.y = OpTraits<OpT>::pack2(__uint_as_float(rb[8 * k + 2]) * inv, __uint_as_float(rb[8 * k + 3]) * inv);
+          q.z = OpTraits<OpT>::pack2(__uint_as_float(rb[8 * k + 4]) * inv, __uint_as_float(rb[8 * k + 5]) * inv);
+          q.w = OpTraits<OpT>::pack2(__uint_as_float(rb[8 * k + 6]) * inv, __uint_as_float(rb[8 * k + 7]) * inv);
+          *reinterpret_cast<uint4*>(so + row * 128 + (((4 + k) ^ (row & 7)) << 4)) = q;
+        }
+        fence_proxy_async_smem();
+        if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (elected) {
+          tma_store_3d(&mapOut, so, h * AT_HD, qt * AT_BM, b);
+          bulk_commit();
         }
       }
+      ATT_TRACE(5);
     }
+    if ((warp & 3) == 0 && lane == 0) bulk_wait<0>();   // the last stores have landed before the CTA's smem goes away
   }
 
   tc_fence_before();
@@ -506,8 +566,8 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
 }
 
 template <typename OpT>
-static int launch_attn_t256(const CUtensorMap& mqk, const CUtensorMap& mvt, const int* lens, int B, int T, int H, int d,
-                            void* out, long long out_ld, cudaStream_t s) {
+static int launch_attn_t256(const CUtensorMap& mqk, const CUtensorMap& mout, const int* lens, int B, int T, int H,
+                            int d, cudaStream_t s) {
   auto kern = self_attention_t256_kernel<OpT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -529,8 +589,7 @@ static int launch_attn_t256(const CUtensorMap& mqk, const CUtensorMap& mvt, cons
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mqk, mvt, lens, T, d, H, nqt, n_items, reinterpret_cast<OpT*>(out),
-                                     out_ld);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mqk, mout, lens, T, d, H, nqt, n_items);
   if (e != cudaSuccess) return fail(e, "self_attention_t256_kernel launch");
   return 0;
 }
@@ -538,6 +597,12 @@ static int launch_attn_t256(const CUtensorMap& mqk, const CUtensorMap& mvt, cons
 }  // namespace mm
 
 using namespace mm;
+
+#ifdef MM_ATT_TRACE
+extern "C" int mm_debug_att_trace(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, g_att_trace, sizeof(long long) * 148 * 2 * 8 * 6);
+}
+#endif
 
 extern "C" int mm_self_attention(const void* qkv, int64_t qkv_ld, const int32_t* seq_lens, int32_t batch, int32_t seq,
                                  int32_t heads, void* out, int64_t out_ld, int32_t dtype, void* stream) {
@@ -553,9 +618,14 @@ extern "C" int mm_self_attention(const void* qkv, int64_t qkv_ld, const int32_t*
   if (rc) return rc;
   const CUtensorMap& mvt = mqk;   // V is read from the same [B*T, 3d] tensor (columns [2d, 3d)) as an MN-major operand
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (seq <= AT_KC)   // single key chunk: persistent warp-specialised kernel
-    return f16 ? launch_attn_t256<__half>(mqk, mvt, seq_lens, batch, seq, heads, d, out, out_ld, s)
-               : launch_attn_t256<__nv_bfloat16>(mqk, mvt, seq_lens, batch, seq, heads, d, out, out_ld, s);
+  if (seq <= AT_KC) {   // single key chunk: persistent warp-specialised kernel, output through TMA ([B][T][d] view)
+    CUtensorMap mout;
+    rc = make_tmap_3d(&mout, out, f16, (uint64_t)d, (uint64_t)seq, (uint64_t)batch, (uint64_t)out_ld,
+                      (uint64_t)seq * out_ld, 128);
+    if (rc) return rc;
+    return f16 ? launch_attn_t256<__half>(mqk, mout, seq_lens, batch, seq, heads, d, s)
+               : launch_attn_t256<__nv_bfloat16>(mqk, mout, seq_lens, batch, seq, heads, d, s);
+  }
   return f16 ? launch_attn<__half>(mqk, mvt, seq_lens, batch, seq, heads, d, out, out_ld, s)
              : launch_attn<__nv_bfloat16>(mqk, mvt, seq_lens, batch, seq, heads, d, out, out_ld, s);
 }
