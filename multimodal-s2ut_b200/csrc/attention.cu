@@ -228,15 +228,16 @@ static int launch_attn(const CUtensorMap& mqk, const CUtensorMap& mvt, const int
 // ===================================================================================================
 // Persistent, warp-specialised variant for T <= 256 (utterances up to ~10 s: one key chunk per query tile).
 //
-// One CTA per SM walks a list of (utterance, head, 128-query tile) items.  Roles (320 threads):
-//   warp 8      TMA producer: Q / K / V^T of item i into a 2-stage shared-memory ring
-//   warp 9      MMA issuer:   S_i = Q K^T (SS) as soon as stage i has landed and TMEM region (i & 1) is free;
+// One CTA per SM walks a list of (utterance, head, 128-query tile) items.  Roles (576 threads):
+//   warp 16     TMA producer: Q / K / V^T of item i into a 2-stage shared-memory ring
+//   warp 17     MMA issuer:   S_i = Q K^T (SS) as soon as stage i has landed and TMEM region (i & 1) is free;
 //                             O_i = P_i V (TS: P is read from TMEM) once softmax group (i & 1) has published P_i
-//   warps 0-3   softmax group 0 (even items)      } each thread owns one query row = one TMEM lane:
-//   warps 4-7   softmax group 1 (odd items)       } row max, exp2, row sum, P written back to TMEM as packed
+//   warps 0-7   softmax group 0 (even items)      } two threads per query row (= TMEM lane): warps 0-3 / 8-11 own
+//   warps 8-15  softmax group 1 (odd items)       } keys 0-127, warps 4-7 / 12-15 keys 128-255.  Row max and row sum
+//                                                   are combined through shared memory; P goes back to TMEM as packed
 //                                                   16-bit over the already-consumed S columns, then O / l -> HBM
-// The two groups ping-pong: while one waits for its MMAs the other keeps the MUFU/ALU pipes busy, and the
-// producer runs one item ahead, so TMA latency, tensor work and softmax overlap instead of serialising.
+// The two groups ping-pong, and four softmax warps per scheduler hide the TMEM / MUFU latencies of one another
+// (the per-item dependency chain, not bandwidth, bounded the 8-warp version); the producer runs one item ahead.
 // TMEM: region g = columns [256 g, 256 g + 256): S (fp32, 256 keys) -> P(keys 0-127) in [0,64), O in [64,128),
 // P(keys 128-255) in [128,192).  P V for the first 128 keys is issued as soon as that half of P is in TMEM, while the
 // group is still exponentiating the second half.  O leaves through a swizzled 16 KB staging tile and one TMA store
@@ -245,8 +246,9 @@ static int launch_attn(const CUtensorMap& mqk, const CUtensorMap& mvt, const int
 constexpr int PA_STAGE_BYTES = AT_Q_BYTES + AT_K_BYTES + AT_V_BYTES;   // 80 KB
 constexpr int PA_MAX_LENS = 1024;   // utterance lengths staged in shared memory (larger batches read them from global)
 constexpr int PA_OUT_BYTES = AT_BM * AT_HD * 2;   // 16 KB staging tile per softmax group
-constexpr int PA_SMEM_BYTES = 2 * PA_STAGE_BYTES + 2 * PA_OUT_BYTES + 256 + PA_MAX_LENS * 4 + 1024;
-constexpr int PA_THREADS = 320;
+constexpr int PA_XCH_BYTES = 2 * 2 * 2 * AT_BM * 4;   // [group][max | sum][key half][row] floats
+constexpr int PA_SMEM_BYTES = 2 * PA_STAGE_BYTES + 2 * PA_OUT_BYTES + 256 + PA_MAX_LENS * 4 + PA_XCH_BYTES + 1024;
+constexpr int PA_THREADS = 576;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -291,7 +293,7 @@ __device__ __forceinline__ float max_chunk(const uint32_t (&r)[32], int valid) {
 __device__ long long g_att_trace[148 * 2 * 8 * 6];
 #define ATT_TRACE(slot)                                                                              \
   do {                                                                                               \
-    if ((warp & 3) == 0 && lane == 0 && (i >> 1) < 8)                                                \
+    if ((warp & 7) == 0 && lane == 0 && (i >> 1) < 8)                                                \
       g_att_trace[((blockIdx.x * 2 + g) * 8 + (i >> 1)) * 6 + (slot)] = clock64();                   \
   } while (0)
 #else
@@ -316,6 +318,7 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
   uint64_t* reg_free = bars + 16;   // [2] softmax group has read O -> MMA may overwrite the TMEM region
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
   int* s_lens = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 256);
+  float* s_xch = reinterpret_cast<float*>(s_lens + PA_MAX_LENS);
   const int n_batch = n_items / (nqt * H);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -334,11 +337,11 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
       mbar_init(&p_half[2 * i], 4);
       mbar_init(&p_half[2 * i + 1], 4);
       mbar_init(&o_full[i], 1);
-      mbar_init(&reg_free[i], 4);
+      mbar_init(&reg_free[i], 8);
     }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  if (warp == 17) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -348,7 +351,7 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
   for (int i = threadIdx.x; i < n_batch && i < PA_MAX_LENS; i += PA_THREADS) s_lens[i] = seq_lens[i];
   __syncthreads();
 
-  if (warp == 8) {
+  if (warp == 16) {
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       for (int i = 0; i < n_local; ++i) {
@@ -369,7 +372,7 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
         tma_load_3d(sV + AT_V_BYTES / 2, &mapQK, &v_full[s], 2 * d_model + h * AT_HD, 128, b);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 17) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc(AT_BM, AT_KC, OpTraits<OpT>::fmt);
@@ -438,9 +441,15 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
     }
   } else {
     // ---------------- softmax + epilogue groups ----------------
-    const int g = warp >> 2;
+    const int g = warp >> 3;                   // item parity served by this group
+    const int hf = (warp >> 2) & 1;            // key half: chunks 4 hf .. 4 hf + 3 of the 8 32-key chunks
     const int row = (warp & 3) * 32 + lane;
     const uint32_t t_row = tmem_base + 256 * g + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    float* x_max = s_xch + g * 4 * AT_BM;      // [2 halves][128 rows]
+    float* x_sum = x_max + 2 * AT_BM;
+    auto group_sync = [&]() {
+      if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 2, 256;" ::: "memory");
+    };
     for (int i = g; i < n_local; i += 2) {
       const int item = blockIdx.x + i * gridDim.x;
       const int qt = item % nqt, h = (item / nqt) % H, b = item / (nqt * H);
@@ -449,36 +458,36 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
       const int nch = (len + 31) >> 5;        // chunks holding at least one valid key
       const int nfull = len >> 5;             // chunks that need no masking
       const int rem = len & 31;               // valid keys in chunk `nfull` when rem > 0
+      const int c0 = 4 * hf;                  // my chunks: c0 .. c0 + 3
       ATT_TRACE(0);
       mbar_wait(&s_full[g], u & 1);
       tc_fence_after();
       ATT_TRACE(1);
       uint32_t ra[32], rb[32];
-      // ---- sweep 1: row maximum (four TMEM loads in flight) ----
+      // ---- sweep 1: maximum over my 128 keys, then over the row ----
       float m = -INFINITY;
-      {
-        uint32_t rc[32], rd[32];
 #pragma unroll 1
-        for (int cc = 0; cc < nch; cc += 4) {
-          tmem_ld32(t_row + cc * 32, ra);
-          if (cc + 1 < nch) tmem_ld32(t_row + (cc + 1) * 32, rb);
-          if (cc + 2 < nch) tmem_ld32(t_row + (cc + 2) * 32, rc);
-          if (cc + 3 < nch) tmem_ld32(t_row + (cc + 3) * 32, rd);
-          tmem_ld_wait();
-          m = fmaxf(m, cc < nfull ? max_chunk<false>(ra, 32) : max_chunk<true>(ra, rem));
-          if (cc + 1 < nch) m = fmaxf(m, cc + 1 < nfull ? max_chunk<false>(rb, 32) : max_chunk<true>(rb, rem));
-          if (cc + 2 < nch) m = fmaxf(m, cc + 2 < nfull ? max_chunk<false>(rc, 32) : max_chunk<true>(rc, rem));
-          if (cc + 3 < nch) m = fmaxf(m, cc + 3 < nfull ? max_chunk<false>(rd, 32) : max_chunk<true>(rd, rem));
-        }
+      for (int cc = c0; cc < c0 + 4 && cc < nch; cc += 2) {
+        tmem_ld32(t_row + cc * 32, ra);
+        if (cc + 1 < nch) tmem_ld32(t_row + (cc + 1) * 32, rb);
+        tmem_ld_wait();
+        m = fmaxf(m, cc < nfull ? max_chunk<false>(ra, 32) : max_chunk<true>(ra, rem));
+        if (cc + 1 < nch) m = fmaxf(m, cc + 1 < nfull ? max_chunk<false>(rb, 32) : max_chunk<true>(rb, rem));
       }
+      if (c0 < nch) {   // prefetch my first chunk for sweep 2 across the exchange
+        tmem_ld32(t_row + c0 * 32, ra);
+      }
+      x_max[hf * AT_BM + row] = m;
+      group_sync();
+      m = fmaxf(m, x_max[(hf ^ 1) * AT_BM + row]);
       const float mb = m * L2E;
       ATT_TRACE(2);
-      // ---- sweep 2: probabilities (next chunk prefetched while the current one goes through MUFU) ----
+      // ---- sweep 2: probabilities of my 128 keys (next chunk prefetched while the current one goes through MUFU) ----
       float l = 0.f;
-      tmem_ld32(t_row, ra);
       tmem_ld_wait();
+      const uint32_t p_col = t_row + 128 * hf;   // P(keys 0-127) -> columns [0,64), P(keys 128-255) -> [128,192)
 #pragma unroll 1
-      for (int cc = 0; cc < AT_KC / 32; cc += 2) {
+      for (int cc = c0; cc < c0 + 4; cc += 2) {
         uint32_t pk[16];
         if (cc + 1 < nch) tmem_ld32(t_row + (cc + 1) * 32, rb);
         if (cc < nch) {
@@ -488,9 +497,8 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
           for (int k = 0; k < 16; ++k) pk[k] = 0u;
         }
         tmem_ld_wait();
-        const uint32_t p_col = t_row + (cc < 4 ? 16 * cc : 128 + 16 * (cc - 4));
-        tmem_st16(p_col, pk);                 // P over S columns that have already been consumed
-        if (cc + 2 < nch) tmem_ld32(t_row + (cc + 2) * 32, ra);
+        tmem_st16(p_col + 16 * (cc - c0), pk);    // P over S columns that have already been consumed
+        if (cc + 2 < c0 + 4 && cc + 2 < nch) tmem_ld32(t_row + (cc + 2) * 32, ra);
         if (cc + 1 < nch) {
           l += cc + 1 < nfull ? softmax_chunk<OpT, false>(rb, pk, mb, 32) : softmax_chunk<OpT, true>(rb, pk, mb, rem);
         } else {
@@ -498,35 +506,29 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
           for (int k = 0; k < 16; ++k) pk[k] = 0u;
         }
         tmem_ld_wait();
-        tmem_st16(p_col + 16, pk);
-        if (cc == 2) {                        // keys 0-127 of P are complete: their P V can start now
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&p_half[2 * g]);
-        }
+        tmem_st16(p_col + 16 * (cc + 1 - c0), pk);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_half[2 * g + 1]);
+      if (lane == 0) mbar_arrive(&p_half[2 * g + hf]);   // my 128 keys of P are in TMEM: their P V can start
+      x_sum[hf * AT_BM + row] = l;
       ATT_TRACE(3);
 
       mbar_wait(&o_full[g], u & 1);
       tc_fence_after();
       ATT_TRACE(4);
       {
-        const float inv = 1.0f / l;
-        tmem_ld32(t_row + 64, ra);
-        tmem_ld32(t_row + 96, rb);
+        tmem_ld32(t_row + 64 + 32 * hf, ra);        // my 32 of the 64 output columns
+        uint8_t* so = sOut + g * PA_OUT_BYTES;
+        const bool elected = (warp & 7) == 0 && lane == 0;
+        if (elected) bulk_wait_read<0>();           // the previous item's store has finished reading the tile
+        group_sync();                               // ... and both halves of the row sum are visible
+        const float inv = 1.0f / (l + x_sum[(hf ^ 1) * AT_BM + row]);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&reg_free[g]);   // O is in registers: the TMEM region may be reused
-        uint8_t* so = sOut + g * PA_OUT_BYTES;
-        const bool elected = (warp & 3) == 0 && lane == 0;
-        if (elected) bulk_wait_read<0>();           // the previous item's store has finished reading the tile
-        if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           uint4 q;
@@ -534,19 +536,10 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
           q.y = OpTraits<OpT>::pack2(__uint_as_float(ra[8 * k + 2]) * inv, __uint_as_float(ra[8 * k + 3]) * inv);
           q.z = OpTraits<OpT>::pack2(__uint_as_float(ra[8 * k + 4]) * inv, __uint_as_float(ra[8 * k + 5]) * inv);
           q.w = OpTraits<OpT>::pack2(__uint_as_float(ra[8 * k + 6]) * inv, __uint_as_float(ra[8 * k + 7]) * inv);
-          *reinterpret_cast<uint4*>(so + row * 128 + ((k ^ (row & 7)) << 4)) = q;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint4 q;
-          q.x = OpTraits<OpT>::pack2(__uint_as_float(rb[8 * k + 0]) * inv, __uint_as_float(rb[8 * k + 1]) * inv);
-          q.y = OpTraits<OpT>::pack2(__uint_as_float(rb[8 * k + 2]) * inv, __uint_as_float(rb[8 * k + 3]) * inv);
-          q.z = OpTraits<OpT>::pack2(__uint_as_float(rb[8 * k + 4]) * inv, __uint_as_float(rb[8 * k + 5]) * inv);
-          q.w = OpTraits<OpT>::pack2(__uint_as_float(rb[8 * k + 6]) * inv, __uint_as_float(rb[8 * k + 7]) * inv);
-          *reinterpret_cast<uint4*>(so + row * 128 + (((4 + k) ^ (row & 7)) << 4)) = q;
+          *reinterpret_cast<uint4*>(so + row * 128 + (((4 * hf + k) ^ (row & 7)) << 4)) = q;
         }
         fence_proxy_async_smem();
-        if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+        group_sync();
         if (elected) {
           tma_store_3d(&mapOut, so, h * AT_HD, qt * AT_BM, b);
           bulk_commit();
@@ -554,12 +547,12 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
       }
       ATT_TRACE(5);
     }
-    if ((warp & 3) == 0 && lane == 0) bulk_wait<0>();   // the last stores have landed before the CTA's smem goes away
+    if ((warp & 7) == 0 && lane == 0) bulk_wait<0>();   // the last stores have landed before the CTA's smem goes away
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 17) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
