@@ -43,6 +43,16 @@ __device__ __forceinline__ uint4* ln_slab_chunk(uint8_t* slab, int row, int c) {
   return reinterpret_cast<uint4*>(slab + row * 128 + ((c ^ (row & 7)) << 4));
 }
 
+#ifdef MM_LN_TRACE
+__device__ long long g_ln_trace[148 * 2 * 8];
+#define LN_TRACE(slot)                                                                      \
+  do {                                                                                      \
+    if (ht == 0 && it == 0) g_ln_trace[(blockIdx.x * 2 + h) * 8 + (slot)] = clock64();       \
+  } while (0)
+#else
+#define LN_TRACE(slot)
+#endif
+
 template <typename OpT>
 __global__ void __launch_bounds__(256, 1)
 gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
@@ -100,6 +110,9 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   // while the activations between them are read exactly once; ask L2 to keep the former and drop the latter first.
   const uint64_t pol_x = (p.l2_hints & 1) ? l2_policy_evict_last() : l2_policy_evict_normal();
   const uint64_t pol_a = (p.l2_hints & 2) ? l2_policy_evict_first() : l2_policy_evict_normal();
+#ifdef MM_LN_TRACE
+  if (ht == 0) g_ln_trace[(blockIdx.x * 2 + h) * 8 + 0] = clock64();
+#endif
 
   for (int tile = pid; tile < p.num_tiles; tile += npairs, ++it) {
     const int row0 = tile * 256 + rank * Cfg::BM;
@@ -143,6 +156,7 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     // ===================== phase B: epilogue on all 8 warps =====================
     mbar_wait(tfull, it & 1);     // accumulator complete => every MMA has finished reading the operand ring
     tc_fence_after();
+    LN_TRACE(1);
     if (ht == 0) {                // this half's residual slabs 0..5 (slabs 6, 7 recycle buffers 0, 1)
 #pragma unroll 1
       for (int j = 0; j < 6; ++j) {
@@ -208,6 +222,7 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       }
     }
     tmem_st_wait();
+    LN_TRACE(2);
     // Row statistics: the two halves exchange (sum, sum of squares).  Raw-moment variance in fp32 is accurate to
     // ~1e-6 here because the residual stream has |mean| <~ std (checked against a two-pass fp64 LayerNorm);
     // it saves a full extra sweep over the accumulator in TMEM.
@@ -217,6 +232,7 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     const float mean = (sum + stat[(h ^ 1) * 128 + lrow]) * (1.0f / Cfg::N);
     const float ex2 = (sumsq + stat[256 + (h ^ 1) * 128 + lrow]) * (1.0f / Cfg::N);
     const float rstd = rsqrtf(fmaxf(ex2 - mean * mean, 0.f) + p.eps);
+    LN_TRACE(3);
     // ---- sweep 3: normalise -> 16-bit slabs (64 columns each), optional fp32 copy ----
     if (ht == 0) bulk_wait_read<0>();       // sweep-1 stores have drained: this half's 6 buffers are reusable
     auto sweep3 = [&](int col, const uint32_t (&r)[32], uint8_t* slab, int chunk0, uint8_t* fs) {
@@ -274,12 +290,17 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       }
     }
     // the operand ring and TMEM are handed back to the mainloop of the next tile (both CTAs)
+    LN_TRACE(4);
     if (ht == 0) bulk_wait_read<0>();
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
+    LN_TRACE(5);
   }
   if ((threadIdx.x & 127) == 0) bulk_wait<0>();
+#ifdef MM_LN_TRACE
+  if (ht == 0) g_ln_trace[(blockIdx.x * 2 + h) * 8 + 6] = clock64();
+#endif
 
   tc_fence_before();
   cluster_sync_all();
@@ -702,6 +723,12 @@ static int launch_ln2_gemm(const CUtensorMap& mA, const CUtensorMap& mW, const C
 }
 
 }  // namespace mm
+
+#ifdef MM_LN_TRACE
+extern "C" int mm_debug_ln_trace(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, mm::g_ln_trace, sizeof(long long) * 148 * 2 * 8);
+}
+#endif
 
 extern "C" int mm_gemm_resid_ln(const void* a, int64_t a_ld, const void* w, int64_t w_ld, int32_t rows, int32_t k,
                                 int32_t n, const float* bias, float* x, const float* gamma, const float* beta,
