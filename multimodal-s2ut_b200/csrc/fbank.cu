@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(FB_THREADS, 3) fbank_kernel(const WavT* __rest
                                                               const long long* __restrict__ n_samples,
                                                               long long wav_stride, float* __restrict__ feats,
                                                               int max_frames, const float* __restrict__ tables) {
+  pdl_launch_dependents();   // programmatic dependent launch: see host.cuh launch_pdl
+  pdl_wait();
   extern __shared__ __align__(16) float fsm[];
   float* s_wave = fsm;
   float* s_work = s_wave + FB_WAVE;
@@ -244,6 +246,8 @@ __global__ void __launch_bounds__(CS_THREADS) cmvn_stats_kernel(const float* __r
                                                                 const long long* __restrict__ lens,
                                                                 int lengths_are_samples, int max_frames,
                                                                 float* __restrict__ mean_std) {
+  pdl_launch_dependents();   // programmatic dependent launch: see host.cuh launch_pdl
+  pdl_wait();
   // All 256 threads stream [64 frames x 80 bins] tiles into shared memory with 16-byte cp.async (coalesced, next
   // tile in flight while the current one is consumed); threads 0..79 then replay numpy's frame-sequential fp32
   // accumulation from shared memory, so the only serial chain is two dependent adds per frame.
@@ -380,7 +384,7 @@ static int launch_fbank(const WavT* wav, const int64_t* n_samples, int32_t batch
   }
   const int n_chunks = (max_frames + FB_FRAMES_PER_CTA - 1) / FB_FRAMES_PER_CTA;
   dim3 grid(n_chunks, batch);
-  fbank_kernel<WavT><<<grid, FB_THREADS, FB_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(fbank_kernel<WavT>, dim3(grid), dim3(FB_THREADS), FB_SMEM_BYTES, static_cast<cudaStream_t>(stream), 
       wav, reinterpret_cast<const long long*>(n_samples), wav_stride, feats, max_frames, tables);
   MM_CHECK_LAUNCH("fbank_kernel launch");
   return 0;
@@ -400,7 +404,7 @@ extern "C" int mm_cmvn_stats(const float* feats, const int64_t* lens, int32_t le
                              int32_t max_frames, float* mean_std, void* stream) {
   if (!feats || !lens || !mean_std) return bad_arg("cmvn_stats: null pointer");
   if (batch <= 0 || max_frames <= 0) return 0;
-  cmvn_stats_kernel<<<batch, CS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(cmvn_stats_kernel, dim3(batch), dim3(CS_THREADS), 0, static_cast<cudaStream_t>(stream), 
       feats, reinterpret_cast<const long long*>(lens), lengths_are_samples, max_frames, mean_std);
   MM_CHECK_LAUNCH("cmvn_stats_kernel launch");
   return 0;

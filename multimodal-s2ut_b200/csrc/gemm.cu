@@ -342,8 +342,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
           uint32_t ra[32], rg[32];
           tmem_ld32(taddr + j0, ra);
           tmem_ld32(taddr + HALF + j0, rg);
-          tmem_ld_wait();
           const int oc = n_tile * HALF + j0;
+          // valid position t -> sinusoidal row t + 2; padded positions get the zero row.  The table reads are issued
+          // before the TMEM wait so their L2 latency hides behind it and the sigmoid arithmetic.
+          float4 pq[8];
+          if (rvalid && r < slen) {
+            const float4* pe = reinterpret_cast<const float4*>(p.pos + (long long)(r + 2) * n_out + oc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pq[i] = __ldg(pe + i);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          tmem_ld_wait();
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -351,14 +362,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
             const float g = __uint_as_float(rg[i]) + sBias[HALF + j0 + i];
             v[i] = a * sigmoidf_(g) * p.scale;
           }
-          if (rvalid && r < slen) {   // valid position t -> sinusoidal row t + 2; padded positions get the zero row
-            const float4* pe = reinterpret_cast<const float4*>(p.pos + (long long)(r + 2) * n_out + oc);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 q = __ldg(pe + i);
-              v[4 * i] += q.x, v[4 * i + 1] += q.y, v[4 * i + 2] += q.z, v[4 * i + 3] += q.w;
-            }
-          }
+          for (int i = 0; i < 8; ++i)
+            v[4 * i] += pq[i].x, v[4 * i + 1] += pq[i].y, v[4 * i + 2] += pq[i].z, v[4 * i + 3] += pq[i].w;
           slab_write_f32(slab, lrow, v);
           fence_proxy_async_smem();
           asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -439,18 +445,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
           }
           uint32_t ra[32];
           tmem_ld32(taddr + c0, ra);
-          tmem_ld_wait();
-          mbar_wait(&auxfull[b], (aux_phase >> b) & 1);
-          aux_phase ^= (1u << b);
-          float v[32], x[32];
-          slab_read_f32(slab, lrow, x);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]) + sBias[c0 + i];
-          if constexpr (MODE == MM_EPI_RESID_F32) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += x[i];
-          } else {
-            float o[32];
+          float o[32];
+          if constexpr (MODE == MM_EPI_GATE) {   // issued before the waits below: the L2 latency hides behind them
             if (rvalid) {
               const float4* op = reinterpret_cast<const float4*>(p.aux1 + arow * p.aux_ld + col);
 #pragma unroll
@@ -462,6 +458,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
 #pragma unroll
               for (int i = 0; i < 32; ++i) o[i] = 0.f;
             }
+          }
+          tmem_ld_wait();
+          mbar_wait(&auxfull[b], (aux_phase >> b) & 1);
+          aux_phase ^= (1u << b);
+          float v[32], x[32];
+          slab_read_f32(slab, lrow, x);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]) + sBias[c0 + i];
+          if constexpr (MODE == MM_EPI_RESID_F32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += x[i];
+          } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const float g = sigmoidf_(v[i]);

@@ -15,6 +15,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                          const float* __restrict__ beta, long long rows,
                                                          OpT* __restrict__ out_op, float* __restrict__ out_f32,
                                                          float eps) {
+  pdl_launch_dependents();   // programmatic dependent launch: see host.cuh launch_pdl
+  pdl_wait();
   constexpr int V = DIM / 128;  // float4 per lane
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -62,10 +64,10 @@ static int launch_ln(const float* x, const float* g, const float* b, long long r
   const unsigned grid = (unsigned)((rows + rows_per_block - 1) / rows_per_block);
   OpT* o = reinterpret_cast<OpT*>(out_op);
   switch (dim) {
-    case 256: layernorm_kernel<256, OpT><<<grid, 256, 0, s>>>(x, g, b, rows, o, out_f32, eps); break;
-    case 512: layernorm_kernel<512, OpT><<<grid, 256, 0, s>>>(x, g, b, rows, o, out_f32, eps); break;
-    case 768: layernorm_kernel<768, OpT><<<grid, 256, 0, s>>>(x, g, b, rows, o, out_f32, eps); break;
-    case 1024: layernorm_kernel<1024, OpT><<<grid, 256, 0, s>>>(x, g, b, rows, o, out_f32, eps); break;
+    case 256: launch_pdl(layernorm_kernel<256, OpT>, dim3(grid), dim3(256), 0, s, x, g, b, rows, o, out_f32, eps); break;
+    case 512: launch_pdl(layernorm_kernel<512, OpT>, dim3(grid), dim3(256), 0, s, x, g, b, rows, o, out_f32, eps); break;
+    case 768: launch_pdl(layernorm_kernel<768, OpT>, dim3(grid), dim3(256), 0, s, x, g, b, rows, o, out_f32, eps); break;
+    case 1024: launch_pdl(layernorm_kernel<1024, OpT>, dim3(grid), dim3(256), 0, s, x, g, b, rows, o, out_f32, eps); break;
     default: return bad_arg("layernorm dim must be 256, 512, 768 or 1024");
   }
   MM_CHECK_LAUNCH("layernorm_kernel launch");
@@ -81,6 +83,8 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
                                                             long long rows, int n_keys,
                                                             const uint8_t* __restrict__ key_mask, int rows_per_seq,
                                                             OpT* __restrict__ probs, long long ld_out) {
+  pdl_launch_dependents();   // programmatic dependent launch: see host.cuh launch_pdl
+  pdl_wait();
   constexpr int MAXV = 32;  // up to 1024 keys
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -125,6 +129,8 @@ __global__ void __launch_bounds__(256) softmax_rows_vec_kernel(const float* __re
                                                                 long long rows, int n_keys,
                                                                 const uint8_t* __restrict__ key_mask, int rows_per_seq,
                                                                 OpT* __restrict__ probs, long long ld_out) {
+  pdl_launch_dependents();   // programmatic dependent launch: see host.cuh launch_pdl
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -174,7 +180,7 @@ template <int V4, typename OpT>
 static void launch_softmax_vec(const float* scores, long long ld_in, long long rows, int n_keys, const uint8_t* key_mask,
                                int rows_per_seq, void* probs, long long ld_out, cudaStream_t s) {
   const unsigned grid = (unsigned)((rows + 7) / 8);
-  softmax_rows_vec_kernel<V4, OpT><<<grid, 256, 0, s>>>(scores, ld_in, rows, n_keys, key_mask, rows_per_seq,
+  launch_pdl(softmax_rows_vec_kernel<V4, OpT>, dim3(grid), dim3(256), 0, s, scores, ld_in, rows, n_keys, key_mask, rows_per_seq,
                                                         reinterpret_cast<OpT*>(probs), ld_out);
 }
 template <typename OpT>
@@ -196,6 +202,8 @@ static void dispatch_softmax_vec(const float* scores, long long ld_in, long long
 template <typename OpT>
 __global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ x, OpT* __restrict__ out,
                                                        long long n) {
+  pdl_launch_dependents();   // programmatic dependent launch: see host.cuh launch_pdl
+  pdl_wait();
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -234,6 +242,8 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const float* __restrict
                                                           int max_frames, float* __restrict__ out_f32,
                                                           OpT* __restrict__ out_op, int op_frames, int op_row_offset,
                                                           int rows_per_block) {
+  pdl_launch_dependents();   // programmatic dependent launch: see host.cuh launch_pdl
+  pdl_wait();
   __shared__ float s_mean[80], s_std[80];
   const int b = blockIdx.y;
   const int nfr = min(frames_of(lens[b], lengths_are_samples), max_frames);
@@ -276,6 +286,8 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const float* __restrict
 
 __global__ void seq_lens_kernel(const long long* __restrict__ lens, int lengths_are_samples, int batch, int n_layers,
                                 int* __restrict__ out) {
+  pdl_launch_dependents();   // programmatic dependent launch: see host.cuh launch_pdl
+  pdl_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
   int n = frames_of(lens[b], lengths_are_samples);
@@ -315,10 +327,10 @@ extern "C" int mm_softmax_rows(const float* scores, int64_t ld_in, int64_t rows,
     return 0;
   }
   if (dtype == MM_DTYPE_F16)
-    softmax_rows_kernel<__half><<<grid, 256, 0, s>>>(scores, ld_in, rows, n_keys, key_mask, rows_per_seq,
+    launch_pdl(softmax_rows_kernel<__half>, dim3(grid), dim3(256), 0, s, scores, ld_in, rows, n_keys, key_mask, rows_per_seq,
                                                      reinterpret_cast<__half*>(probs), ld_out);
   else
-    softmax_rows_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(scores, ld_in, rows, n_keys, key_mask, rows_per_seq,
+    launch_pdl(softmax_rows_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, scores, ld_in, rows, n_keys, key_mask, rows_per_seq,
                                                             reinterpret_cast<__nv_bfloat16*>(probs), ld_out);
   MM_CHECK_LAUNCH("softmax_rows_kernel launch");
   return 0;
@@ -333,9 +345,9 @@ extern "C" int mm_convert_f32(const float* x, void* out, int64_t n, int32_t dtyp
   if (blocks < 1) blocks = 1;
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
   if (dtype == MM_DTYPE_F16)
-    convert_kernel<__half><<<(unsigned)blocks, 256, 0, s>>>(x, reinterpret_cast<__half*>(out), n);
+    launch_pdl(convert_kernel<__half>, dim3((unsigned)blocks), dim3(256), 0, s, x, reinterpret_cast<__half*>(out), n);
   else
-    convert_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>(x, reinterpret_cast<__nv_bfloat16*>(out), n);
+    launch_pdl(convert_kernel<__nv_bfloat16>, dim3((unsigned)blocks), dim3(256), 0, s, x, reinterpret_cast<__nv_bfloat16*>(out), n);
   MM_CHECK_LAUNCH("convert_kernel launch");
   return 0;
 }
@@ -352,11 +364,11 @@ extern "C" int mm_cmvn_apply(const float* feats, const float* mean_std, const in
   dim3 grid((total_rows + rows_per_block - 1) / rows_per_block, batch);
   const long long* l = reinterpret_cast<const long long*>(lens);
   if (dtype == MM_DTYPE_F16)
-    cmvn_apply_kernel<__half><<<grid, 256, 0, s>>>(feats, mean_std, l, lengths_are_samples, max_frames, out_f32,
+    launch_pdl(cmvn_apply_kernel<__half>, dim3(grid), dim3(256), 0, s, feats, mean_std, l, lengths_are_samples, max_frames, out_f32,
                                                    reinterpret_cast<__half*>(out_op), op_frames, op_row_offset,
                                                    rows_per_block);
   else
-    cmvn_apply_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(feats, mean_std, l, lengths_are_samples, max_frames,
+    launch_pdl(cmvn_apply_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, feats, mean_std, l, lengths_are_samples, max_frames,
                                                           out_f32, reinterpret_cast<__nv_bfloat16*>(out_op),
                                                           op_frames, op_row_offset, rows_per_block);
   MM_CHECK_LAUNCH("cmvn_apply_kernel launch");
@@ -367,7 +379,7 @@ extern "C" int mm_seq_lens(const int64_t* lens, int32_t lengths_are_samples, int
                            int32_t* out_lens, void* stream) {
   if (!lens || !out_lens) return bad_arg("seq_lens: null pointer");
   if (batch <= 0) return 0;
-  seq_lens_kernel<<<(batch + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(seq_lens_kernel, dim3((batch + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const long long*>(lens), lengths_are_samples, batch, n_layers, out_lens);
   MM_CHECK_LAUNCH("seq_lens_kernel launch");
   return 0;
