@@ -306,18 +306,37 @@ def run_ours(a):
             ach = work / (ms * 1e-3) / (1e12 if tensor else 1e9) if ms > 0 else 0.0
             kern[name] = {"launches_per_step": cnt // reps, "ms_per_step": ms / reps, "share": ms / total_ms,
                           "achieved": ach, "unit": "TFLOP/s" if tensor else "GB/s"}
-        gemm_ms = sum(v[0] for k, v in fam.items() if k.startswith("gemm"))
-        gemm_fl = sum(v[1] for k, v in fam.items() if k.startswith("gemm"))
-        gemm_n = sum(v[2] for k, v in fam.items() if k.startswith("gemm"))
+        # dominant kernel = gemm_kernel (one template, eight epilogue instantiations: every "gemm[...]" family);
+        # the fused GEMM+LayerNorm kernel is a different kernel and is reported next to it
+        gemm_ms = sum(v[0] for k, v in fam.items() if k.startswith("gemm["))
+        gemm_fl = sum(v[1] for k, v in fam.items() if k.startswith("gemm["))
+        gemm_n = sum(v[2] for k, v in fam.items() if k.startswith("gemm["))
         ach = gemm_fl / (gemm_ms * 1e-3) / 1e12
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        traffic, traffic_ln, traffic_src = None, None, None
+        tpath = os.path.join(ROOT, "profiles", "r01", "ncu_full_v12_traffic.json")
+        if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum per launch from one ncu --set full capture
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic = tj["gemm_kernel_per_launch_mean_mb"]["value"] * 1e6
+            traffic_ln = tj["gemm_resid_ln_per_launch_mean_mb"]["value"] * 1e6
+            traffic_src = "profiles/r01/ncu_full_v12_traffic.json (cold-L2 replays: reads are compulsory, writes stay in L2)"
         roofline = {
             "bound": "tensor", "kernel": "gemm_kernel (tcgen05/TMA persistent GEMM, all epilogues)",
-            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+            "traffic_source": traffic_src,
             "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
             "launches_per_step": gemm_n // reps, "share_of_step": gemm_ms / total_ms,
-            "how": "algorithmic FLOPs (2*M*N*K per launch) / CUDA-event time per launch, eager instrumented pass",
+            "how": "algorithmic FLOPs (2*M*N*K per launch) / CUDA-event time per launch, eager instrumented pass "
+                   "(each forward enqueued behind a device spin so host launch latency is not timed)",
         }
+        ln = fam.get("gemm_resid_ln")
+        if ln:
+            ach_ln = ln[1] / (ln[0] * 1e-3) / 1e12
+            roofline["second_kernel"] = {
+                "kernel": "gemm_resid_ln_kernel (GEMM + residual + LayerNorm, 256x512 pair tiles)", "bound": "tensor",
+                "achieved": ach_ln, "peak": peak, "unit": "TFLOP/s", "frac": ach_ln / peak, "traffic": traffic_ln,
+                "launches_per_step": ln[2] // reps, "share_of_step": ln[0] / total_ms}
         fb = kern.get("fbank")
         if fb:
             roofline["hbm_kernels"] = {k: {"achieved_gbs": kern[k]["achieved"],

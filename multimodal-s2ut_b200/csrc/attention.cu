@@ -1,14 +1,17 @@
 // Multi-head self-attention core on tcgen05: O = softmax_fp32(Q K^T + key-padding mask) V, head_dim 64.
+// q, k, v are column blocks of ONE [B*T, 3d] tensor (the QKV GEMM output); q arrives pre-scaled by head_dim^-0.5
+// (fused into that GEMM's epilogue).  Reference: fairseq/modules/multihead_attention.py (encoder self-attention,
+// key_padding_mask), as called from TransformerEncoderLayerBase.forward.
 //
-// One CTA (128 threads) = one (utterance, head, 128-query tile).  Keys are processed in chunks of 256:
-//   S = Q K^T      tcgen05.mma M=128 N=256 K=64, fp32 scores in TMEM columns [0,256)
-//   softmax        thread i owns score row i (TMEM lane i): no cross-thread reductions at all
-//   P              written as 16-bit into shared memory in the 128B-swizzled K-major layout UMMA expects
-//   O += P V       tcgen05.mma M=128 N=64 K=256 (A = P from smem, B = V^T tile), O in TMEM columns [256,320)
-// For T <= 256 (utterances up to ~10 s) there is a single chunk and S is computed once.  Longer sequences
-// use a two-sweep schedule (sweep 1: row maxima only; sweep 2: exp / P V) so O never needs rescaling.
-// q arrives pre-scaled by head_dim^-0.5 (fused into the QKV GEMM epilogue), V arrives transposed
-// ([B][d][T_pad], zero beyond T) so both MMAs use K-major operands loaded by TMA.
+// Two kernels:
+//  * self_attention_t256_kernel (T <= 256, i.e. utterances up to ~10 s at 4x subsampling): persistent, warp-specialised,
+//    S / P / O all live in TMEM; described in front of the kernel below.  This is the one the bench runs.
+//  * self_attention_kernel (any T): one CTA (128 threads) per (utterance, head, 128-query tile), keys in chunks of 256:
+//      S = Q K^T      tcgen05.mma M=128 N=256 K=64, fp32 scores in TMEM columns [0,256)
+//      softmax        thread i owns score row i (TMEM lane i): no cross-thread reductions
+//      P              written as 16-bit into shared memory in the 128B-swizzled K-major layout UMMA expects
+//      O += P V       tcgen05.mma M=128 N=64 K=256 (A = P from smem, B = V rows as an MN-major operand)
+//    with a two-sweep schedule (sweep 1: row maxima only; sweep 2: exp / P V) so O never needs rescaling.
 #include "common.cuh"
 #include "host.cuh"
 #include "../../include/mms2ut_b200.h"

@@ -94,6 +94,10 @@ __device__ __forceinline__ void slab_read_f32(uint8_t* slab, int row, float* v) 
   }
 }
 
+#ifdef MM_GEMM_TRACE
+__device__ long long g_gemm_trace[148 * 4];   // per CTA: clock64 start / end, globaltimer start / end
+#endif
+
 template <int MODE, typename OpT>
 __global__ void __launch_bounds__(256, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
@@ -143,6 +147,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();   // the next kernel may start its prologue on SMs this grid no longer needs
   pdl_wait();                // everything above overlapped the previous kernel's tail; its outputs are visible now
+#ifdef MM_GEMM_TRACE
+  if (threadIdx.x == 128) {
+    g_gemm_trace[blockIdx.x * 4 + 0] = clock64();
+    g_gemm_trace[blockIdx.x * 4 + 2] = (long long)globaltimer_ns();
+  }
+#endif
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -497,6 +507,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
       if (++as == 2) as = 0, aphase ^= 1;
     }
     if (et == 0) bulk_wait<0>();   // all TMA stores of this CTA complete before its smem goes away
+#ifdef MM_GEMM_TRACE
+    if (et == 0) {
+      g_gemm_trace[blockIdx.x * 4 + 1] = clock64();
+      g_gemm_trace[blockIdx.x * 4 + 3] = (long long)globaltimer_ns();
+    }
+#endif
   }
 
   tc_fence_before();
@@ -608,6 +624,12 @@ static int dispatch_mode(int mode, const GemmMaps& m, const GemmDev& p, cudaStre
 }
 
 }  // namespace mm
+
+#ifdef MM_GEMM_TRACE
+extern "C" int mm_debug_gemm_trace(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, mm::g_gemm_trace, sizeof(long long) * 148 * 4);
+}
+#endif
 
 extern "C" int mm_gemm(const mm_gemm_args* a, void* stream) {
   using namespace mm;

@@ -342,386 +342,6 @@ static int launch_ln_gemm(const CUtensorMap& mA, const CUtensorMap& mW, const CU
   return 0;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Version 2: the epilogue of one row block overlaps the mainloop of the next.
-//
-// In the kernel above every CTA pair owns whole rows, so all 512 TMEM columns hold one accumulator and the (HBM-bound)
-// epilogue cannot start before, nor overlap with, any (tensor-bound) mainloop: the two phases serialise GPU-wide.
-// Here a cluster of FOUR CTAs owns a 256-row block: pair 0 (ranks 0,1) accumulates columns [0,256), pair 1 (ranks 2,3)
-// columns [256,512), each as an ordinary cta_group::2 256x256 tile.  An accumulator is 256 TMEM columns, so two fit
-// and the MMA warp runs one row block ahead of the epilogue.  The only coupling between the pairs is the LayerNorm
-// row statistics: every thread writes its partial (sum, sum of squares) into its own CTA and into the CTA that holds
-// the other half of the same rows (rank ^ 2) through distributed shared memory, then both reduce the four partials
-// in the same order.
-//
-// Warps: 0 operand TMA producer, 1 MMA issuer (pair leader), 2 TMEM allocator, 3 slab-ring producer,
-// 4-7 / 8-11 two epilogue groups (thread = row; group g takes the 32-column residual chunks j = g, g+2, g+4, g+6 and
-// the 64-column output chunks d = g, g+2 of this CTA's 256 columns).
-// Slab ring: RING x 16 KB buffers handed out in item order (per row block: 8 residual chunks, TMA-loaded by warp 3,
-// then 4 blank buffers for the 16-bit output chunks); a buffer returns to the ring when the TMA store that reads it
-// has drained.
-// ---------------------------------------------------------------------------------------------------------------
-#ifndef MM_LN2_STAGES
-#define MM_LN2_STAGES 3
-#endif
-#ifndef MM_LN2_RING
-#define MM_LN2_RING 7
-#endif
-struct Ln2Cfg {
-  static constexpr int BM = 128, BN = 256, BK = 64, STAGES = MM_LN2_STAGES, RING = MM_LN2_RING;
-  static constexpr int A_BYTES = BM * BK * 2;            // 16 KB
-  static constexpr int B_BYTES = (BN / 2) * BK * 2;      // 16 KB: this CTA's half of the pair's 256 W rows
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SLAB_BYTES = BM * 128;            // 16 KB
-  static constexpr int STAT_BYTES = 2 * 4 * BM * 8;      // [accumulator stage][source group][row] float2
-  static constexpr int BAR_BYTES = 512;
-  static constexpr int THREADS = 384;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RING * SLAB_BYTES + STAT_BYTES + BAR_BYTES + 1024;
-  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-};
-
-template <typename OpT>
-__global__ void __launch_bounds__(Ln2Cfg::THREADS, 1)
-gemm_resid_ln2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
-                      const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapH,
-                      const LnDev p) {
-  using Cfg = Ln2Cfg;
-  constexpr int STAGES = Cfg::STAGES, RING = Cfg::RING;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* ops = smem;                                         // STAGES x (A | B)
-  uint8_t* slabs = ops + STAGES * Cfg::STAGE_BYTES;            // RING x 16 KB
-  float2* stat = reinterpret_cast<float2*>(slabs + RING * Cfg::SLAB_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stat) + Cfg::STAT_BYTES);
-  uint64_t* full = bars;                   // [STAGES] TMA -> MMA (leader's copy)
-  uint64_t* empty = full + STAGES;         // [STAGES] MMA -> TMA (multicast commit)
-  uint64_t* tfull = empty + STAGES;        // [2] accumulator complete (multicast commit)
-  uint64_t* tempty = tfull + 2;            // [2] accumulator drained by both CTAs (leader's copy)
-  uint64_t* rfull = tempty + 2;            // [RING] slab ready for the epilogue
-  uint64_t* rempty = rfull + RING;         // [RING] slab back in the ring
-  uint64_t* statbar = rempty + RING;       // [2] row statistics of all four sources have landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(statbar + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();         // 0..3
-  const int ph = rank >> 1;                        // which 256-column half this pair accumulates
-  const int pr = rank & 1;                         // rank inside the pair (0 = MMA leader)
-  const uint32_t leader = rank & 2u;
-  const int qid = blockIdx.x >> 2, nquads = gridDim.x >> 2;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&mapA);
-    tma_prefetch_desc(&mapW);
-    tma_prefetch_desc(&mapX);
-    tma_prefetch_desc(&mapH);
-    for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 16);     // 8 epilogue warps x 2 CTAs
-      mbar_init(&statbar[i], 16);    // 8 local warps + 8 warps of CTA rank^2
-    }
-    for (int i = 0; i < RING; ++i) {
-      mbar_init(&rfull[i], 1);
-      mbar_init(&rempty[i], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc_2sm(tmem_slot, 512);
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_launch_dependents();
-  pdl_wait();
-
-  if (warp == 0) {
-    // ===================== operand producer (every CTA) =====================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      const int wrow0 = ph * Cfg::BN + pr * (Cfg::BN / 2);
-      for (int rb = qid; rb < p.num_tiles; rb += nquads) {
-        const int row0 = rb * 256 + pr * Cfg::BM;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          if (pr == 0) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
-          uint8_t* st = ops + stage * Cfg::STAGE_BYTES;
-          tma_load_3d_2sm(st, &mapA, &full[stage], kb * Cfg::BK, row0, 0);
-          tma_load_3d_2sm(st + Cfg::A_BYTES, &mapW, &full[stage], kb * Cfg::BK, wrow0, 0);
-          if (++stage == STAGES) stage = 0, phase ^= 1;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (leader of each pair) =====================
-    if (pr == 0 && lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(256, Cfg::BN, OpTraits<OpT>::fmt);
-      const uint16_t mask = static_cast<uint16_t>(3u << leader);
-      uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-      const int k_tail = p.k - (p.num_kb - 1) * Cfg::BK;
-      const int tail_steps = (k_tail + 15) >> 4;
-      for (int rb = qid; rb < p.num_tiles; rb += nquads) {
-        mbar_wait(&tempty[as], aphase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * Cfg::BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          uint8_t* st = ops + stage * Cfg::STAGE_BYTES;
-          const uint64_t adesc = umma_desc_sw128(smem_u32(st));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(st + Cfg::A_BYTES));
-          const int steps = (kb == p.num_kb - 1) ? tail_steps : 4;
-          for (int kk = 0; kk < steps; ++kk)
-            umma_f16_2sm(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb | kk) != 0);
-          umma_commit_2sm(&empty[stage], mask);
-          if (++stage == STAGES) stage = 0, phase ^= 1;
-        }
-        umma_commit_2sm(&tfull[as], mask);
-        if (++as == 2) as = 0, aphase ^= 1;
-      }
-    }
-  } else if (warp == 3) {
-    // ===================== slab ring producer =====================
-    if (lane == 0) {
-      uint32_t slot = 0, par = 0;
-      for (int rb = qid; rb < p.num_tiles; rb += nquads) {
-        const int row0 = rb * 256 + pr * Cfg::BM;
-#pragma unroll 1
-        for (int item = 0; item < 12; ++item) {
-          mbar_wait(&rempty[slot], par ^ 1);
-          if (item < 8) {
-            mbar_expect_tx(&rfull[slot], Cfg::SLAB_BYTES);
-            tma_load_3d(slabs + slot * Cfg::SLAB_BYTES, &mapX, &rfull[slot], ph * Cfg::BN + 32 * item, row0, 0);
-          } else {
-            mbar_arrive(&rfull[slot]);
-          }
-          if (++slot == RING) slot = 0, par ^= 1;
-        }
-      }
-    }
-  } else if (warp >= 4) {
-    // ===================== epilogue: two groups of four warps =====================
-    const int g = (warp - 4) >> 2;
-    const int quad = warp & 3;                       // TMEM lane quadrant
-    const int gt = threadIdx.x - 128 - 128 * g;      // 0..127 inside the group
-    const int lrow = quad * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t tempty_leader = mapa_u32(&tempty[0], leader);
-    const uint32_t stat_peer = mapa_u32(stat, rank ^ 2u);
-    const uint32_t statbar_peer = mapa_u32(&statbar[0], rank ^ 2u);
-    const int src = 2 * ph + g;                      // who I am among the four partial sums of a row
-    uint32_t as = 0, aphase = 0;
-    uint32_t slot = g % RING, par = (g / RING) & 1;  // my first item is n = g
-    int prev_slot = -1;
-    auto next_item = [&]() {
-      slot += 2;
-      if (slot >= RING) slot -= RING, par ^= 1;
-    };
-    auto group_sync = [&]() {
-      if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
-    };
-    // store the slab just completed by the group; the slab stored one item earlier goes back to the ring
-    auto store_and_recycle = [&](const CUtensorMap* map, int col, int row0) {
-      tma_store_3d(map, slabs + slot * Cfg::SLAB_BYTES, col, row0, 0);
-      bulk_commit();
-      if (prev_slot >= 0) {
-        bulk_wait_read<1>();
-        mbar_arrive(&rempty[prev_slot]);
-      }
-      prev_slot = static_cast<int>(slot);
-    };
-
-    for (int rb = qid; rb < p.num_tiles; rb += nquads) {
-      const int row0 = rb * 256 + pr * Cfg::BM;
-      mbar_wait(&tfull[as], aphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + as * Cfg::BN + lane_off;
-
-      // ---- sweep 1: v = acc + bias + x ; new residual out ; row sums ----
-      float sum = 0.f, sumsq = 0.f;
-      uint32_t ra[32], rq[32];
-      auto sweep1 = [&](int j, uint32_t (&r)[32]) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + ph * Cfg::BN + 32 * j);
-        float4 bq[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) bq[c] = __ldg(b4 + c);
-        uint8_t* slab = slabs + slot * Cfg::SLAB_BYTES;
-        mbar_wait(&rfull[slot], par);
-        uint4 xq[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) xq[c] = *ln_slab_chunk(slab, lrow, c);
-        uint32_t lo[16], hi[16];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float v0 = __uint_as_float(r[4 * c + 0]) + bq[c].x + __uint_as_float(xq[c].x);
-          const float v1 = __uint_as_float(r[4 * c + 1]) + bq[c].y + __uint_as_float(xq[c].y);
-          const float v2 = __uint_as_float(r[4 * c + 2]) + bq[c].z + __uint_as_float(xq[c].z);
-          const float v3 = __uint_as_float(r[4 * c + 3]) + bq[c].w + __uint_as_float(xq[c].w);
-          sum += (v0 + v1) + (v2 + v3);
-          sumsq += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
-          uint32_t* dst = c < 4 ? &lo[4 * c] : &hi[4 * (c - 4)];
-          dst[0] = __float_as_uint(v0), dst[1] = __float_as_uint(v1);
-          dst[2] = __float_as_uint(v2), dst[3] = __float_as_uint(v3);
-          *ln_slab_chunk(slab, lrow, c) = make_uint4(dst[0], dst[1], dst[2], dst[3]);
-        }
-        tmem_st16(taddr + 32 * j, lo);          // v stays in TMEM for sweep 2
-        tmem_st16(taddr + 32 * j + 16, hi);
-        fence_proxy_async_smem();
-        group_sync();
-        if (gt == 0) store_and_recycle(&mapX, ph * Cfg::BN + 32 * j, row0);
-        next_item();
-      };
-      tmem_ld32(taddr + 32 * g, ra);
-      tmem_ld_wait();
-      tmem_ld32(taddr + 32 * (g + 2), rq);
-      sweep1(g, ra);
-      tmem_ld_wait();
-      tmem_ld32(taddr + 32 * (g + 4), ra);
-      sweep1(g + 2, rq);
-      tmem_ld_wait();
-      tmem_ld32(taddr + 32 * (g + 6), rq);
-      sweep1(g + 4, ra);
-      tmem_ld_wait();
-      sweep1(g + 6, rq);
-
-      // ---- row statistics: two local groups + the two groups of the CTA holding the other 256 columns ----
-      tmem_st_wait();
-      tc_fence_before();
-      const int sidx = (as * 4 + src) * Cfg::BM + lrow;
-      stat[sidx] = make_float2(sum, sumsq);
-      st_cluster_f32x2(stat_peer + sidx * 8, sum, sumsq);
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&statbar[as]);
-        mbar_arrive_release_cluster(statbar_peer + 8 * as);
-      }
-      mbar_wait_cluster(&statbar[as], aphase);
-      tc_fence_after();
-      const float2* sb = stat + as * 4 * Cfg::BM + lrow;
-      const float2 s0 = sb[0], s1 = sb[Cfg::BM], s2 = sb[2 * Cfg::BM], s3 = sb[3 * Cfg::BM];
-      const float mean = ((s0.x + s1.x) + (s2.x + s3.x)) * (1.0f / 512.0f);
-      const float ex2 = ((s0.y + s1.y) + (s2.y + s3.y)) * (1.0f / 512.0f);
-      const float rstd = rsqrtf(fmaxf(ex2 - mean * mean, 0.f) + p.eps);
-
-      // ---- sweep 2: normalise -> 16-bit output chunks of 64 columns ----
-      tmem_ld32(taddr + 64 * g, ra);
-      tmem_ld32(taddr + 64 * g + 32, rq);
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int d = g + 2 * i;
-        const int col = ph * Cfg::BN + 64 * d;
-        tmem_ld_wait();
-        uint4 q[8];
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const uint32_t* r = hh ? rq : ra;
-          const float4* g4 = reinterpret_cast<const float4*>(p.gamma + col + 32 * hh);
-          const float4* be4 = reinterpret_cast<const float4*>(p.beta + col + 32 * hh);
-          float y[32];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 gg = __ldg(g4 + c), be = __ldg(be4 + c);
-            y[4 * c + 0] = fmaf((__uint_as_float(r[4 * c + 0]) - mean) * rstd, gg.x, be.x);
-            y[4 * c + 1] = fmaf((__uint_as_float(r[4 * c + 1]) - mean) * rstd, gg.y, be.y);
-            y[4 * c + 2] = fmaf((__uint_as_float(r[4 * c + 2]) - mean) * rstd, gg.z, be.z);
-            y[4 * c + 3] = fmaf((__uint_as_float(r[4 * c + 3]) - mean) * rstd, gg.w, be.w);
-          }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            q[4 * hh + c].x = OpTraits<OpT>::pack2(y[8 * c + 0], y[8 * c + 1]);
-            q[4 * hh + c].y = OpTraits<OpT>::pack2(y[8 * c + 2], y[8 * c + 3]);
-            q[4 * hh + c].z = OpTraits<OpT>::pack2(y[8 * c + 4], y[8 * c + 5]);
-            q[4 * hh + c].w = OpTraits<OpT>::pack2(y[8 * c + 6], y[8 * c + 7]);
-          }
-        }
-        if (i == 0) {
-          tmem_ld32(taddr + 64 * (g + 2), ra);
-          tmem_ld32(taddr + 64 * (g + 2) + 32, rq);
-        } else {
-          // the accumulator stage is drained: hand it back to the MMA warp of the pair leader
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * as);
-        }
-        uint8_t* slab = slabs + slot * Cfg::SLAB_BYTES;
-        mbar_wait(&rfull[slot], par);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) *ln_slab_chunk(slab, lrow, c) = q[c];
-        fence_proxy_async_smem();
-        group_sync();
-        if (gt == 0) store_and_recycle(&mapH, col, row0);
-        next_item();
-      }
-      if (++as == 2) as = 0, aphase ^= 1;
-    }
-    if (gt == 0) bulk_wait<0>();
-  }
-
-  tc_fence_before();
-  cluster_sync_all();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc_2sm(tmem_base, 512);
-  }
-}
-
-// co-resident clusters of four CTAs (GPC packing can leave a few SMs unused); 0 = unsupported
-template <typename OpT>
-static int ln2_max_quads() {
-  static int cached = -1;
-  if (cached >= 0) return cached;
-  auto kern = gemm_resid_ln2_kernel<OpT>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Ln2Cfg::SMEM_BYTES) != cudaSuccess) {
-    cudaGetLastError();
-    return cached = 0;
-  }
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(kNumSMs / 4 * 4);
-  cfg.blockDim = dim3(Ln2Cfg::THREADS);
-  cfg.dynamicSmemBytes = Ln2Cfg::SMEM_BYTES;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 4;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
-    cudaGetLastError();
-    n = 0;
-  }
-  if (n > kNumSMs / 4) n = kNumSMs / 4;
-  return cached = n;
-}
-
-template <typename OpT>
-static int launch_ln2_gemm(const CUtensorMap& mA, const CUtensorMap& mW, const CUtensorMap& mX, const CUtensorMap& mH,
-                           const LnDev& p, int quads, cudaStream_t s) {
-  auto kern = gemm_resid_ln2_kernel<OpT>;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(4 * quads);
-  cfg.blockDim = dim3(Ln2Cfg::THREADS);
-  cfg.dynamicSmemBytes = Ln2Cfg::SMEM_BYTES;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 4;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 2;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mA, mW, mX, mH, p);
-  if (e != cudaSuccess) return fail(e, "gemm_resid_ln2_kernel launch");
-  return 0;
-}
-
 }  // namespace mm
 
 #ifdef MM_LN_TRACE
@@ -760,17 +380,6 @@ extern "C" int mm_gemm_resid_ln(const void* a, int64_t a_ld, const void* w, int6
   static const int l2_hints = getenv("MM_LN_L2_HINTS") ? atoi(getenv("MM_LN_L2_HINTS")) : 3;
   p.l2_hints = l2_hints;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // The overlapped four-CTA version writes the 16-bit output only; the optional fp32 copy (last encoder LayerNorm)
-  // and devices that cannot co-schedule enough four-CTA clusters take the whole-row kernel.
-  static const bool use_v2 = getenv("MM_LN_V2") != nullptr;
-  if (!h_f32 && use_v2) {
-    const int quads_max = f16 ? ln2_max_quads<__half>() : ln2_max_quads<__nv_bfloat16>();
-    if (quads_max >= 16) {
-      const int quads = p.num_tiles < quads_max ? p.num_tiles : quads_max;
-      return f16 ? launch_ln2_gemm<__half>(mA, mW, mX, mH, p, quads, s)
-                 : launch_ln2_gemm<__nv_bfloat16>(mA, mW, mX, mH, p, quads, s);
-    }
-  }
   return f16 ? launch_ln_gemm<__half>(mA, mW, mX, mH, mHf, p, s)
              : launch_ln_gemm<__nv_bfloat16>(mA, mW, mX, mH, mHf, p, s);
 }

@@ -1,5 +1,15 @@
 """Shared comparison helpers for the tests."""
+import os
+
 import numpy as np
+
+
+def record(name: str, value, bound=None) -> None:
+    """Append a measured parity number to $MM_PARITY_REPORT (profiles/rNN/parity.txt is produced this way)."""
+    path = os.environ.get("MM_PARITY_REPORT")
+    if path:
+        with open(path, "a") as f:
+            f.write(f"{name}: {value:.6g}" + (f"   (bound {bound:g})" if bound is not None else "") + "\n")
 
 
 def fbank_errors(got: np.ndarray, ref: np.ndarray):

@@ -2,6 +2,8 @@
 import pytest
 import torch
 
+from _util import record
+
 from test_gpu_encoder import TOL, _build, _compare, _oracle
 
 pytestmark = pytest.mark.gpu
@@ -26,6 +28,7 @@ def test_large_config4_detr_feats(cuda):
     out = enc(wav.cuda(), lens.cuda(), None, None, None, imgs_list=[imgs.cuda()], img_masks_list=[None])
     torch.cuda.synchronize()
     err = _compare(out, ref)
+    record("configs[4] large (16 layers, d=1024) B=3x4s, 100x256 image feats: fused states max-abs err", err, TOL)
     assert err < TOL, err
 
 

@@ -6,6 +6,8 @@ Tolerances are the north_star ones: fused / encoder states within 2e-2 max-abs o
 import pytest
 import torch
 
+from _util import record
+
 pytestmark = pytest.mark.gpu
 
 TOL = 2e-2
@@ -73,6 +75,7 @@ def test_small_config0_parity(cuda, attn_type, gate):
               return_all_hiddens=True)
     torch.cuda.synchronize()
     err = _compare(out, ref)
+    record(f"configs[0] small B=4x5s ragged+zero utt, {attn_type}, gate={gate}: fused states max-abs err", err, TOL)
     assert err < TOL, err
     # per-layer states (fp32 residual stream): tighter than the final tolerance early on
     mask = ref["encoder_padding_mask"][0]
@@ -154,6 +157,7 @@ def test_base_config1_shape_parity(cuda):
     out = enc(wav.cuda(), lens.cuda(), None, None, None, imgs_list=[imgs.cuda()], img_masks_list=[None])
     torch.cuda.synchronize()
     err = _compare(out, ref)
+    record("configs[1] base B=8x10s ragged+zero utt, selective_attention: fused states max-abs err", err, TOL)
     assert err < TOL, err
 
 
@@ -169,7 +173,9 @@ def test_fp16_operands_tighter(cuda):
     enc.cuda()
     out = enc(wav.cuda(), lens.cuda(), None, None, None, imgs_list=[imgs.cuda()], img_masks_list=[None])
     torch.cuda.synchronize()
-    assert _compare(out, ref) < 4e-3
+    err = _compare(out, ref)
+    record("configs[0] small, fp16 operands: fused states max-abs err", err, 4e-3)
+    assert err < 4e-3
 
 
 def test_decoder_unit_argmax_agreement(cuda):
@@ -196,4 +202,5 @@ def test_decoder_unit_argmax_agreement(cuda):
         l_gpu = odec.unit_decoder_forward(dsd, prev, out["encoder_out"][0].float().cpu(), mask,
                                           args.decoder_attention_heads)
     agree = (l_ref.argmax(-1) == l_gpu.argmax(-1)).float().mean().item()
+    record("S2UT decoder unit arg-max agreement (base, 6 utt x 80 units, teacher forced)", agree, 0.99)
     assert agree >= 0.99, agree

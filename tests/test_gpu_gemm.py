@@ -210,8 +210,7 @@ def test_gemm_full_size_linearity(cuda):
 def test_gemm_resid_ln_fused(cuda, M, Kd, want_f32):
     """x += a W^T + b and h = LayerNorm(x) in one kernel (20000 rows -> some CTA pairs take two tiles).
 
-    Without the fp32 copy the four-CTA overlapped kernel runs (40000 rows -> up to five row blocks per cluster,
-    both accumulator stages and the slab ring wrap several times)."""
+    40000 rows -> three row blocks per CTA pair; K=576 exercises nine k-blocks (ring wrap) and 2048 the fc2 shape."""
     from mm_s2ut_b200 import kernels as K
 
     dt, N = torch.bfloat16, 512
