@@ -44,10 +44,10 @@ __device__ __forceinline__ uint4* ln_slab_chunk(uint8_t* slab, int row, int c) {
 }
 
 #ifdef MM_LN_TRACE
-__device__ long long g_ln_trace[148 * 2 * 8];
+__device__ long long g_ln_trace[148 * 2 * 16];
 #define LN_TRACE(slot)                                                                      \
   do {                                                                                      \
-    if (ht == 0 && it == 0) g_ln_trace[(blockIdx.x * 2 + h) * 8 + (slot)] = clock64();       \
+    if (ht == 0 && it == 0) g_ln_trace[(blockIdx.x * 2 + h) * 16 + (slot)] = clock64();       \
   } while (0)
 #else
 #define LN_TRACE(slot)
@@ -70,7 +70,10 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   uint64_t* tfull = empty + STAGES;       // [1] accumulator complete (multicast commit)
   uint64_t* auxfull = tfull + 1;          // [12] residual slab landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(auxfull + 12);
-  float* stat = reinterpret_cast<float*>(extra);              // [2 halves][128 rows]
+  float* stat = reinterpret_cast<float*>(extra);              // [sum | sumsq][2 halves][128 rows]
+  float* s_bias = stat + 512;                                 // [512] bias, gamma, beta: read once from global; the
+  float* s_gamma = s_bias + 512;                              // epilogue then takes them as shared-memory broadcasts
+  float* s_beta = s_gamma + 512;                              // (their L2 latency was exposed in every 32-column step)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -90,6 +93,11 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2sm(tmem_slot, 512);
+  for (int i = threadIdx.x; i < 512; i += 256) {   // parameters, not activations: safe to read before pdl_wait()
+    s_bias[i] = __ldg(p.bias + i);
+    s_gamma[i] = __ldg(p.gamma + i);
+    s_beta[i] = __ldg(p.beta + i);
+  }
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -111,7 +119,7 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   const uint64_t pol_x = (p.l2_hints & 1) ? l2_policy_evict_last() : l2_policy_evict_normal();
   const uint64_t pol_a = (p.l2_hints & 2) ? l2_policy_evict_first() : l2_policy_evict_normal();
 #ifdef MM_LN_TRACE
-  if (ht == 0) g_ln_trace[(blockIdx.x * 2 + h) * 8 + 0] = clock64();
+  if (ht == 0) g_ln_trace[(blockIdx.x * 2 + h) * 16 + 0] = clock64();
 #endif
 
   for (int tile = pid; tile < p.num_tiles; tile += npairs, ++it) {
@@ -170,10 +178,10 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     auto sweep1 = [&](int j, uint32_t (&r)[32]) {
       const int b = j < 6 ? j : j - 6;
       uint8_t* slab = slab_ptr(b);
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + 256 * h + 32 * j);
+      const float4* b4 = reinterpret_cast<const float4*>(s_bias + 256 * h + 32 * j);
       float4 bq[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) bq[c] = __ldg(b4 + c);
+      for (int c = 0; c < 8; ++c) bq[c] = b4[c];
       mbar_wait(&aux[b], (aux_phase >> b) & 1);
       aux_phase ^= (1u << b);
       uint4 xq[8];
@@ -234,14 +242,18 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     const float rstd = rsqrtf(fmaxf(ex2 - mean * mean, 0.f) + p.eps);
     LN_TRACE(3);
     // ---- sweep 3: normalise -> 16-bit slabs (64 columns each), optional fp32 copy ----
-    if (ht == 0) bulk_wait_read<0>();       // sweep-1 stores have drained: this half's 6 buffers are reusable
+    // Sweep-1 store groups used buffers {0,1} {2,3} {4,5} {0,1}.  Without the fp32 copy a step needs one buffer, so
+    // step 0 takes buffer 3 and only the last group may still be reading; with the copy it needs three: drain all.
+    if (ht == 0) {
+      if (p.want_f32) bulk_wait_read<0>(); else bulk_wait_read<1>();
+    }
     auto sweep3 = [&](int col, const uint32_t (&r)[32], uint8_t* slab, int chunk0, uint8_t* fs) {
-      const float4* g4 = reinterpret_cast<const float4*>(p.gamma + col);
-      const float4* be4 = reinterpret_cast<const float4*>(p.beta + col);
+      const float4* g4 = reinterpret_cast<const float4*>(s_gamma + col);
+      const float4* be4 = reinterpret_cast<const float4*>(s_beta + col);
       float y[32];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        const float4 g = __ldg(g4 + c), be = __ldg(be4 + c);
+        const float4 g = g4[c], be = be4[c];
         y[4 * c + 0] = fmaf((__uint_as_float(r[4 * c + 0]) - mean) * rstd, g.x, be.x);
         y[4 * c + 1] = fmaf((__uint_as_float(r[4 * c + 1]) - mean) * rstd, g.y, be.y);
         y[4 * c + 2] = fmaf((__uint_as_float(r[4 * c + 2]) - mean) * rstd, g.z, be.z);
@@ -266,20 +278,26 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     tmem_ld32(taddr, ra);
 #pragma unroll 1
     for (int j = 0; j < 4; ++j) {
-      const int sb = 3 * (j & 1);             // buffers {0,1,2} / {3,4,5} alternate
+      const int sb = 3 * ((j + 1) & 1);       // buffers {3,4,5} / {0,1,2} alternate
       uint8_t* slab = slab_ptr(sb);
       uint8_t* f0 = slab_ptr(sb + 1);
       uint8_t* f1 = slab_ptr(sb + 2);
+      if (j == 1) LN_TRACE(7);
       if (ht == 0) bulk_wait_read<1>();       // the group that used these buffers two iterations ago has drained
       if (h == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (j == 1) LN_TRACE(8);
       tmem_ld_wait();
       tmem_ld32(taddr + 64 * j + 32, rb);
+      if (j == 1) LN_TRACE(9);
       sweep3(256 * h + 64 * j, ra, slab, 0, f0);
+      if (j == 1) LN_TRACE(10);
       tmem_ld_wait();
       if (j + 1 < 4) tmem_ld32(taddr + 64 * (j + 1), ra);
       sweep3(256 * h + 64 * j + 32, rb, slab, 4, f1);
+      if (j == 1) LN_TRACE(11);
       fence_proxy_async_smem();
       if (h == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (j == 1) LN_TRACE(12);
       if (ht == 0) {
         tma_store_3d(&mapH, slab, 256 * h + 64 * j, row0, 0);
         if (p.want_f32) {
@@ -299,7 +317,7 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   }
   if ((threadIdx.x & 127) == 0) bulk_wait<0>();
 #ifdef MM_LN_TRACE
-  if (ht == 0) g_ln_trace[(blockIdx.x * 2 + h) * 8 + 6] = clock64();
+  if (ht == 0) g_ln_trace[(blockIdx.x * 2 + h) * 16 + 6] = clock64();
 #endif
 
   tc_fence_before();
@@ -346,7 +364,7 @@ static int launch_ln_gemm(const CUtensorMap& mA, const CUtensorMap& mW, const CU
 
 #ifdef MM_LN_TRACE
 extern "C" int mm_debug_ln_trace(long long* host) {
-  return (int)cudaMemcpyFromSymbol(host, mm::g_ln_trace, sizeof(long long) * 148 * 2 * 8);
+  return (int)cudaMemcpyFromSymbol(host, mm::g_ln_trace, sizeof(long long) * 148 * 2 * 16);
 }
 #endif
 

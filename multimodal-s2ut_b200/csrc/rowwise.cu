@@ -256,30 +256,44 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const float* __restrict
   // rows handled by this block: [row0, row0 + rows_per_block) of the LARGER of the two output extents
   const int total_rows = max(op_frames, max_frames);
   const int row0 = blockIdx.x * rows_per_block;
-  for (int idx = threadIdx.x; idx < rows_per_block * 20; idx += blockDim.x) {
-    const int row = row0 + idx / 20;
-    const int c4 = idx % 20;
-    if (row >= total_rows) break;
-    // fp32 output row `row` <-> utterance frame `row`; operand row `row` <-> frame `row - op_row_offset`
-    if (out_f32 != nullptr && row < max_frames) {
-      float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < nfr) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(feats + ((long long)b * max_frames + row) * 80) + c4);
-        y = ident ? v : cmvn4(v, s_mean, s_std, c4);
-      }
-      reinterpret_cast<float4*>(out_f32 + ((long long)b * max_frames + row) * 80)[c4] = y;
-    }
-    if (out_op != nullptr && row < op_frames) {
+  // Batches of four (row, float4-column) items per thread: all loads of a batch are in flight before the first store
+  // (one load at a time left this kernel latency-bound at a third of the HBM rate).
+  constexpr int NI = 4;
+  const int items = rows_per_block * 20;
+  for (int base = threadIdx.x; base < items; base += NI * blockDim.x) {
+    float4 vf[NI], vo[NI];
+    int rowi[NI];
+#pragma unroll
+    for (int u = 0; u < NI; ++u) {
+      const int idx = base + u * blockDim.x;
+      const int row = row0 + idx / 20, c4 = idx % 20;
+      rowi[u] = (idx < items && row < total_rows) ? row : -1;
+      vf[u] = vo[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rowi[u] < 0) continue;
+      // fp32 output row `row` <-> utterance frame `row`; operand row `row` <-> frame `row - op_row_offset`
+      if (out_f32 != nullptr && row < nfr)
+        vf[u] = __ldg(reinterpret_cast<const float4*>(feats + ((long long)b * max_frames + row) * 80) + c4);
       const int fr = row - op_row_offset;
-      float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (fr >= 0 && fr < nfr) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(feats + ((long long)b * max_frames + fr) * 80) + c4);
-        y = ident ? v : cmvn4(v, s_mean, s_std, c4);
+      if (out_op != nullptr && fr >= 0 && fr < nfr)
+        vo[u] = __ldg(reinterpret_cast<const float4*>(feats + ((long long)b * max_frames + fr) * 80) + c4);
+    }
+#pragma unroll
+    for (int u = 0; u < NI; ++u) {
+      if (rowi[u] < 0) continue;
+      const int idx = base + u * blockDim.x;
+      const int row = rowi[u], c4 = idx % 20;
+      if (out_f32 != nullptr && row < max_frames) {
+        const float4 y = (row < nfr && !ident) ? cmvn4(vf[u], s_mean, s_std, c4) : vf[u];
+        reinterpret_cast<float4*>(out_f32 + ((long long)b * max_frames + row) * 80)[c4] = y;
       }
-      uint2 pk;
-      pk.x = OpTraits<OpT>::pack2(y.x, y.y);
-      pk.y = OpTraits<OpT>::pack2(y.z, y.w);
-      reinterpret_cast<uint2*>(out_op + ((long long)b * op_frames + row) * 80)[c4] = pk;
+      if (out_op != nullptr && row < op_frames) {
+        const int fr = row - op_row_offset;
+        const float4 y = (fr >= 0 && fr < nfr && !ident) ? cmvn4(vo[u], s_mean, s_std, c4) : vo[u];
+        uint2 pk;
+        pk.x = OpTraits<OpT>::pack2(y.x, y.y);
+        pk.y = OpTraits<OpT>::pack2(y.z, y.w);
+        reinterpret_cast<uint2*>(out_op + ((long long)b * op_frames + row) * 80)[c4] = pk;
+      }
     }
   }
 }

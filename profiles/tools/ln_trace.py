@@ -50,23 +50,28 @@ for which in ("out_proj K=512", "fc2 K=2048"):
         layer()
     layer(stop_after_out_proj=which.startswith("out"))
     torch.cuda.synchronize()
-    buf = np.zeros(148 * 2 * 8, dtype=np.int64)
+    buf = np.zeros(148 * 2 * 16, dtype=np.int64)
     assert lib.mm_debug_ln_trace(buf.ctypes.data) == 0
-    t = buf.reshape(148, 2, 8)[:126]
+    t = buf.reshape(148, 2, 16)[:126]
     print(f"{which}: mean cycles over {t.shape[0]} CTAs x 2 halves")
     for k in range(6):
         dlt = t[:, :, k + 1] - t[:, :, k]
         print(f"  {names[k]:34s} mean {dlt.mean():8.0f}  min {dlt.min():8.0f}  max {dlt.max():8.0f}")
     print(f"  total traced {np.mean(t[:, :, 6] - t[:, :, 0]):8.0f} cycles")
+    sub = ["step-1 start -> wait_read+bar", "tmem wait + issue", "normalise cols 0-31", "tmem wait + normalise cols 32-63",
+           "fence + bar"]
+    for k in range(5):
+        dlt = t[:, :, 8 + k] - t[:, :, 7 + k]
+        print(f"    sweep-2 step 1: {sub[k]:34s} mean {dlt.mean():7.0f}  max {dlt.max():7.0f}")
 
 # hot-L2 bound: the same kernel back to back (x, a, h all resident)
 for Kd, a_, w_, b_ in ((512, att, wo, bo), (2048, f, w2, b2)):
     for _ in range(4):
         K.gemm_resid_ln(a_, w_, b_, x, g, be, h)
     torch.cuda.synchronize()
-    buf = np.zeros(148 * 2 * 8, dtype=np.int64)
+    buf = np.zeros(148 * 2 * 16, dtype=np.int64)
     assert lib.mm_debug_ln_trace(buf.ctypes.data) == 0
-    t = buf.reshape(148, 2, 8)[:126]
+    t = buf.reshape(148, 2, 16)[:126]
     print(f"back-to-back K={Kd} (everything L2-resident):")
     for k in range(5):
         dlt = t[:, :, k + 1] - t[:, :, k]

@@ -1,14 +1,10 @@
 mkdir -p gpurun_out
-rm -f gpurun_out/parity.txt
-MM_PARITY_REPORT=$PWD/gpurun_out/parity.txt timeout 900 python -m pytest tests -q -m gpu --timeout 300 > gpurun_out/gpu_tests.log 2>&1
+timeout 900 python -m pytest tests -q -m gpu --timeout 300 -x > gpurun_out/gpu_tests.log 2>&1
 echo "gpu tests exit $?"; tail -3 gpurun_out/gpu_tests.log
-timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
-echo "bench exit $?"; tail -2 gpurun_out/bench_default.err
-timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
-echo "ref exit $?"; cat gpurun_out/bench_reference.json | cut -c1-400
-python -c "
-import sys; sys.path.insert(0,'.')
-import __graft_entry__ as g
-g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -2 gpurun_out/smoke.log
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_v16.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu.log 2>&1
-echo "ncu exit $?"; wc -l gpurun_out/launches_v16.csv
+timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench17.json 2> gpurun_out/bench17.err
+echo "bench exit $?"; tail -3 gpurun_out/bench17.err; python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench17.json'))
+print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'],'roof',d['roofline']['achieved'],d['roofline']['frac'])
+for k,v in d['kernels'].items(): print(k, round(v['ms_per_step'],4), v['launches_per_step'])
+PY
