@@ -37,7 +37,6 @@ struct LnDev {
   float eps;
   int want_f32;
   int l2_hints;   // bit 0: residual stream evict_last, bit 1: A operand evict_first
-  int rows_cta;   // rows owned by one CTA (<= 128): the TMA boxes carry this many rows, see mm_gemm_resid_ln
 };
 
 __device__ __forceinline__ uint4* ln_slab_chunk(uint8_t* slab, int row, int c) {
@@ -124,12 +123,12 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #endif
 
   for (int tile = pid; tile < p.num_tiles; tile += npairs, ++it) {
-    const int row0 = (tile * 2 + rank) * p.rows_cta;
+    const int row0 = tile * 256 + rank * Cfg::BM;
     // ===================== phase A: mainloop (one producer thread per CTA, one MMA thread per pair) ==========
     if (warp == 0 && lane == 0) {
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
-        if (rank == 0) mbar_expect_tx(&full[stage], 2 * (p.rows_cta * 128 + Cfg::B_BYTES));
+        if (rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
         uint8_t* st = ring + stage * Cfg::STAGE_BYTES;
         tma_load_3d_2sm_hint(st, &mapA, &full[stage], kb * Cfg::BK, row0, 0, pol_a);
         tma_load_3d_2sm(st + Cfg::A_BYTES, &mapW, &full[stage], kb * Cfg::BK, rank * 128, 0);
@@ -169,7 +168,7 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     if (ht == 0) {                // this half's residual slabs 0..5 (slabs 6, 7 recycle buffers 0, 1)
 #pragma unroll 1
       for (int j = 0; j < 6; ++j) {
-        mbar_expect_tx(&aux[j], p.rows_cta * 128);
+        mbar_expect_tx(&aux[j], Cfg::SLAB_BYTES);
         tma_load_3d_hint(slab_ptr(j), &mapX, &aux[j], 256 * h + 32 * j, row0, 0, pol_x);
       }
     }
@@ -212,7 +211,7 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         bulk_wait_read<1>();
 #pragma unroll 1
         for (int q = 0; q < 2; ++q) {
-          mbar_expect_tx(&aux[q], p.rows_cta * 128);
+          mbar_expect_tx(&aux[q], Cfg::SLAB_BYTES);
           tma_load_3d_hint(slab_ptr(q), &mapX, &aux[q], 256 * h + 32 * (6 + q), row0, 0, pol_x);
         }
       }
@@ -377,35 +376,24 @@ extern "C" int mm_gemm_resid_ln(const void* a, int64_t a_ld, const void* w, int6
   if (n != LnCfg::N) return bad_arg("gemm_resid_ln: n must be 512 (full rows in one accumulator)");
   if (rows <= 0 || k <= 0) return bad_arg("gemm_resid_ln: extents");
   const int f16 = dtype == MM_DTYPE_F16;
-  // Rows per CTA.  One wave (<= 74 tiles of 256 rows) that would leave CTA pairs idle is re-cut so that all 74 pairs
-  // get an equal share: the UMMA still spans 128 lanes per CTA, but the TMA boxes (A rows, residual in/out, LN out)
-  // carry only rows_cta rows, and the epilogue - which runs at the per-SM L2 rate - moves proportionally less per SM.
-  const int max_pairs = kNumSMs / 2;
-  const int tiles256 = (rows + 255) / 256;
-  int rows_cta = 128;
-  if (tiles256 <= max_pairs && tiles256 > max_pairs / 2) {
-    rows_cta = ((rows + 2 * max_pairs - 1) / (2 * max_pairs) + 7) & ~7;
-    if (rows_cta > 128) rows_cta = 128;
-  }
   CUtensorMap mA, mW, mX, mH, mHf;
-  int rc = make_tmap_3d(&mA, a, f16, (uint64_t)k, (uint64_t)rows, 1, (uint64_t)a_ld, 0, (uint32_t)rows_cta);
+  int rc = make_tmap_3d(&mA, a, f16, (uint64_t)k, (uint64_t)rows, 1, (uint64_t)a_ld, 0, 128);
   if (rc) return rc;
   rc = make_tmap_3d(&mW, w, f16, (uint64_t)k, (uint64_t)n, 1, (uint64_t)w_ld, 0, 128);
   if (rc) return rc;
-  rc = make_tmap_3d_ex(&mX, x, 2, (uint64_t)n, (uint64_t)rows, 1, (uint64_t)n, 0, 32, (uint32_t)rows_cta);
+  rc = make_tmap_3d_ex(&mX, x, 2, (uint64_t)n, (uint64_t)rows, 1, (uint64_t)n, 0, 32, 128);
   if (rc) return rc;
-  rc = make_tmap_3d_ex(&mH, h_op, f16 ? 1 : 0, (uint64_t)n, (uint64_t)rows, 1, (uint64_t)n, 0, 64, (uint32_t)rows_cta);
+  rc = make_tmap_3d_ex(&mH, h_op, f16 ? 1 : 0, (uint64_t)n, (uint64_t)rows, 1, (uint64_t)n, 0, 64, 128);
   if (rc) return rc;
   if (h_f32) {
-    rc = make_tmap_3d_ex(&mHf, h_f32, 2, (uint64_t)n, (uint64_t)rows, 1, (uint64_t)n, 0, 32, (uint32_t)rows_cta);
+    rc = make_tmap_3d_ex(&mHf, h_f32, 2, (uint64_t)n, (uint64_t)rows, 1, (uint64_t)n, 0, 32, 128);
     if (rc) return rc;
   } else {
     mHf = mX;
   }
   LnDev p;
   memset(&p, 0, sizeof(p));
-  p.rows = rows, p.k = k, p.num_kb = (k + 63) / 64, p.rows_cta = rows_cta;
-  p.num_tiles = (rows + 2 * rows_cta - 1) / (2 * rows_cta);
+  p.rows = rows, p.k = k, p.num_kb = (k + 63) / 64, p.num_tiles = (rows + 255) / 256;
   p.bias = bias, p.gamma = gamma, p.beta = beta, p.eps = eps, p.want_f32 = h_f32 != nullptr;
   static const int l2_hints = getenv("MM_LN_L2_HINTS") ? atoi(getenv("MM_LN_L2_HINTS")) : 3;
   p.l2_hints = l2_hints;

@@ -211,8 +211,7 @@ def test_gemm_full_size_linearity(cuda):
 def test_gemm_resid_ln_fused(cuda, M, Kd, want_f32):
     """x += a W^T + b and h = LayerNorm(x) in one kernel (20000 rows -> some CTA pairs take two tiles).
 
-    16000 / 12000 / 9700 rows are single waves re-cut to 112 / 88 / 72 rows per CTA (TMA boxes shorter than the
-    128-lane accumulator); 40000 rows -> three row blocks per CTA pair; K=576 exercises nine k-blocks (ring wrap) and 2048 the fc2 shape."""
+    40000 rows -> three row blocks per CTA pair; K=576 exercises nine k-blocks (ring wrap) and 2048 the fc2 shape."""
     from mm_s2ut_b200 import kernels as K
 
     dt, N = torch.bfloat16, 512
