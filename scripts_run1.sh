@@ -1,11 +1,12 @@
 mkdir -p gpurun_out
-MM_GEMM_DIRECT=1 timeout 600 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_encoder.py -q -m gpu --timeout 120 -x > gpurun_out/direct_tests.log 2>&1
-echo "tests exit $?"; tail -3 gpurun_out/direct_tests.log
-for d in 1 0 1 0; do
-echo "== direct $d"
-MM_GEMM_DIRECT=$d timeout 300 python profiles/tools/gemm_sweep.py 2>&1 | grep -E "^relu_op" | grep -E "K=  512|K= 2048"
-MM_GEMM_DIRECT=$d timeout 600 python bench.py --steps 100 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read())
-print('value',d['value'],'ms',d['ms_per_step'], 'op', d['kernels']['gemm[op]']['ms_per_step'], 'relu', d['kernels']['gemm[relu_op]']['ms_per_step'])"
-done
+rm -f gpurun_out/parity.txt
+MM_PARITY_REPORT=$PWD/gpurun_out/parity.txt timeout 900 python -m pytest tests -q -m gpu --timeout 300 > gpurun_out/gpu_tests.log 2>&1
+echo "gpu tests exit $?"; tail -3 gpurun_out/gpu_tests.log
+timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
+echo "bench exit $?"; tail -2 gpurun_out/bench_default.err
+python -c "
+import json
+d=json.load(open('gpurun_out/bench_default.json'))
+print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'],'roof',d['roofline']['frac'],d['clocks'])"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_v18.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu.log 2>&1
+echo "ncu exit $?"; wc -l gpurun_out/launches_v18.csv
