@@ -3,15 +3,12 @@
 // (fused into that GEMM's epilogue).  Reference: fairseq/modules/multihead_attention.py (encoder self-attention,
 // key_padding_mask), as called from TransformerEncoderLayerBase.forward.
 //
-// Two kernels:
-//  * self_attention_t256_kernel (T <= 256, i.e. utterances up to ~10 s at 4x subsampling): persistent, warp-specialised,
-//    S / P / O all live in TMEM; described in front of the kernel below.  This is the one the bench runs.
-//  * self_attention_kernel (any T): one CTA (128 threads) per (utterance, head, 128-query tile), keys in chunks of 256:
-//      S = Q K^T      tcgen05.mma M=128 N=256 K=64, fp32 scores in TMEM columns [0,256)
-//      softmax        thread i owns score row i (TMEM lane i): no cross-thread reductions
-//      P              written as 16-bit into shared memory in the 128B-swizzled K-major layout UMMA expects
-//      O += P V       tcgen05.mma M=128 N=64 K=256 (A = P from smem, B = V rows as an MN-major operand)
-//    with a two-sweep schedule (sweep 1: row maxima only; sweep 2: exp / P V) so O never needs rescaling.
+// Two persistent, warp-specialised kernels (one CTA per SM walks a list of (utterance, head, 128-query tile) items;
+// TMA producer warp, MMA warp, two ping-pong softmax groups of 8 warps; S, P and O live in TMEM; O leaves by TMA store):
+//  * self_attention_t256_kernel  T <= 256 (utterances up to ~10 s at 4x subsampling): one 256-key chunk, plain softmax.
+//    This is the one the bench runs.
+//  * self_attention_long_kernel  any T: 128-key chunks, online softmax (running maximum, O rescaled in TMEM), chunks
+//    beyond an utterance's length skipped.
 #include "common.cuh"
 #include "host.cuh"
 #include "../../include/mms2ut_b200.h"
@@ -22,211 +19,6 @@ constexpr int AT_BM = 128, AT_HD = 64, AT_KC = 256;
 constexpr int AT_Q_BYTES = AT_BM * AT_HD * 2;        // 16 KB
 constexpr int AT_K_BYTES = AT_KC * AT_HD * 2;        // 32 KB
 constexpr int AT_V_BYTES = AT_HD * AT_KC * 2;        // 32 KB (4 blocks of 64 keys)
-constexpr int AT_P_BYTES = AT_BM * AT_KC * 2;        // 64 KB (4 blocks of 64 keys)
-constexpr int AT_SMEM_BYTES = AT_Q_BYTES + AT_K_BYTES + AT_V_BYTES + AT_P_BYTES + 64 + 1024;
-constexpr int AT_TMEM_COLS = 512;
-constexpr int AT_O_COL = 256;
-
-template <typename OpT>
-__global__ void __launch_bounds__(128, 1)
-self_attention_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant__ CUtensorMap mapVT,
-                      const int* __restrict__ seq_lens, int T, int d_model, OpT* __restrict__ out, long long out_ld) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + AT_Q_BYTES;
-  uint8_t* sV = sK + AT_K_BYTES;
-  uint8_t* sP = sV + AT_V_BYTES;
-  uint64_t* bar_tma = reinterpret_cast<uint64_t*>(sP + AT_P_BYTES);
-  uint64_t* bar_mma = bar_tma + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int len = min(seq_lens[b], T);
-  const int nchunks = max(1, (len + AT_KC - 1) / AT_KC);
-  constexpr float L2E = 1.4426950408889634f;
-
-  if (tid == 0) {
-    tma_prefetch_desc(&mapQK);
-    tma_prefetch_desc(&mapVT);
-    mbar_init(bar_tma, 1);
-    mbar_init(bar_mma, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, AT_TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-
-  uint32_t tma_phase = 0, mma_phase = 0;
-  constexpr uint32_t idesc_s = umma_idesc(AT_BM, AT_KC, OpTraits<OpT>::fmt);
-  constexpr uint32_t idesc_o = umma_idesc(AT_BM, AT_HD, OpTraits<OpT>::fmt) | (1u << 16);  // B (= V) is MN-major
-
-  auto load_and_scores = [&](int c, bool with_q, bool with_v) {
-    if (tid == 0) {
-      mbar_expect_tx(bar_tma, (with_q ? AT_Q_BYTES : 0) + AT_K_BYTES + (with_v ? AT_V_BYTES : 0));
-      if (with_q) tma_load_3d(sQ, &mapQK, bar_tma, h * AT_HD, qt * AT_BM, b);
-      tma_load_3d(sK, &mapQK, bar_tma, d_model + h * AT_HD, c * AT_KC, b);
-      tma_load_3d(sK + AT_K_BYTES / 2, &mapQK, bar_tma, d_model + h * AT_HD, c * AT_KC + 128, b);
-      if (with_v) {   // V rows = keys, 64 values (128 B) each: MN-major B operand of the PV MMA
-        tma_load_3d(sV, &mapQK, bar_tma, 2 * d_model + h * AT_HD, c * AT_KC, b);
-        tma_load_3d(sV + AT_V_BYTES / 2, &mapQK, bar_tma, 2 * d_model + h * AT_HD, c * AT_KC + 128, b);
-      }
-    }
-    mbar_wait(bar_tma, tma_phase);
-    tma_phase ^= 1;
-    if (tid == 0) {
-      tc_fence_after();
-      const uint64_t adesc = umma_desc_sw128(smem_u32(sQ));
-      const uint64_t bdesc = umma_desc_sw128(smem_u32(sK));
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) umma_f16(tmem_base, adesc + 2 * kk, bdesc + 2 * kk, idesc_s, kk != 0);
-      umma_commit(bar_mma);
-    }
-    mbar_wait(bar_mma, mma_phase);
-    mma_phase ^= 1;
-    tc_fence_after();
-  };
-
-  auto row_max_of_chunk = [&](int c, float m) {
-#pragma unroll 1
-    for (int cc = 0; cc < AT_KC / 32; ++cc) {
-      if (c * AT_KC + cc * 32 >= len) break;  // uniform
-      uint32_t r[32];
-      tmem_ld32(t_row + cc * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int key = c * AT_KC + cc * 32 + i;
-        if (key < len) m = fmaxf(m, __uint_as_float(r[i]));
-      }
-    }
-    return m;
-  };
-
-  float m = -INFINITY, l = 0.f;
-  bool q_loaded = false;
-  if (nchunks > 1) {
-    for (int c = 0; c < nchunks; ++c) {
-      load_and_scores(c, !q_loaded, false);
-      q_loaded = true;
-      m = row_max_of_chunk(c, m);
-      tc_fence_before();
-      __syncthreads();
-    }
-  }
-  for (int c = 0; c < nchunks; ++c) {
-    load_and_scores(c, !q_loaded, true);
-    q_loaded = true;
-    if (nchunks == 1) m = row_max_of_chunk(0, m);
-    const float mb = (m == -INFINITY) ? 0.f : m * L2E;
-    const int row = warp * 32 + lane;
-#pragma unroll 1
-    for (int cc = 0; cc < AT_KC / 32; ++cc) {
-      uint32_t r[32];
-      uint32_t pk[16];
-      if (c * AT_KC + cc * 32 < len) {  // uniform
-        tmem_ld32(t_row + cc * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const int key = c * AT_KC + cc * 32 + i;
-          float p0 = key < len ? exp2f(fmaf(__uint_as_float(r[i]), L2E, -mb)) : 0.f;
-          float p1 = key + 1 < len ? exp2f(fmaf(__uint_as_float(r[i + 1]), L2E, -mb)) : 0.f;
-          pk[i >> 1] = OpTraits<OpT>::pack2(p0, p1);
-          l += p0 + p1;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = 0u;
-      }
-      uint8_t* prow = sP + (cc >> 1) * (AT_P_BYTES / 4) + row * 128;
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        const int chunk16 = (cc & 1) * 4 + q4;
-        *reinterpret_cast<uint4*>(prow + ((chunk16 ^ (row & 7)) << 4)) =
-            make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
-      }
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint64_t adesc = umma_desc_sw128(smem_u32(sP));
-      const uint64_t bdesc = umma_desc_sw128(smem_u32(sV));
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          umma_f16(tmem_base + AT_O_COL, adesc + (uint64_t)((j * (AT_P_BYTES / 4)) >> 4) + 2 * kk,
-                   bdesc + (uint64_t)(((j * 64 + kk * 16) * 128) >> 4), idesc_o, (c | j | kk) != 0);
-        }
-      }
-      umma_commit(bar_mma);
-    }
-    mbar_wait(bar_mma, mma_phase);
-    mma_phase ^= 1;
-    tc_fence_after();
-  }
-
-  // ---- epilogue: O / l -> 16-bit, 128 contiguous bytes per row ----
-  {
-    const int row = warp * 32 + lane;
-    const int t = qt * AT_BM + row;
-    const float inv = l > 0.f ? 1.0f / l : 0.f;
-    uint32_t r0[32], r1[32];
-    tmem_ld32(t_row + AT_O_COL, r0);
-    tmem_ld32(t_row + AT_O_COL + 32, r1);
-    tmem_ld_wait();
-    if (t < T) {
-      uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * T + t) * out_ld + h * AT_HD);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint4 q;
-        q.x = OpTraits<OpT>::pack2(__uint_as_float(r0[8 * i + 0]) * inv, __uint_as_float(r0[8 * i + 1]) * inv);
-        q.y = OpTraits<OpT>::pack2(__uint_as_float(r0[8 * i + 2]) * inv, __uint_as_float(r0[8 * i + 3]) * inv);
-        q.z = OpTraits<OpT>::pack2(__uint_as_float(r0[8 * i + 4]) * inv, __uint_as_float(r0[8 * i + 5]) * inv);
-        q.w = OpTraits<OpT>::pack2(__uint_as_float(r0[8 * i + 6]) * inv, __uint_as_float(r0[8 * i + 7]) * inv);
-        dst[i] = q;
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint4 q;
-        q.x = OpTraits<OpT>::pack2(__uint_as_float(r1[8 * i + 0]) * inv, __uint_as_float(r1[8 * i + 1]) * inv);
-        q.y = OpTraits<OpT>::pack2(__uint_as_float(r1[8 * i + 2]) * inv, __uint_as_float(r1[8 * i + 3]) * inv);
-        q.z = OpTraits<OpT>::pack2(__uint_as_float(r1[8 * i + 4]) * inv, __uint_as_float(r1[8 * i + 5]) * inv);
-        q.w = OpTraits<OpT>::pack2(__uint_as_float(r1[8 * i + 6]) * inv, __uint_as_float(r1[8 * i + 7]) * inv);
-        dst[4 + i] = q;
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, AT_TMEM_COLS);
-  }
-}
-
-template <typename OpT>
-static int launch_attn(const CUtensorMap& mqk, const CUtensorMap& mvt, const int* lens, int B, int T, int H, int d,
-                       void* out, long long out_ld, cudaStream_t s) {
-  auto kern = self_attention_kernel<OpT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
-    if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute(self_attention)");
-    attr_set = true;
-  }
-  dim3 grid((T + AT_BM - 1) / AT_BM, H, B);
-  kern<<<grid, 128, AT_SMEM_BYTES, s>>>(mqk, mvt, lens, T, d, reinterpret_cast<OpT*>(out), out_ld);
-  MM_CHECK_LAUNCH("self_attention_kernel launch");
-  return 0;
-}
 
 // ===================================================================================================
 // Persistent, warp-specialised variant for T <= 256 (utterances up to ~10 s: one key chunk per query tile).
@@ -590,6 +382,322 @@ static int launch_attn_t256(const CUtensorMap& mqk, const CUtensorMap& mout, con
   return 0;
 }
 
+
+// ===================================================================================================
+// Persistent variant for T > 256: the same roles and the same two ping-pong softmax groups, but keys arrive in chunks
+// of 128 and the softmax is ONLINE (running row maximum m, running sum l, O rescaled by exp2(m_old - m_new) when the
+// maximum moves), so S / P / O of a group fit in 192 TMEM columns for any T:
+//   region g = columns [256 g, 256 g + 256):  S chunk (fp32, 128 keys) in [0,128) -> P (packed 16-bit) in [0,64),
+//   O (fp32, 64 values) in [128,192), accumulated over the chunks by the P V UMMAs.
+// Per chunk and group: S = Q K_c^T (SS UMMA) -> each of the 256 threads takes 64 scores of its row (two threads per
+// row, row maximum combined through shared memory) -> P to TMEM, O rescaled in TMEM only by warps that saw their
+// maximum move -> O += P V_c (TS UMMA, V_c rows as MN-major B).  The next chunk's S UMMA is issued right behind the
+// P V UMMAs (the tensor pipe executes in order, so it cannot overtake their reads of P).  Chunks that lie entirely
+// beyond an utterance's length are skipped, so ragged batches cost what their real lengths cost.
+// Shared memory: per group a Q tile (16 KB) and a 2-stage ring of (K_c | V_c) (32 KB per stage), plus the staging
+// tile for the TMA store of O.
+// ===================================================================================================
+constexpr int PL_KC = 128;                                   // keys per chunk
+constexpr int PL_KV_BYTES = 2 * PL_KC * AT_HD * 2;           // K_c + V_c: 32 KB
+constexpr int PL_SMEM_BYTES = 2 * AT_Q_BYTES + 2 * 2 * PL_KV_BYTES + 2 * PA_OUT_BYTES + 256 + PA_MAX_LENS * 4 +
+                              PA_XCH_BYTES + 1024;
+static_assert(PL_SMEM_BYTES <= 232448, "shared memory budget");
+
+template <typename OpT>
+__global__ void __launch_bounds__(PA_THREADS, 1)
+self_attention_long_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapKV,
+                           const __grid_constant__ CUtensorMap mapOut, const int* __restrict__ seq_lens, int T,
+                           int d_model, int H, int nqt, int n_items) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                                  // [2 groups] 16 KB
+  uint8_t* sKV = sQ + 2 * AT_Q_BYTES;                  // [2 groups][2 stages] (K_c 16 KB | V_c 16 KB)
+  uint8_t* sOut = sKV + 4 * PL_KV_BYTES;               // [2 groups] 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + 2 * PA_OUT_BYTES);
+  uint64_t* q_full = bars;            // [2]     TMA Q -> MMA
+  uint64_t* q_empty = bars + 2;       // [2]     last S UMMA of the item done -> TMA
+  uint64_t* kv_full = bars + 4;       // [2][2]  TMA (K_c, V_c) -> MMA
+  uint64_t* kv_empty = bars + 8;      // [2][2]  P V_c done -> TMA
+  uint64_t* s_full = bars + 12;       // [2]     S_c done -> softmax group
+  uint64_t* p_full = bars + 14;       // [2]     softmax group (8 warps): P_c stored, O rescaled -> MMA
+  uint64_t* o_done = bars + 16;       // [2]     P V_c done -> softmax group
+  uint64_t* reg_free = bars + 18;     // [2]     group has read the final O -> MMA may start the next item there
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  int* s_lens = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 256);
+  float* s_xch = reinterpret_cast<float*>(s_lens + PA_MAX_LENS);
+  const int n_batch = n_items / (nqt * H);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_local = (int)blockIdx.x < n_items ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  constexpr float L2E = 1.4426950408889634f;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapKV);
+    tma_prefetch_desc(&mapOut);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 8);
+      mbar_init(&o_done[i], 1);
+      mbar_init(&reg_free[i], 8);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 17) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int i = threadIdx.x; i < n_batch && i < PA_MAX_LENS; i += PA_THREADS) s_lens[i] = seq_lens[i];
+  __syncthreads();
+  auto len_of = [&](int b) { return max(1, min(b < PA_MAX_LENS ? s_lens[b] : seq_lens[b], T)); };
+  auto item_coords = [&](int i, int& qt, int& h, int& b) {
+    const int item = blockIdx.x + i * gridDim.x;
+    qt = item % nqt, h = (item / nqt) % H, b = item / (nqt * H);
+  };
+
+  if (warp == 16) {
+    // ---------------- TMA producer: the two groups' (item, chunk) streams, interleaved chunk by chunk ----------------
+    if (lane == 0) {
+      int it[2] = {0, 1}, ch[2] = {0, 0};          // next item / chunk per group
+      uint32_t kv_n[2] = {0, 0}, q_n[2] = {0, 0};   // loads issued so far (-> stage and parity)
+      while (it[0] < n_local || it[1] < n_local) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (it[g] >= n_local) continue;
+          int qt, h, b;
+          item_coords(it[g], qt, h, b);
+          const int nc = (len_of(b) + PL_KC - 1) / PL_KC;
+          if (ch[g] == 0) {
+            mbar_wait(&q_empty[g], (q_n[g] & 1) ^ 1);
+            mbar_expect_tx(&q_full[g], AT_Q_BYTES);
+            tma_load_3d(sQ + g * AT_Q_BYTES, &mapQ, &q_full[g], h * AT_HD, qt * AT_BM, b);
+            ++q_n[g];
+          }
+          const uint32_t st = kv_n[g] & 1;
+          uint8_t* kv = sKV + (2 * g + st) * PL_KV_BYTES;
+          mbar_wait(&kv_empty[2 * g + st], ((kv_n[g] >> 1) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[2 * g + st], PL_KV_BYTES);
+          tma_load_3d(kv, &mapKV, &kv_full[2 * g + st], d_model + h * AT_HD, ch[g] * PL_KC, b);
+          tma_load_3d(kv + PL_KV_BYTES / 2, &mapKV, &kv_full[2 * g + st], 2 * d_model + h * AT_HD, ch[g] * PL_KC, b);
+          ++kv_n[g];
+          if (++ch[g] == nc) ch[g] = 0, it[g] += 2;
+        }
+      }
+    }
+  } else if (warp == 17) {
+    // ---------------- MMA issuer: per group a two-state machine (S of chunk c, then P V of chunk c) ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc(AT_BM, PL_KC, OpTraits<OpT>::fmt);
+      constexpr uint32_t idesc_o = umma_idesc(AT_BM, AT_HD, OpTraits<OpT>::fmt) | (1u << 16);  // B (= V) is MN-major
+      int it[2] = {0, 1}, ch[2] = {0, 0}, nc[2] = {0, 0};
+      bool need_pv[2] = {false, false};
+      uint32_t kv_n[2] = {0, 0}, q_n[2] = {0, 0}, pv_n[2] = {0, 0};
+      const uint64_t t0 = globaltimer_ns();
+      while (it[0] < n_local || it[1] < n_local) {
+        bool progressed = false;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (it[g] >= n_local) continue;
+          const uint32_t st = kv_n[g] & 1;
+          uint8_t* kv = sKV + (2 * g + st) * PL_KV_BYTES;
+          if (!need_pv[g]) {
+            if (ch[g] == 0) {
+              if (!mbar_test(&q_full[g], q_n[g] & 1) || !mbar_test(&reg_free[g], (q_n[g] & 1) ^ 1)) continue;
+              int qt, h, b;
+              item_coords(it[g], qt, h, b);
+              nc[g] = (len_of(b) + PL_KC - 1) / PL_KC;
+            }
+            if (!mbar_test(&kv_full[2 * g + st], (kv_n[g] >> 1) & 1)) continue;
+            tc_fence_after();
+            const uint64_t adesc = umma_desc_sw128(smem_u32(sQ + g * AT_Q_BYTES));
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(kv));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16(tmem_base + 256 * g, adesc + 2 * kk, bdesc + 2 * kk, idesc_s, kk != 0);
+            umma_commit(&s_full[g]);
+            if (ch[g] + 1 == nc[g]) {   // last S of the item: the Q tile may be replaced
+              umma_commit(&q_empty[g]);
+              ++q_n[g];
+            }
+            need_pv[g] = true;
+            progressed = true;
+          } else {
+            if (!mbar_test(&p_full[g], pv_n[g] & 1)) continue;
+            tc_fence_after();
+            const uint64_t vdesc = umma_desc_sw128(smem_u32(kv + PL_KV_BYTES / 2));
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)   // 16 keys per step: 8 packed P columns, 16 V rows of 128 B
+                umma_f16_ts(tmem_base + 256 * g + 128, tmem_base + 256 * g + 8 * (4 * j + kk),
+                            vdesc + (uint64_t)(((j * 64 + kk * 16) * 128) >> 4), idesc_o, (ch[g] | j | kk) != 0);
+            }
+            umma_commit(&o_done[g]);
+            umma_commit(&kv_empty[2 * g + st]);
+            ++pv_n[g];
+            ++kv_n[g];
+            need_pv[g] = false;
+            if (++ch[g] == nc[g]) ch[g] = 0, it[g] += 2;
+            progressed = true;
+          }
+        }
+        if (!progressed && globaltimer_ns() - t0 > 8000000000ull) {
+          printf("mm: long attention issuer timeout block %d items %d %d chunks %d %d\n", blockIdx.x, it[0], it[1], ch[0],
+                 ch[1]);
+          __trap();
+        }
+      }
+    }
+  } else {
+    // ---------------- softmax + epilogue groups ----------------
+    const int g = warp >> 3;
+    const int hf = (warp >> 2) & 1;            // which 64 keys of a chunk / which 32 output columns
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t t_row = tmem_base + 256 * g + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    float* x_max = s_xch + g * 4 * AT_BM;      // [2 halves][128 rows]
+    float* x_sum = x_max + 2 * AT_BM;
+    auto group_sync = [&]() {
+      if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 2, 256;" ::: "memory");
+    };
+    uint32_t s_n = 0, o_n = 0;                 // S chunks / P V chunks seen by this group (-> parities)
+    for (int i = g; i < n_local; i += 2) {
+      int qt, h, b;
+      item_coords(i, qt, h, b);
+      const int len = len_of(b);
+      const int nc = (len + PL_KC - 1) / PL_KC;
+      float m = -INFINITY, l = 0.f;
+      for (int c = 0; c < nc; ++c) {
+        const int valid = min(64, max(0, len - c * PL_KC - 64 * hf));   // valid keys among my 64
+        mbar_wait(&s_full[g], s_n & 1);
+        ++s_n;
+        tc_fence_after();
+        uint32_t ra[32], rb[32];
+        tmem_ld32(t_row + 64 * hf, ra);
+        tmem_ld32(t_row + 64 * hf + 32, rb);
+        tmem_ld_wait();
+        float mloc = valid >= 32 ? max_chunk<false>(ra, 32) : max_chunk<true>(ra, valid);
+        if (valid > 32) mloc = fmaxf(mloc, valid >= 64 ? max_chunk<false>(rb, 32) : max_chunk<true>(rb, valid - 32));
+        x_max[hf * AT_BM + row] = mloc;
+        group_sync();                            // both halves hold their S in registers: P may overwrite it
+        const float m_new = fmaxf(m, fmaxf(mloc, x_max[(hf ^ 1) * AT_BM + row]));
+        const float alpha = ex2_approx((m - m_new) * L2E);   // 0 for the first chunk (m = -inf)
+        m = m_new;
+        const float mb = m * L2E;
+        uint32_t pk[16];
+        float lc;
+        if (valid >= 32) lc = softmax_chunk<OpT, false>(ra, pk, mb, 32);
+        else lc = softmax_chunk<OpT, true>(ra, pk, mb, valid);
+        tmem_st16(t_row + 32 * hf, pk);
+        if (valid >= 64) lc += softmax_chunk<OpT, false>(rb, pk, mb, 32);
+        else lc += softmax_chunk<OpT, true>(rb, pk, mb, max(valid - 32, 0));
+        tmem_st16(t_row + 32 * hf + 16, pk);
+        l = l * alpha + lc;
+        // O <- alpha O, only in warps where some row's maximum moved; P V of the previous chunk must have landed
+        if (c > 0) {
+          mbar_wait(&o_done[g], o_n & 1);
+          ++o_n;
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+            tmem_ld32(t_row + 128 + 32 * hf, ra);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) ra[k] = __float_as_uint(__uint_as_float(ra[k]) * alpha);
+            uint32_t lo[16], hi[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) lo[k] = ra[k], hi[k] = ra[16 + k];
+            tmem_st16(t_row + 128 + 32 * hf, lo);
+            tmem_st16(t_row + 128 + 32 * hf + 16, hi);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g]);
+        // the next chunk's x_max write happens after the next S wait; the read above finished before p_full fired
+        // for this warp, but the OTHER half may still be reading: order through the group barrier of the next chunk
+      }
+      x_sum[hf * AT_BM + row] = l;
+      mbar_wait(&o_done[g], o_n & 1);
+      ++o_n;
+      tc_fence_after();
+      {
+        uint32_t ra[32];
+        tmem_ld32(t_row + 128 + 32 * hf, ra);
+        uint8_t* so = sOut + g * PA_OUT_BYTES;
+        const bool elected = (warp & 7) == 0 && lane == 0;
+        if (elected) bulk_wait_read<0>();
+        group_sync();
+        const float inv = 1.0f / (l + x_sum[(hf ^ 1) * AT_BM + row]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&reg_free[g]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint4 q;
+          q.x = OpTraits<OpT>::pack2(__uint_as_float(ra[8 * k + 0]) * inv, __uint_as_float(ra[8 * k + 1]) * inv);
+          q.y = OpTraits<OpT>::pack2(__uint_as_float(ra[8 * k + 2]) * inv, __uint_as_float(ra[8 * k + 3]) * inv);
+          q.z = OpTraits<OpT>::pack2(__uint_as_float(ra[8 * k + 4]) * inv, __uint_as_float(ra[8 * k + 5]) * inv);
+          q.w = OpTraits<OpT>::pack2(__uint_as_float(ra[8 * k + 6]) * inv, __uint_as_float(ra[8 * k + 7]) * inv);
+          *reinterpret_cast<uint4*>(so + row * 128 + (((4 * hf + k) ^ (row & 7)) << 4)) = q;
+        }
+        fence_proxy_async_smem();
+        group_sync();
+        if (elected) {
+          tma_store_3d(&mapOut, so, h * AT_HD, qt * AT_BM, b);
+          bulk_commit();
+        }
+      }
+    }
+    if ((warp & 7) == 0 && lane == 0) bulk_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <typename OpT>
+static int launch_attn_long(const CUtensorMap& mq, const CUtensorMap& mkv, const CUtensorMap& mout, const int* lens,
+                            int B, int T, int H, int d, cudaStream_t s) {
+  auto kern = self_attention_long_kernel<OpT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PL_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute(self_attention_long)");
+    attr_set = true;
+  }
+  const int nqt = (T + AT_BM - 1) / AT_BM;
+  const int n_items = B * H * nqt;
+  const int grid = n_items < kNumSMs ? n_items : kNumSMs;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(PA_THREADS);
+  cfg.dynamicSmemBytes = PL_SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mq, mkv, mout, lens, T, d, H, nqt, n_items);
+  if (e != cudaSuccess) return fail(e, "self_attention_long_kernel launch");
+  return 0;
+}
+
 }  // namespace mm
 
 using namespace mm;
@@ -612,7 +720,6 @@ extern "C" int mm_self_attention(const void* qkv, int64_t qkv_ld, const int32_t*
   int rc = make_tmap_3d(&mqk, qkv, f16, (uint64_t)(3 * d), (uint64_t)seq, (uint64_t)batch, (uint64_t)qkv_ld,
                         (uint64_t)seq * qkv_ld, 128);
   if (rc) return rc;
-  const CUtensorMap& mvt = mqk;   // V is read from the same [B*T, 3d] tensor (columns [2d, 3d)) as an MN-major operand
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (seq <= AT_KC) {   // single key chunk: persistent warp-specialised kernel, output through TMA ([B][T][d] view)
     CUtensorMap mout;
@@ -622,6 +729,11 @@ extern "C" int mm_self_attention(const void* qkv, int64_t qkv_ld, const int32_t*
     return f16 ? launch_attn_t256<__half>(mqk, mout, seq_lens, batch, seq, heads, d, s)
                : launch_attn_t256<__nv_bfloat16>(mqk, mout, seq_lens, batch, seq, heads, d, s);
   }
-  return f16 ? launch_attn<__half>(mqk, mvt, seq_lens, batch, seq, heads, d, out, out_ld, s)
-             : launch_attn<__nv_bfloat16>(mqk, mvt, seq_lens, batch, seq, heads, d, out, out_ld, s);
+  // T > 256: persistent online-softmax kernel, 128-key chunks; mqk (box 64 x 128) serves Q, K and V chunks alike
+  CUtensorMap mout;
+  rc = make_tmap_3d(&mout, out, f16, (uint64_t)d, (uint64_t)seq, (uint64_t)batch, (uint64_t)out_ld,
+                    (uint64_t)seq * out_ld, 128);
+  if (rc) return rc;
+  return f16 ? launch_attn_long<__half>(mqk, mqk, mout, seq_lens, batch, seq, heads, d, s)
+             : launch_attn_long<__nv_bfloat16>(mqk, mqk, mout, seq_lens, batch, seq, heads, d, s);
 }

@@ -133,7 +133,8 @@ def test_fbank_cmvn_end_to_end(cuda):
     assert (o32.cpu() - torch.from_numpy(ref)).abs().max().item() < 3e-2
 
 
-@pytest.mark.parametrize("T,lens", [(250, [250, 173, 1]), (125, [125, 80]), (300, [300, 257, 40]), (750, [750, 512])])
+@pytest.mark.parametrize("T,lens", [(250, [250, 173, 1]), (125, [125, 80]), (300, [300, 257, 40]), (750, [750, 512]),
+                                    (600, [600, 130, 128, 129, 1, 385]), (1030, [1030, 7, 512])])
 def test_self_attention(cuda, T, lens):
     from mm_s2ut_b200 import kernels as K
 
