@@ -721,7 +721,9 @@ extern "C" int mm_self_attention(const void* qkv, int64_t qkv_ld, const int32_t*
                         (uint64_t)seq * qkv_ld, 128);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (seq <= AT_KC) {   // single key chunk: persistent warp-specialised kernel, output through TMA ([B][T][d] view)
+  // 129..256 keys: one 256-key chunk is cheapest (23.5 vs 27 us at the bench shape); up to 128 keys the chunked kernel
+  // needs a single 128-key chunk (16.5 vs 20 us at T = 125), beyond 256 it is the only one
+  if (seq > PL_KC && seq <= AT_KC) {   // single 256-key chunk: persistent warp-specialised kernel, output through TMA ([B][T][d] view)
     CUtensorMap mout;
     rc = make_tmap_3d(&mout, out, f16, (uint64_t)d, (uint64_t)seq, (uint64_t)batch, (uint64_t)out_ld,
                       (uint64_t)seq * out_ld, 128);

@@ -441,6 +441,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
         }
       } else {  // MM_EPI_RESID_F32 / MM_EPI_GATE: in-place update of TMA-loaded fp32 slabs
         const long long arow = (long long)bi * p.rows + r;
+        // gate: the attention output `o` of this row comes straight from global memory (each thread its own 128 B);
+        // the loads for chunk c + 1 are issued while chunk c is processed, a full chunk ahead of their use
+        float o[32], o_next[32];
+        auto load_o = [&](int col, float (&dst)[32]) {
+          if (rvalid && col < p.n) {
+            const float4* op = reinterpret_cast<const float4*>(p.aux1 + arow * p.aux_ld + col);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 q = __ldg(op + i);
+              dst[4 * i] = q.x, dst[4 * i + 1] = q.y, dst[4 * i + 2] = q.z, dst[4 * i + 3] = q.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dst[i] = 0.f;
+          }
+        };
+        if constexpr (MODE == MM_EPI_GATE) load_o(col_tile, o_next);
 #pragma unroll 1
         for (int c0 = 0, s = 0; c0 < BN; c0 += 32, ++s) {
           const int col = col_tile + c0;
@@ -455,19 +472,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
           }
           uint32_t ra[32];
           tmem_ld32(taddr + c0, ra);
-          float o[32];
-          if constexpr (MODE == MM_EPI_GATE) {   // issued before the waits below: the L2 latency hides behind them
-            if (rvalid) {
-              const float4* op = reinterpret_cast<const float4*>(p.aux1 + arow * p.aux_ld + col);
+          if constexpr (MODE == MM_EPI_GATE) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 q = __ldg(op + i);
-                o[4 * i] = q.x, o[4 * i + 1] = q.y, o[4 * i + 2] = q.z, o[4 * i + 3] = q.w;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = 0.f;
-            }
+            for (int i = 0; i < 32; ++i) o[i] = o_next[i];
+            if (c0 + 32 < BN) load_o(col + 32, o_next);
           }
           tmem_ld_wait();
           mbar_wait(&auxfull[b], (aux_phase >> b) & 1);
