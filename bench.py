@@ -167,7 +167,7 @@ def run_ours(a):
     import torch.distributed as dist
 
     import mm_s2ut_b200  # noqa: F401
-    from mm_s2ut_b200 import kernels as K, synth
+    from mm_s2ut_b200 import hostmem, kernels as K, synth
     from mm_s2ut_b200.config import DEFAULT_YAML, make_args
     from mm_s2ut_b200.graph import GraphedEncoder
     from mm_s2ut_b200.models.mm_s2s_transformer import MM_S2STransformerEncoder
@@ -179,6 +179,8 @@ def run_ours(a):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # pinned staging buffers must live on the GPU's own NUMA node (see hostmem.py): bind before they are allocated
+    numa_node = hostmem.bind_to_gpu_numa_node(local) if os.environ.get("MM_BENCH_NUMA", "1") != "0" else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -361,6 +363,7 @@ def run_ours(a):
             "gpu_launches": launches_per_fwd * a.steps,
             "launches_per_step": launches_per_fwd,
             "clocks": clocks,
+            "host_numa_node": numa_node,
             "roofline": roofline,
             "tensor_flops_per_step": flops,
             "step_tensor_frac_of_peak": flops / (ms_dev / a.steps * 1e-3) / 1e12 / peak,
