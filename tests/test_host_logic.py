@@ -180,3 +180,19 @@ def test_bench_reference_arm_contract():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "audio-s/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_hostmem_cpulist_and_missing_gpu():
+    """NUMA helper: sysfs cpulist parsing; without a driver (this container) it reports "unknown" and binds nothing."""
+    import os
+
+    from mm_s2ut_b200 import hostmem
+
+    assert hostmem._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert hostmem._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    node = hostmem.bind_to_gpu_numa_node(0)
+    assert node is None or isinstance(node, int)
+    if node is None:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
