@@ -196,3 +196,31 @@ def test_hostmem_cpulist_and_missing_gpu():
     if node is None:
         assert os.sched_getaffinity(0) == before
     os.sched_setaffinity(0, before)
+
+
+def test_committed_bench_line_has_contract_keys():
+    """The round's committed default bench line (profiles/rNN/bench_*default_n1.json) carries every key of the bench
+    contract, with the roofline fraction consistent with its own achieved / peak."""
+    import glob
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = sorted(glob.glob(os.path.join(root, "profiles", "r*", "bench_*default_n1.json")))
+    assert files, "no committed default bench line"
+    d = json.load(open(files[-1]))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0 and d["vs_baseline"] is None
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in d["e2e"], k
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["value"] != d["value"]
+    r = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r, k
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-6 and r["traffic"] is not None
+    for k in ("value", "unit", "cores", "kind", "sample"):
+        assert k in d["cpu_baseline"], k
+    assert "sm_mhz" in d["clocks"] and "reasons" in d["clocks"]
