@@ -206,7 +206,10 @@ def test_committed_bench_line_has_contract_keys():
     import os
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    files = sorted(glob.glob(os.path.join(root, "profiles", "r*", "bench_*default_n1.json")))
+    import re
+
+    files = sorted(glob.glob(os.path.join(root, "profiles", "r*", "bench_*default_n1.json")),
+                   key=lambda f: [int(t) for t in re.findall(r"\d+", f)])   # r01 < r02, v4 < v19
     assert files, "no committed default bench line"
     d = json.load(open(files[-1]))
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
