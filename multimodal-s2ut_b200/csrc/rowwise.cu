@@ -248,18 +248,15 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const float* __restrict
   const int b = blockIdx.y;
   const int nfr = min(frames_of(lens[b], lengths_are_samples), max_frames);
   const bool ident = mean_std == nullptr;   // input already normalised: copy / pad only
-  if (threadIdx.x < 80) {
-    s_mean[threadIdx.x] = ident ? 0.f : mean_std[(long long)b * 160 + threadIdx.x];
-    s_std[threadIdx.x] = ident ? 1.f : mean_std[(long long)b * 160 + 80 + threadIdx.x];
-  }
-  __syncthreads();
   // rows handled by this block: [row0, row0 + rows_per_block) of the LARGER of the two output extents
   const int total_rows = max(op_frames, max_frames);
   const int row0 = blockIdx.x * rows_per_block;
-  // Batches of four (row, float4-column) items per thread: all loads of a batch are in flight before the first store
-  // (one load at a time left this kernel latency-bound at a third of the HBM rate).
-  constexpr int NI = 4;
+  // Batches of five (row, float4-column) items per thread.  All feature loads of a batch are issued before anything
+  // else - the statistics are fetched while they are in flight - so the kernel is one memory round trip deep
+  // (one load at a time had left it latency-bound at a third of the HBM rate).
+  constexpr int NI = 5;
   const int items = rows_per_block * 20;
+  bool stats_ready = false;
   for (int base = threadIdx.x; base < items; base += NI * blockDim.x) {
     float4 vf[NI], vo[NI];
     int rowi[NI];
@@ -276,6 +273,14 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const float* __restrict
       const int fr = row - op_row_offset;
       if (out_op != nullptr && fr >= 0 && fr < nfr)
         vo[u] = __ldg(reinterpret_cast<const float4*>(feats + ((long long)b * max_frames + fr) * 80) + c4);
+    }
+    if (!stats_ready) {   // uniform: first trip only
+      if (threadIdx.x < 80) {
+        s_mean[threadIdx.x] = ident ? 0.f : mean_std[(long long)b * 160 + threadIdx.x];
+        s_std[threadIdx.x] = ident ? 1.f : mean_std[(long long)b * 160 + 80 + threadIdx.x];
+      }
+      __syncthreads();
+      stats_ready = true;
     }
 #pragma unroll
     for (int u = 0; u < NI; ++u) {
@@ -373,7 +378,7 @@ extern "C" int mm_cmvn_apply(const float* feats, const float* mean_std, const in
   if (batch <= 0 || max_frames <= 0) return 0;
   if (!out_op) op_frames = 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int rows_per_block = 64;
+  const int rows_per_block = 64;   // 64 rows x 20 float4 = 1280 items: one batch of five per thread, 1024 blocks = one wave
   const int total_rows = op_frames > max_frames ? op_frames : max_frames;
   dim3 grid((total_rows + rows_per_block - 1) / rows_per_block, batch);
   const long long* l = reinterpret_cast<const long long*>(lens);
