@@ -137,6 +137,15 @@ int mm_gemm_resid_ln(const void* a, int64_t a_ld, const void* w, int64_t w_ld, i
 int mm_layernorm(const float* x, const float* gamma, const float* beta, int64_t rows, int32_t dim, void* out_op,
                  float* out_f32, int32_t dtype, float eps, void* stream);
 
+/* LayerNorm of rows gathered from a device-resident 16-bit feature store (x_dtype = MM_DTYPE_F16 / MM_DTYPE_BF16):
+ * output row r = LayerNorm(x[index[r / rows_per_index] * rows_per_index + r % rows_per_index]); index == NULL: rows in
+ * order.  This is image_pre_norm_module (mm_s2s_transformer.py:595) applied to the batch that the reference's
+ * ImageDataset.__getitem__ (data/speech_to_speech_dataset.py:56-65) would have collated from host memory: the
+ * features stay on the GPU and are read once, in 16 bit.  Output is the 16-bit GEMM operand only. */
+int mm_layernorm_gather(const void* x, int32_t x_dtype, const int64_t* index, int32_t rows_per_index,
+                        const float* gamma, const float* beta, int64_t rows, int32_t dim, void* out_op, int32_t dtype,
+                        float eps, void* stream);
+
 /* Multi-head self-attention core (fairseq MultiheadAttention: softmax_fp32(q k^T + key-padding mask) v).
  * qkv: [B*T, qkv_ld] 16-bit, q (pre-scaled by head_dim^-0.5) at columns [0, d), k at [d, 2d), v at [2d, 3d)
  * (exactly what the QKV projection GEMM writes); seq_lens [B] int32 valid keys; out [B*T, out_ld] 16-bit.

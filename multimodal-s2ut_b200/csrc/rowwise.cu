@@ -74,6 +74,80 @@ static int launch_ln(const float* x, const float* g, const float* b, long long r
   return 0;
 }
 
+// LayerNorm over rows GATHERED from a device-resident 16-bit feature store: output row r is input row
+// index[r / rows_per_index] * rows_per_index + r % rows_per_index.  This is the image pre-norm of a batch whose ViT
+// features live on the GPU (ImageFeatureStore) - the batch is never materialised, the store is read once, in 16 bit.
+template <int DIM, typename InT, typename OpT>
+__global__ void __launch_bounds__(256) layernorm_gather_kernel(const InT* __restrict__ x,
+                                                                const long long* __restrict__ index,
+                                                                int rows_per_index, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, long long rows,
+                                                                OpT* __restrict__ out_op, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int V = DIM / 256;  // 8 values (one 128-bit load) per lane per step
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const long long src = index ? index[row / rows_per_index] * rows_per_index + row % rows_per_index : row;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + src * DIM);
+  float v[V][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const uint4 q = __ldcs(xr + lane + 32 * i);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const InT lo = reinterpret_cast<const InT*>(&w[j])[0], hi = reinterpret_cast<const InT*>(&w[j])[1];
+      v[i][2 * j] = OpTraits<InT>::to_float(lo);
+      v[i][2 * j + 1] = OpTraits<InT>::to_float(hi);
+      s += v[i][2 * j] + v[i][2 * j + 1];
+    }
+  }
+  const float mean = warp_sum(s) * (1.0f / DIM);
+  float q2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[i][j] -= mean;
+      q2 += v[i][j] * v[i][j];
+    }
+  const float rstd = rsqrtf(warp_sum(q2) * (1.0f / DIM) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  uint4* orow = reinterpret_cast<uint4*>(out_op + row * DIM);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c8 = lane + 32 * i;   // group of 8 columns
+    const float4 g0 = __ldg(g4 + 2 * c8), g1 = __ldg(g4 + 2 * c8 + 1), b0 = __ldg(b4 + 2 * c8), b1 = __ldg(b4 + 2 * c8 + 1);
+    uint4 o;
+    o.x = OpTraits<OpT>::pack2(fmaf(v[i][0] * rstd, g0.x, b0.x), fmaf(v[i][1] * rstd, g0.y, b0.y));
+    o.y = OpTraits<OpT>::pack2(fmaf(v[i][2] * rstd, g0.z, b0.z), fmaf(v[i][3] * rstd, g0.w, b0.w));
+    o.z = OpTraits<OpT>::pack2(fmaf(v[i][4] * rstd, g1.x, b1.x), fmaf(v[i][5] * rstd, g1.y, b1.y));
+    o.w = OpTraits<OpT>::pack2(fmaf(v[i][6] * rstd, g1.z, b1.z), fmaf(v[i][7] * rstd, g1.w, b1.w));
+    orow[c8] = o;
+  }
+}
+
+template <typename InT, typename OpT>
+static int launch_ln_gather(const void* x, const long long* index, int rows_per_index, const float* g, const float* b,
+                            long long rows, int dim, void* out_op, float eps, cudaStream_t s) {
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  const InT* xi = reinterpret_cast<const InT*>(x);
+  OpT* o = reinterpret_cast<OpT*>(out_op);
+  switch (dim) {
+    case 256: launch_pdl(layernorm_gather_kernel<256, InT, OpT>, dim3(grid), dim3(256), 0, s, xi, index, rows_per_index, g, b, rows, o, eps); break;
+    case 512: launch_pdl(layernorm_gather_kernel<512, InT, OpT>, dim3(grid), dim3(256), 0, s, xi, index, rows_per_index, g, b, rows, o, eps); break;
+    case 768: launch_pdl(layernorm_gather_kernel<768, InT, OpT>, dim3(grid), dim3(256), 0, s, xi, index, rows_per_index, g, b, rows, o, eps); break;
+    case 1024: launch_pdl(layernorm_gather_kernel<1024, InT, OpT>, dim3(grid), dim3(256), 0, s, xi, index, rows_per_index, g, b, rows, o, eps); break;
+    default: return bad_arg("layernorm_gather dim must be 256, 512, 768 or 1024");
+  }
+  MM_CHECK_LAUNCH("layernorm_gather_kernel launch");
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Row softmax over image keys: scores fp32 [rows, ld_in] -> probabilities 16-bit [rows, ld_out].
 // One warp per row; the row (<= 1024 keys) lives in registers.
@@ -325,6 +399,23 @@ extern "C" int mm_layernorm(const float* x, const float* gamma, const float* bet
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return dtype == MM_DTYPE_F16 ? launch_ln<__half>(x, gamma, beta, rows, dim, out_op, out_f32, eps, s)
                                : launch_ln<__nv_bfloat16>(x, gamma, beta, rows, dim, out_op, out_f32, eps, s);
+}
+
+extern "C" int mm_layernorm_gather(const void* x, int32_t x_dtype, const int64_t* index, int32_t rows_per_index,
+                                   const float* gamma, const float* beta, int64_t rows, int32_t dim, void* out_op,
+                                   int32_t dtype, float eps, void* stream) {
+  if (!x || !gamma || !beta || !out_op) return bad_arg("layernorm_gather: null pointer");
+  if (index && rows_per_index <= 0) return bad_arg("layernorm_gather: rows_per_index");
+  if (x_dtype != MM_DTYPE_F16 && x_dtype != MM_DTYPE_BF16) return bad_arg("layernorm_gather: 16-bit input only");
+  if (rows <= 0) return 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long* idx = reinterpret_cast<const long long*>(index);
+  const bool in16 = x_dtype == MM_DTYPE_F16, out16 = dtype == MM_DTYPE_F16;
+  if (in16)
+    return out16 ? launch_ln_gather<__half, __half>(x, idx, rows_per_index, gamma, beta, rows, dim, out_op, eps, s)
+                 : launch_ln_gather<__half, __nv_bfloat16>(x, idx, rows_per_index, gamma, beta, rows, dim, out_op, eps, s);
+  return out16 ? launch_ln_gather<__nv_bfloat16, __half>(x, idx, rows_per_index, gamma, beta, rows, dim, out_op, eps, s)
+               : launch_ln_gather<__nv_bfloat16, __nv_bfloat16>(x, idx, rows_per_index, gamma, beta, rows, dim, out_op, eps, s);
 }
 
 extern "C" int mm_softmax_rows(const float* scores, int64_t ld_in, int64_t rows, int32_t n_keys,

@@ -23,6 +23,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import kernels as K
+from .feature_store import StoredImages
 from .models.modules import SinusoidalPositionalEmbedding
 
 
@@ -252,12 +253,18 @@ class EncoderEngine:
         extra = 1 if F["bias_kv"] is not None else 0
         Tk = Tk_img + extra
         Tkp = _round_up(Tk, 8)
-        img = img.to(self.device, non_blocking=True).float().contiguous()
         img_op = self.buf(f"img_op{j}", (B * Tk_img, dk), op)
-        if self.img_ln is not None:
-            K.layernorm(img.view(B * Tk_img, dk), self.img_ln[0], self.img_ln[1], out_op=img_op)
+        if isinstance(img, StoredImages):   # features resident on the GPU in 16 bit: gather + pre-norm in one pass
+            if self.img_ln is None:
+                raise NotImplementedError("ImageFeatureStore batches need image_pre_norm: True (the gather is fused "
+                                          "into the pre-norm kernel)")
+            K.layernorm_gather(img.store.data, img.index, Tk_img, self.img_ln[0], self.img_ln[1], img_op)
         else:
-            K.convert(img.view(B * Tk_img, dk), img_op)
+            img = img.to(self.device, non_blocking=True).float().contiguous()
+            if self.img_ln is not None:
+                K.layernorm(img.view(B * Tk_img, dk), self.img_ln[0], self.img_ln[1], out_op=img_op)
+            else:
+                K.convert(img.view(B * Tk_img, dk), img_op)
         kbuf = self.buf(f"k{j}", (B, Tk, d), op)
         vt = self.buf(f"vt_img{j}", (B, d, Tkp), op, zero=True)
         if extra == 0:   # keys are contiguous over the batch: one flat GEMM over all B * Tk image tokens
@@ -338,8 +345,8 @@ class EncoderEngine:
                 text_op.zero_()
             outs = []
             for j, (img, img_mask) in enumerate(zip(imgs_list, img_masks_list)):
-                if drop_image:
-                    img = torch.zeros_like(img)
+                if drop_image:   # modality dropout: every image tensor zeroed (reference :504-505)
+                    img = torch.zeros(tuple(img.shape), dtype=torch.float32, device=self.device)
                 res = torch.empty(T, B, self.d, dtype=torch.float32, device=self.device)
                 self.fuse(j, text_f32, text_op, img, img_mask, B, T, res)
                 outs.append(res)

@@ -13,10 +13,14 @@ from typing import List, Optional
 
 import torch
 
+from .feature_store import StoredImages
+
 
 class GraphedEncoder:
     def __init__(self, enc, batch: int, n_samples: int, img_shapes: List[tuple], warmup: int = 2,
-                 wav_dtype: torch.dtype = torch.float32):
+                 wav_dtype: torch.dtype = torch.float32, stores: Optional[list] = None):
+        """stores: optional list (one entry per image type) of ImageFeatureStore or None.  For a store the static
+        input is a [batch] int64 index vector instead of a [batch, Tk, Dk] fp32 feature tensor."""
         if enc.training:
             raise RuntimeError("graph capture is for eval-mode forwards (modality dropout draws are per batch)")
         self.enc = enc
@@ -24,7 +28,10 @@ class GraphedEncoder:
         self.device = dev
         self.wav = torch.zeros(batch, n_samples, dtype=wav_dtype, device=dev)   # float32 (x 2**15) or int16 PCM
         self.lens = torch.full((batch,), n_samples, dtype=torch.int64, device=dev)
-        self.imgs = [torch.zeros(batch, *s, dtype=torch.float32, device=dev) for s in img_shapes]
+        self.stores = list(stores) if stores is not None else [None for _ in img_shapes]
+        self.imgs = [torch.zeros(batch, *s, dtype=torch.float32, device=dev) if st is None else
+                     StoredImages(st, torch.zeros(batch, dtype=torch.int64, device=dev))
+                     for s, st in zip(img_shapes, self.stores)]
         self.masks: List[Optional[torch.Tensor]] = [None for _ in img_shapes]
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.out = None
@@ -50,8 +57,8 @@ class GraphedEncoder:
         """Async copies into the static buffers on the current stream (H2D when the sources are pinned host)."""
         self.wav.copy_(wav, non_blocking=True)
         self.lens.copy_(lens, non_blocking=True)
-        for dst, src in zip(self.imgs, imgs):
-            dst.copy_(src, non_blocking=True)
+        for dst, src in zip(self.imgs, imgs):   # feature tensors, or index vectors for store-backed image types
+            (dst.index if isinstance(dst, StoredImages) else dst).copy_(src, non_blocking=True)
 
     def replay(self):
         if self.graph is None:

@@ -191,6 +191,23 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_op: 
                                     eps, _stream()), "mm_layernorm")
 
 
+def layernorm_gather(store: torch.Tensor, index: Optional[torch.Tensor], rows_per_index: int, gamma: torch.Tensor,
+                     beta: torch.Tensor, out_op: torch.Tensor, eps: float = 1e-5) -> None:
+    """out_op[r] = LayerNorm(store[index[r // rows_per_index], r % rows_per_index]): store [N, rows_per_index, dim]
+    16-bit on the device, index [B] int64 (None: rows in order)."""
+    assert store.dtype in _DT and store.is_contiguous() and out_op.is_contiguous()
+    dim = store.shape[-1]
+    rows = out_op.shape[0]
+    assert out_op.shape[1] == dim and gamma.dtype == beta.dtype == torch.float32
+    if index is not None:
+        assert index.dtype == torch.int64 and index.numel() * rows_per_index == rows
+    lib = _lib.load()
+    with _Launch("layernorm_gather", float(store.element_size() * rows * dim + out_op.element_size() * rows * dim)):
+        _lib.check(lib.mm_layernorm_gather(_ptr(store), dtype_code(store.dtype), _ptr(index), rows_per_index,
+                                           _ptr(gamma), _ptr(beta), rows, dim, _ptr(out_op), dtype_code(out_op.dtype),
+                                           eps, _stream()), "mm_layernorm_gather")
+
+
 def self_attention(qkv: torch.Tensor, seq_lens_: torch.Tensor, batch: int, seq: int, heads: int,
                    out: torch.Tensor) -> None:
     """qkv [B*T, 3d] (q pre-scaled | k | v) -> out [B*T, d]; head_dim 64."""
