@@ -169,6 +169,7 @@ def run_ours(a):
     import mm_s2ut_b200  # noqa: F401
     from mm_s2ut_b200 import hostmem, kernels as K, synth
     from mm_s2ut_b200.config import DEFAULT_YAML, make_args
+    from mm_s2ut_b200.feature_store import ImageFeatureStore
     from mm_s2ut_b200.graph import GraphedEncoder
     from mm_s2ut_b200.models.mm_s2s_transformer import MM_S2STransformerEncoder
 
@@ -280,6 +281,43 @@ def run_ours(a):
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     e2e_value = audio_s / (e2e_ms * 1e-3)
 
+    # ---------------- e2e with the image features resident on the device (ImageFeatureStore) ----------
+    # The "dataset" is the two input sets' 2 x BATCH images held on the GPU in fp16; a step's image input is the
+    # int64 index vector its collater would have used, so H2D carries the PCM waveform, the lengths and 512 bytes.
+    store = ImageFeatureStore(torch.cat([host_sets[0][2], host_sets[1][2]], 0), dev)
+    idx_host = [torch.arange(j * BATCH, (j + 1) * BATCH, dtype=torch.int64).pin_memory() for j in range(2)]
+    ges = [GraphedEncoder(enc, BATCH, n_samples, [(IMG_TOKENS, IMG_DIM)], wav_dtype=torch.int16, stores=[store])
+           for _ in range(2)]
+    for j, g in enumerate(ges):
+        g.load_inputs(host_sets[j][3].to(dev), dev_sets[j][1], [idx_host[j]])
+        g.capture()
+    torch.cuda.synchronize()
+    h2d_store = sum(t.numel() * t.element_size() for t in (host_sets[0][3], host_sets[0][1], idx_host[0]))
+
+    def e2e_store_steps(n):
+        for j in range(2):
+            free[j].record(main)
+        for i in range(n):
+            j = i & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(free[j])
+                ges[j].load_inputs(host_sets[j][3], host_sets[j][1], [idx_host[j]])
+                ready[j].record(copy_stream)
+            main.wait_event(ready[j])
+            out = ges[j].replay()
+            chk = out["encoder_out"][0].sum()
+            result_host[j:j + 1].copy_(chk.reshape(1), non_blocking=True)
+            free[j].record(main)
+        main.synchronize()
+
+    e2e_store_steps(max(2, a.warmup))
+    barrier()
+    t0 = time.perf_counter()
+    e2e_store_steps(a.steps)
+    barrier()
+    e2e_store_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_store_value = audio_s / (e2e_store_ms * 1e-3)
+
     line = None
     if rank == 0:
         # ---------------- instrumented pass: per-kernel device time (CUDA events on the launch stream) ------------
@@ -360,6 +398,13 @@ def run_ours(a):
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / a.steps,
                     "how": "pinned host int16 PCM waveform + fp32 image features -> cudaMemcpyAsync on a copy stream "
                            "(double-buffered, overlapping the previous step) -> graph replay -> checksum D2H"},
+            "e2e_feature_store": {
+                "value": e2e_store_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d_store, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_store_ms / a.steps,
+                "how": "same loop, but the image features live on the GPU in fp16 (ImageFeatureStore, SURVEY 8f-4) and "
+                       "a step's image input is its int64 index vector: H2D = int16 PCM + lengths + 512 B of indices; "
+                       "the image pre-norm gathers the rows from the store (mm_layernorm_gather).  NOT the headline: "
+                       "the reference ships fp32 features from host memory every step, which is what `e2e` measures"},
             "gpu_launches": launches_per_fwd * a.steps,
             "launches_per_step": launches_per_fwd,
             "clocks": clocks,
