@@ -153,6 +153,17 @@ int mm_layernorm_gather(const void* x, int32_t x_dtype, const int64_t* index, in
 int mm_self_attention(const void* qkv, int64_t qkv_ld, const int32_t* seq_lens, int32_t batch, int32_t seq,
                       int32_t heads, void* out, int64_t out_ld, int32_t dtype, void* stream);
 
+/* General form: queries, keys and values from three tensors (or column blocks of one), q_len query rows and kv_len
+ * key rows per batch element, kv_lens[b] valid keys (NULL: all), optional causal mask (key j visible to query i iff
+ * j <= i; needs q_len == kv_len).  q is expected pre-scaled by head_dim^-0.5.  Rows are [batch][len][ld] with the
+ * heads' 64-wide column blocks starting at *_col0.  Serves the S2UT decoder's causal self-attention and its
+ * encoder attention (fairseq TransformerDecoderLayerBase.forward: self_attn / encoder_attn), i.e. the first
+ * consumer of this path's output (mm_s2s_transformer.py:693-696).  Any lengths; runs the chunked online-softmax
+ * kernel. */
+int mm_attention(const void* q, int64_t q_ld, int32_t q_col0, int32_t q_len, const void* k, int64_t k_ld, int32_t k_col0,
+                 const void* v, int64_t v_ld, int32_t v_col0, int32_t kv_len, const int32_t* kv_lens, int32_t batch,
+                 int32_t heads, int32_t causal, void* out, int64_t out_ld, int32_t dtype, void* stream);
+
 /* Row softmax for the speech->image attention (fuse.py:88-111): scores fp32 [rows, ld_in] -> probabilities
  * 16-bit [rows, ld_out]; columns [n_keys, ld_out) written as 0.  key_mask: optional [n_seqs, n_keys] uint8
  * (1 = padded key -> -inf); rows_per_seq maps a row to its sequence. */

@@ -405,9 +405,14 @@ static_assert(PL_SMEM_BYTES <= 232448, "shared memory budget");
 
 template <typename OpT>
 __global__ void __launch_bounds__(PA_THREADS, 1)
-self_attention_long_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapKV,
-                           const __grid_constant__ CUtensorMap mapOut, const int* __restrict__ seq_lens, int T,
-                           int d_model, int H, int nqt, int n_items) {
+self_attention_long_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                           const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapOut,
+                           const int* __restrict__ seq_lens, int T, int q_col0, int k_col0, int v_col0, int causal,
+                           int H, int nqt, int n_items) {
+  // Q, K, V may be three different tensors (decoder cross-attention: queries from the decoder states, keys / values
+  // from the projected encoder states) or column blocks of one (self-attention: q | k | v of the QKV GEMM).  T is
+  // the key extent, seq_lens[b] (NULL: T) the number of valid keys of utterance b; the number of query rows only
+  // enters through nqt and the bounds of mapQ / mapOut.  causal: key k is visible to query row q iff k <= q.
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                                  // [2 groups] 16 KB
@@ -433,7 +438,8 @@ self_attention_long_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
 
   if (tid == 0) {
     tma_prefetch_desc(&mapQ);
-    tma_prefetch_desc(&mapKV);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
     tma_prefetch_desc(&mapOut);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
@@ -456,12 +462,17 @@ self_attention_long_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
   pdl_wait();
-  for (int i = threadIdx.x; i < n_batch && i < PA_MAX_LENS; i += PA_THREADS) s_lens[i] = seq_lens[i];
+  for (int i = threadIdx.x; i < n_batch && i < PA_MAX_LENS; i += PA_THREADS) s_lens[i] = seq_lens ? seq_lens[i] : T;
   __syncthreads();
-  auto len_of = [&](int b) { return max(1, min(b < PA_MAX_LENS ? s_lens[b] : seq_lens[b], T)); };
+  auto len_of = [&](int b) { return max(1, min(b < PA_MAX_LENS ? s_lens[b] : (seq_lens ? seq_lens[b] : T), T)); };
   auto item_coords = [&](int i, int& qt, int& h, int& b) {
     const int item = blockIdx.x + i * gridDim.x;
     qt = item % nqt, h = (item / nqt) % H, b = item / (nqt * H);
+  };
+  // key chunks of an item: up to the utterance length, and under a causal mask up to the query tile's diagonal chunk
+  auto chunks_of = [&](int b, int qt) {
+    const int nc = (len_of(b) + PL_KC - 1) / PL_KC;
+    return causal ? min(nc, qt + 1) : nc;
   };
 
   if (warp == 16) {
@@ -475,19 +486,19 @@ self_attention_long_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
           if (it[g] >= n_local) continue;
           int qt, h, b;
           item_coords(it[g], qt, h, b);
-          const int nc = (len_of(b) + PL_KC - 1) / PL_KC;
+          const int nc = chunks_of(b, qt);
           if (ch[g] == 0) {
             mbar_wait(&q_empty[g], (q_n[g] & 1) ^ 1);
             mbar_expect_tx(&q_full[g], AT_Q_BYTES);
-            tma_load_3d(sQ + g * AT_Q_BYTES, &mapQ, &q_full[g], h * AT_HD, qt * AT_BM, b);
+            tma_load_3d(sQ + g * AT_Q_BYTES, &mapQ, &q_full[g], q_col0 + h * AT_HD, qt * AT_BM, b);
             ++q_n[g];
           }
           const uint32_t st = kv_n[g] & 1;
           uint8_t* kv = sKV + (2 * g + st) * PL_KV_BYTES;
           mbar_wait(&kv_empty[2 * g + st], ((kv_n[g] >> 1) & 1) ^ 1);
           mbar_expect_tx(&kv_full[2 * g + st], PL_KV_BYTES);
-          tma_load_3d(kv, &mapKV, &kv_full[2 * g + st], d_model + h * AT_HD, ch[g] * PL_KC, b);
-          tma_load_3d(kv + PL_KV_BYTES / 2, &mapKV, &kv_full[2 * g + st], 2 * d_model + h * AT_HD, ch[g] * PL_KC, b);
+          tma_load_3d(kv, &mapK, &kv_full[2 * g + st], k_col0 + h * AT_HD, ch[g] * PL_KC, b);
+          tma_load_3d(kv + PL_KV_BYTES / 2, &mapV, &kv_full[2 * g + st], v_col0 + h * AT_HD, ch[g] * PL_KC, b);
           ++kv_n[g];
           if (++ch[g] == nc) ch[g] = 0, it[g] += 2;
         }
@@ -514,7 +525,7 @@ self_attention_long_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
               if (!mbar_test(&q_full[g], q_n[g] & 1) || !mbar_test(&reg_free[g], (q_n[g] & 1) ^ 1)) continue;
               int qt, h, b;
               item_coords(it[g], qt, h, b);
-              nc[g] = (len_of(b) + PL_KC - 1) / PL_KC;
+              nc[g] = chunks_of(b, qt);
             }
             if (!mbar_test(&kv_full[2 * g + st], (kv_n[g] >> 1) & 1)) continue;
             tc_fence_after();
@@ -573,10 +584,11 @@ self_attention_long_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
       int qt, h, b;
       item_coords(i, qt, h, b);
       const int len = len_of(b);
-      const int nc = (len + PL_KC - 1) / PL_KC;
+      const int nc = chunks_of(b, qt);
       float m = -INFINITY, l = 0.f;
       for (int c = 0; c < nc; ++c) {
-        const int valid = min(64, max(0, len - c * PL_KC - 64 * hf));   // valid keys among my 64
+        int valid = min(64, max(0, len - c * PL_KC - 64 * hf));   // valid keys among my 64
+        if (causal && c == qt) valid = min(valid, max(0, row + 1 - 64 * hf));   // diagonal chunk: keys <= my query row
         mbar_wait(&s_full[g], s_n & 1);
         ++s_n;
         tc_fence_after();
@@ -670,8 +682,9 @@ self_attention_long_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
 }
 
 template <typename OpT>
-static int launch_attn_long(const CUtensorMap& mq, const CUtensorMap& mkv, const CUtensorMap& mout, const int* lens,
-                            int B, int T, int H, int d, cudaStream_t s) {
+static int launch_attn_long(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mout,
+                            const int* lens, int B, int Tq, int Tk, int q_col0, int k_col0, int v_col0, int causal,
+                            int H, cudaStream_t s) {
   auto kern = self_attention_long_kernel<OpT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -679,7 +692,7 @@ static int launch_attn_long(const CUtensorMap& mq, const CUtensorMap& mkv, const
     if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute(self_attention_long)");
     attr_set = true;
   }
-  const int nqt = (T + AT_BM - 1) / AT_BM;
+  const int nqt = (Tq + AT_BM - 1) / AT_BM;
   const int n_items = B * H * nqt;
   const int grid = n_items < kNumSMs ? n_items : kNumSMs;
   cudaLaunchConfig_t cfg;
@@ -693,7 +706,8 @@ static int launch_attn_long(const CUtensorMap& mq, const CUtensorMap& mkv, const
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mq, mkv, mout, lens, T, d, H, nqt, n_items);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mq, mk, mv, mout, lens, Tk, q_col0, k_col0, v_col0, causal, H, nqt,
+                                     n_items);
   if (e != cudaSuccess) return fail(e, "self_attention_long_kernel launch");
   return 0;
 }
@@ -736,6 +750,38 @@ extern "C" int mm_self_attention(const void* qkv, int64_t qkv_ld, const int32_t*
   rc = make_tmap_3d(&mout, out, f16, (uint64_t)d, (uint64_t)seq, (uint64_t)batch, (uint64_t)out_ld,
                     (uint64_t)seq * out_ld, 128);
   if (rc) return rc;
-  return f16 ? launch_attn_long<__half>(mqk, mqk, mout, seq_lens, batch, seq, heads, d, s)
-             : launch_attn_long<__nv_bfloat16>(mqk, mqk, mout, seq_lens, batch, seq, heads, d, s);
+  return f16 ? launch_attn_long<__half>(mqk, mqk, mqk, mout, seq_lens, batch, seq, seq, 0, d, 2 * d, 0, heads, s)
+             : launch_attn_long<__nv_bfloat16>(mqk, mqk, mqk, mout, seq_lens, batch, seq, seq, 0, d, 2 * d, 0, heads, s);
+}
+
+extern "C" int mm_attention(const void* q, int64_t q_ld, int32_t q_col0, int32_t q_len, const void* k, int64_t k_ld,
+                            int32_t k_col0, const void* v, int64_t v_ld, int32_t v_col0, int32_t kv_len,
+                            const int32_t* kv_lens, int32_t batch, int32_t heads, int32_t causal, void* out,
+                            int64_t out_ld, int32_t dtype, void* stream) {
+  if (!q || !k || !v || !out) return bad_arg("attention: null pointer");
+  if (batch <= 0 || q_len <= 0 || kv_len <= 0 || heads <= 0) return bad_arg("attention: extents");
+  const int d = heads * AT_HD;
+  if ((q_ld % 8) || (k_ld % 8) || (v_ld % 8) || (out_ld % 8) || out_ld < d || q_ld < q_col0 + d || k_ld < k_col0 + d ||
+      v_ld < v_col0 + d || (q_col0 % 8) || (k_col0 % 8) || (v_col0 % 8))
+    return bad_arg("attention: leading dims / column offsets (head_dim must be 64)");
+  if (causal && q_len != kv_len) return bad_arg("attention: a causal mask needs q_len == kv_len");
+  const int f16 = dtype == MM_DTYPE_F16;
+  CUtensorMap mq, mk, mv, mout;
+  int rc = make_tmap_3d(&mq, q, f16, (uint64_t)q_ld, (uint64_t)q_len, (uint64_t)batch, (uint64_t)q_ld,
+                        (uint64_t)q_len * q_ld, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&mk, k, f16, (uint64_t)k_ld, (uint64_t)kv_len, (uint64_t)batch, (uint64_t)k_ld,
+                    (uint64_t)kv_len * k_ld, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&mv, v, f16, (uint64_t)v_ld, (uint64_t)kv_len, (uint64_t)batch, (uint64_t)v_ld,
+                    (uint64_t)kv_len * v_ld, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&mout, out, f16, (uint64_t)d, (uint64_t)q_len, (uint64_t)batch, (uint64_t)out_ld,
+                    (uint64_t)q_len * out_ld, 128);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return f16 ? launch_attn_long<__half>(mq, mk, mv, mout, kv_lens, batch, q_len, kv_len, q_col0, k_col0, v_col0,
+                                         causal != 0, heads, s)
+             : launch_attn_long<__nv_bfloat16>(mq, mk, mv, mout, kv_lens, batch, q_len, kv_len, q_col0, k_col0,
+                                                 v_col0, causal != 0, heads, s);
 }

@@ -218,6 +218,23 @@ def self_attention(qkv: torch.Tensor, seq_lens_: torch.Tensor, batch: int, seq: 
                                          out.stride(-2), dtype_code(qkv.dtype), _stream()), "mm_self_attention")
 
 
+def attention(q: torch.Tensor, q_col0: int, q_len: int, k: torch.Tensor, k_col0: int, v: torch.Tensor, v_col0: int,
+              kv_len: int, kv_lens: Optional[torch.Tensor], batch: int, heads: int, out: torch.Tensor,
+              causal: bool = False) -> None:
+    """General attention core (see ``mm_attention``): q [batch*q_len, ld] (pre-scaled), k / v [batch*kv_len, ld],
+    head h in columns [col0 + 64 h, col0 + 64 h + 64); out [batch*q_len, heads*64]."""
+    assert q.dtype == k.dtype == v.dtype == out.dtype and q.dtype in _DT
+    assert all(t.dim() == 2 and t.stride(1) == 1 for t in (q, k, v, out))
+    assert q.shape[0] == batch * q_len and k.shape[0] == batch * kv_len and v.shape[0] == batch * kv_len
+    if kv_lens is not None:
+        assert kv_lens.dtype == torch.int32 and kv_lens.numel() == batch
+    lib = _lib.load()
+    with _Launch("attention", 4.0 * batch * heads * q_len * kv_len * 64 * (0.5 if causal else 1.0)):
+        _lib.check(lib.mm_attention(_ptr(q), q.stride(0), q_col0, q_len, _ptr(k), k.stride(0), k_col0, _ptr(v),
+                                    v.stride(0), v_col0, kv_len, _ptr(kv_lens), batch, heads, int(causal), _ptr(out),
+                                    out.stride(0), dtype_code(q.dtype), _stream()), "mm_attention")
+
+
 def softmax_rows(scores: torch.Tensor, ld_in: int, rows: int, n_keys: int, probs: torch.Tensor, ld_out: int,
                  key_mask: Optional[torch.Tensor] = None, rows_per_seq: int = 0) -> None:
     assert scores.dtype == torch.float32
