@@ -137,6 +137,14 @@ int mm_gemm_resid_ln(const void* a, int64_t a_ld, const void* w, int64_t w_ld, i
 int mm_layernorm(const float* x, const float* gamma, const float* beta, int64_t rows, int32_t dim, void* out_op,
                  float* out_f32, int32_t dtype, float eps, void* stream);
 
+/* Decoder input embedding: out[b, t] = scale * table[tokens[b, t]] + pos_table[position], position as fairseq
+ * utils.make_positions (padding_idx + running count of non-pad tokens; pad tokens take row padding_idx = zeros).
+ * fairseq TransformerDecoderBase.extract_features_scriptable (embed_scale * embed_tokens + embed_positions), the
+ * input side of the S2UT unit decoder called at mm_s2s_transformer.py:693-696.  fp32 in, fp32 out [batch*length, dim]. */
+int mm_embed_tokens(const int64_t* tokens, int32_t padding_idx, const float* table, int32_t vocab, float scale,
+                    const float* pos_table, int32_t pos_rows, int32_t batch, int32_t length, int32_t dim, float* out,
+                    void* stream);
+
 /* LayerNorm of rows gathered from a device-resident 16-bit feature store (x_dtype = MM_DTYPE_F16 / MM_DTYPE_BF16):
  * output row r = LayerNorm(x[index[r / rows_per_index] * rows_per_index + r % rows_per_index]); index == NULL: rows in
  * order.  This is image_pre_norm_module (mm_s2s_transformer.py:595) applied to the batch that the reference's

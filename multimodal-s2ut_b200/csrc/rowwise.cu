@@ -401,6 +401,54 @@ extern "C" int mm_layernorm(const float* x, const float* gamma, const float* bet
                                : launch_ln<__nv_bfloat16>(x, gamma, beta, rows, dim, out_op, out_f32, eps, s);
 }
 
+namespace mm {
+// Decoder input embedding (fairseq TransformerDecoderBase.extract_features_scriptable): x = scale * E[token] +
+// sinusoidal[position], position = padding_idx + (number of non-pad tokens up to and including this one) for real
+// tokens and padding_idx (the all-zero table row) for pad tokens (fairseq utils.make_positions).
+// One block per (position, sequence): the 128 threads first count the non-pad tokens of the prefix, then write the row.
+__global__ void __launch_bounds__(128) embed_tokens_kernel(const long long* __restrict__ tokens, int padding_idx,
+                                                           const float* __restrict__ table, int vocab, float scale,
+                                                           const float* __restrict__ pos_table, int pos_rows, int L,
+                                                           int dim, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ int s_cnt[4];
+  const int t = blockIdx.x, b = blockIdx.y;
+  const long long* row = tokens + (long long)b * L;
+  int cnt = 0;
+  for (int i = threadIdx.x; i <= t; i += 128) cnt += row[i] != padding_idx;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  const long long tok = row[t];
+  const int total = s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3];
+  int pos = tok != padding_idx ? padding_idx + total : padding_idx;
+  pos = min(pos, pos_rows - 1);
+  const long long tk = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
+  const float4* e = reinterpret_cast<const float4*>(table + tk * dim);
+  const float4* pe = reinterpret_cast<const float4*>(pos_table + (long long)pos * dim);
+  float4* o4 = reinterpret_cast<float4*>(out + ((long long)b * L + t) * dim);
+  for (int i = threadIdx.x; i < dim / 4; i += 128) {
+    const float4 a = __ldg(e + i), p = __ldg(pe + i);
+    o4[i] = make_float4(fmaf(scale, a.x, p.x), fmaf(scale, a.y, p.y), fmaf(scale, a.z, p.z), fmaf(scale, a.w, p.w));
+  }
+}
+}  // namespace mm
+
+extern "C" int mm_embed_tokens(const int64_t* tokens, int32_t padding_idx, const float* table, int32_t vocab, float scale,
+                               const float* pos_table, int32_t pos_rows, int32_t batch, int32_t length, int32_t dim,
+                               float* out, void* stream) {
+  if (!tokens || !table || !pos_table || !out) return bad_arg("embed_tokens: null pointer");
+  if (dim % 4 || vocab <= 0 || pos_rows <= padding_idx) return bad_arg("embed_tokens: dims");
+  if (batch <= 0 || length <= 0) return 0;
+  mm::launch_pdl(mm::embed_tokens_kernel, dim3(length, batch), dim3(128), 0, static_cast<cudaStream_t>(stream),
+                 reinterpret_cast<const long long*>(tokens), padding_idx, table, vocab, scale, pos_table, pos_rows,
+                 length, dim, out);
+  MM_CHECK_LAUNCH("embed_tokens_kernel launch");
+  return 0;
+}
+
 extern "C" int mm_layernorm_gather(const void* x, int32_t x_dtype, const int64_t* index, int32_t rows_per_index,
                                    const float* gamma, const float* beta, int64_t rows, int32_t dim, void* out_op,
                                    int32_t dtype, float eps, void* stream) {

@@ -218,6 +218,20 @@ def self_attention(qkv: torch.Tensor, seq_lens_: torch.Tensor, batch: int, seq: 
                                          out.stride(-2), dtype_code(qkv.dtype), _stream()), "mm_self_attention")
 
 
+def embed_tokens(tokens: torch.Tensor, padding_idx: int, table: torch.Tensor, scale: float, pos_table: torch.Tensor,
+                 out: torch.Tensor) -> None:
+    """out [B*L, d] fp32 = scale * table[tokens] + pos_table[fairseq positions(tokens)]."""
+    assert tokens.dtype == torch.int64 and tokens.dim() == 2 and tokens.is_contiguous()
+    assert table.dtype == pos_table.dtype == out.dtype == torch.float32
+    assert table.is_contiguous() and pos_table.is_contiguous() and out.is_contiguous()
+    B, L = tokens.shape
+    lib = _lib.load()
+    with _Launch("embed_tokens", 8.0 * B * L * table.shape[1]):
+        _lib.check(lib.mm_embed_tokens(_ptr(tokens), padding_idx, _ptr(table), table.shape[0], scale, _ptr(pos_table),
+                                       pos_table.shape[0], B, L, table.shape[1], _ptr(out), _stream()),
+                   "mm_embed_tokens")
+
+
 def attention(q: torch.Tensor, q_col0: int, q_len: int, k: torch.Tensor, k_col0: int, v: torch.Tensor, v_col0: int,
               kv_len: int, kv_lens: Optional[torch.Tensor], batch: int, heads: int, out: torch.Tensor,
               causal: bool = False) -> None:
