@@ -145,6 +145,14 @@ int mm_embed_tokens(const int64_t* tokens, int32_t padding_idx, const float* tab
                     const float* pos_table, int32_t pos_rows, int32_t batch, int32_t length, int32_t dim, float* out,
                     void* stream);
 
+/* Label-smoothed cross entropy terms of the unit logits: per row nll = -log_softmax(logits)[target] and
+ * smooth = -sum_v log_softmax(logits)[v] (0 for rows whose target is padding_idx), plus their sums in sums[0..1]
+ * (deterministic order).  The caller forms fairseq's loss = (1 - eps - eps_i) * sum_nll + eps_i * sum_smooth with
+ * eps_i = eps / (vocab - 1)  (fairseq label_smoothed_nll_loss, used by the reference's criterion,
+ * criterions/speech_to_speech_criterion.py:58-72).  logits fp32 [rows, ld], target int64 [rows]. */
+int mm_label_smoothed_nll(const float* logits, int64_t ld, int32_t vocab, const int64_t* target, int32_t padding_idx,
+                          int64_t rows, float* row_nll, float* row_smooth, float* sums, void* stream);
+
 /* LayerNorm of rows gathered from a device-resident 16-bit feature store (x_dtype = MM_DTYPE_F16 / MM_DTYPE_BF16):
  * output row r = LayerNorm(x[index[r / rows_per_index] * rows_per_index + r % rows_per_index]); index == NULL: rows in
  * order.  This is image_pre_norm_module (mm_s2s_transformer.py:595) applied to the batch that the reference's

@@ -449,6 +449,75 @@ extern "C" int mm_embed_tokens(const int64_t* tokens, int32_t padding_idx, const
   return 0;
 }
 
+namespace mm {
+// Label-smoothed cross entropy of the unit logits (fairseq label_smoothed_nll_loss behind the reference's criterion,
+// mm_s2ut/criterions/speech_to_speech_criterion.py:58-72 -> RdropLabelSmoothedCrossEntropyCriterion.compute_loss):
+// per row  lprobs = log_softmax(logits) in fp32,  nll = -lprobs[target],  smooth = -sum_v lprobs[v];  rows whose target
+// is the padding index contribute 0.  One warp per row (V <= a few thousand), two-pass log-sum-exp from registers.
+__global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ logits, long long ld, int vocab,
+                                                      const long long* __restrict__ target, int padding_idx,
+                                                      long long rows, float* __restrict__ row_nll,
+                                                      float* __restrict__ row_smooth) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* x = logits + row * ld;
+  const long long tgt = target[row];
+  float mx = -INFINITY, sum = 0.f;
+  for (int c = lane; c < vocab; c += 32) {
+    const float v = x[c];
+    mx = fmaxf(mx, v);
+    sum += v;
+  }
+  mx = warp_max(mx);
+  sum = warp_sum(sum);
+  float se = 0.f;
+  for (int c = lane; c < vocab; c += 32) se += __expf(x[c] - mx);
+  se = warp_sum(se);
+  const float lse = mx + logf(se);
+  if (lane == 0) {
+    const bool pad = tgt == padding_idx || tgt < 0 || tgt >= vocab;
+    row_nll[row] = pad ? 0.f : lse - x[tgt];
+    row_smooth[row] = pad ? 0.f : (float)vocab * lse - sum;
+  }
+}
+// deterministic sum of the per-row terms (fixed tree order) -> out[0] = sum nll, out[1] = sum smooth
+__global__ void __launch_bounds__(1024) ce_reduce_kernel(const float* __restrict__ row_nll,
+                                                         const float* __restrict__ row_smooth, long long rows,
+                                                         float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ double s_a[1024], s_b[1024];
+  double a = 0.0, b = 0.0;
+  for (long long i = threadIdx.x; i < rows; i += 1024) a += row_nll[i], b += row_smooth[i];
+  s_a[threadIdx.x] = a, s_b[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s_a[threadIdx.x] += s_a[threadIdx.x + o], s_b[threadIdx.x] += s_b[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)s_a[0], out[1] = (float)s_b[0];
+}
+}  // namespace mm
+
+extern "C" int mm_label_smoothed_nll(const float* logits, int64_t ld, int32_t vocab, const int64_t* target,
+                                     int32_t padding_idx, int64_t rows, float* row_nll, float* row_smooth,
+                                     float* sums, void* stream) {
+  if (!logits || !target || !row_nll || !row_smooth || !sums) return bad_arg("label_smoothed_nll: null pointer");
+  if (vocab <= 0 || ld < vocab) return bad_arg("label_smoothed_nll: vocab / ld");
+  if (rows <= 0) return 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  mm::launch_pdl(mm::ce_rows_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, s, logits, (long long)ld, vocab,
+                 reinterpret_cast<const long long*>(target), padding_idx, (long long)rows, row_nll, row_smooth);
+  MM_CHECK_LAUNCH("ce_rows_kernel launch");
+  mm::launch_pdl(mm::ce_reduce_kernel, dim3(1), dim3(1024), 0, s, (const float*)row_nll, (const float*)row_smooth,
+                 (long long)rows, sums);
+  MM_CHECK_LAUNCH("ce_reduce_kernel launch");
+  return 0;
+}
+
 extern "C" int mm_layernorm_gather(const void* x, int32_t x_dtype, const int64_t* index, int32_t rows_per_index,
                                    const float* gamma, const float* beta, int64_t rows, int32_t dim, void* out_op,
                                    int32_t dtype, float eps, void* stream) {

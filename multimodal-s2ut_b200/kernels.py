@@ -218,6 +218,24 @@ def self_attention(qkv: torch.Tensor, seq_lens_: torch.Tensor, batch: int, seq: 
                                          out.stride(-2), dtype_code(qkv.dtype), _stream()), "mm_self_attention")
 
 
+def label_smoothed_nll(logits: torch.Tensor, vocab: int, target: torch.Tensor, padding_idx: int, epsilon: float):
+    """fairseq ``label_smoothed_nll_loss(log_softmax(logits), target, epsilon, ignore_index=padding_idx)`` summed over
+    rows: returns (loss, nll_loss) as 0-d device tensors.  logits fp32 [rows, ld >= vocab], target int64 [rows]."""
+    assert logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1
+    assert target.dtype == torch.int64 and target.numel() == logits.shape[0] and target.is_contiguous()
+    rows = logits.shape[0]
+    row_nll = torch.empty(rows, dtype=torch.float32, device=logits.device)
+    row_smooth = torch.empty(rows, dtype=torch.float32, device=logits.device)
+    sums = torch.empty(2, dtype=torch.float32, device=logits.device)
+    lib = _lib.load()
+    with _Launch("label_smoothed_nll", 4.0 * rows * vocab):
+        _lib.check(lib.mm_label_smoothed_nll(_ptr(logits), logits.stride(0), vocab, _ptr(target), padding_idx, rows,
+                                             _ptr(row_nll), _ptr(row_smooth), _ptr(sums), _stream()),
+                   "mm_label_smoothed_nll")
+    eps_i = epsilon / (vocab - 1)
+    return (1.0 - epsilon - eps_i) * sums[0] + eps_i * sums[1], sums[0]
+
+
 def embed_tokens(tokens: torch.Tensor, padding_idx: int, table: torch.Tensor, scale: float, pos_table: torch.Tensor,
                  out: torch.Tensor) -> None:
     """out [B*L, d] fp32 = scale * table[tokens] + pos_table[fairseq positions(tokens)]."""

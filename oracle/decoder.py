@@ -89,3 +89,20 @@ def unit_decoder_forward(sd: Dict[str, Tensor], prev_output_tokens: Tensor, enco
         i += 1
     x = F.layer_norm(x, (d,), sd["layer_norm.weight"], sd["layer_norm.bias"], 1e-5).transpose(0, 1)
     return F.linear(x, sd["embed_tokens.weight"])
+
+
+def label_smoothed_nll_loss(logits: Tensor, target: Tensor, epsilon: float, padding_idx: int = 1):
+    """fairseq ``label_smoothed_nll_loss`` (fairseq/criterions/label_smoothed_cross_entropy.py) on
+    ``lprobs = log_softmax(logits.float())`` with ``ignore_index=padding_idx`` and ``reduce=True``: what the
+    reference's criterion computes for the unit targets (mm_s2ut/criterions/speech_to_speech_criterion.py:58-72 via
+    RdropLabelSmoothedCrossEntropyCriterion.compute_loss; scripts pass --label-smoothing 0.2).  Restated from the
+    fairseq source as recalled (fairseq is not on this box): unpinned.  Returns (loss, nll_loss)."""
+    lprobs = F.log_softmax(logits.float(), dim=-1).view(-1, logits.shape[-1])
+    t = target.reshape(-1, 1)
+    nll = -lprobs.gather(dim=-1, index=t)
+    smooth = -lprobs.sum(dim=-1, keepdim=True)
+    pad = t.eq(padding_idx)
+    nll = nll.masked_fill(pad, 0.0).sum()
+    smooth = smooth.masked_fill(pad, 0.0).sum()
+    eps_i = epsilon / (lprobs.size(-1) - 1)
+    return (1.0 - epsilon - eps_i) * nll + eps_i * smooth, nll
