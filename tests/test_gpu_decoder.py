@@ -80,3 +80,39 @@ def test_label_smoothed_nll(cuda):
     torch.cuda.synchronize()
     assert abs(loss.item() - ref_loss.item()) / abs(ref_loss.item()) < 2e-5
     assert abs(nll.item() - ref_nll.item()) / abs(ref_nll.item()) < 2e-5
+
+
+def test_model_forward_mirrors_reference_surface(cuda):
+    """MM_S2UTTransformerModel.forward: 9 encoder kwargs through, decoder on the encoder output, encoder states attached
+    when return_all_hiddens (reference mm_s2s_transformer.py:667-700); logits agree with oracle encoder + oracle decoder."""
+    from mm_s2ut_b200 import synth
+    from mm_s2ut_b200.config import DEFAULT_YAML, load_mm_config, make_args
+    from mm_s2ut_b200.models.mm_s2ut_model import MM_S2UTTransformerModel
+    from oracle import decoder as odec
+    from test_gpu_encoder import _oracle
+
+    torch.manual_seed(2)
+    args = make_args("small", multimodal_translation_config_yaml=str(DEFAULT_YAML))
+    model = MM_S2UTTransformerModel(args, build_unused_projections=False).eval()
+    keys = set(model.state_dict().keys())
+    assert "decoder.embed_tokens.weight" in keys and "decoder.output_projection.weight" in keys
+    assert "decoder.layers.0.encoder_attn.k_proj.weight" in keys and "encoder.layer_norm.weight" in keys
+    wavs, _ = synth.synth_batch(0, 3, 4.0, ragged=True)
+    imgs = synth.synth_images(0, 3)
+    ref_enc = _oracle(model.encoder, args, load_mm_config(DEFAULT_YAML), wavs, imgs)
+    dsd = {k: v.detach().clone() for k, v in model.decoder.state_dict().items() if not k.startswith("output_projection.")}
+    g = torch.Generator().manual_seed(4)
+    prev = torch.randint(4, 1004, (3, 40), generator=g)
+    prev[:, 0] = 2
+    with torch.no_grad():
+        l_ref = odec.unit_decoder_forward(dsd, prev, ref_enc["encoder_out"][0], ref_enc["encoder_padding_mask"][0],
+                                          args.decoder_attention_heads)
+    wav, lens = synth.pad_waveforms(wavs)
+    model.cuda()
+    logits, extra = model(wav.cuda(), lens.cuda(), prev.cuda(), None, None, None, imgs_list=[imgs.cuda()],
+                          img_masks_list=[None], return_all_hiddens=True)
+    torch.cuda.synchronize()
+    assert logits.shape == l_ref.shape
+    assert len(extra["encoder_states"]) == args.encoder_layers and len(extra["encoder_padding_mask"]) == 1
+    agree = (logits.float().cpu().argmax(-1) == l_ref.argmax(-1)).float().mean().item()
+    assert agree >= 0.99, agree
