@@ -265,6 +265,7 @@ class EncoderEngine:
                 K.layernorm(img.view(B * Tk_img, dk), self.img_ln[0], self.img_ln[1], out_op=img_op)
             else:
                 K.convert(img.view(B * Tk_img, dk), img_op)
+        new_kv = (f"k{j}", (B, Tk, d), op) not in self._buf
         kbuf = self.buf(f"k{j}", (B, Tk, d), op)
         vt = self.buf(f"vt_img{j}", (B, d, Tkp), op, zero=True)
         if extra == 0:   # keys are contiguous over the batch: one flat GEMM over all B * Tk image tokens
@@ -274,7 +275,10 @@ class EncoderEngine:
             K.gemm(a0=img_op, a0_ld=dk, a0_bs=Tk_img * dk, rows=Tk_img, batches=B, w=F["wkv"], n=2 * d, k=dk,
                    mode=K.EPI_OP, bias=F["bkv"], out0=kbuf, out0_ld=d, out0_bs=Tk * d, vt=vt, vt_col0=d, vt_rows=d,
                    vt_ld=Tkp, block_n=bn)
-        if extra:  # learned bias_k / bias_v appended as key/value number Tk_img (nn.MultiheadAttention add_bias_kv)
+        if extra and new_kv:
+            # learned bias_k / bias_v are key / value number Tk_img (nn.MultiheadAttention add_bias_kv).  The K|V GEMM
+            # only ever writes keys < Tk_img (its output map and the transposed-V store stop there), so the extra
+            # key / value is written ONCE, when the workspace is created, not per forward.
             kbuf[:, Tk_img, :] = F["bias_kv"][0]
             vt[:, :, Tk_img] = F["bias_kv"][1]
         q = self.buf("q_img", (M, d), op)

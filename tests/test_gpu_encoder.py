@@ -77,6 +77,10 @@ def test_small_config0_parity(cuda, attn_type, gate):
     err = _compare(out, ref)
     record(f"configs[0] small B=4x5s ragged+zero utt, {attn_type}, gate={gate}: fused states max-abs err", err, TOL)
     assert err < TOL, err
+    # second forward on the cached workspaces (the learned bias_k / bias_v key is written only when they are created)
+    out2 = enc(wav.cuda(), lens.cuda(), None, None, None, imgs_list=[imgs.cuda()], img_masks_list=[None])
+    torch.cuda.synchronize()
+    assert torch.equal(out2["encoder_out"][0], out["encoder_out"][0])
     # per-layer states (fp32 residual stream): tighter than the final tolerance early on
     mask = ref["encoder_padding_mask"][0]
     valid = (~mask).t().unsqueeze(-1)
