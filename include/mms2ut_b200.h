@@ -61,6 +61,9 @@ int mm_cmvn_apply(const float* feats, const float* mean_std, const int64_t* n_sa
  * frames = 1 + (n - 400) / 160 when lengths_are_samples.  (fairseq Conv1dSubsampler.get_out_seq_lens_tensor) */
 int mm_seq_lens(const int64_t* n_samples_or_frames, int32_t lengths_are_samples, int32_t batch, int32_t n_layers,
                 int32_t* out_lens, void* stream);
+/* mask[b, t] = (t >= seq_lens[b]) as bytes (PyTorch bool layout): fairseq lengths_to_padding_mask applied to the
+ * subsampled lengths, i.e. the encoder_padding_mask of the encoder-out dict (mm_s2s_transformer.py:378-562). */
+int mm_padding_mask(const int32_t* seq_lens, int32_t batch, int32_t T, uint8_t* mask, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * tcgen05 GEMM with fused epilogues:  acc[r, c] = sum_k A[r, k] * W[c, k]   (fp32 accumulation in TMEM)

@@ -104,6 +104,7 @@ EXPORTS = {
                                 C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "mm_seq_lens": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "mm_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+    "mm_padding_mask": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "mm_label_smoothed_nll": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "mm_embed_tokens": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_int32,

@@ -602,6 +602,28 @@ extern "C" int mm_cmvn_apply(const float* feats, const float* mean_std, const in
   return 0;
 }
 
+namespace mm {
+// encoder_padding_mask[b, t] = t >= seq_lens[b]  (fairseq lengths_to_padding_mask on the subsampled lengths)
+__global__ void __launch_bounds__(256) padding_mask_kernel(const int* __restrict__ seq_lens, int T, long long total,
+                                                           uint8_t* __restrict__ mask) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  mask[i] = (int)(i % T) >= seq_lens[i / T];
+}
+}  // namespace mm
+
+extern "C" int mm_padding_mask(const int32_t* seq_lens, int32_t batch, int32_t T, uint8_t* mask, void* stream) {
+  if (!seq_lens || !mask) return bad_arg("padding_mask: null pointer");
+  if (batch <= 0 || T <= 0) return 0;
+  const long long total = (long long)batch * T;
+  mm::launch_pdl(mm::padding_mask_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0,
+                 static_cast<cudaStream_t>(stream), seq_lens, T, total, mask);
+  MM_CHECK_LAUNCH("padding_mask_kernel launch");
+  return 0;
+}
+
 extern "C" int mm_seq_lens(const int64_t* lens, int32_t lengths_are_samples, int32_t batch, int32_t n_layers,
                            int32_t* out_lens, void* stream) {
   if (!lens || !out_lens) return bad_arg("seq_lens: null pointer");

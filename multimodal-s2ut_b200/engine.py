@@ -342,7 +342,8 @@ class EncoderEngine:
                 states.append(x.view(B, T, self.d).transpose(0, 1).contiguous())
         if not self.fused_ln:
             K.layernorm(x, self.ln_g, self.ln_b, out_op=text_op, out_f32=text_f32)
-        mask = torch.arange(T, device=self.device)[None, :] >= seq_lens[:, None]
+        mask = torch.empty(B, T, dtype=torch.bool, device=self.device)
+        K.padding_mask(seq_lens, T, mask)
         if imgs_list and self.fusion:
             if drop_audio:
                 text_f32.zero_()

@@ -125,6 +125,15 @@ def seq_lens(lens: torch.Tensor, lengths_are_samples: bool, n_layers: int, out: 
                                    _stream()), "mm_seq_lens")
 
 
+def padding_mask(seq_lens: torch.Tensor, T: int, out: torch.Tensor) -> None:
+    """out [B, T] bool = t >= seq_lens[b]."""
+    assert seq_lens.dtype == torch.int32 and out.dtype == torch.bool and out.is_contiguous()
+    assert out.shape == (seq_lens.numel(), T)
+    lib = _lib.load()
+    with _Launch("padding_mask"):
+        _lib.check(lib.mm_padding_mask(_ptr(seq_lens), seq_lens.numel(), T, _ptr(out), _stream()), "mm_padding_mask")
+
+
 def gemm(*, a0: torch.Tensor, w: torch.Tensor, rows: int, n: int, k: int, mode: int, out0: torch.Tensor,
          a0_ld: int, out0_ld: int, batches: int = 1, a0_bs: int = 0, a1: Optional[torch.Tensor] = None,
          a1_ld: int = 0, a1_bs: int = 0, k_split: int = 0, w_ld: Optional[int] = None, w_bs: int = 0,
