@@ -192,6 +192,59 @@ int mm_softmax_rows(const float* scores, int64_t ld_in, int64_t rows, int32_t n_
 /* fp32 -> 16-bit operand conversion (weights / image features); n elements. */
 int mm_convert_f32(const float* x, void* out, int64_t n, int32_t dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training-step variant (BASELINE configs[2]): backward of the same path + optimizer.  The reference gets all of this
+ * from PyTorch autograd over the modules named above (fairseq_cli/train -> task.train_step -> loss.backward();
+ * optimizer = fairseq Adam, scripts/textless/1_train.sh) -- these are the `_bwd` twins SURVEY.md 8(b) asks for.
+ * Every dense contraction of the backward pass (dgrad = dY W, wgrad = dY^T X) runs on mm_gemm; the entry points below
+ * are the memory-bound pieces between them.
+ *
+ * mm_pack_t: 16-bit operand copies of `in` ([batches][rows][cols], fp32 or 16-bit, batch z at
+ *   (z / nb1) * in_bs0 + (z % nb1) * in_bs1), multiplied by `scale`, optionally zeroed where mask <= 0 (ReLU backward):
+ *   out_n [..][rows][n_ld] straight and/or out_t [..][cols][t_ld] TRANSPOSED, whose columns [rows, t_cols_pad) are
+ *   written as 0 (split-K padding of the wgrad GEMMs).  Also splits / merges attention heads (nb1 = heads).
+ * mm_rowsum: out[r] (+)= sum_c in[r, c]  (bias gradient from the transposed output gradient).
+ * mm_reduce_partials: out[i] (+)= sum_s part[s * stride + i]  (split-K partials, LayerNorm parameter partials).
+ * mm_layernorm_bwd: dx = resid + LN'(dy) (dx / resid optional), partials [mm_layernorm_bwd_blocks()][2][dim] =
+ *   per-block (sum dy * xhat, sum dy).
+ * mm_softmax_bwd: P = softmax(scores[:, :valid]), dscores = P o (dprobs - rowsum(P o dprobs)), both 16-bit,
+ *   rows [batch][rows_per_batch], valid = kv_lens[batch / heads] (NULL: n_keys); columns [valid, ld_out) = 0.
+ * mm_glu_bwd: pre fp32 [rows, 2n] = (a | b), dy fp32 [rows, n] -> dpre 16-bit [rows, 2n]   (F.glu backward, x scale).
+ * mm_gate_bwd: selective gate backward (mm_s2s_transformer.py:612-618): z = pre-sigmoid gate incl. bias ->
+ *   dz 16-bit [B*T, d], dcat fp32 [B*T, 2d] = (dres g | dres (1-g)); dres is T x B x C.
+ * mm_tbc_to_btc: T x B x C fp32 -> token-major fp32.
+ * mm_col2im_k5s2: input gradient of Conv1d(k=5, stride 2, pad 2) from the per-window gradient [B, T_out, 5*C].
+ * mm_grad_clip_coef: norm_coef[0] = ||grad_scale * grad||_2, norm_coef[1] = grad_scale * min(1, max_norm / (norm + 1e-6))
+ *   (fairseq clip_grad_norm_; max_norm <= 0: no clipping); partials: mm_sumsq_blocks() floats.
+ * mm_adam: fairseq.optim.adam.Adam.step on a flat fp32 buffer; the gradient is multiplied by norm_coef[1] (NULL: 1).
+ * --------------------------------------------------------------------------------------------- */
+int mm_pack_t(const void* in, int32_t in_is_f32, int64_t in_ld, int64_t in_bs0, int64_t in_bs1, int32_t nb1,
+              const void* mask, int64_t mask_ld, int32_t rows, int32_t cols, int32_t batches, float scale, void* out_n,
+              int64_t n_ld, int64_t n_bs0, int64_t n_bs1, void* out_t, int64_t t_ld, int64_t t_bs0, int64_t t_bs1,
+              int32_t t_cols_pad, int32_t dtype, void* stream);
+int mm_rowsum(const void* in, int64_t ld, int32_t rows, int32_t cols, float* out, int32_t accumulate, int32_t dtype,
+              void* stream);
+int mm_reduce_partials(const float* part, int32_t n_partials, int64_t stride, int64_t n, float* out, int32_t accumulate,
+                       void* stream);
+int mm_layernorm_bwd_blocks(void);
+int mm_layernorm_bwd(const float* x, const float* gamma, const float* dy, int64_t rows, int32_t dim, float eps,
+                     const float* resid, float* dx, float* partials, void* stream);
+int mm_softmax_bwd(const float* scores, const float* dprobs, int64_t ld_in, int64_t rows, int32_t rows_per_batch,
+                   int32_t n_keys, const int32_t* kv_lens, int32_t heads, void* probs, void* dscores, int64_t ld_out,
+                   int32_t dtype, void* stream);
+int mm_glu_bwd(const float* pre, const float* dy, int64_t rows, int32_t n, float scale, void* dpre, int32_t dtype,
+               void* stream);
+int mm_gate_bwd(const float* z, const float* dres_tbc, const float* text, const float* attn, int32_t batch, int32_t seq,
+                int32_t dim, void* dz, float* dcat, int32_t dtype, void* stream);
+int mm_tbc_to_btc(const float* in_tbc, int32_t batch, int32_t seq, int32_t dim, float* out, void* stream);
+int mm_col2im_k5s2(const float* dcol, int32_t batch, int32_t t_out, int32_t t_in, int32_t channels, float* dx,
+                   void* stream);
+int mm_sumsq_blocks(void);
+int mm_grad_clip_coef(const float* grad, int64_t n, float grad_scale, float max_norm, float* partials, float* norm_coef,
+                      void* stream);
+int mm_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+            float beta2, float eps, float weight_decay, int32_t step, const float* norm_coef, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

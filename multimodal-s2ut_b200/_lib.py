@@ -17,7 +17,7 @@ _PKG = Path(__file__).resolve().parent
 CSRC = _PKG / "csrc"
 INCLUDE = _PKG.parent / "include"
 LIB_PATH = _PKG / "libmms2ut_b200.so"
-SOURCES = ["abi.cu", "gemm.cu", "gemm_ln.cu", "rowwise.cu", "fbank.cu", "attention.cu"]
+SOURCES = ["abi.cu", "gemm.cu", "gemm_ln.cu", "rowwise.cu", "fbank.cu", "attention.cu", "backward.cu"]
 ABI_VERSION = 1
 
 NVCC_FLAGS = [
@@ -124,6 +124,26 @@ EXPORTS = {
     "mm_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                   C.c_int64, C.c_int32, C.c_void_p]),
     "mm_convert_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    # training-step variant (csrc/backward.cu)
+    "mm_pack_t": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,
+                            C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                            C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "mm_rowsum": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "mm_reduce_partials": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mm_layernorm_bwd_blocks": (C.c_int, []),
+    "mm_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mm_softmax_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                 C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "mm_glu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mm_gate_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                              C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mm_tbc_to_btc": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mm_col2im_k5s2": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mm_sumsq_blocks": (C.c_int, []),
+    "mm_grad_clip_coef": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mm_adam": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float,
+                          C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

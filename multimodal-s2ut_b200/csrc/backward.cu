@@ -1,0 +1,553 @@
+// Backward-pass and optimizer kernels of the training-step variant (BASELINE configs[2]): the HBM-bound pieces that sit
+// between the tcgen05 GEMMs (gemm.cu serves every dgrad / wgrad contraction):
+//   pack_t           16-bit operand copies of a gradient / activation, straight and TRANSPOSED (the wgrad GEMMs contract
+//                    over tokens, so both operands are needed token-contiguous), optional ReLU mask, head split / merge
+//   rowsum           bias gradients = row sums of the transposed gradient
+//   reduce_partials  deterministic split-K / per-block partial reduction into the fp32 gradient
+//   layernorm_bwd    dx (+ residual gradient), per-block dgamma / dbeta partials
+//   softmax_bwd      P and dS = P o (dP - rowsum(P o dP)) from recomputed scores
+//   glu_bwd, gate_bwd, col2im_k5s2   element-wise backward of GLU, the selective gate and the stride-2 k=5 conv gather
+//   adam, sumsq, clip_coef           fairseq Adam on fp32 master parameters with global-norm clipping
+// All plain CUDA-core kernels: warp-per-row or tile-per-block, fp32 arithmetic, deterministic reductions.
+#include "common.cuh"
+#include "host.cuh"
+#include "../../include/mms2ut_b200.h"
+
+namespace mm {
+
+__device__ __forceinline__ float sigmoid_exact(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------------
+// pack_t: tile 64 rows x 64 cols through shared memory (fp32), 256 threads.
+// ---------------------------------------------------------------------------------------------------
+struct PackArgs {
+  const void* in;
+  const void* mask;
+  void* out_n;
+  void* out_t;
+  long long in_ld, in_bs0, in_bs1, mask_ld;
+  long long n_ld, n_bs0, n_bs1;
+  long long t_ld, t_bs0, t_bs1;
+  int rows, cols, nb1, t_cols_pad, in_is_f32;
+  float scale;
+};
+
+template <typename OpT>
+__global__ void __launch_bounds__(256) pack_t_kernel(PackArgs a) {
+  __shared__ float tile[64][65];
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int b0 = blockIdx.z / a.nb1, b1 = blockIdx.z % a.nb1;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 column pairs x 8 row groups
+  const long long in_off = (long long)b0 * a.in_bs0 + (long long)b1 * a.in_bs1;
+  const int c = c0 + 2 * tx;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int rl = ty + 8 * j, r = r0 + rl;
+    float v0 = 0.f, v1 = 0.f;
+    if (r < a.rows && c < a.cols) {
+      const long long idx = in_off + (long long)r * a.in_ld + c;
+      if (a.in_is_f32) {
+        const float2 t = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(a.in) + idx);
+        v0 = t.x, v1 = t.y;
+      } else {
+        const OpT* p = reinterpret_cast<const OpT*>(a.in) + idx;
+        v0 = OpTraits<OpT>::to_float(p[0]), v1 = OpTraits<OpT>::to_float(p[1]);
+      }
+      v0 *= a.scale, v1 *= a.scale;
+      if (a.mask) {
+        const OpT* m = reinterpret_cast<const OpT*>(a.mask) + (long long)r * a.mask_ld + c;
+        if (!(OpTraits<OpT>::to_float(m[0]) > 0.f)) v0 = 0.f;
+        if (!(OpTraits<OpT>::to_float(m[1]) > 0.f)) v1 = 0.f;
+      }
+      if (a.out_n) {
+        OpT* o = reinterpret_cast<OpT*>(a.out_n) + (long long)b0 * a.n_bs0 + (long long)b1 * a.n_bs1 +
+                 (long long)r * a.n_ld + c;
+        *reinterpret_cast<uint32_t*>(o) = OpTraits<OpT>::pack2(v0, v1);
+      }
+    }
+    tile[rl][2 * tx] = v0;
+    tile[rl][2 * tx + 1] = v1;
+  }
+  if (!a.out_t) return;
+  __syncthreads();
+  // transposed store: output row = input column, 32 pairs of consecutive input rows per warp
+  OpT* ot = reinterpret_cast<OpT*>(a.out_t) + (long long)b0 * a.t_bs0 + (long long)b1 * a.t_bs1;
+  const int r = r0 + 2 * tx;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int cl = ty + 8 * j, cc = c0 + cl;
+    if (cc < a.cols && r < a.t_cols_pad) {
+      // rows >= a.rows were loaded as zeros: the padding columns of the transposed copy are written as 0
+      *reinterpret_cast<uint32_t*>(ot + (long long)cc * a.t_ld + r) =
+          OpTraits<OpT>::pack2(tile[2 * tx][cl], tile[2 * tx + 1][cl]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// rowsum: out[r] (+)= sum_c in[r, c], warp per row, 16-bit input.
+// ---------------------------------------------------------------------------------------------------
+template <typename OpT>
+__global__ void __launch_bounds__(256) rowsum_kernel(const OpT* __restrict__ in, long long ld, int rows, int cols,
+                                                      float* __restrict__ out, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const OpT* p = in + (long long)row * ld;
+  float s0 = 0.f, s1 = 0.f;
+  for (int c = 2 * lane; c < cols; c += 64) {
+    s0 += OpTraits<OpT>::to_float(p[c]);
+    if (c + 1 < cols) s1 += OpTraits<OpT>::to_float(p[c + 1]);
+  }
+  const float s = warp_sum(s0 + s1);
+  if (lane == 0) out[row] = accumulate ? out[row] + s : s;
+}
+
+// out[i] (+)= sum_s part[s * stride + i]
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int S, long long stride,
+                                                               long long n, float* __restrict__ out, int accumulate) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int k = 0; k < S; ++k) s += part[(long long)k * stride + i];
+  out[i] = accumulate ? out[i] + s : s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm backward: warp per row (grid-stride), row in registers.
+//   xhat = (x - mean) * rstd ; dyg = dy * gamma ; dx = rstd * (dyg - mean(dyg) - xhat * mean(dyg * xhat))
+//   dx_out = (resid ? resid : 0) + dx ; partials[block] = (sum_r dy * xhat, sum_r dy)
+// ---------------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ dy, long long rows, float eps,
+                                                             const float* resid, float* dx_out,
+                                                             float* __restrict__ partials) {
+  constexpr int V = DIM / 128;
+  __shared__ float red[8][DIM];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 ag[V], ab[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) ag[i] = make_float4(0.f, 0.f, 0.f, 0.f), ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < rows; row += (long long)gridDim.x * 8) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * DIM);
+    const float4* dr = reinterpret_cast<const float4*>(dy + row * DIM);
+    float4 v[V], d[V];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      v[i] = xr[lane + 32 * i];
+      d[i] = dr[lane + 32 * i];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / DIM);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      v[i].x -= mean, v[i].y -= mean, v[i].z -= mean, v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / DIM) + eps);
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float4 g = __ldg(g4 + lane + 32 * i);
+      v[i].x *= rstd, v[i].y *= rstd, v[i].z *= rstd, v[i].w *= rstd;   // xhat
+      ag[i].x += d[i].x * v[i].x, ag[i].y += d[i].y * v[i].y, ag[i].z += d[i].z * v[i].z, ag[i].w += d[i].w * v[i].w;
+      ab[i].x += d[i].x, ab[i].y += d[i].y, ab[i].z += d[i].z, ab[i].w += d[i].w;
+      d[i].x *= g.x, d[i].y *= g.y, d[i].z *= g.z, d[i].w *= g.w;       // dyg
+      c1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+      c2 += (d[i].x * v[i].x + d[i].y * v[i].y) + (d[i].z * v[i].z + d[i].w * v[i].w);
+    }
+    c1 = warp_sum(c1) * (1.0f / DIM);
+    c2 = warp_sum(c2) * (1.0f / DIM);
+    if (dx_out) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float4 o;
+        o.x = rstd * (d[i].x - c1 - v[i].x * c2);
+        o.y = rstd * (d[i].y - c1 - v[i].y * c2);
+        o.z = rstd * (d[i].z - c1 - v[i].z * c2);
+        o.w = rstd * (d[i].w - c1 - v[i].w * c2);
+        if (resid) {
+          const float4 r = reinterpret_cast<const float4*>(resid + row * DIM)[lane + 32 * i];
+          o.x += r.x, o.y += r.y, o.z += r.z, o.w += r.w;
+        }
+        reinterpret_cast<float4*>(dx_out + row * DIM)[lane + 32 * i] = o;
+      }
+    }
+  }
+  // block reduction of the parameter-gradient partials (fixed order: warp 0..7)
+  float* out = partials + (long long)blockIdx.x * 2 * DIM;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+      reinterpret_cast<float4*>(&red[warp][0])[lane + 32 * i] = pass == 0 ? ag[i] : ab[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < DIM; c += 256) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][c];
+      out[pass * DIM + c] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// softmax backward from recomputed scores: warp per query row.
+//   P = softmax(S[:, :valid]) ; D = sum_k P dP ; dS = P (dP - D)   (keys >= valid: P = dS = 0 up to ld_out)
+// rows are laid out [batch][rows_per_batch]; valid keys of a batch = kv_lens[batch / heads] (or n_keys).
+// ---------------------------------------------------------------------------------------------------
+template <typename OpT>
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ S, const float* __restrict__ dP,
+                                                           long long ld_in, long long rows, int rows_per_batch,
+                                                           int n_keys, const int* __restrict__ kv_lens, int heads,
+                                                           OpT* __restrict__ P, OpT* __restrict__ dS, long long ld_out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  int valid = n_keys;
+  if (kv_lens) {
+    const int v = kv_lens[(row / rows_per_batch) / heads];
+    valid = v < n_keys ? v : n_keys;
+  }
+  const float* s = S + row * ld_in;
+  const float* d = dP + row * ld_in;
+  float mx = -INFINITY;
+  for (int k = lane; k < valid; k += 32) mx = fmaxf(mx, s[k]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int k = lane; k < valid; k += 32) sum += __expf(s[k] - mx);
+  sum = warp_sum(sum);
+  const float inv = valid > 0 ? 1.0f / sum : 0.f;
+  float dot = 0.f;
+  for (int k = lane; k < valid; k += 32) dot += __expf(s[k] - mx) * inv * d[k];
+  dot = warp_sum(dot);
+  OpT* po = P ? P + row * ld_out : nullptr;
+  OpT* go = dS + row * ld_out;
+  for (int k = lane; k < ld_out; k += 32) {
+    float p = 0.f, g = 0.f;
+    if (k < valid) {
+      p = __expf(s[k] - mx) * inv;
+      g = p * (d[k] - dot);
+    }
+    if (po) po[k] = OpTraits<OpT>::cvt(p);
+    go[k] = OpTraits<OpT>::cvt(g);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GLU backward: y = a * sigmoid(b), pre = [a | b] (fp32, 2n columns); dpre = [dy s sig(b) | dy s a sig(b)(1-sig(b))]
+// ---------------------------------------------------------------------------------------------------
+template <typename OpT>
+__global__ void __launch_bounds__(256) glu_bwd_kernel(const float* __restrict__ pre, const float* __restrict__ dy,
+                                                       long long rows, int n, float scale, OpT* __restrict__ dpre) {
+  const long long total = rows * (long long)(n / 2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (n / 2);
+    const int c = (int)(i - r * (n / 2)) * 2;
+    const float2 a = *reinterpret_cast<const float2*>(pre + r * 2 * n + c);
+    const float2 b = *reinterpret_cast<const float2*>(pre + r * 2 * n + n + c);
+    float2 g = *reinterpret_cast<const float2*>(dy + r * n + c);
+    g.x *= scale, g.y *= scale;
+    const float s0 = sigmoid_exact(b.x), s1 = sigmoid_exact(b.y);
+    *reinterpret_cast<uint32_t*>(dpre + r * 2 * n + c) = OpTraits<OpT>::pack2(g.x * s0, g.y * s1);
+    *reinterpret_cast<uint32_t*>(dpre + r * 2 * n + n + c) =
+        OpTraits<OpT>::pack2(g.x * a.x * s0 * (1.f - s0), g.y * a.y * s1 * (1.f - s1));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// selective-gate backward: res = (1-g) text + g attn, g = sigmoid(z)  (z includes the bias)
+//   dz = dres (attn - text) g (1-g) ; dcat = [dres g | dres (1-g)]   (dcat then receives += dz Wg by the RESID GEMM)
+// dres is T x B x C (fairseq layout of the fused states), everything else token-major [B*T, C].
+// ---------------------------------------------------------------------------------------------------
+template <typename OpT>
+__global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__ z, const float* __restrict__ dres,
+                                                        const float* __restrict__ text, const float* __restrict__ attn,
+                                                        int B, int T, int d, OpT* __restrict__ dz,
+                                                        float* __restrict__ dcat) {
+  const long long total = (long long)B * T * (d / 2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (d / 2);
+    const int c = (int)(i - r * (d / 2)) * 2;
+    const int b = (int)(r / T), t = (int)(r - (long long)b * T);
+    const float2 g_ = *reinterpret_cast<const float2*>(dres + ((long long)t * B + b) * d + c);
+    const float2 zz = *reinterpret_cast<const float2*>(z + r * d + c);
+    const float2 tx = *reinterpret_cast<const float2*>(text + r * d + c);
+    const float2 at = *reinterpret_cast<const float2*>(attn + r * d + c);
+    const float g0 = sigmoid_exact(zz.x), g1 = sigmoid_exact(zz.y);
+    *reinterpret_cast<uint32_t*>(dz + r * d + c) =
+        OpTraits<OpT>::pack2(g_.x * (at.x - tx.x) * g0 * (1.f - g0), g_.y * (at.y - tx.y) * g1 * (1.f - g1));
+    *reinterpret_cast<float2*>(dcat + r * 2 * d + c) = make_float2(g_.x * g0, g_.y * g1);
+    *reinterpret_cast<float2*>(dcat + r * 2 * d + d + c) = make_float2(g_.x * (1.f - g0), g_.y * (1.f - g1));
+  }
+}
+
+// T x B x C fp32 -> token-major [B*T, C] fp32 (gradient of the un-gated `text + attn` residual mode and of the
+// no-fusion path, where the fused states are a plain transpose of the final LayerNorm output)
+__global__ void __launch_bounds__(256) tbc_to_btc_kernel(const float* __restrict__ in, int B, int T, int d,
+                                                          float* __restrict__ out) {
+  const long long total = (long long)B * T * (d / 4);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (d / 4);
+    const int c = (int)(i - r * (d / 4)) * 4;
+    const int b = (int)(r / T), t = (int)(r - (long long)b * T);
+    *reinterpret_cast<float4*>(out + r * d + c) = *reinterpret_cast<const float4*>(in + ((long long)t * B + b) * d + c);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// col2im of a k=5, stride-2, pad-2 Conv1d: dx[b, s, c] = sum over taps k with (s + 2 - k) even, t = (s+2-k)/2 in range
+// of dcol[b, t, k, c].   dcol fp32 [B, T_out, 5*C], dx fp32 [B, T_in, C].
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) col2im_k5s2_kernel(const float* __restrict__ dcol, int B, int T_out, int T_in,
+                                                           int C, float* __restrict__ dx) {
+  const long long total = (long long)B * T_in * (C / 4);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (C / 4);
+    const int c = (int)(i - r * (C / 4)) * 4;
+    const int b = (int)(r / T_in), s = (int)(r - (long long)b * T_in);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int u = s + 2 - k;
+      if (u < 0 || (u & 1)) continue;
+      const int t = u >> 1;
+      if (t >= T_out) continue;
+      const float4 v = *reinterpret_cast<const float4*>(dcol + (((long long)b * T_out + t) * 5 + k) * C + c);
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(dx + r * C + c) = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Optimizer: sum of squares (per-block partials), clip coefficient, fairseq Adam.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ partials) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    s += g[i] * g[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partials[blockIdx.x] = t;
+  }
+}
+
+// out[0] = grad norm (after grad_scale), out[1] = multiplier to apply to the raw gradient: grad_scale * min(1, max_norm/(norm+1e-6))
+__global__ void clip_coef_kernel(const float* __restrict__ partials, int S, float grad_scale, float max_norm,
+                                 float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double t = 0.0;
+  for (int i = 0; i < S; ++i) t += (double)partials[i];
+  const float norm = sqrtf((float)t) * grad_scale;
+  float coef = grad_scale;
+  if (max_norm > 0.f) coef *= fminf(1.0f, max_norm / (norm + 1e-6f));
+  out[0] = norm;
+  out[1] = coef;
+}
+
+// fairseq.optim.adam.Adam.step: m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; denom = sqrt(v) + eps ;
+// step_size = lr sqrt(1-b2^t) / (1-b1^t) ; p -= wd lr p ; p -= step_size m / denom
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                    float* __restrict__ m, float* __restrict__ v, long long n, float lr,
+                                                    float beta1, float beta2, float eps, float weight_decay,
+                                                    float step_size, const float* __restrict__ coef) {
+  const float gs = coef ? coef[1] : 1.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gs;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi, v[i] = vi;
+    float pi = p[i];
+    if (weight_decay != 0.f) pi -= weight_decay * lr * pi;
+    p[i] = pi - step_size * mi / (sqrtf(vi) + eps);
+  }
+}
+
+static inline unsigned grid_for(long long total, int per_block = 256) {
+  long long g = (total + per_block - 1) / per_block;
+  const long long cap = (long long)kNumSMs * 16;
+  return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace mm
+
+using namespace mm;
+
+extern "C" int mm_pack_t(const void* in, int32_t in_is_f32, int64_t in_ld, int64_t in_bs0, int64_t in_bs1, int32_t nb1,
+                         const void* mask, int64_t mask_ld, int32_t rows, int32_t cols, int32_t batches, float scale,
+                         void* out_n, int64_t n_ld, int64_t n_bs0, int64_t n_bs1, void* out_t, int64_t t_ld,
+                         int64_t t_bs0, int64_t t_bs1, int32_t t_cols_pad, int32_t dtype, void* stream) {
+  if (!in || (!out_n && !out_t)) return bad_arg("pack_t: null operand");
+  if (rows <= 0 || cols <= 0 || batches <= 0 || nb1 <= 0) return bad_arg("pack_t: non-positive extent");
+  if ((cols & 1) || (in_ld & 1) || (in_bs0 & 1) || (in_bs1 & 1) || (n_ld & 1) || (t_ld & 1) || (mask_ld & 1) ||
+      (n_bs0 & 1) || (n_bs1 & 1) || (t_bs0 & 1) || (t_bs1 & 1))
+    return bad_arg("pack_t: cols and strides must be even");
+  if (mask && batches != 1) return bad_arg("pack_t: mask needs batches == 1");
+  if (dtype != MM_DTYPE_BF16 && dtype != MM_DTYPE_F16) return bad_arg("dtype");
+  const int rows_even = rows + (rows & 1);
+  if (out_t) {
+    if (t_cols_pad < rows_even) t_cols_pad = rows_even;
+    if ((t_cols_pad & 1) || t_ld < t_cols_pad) return bad_arg("pack_t: t_cols_pad must be even and <= t_ld");
+  } else {
+    t_cols_pad = rows;
+  }
+  PackArgs a;
+  a.in = in, a.mask = mask, a.out_n = out_n, a.out_t = out_t;
+  a.in_ld = in_ld, a.in_bs0 = in_bs0, a.in_bs1 = in_bs1, a.mask_ld = mask_ld;
+  a.n_ld = n_ld, a.n_bs0 = n_bs0, a.n_bs1 = n_bs1, a.t_ld = t_ld, a.t_bs0 = t_bs0, a.t_bs1 = t_bs1;
+  a.rows = rows, a.cols = cols, a.nb1 = nb1, a.t_cols_pad = t_cols_pad, a.in_is_f32 = in_is_f32, a.scale = scale;
+  const int span = t_cols_pad > rows ? t_cols_pad : rows;
+  dim3 grid((span + 63) / 64, (cols + 63) / 64, batches);
+  if (grid.y > 65535 || grid.z > 65535) return bad_arg("pack_t: grid too large");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == MM_DTYPE_F16)
+    pack_t_kernel<__half><<<grid, 256, 0, s>>>(a);
+  else
+    pack_t_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(a);
+  MM_CHECK_LAUNCH("pack_t_kernel launch");
+  return 0;
+}
+
+extern "C" int mm_rowsum(const void* in, int64_t ld, int32_t rows, int32_t cols, float* out, int32_t accumulate,
+                         int32_t dtype, void* stream) {
+  if (!in || !out || rows <= 0 || cols <= 0) return bad_arg("rowsum");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (rows + 7) / 8;
+  if (dtype == MM_DTYPE_F16)
+    rowsum_kernel<__half><<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(in), ld, rows, cols, out, accumulate);
+  else
+    rowsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(in), ld, rows, cols, out,
+                                                       accumulate);
+  MM_CHECK_LAUNCH("rowsum_kernel launch");
+  return 0;
+}
+
+extern "C" int mm_reduce_partials(const float* part, int32_t n_partials, int64_t stride, int64_t n, float* out,
+                                  int32_t accumulate, void* stream) {
+  if (!part || !out || n_partials <= 0 || n <= 0) return bad_arg("reduce_partials");
+  reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      part, n_partials, stride, n, out, accumulate);
+  MM_CHECK_LAUNCH("reduce_partials_kernel launch");
+  return 0;
+}
+
+extern "C" int mm_layernorm_bwd_blocks(void) { return 2 * kNumSMs; }
+
+extern "C" int mm_layernorm_bwd(const float* x, const float* gamma, const float* dy, int64_t rows, int32_t dim, float eps,
+                                const float* resid, float* dx, float* partials, void* stream) {
+  if (!x || !gamma || !dy || !partials || rows <= 0) return bad_arg("layernorm_bwd");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = 2 * kNumSMs;
+  switch (dim) {
+    case 256: layernorm_bwd_kernel<256><<<grid, 256, 0, s>>>(x, gamma, dy, rows, eps, resid, dx, partials); break;
+    case 512: layernorm_bwd_kernel<512><<<grid, 256, 0, s>>>(x, gamma, dy, rows, eps, resid, dx, partials); break;
+    case 768: layernorm_bwd_kernel<768><<<grid, 256, 0, s>>>(x, gamma, dy, rows, eps, resid, dx, partials); break;
+    case 1024: layernorm_bwd_kernel<1024><<<grid, 256, 0, s>>>(x, gamma, dy, rows, eps, resid, dx, partials); break;
+    default: return bad_arg("layernorm_bwd dim must be 256, 512, 768 or 1024");
+  }
+  MM_CHECK_LAUNCH("layernorm_bwd_kernel launch");
+  return 0;
+}
+
+extern "C" int mm_softmax_bwd(const float* scores, const float* dprobs, int64_t ld_in, int64_t rows,
+                              int32_t rows_per_batch, int32_t n_keys, const int32_t* kv_lens, int32_t heads, void* probs,
+                              void* dscores, int64_t ld_out, int32_t dtype, void* stream) {
+  if (!scores || !dprobs || !dscores || rows <= 0 || n_keys <= 0 || rows_per_batch <= 0 || heads <= 0)
+    return bad_arg("softmax_bwd");
+  if (ld_out < n_keys || ld_in < n_keys) return bad_arg("softmax_bwd: leading dimensions");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (dtype == MM_DTYPE_F16)
+    softmax_bwd_kernel<__half><<<grid, 256, 0, s>>>(scores, dprobs, ld_in, rows, rows_per_batch, n_keys, kv_lens, heads,
+                                                    reinterpret_cast<__half*>(probs),
+                                                    reinterpret_cast<__half*>(dscores), ld_out);
+  else
+    softmax_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(scores, dprobs, ld_in, rows, rows_per_batch, n_keys, kv_lens,
+                                                           heads, reinterpret_cast<__nv_bfloat16*>(probs),
+                                                           reinterpret_cast<__nv_bfloat16*>(dscores), ld_out);
+  MM_CHECK_LAUNCH("softmax_bwd_kernel launch");
+  return 0;
+}
+
+extern "C" int mm_glu_bwd(const float* pre, const float* dy, int64_t rows, int32_t n, float scale, void* dpre,
+                          int32_t dtype, void* stream) {
+  if (!pre || !dy || !dpre || rows <= 0 || n <= 0 || (n & 1)) return bad_arg("glu_bwd");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = grid_for(rows * (long long)(n / 2));
+  if (dtype == MM_DTYPE_F16)
+    glu_bwd_kernel<__half><<<grid, 256, 0, s>>>(pre, dy, rows, n, scale, reinterpret_cast<__half*>(dpre));
+  else
+    glu_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(pre, dy, rows, n, scale, reinterpret_cast<__nv_bfloat16*>(dpre));
+  MM_CHECK_LAUNCH("glu_bwd_kernel launch");
+  return 0;
+}
+
+extern "C" int mm_gate_bwd(const float* z, const float* dres_tbc, const float* text, const float* attn, int32_t batch,
+                           int32_t seq, int32_t dim, void* dz, float* dcat, int32_t dtype, void* stream) {
+  if (!z || !dres_tbc || !text || !attn || !dz || !dcat || batch <= 0 || seq <= 0 || dim <= 0 || (dim & 1))
+    return bad_arg("gate_bwd");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = grid_for((long long)batch * seq * (dim / 2));
+  if (dtype == MM_DTYPE_F16)
+    gate_bwd_kernel<__half><<<grid, 256, 0, s>>>(z, dres_tbc, text, attn, batch, seq, dim,
+                                                 reinterpret_cast<__half*>(dz), dcat);
+  else
+    gate_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(z, dres_tbc, text, attn, batch, seq, dim,
+                                                        reinterpret_cast<__nv_bfloat16*>(dz), dcat);
+  MM_CHECK_LAUNCH("gate_bwd_kernel launch");
+  return 0;
+}
+
+extern "C" int mm_tbc_to_btc(const float* in_tbc, int32_t batch, int32_t seq, int32_t dim, float* out, void* stream) {
+  if (!in_tbc || !out || batch <= 0 || seq <= 0 || dim <= 0 || (dim & 3)) return bad_arg("tbc_to_btc");
+  tbc_to_btc_kernel<<<grid_for((long long)batch * seq * (dim / 4)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in_tbc, batch, seq, dim, out);
+  MM_CHECK_LAUNCH("tbc_to_btc_kernel launch");
+  return 0;
+}
+
+extern "C" int mm_col2im_k5s2(const float* dcol, int32_t batch, int32_t t_out, int32_t t_in, int32_t channels, float* dx,
+                              void* stream) {
+  if (!dcol || !dx || batch <= 0 || t_out <= 0 || t_in <= 0 || channels <= 0 || (channels & 3)) return bad_arg("col2im");
+  col2im_k5s2_kernel<<<grid_for((long long)batch * t_in * (channels / 4)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dcol, batch, t_out, t_in, channels, dx);
+  MM_CHECK_LAUNCH("col2im_k5s2_kernel launch");
+  return 0;
+}
+
+extern "C" int mm_sumsq_blocks(void) { return 4 * kNumSMs; }
+
+extern "C" int mm_grad_clip_coef(const float* grad, int64_t n, float grad_scale, float max_norm, float* partials,
+                                 float* norm_coef, void* stream) {
+  if (!grad || !partials || !norm_coef || n <= 0) return bad_arg("grad_clip_coef");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int blocks = 4 * kNumSMs;
+  sumsq_kernel<<<blocks, 256, 0, s>>>(grad, n, partials);
+  MM_CHECK_LAUNCH("sumsq_kernel launch");
+  clip_coef_kernel<<<1, 32, 0, s>>>(partials, blocks, grad_scale, max_norm, norm_coef);
+  MM_CHECK_LAUNCH("clip_coef_kernel launch");
+  return 0;
+}
+
+extern "C" int mm_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                       float beta1, float beta2, float eps, float weight_decay, int32_t step, const float* norm_coef,
+                       void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || n <= 0 || step <= 0) return bad_arg("adam");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr * sqrt(bc2) / bc1);
+  adam_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
+                                                                          beta2, eps, weight_decay, step_size, norm_coef);
+  MM_CHECK_LAUNCH("adam_kernel launch");
+  return 0;
+}

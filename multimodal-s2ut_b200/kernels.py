@@ -293,3 +293,132 @@ def convert(x: torch.Tensor, out: torch.Tensor) -> None:
     with _Launch("convert", 6.0 * x.numel()):
         _lib.check(lib.mm_convert_f32(_ptr(x), _ptr(out), x.numel(), dtype_code(out.dtype), _stream()),
                    "mm_convert_f32")
+
+
+# ----------------------------------------------------------------------------------------------------------
+# training-step variant (csrc/backward.cu): see include/mms2ut_b200.h
+# ----------------------------------------------------------------------------------------------------------
+def pack_t(x: torch.Tensor, *, rows: int, cols: int, in_ld: int, out_n: Optional[torch.Tensor] = None, n_ld: int = 0,
+           out_t: Optional[torch.Tensor] = None, t_ld: int = 0, t_cols_pad: int = 0, batches: int = 1, nb1: int = 1,
+           in_bs0: int = 0, in_bs1: int = 0, n_bs0: int = 0, n_bs1: int = 0, t_bs0: int = 0, t_bs1: int = 0,
+           mask: Optional[torch.Tensor] = None, mask_ld: int = 0, scale: float = 1.0) -> None:
+    """16-bit straight (out_n) and/or transposed (out_t, zero-padded to t_cols_pad columns) copies of x (fp32/16-bit)."""
+    outs = [t for t in (out_n, out_t) if t is not None]
+    assert outs and all(t.dtype == outs[0].dtype for t in outs)
+    assert x.dtype == torch.float32 or x.dtype == outs[0].dtype
+    if mask is not None:
+        assert mask.dtype == outs[0].dtype
+    lib = _lib.load()
+    with _Launch("pack_t", float(x.element_size() * rows * cols * batches +
+                                 2 * rows * cols * batches * len(outs))):
+        _lib.check(lib.mm_pack_t(_ptr(x), int(x.dtype == torch.float32), in_ld, in_bs0, in_bs1, nb1, _ptr(mask), mask_ld,
+                                 rows, cols, batches, scale, _ptr(out_n), n_ld, n_bs0, n_bs1, _ptr(out_t), t_ld, t_bs0,
+                                 t_bs1, t_cols_pad, dtype_code(outs[0].dtype), _stream()), "mm_pack_t")
+
+
+def rowsum(x: torch.Tensor, ld: int, rows: int, cols: int, out: torch.Tensor, accumulate: bool = False) -> None:
+    assert out.dtype == torch.float32 and out.numel() >= rows
+    lib = _lib.load()
+    with _Launch("rowsum", 2.0 * rows * cols):
+        _lib.check(lib.mm_rowsum(_ptr(x), ld, rows, cols, _ptr(out), int(accumulate), dtype_code(x.dtype), _stream()),
+                   "mm_rowsum")
+
+
+def reduce_partials(part: torch.Tensor, n_partials: int, stride: int, n: int, out: torch.Tensor,
+                    accumulate: bool = False, part_offset: int = 0) -> None:
+    assert part.dtype == torch.float32 and out.dtype == torch.float32 and out.numel() >= n
+    lib = _lib.load()
+    with _Launch("reduce_partials", 4.0 * n * n_partials):
+        _lib.check(lib.mm_reduce_partials(_ptr(part) + 4 * part_offset, n_partials, stride, n, _ptr(out),
+                                          int(accumulate), _stream()), "mm_reduce_partials")
+
+
+def layernorm_bwd_blocks() -> int:
+    return _lib.load().mm_layernorm_bwd_blocks()
+
+
+def layernorm_bwd(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, partials: torch.Tensor,
+                  dx: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None, eps: float = 1e-5) -> None:
+    """dx = resid + LayerNorm'(dy); partials [blocks, 2, dim] per-block (dgamma, dbeta) sums."""
+    dim = x.shape[-1]
+    rows = x.numel() // dim
+    for t in (x, gamma, dy, partials, dx, resid):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
+    assert dy.numel() == x.numel() and partials.numel() >= layernorm_bwd_blocks() * 2 * dim
+    lib = _lib.load()
+    with _Launch("layernorm_bwd", 4.0 * x.numel() * (2 + (dx is not None) + (resid is not None))):
+        _lib.check(lib.mm_layernorm_bwd(_ptr(x), _ptr(gamma), _ptr(dy), rows, dim, eps, _ptr(resid), _ptr(dx),
+                                        _ptr(partials), _stream()), "mm_layernorm_bwd")
+
+
+def softmax_bwd(scores: torch.Tensor, dprobs: torch.Tensor, ld_in: int, rows: int, rows_per_batch: int, n_keys: int,
+                dscores: torch.Tensor, ld_out: int, probs: Optional[torch.Tensor] = None,
+                kv_lens: Optional[torch.Tensor] = None, heads: int = 1) -> None:
+    assert scores.dtype == dprobs.dtype == torch.float32
+    assert kv_lens is None or kv_lens.dtype == torch.int32
+    assert probs is None or probs.dtype == dscores.dtype
+    lib = _lib.load()
+    with _Launch("softmax_bwd", 8.0 * rows * n_keys + 4.0 * rows * ld_out):
+        _lib.check(lib.mm_softmax_bwd(_ptr(scores), _ptr(dprobs), ld_in, rows, rows_per_batch, n_keys, _ptr(kv_lens),
+                                      heads, _ptr(probs), _ptr(dscores), ld_out, dtype_code(dscores.dtype), _stream()),
+                   "mm_softmax_bwd")
+
+
+def glu_bwd(pre: torch.Tensor, dy: torch.Tensor, rows: int, n: int, dpre: torch.Tensor, scale: float = 1.0) -> None:
+    assert pre.dtype == dy.dtype == torch.float32 and pre.is_contiguous() and dy.is_contiguous() and dpre.is_contiguous()
+    assert pre.numel() == rows * 2 * n and dy.numel() == rows * n and dpre.numel() == rows * 2 * n
+    lib = _lib.load()
+    with _Launch("glu_bwd", 16.0 * rows * n):
+        _lib.check(lib.mm_glu_bwd(_ptr(pre), _ptr(dy), rows, n, scale, _ptr(dpre), dtype_code(dpre.dtype), _stream()),
+                   "mm_glu_bwd")
+
+
+def gate_bwd(z: torch.Tensor, dres_tbc: torch.Tensor, text: torch.Tensor, attn: torch.Tensor, B: int, T: int, d: int,
+             dz: torch.Tensor, dcat: torch.Tensor) -> None:
+    for t in (z, dres_tbc, text, attn, dcat):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    assert dcat.numel() == B * T * 2 * d and dz.numel() == B * T * d and dz.is_contiguous()
+    lib = _lib.load()
+    with _Launch("gate_bwd", 26.0 * B * T * d):
+        _lib.check(lib.mm_gate_bwd(_ptr(z), _ptr(dres_tbc), _ptr(text), _ptr(attn), B, T, d, _ptr(dz), _ptr(dcat),
+                                   dtype_code(dz.dtype), _stream()), "mm_gate_bwd")
+
+
+def tbc_to_btc(x_tbc: torch.Tensor, B: int, T: int, d: int, out: torch.Tensor) -> None:
+    assert x_tbc.dtype == out.dtype == torch.float32 and x_tbc.is_contiguous() and out.is_contiguous()
+    lib = _lib.load()
+    with _Launch("tbc_to_btc", 8.0 * B * T * d):
+        _lib.check(lib.mm_tbc_to_btc(_ptr(x_tbc), B, T, d, _ptr(out), _stream()), "mm_tbc_to_btc")
+
+
+def col2im_k5s2(dcol: torch.Tensor, B: int, t_out: int, t_in: int, C_: int, dx: torch.Tensor) -> None:
+    assert dcol.dtype == dx.dtype == torch.float32 and dcol.is_contiguous() and dx.is_contiguous()
+    assert dcol.numel() == B * t_out * 5 * C_ and dx.numel() == B * t_in * C_
+    lib = _lib.load()
+    with _Launch("col2im_k5s2", 4.0 * (dcol.numel() + dx.numel())):
+        _lib.check(lib.mm_col2im_k5s2(_ptr(dcol), B, t_out, t_in, C_, _ptr(dx), _stream()), "mm_col2im_k5s2")
+
+
+def grad_clip_coef(grad: torch.Tensor, grad_scale: float, max_norm: float, partials: torch.Tensor,
+                   norm_coef: torch.Tensor) -> None:
+    """norm_coef[0] = ||grad_scale * grad||, norm_coef[1] = grad_scale * min(1, max_norm / (norm + 1e-6))."""
+    assert grad.dtype == torch.float32 and grad.is_contiguous() and norm_coef.numel() >= 2
+    lib = _lib.load()
+    assert partials.numel() >= lib.mm_sumsq_blocks()
+    with _Launch("grad_clip_coef", 4.0 * grad.numel()):
+        _lib.check(lib.mm_grad_clip_coef(_ptr(grad), grad.numel(), grad_scale, max_norm, _ptr(partials),
+                                         _ptr(norm_coef), _stream()), "mm_grad_clip_coef")
+    global launch_count
+    launch_count += 1   # two kernels
+
+
+def adam(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, *, lr: float,
+         betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, step: int = 1,
+         norm_coef: Optional[torch.Tensor] = None) -> None:
+    """fairseq Adam step on flat fp32 buffers (in place)."""
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == param.numel()
+    lib = _lib.load()
+    with _Launch("adam", 28.0 * param.numel()):
+        _lib.check(lib.mm_adam(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), lr, betas[0],
+                               betas[1], eps, weight_decay, step, _ptr(norm_coef), _stream()), "mm_adam")

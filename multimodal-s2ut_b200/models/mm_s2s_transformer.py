@@ -155,6 +155,14 @@ class MM_S2STransformerEncoder(S2TTransformerEncoderParams):
             self._engine = EncoderEngine(self)
         return self._engine
 
+    def train_engine(self):
+        """Engine of the training-step variant (activations kept, backward kernels, flat fp32 parameters)."""
+        from ..training import TrainEngine
+
+        if not isinstance(self._engine, TrainEngine):
+            self._engine = TrainEngine(self, getattr(self, "op_dtype", None))
+        return self._engine
+
     def _apply(self, fn, *a, **k):  # .to()/.cuda()/.half(): packed device weights are stale
         self._engine = None
         return super()._apply(fn, *a, **k)
@@ -182,6 +190,16 @@ class MM_S2STransformerEncoder(S2TTransformerEncoderParams):
                     drop_audio = True        # reference: NameError at :500; intent = zero the speech states
                 else:
                     drop_image = True        # (:504-505) every image tensor zeroed
+        if self.training and torch.is_grad_enabled():
+            # training step: autograd reaches the path through one Function on the fused states
+            from ..training import EncoderOutGrad
+
+            eng = self.train_engine()
+            out = eng.forward_train(src_tokens, src_lengths, imgs_list if fuse else [], img_masks_list if fuse else [],
+                                    drop_audio=drop_audio, drop_image=drop_image)
+            trigger = torch.zeros((), device=eng.device, requires_grad=True)
+            out["encoder_out"] = [EncoderOutGrad.apply(trigger, out["encoder_out"][0], eng)]
+            return out
         return eng.forward(src_tokens, src_lengths, imgs_list if fuse else [], img_masks_list if fuse else [],
                            return_all_hiddens=return_all_hiddens, drop_audio=drop_audio, drop_image=drop_image,
                            training=self.training)

@@ -1,0 +1,634 @@
+"""Training-step variant of the fbank -> fused-encoder path (BASELINE configs[2]): forward that keeps the
+activations, backward down to every encoder parameter, gradient all-reduce, fairseq Adam.
+
+What the reference does here is plain PyTorch autograd over the modules of the path (fairseq ``train_step``:
+``loss.backward()`` -> DDP all-reduce -> ``clip_grad_norm_`` -> ``Adam.step``; scripts/textless/1_train.sh).  The
+boundary of THIS path is the gradient of the fused encoder states, ``d loss / d encoder_out[0]`` ``[T, B, C]``, which
+the decoder + criterion hand back ("the encoder nn.Module.forward and an autograd.Function wrapper for
+training").  ``TrainEngine.backward`` turns it into the gradient of every encoder parameter:
+
+  fusion   (mm_s2s_transformer.py:594-622, fuse.py:65-117 / :145-167)  gate -> proj -> P V -> softmax -> q k^T -> q / k|v
+            projections -> image pre-norm parameters
+  encoder  final LayerNorm -> L x [fc2 -> ReLU -> fc1 -> LN2 ; out_proj -> self-attention -> QKV -> LN1]
+  front    x sqrt(d) -> GLU -> Conv1d #2 (col2im) -> GLU -> Conv1d #1          (fbank / CMVN have no parameters)
+
+Every contraction is the tcgen05 GEMM of the forward pass (``mm_gemm``): dgrad = dY W uses a transposed 16-bit copy
+of the weight, wgrad = dY^T X contracts over tokens with split-K partials (``mm_pack_t`` makes the token-contiguous
+operand copies, ``mm_reduce_partials`` sums them deterministically).  Attention backward recomputes the scores per
+head (S = q k^T, dP = dO v^T -> ``mm_softmax_bwd`` -> dV = P^T dO, dK = dS^T q, dQ = dS k).  fp32 residual-stream
+gradients, 16-bit GEMM operands, fp32 parameter gradients / Adam state in flat buffers.
+
+Parameters and gradients live in two flat fp32 buffers (``flat_p`` / ``flat_g``; every ``nn.Parameter`` of the encoder
+is re-pointed to a view), ordered so that the packed layouts the kernels produce (q|k|v, k|v, LayerNorm weight|bias)
+are contiguous slices.  ``all_reduce_grads`` runs NCCL (or gloo) over ``flat_g`` in buckets; ``adam_step`` is one kernel.
+
+Not built (raises): element-wise dropout in training mode, image key masks, several image-feature types, and the
+device feature store in the backward pass.  Modality dropout (per-batch image zeroing) works.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import kernels as K
+from .engine import EncoderEngine, _even, _round_up, sub_len
+from .feature_store import StoredImages
+
+
+def _split_k(n: int, kin: int, mp: int) -> int:
+    """Number of K-splits of a wgrad GEMM [n, kin] contracting over mp tokens: fill the 74 CTA pairs."""
+    tiles = ((n + 255) // 256) * ((kin + 255) // 256)
+    s = 1
+    while s < 16 and tiles * s < 74 and (mp // 64) % (2 * s) == 0:
+        s *= 2
+    return s
+
+
+def all_reduce_flat(flat: torch.Tensor, bucket_elems: int = 8 * 1024 * 1024) -> int:
+    """Bucketed asynchronous SUM all-reduce of a flat gradient buffer over the default process group."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 1
+    works = [dist.all_reduce(flat[o:o + bucket_elems], op=dist.ReduceOp.SUM, async_op=True)
+             for o in range(0, flat.numel(), bucket_elems)]
+    for wk in works:
+        wk.wait()
+    return dist.get_world_size()
+
+
+class EncoderOutGrad(torch.autograd.Function):
+    """Autograd boundary of the path: identity on the fused states in forward; in backward the incoming
+    ``d loss / d encoder_out`` is handed to ``TrainEngine.backward`` which fills the parameters' ``.grad``."""
+
+    @staticmethod
+    def forward(ctx, trigger, out, eng):
+        ctx.eng = eng
+        return out.view_as(out)
+
+    @staticmethod
+    def backward(ctx, grad):
+        eng = ctx.eng
+        acc = eng.grads_attached()
+        eng.backward(grad, accumulate=acc)
+        if not acc:
+            eng.attach_grads()
+        return None, None, None
+
+
+class TrainEngine(EncoderEngine):
+    def __init__(self, enc, op_dtype: Optional[torch.dtype] = None, block_n: int = 256):
+        self._flatten(enc)
+        super().__init__(enc, op_dtype, block_n)
+        self.fused_ln = False          # per-sub-layer residual buffers are kept for the backward pass
+        self._saved = None
+        self.step_count = 0
+        n = self.flat_p.numel()
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.norm_coef = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self._sumsq_partials = torch.zeros(K._lib.load().mm_sumsq_blocks(), dtype=torch.float32, device=self.device)
+        self._ln_blocks = K.layernorm_bwd_blocks()
+        self._pack_train()
+
+    # ------------------------------------------------------------------------------------------
+    # flat parameter / gradient buffers
+    # ------------------------------------------------------------------------------------------
+    def _flatten(self, enc) -> None:
+        order: List[torch.nn.Parameter] = []
+        seen = set()
+
+        def add(*ps):
+            for p in ps:
+                if p is not None and id(p) not in seen:
+                    seen.add(id(p))
+                    order.append(p)
+
+        for c in enc.subsample.conv_layers:
+            add(c.weight, c.bias)
+        for L in enc.transformer_layers:
+            a = L.self_attn
+            add(L.self_attn_layer_norm.weight, L.self_attn_layer_norm.bias)
+            add(a.q_proj.weight, a.k_proj.weight, a.v_proj.weight, a.q_proj.bias, a.k_proj.bias, a.v_proj.bias)
+            add(a.out_proj.weight, a.out_proj.bias, L.final_layer_norm.weight, L.final_layer_norm.bias)
+            add(L.fc1.weight, L.fc1.bias, L.fc2.weight, L.fc2.bias)
+        add(enc.layer_norm.weight, enc.layer_norm.bias)
+        if enc.multimodal_translation_flag and enc.multimodal_attention_type is not None:
+            for j in range(len(enc.gate_denses)):
+                if enc.multimodal_attention_type == "selective_attention":
+                    s = enc.selective_attns[j]
+                    add(s.q_proj.weight, s.q_proj.bias, s.k_proj.weight, s.v_proj.weight, s.k_proj.bias, s.v_proj.bias,
+                        s.proj.weight, s.proj.bias)
+                else:
+                    m = enc.multimodal_attns[j]
+                    add(m.q_proj_weight, m.k_proj_weight, m.v_proj_weight, m.in_proj_bias, m.bias_k, m.bias_v,
+                        m.out_proj.weight, m.out_proj.bias)
+                add(enc.gate_denses[j].weight, enc.gate_denses[j].bias)
+            pn = enc.image_pre_norm_module
+            if not isinstance(pn, torch.nn.Identity):
+                add(pn.weight, pn.bias)
+        add(*enc.parameters())     # anything else (the reference's always-present unused projections): zero gradient
+        dev = order[0].device
+        if self._require_cuda and dev.type != "cuda":
+            raise RuntimeError("TrainEngine needs the encoder on a CUDA device (no CPU fallback)")
+        offs, total = [], 0
+        for p in order:
+            offs.append(total)
+            total += _round_up(p.numel(), 4)
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._slices: Dict[int, Tuple[int, int]] = {}
+        with torch.no_grad():
+            for p, o in zip(order, offs):
+                n = p.numel()
+                self.flat_p[o:o + n].copy_(p.detach().reshape(-1).float())
+                p.data = self.flat_p[o:o + n].view(p.shape)
+                p.grad = self.flat_g[o:o + n].view(p.shape)
+                self._slices[id(p)] = (o, n)
+        self.params = order
+
+    def g(self, *params) -> torch.Tensor:
+        """Flat fp32 gradient slice spanning the given (adjacent, in this order) parameters."""
+        o0, n0 = self._slices[id(params[0])]
+        end = o0 + n0
+        for p in params[1:]:
+            o, n = self._slices[id(p)]
+            assert o == end, "parameters are not adjacent in the flat buffer"
+            end = o + n
+        return self.flat_g[o0:end]
+
+    def w(self, *params) -> torch.Tensor:
+        o0, n0 = self._slices[id(params[0])]
+        end = o0 + n0
+        for p in params[1:]:
+            o, n = self._slices[id(p)]
+            assert o == end
+            end = o + n
+        return self.flat_p[o0:end]
+
+    # ------------------------------------------------------------------------------------------
+    # 16-bit operand copies for the backward pass (transposed weights, un-permuted conv weights)
+    # ------------------------------------------------------------------------------------------
+    def _wt(self, name: str, src_f32: torch.Tensor, n: int, k: int) -> torch.Tensor:
+        """[k, n] 16-bit transposed copy of the fp32 weight [n, k] (the W operand of a dgrad GEMM)."""
+        t = self.buf("wt_" + name, (k, _even(n)), self.op_dtype, zero=True)
+        K.pack_t(src_f32, rows=n, cols=k, in_ld=k, out_t=t, t_ld=_even(n))
+        return t
+
+    def _pack_train(self) -> None:
+        enc, d = self.enc, self.d
+        self.conv_bwd = []
+        for i, c in enumerate(enc.subsample.conv_layers):
+            cout, cin, k = c.weight.shape
+            wp = self.w(c.weight).view(cout, cin, k).permute(0, 2, 1).reshape(cout, k * cin).contiguous()  # layout glue
+            w_plain = self.buf(f"convw_plain{i}", (cout, k * cin), self.op_dtype)
+            K.convert(wp, w_plain)
+            self.conv_bwd.append(dict(w=w_plain, wt=self._wt(f"conv{i}", wp, cout, k * cin), b=self.w(c.bias),
+                                      p=c, cin=cin, cout=cout, k=k))
+        self.layers_bwd = []
+        for i, L in enumerate(enc.transformer_layers):
+            a = L.self_attn
+            self.layers_bwd.append(dict(
+                wqkv_t=self._wt(f"qkv{i}", self.w(a.q_proj.weight, a.k_proj.weight, a.v_proj.weight), 3 * d, d),
+                wo_t=self._wt(f"o{i}", self.w(a.out_proj.weight), d, d),
+                w1_t=self._wt(f"fc1{i}", self.w(L.fc1.weight), self.ffn, d),
+                w2_t=self._wt(f"fc2{i}", self.w(L.fc2.weight), d, self.ffn), mod=L))
+        self.fusion_bwd = []
+        for j, F in enumerate(self.fusion):
+            dk = F["dk"]
+            if enc.multimodal_attention_type == "selective_attention":
+                s = enc.selective_attns[j]
+                ps = dict(wq=(s.q_proj.weight,), bq=(s.q_proj.bias,), wkv=(s.k_proj.weight, s.v_proj.weight),
+                          bkv=(s.k_proj.bias, s.v_proj.bias), wp=(s.proj.weight,), bp=(s.proj.bias,), bias_kv=None)
+            else:
+                m = enc.multimodal_attns[j]
+                ps = dict(wq=(m.q_proj_weight,), wkv=(m.k_proj_weight, m.v_proj_weight), in_b=(m.in_proj_bias,),
+                          wp=(m.out_proj.weight,), bp=(m.out_proj.bias,), bias_kv=(m.bias_k, m.bias_v))
+            gd = enc.gate_denses[j]
+            ps.update(wg=(gd.weight,), bg=(gd.bias,))
+            self.fusion_bwd.append(dict(
+                p=ps, wq_t=self._wt(f"fq{j}", self.w(*ps["wq"]), d, d), wkv_t=self._wt(f"fkv{j}", self.w(*ps["wkv"]), 2 * d, dk),
+                wp_t=self._wt(f"fp{j}", self.w(*ps["wp"]), d, d), wg_t=self._wt(f"fg{j}", self.w(*ps["wg"]), d, 2 * d)))
+
+    def repack(self) -> None:
+        """Refresh every 16-bit operand copy from the fp32 master parameters (after an optimizer step)."""
+        self._pack()
+        self._pack_train()
+        for j, F in enumerate(self.fusion):     # learned extra key / value rows live in the cached K / V^T workspaces
+            if F["bias_kv"] is None:
+                continue
+            for (name, shape, _), t in self._buf.items():
+                if name == f"k{j}":
+                    t[:, shape[1] - 1, :] = F["bias_kv"][0]
+                elif name == f"vt_img{j}":
+                    for (n2, s2, _2) in self._buf:
+                        if n2 == f"k{j}" and s2[0] == shape[0]:
+                            t[:, :, s2[1] - 1] = F["bias_kv"][1]
+
+    def grads_attached(self) -> bool:
+        """True when every ``param.grad`` still is this engine's view of ``flat_g`` (an optimizer's
+        ``zero_grad(set_to_none=True)`` detaches them)."""
+        return all(p.grad is not None and p.grad.data_ptr() == self.flat_g.data_ptr() + 4 * self._slices[id(p)][0]
+                   for p in self.params)
+
+    def attach_grads(self) -> None:
+        for p in self.params:
+            o, n = self._slices[id(p)]
+            p.grad = self.flat_g[o:o + n].view(p.shape)
+
+    # ------------------------------------------------------------------------------------------
+    # forward (activations kept)
+    # ------------------------------------------------------------------------------------------
+    def _layer_train(self, i: int, x_in: torch.Tensor, B: int, T: int, seq_lens: torch.Tensor):
+        L, d, M, op, bn = self.layers[i], self.d, B * T, self.op_dtype, self.block_n
+        s = dict(x_in=x_in, h1=self.buf(f"t_h1_{i}", (M, d), op), qkv=self.buf(f"t_qkv_{i}", (M, 3 * d), op),
+                 att=self.buf(f"t_att_{i}", (M, d), op), x_mid=self.buf(f"t_xmid_{i}", (M, d), torch.float32),
+                 h2=self.buf(f"t_h2_{i}", (M, d), op), f=self.buf(f"t_f_{i}", (M, self.ffn), op),
+                 x_out=self.buf(f"t_xout_{i}", (M, d), torch.float32))
+        K.layernorm(x_in, L["ln1_g"], L["ln1_b"], out_op=s["h1"])
+        K.gemm(a0=s["h1"], a0_ld=d, rows=M, w=L["wqkv"], n=3 * d, k=d, mode=K.EPI_OP, bias=L["bqkv"], scale=64 ** -0.5,
+               scale_cols=d, out0=s["qkv"], out0_ld=3 * d, block_n=bn)
+        K.self_attention(s["qkv"], seq_lens, B, T, self.heads, s["att"])
+        K.gemm(a0=s["att"], a0_ld=d, rows=M, w=L["wo"], n=d, k=d, mode=K.EPI_RESID_F32, bias=L["bo"], aux0=x_in,
+               aux_ld=d, out0=s["x_mid"], out0_ld=d, block_n=bn)
+        K.layernorm(s["x_mid"], L["ln2_g"], L["ln2_b"], out_op=s["h2"])
+        K.gemm(a0=s["h2"], a0_ld=d, rows=M, w=L["w1"], n=self.ffn, k=d, mode=K.EPI_RELU_OP, bias=L["b1"], out0=s["f"],
+               out0_ld=self.ffn, block_n=bn)
+        K.gemm(a0=s["f"], a0_ld=self.ffn, rows=M, w=L["w2"], n=d, k=self.ffn, mode=K.EPI_RESID_F32, bias=L["b2"],
+               aux0=s["x_mid"], aux_ld=d, out0=s["x_out"], out0_ld=d, block_n=bn)
+        return s
+
+    @torch.no_grad()
+    def forward_train(self, src_tokens, src_lengths, imgs_list: List[torch.Tensor], img_masks_list: List,
+                      drop_audio: bool = False, drop_image: bool = False):
+        enc = self.enc
+        if max(enc.dropout_p, getattr(enc, "SA_image_dropout", 0.0), getattr(enc, "SA_text_dropout", 0.0),
+               getattr(enc, "SA_attention_dropout", 0.0)) > 0:
+            raise NotImplementedError("element-wise dropout masks are not built: set the dropout probabilities to 0 "
+                                      "(modality dropout is supported)")
+        if len(imgs_list) > 1:
+            raise NotImplementedError("the backward pass handles one image-feature type")
+        if any(m is not None for m in img_masks_list):
+            raise NotImplementedError("image key masks are not supported in the backward pass")
+        if drop_audio:
+            raise NotImplementedError("audio-drop branch (broken in the reference, :500) has no backward here")
+        x1, m, seq_lens, _ = self.frontend(src_tokens, src_lengths)
+        B = x1.shape[0]
+        x, T = self.subsample(x1, m, seq_lens)
+        M, d = B * T, self.d
+        saved = dict(B=B, T=T, m=m, x1=x1, seq_lens=seq_lens, layers=[], fused=False)
+        for i in range(self.n_layers):
+            s = self._layer_train(i, x, B, T, seq_lens)
+            saved["layers"].append(s)
+            x = s["x_out"]
+        text_f32 = self.buf("text_f32", (M, d), torch.float32)
+        text_op = self.buf("text_op", (M, d), self.op_dtype)
+        K.layernorm(x, self.ln_g, self.ln_b, out_op=text_op, out_f32=text_f32)
+        saved["x_final"] = x
+        mask = torch.empty(B, T, dtype=torch.bool, device=self.device)
+        K.padding_mask(seq_lens, T, mask)
+        if imgs_list and self.fusion:
+            img = imgs_list[0]
+            if isinstance(img, StoredImages):
+                raise NotImplementedError("ImageFeatureStore batches are forward-only")
+            if drop_image:
+                img = torch.zeros(tuple(img.shape), dtype=torch.float32, device=self.device)
+            img = img.to(self.device, non_blocking=True).float().contiguous()
+            out = torch.empty(T, B, d, dtype=torch.float32, device=self.device)
+            self.fuse(0, text_f32, text_op, img, None, B, T, out)
+            saved.update(fused=True, img=img)
+        else:
+            out = text_f32.view(B, T, d).transpose(0, 1).contiguous()
+        self._saved = saved
+        return {"encoder_out": [out], "encoder_padding_mask": [mask], "encoder_embedding": [], "encoder_states": [],
+                "src_tokens": [], "src_lengths": []}
+
+    # ------------------------------------------------------------------------------------------
+    # backward building blocks
+    # ------------------------------------------------------------------------------------------
+    def _mp(self, M: int) -> int:
+        return _round_up(M, 1024)
+
+    def _wgrad(self, dyt: torch.Tensor, xt: torch.Tensor, n: int, kin: int, mp: int, out: torch.Tensor,
+               accumulate: bool) -> None:
+        """out [n, kin] (+)= dY^T X from the token-contiguous copies dyt [n, mp], xt [kin, mp] (zero beyond M)."""
+        S = _split_k(n, kin, mp)
+        chunk = mp // S
+        part = self.buf("wgrad_part", (16 * 1024 * 1024,), torch.float32)
+        if S * n * kin > part.numel():
+            part = self.buf(f"wgrad_part_{S * n * kin}", (S * n * kin,), torch.float32)
+        K.gemm(a0=dyt, a0_ld=dyt.shape[-1], a0_bs=chunk, rows=n, batches=S, w=xt, w_ld=xt.shape[-1], w_bs=chunk,
+               w_batched=True, n=kin, k=chunk, mode=K.EPI_F32, out0=part, out0_ld=kin, out0_bs=n * kin,
+               block_n=self.block_n)
+        K.reduce_partials(part, S, n * kin, n * kin, out, accumulate)
+
+    def _linear_bwd(self, name: str, dy, dy_is_f32: bool, dy_ld: int, x_op: torch.Tensor, M: int, n: int, kin: int,
+                    gw: torch.Tensor, gb: Optional[torch.Tensor], accumulate: bool, dy_op: Optional[torch.Tensor] = None,
+                    mask: Optional[torch.Tensor] = None, scale: float = 1.0) -> torch.Tensor:
+        """Parameter gradients of y = x W^T + b:  gw [n, kin] (+)= dy^T x, gb [n] (+)= column sums of dy.
+        Writes the 16-bit copy of dy (masked / scaled) into dy_op when given.  Returns dy_op."""
+        mp = self._mp(M)
+        dyt = self.buf(f"t_{n}", (n, mp), self.op_dtype, zero=True)
+        xt = self.buf(f"tx_{kin}", (kin, mp), self.op_dtype, zero=True)
+        K.pack_t(dy, rows=M, cols=n, in_ld=dy_ld, out_n=dy_op, n_ld=n, out_t=dyt, t_ld=mp, mask=mask,
+                 mask_ld=n if mask is not None else 0, scale=scale)
+        K.pack_t(x_op, rows=M, cols=kin, in_ld=x_op.stride(0), out_t=xt, t_ld=mp)
+        self._wgrad(dyt, xt, n, kin, mp, gw, accumulate)
+        if gb is not None:
+            K.rowsum(dyt, mp, n, M, gb, accumulate)
+        return dy_op
+
+    def _ln_param_grads(self, part: torch.Tensor, dim: int, gwb: torch.Tensor, accumulate: bool) -> None:
+        K.reduce_partials(part, self._ln_blocks, 2 * dim, 2 * dim, gwb, accumulate)
+
+    # ------------------------------------------------------------------------------------------
+    # backward
+    # ------------------------------------------------------------------------------------------
+    def _attention_bwd(self, s: dict, datt: torch.Tensor, dqkv: torch.Tensor, B: int, T: int,
+                       seq_lens: torch.Tensor) -> None:
+        """dqkv [M, 3d] (16-bit; q part already x head_dim^-0.5) from datt [M, d] and the saved q|k|v."""
+        d, H, op, bn = self.d, self.heads, self.op_dtype, self.block_n
+        Tp = _round_up(T, 64)
+        BH = B * H
+        qkv = s["qkv"]
+        hm = lambda name: self.buf(name, (BH, Tp, 64), op, zero=True)       # head-major [b, h][t][64]
+        ht = lambda name: self.buf(name, (BH, 64, Tp), op, zero=True)       # transposed  [b, h][64][t]
+        Qh, Kh, Vh, dOh = hm("a_Qh"), hm("a_Kh"), hm("a_Vh"), hm("a_dOh")
+        Qt, Kt, dOt = ht("a_Qt"), ht("a_Kt"), ht("a_dOt")
+        split = dict(rows=T, cols=64, batches=BH, nb1=H, in_bs1=64, n_ld=64, n_bs0=H * Tp * 64, n_bs1=Tp * 64,
+                     t_ld=Tp, t_bs0=H * 64 * Tp, t_bs1=64 * Tp, t_cols_pad=Tp)
+        K.pack_t(qkv, in_ld=3 * d, in_bs0=T * 3 * d, out_n=Qh, out_t=Qt, **split)
+        K.pack_t(qkv[:, d:], in_ld=3 * d, in_bs0=T * 3 * d, out_n=Kh, out_t=Kt, **split)
+        K.pack_t(qkv[:, 2 * d:], in_ld=3 * d, in_bs0=T * 3 * d, out_n=Vh, **{k: v for k, v in split.items()
+                                                                          if not k.startswith("t_")})
+        K.pack_t(datt, in_ld=d, in_bs0=T * d, out_n=dOh, out_t=dOt, **split)
+        S = self.buf("a_S", (BH, Tp, Tp), torch.float32)
+        dP = self.buf("a_dP", (BH, Tp, Tp), torch.float32)
+        sc = dict(rows=Tp, batches=BH, a0_ld=64, a0_bs=Tp * 64, w_ld=64, w_bs=Tp * 64, w_batched=True, n=T, k=64,
+                  mode=K.EPI_F32, out0_ld=Tp, out0_bs=Tp * Tp, block_n=bn)
+        K.gemm(a0=Qh, w=Kh, out0=S, **sc)
+        K.gemm(a0=dOh, w=Vh, out0=dP, **sc)
+        P = self.buf("a_P", (BH, Tp, Tp), op)
+        dS = self.buf("a_dS", (BH, Tp, Tp), op)
+        K.softmax_bwd(S, dP, Tp, BH * Tp, Tp, T, dS, Tp, probs=P, kv_lens=seq_lens, heads=H)
+        Pt = self.buf("a_Pt", (BH, Tp, Tp), op)
+        dSt = self.buf("a_dSt", (BH, Tp, Tp), op)
+        tr = dict(rows=Tp, cols=Tp, in_ld=Tp, batches=BH, in_bs0=Tp * Tp, t_ld=Tp, t_bs0=Tp * Tp, t_cols_pad=Tp)
+        K.pack_t(P, out_t=Pt, **tr)
+        K.pack_t(dS, out_t=dSt, **tr)
+        dQh, dKh, dVh = hm("a_dQh"), hm("a_dKh"), hm("a_dVh")
+        og = dict(rows=T, batches=BH, a0_ld=Tp, a0_bs=Tp * Tp, w_ld=Tp, w_bs=64 * Tp, w_batched=True, n=64, k=Tp,
+                  mode=K.EPI_OP, out0_ld=64, out0_bs=Tp * 64, block_n=bn)
+        K.gemm(a0=Pt, w=dOt, out0=dVh, **og)
+        K.gemm(a0=dSt, w=Qt, out0=dKh, **og)
+        K.gemm(a0=dS, w=Kt, out0=dQh, scale=64 ** -0.5, scale_cols=64, **og)
+        merge = dict(rows=T, cols=64, in_ld=64, batches=BH, nb1=H, in_bs0=H * Tp * 64, in_bs1=Tp * 64, n_ld=3 * d,
+                     n_bs0=T * 3 * d, n_bs1=64)
+        K.pack_t(dQh, out_n=dqkv, **merge)
+        K.pack_t(dKh, out_n=dqkv[:, d:], **merge)
+        K.pack_t(dVh, out_n=dqkv[:, 2 * d:], **merge)
+
+    def _layer_bwd(self, i: int, g: torch.Tensor, B: int, T: int, seq_lens: torch.Tensor, accumulate: bool) -> torch.Tensor:
+        """g = d loss / d x_out [M, d] fp32 (overwritten); returns d loss / d x_in (same buffer)."""
+        s, Lb, L = self._saved["layers"][i], self.layers_bwd[i], self.layers[i]
+        mod = Lb["mod"]
+        a = mod.self_attn
+        d, ffn, M, op, bn = self.d, self.ffn, B * T, self.op_dtype, self.block_n
+        lnp = self.buf("ln_part", (self._ln_blocks * 2 * max(d, 1024),), torch.float32)
+        # ---- FFN: x_out = x_mid + fc2(relu(fc1(LN2(x_mid))))
+        g_op = self.buf("b_g_op", (M, d), op)
+        self._linear_bwd("fc2", g, True, d, s["f"], M, d, ffn, self.g(mod.fc2.weight), self.g(mod.fc2.bias), accumulate,
+                         dy_op=g_op)
+        dF = self.buf("b_dF", (M, ffn), op)
+        K.gemm(a0=g_op, a0_ld=d, rows=M, w=Lb["w2_t"], n=ffn, k=d, mode=K.EPI_OP, out0=dF, out0_ld=ffn, block_n=bn)
+        # ReLU mask applied while packing; dF is rewritten in place (masked) for the dgrad GEMM below
+        self._linear_bwd("fc1", dF, False, ffn, s["h2"], M, ffn, d, self.g(mod.fc1.weight), self.g(mod.fc1.bias),
+                         accumulate, dy_op=dF, mask=s["f"])
+        dh = self.buf("b_dh", (M, d), torch.float32)
+        K.gemm(a0=dF, a0_ld=ffn, rows=M, w=Lb["w1_t"], n=d, k=ffn, mode=K.EPI_F32, out0=dh, out0_ld=d, block_n=bn)
+        K.layernorm_bwd(s["x_mid"], L["ln2_g"], dh, lnp, dx=g, resid=g)
+        self._ln_param_grads(lnp, d, self.g(mod.final_layer_norm.weight, mod.final_layer_norm.bias), accumulate)
+        # ---- attention: x_mid = x_in + out_proj(attn(LN1(x_in)))
+        self._linear_bwd("o", g, True, d, s["att"], M, d, d, self.g(a.out_proj.weight), self.g(a.out_proj.bias),
+                         accumulate, dy_op=g_op)
+        datt = self.buf("b_datt", (M, d), op)
+        K.gemm(a0=g_op, a0_ld=d, rows=M, w=Lb["wo_t"], n=d, k=d, mode=K.EPI_OP, out0=datt, out0_ld=d, block_n=bn)
+        dqkv = self.buf("b_dqkv", (M, 3 * d), op)
+        self._attention_bwd(s, datt, dqkv, B, T, seq_lens)
+        self._linear_bwd("qkv", dqkv, False, 3 * d, s["h1"], M, 3 * d, d,
+                         self.g(a.q_proj.weight, a.k_proj.weight, a.v_proj.weight),
+                         self.g(a.q_proj.bias, a.k_proj.bias, a.v_proj.bias), accumulate)
+        K.gemm(a0=dqkv, a0_ld=3 * d, rows=M, w=Lb["wqkv_t"], n=d, k=3 * d, mode=K.EPI_F32, out0=dh, out0_ld=d,
+               block_n=bn)
+        K.layernorm_bwd(s["x_in"], L["ln1_g"], dh, lnp, dx=g, resid=g)
+        self._ln_param_grads(lnp, d, self.g(mod.self_attn_layer_norm.weight, mod.self_attn_layer_norm.bias), accumulate)
+        return g
+
+    def _fusion_bwd(self, dres: torch.Tensor, gtext: torch.Tensor, B: int, T: int, accumulate: bool) -> None:
+        """dres [T, B, d] -> gtext [M, d] = d loss / d text (the final LayerNorm output) + fusion parameter grads."""
+        enc, F, Fb = self.enc, self.fusion[0], self.fusion_bwd[0]
+        ps = Fb["p"]
+        d, M, op, bn, dk = self.d, B * T, self.op_dtype, self.block_n, F["dk"]
+        img = self._saved["img"]
+        Tk_img = img.shape[1]
+        extra = 1 if F["bias_kv"] is not None else 0
+        Tk = Tk_img + extra
+        Tkp = _round_up(Tk, 8)
+        Tp = _round_up(T, 64)
+        text_f32, text_op = self.buf("text_f32", (M, d), torch.float32), self.buf("text_op", (M, d), op)
+        o = self.buf("o_img", (M, d), op)
+        q = self.buf("q_img", (M, d), op)
+        kbuf = self.buf("k0", (B, Tk, d), op)
+        vt = self.buf("vt_img0", (B, d, Tkp), op)
+        S = self.buf("S0", (B, T, Tkp), torch.float32)
+        P = self.buf("P0", (B, T, Tkp), op)
+        img_op = self.buf("img_op0", (B * Tk_img, dk), op)
+        da_op = self.buf("f_da_op", (M, d), op)
+        if enc.use_selective_gate:
+            a_f32, a_op = self.buf("attn_f32", (M, d), torch.float32), self.buf("attn_op", (M, d), op)
+            z = self.buf("f_z", (M, d), torch.float32)
+            K.gemm(a0=a_op, a0_ld=d, a1=text_op, a1_ld=d, k_split=d, rows=M, w=F["wg"], n=d, k=2 * d, mode=K.EPI_F32,
+                   bias=F["bg"], out0=z, out0_ld=d, block_n=bn)
+            dz = self.buf("f_dz", (M, d), op)
+            dcat = self.buf("f_dcat", (M, 2 * d), torch.float32)
+            K.gate_bwd(z, dres, text_f32, a_f32, B, T, d, dz, dcat)
+            # gate Linear(2d -> d) on [attn | text]: wgrad with the concatenated operand built row-block by row-block
+            mp = self._mp(M)
+            dzt = self.buf(f"t_{d}", (d, mp), op, zero=True)
+            xt = self.buf(f"tx_{2 * d}", (2 * d, mp), op, zero=True)
+            K.pack_t(dz, rows=M, cols=d, in_ld=d, out_t=dzt, t_ld=mp)
+            K.pack_t(a_op, rows=M, cols=d, in_ld=d, out_t=xt, t_ld=mp)
+            K.pack_t(text_op, rows=M, cols=d, in_ld=d, out_t=xt[d:], t_ld=mp)
+            self._wgrad(dzt, xt, d, 2 * d, mp, self.g(*ps["wg"]), accumulate)
+            K.rowsum(dzt, mp, d, M, self.g(*ps["bg"]), accumulate)
+            K.gemm(a0=dz, a0_ld=d, rows=M, w=Fb["wg_t"], n=2 * d, k=d, mode=K.EPI_RESID_F32, aux0=dcat, aux_ld=2 * d,
+                   out0=dcat, out0_ld=2 * d, block_n=bn)
+            da, da_ld, dtext_part, dtext_ld = dcat, 2 * d, dcat[:, d:], 2 * d
+        else:   # res = text + attn
+            dflat = self.buf("f_dflat", (M, d), torch.float32)
+            K.tbc_to_btc(dres, B, T, d, dflat)
+            da, da_ld, dtext_part, dtext_ld = dflat, d, dflat, d
+        # ---- proj: attn = o Wp^T + bp
+        self._linear_bwd("fproj", da, True, da_ld, o, M, d, d, self.g(*ps["wp"]), self.g(*ps["bp"]), accumulate,
+                         dy_op=da_op)
+        do = self.buf("f_do", (M, d), op)
+        K.gemm(a0=da_op, a0_ld=d, rows=M, w=Fb["wp_t"], n=d, k=d, mode=K.EPI_OP, out0=do, out0_ld=d, block_n=bn)
+        # ---- o = P V ; P = softmax(q k^T)
+        vbuf = self.buf("f_v", (B, Tkp, d), op)
+        K.pack_t(vt, rows=d, cols=Tkp, in_ld=Tkp, batches=B, in_bs0=d * Tkp, out_t=vbuf, t_ld=d, t_bs0=Tkp * d,
+                 t_cols_pad=d)
+        dP = self.buf("f_dP", (B, T, Tkp), torch.float32)
+        K.gemm(a0=do, a0_ld=d, a0_bs=T * d, rows=T, batches=B, w=vbuf, w_ld=d, w_bs=Tkp * d, w_batched=True, n=Tk, k=d,
+               mode=K.EPI_F32, out0=dP, out0_ld=Tkp, out0_bs=T * Tkp, block_n=bn)
+        dS = self.buf("f_dS", (B, T, Tkp), op)
+        K.softmax_bwd(S, dP, Tkp, M, T, Tk, dS, Tkp)
+        Pt = self.buf("f_Pt", (B, Tkp, Tp), op, zero=True)
+        dSt = self.buf("f_dSt", (B, Tkp, Tp), op, zero=True)
+        dot = self.buf("f_dot", (B, d, Tp), op, zero=True)
+        qt = self.buf("f_qt", (B, d, Tp), op, zero=True)
+        kt = self.buf("f_kt", (B, d, Tkp), op, zero=True)
+        tr = dict(rows=T, cols=Tkp, in_ld=Tkp, batches=B, in_bs0=T * Tkp, t_ld=Tp, t_bs0=Tkp * Tp, t_cols_pad=Tp)
+        K.pack_t(P, out_t=Pt, **tr)
+        K.pack_t(dS, out_t=dSt, **tr)
+        tq = dict(rows=T, cols=d, in_ld=d, batches=B, in_bs0=T * d, t_ld=Tp, t_bs0=d * Tp, t_cols_pad=Tp)
+        K.pack_t(do, out_t=dot, **tq)
+        K.pack_t(q, out_t=qt, **tq)
+        K.pack_t(kbuf, rows=Tk, cols=d, in_ld=d, batches=B, in_bs0=Tk * d, out_t=kt, t_ld=Tkp, t_bs0=d * Tkp,
+                 t_cols_pad=Tkp)
+        dkv = self.buf("f_dkv", (B, Tk, 2 * d), op)
+        kvg = dict(rows=Tk, batches=B, a0_ld=Tp, a0_bs=Tkp * Tp, w_ld=Tp, w_bs=d * Tp, w_batched=True, n=d, k=Tp,
+                   mode=K.EPI_OP, out0_ld=2 * d, out0_bs=Tk * 2 * d, block_n=bn)
+        K.gemm(a0=dSt, w=qt, out0=dkv, **kvg)                        # dK = dS^T q
+        K.gemm(a0=Pt, w=dot, out0=dkv.view(-1)[d:], **kvg)           # dV = P^T dO
+        dq = self.buf("f_dq", (M, d), op)
+        K.gemm(a0=dS, a0_ld=Tkp, a0_bs=T * Tkp, rows=T, batches=B, w=kt, w_ld=Tkp, w_bs=d * Tkp, w_batched=True, n=d,
+               k=Tkp, mode=K.EPI_OP, scale=d ** -0.5, scale_cols=d, out0=dq, out0_ld=d, out0_bs=T * d, block_n=bn)
+        # ---- q projection: parameter grads + text gradient
+        gbq = self.g(*ps["bq"]) if extra == 0 else self.g(*ps["in_b"])[:d]
+        self._linear_bwd("fq", dq, False, d, text_op, M, d, d, self.g(*ps["wq"]), gbq, accumulate)
+        K.gemm(a0=dq, a0_ld=d, rows=M, w=Fb["wq_t"], n=d, k=d, mode=K.EPI_RESID_F32, aux0=dtext_part, aux_ld=dtext_ld,
+               out0=gtext, out0_ld=d, block_n=bn)
+        # ---- k|v projection over the image tokens (the learned extra key/value row is excluded: zero column)
+        Tke = _even(Tk)
+        Mi = B * Tke
+        mpi = self._mp(Mi)
+        dkvt = self.buf(f"ti_{2 * d}", (2 * d, mpi), op, zero=True)
+        imt = self.buf(f"tix_{dk}", (dk, mpi), op, zero=True)
+        K.pack_t(dkv, rows=Tk_img, cols=2 * d, in_ld=2 * d, batches=B, in_bs0=Tk * 2 * d, out_t=dkvt, t_ld=mpi, t_bs0=Tke,
+                 t_cols_pad=Tke)
+        K.pack_t(img_op, rows=Tk_img, cols=dk, in_ld=dk, batches=B, in_bs0=Tk_img * dk, out_t=imt, t_ld=mpi, t_bs0=Tke,
+                 t_cols_pad=Tke)
+        self._wgrad(dkvt, imt, 2 * d, dk, mpi, self.g(*ps["wkv"]), accumulate)
+        gbkv = self.g(*ps["bkv"]) if extra == 0 else self.g(*ps["in_b"])[d:]
+        K.rowsum(dkvt, mpi, 2 * d, Mi, gbkv, accumulate)
+        if extra:   # learned bias_k | bias_v: key / value number Tk_img of every utterance
+            Bp = _round_up(B, 2)
+            bt = self.buf("f_bkv_t", (2 * d, Bp), op, zero=True)
+            K.pack_t(dkv.view(-1)[Tk_img * 2 * d:], rows=B, cols=2 * d, in_ld=Tk * 2 * d, out_t=bt, t_ld=Bp, t_cols_pad=Bp)
+            K.rowsum(bt, Bp, 2 * d, B, self.g(*ps["bias_kv"]), accumulate)
+        if self.img_ln is not None:
+            dimg = self.buf("f_dimg", (B * Tk_img, dk), torch.float32)
+            K.gemm(a0=dkv, a0_ld=2 * d, a0_bs=Tk * 2 * d, rows=Tk_img, batches=B, w=Fb["wkv_t"], n=dk, k=2 * d,
+                   mode=K.EPI_F32, out0=dimg, out0_ld=dk, out0_bs=Tk_img * dk, block_n=bn)
+            lnp = self.buf("ln_part", (self._ln_blocks * 2 * max(d, 1024),), torch.float32)
+            K.layernorm_bwd(img.view(B * Tk_img, dk), self.img_ln[0], dimg, lnp)
+            pn = enc.image_pre_norm_module
+            self._ln_param_grads(lnp, dk, self.g(pn.weight, pn.bias), accumulate)
+
+    def _conv_bwd(self, g: torch.Tensor, B: int, T: int, accumulate: bool) -> None:
+        """g = d loss / d x0 [B*T, d] (x0 = glu(conv2) * sqrt(d) + positions) -> conv parameter gradients."""
+        sv, op, bn, d = self._saved, self.op_dtype, self.block_n, self.d
+        c1, c2 = self.conv_bwd
+        m, x1 = sv["m"], sv["x1"]
+        m_alloc = x1.shape[1]
+        T1, mid = sub_len(m), c1["cout"] // 2
+        T1_alloc = _even(T1 + 4)
+        x2 = self.buf("x2", (B, T1_alloc, mid), op, zero=True)
+
+        def conv_param_grads(c, dpre, xin, in_ld, in_bs, Tout, kin):
+            Te = _even(Tout)
+            mp = self._mp(B * Te)
+            n = c["cout"]
+            dyt = self.buf(f"tc_{n}_{mp}", (n, mp), op, zero=True)
+            xt = self.buf(f"tcx_{kin}_{mp}", (kin, mp), op, zero=True)
+            K.pack_t(dpre, rows=Tout, cols=n, in_ld=n, batches=B, in_bs0=Tout * n, out_t=dyt, t_ld=mp, t_bs0=Te,
+                     t_cols_pad=Te)
+            K.pack_t(xin, rows=Tout, cols=kin, in_ld=in_ld, batches=B, in_bs0=in_bs, out_t=xt, t_ld=mp, t_bs0=Te,
+                     t_cols_pad=Te)
+            gw = self.buf(f"convgw_{n}_{kin}", (n, kin), torch.float32)
+            self._wgrad(dyt, xt, n, kin, mp, gw, False)
+            # layout glue: [cout, tap, cin] (GEMM operand order) -> Conv1d.weight [cout, cin, tap]
+            gview = gw.view(n, c["k"], c["cin"]).permute(0, 2, 1)
+            gflat = self.g(c["p"].weight).view(n, c["cin"], c["k"])
+            if accumulate:
+                gflat.add_(gview)
+            else:
+                gflat.copy_(gview)
+            K.rowsum(dyt, mp, n, B * Te, self.g(c["p"].bias), accumulate)
+
+        # ---- conv 2 + GLU (+ x sqrt(d))
+        M = B * T
+        pre2 = self.buf("c_pre2", (M, c2["cout"]), torch.float32)
+        K.gemm(a0=x2, a0_ld=2 * mid, a0_bs=T1_alloc * mid, rows=T, batches=B, w=c2["w"], n=c2["cout"], k=c2["k"] * mid,
+               mode=K.EPI_F32, bias=c2["b"], out0=pre2, out0_ld=c2["cout"], out0_bs=T * c2["cout"], block_n=bn)
+        dpre2 = self.buf("c_dpre2", (M, c2["cout"]), op)
+        K.glu_bwd(pre2, g, M, d, dpre2, scale=self.embed_scale)
+        conv_param_grads(c2, dpre2, x2, 2 * mid, T1_alloc * mid, T, c2["k"] * mid)
+        dcol = self.buf("c_dcol", (M, c2["k"] * mid), torch.float32)
+        K.gemm(a0=dpre2, a0_ld=c2["cout"], rows=M, w=c2["wt"], n=c2["k"] * mid, k=c2["cout"], mode=K.EPI_F32, out0=dcol,
+               out0_ld=c2["k"] * mid, block_n=bn)
+        dglu1 = self.buf("c_dglu1", (B * T1, mid), torch.float32)
+        K.col2im_k5s2(dcol, B, T, T1, mid, dglu1)
+        # ---- conv 1 + GLU
+        M1 = B * T1
+        pre1 = self.buf("c_pre1", (M1, c1["cout"]), torch.float32)
+        K.gemm(a0=x1, a0_ld=2 * c1["cin"], a0_bs=m_alloc * c1["cin"], rows=T1, batches=B, w=c1["w"], n=c1["cout"],
+               k=c1["k"] * c1["cin"], mode=K.EPI_F32, bias=c1["b"], out0=pre1, out0_ld=c1["cout"],
+               out0_bs=T1 * c1["cout"], block_n=bn)
+        dpre1 = self.buf("c_dpre1", (M1, c1["cout"]), op)
+        K.glu_bwd(pre1, dglu1, M1, mid, dpre1)
+        conv_param_grads(c1, dpre1, x1, 2 * c1["cin"], m_alloc * c1["cin"], T1, c1["k"] * c1["cin"])
+
+    @torch.no_grad()
+    def backward(self, grad_out: torch.Tensor, accumulate: bool = False) -> None:
+        """grad_out = d loss / d encoder_out[0]  [T, B, d] fp32.  Fills (or accumulates into) every ``param.grad``."""
+        sv = self._saved
+        if sv is None:
+            raise RuntimeError("backward() needs a preceding forward_train()")
+        B, T, d = sv["B"], sv["T"], self.d
+        M = B * T
+        grad_out = grad_out.to(device=self.device, dtype=torch.float32).contiguous()
+        assert tuple(grad_out.shape) == (T, B, d)
+        gtext = self.buf("b_gtext", (M, d), torch.float32)
+        if sv["fused"]:
+            self._fusion_bwd(grad_out, gtext, B, T, accumulate)
+        else:
+            K.tbc_to_btc(grad_out, B, T, d, gtext)
+        lnp = self.buf("ln_part", (self._ln_blocks * 2 * max(d, 1024),), torch.float32)
+        g = self.buf("b_g", (M, d), torch.float32)
+        K.layernorm_bwd(sv["x_final"], self.ln_g, gtext, lnp, dx=g)
+        self._ln_param_grads(lnp, d, self.g(self.enc.layer_norm.weight, self.enc.layer_norm.bias), accumulate)
+        for i in reversed(range(self.n_layers)):
+            self._layer_bwd(i, g, B, T, sv["seq_lens"], accumulate)
+        self._conv_bwd(g, B, T, accumulate)
+
+    # ------------------------------------------------------------------------------------------
+    # gradient exchange + optimizer
+    # ------------------------------------------------------------------------------------------
+    def all_reduce_grads(self, bucket_elems: int = 8 * 1024 * 1024) -> int:
+        """Sum ``flat_g`` over the ranks of the default process group, in buckets (async, then waited); returns the
+        world size (fairseq then multiplies the gradients by world_size / sample_size: pass that as ``grad_scale`` to
+        ``adam_step``).  The only collective of the path: NCCL over NVLink on the GPU box, gloo in
+        the CPU tests (``all_reduce_flat``)."""
+        return all_reduce_flat(self.flat_g, bucket_elems)
+
+    def adam_step(self, lr: float, betas=(0.9, 0.98), eps: float = 1e-8, weight_decay: float = 0.0,
+                  clip_norm: float = 0.0, grad_scale: float = 1.0) -> None:
+        """fairseq: multiply_grads(grad_scale) -> clip_grad_norm_(clip_norm) -> Adam.step, then refresh operand copies."""
+        self.step_count += 1
+        K.grad_clip_coef(self.flat_g, grad_scale, clip_norm, self._sumsq_partials, self.norm_coef)
+        K.adam(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, lr=lr, betas=betas, eps=eps,
+               weight_decay=weight_decay, step=self.step_count, norm_coef=self.norm_coef)
+        self.repack()

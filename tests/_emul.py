@@ -1,0 +1,319 @@
+"""CPU emulation of the C-ABI kernel wrappers (``mm_s2ut_b200.kernels``) -- TEST INFRASTRUCTURE ONLY.
+
+The engines (``engine.py`` / ``training.py``) are host logic: they choose buffers, strides, batch offsets and the
+order of launches.  This module re-states every wrapper they call as plain PyTorch on CPU tensors, honouring the same
+pointer / leading-dimension / batch-stride arguments (``as_strided`` over the tensor's storage), so that the host
+logic -- in particular the whole backward orchestration -- can be checked against autograd over the oracle WITHOUT a
+GPU (``tests/test_host_training.py``).  It is never imported by the package; the product path has no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+EPI_OP, EPI_RELU_OP, EPI_RESID_F32, EPI_GLU_OP, EPI_GLU_POS_F32, EPI_F32_OP, EPI_GATE, EPI_F32 = range(8)
+launch_count = 0
+timing = None
+
+
+def _v(t, sizes, strides, extra_offset=0):
+    """Strided view over t's storage starting at t's first element (+ extra_offset elements)."""
+    return t.as_strided(tuple(int(s) for s in sizes), tuple(int(s) for s in strides), t.storage_offset() + extra_offset)
+
+
+def dtype_code(dt):
+    return {torch.bfloat16: 0, torch.float16: 1}[dt]
+
+
+def fbank_tables(device):
+    return torch.zeros(1)
+
+
+def _frames(n):
+    return 0 if n < 400 else 1 + (n - 400) // 160
+
+
+def fbank(wav, n_samples, feats, tables):
+    from oracle import fbank as ofb
+
+    for b in range(wav.shape[0]):
+        n = int(n_samples[b])
+        f = ofb.kaldi_fbank_ta(wav[b, :n].float().numpy())
+        feats[b, : f.shape[0]] = torch.from_numpy(f)
+
+
+def _lens_frames(lens, is_samples):
+    return [(_frames(int(v)) if is_samples else int(v)) for v in lens]
+
+
+def cmvn_stats(feats, lens, lengths_are_samples, mean_std):
+    for b, m in enumerate(_lens_frames(lens, lengths_are_samples)):
+        x = feats[b, :m].numpy()
+        mean = x.mean(0)
+        var = (x ** 2).sum(0) / m - mean ** 2
+        mean_std.view(-1, 2, 80)[b, 0] = torch.from_numpy(mean)
+        mean_std.view(-1, 2, 80)[b, 1] = torch.from_numpy(np.sqrt(np.maximum(var, 1e-10)))
+
+
+def cmvn_apply(feats, stats, lens, lengths_are_samples, out_f32, out_op, op_row_offset=0):
+    if out_op is not None:
+        out_op.zero_()
+    if out_f32 is not None:
+        out_f32.zero_()
+    for b, m in enumerate(_lens_frames(lens, lengths_are_samples)):
+        x = feats[b, :m]
+        if stats is not None:
+            x = (x - stats.view(-1, 2, 80)[b, 0]) / stats.view(-1, 2, 80)[b, 1]
+        if out_f32 is not None:
+            out_f32[b, :m] = x
+        if out_op is not None:
+            out_op[b, op_row_offset:op_row_offset + m] = x.to(out_op.dtype)
+
+
+def seq_lens(lens, lengths_are_samples, n_layers, out):
+    for b, m in enumerate(_lens_frames(lens, lengths_are_samples)):
+        for _ in range(n_layers):
+            m = (m - 1) // 2 + 1
+        out[b] = m
+
+
+def padding_mask(seq_lens_, T, out):
+    out.copy_(torch.arange(T)[None, :] >= seq_lens_[:, None])
+
+
+def gemm(*, a0, w, rows, n, k, mode, out0, a0_ld, out0_ld, batches=1, a0_bs=0, a1=None, a1_ld=0, a1_bs=0, k_split=0,
+         w_ld=None, w_bs=0, w_batched=False, bias=None, scale=1.0, scale_cols=0, out0_bs=0, out1=None, out1_ld=0,
+         out1_bs=0, aux0=None, aux1=None, aux_ld=0, rows_per_seq=0, out_tbc=False, n_seqs=0, out_row_offset=0, vt=None,
+         vt_col0=0, vt_rows=0, vt_ld=0, pos=None, seq_lens=None, block_n=0):
+    global launch_count
+    launch_count += 1
+    w_ld = k if w_ld is None else w_ld
+    k0 = k_split if a1 is not None else k
+    A = _v(a0, (batches, rows, k0), (a0_bs, a0_ld, 1)).float()
+    if a1 is not None:
+        A = torch.cat([A, _v(a1, (batches, rows, k - k0), (a1_bs, a1_ld, 1)).float()], -1)
+    W = _v(w, (batches if w_batched else 1, n, k), (w_bs if w_batched else 0, w_ld, 1)).float()
+    acc = A @ W.transpose(-1, -2)
+    if bias is not None:
+        acc = acc + bias[:n]
+    op = w.dtype
+
+    def out_view(t, cols, ld, bs, rows_=rows, roff=0):
+        if out_tbc:
+            return _v(t, (batches, rows_, cols), (ld, n_seqs * ld, 1))
+        return _v(t, (batches, rows_, cols), (bs, ld, 1), roff * ld)
+
+    if mode in (EPI_OP, EPI_RELU_OP):
+        if mode == EPI_OP and scale_cols > 0:
+            acc[..., :scale_cols] *= scale
+        if mode == EPI_RELU_OP:
+            acc = acc.relu()
+        n_out = vt_col0 if (mode == EPI_OP and vt is not None) else n
+        if n_out > 0:
+            out_view(out0, n_out, out0_ld, out0_bs, roff=out_row_offset).copy_(acc[..., :n_out].to(op))
+        if mode == EPI_OP and vt is not None:
+            tail = acc[..., vt_col0:].to(op)                                  # [batches, rows, n - vt_col0]
+            if rows_per_seq > 0:
+                tail = tail.reshape(rows // rows_per_seq, rows_per_seq, -1)
+            V = _v(vt, (tail.shape[0], tail.shape[2], tail.shape[1]), (vt_rows * vt_ld, vt_ld, 1))
+            V.copy_(tail.transpose(1, 2))
+    elif mode in (EPI_GLU_OP, EPI_GLU_POS_F32):
+        t = acc.reshape(batches, rows, n // 256, 2, 128)
+        y = (t[..., 0, :] * torch.sigmoid(t[..., 1, :])).reshape(batches, rows, n // 2)
+        if mode == EPI_GLU_OP:
+            out_view(out0, n // 2, out0_ld, out0_bs, roff=out_row_offset).copy_(y.to(op))
+        else:
+            y = y * scale
+            for b in range(batches):
+                L = min(int(seq_lens[b]), rows) if seq_lens is not None else rows
+                y[b, :L] += pos[2:2 + L, : n // 2]
+            out_view(out0, n // 2, out0_ld, out0_bs).copy_(y)
+    elif mode == EPI_F32:
+        out_view(out0, n, out0_ld, out0_bs).copy_(acc)
+    elif mode == EPI_F32_OP:
+        out_view(out0, n, out0_ld, out0_bs).copy_(acc)
+        _v(out1, (batches, rows, n), (out1_bs, out1_ld, 1)).copy_(acc.to(op))
+    elif mode == EPI_RESID_F32:
+        x = _v(aux0, (batches, rows, n), (rows * aux_ld, aux_ld, 1)).clone()
+        out_view(out0, n, out0_ld, out0_bs).copy_(acc + x)
+    elif mode == EPI_GATE:
+        x = _v(aux0, (batches, rows, n), (rows * aux_ld, aux_ld, 1))
+        o = _v(aux1, (batches, rows, n), (rows * aux_ld, aux_ld, 1))
+        g = torch.sigmoid(acc)
+        out_view(out0, n, out0_ld, out0_bs).copy_((1 - g) * x + g * o)
+    else:
+        raise ValueError(mode)
+
+
+def gemm_resid_ln(*a, **k):
+    raise NotImplementedError("the training path does not use the fused GEMM+LN kernel")
+
+
+def layernorm(x, gamma, beta, out_op=None, out_f32=None, eps=1e-5):
+    dim = x.shape[-1]
+    y = torch.nn.functional.layer_norm(x.reshape(-1, dim), (dim,), gamma, beta, eps)
+    if out_op is not None:
+        out_op.view(-1, dim).copy_(y.to(out_op.dtype))
+    if out_f32 is not None:
+        out_f32.view(-1, dim).copy_(y)
+
+
+def self_attention(qkv, seq_lens_, batch, seq, heads, out):
+    d = heads * 64
+    x = qkv.float().view(batch, seq, 3, heads, 64)
+    q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    s = q @ k.transpose(-1, -2)
+    mask = torch.arange(seq)[None, :] >= seq_lens_[:, None]
+    s = s.masked_fill(mask[:, None, None, :], float("-inf"))
+    p = s.softmax(-1).to(qkv.dtype).float()
+    o = (p @ v).permute(0, 2, 1, 3).reshape(batch * seq, d)
+    out.copy_(o.to(out.dtype))
+
+
+def softmax_rows(scores, ld_in, rows, n_keys, probs, ld_out, key_mask=None, rows_per_seq=0):
+    assert key_mask is None
+    s = _v(scores, (rows, n_keys), (ld_in, 1))
+    P = _v(probs, (rows, ld_out), (ld_out, 1))
+    P.zero_()
+    P[:, :n_keys] = s.softmax(-1).to(probs.dtype)
+
+
+def convert(x, out):
+    out.view(-1).copy_(x.reshape(-1).to(out.dtype))
+
+
+# ---- training-step variant --------------------------------------------------------------------------------
+def pack_t(x, *, rows, cols, in_ld, out_n=None, n_ld=0, out_t=None, t_ld=0, t_cols_pad=0, batches=1, nb1=1, in_bs0=0,
+           in_bs1=0, n_bs0=0, n_bs1=0, t_bs0=0, t_bs1=0, mask=None, mask_ld=0, scale=1.0):
+    global launch_count
+    launch_count += 1
+    assert cols % 2 == 0 and all(s % 2 == 0 for s in (in_ld, in_bs0, in_bs1, n_ld, t_ld, n_bs0, n_bs1, t_bs0, t_bs1))
+    op = (out_n if out_n is not None else out_t).dtype
+    rows_even = rows + (rows & 1)
+    if out_t is not None:
+        t_cols_pad = max(t_cols_pad, rows_even)
+        assert t_cols_pad % 2 == 0 and t_ld >= t_cols_pad
+    for z in range(batches):
+        b0, b1 = divmod(z, nb1)
+        v = _v(x, (rows, cols), (in_ld, 1), b0 * in_bs0 + b1 * in_bs1).float() * scale
+        if mask is not None:
+            v = v * (_v(mask, (rows, cols), (mask_ld, 1)).float() > 0)
+        v = v.to(op)
+        if out_n is not None:
+            _v(out_n, (rows, cols), (n_ld, 1), b0 * n_bs0 + b1 * n_bs1).copy_(v)
+        if out_t is not None:
+            T = _v(out_t, (cols, t_cols_pad), (t_ld, 1), b0 * t_bs0 + b1 * t_bs1)
+            T[:, :rows] = v.t()
+            T[:, rows:] = 0
+
+
+def rowsum(x, ld, rows, cols, out, accumulate=False):
+    s = _v(x, (rows, cols), (ld, 1)).float().sum(1)
+    out[:rows] = out[:rows] + s if accumulate else s
+
+
+def reduce_partials(part, n_partials, stride, n, out, accumulate=False, part_offset=0):
+    s = _v(part, (n_partials, n), (stride, 1), part_offset).sum(0)
+    out.view(-1)[:n] = out.view(-1)[:n] + s if accumulate else s
+
+
+def layernorm_bwd_blocks():
+    return 4
+
+
+def layernorm_bwd(x, gamma, dy, partials, dx=None, resid=None, eps=1e-5):
+    dim = x.shape[-1]
+    xr = x.reshape(-1, dim)
+    dyr = dy.reshape(-1, dim)
+    mean = xr.mean(1, keepdim=True)
+    rstd = torch.rsqrt(((xr - mean) ** 2).mean(1, keepdim=True) + eps)
+    xhat = (xr - mean) * rstd
+    dyg = dyr * gamma
+    d = rstd * (dyg - dyg.mean(1, keepdim=True) - xhat * (dyg * xhat).mean(1, keepdim=True))
+    if dx is not None:
+        dx.view(-1, dim).copy_(d + (resid.reshape(-1, dim) if resid is not None else 0))
+    p = partials[: layernorm_bwd_blocks() * 2 * dim].view(layernorm_bwd_blocks(), 2, dim)
+    p.zero_()
+    p[0, 0] = (dyr * xhat).sum(0)
+    p[0, 1] = dyr.sum(0)
+
+
+def softmax_bwd(scores, dprobs, ld_in, rows, rows_per_batch, n_keys, dscores, ld_out, probs=None, kv_lens=None, heads=1):
+    S = _v(scores, (rows, n_keys), (ld_in, 1))
+    D = _v(dprobs, (rows, n_keys), (ld_in, 1))
+    G = _v(dscores, (rows, ld_out), (ld_out, 1))
+    G.zero_()
+    if probs is not None:
+        Pv = _v(probs, (rows, ld_out), (ld_out, 1))
+        Pv.zero_()
+    for r0 in range(0, rows, rows_per_batch):
+        valid = n_keys if kv_lens is None else min(n_keys, int(kv_lens[(r0 // rows_per_batch) // heads]))
+        sl = slice(r0, min(rows, r0 + rows_per_batch))
+        p = S[sl, :valid].softmax(-1)
+        g = p * (D[sl, :valid] - (p * D[sl, :valid]).sum(1, keepdim=True))
+        G[sl, :valid] = g.to(dscores.dtype)
+        if probs is not None:
+            Pv[sl, :valid] = p.to(probs.dtype)
+
+
+def glu_bwd(pre, dy, rows, n, dpre, scale=1.0):
+    a, b = pre.view(rows, 2 * n)[:, :n], pre.view(rows, 2 * n)[:, n:]
+    g = dy.view(rows, n) * scale
+    s = torch.sigmoid(b)
+    dpre.view(rows, 2 * n)[:, :n] = (g * s).to(dpre.dtype)
+    dpre.view(rows, 2 * n)[:, n:] = (g * a * s * (1 - s)).to(dpre.dtype)
+
+
+def gate_bwd(z, dres_tbc, text, attn, B, T, d, dz, dcat):
+    dres = dres_tbc.view(T, B, d).transpose(0, 1).reshape(B * T, d)
+    g = torch.sigmoid(z.view(B * T, d))
+    dz.view(B * T, d).copy_((dres * (attn.view(B * T, d) - text.view(B * T, d)) * g * (1 - g)).to(dz.dtype))
+    dcat.view(B * T, 2 * d)[:, :d] = dres * g
+    dcat.view(B * T, 2 * d)[:, d:] = dres * (1 - g)
+
+
+def tbc_to_btc(x_tbc, B, T, d, out):
+    out.view(B, T, d).copy_(x_tbc.view(T, B, d).transpose(0, 1))
+
+
+def col2im_k5s2(dcol, B, t_out, t_in, C_, dx):
+    dc = dcol.view(B, t_out, 5, C_)
+    o = dx.view(B, t_in, C_)
+    o.zero_()
+    for t in range(t_out):
+        for k in range(5):
+            s = 2 * t + k - 2
+            if 0 <= s < t_in:
+                o[:, s] += dc[:, t, k]
+
+
+def grad_clip_coef(grad, grad_scale, max_norm, partials, norm_coef):
+    norm = grad.double().norm().item() * grad_scale
+    coef = grad_scale * (min(1.0, max_norm / (norm + 1e-6)) if max_norm > 0 else 1.0)
+    norm_coef[0], norm_coef[1] = norm, coef
+
+
+def adam(param, grad, exp_avg, exp_avg_sq, *, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, step=1,
+         norm_coef=None):
+    g = grad * (norm_coef[1] if norm_coef is not None else 1.0)
+    exp_avg.mul_(betas[0]).add_(g, alpha=1 - betas[0])
+    exp_avg_sq.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
+    step_size = lr * math.sqrt(1 - betas[1] ** step) / (1 - betas[0] ** step)
+    if weight_decay:
+        param.mul_(1 - weight_decay * lr)
+    param.addcdiv_(exp_avg, exp_avg_sq.sqrt() + eps, value=-step_size)
+
+
+class _FakeLib:
+    @staticmethod
+    def load():
+        class L:
+            @staticmethod
+            def mm_sumsq_blocks():
+                return 4
+        return L
+
+
+_lib = _FakeLib

@@ -1,0 +1,265 @@
+"""Training-step variant (BASELINE configs[2]): the backward kernels, the encoder backward pass against PyTorch
+autograd over the fp32 CPU oracle, fairseq Adam.
+
+Tolerances: every parameter gradient within REL (relative L2 error over the tensor; bf16 GEMM operands against an
+fp32 reference) and cosine similarity above COS; element-wise kernels against their fp32 PyTorch formula.
+"""
+import numpy as np
+import pytest
+import torch
+
+from _util import record
+
+pytestmark = pytest.mark.gpu
+
+REL = 8e-2      # bf16 operands: measured 1.5-5.5e-2 (largest through the ReLU mask of fc1); fp16 operands 0.5-1.8e-2
+COS = 0.995
+ZERO = 1e-4     # gradients that are zero in exact arithmetic (key-projection biases: softmax is shift-invariant)
+
+
+def _rel(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# kernels
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("f32_in", [True, False])
+def test_pack_t_transpose_mask_pad(cuda, f32_in):
+    from mm_s2ut_b200 import kernels as K
+
+    g = torch.Generator().manual_seed(0)
+    rows, cols, pad = 333, 130, 384
+    x = torch.randn(rows, cols + 6, generator=g)
+    mask = torch.randn(rows, cols, generator=g)
+    xin = (x if f32_in else x.bfloat16()).cuda()
+    m = mask.bfloat16().cuda()
+    out_n = torch.full((rows, cols), 7.0, dtype=torch.bfloat16, device=cuda)
+    out_t = torch.full((cols, pad), 7.0, dtype=torch.bfloat16, device=cuda)
+    K.pack_t(xin, rows=rows, cols=cols, in_ld=cols + 6, out_n=out_n, n_ld=cols, out_t=out_t, t_ld=pad, t_cols_pad=pad,
+             mask=m, mask_ld=cols, scale=0.5)
+    ref = (xin.float()[:, :cols] * 0.5 * (m.float() > 0)).bfloat16()
+    assert torch.equal(out_n, ref)
+    assert torch.equal(out_t[:, :rows], ref.t())
+    assert (out_t[:, rows:] == 0).all()
+
+
+def test_pack_t_head_split_and_merge(cuda):
+    from mm_s2ut_b200 import kernels as K
+
+    B, T, H, Tp = 3, 50, 4, 64
+    d = 64 * H
+    qkv = torch.randn(B * T, 3 * d, generator=torch.Generator().manual_seed(1)).bfloat16().cuda()
+    Kh = torch.zeros(B * H, Tp, 64, dtype=torch.bfloat16, device=cuda)
+    Kt = torch.zeros(B * H, 64, Tp, dtype=torch.bfloat16, device=cuda)
+    K.pack_t(qkv[:, d:], rows=T, cols=64, in_ld=3 * d, batches=B * H, nb1=H, in_bs0=T * 3 * d, in_bs1=64, out_n=Kh,
+             n_ld=64, n_bs0=H * Tp * 64, n_bs1=Tp * 64, out_t=Kt, t_ld=Tp, t_bs0=H * 64 * Tp, t_bs1=64 * Tp,
+             t_cols_pad=Tp)
+    ref = qkv[:, d:2 * d].view(B, T, H, 64).permute(0, 2, 1, 3).reshape(B * H, T, 64)
+    assert torch.equal(Kh[:, :T], ref) and (Kh[:, T:] == 0).all()
+    assert torch.equal(Kt[:, :, :T], ref.transpose(1, 2)) and (Kt[:, :, T:] == 0).all()
+    back = torch.zeros(B * T, 3 * d, dtype=torch.bfloat16, device=cuda)
+    K.pack_t(Kh, rows=T, cols=64, in_ld=64, batches=B * H, nb1=H, in_bs0=H * Tp * 64, in_bs1=Tp * 64, out_n=back[:, d:],
+             n_ld=3 * d, n_bs0=T * 3 * d, n_bs1=64)
+    assert torch.equal(back[:, d:2 * d], qkv[:, d:2 * d]) and (back[:, :d] == 0).all() and (back[:, 2 * d:] == 0).all()
+
+
+@pytest.mark.parametrize("dim", [256, 512, 768, 1024])
+def test_layernorm_bwd_vs_autograd(cuda, dim):
+    from mm_s2ut_b200 import kernels as K
+
+    g = torch.Generator().manual_seed(dim)
+    rows = 1234
+    x = (torch.randn(rows, dim, generator=g) * 2 + 0.3).requires_grad_()
+    gamma = (1 + 0.1 * torch.randn(dim, generator=g)).requires_grad_()
+    beta = torch.randn(dim, generator=g).requires_grad_()
+    dy = torch.randn(rows, dim, generator=g)
+    resid = torch.randn(rows, dim, generator=g)
+    torch.nn.functional.layer_norm(x, (dim,), gamma, beta, 1e-5).backward(dy)
+    part = torch.empty(K.layernorm_bwd_blocks() * 2 * dim, device=cuda)
+    dx = torch.empty(rows, dim, device=cuda)
+    K.layernorm_bwd(x.detach().cuda(), gamma.detach().cuda(), dy.cuda(), part, dx=dx, resid=resid.cuda())
+    gwb = torch.empty(2 * dim, device=cuda)
+    K.reduce_partials(part, K.layernorm_bwd_blocks(), 2 * dim, 2 * dim, gwb)
+    assert torch.allclose(dx.cpu(), x.grad + resid, atol=2e-5, rtol=1e-4)
+    assert torch.allclose(gwb[:dim].cpu(), gamma.grad, atol=2e-3, rtol=1e-4)
+    assert torch.allclose(gwb[dim:].cpu(), beta.grad, atol=2e-3, rtol=1e-4)
+
+
+def test_softmax_bwd_vs_autograd(cuda):
+    from mm_s2ut_b200 import kernels as K
+
+    g = torch.Generator().manual_seed(3)
+    B, H, Tp, T = 2, 2, 64, 50
+    lens = torch.tensor([50, 37], dtype=torch.int32)
+    S = (torch.randn(B * H, Tp, Tp, generator=g) * 3)
+    dP = torch.randn(B * H, Tp, Tp, generator=g)
+    P = torch.full((B * H, Tp, Tp), 9.0, dtype=torch.bfloat16, device=cuda)
+    dS = torch.full((B * H, Tp, Tp), 9.0, dtype=torch.bfloat16, device=cuda)
+    K.softmax_bwd(S.cuda(), dP.cuda(), Tp, B * H * Tp, Tp, T, dS, Tp, probs=P, kv_lens=lens.cuda(), heads=H)
+    for bh in range(B * H):
+        v = int(lens[bh // H])
+        s = S[bh, :, :v].clone().requires_grad_()
+        p = s.softmax(-1)
+        p.backward(dP[bh, :, :v])
+        assert torch.allclose(P[bh, :, :v].float().cpu(), p.detach(), atol=4e-3)
+        assert torch.allclose(dS[bh, :, :v].float().cpu(), s.grad, atol=1e-2, rtol=1e-2)
+        assert (P[bh, :, v:] == 0).all() and (dS[bh, :, v:] == 0).all()
+
+
+def test_glu_gate_col2im_bwd_vs_autograd(cuda):
+    from mm_s2ut_b200 import kernels as K
+
+    g = torch.Generator().manual_seed(4)
+    rows, n = 301, 128
+    pre = torch.randn(rows, 2 * n, generator=g).requires_grad_()
+    dy = torch.randn(rows, n, generator=g)
+    (torch.nn.functional.glu(pre, dim=1) * 3.0).backward(dy)
+    dpre = torch.empty(rows, 2 * n, dtype=torch.bfloat16, device=cuda)
+    K.glu_bwd(pre.detach().cuda(), dy.cuda(), rows, n, dpre, scale=3.0)
+    assert torch.allclose(dpre.float().cpu(), pre.grad, atol=2e-2, rtol=1e-2)
+    # selective gate
+    B, T, d = 3, 21, 64
+    z = torch.randn(B * T, d, generator=g).requires_grad_()
+    text = torch.randn(B * T, d, generator=g).requires_grad_()
+    attn = torch.randn(B * T, d, generator=g).requires_grad_()
+    dres = torch.randn(T, B, d, generator=g)
+    gate = torch.sigmoid(z)
+    res = ((1 - gate) * text + gate * attn).view(B, T, d).transpose(0, 1)
+    res.backward(dres)
+    dz = torch.empty(B * T, d, dtype=torch.bfloat16, device=cuda)
+    dcat = torch.empty(B * T, 2 * d, device=cuda)
+    K.gate_bwd(z.detach().cuda(), dres.cuda(), text.detach().cuda(), attn.detach().cuda(), B, T, d, dz, dcat)
+    assert torch.allclose(dz.float().cpu(), z.grad, atol=2e-2, rtol=1e-2)
+    assert torch.allclose(dcat[:, :d].cpu(), attn.grad, atol=1e-5) and torch.allclose(dcat[:, d:].cpu(), text.grad, atol=1e-5)
+    # col2im of Conv1d(k5, s2, p2)
+    Bc, Tin, C = 2, 37, 8
+    Tout = (Tin - 1) // 2 + 1
+    x = torch.randn(Bc, C, Tin, generator=g).requires_grad_()
+    w = torch.randn(16, C, 5, generator=g)
+    y = torch.nn.functional.conv1d(x, w, stride=2, padding=2)          # [B, 16, Tout]
+    dyc = torch.randn(Bc, 16, Tout, generator=g)
+    y.backward(dyc)
+    wflat = w.permute(0, 2, 1).reshape(16, 5 * C)                       # [n, tap*C + c]
+    dcol = (dyc.transpose(1, 2) @ wflat).contiguous()                   # [B, Tout, 5*C]
+    dx = torch.empty(Bc, Tin, C, device=cuda)
+    K.col2im_k5s2(dcol.cuda(), Bc, Tout, Tin, C, dx)
+    assert torch.allclose(dx.cpu(), x.grad.transpose(1, 2), atol=1e-4)
+
+
+def test_adam_matches_fairseq_restatement(cuda):
+    from mm_s2ut_b200 import kernels as K
+    from oracle import adam as oadam
+
+    rng = np.random.default_rng(0)
+    n = 100003 * 4
+    p, g = rng.standard_normal(n).astype(np.float32), (rng.standard_normal(n) * 3).astype(np.float32)
+    m, v = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    dp, dg, dm, dv = (torch.from_numpy(a.copy()).cuda() for a in (p, g, m, v))
+    part = torch.empty(4 * 148, device=cuda)
+    nc = torch.empty(2, device=cuda)
+    for step in (1, 2, 3):
+        K.grad_clip_coef(dg, 0.5, 10.0, part, nc)
+        K.adam(dp, dg, dm, dv, lr=5e-4, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.01, step=step, norm_coef=nc)
+        norm, coef = oadam.clip_coef(g, 0.5, 10.0)
+        p, m, v = oadam.adam_step(p, g, m, v, lr=5e-4, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.01, step=step,
+                                  grad_mul=coef)
+        assert abs(nc[0].item() - norm) / norm < 1e-5 and abs(nc[1].item() - coef) / coef < 1e-5
+        assert np.allclose(dp.cpu().numpy(), p, atol=2e-6, rtol=1e-5)
+        assert np.allclose(dv.cpu().numpy(), v, atol=1e-7, rtol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# encoder backward against autograd over the fp32 oracle
+# ---------------------------------------------------------------------------------------------------------
+def _train_setup(attn_type, gate, preset="small", B=3, dur=2.0, drop_image=False):
+    from mm_s2ut_b200 import synth
+    from oracle import fbank as ofb, fusion as ofu
+    from test_gpu_encoder import _build
+
+    enc, args, cfg = _build(preset, attn_type, gate)
+    enc.dropout_p = 0.0
+    enc.SA_image_dropout = enc.SA_attention_dropout = enc.SA_text_dropout = 0.0
+    wavs, _ = synth.synth_batch(2, B, dur, ragged=True)
+    imgs = synth.synth_images(2, B)
+    sd = {k: v.detach().clone().float().requires_grad_(v.is_floating_point()) for k, v in enc.state_dict().items()}
+    feats, flens = ofb.features_from_waveforms(wavs)
+    img_o = torch.zeros_like(imgs) if drop_image else imgs
+    ref = ofu.mm_encoder_forward(sd, cfg, torch.from_numpy(feats), torch.from_numpy(flens), [img_o], [None],
+                                 args.encoder_attention_heads)
+    out_ref = ref["encoder_out"][0]
+    mask = ref["encoder_padding_mask"][0]                    # [B, T]
+    R = torch.randn(out_ref.shape, generator=torch.Generator().manual_seed(11))
+    R = R * (~mask).t().unsqueeze(-1)                        # the decoder never attends to padded states
+    (out_ref * R).sum().backward()
+    ref_grads = {k: v.grad for k, v in sd.items() if v.requires_grad and v.grad is not None}
+    wav, lens = synth.pad_waveforms(wavs)
+    return enc, wav, lens, imgs, R, ref_grads, out_ref.detach(), mask
+
+
+@pytest.mark.parametrize("attn_type,gate,drop_image", [("selective_attention", True, False),
+                                                       ("multimodal_attention", True, False),
+                                                       ("selective_attention", False, False),
+                                                       ("selective_attention", True, True)])
+def test_encoder_backward_matches_autograd_oracle(cuda, attn_type, gate, drop_image):
+    from mm_s2ut_b200.training import TrainEngine
+
+    enc, wav, lens, imgs, R, ref_grads, out_ref, mask = _train_setup(attn_type, gate, drop_image=drop_image)
+    enc.cuda().train()
+    eng = enc.train_engine()
+    assert isinstance(eng, TrainEngine)
+    out = eng.forward_train(wav.cuda(), lens.cuda(), [imgs.cuda()], [None], drop_image=drop_image)
+    x = out["encoder_out"][0].cpu()
+    valid = (~mask).t().unsqueeze(-1)
+    ferr = ((x - out_ref).abs() * valid).max().item()
+    assert ferr < 2e-2, ferr
+    eng.backward(R.cuda())
+    torch.cuda.synchronize()
+    worst, worst_name = 0.0, ""
+    names = dict(enc.named_parameters())
+    checked = 0
+    for k, gref in ref_grads.items():
+        if k not in names or gref.norm() < ZERO:
+            continue
+        got = names[k].grad
+        assert got is not None and torch.isfinite(got).all(), k
+        rel = _rel(got, gref)
+        cos = torch.nn.functional.cosine_similarity(got.flatten().double().cpu(), gref.flatten().double(), dim=0).item()
+        if rel > worst:
+            worst, worst_name = rel, k
+        assert rel < REL and cos > COS, (k, rel, cos)
+        checked += 1
+    assert checked >= 6 * 15 + 2 + 4
+    record(f"configs[2] backward, small B=3x2s ragged, {attn_type}, gate={gate}, drop_image={drop_image}: worst "
+           f"parameter-gradient relative L2 error ({worst_name}, {checked} tensors)", worst, REL)
+
+
+def test_autograd_function_and_adam_step(cuda):
+    """The module API in .train(): loss.backward() reaches the kernels through EncoderOutGrad; one Adam step moves
+    every used parameter and the next forward sees the refreshed operand copies."""
+    enc, wav, lens, imgs, R, ref_grads, out_ref, mask = _train_setup("selective_attention", True)
+    enc.cuda().train()
+    out = enc(wav.cuda(), lens.cuda(), None, None, None, imgs_list=[imgs.cuda()], img_masks_list=[None])
+    y = out["encoder_out"][0]
+    assert y.requires_grad
+    (y * R.cuda()).sum().backward()
+    eng = enc.train_engine()
+    k = "transformer_layers.0.fc1.weight"
+    g1 = dict(enc.named_parameters())[k].grad.clone()
+    assert _rel(g1, ref_grads[k]) < REL
+    p0 = eng.flat_p.clone()
+    eng.adam_step(lr=1e-3, clip_norm=10.0)
+    torch.cuda.synchronize()
+    assert eng.norm_coef[0].item() > 0
+    moved = (eng.flat_p != p0)
+    used = eng.flat_g != 0
+    assert moved[used].float().mean().item() > 0.999
+    out2 = enc(wav.cuda(), lens.cuda(), None, None, None, imgs_list=[imgs.cuda()], img_masks_list=[None])
+    loss1, loss2 = (y.detach() * R.cuda()).sum().item(), (out2["encoder_out"][0].detach() * R.cuda()).sum().item()
+    assert loss2 < loss1, (loss1, loss2)      # one descent step on a linear functional of the output
+    # gradient accumulation: a second backward adds onto the attached gradients
+    g_before = dict(enc.named_parameters())[k].grad.clone()
+    (out2["encoder_out"][0] * R.cuda()).sum().backward()
+    g_after = dict(enc.named_parameters())[k].grad
+    assert (g_after - g_before).abs().max().item() > 0

@@ -1,0 +1,110 @@
+"""Host logic of the training-step variant, checked on CPU: the backward ORCHESTRATION of ``training.TrainEngine``
+(buffers, strides, batch offsets, launch order, flat parameter layout) runs against emulated kernels
+(``tests/_emul.py``: the same wrapper signatures restated in PyTorch) and must reproduce PyTorch autograd over the fp32
+oracle.  The CUDA kernels themselves are covered by ``test_gpu_training.py``; plus the gradient all-reduce under gloo.
+"""
+import os
+import socket
+
+import pytest
+import torch
+
+import _emul
+
+
+def _emulated(monkeypatch):
+    import mm_s2ut_b200  # noqa: F401
+    from mm_s2ut_b200 import engine, training
+
+    monkeypatch.setattr(engine, "K", _emul)
+    monkeypatch.setattr(training, "K", _emul)
+    monkeypatch.setattr(engine.EncoderEngine, "_require_cuda", False)
+
+
+@pytest.mark.parametrize("attn_type,gate,drop_image", [("selective_attention", True, False),
+                                                       ("multimodal_attention", True, False),
+                                                       ("selective_attention", False, True)])
+def test_backward_orchestration_matches_autograd_oracle(monkeypatch, attn_type, gate, drop_image):
+    from test_gpu_training import REL, ZERO, _rel, _train_setup
+
+    _emulated(monkeypatch)
+    enc, wav, lens, imgs, R, ref_grads, out_ref, mask = _train_setup(attn_type, gate, B=2, dur=1.0,
+                                                                      drop_image=drop_image)
+    enc.train()
+    eng = enc.train_engine()
+    out = eng.forward_train(wav, lens, [imgs], [None], drop_image=drop_image)
+    valid = (~mask).t().unsqueeze(-1)
+    assert ((out["encoder_out"][0] - out_ref).abs() * valid).max().item() < 2e-2
+    eng.backward(R)
+    names = dict(enc.named_parameters())
+    checked = 0
+    for k, gref in ref_grads.items():
+        if k not in names or gref.norm() < ZERO:
+            continue
+        rel = _rel(names[k].grad, gref)
+        assert rel < REL, (k, rel)
+        checked += 1
+    assert checked >= 6 * 15 + 2 + 4
+    # accumulate=True adds the same gradient once more
+    g1 = eng.flat_g.clone()
+    eng.backward(R, accumulate=True)
+    assert _rel(eng.flat_g, 2 * g1) < 1e-2
+    # Adam step + operand refresh: the linear functional of the output goes down
+    l1 = (out["encoder_out"][0] * R).sum().item()
+    eng.backward(R)
+    eng.adam_step(lr=1e-3, clip_norm=10.0)
+    out2 = eng.forward_train(wav, lens, [imgs], [None], drop_image=drop_image)
+    assert (out2["encoder_out"][0] * R).sum().item() < l1
+
+
+def test_autograd_function_boundary(monkeypatch):
+    from test_gpu_training import REL, ZERO, _rel, _train_setup
+
+    _emulated(monkeypatch)
+    enc, wav, lens, imgs, R, ref_grads, out_ref, mask = _train_setup("selective_attention", True, B=2, dur=1.0)
+    enc.train()
+    out = enc(wav, lens, None, None, None, imgs_list=[imgs], img_masks_list=[None])
+    y = out["encoder_out"][0]
+    assert y.requires_grad
+    (y * R).sum().backward()
+    k = "transformer_layers.5.fc2.weight"
+    p = dict(enc.named_parameters())[k]
+    assert _rel(p.grad, ref_grads[k]) < REL
+    for q in enc.parameters():      # an optimizer's zero_grad(set_to_none=True)
+        q.grad = None
+    out = enc(wav, lens, None, None, None, imgs_list=[imgs], img_masks_list=[None])
+    (out["encoder_out"][0] * R).sum().backward()
+    assert _rel(p.grad, ref_grads[k]) < REL and enc.train_engine().grads_attached()
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    import mm_s2ut_b200  # noqa: F401
+    from mm_s2ut_b200.training import all_reduce_flat
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    n = all_reduce_flat(flat, bucket_elems=256)
+    q.put((rank, n, flat.sum().item()))
+    dist.destroy_process_group()
+
+
+def test_gradient_all_reduce_gloo_world2():
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(60)
+    expect = float(sum(range(1000)) * 3)
+    assert [r[1] for r in res] == [2, 2] and all(abs(r[2] - expect) < 1e-3 * expect for r in res)
