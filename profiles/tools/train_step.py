@@ -1,0 +1,118 @@
+"""Training-step variant at BASELINE configs[2]'s shape (base model, 64 x 10 s + 577 x 768 image features per GPU):
+forward (activations kept) + backward + gradient all-reduce + fairseq Adam, timed with CUDA events (eager launches
+behind a device spin so host latency is not timed); per-kernel-family breakdown of one step.
+
+    python profiles/tools/train_step.py [--steps 10] [--batch 64] [--seconds 10]
+    torchrun --nproc-per-node N ... profiles/tools/train_step.py          (adds the NCCL gradient all-reduce)
+
+Element-wise dropout masks are not built (dropout probabilities are set to 0); modality dropout is on at 0.5
+(image-drop branch, per-batch numpy draw like the reference).
+"""
+import argparse
+import json
+import os
+import sys
+from collections import defaultdict
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--preset", default="base")
+    a = ap.parse_args()
+    import mm_s2ut_b200  # noqa: F401
+    from mm_s2ut_b200 import kernels as K
+    from mm_s2ut_b200.config import DEFAULT_YAML, load_mm_config, make_args
+    from mm_s2ut_b200.models.mm_s2s_transformer import MM_S2STransformerEncoder
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = dict(load_mm_config(DEFAULT_YAML))
+    cfg.update(modality_dropout=0.5, audio_dropout=-0.5, SA_image_dropout=0.0, SA_attention_dropout=0.0)
+    torch.manual_seed(0)
+    args = make_args(a.preset, multimodal_translation_config_yaml=cfg)
+    enc = MM_S2STransformerEncoder(args, build_unused_projections=False).to(dev).train()
+    enc.dropout_p = 0.0
+    eng = enc.train_engine()
+    B, n = a.batch, int(16000 * a.seconds)
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    wav = (torch.randn(B, n, device=dev, generator=g) * 3000).clamp_(-32768, 32767)
+    lens = torch.full((B,), n, dtype=torch.int64, device=dev)
+    imgs = torch.randn(B, 577, 768, device=dev, generator=g)
+    rng = np.random.RandomState(0)
+
+    def step(grad_out=None):
+        drop_image = rng.random() < 0.5 and rng.random() >= -0.5
+        out = eng.forward_train(wav, lens, [imgs], [None], drop_image=drop_image)
+        y = out["encoder_out"][0]
+        if grad_out is None:
+            grad_out = torch.randn(y.shape, device=dev, generator=g) * 1e-3
+        eng.backward(grad_out)
+        ws = eng.all_reduce_grads()
+        eng.adam_step(lr=5e-4, betas=(0.9, 0.98), clip_norm=10.0, grad_scale=1.0 / ws)
+        return grad_out
+
+    go = step()
+    for _ in range(a.warmup):
+        step(go)
+    torch.cuda.synchronize()
+    n0 = K.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(200_000_000)      # ~0.1 s device spin: the launches below queue up behind it
+    e0.record()
+    for _ in range(a.steps):
+        step(go)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    launches = (K.launch_count - n0) // a.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    # per-family breakdown of one step
+    K.timing = []
+    step(go)
+    torch.cuda.synchronize()
+    fam = defaultdict(lambda: [0.0, 0, 0.0])
+    for name, s, e, work in K.timing:
+        f = fam[name]
+        f[0] += s.elapsed_time(e)
+        f[1] += 1
+        f[2] += work
+    K.timing = None
+    if rank == 0:
+        tot = sum(v[0] for v in fam.values())
+        print(f"{'kernel family':24s} {'launches':>8s} {'ms':>9s} {'share':>7s} {'rate':>14s}")
+        for name, (t, c, wk) in sorted(fam.items(), key=lambda kv: -kv[1][0]):
+            rate = f"{wk / t / 1e9:9.1f} TF/s" if name.startswith("gemm") or "attention" in name else f"{wk / t / 1e6:9.0f} GB/s"
+            print(f"{name:24s} {c:8d} {t:9.3f} {100 * t / tot:6.1f}% {rate:>14s}")
+        audio_s = B * a.seconds * world
+        line = dict(metric="audio-sec trained/sec (fbank -> fused enc fwd + bwd + all-reduce + Adam)",
+                    value=audio_s / (ms * 1e-3), unit="audio-s/s", n_gpus=world, steps=a.steps, ms_per_step=ms,
+                    launches_per_step=launches, eager_sum_ms=tot, batch_per_gpu=B, utt_seconds=a.seconds,
+                    preset=a.preset, params=int(eng.flat_p.numel()),
+                    note="element-wise dropout off (masks not built); modality dropout 0.5; synthetic d loss/d encoder_out")
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
