@@ -121,6 +121,17 @@ typedef struct mm_gemm_args {
   int64_t vt_ld;
   const float* pos;     /* GLU_POS: [>= rows+2][n/2] sinusoidal table */
   const int32_t* seq_lens; /* GLU_POS: valid length per sequence */
+  /* Operand layouts of the backward pass (all 0 in the forward pass):
+   *   a_mn / w_mn     the operand is MN-major: memory is [contraction index][row], ld = elements between contraction
+   *                   indices.  dgrad (dX = dY W) reads W [n_out, k_in] as stored; wgrad (dW = dY^T X) reads dY and X as
+   *                   stored -- no transposed copies.  Needs k % 64 == 0 unless the operand ends at k.
+   *   a_kbatch / w_kbatch  (MN-major only) the batch index advances the contraction index by k (split-K over tokens):
+   *                   batch b covers contraction rows [b k, (b+1) k) of a tensor with *_k_total rows (zero beyond).
+   *   heads, head_stride, a_hm / w_hm / out_hm   batch index = (sequence, head): the operand / output is
+   *                   [sequence][rows][heads * head_stride] and head h uses the column block starting at h * head_stride
+   *                   (attention backward straight from / into the q|k|v layout).  out_hm: MM_EPI_OP, n % 64 == 0. */
+  int32_t a_mn, w_mn, a_kbatch, w_kbatch, a_hm, w_hm, out_hm, heads, head_stride;
+  int64_t a_k_total, w_k_total;
 } mm_gemm_args;
 
 int mm_gemm(const mm_gemm_args* args, void* stream);
@@ -216,7 +227,8 @@ int mm_convert_f32(const float* x, void* out, int64_t n, int32_t dtype, void* st
  * mm_col2im_k5s2: input gradient of Conv1d(k=5, stride 2, pad 2) from the per-window gradient [B, T_out, 5*C].
  * mm_grad_clip_coef: norm_coef[0] = ||grad_scale * grad||_2, norm_coef[1] = grad_scale * min(1, max_norm / (norm + 1e-6))
  *   (fairseq clip_grad_norm_; max_norm <= 0: no clipping); partials: mm_sumsq_blocks() floats.
- * mm_adam: fairseq.optim.adam.Adam.step on a flat fp32 buffer; the gradient is multiplied by norm_coef[1] (NULL: 1).
+ * mm_adam: fairseq.optim.adam.Adam.step on a flat fp32 buffer; the gradient is multiplied by norm_coef[1] (NULL: 1);
+ *   param_op (optional): 16-bit copy of the updated parameters, written in the same pass (the GEMM operand copies).
  * --------------------------------------------------------------------------------------------- */
 int mm_pack_t(const void* in, int32_t in_is_f32, int64_t in_ld, int64_t in_bs0, int64_t in_bs1, int32_t nb1,
               const void* mask, int64_t mask_ld, int32_t rows, int32_t cols, int32_t batches, float scale, void* out_n,
@@ -243,7 +255,8 @@ int mm_sumsq_blocks(void);
 int mm_grad_clip_coef(const float* grad, int64_t n, float grad_scale, float max_norm, float* partials, float* norm_coef,
                       void* stream);
 int mm_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
-            float beta2, float eps, float weight_decay, int32_t step, const float* norm_coef, void* stream);
+            float beta2, float eps, float weight_decay, int32_t step, const float* norm_coef, void* param_op,
+            int32_t dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,7 @@ CSRC = _PKG / "csrc"
 INCLUDE = _PKG.parent / "include"
 LIB_PATH = _PKG / "libmms2ut_b200.so"
 SOURCES = ["abi.cu", "gemm.cu", "gemm_ln.cu", "rowwise.cu", "fbank.cu", "attention.cu", "backward.cu"]
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -86,6 +86,9 @@ class GemmArgs(C.Structure):
         ("rows_per_seq", C.c_int32), ("out_tbc", C.c_int32), ("n_seqs", C.c_int32), ("out_row_offset", C.c_int32),
         ("vt", C.c_void_p), ("vt_col0", C.c_int32), ("vt_rows", C.c_int32), ("vt_ld", C.c_int64),
         ("pos", C.c_void_p), ("seq_lens", C.c_void_p),
+        ("a_mn", C.c_int32), ("w_mn", C.c_int32), ("a_kbatch", C.c_int32), ("w_kbatch", C.c_int32),
+        ("a_hm", C.c_int32), ("w_hm", C.c_int32), ("out_hm", C.c_int32), ("heads", C.c_int32),
+        ("head_stride", C.c_int32), ("a_k_total", C.c_int64), ("w_k_total", C.c_int64),
     ]
 
 
@@ -143,7 +146,7 @@ EXPORTS = {
     "mm_sumsq_blocks": (C.c_int, []),
     "mm_grad_clip_coef": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mm_adam": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float,
-                          C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p]),
+                          C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

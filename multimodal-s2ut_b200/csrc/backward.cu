@@ -18,7 +18,7 @@ namespace mm {
 __device__ __forceinline__ float sigmoid_exact(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 // ---------------------------------------------------------------------------------------------------
-// pack_t: tile 64 rows x 64 cols through shared memory (fp32), 256 threads.
+// pack_t: tile 64 rows x 64 cols through shared memory, 256 threads, 16-byte global loads / stores where aligned.
 // ---------------------------------------------------------------------------------------------------
 struct PackArgs {
   const void* in;
@@ -34,73 +34,141 @@ struct PackArgs {
 
 template <typename OpT>
 __global__ void __launch_bounds__(256) pack_t_kernel(PackArgs a) {
-  __shared__ float tile[64][65];
+  // 64 x 64 tile of 16-bit values, row stride 66 (132 B): the column gathers of the transposed store are 2-way
+  // bank-conflicted at worst; rows are written as 32-bit words.
+  __shared__ __align__(16) uint32_t tile[64 * 33];
   const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
   const int b0 = blockIdx.z / a.nb1, b1 = blockIdx.z % a.nb1;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 column pairs x 8 row groups
   const long long in_off = (long long)b0 * a.in_bs0 + (long long)b1 * a.in_bs1;
-  const int c = c0 + 2 * tx;
+  const long long n_off = (long long)b0 * a.n_bs0 + (long long)b1 * a.n_bs1;
+  const bool in_vec = (((a.in_ld | a.in_bs0 | a.in_bs1) & 7) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(a.in) & 15) == 0);
+  const bool mask_vec = !a.mask || (((a.mask_ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(a.mask) & 15) == 0));
+  const bool n_vec = a.out_n && (((a.n_ld | a.n_bs0 | a.n_bs1) & 7) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(a.out_n) & 15) == 0);
+  // ---- load: 8 consecutive columns per thread, 2 rows per thread
+  const int ch = threadIdx.x & 7;
+  const int c = c0 + ch * 8;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int rl = ty + 8 * j, r = r0 + rl;
-    float v0 = 0.f, v1 = 0.f;
+  for (int h = 0; h < 2; ++h) {
+    const int rl = (threadIdx.x >> 3) + 32 * h, r = r0 + rl;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
     if (r < a.rows && c < a.cols) {
       const long long idx = in_off + (long long)r * a.in_ld + c;
-      if (a.in_is_f32) {
-        const float2 t = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(a.in) + idx);
-        v0 = t.x, v1 = t.y;
+      const bool full = c + 8 <= a.cols;
+      if (full && in_vec) {
+        if (a.in_is_f32) {
+          const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.in) + idx);
+          const float4 x0 = __ldcs(p), x1 = __ldcs(p + 1);
+          v[0] = x0.x, v[1] = x0.y, v[2] = x0.z, v[3] = x0.w, v[4] = x1.x, v[5] = x1.y, v[6] = x1.z, v[7] = x1.w;
+        } else {
+          const uint4 q = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const OpT*>(a.in) + idx));
+          const OpT* e = reinterpret_cast<const OpT*>(&q);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = OpTraits<OpT>::to_float(e[i]);
+        }
       } else {
-        const OpT* p = reinterpret_cast<const OpT*>(a.in) + idx;
-        v0 = OpTraits<OpT>::to_float(p[0]), v1 = OpTraits<OpT>::to_float(p[1]);
+        for (int i = 0; i < 8 && c + i < a.cols; ++i)
+          v[i] = a.in_is_f32 ? reinterpret_cast<const float*>(a.in)[idx + i]
+                             : OpTraits<OpT>::to_float(reinterpret_cast<const OpT*>(a.in)[idx + i]);
       }
-      v0 *= a.scale, v1 *= a.scale;
+      if (a.scale != 1.0f) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] *= a.scale;
+      }
       if (a.mask) {
         const OpT* m = reinterpret_cast<const OpT*>(a.mask) + (long long)r * a.mask_ld + c;
-        if (!(OpTraits<OpT>::to_float(m[0]) > 0.f)) v0 = 0.f;
-        if (!(OpTraits<OpT>::to_float(m[1]) > 0.f)) v1 = 0.f;
-      }
-      if (a.out_n) {
-        OpT* o = reinterpret_cast<OpT*>(a.out_n) + (long long)b0 * a.n_bs0 + (long long)b1 * a.n_bs1 +
-                 (long long)r * a.n_ld + c;
-        *reinterpret_cast<uint32_t*>(o) = OpTraits<OpT>::pack2(v0, v1);
+        if (full && mask_vec) {
+          const uint4 q = __ldcs(reinterpret_cast<const uint4*>(m));
+          const OpT* e = reinterpret_cast<const OpT*>(&q);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (!(OpTraits<OpT>::to_float(e[i]) > 0.f)) v[i] = 0.f;
+        } else {
+          for (int i = 0; i < 8 && c + i < a.cols; ++i)
+            if (!(OpTraits<OpT>::to_float(m[i]) > 0.f)) v[i] = 0.f;
+        }
       }
     }
-    tile[rl][2 * tx] = v0;
-    tile[rl][2 * tx + 1] = v1;
+    uint4 pk;
+    pk.x = OpTraits<OpT>::pack2(v[0], v[1]);
+    pk.y = OpTraits<OpT>::pack2(v[2], v[3]);
+    pk.z = OpTraits<OpT>::pack2(v[4], v[5]);
+    pk.w = OpTraits<OpT>::pack2(v[6], v[7]);
+    if (a.out_n && r < a.rows && c < a.cols) {
+      OpT* o = reinterpret_cast<OpT*>(a.out_n) + n_off + (long long)r * a.n_ld + c;
+      if (c + 8 <= a.cols && n_vec) {
+        *reinterpret_cast<uint4*>(o) = pk;
+      } else {
+        const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+        for (int i = 0; i < 8 && c + i < a.cols; i += 2) *reinterpret_cast<uint32_t*>(o + i) = w[i >> 1];
+      }
+    }
+    uint32_t* t = tile + rl * 33 + ch * 4;
+    t[0] = pk.x, t[1] = pk.y, t[2] = pk.z, t[3] = pk.w;
   }
   if (!a.out_t) return;
   __syncthreads();
-  // transposed store: output row = input column, 32 pairs of consecutive input rows per warp
+  // ---- transposed store: output row = input column; a thread gathers 8 consecutive input rows of one column
   OpT* ot = reinterpret_cast<OpT*>(a.out_t) + (long long)b0 * a.t_bs0 + (long long)b1 * a.t_bs1;
-  const int r = r0 + 2 * tx;
+  const bool t_vec = (((a.t_ld | a.t_bs0 | a.t_bs1) & 7) == 0) && ((a.t_cols_pad & 7) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(a.out_t) & 15) == 0);
+  const uint16_t* t16 = reinterpret_cast<const uint16_t*>(tile);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = lane & 7;
+  const int r = r0 + 8 * j;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int cl = ty + 8 * j, cc = c0 + cl;
-    if (cc < a.cols && r < a.t_cols_pad) {
-      // rows >= a.rows were loaded as zeros: the padding columns of the transposed copy are written as 0
-      *reinterpret_cast<uint32_t*>(ot + (long long)cc * a.t_ld + r) =
-          OpTraits<OpT>::pack2(tile[2 * tx][cl], tile[2 * tx + 1][cl]);
+  for (int pass = 0; pass < 2; ++pass) {
+    const int cl = warp * 8 + pass * 4 + (lane >> 3), cc = c0 + cl;
+    if (cc >= a.cols || r >= a.t_cols_pad) continue;
+    uint16_t e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = t16[(8 * j + i) * 66 + cl];
+    OpT* dst = ot + (long long)cc * a.t_ld + r;
+    if (t_vec) {
+      uint4 pk;
+      pk.x = e[0] | ((uint32_t)e[1] << 16), pk.y = e[2] | ((uint32_t)e[3] << 16);
+      pk.z = e[4] | ((uint32_t)e[5] << 16), pk.w = e[6] | ((uint32_t)e[7] << 16);
+      *reinterpret_cast<uint4*>(dst) = pk;
+    } else {
+      for (int i = 0; i < 8 && r + i < a.t_cols_pad; i += 2)
+        *reinterpret_cast<uint32_t*>(dst + i) = e[i] | ((uint32_t)e[i + 1] << 16);
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// rowsum: out[r] (+)= sum_c in[r, c], warp per row, 16-bit input.
+// rowsum: out[r] (+)= sum_c in[r, c]; one 256-thread block per row, 16-byte loads, fixed-order block reduction.
 // ---------------------------------------------------------------------------------------------------
 template <typename OpT>
 __global__ void __launch_bounds__(256) rowsum_kernel(const OpT* __restrict__ in, long long ld, int rows, int cols,
                                                       float* __restrict__ out, int accumulate) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  __shared__ float red[8];
+  const int row = blockIdx.x;
   const OpT* p = in + (long long)row * ld;
-  float s0 = 0.f, s1 = 0.f;
-  for (int c = 2 * lane; c < cols; c += 64) {
-    s0 += OpTraits<OpT>::to_float(p[c]);
-    if (c + 1 < cols) s1 += OpTraits<OpT>::to_float(p[c + 1]);
+  float s = 0.f;
+  const bool vec = ((ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+  const int cols8 = vec ? (cols & ~7) : 0;
+  for (int c = threadIdx.x * 8; c < cols8; c += 256 * 8) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p + c);
+    const OpT* e = reinterpret_cast<const OpT*>(&q);
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += OpTraits<OpT>::to_float(e[i]);
+    s += t;
   }
-  const float s = warp_sum(s0 + s1);
-  if (lane == 0) out[row] = accumulate ? out[row] + s : s;
+  for (int c = cols8 + threadIdx.x; c < cols; c += 256) s += OpTraits<OpT>::to_float(p[c]);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    out[row] = accumulate ? out[row] + t : t;
+  }
 }
 
 // out[i] (+)= sum_s part[s * stride + i]
@@ -358,10 +426,12 @@ __global__ void clip_coef_kernel(const float* __restrict__ partials, int S, floa
 
 // fairseq.optim.adam.Adam.step: m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; denom = sqrt(v) + eps ;
 // step_size = lr sqrt(1-b2^t) / (1-b1^t) ; p -= wd lr p ; p -= step_size m / denom
+template <typename OpT>
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                     float* __restrict__ m, float* __restrict__ v, long long n, float lr,
                                                     float beta1, float beta2, float eps, float weight_decay,
-                                                    float step_size, const float* __restrict__ coef) {
+                                                    float step_size, const float* __restrict__ coef,
+                                                    OpT* __restrict__ p_op) {
   const float gs = coef ? coef[1] : 1.0f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * gs;
@@ -370,7 +440,9 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     m[i] = mi, v[i] = vi;
     float pi = p[i];
     if (weight_decay != 0.f) pi -= weight_decay * lr * pi;
-    p[i] = pi - step_size * mi / (sqrtf(vi) + eps);
+    pi -= step_size * mi / (sqrtf(vi) + eps);
+    p[i] = pi;
+    if (p_op) p_op[i] = OpTraits<OpT>::cvt(pi);
   }
 }
 
@@ -423,7 +495,7 @@ extern "C" int mm_rowsum(const void* in, int64_t ld, int32_t rows, int32_t cols,
                          int32_t dtype, void* stream) {
   if (!in || !out || rows <= 0 || cols <= 0) return bad_arg("rowsum");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const unsigned grid = (rows + 7) / 8;
+  const unsigned grid = rows;
   if (dtype == MM_DTYPE_F16)
     rowsum_kernel<__half><<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(in), ld, rows, cols, out, accumulate);
   else
@@ -542,12 +614,19 @@ extern "C" int mm_grad_clip_coef(const float* grad, int64_t n, float grad_scale,
 
 extern "C" int mm_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                        float beta1, float beta2, float eps, float weight_decay, int32_t step, const float* norm_coef,
-                       void* stream) {
+                       void* param_op, int32_t dtype, void* stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq || n <= 0 || step <= 0) return bad_arg("adam");
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
   const float step_size = (float)((double)lr * sqrt(bc2) / bc1);
-  adam_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
-                                                                          beta2, eps, weight_decay, step_size, norm_coef);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == MM_DTYPE_F16)
+    adam_kernel<__half><<<grid_for(n), 256, 0, s>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                    weight_decay, step_size, norm_coef,
+                                                    reinterpret_cast<__half*>(param_op));
+  else
+    adam_kernel<__nv_bfloat16><<<grid_for(n), 256, 0, s>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                           weight_decay, step_size, norm_coef,
+                                                           reinterpret_cast<__nv_bfloat16*>(param_op));
   MM_CHECK_LAUNCH("adam_kernel launch");
   return 0;
 }

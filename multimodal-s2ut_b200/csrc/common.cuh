@@ -311,6 +311,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                     // SWIZZLE_128B
   return d;
 }
+// MN-major operand tile, 128-byte swizzle: 64-element (128 B) runs along the rows (MN) dimension, one 128 B line per
+// contraction index, 8-line atoms of 1024 B (stride byte offset); the next 64-wide block of rows starts `block_bytes`
+// further (leading byte offset).  Each block is what one TMA box {64 rows, kblock} with SWIZZLE_128B writes.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t block_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(block_bytes >> 4) << 16;      // leading byte offset: next 64 rows
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;             // stride byte offset: next 8 contraction indices
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // kind::f16 instruction descriptor: fp32 accumulate, A/B both K-major, fmt 0 = f16, 1 = bf16
 __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int fmt) {
   return (1u << 4) | (static_cast<uint32_t>(fmt) << 7) | (static_cast<uint32_t>(fmt) << 10) |

@@ -38,6 +38,9 @@ struct GemmDev {
   long long vt_ld;
   const float* pos;
   const int* seq_lens;
+  // operand layout extensions (backward pass): MN-major operands (memory is [contraction][rows]), split-K batches that
+  // advance the contraction coordinate, and (batch, head) decomposition of the batch index with per-head column offsets
+  int a_mn, w_mn, a_kbatch, w_kbatch, a_hm, w_hm, out_hm, heads, head_stride;
 };
 
 struct GemmCfg {
@@ -164,15 +167,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
         const int bi = mp / p.m_pairs_per_batch;
         const int row0 = (mp % p.m_pairs_per_batch) * (2 * Cfg::BM) + rank * Cfg::BM;
         const int wrow0 = n_tile * BN + rank * (BN / 2);
+        const int hb = p.heads > 0 ? bi / p.heads : bi, hcol = p.heads > 0 ? (bi % p.heads) * p.head_stride : 0;
+        const int a_b = p.a_hm ? hb : bi, a_c = p.a_hm ? hcol : 0;
+        const int w_b = p.w_batched ? (p.w_hm ? hb : bi) : 0, w_c = p.w_hm ? hcol : 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           if (rank == 0) mbar_expect_tx(&full[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
-          if (kb < p.kb_split)
-            tma_load_3d_2sm(sA + stage * Cfg::A_BYTES, &mapA0, &full[stage], kb * Cfg::BK, row0, bi);
-          else
-            tma_load_3d_2sm(sA + stage * Cfg::A_BYTES, &mapA1, &full[stage], (kb - p.kb_split) * Cfg::BK, row0, bi);
-          tma_load_3d_2sm(sB + stage * Cfg::B_BYTES, &mapW, &full[stage], kb * Cfg::BK, wrow0,
-                          p.w_batched ? bi : 0);
+          uint8_t* dA = sA + stage * Cfg::A_BYTES;
+          uint8_t* dB = sB + stage * Cfg::B_BYTES;
+          if (p.a_mn) {
+            // MN-major A: two 64 (rows) x 64 (contraction) boxes, 8 KB each; memory rows are contraction indices
+            const int kc = kb * Cfg::BK + (p.a_kbatch ? bi * p.k : 0);
+            const int bz = p.a_kbatch ? 0 : a_b;
+            tma_load_3d_2sm(dA, &mapA0, &full[stage], row0 + a_c, kc, bz);
+            tma_load_3d_2sm(dA + Cfg::A_BYTES / 2, &mapA0, &full[stage], row0 + 64 + a_c, kc, bz);
+          } else if (kb < p.kb_split) {
+            tma_load_3d_2sm(dA, &mapA0, &full[stage], kb * Cfg::BK + a_c, row0, a_b);
+          } else {
+            tma_load_3d_2sm(dA, &mapA1, &full[stage], (kb - p.kb_split) * Cfg::BK, row0, bi);
+          }
+          if (p.w_mn) {
+            const int kc = kb * Cfg::BK + (p.w_kbatch ? bi * p.k : 0);
+            const int bz = p.w_kbatch ? 0 : w_b;
+            tma_load_3d_2sm(dB, &mapW, &full[stage], wrow0 + w_c, kc, bz);
+            tma_load_3d_2sm(dB + Cfg::B_BYTES / 2, &mapW, &full[stage], wrow0 + 64 + w_c, kc, bz);
+          } else {
+            tma_load_3d_2sm(dB, &mapW, &full[stage], kb * Cfg::BK + w_c, wrow0, w_b);
+          }
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
       }
@@ -180,7 +201,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (rank == 0 && lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(2 * Cfg::BM, BN, OpTraits<OpT>::fmt);
+      // bit 15 / 16: A / B operand is MN-major
+      const uint32_t idesc = umma_idesc(2 * Cfg::BM, BN, OpTraits<OpT>::fmt) | (p.a_mn ? (1u << 15) : 0u) |
+                             (p.w_mn ? (1u << 16) : 0u);
+      // per K=16 step: +32 B inside the 128 B swizzle row (K-major) or +16 rows of 128 B (MN-major)
+      const uint64_t a_step = p.a_mn ? 128 : 2, b_step = p.w_mn ? 128 : 2;
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       const int k_tail = p.k - (p.num_kb - 1) * Cfg::BK;          // valid K in the last k-block
       const int tail_steps = (k_tail + 15) >> 4;
@@ -191,11 +216,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
+          const uint32_t aaddr = smem_u32(sA + stage * Cfg::A_BYTES), baddr = smem_u32(sB + stage * Cfg::B_BYTES);
+          const uint64_t adesc = p.a_mn ? umma_desc_sw128_mn(aaddr, Cfg::A_BYTES / 2) : umma_desc_sw128(aaddr);
+          const uint64_t bdesc = p.w_mn ? umma_desc_sw128_mn(baddr, Cfg::B_BYTES / 2) : umma_desc_sw128(baddr);
           const int steps = (kb == p.num_kb - 1) ? tail_steps : 4;
-          for (int kk = 0; kk < steps; ++kk)  // +32 B per K=16 step inside the 128 B swizzle row
-            umma_f16_2sm(tmem_d, adesc + 2 * kk, bdesc + 2 * kk, idesc, (kb | kk) != 0);
+          for (int kk = 0; kk < steps; ++kk)
+            umma_f16_2sm(tmem_d, adesc + a_step * kk, bdesc + b_step * kk, idesc, (kb | kk) != 0);
           umma_commit_2sm(&empty[stage], 3);
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
@@ -222,6 +248,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
       const int r = row0 + lrow;                                         // row within the batch
       const bool rvalid = r < p.rows;
       const int col_tile = n_tile * BN;
+      const int ob = p.out_hm ? bi / p.heads : bi;                       // output batch / column offset (head mode)
+      const int ocol = p.out_hm ? (bi % p.heads) * p.head_stride : 0;
 
       asm volatile("bar.sync 1, 128;" ::: "memory");   // every thread is done with the previous tile's bias
       for (int i = et; i < BN; i += 128) {
@@ -303,7 +331,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
             fence_proxy_async_smem();
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (et == 0) {
-              tma_store_3d(&mapOut0, slab, col, row0 + p.out_row_offset, bi);
+              tma_store_3d(&mapOut0, slab, col + ocol, row0 + p.out_row_offset, ob);
               bulk_commit();
             }
             ++slab_ctr;
@@ -664,10 +692,35 @@ extern "C" int mm_gemm(const mm_gemm_args* a, void* stream) {
   }
   if ((mode == MM_EPI_RESID_F32 || mode == MM_EPI_GATE) && (a->n % 32)) return bad_arg("RESID/GATE need n % 32 == 0");
 
+  const bool layouts = a->a_mn || a->w_mn || a->a_hm || a->w_hm || a->out_hm;
+  if (layouts) {
+    if (a->a1) return bad_arg("MN-major / head-mode operands exclude the split A operand");
+    if ((a->a_hm || a->w_hm || a->out_hm) && (a->heads <= 0 || a->head_stride <= 0 || a->batches % a->heads))
+      return bad_arg("head mode needs heads > 0, head_stride > 0 and batches % heads == 0");
+    if (a->out_hm && (mode != MM_EPI_OP || a->vt || a->n % 64)) return bad_arg("out_hm needs MM_EPI_OP and n % 64 == 0");
+    if ((a->a_kbatch && !a->a_mn) || (a->w_kbatch && !a->w_mn)) return bad_arg("kbatch needs an MN-major operand");
+    if ((a->a_kbatch || a->w_kbatch) && a->k % 64) return bad_arg("split-K batches need k % 64 == 0");
+    if (a->w_hm && !a->w_batched) return bad_arg("w_hm needs w_batched");
+  }
   GemmMaps m;
   const int f16 = a->dtype == MM_DTYPE_F16;
   const uint64_t rows = (uint64_t)a->rows, nb = (uint64_t)a->batches;
-  int rc = make_tmap_3d(&m.a0, a->a0, f16, (uint64_t)k0, rows, nb, (uint64_t)a->a0_ld, (uint64_t)a->a0_bs, 128);
+  const uint64_t hw = (uint64_t)a->heads * (uint64_t)a->head_stride;      // column extent of a head-mode tensor
+  const uint64_t nseq = a->heads > 0 ? nb / (uint64_t)a->heads : nb;
+  int rc;
+  if (a->a_mn) {
+    // memory [batch][contraction][rows]: dim0 = rows (or all heads' columns), dim1 = contraction indices
+    const uint64_t d0 = a->a_hm ? hw : rows;
+    if (a->a_kbatch)
+      rc = make_tmap_3d_ex(&m.a0, a->a0, f16 ? 1 : 0, d0, (uint64_t)(a->a_k_total > 0 ? a->a_k_total : nb * k0), 1,
+                           (uint64_t)a->a0_ld, 0, 64, 64);
+    else
+      rc = make_tmap_3d_ex(&m.a0, a->a0, f16 ? 1 : 0, d0, (uint64_t)k0, a->a_hm ? nseq : nb, (uint64_t)a->a0_ld,
+                           (uint64_t)a->a0_bs, 64, 64);
+  } else {
+    rc = make_tmap_3d(&m.a0, a->a0, f16, a->a_hm ? hw : (uint64_t)k0, rows, a->a_hm ? nseq : nb, (uint64_t)a->a0_ld,
+                      (uint64_t)a->a0_bs, 128);
+  }
   if (rc) return rc;
   if (a->a1) {
     rc = make_tmap_3d(&m.a1, a->a1, f16, (uint64_t)(a->k - k0), rows, nb, (uint64_t)a->a1_ld, (uint64_t)a->a1_bs, 128);
@@ -675,8 +728,19 @@ extern "C" int mm_gemm(const mm_gemm_args* a, void* stream) {
   } else {
     m.a1 = m.a0;
   }
-  rc = make_tmap_3d(&m.w, a->w, f16, (uint64_t)a->k, (uint64_t)a->n, (uint64_t)(a->w_batched ? a->batches : 1),
-                    (uint64_t)a->w_ld, (uint64_t)a->w_bs, 128);
+  const uint64_t wb = a->w_batched ? (a->w_hm ? nseq : nb) : 1;
+  if (a->w_mn) {
+    const uint64_t d0 = a->w_hm ? hw : (uint64_t)a->n;
+    if (a->w_kbatch)
+      rc = make_tmap_3d_ex(&m.w, a->w, f16 ? 1 : 0, d0, (uint64_t)(a->w_k_total > 0 ? a->w_k_total : nb * a->k), 1,
+                           (uint64_t)a->w_ld, 0, 64, 64);
+    else
+      rc = make_tmap_3d_ex(&m.w, a->w, f16 ? 1 : 0, d0, (uint64_t)a->k, wb, (uint64_t)a->w_ld, (uint64_t)a->w_bs, 64,
+                           64);
+  } else {
+    rc = make_tmap_3d(&m.w, a->w, f16, a->w_hm ? hw : (uint64_t)a->k, (uint64_t)a->n, wb, (uint64_t)a->w_ld,
+                      (uint64_t)a->w_bs, 128);
+  }
   if (rc) return rc;
 
   // outputs: 3-D maps (columns, rows, batch); T x B x C stores are just another stride pair
@@ -687,8 +751,8 @@ extern "C" int mm_gemm(const mm_gemm_args* a, void* stream) {
   uint64_t s1 = (uint64_t)a->out0_ld, s2 = (uint64_t)a->out0_bs;
   if (a->out_tbc) s1 = (uint64_t)a->n_seqs * a->out0_ld, s2 = (uint64_t)a->out0_ld;
   if (n_out > 0) {
-    rc = make_tmap_3d_ex(&m.out0, a->out0, out_op ? (f16 ? 1 : 0) : 2, n_out, out_rows, nb, s1, s2, out_op ? 64 : 32,
-                         128);
+    rc = make_tmap_3d_ex(&m.out0, a->out0, out_op ? (f16 ? 1 : 0) : 2, a->out_hm ? hw : n_out, out_rows,
+                         a->out_hm ? nseq : nb, s1, s2, out_op ? 64 : 32, 128);
     if (rc) return rc;
   } else {
     m.out0 = m.a0;  // every column goes to vt; never used
@@ -722,6 +786,8 @@ extern "C" int mm_gemm(const mm_gemm_args* a, void* stream) {
   p.rows_per_seq = a->rows_per_seq, p.out_row_offset = a->out_row_offset;
   p.vt = a->vt, p.vt_col0 = a->vt_col0, p.vt_rows = a->vt_rows, p.vt_ld = a->vt_ld;
   p.pos = a->pos, p.seq_lens = a->seq_lens;
+  p.a_mn = a->a_mn, p.w_mn = a->w_mn, p.a_kbatch = a->a_kbatch, p.w_kbatch = a->w_kbatch;
+  p.a_hm = a->a_hm, p.w_hm = a->w_hm, p.out_hm = a->out_hm, p.heads = a->heads, p.head_stride = a->head_stride;
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return f16 ? dispatch_mode<__half>(mode, m, p, s) : dispatch_mode<__nv_bfloat16>(mode, m, p, s);

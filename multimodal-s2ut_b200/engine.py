@@ -91,7 +91,7 @@ class EncoderEngine:
             idx += [a, half + a]
         return torch.cat(idx).to(self.device)
 
-    def _pack(self) -> None:
+    def _pack_conv(self) -> None:
         enc = self.enc
         convs = enc.subsample.conv_layers
         if len(convs) != 2 or any(c.kernel_size[0] != 5 for c in convs):
@@ -104,6 +104,10 @@ class EncoderEngine:
             perm = self._glu_perm(cout)
             w = c.weight.detach().float().permute(0, 2, 1).reshape(cout, k * cin)[perm]   # [n, tap*cin + ci]
             self.conv.append(dict(w=self._op(w), b=self._f32(c.bias)[perm].contiguous(), cin=cin, cout=cout, k=k))
+
+    def _pack(self) -> None:
+        enc = self.enc
+        self._pack_conv()
         self.layers = []
         for L in enc.transformer_layers:
             a = L.self_attn

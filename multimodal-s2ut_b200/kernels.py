@@ -42,6 +42,7 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 # Optional per-launch device timing (bench.py's instrumented pass): when `timing` is a list, every wrapper
 # brackets its launch with CUDA events on the launching stream and appends (name, start, end, work) to it.
 timing = None
+scope = ""      # set by the engines around a phase: timed launches are reported as "name@scope"
 
 
 class _Launch:
@@ -62,7 +63,7 @@ class _Launch:
         if timing is not None and exc[0] is None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            timing.append((self.name, self.e0, e1, self.work))
+            timing.append((self.name + ("@" + scope if scope else ""), self.e0, e1, self.work))
         return False
 
 
@@ -142,7 +143,10 @@ def gemm(*, a0: torch.Tensor, w: torch.Tensor, rows: int, n: int, k: int, mode: 
          aux0: Optional[torch.Tensor] = None, aux1: Optional[torch.Tensor] = None, aux_ld: int = 0,
          rows_per_seq: int = 0, out_tbc: bool = False, n_seqs: int = 0, out_row_offset: int = 0,
          vt: Optional[torch.Tensor] = None, vt_col0: int = 0, vt_rows: int = 0, vt_ld: int = 0,
-         pos: Optional[torch.Tensor] = None, seq_lens: Optional[torch.Tensor] = None, block_n: int = 0) -> None:
+         pos: Optional[torch.Tensor] = None, seq_lens: Optional[torch.Tensor] = None, block_n: int = 0,
+         a_mn: bool = False, w_mn: bool = False, a_kbatch: bool = False, w_kbatch: bool = False, a_hm: bool = False,
+         w_hm: bool = False, out_hm: bool = False, heads: int = 0, head_stride: int = 0, a_k_total: int = 0,
+         w_k_total: int = 0) -> None:
     """acc = A @ W^T with a fused epilogue; see ``mm_gemm_args`` in include/mms2ut_b200.h."""
     if a0.dtype != w.dtype or (a1 is not None and a1.dtype != w.dtype):
         raise TypeError("A and W must share the 16-bit operand dtype")
@@ -164,6 +168,9 @@ def gemm(*, a0: torch.Tensor, w: torch.Tensor, rows: int, n: int, k: int, mode: 
     g.rows_per_seq, g.out_tbc, g.n_seqs, g.out_row_offset = rows_per_seq, int(out_tbc), n_seqs, out_row_offset
     g.vt, g.vt_col0, g.vt_rows, g.vt_ld = _ptr(vt), vt_col0, vt_rows, vt_ld
     g.pos, g.seq_lens = _ptr(pos), _ptr(seq_lens)
+    g.a_mn, g.w_mn, g.a_kbatch, g.w_kbatch = int(a_mn), int(w_mn), int(a_kbatch), int(w_kbatch)
+    g.a_hm, g.w_hm, g.out_hm, g.heads, g.head_stride = int(a_hm), int(w_hm), int(out_hm), heads, head_stride
+    g.a_k_total, g.w_k_total = a_k_total, w_k_total
     lib = _lib.load()
     with _Launch(f"gemm[{EPI_NAMES[mode]}]", 2.0 * rows * batches * n * k):          # algorithmic FLOPs
         _lib.check(lib.mm_gemm(C.byref(g), _stream()), "mm_gemm")
@@ -414,11 +421,13 @@ def grad_clip_coef(grad: torch.Tensor, grad_scale: float, max_norm: float, parti
 
 def adam(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, *, lr: float,
          betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, step: int = 1,
-         norm_coef: Optional[torch.Tensor] = None) -> None:
-    """fairseq Adam step on flat fp32 buffers (in place)."""
+         norm_coef: Optional[torch.Tensor] = None, param_op: Optional[torch.Tensor] = None) -> None:
+    """fairseq Adam step on flat fp32 buffers (in place); param_op: 16-bit copy of the new parameters (same pass)."""
+    assert param_op is None or (param_op.numel() == param.numel() and param_op.is_contiguous())
     for t in (param, grad, exp_avg, exp_avg_sq):
         assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == param.numel()
     lib = _lib.load()
     with _Launch("adam", 28.0 * param.numel()):
         _lib.check(lib.mm_adam(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), lr, betas[0],
-                               betas[1], eps, weight_decay, step, _ptr(norm_coef), _stream()), "mm_adam")
+                               betas[1], eps, weight_decay, step, _ptr(norm_coef), _ptr(param_op),
+                               dtype_code(param_op.dtype) if param_op is not None else 0, _stream()), "mm_adam")

@@ -46,6 +46,20 @@ def _split_k(n: int, kin: int, mp: int) -> int:
     return s
 
 
+class _scope:
+    """Tags the launches of a phase in the per-launch timing list (``kernels.timing``)."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        self.prev, K.scope = K.scope, self.name
+
+    def __exit__(self, *exc):
+        K.scope = self.prev
+        return False
+
+
 def all_reduce_flat(flat: torch.Tensor, bucket_elems: int = 8 * 1024 * 1024) -> int:
     """Bucketed asynchronous SUM all-reduce of a flat gradient buffer over the default process group."""
     import torch.distributed as dist
@@ -136,7 +150,7 @@ class TrainEngine(EncoderEngine):
         offs, total = [], 0
         for p in order:
             offs.append(total)
-            total += _round_up(p.numel(), 4)
+            total += _round_up(p.numel(), 8)    # 16-byte aligned slices of the 16-bit copy too (TMA bases)
         self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
         self._slices: Dict[int, Tuple[int, int]] = {}
@@ -171,10 +185,52 @@ class TrainEngine(EncoderEngine):
     # ------------------------------------------------------------------------------------------
     # 16-bit operand copies for the backward pass (transposed weights, un-permuted conv weights)
     # ------------------------------------------------------------------------------------------
-    def _wt(self, name: str, src_f32: torch.Tensor, n: int, k: int) -> torch.Tensor:
-        """[k, n] 16-bit transposed copy of the fp32 weight [n, k] (the W operand of a dgrad GEMM)."""
+    def opw(self, *params) -> torch.Tensor:
+        """16-bit operand copy of the given (adjacent) parameters: a slice of ``flat_op`` (written by the Adam kernel)."""
+        o0, n0 = self._slices[id(params[0])]
+        end = o0 + n0
+        for p in params[1:]:
+            o, n = self._slices[id(p)]
+            assert o == end
+            end = o + n
+        return self.flat_op[o0:end]
+
+    def _pack(self) -> None:
+        """Forward operand set.  Linear weights are views of ``flat_op`` and biases / LayerNorm parameters views of
+        ``flat_p`` (so an optimizer step needs no re-packing of them); conv weights keep their GLU tile permutation."""
+        if not hasattr(self, "flat_op"):
+            self.flat_op = torch.empty(self.flat_p.numel(), dtype=self.op_dtype, device=self.device)
+            K.convert(self.flat_p, self.flat_op)
+        if getattr(self, "_linked", False):
+            self._pack_conv()
+            return
+        super()._pack()
+        enc, d = self.enc, self.d
+        for L, mod in zip(self.layers, enc.transformer_layers):
+            a = mod.self_attn
+            L.update(wqkv=self.opw(a.q_proj.weight, a.k_proj.weight, a.v_proj.weight).view(3 * d, d),
+                     bqkv=self.w(a.q_proj.bias, a.k_proj.bias, a.v_proj.bias),
+                     wo=self.opw(a.out_proj.weight).view(d, d), w1=self.opw(mod.fc1.weight).view(self.ffn, d),
+                     w2=self.opw(mod.fc2.weight).view(d, self.ffn))
+        for j, F in enumerate(self.fusion):
+            dk = F["dk"]
+            g = enc.gate_denses[j]
+            if enc.multimodal_attention_type == "selective_attention":
+                s = enc.selective_attns[j]
+                F.update(wq=self.opw(s.q_proj.weight).view(d, d), wkv=self.opw(s.k_proj.weight, s.v_proj.weight).view(2 * d, dk),
+                         bkv=self.w(s.k_proj.bias, s.v_proj.bias), wp=self.opw(s.proj.weight).view(d, d))
+            else:
+                m = enc.multimodal_attns[j]
+                F.update(wq=self.opw(m.q_proj_weight).view(d, d), wkv=self.opw(m.k_proj_weight, m.v_proj_weight).view(2 * d, dk),
+                         bq=self.w(m.in_proj_bias)[:d], bkv=self.w(m.in_proj_bias)[d:], wp=self.opw(m.out_proj.weight).view(d, d),
+                         bias_kv=(self.opw(m.bias_k), self.opw(m.bias_v)))
+            F.update(wg=self.opw(g.weight).view(d, 2 * d))
+        self._linked = True
+
+    def _wt(self, name: str, src: torch.Tensor, n: int, k: int) -> torch.Tensor:
+        """[k, n] 16-bit transposed copy of the weight [n, k] (the W operand of a dgrad GEMM)."""
         t = self.buf("wt_" + name, (k, _even(n)), self.op_dtype, zero=True)
-        K.pack_t(src_f32, rows=n, cols=k, in_ld=k, out_t=t, t_ld=_even(n))
+        K.pack_t(src, rows=n, cols=k, in_ld=k, out_t=t, t_ld=_even(n))
         return t
 
     def _pack_train(self) -> None:
@@ -191,10 +247,10 @@ class TrainEngine(EncoderEngine):
         for i, L in enumerate(enc.transformer_layers):
             a = L.self_attn
             self.layers_bwd.append(dict(
-                wqkv_t=self._wt(f"qkv{i}", self.w(a.q_proj.weight, a.k_proj.weight, a.v_proj.weight), 3 * d, d),
-                wo_t=self._wt(f"o{i}", self.w(a.out_proj.weight), d, d),
-                w1_t=self._wt(f"fc1{i}", self.w(L.fc1.weight), self.ffn, d),
-                w2_t=self._wt(f"fc2{i}", self.w(L.fc2.weight), d, self.ffn), mod=L))
+                wqkv_t=self._wt(f"qkv{i}", self.opw(a.q_proj.weight, a.k_proj.weight, a.v_proj.weight), 3 * d, d),
+                wo_t=self._wt(f"o{i}", self.opw(a.out_proj.weight), d, d),
+                w1_t=self._wt(f"fc1{i}", self.opw(L.fc1.weight), self.ffn, d),
+                w2_t=self._wt(f"fc2{i}", self.opw(L.fc2.weight), d, self.ffn), mod=L))
         self.fusion_bwd = []
         for j, F in enumerate(self.fusion):
             dk = F["dk"]
@@ -209,8 +265,9 @@ class TrainEngine(EncoderEngine):
             gd = enc.gate_denses[j]
             ps.update(wg=(gd.weight,), bg=(gd.bias,))
             self.fusion_bwd.append(dict(
-                p=ps, wq_t=self._wt(f"fq{j}", self.w(*ps["wq"]), d, d), wkv_t=self._wt(f"fkv{j}", self.w(*ps["wkv"]), 2 * d, dk),
-                wp_t=self._wt(f"fp{j}", self.w(*ps["wp"]), d, d), wg_t=self._wt(f"fg{j}", self.w(*ps["wg"]), d, 2 * d)))
+                p=ps, wq_t=self._wt(f"fq{j}", self.opw(*ps["wq"]), d, d),
+                wkv_t=self._wt(f"fkv{j}", self.opw(*ps["wkv"]), 2 * d, dk),
+                wp_t=self._wt(f"fp{j}", self.opw(*ps["wp"]), d, d), wg_t=self._wt(f"fg{j}", self.opw(*ps["wg"]), d, 2 * d)))
 
     def repack(self) -> None:
         """Refresh every 16-bit operand copy from the fp32 master parameters (after an optimizer step)."""
@@ -416,7 +473,8 @@ class TrainEngine(EncoderEngine):
         datt = self.buf("b_datt", (M, d), op)
         K.gemm(a0=g_op, a0_ld=d, rows=M, w=Lb["wo_t"], n=d, k=d, mode=K.EPI_OP, out0=datt, out0_ld=d, block_n=bn)
         dqkv = self.buf("b_dqkv", (M, 3 * d), op)
-        self._attention_bwd(s, datt, dqkv, B, T, seq_lens)
+        with _scope("attn"):
+            self._attention_bwd(s, datt, dqkv, B, T, seq_lens)
         self._linear_bwd("qkv", dqkv, False, 3 * d, s["h1"], M, 3 * d, d,
                          self.g(a.q_proj.weight, a.k_proj.weight, a.v_proj.weight),
                          self.g(a.q_proj.bias, a.k_proj.bias, a.v_proj.bias), accumulate)
@@ -603,7 +661,8 @@ class TrainEngine(EncoderEngine):
         assert tuple(grad_out.shape) == (T, B, d)
         gtext = self.buf("b_gtext", (M, d), torch.float32)
         if sv["fused"]:
-            self._fusion_bwd(grad_out, gtext, B, T, accumulate)
+            with _scope("fusion"):
+                self._fusion_bwd(grad_out, gtext, B, T, accumulate)
         else:
             K.tbc_to_btc(grad_out, B, T, d, gtext)
         lnp = self.buf("ln_part", (self._ln_blocks * 2 * max(d, 1024),), torch.float32)
@@ -611,8 +670,10 @@ class TrainEngine(EncoderEngine):
         K.layernorm_bwd(sv["x_final"], self.ln_g, gtext, lnp, dx=g)
         self._ln_param_grads(lnp, d, self.g(self.enc.layer_norm.weight, self.enc.layer_norm.bias), accumulate)
         for i in reversed(range(self.n_layers)):
-            self._layer_bwd(i, g, B, T, sv["seq_lens"], accumulate)
-        self._conv_bwd(g, B, T, accumulate)
+            with _scope("layer"):
+                self._layer_bwd(i, g, B, T, sv["seq_lens"], accumulate)
+        with _scope("conv"):
+            self._conv_bwd(g, B, T, accumulate)
 
     # ------------------------------------------------------------------------------------------
     # gradient exchange + optimizer
@@ -628,7 +689,11 @@ class TrainEngine(EncoderEngine):
                   clip_norm: float = 0.0, grad_scale: float = 1.0) -> None:
         """fairseq: multiply_grads(grad_scale) -> clip_grad_norm_(clip_norm) -> Adam.step, then refresh operand copies."""
         self.step_count += 1
+        with _scope("optim"):
+            self._adam(lr, betas, eps, weight_decay, clip_norm, grad_scale)
+
+    def _adam(self, lr, betas, eps, weight_decay, clip_norm, grad_scale) -> None:
         K.grad_clip_coef(self.flat_g, grad_scale, clip_norm, self._sumsq_partials, self.norm_coef)
         K.adam(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, lr=lr, betas=betas, eps=eps,
-               weight_decay=weight_decay, step=self.step_count, norm_coef=self.norm_coef)
+               weight_decay=weight_decay, step=self.step_count, norm_coef=self.norm_coef, param_op=self.flat_op)
         self.repack()

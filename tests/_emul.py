@@ -16,6 +16,7 @@ import torch
 EPI_OP, EPI_RELU_OP, EPI_RESID_F32, EPI_GLU_OP, EPI_GLU_POS_F32, EPI_F32_OP, EPI_GATE, EPI_F32 = range(8)
 launch_count = 0
 timing = None
+scope = ""
 
 
 def _v(t, sizes, strides, extra_offset=0):
@@ -296,7 +297,7 @@ def grad_clip_coef(grad, grad_scale, max_norm, partials, norm_coef):
 
 
 def adam(param, grad, exp_avg, exp_avg_sq, *, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, step=1,
-         norm_coef=None):
+         norm_coef=None, param_op=None):
     g = grad * (norm_coef[1] if norm_coef is not None else 1.0)
     exp_avg.mul_(betas[0]).add_(g, alpha=1 - betas[0])
     exp_avg_sq.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
@@ -304,6 +305,8 @@ def adam(param, grad, exp_avg, exp_avg_sq, *, lr, betas=(0.9, 0.999), eps=1e-8, 
     if weight_decay:
         param.mul_(1 - weight_decay * lr)
     param.addcdiv_(exp_avg, exp_avg_sq.sqrt() + eps, value=-step_size)
+    if param_op is not None:
+        param_op.copy_(param.to(param_op.dtype))
 
 
 class _FakeLib:

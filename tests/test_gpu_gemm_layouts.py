@@ -1,0 +1,81 @@
+"""Operand layouts the backward pass adds to the tcgen05 GEMM (``mm_gemm``): MN-major A / W operands (dgrad and wgrad
+read activations, gradients and weights as stored, no transposed copies), split-K batches over the contraction index,
+and (sequence, head) batch decomposition straight from / into the q|k|v layout.  Reference: fp32 matmul of the same
+16-bit operands."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rnd(*shape, seed=0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)).bfloat16().cuda()
+
+
+def _close(got, ref, tol=2e-2):
+    err = (got.float() - ref).abs().max().item()
+    assert err <= tol * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("M,N,Kc", [(300, 320, 192), (1000, 64, 512), (77, 1536, 64)])
+def test_dgrad_w_mn_major(cuda, M, N, Kc):
+    """out[m, n] = sum_c A[m, c] W[c, n]: W stored [contraction, n] (PyTorch Linear weight [out=c, in=n] as is)."""
+    from mm_s2ut_b200 import kernels as K
+
+    A, W = _rnd(M, Kc, seed=1), _rnd(Kc, N, seed=2)
+    out = torch.zeros(M, N, dtype=torch.float32, device=cuda)
+    K.gemm(a0=A, a0_ld=Kc, rows=M, w=W, w_ld=N, n=N, k=Kc, mode=K.EPI_F32, out0=out, out0_ld=N, w_mn=True)
+    _close(out, A.float() @ W.float())
+    out_op = torch.zeros(M, N, dtype=torch.bfloat16, device=cuda)
+    K.gemm(a0=A, a0_ld=Kc, rows=M, w=W, w_ld=N, n=N, k=Kc, mode=K.EPI_OP, out0=out_op, out0_ld=N, w_mn=True)
+    _close(out_op, A.float() @ W.float(), 3e-2)
+
+
+@pytest.mark.parametrize("M,N,Kin,S", [(1000, 384, 200, 4), (4096, 512, 512, 8), (130, 64, 1024, 1)])
+def test_wgrad_both_mn_major_split_k(cuda, M, N, Kin, S):
+    """dW[n, k] = sum_m dY[m, n] X[m, k], contraction over tokens split into S batches of `chunk` tokens."""
+    from mm_s2ut_b200 import kernels as K
+
+    dY, X = _rnd(M, N, seed=3), _rnd(M, Kin, seed=4)
+    chunk = ((M + S - 1) // S + 63) // 64 * 64
+    part = torch.full((S, N, Kin), 7.0, dtype=torch.float32, device=cuda)
+    K.gemm(a0=dY, a0_ld=N, rows=N, batches=S, w=X, w_ld=Kin, w_batched=True, n=Kin, k=chunk, mode=K.EPI_F32, out0=part,
+           out0_ld=Kin, out0_bs=N * Kin, a_mn=True, w_mn=True, a_kbatch=True, w_kbatch=True, a_k_total=M, w_k_total=M)
+    _close(part.sum(0), dY.float().t() @ X.float(), 2e-2)
+
+
+def test_attention_backward_gemms_head_mode(cuda):
+    from mm_s2ut_b200 import kernels as K
+
+    B, H, T = 3, 4, 50
+    d, Tp = 64 * H, 64
+    qkv = _rnd(B * T, 3 * d, seed=5)
+    dO = _rnd(B * T, d, seed=6)
+    q, k, v = (qkv[:, i * d:(i + 1) * d].float().view(B, T, H, 64).permute(0, 2, 1, 3) for i in range(3))   # [B,H,T,64]
+    do = dO.float().view(B, T, H, 64).permute(0, 2, 1, 3)
+    # S = q k^T and dP = dO v^T per (sequence, head), straight from the q|k|v layout
+    S = torch.zeros(B * H, Tp, Tp, device=cuda)
+    K.gemm(a0=qkv, a0_ld=3 * d, a0_bs=T * 3 * d, rows=T, batches=B * H, w=qkv[:, d:], w_ld=3 * d, w_bs=T * 3 * d,
+           w_batched=True, n=T, k=64, mode=K.EPI_F32, out0=S, out0_ld=Tp, out0_bs=Tp * Tp, a_hm=True, w_hm=True,
+           heads=H, head_stride=64)
+    _close(S.view(B, H, Tp, Tp)[:, :, :T, :T], q @ k.transpose(-1, -2))
+    dP = torch.zeros(B * H, Tp, Tp, device=cuda)
+    K.gemm(a0=dO, a0_ld=d, a0_bs=T * d, rows=T, batches=B * H, w=qkv[:, 2 * d:], w_ld=3 * d, w_bs=T * 3 * d,
+           w_batched=True, n=T, k=64, mode=K.EPI_F32, out0=dP, out0_ld=Tp, out0_bs=Tp * Tp, a_hm=True, w_hm=True,
+           heads=H, head_stride=64)
+    _close(dP.view(B, H, Tp, Tp)[:, :, :T, :T], do @ v.transpose(-1, -2))
+    # dV = P^T dO, dK = dS^T q (A MN-major from [q][k] buffers), dQ = dS k (W MN-major), into the q|k|v layout
+    P = torch.zeros(B * H, Tp, Tp, dtype=torch.bfloat16, device=cuda)
+    P[:, :T, :T] = _rnd(B * H, T, T, seed=7)
+    Pf = P.float().view(B, H, Tp, Tp)[:, :, :T, :T]
+    dqkv = torch.zeros(B * T, 3 * d, dtype=torch.bfloat16, device=cuda)
+    og = dict(rows=T, batches=B * H, w_batched=True, n=64, mode=K.EPI_OP, out0_ld=3 * d, out0_bs=T * 3 * d, out_hm=True,
+              heads=H, head_stride=64, w_mn=True, w_hm=True)
+    K.gemm(a0=P, a0_ld=Tp, a0_bs=Tp * Tp, a_mn=True, k=Tp, w=dO, w_ld=d, w_bs=T * d, out0=dqkv[:, 2 * d:], **og)
+    K.gemm(a0=P, a0_ld=Tp, a0_bs=Tp * Tp, a_mn=True, k=Tp, w=qkv, w_ld=3 * d, w_bs=T * 3 * d, out0=dqkv[:, d:], **og)
+    K.gemm(a0=P, a0_ld=Tp, a0_bs=Tp * Tp, k=Tp, w=qkv[:, d:], w_ld=3 * d, w_bs=T * 3 * d, out0=dqkv, scale=0.125,
+           scale_cols=64, **og)
+    back = lambda x: x.permute(0, 2, 1, 3).reshape(B * T, d)
+    _close(dqkv[:, 2 * d:], back(Pf.transpose(-1, -2) @ do), 3e-2)
+    _close(dqkv[:, d:2 * d], back(Pf.transpose(-1, -2) @ q), 3e-2)
+    _close(dqkv[:, :d], back(Pf @ k) * 0.125, 3e-2)
