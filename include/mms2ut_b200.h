@@ -215,11 +215,14 @@ int mm_convert_f32(const float* x, void* out, int64_t n, int32_t dtype, void* st
  *   out_n [..][rows][n_ld] straight and/or out_t [..][cols][t_ld] TRANSPOSED, whose columns [rows, t_cols_pad) are
  *   written as 0 (split-K padding of the wgrad GEMMs).  Also splits / merges attention heads (nb1 = heads).
  * mm_rowsum: out[r] (+)= sum_c in[r, c]  (bias gradient from the transposed output gradient).
+ * mm_colsum: partials [mm_colsum_blocks(rows)][cols] = per-512-row-chunk column sums of a 16-bit [rows, cols] matrix
+ *   (bias gradients; rows with r % period >= valid are skipped when period > 0); summed by mm_reduce_partials.
  * mm_reduce_partials: out[i] (+)= sum_s part[s * stride + i]  (split-K partials, LayerNorm parameter partials).
- * mm_layernorm_bwd: dx = resid + LN'(dy) (dx / resid optional), partials [mm_layernorm_bwd_blocks()][2][dim] =
+ * mm_layernorm_bwd: dx = resid + LN'(dy) (dx / resid optional; dx_op: 16-bit copy of dx), partials [mm_layernorm_bwd_blocks()][2][dim] =
  *   per-block (sum dy * xhat, sum dy).
  * mm_softmax_bwd: P = softmax(scores[:, :valid]), dscores = P o (dprobs - rowsum(P o dprobs)), both 16-bit,
- *   rows [batch][rows_per_batch], valid = kv_lens[batch / heads] (NULL: n_keys); columns [valid, ld_out) = 0.
+ *   rows [batch][rows_per_batch] of which the first valid_rows are processed (0: all), valid = kv_lens[batch / heads]
+ *   (NULL: n_keys); columns [valid, ld_out) = 0.
  * mm_glu_bwd: pre fp32 [rows, 2n] = (a | b), dy fp32 [rows, n] -> dpre 16-bit [rows, 2n]   (F.glu backward, x scale).
  * mm_gate_bwd: selective gate backward (mm_s2s_transformer.py:612-618): z = pre-sigmoid gate incl. bias ->
  *   dz 16-bit [B*T, d], dcat fp32 [B*T, 2d] = (dres g | dres (1-g)); dres is T x B x C.
@@ -240,10 +243,13 @@ int mm_reduce_partials(const float* part, int32_t n_partials, int64_t stride, in
                        void* stream);
 int mm_layernorm_bwd_blocks(void);
 int mm_layernorm_bwd(const float* x, const float* gamma, const float* dy, int64_t rows, int32_t dim, float eps,
-                     const float* resid, float* dx, float* partials, void* stream);
+                     const float* resid, float* dx, float* partials, void* dx_op, int32_t dtype, void* stream);
 int mm_softmax_bwd(const float* scores, const float* dprobs, int64_t ld_in, int64_t rows, int32_t rows_per_batch,
                    int32_t n_keys, const int32_t* kv_lens, int32_t heads, void* probs, void* dscores, int64_t ld_out,
-                   int32_t dtype, void* stream);
+                   int32_t valid_rows, int32_t dtype, void* stream);
+int mm_colsum_blocks(int32_t rows);
+int mm_colsum(const void* in, int64_t ld, int32_t rows, int32_t cols, int32_t period, int32_t valid, float* partials,
+              int32_t dtype, void* stream);
 int mm_glu_bwd(const float* pre, const float* dy, int64_t rows, int32_t n, float scale, void* dpre, int32_t dtype,
                void* stream);
 int mm_gate_bwd(const float* z, const float* dres_tbc, const float* text, const float* attn, int32_t batch, int32_t seq,

@@ -181,16 +181,47 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
   out[i] = accumulate ? out[i] + s : s;
 }
 
+// column sums of a 16-bit [rows, cols] matrix (bias gradients): block = 64 columns x one chunk of rows; partials
+// [gridDim.y][cols], summed by reduce_partials.  Rows with (r % period) >= valid are skipped when period > 0.
+template <typename OpT>
+__global__ void __launch_bounds__(256) colsum_kernel(const OpT* __restrict__ in, long long ld, int rows, int cols,
+                                                      int rows_per_block, int period, int valid,
+                                                      float* __restrict__ partials) {
+  __shared__ float red[8][64];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + 2 * tx;
+  const int r_begin = blockIdx.y * rows_per_block;
+  const int r_end = min(rows, r_begin + rows_per_block);
+  float s0 = 0.f, s1 = 0.f;
+  if (c < cols) {
+    for (int r = r_begin + ty; r < r_end; r += 8) {
+      if (period > 0 && (r % period) >= valid) continue;
+      const uint32_t q = *reinterpret_cast<const uint32_t*>(in + (long long)r * ld + c);
+      const OpT* e = reinterpret_cast<const OpT*>(&q);
+      s0 += OpTraits<OpT>::to_float(e[0]);
+      s1 += OpTraits<OpT>::to_float(e[1]);
+    }
+  }
+  red[ty][2 * tx] = s0, red[ty][2 * tx + 1] = s1;
+  __syncthreads();
+  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    partials[(long long)blockIdx.y * cols + blockIdx.x * 64 + threadIdx.x] = t;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // LayerNorm backward: warp per row (grid-stride), row in registers.
 //   xhat = (x - mean) * rstd ; dyg = dy * gamma ; dx = rstd * (dyg - mean(dyg) - xhat * mean(dyg * xhat))
 //   dx_out = (resid ? resid : 0) + dx ; partials[block] = (sum_r dy * xhat, sum_r dy)
 // ---------------------------------------------------------------------------------------------------
-template <int DIM>
+template <int DIM, typename OpT>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                              const float* __restrict__ dy, long long rows, float eps,
                                                              const float* resid, float* dx_out,
-                                                             float* __restrict__ partials) {
+                                                             float* __restrict__ partials, OpT* __restrict__ dx_op) {
   constexpr int V = DIM / 128;
   __shared__ float red[8][DIM];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -243,6 +274,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
           o.x += r.x, o.y += r.y, o.z += r.z, o.w += r.w;
         }
         reinterpret_cast<float4*>(dx_out + row * DIM)[lane + 32 * i] = o;
+        if (dx_op) {   // 16-bit copy of the gradient: the A operand of the next dgrad / wgrad GEMMs
+          uint2 pk;
+          pk.x = OpTraits<OpT>::pack2(o.x, o.y);
+          pk.y = OpTraits<OpT>::pack2(o.z, o.w);
+          reinterpret_cast<uint2*>(dx_op + row * DIM)[lane + 32 * i] = pk;
+        }
       }
     }
   }
@@ -273,10 +310,11 @@ template <typename OpT>
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ S, const float* __restrict__ dP,
                                                            long long ld_in, long long rows, int rows_per_batch,
                                                            int n_keys, const int* __restrict__ kv_lens, int heads,
-                                                           OpT* __restrict__ P, OpT* __restrict__ dS, long long ld_out) {
+                                                           OpT* __restrict__ P, OpT* __restrict__ dS, long long ld_out,
+                                                           int valid_rows) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  if (row >= rows || (int)(row % rows_per_batch) >= valid_rows) return;
   int valid = n_keys;
   if (kv_lens) {
     const int v = kv_lens[(row / rows_per_batch) / heads];
@@ -505,6 +543,23 @@ extern "C" int mm_rowsum(const void* in, int64_t ld, int32_t rows, int32_t cols,
   return 0;
 }
 
+extern "C" int mm_colsum_blocks(int32_t rows) { return (rows + 511) / 512; }
+
+extern "C" int mm_colsum(const void* in, int64_t ld, int32_t rows, int32_t cols, int32_t period, int32_t valid,
+                         float* partials, int32_t dtype, void* stream) {
+  if (!in || !partials || rows <= 0 || cols <= 0 || (cols & 1) || (ld & 1)) return bad_arg("colsum");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  dim3 grid((cols + 63) / 64, (rows + 511) / 512);
+  if (dtype == MM_DTYPE_F16)
+    colsum_kernel<__half><<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(in), ld, rows, cols, 512, period, valid,
+                                               partials);
+  else
+    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(in), ld, rows, cols, 512,
+                                                       period, valid, partials);
+  MM_CHECK_LAUNCH("colsum_kernel launch");
+  return 0;
+}
+
 extern "C" int mm_reduce_partials(const float* part, int32_t n_partials, int64_t stride, int64_t n, float* out,
                                   int32_t accumulate, void* stream) {
   if (!part || !out || n_partials <= 0 || n <= 0) return bad_arg("reduce_partials");
@@ -516,25 +571,39 @@ extern "C" int mm_reduce_partials(const float* part, int32_t n_partials, int64_t
 
 extern "C" int mm_layernorm_bwd_blocks(void) { return 2 * kNumSMs; }
 
-extern "C" int mm_layernorm_bwd(const float* x, const float* gamma, const float* dy, int64_t rows, int32_t dim, float eps,
-                                const float* resid, float* dx, float* partials, void* stream) {
-  if (!x || !gamma || !dy || !partials || rows <= 0) return bad_arg("layernorm_bwd");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+template <typename OpT>
+static int launch_ln_bwd(const float* x, const float* gamma, const float* dy, long long rows, int dim, float eps,
+                         const float* resid, float* dx, float* partials, void* dx_op, cudaStream_t s) {
   const unsigned grid = 2 * kNumSMs;
+  OpT* o = reinterpret_cast<OpT*>(dx_op);
   switch (dim) {
-    case 256: layernorm_bwd_kernel<256><<<grid, 256, 0, s>>>(x, gamma, dy, rows, eps, resid, dx, partials); break;
-    case 512: layernorm_bwd_kernel<512><<<grid, 256, 0, s>>>(x, gamma, dy, rows, eps, resid, dx, partials); break;
-    case 768: layernorm_bwd_kernel<768><<<grid, 256, 0, s>>>(x, gamma, dy, rows, eps, resid, dx, partials); break;
-    case 1024: layernorm_bwd_kernel<1024><<<grid, 256, 0, s>>>(x, gamma, dy, rows, eps, resid, dx, partials); break;
+    case 256: layernorm_bwd_kernel<256, OpT><<<grid, 256, 0, s>>>(x, gamma, dy, rows, eps, resid, dx, partials, o); break;
+    case 512: layernorm_bwd_kernel<512, OpT><<<grid, 256, 0, s>>>(x, gamma, dy, rows, eps, resid, dx, partials, o); break;
+    case 768: layernorm_bwd_kernel<768, OpT><<<grid, 256, 0, s>>>(x, gamma, dy, rows, eps, resid, dx, partials, o); break;
+    case 1024: layernorm_bwd_kernel<1024, OpT><<<grid, 256, 0, s>>>(x, gamma, dy, rows, eps, resid, dx, partials, o); break;
     default: return bad_arg("layernorm_bwd dim must be 256, 512, 768 or 1024");
   }
+  return 0;
+}
+
+extern "C" int mm_layernorm_bwd(const float* x, const float* gamma, const float* dy, int64_t rows, int32_t dim, float eps,
+                                const float* resid, float* dx, float* partials, void* dx_op, int32_t dtype,
+                                void* stream) {
+  if (!x || !gamma || !dy || !partials || rows <= 0) return bad_arg("layernorm_bwd");
+  if (dx_op && !dx) return bad_arg("layernorm_bwd: dx_op needs dx");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int rc = dtype == MM_DTYPE_F16 ? launch_ln_bwd<__half>(x, gamma, dy, rows, dim, eps, resid, dx, partials, dx_op, s)
+                                       : launch_ln_bwd<__nv_bfloat16>(x, gamma, dy, rows, dim, eps, resid, dx, partials,
+                                                                      dx_op, s);
+  if (rc) return rc;
   MM_CHECK_LAUNCH("layernorm_bwd_kernel launch");
   return 0;
 }
 
 extern "C" int mm_softmax_bwd(const float* scores, const float* dprobs, int64_t ld_in, int64_t rows,
                               int32_t rows_per_batch, int32_t n_keys, const int32_t* kv_lens, int32_t heads, void* probs,
-                              void* dscores, int64_t ld_out, int32_t dtype, void* stream) {
+                              void* dscores, int64_t ld_out, int32_t valid_rows, int32_t dtype, void* stream) {
+  if (valid_rows <= 0) valid_rows = rows_per_batch;
   if (!scores || !dprobs || !dscores || rows <= 0 || n_keys <= 0 || rows_per_batch <= 0 || heads <= 0)
     return bad_arg("softmax_bwd");
   if (ld_out < n_keys || ld_in < n_keys) return bad_arg("softmax_bwd: leading dimensions");
@@ -543,11 +612,11 @@ extern "C" int mm_softmax_bwd(const float* scores, const float* dprobs, int64_t 
   if (dtype == MM_DTYPE_F16)
     softmax_bwd_kernel<__half><<<grid, 256, 0, s>>>(scores, dprobs, ld_in, rows, rows_per_batch, n_keys, kv_lens, heads,
                                                     reinterpret_cast<__half*>(probs),
-                                                    reinterpret_cast<__half*>(dscores), ld_out);
+                                                    reinterpret_cast<__half*>(dscores), ld_out, valid_rows);
   else
     softmax_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(scores, dprobs, ld_in, rows, rows_per_batch, n_keys, kv_lens,
                                                            heads, reinterpret_cast<__nv_bfloat16*>(probs),
-                                                           reinterpret_cast<__nv_bfloat16*>(dscores), ld_out);
+                                                           reinterpret_cast<__nv_bfloat16*>(dscores), ld_out, valid_rows);
   MM_CHECK_LAUNCH("softmax_bwd_kernel launch");
   return 0;
 }

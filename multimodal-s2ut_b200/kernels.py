@@ -344,9 +344,28 @@ def layernorm_bwd_blocks() -> int:
     return _lib.load().mm_layernorm_bwd_blocks()
 
 
+def colsum_blocks(rows: int) -> int:
+    return (rows + 511) // 512
+
+
+def colsum(x: torch.Tensor, ld: int, rows: int, cols: int, partials: torch.Tensor, period: int = 0,
+           valid: int = 0) -> int:
+    """partials [colsum_blocks(rows), cols] = per-chunk column sums of the 16-bit matrix x [rows, cols]; returns the
+    number of partial rows (sum them with ``reduce_partials``)."""
+    nb = colsum_blocks(rows)
+    assert partials.dtype == torch.float32 and partials.numel() >= nb * cols
+    lib = _lib.load()
+    with _Launch("colsum", 2.0 * rows * cols):
+        _lib.check(lib.mm_colsum(_ptr(x), ld, rows, cols, period, valid, _ptr(partials), dtype_code(x.dtype), _stream()),
+                   "mm_colsum")
+    return nb
+
+
 def layernorm_bwd(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, partials: torch.Tensor,
-                  dx: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None, eps: float = 1e-5) -> None:
-    """dx = resid + LayerNorm'(dy); partials [blocks, 2, dim] per-block (dgamma, dbeta) sums."""
+                  dx: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None, eps: float = 1e-5,
+                  dx_op: Optional[torch.Tensor] = None) -> None:
+    """dx = resid + LayerNorm'(dy) (dx_op: its 16-bit copy); partials [blocks, 2, dim] per-block (dgamma, dbeta) sums."""
+    assert dx_op is None or (dx_op.is_contiguous() and dx_op.numel() == x.numel())
     dim = x.shape[-1]
     rows = x.numel() // dim
     for t in (x, gamma, dy, partials, dx, resid):
@@ -355,19 +374,22 @@ def layernorm_bwd(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, partia
     lib = _lib.load()
     with _Launch("layernorm_bwd", 4.0 * x.numel() * (2 + (dx is not None) + (resid is not None))):
         _lib.check(lib.mm_layernorm_bwd(_ptr(x), _ptr(gamma), _ptr(dy), rows, dim, eps, _ptr(resid), _ptr(dx),
-                                        _ptr(partials), _stream()), "mm_layernorm_bwd")
+                                        _ptr(partials), _ptr(dx_op),
+                                        dtype_code(dx_op.dtype) if dx_op is not None else 0, _stream()),
+                   "mm_layernorm_bwd")
 
 
 def softmax_bwd(scores: torch.Tensor, dprobs: torch.Tensor, ld_in: int, rows: int, rows_per_batch: int, n_keys: int,
                 dscores: torch.Tensor, ld_out: int, probs: Optional[torch.Tensor] = None,
-                kv_lens: Optional[torch.Tensor] = None, heads: int = 1) -> None:
+                kv_lens: Optional[torch.Tensor] = None, heads: int = 1, valid_rows: int = 0) -> None:
     assert scores.dtype == dprobs.dtype == torch.float32
     assert kv_lens is None or kv_lens.dtype == torch.int32
     assert probs is None or probs.dtype == dscores.dtype
     lib = _lib.load()
     with _Launch("softmax_bwd", 8.0 * rows * n_keys + 4.0 * rows * ld_out):
         _lib.check(lib.mm_softmax_bwd(_ptr(scores), _ptr(dprobs), ld_in, rows, rows_per_batch, n_keys, _ptr(kv_lens),
-                                      heads, _ptr(probs), _ptr(dscores), ld_out, dtype_code(dscores.dtype), _stream()),
+                                      heads, _ptr(probs), _ptr(dscores), ld_out, valid_rows, dtype_code(dscores.dtype),
+                                      _stream()),
                    "mm_softmax_bwd")
 
 

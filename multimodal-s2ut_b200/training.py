@@ -227,33 +227,19 @@ class TrainEngine(EncoderEngine):
             F.update(wg=self.opw(g.weight).view(d, 2 * d))
         self._linked = True
 
-    def _wt(self, name: str, src: torch.Tensor, n: int, k: int) -> torch.Tensor:
-        """[k, n] 16-bit transposed copy of the weight [n, k] (the W operand of a dgrad GEMM)."""
-        t = self.buf("wt_" + name, (k, _even(n)), self.op_dtype, zero=True)
-        K.pack_t(src, rows=n, cols=k, in_ld=k, out_t=t, t_ld=_even(n))
-        return t
-
     def _pack_train(self) -> None:
-        enc, d = self.enc, self.d
+        """Backward-only operand copies: un-permuted conv weights (the forward copies are GLU-tile permuted).  Every
+        other backward GEMM reads the forward operand copies as stored (MN-major W operand for dgrad)."""
+        enc = self.enc
         self.conv_bwd = []
         for i, c in enumerate(enc.subsample.conv_layers):
             cout, cin, k = c.weight.shape
             wp = self.w(c.weight).view(cout, cin, k).permute(0, 2, 1).reshape(cout, k * cin).contiguous()  # layout glue
             w_plain = self.buf(f"convw_plain{i}", (cout, k * cin), self.op_dtype)
             K.convert(wp, w_plain)
-            self.conv_bwd.append(dict(w=w_plain, wt=self._wt(f"conv{i}", wp, cout, k * cin), b=self.w(c.bias),
-                                      p=c, cin=cin, cout=cout, k=k))
-        self.layers_bwd = []
-        for i, L in enumerate(enc.transformer_layers):
-            a = L.self_attn
-            self.layers_bwd.append(dict(
-                wqkv_t=self._wt(f"qkv{i}", self.opw(a.q_proj.weight, a.k_proj.weight, a.v_proj.weight), 3 * d, d),
-                wo_t=self._wt(f"o{i}", self.opw(a.out_proj.weight), d, d),
-                w1_t=self._wt(f"fc1{i}", self.opw(L.fc1.weight), self.ffn, d),
-                w2_t=self._wt(f"fc2{i}", self.opw(L.fc2.weight), d, self.ffn), mod=L))
+            self.conv_bwd.append(dict(w=w_plain, b=self.w(c.bias), p=c, cin=cin, cout=cout, k=k))
         self.fusion_bwd = []
         for j, F in enumerate(self.fusion):
-            dk = F["dk"]
             if enc.multimodal_attention_type == "selective_attention":
                 s = enc.selective_attns[j]
                 ps = dict(wq=(s.q_proj.weight,), bq=(s.q_proj.bias,), wkv=(s.k_proj.weight, s.v_proj.weight),
@@ -264,10 +250,7 @@ class TrainEngine(EncoderEngine):
                           wp=(m.out_proj.weight,), bp=(m.out_proj.bias,), bias_kv=(m.bias_k, m.bias_v))
             gd = enc.gate_denses[j]
             ps.update(wg=(gd.weight,), bg=(gd.bias,))
-            self.fusion_bwd.append(dict(
-                p=ps, wq_t=self._wt(f"fq{j}", self.opw(*ps["wq"]), d, d),
-                wkv_t=self._wt(f"fkv{j}", self.opw(*ps["wkv"]), 2 * d, dk),
-                wp_t=self._wt(f"fp{j}", self.opw(*ps["wp"]), d, d), wg_t=self._wt(f"fg{j}", self.opw(*ps["wg"]), d, 2 * d)))
+            self.fusion_bwd.append(dict(p=ps))
 
     def repack(self) -> None:
         """Refresh every 16-bit operand copy from the fp32 master parameters (after an optimizer step)."""
@@ -368,34 +351,52 @@ class TrainEngine(EncoderEngine):
     def _mp(self, M: int) -> int:
         return _round_up(M, 1024)
 
+    def _partials(self, n: int) -> torch.Tensor:
+        part = self.buf("wgrad_part", (16 * 1024 * 1024,), torch.float32)
+        return part if n <= part.numel() else self.buf(f"wgrad_part_{n}", (n,), torch.float32)
+
     def _wgrad(self, dyt: torch.Tensor, xt: torch.Tensor, n: int, kin: int, mp: int, out: torch.Tensor,
                accumulate: bool) -> None:
-        """out [n, kin] (+)= dY^T X from the token-contiguous copies dyt [n, mp], xt [kin, mp] (zero beyond M)."""
+        """out [n, kin] (+)= dY^T X from TRANSPOSED token-contiguous copies dyt [n, mp], xt [kin, mp] (zero beyond M).
+        Only the conv layers use this form (their X operand is a strided window view per utterance)."""
         S = _split_k(n, kin, mp)
         chunk = mp // S
-        part = self.buf("wgrad_part", (16 * 1024 * 1024,), torch.float32)
-        if S * n * kin > part.numel():
-            part = self.buf(f"wgrad_part_{S * n * kin}", (S * n * kin,), torch.float32)
+        part = self._partials(S * n * kin)
         K.gemm(a0=dyt, a0_ld=dyt.shape[-1], a0_bs=chunk, rows=n, batches=S, w=xt, w_ld=xt.shape[-1], w_bs=chunk,
                w_batched=True, n=kin, k=chunk, mode=K.EPI_F32, out0=part, out0_ld=kin, out0_bs=n * kin,
                block_n=self.block_n)
         K.reduce_partials(part, S, n * kin, n * kin, out, accumulate)
 
-    def _linear_bwd(self, name: str, dy, dy_is_f32: bool, dy_ld: int, x_op: torch.Tensor, M: int, n: int, kin: int,
-                    gw: torch.Tensor, gb: Optional[torch.Tensor], accumulate: bool, dy_op: Optional[torch.Tensor] = None,
-                    mask: Optional[torch.Tensor] = None, scale: float = 1.0) -> torch.Tensor:
-        """Parameter gradients of y = x W^T + b:  gw [n, kin] (+)= dy^T x, gb [n] (+)= column sums of dy.
-        Writes the 16-bit copy of dy (masked / scaled) into dy_op when given.  Returns dy_op."""
-        mp = self._mp(M)
-        dyt = self.buf(f"t_{n}", (n, mp), self.op_dtype, zero=True)
-        xt = self.buf(f"tx_{kin}", (kin, mp), self.op_dtype, zero=True)
-        K.pack_t(dy, rows=M, cols=n, in_ld=dy_ld, out_n=dy_op, n_ld=n, out_t=dyt, t_ld=mp, mask=mask,
-                 mask_ld=n if mask is not None else 0, scale=scale)
-        K.pack_t(x_op, rows=M, cols=kin, in_ld=x_op.stride(0), out_t=xt, t_ld=mp)
-        self._wgrad(dyt, xt, n, kin, mp, gw, accumulate)
+    def _wgrad_mn(self, dy_op: torch.Tensor, dy_ld: int, x_ops, M: int, n: int, gw: torch.Tensor, accumulate: bool) -> None:
+        """gw [n, sum kin] (+)= dy^T [x_0 | x_1 | ...]: both operands read as stored (MN-major), the token contraction
+        split into S batches; x_ops = [(tensor [M, kin], ld, kin), ...] fill consecutive column blocks of gw."""
+        kin_all = sum(x[2] for x in x_ops)
+        S = 1
+        tiles = ((n + 255) // 256) * sum((x[2] + 255) // 256 for x in x_ops)
+        while S < 16 and tiles * S < 74 and M // (2 * S) >= 256:
+            S *= 2
+        chunk = _round_up((M + S - 1) // S, 64)
+        part = self._partials(S * n * kin_all)
+        col = 0
+        for x, x_ld, kin in x_ops:
+            K.gemm(a0=dy_op, a0_ld=dy_ld, rows=n, batches=S, w=x, w_ld=x_ld, w_batched=True, n=kin, k=chunk,
+                   mode=K.EPI_F32, out0=part[col:], out0_ld=kin_all, out0_bs=n * kin_all, block_n=self.block_n,
+                   a_mn=True, w_mn=True, a_kbatch=True, w_kbatch=True, a_k_total=M, w_k_total=M)
+            col += kin
+        K.reduce_partials(part, S, n * kin_all, n * kin_all, gw, accumulate)
+
+    def _bias_grad(self, dy_op: torch.Tensor, dy_ld: int, M: int, n: int, gb: torch.Tensor, accumulate: bool,
+                   period: int = 0, valid: int = 0) -> None:
+        part = self.buf("colsum_part", (K.colsum_blocks(M) * n,), torch.float32)
+        nb = K.colsum(dy_op, dy_ld, M, n, part, period, valid)
+        K.reduce_partials(part, nb, n, n, gb, accumulate)
+
+    def _linear_bwd(self, dy_op: torch.Tensor, dy_ld: int, x_op: torch.Tensor, M: int, n: int, kin: int,
+                    gw: torch.Tensor, gb: Optional[torch.Tensor], accumulate: bool) -> None:
+        """Parameter gradients of y = x W^T + b from the 16-bit dy [M, n] and x [M, kin]."""
+        self._wgrad_mn(dy_op, dy_ld, [(x_op, x_op.stride(0), kin)], M, n, gw, accumulate)
         if gb is not None:
-            K.rowsum(dyt, mp, n, M, gb, accumulate)
-        return dy_op
+            self._bias_grad(dy_op, dy_ld, M, n, gb, accumulate)
 
     def _ln_param_grads(self, part: torch.Tensor, dim: int, gwb: torch.Tensor, accumulate: bool) -> None:
         K.reduce_partials(part, self._ln_blocks, 2 * dim, 2 * dim, gwb, accumulate)
@@ -405,84 +406,62 @@ class TrainEngine(EncoderEngine):
     # ------------------------------------------------------------------------------------------
     def _attention_bwd(self, s: dict, datt: torch.Tensor, dqkv: torch.Tensor, B: int, T: int,
                        seq_lens: torch.Tensor) -> None:
-        """dqkv [M, 3d] (16-bit; q part already x head_dim^-0.5) from datt [M, d] and the saved q|k|v."""
+        """dqkv [M, 3d] (16-bit; q part already x head_dim^-0.5) from datt [M, d] and the saved q|k|v.  All five
+        contractions read q|k|v / datt and write dqkv in place of their (sequence, head) column blocks."""
         d, H, op, bn = self.d, self.heads, self.op_dtype, self.block_n
         Tp = _round_up(T, 64)
         BH = B * H
         qkv = s["qkv"]
-        hm = lambda name: self.buf(name, (BH, Tp, 64), op, zero=True)       # head-major [b, h][t][64]
-        ht = lambda name: self.buf(name, (BH, 64, Tp), op, zero=True)       # transposed  [b, h][64][t]
-        Qh, Kh, Vh, dOh = hm("a_Qh"), hm("a_Kh"), hm("a_Vh"), hm("a_dOh")
-        Qt, Kt, dOt = ht("a_Qt"), ht("a_Kt"), ht("a_dOt")
-        split = dict(rows=T, cols=64, batches=BH, nb1=H, in_bs1=64, n_ld=64, n_bs0=H * Tp * 64, n_bs1=Tp * 64,
-                     t_ld=Tp, t_bs0=H * 64 * Tp, t_bs1=64 * Tp, t_cols_pad=Tp)
-        K.pack_t(qkv, in_ld=3 * d, in_bs0=T * 3 * d, out_n=Qh, out_t=Qt, **split)
-        K.pack_t(qkv[:, d:], in_ld=3 * d, in_bs0=T * 3 * d, out_n=Kh, out_t=Kt, **split)
-        K.pack_t(qkv[:, 2 * d:], in_ld=3 * d, in_bs0=T * 3 * d, out_n=Vh, **{k: v for k, v in split.items()
-                                                                          if not k.startswith("t_")})
-        K.pack_t(datt, in_ld=d, in_bs0=T * d, out_n=dOh, out_t=dOt, **split)
+        hd = dict(heads=H, head_stride=64, batches=BH, w_batched=True, block_n=bn)
         S = self.buf("a_S", (BH, Tp, Tp), torch.float32)
         dP = self.buf("a_dP", (BH, Tp, Tp), torch.float32)
-        sc = dict(rows=Tp, batches=BH, a0_ld=64, a0_bs=Tp * 64, w_ld=64, w_bs=Tp * 64, w_batched=True, n=T, k=64,
-                  mode=K.EPI_F32, out0_ld=Tp, out0_bs=Tp * Tp, block_n=bn)
-        K.gemm(a0=Qh, w=Kh, out0=S, **sc)
-        K.gemm(a0=dOh, w=Vh, out0=dP, **sc)
+        sc = dict(rows=T, n=T, k=64, mode=K.EPI_F32, out0_ld=Tp, out0_bs=Tp * Tp, a_hm=True, w_hm=True, **hd)
+        K.gemm(a0=qkv, a0_ld=3 * d, a0_bs=T * 3 * d, w=qkv[:, d:], w_ld=3 * d, w_bs=T * 3 * d, out0=S, **sc)
+        K.gemm(a0=datt, a0_ld=d, a0_bs=T * d, w=qkv[:, 2 * d:], w_ld=3 * d, w_bs=T * 3 * d, out0=dP, **sc)
         P = self.buf("a_P", (BH, Tp, Tp), op)
         dS = self.buf("a_dS", (BH, Tp, Tp), op)
-        K.softmax_bwd(S, dP, Tp, BH * Tp, Tp, T, dS, Tp, probs=P, kv_lens=seq_lens, heads=H)
-        Pt = self.buf("a_Pt", (BH, Tp, Tp), op)
-        dSt = self.buf("a_dSt", (BH, Tp, Tp), op)
-        tr = dict(rows=Tp, cols=Tp, in_ld=Tp, batches=BH, in_bs0=Tp * Tp, t_ld=Tp, t_bs0=Tp * Tp, t_cols_pad=Tp)
-        K.pack_t(P, out_t=Pt, **tr)
-        K.pack_t(dS, out_t=dSt, **tr)
-        dQh, dKh, dVh = hm("a_dQh"), hm("a_dKh"), hm("a_dVh")
-        og = dict(rows=T, batches=BH, a0_ld=Tp, a0_bs=Tp * Tp, w_ld=Tp, w_bs=64 * Tp, w_batched=True, n=64, k=Tp,
-                  mode=K.EPI_OP, out0_ld=64, out0_bs=Tp * 64, block_n=bn)
-        K.gemm(a0=Pt, w=dOt, out0=dVh, **og)
-        K.gemm(a0=dSt, w=Qt, out0=dKh, **og)
-        K.gemm(a0=dS, w=Kt, out0=dQh, scale=64 ** -0.5, scale_cols=64, **og)
-        merge = dict(rows=T, cols=64, in_ld=64, batches=BH, nb1=H, in_bs0=H * Tp * 64, in_bs1=Tp * 64, n_ld=3 * d,
-                     n_bs0=T * 3 * d, n_bs1=64)
-        K.pack_t(dQh, out_n=dqkv, **merge)
-        K.pack_t(dKh, out_n=dqkv[:, d:], **merge)
-        K.pack_t(dVh, out_n=dqkv[:, 2 * d:], **merge)
+        K.softmax_bwd(S, dP, Tp, BH * Tp, Tp, T, dS, Tp, probs=P, kv_lens=seq_lens, heads=H, valid_rows=T)
+        og = dict(rows=T, n=64, k=T, mode=K.EPI_OP, out0_ld=3 * d, out0_bs=T * 3 * d, out_hm=True, w_mn=True, w_hm=True,
+                  a0_ld=Tp, a0_bs=Tp * Tp, **hd)
+        K.gemm(a0=P, a_mn=True, w=datt, w_ld=d, w_bs=T * d, out0=dqkv[:, 2 * d:], **og)          # dV = P^T dO
+        K.gemm(a0=dS, a_mn=True, w=qkv, w_ld=3 * d, w_bs=T * 3 * d, out0=dqkv[:, d:], **og)      # dK = dS^T q
+        K.gemm(a0=dS, w=qkv[:, d:], w_ld=3 * d, w_bs=T * 3 * d, out0=dqkv, scale=64 ** -0.5,     # dQ = dS k
+               scale_cols=64, **og)
 
-    def _layer_bwd(self, i: int, g: torch.Tensor, B: int, T: int, seq_lens: torch.Tensor, accumulate: bool) -> torch.Tensor:
-        """g = d loss / d x_out [M, d] fp32 (overwritten); returns d loss / d x_in (same buffer)."""
-        s, Lb, L = self._saved["layers"][i], self.layers_bwd[i], self.layers[i]
-        mod = Lb["mod"]
+    def _layer_bwd(self, i: int, g: torch.Tensor, g_op: torch.Tensor, B: int, T: int, seq_lens: torch.Tensor,
+                   accumulate: bool) -> None:
+        """g = d loss / d x_out [M, d] fp32 with its 16-bit copy g_op; both are overwritten with d loss / d x_in."""
+        s, L = self._saved["layers"][i], self.layers[i]
+        mod = self.enc.transformer_layers[i]
         a = mod.self_attn
         d, ffn, M, op, bn = self.d, self.ffn, B * T, self.op_dtype, self.block_n
         lnp = self.buf("ln_part", (self._ln_blocks * 2 * max(d, 1024),), torch.float32)
         # ---- FFN: x_out = x_mid + fc2(relu(fc1(LN2(x_mid))))
-        g_op = self.buf("b_g_op", (M, d), op)
-        self._linear_bwd("fc2", g, True, d, s["f"], M, d, ffn, self.g(mod.fc2.weight), self.g(mod.fc2.bias), accumulate,
-                         dy_op=g_op)
+        self._linear_bwd(g_op, d, s["f"], M, d, ffn, self.g(mod.fc2.weight), self.g(mod.fc2.bias), accumulate)
         dF = self.buf("b_dF", (M, ffn), op)
-        K.gemm(a0=g_op, a0_ld=d, rows=M, w=Lb["w2_t"], n=ffn, k=d, mode=K.EPI_OP, out0=dF, out0_ld=ffn, block_n=bn)
-        # ReLU mask applied while packing; dF is rewritten in place (masked) for the dgrad GEMM below
-        self._linear_bwd("fc1", dF, False, ffn, s["h2"], M, ffn, d, self.g(mod.fc1.weight), self.g(mod.fc1.bias),
-                         accumulate, dy_op=dF, mask=s["f"])
+        K.gemm(a0=g_op, a0_ld=d, rows=M, w=L["w2"], w_ld=ffn, w_mn=True, n=ffn, k=d, mode=K.EPI_OP, out0=dF,
+               out0_ld=ffn, block_n=bn)
+        K.pack_t(dF, rows=M, cols=ffn, in_ld=ffn, out_n=dF, n_ld=ffn, mask=s["f"], mask_ld=ffn)   # ReLU mask, in place
+        self._linear_bwd(dF, ffn, s["h2"], M, ffn, d, self.g(mod.fc1.weight), self.g(mod.fc1.bias), accumulate)
         dh = self.buf("b_dh", (M, d), torch.float32)
-        K.gemm(a0=dF, a0_ld=ffn, rows=M, w=Lb["w1_t"], n=d, k=ffn, mode=K.EPI_F32, out0=dh, out0_ld=d, block_n=bn)
-        K.layernorm_bwd(s["x_mid"], L["ln2_g"], dh, lnp, dx=g, resid=g)
+        K.gemm(a0=dF, a0_ld=ffn, rows=M, w=L["w1"], w_ld=d, w_mn=True, n=d, k=ffn, mode=K.EPI_F32, out0=dh, out0_ld=d,
+               block_n=bn)
+        K.layernorm_bwd(s["x_mid"], L["ln2_g"], dh, lnp, dx=g, resid=g, dx_op=g_op)
         self._ln_param_grads(lnp, d, self.g(mod.final_layer_norm.weight, mod.final_layer_norm.bias), accumulate)
         # ---- attention: x_mid = x_in + out_proj(attn(LN1(x_in)))
-        self._linear_bwd("o", g, True, d, s["att"], M, d, d, self.g(a.out_proj.weight), self.g(a.out_proj.bias),
-                         accumulate, dy_op=g_op)
+        self._linear_bwd(g_op, d, s["att"], M, d, d, self.g(a.out_proj.weight), self.g(a.out_proj.bias), accumulate)
         datt = self.buf("b_datt", (M, d), op)
-        K.gemm(a0=g_op, a0_ld=d, rows=M, w=Lb["wo_t"], n=d, k=d, mode=K.EPI_OP, out0=datt, out0_ld=d, block_n=bn)
+        K.gemm(a0=g_op, a0_ld=d, rows=M, w=L["wo"], w_ld=d, w_mn=True, n=d, k=d, mode=K.EPI_OP, out0=datt, out0_ld=d,
+               block_n=bn)
         dqkv = self.buf("b_dqkv", (M, 3 * d), op)
         with _scope("attn"):
             self._attention_bwd(s, datt, dqkv, B, T, seq_lens)
-        self._linear_bwd("qkv", dqkv, False, 3 * d, s["h1"], M, 3 * d, d,
-                         self.g(a.q_proj.weight, a.k_proj.weight, a.v_proj.weight),
+        self._linear_bwd(dqkv, 3 * d, s["h1"], M, 3 * d, d, self.g(a.q_proj.weight, a.k_proj.weight, a.v_proj.weight),
                          self.g(a.q_proj.bias, a.k_proj.bias, a.v_proj.bias), accumulate)
-        K.gemm(a0=dqkv, a0_ld=3 * d, rows=M, w=Lb["wqkv_t"], n=d, k=3 * d, mode=K.EPI_F32, out0=dh, out0_ld=d,
-               block_n=bn)
-        K.layernorm_bwd(s["x_in"], L["ln1_g"], dh, lnp, dx=g, resid=g)
+        K.gemm(a0=dqkv, a0_ld=3 * d, rows=M, w=L["wqkv"], w_ld=d, w_mn=True, n=d, k=3 * d, mode=K.EPI_F32, out0=dh,
+               out0_ld=d, block_n=bn)
+        K.layernorm_bwd(s["x_in"], L["ln1_g"], dh, lnp, dx=g, resid=g, dx_op=g_op)
         self._ln_param_grads(lnp, d, self.g(mod.self_attn_layer_norm.weight, mod.self_attn_layer_norm.bias), accumulate)
-        return g
 
     def _fusion_bwd(self, dres: torch.Tensor, gtext: torch.Tensor, B: int, T: int, accumulate: bool) -> None:
         """dres [T, B, d] -> gtext [M, d] = d loss / d text (the final LayerNorm output) + fusion parameter grads."""
@@ -494,7 +473,6 @@ class TrainEngine(EncoderEngine):
         extra = 1 if F["bias_kv"] is not None else 0
         Tk = Tk_img + extra
         Tkp = _round_up(Tk, 8)
-        Tp = _round_up(T, 64)
         text_f32, text_op = self.buf("text_f32", (M, d), torch.float32), self.buf("text_op", (M, d), op)
         o = self.buf("o_img", (M, d), op)
         q = self.buf("q_img", (M, d), op)
@@ -512,84 +490,60 @@ class TrainEngine(EncoderEngine):
             dz = self.buf("f_dz", (M, d), op)
             dcat = self.buf("f_dcat", (M, 2 * d), torch.float32)
             K.gate_bwd(z, dres, text_f32, a_f32, B, T, d, dz, dcat)
-            # gate Linear(2d -> d) on [attn | text]: wgrad with the concatenated operand built row-block by row-block
-            mp = self._mp(M)
-            dzt = self.buf(f"t_{d}", (d, mp), op, zero=True)
-            xt = self.buf(f"tx_{2 * d}", (2 * d, mp), op, zero=True)
-            K.pack_t(dz, rows=M, cols=d, in_ld=d, out_t=dzt, t_ld=mp)
-            K.pack_t(a_op, rows=M, cols=d, in_ld=d, out_t=xt, t_ld=mp)
-            K.pack_t(text_op, rows=M, cols=d, in_ld=d, out_t=xt[d:], t_ld=mp)
-            self._wgrad(dzt, xt, d, 2 * d, mp, self.g(*ps["wg"]), accumulate)
-            K.rowsum(dzt, mp, d, M, self.g(*ps["bg"]), accumulate)
-            K.gemm(a0=dz, a0_ld=d, rows=M, w=Fb["wg_t"], n=2 * d, k=d, mode=K.EPI_RESID_F32, aux0=dcat, aux_ld=2 * d,
-                   out0=dcat, out0_ld=2 * d, block_n=bn)
+            # gate Linear(2d -> d) on [attn | text]: the two operand halves fill the two column blocks of dWg
+            self._wgrad_mn(dz, d, [(a_op, d, d), (text_op, d, d)], M, d, self.g(*ps["wg"]), accumulate)
+            self._bias_grad(dz, d, M, d, self.g(*ps["bg"]), accumulate)
+            K.gemm(a0=dz, a0_ld=d, rows=M, w=F["wg"], w_ld=2 * d, w_mn=True, n=2 * d, k=d, mode=K.EPI_RESID_F32,
+                   aux0=dcat, aux_ld=2 * d, out0=dcat, out0_ld=2 * d, block_n=bn)
             da, da_ld, dtext_part, dtext_ld = dcat, 2 * d, dcat[:, d:], 2 * d
         else:   # res = text + attn
             dflat = self.buf("f_dflat", (M, d), torch.float32)
             K.tbc_to_btc(dres, B, T, d, dflat)
             da, da_ld, dtext_part, dtext_ld = dflat, d, dflat, d
         # ---- proj: attn = o Wp^T + bp
-        self._linear_bwd("fproj", da, True, da_ld, o, M, d, d, self.g(*ps["wp"]), self.g(*ps["bp"]), accumulate,
-                         dy_op=da_op)
+        K.pack_t(da, rows=M, cols=d, in_ld=da_ld, out_n=da_op, n_ld=d)
+        self._linear_bwd(da_op, d, o, M, d, d, self.g(*ps["wp"]), self.g(*ps["bp"]), accumulate)
         do = self.buf("f_do", (M, d), op)
-        K.gemm(a0=da_op, a0_ld=d, rows=M, w=Fb["wp_t"], n=d, k=d, mode=K.EPI_OP, out0=do, out0_ld=d, block_n=bn)
-        # ---- o = P V ; P = softmax(q k^T)
-        vbuf = self.buf("f_v", (B, Tkp, d), op)
-        K.pack_t(vt, rows=d, cols=Tkp, in_ld=Tkp, batches=B, in_bs0=d * Tkp, out_t=vbuf, t_ld=d, t_bs0=Tkp * d,
-                 t_cols_pad=d)
+        K.gemm(a0=da_op, a0_ld=d, rows=M, w=F["wp"], w_ld=d, w_mn=True, n=d, k=d, mode=K.EPI_OP, out0=do, out0_ld=d,
+               block_n=bn)
+        # ---- o = P V ; P = softmax(q k^T): V^T, P, dS, q, k are all read as stored
+        bt = dict(batches=B, w_batched=True, block_n=bn)
         dP = self.buf("f_dP", (B, T, Tkp), torch.float32)
-        K.gemm(a0=do, a0_ld=d, a0_bs=T * d, rows=T, batches=B, w=vbuf, w_ld=d, w_bs=Tkp * d, w_batched=True, n=Tk, k=d,
-               mode=K.EPI_F32, out0=dP, out0_ld=Tkp, out0_bs=T * Tkp, block_n=bn)
+        K.gemm(a0=do, a0_ld=d, a0_bs=T * d, rows=T, w=vt, w_ld=Tkp, w_bs=d * Tkp, w_mn=True, n=Tk, k=d, mode=K.EPI_F32,
+               out0=dP, out0_ld=Tkp, out0_bs=T * Tkp, **bt)                                        # dP = dO V^T
         dS = self.buf("f_dS", (B, T, Tkp), op)
         K.softmax_bwd(S, dP, Tkp, M, T, Tk, dS, Tkp)
-        Pt = self.buf("f_Pt", (B, Tkp, Tp), op, zero=True)
-        dSt = self.buf("f_dSt", (B, Tkp, Tp), op, zero=True)
-        dot = self.buf("f_dot", (B, d, Tp), op, zero=True)
-        qt = self.buf("f_qt", (B, d, Tp), op, zero=True)
-        kt = self.buf("f_kt", (B, d, Tkp), op, zero=True)
-        tr = dict(rows=T, cols=Tkp, in_ld=Tkp, batches=B, in_bs0=T * Tkp, t_ld=Tp, t_bs0=Tkp * Tp, t_cols_pad=Tp)
-        K.pack_t(P, out_t=Pt, **tr)
-        K.pack_t(dS, out_t=dSt, **tr)
-        tq = dict(rows=T, cols=d, in_ld=d, batches=B, in_bs0=T * d, t_ld=Tp, t_bs0=d * Tp, t_cols_pad=Tp)
-        K.pack_t(do, out_t=dot, **tq)
-        K.pack_t(q, out_t=qt, **tq)
-        K.pack_t(kbuf, rows=Tk, cols=d, in_ld=d, batches=B, in_bs0=Tk * d, out_t=kt, t_ld=Tkp, t_bs0=d * Tkp,
-                 t_cols_pad=Tkp)
         dkv = self.buf("f_dkv", (B, Tk, 2 * d), op)
-        kvg = dict(rows=Tk, batches=B, a0_ld=Tp, a0_bs=Tkp * Tp, w_ld=Tp, w_bs=d * Tp, w_batched=True, n=d, k=Tp,
-                   mode=K.EPI_OP, out0_ld=2 * d, out0_bs=Tk * 2 * d, block_n=bn)
-        K.gemm(a0=dSt, w=qt, out0=dkv, **kvg)                        # dK = dS^T q
-        K.gemm(a0=Pt, w=dot, out0=dkv.view(-1)[d:], **kvg)           # dV = P^T dO
+        kvg = dict(rows=Tk, a0_ld=Tkp, a0_bs=T * Tkp, a_mn=True, w_ld=d, w_bs=T * d, w_mn=True, n=d, k=T, mode=K.EPI_OP,
+                   out0_ld=2 * d, out0_bs=Tk * 2 * d, **bt)
+        K.gemm(a0=dS, w=q, out0=dkv, **kvg)                                                       # dK = dS^T q
+        K.gemm(a0=P, w=do, out0=dkv.view(-1)[d:], **kvg)                                          # dV = P^T dO
         dq = self.buf("f_dq", (M, d), op)
-        K.gemm(a0=dS, a0_ld=Tkp, a0_bs=T * Tkp, rows=T, batches=B, w=kt, w_ld=Tkp, w_bs=d * Tkp, w_batched=True, n=d,
-               k=Tkp, mode=K.EPI_OP, scale=d ** -0.5, scale_cols=d, out0=dq, out0_ld=d, out0_bs=T * d, block_n=bn)
+        K.gemm(a0=dS, a0_ld=Tkp, a0_bs=T * Tkp, rows=T, w=kbuf, w_ld=d, w_bs=Tk * d, w_mn=True, n=d, k=Tk, mode=K.EPI_OP,
+               scale=d ** -0.5, scale_cols=d, out0=dq, out0_ld=d, out0_bs=T * d, **bt)            # dq = dS k
         # ---- q projection: parameter grads + text gradient
         gbq = self.g(*ps["bq"]) if extra == 0 else self.g(*ps["in_b"])[:d]
-        self._linear_bwd("fq", dq, False, d, text_op, M, d, d, self.g(*ps["wq"]), gbq, accumulate)
-        K.gemm(a0=dq, a0_ld=d, rows=M, w=Fb["wq_t"], n=d, k=d, mode=K.EPI_RESID_F32, aux0=dtext_part, aux_ld=dtext_ld,
-               out0=gtext, out0_ld=d, block_n=bn)
-        # ---- k|v projection over the image tokens (the learned extra key/value row is excluded: zero column)
-        Tke = _even(Tk)
-        Mi = B * Tke
-        mpi = self._mp(Mi)
-        dkvt = self.buf(f"ti_{2 * d}", (2 * d, mpi), op, zero=True)
-        imt = self.buf(f"tix_{dk}", (dk, mpi), op, zero=True)
-        K.pack_t(dkv, rows=Tk_img, cols=2 * d, in_ld=2 * d, batches=B, in_bs0=Tk * 2 * d, out_t=dkvt, t_ld=mpi, t_bs0=Tke,
-                 t_cols_pad=Tke)
-        K.pack_t(img_op, rows=Tk_img, cols=dk, in_ld=dk, batches=B, in_bs0=Tk_img * dk, out_t=imt, t_ld=mpi, t_bs0=Tke,
-                 t_cols_pad=Tke)
-        self._wgrad(dkvt, imt, 2 * d, dk, mpi, self.g(*ps["wkv"]), accumulate)
+        self._linear_bwd(dq, d, text_op, M, d, d, self.g(*ps["wq"]), gbq, accumulate)
+        K.gemm(a0=dq, a0_ld=d, rows=M, w=F["wq"], w_ld=d, w_mn=True, n=d, k=d, mode=K.EPI_RESID_F32, aux0=dtext_part,
+               aux_ld=dtext_ld, out0=gtext, out0_ld=d, block_n=bn)
+        # ---- k|v projection over the image tokens
         gbkv = self.g(*ps["bkv"]) if extra == 0 else self.g(*ps["in_b"])[d:]
-        K.rowsum(dkvt, mpi, 2 * d, Mi, gbkv, accumulate)
-        if extra:   # learned bias_k | bias_v: key / value number Tk_img of every utterance
-            Bp = _round_up(B, 2)
-            bt = self.buf("f_bkv_t", (2 * d, Bp), op, zero=True)
-            K.pack_t(dkv.view(-1)[Tk_img * 2 * d:], rows=B, cols=2 * d, in_ld=Tk * 2 * d, out_t=bt, t_ld=Bp, t_cols_pad=Bp)
-            K.rowsum(bt, Bp, 2 * d, B, self.g(*ps["bias_kv"]), accumulate)
+        if extra == 0:
+            self._linear_bwd(dkv, 2 * d, img_op, B * Tk_img, 2 * d, dk, self.g(*ps["wkv"]), gbkv, accumulate)
+        else:
+            # the learned extra key / value row of every utterance is not a projected image token: contract per utterance
+            # over its Tk_img image rows (batched MN-major operands), then sum the per-utterance partials
+            part = self._partials(B * 2 * d * dk)
+            K.gemm(a0=dkv, a0_ld=2 * d, a0_bs=Tk * 2 * d, a_mn=True, rows=2 * d, w=img_op, w_ld=dk, w_bs=Tk_img * dk,
+                   w_mn=True, n=dk, k=Tk_img, mode=K.EPI_F32, out0=part, out0_ld=dk, out0_bs=2 * d * dk, **bt)
+            K.reduce_partials(part, B, 2 * d * dk, 2 * d * dk, self.g(*ps["wkv"]), accumulate)
+            self._bias_grad(dkv, 2 * d, B * Tk, 2 * d, gbkv, accumulate, period=Tk, valid=Tk_img)
+            # learned bias_k | bias_v: key / value number Tk_img of every utterance
+            self._bias_grad(dkv.view(-1)[Tk_img * 2 * d:], Tk * 2 * d, B, 2 * d, self.g(*ps["bias_kv"]), accumulate)
         if self.img_ln is not None:
             dimg = self.buf("f_dimg", (B * Tk_img, dk), torch.float32)
-            K.gemm(a0=dkv, a0_ld=2 * d, a0_bs=Tk * 2 * d, rows=Tk_img, batches=B, w=Fb["wkv_t"], n=dk, k=2 * d,
-                   mode=K.EPI_F32, out0=dimg, out0_ld=dk, out0_bs=Tk_img * dk, block_n=bn)
+            K.gemm(a0=dkv, a0_ld=2 * d, a0_bs=Tk * 2 * d, rows=Tk_img, batches=B, w=F["wkv"], w_ld=dk, w_mn=True, n=dk,
+                   k=2 * d, mode=K.EPI_F32, out0=dimg, out0_ld=dk, out0_bs=Tk_img * dk, block_n=bn)
             lnp = self.buf("ln_part", (self._ln_blocks * 2 * max(d, 1024),), torch.float32)
             K.layernorm_bwd(img.view(B * Tk_img, dk), self.img_ln[0], dimg, lnp)
             pn = enc.image_pre_norm_module
@@ -635,8 +589,8 @@ class TrainEngine(EncoderEngine):
         K.glu_bwd(pre2, g, M, d, dpre2, scale=self.embed_scale)
         conv_param_grads(c2, dpre2, x2, 2 * mid, T1_alloc * mid, T, c2["k"] * mid)
         dcol = self.buf("c_dcol", (M, c2["k"] * mid), torch.float32)
-        K.gemm(a0=dpre2, a0_ld=c2["cout"], rows=M, w=c2["wt"], n=c2["k"] * mid, k=c2["cout"], mode=K.EPI_F32, out0=dcol,
-               out0_ld=c2["k"] * mid, block_n=bn)
+        K.gemm(a0=dpre2, a0_ld=c2["cout"], rows=M, w=c2["w"], w_ld=c2["k"] * mid, w_mn=True, n=c2["k"] * mid,
+               k=c2["cout"], mode=K.EPI_F32, out0=dcol, out0_ld=c2["k"] * mid, block_n=bn)
         dglu1 = self.buf("c_dglu1", (B * T1, mid), torch.float32)
         K.col2im_k5s2(dcol, B, T, T1, mid, dglu1)
         # ---- conv 1 + GLU
@@ -667,11 +621,12 @@ class TrainEngine(EncoderEngine):
             K.tbc_to_btc(grad_out, B, T, d, gtext)
         lnp = self.buf("ln_part", (self._ln_blocks * 2 * max(d, 1024),), torch.float32)
         g = self.buf("b_g", (M, d), torch.float32)
-        K.layernorm_bwd(sv["x_final"], self.ln_g, gtext, lnp, dx=g)
+        g_op = self.buf("b_g_op", (M, d), self.op_dtype)
+        K.layernorm_bwd(sv["x_final"], self.ln_g, gtext, lnp, dx=g, dx_op=g_op)
         self._ln_param_grads(lnp, d, self.g(self.enc.layer_norm.weight, self.enc.layer_norm.bias), accumulate)
         for i in reversed(range(self.n_layers)):
             with _scope("layer"):
-                self._layer_bwd(i, g, B, T, sv["seq_lens"], accumulate)
+                self._layer_bwd(i, g, g_op, B, T, sv["seq_lens"], accumulate)
         with _scope("conv"):
             self._conv_bwd(g, B, T, accumulate)
 

@@ -84,24 +84,52 @@ def padding_mask(seq_lens_, T, out):
     out.copy_(torch.arange(T)[None, :] >= seq_lens_[:, None])
 
 
+def _operand(t, mn, kbatch, hm, rows, k, ld, bs, batches, heads, hs, k_total):
+    """[batches, rows, k] fp32 view of a GEMM operand under the layout flags of mm_gemm_args."""
+    if mn and kbatch:
+        kt = k_total if k_total > 0 else batches * k
+        full = torch.zeros(batches * k, rows)
+        take = min(kt, batches * k)
+        full[:take] = _v(t, (take, rows), (ld, 1)).float()
+        return full.view(batches, k, rows).transpose(1, 2)
+    if hm:
+        nseq = batches // heads
+        if mn:
+            x = _v(t, (nseq, heads, k, rows), (bs, hs, ld, 1))
+            return x.reshape(batches, k, rows).float().transpose(1, 2)
+        return _v(t, (nseq, heads, rows, k), (bs, hs, ld, 1)).reshape(batches, rows, k).float()
+    if mn:
+        return _v(t, (batches, k, rows), (bs, ld, 1)).float().transpose(1, 2)
+    return _v(t, (batches, rows, k), (bs, ld, 1)).float()
+
+
 def gemm(*, a0, w, rows, n, k, mode, out0, a0_ld, out0_ld, batches=1, a0_bs=0, a1=None, a1_ld=0, a1_bs=0, k_split=0,
          w_ld=None, w_bs=0, w_batched=False, bias=None, scale=1.0, scale_cols=0, out0_bs=0, out1=None, out1_ld=0,
          out1_bs=0, aux0=None, aux1=None, aux_ld=0, rows_per_seq=0, out_tbc=False, n_seqs=0, out_row_offset=0, vt=None,
-         vt_col0=0, vt_rows=0, vt_ld=0, pos=None, seq_lens=None, block_n=0):
+         vt_col0=0, vt_rows=0, vt_ld=0, pos=None, seq_lens=None, block_n=0, a_mn=False, w_mn=False, a_kbatch=False,
+         w_kbatch=False, a_hm=False, w_hm=False, out_hm=False, heads=0, head_stride=0, a_k_total=0, w_k_total=0):
     global launch_count
     launch_count += 1
     w_ld = k if w_ld is None else w_ld
     k0 = k_split if a1 is not None else k
-    A = _v(a0, (batches, rows, k0), (a0_bs, a0_ld, 1)).float()
+    if a_kbatch or w_kbatch:
+        assert k % 64 == 0
+    A = _operand(a0, a_mn, a_kbatch, a_hm, rows, k0, a0_ld, a0_bs, batches, heads, head_stride, a_k_total)
     if a1 is not None:
         A = torch.cat([A, _v(a1, (batches, rows, k - k0), (a1_bs, a1_ld, 1)).float()], -1)
-    W = _v(w, (batches if w_batched else 1, n, k), (w_bs if w_batched else 0, w_ld, 1)).float()
+    if w_batched:
+        W = _operand(w, w_mn, w_kbatch, w_hm, n, k, w_ld, w_bs, batches, heads, head_stride, w_k_total)
+    else:
+        W = _operand(w, w_mn, False, False, n, k, w_ld, 0, 1, 0, 0, 0)
     acc = A @ W.transpose(-1, -2)
     if bias is not None:
         acc = acc + bias[:n]
     op = w.dtype
 
     def out_view(t, cols, ld, bs, rows_=rows, roff=0):
+        if out_hm:
+            assert mode == EPI_OP and n % 64 == 0
+            return _HeadView(t, batches, heads, rows_, cols, bs, ld, head_stride)
         if out_tbc:
             return _v(t, (batches, rows_, cols), (ld, n_seqs * ld, 1))
         return _v(t, (batches, rows_, cols), (bs, ld, 1), roff * ld)
@@ -146,6 +174,17 @@ def gemm(*, a0, w, rows, n, k, mode, out0, a0_ld, out0_ld, batches=1, a0_bs=0, a
         out_view(out0, n, out0_ld, out0_bs).copy_((1 - g) * x + g * o)
     else:
         raise ValueError(mode)
+
+
+class _HeadView:
+    """copy_ target for head-mode outputs: [batches = (seq, head), rows, cols] -> t[seq][row][head * hs + col]."""
+
+    def __init__(self, t, batches, heads, rows, cols, bs, ld, hs):
+        self.v = _v(t, (batches // heads, heads, rows, cols), (bs, hs, ld, 1))
+        self.shape = (batches // heads, heads, rows, cols)
+
+    def copy_(self, src):
+        self.v.copy_(src.reshape(self.shape))
 
 
 def gemm_resid_ln(*a, **k):
@@ -215,6 +254,21 @@ def rowsum(x, ld, rows, cols, out, accumulate=False):
     out[:rows] = out[:rows] + s if accumulate else s
 
 
+def colsum_blocks(rows):
+    return (rows + 511) // 512
+
+
+def colsum(x, ld, rows, cols, partials, period=0, valid=0):
+    nb = colsum_blocks(rows)
+    v = _v(x, (rows, cols), (ld, 1)).float()
+    if period > 0:
+        v = v * ((torch.arange(rows) % period) < valid)[:, None]
+    p = partials[: nb * cols].view(nb, cols)
+    p.zero_()
+    p[0] = v.sum(0)
+    return nb
+
+
 def reduce_partials(part, n_partials, stride, n, out, accumulate=False, part_offset=0):
     s = _v(part, (n_partials, n), (stride, 1), part_offset).sum(0)
     out.view(-1)[:n] = out.view(-1)[:n] + s if accumulate else s
@@ -224,7 +278,7 @@ def layernorm_bwd_blocks():
     return 4
 
 
-def layernorm_bwd(x, gamma, dy, partials, dx=None, resid=None, eps=1e-5):
+def layernorm_bwd(x, gamma, dy, partials, dx=None, resid=None, eps=1e-5, dx_op=None):
     dim = x.shape[-1]
     xr = x.reshape(-1, dim)
     dyr = dy.reshape(-1, dim)
@@ -235,23 +289,28 @@ def layernorm_bwd(x, gamma, dy, partials, dx=None, resid=None, eps=1e-5):
     d = rstd * (dyg - dyg.mean(1, keepdim=True) - xhat * (dyg * xhat).mean(1, keepdim=True))
     if dx is not None:
         dx.view(-1, dim).copy_(d + (resid.reshape(-1, dim) if resid is not None else 0))
+        if dx_op is not None:
+            dx_op.view(-1, dim).copy_(dx.view(-1, dim).to(dx_op.dtype))
     p = partials[: layernorm_bwd_blocks() * 2 * dim].view(layernorm_bwd_blocks(), 2, dim)
     p.zero_()
     p[0, 0] = (dyr * xhat).sum(0)
     p[0, 1] = dyr.sum(0)
 
 
-def softmax_bwd(scores, dprobs, ld_in, rows, rows_per_batch, n_keys, dscores, ld_out, probs=None, kv_lens=None, heads=1):
+def softmax_bwd(scores, dprobs, ld_in, rows, rows_per_batch, n_keys, dscores, ld_out, probs=None, kv_lens=None, heads=1,
+                valid_rows=0):
     S = _v(scores, (rows, n_keys), (ld_in, 1))
     D = _v(dprobs, (rows, n_keys), (ld_in, 1))
     G = _v(dscores, (rows, ld_out), (ld_out, 1))
-    G.zero_()
     if probs is not None:
         Pv = _v(probs, (rows, ld_out), (ld_out, 1))
-        Pv.zero_()
+    vr = valid_rows if valid_rows > 0 else rows_per_batch
     for r0 in range(0, rows, rows_per_batch):
         valid = n_keys if kv_lens is None else min(n_keys, int(kv_lens[(r0 // rows_per_batch) // heads]))
-        sl = slice(r0, min(rows, r0 + rows_per_batch))
+        sl = slice(r0, min(rows, r0 + vr))
+        G[sl] = 0
+        if probs is not None:
+            Pv[sl] = 0
         p = S[sl, :valid].softmax(-1)
         g = p * (D[sl, :valid] - (p * D[sl, :valid]).sum(1, keepdim=True))
         G[sl, :valid] = g.to(dscores.dtype)
