@@ -229,7 +229,11 @@ int mm_convert_f32(const float* x, void* out, int64_t n, int32_t dtype, void* st
  * mm_tbc_to_btc: T x B x C fp32 -> token-major fp32.
  * mm_col2im_k5s2: input gradient of Conv1d(k=5, stride 2, pad 2) from the per-window gradient [B, T_out, 5*C].
  * mm_grad_clip_coef: norm_coef[0] = ||grad_scale * grad||_2, norm_coef[1] = grad_scale * min(1, max_norm / (norm + 1e-6))
- *   (fairseq clip_grad_norm_; max_norm <= 0: no clipping); partials: mm_sumsq_blocks() floats.
+ *   (fairseq clip_grad_norm_; max_norm <= 0: no clipping); partials: mm_sumsq_blocks() floats.  norm_coef has 8 floats:
+ *   [0] norm, [1] multiplier (outputs); with dev_hyper != 0 the kernels read the per-step hyper-parameters from it
+ *   instead of their by-value arguments, so that a captured CUDA graph can be replayed with new values:
+ *   [2] Adam step_size = lr sqrt(1-b2^t)/(1-b1^t), [3] weight_decay * lr, [4] grad_scale, [5] max_norm.
+ *   (mm_adam takes them from the device when step == 0.)
  * mm_adam: fairseq.optim.adam.Adam.step on a flat fp32 buffer; the gradient is multiplied by norm_coef[1] (NULL: 1);
  *   param_op (optional): 16-bit copy of the updated parameters, written in the same pass (the GEMM operand copies).
  * --------------------------------------------------------------------------------------------- */
@@ -259,7 +263,7 @@ int mm_col2im_k5s2(const float* dcol, int32_t batch, int32_t t_out, int32_t t_in
                    void* stream);
 int mm_sumsq_blocks(void);
 int mm_grad_clip_coef(const float* grad, int64_t n, float grad_scale, float max_norm, float* partials, float* norm_coef,
-                      void* stream);
+                      int32_t dev_hyper, void* stream);
 int mm_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
             float beta2, float eps, float weight_decay, int32_t step, const float* norm_coef, void* param_op,
             int32_t dtype, void* stream);

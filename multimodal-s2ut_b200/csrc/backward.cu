@@ -451,8 +451,9 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 
 // out[0] = grad norm (after grad_scale), out[1] = multiplier to apply to the raw gradient: grad_scale * min(1, max_norm/(norm+1e-6))
 __global__ void clip_coef_kernel(const float* __restrict__ partials, int S, float grad_scale, float max_norm,
-                                 float* __restrict__ out) {
+                                 float* __restrict__ out, int dev_hyper) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (dev_hyper) grad_scale = out[4], max_norm = out[5];   // per-step values written by the host before a graph replay
   double t = 0.0;
   for (int i = 0; i < S; ++i) t += (double)partials[i];
   const float norm = sqrtf((float)t) * grad_scale;
@@ -469,15 +470,17 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                     float* __restrict__ m, float* __restrict__ v, long long n, float lr,
                                                     float beta1, float beta2, float eps, float weight_decay,
                                                     float step_size, const float* __restrict__ coef,
-                                                    OpT* __restrict__ p_op) {
+                                                    OpT* __restrict__ p_op, int dev_hyper) {
   const float gs = coef ? coef[1] : 1.0f;
+  float wd_lr = weight_decay * lr;
+  if (dev_hyper) step_size = coef[2], wd_lr = coef[3];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * gs;
     const float mi = beta1 * m[i] + (1.f - beta1) * gi;
     const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
     m[i] = mi, v[i] = vi;
     float pi = p[i];
-    if (weight_decay != 0.f) pi -= weight_decay * lr * pi;
+    if (wd_lr != 0.f) pi -= wd_lr * pi;
     pi -= step_size * mi / (sqrtf(vi) + eps);
     p[i] = pi;
     if (p_op) p_op[i] = OpTraits<OpT>::cvt(pi);
@@ -670,13 +673,13 @@ extern "C" int mm_col2im_k5s2(const float* dcol, int32_t batch, int32_t t_out, i
 extern "C" int mm_sumsq_blocks(void) { return 4 * kNumSMs; }
 
 extern "C" int mm_grad_clip_coef(const float* grad, int64_t n, float grad_scale, float max_norm, float* partials,
-                                 float* norm_coef, void* stream) {
+                                 float* norm_coef, int32_t dev_hyper, void* stream) {
   if (!grad || !partials || !norm_coef || n <= 0) return bad_arg("grad_clip_coef");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int blocks = 4 * kNumSMs;
   sumsq_kernel<<<blocks, 256, 0, s>>>(grad, n, partials);
   MM_CHECK_LAUNCH("sumsq_kernel launch");
-  clip_coef_kernel<<<1, 32, 0, s>>>(partials, blocks, grad_scale, max_norm, norm_coef);
+  clip_coef_kernel<<<1, 32, 0, s>>>(partials, blocks, grad_scale, max_norm, norm_coef, dev_hyper);
   MM_CHECK_LAUNCH("clip_coef_kernel launch");
   return 0;
 }
@@ -684,18 +687,23 @@ extern "C" int mm_grad_clip_coef(const float* grad, int64_t n, float grad_scale,
 extern "C" int mm_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                        float beta1, float beta2, float eps, float weight_decay, int32_t step, const float* norm_coef,
                        void* param_op, int32_t dtype, void* stream) {
-  if (!param || !grad || !exp_avg || !exp_avg_sq || n <= 0 || step <= 0) return bad_arg("adam");
-  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-  const float step_size = (float)((double)lr * sqrt(bc2) / bc1);
+  if (!param || !grad || !exp_avg || !exp_avg_sq || n <= 0 || step < 0) return bad_arg("adam");
+  if (step == 0 && !norm_coef) return bad_arg("adam: step 0 reads step_size / wd*lr from norm_coef[2..3]");
+  const int dev_hyper = step == 0;
+  float step_size = 0.f;
+  if (step > 0) {
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    step_size = (float)((double)lr * sqrt(bc2) / bc1);
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == MM_DTYPE_F16)
     adam_kernel<__half><<<grid_for(n), 256, 0, s>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                     weight_decay, step_size, norm_coef,
-                                                    reinterpret_cast<__half*>(param_op));
+                                                    reinterpret_cast<__half*>(param_op), dev_hyper);
   else
     adam_kernel<__nv_bfloat16><<<grid_for(n), 256, 0, s>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                            weight_decay, step_size, norm_coef,
-                                                           reinterpret_cast<__nv_bfloat16*>(param_op));
+                                                           reinterpret_cast<__nv_bfloat16*>(param_op), dev_hyper);
   MM_CHECK_LAUNCH("adam_kernel launch");
   return 0;
 }

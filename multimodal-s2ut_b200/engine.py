@@ -84,6 +84,12 @@ class EncoderEngine:
 
     def _glu_perm(self, n: int) -> torch.Tensor:
         """Row order that puts each GLU value column and its gate column in the same BN-wide tile."""
+        cache = self.__dict__.setdefault("_perm_cache", {})
+        if n not in cache:
+            cache[n] = self._glu_perm_build(n)
+        return cache[n]
+
+    def _glu_perm_build(self, n: int) -> torch.Tensor:
         bn, half = self.block_n, n // 2
         idx = []
         for t in range(n // bn):
@@ -97,13 +103,19 @@ class EncoderEngine:
         if len(convs) != 2 or any(c.kernel_size[0] != 5 for c in convs):
             raise NotImplementedError("Conv1dSubsampler kernels are built for conv_kernel_sizes='5,5'")
         self.conv = []
-        for c in convs:
+        for i, c in enumerate(convs):
             cout, cin, k = c.weight.shape
             if cout % self.block_n or (cin * 2) % 16:
                 raise NotImplementedError("conv channel counts must be multiples of the GEMM tile")
             perm = self._glu_perm(cout)
             w = c.weight.detach().float().permute(0, 2, 1).reshape(cout, k * cin)[perm]   # [n, tap*cin + ci]
-            self.conv.append(dict(w=self._op(w), b=self._f32(c.bias)[perm].contiguous(), cin=cin, cout=cout, k=k))
+            # persistent buffers, rewritten in place: a captured CUDA graph keeps reading the same addresses after
+            # the training engine refreshes them
+            w_op = self.buf(f"conv_w_op{i}", (cout, k * cin), self.op_dtype)
+            K.convert(w.contiguous(), w_op)
+            b = self.buf(f"conv_b{i}", (cout,), torch.float32)
+            b.copy_(c.bias.detach().float()[perm])
+            self.conv.append(dict(w=w_op, b=b, cin=cin, cout=cout, k=k))
 
     def _pack(self) -> None:
         enc = self.enc

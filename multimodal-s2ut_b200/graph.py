@@ -69,3 +69,92 @@ class GraphedEncoder:
     def __call__(self, wav, lens, imgs):
         self.load_inputs(wav, lens, imgs)
         return self.replay()
+
+
+class GraphedTrainStep:
+    """CUDA-graph replay of the training step (``training.TrainEngine``) for a fixed batch shape.
+
+    Two graphs hold forward (activations kept) + backward, one per outcome of the per-batch modality-dropout draw
+    (images kept / every image tensor zeroed, reference mm_s2s_transformer.py:496-505); a third holds gradient
+    clipping + fairseq Adam + the operand refresh.  The gradient all-reduce runs between them (NCCL, outside the
+    graphs).  Per-step hyper-parameters (Adam step size, weight decay x lr, gradient scale, clip norm) are written to
+    the device before the optimizer graph is replayed, so learning-rate schedules and fairseq's
+    ``world_size / sample_size`` gradient normalisation work under replay.
+    """
+
+    def __init__(self, enc, batch: int, n_samples: int, img_shape: tuple, wav_dtype: torch.dtype = torch.float32,
+                 betas=(0.9, 0.98), eps: float = 1e-8):
+        self.enc = enc
+        self.eng = enc.train_engine()
+        dev = self.eng.device
+        self.device = dev
+        self.betas, self.eps = betas, eps
+        self.wav = torch.zeros(batch, n_samples, dtype=wav_dtype, device=dev)
+        self.lens = torch.full((batch,), n_samples, dtype=torch.int64, device=dev)
+        self.img = torch.zeros(batch, *img_shape, dtype=torch.float32, device=dev)
+        self.grad_out: Optional[torch.Tensor] = None
+        self.out = {}
+        self.graphs = {}
+        self.opt_graph: Optional[torch.cuda.CUDAGraph] = None
+        # pinned staging ring for the per-step hyper-parameters: a slot is rewritten only after its H2D copy has run
+        self._hyper_host = [torch.zeros(4, dtype=torch.float32).pin_memory() for _ in range(8)]
+        self._hyper_done = [None] * 8
+        self._hyper_i = 0
+
+    def _fwd_bwd(self, drop_image: bool):
+        out = self.eng.forward_train(self.wav, self.lens, [self.img], [None], drop_image=drop_image)
+        if self.grad_out is None:
+            self.grad_out = torch.zeros_like(out["encoder_out"][0])
+        self.eng.backward(self.grad_out)
+        return out
+
+    def capture(self) -> None:
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):          # eager pass: allocates every workspace, sets kernel attributes
+            for drop in (False, True):
+                self._fwd_bwd(drop)
+            self.eng.norm_coef[2:6] = torch.tensor([0.0, 0.0, 1.0, 0.0], device=self.device)   # a no-op optimizer step
+            self.eng.adam_step_device_hyper(self.betas, self.eps)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        self.eng.exp_avg.zero_()
+        self.eng.exp_avg_sq.zero_()
+        pool = None
+        for drop in (False, True):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                self.out[drop] = self._fwd_bwd(drop)
+            pool = g.pool()
+            self.graphs[drop] = g
+        self.opt_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.opt_graph, pool=pool):
+            self.eng.adam_step_device_hyper(self.betas, self.eps)
+
+    def forward_backward(self, drop_image: bool = False):
+        """Replays forward + backward on the static inputs (``wav``, ``lens``, ``img``, ``grad_out``)."""
+        if self.opt_graph is None:
+            self.capture()
+        self.graphs[bool(drop_image)].replay()
+        return self.out[bool(drop_image)]
+
+    def optimizer_step(self, lr: float, weight_decay: float = 0.0, clip_norm: float = 0.0,
+                       grad_scale: float = 1.0) -> None:
+        vals = self.eng.hyper_values(lr, self.betas, weight_decay, clip_norm, grad_scale)
+        i = self._hyper_i
+        self._hyper_i = (i + 1) % len(self._hyper_host)
+        if self._hyper_done[i] is not None:
+            self._hyper_done[i].synchronize()
+        self._hyper_host[i].copy_(torch.tensor(vals, dtype=torch.float32))
+        self.eng.norm_coef[2:6].copy_(self._hyper_host[i], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._hyper_done[i] = ev
+        self.opt_graph.replay()
+
+    def step(self, lr: float, drop_image: bool = False, weight_decay: float = 0.0, clip_norm: float = 0.0):
+        """forward + backward -> gradient all-reduce -> optimizer, on the static inputs."""
+        out = self.forward_backward(drop_image)
+        ws = self.eng.all_reduce_grads()
+        self.optimizer_step(lr, weight_decay, clip_norm, grad_scale=1.0 / ws)
+        return out

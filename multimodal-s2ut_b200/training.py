@@ -102,7 +102,7 @@ class TrainEngine(EncoderEngine):
         n = self.flat_p.numel()
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=self.device)
-        self.norm_coef = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self.norm_coef = torch.zeros(8, dtype=torch.float32, device=self.device)   # see mm_grad_clip_coef
         self._sumsq_partials = torch.zeros(K._lib.load().mm_sumsq_blocks(), dtype=torch.float32, device=self.device)
         self._ln_blocks = K.layernorm_bwd_blocks()
         self._pack_train()
@@ -645,10 +645,27 @@ class TrainEngine(EncoderEngine):
         """fairseq: multiply_grads(grad_scale) -> clip_grad_norm_(clip_norm) -> Adam.step, then refresh operand copies."""
         self.step_count += 1
         with _scope("optim"):
-            self._adam(lr, betas, eps, weight_decay, clip_norm, grad_scale)
+            K.grad_clip_coef(self.flat_g, grad_scale, clip_norm, self._sumsq_partials, self.norm_coef)
+            K.adam(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, lr=lr, betas=betas, eps=eps,
+                   weight_decay=weight_decay, step=self.step_count, norm_coef=self.norm_coef, param_op=self.flat_op)
+            self.repack()
 
-    def _adam(self, lr, betas, eps, weight_decay, clip_norm, grad_scale) -> None:
-        K.grad_clip_coef(self.flat_g, grad_scale, clip_norm, self._sumsq_partials, self.norm_coef)
-        K.adam(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, lr=lr, betas=betas, eps=eps,
-               weight_decay=weight_decay, step=self.step_count, norm_coef=self.norm_coef, param_op=self.flat_op)
-        self.repack()
+    def hyper_values(self, lr: float, betas, weight_decay: float, clip_norm: float, grad_scale: float) -> List[float]:
+        """The six per-step floats of ``norm_coef[2:6]`` for the NEXT optimizer step (advances the step counter)."""
+        import numpy as np
+
+        self.step_count += 1
+        t = self.step_count
+        # the same arithmetic as mm_adam's host side (fp32 arguments, double bias corrections): replay == eager, bit for bit
+        b1, b2, lr32 = float(np.float32(betas[0])), float(np.float32(betas[1])), float(np.float32(lr))
+        step_size = lr32 * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
+        return [step_size, float(np.float32(weight_decay) * np.float32(lr)), grad_scale, clip_norm]
+
+    def adam_step_device_hyper(self, betas=(0.9, 0.98), eps: float = 1e-8) -> None:
+        """Same optimizer step with step_size / wd*lr / grad_scale / clip_norm read from ``norm_coef[2:6]`` on the device:
+        the form that is captured into a CUDA graph (``graph.GraphedTrainStep`` writes the values before each replay)."""
+        with _scope("optim"):
+            K.grad_clip_coef(self.flat_g, 1.0, 0.0, self._sumsq_partials, self.norm_coef, dev_hyper=True)
+            K.adam(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, lr=0.0, betas=betas, eps=eps,
+                   weight_decay=0.0, step=0, norm_coef=self.norm_coef, param_op=self.flat_op)
+            self.repack()

@@ -349,7 +349,9 @@ def col2im_k5s2(dcol, B, t_out, t_in, C_, dx):
                 o[:, s] += dc[:, t, k]
 
 
-def grad_clip_coef(grad, grad_scale, max_norm, partials, norm_coef):
+def grad_clip_coef(grad, grad_scale, max_norm, partials, norm_coef, dev_hyper=False):
+    if dev_hyper:
+        grad_scale, max_norm = float(norm_coef[4]), float(norm_coef[5])
     norm = grad.double().norm().item() * grad_scale
     coef = grad_scale * (min(1.0, max_norm / (norm + 1e-6)) if max_norm > 0 else 1.0)
     norm_coef[0], norm_coef[1] = norm, coef
@@ -360,9 +362,13 @@ def adam(param, grad, exp_avg, exp_avg_sq, *, lr, betas=(0.9, 0.999), eps=1e-8, 
     g = grad * (norm_coef[1] if norm_coef is not None else 1.0)
     exp_avg.mul_(betas[0]).add_(g, alpha=1 - betas[0])
     exp_avg_sq.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
-    step_size = lr * math.sqrt(1 - betas[1] ** step) / (1 - betas[0] ** step)
-    if weight_decay:
-        param.mul_(1 - weight_decay * lr)
+    wd_lr = weight_decay * lr
+    if step == 0:
+        step_size, wd_lr = float(norm_coef[2]), float(norm_coef[3])
+    else:
+        step_size = lr * math.sqrt(1 - betas[1] ** step) / (1 - betas[0] ** step)
+    if wd_lr:
+        param.mul_(1 - wd_lr)
     param.addcdiv_(exp_avg, exp_avg_sq.sqrt() + eps, value=-step_size)
     if param_op is not None:
         param_op.copy_(param.to(param_op.dtype))
