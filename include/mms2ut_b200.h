@@ -57,6 +57,14 @@ int mm_cmvn_stats(const float* feats, const int64_t* n_samples_or_frames, int32_
 int mm_cmvn_apply(const float* feats, const float* mean_std, const int64_t* n_samples_or_frames,
                   int32_t lengths_are_samples, int32_t batch, int32_t max_frames, float* out_f32, void* out_op,
                   int32_t op_frames, int32_t op_row_offset, int32_t dtype, void* stream);
+/* mm_cmvn_apply with the train-time SpecAugment of the reference's data config (`_train: [utterance_cmvn, specaugment]`,
+ * fairseq SpecAugmentTransform applied at mm_s2ut/data/speech_to_speech_dataset.py:271-273) fused into the same pass:
+ * spec_masks [B][2 * (n_fmask + n_tmask)] int32 = n_fmask (f0, f) frequency bands then n_tmask (t0, t) frame ranges per
+ * utterance, drawn on the host with the reference's numpy calls; masked cells are written as mask_value. */
+int mm_cmvn_apply_specaug(const float* feats, const float* mean_std, const int64_t* n_samples_or_frames,
+                          int32_t lengths_are_samples, int32_t batch, int32_t max_frames, float* out_f32, void* out_op,
+                          int32_t op_frames, int32_t op_row_offset, int32_t dtype, const int32_t* spec_masks,
+                          int32_t n_fmask, int32_t n_tmask, float mask_value, void* stream);
 /* out_lens[b] = conv-subsampled length of utterance b (int32): frames -> floor((L-1)/2+1) n_layers times;
  * frames = 1 + (n - 400) / 160 when lengths_are_samples.  (fairseq Conv1dSubsampler.get_out_seq_lens_tensor) */
 int mm_seq_lens(const int64_t* n_samples_or_frames, int32_t lengths_are_samples, int32_t batch, int32_t n_layers,

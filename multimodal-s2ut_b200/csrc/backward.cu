@@ -306,7 +306,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 //   P = softmax(S[:, :valid]) ; D = sum_k P dP ; dS = P (dP - D)   (keys >= valid: P = dS = 0 up to ld_out)
 // rows are laid out [batch][rows_per_batch]; valid keys of a batch = kv_lens[batch / heads] (or n_keys).
 // ---------------------------------------------------------------------------------------------------
-template <typename OpT>
+// NPL = keys per lane held in registers (n_keys <= 32 * NPL): scores and dP are read once.
+template <int NPL, typename OpT>
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ S, const float* __restrict__ dP,
                                                            long long ld_in, long long rows, int rows_per_batch,
                                                            int n_keys, const int* __restrict__ kv_lens, int heads,
@@ -322,27 +323,71 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
   }
   const float* s = S + row * ld_in;
   const float* d = dP + row * ld_in;
+  // lane owns key pairs (2 * (lane + 32 i), +1): 8-byte loads, 4-byte stores
+  float sv[NPL], dv[NPL];
   float mx = -INFINITY;
-  for (int k = lane; k < valid; k += 32) mx = fmaxf(mx, s[k]);
+#pragma unroll
+  for (int i = 0; i < NPL / 2; ++i) {
+    const int k = 2 * (lane + 32 * i);
+    float2 a = make_float2(-INFINITY, -INFINITY), g = make_float2(0.f, 0.f);
+    if (k + 1 < valid) {
+      a = __ldcs(reinterpret_cast<const float2*>(s + k));
+      g = __ldcs(reinterpret_cast<const float2*>(d + k));
+    } else if (k < valid) {
+      a.x = s[k], g.x = d[k];
+    }
+    sv[2 * i] = a.x, sv[2 * i + 1] = a.y, dv[2 * i] = g.x, dv[2 * i + 1] = g.y;
+    mx = fmaxf(mx, fmaxf(a.x, a.y));
+  }
   mx = warp_max(mx);
   float sum = 0.f;
-  for (int k = lane; k < valid; k += 32) sum += __expf(s[k] - mx);
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    sv[i] = (sv[i] == -INFINITY) ? 0.f : __expf(sv[i] - mx);
+    sum += sv[i];
+  }
   sum = warp_sum(sum);
   const float inv = valid > 0 ? 1.0f / sum : 0.f;
   float dot = 0.f;
-  for (int k = lane; k < valid; k += 32) dot += __expf(s[k] - mx) * inv * d[k];
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    sv[i] *= inv;
+    dot += sv[i] * dv[i];
+  }
   dot = warp_sum(dot);
   OpT* po = P ? P + row * ld_out : nullptr;
   OpT* go = dS + row * ld_out;
-  for (int k = lane; k < ld_out; k += 32) {
-    float p = 0.f, g = 0.f;
-    if (k < valid) {
-      p = __expf(s[k] - mx) * inv;
-      g = p * (d[k] - dot);
+#pragma unroll
+  for (int i = 0; i < NPL / 2; ++i) {
+    const int k = 2 * (lane + 32 * i);
+    if (k + 1 < ld_out) {
+      if (po) *reinterpret_cast<uint32_t*>(po + k) = OpTraits<OpT>::pack2(sv[2 * i], sv[2 * i + 1]);
+      *reinterpret_cast<uint32_t*>(go + k) =
+          OpTraits<OpT>::pack2(sv[2 * i] * (dv[2 * i] - dot), sv[2 * i + 1] * (dv[2 * i + 1] - dot));
+    } else if (k < ld_out) {
+      if (po) po[k] = OpTraits<OpT>::cvt(sv[2 * i]);
+      go[k] = OpTraits<OpT>::cvt(sv[2 * i] * (dv[2 * i] - dot));
     }
-    if (po) po[k] = OpTraits<OpT>::cvt(p);
-    go[k] = OpTraits<OpT>::cvt(g);
   }
+  // columns beyond the register span (ld_out > 32 * NPL cannot happen: checked on the host)
+}
+
+template <typename OpT>
+static int launch_softmax_bwd(const float* S, const float* dP, long long ld_in, long long rows, int rpb, int n_keys,
+                              const int* kv_lens, int heads, void* P, void* dS, long long ld_out, int valid_rows,
+                              cudaStream_t s) {
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  OpT* p = reinterpret_cast<OpT*>(P);
+  OpT* g = reinterpret_cast<OpT*>(dS);
+  if (ld_out <= 256)
+    softmax_bwd_kernel<8, OpT><<<grid, 256, 0, s>>>(S, dP, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows);
+  else if (ld_out <= 640)
+    softmax_bwd_kernel<20, OpT><<<grid, 256, 0, s>>>(S, dP, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows);
+  else if (ld_out <= 2048)
+    softmax_bwd_kernel<64, OpT><<<grid, 256, 0, s>>>(S, dP, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows);
+  else
+    return bad_arg("softmax_bwd: at most 2048 keys");
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -610,16 +655,15 @@ extern "C" int mm_softmax_bwd(const float* scores, const float* dprobs, int64_t 
   if (!scores || !dprobs || !dscores || rows <= 0 || n_keys <= 0 || rows_per_batch <= 0 || heads <= 0)
     return bad_arg("softmax_bwd");
   if (ld_out < n_keys || ld_in < n_keys) return bad_arg("softmax_bwd: leading dimensions");
+  if ((ld_in & 1) || (ld_out & 1) || (reinterpret_cast<uintptr_t>(scores) & 7) || (reinterpret_cast<uintptr_t>(dprobs) & 7))
+    return bad_arg("softmax_bwd: leading dimensions must be even and the fp32 inputs 8-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const unsigned grid = (unsigned)((rows + 7) / 8);
-  if (dtype == MM_DTYPE_F16)
-    softmax_bwd_kernel<__half><<<grid, 256, 0, s>>>(scores, dprobs, ld_in, rows, rows_per_batch, n_keys, kv_lens, heads,
-                                                    reinterpret_cast<__half*>(probs),
-                                                    reinterpret_cast<__half*>(dscores), ld_out, valid_rows);
-  else
-    softmax_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(scores, dprobs, ld_in, rows, rows_per_batch, n_keys, kv_lens,
-                                                           heads, reinterpret_cast<__nv_bfloat16*>(probs),
-                                                           reinterpret_cast<__nv_bfloat16*>(dscores), ld_out, valid_rows);
+  const int rc = dtype == MM_DTYPE_F16
+                     ? launch_softmax_bwd<__half>(scores, dprobs, ld_in, rows, rows_per_batch, n_keys, kv_lens, heads,
+                                                  probs, dscores, ld_out, valid_rows, s)
+                     : launch_softmax_bwd<__nv_bfloat16>(scores, dprobs, ld_in, rows, rows_per_batch, n_keys, kv_lens,
+                                                         heads, probs, dscores, ld_out, valid_rows, s);
+  if (rc) return rc;
   MM_CHECK_LAUNCH("softmax_bwd_kernel launch");
   return 0;
 }

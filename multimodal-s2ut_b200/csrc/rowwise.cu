@@ -315,10 +315,28 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const float* __restrict
                                                           const long long* __restrict__ lens, int lengths_are_samples,
                                                           int max_frames, float* __restrict__ out_f32,
                                                           OpT* __restrict__ out_op, int op_frames, int op_row_offset,
-                                                          int rows_per_block) {
+                                                          int rows_per_block, const int* __restrict__ spec, int n_fmask,
+                                                          int n_tmask, float mask_value) {
   pdl_launch_dependents();   // programmatic dependent launch: see host.cuh launch_pdl
   pdl_wait();
   __shared__ float s_mean[80], s_std[80];
+  // SpecAugment (fairseq SpecAugmentTransform, applied after CMVN): per utterance n_fmask (f0, f) frequency bands and
+  // n_tmask (t0, t) frame ranges, drawn on the host, overwritten with mask_value while the features are written
+  const int* sp = spec ? spec + (long long)blockIdx.y * 2 * (n_fmask + n_tmask) : nullptr;
+  auto specaug = [&](float4 y, int frame, int c4) {
+    for (int i = 0; i < n_tmask; ++i) {
+      const int t0 = sp[2 * (n_fmask + i)], t = sp[2 * (n_fmask + i) + 1];
+      if (frame >= t0 && frame < t0 + t) return make_float4(mask_value, mask_value, mask_value, mask_value);
+    }
+    for (int i = 0; i < n_fmask; ++i) {
+      const int f0 = sp[2 * i], f1 = f0 + sp[2 * i + 1], c = 4 * c4;
+      if (c >= f0 && c < f1) y.x = mask_value;
+      if (c + 1 >= f0 && c + 1 < f1) y.y = mask_value;
+      if (c + 2 >= f0 && c + 2 < f1) y.z = mask_value;
+      if (c + 3 >= f0 && c + 3 < f1) y.w = mask_value;
+    }
+    return y;
+  };
   const int b = blockIdx.y;
   const int nfr = min(frames_of(lens[b], lengths_are_samples), max_frames);
   const bool ident = mean_std == nullptr;   // input already normalised: copy / pad only
@@ -362,12 +380,14 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const float* __restrict
       const int idx = base + u * blockDim.x;
       const int row = rowi[u], c4 = idx % 20;
       if (out_f32 != nullptr && row < max_frames) {
-        const float4 y = (row < nfr && !ident) ? cmvn4(vf[u], s_mean, s_std, c4) : vf[u];
+        float4 y = (row < nfr && !ident) ? cmvn4(vf[u], s_mean, s_std, c4) : vf[u];
+        if (sp && row < nfr) y = specaug(y, row, c4);
         reinterpret_cast<float4*>(out_f32 + ((long long)b * max_frames + row) * 80)[c4] = y;
       }
       if (out_op != nullptr && row < op_frames) {
         const int fr = row - op_row_offset;
-        const float4 y = (fr >= 0 && fr < nfr && !ident) ? cmvn4(vo[u], s_mean, s_std, c4) : vo[u];
+        float4 y = (fr >= 0 && fr < nfr && !ident) ? cmvn4(vo[u], s_mean, s_std, c4) : vo[u];
+        if (sp && fr >= 0 && fr < nfr) y = specaug(y, fr, c4);
         uint2 pk;
         pk.x = OpTraits<OpT>::pack2(y.x, y.y);
         pk.y = OpTraits<OpT>::pack2(y.z, y.w);
@@ -582,7 +602,18 @@ extern "C" int mm_convert_f32(const float* x, void* out, int64_t n, int32_t dtyp
 extern "C" int mm_cmvn_apply(const float* feats, const float* mean_std, const int64_t* lens,
                              int32_t lengths_are_samples, int32_t batch, int32_t max_frames, float* out_f32,
                              void* out_op, int32_t op_frames, int32_t op_row_offset, int32_t dtype, void* stream) {
+  return mm_cmvn_apply_specaug(feats, mean_std, lens, lengths_are_samples, batch, max_frames, out_f32, out_op, op_frames,
+                               op_row_offset, dtype, nullptr, 0, 0, 0.f, stream);
+}
+
+extern "C" int mm_cmvn_apply_specaug(const float* feats, const float* mean_std, const int64_t* lens,
+                                     int32_t lengths_are_samples, int32_t batch, int32_t max_frames, float* out_f32,
+                                     void* out_op, int32_t op_frames, int32_t op_row_offset, int32_t dtype,
+                                     const int32_t* spec_masks, int32_t n_fmask, int32_t n_tmask, float mask_value,
+                                     void* stream) {
   if (!feats || !lens || (!out_f32 && !out_op)) return bad_arg("cmvn: null pointer");
+  if (spec_masks && (n_fmask < 0 || n_tmask < 0 || n_fmask + n_tmask <= 0)) return bad_arg("cmvn: specaugment mask counts");
+  if (!spec_masks) n_fmask = n_tmask = 0;
   if (batch <= 0 || max_frames <= 0) return 0;
   if (!out_op) op_frames = 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -593,11 +624,12 @@ extern "C" int mm_cmvn_apply(const float* feats, const float* mean_std, const in
   if (dtype == MM_DTYPE_F16)
     launch_pdl(cmvn_apply_kernel<__half>, dim3(grid), dim3(256), 0, s, feats, mean_std, l, lengths_are_samples, max_frames, out_f32,
                                                    reinterpret_cast<__half*>(out_op), op_frames, op_row_offset,
-                                                   rows_per_block);
+                                                   rows_per_block, spec_masks, n_fmask, n_tmask, mask_value);
   else
     launch_pdl(cmvn_apply_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, feats, mean_std, l, lengths_are_samples, max_frames,
                                                           out_f32, reinterpret_cast<__nv_bfloat16*>(out_op),
-                                                          op_frames, op_row_offset, rows_per_block);
+                                                          op_frames, op_row_offset, rows_per_block, spec_masks, n_fmask,
+                                                          n_tmask, mask_value);
   MM_CHECK_LAUNCH("cmvn_apply_kernel launch");
   return 0;
 }

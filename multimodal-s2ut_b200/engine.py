@@ -177,8 +177,10 @@ class EncoderEngine:
     # ------------------------------------------------------------------------------------------
     # stages
     # ------------------------------------------------------------------------------------------
-    def frontend(self, src_tokens: torch.Tensor, src_lengths: torch.Tensor, want_features: bool = False):
-        """Raw waveform [B, N] (or features [B, m, 80]) -> conv-ready operand buffer x1 [B, m_alloc, 80]."""
+    def frontend(self, src_tokens: torch.Tensor, src_lengths: torch.Tensor, want_features: bool = False,
+                 specaug=None):
+        """Raw waveform [B, N] (or features [B, m, 80]) -> conv-ready operand buffer x1 [B, m_alloc, 80].
+        specaug = (mask table int32 [B, 2 (nf + nt)], nf, nt, mask_value): SpecAugment fused into the CMVN pass."""
         dev, op = self.device, self.op_dtype
         src_tokens = src_tokens.to(dev, non_blocking=True)
         lens = src_lengths.to(device=dev, dtype=torch.int64, non_blocking=True)
@@ -204,7 +206,13 @@ class EncoderEngine:
         x1 = self.buf("x1", (B, m_alloc, 80), op)
         if want_features:
             feats_norm = torch.empty(B, m, 80, dtype=torch.float32, device=dev)
-        K.cmvn_apply(raw, stats, lens, is_samples, feats_norm, x1, op_row_offset=2)
+        if specaug is not None:
+            tab, nf, nt, mv = specaug
+            K.cmvn_apply(raw, stats, lens, is_samples, feats_norm, x1, op_row_offset=2,
+                         spec_masks=tab.to(device=dev, dtype=torch.int32).contiguous(), n_fmask=nf, n_tmask=nt,
+                         mask_value=mv)
+        else:
+            K.cmvn_apply(raw, stats, lens, is_samples, feats_norm, x1, op_row_offset=2)
         seq_lens = self.buf("seq_lens", (B,), torch.int32)
         K.seq_lens(lens, is_samples, 2, seq_lens)
         return x1, m, seq_lens, feats_norm

@@ -99,7 +99,13 @@ def cmvn_stats(feats: torch.Tensor, lens: torch.Tensor, lengths_are_samples: boo
 
 
 def cmvn_apply(feats: torch.Tensor, stats: Optional[torch.Tensor], lens: torch.Tensor, lengths_are_samples: bool,
-               out_f32: Optional[torch.Tensor], out_op: Optional[torch.Tensor], op_row_offset: int = 0) -> None:
+               out_f32: Optional[torch.Tensor], out_op: Optional[torch.Tensor], op_row_offset: int = 0,
+               spec_masks: Optional[torch.Tensor] = None, n_fmask: int = 0, n_tmask: int = 0,
+               mask_value: float = 0.0) -> None:
+    """CMVN + zero padding (+ SpecAugment: spec_masks [B, 2 (n_fmask + n_tmask)] int32, see the header)."""
+    if spec_masks is not None:
+        assert spec_masks.dtype == torch.int32 and spec_masks.is_contiguous()
+        assert spec_masks.numel() == feats.shape[0] * 2 * (n_fmask + n_tmask)
     assert feats.dtype == torch.float32 and feats.is_contiguous() and feats.shape[2] == 80
     assert stats is None or stats.dtype == torch.float32
     B, m = feats.shape[0], feats.shape[1]
@@ -113,9 +119,9 @@ def cmvn_apply(feats: torch.Tensor, stats: Optional[torch.Tensor], lens: torch.T
     work = 4.0 * feats.numel() + (4.0 * out_f32.numel() if out_f32 is not None else 0.0) + \
         (2.0 * out_op.numel() if out_op is not None else 0.0)
     with _Launch("cmvn_apply", work):
-        _lib.check(lib.mm_cmvn_apply(_ptr(feats), _ptr(stats), _ptr(lens), int(lengths_are_samples), B, m,
-                                     _ptr(out_f32), _ptr(out_op), op_frames, op_row_offset, dt, _stream()),
-                   "mm_cmvn_apply")
+        _lib.check(lib.mm_cmvn_apply_specaug(_ptr(feats), _ptr(stats), _ptr(lens), int(lengths_are_samples), B, m,
+                                             _ptr(out_f32), _ptr(out_op), op_frames, op_row_offset, dt, _ptr(spec_masks),
+                                             n_fmask, n_tmask, mask_value, _stream()), "mm_cmvn_apply")
 
 
 def seq_lens(lens: torch.Tensor, lengths_are_samples: bool, n_layers: int, out: torch.Tensor) -> None:

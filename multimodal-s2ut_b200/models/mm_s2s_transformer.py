@@ -143,6 +143,9 @@ class MM_S2STransformerEncoder(S2TTransformerEncoderParams):
         self.num_updates = None
         self.freezing_updates = getattr(args, "freezing_updates", None)
         self.modality_rng = np.random  # the reference draws from the global numpy RNG (:497)
+        # train-time SpecAugment of the reference's data config, moved to the device with fbank + CMVN
+        # (data.specaugment.SpecAugmentTransform or None); set e.g. enc.specaugment = SpecAugmentTransform.from_policy("lb")
+        self.specaugment = None
         self._engine = None
         logger.info(f"multimodal_translation_flag = {self.multimodal_translation_flag}")
         logger.info(f"is_fusion_top = {self.is_fusion_top}")
@@ -195,8 +198,17 @@ class MM_S2STransformerEncoder(S2TTransformerEncoderParams):
             from ..training import EncoderOutGrad
 
             eng = self.train_engine()
+            specaug = None
+            if self.specaugment is not None:
+                from ..engine import num_frames
+
+                raw = src_tokens.dim() == 2
+                frames = [num_frames(int(n)) if raw else int(n) for n in src_lengths.tolist()]   # host sync: training only
+                sa = self.specaugment
+                specaug = (torch.from_numpy(sa.draw_batch(frames, 80, self.modality_rng)), sa.freq_mask_n,
+                           sa.time_mask_n, sa.mask_value)
             out = eng.forward_train(src_tokens, src_lengths, imgs_list if fuse else [], img_masks_list if fuse else [],
-                                    drop_audio=drop_audio, drop_image=drop_image)
+                                    drop_audio=drop_audio, drop_image=drop_image, specaug=specaug)
             trigger = torch.zeros((), device=eng.device, requires_grad=True)
             out["encoder_out"] = [EncoderOutGrad.apply(trigger, out["encoder_out"][0], eng)]
             return out

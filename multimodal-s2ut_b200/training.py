@@ -302,7 +302,7 @@ class TrainEngine(EncoderEngine):
 
     @torch.no_grad()
     def forward_train(self, src_tokens, src_lengths, imgs_list: List[torch.Tensor], img_masks_list: List,
-                      drop_audio: bool = False, drop_image: bool = False):
+                      drop_audio: bool = False, drop_image: bool = False, specaug=None):
         enc = self.enc
         if max(enc.dropout_p, getattr(enc, "SA_image_dropout", 0.0), getattr(enc, "SA_text_dropout", 0.0),
                getattr(enc, "SA_attention_dropout", 0.0)) > 0:
@@ -314,7 +314,7 @@ class TrainEngine(EncoderEngine):
             raise NotImplementedError("image key masks are not supported in the backward pass")
         if drop_audio:
             raise NotImplementedError("audio-drop branch (broken in the reference, :500) has no backward here")
-        x1, m, seq_lens, _ = self.frontend(src_tokens, src_lengths)
+        x1, m, seq_lens, _ = self.frontend(src_tokens, src_lengths, specaug=specaug)
         B = x1.shape[0]
         x, T = self.subsample(x1, m, seq_lens)
         M, d = B * T, self.d

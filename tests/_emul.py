@@ -58,7 +58,8 @@ def cmvn_stats(feats, lens, lengths_are_samples, mean_std):
         mean_std.view(-1, 2, 80)[b, 1] = torch.from_numpy(np.sqrt(np.maximum(var, 1e-10)))
 
 
-def cmvn_apply(feats, stats, lens, lengths_are_samples, out_f32, out_op, op_row_offset=0):
+def cmvn_apply(feats, stats, lens, lengths_are_samples, out_f32, out_op, op_row_offset=0, spec_masks=None, n_fmask=0,
+               n_tmask=0, mask_value=0.0):
     if out_op is not None:
         out_op.zero_()
     if out_f32 is not None:
@@ -67,6 +68,13 @@ def cmvn_apply(feats, stats, lens, lengths_are_samples, out_f32, out_op, op_row_
         x = feats[b, :m]
         if stats is not None:
             x = (x - stats.view(-1, 2, 80)[b, 0]) / stats.view(-1, 2, 80)[b, 1]
+        if spec_masks is not None:
+            x = x.clone()
+            row = spec_masks.view(len(lens), -1)[b].tolist()
+            for i in range(n_fmask):
+                x[:, row[2 * i]:row[2 * i] + row[2 * i + 1]] = mask_value
+            for i in range(n_fmask, n_fmask + n_tmask):
+                x[row[2 * i]:row[2 * i] + row[2 * i + 1]] = mask_value
         if out_f32 is not None:
             out_f32[b, :m] = x
         if out_op is not None:

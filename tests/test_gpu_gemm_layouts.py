@@ -65,15 +65,16 @@ def test_attention_backward_gemms_head_mode(cuda):
            heads=H, head_stride=64)
     _close(dP.view(B, H, Tp, Tp)[:, :, :T, :T], do @ v.transpose(-1, -2))
     # dV = P^T dO, dK = dS^T q (A MN-major from [q][k] buffers), dQ = dS k (W MN-major), into the q|k|v layout
-    P = torch.zeros(B * H, Tp, Tp, dtype=torch.bfloat16, device=cuda)
+    P = torch.full((B * H, Tp, Tp), float("nan"), dtype=torch.bfloat16, device=cuda)   # padding is never read
     P[:, :T, :T] = _rnd(B * H, T, T, seed=7)
     Pf = P.float().view(B, H, Tp, Tp)[:, :, :T, :T]
     dqkv = torch.zeros(B * T, 3 * d, dtype=torch.bfloat16, device=cuda)
     og = dict(rows=T, batches=B * H, w_batched=True, n=64, mode=K.EPI_OP, out0_ld=3 * d, out0_bs=T * 3 * d, out_hm=True,
               heads=H, head_stride=64, w_mn=True, w_hm=True)
-    K.gemm(a0=P, a0_ld=Tp, a0_bs=Tp * Tp, a_mn=True, k=Tp, w=dO, w_ld=d, w_bs=T * d, out0=dqkv[:, 2 * d:], **og)
-    K.gemm(a0=P, a0_ld=Tp, a0_bs=Tp * Tp, a_mn=True, k=Tp, w=qkv, w_ld=3 * d, w_bs=T * 3 * d, out0=dqkv[:, d:], **og)
-    K.gemm(a0=P, a0_ld=Tp, a0_bs=Tp * Tp, k=Tp, w=qkv[:, d:], w_ld=3 * d, w_bs=T * 3 * d, out0=dqkv, scale=0.125,
+    # k = T: contraction rows T .. 63 of the last k-block are out of bounds for every operand -> zero-filled by TMA
+    K.gemm(a0=P, a0_ld=Tp, a0_bs=Tp * Tp, a_mn=True, k=T, w=dO, w_ld=d, w_bs=T * d, out0=dqkv[:, 2 * d:], **og)
+    K.gemm(a0=P, a0_ld=Tp, a0_bs=Tp * Tp, a_mn=True, k=T, w=qkv, w_ld=3 * d, w_bs=T * 3 * d, out0=dqkv[:, d:], **og)
+    K.gemm(a0=P, a0_ld=Tp, a0_bs=Tp * Tp, k=T, w=qkv[:, d:], w_ld=3 * d, w_bs=T * 3 * d, out0=dqkv, scale=0.125,
            scale_cols=64, **og)
     back = lambda x: x.permute(0, 2, 1, 3).reshape(B * T, d)
     _close(dqkv[:, 2 * d:], back(Pf.transpose(-1, -2) @ do), 3e-2)

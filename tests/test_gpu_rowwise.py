@@ -157,3 +157,37 @@ def test_self_attention(cuda, T, lens):
     s = s.masked_fill(mask[:, None, None, :], float("-inf"))
     ref = (torch.softmax(s, -1) @ vf).permute(0, 2, 1, 3).reshape(B * T, d)
     assert (out.float() - ref).abs().max().item() < 3e-2
+
+
+def test_specaugment_fused_into_cmvn_matches_oracle(cuda):
+    """CMVN + SpecAugment in one pass == oracle CMVN followed by the oracle (fairseq) SpecAugment, same draws."""
+    import numpy as np
+
+    from mm_s2ut_b200 import kernels as K
+    from mm_s2ut_b200.data.specaugment import SpecAugmentTransform
+    from oracle.fbank import utterance_cmvn
+    from oracle.specaugment import spec_augment
+
+    rng = np.random.RandomState(3)
+    frames = [300, 211, 64]
+    B, m = len(frames), max(frames)
+    raw = rng.randn(B, m, 80).astype(np.float32) * 2 + 1
+    sa = SpecAugmentTransform.from_policy("ld")
+    tab = sa.draw_batch(frames, 80, np.random.RandomState(11))
+    ref_rng = np.random.RandomState(11)
+    feats = torch.from_numpy(raw).cuda()
+    lens = torch.tensor(frames, dtype=torch.int64, device=cuda)
+    stats = torch.empty(B, 2, 80, device=cuda)
+    K.cmvn_stats(feats, lens, False, stats)
+    out = torch.full((B, m, 80), 9.0, device=cuda)
+    out_op = torch.full((B, m + 4, 80), 9.0, dtype=torch.bfloat16, device=cuda)
+    K.cmvn_apply(feats, stats, lens, False, out, out_op, op_row_offset=2, spec_masks=torch.from_numpy(tab).cuda(),
+                 n_fmask=sa.freq_mask_n, n_tmask=sa.time_mask_n, mask_value=sa.mask_value)
+    for b, n in enumerate(frames):
+        ref = spec_augment(utterance_cmvn(raw[b, :n]), freq_mask_n=2, freq_mask_f=27, time_mask_n=2, time_mask_t=100,
+                           time_mask_p=1.0, mask_value=0.0, rng=ref_rng)
+        got = out[b, :n].cpu().numpy()
+        assert np.array_equal(got == 0.0, ref == 0.0)
+        assert np.allclose(got, ref, atol=1e-5)
+        assert (out[b, n:] == 0).all()
+        assert torch.equal(out_op[b, 2:2 + n].float().cpu(), torch.from_numpy(got).bfloat16().float())

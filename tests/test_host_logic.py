@@ -227,3 +227,29 @@ def test_committed_bench_line_has_contract_keys():
     for k in ("value", "unit", "cores", "kind", "sample"):
         assert k in d["cpu_baseline"], k
     assert "sm_mhz" in d["clocks"] and "reasons" in d["clocks"]
+
+
+def test_specaugment_draws_follow_the_reference_call_sequence():
+    """data.specaugment draws the masks with the oracle's (= fairseq's) numpy calls in the same order, incl. early exits."""
+    import numpy as np
+
+    import mm_s2ut_b200  # noqa: F401
+    from mm_s2ut_b200.data.specaugment import POLICIES, SpecAugmentTransform
+    from oracle.specaugment import spec_augment
+
+    for name, pol in POLICIES.items():
+        sa = SpecAugmentTransform.from_policy(name)
+        kw = dict(freq_mask_n=pol["freq_mask_N"], freq_mask_f=pol["freq_mask_F"], time_mask_n=pol["time_mask_N"],
+                  time_mask_t=pol["time_mask_T"], time_mask_p=pol["time_mask_p"], mask_value=0.0)
+        for frames in (998, 37, 3, 0):
+            x = np.random.RandomState(frames).randn(frames, 80).astype(np.float32) + 3.0
+            ref = spec_augment(x, rng=np.random.RandomState(7), **kw)
+            fm, tm = sa.draw(frames, 80, np.random.RandomState(7))
+            got = x.copy()
+            for f0, f in fm:
+                got[:, f0:f0 + f] = 0.0
+            for t0, t in tm:
+                got[t0:t0 + t] = 0.0
+            assert np.array_equal(got, ref), (name, frames)
+    tab = SpecAugmentTransform.from_policy("ld").draw_batch([998, 500], 80, np.random.RandomState(0))
+    assert tab.shape == (2, 8) and tab.dtype == np.int32
