@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--preset", default="base")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches only (for an ncu launch list)")
     a = ap.parse_args()
     import mm_s2ut_b200  # noqa: F401
     from mm_s2ut_b200 import kernels as K
@@ -74,6 +75,11 @@ def main():
     torch.cuda.synchronize()
     # ---- CUDA-graph replay of the same step (one graph for forward + backward per dropout outcome, one for the optimizer)
     from mm_s2ut_b200.graph import GraphedTrainStep
+    if a.no_graph:
+        for _ in range(a.steps):
+            step(go)
+        torch.cuda.synchronize()
+        return
     gs = GraphedTrainStep(enc, B, n, (577, 768))
     gs.wav.copy_(wav)
     gs.img.copy_(imgs)
