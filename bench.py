@@ -181,7 +181,7 @@ def train_step_probe(dev, world, rank, wav, img, steps=20, warmup=3):
     args = make_args(PRESET, multimodal_translation_config_yaml=cfg)
     enc = MM_S2STransformerEncoder(args, build_unused_projections=False).to(dev).train()
     enc.dropout_p = 0.0            # element-wise dropout masks are not built; modality dropout is on
-    gs = GraphedTrainStep(enc, wav.shape[0], wav.shape[1], tuple(img.shape[1:]))
+    gs = GraphedTrainStep(enc, wav.shape[0], wav.shape[1], tuple(img.shape[1:]), overlap_reduce=world > 1)
     gs.wav.copy_(wav)
     gs.img.copy_(img)
     g = torch.Generator(device=dev).manual_seed(5 + rank)
@@ -211,7 +211,8 @@ def train_step_probe(dev, world, rank, wav, img, steps=20, warmup=3):
     audio_s = wav.shape[0] * DUR_S * world
     out = {"value": audio_s / (ms * 1e-3), "unit": "audio-s/s trained", "ms_per_step": ms, "steps": steps,
            "launches_per_step_approx": launches // 2, "params": int(gs.eng.flat_p.numel()), "grad_norm_last": norm,
-           "collective": "NCCL all-reduce of the flat fp32 gradient (%d MB), after backward" % (gs.eng.flat_g.numel() * 4 >> 20)
+           "collective": "NCCL all-reduce of the flat fp32 gradient (%d MB) in per-layer buckets on a side stream, captured "
+                         "in the backward graph and overlapped with it" % (gs.eng.flat_g.numel() * 4 >> 20)
            if world > 1 else "none (1 GPU)",
            "what": "BASELINE configs[2]: forward (activations kept) + backward of every encoder/fusion/conv parameter + "
                    "gradient all-reduce + fairseq Adam with clip-norm, batch 64 x 10 s per GPU, modality dropout 0.5 "

@@ -83,12 +83,13 @@ class GraphedTrainStep:
     """
 
     def __init__(self, enc, batch: int, n_samples: int, img_shape: tuple, wav_dtype: torch.dtype = torch.float32,
-                 betas=(0.9, 0.98), eps: float = 1e-8):
+                 betas=(0.9, 0.98), eps: float = 1e-8, overlap_reduce: bool = False):
         self.enc = enc
         self.eng = enc.train_engine()
         dev = self.eng.device
         self.device = dev
         self.betas, self.eps = betas, eps
+        self.overlap_reduce = overlap_reduce
         self.wav = torch.zeros(batch, n_samples, dtype=wav_dtype, device=dev)
         self.lens = torch.full((batch,), n_samples, dtype=torch.int64, device=dev)
         self.img = torch.zeros(batch, *img_shape, dtype=torch.float32, device=dev)
@@ -105,7 +106,9 @@ class GraphedTrainStep:
         out = self.eng.forward_train(self.wav, self.lens, [self.img], [None], drop_image=drop_image)
         if self.grad_out is None:
             self.grad_out = torch.zeros_like(out["encoder_out"][0])
-        self.eng.backward(self.grad_out)
+        # with several ranks the bucketed gradient all-reduce is part of the captured graph (side stream, forked from
+        # and joined to the capture stream), overlapping the rest of the backward pass
+        self.eng.backward(self.grad_out, overlap_reduce=self.overlap_reduce)
         return out
 
     def capture(self) -> None:
@@ -155,6 +158,10 @@ class GraphedTrainStep:
     def step(self, lr: float, drop_image: bool = False, weight_decay: float = 0.0, clip_norm: float = 0.0):
         """forward + backward -> gradient all-reduce -> optimizer, on the static inputs."""
         out = self.forward_backward(drop_image)
+        import torch.distributed as dist
+
+        if self.overlap_reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self.eng._reduced = True      # the captured graph holds the collectives (python state is not replayed)
         ws = self.eng.all_reduce_grads()
         self.optimizer_step(lr, weight_decay, clip_norm, grad_scale=1.0 / ws)
         return out

@@ -46,6 +46,20 @@ def _split_k(n: int, kin: int, mp: int) -> int:
     return s
 
 
+def _best_split(tiles: int, M: int, pairs: int = 74, max_split: int = 32, min_chunk: int = 512) -> int:
+    """Split-K factor of a wgrad GEMM with `tiles` 256 x 256 output tiles contracting over M tokens: the persistent
+    kernel runs one tile per CTA pair per wave, so pick the split whose tile count fills whole waves of the 74 pairs
+    best (within 3 %: the fewest partials), keeping every chunk at least `min_chunk` tokens long."""
+    effs = []
+    for s in range(1, max_split + 1):
+        if s > 1 and M // s < min_chunk:
+            break
+        work = tiles * s
+        effs.append((s, work / (((work + pairs - 1) // pairs) * pairs)))
+    top = max(e for _, e in effs)
+    return next(s for s, e in effs if e >= top - 0.03)      # fewer, longer chunks when the fill is within 3 %
+
+
 class _scope:
     """Tags the launches of a phase in the per-launch timing list (``kernels.timing``)."""
 
@@ -162,6 +176,17 @@ class TrainEngine(EncoderEngine):
                 p.grad = self.flat_g[o:o + n].view(p.shape)
                 self._slices[id(p)] = (o, n)
         self.params = order
+        # gradient buckets in the order the backward pass completes them: top (final LayerNorm, fusion, everything
+        # else), layers L-1 .. 0, conv.  Flat layout: [conv | layer 0 .. L-1 | top]
+        off = {id(p): o for p, o in zip(order, offs)}
+        l_lo = [off[id(L.self_attn_layer_norm.weight)] for L in enc.transformer_layers]
+        top_lo = off[id(enc.layer_norm.weight)]
+        self.bucket_conv = (0, l_lo[0] if l_lo else top_lo)
+        self.bucket_layers = [(lo, (l_lo[i + 1] if i + 1 < len(l_lo) else top_lo)) for i, lo in enumerate(l_lo)]
+        self.bucket_top = (top_lo, total)
+        self._reduce_works = []
+        self._reduced = False
+        self._comm_stream = None
 
     def g(self, *params) -> torch.Tensor:
         """Flat fp32 gradient slice spanning the given (adjacent, in this order) parameters."""
@@ -371,10 +396,8 @@ class TrainEngine(EncoderEngine):
         """gw [n, sum kin] (+)= dy^T [x_0 | x_1 | ...]: both operands read as stored (MN-major), the token contraction
         split into S batches; x_ops = [(tensor [M, kin], ld, kin), ...] fill consecutive column blocks of gw."""
         kin_all = sum(x[2] for x in x_ops)
-        S = 1
         tiles = ((n + 255) // 256) * sum((x[2] + 255) // 256 for x in x_ops)
-        while S < 16 and tiles * S < 74 and M // (2 * S) >= 256:
-            S *= 2
+        S = _best_split(tiles, M)
         chunk = _round_up((M + S - 1) // S, 64)
         part = self._partials(S * n * kin_all)
         col = 0
@@ -603,12 +626,47 @@ class TrainEngine(EncoderEngine):
         K.glu_bwd(pre1, dglu1, M1, mid, dpre1)
         conv_param_grads(c1, dpre1, x1, 2 * c1["cin"], m_alloc * c1["cin"], T1, c1["k"] * c1["cin"])
 
+    def _reduce_async(self, lo: int, hi: int) -> None:
+        """All-reduce flat_g[lo:hi] over the ranks while the backward pass continues: the collective is issued on a side
+        stream behind an event that marks the bucket complete (NCCL over NVLink; plain blocking call under gloo)."""
+        import torch.distributed as dist
+
+        if hi <= lo:
+            return
+        bucket = self.flat_g[lo:hi]
+        if self.device.type != "cuda":
+            dist.all_reduce(bucket, op=dist.ReduceOp.SUM)
+            return
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self._comm_stream):
+            self._comm_stream.wait_event(ev)
+            self._reduce_works.append(dist.all_reduce(bucket, op=dist.ReduceOp.SUM, async_op=True))
+
+    def _reduce_join(self) -> None:
+        for wk in self._reduce_works:
+            wk.wait()
+        self._reduce_works = []
+        if self._comm_stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
+        self._reduced = True
+
     @torch.no_grad()
-    def backward(self, grad_out: torch.Tensor, accumulate: bool = False) -> None:
-        """grad_out = d loss / d encoder_out[0]  [T, B, d] fp32.  Fills (or accumulates into) every ``param.grad``."""
+    def backward(self, grad_out: torch.Tensor, accumulate: bool = False, overlap_reduce: bool = False) -> None:
+        """grad_out = d loss / d encoder_out[0]  [T, B, d] fp32.  Fills (or accumulates into) every ``param.grad``.
+        overlap_reduce: all-reduce each gradient bucket (top, every layer, conv) over the process group as soon as the
+        backward pass has completed it, overlapping the collective with the remaining backward kernels."""
+        import torch.distributed as dist
+
         sv = self._saved
         if sv is None:
             raise RuntimeError("backward() needs a preceding forward_train()")
+        overlap = overlap_reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if overlap and accumulate:
+            raise ValueError("overlap_reduce reduces fresh gradients: use it on the last micro-batch only, without accumulate")
+        self._reduced = False
         B, T, d = sv["B"], sv["T"], self.d
         M = B * T
         grad_out = grad_out.to(device=self.device, dtype=torch.float32).contiguous()
@@ -624,11 +682,18 @@ class TrainEngine(EncoderEngine):
         g_op = self.buf("b_g_op", (M, d), self.op_dtype)
         K.layernorm_bwd(sv["x_final"], self.ln_g, gtext, lnp, dx=g, dx_op=g_op)
         self._ln_param_grads(lnp, d, self.g(self.enc.layer_norm.weight, self.enc.layer_norm.bias), accumulate)
+        if overlap:
+            self._reduce_async(*self.bucket_top)
         for i in reversed(range(self.n_layers)):
             with _scope("layer"):
                 self._layer_bwd(i, g, g_op, B, T, sv["seq_lens"], accumulate)
+            if overlap:
+                self._reduce_async(*self.bucket_layers[i])
         with _scope("conv"):
             self._conv_bwd(g, B, T, accumulate)
+        if overlap:
+            self._reduce_async(*self.bucket_conv)
+            self._reduce_join()
 
     # ------------------------------------------------------------------------------------------
     # gradient exchange + optimizer
@@ -637,7 +702,12 @@ class TrainEngine(EncoderEngine):
         """Sum ``flat_g`` over the ranks of the default process group, in buckets (async, then waited); returns the
         world size (fairseq then multiplies the gradients by world_size / sample_size: pass that as ``grad_scale`` to
         ``adam_step``).  The only collective of the path: NCCL over NVLink on the GPU box, gloo in
-        the CPU tests (``all_reduce_flat``)."""
+        the CPU tests (``all_reduce_flat``).  A no-op when ``backward(overlap_reduce=True)`` already reduced them."""
+        import torch.distributed as dist
+
+        if self._reduced:
+            self._reduced = False
+            return dist.get_world_size() if dist.is_initialized() else 1
         return all_reduce_flat(self.flat_g, bucket_elems)
 
     def adam_step(self, lr: float, betas=(0.9, 0.98), eps: float = 1e-8, weight_decay: float = 0.0,

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--preset", default="base")
     ap.add_argument("--no-graph", action="store_true", help="eager launches only (for an ncu launch list)")
+    ap.add_argument("--no-overlap", action="store_true", help="all-reduce after the backward graph instead of inside it")
     a = ap.parse_args()
     import mm_s2ut_b200  # noqa: F401
     from mm_s2ut_b200 import kernels as K
@@ -80,7 +81,7 @@ def main():
             step(go)
         torch.cuda.synchronize()
         return
-    gs = GraphedTrainStep(enc, B, n, (577, 768))
+    gs = GraphedTrainStep(enc, B, n, (577, 768), overlap_reduce=(world > 1 and not a.no_overlap))
     gs.wav.copy_(wav)
     gs.img.copy_(imgs)
     gs.grad_out = go.clone()
@@ -135,10 +136,14 @@ def main():
                     value=audio_s / (graph_ms * 1e-3), unit="audio-s/s", n_gpus=world, steps=a.steps,
                     ms_per_step=graph_ms, eager_ms_per_step=ms,
                     launches_per_step=launches, eager_sum_ms=tot, batch_per_gpu=B, utt_seconds=a.seconds,
-                    preset=a.preset, params=int(eng.flat_p.numel()),
+                    preset=a.preset, params=int(eng.flat_p.numel()), overlap_reduce=bool(world > 1 and not a.no_overlap),
                     note="element-wise dropout off (masks not built); modality dropout 0.5; synthetic d loss/d encoder_out")
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # graphs that hold captured NCCL kernels must be gone before the communicator is torn down
+        del gs
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 

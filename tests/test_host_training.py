@@ -91,6 +91,62 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _overlap_worker(rank, world, port, q):
+    import sys
+    from pathlib import Path
+
+    import torch.distributed as dist
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    import _emul as emul
+    import mm_s2ut_b200  # noqa: F401
+    from mm_s2ut_b200 import engine, training
+    from test_gpu_training import _train_setup
+
+    engine.K = training.K = emul
+    engine.EncoderEngine._require_cuda = False
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    enc, wav, lens, imgs, R, *_ = _train_setup("selective_attention", True, B=2, dur=1.0)
+    enc.train()
+    eng = enc.train_engine()
+    R = R * (1.0 + rank)                      # different gradients on the two ranks
+    eng.forward_train(wav, lens, [imgs], [None])
+    eng.backward(R)
+    local = eng.flat_g.clone()
+    both = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(both, local)
+    eng.backward(R, overlap_reduce=True)      # buckets reduced as the backward pass completes them
+    ws = eng.all_reduce_grads()               # already reduced: no second collective
+    cover = sorted([eng.bucket_conv, eng.bucket_top] + eng.bucket_layers)
+    tiled = cover[0][0] == 0 and cover[-1][1] == eng.flat_g.numel() and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+    err = (eng.flat_g - sum(both)).abs().max().item() / sum(both).abs().max().item()
+    q.put((rank, ws, tiled, err))
+    dist.destroy_process_group()
+
+
+def test_overlapped_bucket_all_reduce_gloo_world2():
+    """backward(overlap_reduce=True) under gloo, world_size 2: every bucket is reduced exactly once and the buckets
+    tile the flat gradient buffer (the N > 1 path of SURVEY.md 8e, run on CPU with the emulated kernels)."""
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_overlap_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in ps)
+    for p in ps:
+        p.join(60)
+    for rank, ws, tiled, err in res:
+        assert ws == 2 and tiled and err < 1e-6, (rank, ws, tiled, err)
+
+
 def test_gradient_all_reduce_gloo_world2():
     import torch.multiprocessing as mp
 
