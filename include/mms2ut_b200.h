@@ -230,7 +230,7 @@ int mm_convert_f32(const float* x, void* out, int64_t n, int32_t dtype, void* st
  *   per-block (sum dy * xhat, sum dy).
  * mm_softmax_bwd: P = softmax(scores[:, :valid]), dscores = P o (dprobs - rowsum(P o dprobs)), both 16-bit,
  *   rows [batch][rows_per_batch] of which the first valid_rows are processed (0: all), valid = kv_lens[batch / heads]
- *   (NULL: n_keys); columns [valid, ld_out) = 0.
+ *   (NULL: n_keys), further limited to the query's own index + 1 when causal; columns [valid, ld_out) = 0.
  * mm_glu_bwd: pre fp32 [rows, 2n] = (a | b), dy fp32 [rows, n] -> dpre 16-bit [rows, 2n]   (F.glu backward, x scale).
  * mm_gate_bwd: selective gate backward (mm_s2s_transformer.py:612-618): z = pre-sigmoid gate incl. bias ->
  *   dz 16-bit [B*T, d], dcat fp32 [B*T, 2d] = (dres g | dres (1-g)); dres is T x B x C.
@@ -258,7 +258,15 @@ int mm_layernorm_bwd(const float* x, const float* gamma, const float* dy, int64_
                      const float* resid, float* dx, float* partials, void* dx_op, int32_t dtype, void* stream);
 int mm_softmax_bwd(const float* scores, const float* dprobs, int64_t ld_in, int64_t rows, int32_t rows_per_batch,
                    int32_t n_keys, const int32_t* kv_lens, int32_t heads, void* probs, void* dscores, int64_t ld_out,
-                   int32_t valid_rows, int32_t dtype, void* stream);
+                   int32_t valid_rows, int32_t causal, int32_t dtype, void* stream);
+/* Backward of mm_label_smoothed_nll summed over rows (fairseq label_smoothed_nll_loss, reduce=True), times grad_scale:
+ * dlogits 16-bit [rows, ld_out] (columns >= vocab and padding rows are 0) -- the A operand of the tied output
+ * projection's dgrad / wgrad.  mm_embed_tokens_bwd: table_grad[token] += scale * dx[row] (atomic; padding rows skipped). */
+int mm_label_smoothed_nll_bwd(const float* logits, int64_t ld, int32_t vocab, const int64_t* target, int32_t padding_idx,
+                              int64_t rows, float epsilon, float grad_scale, void* dlogits, int64_t ld_out, int32_t dtype,
+                              void* stream);
+int mm_embed_tokens_bwd(const int64_t* tokens, int32_t padding_idx, const float* dx, int64_t rows, int32_t dim,
+                        float scale, float* table_grad, void* stream);
 int mm_colsum_blocks(int32_t rows);
 int mm_colsum(const void* in, int64_t ld, int32_t rows, int32_t cols, int32_t period, int32_t valid, float* partials,
               int32_t dtype, void* stream);

@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
                                                            long long ld_in, long long rows, int rows_per_batch,
                                                            int n_keys, const int* __restrict__ kv_lens, int heads,
                                                            OpT* __restrict__ P, OpT* __restrict__ dS, long long ld_out,
-                                                           int valid_rows) {
+                                                           int valid_rows, int causal) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows || (int)(row % rows_per_batch) >= valid_rows) return;
@@ -321,6 +321,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
     const int v = kv_lens[(row / rows_per_batch) / heads];
     valid = v < n_keys ? v : n_keys;
   }
+  if (causal) valid = min(valid, (int)(row % rows_per_batch) + 1);   // key j visible to query i iff j <= i
   const float* s = S + row * ld_in;
   const float* d = dP + row * ld_in;
   // lane owns key pairs (2 * (lane + 32 i), +1): 8-byte loads, 4-byte stores
@@ -375,16 +376,16 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
 template <typename OpT>
 static int launch_softmax_bwd(const float* S, const float* dP, long long ld_in, long long rows, int rpb, int n_keys,
                               const int* kv_lens, int heads, void* P, void* dS, long long ld_out, int valid_rows,
-                              cudaStream_t s) {
+                              int causal, cudaStream_t s) {
   const unsigned grid = (unsigned)((rows + 7) / 8);
   OpT* p = reinterpret_cast<OpT*>(P);
   OpT* g = reinterpret_cast<OpT*>(dS);
   if (ld_out <= 256)
-    softmax_bwd_kernel<8, OpT><<<grid, 256, 0, s>>>(S, dP, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows);
+    softmax_bwd_kernel<8, OpT><<<grid, 256, 0, s>>>(S, dP, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows, causal);
   else if (ld_out <= 640)
-    softmax_bwd_kernel<20, OpT><<<grid, 256, 0, s>>>(S, dP, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows);
+    softmax_bwd_kernel<20, OpT><<<grid, 256, 0, s>>>(S, dP, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows, causal);
   else if (ld_out <= 2048)
-    softmax_bwd_kernel<64, OpT><<<grid, 256, 0, s>>>(S, dP, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows);
+    softmax_bwd_kernel<64, OpT><<<grid, 256, 0, s>>>(S, dP, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows, causal);
   else
     return bad_arg("softmax_bwd: at most 2048 keys");
   return 0;
@@ -532,6 +533,59 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// label-smoothed cross entropy backward (fairseq label_smoothed_nll_loss, reduce=True):
+//   loss = (1 - eps - eps_i) * nll + eps_i * smooth, eps_i = eps / (V - 1)
+//   d loss / d logit_j = (1 - eps - eps_i) (p_j - [j == t]) + eps_i (V p_j - 1)   (0 for rows whose target is padding)
+// warp per row; dlogits 16-bit [rows, ld_out], columns [vocab, ld_out) = 0.
+// ---------------------------------------------------------------------------------------------------
+template <typename OpT>
+__global__ void __launch_bounds__(256) ce_bwd_kernel(const float* __restrict__ logits, long long ld, int vocab,
+                                                      const long long* __restrict__ target, int padding_idx, long long rows,
+                                                      float eps, float grad_scale, OpT* __restrict__ dlogits,
+                                                      long long ld_out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* x = logits + row * ld;
+  OpT* o = dlogits + row * ld_out;
+  const long long t = target[row];
+  if (t == padding_idx) {
+    for (int j = lane; j < ld_out; j += 32) o[j] = OpTraits<OpT>::cvt(0.f);
+    return;
+  }
+  float mx = -INFINITY;
+  for (int j = lane; j < vocab; j += 32) mx = fmaxf(mx, x[j]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < vocab; j += 32) sum += __expf(x[j] - mx);
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  const float eps_i = eps / (float)(vocab - 1);
+  const float a = 1.0f - eps - eps_i;
+  for (int j = lane; j < ld_out; j += 32) {
+    float g = 0.f;
+    if (j < vocab) {
+      const float p = __expf(x[j] - mx) * inv;
+      g = a * (p - (j == t ? 1.0f : 0.0f)) + eps_i * ((float)vocab * p - 1.0f);
+    }
+    o[j] = OpTraits<OpT>::cvt(g * grad_scale);
+  }
+}
+
+// embedding backward: table_grad[token] += scale * dx[row] for non-padding tokens (atomic adds; nn.Embedding with
+// padding_idx gives that row no gradient)
+__global__ void __launch_bounds__(128) embed_bwd_kernel(const long long* __restrict__ tokens, int padding_idx,
+                                                         const float* __restrict__ dx, long long rows, int dim,
+                                                         float scale, float* __restrict__ table_grad) {
+  const long long row = blockIdx.x;
+  if (row >= rows) return;
+  const long long tok = tokens[row];
+  if (tok == padding_idx) return;
+  for (int c = threadIdx.x; c < dim; c += blockDim.x)
+    atomicAdd(table_grad + tok * dim + c, scale * dx[row * dim + c]);
+}
+
 static inline unsigned grid_for(long long total, int per_block = 256) {
   long long g = (total + per_block - 1) / per_block;
   const long long cap = (long long)kNumSMs * 16;
@@ -650,7 +704,8 @@ extern "C" int mm_layernorm_bwd(const float* x, const float* gamma, const float*
 
 extern "C" int mm_softmax_bwd(const float* scores, const float* dprobs, int64_t ld_in, int64_t rows,
                               int32_t rows_per_batch, int32_t n_keys, const int32_t* kv_lens, int32_t heads, void* probs,
-                              void* dscores, int64_t ld_out, int32_t valid_rows, int32_t dtype, void* stream) {
+                              void* dscores, int64_t ld_out, int32_t valid_rows, int32_t causal, int32_t dtype,
+                              void* stream) {
   if (valid_rows <= 0) valid_rows = rows_per_batch;
   if (!scores || !dprobs || !dscores || rows <= 0 || n_keys <= 0 || rows_per_batch <= 0 || heads <= 0)
     return bad_arg("softmax_bwd");
@@ -660,11 +715,38 @@ extern "C" int mm_softmax_bwd(const float* scores, const float* dprobs, int64_t 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int rc = dtype == MM_DTYPE_F16
                      ? launch_softmax_bwd<__half>(scores, dprobs, ld_in, rows, rows_per_batch, n_keys, kv_lens, heads,
-                                                  probs, dscores, ld_out, valid_rows, s)
+                                                  probs, dscores, ld_out, valid_rows, causal, s)
                      : launch_softmax_bwd<__nv_bfloat16>(scores, dprobs, ld_in, rows, rows_per_batch, n_keys, kv_lens,
-                                                         heads, probs, dscores, ld_out, valid_rows, s);
+                                                         heads, probs, dscores, ld_out, valid_rows, causal, s);
   if (rc) return rc;
   MM_CHECK_LAUNCH("softmax_bwd_kernel launch");
+  return 0;
+}
+
+extern "C" int mm_label_smoothed_nll_bwd(const float* logits, int64_t ld, int32_t vocab, const int64_t* target,
+                                         int32_t padding_idx, int64_t rows, float epsilon, float grad_scale,
+                                         void* dlogits, int64_t ld_out, int32_t dtype, void* stream) {
+  if (!logits || !target || !dlogits || rows <= 0 || vocab <= 1 || ld < vocab || ld_out < vocab)
+    return bad_arg("label_smoothed_nll_bwd");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  const long long* t = reinterpret_cast<const long long*>(target);
+  if (dtype == MM_DTYPE_F16)
+    ce_bwd_kernel<__half><<<grid, 256, 0, s>>>(logits, ld, vocab, t, padding_idx, rows, epsilon, grad_scale,
+                                               reinterpret_cast<__half*>(dlogits), ld_out);
+  else
+    ce_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(logits, ld, vocab, t, padding_idx, rows, epsilon, grad_scale,
+                                                      reinterpret_cast<__nv_bfloat16*>(dlogits), ld_out);
+  MM_CHECK_LAUNCH("ce_bwd_kernel launch");
+  return 0;
+}
+
+extern "C" int mm_embed_tokens_bwd(const int64_t* tokens, int32_t padding_idx, const float* dx, int64_t rows, int32_t dim,
+                                   float scale, float* table_grad, void* stream) {
+  if (!tokens || !dx || !table_grad || rows <= 0 || dim <= 0) return bad_arg("embed_tokens_bwd");
+  embed_bwd_kernel<<<(unsigned)rows, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(tokens), padding_idx, dx, rows, dim, scale, table_grad);
+  MM_CHECK_LAUNCH("embed_bwd_kernel launch");
   return 0;
 }
 

@@ -387,15 +387,16 @@ def layernorm_bwd(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, partia
 
 def softmax_bwd(scores: torch.Tensor, dprobs: torch.Tensor, ld_in: int, rows: int, rows_per_batch: int, n_keys: int,
                 dscores: torch.Tensor, ld_out: int, probs: Optional[torch.Tensor] = None,
-                kv_lens: Optional[torch.Tensor] = None, heads: int = 1, valid_rows: int = 0) -> None:
+                kv_lens: Optional[torch.Tensor] = None, heads: int = 1, valid_rows: int = 0,
+                causal: bool = False) -> None:
     assert scores.dtype == dprobs.dtype == torch.float32
     assert kv_lens is None or kv_lens.dtype == torch.int32
     assert probs is None or probs.dtype == dscores.dtype
     lib = _lib.load()
     with _Launch("softmax_bwd", 8.0 * rows * n_keys + 4.0 * rows * ld_out):
         _lib.check(lib.mm_softmax_bwd(_ptr(scores), _ptr(dprobs), ld_in, rows, rows_per_batch, n_keys, _ptr(kv_lens),
-                                      heads, _ptr(probs), _ptr(dscores), ld_out, valid_rows, dtype_code(dscores.dtype),
-                                      _stream()),
+                                      heads, _ptr(probs), _ptr(dscores), ld_out, valid_rows, int(causal),
+                                      dtype_code(dscores.dtype), _stream()),
                    "mm_softmax_bwd")
 
 
@@ -460,3 +461,28 @@ def adam(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg
         _lib.check(lib.mm_adam(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), lr, betas[0],
                                betas[1], eps, weight_decay, step, _ptr(norm_coef), _ptr(param_op),
                                dtype_code(param_op.dtype) if param_op is not None else 0, _stream()), "mm_adam")
+
+
+def label_smoothed_nll_bwd(logits: torch.Tensor, vocab: int, target: torch.Tensor, padding_idx: int, epsilon: float,
+                           dlogits: torch.Tensor, grad_scale: float = 1.0) -> None:
+    """dlogits (16-bit [rows, ld_out]) = grad_scale * d label_smoothed_nll_loss(sum) / d logits."""
+    assert logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1
+    assert target.dtype == torch.int64 and target.is_contiguous() and target.numel() == logits.shape[0]
+    assert dlogits.dim() == 2 and dlogits.stride(1) == 1 and dlogits.shape[0] == logits.shape[0]
+    lib = _lib.load()
+    with _Launch("label_smoothed_nll_bwd", 4.0 * logits.shape[0] * vocab + 2.0 * dlogits.numel()):
+        _lib.check(lib.mm_label_smoothed_nll_bwd(_ptr(logits), logits.stride(0), vocab, _ptr(target), padding_idx,
+                                                 logits.shape[0], epsilon, grad_scale, _ptr(dlogits), dlogits.stride(0),
+                                                 dtype_code(dlogits.dtype), _stream()), "mm_label_smoothed_nll_bwd")
+
+
+def embed_tokens_bwd(tokens: torch.Tensor, padding_idx: int, dx: torch.Tensor, scale: float,
+                     table_grad: torch.Tensor) -> None:
+    """table_grad[token] += scale * dx[row] for the non-padding tokens (atomic adds)."""
+    assert tokens.dtype == torch.int64 and tokens.is_contiguous() and dx.dtype == table_grad.dtype == torch.float32
+    assert dx.is_contiguous() and table_grad.is_contiguous()
+    rows, dim = tokens.numel(), dx.shape[-1]
+    lib = _lib.load()
+    with _Launch("embed_tokens_bwd", 8.0 * rows * dim):
+        _lib.check(lib.mm_embed_tokens_bwd(_ptr(tokens), padding_idx, _ptr(dx), rows, dim, scale, _ptr(table_grad),
+                                           _stream()), "mm_embed_tokens_bwd")

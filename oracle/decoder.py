@@ -71,7 +71,9 @@ def unit_decoder_forward(sd: Dict[str, Tensor], prev_output_tokens: Tensor, enco
     d = encoder_out.shape[-1]
     B, L = prev_output_tokens.shape
     pos = make_positions(prev_output_tokens.ne(1), 1)
-    x = math.sqrt(d) * sd["embed_tokens.weight"][prev_output_tokens] + sinusoidal_table(L + 2, d, 1)[pos]
+    # nn.Embedding(V, d, padding_idx=1): same values as plain indexing, no gradient for the padding row
+    x = math.sqrt(d) * F.embedding(prev_output_tokens, sd["embed_tokens.weight"], padding_idx=1) + \
+        sinusoidal_table(L + 2, d, 1)[pos]
     x = x.transpose(0, 1)
     i = 0
     while f"layers.{i}.fc1.weight" in sd:

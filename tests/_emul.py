@@ -228,6 +228,54 @@ def softmax_rows(scores, ld_in, rows, n_keys, probs, ld_out, key_mask=None, rows
     P[:, :n_keys] = s.softmax(-1).to(probs.dtype)
 
 
+def attention(q, q_col0, q_len, k, k_col0, v, v_col0, kv_len, kv_lens, batch, heads, out, causal=False):
+    d = heads * 64
+    Q = q[:, q_col0:q_col0 + d].float().view(batch, q_len, heads, 64).permute(0, 2, 1, 3)
+    Kx = k[:, k_col0:k_col0 + d].float().view(batch, kv_len, heads, 64).permute(0, 2, 1, 3)
+    V = v[:, v_col0:v_col0 + d].float().view(batch, kv_len, heads, 64).permute(0, 2, 1, 3)
+    s = Q @ Kx.transpose(-1, -2)
+    if kv_lens is not None:
+        s = s.masked_fill((torch.arange(kv_len)[None, :] >= kv_lens[:, None])[:, None, None, :], float("-inf"))
+    if causal:
+        s = s.masked_fill(torch.arange(kv_len)[None, :] > torch.arange(q_len)[:, None], float("-inf"))
+    p = s.softmax(-1).to(q.dtype).float()
+    out.copy_((p @ V).permute(0, 2, 1, 3).reshape(batch * q_len, d).to(out.dtype))
+
+
+def embed_tokens(tokens, padding_idx, table, scale, pos_table, out):
+    B, L = tokens.shape
+    ne = tokens.ne(padding_idx)
+    pos = torch.cumsum(ne, 1) * ne + padding_idx
+    out.view(B, L, -1).copy_(scale * table[tokens] + pos_table[pos])
+
+
+def label_smoothed_nll(logits, vocab, target, padding_idx, epsilon):
+    lp = torch.log_softmax(logits[:, :vocab], -1)
+    t = target.view(-1, 1)
+    pad = t.eq(padding_idx)
+    nll = (-lp.gather(1, t)).masked_fill(pad, 0).sum()
+    smooth = (-lp.sum(1, keepdim=True)).masked_fill(pad, 0).sum()
+    eps_i = epsilon / (vocab - 1)
+    return (1 - epsilon - eps_i) * nll + eps_i * smooth, nll
+
+
+def label_smoothed_nll_bwd(logits, vocab, target, padding_idx, epsilon, dlogits, grad_scale=1.0):
+    p = torch.softmax(logits[:, :vocab], -1)
+    t = target.view(-1)
+    eps_i = epsilon / (vocab - 1)
+    onehot = torch.nn.functional.one_hot(t, vocab).float()
+    g = (1 - epsilon - eps_i) * (p - onehot) + eps_i * (vocab * p - 1)
+    g = g * t.ne(padding_idx)[:, None] * grad_scale
+    dlogits.zero_()
+    dlogits[:, :vocab] = g.to(dlogits.dtype)
+
+
+def embed_tokens_bwd(tokens, padding_idx, dx, scale, table_grad):
+    t = tokens.view(-1)
+    keep = t.ne(padding_idx)
+    table_grad.view(-1, dx.shape[-1]).index_add_(0, t[keep], scale * dx.view(t.numel(), -1)[keep])
+
+
 def convert(x, out):
     out.view(-1).copy_(x.reshape(-1).to(out.dtype))
 
@@ -306,7 +354,7 @@ def layernorm_bwd(x, gamma, dy, partials, dx=None, resid=None, eps=1e-5, dx_op=N
 
 
 def softmax_bwd(scores, dprobs, ld_in, rows, rows_per_batch, n_keys, dscores, ld_out, probs=None, kv_lens=None, heads=1,
-                valid_rows=0):
+                valid_rows=0, causal=False):
     S = _v(scores, (rows, n_keys), (ld_in, 1))
     D = _v(dprobs, (rows, n_keys), (ld_in, 1))
     G = _v(dscores, (rows, ld_out), (ld_out, 1))
@@ -319,7 +367,11 @@ def softmax_bwd(scores, dprobs, ld_in, rows, rows_per_batch, n_keys, dscores, ld
         G[sl] = 0
         if probs is not None:
             Pv[sl] = 0
-        p = S[sl, :valid].softmax(-1)
+        sc = S[sl, :valid].clone()
+        if causal:
+            nq = sc.shape[0]
+            sc = sc.masked_fill(torch.arange(valid)[None, :] > torch.arange(nq)[:, None], float("-inf"))
+        p = sc.softmax(-1)
         g = p * (D[sl, :valid] - (p * D[sl, :valid]).sum(1, keepdim=True))
         G[sl, :valid] = g.to(dscores.dtype)
         if probs is not None:

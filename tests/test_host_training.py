@@ -164,3 +164,70 @@ def test_gradient_all_reduce_gloo_world2():
         p.join(60)
     expect = float(sum(range(1000)) * 3)
     assert [r[1] for r in res] == [2, 2] and all(abs(r[2] - expect) < 1e-3 * expect for r in res)
+
+
+def _decoder_setup(B=2, L=9, T=13, d=128, heads=2, ffn=256, layers=2, vocab=37, seed=0):
+    from oracle import decoder as odec
+
+    g = torch.Generator().manual_seed(seed)
+    sd = odec.init_decoder(d, ffn, layers, vocab, seed)
+    for k in sd:      # non-trivial biases / LayerNorm affine so that every gradient is exercised
+        if k.endswith(".bias") or "layer_norm" in k:
+            sd[k] = sd[k] + 0.1 * torch.randn(sd[k].shape, generator=g)
+    prev = torch.randint(4, vocab, (B, L), generator=g)
+    target = torch.randint(4, vocab, (B, L), generator=g)
+    target[0, -2:] = 1                                     # padded targets are ignored by the criterion
+    enc = torch.randn(T, B, d, generator=g)
+    mask = torch.zeros(B, T, dtype=torch.bool)
+    mask[1, T - 4:] = True
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    encg = enc.clone().requires_grad_(True)
+    logits = odec.unit_decoder_forward(sdg, prev, encg, mask, heads)
+    loss, nll = odec.label_smoothed_nll_loss(logits, target, 0.2)
+    loss.backward()
+    ref = {k: v.grad for k, v in sdg.items()}
+    return sd, prev, target, enc, mask, heads, logits.detach(), loss.item(), nll.item(), ref, encg.grad
+
+
+def _check_decoder(eng, setup, REL, ZERO, _rel):
+    sd, prev, target, enc, mask, heads, logits_ref, loss_ref, nll_ref, ref, denc_ref = setup
+    dev = eng.device
+    logits = eng.forward_train(prev.to(dev), enc.to(dev), mask.to(dev))
+    assert (logits.cpu() - logits_ref).abs().max().item() < 0.15
+    loss, nll, d_enc = eng.loss_backward(target.to(dev), 0.2)
+    assert abs(loss.item() - loss_ref) / abs(loss_ref) < 2e-2 and abs(nll.item() - nll_ref) / abs(nll_ref) < 2e-2
+    assert tuple(d_enc.shape) == tuple(enc.shape)
+    valid = (~mask).t().unsqueeze(-1)
+    assert _rel(d_enc.cpu() * valid, denc_ref * valid) < REL
+    assert (d_enc.cpu() * ~valid).abs().max().item() == 0.0          # padded encoder states receive no gradient
+    worst, checked = 0.0, 0
+    for k, got in eng.grads().items():
+        if ref[k].norm() < ZERO:
+            continue
+        r = _rel(got, ref[k])
+        worst = max(worst, r)
+        assert r < REL, (k, r)
+        checked += 1
+    assert checked >= len(ref) - 2 * eng.n_layers
+    return worst
+
+
+def test_decoder_backward_orchestration_matches_autograd_oracle(monkeypatch):
+    """Unit decoder + label-smoothed CE: forward_train / loss_backward on the emulated kernels against autograd over
+    the oracle decoder and criterion (parameter gradients, loss values, d loss / d encoder_out)."""
+    from test_gpu_training import REL, ZERO, _rel
+
+    _emulated(monkeypatch)
+    import mm_s2ut_b200.decoder_training as dt
+
+    monkeypatch.setattr(dt, "K", _emul)
+    monkeypatch.setattr(dt.UnitDecoderTrainEngine, "_require_cuda", False)
+    setup = _decoder_setup()
+    eng = dt.UnitDecoderTrainEngine(setup[0], setup[5], "cpu")
+    _check_decoder(eng, setup, REL, ZERO, _rel)
+    # one Adam step lowers the loss on the same batch
+    l0 = setup[7]
+    eng.adam_step(lr=2e-3, clip_norm=10.0)
+    eng.forward_train(setup[1], setup[3], setup[4])
+    l1, _, _ = eng.loss_backward(setup[2], 0.2)
+    assert l1.item() < l0
