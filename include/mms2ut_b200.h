@@ -241,7 +241,8 @@ int mm_convert_f32(const float* x, void* out, int64_t n, int32_t dtype, void* st
  *   [0] norm, [1] multiplier (outputs); with dev_hyper != 0 the kernels read the per-step hyper-parameters from it
  *   instead of their by-value arguments, so that a captured CUDA graph can be replayed with new values:
  *   [2] Adam step_size = lr sqrt(1-b2^t)/(1-b1^t), [3] weight_decay * lr, [4] grad_scale, [5] max_norm.
- *   (mm_adam takes them from the device when step == 0.)
+ *   (mm_adam takes them from the device when step == 0.)  extra_norm (optional): extra_norm[0] = the already scaled
+ *   norm of another gradient buffer (e.g. the decoder's), combined into a joint norm before the clip coefficient.
  * mm_adam: fairseq.optim.adam.Adam.step on a flat fp32 buffer; the gradient is multiplied by norm_coef[1] (NULL: 1);
  *   param_op (optional): 16-bit copy of the updated parameters, written in the same pass (the GEMM operand copies).
  * --------------------------------------------------------------------------------------------- */
@@ -279,7 +280,7 @@ int mm_col2im_k5s2(const float* dcol, int32_t batch, int32_t t_out, int32_t t_in
                    void* stream);
 int mm_sumsq_blocks(void);
 int mm_grad_clip_coef(const float* grad, int64_t n, float grad_scale, float max_norm, float* partials, float* norm_coef,
-                      int32_t dev_hyper, void* stream);
+                      int32_t dev_hyper, const float* extra_norm, void* stream);
 int mm_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
             float beta2, float eps, float weight_decay, int32_t step, const float* norm_coef, void* param_op,
             int32_t dtype, void* stream);

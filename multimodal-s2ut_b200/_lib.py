@@ -155,7 +155,7 @@ EXPORTS = {
     "mm_col2im_k5s2": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "mm_sumsq_blocks": (C.c_int, []),
     "mm_grad_clip_coef": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int32,
-                                    C.c_void_p]),
+                                    C.c_void_p, C.c_void_p]),
     "mm_adam": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float,
                           C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
 }

@@ -497,12 +497,13 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 
 // out[0] = grad norm (after grad_scale), out[1] = multiplier to apply to the raw gradient: grad_scale * min(1, max_norm/(norm+1e-6))
 __global__ void clip_coef_kernel(const float* __restrict__ partials, int S, float grad_scale, float max_norm,
-                                 float* __restrict__ out, int dev_hyper) {
+                                 float* __restrict__ out, int dev_hyper, const float* __restrict__ extra_norm) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (dev_hyper) grad_scale = out[4], max_norm = out[5];   // per-step values written by the host before a graph replay
   double t = 0.0;
   for (int i = 0; i < S; ++i) t += (double)partials[i];
-  const float norm = sqrtf((float)t) * grad_scale;
+  float norm = sqrtf((float)t) * grad_scale;
+  if (extra_norm) norm = sqrtf(norm * norm + extra_norm[0] * extra_norm[0]);   // joint norm with another flat buffer
   float coef = grad_scale;
   if (max_norm > 0.f) coef *= fminf(1.0f, max_norm / (norm + 1e-6f));
   out[0] = norm;
@@ -799,13 +800,13 @@ extern "C" int mm_col2im_k5s2(const float* dcol, int32_t batch, int32_t t_out, i
 extern "C" int mm_sumsq_blocks(void) { return 4 * kNumSMs; }
 
 extern "C" int mm_grad_clip_coef(const float* grad, int64_t n, float grad_scale, float max_norm, float* partials,
-                                 float* norm_coef, int32_t dev_hyper, void* stream) {
+                                 float* norm_coef, int32_t dev_hyper, const float* extra_norm, void* stream) {
   if (!grad || !partials || !norm_coef || n <= 0) return bad_arg("grad_clip_coef");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int blocks = 4 * kNumSMs;
   sumsq_kernel<<<blocks, 256, 0, s>>>(grad, n, partials);
   MM_CHECK_LAUNCH("sumsq_kernel launch");
-  clip_coef_kernel<<<1, 32, 0, s>>>(partials, blocks, grad_scale, max_norm, norm_coef, dev_hyper);
+  clip_coef_kernel<<<1, 32, 0, s>>>(partials, blocks, grad_scale, max_norm, norm_coef, dev_hyper, extra_norm);
   MM_CHECK_LAUNCH("clip_coef_kernel launch");
   return 0;
 }

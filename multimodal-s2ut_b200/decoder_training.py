@@ -333,6 +333,22 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
         K.tbc_to_btc(denc, T, B, d, d_enc)       # [B, T, d] -> [T, B, d]: the same index swap with the roles exchanged
         return loss, nll, d_enc
 
+    def grad_norm(self, grad_scale: float = 1.0, dev_hyper: bool = False) -> torch.Tensor:
+        """norm_coef[0] = ||grad_scale * flat_g|| on the device (no clipping): the decoder's share of the model's joint
+        gradient norm, handed to the encoder engine's ``adam_step(extra_norm=...)``."""
+        K.grad_clip_coef(self.flat_g, grad_scale, 0.0, self._sumsq_partials, self.norm_coef, dev_hyper=dev_hyper)
+        return self.norm_coef
+
+    def adam_apply(self, norm_coef: torch.Tensor, lr: float = 0.0, betas=(0.9, 0.98), eps: float = 1e-8,
+                   weight_decay: float = 0.0, step: Optional[int] = None) -> None:
+        """Adam with the clip multiplier (and, for step == 0, the per-step hyper-parameters) of ``norm_coef`` -- the
+        ENCODER engine's array when the two engines are clipped jointly (fairseq clips the whole model's norm)."""
+        if step is None:
+            self.step_count += 1
+            step = self.step_count
+        K.adam(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, lr=lr, betas=betas, eps=eps,
+               weight_decay=weight_decay, step=step, norm_coef=norm_coef, param_op=self.flat_op)
+
     def adam_step(self, lr: float, betas=(0.9, 0.98), eps: float = 1e-8, weight_decay: float = 0.0,
                   clip_norm: float = 0.0, grad_scale: float = 1.0) -> None:
         self.step_count += 1

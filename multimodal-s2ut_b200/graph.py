@@ -117,12 +117,12 @@ class GraphedTrainStep:
         with torch.cuda.stream(s):          # eager pass: allocates every workspace, sets kernel attributes
             for drop in (False, True):
                 self._fwd_bwd(drop)
-            self.eng.norm_coef[2:6] = torch.tensor([0.0, 0.0, 1.0, 0.0], device=self.device)   # a no-op optimizer step
-            self.eng.adam_step_device_hyper(self.betas, self.eps)
+            for nc in self._hyper_targets():
+                nc[2:6] = torch.tensor([0.0, 0.0, 1.0, 0.0], device=self.device)   # a no-op optimizer step
+            self._optimizer()
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
-        self.eng.exp_avg.zero_()
-        self.eng.exp_avg_sq.zero_()
+        self._reset_moments()
         pool = None
         for drop in (False, True):
             g = torch.cuda.CUDAGraph()
@@ -132,7 +132,18 @@ class GraphedTrainStep:
             self.graphs[drop] = g
         self.opt_graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.opt_graph, pool=pool):
-            self.eng.adam_step_device_hyper(self.betas, self.eps)
+            self._optimizer()
+
+    # hooks the encoder + decoder step overrides
+    def _optimizer(self) -> None:
+        self.eng.adam_step_device_hyper(self.betas, self.eps)
+
+    def _hyper_targets(self):
+        return [self.eng.norm_coef]
+
+    def _reset_moments(self) -> None:
+        self.eng.exp_avg.zero_()
+        self.eng.exp_avg_sq.zero_()
 
     def forward_backward(self, drop_image: bool = False):
         """Replays forward + backward on the static inputs (``wav``, ``lens``, ``img``, ``grad_out``)."""
@@ -149,7 +160,10 @@ class GraphedTrainStep:
         if self._hyper_done[i] is not None:
             self._hyper_done[i].synchronize()
         self._hyper_host[i].copy_(torch.tensor(vals, dtype=torch.float32))
-        self.eng.norm_coef[2:6].copy_(self._hyper_host[i], non_blocking=True)
+        for k, nc in enumerate(self._hyper_targets()):
+            nc[2:6].copy_(self._hyper_host[i], non_blocking=True)
+            if k > 0:
+                nc[5].zero_()     # only the first (encoder) engine clips: it holds the joint norm
         ev = torch.cuda.Event()
         ev.record()
         self._hyper_done[i] = ev
@@ -165,3 +179,67 @@ class GraphedTrainStep:
         ws = self.eng.all_reduce_grads()
         self.optimizer_step(lr, weight_decay, clip_norm, grad_scale=1.0 / ws)
         return out
+
+
+class GraphedModelTrainStep(GraphedTrainStep):
+    """The complete BASELINE configs[2] step under CUDA-graph replay: encoder (``TrainEngine``) + S2UT unit decoder +
+    label-smoothed cross entropy (``decoder_training.UnitDecoderTrainEngine``), chained by ``d loss / d encoder_out``
+    with no autograd:  waveform -> fused states -> logits -> loss -> decoder backward -> encoder backward ->
+    (gradient all-reduce) -> joint-norm clipping -> Adam on both engines.  Static inputs: ``wav``, ``lens``, ``img``,
+    ``prev_tokens``, ``target``."""
+
+    def __init__(self, enc, dec_engine, batch: int, n_samples: int, img_shape: tuple, tgt_len: int,
+                 label_smoothing: float = 0.2, **kw):
+        super().__init__(enc, batch, n_samples, img_shape, **kw)
+        self.dec = dec_engine
+        self.label_smoothing = label_smoothing
+        self.prev_tokens = torch.full((batch, tgt_len), 4, dtype=torch.int64, device=self.device)
+        self.target = torch.full((batch, tgt_len), 4, dtype=torch.int64, device=self.device)
+        self.loss = {}
+        self.grad_out = False      # unused: the decoder supplies d loss / d encoder_out
+
+    def _fwd_bwd(self, drop_image: bool):
+        import torch.distributed as dist
+
+        out = self.eng.forward_train(self.wav, self.lens, [self.img], [None], drop_image=drop_image)
+        self.dec.forward_train(self.prev_tokens, out["encoder_out"][0], out["encoder_padding_mask"][0])
+        loss, nll, d_enc = self.dec.loss_backward(self.target, self.label_smoothing)
+        multi = self.overlap_reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if multi:       # the decoder's gradients travel while the encoder's backward runs
+            self.eng._reduce_works = []
+            ev = torch.cuda.Event()
+            ev.record()
+            if self.eng._comm_stream is None:
+                self.eng._comm_stream = torch.cuda.Stream(device=self.device)
+            with torch.cuda.stream(self.eng._comm_stream):
+                self.eng._comm_stream.wait_event(ev)
+                self.eng._reduce_works.append(dist.all_reduce(self.dec.flat_g, op=dist.ReduceOp.SUM, async_op=True))
+        self.eng.backward(d_enc, overlap_reduce=self.overlap_reduce)
+        self.loss[bool(drop_image)] = (loss, nll)
+        return out
+
+    def _optimizer(self) -> None:
+        self.dec.grad_norm(dev_hyper=True)
+        self.eng.adam_step_device_hyper(self.betas, self.eps, extra_norm=self.dec.norm_coef)
+        self.dec.adam_apply(self.eng.norm_coef, betas=self.betas, eps=self.eps, step=0)
+
+    def _hyper_targets(self):
+        return [self.eng.norm_coef, self.dec.norm_coef]
+
+    def _reset_moments(self) -> None:
+        super()._reset_moments()
+        self.dec.exp_avg.zero_()
+        self.dec.exp_avg_sq.zero_()
+
+    def step(self, lr: float, drop_image: bool = False, weight_decay: float = 0.0, clip_norm: float = 0.0):
+        import torch.distributed as dist
+
+        out = self.forward_backward(drop_image)
+        ws = 1
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            ws = dist.get_world_size()
+            if not self.overlap_reduce:
+                self.eng.all_reduce_grads()
+                dist.all_reduce(self.dec.flat_g, op=dist.ReduceOp.SUM)
+        self.optimizer_step(lr, weight_decay, clip_norm, grad_scale=1.0 / ws)
+        return out, self.loss[bool(drop_image)]

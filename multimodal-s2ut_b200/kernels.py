@@ -436,7 +436,7 @@ def col2im_k5s2(dcol: torch.Tensor, B: int, t_out: int, t_in: int, C_: int, dx: 
 
 
 def grad_clip_coef(grad: torch.Tensor, grad_scale: float, max_norm: float, partials: torch.Tensor,
-                   norm_coef: torch.Tensor, dev_hyper: bool = False) -> None:
+                   norm_coef: torch.Tensor, dev_hyper: bool = False, extra_norm: Optional[torch.Tensor] = None) -> None:
     """norm_coef[0] = ||grad_scale * grad||, norm_coef[1] = grad_scale * min(1, max_norm / (norm + 1e-6)).
     dev_hyper: grad_scale / max_norm are read from norm_coef[4] / [5] on the device (CUDA-graph replays)."""
     assert grad.dtype == torch.float32 and grad.is_contiguous() and norm_coef.numel() >= (8 if dev_hyper else 2)
@@ -444,7 +444,8 @@ def grad_clip_coef(grad: torch.Tensor, grad_scale: float, max_norm: float, parti
     assert partials.numel() >= lib.mm_sumsq_blocks()
     with _Launch("grad_clip_coef", 4.0 * grad.numel()):
         _lib.check(lib.mm_grad_clip_coef(_ptr(grad), grad.numel(), grad_scale, max_norm, _ptr(partials),
-                                         _ptr(norm_coef), int(dev_hyper), _stream()), "mm_grad_clip_coef")
+                                         _ptr(norm_coef), int(dev_hyper), _ptr(extra_norm), _stream()),
+                   "mm_grad_clip_coef")
     global launch_count
     launch_count += 1   # two kernels
 

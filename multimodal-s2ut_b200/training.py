@@ -711,11 +711,14 @@ class TrainEngine(EncoderEngine):
         return all_reduce_flat(self.flat_g, bucket_elems)
 
     def adam_step(self, lr: float, betas=(0.9, 0.98), eps: float = 1e-8, weight_decay: float = 0.0,
-                  clip_norm: float = 0.0, grad_scale: float = 1.0) -> None:
-        """fairseq: multiply_grads(grad_scale) -> clip_grad_norm_(clip_norm) -> Adam.step, then refresh operand copies."""
+                  clip_norm: float = 0.0, grad_scale: float = 1.0, extra_norm: Optional[torch.Tensor] = None) -> None:
+        """fairseq: multiply_grads(grad_scale) -> clip_grad_norm_(clip_norm) -> Adam.step, then refresh operand copies.
+        extra_norm[0]: scaled gradient norm of the rest of the model (the decoder engine's ``grad_norm()``), so that
+        the clip coefficient in ``norm_coef[1]`` is the whole model's, as in fairseq."""
         self.step_count += 1
         with _scope("optim"):
-            K.grad_clip_coef(self.flat_g, grad_scale, clip_norm, self._sumsq_partials, self.norm_coef)
+            K.grad_clip_coef(self.flat_g, grad_scale, clip_norm, self._sumsq_partials, self.norm_coef,
+                             extra_norm=extra_norm)
             K.adam(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, lr=lr, betas=betas, eps=eps,
                    weight_decay=weight_decay, step=self.step_count, norm_coef=self.norm_coef, param_op=self.flat_op)
             self.repack()
@@ -731,11 +734,12 @@ class TrainEngine(EncoderEngine):
         step_size = lr32 * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
         return [step_size, float(np.float32(weight_decay) * np.float32(lr)), grad_scale, clip_norm]
 
-    def adam_step_device_hyper(self, betas=(0.9, 0.98), eps: float = 1e-8) -> None:
+    def adam_step_device_hyper(self, betas=(0.9, 0.98), eps: float = 1e-8, extra_norm: Optional[torch.Tensor] = None) -> None:
         """Same optimizer step with step_size / wd*lr / grad_scale / clip_norm read from ``norm_coef[2:6]`` on the device:
         the form that is captured into a CUDA graph (``graph.GraphedTrainStep`` writes the values before each replay)."""
         with _scope("optim"):
-            K.grad_clip_coef(self.flat_g, 1.0, 0.0, self._sumsq_partials, self.norm_coef, dev_hyper=True)
+            K.grad_clip_coef(self.flat_g, 1.0, 0.0, self._sumsq_partials, self.norm_coef, dev_hyper=True,
+                             extra_norm=extra_norm)
             K.adam(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, lr=0.0, betas=betas, eps=eps,
                    weight_decay=0.0, step=0, norm_coef=self.norm_coef, param_op=self.flat_op)
             self.repack()

@@ -22,6 +22,75 @@ ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 
 
+def model_step(a, enc, eng, wav, lens, imgs, dev, world, rank, rng):
+    """Encoder + 6-layer S2UT unit decoder (V = 1004) + label-smoothed CE: the complete configs[2] step."""
+    import torch.distributed as dist
+
+    from mm_s2ut_b200 import kernels as K
+    from mm_s2ut_b200.decoder_training import UnitDecoderTrainEngine
+    from mm_s2ut_b200.graph import GraphedModelTrainStep
+    from oracle.decoder import init_decoder        # weights only (seeded fairseq-style init); nothing is computed with it
+
+    B, n = wav.shape
+    d, ffn = enc.embed_dim, enc.ffn_dim
+    dec = UnitDecoderTrainEngine(init_decoder(d, ffn, 6, 1004, seed=1), enc.num_heads, dev)
+    gs = GraphedModelTrainStep(enc, dec, B, n, (577, 768), a.tgt_len, overlap_reduce=(world > 1 and not a.no_overlap))
+    g = torch.Generator(device=dev).manual_seed(3 + rank)
+    gs.wav.copy_(wav)
+    gs.img.copy_(imgs)
+    gs.prev_tokens.copy_(torch.randint(4, 1004, (B, a.tgt_len), device=dev, generator=g))
+    gs.target.copy_(torch.randint(4, 1004, (B, a.tgt_len), device=dev, generator=g))
+    gs._fwd_bwd(False)                     # first call: workspaces, kernel attributes
+    torch.cuda.synchronize()
+    n0 = K.launch_count
+    K.timing = []
+    gs._fwd_bwd(False)
+    torch.cuda.synchronize()
+    timing, K.timing = K.timing, None
+    launches = K.launch_count - n0
+    gs.capture()
+    losses = []
+    for _ in range(a.warmup):
+        _, (loss, _) = gs.step(5e-4, drop_image=rng.random() < 0.5, clip_norm=10.0)
+    losses.append(loss.item())
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        _, (loss, _) = gs.step(5e-4, drop_image=rng.random() < 0.5, clip_norm=10.0)
+    e1.record()
+    torch.cuda.synchronize()
+    losses.append(loss.item())
+    ms = e0.elapsed_time(e1) / a.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    if rank == 0:
+        fam = defaultdict(lambda: [0.0, 0])
+        for name, s, e, work in timing:
+            fam[name][0] += s.elapsed_time(e)
+            fam[name][1] += 1
+        tot = sum(v[0] for v in fam.values())
+        print(f"{'kernel family (forward + backward, eager)':44s} {'launches':>8s} {'ms':>9s} {'share':>7s}")
+        for name, (t, c) in sorted(fam.items(), key=lambda kv: -kv[1][0])[:24]:
+            print(f"{name:44s} {c:8d} {t:9.3f} {100 * t / tot:6.1f}%")
+        ntok = B * a.tgt_len
+        line = dict(metric="audio-sec trained/sec (complete model step: encoder + unit decoder + label-smoothed CE)",
+                    value=B * a.seconds * world / (ms * 1e-3), unit="audio-s/s", n_gpus=world, steps=a.steps, ms_per_step=ms,
+                    fwd_bwd_launches=launches, eager_fwd_bwd_sum_ms=tot, batch_per_gpu=B, utt_seconds=a.seconds,
+                    tgt_units_per_utt=a.tgt_len, encoder_params=int(eng.flat_p.numel()), decoder_params=int(dec.flat_p.numel()),
+                    loss_per_unit_first=losses[0] / ntok, loss_per_unit_last=losses[-1] / ntok,
+                    overlap_reduce=bool(world > 1 and not a.no_overlap),
+                    note="element-wise dropout off (masks not built); modality dropout 0.5; random target units")
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        del gs
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
@@ -31,6 +100,8 @@ def main():
     ap.add_argument("--preset", default="base")
     ap.add_argument("--no-graph", action="store_true", help="eager launches only (for an ncu launch list)")
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce after the backward graph instead of inside it")
+    ap.add_argument("--model", action="store_true", help="complete model step: + 6-layer unit decoder + label-smoothed CE")
+    ap.add_argument("--tgt-len", type=int, default=500, help="target units per utterance (50 Hz units x 10 s)")
     a = ap.parse_args()
     import mm_s2ut_b200  # noqa: F401
     from mm_s2ut_b200 import kernels as K
@@ -58,6 +129,8 @@ def main():
     lens = torch.full((B,), n, dtype=torch.int64, device=dev)
     imgs = torch.randn(B, 577, 768, device=dev, generator=g)
     rng = np.random.RandomState(0)
+    if a.model:
+        return model_step(a, enc, eng, wav, lens, imgs, dev, world, rank, rng)
 
     def step(grad_out=None):
         drop_image = rng.random() < 0.5 and rng.random() >= -0.5

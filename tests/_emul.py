@@ -409,10 +409,12 @@ def col2im_k5s2(dcol, B, t_out, t_in, C_, dx):
                 o[:, s] += dc[:, t, k]
 
 
-def grad_clip_coef(grad, grad_scale, max_norm, partials, norm_coef, dev_hyper=False):
+def grad_clip_coef(grad, grad_scale, max_norm, partials, norm_coef, dev_hyper=False, extra_norm=None):
     if dev_hyper:
         grad_scale, max_norm = float(norm_coef[4]), float(norm_coef[5])
     norm = grad.double().norm().item() * grad_scale
+    if extra_norm is not None:
+        norm = math.sqrt(norm * norm + float(extra_norm[0]) ** 2)
     coef = grad_scale * (min(1.0, max_norm / (norm + 1e-6)) if max_norm > 0 else 1.0)
     norm_coef[0], norm_coef[1] = norm, coef
 

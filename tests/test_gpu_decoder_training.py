@@ -112,3 +112,62 @@ def test_full_model_training_step_chain(cuda):
     deng.forward_train(prev.cuda(), out["encoder_out"][0], out["encoder_padding_mask"][0])
     loss2, _, _ = deng.loss_backward(target.cuda(), 0.2)
     assert loss2.item() < loss.item()
+
+
+def test_graphed_model_train_step_matches_eager(cuda):
+    """GraphedModelTrainStep (encoder + decoder + criterion + joint-norm clipping + Adam under CUDA-graph replay)
+    reproduces the same step issued eagerly.  Not bit-for-bit: the embedding gradient is accumulated with atomic adds
+    (rows that share a token), whose order -- and therefore last-bit rounding -- differs from run to run."""
+    from mm_s2ut_b200 import synth
+    from mm_s2ut_b200.decoder_training import UnitDecoderTrainEngine
+    from mm_s2ut_b200.graph import GraphedModelTrainStep
+    from oracle import decoder as odec
+    from test_gpu_encoder import _build
+
+    B, Lu = 2, 24
+    wavs, _ = synth.synth_batch(4, B, 1.5, ragged=False)
+    wav, lens = synth.pad_waveforms(wavs)
+    imgs = synth.synth_images(4, B)
+    g = torch.Generator().manual_seed(3)
+    prev = torch.randint(4, 104, (B, Lu), generator=g)
+    target = torch.randint(4, 104, (B, Lu), generator=g)
+    res = {}
+    for mode in ("eager", "graph"):
+        enc, args, cfg = _build("small", "selective_attention", True)
+        enc.dropout_p = 0.0
+        enc.SA_image_dropout = enc.SA_attention_dropout = enc.SA_text_dropout = 0.0
+        enc.cuda().train()
+        eeng = enc.train_engine()
+        deng = UnitDecoderTrainEngine(odec.init_decoder(args.encoder_embed_dim, 512, 2, 104, seed=2),
+                                      args.encoder_attention_heads, cuda)
+        losses = []
+        if mode == "eager":
+            for it in range(3):
+                out = eeng.forward_train(wav.cuda(), lens.cuda(), [imgs.cuda()], [None], drop_image=(it == 1))
+                deng.forward_train(prev.cuda(), out["encoder_out"][0], out["encoder_padding_mask"][0])
+                loss, _, d_enc = deng.loss_backward(target.cuda(), 0.2)
+                eeng.backward(d_enc)
+                deng.grad_norm(grad_scale=0.5)
+                eeng.adam_step(lr=1e-3, betas=(0.9, 0.98), clip_norm=1.0, weight_decay=0.01, grad_scale=0.5,
+                               extra_norm=deng.norm_coef)
+                deng.adam_apply(eeng.norm_coef, lr=1e-3, betas=(0.9, 0.98), weight_decay=0.01)
+                losses.append(loss.item())
+        else:
+            gs = GraphedModelTrainStep(enc, deng, B, wav.shape[1], tuple(imgs.shape[1:]), Lu)
+            gs.wav.copy_(wav.cuda())
+            gs.img.copy_(imgs.cuda())
+            gs.prev_tokens.copy_(prev.cuda())
+            gs.target.copy_(target.cuda())
+            gs.capture()
+            for it in range(3):
+                gs.forward_backward(drop_image=(it == 1))
+                losses.append(gs.loss[it == 1][0].item())
+                gs.optimizer_step(1e-3, weight_decay=0.01, clip_norm=1.0, grad_scale=0.5)
+        torch.cuda.synchronize()
+        res[mode] = (eeng.flat_p.clone(), deng.flat_p.clone(), losses, eeng.norm_coef[:2].clone())
+    assert all(abs(a - b) <= 1e-4 * abs(a) for a, b in zip(res["eager"][2], res["graph"][2])), (res["eager"][2], res["graph"][2])
+    for i in (0, 1):     # Adam moves a parameter by at most ~lr per step: a sign flip of a near-zero gradient costs 2 lr
+        diff = (res["eager"][i] - res["graph"][i]).abs()
+        assert diff.max().item() <= 3 * 2e-3 and diff.mean().item() < 2e-5, (i, diff.max().item(), diff.mean().item())
+    assert torch.allclose(res["eager"][3], res["graph"][3], rtol=1e-3)
+    assert res["eager"][2][2] < res["eager"][2][0]            # the loss goes down over the three steps
