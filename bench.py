@@ -217,8 +217,52 @@ def train_step_probe(dev, world, rank, wav, img, steps=20, warmup=3):
            "what": "BASELINE configs[2]: forward (activations kept) + backward of every encoder/fusion/conv parameter + "
                    "gradient all-reduce + fairseq Adam with clip-norm, batch 64 x 10 s per GPU, modality dropout 0.5 "
                    "(image-drop branch), synthetic d loss/d encoder_out; element-wise dropout off (masks not built)"}
-    del gs, enc
+    del gs
     torch.cuda.empty_cache()
+    # ---- the complete model step: + 6-layer unit decoder (V = 1004, 500 target units per 10 s) + label-smoothed CE
+    try:
+        from mm_s2ut_b200.graph import GraphedModelTrainStep
+        from mm_s2ut_b200.models.mm_s2ut_model import MM_S2UTTransformerModel
+
+        torch.manual_seed(0)
+        model = MM_S2UTTransformerModel(args, target_code_size=1000, build_unused_projections=False).to(dev).train()
+        model.encoder.dropout_p = 0.0
+        tgt_len = int(50 * DUR_S)
+        gm = GraphedModelTrainStep(model.encoder, model.decoder_train_engine(), wav.shape[0], wav.shape[1],
+                                   tuple(img.shape[1:]), tgt_len, overlap_reduce=world > 1)
+        gm.wav.copy_(wav)
+        gm.img.copy_(img)
+        gm.prev_tokens.copy_(torch.randint(4, 1004, (wav.shape[0], tgt_len), device=dev, generator=g))
+        gm.target.copy_(torch.randint(4, 1004, (wav.shape[0], tgt_len), device=dev, generator=g))
+        gm.capture()
+        for _ in range(warmup):
+            gm.step(5e-4, drop_image=rng.random() < 0.5, clip_norm=10.0)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        msteps = max(steps // 2, 5)
+        e0.record()
+        for _ in range(msteps):
+            _, (loss, _) = gm.step(5e-4, drop_image=rng.random() < 0.5, clip_norm=10.0)
+        e1.record()
+        torch.cuda.synchronize()
+        mms = e0.elapsed_time(e1) / msteps
+        if world > 1:
+            t = torch.tensor([mms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            mms = t.item()
+        out["model_step"] = {
+            "value": audio_s / (mms * 1e-3), "unit": "audio-s/s trained", "ms_per_step": mms, "steps": msteps,
+            "tgt_units_per_utt": tgt_len, "decoder_params": int(gm.dec.flat_p.numel()),
+            "loss_per_unit": loss.item() / (wav.shape[0] * tgt_len),
+            "what": "the same plus the 6-layer S2UT unit decoder (V = 1004) and fairseq's label-smoothed cross entropy "
+                    "(0.2): waveform -> loss -> every parameter gradient -> joint-norm clipping -> Adam on both engines, "
+                    "no autograd; random target units"}
+        del gm, model
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out["model_step"] = {"error": f"{type(e).__name__}: {e}"}
+    del enc
     return out
 
 

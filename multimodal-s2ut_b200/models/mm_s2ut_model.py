@@ -82,6 +82,57 @@ class MM_S2UTTransformerModel(nn.Module):
                                                      padding_idx=self.decoder.padding_idx)
         return self._decoder_engine
 
+    # ---- training-step variant (BASELINE configs[2]) -------------------------------------
+    def decoder_train_engine(self):
+        """``decoder_training.UnitDecoderTrainEngine`` over this model's decoder parameters (its own flat fp32 copy:
+        call ``sync_decoder_parameters()`` before saving a checkpoint)."""
+        from ..decoder_training import UnitDecoderTrainEngine
+
+        if not isinstance(self._decoder_engine, UnitDecoderTrainEngine):
+            dev = self.decoder.embed_tokens.weight.device
+            sd = {k: v for k, v in self.decoder.state_dict().items() if not k.startswith("output_projection.")}
+            self._decoder_engine = UnitDecoderTrainEngine(sd, self.decoder.num_heads, dev,
+                                                          op_dtype=getattr(self.encoder, "op_dtype", torch.bfloat16),
+                                                          padding_idx=self.decoder.padding_idx)
+        return self._decoder_engine
+
+    @torch.no_grad()
+    def sync_decoder_parameters(self) -> None:
+        """Write the decoder engine's trained fp32 parameters back into ``self.decoder`` (state_dict / checkpoints)."""
+        eng = self._decoder_engine
+        if eng is None or not hasattr(eng, "flat_p"):
+            return
+        params = dict(self.decoder.named_parameters())
+        for name in eng.names:
+            src = eng.p(name)
+            dst = params[name]
+            dst.copy_(src[: dst.shape[0]] if name == "embed_tokens.weight" else src.view(dst.shape))
+
+    @torch.no_grad()
+    def train_step(self, src_tokens, src_lengths, prev_output_tokens, target, imgs_list=[], img_masks_list=[],
+                   label_smoothing: float = 0.2, drop_image: bool = False):
+        """Forward + backward of the whole model on the CUDA kernels, no autograd: encoder (activations kept) -> unit
+        decoder -> fairseq label-smoothed cross entropy -> decoder backward -> ``d loss / d encoder_out`` -> encoder
+        backward.  Returns (loss, nll_loss) as device scalars; gradients are in the two engines' ``flat_g`` (the
+        encoder's also as ``param.grad``).  Follow with ``optimizer_step``."""
+        eeng, deng = self.encoder.train_engine(), self.decoder_train_engine()
+        fuse = bool(imgs_list)
+        out = eeng.forward_train(src_tokens, src_lengths, imgs_list if fuse else [], img_masks_list if fuse else [],
+                                 drop_image=drop_image)
+        mask = out["encoder_padding_mask"][0] if out["encoder_padding_mask"] else None
+        deng.forward_train(prev_output_tokens, out["encoder_out"][0], mask)
+        loss, nll, d_enc = deng.loss_backward(target, label_smoothing)
+        eeng.backward(d_enc)
+        return loss, nll
+
+    def optimizer_step(self, lr: float, betas=(0.9, 0.98), eps: float = 1e-8, weight_decay: float = 0.0,
+                       clip_norm: float = 0.0, grad_scale: float = 1.0) -> None:
+        """fairseq's update on both engines: gradient scaling, clipping by the WHOLE model's norm, Adam."""
+        eeng, deng = self.encoder.train_engine(), self.decoder_train_engine()
+        deng.grad_norm(grad_scale=grad_scale)
+        eeng.adam_step(lr, betas, eps, weight_decay, clip_norm, grad_scale, extra_norm=deng.norm_coef)
+        deng.adam_apply(eeng.norm_coef, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+
     def forward_encoder(self, src_tokens, src_lengths, src_audio_path=None, img_path=None, img_tensor=None,
                         imgs_list=[], img_masks_list=[], speaker=None, **kwargs):
         return self.encoder(src_tokens, src_lengths=src_lengths, src_audio_path=src_audio_path, img_path=img_path,
@@ -92,7 +143,8 @@ class MM_S2UTTransformerModel(nn.Module):
                 imgs_list=[], img_masks_list=[], tgt_speaker=None, return_all_hiddens=False,
                 **kwargs) -> Tuple[torch.Tensor, Dict[str, List]]:
         if self.training:
-            raise NotImplementedError("training (dropout / backward) is not built; call .eval()")
+            raise NotImplementedError("forward() is the inference path; the training step of the whole model is "
+                                      "train_step() / optimizer_step() (DESIGN.md section 9)")
         encoder_out = self.forward_encoder(src_tokens, src_lengths=src_lengths, src_audio_path=src_audio_path,
                                            img_path=img_path, img_tensor=img_tensor, imgs_list=imgs_list,
                                            img_masks_list=img_masks_list, speaker=tgt_speaker,

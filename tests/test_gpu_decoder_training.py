@@ -171,3 +171,39 @@ def test_graphed_model_train_step_matches_eager(cuda):
         assert diff.max().item() <= 3 * 2e-3 and diff.mean().item() < 2e-5, (i, diff.max().item(), diff.mean().item())
     assert torch.allclose(res["eager"][3], res["graph"][3], rtol=1e-3)
     assert res["eager"][2][2] < res["eager"][2][0]            # the loss goes down over the three steps
+
+
+def test_model_train_step_api(cuda):
+    """MM_S2UTTransformerModel.train_step / optimizer_step: the stand-alone model trains on the CUDA kernels (loss goes
+    down on a fixed batch) and the decoder's trained parameters are written back for checkpoints."""
+    from mm_s2ut_b200 import synth
+    from mm_s2ut_b200.config import DEFAULT_YAML, load_mm_config, make_args
+    from mm_s2ut_b200.models.mm_s2ut_model import MM_S2UTTransformerModel
+
+    cfg = dict(load_mm_config(DEFAULT_YAML))
+    cfg.update(SA_image_dropout=0.0, SA_attention_dropout=0.0)
+    torch.manual_seed(0)
+    args = make_args("small", multimodal_translation_config_yaml=cfg)
+    args.decoder_layers = 2
+    model = MM_S2UTTransformerModel(args, target_code_size=100, build_unused_projections=False).cuda().train()
+    model.encoder.dropout_p = 0.0
+    B, Lu = 2, 20
+    wavs, _ = synth.synth_batch(5, B, 1.5, ragged=True)
+    wav, lens = synth.pad_waveforms(wavs)
+    imgs = synth.synth_images(5, B).cuda()
+    g = torch.Generator().manual_seed(1)
+    prev = torch.randint(4, 104, (B, Lu), generator=g).cuda()
+    target = torch.randint(4, 104, (B, Lu), generator=g).cuda()
+    before = model.decoder.layers[0].fc1.weight.detach().clone()
+    losses = []
+    for _ in range(4):
+        loss, nll = model.train_step(wav.cuda(), lens.cuda(), prev, target, imgs_list=[imgs], img_masks_list=[None])
+        model.optimizer_step(lr=1e-3, clip_norm=10.0)
+        losses.append(loss.item())
+    assert losses[-1] < losses[0], losses
+    model.sync_decoder_parameters()
+    after = model.decoder.layers[0].fc1.weight.detach()
+    assert (after - before).abs().max().item() > 0
+    assert torch.equal(after, model.decoder_train_engine().p("layers.0.fc1.weight"))
+    with pytest.raises(NotImplementedError):
+        model(wav.cuda(), lens.cuda(), prev, imgs_list=[imgs], img_masks_list=[None])
