@@ -296,3 +296,67 @@ def test_graphed_train_step_matches_eager(cuda):
     assert torch.equal(res["eager"][1], res["graph"][1])
     assert torch.equal(res["eager"][0], res["graph"][0])
     assert torch.equal(res["eager"][2], res["graph"][2])
+
+
+def _custom_setup(preset, overrides, img_tokens, img_dim, B, dur, attn_type="selective_attention"):
+    """Like _train_setup for an arbitrary architecture / image-feature shape."""
+    from mm_s2ut_b200 import synth
+    from mm_s2ut_b200.config import DEFAULT_YAML, load_mm_config, make_args
+    from mm_s2ut_b200.models.mm_s2s_transformer import MM_S2STransformerEncoder
+    from oracle import fbank as ofb, fusion as ofu
+
+    cfg = dict(load_mm_config(DEFAULT_YAML))
+    cfg.update(multimodal_attention_type=attn_type, image_feat_dim=[img_dim], SA_image_dropout=0.0,
+               SA_attention_dropout=0.0)
+    torch.manual_seed(0)
+    args = make_args(preset, multimodal_translation_config_yaml=cfg, **overrides)
+    enc = MM_S2STransformerEncoder(args, build_unused_projections=False)
+    enc.dropout_p = 0.0
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for n, p in enc.named_parameters():
+            if "layer_norm" in n or "pre_norm" in n:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+            elif n.endswith(".bias"):
+                p.add_(0.05 * torch.randn(p.shape, generator=g))
+    wavs, _ = synth.synth_batch(6, B, dur, ragged=True)
+    imgs = synth.synth_images(6, B, img_tokens, img_dim)
+    sd = {k: v.detach().clone().float().requires_grad_(v.is_floating_point()) for k, v in enc.state_dict().items()}
+    feats, flens = ofb.features_from_waveforms(wavs)
+    ref = ofu.mm_encoder_forward(sd, load_mm_config(cfg), torch.from_numpy(feats), torch.from_numpy(flens), [imgs], [None],
+                                 args.encoder_attention_heads)
+    out_ref, mask = ref["encoder_out"][0], ref["encoder_padding_mask"][0]
+    R = torch.randn(out_ref.shape, generator=torch.Generator().manual_seed(11)) * (~mask).t().unsqueeze(-1)
+    (out_ref * R).sum().backward()
+    wav, lens = synth.pad_waveforms(wavs)
+    return enc, wav, lens, imgs, R, {k: v.grad for k, v in sd.items() if v.requires_grad and v.grad is not None}
+
+
+@pytest.mark.parametrize("name,preset,overrides,img,B,dur", [
+    # configs[4]'s width: d = 1024 (16 heads, ffn 4096), DETR-style 100 x 256 image features; depth cut to 2 layers
+    ("large-width d=1024, DETR 100x256", "large", dict(encoder_layers=2), (100, 256), 2, 1.5),
+    # sequences longer than one 256-key tile: 13 s -> T = 325 (chunked attention forward, 20 keys per lane in softmax_bwd)
+    ("small, 13 s utterances (T = 325)", "small", dict(encoder_layers=2), (577, 768), 2, 13.0),
+    # odd batch, odd subsampled length
+    ("small, B = 3, odd T", "small", dict(encoder_layers=2), (577, 768), 3, 2.53),
+])
+def test_encoder_backward_other_shapes(cuda, name, preset, overrides, img, B, dur):
+    enc, wav, lens, imgs, R, ref_grads = _custom_setup(preset, overrides, img[0], img[1], B, dur)
+    enc.cuda().train()
+    eng = enc.train_engine()
+    eng.forward_train(wav.cuda(), lens.cuda(), [imgs.cuda()], [None])
+    eng.backward(R.cuda())
+    torch.cuda.synchronize()
+    names = dict(enc.named_parameters())
+    worst, checked = 0.0, 0
+    for k, gref in ref_grads.items():
+        if k not in names or gref.norm() < ZERO:
+            continue
+        got = names[k].grad
+        assert torch.isfinite(got).all(), k
+        rel = _rel(got, gref)
+        worst = max(worst, rel)
+        assert rel < REL, (k, rel)
+        checked += 1
+    assert checked >= 2 * 15 + 2 + 4
+    record(f"configs[2] backward, {name}: worst parameter-gradient relative L2 error ({checked} tensors)", worst, REL)
