@@ -153,6 +153,12 @@ int mm_gemm_resid_ln(const void* a, int64_t a_ld, const void* w, int64_t w_ld, i
                      const float* bias, float* x, const float* gamma, const float* beta, float eps, void* h_op,
                      float* h_f32, int32_t dtype, void* stream);
 
+/* Same with the updated residual stream written to x_out instead of over x (x_out == x: in place): the training-step
+ * forward keeps every sub-layer's input for the backward pass. */
+int mm_gemm_resid_ln_out(const void* a, int64_t a_ld, const void* w, int64_t w_ld, int32_t rows, int32_t k, int32_t n,
+                         const float* bias, const float* x, float* x_out, const float* gamma, const float* beta,
+                         float eps, void* h_op, float* h_f32, int32_t dtype, void* stream);
+
 /* LayerNorm over the last dim (eps 1e-5, affine), fp32 in -> 16-bit operand out and/or fp32 out.
  * Replaces F.layer_norm in fairseq TransformerEncoderLayer / final encoder LayerNorm and
  * image_pre_norm_module (mm_s2s_transformer.py:595).  dim in {256, 512, 768, 1024}. */

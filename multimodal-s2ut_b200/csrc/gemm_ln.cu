@@ -57,7 +57,8 @@ template <typename OpT>
 __global__ void __launch_bounds__(256, 1)
 gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                      const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapH,
-                     const __grid_constant__ CUtensorMap mapHf, const LnDev p) {
+                     const __grid_constant__ CUtensorMap mapHf, const __grid_constant__ CUtensorMap mapXo,
+                     const LnDev p) {
   using Cfg = LnCfg;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -224,8 +225,9 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       fence_proxy_async_smem();
       if (h == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
       if (ht == 0) {
-        tma_store_3d_hint(&mapX, slab_ptr(j < 6 ? j : j - 6), 256 * h + 32 * j, row0, 0, pol_x);
-        tma_store_3d_hint(&mapX, slab_ptr(j + 1 < 6 ? j + 1 : j + 1 - 6), 256 * h + 32 * (j + 1), row0, 0, pol_x);
+        // mapXo == mapX: residual stream updated in place; a separate output keeps the input (training: activations kept)
+        tma_store_3d_hint(&mapXo, slab_ptr(j < 6 ? j : j - 6), 256 * h + 32 * j, row0, 0, pol_x);
+        tma_store_3d_hint(&mapXo, slab_ptr(j + 1 < 6 ? j + 1 : j + 1 - 6), 256 * h + 32 * (j + 1), row0, 0, pol_x);
         bulk_commit();
       }
     }
@@ -330,7 +332,7 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 
 template <typename OpT>
 static int launch_ln_gemm(const CUtensorMap& mA, const CUtensorMap& mW, const CUtensorMap& mX, const CUtensorMap& mH,
-                          const CUtensorMap& mHf, const LnDev& p, cudaStream_t s) {
+                          const CUtensorMap& mHf, const CUtensorMap& mXo, const LnDev& p, cudaStream_t s) {
   auto kern = gemm_resid_ln_kernel<OpT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -355,7 +357,7 @@ static int launch_ln_gemm(const CUtensorMap& mA, const CUtensorMap& mW, const CU
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mA, mW, mX, mH, mHf, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mA, mW, mX, mH, mHf, mXo, p);
   if (e != cudaSuccess) return fail(e, "gemm_resid_ln_kernel launch");
   return 0;
 }
@@ -371,17 +373,27 @@ extern "C" int mm_debug_ln_trace(long long* host) {
 extern "C" int mm_gemm_resid_ln(const void* a, int64_t a_ld, const void* w, int64_t w_ld, int32_t rows, int32_t k,
                                 int32_t n, const float* bias, float* x, const float* gamma, const float* beta,
                                 float eps, void* h_op, float* h_f32, int32_t dtype, void* stream) {
+  return mm_gemm_resid_ln_out(a, a_ld, w, w_ld, rows, k, n, bias, x, x, gamma, beta, eps, h_op, h_f32, dtype, stream);
+}
+
+extern "C" int mm_gemm_resid_ln_out(const void* a, int64_t a_ld, const void* w, int64_t w_ld, int32_t rows, int32_t k,
+                                    int32_t n, const float* bias, const float* x, float* x_out, const float* gamma,
+                                    const float* beta, float eps, void* h_op, float* h_f32, int32_t dtype,
+                                    void* stream) {
   using namespace mm;
+  if (!x_out) return bad_arg("gemm_resid_ln: null x_out");
   if (!a || !w || !bias || !x || !gamma || !beta || !h_op) return bad_arg("gemm_resid_ln: null pointer");
   if (n != LnCfg::N) return bad_arg("gemm_resid_ln: n must be 512 (full rows in one accumulator)");
   if (rows <= 0 || k <= 0) return bad_arg("gemm_resid_ln: extents");
   const int f16 = dtype == MM_DTYPE_F16;
-  CUtensorMap mA, mW, mX, mH, mHf;
+  CUtensorMap mA, mW, mX, mH, mHf, mXo;
   int rc = make_tmap_3d(&mA, a, f16, (uint64_t)k, (uint64_t)rows, 1, (uint64_t)a_ld, 0, 128);
   if (rc) return rc;
   rc = make_tmap_3d(&mW, w, f16, (uint64_t)k, (uint64_t)n, 1, (uint64_t)w_ld, 0, 128);
   if (rc) return rc;
   rc = make_tmap_3d_ex(&mX, x, 2, (uint64_t)n, (uint64_t)rows, 1, (uint64_t)n, 0, 32, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d_ex(&mXo, x_out, 2, (uint64_t)n, (uint64_t)rows, 1, (uint64_t)n, 0, 32, 128);
   if (rc) return rc;
   rc = make_tmap_3d_ex(&mH, h_op, f16 ? 1 : 0, (uint64_t)n, (uint64_t)rows, 1, (uint64_t)n, 0, 64, 128);
   if (rc) return rc;
@@ -398,6 +410,6 @@ extern "C" int mm_gemm_resid_ln(const void* a, int64_t a_ld, const void* w, int6
   static const int l2_hints = getenv("MM_LN_L2_HINTS") ? atoi(getenv("MM_LN_L2_HINTS")) : 3;
   p.l2_hints = l2_hints;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return f16 ? launch_ln_gemm<__half>(mA, mW, mX, mH, mHf, p, s)
-             : launch_ln_gemm<__nv_bfloat16>(mA, mW, mX, mH, mHf, p, s);
+  return f16 ? launch_ln_gemm<__half>(mA, mW, mX, mH, mHf, mXo, p, s)
+             : launch_ln_gemm<__nv_bfloat16>(mA, mW, mX, mH, mHf, mXo, p, s);
 }

@@ -184,8 +184,12 @@ def gemm(*, a0: torch.Tensor, w: torch.Tensor, rows: int, n: int, k: int, mode: 
 
 def gemm_resid_ln(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor,
                   beta: torch.Tensor, h_op: torch.Tensor, h_f32: Optional[torch.Tensor] = None,
-                  eps: float = 1e-5) -> None:
-    """x += a @ w.T + bias (fp32, in place); h_op (and h_f32) = LayerNorm(x) * gamma + beta.  n = 512 only."""
+                  eps: float = 1e-5, x_out: Optional[torch.Tensor] = None) -> None:
+    """x_out (default: x, in place) = x + a @ w.T + bias (fp32); h_op (and h_f32) = LayerNorm(x_out) * gamma + beta.
+    n = 512 only."""
+    if x_out is None:
+        x_out = x
+    assert x_out.dtype == torch.float32 and x_out.is_contiguous() and x_out.shape == x.shape
     rows, k = a.shape
     n = w.shape[0]
     assert a.dtype == w.dtype == h_op.dtype and a.is_contiguous() and w.is_contiguous() and w.shape[1] == k
@@ -193,9 +197,9 @@ def gemm_resid_ln(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, x: torch
     assert all(t.dtype == torch.float32 and t.numel() == n for t in (bias, gamma, beta))
     lib = _lib.load()
     with _Launch("gemm_resid_ln", 2.0 * rows * n * k):
-        _lib.check(lib.mm_gemm_resid_ln(_ptr(a), k, _ptr(w), k, rows, k, n, _ptr(bias), _ptr(x), _ptr(gamma),
-                                        _ptr(beta), eps, _ptr(h_op), _ptr(h_f32), dtype_code(w.dtype), _stream()),
-                   "mm_gemm_resid_ln")
+        _lib.check(lib.mm_gemm_resid_ln_out(_ptr(a), k, _ptr(w), k, rows, k, n, _ptr(bias), _ptr(x), _ptr(x_out),
+                                            _ptr(gamma), _ptr(beta), eps, _ptr(h_op), _ptr(h_f32), dtype_code(w.dtype),
+                                            _stream()), "mm_gemm_resid_ln")
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_op: Optional[torch.Tensor] = None,

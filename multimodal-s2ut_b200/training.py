@@ -110,7 +110,9 @@ class TrainEngine(EncoderEngine):
     def __init__(self, enc, op_dtype: Optional[torch.dtype] = None, block_n: int = 256):
         self._flatten(enc)
         super().__init__(enc, op_dtype, block_n)
-        self.fused_ln = False          # per-sub-layer residual buffers are kept for the backward pass
+        self.fused_ln = False          # (inference path of this engine: un-fused)
+        # training forward: fused GEMM + residual + LayerNorm with a separate output buffer (needs n == 512)
+        self.train_fused_ln = self.d == 512 and getattr(enc, "fuse_layernorm", True)
         self._saved = None
         self.step_count = 0
         n = self.flat_p.numel()
@@ -306,23 +308,37 @@ class TrainEngine(EncoderEngine):
     # ------------------------------------------------------------------------------------------
     # forward (activations kept)
     # ------------------------------------------------------------------------------------------
-    def _layer_train(self, i: int, x_in: torch.Tensor, B: int, T: int, seq_lens: torch.Tensor):
+    def _layer_train(self, i: int, x_in: torch.Tensor, B: int, T: int, seq_lens: torch.Tensor, h_next=None,
+                     h_next_f32=None):
+        """One pre-LN encoder layer with every sub-layer input kept.  d_model == 512: the two residual updates and the
+        LayerNorms that follow them are the fused GEMM+LN kernel with a separate output (on entry ``t_h1_i`` holds
+        LN1(x_in); on exit ``h_next`` holds the next LayerNorm of x_out); otherwise GEMM + stand-alone LayerNorm."""
         L, d, M, op, bn = self.layers[i], self.d, B * T, self.op_dtype, self.block_n
         s = dict(x_in=x_in, h1=self.buf(f"t_h1_{i}", (M, d), op), qkv=self.buf(f"t_qkv_{i}", (M, 3 * d), op),
                  att=self.buf(f"t_att_{i}", (M, d), op), x_mid=self.buf(f"t_xmid_{i}", (M, d), torch.float32),
                  h2=self.buf(f"t_h2_{i}", (M, d), op), f=self.buf(f"t_f_{i}", (M, self.ffn), op),
                  x_out=self.buf(f"t_xout_{i}", (M, d), torch.float32))
-        K.layernorm(x_in, L["ln1_g"], L["ln1_b"], out_op=s["h1"])
+        fused = self.train_fused_ln
+        if not fused:
+            K.layernorm(x_in, L["ln1_g"], L["ln1_b"], out_op=s["h1"])
         K.gemm(a0=s["h1"], a0_ld=d, rows=M, w=L["wqkv"], n=3 * d, k=d, mode=K.EPI_OP, bias=L["bqkv"], scale=64 ** -0.5,
                scale_cols=d, out0=s["qkv"], out0_ld=3 * d, block_n=bn)
         K.self_attention(s["qkv"], seq_lens, B, T, self.heads, s["att"])
-        K.gemm(a0=s["att"], a0_ld=d, rows=M, w=L["wo"], n=d, k=d, mode=K.EPI_RESID_F32, bias=L["bo"], aux0=x_in,
-               aux_ld=d, out0=s["x_mid"], out0_ld=d, block_n=bn)
-        K.layernorm(s["x_mid"], L["ln2_g"], L["ln2_b"], out_op=s["h2"])
+        if fused:
+            K.gemm_resid_ln(s["att"], L["wo"], L["bo"], x_in, L["ln2_g"], L["ln2_b"], s["h2"], x_out=s["x_mid"])
+        else:
+            K.gemm(a0=s["att"], a0_ld=d, rows=M, w=L["wo"], n=d, k=d, mode=K.EPI_RESID_F32, bias=L["bo"], aux0=x_in,
+                   aux_ld=d, out0=s["x_mid"], out0_ld=d, block_n=bn)
+            K.layernorm(s["x_mid"], L["ln2_g"], L["ln2_b"], out_op=s["h2"])
         K.gemm(a0=s["h2"], a0_ld=d, rows=M, w=L["w1"], n=self.ffn, k=d, mode=K.EPI_RELU_OP, bias=L["b1"], out0=s["f"],
                out0_ld=self.ffn, block_n=bn)
-        K.gemm(a0=s["f"], a0_ld=self.ffn, rows=M, w=L["w2"], n=d, k=self.ffn, mode=K.EPI_RESID_F32, bias=L["b2"],
-               aux0=s["x_mid"], aux_ld=d, out0=s["x_out"], out0_ld=d, block_n=bn)
+        if fused:
+            last = i + 1 == self.n_layers
+            ng, nb_ = (self.ln_g, self.ln_b) if last else (self.layers[i + 1]["ln1_g"], self.layers[i + 1]["ln1_b"])
+            K.gemm_resid_ln(s["f"], L["w2"], L["b2"], s["x_mid"], ng, nb_, h_next, h_next_f32, x_out=s["x_out"])
+        else:
+            K.gemm(a0=s["f"], a0_ld=self.ffn, rows=M, w=L["w2"], n=d, k=self.ffn, mode=K.EPI_RESID_F32, bias=L["b2"],
+                   aux0=s["x_mid"], aux_ld=d, out0=s["x_out"], out0_ld=d, block_n=bn)
         return s
 
     @torch.no_grad()
@@ -344,13 +360,18 @@ class TrainEngine(EncoderEngine):
         x, T = self.subsample(x1, m, seq_lens)
         M, d = B * T, self.d
         saved = dict(B=B, T=T, m=m, x1=x1, seq_lens=seq_lens, layers=[], fused=False)
-        for i in range(self.n_layers):
-            s = self._layer_train(i, x, B, T, seq_lens)
-            saved["layers"].append(s)
-            x = s["x_out"]
         text_f32 = self.buf("text_f32", (M, d), torch.float32)
         text_op = self.buf("text_op", (M, d), self.op_dtype)
-        K.layernorm(x, self.ln_g, self.ln_b, out_op=text_op, out_f32=text_f32)
+        if self.train_fused_ln:    # LN1 of layer 0 is the only stand-alone LayerNorm
+            K.layernorm(x, self.layers[0]["ln1_g"], self.layers[0]["ln1_b"], out_op=self.buf("t_h1_0", (M, d), self.op_dtype))
+        for i in range(self.n_layers):
+            last = i + 1 == self.n_layers
+            h_next = text_op if last else self.buf(f"t_h1_{i + 1}", (M, d), self.op_dtype)
+            s = self._layer_train(i, x, B, T, seq_lens, h_next=h_next, h_next_f32=text_f32 if last else None)
+            saved["layers"].append(s)
+            x = s["x_out"]
+        if not self.train_fused_ln:
+            K.layernorm(x, self.ln_g, self.ln_b, out_op=text_op, out_f32=text_f32)
         saved["x_final"] = x
         mask = torch.empty(B, T, dtype=torch.bool, device=self.device)
         K.padding_mask(seq_lens, T, mask)

@@ -339,6 +339,8 @@ def _custom_setup(preset, overrides, img_tokens, img_dim, B, dur, attn_type="sel
     ("small, 13 s utterances (T = 325)", "small", dict(encoder_layers=2), (577, 768), 2, 13.0),
     # odd batch, odd subsampled length
     ("small, B = 3, odd T", "small", dict(encoder_layers=2), (577, 768), 3, 2.53),
+    # d = 512: the training forward runs the fused GEMM + residual + LayerNorm kernel with a separate output buffer
+    ("base width d=512 (fused GEMM+LN forward), 3 layers", "base", dict(encoder_layers=3), (577, 768), 2, 2.0),
 ])
 def test_encoder_backward_other_shapes(cuda, name, preset, overrides, img, B, dur):
     enc, wav, lens, imgs, R, ref_grads = _custom_setup(preset, overrides, img[0], img[1], B, dur)

@@ -231,3 +231,21 @@ def test_decoder_backward_orchestration_matches_autograd_oracle(monkeypatch):
     eng.forward_train(setup[1], setup[3], setup[4])
     l1, _, _ = eng.loss_backward(setup[2], 0.2)
     assert l1.item() < l0
+
+
+def test_backward_orchestration_d512_fused_forward(monkeypatch):
+    """d_model = 512: the training forward takes the fused GEMM + residual + LayerNorm path (separate output buffers);
+    same autograd check on the emulated kernels."""
+    from test_gpu_training import REL, ZERO, _custom_setup, _rel
+
+    _emulated(monkeypatch)
+    enc, wav, lens, imgs, R, ref_grads = _custom_setup("base", dict(encoder_layers=2), 50, 768, 2, 1.0)
+    enc.train()
+    eng = enc.train_engine()
+    assert eng.train_fused_ln
+    eng.forward_train(wav, lens, [imgs], [None])
+    eng.backward(R)
+    names = dict(enc.named_parameters())
+    for k, gref in ref_grads.items():
+        if k in names and gref.norm() >= ZERO:
+            assert _rel(names[k].grad, gref) < REL, k
