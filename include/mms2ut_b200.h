@@ -234,7 +234,8 @@ int mm_convert_f32(const float* x, void* out, int64_t n, int32_t dtype, void* st
  * mm_reduce_partials: out[i] (+)= sum_s part[s * stride + i]  (split-K partials, LayerNorm parameter partials).
  * mm_layernorm_bwd: dx = resid + LN'(dy) (dx / resid optional; dx_op: 16-bit copy of dx), partials [mm_layernorm_bwd_blocks()][2][dim] =
  *   per-block (sum dy * xhat, sum dy).
- * mm_softmax_bwd: P = softmax(scores[:, :valid]), dscores = P o (dprobs - rowsum(P o dprobs)), both 16-bit,
+ * mm_softmax_bwd: P = softmax(scores[:, :valid]), dscores = P o (dprobs - rowsum(P o dprobs)), both 16-bit; dprobs is
+ *   fp32 or (dprobs_is_op) 16-bit with its own leading dimension,
  *   rows [batch][rows_per_batch] of which the first valid_rows are processed (0: all), valid = kv_lens[batch / heads]
  *   (NULL: n_keys), further limited to the query's own index + 1 when causal; columns [valid, ld_out) = 0.
  * mm_glu_bwd: pre fp32 [rows, 2n] = (a | b), dy fp32 [rows, n] -> dpre 16-bit [rows, 2n]   (F.glu backward, x scale).
@@ -263,7 +264,8 @@ int mm_reduce_partials(const float* part, int32_t n_partials, int64_t stride, in
 int mm_layernorm_bwd_blocks(void);
 int mm_layernorm_bwd(const float* x, const float* gamma, const float* dy, int64_t rows, int32_t dim, float eps,
                      const float* resid, float* dx, float* partials, void* dx_op, int32_t dtype, void* stream);
-int mm_softmax_bwd(const float* scores, const float* dprobs, int64_t ld_in, int64_t rows, int32_t rows_per_batch,
+int mm_softmax_bwd(const float* scores, const void* dprobs, int32_t dprobs_is_op, int64_t ld_dprobs, int64_t ld_in,
+                   int64_t rows, int32_t rows_per_batch,
                    int32_t n_keys, const int32_t* kv_lens, int32_t heads, void* probs, void* dscores, int64_t ld_out,
                    int32_t valid_rows, int32_t causal, int32_t dtype, void* stream);
 /* Backward of mm_label_smoothed_nll summed over rows (fairseq label_smoothed_nll_loss, reduce=True), times grad_scale:

@@ -308,7 +308,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 // ---------------------------------------------------------------------------------------------------
 // NPL = keys per lane held in registers (n_keys <= 32 * NPL): scores and dP are read once.
 template <int NPL, typename OpT>
-__global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ S, const float* __restrict__ dP,
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ S, const void* __restrict__ dPv,
+                                                           int dp_is_op, long long ld_dp,
                                                            long long ld_in, long long rows, int rows_per_batch,
                                                            int n_keys, const int* __restrict__ kv_lens, int heads,
                                                            OpT* __restrict__ P, OpT* __restrict__ dS, long long ld_out,
@@ -323,7 +324,9 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
   }
   if (causal) valid = min(valid, (int)(row % rows_per_batch) + 1);   // key j visible to query i iff j <= i
   const float* s = S + row * ld_in;
-  const float* d = dP + row * ld_in;
+  // dP is fp32, or 16-bit (written by the GEMM's 16-bit epilogue: half the traffic of the dP = dO v^T round trip)
+  const float* d = reinterpret_cast<const float*>(dPv) + row * ld_dp;
+  const OpT* d16 = reinterpret_cast<const OpT*>(dPv) + row * ld_dp;
   // lane owns key pairs (2 * (lane + 32 i), +1): 8-byte loads, 4-byte stores
   float sv[NPL], dv[NPL];
   float mx = -INFINITY;
@@ -333,9 +336,15 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
     float2 a = make_float2(-INFINITY, -INFINITY), g = make_float2(0.f, 0.f);
     if (k + 1 < valid) {
       a = __ldcs(reinterpret_cast<const float2*>(s + k));
-      g = __ldcs(reinterpret_cast<const float2*>(d + k));
+      if (dp_is_op) {
+        const uint32_t q = __ldcs(reinterpret_cast<const uint32_t*>(d16 + k));
+        const OpT* e = reinterpret_cast<const OpT*>(&q);
+        g = make_float2(OpTraits<OpT>::to_float(e[0]), OpTraits<OpT>::to_float(e[1]));
+      } else {
+        g = __ldcs(reinterpret_cast<const float2*>(d + k));
+      }
     } else if (k < valid) {
-      a.x = s[k], g.x = d[k];
+      a.x = s[k], g.x = dp_is_op ? OpTraits<OpT>::to_float(d16[k]) : d[k];
     }
     sv[2 * i] = a.x, sv[2 * i + 1] = a.y, dv[2 * i] = g.x, dv[2 * i + 1] = g.y;
     mx = fmaxf(mx, fmaxf(a.x, a.y));
@@ -374,18 +383,19 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
 }
 
 template <typename OpT>
-static int launch_softmax_bwd(const float* S, const float* dP, long long ld_in, long long rows, int rpb, int n_keys,
+static int launch_softmax_bwd(const float* S, const void* dP, int dp_is_op, long long ld_dp, long long ld_in,
+                              long long rows, int rpb, int n_keys,
                               const int* kv_lens, int heads, void* P, void* dS, long long ld_out, int valid_rows,
                               int causal, cudaStream_t s) {
   const unsigned grid = (unsigned)((rows + 7) / 8);
   OpT* p = reinterpret_cast<OpT*>(P);
   OpT* g = reinterpret_cast<OpT*>(dS);
   if (ld_out <= 256)
-    softmax_bwd_kernel<8, OpT><<<grid, 256, 0, s>>>(S, dP, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows, causal);
+    softmax_bwd_kernel<8, OpT><<<grid, 256, 0, s>>>(S, dP, dp_is_op, ld_dp, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows, causal);
   else if (ld_out <= 640)
-    softmax_bwd_kernel<20, OpT><<<grid, 256, 0, s>>>(S, dP, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows, causal);
+    softmax_bwd_kernel<20, OpT><<<grid, 256, 0, s>>>(S, dP, dp_is_op, ld_dp, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows, causal);
   else if (ld_out <= 2048)
-    softmax_bwd_kernel<64, OpT><<<grid, 256, 0, s>>>(S, dP, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows, causal);
+    softmax_bwd_kernel<64, OpT><<<grid, 256, 0, s>>>(S, dP, dp_is_op, ld_dp, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows, causal);
   else
     return bad_arg("softmax_bwd: at most 2048 keys");
   return 0;
@@ -703,7 +713,8 @@ extern "C" int mm_layernorm_bwd(const float* x, const float* gamma, const float*
   return 0;
 }
 
-extern "C" int mm_softmax_bwd(const float* scores, const float* dprobs, int64_t ld_in, int64_t rows,
+extern "C" int mm_softmax_bwd(const float* scores, const void* dprobs, int32_t dprobs_is_op, int64_t ld_dprobs,
+                              int64_t ld_in, int64_t rows,
                               int32_t rows_per_batch, int32_t n_keys, const int32_t* kv_lens, int32_t heads, void* probs,
                               void* dscores, int64_t ld_out, int32_t valid_rows, int32_t causal, int32_t dtype,
                               void* stream) {
@@ -711,13 +722,14 @@ extern "C" int mm_softmax_bwd(const float* scores, const float* dprobs, int64_t 
   if (!scores || !dprobs || !dscores || rows <= 0 || n_keys <= 0 || rows_per_batch <= 0 || heads <= 0)
     return bad_arg("softmax_bwd");
   if (ld_out < n_keys || ld_in < n_keys) return bad_arg("softmax_bwd: leading dimensions");
-  if ((ld_in & 1) || (ld_out & 1) || (reinterpret_cast<uintptr_t>(scores) & 7) || (reinterpret_cast<uintptr_t>(dprobs) & 7))
-    return bad_arg("softmax_bwd: leading dimensions must be even and the fp32 inputs 8-byte aligned");
+  if ((ld_in & 1) || (ld_out & 1) || (ld_dprobs & 1) || ld_dprobs < n_keys ||
+      (reinterpret_cast<uintptr_t>(scores) & 7) || (reinterpret_cast<uintptr_t>(dprobs) & 7))
+    return bad_arg("softmax_bwd: leading dimensions must be even and the inputs 8-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int rc = dtype == MM_DTYPE_F16
-                     ? launch_softmax_bwd<__half>(scores, dprobs, ld_in, rows, rows_per_batch, n_keys, kv_lens, heads,
+                     ? launch_softmax_bwd<__half>(scores, dprobs, dprobs_is_op, ld_dprobs, ld_in, rows, rows_per_batch, n_keys, kv_lens, heads,
                                                   probs, dscores, ld_out, valid_rows, causal, s)
-                     : launch_softmax_bwd<__nv_bfloat16>(scores, dprobs, ld_in, rows, rows_per_batch, n_keys, kv_lens,
+                     : launch_softmax_bwd<__nv_bfloat16>(scores, dprobs, dprobs_is_op, ld_dprobs, ld_in, rows, rows_per_batch, n_keys, kv_lens,
                                                          heads, probs, dscores, ld_out, valid_rows, causal, s);
   if (rc) return rc;
   MM_CHECK_LAUNCH("softmax_bwd_kernel launch");

@@ -226,10 +226,10 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
         Lp, Tp = _round_up(Lq, 64), _round_up(Tk, 64)
         hd = dict(heads=H, head_stride=64, batches=BH, w_batched=True, block_n=bn)
         S = self.buf("a_S", (BH, Lp, Tp), torch.float32)
-        dP = self.buf("a_dP", (BH, Lp, Tp), torch.float32)
-        sc = dict(rows=Lq, n=Tk, k=64, mode=K.EPI_F32, out0_ld=Tp, out0_bs=Lp * Tp, a_hm=True, w_hm=True, **hd)
-        K.gemm(a0=q, a0_ld=q_ld, a0_bs=q_bs, w=k, w_ld=kv_ld, w_bs=kv_bs, out0=S, **sc)
-        K.gemm(a0=dO, a0_ld=d, a0_bs=Lq * d, w=v, w_ld=kv_ld, w_bs=kv_bs, out0=dP, **sc)
+        dP = self.buf("a_dP16", (BH, Lp, Tp), op)      # 16-bit gradient; the scores stay fp32
+        sc = dict(rows=Lq, n=Tk, k=64, out0_ld=Tp, out0_bs=Lp * Tp, a_hm=True, w_hm=True, **hd)
+        K.gemm(a0=q, a0_ld=q_ld, a0_bs=q_bs, w=k, w_ld=kv_ld, w_bs=kv_bs, out0=S, mode=K.EPI_F32, **sc)
+        K.gemm(a0=dO, a0_ld=d, a0_bs=Lq * d, w=v, w_ld=kv_ld, w_bs=kv_bs, out0=dP, mode=K.EPI_OP, **sc)
         P = self.buf("a_P", (BH, Lp, Tp), op)
         dS = self.buf("a_dS", (BH, Lp, Tp), op)
         K.softmax_bwd(S, dP, Tp, BH * Lp, Lp, Tk, dS, Tp, probs=P, kv_lens=kv_lens, heads=H, valid_rows=Lq, causal=causal)

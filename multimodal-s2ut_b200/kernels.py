@@ -392,13 +392,16 @@ def layernorm_bwd(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, partia
 def softmax_bwd(scores: torch.Tensor, dprobs: torch.Tensor, ld_in: int, rows: int, rows_per_batch: int, n_keys: int,
                 dscores: torch.Tensor, ld_out: int, probs: Optional[torch.Tensor] = None,
                 kv_lens: Optional[torch.Tensor] = None, heads: int = 1, valid_rows: int = 0,
-                causal: bool = False) -> None:
-    assert scores.dtype == dprobs.dtype == torch.float32
+                causal: bool = False, ld_dprobs: Optional[int] = None) -> None:
+    assert scores.dtype == torch.float32 and (dprobs.dtype == torch.float32 or dprobs.dtype == dscores.dtype)
+    dp_is_op = dprobs.dtype != torch.float32
+    ld_dp = ld_in if ld_dprobs is None else ld_dprobs
     assert kv_lens is None or kv_lens.dtype == torch.int32
     assert probs is None or probs.dtype == dscores.dtype
     lib = _lib.load()
     with _Launch("softmax_bwd", 8.0 * rows * n_keys + 4.0 * rows * ld_out):
-        _lib.check(lib.mm_softmax_bwd(_ptr(scores), _ptr(dprobs), ld_in, rows, rows_per_batch, n_keys, _ptr(kv_lens),
+        _lib.check(lib.mm_softmax_bwd(_ptr(scores), _ptr(dprobs), int(dp_is_op), ld_dp, ld_in, rows, rows_per_batch, n_keys,
+                                      _ptr(kv_lens),
                                       heads, _ptr(probs), _ptr(dscores), ld_out, valid_rows, int(causal),
                                       dtype_code(dscores.dtype), _stream()),
                    "mm_softmax_bwd")

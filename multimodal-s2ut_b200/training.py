@@ -458,10 +458,10 @@ class TrainEngine(EncoderEngine):
         qkv = s["qkv"]
         hd = dict(heads=H, head_stride=64, batches=BH, w_batched=True, block_n=bn)
         S = self.buf("a_S", (BH, Tp, Tp), torch.float32)
-        dP = self.buf("a_dP", (BH, Tp, Tp), torch.float32)
-        sc = dict(rows=T, n=T, k=64, mode=K.EPI_F32, out0_ld=Tp, out0_bs=Tp * Tp, a_hm=True, w_hm=True, **hd)
-        K.gemm(a0=qkv, a0_ld=3 * d, a0_bs=T * 3 * d, w=qkv[:, d:], w_ld=3 * d, w_bs=T * 3 * d, out0=S, **sc)
-        K.gemm(a0=datt, a0_ld=d, a0_bs=T * d, w=qkv[:, 2 * d:], w_ld=3 * d, w_bs=T * 3 * d, out0=dP, **sc)
+        dP = self.buf("a_dP16", (BH, Tp, Tp), op)      # 16-bit: it is a gradient (dS is 16-bit anyway); S stays fp32
+        sc = dict(rows=T, n=T, k=64, out0_ld=Tp, out0_bs=Tp * Tp, a_hm=True, w_hm=True, **hd)
+        K.gemm(a0=qkv, a0_ld=3 * d, a0_bs=T * 3 * d, w=qkv[:, d:], w_ld=3 * d, w_bs=T * 3 * d, out0=S, mode=K.EPI_F32, **sc)
+        K.gemm(a0=datt, a0_ld=d, a0_bs=T * d, w=qkv[:, 2 * d:], w_ld=3 * d, w_bs=T * 3 * d, out0=dP, mode=K.EPI_OP, **sc)
         P = self.buf("a_P", (BH, Tp, Tp), op)
         dS = self.buf("a_dS", (BH, Tp, Tp), op)
         K.softmax_bwd(S, dP, Tp, BH * Tp, Tp, T, dS, Tp, probs=P, kv_lens=seq_lens, heads=H, valid_rows=T)

@@ -361,9 +361,9 @@ def layernorm_bwd(x, gamma, dy, partials, dx=None, resid=None, eps=1e-5, dx_op=N
 
 
 def softmax_bwd(scores, dprobs, ld_in, rows, rows_per_batch, n_keys, dscores, ld_out, probs=None, kv_lens=None, heads=1,
-                valid_rows=0, causal=False):
+                valid_rows=0, causal=False, ld_dprobs=None):
     S = _v(scores, (rows, n_keys), (ld_in, 1))
-    D = _v(dprobs, (rows, n_keys), (ld_in, 1))
+    D = _v(dprobs, (rows, n_keys), (ld_in if ld_dprobs is None else ld_dprobs, 1)).float()
     G = _v(dscores, (rows, ld_out), (ld_out, 1))
     if probs is not None:
         Pv = _v(probs, (rows, ld_out), (ld_out, 1))
