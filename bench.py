@@ -180,7 +180,7 @@ def train_step_probe(dev, world, rank, wav, img, steps=20, warmup=3):
     torch.manual_seed(0)
     args = make_args(PRESET, multimodal_translation_config_yaml=cfg)
     enc = MM_S2STransformerEncoder(args, build_unused_projections=False).to(dev).train()
-    enc.dropout_p = 0.0            # element-wise dropout masks are not built; modality dropout is on
+    enc.dropout_p = enc.activation_dropout_p = enc.attention_dropout_p = 0.0   # the probe runs without element-wise dropout; modality dropout is on
     gs = GraphedTrainStep(enc, wav.shape[0], wav.shape[1], tuple(img.shape[1:]), overlap_reduce=world > 1)
     gs.wav.copy_(wav)
     gs.img.copy_(img)
@@ -226,7 +226,7 @@ def train_step_probe(dev, world, rank, wav, img, steps=20, warmup=3):
 
         torch.manual_seed(0)
         model = MM_S2UTTransformerModel(args, target_code_size=1000, build_unused_projections=False).to(dev).train()
-        model.encoder.dropout_p = 0.0
+        model.encoder.dropout_p = model.encoder.activation_dropout_p = model.encoder.attention_dropout_p = 0.0
         tgt_len = int(50 * DUR_S)
         gm = GraphedModelTrainStep(model.encoder, model.decoder_train_engine(), wav.shape[0], wav.shape[1],
                                    tuple(img.shape[1:]), tgt_len, overlap_reduce=world > 1)

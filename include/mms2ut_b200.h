@@ -286,6 +286,12 @@ int mm_gate_bwd(const float* z, const float* dres_tbc, const float* text, const 
 int mm_tbc_to_btc(const float* in_tbc, int32_t batch, int32_t seq, int32_t dim, float* out, void* stream);
 int mm_col2im_k5s2(const float* dcol, int32_t batch, int32_t t_out, int32_t t_in, int32_t channels, float* dx,
                    void* stream);
+/* Element-wise dropout of the training forward / backward (fairseq FairseqDropout at the encoder's embedding, residual
+ * and activation sites; SA_image_dropout, mm_s2s_transformer.py:596): out = (resid ? resid : 0) + (keep ? x / (1-p) : 0),
+ * keep = f(seed + *seed_dev, site, element index) -- a pure function, regenerated in the backward pass (seed_dev:
+ * optional device-resident per-step seed, so that CUDA-graph replays draw fresh masks).  x / out fp32 or 16-bit. */
+int mm_dropout(const void* x, int32_t x_is_f32, const float* resid, void* out, int64_t n, float p, uint64_t seed,
+               const uint64_t* seed_dev, uint32_t site, int32_t dtype, void* stream);
 int mm_sumsq_blocks(void);
 int mm_grad_clip_coef(const float* grad, int64_t n, float grad_scale, float max_norm, float* partials, float* norm_coef,
                       int32_t dev_hyper, const float* extra_norm, void* stream);

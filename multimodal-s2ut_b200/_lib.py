@@ -156,6 +156,8 @@ EXPORTS = {
                               C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "mm_tbc_to_btc": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "mm_col2im_k5s2": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mm_dropout": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_uint64, C.c_void_p,
+                             C.c_uint32, C.c_int32, C.c_void_p]),
     "mm_sumsq_blocks": (C.c_int, []),
     "mm_grad_clip_coef": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int32,
                                     C.c_void_p, C.c_void_p]),

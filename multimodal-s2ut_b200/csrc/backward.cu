@@ -597,6 +597,37 @@ __global__ void __launch_bounds__(128) embed_bwd_kernel(const long long* __restr
     atomicAdd(table_grad + tok * dim + c, scale * dx[row * dim + c]);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Element-wise dropout (fairseq FairseqDropout = F.dropout in training): y = keep ? x / (1 - p) : 0 with a counter-based
+// mask: keep(seed, site, i) is a pure function, so the backward pass (and the parity tests) regenerate the same mask
+// from (seed, site) instead of storing it.  Not torch's Philox stream (a drop-in cannot share torch's generator state
+// with a fused kernel anyway); splitmix64 finaliser of the element counter.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned site, unsigned long long i, float p) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(site + 1) + i * 0xD1342543DE82EF95ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (float)(z >> 40) * (1.0f / 16777216.0f) >= p;      // 24 uniform bits
+}
+
+// out = resid + dropout(x)  (resid optional); x / out fp32 or 16-bit (same type), n elements, in place allowed
+template <typename T, typename OpT>
+__global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, const float* __restrict__ resid,
+                                                       T* __restrict__ out, long long n, float p,
+                                                       unsigned long long seed, const unsigned long long* seed_dev,
+                                                       unsigned site) {
+  if (seed_dev) seed += *seed_dev;      // per-step seed held in device memory: CUDA-graph replays get fresh masks
+  const float inv = 1.0f / (1.0f - p);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v;
+    if constexpr (sizeof(T) == 4) v = (float)x[i]; else v = OpTraits<OpT>::to_float(reinterpret_cast<const OpT*>(x)[i]);
+    v = dropout_keep(seed, site, (unsigned long long)i, p) ? v * inv : 0.f;
+    if (resid) v += resid[i];
+    if constexpr (sizeof(T) == 4) out[i] = (T)v; else reinterpret_cast<OpT*>(out)[i] = OpTraits<OpT>::cvt(v);
+  }
+}
+
 static inline unsigned grid_for(long long total, int per_block = 256) {
   long long g = (total + per_block - 1) / per_block;
   const long long cap = (long long)kNumSMs * 16;
@@ -760,6 +791,29 @@ extern "C" int mm_embed_tokens_bwd(const int64_t* tokens, int32_t padding_idx, c
   embed_bwd_kernel<<<(unsigned)rows, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const long long*>(tokens), padding_idx, dx, rows, dim, scale, table_grad);
   MM_CHECK_LAUNCH("embed_bwd_kernel launch");
+  return 0;
+}
+
+extern "C" int mm_dropout(const void* x, int32_t x_is_f32, const float* resid, void* out, int64_t n, float p,
+                          uint64_t seed, const uint64_t* seed_dev, uint32_t site, int32_t dtype, void* stream) {
+  if (!x || !out || n <= 0 || p < 0.f || p >= 1.f) return bad_arg("dropout");
+  if (resid && !x_is_f32) return bad_arg("dropout: the residual form is fp32");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = grid_for(n);
+  if (x_is_f32)
+    dropout_kernel<float, __nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x), resid,
+                                                              reinterpret_cast<float*>(out), n, p, seed,
+                                                              reinterpret_cast<const unsigned long long*>(seed_dev), site);
+  else if (dtype == MM_DTYPE_F16)
+    dropout_kernel<__half, __half><<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(x), nullptr,
+                                                        reinterpret_cast<__half*>(out), n, p, seed,
+                                                        reinterpret_cast<const unsigned long long*>(seed_dev), site);
+  else
+    dropout_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), nullptr,
+                                                                      reinterpret_cast<__nv_bfloat16*>(out), n, p, seed,
+                                                                      reinterpret_cast<const unsigned long long*>(seed_dev),
+                                                                      site);
+  MM_CHECK_LAUNCH("dropout_kernel launch");
   return 0;
 }
 

@@ -269,8 +269,9 @@ class EncoderEngine:
                    aux0=x, aux_ld=d, out0=x, out0_ld=d, block_n=bn)
 
     def fuse(self, j: int, text_f32: torch.Tensor, text_op: torch.Tensor, img: torch.Tensor,
-             img_mask: Optional[torch.Tensor], B: int, T: int, out_tbc: torch.Tensor) -> None:
-        """fuse_img_feat for image type j; writes the fused states into out_tbc [T, B, d] fp32."""
+             img_mask: Optional[torch.Tensor], B: int, T: int, out_tbc: torch.Tensor, img_dropout=None) -> None:
+        """fuse_img_feat for image type j; writes the fused states into out_tbc [T, B, d] fp32.
+        img_dropout = (p, seed, seed_dev, site): SA_image_dropout on the pre-normed image (training, :596)."""
         enc, F, d, op, bn = self.enc, self.fusion[j], self.d, self.op_dtype, self.block_n
         M = B * T
         Tk_img, dk = img.shape[1], img.shape[2]
@@ -291,6 +292,8 @@ class EncoderEngine:
                 K.layernorm(img.view(B * Tk_img, dk), self.img_ln[0], self.img_ln[1], out_op=img_op)
             else:
                 K.convert(img.view(B * Tk_img, dk), img_op)
+        if img_dropout is not None and img_dropout[0] > 0:
+            K.dropout(img_op, img_op, img_dropout[0], img_dropout[1], img_dropout[3], seed_dev=img_dropout[2])
         new_kv = (f"k{j}", (B, Tk, d), op) not in self._buf
         kbuf = self.buf(f"k{j}", (B, Tk, d), op)
         vt = self.buf(f"vt_img{j}", (B, d, Tkp), op, zero=True)

@@ -94,6 +94,9 @@ class GraphedTrainStep:
         self.lens = torch.full((batch,), n_samples, dtype=torch.int64, device=dev)
         self.img = torch.zeros(batch, *img_shape, dtype=torch.float32, device=dev)
         self.grad_out: Optional[torch.Tensor] = None
+        # element-wise dropout under replay: the masks are keyed on base seed + this device scalar, advanced per step
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.base_seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
         self.out = {}
         self.graphs = {}
         self.opt_graph: Optional[torch.cuda.CUDAGraph] = None
@@ -103,7 +106,8 @@ class GraphedTrainStep:
         self._hyper_i = 0
 
     def _fwd_bwd(self, drop_image: bool):
-        out = self.eng.forward_train(self.wav, self.lens, [self.img], [None], drop_image=drop_image)
+        out = self.eng.forward_train(self.wav, self.lens, [self.img], [None], drop_image=drop_image,
+                                     dropout_seed=self.base_seed, dropout_seed_dev=self.seed_dev)
         if self.grad_out is None:
             self.grad_out = torch.zeros_like(out["encoder_out"][0])
         # with several ranks the bucketed gradient all-reduce is part of the captured graph (side stream, forked from
@@ -149,6 +153,7 @@ class GraphedTrainStep:
         """Replays forward + backward on the static inputs (``wav``, ``lens``, ``img``, ``grad_out``)."""
         if self.opt_graph is None:
             self.capture()
+        self.seed_dev.add_(0x632BE5AB)        # fresh dropout masks for this step (stream-ordered before the replay)
         self.graphs[bool(drop_image)].replay()
         return self.out[bool(drop_image)]
 
@@ -201,7 +206,8 @@ class GraphedModelTrainStep(GraphedTrainStep):
     def _fwd_bwd(self, drop_image: bool):
         import torch.distributed as dist
 
-        out = self.eng.forward_train(self.wav, self.lens, [self.img], [None], drop_image=drop_image)
+        out = self.eng.forward_train(self.wav, self.lens, [self.img], [None], drop_image=drop_image,
+                                     dropout_seed=self.base_seed, dropout_seed_dev=self.seed_dev)
         self.dec.forward_train(self.prev_tokens, out["encoder_out"][0], out["encoder_padding_mask"][0])
         loss, nll, d_enc = self.dec.loss_backward(self.target, self.label_smoothing)
         multi = self.overlap_reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1

@@ -494,3 +494,18 @@ def embed_tokens_bwd(tokens: torch.Tensor, padding_idx: int, dx: torch.Tensor, s
     with _Launch("embed_tokens_bwd", 8.0 * rows * dim):
         _lib.check(lib.mm_embed_tokens_bwd(_ptr(tokens), padding_idx, _ptr(dx), rows, dim, scale, _ptr(table_grad),
                                            _stream()), "mm_embed_tokens_bwd")
+
+
+def dropout(x: torch.Tensor, out: torch.Tensor, p: float, seed: int, site: int,
+            resid: Optional[torch.Tensor] = None, seed_dev: Optional[torch.Tensor] = None) -> None:
+    """out = (resid or 0) + dropout(x) with the counter-based mask keep(seed + seed_dev[0], site, element); in place
+    allowed.  seed_dev: optional int64 device scalar (per-step seed under CUDA-graph replay)."""
+    assert seed_dev is None or (seed_dev.dtype == torch.int64 and seed_dev.numel() >= 1)
+    assert x.dtype == out.dtype and x.is_contiguous() and out.is_contiguous() and x.numel() == out.numel()
+    assert resid is None or (resid.dtype == torch.float32 and resid.is_contiguous() and x.dtype == torch.float32)
+    lib = _lib.load()
+    with _Launch("dropout", float(x.element_size() * x.numel() * (2 + (resid is not None)))):
+        _lib.check(lib.mm_dropout(_ptr(x), int(x.dtype == torch.float32), _ptr(resid), _ptr(out), x.numel(), p,
+                                  seed & 0xFFFFFFFFFFFFFFFF, _ptr(seed_dev), site,
+                                  0 if x.dtype == torch.float32 else dtype_code(x.dtype),
+                                  _stream()), "mm_dropout")

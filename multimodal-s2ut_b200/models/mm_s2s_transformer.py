@@ -61,6 +61,9 @@ class S2TTransformerEncoderParams(nn.Module):
         self.embed_scale = 1.0 if args.no_scale_embedding else math.sqrt(d)
         self.padding_idx = 1
         self.dropout_p = args.dropout
+        # fairseq: activation_dropout, falling back to relu_dropout when it is 0; attention_dropout inside the MHA
+        self.activation_dropout_p = float(getattr(args, "activation_dropout", 0.0) or getattr(args, "relu_dropout", 0.0) or 0.0)
+        self.attention_dropout_p = float(getattr(args, "attention_dropout", 0.0) or 0.0)
         self.subsample = Conv1dSubsampler(
             args.input_feat_per_channel * args.input_channels, args.conv_channels, d,
             [int(k) for k in args.conv_kernel_sizes.split(",")])

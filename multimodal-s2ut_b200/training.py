@@ -22,8 +22,10 @@ Parameters and gradients live in two flat fp32 buffers (``flat_p`` / ``flat_g``;
 is re-pointed to a view), ordered so that the packed layouts the kernels produce (q|k|v, k|v, LayerNorm weight|bias)
 are contiguous slices.  ``all_reduce_grads`` runs NCCL (or gloo) over ``flat_g`` in buckets; ``adam_step`` is one kernel.
 
-Not built (raises): element-wise dropout in training mode, image key masks, several image-feature types, and the
-device feature store in the backward pass.  Modality dropout (per-batch image zeroing) works.
+Element-wise dropout (embedding, residual and activation sites, SA_image_dropout) uses counter-based masks that the
+backward pass regenerates (``mm_dropout``); modality dropout (per-batch image zeroing) works.  Not built (raises):
+dropout on attention probabilities, SA_text_dropout, image key masks, several image-feature types, and the device
+feature store in the backward pass.
 """
 from __future__ import annotations
 
@@ -44,6 +46,15 @@ def _split_k(n: int, kin: int, mp: int) -> int:
     while s < 16 and tiles * s < 74 and (mp // 64) % (2 * s) == 0:
         s *= 2
     return s
+
+
+# dropout sites (the counter-based mask is a function of (seed, site, element index))
+SITE_EMBED, SITE_IMAGE = 0, 8
+
+
+def site_layer(i: int, which: int) -> int:
+    """which: 0 = after the self-attention out_proj, 1 = after ReLU (activation dropout), 2 = after fc2."""
+    return 16 * (i + 1) + which
 
 
 def _best_split(tiles: int, M: int, pairs: int = 74, max_split: int = 32, min_chunk: int = 512) -> int:
@@ -318,7 +329,8 @@ class TrainEngine(EncoderEngine):
                  att=self.buf(f"t_att_{i}", (M, d), op), x_mid=self.buf(f"t_xmid_{i}", (M, d), torch.float32),
                  h2=self.buf(f"t_h2_{i}", (M, d), op), f=self.buf(f"t_f_{i}", (M, self.ffn), op),
                  x_out=self.buf(f"t_xout_{i}", (M, d), torch.float32))
-        fused = self.train_fused_ln
+        p_drop, p_act, seed, seed_dev = self._drop
+        fused = self.train_fused_ln and p_drop == 0
         if not fused:
             K.layernorm(x_in, L["ln1_g"], L["ln1_b"], out_op=s["h1"])
         K.gemm(a0=s["h1"], a0_ld=d, rows=M, w=L["wqkv"], n=3 * d, k=d, mode=K.EPI_OP, bias=L["bqkv"], scale=64 ** -0.5,
@@ -326,16 +338,29 @@ class TrainEngine(EncoderEngine):
         K.self_attention(s["qkv"], seq_lens, B, T, self.heads, s["att"])
         if fused:
             K.gemm_resid_ln(s["att"], L["wo"], L["bo"], x_in, L["ln2_g"], L["ln2_b"], s["h2"], x_out=s["x_mid"])
+        elif p_drop > 0:     # x_mid = x_in + dropout(out_proj(att))
+            y = self.buf("t_y", (M, d), torch.float32)
+            K.gemm(a0=s["att"], a0_ld=d, rows=M, w=L["wo"], n=d, k=d, mode=K.EPI_F32, bias=L["bo"], out0=y, out0_ld=d,
+                   block_n=bn)
+            K.dropout(y, s["x_mid"], p_drop, seed, site_layer(i, 0), resid=x_in, seed_dev=seed_dev)
+            K.layernorm(s["x_mid"], L["ln2_g"], L["ln2_b"], out_op=s["h2"])
         else:
             K.gemm(a0=s["att"], a0_ld=d, rows=M, w=L["wo"], n=d, k=d, mode=K.EPI_RESID_F32, bias=L["bo"], aux0=x_in,
                    aux_ld=d, out0=s["x_mid"], out0_ld=d, block_n=bn)
             K.layernorm(s["x_mid"], L["ln2_g"], L["ln2_b"], out_op=s["h2"])
         K.gemm(a0=s["h2"], a0_ld=d, rows=M, w=L["w1"], n=self.ffn, k=d, mode=K.EPI_RELU_OP, bias=L["b1"], out0=s["f"],
                out0_ld=self.ffn, block_n=bn)
+        if p_act > 0:
+            K.dropout(s["f"], s["f"], p_act, seed, site_layer(i, 1), seed_dev=seed_dev)
         if fused:
             last = i + 1 == self.n_layers
             ng, nb_ = (self.ln_g, self.ln_b) if last else (self.layers[i + 1]["ln1_g"], self.layers[i + 1]["ln1_b"])
             K.gemm_resid_ln(s["f"], L["w2"], L["b2"], s["x_mid"], ng, nb_, h_next, h_next_f32, x_out=s["x_out"])
+        elif p_drop > 0:     # x_out = x_mid + dropout(fc2(f))
+            y = self.buf("t_y", (M, d), torch.float32)
+            K.gemm(a0=s["f"], a0_ld=self.ffn, rows=M, w=L["w2"], n=d, k=self.ffn, mode=K.EPI_F32, bias=L["b2"], out0=y,
+                   out0_ld=d, block_n=bn)
+            K.dropout(y, s["x_out"], p_drop, seed, site_layer(i, 2), resid=s["x_mid"], seed_dev=seed_dev)
         else:
             K.gemm(a0=s["f"], a0_ld=self.ffn, rows=M, w=L["w2"], n=d, k=self.ffn, mode=K.EPI_RESID_F32, bias=L["b2"],
                    aux0=s["x_mid"], aux_ld=d, out0=s["x_out"], out0_ld=d, block_n=bn)
@@ -343,12 +368,23 @@ class TrainEngine(EncoderEngine):
 
     @torch.no_grad()
     def forward_train(self, src_tokens, src_lengths, imgs_list: List[torch.Tensor], img_masks_list: List,
-                      drop_audio: bool = False, drop_image: bool = False, specaug=None):
+                      drop_audio: bool = False, drop_image: bool = False, specaug=None,
+                      dropout_seed: Optional[int] = None, dropout_seed_dev: Optional[torch.Tensor] = None):
+        """dropout_seed (+ the int64 device scalar dropout_seed_dev, for CUDA-graph replay) seeds the element-wise
+        dropout masks of this step; default: a counter advanced per call on top of torch.initial_seed()."""
         enc = self.enc
-        if max(enc.dropout_p, getattr(enc, "SA_image_dropout", 0.0), getattr(enc, "SA_text_dropout", 0.0),
+        if max(getattr(enc, "attention_dropout_p", 0.0), getattr(enc, "SA_text_dropout", 0.0),
                getattr(enc, "SA_attention_dropout", 0.0)) > 0:
-            raise NotImplementedError("element-wise dropout masks are not built: set the dropout probabilities to 0 "
-                                      "(modality dropout is supported)")
+            raise NotImplementedError(
+                "dropout on attention probabilities (--attention-dropout, SA_attention_dropout) and SA_text_dropout are "
+                "not built: set them to 0.  --dropout, --activation-dropout / --relu-dropout, SA_image_dropout and "
+                "modality dropout are supported")
+        p_drop, p_act = float(enc.dropout_p), float(getattr(enc, "activation_dropout_p", 0.0))
+        p_img = float(getattr(enc, "SA_image_dropout", 0.0) or 0.0)
+        if dropout_seed is None:
+            self._drop_calls = getattr(self, "_drop_calls", 0) + 1
+            dropout_seed = (torch.initial_seed() + 0x51ED270B * self._drop_calls) & 0x7FFFFFFFFFFFFFFF
+        self._drop = (p_drop, p_act, int(dropout_seed), dropout_seed_dev)
         if len(imgs_list) > 1:
             raise NotImplementedError("the backward pass handles one image-feature type")
         if any(m is not None for m in img_masks_list):
@@ -359,10 +395,13 @@ class TrainEngine(EncoderEngine):
         B = x1.shape[0]
         x, T = self.subsample(x1, m, seq_lens)
         M, d = B * T, self.d
-        saved = dict(B=B, T=T, m=m, x1=x1, seq_lens=seq_lens, layers=[], fused=False)
+        if p_drop > 0:      # S2TTransformerEncoder: x = dropout_module(embed_scale * x + positions)
+            K.dropout(x, x, p_drop, self._drop[2], SITE_EMBED, seed_dev=dropout_seed_dev)
+        saved = dict(B=B, T=T, m=m, x1=x1, seq_lens=seq_lens, layers=[], fused=False, drop=self._drop, p_img=p_img)
         text_f32 = self.buf("text_f32", (M, d), torch.float32)
         text_op = self.buf("text_op", (M, d), self.op_dtype)
-        if self.train_fused_ln:    # LN1 of layer 0 is the only stand-alone LayerNorm
+        fused_fwd = self.train_fused_ln and p_drop == 0
+        if fused_fwd:              # LN1 of layer 0 is the only stand-alone LayerNorm
             K.layernorm(x, self.layers[0]["ln1_g"], self.layers[0]["ln1_b"], out_op=self.buf("t_h1_0", (M, d), self.op_dtype))
         for i in range(self.n_layers):
             last = i + 1 == self.n_layers
@@ -370,7 +409,7 @@ class TrainEngine(EncoderEngine):
             s = self._layer_train(i, x, B, T, seq_lens, h_next=h_next, h_next_f32=text_f32 if last else None)
             saved["layers"].append(s)
             x = s["x_out"]
-        if not self.train_fused_ln:
+        if not fused_fwd:
             K.layernorm(x, self.ln_g, self.ln_b, out_op=text_op, out_f32=text_f32)
         saved["x_final"] = x
         mask = torch.empty(B, T, dtype=torch.bool, device=self.device)
@@ -383,7 +422,8 @@ class TrainEngine(EncoderEngine):
                 img = torch.zeros(tuple(img.shape), dtype=torch.float32, device=self.device)
             img = img.to(self.device, non_blocking=True).float().contiguous()
             out = torch.empty(T, B, d, dtype=torch.float32, device=self.device)
-            self.fuse(0, text_f32, text_op, img, None, B, T, out)
+            self.fuse(0, text_f32, text_op, img, None, B, T, out,
+                      img_dropout=(p_img, self._drop[2], dropout_seed_dev, SITE_IMAGE))
             saved.update(fused=True, img=img)
         else:
             out = text_f32.view(B, T, d).transpose(0, 1).contiguous()
@@ -480,22 +520,34 @@ class TrainEngine(EncoderEngine):
         a = mod.self_attn
         d, ffn, M, op, bn = self.d, self.ffn, B * T, self.op_dtype, self.block_n
         lnp = self.buf("ln_part", (self._ln_blocks * 2 * max(d, 1024),), torch.float32)
-        # ---- FFN: x_out = x_mid + fc2(relu(fc1(LN2(x_mid))))
-        self._linear_bwd(g_op, d, s["f"], M, d, ffn, self.g(mod.fc2.weight), self.g(mod.fc2.bias), accumulate)
+        p_drop, p_act, seed, seed_dev = self._saved["drop"]
+        gm = g_op
+        if p_drop > 0:       # gradient entering fc2 = g o mask / (1 - p); the residual branch keeps g itself
+            gm = self.buf("b_gm_op", (M, d), op)
+            K.dropout(g_op, gm, p_drop, seed, site_layer(i, 2), seed_dev=seed_dev)
+        # ---- FFN: x_out = x_mid + dropout(fc2(dropout(relu(fc1(LN2(x_mid))))))
+        self._linear_bwd(gm, d, s["f"], M, d, ffn, self.g(mod.fc2.weight), self.g(mod.fc2.bias), accumulate)
         dF = self.buf("b_dF", (M, ffn), op)
-        K.gemm(a0=g_op, a0_ld=d, rows=M, w=L["w2"], w_ld=ffn, w_mn=True, n=ffn, k=d, mode=K.EPI_OP, out0=dF,
+        K.gemm(a0=gm, a0_ld=d, rows=M, w=L["w2"], w_ld=ffn, w_mn=True, n=ffn, k=d, mode=K.EPI_OP, out0=dF,
                out0_ld=ffn, block_n=bn)
-        K.pack_t(dF, rows=M, cols=ffn, in_ld=ffn, out_n=dF, n_ld=ffn, mask=s["f"], mask_ld=ffn)   # ReLU mask, in place
+        # ReLU (and activation-dropout) mask in place: the kept activation is > 0 exactly where ReLU passed and the
+        # dropout kept it; the surviving gradient is scaled by 1 / (1 - p_act)
+        K.pack_t(dF, rows=M, cols=ffn, in_ld=ffn, out_n=dF, n_ld=ffn, mask=s["f"], mask_ld=ffn,
+                 scale=1.0 / (1.0 - p_act))
         self._linear_bwd(dF, ffn, s["h2"], M, ffn, d, self.g(mod.fc1.weight), self.g(mod.fc1.bias), accumulate)
         dh = self.buf("b_dh", (M, d), torch.float32)
         K.gemm(a0=dF, a0_ld=ffn, rows=M, w=L["w1"], w_ld=d, w_mn=True, n=d, k=ffn, mode=K.EPI_F32, out0=dh, out0_ld=d,
                block_n=bn)
         K.layernorm_bwd(s["x_mid"], L["ln2_g"], dh, lnp, dx=g, resid=g, dx_op=g_op)
         self._ln_param_grads(lnp, d, self.g(mod.final_layer_norm.weight, mod.final_layer_norm.bias), accumulate)
-        # ---- attention: x_mid = x_in + out_proj(attn(LN1(x_in)))
-        self._linear_bwd(g_op, d, s["att"], M, d, d, self.g(a.out_proj.weight), self.g(a.out_proj.bias), accumulate)
+        # ---- attention: x_mid = x_in + dropout(out_proj(attn(LN1(x_in))))
+        gm = g_op
+        if p_drop > 0:
+            gm = self.buf("b_gm_op", (M, d), op)
+            K.dropout(g_op, gm, p_drop, seed, site_layer(i, 0), seed_dev=seed_dev)
+        self._linear_bwd(gm, d, s["att"], M, d, d, self.g(a.out_proj.weight), self.g(a.out_proj.bias), accumulate)
         datt = self.buf("b_datt", (M, d), op)
-        K.gemm(a0=g_op, a0_ld=d, rows=M, w=L["wo"], w_ld=d, w_mn=True, n=d, k=d, mode=K.EPI_OP, out0=datt, out0_ld=d,
+        K.gemm(a0=gm, a0_ld=d, rows=M, w=L["wo"], w_ld=d, w_mn=True, n=d, k=d, mode=K.EPI_OP, out0=datt, out0_ld=d,
                block_n=bn)
         dqkv = self.buf("b_dqkv", (M, 3 * d), op)
         with _scope("attn"):
@@ -589,6 +641,9 @@ class TrainEngine(EncoderEngine):
             K.gemm(a0=dkv, a0_ld=2 * d, a0_bs=Tk * 2 * d, rows=Tk_img, batches=B, w=F["wkv"], w_ld=dk, w_mn=True, n=dk,
                    k=2 * d, mode=K.EPI_F32, out0=dimg, out0_ld=dk, out0_bs=Tk_img * dk, block_n=bn)
             lnp = self.buf("ln_part", (self._ln_blocks * 2 * max(d, 1024),), torch.float32)
+            if self._saved["p_img"] > 0:     # SA_image_dropout sat between the pre-norm and the K|V projection
+                _, _, seed, seed_dev = self._saved["drop"]
+                K.dropout(dimg, dimg, self._saved["p_img"], seed, SITE_IMAGE, seed_dev=seed_dev)
             K.layernorm_bwd(img.view(B * Tk_img, dk), self.img_ln[0], dimg, lnp)
             pn = enc.image_pre_norm_module
             self._ln_param_grads(lnp, dk, self.g(pn.weight, pn.bias), accumulate)
@@ -711,6 +766,8 @@ class TrainEngine(EncoderEngine):
             if overlap:
                 self._reduce_async(*self.bucket_layers[i])
         with _scope("conv"):
+            if sv["drop"][0] > 0:      # dropout after the scaled, position-added subsampler output
+                K.dropout(g, g, sv["drop"][0], sv["drop"][2], SITE_EMBED, seed_dev=sv["drop"][3])
             self._conv_bwd(g, B, T, accumulate)
         if overlap:
             self._reduce_async(*self.bucket_conv)

@@ -67,11 +67,13 @@ def multimodal_attention(sd: Dict[str, Tensor], p: str, text: Tensor, img: Tenso
 
 
 def fuse_img_feat(sd, prefix: str, mm_cfg, text: Tensor, idx: int, image: Tensor,
-                  image_mask: Optional[Tensor], rnd: Callable = _id) -> Tensor:
-    """text [T,B,d], image [Tk,B,Dk] -> fused [T,B,d] (eval mode: the three dropouts are identity)."""
+                  image_mask: Optional[Tensor], rnd: Callable = _id, drop: Callable = lambda site, x: x) -> Tensor:
+    """text [T,B,d], image [Tk,B,Dk] -> fused [T,B,d].  ``drop(("image",), x)`` = SA_image_dropout (:596); identity in
+    eval mode (SA_text_dropout / SA_attention_dropout are not modelled: the device path requires them to be 0)."""
     if mm_cfg.image_pre_norm:
         image = F.layer_norm(image, (image.shape[-1],), sd[prefix + "image_pre_norm_module.weight"],
                              sd[prefix + "image_pre_norm_module.bias"], 1e-5)
+    image = drop(("image",), image)
     kind = mm_cfg.multimodal_attention_type
     if kind == "selective_attention":
         out, _ = selective_attention(sd, f"{prefix}selective_attns.{idx}.", text, image, image, image_mask, rnd)
@@ -90,7 +92,7 @@ def fuse_img_feat(sd, prefix: str, mm_cfg, text: Tensor, idx: int, image: Tensor
 def mm_encoder_forward(sd, mm_cfg, src_tokens: Tensor, src_lengths: Tensor, imgs_list: List[Tensor],
                        img_masks_list: List[Optional[Tensor]], num_heads: int, prefix: str = "",
                        return_all_hiddens: bool = False, training: bool = False,
-                       draws: Optional[tuple] = None, rnd: Callable = _id):
+                       draws: Optional[tuple] = None, rnd: Callable = _id, drop: Callable = lambda site, x: x):
     """MM_S2STransformerEncoder.forward on the plain-S2T + fusion-at-top branch.
 
     ``training`` only switches the modality-dropout glue on (ordinary dropouts stay off so the result
@@ -99,7 +101,7 @@ def mm_encoder_forward(sd, mm_cfg, src_tokens: Tensor, src_lengths: Tensor, imgs
     raises NameError (:500); the evident intent -- zero the speech states -- is what is restated.
     A batch without padding makes the reference raise IndexError (:527); here it is an all-False mask.
     """
-    out = s2t_encoder_forward(sd, src_tokens, src_lengths, num_heads, prefix, return_all_hiddens, rnd=rnd)
+    out = s2t_encoder_forward(sd, src_tokens, src_lengths, num_heads, prefix, return_all_hiddens, rnd=rnd, drop=drop)
     if mm_cfg is None or not mm_cfg.is_fusion_top or not imgs_list:
         return out
     imgs_list = list(imgs_list)
@@ -112,7 +114,8 @@ def mm_encoder_forward(sd, mm_cfg, src_tokens: Tensor, src_lengths: Tensor, imgs
                 imgs_list = [torch.zeros_like(i) for i in imgs_list]
     xs = []
     for idx, (img, img_mask) in enumerate(zip(imgs_list, img_masks_list)):
-        xs.append(fuse_img_feat(sd, prefix, mm_cfg, out["encoder_out"][0], idx, img.transpose(0, 1), img_mask, rnd))
+        xs.append(fuse_img_feat(sd, prefix, mm_cfg, out["encoder_out"][0], idx, img.transpose(0, 1), img_mask, rnd,
+                                drop))
     res = xs[0]
     for x in xs[1:]:
         res = res + x

@@ -86,24 +86,32 @@ def multihead_self_attention(sd, p: str, x: Tensor, key_padding_mask: Tensor, nu
     return F.linear(rnd(a), rnd(sd[p + "out_proj.weight"]), sd[p + "out_proj.bias"])
 
 
-def encoder_layer(sd, p: str, x: Tensor, mask: Tensor, num_heads: int, rnd: Callable = _id) -> Tensor:
-    """Pre-LN TransformerEncoderLayer, ReLU, eval mode (dropout = identity)."""
+def _no_drop(site, x):
+    return x
+
+
+def encoder_layer(sd, p: str, x: Tensor, mask: Tensor, num_heads: int, rnd: Callable = _id,
+                  drop: Callable = _no_drop, index: int = 0) -> Tensor:
+    """Pre-LN TransformerEncoderLayer, ReLU.  ``drop(site, x)`` stands for the layer's three FairseqDropout modules
+    (sites ("attn", i), ("act", i), ("ffn", i): after self-attention, after the activation, after fc2); identity in eval
+    mode.  Attention-probability dropout is not modelled (the device path requires it to be 0)."""
     C = x.shape[-1]
     r = x
     h = F.layer_norm(x, (C,), sd[p + "self_attn_layer_norm.weight"], sd[p + "self_attn_layer_norm.bias"], 1e-5)
     h = multihead_self_attention(sd, p + "self_attn.", h, mask, num_heads, rnd)
-    x = r + h
+    x = r + drop(("attn", index), h)
     r = x
     h = F.layer_norm(x, (C,), sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"], 1e-5)
-    h = F.relu(F.linear(rnd(h), rnd(sd[p + "fc1.weight"]), sd[p + "fc1.bias"]))
+    h = drop(("act", index), F.relu(F.linear(rnd(h), rnd(sd[p + "fc1.weight"]), sd[p + "fc1.bias"])))
     h = F.linear(rnd(h), rnd(sd[p + "fc2.weight"]), sd[p + "fc2.bias"])
-    return r + h
+    return r + drop(("ffn", index), h)
 
 
 def s2t_encoder_forward(sd: Dict[str, Tensor], src_tokens: Tensor, src_lengths: Tensor, num_heads: int,
                         prefix: str = "", return_all_hiddens: bool = False, no_scale_embedding: bool = False,
-                        rnd: Callable = _id) -> Dict[str, List[Tensor]]:
-    """S2TTransformerEncoder._forward in eval mode.  src_tokens [B, T, 80] (post-CMVN, zero-padded)."""
+                        rnd: Callable = _id, drop: Callable = _no_drop) -> Dict[str, List[Tensor]]:
+    """S2TTransformerEncoder._forward.  src_tokens [B, T, 80] (post-CMVN, zero-padded).  ``drop(site, x)``: the
+    training-mode dropout modules (site ("embed",) after the positions, then the layers'); identity = eval mode."""
     x, in_lens = conv1d_subsampler(sd, prefix, src_tokens, src_lengths, rnd)
     T, B, C = x.shape
     x = (1.0 if no_scale_embedding else math.sqrt(C)) * x
@@ -111,10 +119,11 @@ def s2t_encoder_forward(sd: Dict[str, Tensor], src_tokens: Tensor, src_lengths: 
     pos_idx = make_positions(~mask, 1)                       # padded -> 1 (zero row), valid t -> t + 2
     table = sinusoidal_table(T + 2, C, 1)
     x = x + table[pos_idx.reshape(-1)].view(B, T, C).transpose(0, 1)
+    x = drop(("embed",), x)
     states = []
     i = 0
     while f"{prefix}transformer_layers.{i}.fc1.weight" in sd:
-        x = encoder_layer(sd, f"{prefix}transformer_layers.{i}.", x, mask, num_heads, rnd)
+        x = encoder_layer(sd, f"{prefix}transformer_layers.{i}.", x, mask, num_heads, rnd, drop, i)
         if return_all_hiddens:
             states.append(x)
         i += 1

@@ -121,7 +121,7 @@ def main():
     torch.manual_seed(0)
     args = make_args(a.preset, multimodal_translation_config_yaml=cfg)
     enc = MM_S2STransformerEncoder(args, build_unused_projections=False).to(dev).train()
-    enc.dropout_p = 0.0
+    enc.dropout_p = enc.activation_dropout_p = enc.attention_dropout_p = 0.0
     eng = enc.train_engine()
     B, n = a.batch, int(16000 * a.seconds)
     g = torch.Generator(device=dev).manual_seed(1 + rank)

@@ -454,3 +454,14 @@ class _FakeLib:
 
 
 _lib = _FakeLib
+
+
+def dropout(x, out, p, seed, site, resid=None, seed_dev=None):
+    if seed_dev is not None:
+        seed = int(seed) + int(seed_dev.view(-1)[0])
+    g = torch.Generator().manual_seed((int(seed) * 1000003 + int(site)) % (2 ** 63 - 1))
+    keep = torch.rand(x.numel(), generator=g) >= p
+    v = (x.reshape(-1).float() * keep / (1.0 - p))
+    if resid is not None:
+        v = v + resid.reshape(-1)
+    out.view(-1).copy_(v.to(out.dtype))

@@ -59,7 +59,7 @@ def test_full_model_training_step_chain(cuda):
     from test_gpu_encoder import _build
 
     enc, args, cfg = _build("small", "selective_attention", True)
-    enc.dropout_p = 0.0
+    enc.dropout_p = enc.activation_dropout_p = enc.attention_dropout_p = 0.0
     enc.SA_image_dropout = enc.SA_attention_dropout = enc.SA_text_dropout = 0.0
     B, Lu, heads = 3, 30, args.encoder_attention_heads
     d = args.encoder_embed_dim
@@ -134,7 +134,7 @@ def test_graphed_model_train_step_matches_eager(cuda):
     res = {}
     for mode in ("eager", "graph"):
         enc, args, cfg = _build("small", "selective_attention", True)
-        enc.dropout_p = 0.0
+        enc.dropout_p = enc.activation_dropout_p = enc.attention_dropout_p = 0.0
         enc.SA_image_dropout = enc.SA_attention_dropout = enc.SA_text_dropout = 0.0
         enc.cuda().train()
         eeng = enc.train_engine()
@@ -186,7 +186,7 @@ def test_model_train_step_api(cuda):
     args = make_args("small", multimodal_translation_config_yaml=cfg)
     args.decoder_layers = 2
     model = MM_S2UTTransformerModel(args, target_code_size=100, build_unused_projections=False).cuda().train()
-    model.encoder.dropout_p = 0.0
+    model.encoder.dropout_p = model.encoder.activation_dropout_p = model.encoder.attention_dropout_p = 0.0
     B, Lu = 2, 20
     wavs, _ = synth.synth_batch(5, B, 1.5, ragged=True)
     wav, lens = synth.pad_waveforms(wavs)

