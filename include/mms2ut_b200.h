@@ -268,6 +268,14 @@ int mm_softmax_bwd(const float* scores, const void* dprobs, int32_t dprobs_is_op
                    int64_t rows, int32_t rows_per_batch,
                    int32_t n_keys, const int32_t* kv_lens, int32_t heads, void* probs, void* dscores, int64_t ld_out,
                    int32_t valid_rows, int32_t causal, int32_t dtype, void* stream);
+/* The same with attention dropout on the probabilities (fairseq MultiheadAttention dropout_module, fuse.py:111): the mask
+ * m = keep(seed + *seed_dev, site, row * ld_out + k) / (1 - p) is regenerated, probs = P m (the matrix that multiplied V),
+ * dscores = P o (dprobs m - rowsum(P o dprobs m)).  dprobs == NULL and dscores == NULL: the training FORWARD (softmax +
+ * dropout -> probs). */
+int mm_softmax_dropout_bwd(const float* scores, const void* dprobs, int32_t dprobs_is_op, int64_t ld_dprobs, int64_t ld_in,
+                           int64_t rows, int32_t rows_per_batch, int32_t n_keys, const int32_t* kv_lens, int32_t heads,
+                           void* probs, void* dscores, int64_t ld_out, int32_t valid_rows, int32_t causal, float drop_p,
+                           uint64_t seed, const uint64_t* seed_dev, uint32_t site, int32_t dtype, void* stream);
 /* Backward of mm_label_smoothed_nll summed over rows (fairseq label_smoothed_nll_loss, reduce=True), times grad_scale:
  * dlogits 16-bit [rows, ld_out] (columns >= vocab and padding rows are 0) -- the A operand of the tied output
  * projection's dgrad / wgrad.  mm_embed_tokens_bwd: table_grad[token] += scale * dx[row] (atomic; padding rows skipped). */

@@ -144,6 +144,9 @@ EXPORTS = {
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "mm_softmax_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                  C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "mm_softmax_dropout_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                         C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                         C.c_int32, C.c_float, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p]),
     "mm_label_smoothed_nll_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_float,
                                             C.c_float, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "mm_embed_tokens_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p,

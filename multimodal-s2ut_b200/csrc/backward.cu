@@ -306,17 +306,34 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 //   P = softmax(S[:, :valid]) ; D = sum_k P dP ; dS = P (dP - D)   (keys >= valid: P = dS = 0 up to ld_out)
 // rows are laid out [batch][rows_per_batch]; valid keys of a batch = kv_lens[batch / heads] (or n_keys).
 // ---------------------------------------------------------------------------------------------------
+// counter-based dropout mask: see the dropout kernel below
+__device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned site, unsigned long long i, float p) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(site + 1) + i * 0xD1342543DE82EF95ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (float)(z >> 40) * (1.0f / 16777216.0f) >= p;      // 24 uniform bits
+}
+
+
 // NPL = keys per lane held in registers (n_keys <= 32 * NPL): scores and dP are read once.
+// With drop_p > 0 the probabilities carry attention dropout: m = keep(seed, site, row * ld_out + k) / (1 - p);
+// P_out = P m (what multiplied V in the forward pass), dP' = dP m, dS = P (dP' - sum_k P dP').  dPv == NULL: forward
+// use (softmax + dropout -> P_out only).
 template <int NPL, typename OpT>
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ S, const void* __restrict__ dPv,
                                                            int dp_is_op, long long ld_dp,
                                                            long long ld_in, long long rows, int rows_per_batch,
                                                            int n_keys, const int* __restrict__ kv_lens, int heads,
                                                            OpT* __restrict__ P, OpT* __restrict__ dS, long long ld_out,
-                                                           int valid_rows, int causal) {
+                                                           int valid_rows, int causal, float drop_p,
+                                                           unsigned long long seed,
+                                                           const unsigned long long* __restrict__ seed_dev,
+                                                           unsigned site) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows || (int)(row % rows_per_batch) >= valid_rows) return;
+  if (seed_dev) seed += *seed_dev;
   int valid = n_keys;
   if (kv_lens) {
     const int v = kv_lens[(row / rows_per_batch) / heads];
@@ -336,7 +353,8 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
     float2 a = make_float2(-INFINITY, -INFINITY), g = make_float2(0.f, 0.f);
     if (k + 1 < valid) {
       a = __ldcs(reinterpret_cast<const float2*>(s + k));
-      if (dp_is_op) {
+      if (!dPv) {
+      } else if (dp_is_op) {
         const uint32_t q = __ldcs(reinterpret_cast<const uint32_t*>(d16 + k));
         const OpT* e = reinterpret_cast<const OpT*>(&q);
         g = make_float2(OpTraits<OpT>::to_float(e[0]), OpTraits<OpT>::to_float(e[1]));
@@ -344,7 +362,8 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
         g = __ldcs(reinterpret_cast<const float2*>(d + k));
       }
     } else if (k < valid) {
-      a.x = s[k], g.x = dp_is_op ? OpTraits<OpT>::to_float(d16[k]) : d[k];
+      a.x = s[k];
+      if (dPv) g.x = dp_is_op ? OpTraits<OpT>::to_float(d16[k]) : d[k];
     }
     sv[2 * i] = a.x, sv[2 * i + 1] = a.y, dv[2 * i] = g.x, dv[2 * i + 1] = g.y;
     mx = fmaxf(mx, fmaxf(a.x, a.y));
@@ -358,25 +377,34 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
   }
   sum = warp_sum(sum);
   const float inv = valid > 0 ? 1.0f / sum : 0.f;
+  const float dinv = 1.0f / (1.0f - drop_p);
   float dot = 0.f;
+  float mk[NPL];     // attention-dropout multiplier of each element (1 without dropout)
 #pragma unroll
   for (int i = 0; i < NPL; ++i) {
     sv[i] *= inv;
+    mk[i] = 1.0f;
+    if (drop_p > 0.f) {
+      const int k = 2 * (lane + 32 * (i >> 1)) + (i & 1);
+      mk[i] = dropout_keep(seed, site, (unsigned long long)(row * ld_out + k), drop_p) ? dinv : 0.f;
+      dv[i] *= mk[i];
+    }
     dot += sv[i] * dv[i];
   }
   dot = warp_sum(dot);
   OpT* po = P ? P + row * ld_out : nullptr;
-  OpT* go = dS + row * ld_out;
+  OpT* go = dS ? dS + row * ld_out : nullptr;
 #pragma unroll
   for (int i = 0; i < NPL / 2; ++i) {
     const int k = 2 * (lane + 32 * i);
     if (k + 1 < ld_out) {
-      if (po) *reinterpret_cast<uint32_t*>(po + k) = OpTraits<OpT>::pack2(sv[2 * i], sv[2 * i + 1]);
-      *reinterpret_cast<uint32_t*>(go + k) =
-          OpTraits<OpT>::pack2(sv[2 * i] * (dv[2 * i] - dot), sv[2 * i + 1] * (dv[2 * i + 1] - dot));
+      if (po) *reinterpret_cast<uint32_t*>(po + k) = OpTraits<OpT>::pack2(sv[2 * i] * mk[2 * i], sv[2 * i + 1] * mk[2 * i + 1]);
+      if (go)
+        *reinterpret_cast<uint32_t*>(go + k) =
+            OpTraits<OpT>::pack2(sv[2 * i] * (dv[2 * i] - dot), sv[2 * i + 1] * (dv[2 * i + 1] - dot));
     } else if (k < ld_out) {
-      if (po) po[k] = OpTraits<OpT>::cvt(sv[2 * i]);
-      go[k] = OpTraits<OpT>::cvt(sv[2 * i] * (dv[2 * i] - dot));
+      if (po) po[k] = OpTraits<OpT>::cvt(sv[2 * i] * mk[2 * i]);
+      if (go) go[k] = OpTraits<OpT>::cvt(sv[2 * i] * (dv[2 * i] - dot));
     }
   }
   // columns beyond the register span (ld_out > 32 * NPL cannot happen: checked on the host)
@@ -386,16 +414,17 @@ template <typename OpT>
 static int launch_softmax_bwd(const float* S, const void* dP, int dp_is_op, long long ld_dp, long long ld_in,
                               long long rows, int rpb, int n_keys,
                               const int* kv_lens, int heads, void* P, void* dS, long long ld_out, int valid_rows,
-                              int causal, cudaStream_t s) {
+                              int causal, float drop_p, unsigned long long seed, const unsigned long long* seed_dev,
+                              unsigned site, cudaStream_t s) {
   const unsigned grid = (unsigned)((rows + 7) / 8);
   OpT* p = reinterpret_cast<OpT*>(P);
   OpT* g = reinterpret_cast<OpT*>(dS);
   if (ld_out <= 256)
-    softmax_bwd_kernel<8, OpT><<<grid, 256, 0, s>>>(S, dP, dp_is_op, ld_dp, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows, causal);
+    softmax_bwd_kernel<8, OpT><<<grid, 256, 0, s>>>(S, dP, dp_is_op, ld_dp, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows, causal, drop_p, seed, seed_dev, site);
   else if (ld_out <= 640)
-    softmax_bwd_kernel<20, OpT><<<grid, 256, 0, s>>>(S, dP, dp_is_op, ld_dp, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows, causal);
+    softmax_bwd_kernel<20, OpT><<<grid, 256, 0, s>>>(S, dP, dp_is_op, ld_dp, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows, causal, drop_p, seed, seed_dev, site);
   else if (ld_out <= 2048)
-    softmax_bwd_kernel<64, OpT><<<grid, 256, 0, s>>>(S, dP, dp_is_op, ld_dp, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows, causal);
+    softmax_bwd_kernel<64, OpT><<<grid, 256, 0, s>>>(S, dP, dp_is_op, ld_dp, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows, causal, drop_p, seed, seed_dev, site);
   else
     return bad_arg("softmax_bwd: at most 2048 keys");
   return 0;
@@ -603,14 +632,6 @@ __global__ void __launch_bounds__(128) embed_bwd_kernel(const long long* __restr
 // from (seed, site) instead of storing it.  Not torch's Philox stream (a drop-in cannot share torch's generator state
 // with a fused kernel anyway); splitmix64 finaliser of the element counter.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned site, unsigned long long i, float p) {
-  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(site + 1) + i * 0xD1342543DE82EF95ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (float)(z >> 40) * (1.0f / 16777216.0f) >= p;      // 24 uniform bits
-}
-
 // out = resid + dropout(x)  (resid optional); x / out fp32 or 16-bit (same type), n elements, in place allowed
 template <typename T, typename OpT>
 __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, const float* __restrict__ resid,
@@ -745,23 +766,36 @@ extern "C" int mm_layernorm_bwd(const float* x, const float* gamma, const float*
 }
 
 extern "C" int mm_softmax_bwd(const float* scores, const void* dprobs, int32_t dprobs_is_op, int64_t ld_dprobs,
-                              int64_t ld_in, int64_t rows,
-                              int32_t rows_per_batch, int32_t n_keys, const int32_t* kv_lens, int32_t heads, void* probs,
-                              void* dscores, int64_t ld_out, int32_t valid_rows, int32_t causal, int32_t dtype,
-                              void* stream) {
+                              int64_t ld_in, int64_t rows, int32_t rows_per_batch, int32_t n_keys, const int32_t* kv_lens,
+                              int32_t heads, void* probs, void* dscores, int64_t ld_out, int32_t valid_rows, int32_t causal,
+                              int32_t dtype, void* stream) {
+  return mm_softmax_dropout_bwd(scores, dprobs, dprobs_is_op, ld_dprobs, ld_in, rows, rows_per_batch, n_keys, kv_lens,
+                                heads, probs, dscores, ld_out, valid_rows, causal, 0.f, 0, nullptr, 0, dtype, stream);
+}
+
+extern "C" int mm_softmax_dropout_bwd(const float* scores, const void* dprobs, int32_t dprobs_is_op, int64_t ld_dprobs,
+                                      int64_t ld_in, int64_t rows, int32_t rows_per_batch, int32_t n_keys,
+                                      const int32_t* kv_lens, int32_t heads, void* probs, void* dscores, int64_t ld_out,
+                                      int32_t valid_rows, int32_t causal, float drop_p, uint64_t seed,
+                                      const uint64_t* seed_dev, uint32_t site, int32_t dtype, void* stream) {
   if (valid_rows <= 0) valid_rows = rows_per_batch;
-  if (!scores || !dprobs || !dscores || rows <= 0 || n_keys <= 0 || rows_per_batch <= 0 || heads <= 0)
+  if (!scores || (!dscores && !probs) || (dprobs && !dscores) || (!dprobs && dscores) || rows <= 0 || n_keys <= 0 ||
+      rows_per_batch <= 0 || heads <= 0 || drop_p < 0.f || drop_p >= 1.f)
     return bad_arg("softmax_bwd");
   if (ld_out < n_keys || ld_in < n_keys) return bad_arg("softmax_bwd: leading dimensions");
+  if (!dprobs) ld_dprobs = ld_in;
   if ((ld_in & 1) || (ld_out & 1) || (ld_dprobs & 1) || ld_dprobs < n_keys ||
       (reinterpret_cast<uintptr_t>(scores) & 7) || (reinterpret_cast<uintptr_t>(dprobs) & 7))
     return bad_arg("softmax_bwd: leading dimensions must be even and the inputs 8-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned long long* sd = reinterpret_cast<const unsigned long long*>(seed_dev);
   const int rc = dtype == MM_DTYPE_F16
-                     ? launch_softmax_bwd<__half>(scores, dprobs, dprobs_is_op, ld_dprobs, ld_in, rows, rows_per_batch, n_keys, kv_lens, heads,
-                                                  probs, dscores, ld_out, valid_rows, causal, s)
-                     : launch_softmax_bwd<__nv_bfloat16>(scores, dprobs, dprobs_is_op, ld_dprobs, ld_in, rows, rows_per_batch, n_keys, kv_lens,
-                                                         heads, probs, dscores, ld_out, valid_rows, causal, s);
+                     ? launch_softmax_bwd<__half>(scores, dprobs, dprobs_is_op, ld_dprobs, ld_in, rows, rows_per_batch,
+                                                  n_keys, kv_lens, heads, probs, dscores, ld_out, valid_rows, causal,
+                                                  drop_p, seed, sd, site, s)
+                     : launch_softmax_bwd<__nv_bfloat16>(scores, dprobs, dprobs_is_op, ld_dprobs, ld_in, rows,
+                                                         rows_per_batch, n_keys, kv_lens, heads, probs, dscores, ld_out,
+                                                         valid_rows, causal, drop_p, seed, sd, site, s);
   if (rc) return rc;
   MM_CHECK_LAUNCH("softmax_bwd_kernel launch");
   return 0;

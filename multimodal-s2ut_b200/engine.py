@@ -269,9 +269,11 @@ class EncoderEngine:
                    aux0=x, aux_ld=d, out0=x, out0_ld=d, block_n=bn)
 
     def fuse(self, j: int, text_f32: torch.Tensor, text_op: torch.Tensor, img: torch.Tensor,
-             img_mask: Optional[torch.Tensor], B: int, T: int, out_tbc: torch.Tensor, img_dropout=None) -> None:
+             img_mask: Optional[torch.Tensor], B: int, T: int, out_tbc: torch.Tensor, img_dropout=None,
+             attn_dropout=None) -> None:
         """fuse_img_feat for image type j; writes the fused states into out_tbc [T, B, d] fp32.
-        img_dropout = (p, seed, seed_dev, site): SA_image_dropout on the pre-normed image (training, :596)."""
+        img_dropout / attn_dropout = (p, seed, seed_dev, site): SA_image_dropout on the pre-normed image (:596) and
+        SA_attention_dropout on the attention probabilities (fuse.py:111), training only."""
         enc, F, d, op, bn = self.enc, self.fusion[j], self.d, self.op_dtype, self.block_n
         M = B * T
         Tk_img, dk = img.shape[1], img.shape[2]
@@ -323,7 +325,13 @@ class EncoderEngine:
             if extra:
                 mask = torch.nn.functional.pad(mask, (0, 1))
             mask = mask.contiguous()
-        K.softmax_rows(S, Tkp, M, Tk, P, Tkp, key_mask=mask, rows_per_seq=T)
+        if attn_dropout is not None and attn_dropout[0] > 0:
+            if mask is not None:
+                raise NotImplementedError("SA_attention_dropout with an image key mask")
+            K.softmax_bwd(S, None, Tkp, M, T, Tk, None, Tkp, probs=P, drop_p=attn_dropout[0], seed=attn_dropout[1],
+                          seed_dev=attn_dropout[2], site=attn_dropout[3])
+        else:
+            K.softmax_rows(S, Tkp, M, Tk, P, Tkp, key_mask=mask, rows_per_seq=T)
         o = self.buf("o_img", (M, d), op)
         K.gemm(a0=P, a0_ld=Tkp, a0_bs=T * Tkp, rows=T, batches=B, w=vt, w_ld=Tkp, w_bs=d * Tkp, w_batched=True, n=d,
                k=Tkp, mode=K.EPI_OP, out0=o, out0_ld=d, out0_bs=T * d, block_n=bn)

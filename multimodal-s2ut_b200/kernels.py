@@ -389,22 +389,27 @@ def layernorm_bwd(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, partia
                    "mm_layernorm_bwd")
 
 
-def softmax_bwd(scores: torch.Tensor, dprobs: torch.Tensor, ld_in: int, rows: int, rows_per_batch: int, n_keys: int,
-                dscores: torch.Tensor, ld_out: int, probs: Optional[torch.Tensor] = None,
+def softmax_bwd(scores: torch.Tensor, dprobs: Optional[torch.Tensor], ld_in: int, rows: int, rows_per_batch: int,
+                n_keys: int, dscores: Optional[torch.Tensor], ld_out: int, probs: Optional[torch.Tensor] = None,
                 kv_lens: Optional[torch.Tensor] = None, heads: int = 1, valid_rows: int = 0,
-                causal: bool = False, ld_dprobs: Optional[int] = None) -> None:
-    assert scores.dtype == torch.float32 and (dprobs.dtype == torch.float32 or dprobs.dtype == dscores.dtype)
-    dp_is_op = dprobs.dtype != torch.float32
+                causal: bool = False, ld_dprobs: Optional[int] = None, drop_p: float = 0.0, seed: int = 0,
+                seed_dev: Optional[torch.Tensor] = None, site: int = 0) -> None:
+    """probs = softmax(scores) (x attention-dropout mask), dscores = softmax backward of dprobs (see the header).
+    dprobs = dscores = None: forward use (softmax + dropout -> probs)."""
+    assert scores.dtype == torch.float32
+    out_dt = (dscores if dscores is not None else probs).dtype
+    assert dprobs is None or dprobs.dtype == torch.float32 or dprobs.dtype == out_dt
+    dp_is_op = dprobs is not None and dprobs.dtype != torch.float32
     ld_dp = ld_in if ld_dprobs is None else ld_dprobs
     assert kv_lens is None or kv_lens.dtype == torch.int32
-    assert probs is None or probs.dtype == dscores.dtype
+    assert probs is None or probs.dtype == out_dt
+    assert seed_dev is None or seed_dev.dtype == torch.int64
     lib = _lib.load()
-    with _Launch("softmax_bwd", 8.0 * rows * n_keys + 4.0 * rows * ld_out):
-        _lib.check(lib.mm_softmax_bwd(_ptr(scores), _ptr(dprobs), int(dp_is_op), ld_dp, ld_in, rows, rows_per_batch, n_keys,
-                                      _ptr(kv_lens),
-                                      heads, _ptr(probs), _ptr(dscores), ld_out, valid_rows, int(causal),
-                                      dtype_code(dscores.dtype), _stream()),
-                   "mm_softmax_bwd")
+    with _Launch("softmax_bwd" if dprobs is not None else "softmax_dropout", 8.0 * rows * n_keys + 4.0 * rows * ld_out):
+        _lib.check(lib.mm_softmax_dropout_bwd(_ptr(scores), _ptr(dprobs), int(dp_is_op), ld_dp, ld_in, rows, rows_per_batch,
+                                              n_keys, _ptr(kv_lens), heads, _ptr(probs), _ptr(dscores), ld_out, valid_rows,
+                                              int(causal), drop_p, seed & 0xFFFFFFFFFFFFFFFF, _ptr(seed_dev), site,
+                                              dtype_code(out_dt), _stream()), "mm_softmax_dropout_bwd")
 
 
 def glu_bwd(pre: torch.Tensor, dy: torch.Tensor, rows: int, n: int, dpre: torch.Tensor, scale: float = 1.0) -> None:

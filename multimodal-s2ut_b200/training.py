@@ -23,8 +23,9 @@ is re-pointed to a view), ordered so that the packed layouts the kernels produce
 are contiguous slices.  ``all_reduce_grads`` runs NCCL (or gloo) over ``flat_g`` in buckets; ``adam_step`` is one kernel.
 
 Element-wise dropout (embedding, residual and activation sites, SA_image_dropout) uses counter-based masks that the
-backward pass regenerates (``mm_dropout``); modality dropout (per-batch image zeroing) works.  Not built (raises):
-dropout on attention probabilities, SA_text_dropout, image key masks, several image-feature types, and the device
+backward pass regenerates (``mm_dropout``); attention dropout (encoder self-attention, SA_attention_dropout) runs the
+un-fused score / softmax+dropout / P V path in the training forward; modality dropout (per-batch image zeroing) works.
+Not built (raises): SA_text_dropout, image key masks, several image-feature types, and the device
 feature store in the backward pass.
 """
 from __future__ import annotations
@@ -49,11 +50,12 @@ def _split_k(n: int, kin: int, mp: int) -> int:
 
 
 # dropout sites (the counter-based mask is a function of (seed, site, element index))
-SITE_EMBED, SITE_IMAGE = 0, 8
+SITE_EMBED, SITE_IMAGE, SITE_SA_ATTN = 0, 8, 9
 
 
 def site_layer(i: int, which: int) -> int:
-    """which: 0 = after the self-attention out_proj, 1 = after ReLU (activation dropout), 2 = after fc2."""
+    """which: 0 = after the self-attention out_proj, 1 = after ReLU (activation dropout), 2 = after fc2,
+    3 = the self-attention probabilities (attention dropout)."""
     return 16 * (i + 1) + which
 
 
@@ -335,7 +337,21 @@ class TrainEngine(EncoderEngine):
             K.layernorm(x_in, L["ln1_g"], L["ln1_b"], out_op=s["h1"])
         K.gemm(a0=s["h1"], a0_ld=d, rows=M, w=L["wqkv"], n=3 * d, k=d, mode=K.EPI_OP, bias=L["bqkv"], scale=64 ** -0.5,
                scale_cols=d, out0=s["qkv"], out0_ld=3 * d, block_n=bn)
-        K.self_attention(s["qkv"], seq_lens, B, T, self.heads, s["att"])
+        if self._p_attn > 0:
+            # attention dropout: un-fused S = q k^T -> softmax + dropout -> P V on the head-mode GEMMs (the fused
+            # attention kernel has no mask generator); the backward pass regenerates the same mask
+            H, Tp = self.heads, _round_up(T, 64)
+            hd = dict(heads=H, head_stride=64, batches=B * H, w_batched=True, block_n=bn)
+            S = self.buf("a_S", (B * H, Tp, Tp), torch.float32)
+            P = self.buf("a_P", (B * H, Tp, Tp), op)
+            K.gemm(a0=s["qkv"], a0_ld=3 * d, a0_bs=T * 3 * d, w=s["qkv"][:, d:], w_ld=3 * d, w_bs=T * 3 * d, out0=S,
+                   rows=T, n=T, k=64, mode=K.EPI_F32, out0_ld=Tp, out0_bs=Tp * Tp, a_hm=True, w_hm=True, **hd)
+            K.softmax_bwd(S, None, Tp, B * H * Tp, Tp, T, None, Tp, probs=P, kv_lens=seq_lens, heads=H, valid_rows=T,
+                          drop_p=self._p_attn, seed=seed, seed_dev=seed_dev, site=site_layer(i, 3))
+            K.gemm(a0=P, a0_ld=Tp, a0_bs=Tp * Tp, rows=T, k=T, w=s["qkv"][:, 2 * d:], w_ld=3 * d, w_bs=T * 3 * d,
+                   w_mn=True, w_hm=True, n=64, mode=K.EPI_OP, out0=s["att"], out0_ld=d, out0_bs=T * d, out_hm=True, **hd)
+        else:
+            K.self_attention(s["qkv"], seq_lens, B, T, self.heads, s["att"])
         if fused:
             K.gemm_resid_ln(s["att"], L["wo"], L["bo"], x_in, L["ln2_g"], L["ln2_b"], s["h2"], x_out=s["x_mid"])
         elif p_drop > 0:     # x_mid = x_in + dropout(out_proj(att))
@@ -373,12 +389,10 @@ class TrainEngine(EncoderEngine):
         """dropout_seed (+ the int64 device scalar dropout_seed_dev, for CUDA-graph replay) seeds the element-wise
         dropout masks of this step; default: a counter advanced per call on top of torch.initial_seed()."""
         enc = self.enc
-        if max(getattr(enc, "attention_dropout_p", 0.0), getattr(enc, "SA_text_dropout", 0.0),
-               getattr(enc, "SA_attention_dropout", 0.0)) > 0:
-            raise NotImplementedError(
-                "dropout on attention probabilities (--attention-dropout, SA_attention_dropout) and SA_text_dropout are "
-                "not built: set them to 0.  --dropout, --activation-dropout / --relu-dropout, SA_image_dropout and "
-                "modality dropout are supported")
+        if float(getattr(enc, "SA_text_dropout", 0.0) or 0.0) > 0:
+            raise NotImplementedError("SA_text_dropout is not built (the reference's YAML ships 0): set it to 0")
+        self._p_attn = float(getattr(enc, "attention_dropout_p", 0.0) or 0.0)
+        p_sa = float(getattr(enc, "SA_attention_dropout", 0.0) or 0.0)
         p_drop, p_act = float(enc.dropout_p), float(getattr(enc, "activation_dropout_p", 0.0))
         p_img = float(getattr(enc, "SA_image_dropout", 0.0) or 0.0)
         if dropout_seed is None:
@@ -397,7 +411,8 @@ class TrainEngine(EncoderEngine):
         M, d = B * T, self.d
         if p_drop > 0:      # S2TTransformerEncoder: x = dropout_module(embed_scale * x + positions)
             K.dropout(x, x, p_drop, self._drop[2], SITE_EMBED, seed_dev=dropout_seed_dev)
-        saved = dict(B=B, T=T, m=m, x1=x1, seq_lens=seq_lens, layers=[], fused=False, drop=self._drop, p_img=p_img)
+        saved = dict(B=B, T=T, m=m, x1=x1, seq_lens=seq_lens, layers=[], fused=False, drop=self._drop, p_img=p_img,
+                     p_attn=self._p_attn, p_sa=p_sa)
         text_f32 = self.buf("text_f32", (M, d), torch.float32)
         text_op = self.buf("text_op", (M, d), self.op_dtype)
         fused_fwd = self.train_fused_ln and p_drop == 0
@@ -423,7 +438,8 @@ class TrainEngine(EncoderEngine):
             img = img.to(self.device, non_blocking=True).float().contiguous()
             out = torch.empty(T, B, d, dtype=torch.float32, device=self.device)
             self.fuse(0, text_f32, text_op, img, None, B, T, out,
-                      img_dropout=(p_img, self._drop[2], dropout_seed_dev, SITE_IMAGE))
+                      img_dropout=(p_img, self._drop[2], dropout_seed_dev, SITE_IMAGE),
+                      attn_dropout=(p_sa, self._drop[2], dropout_seed_dev, SITE_SA_ATTN))
             saved.update(fused=True, img=img)
         else:
             out = text_f32.view(B, T, d).transpose(0, 1).contiguous()
@@ -489,7 +505,7 @@ class TrainEngine(EncoderEngine):
     # backward
     # ------------------------------------------------------------------------------------------
     def _attention_bwd(self, s: dict, datt: torch.Tensor, dqkv: torch.Tensor, B: int, T: int,
-                       seq_lens: torch.Tensor) -> None:
+                       seq_lens: torch.Tensor, layer_index: int = 0) -> None:
         """dqkv [M, 3d] (16-bit; q part already x head_dim^-0.5) from datt [M, d] and the saved q|k|v.  All five
         contractions read q|k|v / datt and write dqkv in place of their (sequence, head) column blocks."""
         d, H, op, bn = self.d, self.heads, self.op_dtype, self.block_n
@@ -504,7 +520,9 @@ class TrainEngine(EncoderEngine):
         K.gemm(a0=datt, a0_ld=d, a0_bs=T * d, w=qkv[:, 2 * d:], w_ld=3 * d, w_bs=T * 3 * d, out0=dP, mode=K.EPI_OP, **sc)
         P = self.buf("a_P", (BH, Tp, Tp), op)
         dS = self.buf("a_dS", (BH, Tp, Tp), op)
-        K.softmax_bwd(S, dP, Tp, BH * Tp, Tp, T, dS, Tp, probs=P, kv_lens=seq_lens, heads=H, valid_rows=T)
+        _, _, seed, seed_dev = self._saved["drop"]
+        K.softmax_bwd(S, dP, Tp, BH * Tp, Tp, T, dS, Tp, probs=P, kv_lens=seq_lens, heads=H, valid_rows=T,
+                      drop_p=self._saved["p_attn"], seed=seed, seed_dev=seed_dev, site=site_layer(layer_index, 3))
         og = dict(rows=T, n=64, k=T, mode=K.EPI_OP, out0_ld=3 * d, out0_bs=T * 3 * d, out_hm=True, w_mn=True, w_hm=True,
                   a0_ld=Tp, a0_bs=Tp * Tp, **hd)
         K.gemm(a0=P, a_mn=True, w=datt, w_ld=d, w_bs=T * d, out0=dqkv[:, 2 * d:], **og)          # dV = P^T dO
@@ -551,7 +569,7 @@ class TrainEngine(EncoderEngine):
                block_n=bn)
         dqkv = self.buf("b_dqkv", (M, 3 * d), op)
         with _scope("attn"):
-            self._attention_bwd(s, datt, dqkv, B, T, seq_lens)
+            self._attention_bwd(s, datt, dqkv, B, T, seq_lens, i)
         self._linear_bwd(dqkv, 3 * d, s["h1"], M, 3 * d, d, self.g(a.q_proj.weight, a.k_proj.weight, a.v_proj.weight),
                          self.g(a.q_proj.bias, a.k_proj.bias, a.v_proj.bias), accumulate)
         K.gemm(a0=dqkv, a0_ld=3 * d, rows=M, w=L["wqkv"], w_ld=d, w_mn=True, n=d, k=3 * d, mode=K.EPI_F32, out0=dh,
@@ -608,7 +626,8 @@ class TrainEngine(EncoderEngine):
         K.gemm(a0=do, a0_ld=d, a0_bs=T * d, rows=T, w=vt, w_ld=Tkp, w_bs=d * Tkp, w_mn=True, n=Tk, k=d, mode=K.EPI_F32,
                out0=dP, out0_ld=Tkp, out0_bs=T * Tkp, **bt)                                        # dP = dO V^T
         dS = self.buf("f_dS", (B, T, Tkp), op)
-        K.softmax_bwd(S, dP, Tkp, M, T, Tk, dS, Tkp)
+        K.softmax_bwd(S, dP, Tkp, M, T, Tk, dS, Tkp, drop_p=self._saved["p_sa"], seed=self._saved["drop"][2],
+                      seed_dev=self._saved["drop"][3], site=SITE_SA_ATTN)
         dkv = self.buf("f_dkv", (B, Tk, 2 * d), op)
         kvg = dict(rows=Tk, a0_ld=Tkp, a0_bs=T * Tkp, a_mn=True, w_ld=d, w_bs=T * d, w_mn=True, n=d, k=T, mode=K.EPI_OP,
                    out0_ld=2 * d, out0_bs=Tk * 2 * d, **bt)

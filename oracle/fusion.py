@@ -26,7 +26,8 @@ _id = lambda t: t
 
 
 def selective_attention(sd: Dict[str, Tensor], p: str, query: Tensor, key: Tensor, value: Tensor,
-                        key_padding_mask: Optional[Tensor] = None, rnd: Callable = _id):
+                        key_padding_mask: Optional[Tensor] = None, rnd: Callable = _id,
+                        drop: Callable = lambda site, x: x):
     """query [Tq,B,d], key/value [Tk,B,Dk] -> (out [Tq,B,d], attn [B,Tq,Tk]); one head of width d."""
     Tq, B, _ = query.shape
     q = F.linear(rnd(query), rnd(sd[p + "q_proj.weight"]), sd[p + "q_proj.bias"])
@@ -39,13 +40,15 @@ def selective_attention(sd: Dict[str, Tensor], p: str, query: Tensor, key: Tenso
     if key_padding_mask is not None:
         attn = attn.masked_fill(key_padding_mask[:, None, :].to(torch.bool), float("-inf"))
     attn = attn.softmax(dim=-1)
+    attn = drop(("sa_attn_p",), attn)                   # self.attn_drop (fuse.py:111), [B, Tq, Tk]
     x = (rnd(attn) @ rnd(v)).transpose(0, 1).contiguous()
     x = F.linear(rnd(x), rnd(sd[p + "proj.weight"]), sd[p + "proj.bias"])
     return x, attn
 
 
 def multimodal_attention(sd: Dict[str, Tensor], p: str, text: Tensor, img: Tensor,
-                         img_mask: Optional[Tensor] = None, rnd: Callable = _id) -> Tensor:
+                         img_mask: Optional[Tensor] = None, rnd: Callable = _id,
+                         drop: Callable = lambda site, x: x) -> Tensor:
     """nn.MultiheadAttention(embed_dim=d, num_heads=1, kdim=vdim=Dk, add_bias_kv=True), eval mode."""
     Tq, B, d = text.shape
     bq, bk, bv = sd[p + "in_proj_bias"].chunk(3)
@@ -62,6 +65,7 @@ def multimodal_attention(sd: Dict[str, Tensor], p: str, text: Tensor, img: Tenso
     if img_mask is not None:
         attn = attn.masked_fill(img_mask[:, None, :], float("-inf"))
     attn = attn.softmax(dim=-1)
+    attn = drop(("sa_attn_p",), attn)                   # nn.MultiheadAttention(dropout=SA_attention_dropout)
     x = (rnd(attn) @ rnd(v)).transpose(0, 1).contiguous()
     return F.linear(rnd(x), rnd(sd[p + "out_proj.weight"]), sd[p + "out_proj.bias"])
 
@@ -69,16 +73,16 @@ def multimodal_attention(sd: Dict[str, Tensor], p: str, text: Tensor, img: Tenso
 def fuse_img_feat(sd, prefix: str, mm_cfg, text: Tensor, idx: int, image: Tensor,
                   image_mask: Optional[Tensor], rnd: Callable = _id, drop: Callable = lambda site, x: x) -> Tensor:
     """text [T,B,d], image [Tk,B,Dk] -> fused [T,B,d].  ``drop(("image",), x)`` = SA_image_dropout (:596); identity in
-    eval mode (SA_text_dropout / SA_attention_dropout are not modelled: the device path requires them to be 0)."""
+    eval mode; ("sa_attn_p",) = SA_attention_dropout on the probabilities (SA_text_dropout is not modelled)."""
     if mm_cfg.image_pre_norm:
         image = F.layer_norm(image, (image.shape[-1],), sd[prefix + "image_pre_norm_module.weight"],
                              sd[prefix + "image_pre_norm_module.bias"], 1e-5)
     image = drop(("image",), image)
     kind = mm_cfg.multimodal_attention_type
     if kind == "selective_attention":
-        out, _ = selective_attention(sd, f"{prefix}selective_attns.{idx}.", text, image, image, image_mask, rnd)
+        out, _ = selective_attention(sd, f"{prefix}selective_attns.{idx}.", text, image, image, image_mask, rnd, drop)
     elif kind == "multimodal_attention":
-        out = multimodal_attention(sd, f"{prefix}multimodal_attns.{idx}.", text, image, image_mask, rnd)
+        out = multimodal_attention(sd, f"{prefix}multimodal_attns.{idx}.", text, image, image_mask, rnd, drop)
     else:
         raise NotImplementedError(kind)
     if mm_cfg.use_selective_gate:

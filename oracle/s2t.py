@@ -69,7 +69,7 @@ def conv1d_subsampler(sd: Dict[str, Tensor], prefix: str, src_tokens: Tensor, sr
 
 
 def multihead_self_attention(sd, p: str, x: Tensor, key_padding_mask: Tensor, num_heads: int,
-                             rnd: Callable = _id) -> Tensor:
+                             rnd: Callable = _id, drop: Callable = lambda site, x: x, index: int = 0) -> Tensor:
     T, B, C = x.shape
     hd = C // num_heads
     xq = rnd(x)
@@ -82,6 +82,7 @@ def multihead_self_attention(sd, p: str, x: Tensor, key_padding_mask: Tensor, nu
     w = torch.bmm(rnd(q), rnd(k).transpose(1, 2)).view(B, num_heads, T, T)
     w = w.masked_fill(key_padding_mask[:, None, None, :], float("-inf")).view(B * num_heads, T, T)
     w = F.softmax(w.float(), dim=-1)
+    w = drop(("attn_p", index), w)                 # MultiheadAttention.dropout_module on the probabilities [B*H, T, T]
     a = torch.bmm(rnd(w), rnd(v)).transpose(0, 1).contiguous().view(T, B, C)
     return F.linear(rnd(a), rnd(sd[p + "out_proj.weight"]), sd[p + "out_proj.bias"])
 
@@ -94,11 +95,11 @@ def encoder_layer(sd, p: str, x: Tensor, mask: Tensor, num_heads: int, rnd: Call
                   drop: Callable = _no_drop, index: int = 0) -> Tensor:
     """Pre-LN TransformerEncoderLayer, ReLU.  ``drop(site, x)`` stands for the layer's three FairseqDropout modules
     (sites ("attn", i), ("act", i), ("ffn", i): after self-attention, after the activation, after fc2); identity in eval
-    mode.  Attention-probability dropout is not modelled (the device path requires it to be 0)."""
+    mode; ("attn_p", i) is the attention-probability dropout inside the MHA."""
     C = x.shape[-1]
     r = x
     h = F.layer_norm(x, (C,), sd[p + "self_attn_layer_norm.weight"], sd[p + "self_attn_layer_norm.bias"], 1e-5)
-    h = multihead_self_attention(sd, p + "self_attn.", h, mask, num_heads, rnd)
+    h = multihead_self_attention(sd, p + "self_attn.", h, mask, num_heads, rnd, drop, index)
     x = r + drop(("attn", index), h)
     r = x
     h = F.layer_norm(x, (C,), sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"], 1e-5)

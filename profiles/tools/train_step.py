@@ -100,8 +100,8 @@ def main():
     ap.add_argument("--preset", default="base")
     ap.add_argument("--no-graph", action="store_true", help="eager launches only (for an ncu launch list)")
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce after the backward graph instead of inside it")
-    ap.add_argument("--dropout", type=float, default=0.0, help="--dropout / --activation-dropout / SA_image_dropout value "
-                    "(attention-probability dropout stays 0: not built)")
+    ap.add_argument("--dropout", type=float, default=0.0, help="value of --dropout / --activation-dropout / "
+                    "--attention-dropout / SA_image_dropout / SA_attention_dropout")
     ap.add_argument("--model", action="store_true", help="complete model step: + 6-layer unit decoder + label-smoothed CE")
     ap.add_argument("--tgt-len", type=int, default=500, help="target units per utterance (50 Hz units x 10 s)")
     a = ap.parse_args()
@@ -123,8 +123,8 @@ def main():
     torch.manual_seed(0)
     args = make_args(a.preset, multimodal_translation_config_yaml=cfg)
     enc = MM_S2STransformerEncoder(args, build_unused_projections=False).to(dev).train()
-    enc.dropout_p = enc.activation_dropout_p = enc.SA_image_dropout = a.dropout
-    enc.attention_dropout_p = 0.0
+    enc.dropout_p = enc.activation_dropout_p = enc.attention_dropout_p = a.dropout
+    enc.SA_image_dropout = enc.SA_attention_dropout = a.dropout
     eng = enc.train_engine()
     B, n = a.batch, int(16000 * a.seconds)
     g = torch.Generator(device=dev).manual_seed(1 + rank)
@@ -213,7 +213,7 @@ def main():
                     ms_per_step=graph_ms, eager_ms_per_step=ms,
                     launches_per_step=launches, eager_sum_ms=tot, batch_per_gpu=B, utt_seconds=a.seconds,
                     preset=a.preset, params=int(eng.flat_p.numel()), dropout=a.dropout, overlap_reduce=bool(world > 1 and not a.no_overlap),
-                    note="attention-probability dropout off (not built); modality dropout 0.5; synthetic d loss/d encoder_out")
+                    note="modality dropout 0.5; synthetic d loss/d encoder_out")
         print(json.dumps(line), flush=True)
     if world > 1:
         # graphs that hold captured NCCL kernels must be gone before the communicator is torn down

@@ -361,28 +361,36 @@ def layernorm_bwd(x, gamma, dy, partials, dx=None, resid=None, eps=1e-5, dx_op=N
 
 
 def softmax_bwd(scores, dprobs, ld_in, rows, rows_per_batch, n_keys, dscores, ld_out, probs=None, kv_lens=None, heads=1,
-                valid_rows=0, causal=False, ld_dprobs=None):
+                valid_rows=0, causal=False, ld_dprobs=None, drop_p=0.0, seed=0, seed_dev=None, site=0):
     S = _v(scores, (rows, n_keys), (ld_in, 1))
-    D = _v(dprobs, (rows, n_keys), (ld_in if ld_dprobs is None else ld_dprobs, 1)).float()
-    G = _v(dscores, (rows, ld_out), (ld_out, 1))
-    if probs is not None:
-        Pv = _v(probs, (rows, ld_out), (ld_out, 1))
+    D = None if dprobs is None else _v(dprobs, (rows, n_keys), (ld_in if ld_dprobs is None else ld_dprobs, 1)).float()
+    G = None if dscores is None else _v(dscores, (rows, ld_out), (ld_out, 1))
+    Pv = None if probs is None else _v(probs, (rows, ld_out), (ld_out, 1))
+    mult = torch.ones(rows, ld_out)
+    if drop_p > 0:
+        if seed_dev is not None:
+            seed = int(seed) + int(seed_dev.view(-1)[0])
+        g = torch.Generator().manual_seed((int(seed) * 1000003 + int(site)) % (2 ** 63 - 1))
+        mult = ((torch.rand(rows * ld_out, generator=g) >= drop_p).float() / (1.0 - drop_p)).view(rows, ld_out)
     vr = valid_rows if valid_rows > 0 else rows_per_batch
     for r0 in range(0, rows, rows_per_batch):
         valid = n_keys if kv_lens is None else min(n_keys, int(kv_lens[(r0 // rows_per_batch) // heads]))
         sl = slice(r0, min(rows, r0 + vr))
-        G[sl] = 0
-        if probs is not None:
+        if G is not None:
+            G[sl] = 0
+        if Pv is not None:
             Pv[sl] = 0
         sc = S[sl, :valid].clone()
         if causal:
             nq = sc.shape[0]
             sc = sc.masked_fill(torch.arange(valid)[None, :] > torch.arange(nq)[:, None], float("-inf"))
         p = sc.softmax(-1)
-        g = p * (D[sl, :valid] - (p * D[sl, :valid]).sum(1, keepdim=True))
-        G[sl, :valid] = g.to(dscores.dtype)
-        if probs is not None:
-            Pv[sl, :valid] = p.to(probs.dtype)
+        m = mult[sl, :valid]
+        if G is not None:
+            d = D[sl, :valid] * m
+            G[sl, :valid] = (p * (d - (p * d).sum(1, keepdim=True))).to(dscores.dtype)
+        if Pv is not None:
+            Pv[sl, :valid] = (p * m).to(probs.dtype)
 
 
 def glu_bwd(pre, dy, rows, n, dpre, scale=1.0):

@@ -367,18 +367,18 @@ def test_encoder_backward_other_shapes(cuda, name, preset, overrides, img, B, du
 # ---------------------------------------------------------------------------------------------------------
 # element-wise dropout in the training step
 # ---------------------------------------------------------------------------------------------------------
-def _dropout_parity(K, device, p_drop=0.1, p_act=0.15, p_img=0.2, seed=1234, emulated=False):
+def _dropout_parity(K, device, p_drop=0.1, p_act=0.15, p_img=0.2, p_attn=0.1, p_sa=0.1, seed=1234, emulated=False):
     """Forward + backward with dropout on, against autograd over the oracle run with THE SAME masks: the oracle's
     ``drop(site, x)`` hook multiplies by the mask the kernel produces for that site (dumped by running the dropout kernel
     on a tensor of ones), re-laid-out from token-major to the oracle's [T, B, C]."""
     from mm_s2ut_b200 import synth
-    from mm_s2ut_b200.training import SITE_EMBED, SITE_IMAGE, site_layer
+    from mm_s2ut_b200.training import SITE_EMBED, SITE_IMAGE, SITE_SA_ATTN, site_layer
     from oracle import fbank as ofb, fusion as ofu
     from test_gpu_encoder import _build
 
     enc, args, cfg = _build("small", "selective_attention", True)
-    enc.dropout_p, enc.activation_dropout_p, enc.attention_dropout_p = p_drop, p_act, 0.0
-    enc.SA_image_dropout, enc.SA_attention_dropout, enc.SA_text_dropout = p_img, 0.0, 0.0
+    enc.dropout_p, enc.activation_dropout_p, enc.attention_dropout_p = p_drop, p_act, p_attn
+    enc.SA_image_dropout, enc.SA_attention_dropout, enc.SA_text_dropout = p_img, p_sa, 0.0
     B = 2
     wavs, _ = synth.synth_batch(7, B, 1.0 if emulated else 2.0, ragged=True)
     imgs = synth.synth_images(7, B, 50 if emulated else 577, 768)
@@ -393,6 +393,16 @@ def _dropout_parity(K, device, p_drop=0.1, p_act=0.15, p_img=0.2, seed=1234, emu
         return ones.float().cpu()
 
     def drop(site, x):
+        if site[0] == "attn_p":                                  # [B*H, T, T]; device [B*H][Tp][Tp]
+            BH, T, _ = x.shape
+            Tp = (T + 63) // 64 * 64
+            m = mask_for(site_layer(site[1], 3), p_attn, BH * Tp, Tp, torch.float32).view(BH, Tp, Tp)[:, :T, :T]
+            return x * m
+        if site[0] == "sa_attn_p":                               # [B, Tq, Tk]; device [B * Tq][Tkp]
+            Bx, Tq, Tk = x.shape
+            Tkp = (Tk + 7) // 8 * 8
+            m = mask_for(SITE_SA_ATTN, p_sa, Bx * Tq, Tkp, torch.float32).view(Bx, Tq, Tkp)[:, :, :Tk]
+            return x * m
         if site[0] == "image":                                   # oracle layout [Tk, B, Dk]; device [B * Tk, Dk] 16-bit
             Tk, Bx, Dk = x.shape
             m = mask_for(SITE_IMAGE, p_img, Bx * Tk, Dk, torch.bfloat16).view(Bx, Tk, Dk).transpose(0, 1)
@@ -469,8 +479,8 @@ def test_training_step_with_dropout_matches_oracle_with_same_masks(cuda):
     from mm_s2ut_b200 import kernels as K
 
     worst, ferr = _dropout_parity(K, cuda)
-    record("configs[2] backward with dropout 0.1 / activation-dropout 0.15 / SA_image_dropout 0.2 (same masks in the "
-           "oracle): worst parameter-gradient relative L2 error", worst, REL)
+    record("configs[2] backward with dropout 0.1 / activation-dropout 0.15 / attention-dropout 0.1 / SA_image_dropout 0.2 "
+           "/ SA_attention_dropout 0.1 (same masks in the oracle): worst parameter-gradient relative L2 error", worst, REL)
 
 
 def test_graphed_train_step_draws_fresh_dropout_masks(cuda):

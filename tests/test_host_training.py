@@ -252,8 +252,8 @@ def test_backward_orchestration_d512_fused_forward(monkeypatch):
 
 
 def test_dropout_orchestration_matches_oracle_with_same_masks(monkeypatch):
-    """Element-wise dropout sites of the training step (embedding, after attention, activation, after fc2,
-    SA_image_dropout): forward and backward regenerate the same masks; checked on the emulated kernels against autograd
+    """Dropout sites of the training step (embedding, after attention, activation, after fc2, attention probabilities,
+    SA_image_dropout, SA_attention_dropout): forward and backward regenerate the same masks; checked on the emulated kernels against autograd
     over the oracle run with those masks."""
     from test_gpu_training import _dropout_parity
 
@@ -261,12 +261,12 @@ def test_dropout_orchestration_matches_oracle_with_same_masks(monkeypatch):
     _dropout_parity(_emul, torch.device("cpu"), emulated=True)
 
 
-def test_attention_dropout_is_refused(monkeypatch):
+def test_unsupported_dropout_is_refused_not_skipped(monkeypatch):
     from test_gpu_training import _train_setup
 
     _emulated(monkeypatch)
     enc, wav, lens, imgs, *_ = _train_setup("selective_attention", True, B=2, dur=1.0)
-    enc.attention_dropout_p = 0.1
+    enc.SA_text_dropout = 0.1
     enc.train()
     with pytest.raises(NotImplementedError):
         enc.train_engine().forward_train(wav, lens, [imgs], [None])
