@@ -228,7 +228,9 @@ def train_step_probe(dev, world, rank, wav, img, steps=20, warmup=3):
         model = MM_S2UTTransformerModel(args, target_code_size=1000, build_unused_projections=False).to(dev).train()
         model.encoder.dropout_p = model.encoder.activation_dropout_p = model.encoder.attention_dropout_p = 0.0
         tgt_len = int(50 * DUR_S)
-        gm = GraphedModelTrainStep(model.encoder, model.decoder_train_engine(), wav.shape[0], wav.shape[1],
+        deng = model.decoder_train_engine()
+        deng.dropout_p = deng.attention_dropout_p = deng.activation_dropout_p = 0.0      # like the encoder probe above
+        gm = GraphedModelTrainStep(model.encoder, deng, wav.shape[0], wav.shape[1],
                                    tuple(img.shape[1:]), tgt_len, overlap_reduce=world > 1)
         gm.wav.copy_(wav)
         gm.img.copy_(img)

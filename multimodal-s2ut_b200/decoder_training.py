@@ -16,7 +16,9 @@ Same building blocks as the encoder's backward (``training.py``): every contract
 split-K / (sequence, head) operands; softmax backward from recomputed scores (``causal`` for the self-attention,
 encoder key lengths for the encoder attention); ``mm_layernorm_bwd``; plus ``mm_label_smoothed_nll_bwd`` and
 ``mm_embed_tokens_bwd``.  Parameters / gradients / Adam state / 16-bit operand copies are flat buffers; the embedding is
-stored with its rows padded to a multiple of 8 (TMA).  Dropout must be 0 (masks are not built).  No CPU fallback.
+stored with its rows padded to a multiple of 8 (TMA).  Dropout (``dropout_p``, ``attention_dropout_p``,
+``activation_dropout_p``) uses the encoder's counter-based masks (``mm_dropout`` / ``mm_softmax_dropout_bwd``) at
+fairseq's sites.  No CPU fallback.
 """
 from __future__ import annotations
 
@@ -30,8 +32,22 @@ from .decoder import UnitDecoderEngine, _round_up
 from .training import TrainEngine, _scope
 
 
+# dropout sites of the decoder (disjoint from the encoder's: the two engines may share one seed)
+DSITE_EMBED = 1 << 20
+
+
+def dsite_layer(i: int, which: int) -> int:
+    """which: 0 after self-attention, 1 self-attention probabilities, 2 after encoder attention, 3 encoder-attention
+    probabilities, 4 activation, 5 after fc2."""
+    return (1 << 20) + 16 * (i + 1) + which
+
+
 class UnitDecoderTrainEngine(UnitDecoderEngine):
     _require_cuda = True
+    # fairseq TransformerDecoder dropouts (set before forward_train; --dropout, --attention-dropout, --activation-dropout)
+    dropout_p = 0.0
+    attention_dropout_p = 0.0
+    activation_dropout_p = 0.0
 
     # backward helpers shared with the encoder engine (they only use self.buf / block_n / op_dtype / _ln_blocks)
     _partials = TrainEngine._partials
@@ -157,11 +173,46 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
     # ------------------------------------------------------------------------------------------
     # forward (activations kept)
     # ------------------------------------------------------------------------------------------
+    def _resid(self, a, a_ld, w, b, k, x_in, x_out, M, site):
+        """x_out = x_in + dropout(a w^T + b): one GEMM with the residual epilogue, or GEMM -> mm_dropout(+resid)."""
+        d, bn = self.d, self.block_n
+        p, _, _, seed, seed_dev = self._drop
+        if p > 0:
+            y = self.buf("t_y", (M, d), torch.float32)
+            K.gemm(a0=a, a0_ld=a_ld, rows=M, w=w, n=d, k=k, mode=K.EPI_F32, bias=b, out0=y, out0_ld=d, block_n=bn)
+            K.dropout(y, x_out, p, seed, site, resid=x_in, seed_dev=seed_dev)
+        else:
+            K.gemm(a0=a, a0_ld=a_ld, rows=M, w=w, n=d, k=k, mode=K.EPI_RESID_F32, bias=b, aux0=x_in, aux_ld=d, out0=x_out,
+                   out0_ld=d, block_n=bn)
+
+    def _attn_fwd(self, q, q_ld, q_bs, k, v, kv_ld, kv_bs, out, B, Lq, Tk, kv_lens, causal, site):
+        """Attention forward: the fused kernel, or -- with attention dropout -- scores / softmax+dropout / P V on the
+        head-mode GEMMs (the backward pass regenerates the mask from the same site)."""
+        d, H, op, bn = self.d, self.heads, self.op_dtype, self.block_n
+        _, p_attn, _, seed, seed_dev = self._drop
+        BH, Lp, Tp = B * H, _round_up(Lq, 64), _round_up(Tk, 64)
+        hd = dict(heads=H, head_stride=64, batches=BH, w_batched=True, block_n=bn)
+        S = self.buf("a_S", (BH, Lp, Tp), torch.float32)
+        P = self.buf("a_P", (BH, Lp, Tp), op)
+        K.gemm(a0=q, a0_ld=q_ld, a0_bs=q_bs, w=k, w_ld=kv_ld, w_bs=kv_bs, out0=S, rows=Lq, n=Tk, k=64, mode=K.EPI_F32,
+               out0_ld=Tp, out0_bs=Lp * Tp, a_hm=True, w_hm=True, **hd)
+        K.softmax_bwd(S, None, Tp, BH * Lp, Lp, Tk, None, Tp, probs=P, kv_lens=kv_lens, heads=H, valid_rows=Lq,
+                      causal=causal, drop_p=p_attn, seed=seed, seed_dev=seed_dev, site=site)
+        K.gemm(a0=P, a0_ld=Tp, a0_bs=Lp * Tp, rows=Lq, k=Tk, w=v, w_ld=kv_ld, w_bs=kv_bs, w_mn=True, w_hm=True, n=64,
+               mode=K.EPI_OP, out0=out, out0_ld=d, out0_bs=Lq * d, out_hm=True, **hd)
+
     @torch.no_grad()
     def forward_train(self, prev_output_tokens: torch.Tensor, encoder_out: torch.Tensor,
-                      encoder_padding_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      encoder_padding_mask: Optional[torch.Tensor] = None, dropout_seed: Optional[int] = None,
+                      dropout_seed_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
         """prev_output_tokens [B, L] int64, encoder_out [T, B, d] fp32 -> logits [B, L, V] fp32 (a view)."""
         dev, d, op, H, bn = self.device, self.d, self.op_dtype, self.heads, self.block_n
+        if dropout_seed is None:
+            self._drop_calls = getattr(self, "_drop_calls", 0) + 1
+            dropout_seed = (torch.initial_seed() + 0x2545F491 * self._drop_calls) & 0x7FFFFFFFFFFFFFFF
+        self._drop = (float(self.dropout_p), float(self.attention_dropout_p), float(self.activation_dropout_p),
+                      int(dropout_seed), dropout_seed_dev)
+        p_drop, p_attn, p_act, seed, seed_dev = self._drop
         tokens = prev_output_tokens.to(dev).contiguous()
         B, L = tokens.shape
         T = encoder_out.shape[0]
@@ -176,8 +227,10 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
         K.pack_t(enc, rows=T, cols=d, in_ld=B * d, batches=B, in_bs0=d, out_n=enc_btc, n_ld=d, n_bs0=T * d)
         x = self.buf("x0", (M, d), torch.float32)
         K.embed_tokens(tokens, self.padding_idx, self.emb_f32, self.embed_scale, self.pos_table(L + self.padding_idx + 1), x)
+        if p_drop > 0:
+            K.dropout(x, x, p_drop, seed, DSITE_EMBED, seed_dev=seed_dev)
         scale = 64 ** -0.5
-        saved = dict(B=B, L=L, T=T, tokens=tokens, enc_lens=enc_lens, enc_btc=enc_btc, layers=[])
+        saved = dict(B=B, L=L, T=T, tokens=tokens, enc_lens=enc_lens, enc_btc=enc_btc, layers=[], drop=self._drop)
         for i, Lr in enumerate(self.layers):
             s = dict(x0=x, h1=self.buf(f"h1_{i}", (M, d), op), qkv=self.buf(f"qkv_{i}", (M, 3 * d), op),
                      att=self.buf(f"att_{i}", (M, d), op), x1=self.buf(f"x1_{i}", (M, d), torch.float32),
@@ -188,22 +241,29 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
             K.layernorm(s["x0"], Lr["ln1"][0], Lr["ln1"][1], out_op=s["h1"])
             K.gemm(a0=s["h1"], a0_ld=d, rows=M, w=Lr["wqkv"], n=3 * d, k=d, mode=K.EPI_OP, bias=Lr["bqkv"], scale=scale,
                    scale_cols=d, out0=s["qkv"], out0_ld=3 * d, block_n=bn)
-            K.attention(s["qkv"], 0, L, s["qkv"], d, s["qkv"], 2 * d, L, None, B, H, s["att"], causal=True)
-            K.gemm(a0=s["att"], a0_ld=d, rows=M, w=Lr["wo"], n=d, k=d, mode=K.EPI_RESID_F32, bias=Lr["bo"], aux0=s["x0"],
-                   aux_ld=d, out0=s["x1"], out0_ld=d, block_n=bn)
+            if p_attn > 0:
+                self._attn_fwd(s["qkv"], 3 * d, L * 3 * d, s["qkv"][:, d:], s["qkv"][:, 2 * d:], 3 * d, L * 3 * d, s["att"],
+                               B, L, L, None, True, dsite_layer(i, 1))
+            else:
+                K.attention(s["qkv"], 0, L, s["qkv"], d, s["qkv"], 2 * d, L, None, B, H, s["att"], causal=True)
+            self._resid(s["att"], d, Lr["wo"], Lr["bo"], d, s["x0"], s["x1"], M, dsite_layer(i, 0))
             K.layernorm(s["x1"], Lr["ln2"][0], Lr["ln2"][1], out_op=s["h2"])
             K.gemm(a0=s["h2"], a0_ld=d, rows=M, w=Lr["wq"], n=d, k=d, mode=K.EPI_OP, bias=Lr["bq"], scale=scale,
                    scale_cols=d, out0=s["q2"], out0_ld=d, block_n=bn)
             K.gemm(a0=enc_btc, a0_ld=d, rows=B * T, w=Lr["wkv"], n=2 * d, k=d, mode=K.EPI_OP, bias=Lr["bkv"],
                    out0=s["kv2"], out0_ld=2 * d, block_n=bn)
-            K.attention(s["q2"], 0, L, s["kv2"], 0, s["kv2"], d, T, enc_lens, B, H, s["att2"])
-            K.gemm(a0=s["att2"], a0_ld=d, rows=M, w=Lr["wo2"], n=d, k=d, mode=K.EPI_RESID_F32, bias=Lr["bo2"],
-                   aux0=s["x1"], aux_ld=d, out0=s["x2"], out0_ld=d, block_n=bn)
+            if p_attn > 0:
+                self._attn_fwd(s["q2"], d, L * d, s["kv2"], s["kv2"][:, d:], 2 * d, T * 2 * d, s["att2"], B, L, T, enc_lens,
+                               False, dsite_layer(i, 3))
+            else:
+                K.attention(s["q2"], 0, L, s["kv2"], 0, s["kv2"], d, T, enc_lens, B, H, s["att2"])
+            self._resid(s["att2"], d, Lr["wo2"], Lr["bo2"], d, s["x1"], s["x2"], M, dsite_layer(i, 2))
             K.layernorm(s["x2"], Lr["ln3"][0], Lr["ln3"][1], out_op=s["h3"])
             K.gemm(a0=s["h3"], a0_ld=d, rows=M, w=Lr["w1"], n=self.ffn, k=d, mode=K.EPI_RELU_OP, bias=Lr["b1"],
                    out0=s["f"], out0_ld=self.ffn, block_n=bn)
-            K.gemm(a0=s["f"], a0_ld=self.ffn, rows=M, w=Lr["w2"], n=d, k=self.ffn, mode=K.EPI_RESID_F32, bias=Lr["b2"],
-                   aux0=s["x2"], aux_ld=d, out0=s["x3"], out0_ld=d, block_n=bn)
+            if p_act > 0:
+                K.dropout(s["f"], s["f"], p_act, seed, dsite_layer(i, 4), seed_dev=seed_dev)
+            self._resid(s["f"], self.ffn, Lr["w2"], Lr["b2"], self.ffn, s["x2"], s["x3"], M, dsite_layer(i, 5))
             saved["layers"].append(s)
             x = s["x3"]
         h = self.buf("h_out", (M, d), op)
@@ -218,7 +278,8 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
     # ------------------------------------------------------------------------------------------
     # backward
     # ------------------------------------------------------------------------------------------
-    def _attn_bwd(self, q, q_ld, q_bs, k, v, kv_ld, kv_bs, dO, dq, dk, dv, dkv_ld, dkv_bs, B, Lq, Tk, kv_lens, causal):
+    def _attn_bwd(self, q, q_ld, q_bs, k, v, kv_ld, kv_bs, dO, dq, dk, dv, dkv_ld, dkv_bs, B, Lq, Tk, kv_lens, causal,
+                  site=0):
         """Attention backward per (sequence, head): q [B][Lq][..] pre-scaled, k / v [B][Tk][..] (column blocks of the
         given tensors), dO [B*Lq, d] -> dq (x head_dim^-0.5), dk, dv written at their heads' column blocks."""
         d, H, op, bn = self.d, self.heads, self.op_dtype, self.block_n
@@ -232,7 +293,9 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
         K.gemm(a0=dO, a0_ld=d, a0_bs=Lq * d, w=v, w_ld=kv_ld, w_bs=kv_bs, out0=dP, mode=K.EPI_OP, **sc)
         P = self.buf("a_P", (BH, Lp, Tp), op)
         dS = self.buf("a_dS", (BH, Lp, Tp), op)
-        K.softmax_bwd(S, dP, Tp, BH * Lp, Lp, Tk, dS, Tp, probs=P, kv_lens=kv_lens, heads=H, valid_rows=Lq, causal=causal)
+        _, p_attn, _, seed, seed_dev = self._saved["drop"]
+        K.softmax_bwd(S, dP, Tp, BH * Lp, Lp, Tk, dS, Tp, probs=P, kv_lens=kv_lens, heads=H, valid_rows=Lq, causal=causal,
+                      drop_p=p_attn, seed=seed, seed_dev=seed_dev, site=site)
         og = dict(n=64, mode=K.EPI_OP, out_hm=True, w_mn=True, w_hm=True, a0_ld=Tp, a0_bs=Lp * Tp, **hd)
         K.gemm(a0=P, a_mn=True, rows=Tk, k=Lq, w=dO, w_ld=d, w_bs=Lq * d, out0=dv, out0_ld=dkv_ld, out0_bs=dkv_bs, **og)
         K.gemm(a0=dS, a_mn=True, rows=Tk, k=Lq, w=q, w_ld=q_ld, w_bs=q_bs, out0=dk, out0_ld=dkv_ld, out0_bs=dkv_bs, **og)
@@ -267,33 +330,45 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
             self._ln_param_grads(lnp, d, self.g("layer_norm.weight", "layer_norm.bias"), accumulate)
         denc = self.buf("denc_btc", (B * T, d), torch.float32)
         first_kv = True
+        p_drop, p_attn, p_act, seed, seed_dev = sv["drop"]
+
+        def masked(site):       # gradient entering a dropped branch = g o mask / (1 - p); the residual keeps g itself
+            if p_drop == 0:
+                return g_op
+            gm = self.buf("b_gm_op", (M, d), op)
+            K.dropout(g_op, gm, p_drop, seed, site, seed_dev=seed_dev)
+            return gm
+
         for i in reversed(range(self.n_layers)):
             s, Lr = sv["layers"][i], self.layers[i]
             p = Lr["prefix"]
             sa, ea = p + "self_attn.", p + "encoder_attn."
             with _scope("dec_layer"):
                 # ---- FFN
-                self._linear_bwd(g_op, d, s["f"], M, d, ffn, self.g(p + "fc2.weight"), self.g(p + "fc2.bias"), accumulate)
+                gm = masked(dsite_layer(i, 5))
+                self._linear_bwd(gm, d, s["f"], M, d, ffn, self.g(p + "fc2.weight"), self.g(p + "fc2.bias"), accumulate)
                 dF = self.buf("b_dF", (M, ffn), op)
-                K.gemm(a0=g_op, a0_ld=d, rows=M, w=Lr["w2"], w_ld=ffn, w_mn=True, n=ffn, k=d, mode=K.EPI_OP, out0=dF,
+                K.gemm(a0=gm, a0_ld=d, rows=M, w=Lr["w2"], w_ld=ffn, w_mn=True, n=ffn, k=d, mode=K.EPI_OP, out0=dF,
                        out0_ld=ffn, block_n=bn)
-                K.pack_t(dF, rows=M, cols=ffn, in_ld=ffn, out_n=dF, n_ld=ffn, mask=s["f"], mask_ld=ffn)
+                K.pack_t(dF, rows=M, cols=ffn, in_ld=ffn, out_n=dF, n_ld=ffn, mask=s["f"], mask_ld=ffn,
+                         scale=1.0 / (1.0 - p_act))
                 self._linear_bwd(dF, ffn, s["h3"], M, ffn, d, self.g(p + "fc1.weight"), self.g(p + "fc1.bias"), accumulate)
                 K.gemm(a0=dF, a0_ld=ffn, rows=M, w=Lr["w1"], w_ld=d, w_mn=True, n=d, k=ffn, mode=K.EPI_F32, out0=dh,
                        out0_ld=d, block_n=bn)
                 K.layernorm_bwd(s["x2"], Lr["ln3"][0], dh, lnp, dx=g, resid=g, dx_op=g_op)
                 self._ln_param_grads(lnp, d, self.g(p + "final_layer_norm.weight", p + "final_layer_norm.bias"), accumulate)
                 # ---- encoder attention
-                self._linear_bwd(g_op, d, s["att2"], M, d, d, self.g(ea + "out_proj.weight"), self.g(ea + "out_proj.bias"),
+                gm = masked(dsite_layer(i, 2))
+                self._linear_bwd(gm, d, s["att2"], M, d, d, self.g(ea + "out_proj.weight"), self.g(ea + "out_proj.bias"),
                                  accumulate)
                 datt = self.buf("b_datt", (M, d), op)
-                K.gemm(a0=g_op, a0_ld=d, rows=M, w=Lr["wo2"], w_ld=d, w_mn=True, n=d, k=d, mode=K.EPI_OP, out0=datt,
+                K.gemm(a0=gm, a0_ld=d, rows=M, w=Lr["wo2"], w_ld=d, w_mn=True, n=d, k=d, mode=K.EPI_OP, out0=datt,
                        out0_ld=d, block_n=bn)
                 dq2 = self.buf("b_dq2", (M, d), op)
                 dkv2 = self.buf("b_dkv2", (B * T, 2 * d), op)
                 kv2 = s["kv2"]
                 self._attn_bwd(s["q2"], d, L * d, kv2, kv2[:, d:], 2 * d, T * 2 * d, datt, dq2, dkv2, dkv2[:, d:], 2 * d,
-                               T * 2 * d, B, L, T, sv["enc_lens"], False)
+                               T * 2 * d, B, L, T, sv["enc_lens"], False, dsite_layer(i, 3))
                 self._linear_bwd(dq2, d, s["h2"], M, d, d, self.g(ea + "q_proj.weight"), self.g(ea + "q_proj.bias"),
                                  accumulate)
                 K.gemm(a0=dq2, a0_ld=d, rows=M, w=Lr["wq"], w_ld=d, w_mn=True, n=d, k=d, mode=K.EPI_F32, out0=dh,
@@ -311,14 +386,15 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                 self._ln_param_grads(lnp, d, self.g(p + "encoder_attn_layer_norm.weight", p + "encoder_attn_layer_norm.bias"),
                                      accumulate)
                 # ---- causal self-attention
-                self._linear_bwd(g_op, d, s["att"], M, d, d, self.g(sa + "out_proj.weight"), self.g(sa + "out_proj.bias"),
+                gm = masked(dsite_layer(i, 0))
+                self._linear_bwd(gm, d, s["att"], M, d, d, self.g(sa + "out_proj.weight"), self.g(sa + "out_proj.bias"),
                                  accumulate)
-                K.gemm(a0=g_op, a0_ld=d, rows=M, w=Lr["wo"], w_ld=d, w_mn=True, n=d, k=d, mode=K.EPI_OP, out0=datt,
+                K.gemm(a0=gm, a0_ld=d, rows=M, w=Lr["wo"], w_ld=d, w_mn=True, n=d, k=d, mode=K.EPI_OP, out0=datt,
                        out0_ld=d, block_n=bn)
                 dqkv = self.buf("b_dqkv", (M, 3 * d), op)
                 qkv = s["qkv"]
                 self._attn_bwd(qkv, 3 * d, L * 3 * d, qkv[:, d:], qkv[:, 2 * d:], 3 * d, L * 3 * d, datt, dqkv, dqkv[:, d:],
-                               dqkv[:, 2 * d:], 3 * d, L * 3 * d, B, L, L, None, True)
+                               dqkv[:, 2 * d:], 3 * d, L * 3 * d, B, L, L, None, True, dsite_layer(i, 1))
                 self._linear_bwd(dqkv, 3 * d, s["h1"], M, 3 * d, d,
                                  self.g(sa + "q_proj.weight", sa + "k_proj.weight", sa + "v_proj.weight"),
                                  self.g(sa + "q_proj.bias", sa + "k_proj.bias", sa + "v_proj.bias"), accumulate)
@@ -327,7 +403,9 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                 K.layernorm_bwd(s["x0"], Lr["ln1"][0], dh, lnp, dx=g, resid=g, dx_op=g_op)
                 self._ln_param_grads(lnp, d, self.g(p + "self_attn_layer_norm.weight", p + "self_attn_layer_norm.bias"),
                                      accumulate)
-        # ---- embedding: x0 = sqrt(d) * E[tokens] + positions
+        # ---- embedding: x0 = dropout(sqrt(d) * E[tokens] + positions)
+        if p_drop > 0:
+            K.dropout(g, g, p_drop, seed, DSITE_EMBED, seed_dev=seed_dev)
         K.embed_tokens_bwd(sv["tokens"].view(-1), self.padding_idx, g, self.embed_scale, self.g("embed_tokens.weight"))
         d_enc = torch.empty(T, B, d, dtype=torch.float32, device=self.device)
         K.tbc_to_btc(denc, T, B, d, d_enc)       # [B, T, d] -> [T, B, d]: the same index swap with the roles exchanged

@@ -208,7 +208,8 @@ class GraphedModelTrainStep(GraphedTrainStep):
 
         out = self.eng.forward_train(self.wav, self.lens, [self.img], [None], drop_image=drop_image,
                                      dropout_seed=self.base_seed, dropout_seed_dev=self.seed_dev)
-        self.dec.forward_train(self.prev_tokens, out["encoder_out"][0], out["encoder_padding_mask"][0])
+        self.dec.forward_train(self.prev_tokens, out["encoder_out"][0], out["encoder_padding_mask"][0],
+                               dropout_seed=self.base_seed, dropout_seed_dev=self.seed_dev)
         loss, nll, d_enc = self.dec.loss_backward(self.target, self.label_smoothing)
         multi = self.overlap_reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         if multi:       # the decoder's gradients travel while the encoder's backward runs

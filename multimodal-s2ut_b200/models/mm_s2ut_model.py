@@ -94,6 +94,11 @@ class MM_S2UTTransformerModel(nn.Module):
             self._decoder_engine = UnitDecoderTrainEngine(sd, self.decoder.num_heads, dev,
                                                           op_dtype=getattr(self.encoder, "op_dtype", torch.bfloat16),
                                                           padding_idx=self.decoder.padding_idx)
+            a = self.args      # fairseq TransformerDecoder: --dropout, --attention-dropout, --activation-dropout / --relu-dropout
+            self._decoder_engine.dropout_p = float(getattr(a, "dropout", 0.0) or 0.0)
+            self._decoder_engine.attention_dropout_p = float(getattr(a, "attention_dropout", 0.0) or 0.0)
+            self._decoder_engine.activation_dropout_p = float(getattr(a, "activation_dropout", 0.0) or
+                                                              getattr(a, "relu_dropout", 0.0) or 0.0)
         return self._decoder_engine
 
     @torch.no_grad()

@@ -46,7 +46,7 @@ def init_decoder(d: int, ffn: int, layers: int, vocab: int = 1004, seed: int = 0
     return sd
 
 
-def _mha(sd, p, q_in, kv_in, heads, key_padding_mask=None, causal=False):
+def _mha(sd, p, q_in, kv_in, heads, key_padding_mask=None, causal=False, drop=lambda site, x: x, site=None):
     Tq, B, C = q_in.shape
     Tk = kv_in.shape[0]
     hd = C // heads
@@ -61,33 +61,36 @@ def _mha(sd, p, q_in, kv_in, heads, key_padding_mask=None, causal=False):
         w = w + torch.triu(torch.full((Tq, Tk), float("-inf")), 1)[None]
     if key_padding_mask is not None:
         w = w.view(B, heads, Tq, Tk).masked_fill(key_padding_mask[:, None, None, :], float("-inf")).view(B * heads, Tq, Tk)
-    a = torch.bmm(F.softmax(w.float(), dim=-1), v).transpose(0, 1).contiguous().view(Tq, B, C)
+    a = torch.bmm(drop(site, F.softmax(w.float(), dim=-1)), v).transpose(0, 1).contiguous().view(Tq, B, C)
     return F.linear(a, sd[p + "out_proj.weight"], sd[p + "out_proj.bias"])
 
 
 def unit_decoder_forward(sd: Dict[str, Tensor], prev_output_tokens: Tensor, encoder_out: Tensor,
-                         encoder_padding_mask: Tensor, heads: int) -> Tensor:
-    """prev_output_tokens [B, L] int64, encoder_out [T, B, d] -> logits [B, L, V]."""
+                         encoder_padding_mask: Tensor, heads: int, drop=lambda site, x: x) -> Tensor:
+    """prev_output_tokens [B, L] int64, encoder_out [T, B, d] -> logits [B, L, V].  ``drop(site, x)``: the training-mode
+    dropout modules -- ("embed",), per layer i ("self", i), ("self_p", i), ("enc", i), ("enc_p", i), ("act", i), ("ffn", i);
+    identity = eval mode."""
     d = encoder_out.shape[-1]
     B, L = prev_output_tokens.shape
     pos = make_positions(prev_output_tokens.ne(1), 1)
     # nn.Embedding(V, d, padding_idx=1): same values as plain indexing, no gradient for the padding row
     x = math.sqrt(d) * F.embedding(prev_output_tokens, sd["embed_tokens.weight"], padding_idx=1) + \
         sinusoidal_table(L + 2, d, 1)[pos]
-    x = x.transpose(0, 1)
+    x = drop(("embed",), x.transpose(0, 1))
     i = 0
     while f"layers.{i}.fc1.weight" in sd:
         p = f"layers.{i}."
         r = x
         h = F.layer_norm(x, (d,), sd[p + "self_attn_layer_norm.weight"], sd[p + "self_attn_layer_norm.bias"], 1e-5)
-        x = r + _mha(sd, p + "self_attn.", h, h, heads, causal=True)
+        x = r + drop(("self", i), _mha(sd, p + "self_attn.", h, h, heads, causal=True, drop=drop, site=("self_p", i)))
         r = x
         h = F.layer_norm(x, (d,), sd[p + "encoder_attn_layer_norm.weight"], sd[p + "encoder_attn_layer_norm.bias"], 1e-5)
-        x = r + _mha(sd, p + "encoder_attn.", h, encoder_out, heads, key_padding_mask=encoder_padding_mask)
+        x = r + drop(("enc", i), _mha(sd, p + "encoder_attn.", h, encoder_out, heads,
+                                      key_padding_mask=encoder_padding_mask, drop=drop, site=("enc_p", i)))
         r = x
         h = F.layer_norm(x, (d,), sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"], 1e-5)
-        x = r + F.linear(F.relu(F.linear(h, sd[p + "fc1.weight"], sd[p + "fc1.bias"])), sd[p + "fc2.weight"],
-                         sd[p + "fc2.bias"])
+        x = r + drop(("ffn", i), F.linear(drop(("act", i), F.relu(F.linear(h, sd[p + "fc1.weight"], sd[p + "fc1.bias"]))),
+                                          sd[p + "fc2.weight"], sd[p + "fc2.bias"]))
         i += 1
     x = F.layer_norm(x, (d,), sd["layer_norm.weight"], sd["layer_norm.bias"], 1e-5).transpose(0, 1)
     return F.linear(x, sd["embed_tokens.weight"])

@@ -187,6 +187,9 @@ def test_model_train_step_api(cuda):
     args.decoder_layers = 2
     model = MM_S2UTTransformerModel(args, target_code_size=100, build_unused_projections=False).cuda().train()
     model.encoder.dropout_p = model.encoder.activation_dropout_p = model.encoder.attention_dropout_p = 0.0
+    deng = model.decoder_train_engine()
+    assert deng.dropout_p == args.dropout and deng.attention_dropout_p == args.attention_dropout   # taken from the args
+    deng.dropout_p = deng.attention_dropout_p = deng.activation_dropout_p = 0.0                    # deterministic loss curve
     B, Lu = 2, 20
     wavs, _ = synth.synth_batch(5, B, 1.5, ragged=True)
     wav, lens = synth.pad_waveforms(wavs)
@@ -207,3 +210,13 @@ def test_model_train_step_api(cuda):
     assert torch.equal(after, model.decoder_train_engine().p("layers.0.fc1.weight"))
     with pytest.raises(NotImplementedError):
         model(wav.cuda(), lens.cuda(), prev, imgs_list=[imgs], img_masks_list=[None])
+
+
+def test_decoder_training_step_with_dropout_matches_oracle_with_same_masks(cuda):
+    import mm_s2ut_b200.decoder_training as dt
+    from mm_s2ut_b200 import kernels as K
+    from test_host_training import _decoder_dropout_parity
+
+    worst = _decoder_dropout_parity(K, cuda, dt, B=3, L=40, T=50, d=256, heads=4, ffn=512, layers=2, vocab=104, seed=1)
+    record("configs[2] decoder backward with dropout 0.1 / attention-dropout 0.1 / activation-dropout 0.15 (same masks in "
+           "the oracle): worst parameter-gradient relative L2 error", worst, REL)

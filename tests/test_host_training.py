@@ -270,3 +270,64 @@ def test_unsupported_dropout_is_refused_not_skipped(monkeypatch):
     enc.train()
     with pytest.raises(NotImplementedError):
         enc.train_engine().forward_train(wav, lens, [imgs], [None])
+
+
+def _decoder_dropout_parity(K, device, dt, seed=77, **shape):
+    """Decoder training step with dropout at every fairseq site, against autograd over the oracle decoder + criterion run
+    with the same masks (dumped from the kernels' mask function, re-laid-out to the oracle's tensors)."""
+    from oracle import decoder as odec
+    from test_gpu_training import REL, ZERO, _rel
+
+    p_drop, p_attn, p_act = 0.1, 0.1, 0.15
+    sd, prev, target, enc, mask, heads, *_ = _decoder_setup(**shape)
+
+    def mask_for(site, p, rows, cols):
+        ones = torch.ones(rows, cols, dtype=torch.float32, device=device)
+        K.dropout(ones, ones, p, seed, site)
+        return ones.cpu()
+
+    def drop(site, x):
+        kind = site[0]
+        if kind in ("self_p", "enc_p"):                      # [B*H, L, Tk]; device [B*H][Lp][Tp]
+            BH, L, Tk = x.shape
+            Lp, Tp = (L + 63) // 64 * 64, (Tk + 63) // 64 * 64
+            m = mask_for(dt.dsite_layer(site[1], 1 if kind == "self_p" else 3), p_attn, BH * Lp, Tp)
+            return x * m.view(BH, Lp, Tp)[:, :L, :Tk]
+        L, B, C = x.shape                                    # [L, B, C]; device [B * L, C]
+        if kind == "embed":
+            m = mask_for(dt.DSITE_EMBED, p_drop, B * L, C)
+        elif kind == "act":
+            m = mask_for(dt.dsite_layer(site[1], 4), p_act, B * L, C)
+        else:
+            m = mask_for(dt.dsite_layer(site[1], {"self": 0, "enc": 2, "ffn": 5}[kind]), p_drop, B * L, C)
+        return x * m.view(B, L, C).transpose(0, 1)
+
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    encg = enc.clone().requires_grad_(True)
+    logits = odec.unit_decoder_forward(sdg, prev, encg, mask, heads, drop=drop)
+    loss_ref, _ = odec.label_smoothed_nll_loss(logits, target, 0.2)
+    loss_ref.backward()
+    eng = dt.UnitDecoderTrainEngine(sd, heads, device)
+    eng.dropout_p, eng.attention_dropout_p, eng.activation_dropout_p = p_drop, p_attn, p_act
+    eng.forward_train(prev.to(device), enc.to(device), mask.to(device), dropout_seed=seed)
+    loss, _, d_enc = eng.loss_backward(target.to(device), 0.2)
+    assert abs(loss.item() - loss_ref.item()) / loss_ref.item() < 2e-2
+    valid = (~mask).t().unsqueeze(-1)
+    assert _rel(d_enc.cpu() * valid, encg.grad * valid) < REL
+    worst = 0.0
+    for k, got in eng.grads().items():
+        if sdg[k].grad.norm() < ZERO:
+            continue
+        r = _rel(got, sdg[k].grad)
+        worst = max(worst, r)
+        assert r < REL, (k, r)
+    return worst
+
+
+def test_decoder_dropout_orchestration_matches_oracle_with_same_masks(monkeypatch):
+    _emulated(monkeypatch)
+    import mm_s2ut_b200.decoder_training as dt
+
+    monkeypatch.setattr(dt, "K", _emul)
+    monkeypatch.setattr(dt.UnitDecoderTrainEngine, "_require_cuda", False)
+    _decoder_dropout_parity(_emul, torch.device("cpu"), dt)
