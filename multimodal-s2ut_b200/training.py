@@ -25,7 +25,7 @@ are contiguous slices.  ``all_reduce_grads`` runs NCCL (or gloo) over ``flat_g``
 Element-wise dropout (embedding, residual and activation sites, SA_image_dropout) uses counter-based masks that the
 backward pass regenerates (``mm_dropout``); attention dropout (encoder self-attention, SA_attention_dropout) runs the
 un-fused score / softmax+dropout / P V path in the training forward; modality dropout (per-batch image zeroing) works.
-Not built (raises): SA_text_dropout, image key masks, several image-feature types, and the device
+Not built (raises): image key masks, several image-feature types, and the device
 feature store in the backward pass.
 """
 from __future__ import annotations
@@ -50,7 +50,7 @@ def _split_k(n: int, kin: int, mp: int) -> int:
 
 
 # dropout sites (the counter-based mask is a function of (seed, site, element index))
-SITE_EMBED, SITE_IMAGE, SITE_SA_ATTN = 0, 8, 9
+SITE_EMBED, SITE_IMAGE, SITE_SA_ATTN, SITE_TEXT = 0, 8, 9, 10
 
 
 def site_layer(i: int, which: int) -> int:
@@ -389,8 +389,7 @@ class TrainEngine(EncoderEngine):
         """dropout_seed (+ the int64 device scalar dropout_seed_dev, for CUDA-graph replay) seeds the element-wise
         dropout masks of this step; default: a counter advanced per call on top of torch.initial_seed()."""
         enc = self.enc
-        if float(getattr(enc, "SA_text_dropout", 0.0) or 0.0) > 0:
-            raise NotImplementedError("SA_text_dropout is not built (the reference's YAML ships 0): set it to 0")
+        p_text = float(getattr(enc, "SA_text_dropout", 0.0) or 0.0)
         self._p_attn = float(getattr(enc, "attention_dropout_p", 0.0) or 0.0)
         p_sa = float(getattr(enc, "SA_attention_dropout", 0.0) or 0.0)
         p_drop, p_act = float(enc.dropout_p), float(getattr(enc, "activation_dropout_p", 0.0))
@@ -412,7 +411,7 @@ class TrainEngine(EncoderEngine):
         if p_drop > 0:      # S2TTransformerEncoder: x = dropout_module(embed_scale * x + positions)
             K.dropout(x, x, p_drop, self._drop[2], SITE_EMBED, seed_dev=dropout_seed_dev)
         saved = dict(B=B, T=T, m=m, x1=x1, seq_lens=seq_lens, layers=[], fused=False, drop=self._drop, p_img=p_img,
-                     p_attn=self._p_attn, p_sa=p_sa)
+                     p_attn=self._p_attn, p_sa=p_sa, p_text=0.0)
         text_f32 = self.buf("text_f32", (M, d), torch.float32)
         text_op = self.buf("text_op", (M, d), self.op_dtype)
         fused_fwd = self.train_fused_ln and p_drop == 0
@@ -437,6 +436,10 @@ class TrainEngine(EncoderEngine):
                 img = torch.zeros(tuple(img.shape), dtype=torch.float32, device=self.device)
             img = img.to(self.device, non_blocking=True).float().contiguous()
             out = torch.empty(T, B, d, dtype=torch.float32, device=self.device)
+            if p_text > 0:      # SA_text_dropout (:597): the dropped states feed the query, the gate and the mix
+                K.dropout(text_f32, text_f32, p_text, self._drop[2], SITE_TEXT, seed_dev=dropout_seed_dev)
+                K.convert(text_f32, text_op)
+                saved["p_text"] = p_text
             self.fuse(0, text_f32, text_op, img, None, B, T, out,
                       img_dropout=(p_img, self._drop[2], dropout_seed_dev, SITE_IMAGE),
                       attn_dropout=(p_sa, self._drop[2], dropout_seed_dev, SITE_SA_ATTN))
@@ -770,6 +773,8 @@ class TrainEngine(EncoderEngine):
         if sv["fused"]:
             with _scope("fusion"):
                 self._fusion_bwd(grad_out, gtext, B, T, accumulate)
+                if sv["p_text"] > 0:
+                    K.dropout(gtext, gtext, sv["p_text"], sv["drop"][2], SITE_TEXT, seed_dev=sv["drop"][3])
         else:
             K.tbc_to_btc(grad_out, B, T, d, gtext)
         lnp = self.buf("ln_part", (self._ln_blocks * 2 * max(d, 1024),), torch.float32)

@@ -73,11 +73,12 @@ def multimodal_attention(sd: Dict[str, Tensor], p: str, text: Tensor, img: Tenso
 def fuse_img_feat(sd, prefix: str, mm_cfg, text: Tensor, idx: int, image: Tensor,
                   image_mask: Optional[Tensor], rnd: Callable = _id, drop: Callable = lambda site, x: x) -> Tensor:
     """text [T,B,d], image [Tk,B,Dk] -> fused [T,B,d].  ``drop(("image",), x)`` = SA_image_dropout (:596); identity in
-    eval mode; ("sa_attn_p",) = SA_attention_dropout on the probabilities (SA_text_dropout is not modelled)."""
+    eval mode; ("text",) = SA_text_dropout, ("sa_attn_p",) = SA_attention_dropout on the probabilities."""
     if mm_cfg.image_pre_norm:
         image = F.layer_norm(image, (image.shape[-1],), sd[prefix + "image_pre_norm_module.weight"],
                              sd[prefix + "image_pre_norm_module.bias"], 1e-5)
     image = drop(("image",), image)
+    text = drop(("text",), text)                        # SA_text_dropout (:597)
     kind = mm_cfg.multimodal_attention_type
     if kind == "selective_attention":
         out, _ = selective_attention(sd, f"{prefix}selective_attns.{idx}.", text, image, image, image_mask, rnd, drop)

@@ -367,18 +367,19 @@ def test_encoder_backward_other_shapes(cuda, name, preset, overrides, img, B, du
 # ---------------------------------------------------------------------------------------------------------
 # element-wise dropout in the training step
 # ---------------------------------------------------------------------------------------------------------
-def _dropout_parity(K, device, p_drop=0.1, p_act=0.15, p_img=0.2, p_attn=0.1, p_sa=0.1, seed=1234, emulated=False):
+def _dropout_parity(K, device, p_drop=0.1, p_act=0.15, p_img=0.2, p_attn=0.1, p_sa=0.1, p_text=0.1, seed=1234,
+                    emulated=False):
     """Forward + backward with dropout on, against autograd over the oracle run with THE SAME masks: the oracle's
     ``drop(site, x)`` hook multiplies by the mask the kernel produces for that site (dumped by running the dropout kernel
     on a tensor of ones), re-laid-out from token-major to the oracle's [T, B, C]."""
     from mm_s2ut_b200 import synth
-    from mm_s2ut_b200.training import SITE_EMBED, SITE_IMAGE, SITE_SA_ATTN, site_layer
+    from mm_s2ut_b200.training import SITE_EMBED, SITE_IMAGE, SITE_SA_ATTN, SITE_TEXT, site_layer
     from oracle import fbank as ofb, fusion as ofu
     from test_gpu_encoder import _build
 
     enc, args, cfg = _build("small", "selective_attention", True)
     enc.dropout_p, enc.activation_dropout_p, enc.attention_dropout_p = p_drop, p_act, p_attn
-    enc.SA_image_dropout, enc.SA_attention_dropout, enc.SA_text_dropout = p_img, p_sa, 0.0
+    enc.SA_image_dropout, enc.SA_attention_dropout, enc.SA_text_dropout = p_img, p_sa, p_text
     B = 2
     wavs, _ = synth.synth_batch(7, B, 1.0 if emulated else 2.0, ragged=True)
     imgs = synth.synth_images(7, B, 50 if emulated else 577, 768)
@@ -410,6 +411,8 @@ def _dropout_parity(K, device, p_drop=0.1, p_act=0.15, p_img=0.2, p_attn=0.1, p_
         T, Bx, C = x.shape                                       # oracle layout [T, B, C]; device [B * T, C]
         if site[0] == "embed":
             m = mask_for(SITE_EMBED, p_drop, Bx * T, C, torch.float32)
+        elif site[0] == "text":
+            m = mask_for(SITE_TEXT, p_text, Bx * T, C, torch.float32)
         elif site[0] == "act":
             m = mask_for(site_layer(site[1], 1), p_act, Bx * T, C, torch.bfloat16)
         else:

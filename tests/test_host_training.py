@@ -261,17 +261,6 @@ def test_dropout_orchestration_matches_oracle_with_same_masks(monkeypatch):
     _dropout_parity(_emul, torch.device("cpu"), emulated=True)
 
 
-def test_unsupported_dropout_is_refused_not_skipped(monkeypatch):
-    from test_gpu_training import _train_setup
-
-    _emulated(monkeypatch)
-    enc, wav, lens, imgs, *_ = _train_setup("selective_attention", True, B=2, dur=1.0)
-    enc.SA_text_dropout = 0.1
-    enc.train()
-    with pytest.raises(NotImplementedError):
-        enc.train_engine().forward_train(wav, lens, [imgs], [None])
-
-
 def _decoder_dropout_parity(K, device, dt, seed=77, **shape):
     """Decoder training step with dropout at every fairseq site, against autograd over the oracle decoder + criterion run
     with the same masks (dumped from the kernels' mask function, re-laid-out to the oracle's tensors)."""
