@@ -278,12 +278,13 @@ int mm_softmax_dropout_bwd(const float* scores, const void* dprobs, int32_t dpro
                            uint64_t seed, const uint64_t* seed_dev, uint32_t site, int32_t dtype, void* stream);
 /* Backward of mm_label_smoothed_nll summed over rows (fairseq label_smoothed_nll_loss, reduce=True), times grad_scale:
  * dlogits 16-bit [rows, ld_out] (columns >= vocab and padding rows are 0) -- the A operand of the tied output
- * projection's dgrad / wgrad.  mm_embed_tokens_bwd: table_grad[token] += scale * dx[row] (atomic; padding rows skipped). */
+ * projection's dgrad / wgrad.  mm_embed_tokens_bwd: table_grad[v] += scale * sum of dx[row] over rows whose token is v
+ * (one block per vocabulary row, rows summed in order: deterministic; the padding row is skipped). */
 int mm_label_smoothed_nll_bwd(const float* logits, int64_t ld, int32_t vocab, const int64_t* target, int32_t padding_idx,
                               int64_t rows, float epsilon, float grad_scale, void* dlogits, int64_t ld_out, int32_t dtype,
                               void* stream);
 int mm_embed_tokens_bwd(const int64_t* tokens, int32_t padding_idx, const float* dx, int64_t rows, int32_t dim,
-                        float scale, float* table_grad, void* stream);
+                        float scale, float* table_grad, int32_t vocab, void* stream);
 int mm_colsum_blocks(int32_t rows);
 int mm_colsum(const void* in, int64_t ld, int32_t rows, int32_t cols, int32_t period, int32_t valid, float* partials,
               int32_t dtype, void* stream);

@@ -150,7 +150,7 @@ EXPORTS = {
     "mm_label_smoothed_nll_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_float,
                                             C.c_float, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "mm_embed_tokens_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p,
-                                      C.c_void_p]),
+                                      C.c_int32, C.c_void_p]),
     "mm_colsum_blocks": (C.c_int, [C.c_int32]),
     "mm_colsum": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                             C.c_void_p]),

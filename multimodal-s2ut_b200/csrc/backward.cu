@@ -320,7 +320,7 @@ __device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned s
 // With drop_p > 0 the probabilities carry attention dropout: m = keep(seed, site, row * ld_out + k) / (1 - p);
 // P_out = P m (what multiplied V in the forward pass), dP' = dP m, dS = P (dP' - sum_k P dP').  dPv == NULL: forward
 // use (softmax + dropout -> P_out only).
-template <int NPL, typename OpT>
+template <int NPL, typename OpT, bool DROP, bool BWD>
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ S, const void* __restrict__ dPv,
                                                            int dp_is_op, long long ld_dp,
                                                            long long ld_in, long long rows, int rows_per_batch,
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows || (int)(row % rows_per_batch) >= valid_rows) return;
-  if (seed_dev) seed += *seed_dev;
+  if (DROP && seed_dev) seed += *seed_dev;
   int valid = n_keys;
   if (kv_lens) {
     const int v = kv_lens[(row / rows_per_batch) / heads];
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
     float2 a = make_float2(-INFINITY, -INFINITY), g = make_float2(0.f, 0.f);
     if (k + 1 < valid) {
       a = __ldcs(reinterpret_cast<const float2*>(s + k));
-      if (!dPv) {
+      if constexpr (!BWD) {
       } else if (dp_is_op) {
         const uint32_t q = __ldcs(reinterpret_cast<const uint32_t*>(d16 + k));
         const OpT* e = reinterpret_cast<const OpT*>(&q);
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
       }
     } else if (k < valid) {
       a.x = s[k];
-      if (dPv) g.x = dp_is_op ? OpTraits<OpT>::to_float(d16[k]) : d[k];
+      if constexpr (BWD) g.x = dp_is_op ? OpTraits<OpT>::to_float(d16[k]) : d[k];
     }
     sv[2 * i] = a.x, sv[2 * i + 1] = a.y, dv[2 * i] = g.x, dv[2 * i + 1] = g.y;
     mx = fmaxf(mx, fmaxf(a.x, a.y));
@@ -379,12 +379,11 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
   const float inv = valid > 0 ? 1.0f / sum : 0.f;
   const float dinv = 1.0f / (1.0f - drop_p);
   float dot = 0.f;
-  float mk[NPL];     // attention-dropout multiplier of each element (1 without dropout)
+  float mk[DROP ? NPL : 1];     // attention-dropout multiplier of each element (DROP instantiation only)
 #pragma unroll
   for (int i = 0; i < NPL; ++i) {
     sv[i] *= inv;
-    mk[i] = 1.0f;
-    if (drop_p > 0.f) {
+    if constexpr (DROP) {
       const int k = 2 * (lane + 32 * (i >> 1)) + (i & 1);
       mk[i] = dropout_keep(seed, site, (unsigned long long)(row * ld_out + k), drop_p) ? dinv : 0.f;
       dv[i] *= mk[i];
@@ -393,18 +392,23 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
   }
   dot = warp_sum(dot);
   OpT* po = P ? P + row * ld_out : nullptr;
-  OpT* go = dS ? dS + row * ld_out : nullptr;
+  OpT* go = BWD ? dS + row * ld_out : nullptr;
 #pragma unroll
   for (int i = 0; i < NPL / 2; ++i) {
     const int k = 2 * (lane + 32 * i);
     if (k + 1 < ld_out) {
-      if (po) *reinterpret_cast<uint32_t*>(po + k) = OpTraits<OpT>::pack2(sv[2 * i] * mk[2 * i], sv[2 * i + 1] * mk[2 * i + 1]);
-      if (go)
+      if (po) {
+        if constexpr (DROP)
+          *reinterpret_cast<uint32_t*>(po + k) = OpTraits<OpT>::pack2(sv[2 * i] * mk[2 * i], sv[2 * i + 1] * mk[2 * i + 1]);
+        else
+          *reinterpret_cast<uint32_t*>(po + k) = OpTraits<OpT>::pack2(sv[2 * i], sv[2 * i + 1]);
+      }
+      if constexpr (BWD)
         *reinterpret_cast<uint32_t*>(go + k) =
             OpTraits<OpT>::pack2(sv[2 * i] * (dv[2 * i] - dot), sv[2 * i + 1] * (dv[2 * i + 1] - dot));
     } else if (k < ld_out) {
-      if (po) po[k] = OpTraits<OpT>::cvt(sv[2 * i] * mk[2 * i]);
-      if (go) go[k] = OpTraits<OpT>::cvt(sv[2 * i] * (dv[2 * i] - dot));
+      if (po) po[k] = OpTraits<OpT>::cvt(DROP ? sv[2 * i] * mk[DROP ? 2 * i : 0] : sv[2 * i]);
+      if constexpr (BWD) go[k] = OpTraits<OpT>::cvt(sv[2 * i] * (dv[2 * i] - dot));
     }
   }
   // columns beyond the register span (ld_out > 32 * NPL cannot happen: checked on the host)
@@ -419,14 +423,28 @@ static int launch_softmax_bwd(const float* S, const void* dP, int dp_is_op, long
   const unsigned grid = (unsigned)((rows + 7) / 8);
   OpT* p = reinterpret_cast<OpT*>(P);
   OpT* g = reinterpret_cast<OpT*>(dS);
-  if (ld_out <= 256)
-    softmax_bwd_kernel<8, OpT><<<grid, 256, 0, s>>>(S, dP, dp_is_op, ld_dp, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows, causal, drop_p, seed, seed_dev, site);
-  else if (ld_out <= 640)
-    softmax_bwd_kernel<20, OpT><<<grid, 256, 0, s>>>(S, dP, dp_is_op, ld_dp, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows, causal, drop_p, seed, seed_dev, site);
-  else if (ld_out <= 2048)
-    softmax_bwd_kernel<64, OpT><<<grid, 256, 0, s>>>(S, dP, dp_is_op, ld_dp, ld_in, rows, rpb, n_keys, kv_lens, heads, p, g, ld_out, valid_rows, causal, drop_p, seed, seed_dev, site);
-  else
+#define MM_SMB(NPL, DROP)                                                                                                \
+  do {                                                                                                                   \
+    if (dP)                                                                                                              \
+      softmax_bwd_kernel<NPL, OpT, DROP, true><<<grid, 256, 0, s>>>(S, dP, dp_is_op, ld_dp, ld_in, rows, rpb, n_keys,     \
+                                                                     kv_lens, heads, p, g, ld_out, valid_rows, causal,    \
+                                                                     drop_p, seed, seed_dev, site);                       \
+    else                                                                                                                 \
+      softmax_bwd_kernel<NPL, OpT, DROP, false><<<grid, 256, 0, s>>>(S, dP, dp_is_op, ld_dp, ld_in, rows, rpb, n_keys,    \
+                                                                      kv_lens, heads, p, g, ld_out, valid_rows, causal,   \
+                                                                      drop_p, seed, seed_dev, site);                      \
+  } while (0)
+  const bool drop = drop_p > 0.f;
+  if (ld_out <= 256) {
+    if (drop) MM_SMB(8, true); else MM_SMB(8, false);
+  } else if (ld_out <= 640) {
+    if (drop) MM_SMB(20, true); else MM_SMB(20, false);
+  } else if (ld_out <= 2048) {
+    if (drop) MM_SMB(64, true); else MM_SMB(64, false);
+  } else {
     return bad_arg("softmax_bwd: at most 2048 keys");
+  }
+#undef MM_SMB
   return 0;
 }
 
@@ -613,17 +631,56 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const float* __restrict__ l
   }
 }
 
-// embedding backward: table_grad[token] += scale * dx[row] for non-padding tokens (atomic adds; nn.Embedding with
-// padding_idx gives that row no gradient)
-__global__ void __launch_bounds__(128) embed_bwd_kernel(const long long* __restrict__ tokens, int padding_idx,
+// embedding backward, deterministic: one block per vocabulary row scans the token list in order and sums the gradient
+// rows of its token (no atomics: the result does not depend on scheduling).  table_grad[v] += scale * sum_{tokens[r]==v} dx[r]
+// (nn.Embedding with padding_idx gives that row no gradient).  The token list is staged through shared memory.
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const long long* __restrict__ tokens, int padding_idx,
                                                          const float* __restrict__ dx, long long rows, int dim,
                                                          float scale, float* __restrict__ table_grad) {
-  const long long row = blockIdx.x;
-  if (row >= rows) return;
-  const long long tok = tokens[row];
-  if (tok == padding_idx) return;
-  for (int c = threadIdx.x; c < dim; c += blockDim.x)
-    atomicAdd(table_grad + tok * dim + c, scale * dx[row * dim + c]);
+  __shared__ int hits[1024];
+  __shared__ int warp_cnt[8];
+  __shared__ int n_hits;
+  const int v = blockIdx.x;
+  if (v == padding_idx) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};      // dim <= 1024: columns threadIdx.x + 256 j
+  for (long long base = 0; base < rows; base += 1024) {
+    // ordered compaction of the chunk's matching rows: warp w owns rows [128 w, 128 w + 128), four ballots each
+    unsigned m[4];
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long r = base + warp * 128 + q * 32 + lane;
+      m[q] = __ballot_sync(0xffffffffu, r < rows && tokens[r] == v);
+      cnt += __popc(m[q]);
+    }
+    if (lane == 0) warp_cnt[warp] = cnt;
+    __syncthreads();
+    int off = 0;
+    for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+    if (threadIdx.x == 255) n_hits = off + cnt;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if ((m[q] >> lane) & 1u) hits[off + __popc(m[q] & ((1u << lane) - 1u))] = warp * 128 + q * 32 + lane;
+      off += __popc(m[q]);
+    }
+    __syncthreads();
+    const int n = n_hits;
+    for (int h = 0; h < n; ++h) {
+      const float* src = dx + (base + hits[h]) * dim;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = threadIdx.x + 256 * j;
+        if (c < dim) acc[j] += src[c];
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = threadIdx.x + 256 * j;
+    if (c < dim) table_grad[(long long)v * dim + c] += scale * acc[j];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -820,9 +877,9 @@ extern "C" int mm_label_smoothed_nll_bwd(const float* logits, int64_t ld, int32_
 }
 
 extern "C" int mm_embed_tokens_bwd(const int64_t* tokens, int32_t padding_idx, const float* dx, int64_t rows, int32_t dim,
-                                   float scale, float* table_grad, void* stream) {
-  if (!tokens || !dx || !table_grad || rows <= 0 || dim <= 0) return bad_arg("embed_tokens_bwd");
-  embed_bwd_kernel<<<(unsigned)rows, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+                                   float scale, float* table_grad, int32_t vocab, void* stream) {
+  if (!tokens || !dx || !table_grad || rows <= 0 || dim <= 0 || dim > 1024 || vocab <= 0) return bad_arg("embed_tokens_bwd");
+  embed_bwd_kernel<<<(unsigned)vocab, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const long long*>(tokens), padding_idx, dx, rows, dim, scale, table_grad);
   MM_CHECK_LAUNCH("embed_bwd_kernel launch");
   return 0;

@@ -491,14 +491,14 @@ def label_smoothed_nll_bwd(logits: torch.Tensor, vocab: int, target: torch.Tenso
 
 def embed_tokens_bwd(tokens: torch.Tensor, padding_idx: int, dx: torch.Tensor, scale: float,
                      table_grad: torch.Tensor) -> None:
-    """table_grad[token] += scale * dx[row] for the non-padding tokens (atomic adds)."""
+    """table_grad[v] += scale * sum of dx[row] over the rows whose token is v (deterministic; padding row skipped)."""
     assert tokens.dtype == torch.int64 and tokens.is_contiguous() and dx.dtype == table_grad.dtype == torch.float32
     assert dx.is_contiguous() and table_grad.is_contiguous()
     rows, dim = tokens.numel(), dx.shape[-1]
     lib = _lib.load()
     with _Launch("embed_tokens_bwd", 8.0 * rows * dim):
         _lib.check(lib.mm_embed_tokens_bwd(_ptr(tokens), padding_idx, _ptr(dx), rows, dim, scale, _ptr(table_grad),
-                                           _stream()), "mm_embed_tokens_bwd")
+                                           table_grad.numel() // dim, _stream()), "mm_embed_tokens_bwd")
 
 
 def dropout(x: torch.Tensor, out: torch.Tensor, p: float, seed: int, site: int,
