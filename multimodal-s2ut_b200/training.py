@@ -12,20 +12,23 @@ training").  ``TrainEngine.backward`` turns it into the gradient of every encode
   encoder  final LayerNorm -> L x [fc2 -> ReLU -> fc1 -> LN2 ; out_proj -> self-attention -> QKV -> LN1]
   front    x sqrt(d) -> GLU -> Conv1d #2 (col2im) -> GLU -> Conv1d #1          (fbank / CMVN have no parameters)
 
-Every contraction is the tcgen05 GEMM of the forward pass (``mm_gemm``): dgrad = dY W uses a transposed 16-bit copy
-of the weight, wgrad = dY^T X contracts over tokens with split-K partials (``mm_pack_t`` makes the token-contiguous
-operand copies, ``mm_reduce_partials`` sums them deterministically).  Attention backward recomputes the scores per
-head (S = q k^T, dP = dO v^T -> ``mm_softmax_bwd`` -> dV = P^T dO, dK = dS^T q, dQ = dS k).  fp32 residual-stream
-gradients, 16-bit GEMM operands, fp32 parameter gradients / Adam state in flat buffers.
+Every contraction is the tcgen05 GEMM of the forward pass (``mm_gemm``) with the operand layouts the backward pass
+needs, so nothing is transposed or copied: dgrad = dY W reads the Linear weight as stored (MN-major W operand); wgrad =
+dY^T X reads dY and X as stored (both MN-major) and splits the token contraction into the number of batches that fills
+whole waves of the 74 CTA pairs (fp32 partials, summed deterministically by ``mm_reduce_partials``); attention backward
+recomputes the scores per (sequence, head) straight from / into the q|k|v layout (S = q k^T, dP = dO v^T ->
+``mm_softmax_bwd`` -> dV = P^T dO, dK = dS^T q, dQ = dS k).  Only the conv wgrad (strided window operand) still packs
+transposed copies (``mm_pack_t``).  fp32 residual-stream gradients, 16-bit GEMM operands, fp32 parameter gradients /
+Adam state in flat buffers.
 
 Parameters and gradients live in two flat fp32 buffers (``flat_p`` / ``flat_g``; every ``nn.Parameter`` of the encoder
 is re-pointed to a view), ordered so that the packed layouts the kernels produce (q|k|v, k|v, LayerNorm weight|bias)
 are contiguous slices.  ``all_reduce_grads`` runs NCCL (or gloo) over ``flat_g`` in buckets; ``adam_step`` is one kernel.
 
-Element-wise dropout (embedding, residual and activation sites, SA_image_dropout) uses counter-based masks that the
-backward pass regenerates (``mm_dropout``); attention dropout (encoder self-attention, SA_attention_dropout) runs the
-un-fused score / softmax+dropout / P V path in the training forward; modality dropout (per-batch image zeroing) works.
-Not built (raises): image key masks, several image-feature types, and the device
+Element-wise dropout (embedding, residual and activation sites, SA_image_dropout, SA_text_dropout) uses counter-based
+masks that the backward pass regenerates (``mm_dropout``); attention dropout (encoder self-attention,
+SA_attention_dropout) runs the un-fused score / softmax+dropout / P V path in the training forward; modality dropout
+(per-batch image zeroing) works.  Not built (raises): image key masks, several image-feature types, and the device
 feature store in the backward pass.
 """
 from __future__ import annotations
