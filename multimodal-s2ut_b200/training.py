@@ -773,6 +773,9 @@ class TrainEngine(EncoderEngine):
         grad_out = grad_out.to(device=self.device, dtype=torch.float32).contiguous()
         assert tuple(grad_out.shape) == (T, B, d)
         gtext = self.buf("b_gtext", (M, d), torch.float32)
+        if not accumulate and not sv["fused"]:
+            # a batch without image features computes no fusion gradients: they must read 0, not the previous batch's
+            self.flat_g[self.bucket_top[0]:].zero_()
         if sv["fused"]:
             with _scope("fusion"):
                 self._fusion_bwd(grad_out, gtext, B, T, accumulate)

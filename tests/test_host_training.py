@@ -320,3 +320,41 @@ def test_decoder_dropout_orchestration_matches_oracle_with_same_masks(monkeypatc
     monkeypatch.setattr(dt, "K", _emul)
     monkeypatch.setattr(dt.UnitDecoderTrainEngine, "_require_cuda", False)
     _decoder_dropout_parity(_emul, torch.device("cpu"), dt)
+
+
+def test_backward_without_images_matches_autograd_oracle(monkeypatch):
+    """No image features in the batch (the plain S2T branch: fused states = final LayerNorm output): the gradient enters
+    through the T x B x C -> token-major copy instead of the fusion backward."""
+    from oracle import fbank as ofb, fusion as ofu
+    from test_gpu_encoder import _build
+    from test_gpu_training import REL, ZERO, _rel
+
+    _emulated(monkeypatch)
+    from mm_s2ut_b200 import synth
+
+    enc, args, cfg = _build("small", "selective_attention", True)
+    enc.dropout_p = enc.activation_dropout_p = enc.attention_dropout_p = 0.0
+    wavs, _ = synth.synth_batch(9, 2, 1.0, ragged=True)
+    feats, flens = ofb.features_from_waveforms(wavs)
+    sd = {k: v.detach().clone().float().requires_grad_(v.is_floating_point()) for k, v in enc.state_dict().items()}
+    ref = ofu.mm_encoder_forward(sd, cfg, torch.from_numpy(feats), torch.from_numpy(flens), [], [],
+                                 args.encoder_attention_heads)
+    out_ref, mask = ref["encoder_out"][0], ref["encoder_padding_mask"][0]
+    R = torch.randn(out_ref.shape, generator=torch.Generator().manual_seed(3)) * (~mask).t().unsqueeze(-1)
+    (out_ref * R).sum().backward()
+    wav, lens = synth.pad_waveforms(wavs)
+    enc.train()
+    eng = enc.train_engine()
+    eng.flat_g.fill_(7.0)                       # stale gradients of an earlier batch must not survive
+    out = eng.forward_train(wav, lens, [], [])
+    assert ((out["encoder_out"][0] - out_ref.detach()).abs() * (~mask).t().unsqueeze(-1)).max().item() < 2e-2
+    eng.backward(R)
+    names = dict(enc.named_parameters())
+    checked = 0
+    for k, v in sd.items():
+        if v.grad is None or k not in names or v.grad.norm() < ZERO:
+            continue
+        assert _rel(names[k].grad, v.grad) < REL, k
+        checked += 1
+    assert checked >= 6 * 15 + 2 + 4
+    assert all(names[k].grad.abs().max().item() == 0 for k in names if "selective_attns" in k or "gate_denses" in k)
