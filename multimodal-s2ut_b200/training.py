@@ -126,7 +126,7 @@ class TrainEngine(EncoderEngine):
     def __init__(self, enc, op_dtype: Optional[torch.dtype] = None, block_n: int = 256):
         self._flatten(enc)
         super().__init__(enc, op_dtype, block_n)
-        self.fused_ln = False          # (inference path of this engine: un-fused)
+        # (the inference forward of this engine keeps the base class's fused GEMM+LN path)
         # training forward: fused GEMM + residual + LayerNorm with a separate output buffer (needs n == 512)
         self.train_fused_ln = self.d == 512 and getattr(enc, "fuse_layernorm", True)
         self._saved = None

@@ -258,6 +258,12 @@ def test_autograd_function_and_adam_step(cuda):
     out2 = enc(wav.cuda(), lens.cuda(), None, None, None, imgs_list=[imgs.cuda()], img_masks_list=[None])
     loss1, loss2 = (y.detach() * R.cuda()).sum().item(), (out2["encoder_out"][0].detach() * R.cuda()).sum().item()
     assert loss2 < loss1, (loss1, loss2)      # one descent step on a linear functional of the output
+    # the same engine serves inference after training (eval mode: fused kernels, updated operand copies)
+    enc.eval()
+    with torch.no_grad():
+        out_eval = enc(wav.cuda(), lens.cuda(), None, None, None, imgs_list=[imgs.cuda()], img_masks_list=[None])
+    enc.train()
+    assert (out_eval["encoder_out"][0] - out2["encoder_out"][0].detach()).abs().max().item() < 2e-2
     # gradient accumulation: a second backward adds onto the attached gradients
     g_before = dict(enc.named_parameters())[k].grad.clone()
     (out2["encoder_out"][0] * R.cuda()).sum().backward()
