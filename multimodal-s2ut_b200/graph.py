@@ -83,7 +83,9 @@ class GraphedTrainStep:
     """
 
     def __init__(self, enc, batch: int, n_samples: int, img_shape: tuple, wav_dtype: torch.dtype = torch.float32,
-                 betas=(0.9, 0.98), eps: float = 1e-8, overlap_reduce: bool = False):
+                 betas=(0.9, 0.98), eps: float = 1e-8, overlap_reduce: bool = False, specaugment=None):
+        """specaugment: optional ``data.specaugment.SpecAugmentTransform``; its per-utterance masks are drawn on the host
+        before every replay (``enc.modality_rng``, the reference's numpy calls) and copied into a static device table."""
         self.enc = enc
         self.eng = enc.train_engine()
         dev = self.eng.device
@@ -97,6 +99,12 @@ class GraphedTrainStep:
         # element-wise dropout under replay: the masks are keyed on base seed + this device scalar, advanced per step
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.base_seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
+        self.specaugment = specaugment
+        self.spec_tab = None
+        if specaugment is not None:
+            n_masks = specaugment.freq_mask_n + specaugment.time_mask_n
+            self.spec_tab = torch.zeros(batch, 2 * n_masks, dtype=torch.int32, device=dev)
+            self._spec_frames = [0 if n_samples < 400 else 1 + (n_samples - 400) // 160] * batch
         self.out = {}
         self.graphs = {}
         self.opt_graph: Optional[torch.cuda.CUDAGraph] = None
@@ -105,9 +113,13 @@ class GraphedTrainStep:
         self._hyper_done = [None] * 8
         self._hyper_i = 0
 
+    def _specaug(self):
+        sa = self.specaugment
+        return None if sa is None else (self.spec_tab, sa.freq_mask_n, sa.time_mask_n, sa.mask_value)
+
     def _fwd_bwd(self, drop_image: bool):
         out = self.eng.forward_train(self.wav, self.lens, [self.img], [None], drop_image=drop_image,
-                                     dropout_seed=self.base_seed, dropout_seed_dev=self.seed_dev)
+                                     dropout_seed=self.base_seed, dropout_seed_dev=self.seed_dev, specaug=self._specaug())
         if self.grad_out is None:
             self.grad_out = torch.zeros_like(out["encoder_out"][0])
         # with several ranks the bucketed gradient all-reduce is part of the captured graph (side stream, forked from
@@ -154,6 +166,9 @@ class GraphedTrainStep:
         if self.opt_graph is None:
             self.capture()
         self.seed_dev.add_(0x632BE5AB)        # fresh dropout masks for this step (stream-ordered before the replay)
+        if self.specaugment is not None:      # fresh SpecAugment masks: host draws -> the static device table
+            tab = self.specaugment.draw_batch(self._spec_frames, 80, self.enc.modality_rng)
+            self.spec_tab.copy_(torch.from_numpy(tab))
         self.graphs[bool(drop_image)].replay()
         return self.out[bool(drop_image)]
 
@@ -207,7 +222,7 @@ class GraphedModelTrainStep(GraphedTrainStep):
         import torch.distributed as dist
 
         out = self.eng.forward_train(self.wav, self.lens, [self.img], [None], drop_image=drop_image,
-                                     dropout_seed=self.base_seed, dropout_seed_dev=self.seed_dev)
+                                     dropout_seed=self.base_seed, dropout_seed_dev=self.seed_dev, specaug=self._specaug())
         self.dec.forward_train(self.prev_tokens, out["encoder_out"][0], out["encoder_padding_mask"][0],
                                dropout_seed=self.base_seed, dropout_seed_dev=self.seed_dev)
         loss, nll, d_enc = self.dec.loss_backward(self.target, self.label_smoothing)

@@ -510,3 +510,35 @@ def test_graphed_train_step_draws_fresh_dropout_masks(cuda):
     g1 = gs.eng.flat_g.clone()
     o2 = gs.forward_backward()["encoder_out"][0].clone()
     assert not torch.equal(o1, o2) and torch.isfinite(g1).all() and not torch.equal(g1, gs.eng.flat_g)
+
+
+def test_graphed_train_step_with_specaugment(cuda):
+    """SpecAugment under CUDA-graph replay: the mask table is a static device tensor refreshed from host draws before
+    every replay; the normalised features the graph consumes are zero exactly in the drawn bands."""
+    import numpy as np
+
+    from mm_s2ut_b200.data.specaugment import SpecAugmentTransform
+    from mm_s2ut_b200.graph import GraphedTrainStep
+
+    enc, wav, lens, imgs, R, *_ = _train_setup("selective_attention", True)
+    enc.cuda().train()
+    enc.modality_rng = np.random.RandomState(5)
+    sa = SpecAugmentTransform.from_policy("lb")
+    gs = GraphedTrainStep(enc, wav.shape[0], wav.shape[1], tuple(imgs.shape[1:]), specaugment=sa)
+    gs.wav.copy_(wav.cuda())
+    gs.img.copy_(imgs.cuda())
+    gs.grad_out = R.cuda().clone()
+    gs.capture()
+    o1 = gs.forward_backward()["encoder_out"][0].clone()
+    tab1 = gs.spec_tab.cpu().clone()
+    x1 = gs.eng.buf("x1", tuple(gs.eng._saved["x1"].shape), gs.eng.op_dtype).float().cpu()
+    o2 = gs.forward_backward()["encoder_out"][0].clone()
+    assert not torch.equal(tab1, gs.spec_tab.cpu()) and not torch.equal(o1, o2)
+    for b in range(wav.shape[0]):
+        f0, f, t0, t = tab1[b].tolist()
+        feats = x1[b, 2:]                                     # two leading zero frames in the conv operand buffer
+        if f:
+            assert (feats[:, f0:f0 + f] == 0).all()
+        if t:
+            assert (feats[t0:t0 + t] == 0).all()
+        assert (feats[: 50] != 0).any()
