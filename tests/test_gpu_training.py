@@ -531,7 +531,7 @@ def test_graphed_train_step_with_specaugment(cuda):
     gs.capture()
     o1 = gs.forward_backward()["encoder_out"][0].clone()
     tab1 = gs.spec_tab.cpu().clone()
-    x1 = gs.eng.buf("x1", tuple(gs.eng._saved["x1"].shape), gs.eng.op_dtype).float().cpu()
+    x1 = gs.eng._saved["x1"].float().cpu()                    # CMVN output / conv operand buffer of that replay
     o2 = gs.forward_backward()["encoder_out"][0].clone()
     assert not torch.equal(tab1, gs.spec_tab.cpu()) and not torch.equal(o1, o2)
     for b in range(wav.shape[0]):
