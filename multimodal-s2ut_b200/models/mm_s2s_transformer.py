@@ -201,6 +201,11 @@ class MM_S2STransformerEncoder(S2TTransformerEncoderParams):
             from ..training import EncoderOutGrad
 
             eng = self.train_engine()
+            if getattr(self, "_external_optimizer", True):
+                eng.refresh_operands()      # a torch / fairseq optimizer may have stepped the fp32 parameters
+            if eng.grads_attached():        # on this path autograd owns .grad (accumulation, hooks, DDP reducer)
+                for p in eng.params:
+                    p.grad = None
             specaug = None
             if self.specaugment is not None:
                 from ..engine import num_frames
@@ -212,8 +217,7 @@ class MM_S2STransformerEncoder(S2TTransformerEncoderParams):
                            sa.time_mask_n, sa.mask_value)
             out = eng.forward_train(src_tokens, src_lengths, imgs_list if fuse else [], img_masks_list if fuse else [],
                                     drop_audio=drop_audio, drop_image=drop_image, specaug=specaug)
-            trigger = torch.zeros((), device=eng.device, requires_grad=True)
-            out["encoder_out"] = [EncoderOutGrad.apply(trigger, out["encoder_out"][0], eng)]
+            out["encoder_out"] = [EncoderOutGrad.apply(out["encoder_out"][0], eng, *eng.params)]
             return out
         return eng.forward(src_tokens, src_lengths, imgs_list if fuse else [], img_masks_list if fuse else [],
                            return_all_hiddens=return_all_hiddens, drop_audio=drop_audio, drop_image=drop_image,

@@ -104,22 +104,26 @@ def all_reduce_flat(flat: torch.Tensor, bucket_elems: int = 8 * 1024 * 1024) -> 
 
 
 class EncoderOutGrad(torch.autograd.Function):
-    """Autograd boundary of the path: identity on the fused states in forward; in backward the incoming
-    ``d loss / d encoder_out`` is handed to ``TrainEngine.backward`` which fills the parameters' ``.grad``."""
+    """Autograd boundary of the path.  Forward: identity on the fused states.  Backward: the incoming
+    ``d loss / d encoder_out`` goes through ``TrainEngine.backward`` and the parameter gradients are handed back to
+    autograd as the gradients of the Function's parameter inputs -- so ``.grad`` accumulation, ``zero_grad`` in either
+    mode, gradient hooks and DistributedDataParallel's reducer all behave as for any other module."""
 
     @staticmethod
-    def forward(ctx, trigger, out, eng):
+    def forward(ctx, out, eng, *params):
         ctx.eng = eng
         return out.view_as(out)
 
     @staticmethod
     def backward(ctx, grad):
         eng = ctx.eng
-        acc = eng.grads_attached()
-        eng.backward(grad, accumulate=acc)
-        if not acc:
-            eng.attach_grads()
-        return None, None, None
+        eng.backward(grad, accumulate=False)
+        g = eng.flat_g.clone()          # one 4-byte-per-parameter copy: autograd owns what it is given
+        grads = []
+        for p in eng.params:
+            o, n = eng._slices[id(p)]
+            grads.append(g[o:o + n].view(p.shape))
+        return (None, None, *grads)
 
 
 class TrainEngine(EncoderEngine):
@@ -191,7 +195,7 @@ class TrainEngine(EncoderEngine):
                 n = p.numel()
                 self.flat_p[o:o + n].copy_(p.detach().reshape(-1).float())
                 p.data = self.flat_p[o:o + n].view(p.shape)
-                p.grad = self.flat_g[o:o + n].view(p.shape)
+                p.grad = self.flat_g[o:o + n].view(p.shape)      # stand-alone engine API; the module path lets autograd own .grad
                 self._slices[id(p)] = (o, n)
         self.params = order
         # gradient buckets in the order the backward pass completes them: top (final LayerNorm, fusion, everything
@@ -294,6 +298,12 @@ class TrainEngine(EncoderEngine):
             gd = enc.gate_denses[j]
             ps.update(wg=(gd.weight,), bg=(gd.bias,))
             self.fusion_bwd.append(dict(p=ps))
+
+    def refresh_operands(self) -> None:
+        """Re-derive every 16-bit operand copy from the fp32 parameters: for optimizers that update the parameters
+        themselves (torch / fairseq optimizers on the module path); ``adam_step`` does it as part of its own update."""
+        K.convert(self.flat_p, self.flat_op)
+        self.repack()
 
     def repack(self) -> None:
         """Refresh every 16-bit operand copy from the fp32 master parameters (after an optimizer step)."""

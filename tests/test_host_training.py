@@ -74,7 +74,16 @@ def test_autograd_function_boundary(monkeypatch):
         q.grad = None
     out = enc(wav, lens, None, None, None, imgs_list=[imgs], img_masks_list=[None])
     (out["encoder_out"][0] * R).sum().backward()
-    assert _rel(p.grad, ref_grads[k]) < REL and enc.train_engine().grads_attached()
+    assert _rel(p.grad, ref_grads[k]) < REL
+    out = enc(wav, lens, None, None, None, imgs_list=[imgs], img_masks_list=[None])
+    (out["encoder_out"][0] * R).sum().backward()                # no zero_grad in between: autograd accumulates
+    assert _rel(p.grad, 2 * ref_grads[k]) < REL
+    # a torch optimizer steps the fp32 parameters; the next forward re-derives the 16-bit operand copies from them
+    opt = torch.optim.SGD(enc.parameters(), lr=1e-2)
+    l0 = (out["encoder_out"][0].detach() * R).sum().item()
+    opt.step()
+    out = enc(wav, lens, None, None, None, imgs_list=[imgs], img_masks_list=[None])
+    assert (out["encoder_out"][0].detach() * R).sum().item() < l0
 
 
 def _worker(rank, world, port, q):
