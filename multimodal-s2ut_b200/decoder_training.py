@@ -173,10 +173,14 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
     # ------------------------------------------------------------------------------------------
     # forward (activations kept)
     # ------------------------------------------------------------------------------------------
-    def _resid(self, a, a_ld, w, b, k, x_in, x_out, M, site):
-        """x_out = x_in + dropout(a w^T + b): one GEMM with the residual epilogue, or GEMM -> mm_dropout(+resid)."""
+    def _resid(self, a, a_ld, w, b, k, x_in, x_out, M, site, ln=None, h=None):
+        """x_out = x_in + dropout(a w^T + b), then h = LayerNorm_ln(x_out): the fused GEMM + residual + LayerNorm kernel
+        with a separate output (d_model 512, no dropout), else GEMM (-> mm_dropout(+resid)) -> LayerNorm."""
         d, bn = self.d, self.block_n
         p, _, _, seed, seed_dev = self._drop
+        if p == 0 and d == 512 and ln is not None:
+            K.gemm_resid_ln(a, w, b, x_in, ln[0], ln[1], h, x_out=x_out)
+            return
         if p > 0:
             y = self.buf("t_y", (M, d), torch.float32)
             K.gemm(a0=a, a0_ld=a_ld, rows=M, w=w, n=d, k=k, mode=K.EPI_F32, bias=b, out0=y, out0_ld=d, block_n=bn)
@@ -184,6 +188,8 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
         else:
             K.gemm(a0=a, a0_ld=a_ld, rows=M, w=w, n=d, k=k, mode=K.EPI_RESID_F32, bias=b, aux0=x_in, aux_ld=d, out0=x_out,
                    out0_ld=d, block_n=bn)
+        if ln is not None:
+            K.layernorm(x_out, ln[0], ln[1], out_op=h)
 
     def _attn_fwd(self, q, q_ld, q_bs, k, v, kv_ld, kv_bs, out, B, Lq, Tk, kv_lens, causal, site):
         """Attention forward: the fused kernel, or -- with attention dropout -- scores / softmax+dropout / P V on the
@@ -231,6 +237,7 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
             K.dropout(x, x, p_drop, seed, DSITE_EMBED, seed_dev=seed_dev)
         scale = 64 ** -0.5
         saved = dict(B=B, L=L, T=T, tokens=tokens, enc_lens=enc_lens, enc_btc=enc_btc, layers=[], drop=self._drop)
+        h_out = self.buf("h_out", (M, d), op)
         for i, Lr in enumerate(self.layers):
             s = dict(x0=x, h1=self.buf(f"h1_{i}", (M, d), op), qkv=self.buf(f"qkv_{i}", (M, 3 * d), op),
                      att=self.buf(f"att_{i}", (M, d), op), x1=self.buf(f"x1_{i}", (M, d), torch.float32),
@@ -238,7 +245,8 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                      kv2=self.buf(f"kv2_{i}", (B * T, 2 * d), op), att2=self.buf(f"att2_{i}", (M, d), op),
                      x2=self.buf(f"x2_{i}", (M, d), torch.float32), h3=self.buf(f"h3_{i}", (M, d), op),
                      f=self.buf(f"f_{i}", (M, self.ffn), op), x3=self.buf(f"x3_{i}", (M, d), torch.float32))
-            K.layernorm(s["x0"], Lr["ln1"][0], Lr["ln1"][1], out_op=s["h1"])
+            if i == 0:       # later layers: LN1 was produced by the previous layer's fc2 step
+                K.layernorm(s["x0"], Lr["ln1"][0], Lr["ln1"][1], out_op=s["h1"])
             K.gemm(a0=s["h1"], a0_ld=d, rows=M, w=Lr["wqkv"], n=3 * d, k=d, mode=K.EPI_OP, bias=Lr["bqkv"], scale=scale,
                    scale_cols=d, out0=s["qkv"], out0_ld=3 * d, block_n=bn)
             if p_attn > 0:
@@ -246,8 +254,7 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                                B, L, L, None, True, dsite_layer(i, 1))
             else:
                 K.attention(s["qkv"], 0, L, s["qkv"], d, s["qkv"], 2 * d, L, None, B, H, s["att"], causal=True)
-            self._resid(s["att"], d, Lr["wo"], Lr["bo"], d, s["x0"], s["x1"], M, dsite_layer(i, 0))
-            K.layernorm(s["x1"], Lr["ln2"][0], Lr["ln2"][1], out_op=s["h2"])
+            self._resid(s["att"], d, Lr["wo"], Lr["bo"], d, s["x0"], s["x1"], M, dsite_layer(i, 0), Lr["ln2"], s["h2"])
             K.gemm(a0=s["h2"], a0_ld=d, rows=M, w=Lr["wq"], n=d, k=d, mode=K.EPI_OP, bias=Lr["bq"], scale=scale,
                    scale_cols=d, out0=s["q2"], out0_ld=d, block_n=bn)
             K.gemm(a0=enc_btc, a0_ld=d, rows=B * T, w=Lr["wkv"], n=2 * d, k=d, mode=K.EPI_OP, bias=Lr["bkv"],
@@ -257,17 +264,18 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                                False, dsite_layer(i, 3))
             else:
                 K.attention(s["q2"], 0, L, s["kv2"], 0, s["kv2"], d, T, enc_lens, B, H, s["att2"])
-            self._resid(s["att2"], d, Lr["wo2"], Lr["bo2"], d, s["x1"], s["x2"], M, dsite_layer(i, 2))
-            K.layernorm(s["x2"], Lr["ln3"][0], Lr["ln3"][1], out_op=s["h3"])
+            self._resid(s["att2"], d, Lr["wo2"], Lr["bo2"], d, s["x1"], s["x2"], M, dsite_layer(i, 2), Lr["ln3"], s["h3"])
             K.gemm(a0=s["h3"], a0_ld=d, rows=M, w=Lr["w1"], n=self.ffn, k=d, mode=K.EPI_RELU_OP, bias=Lr["b1"],
                    out0=s["f"], out0_ld=self.ffn, block_n=bn)
             if p_act > 0:
                 K.dropout(s["f"], s["f"], p_act, seed, dsite_layer(i, 4), seed_dev=seed_dev)
-            self._resid(s["f"], self.ffn, Lr["w2"], Lr["b2"], self.ffn, s["x2"], s["x3"], M, dsite_layer(i, 5))
+            last = i + 1 == self.n_layers
+            nxt_ln = self.ln_out if last else self.layers[i + 1]["ln1"]
+            nxt_h = h_out if last else self.buf(f"h1_{i + 1}", (M, d), op)
+            self._resid(s["f"], self.ffn, Lr["w2"], Lr["b2"], self.ffn, s["x2"], s["x3"], M, dsite_layer(i, 5), nxt_ln, nxt_h)
             saved["layers"].append(s)
             x = s["x3"]
-        h = self.buf("h_out", (M, d), op)
-        K.layernorm(x, self.ln_out[0], self.ln_out[1], out_op=h)
+        h = h_out
         logits = self.buf("logits", (M, self.vocab_pad), torch.float32)
         K.gemm(a0=h, a0_ld=d, rows=M, w=self.emb_op, n=self.vocab_pad, k=d, mode=K.EPI_F32, out0=logits,
                out0_ld=self.vocab_pad, block_n=bn)

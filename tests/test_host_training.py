@@ -367,3 +367,17 @@ def test_backward_without_images_matches_autograd_oracle(monkeypatch):
         checked += 1
     assert checked >= 6 * 15 + 2 + 4
     assert all(names[k].grad.abs().max().item() == 0 for k in names if "selective_attns" in k or "gate_denses" in k)
+
+
+def test_decoder_backward_d512_fused_forward(monkeypatch):
+    """d_model = 512: the decoder's training forward runs the fused GEMM + residual + LayerNorm kernel (separate output)."""
+    from test_gpu_training import REL, ZERO, _rel
+
+    _emulated(monkeypatch)
+    import mm_s2ut_b200.decoder_training as dt
+
+    monkeypatch.setattr(dt, "K", _emul)
+    monkeypatch.setattr(dt.UnitDecoderTrainEngine, "_require_cuda", False)
+    setup = _decoder_setup(B=2, L=7, T=9, d=512, heads=8, ffn=256, layers=2, vocab=29)
+    eng = dt.UnitDecoderTrainEngine(setup[0], setup[5], "cpu")
+    _check_decoder(eng, setup, REL, ZERO, _rel)
