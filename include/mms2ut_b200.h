@@ -261,6 +261,14 @@ int mm_rowsum(const void* in, int64_t ld, int32_t rows, int32_t cols, float* out
               void* stream);
 int mm_reduce_partials(const float* part, int32_t n_partials, int64_t stride, int64_t n, float* out, int32_t accumulate,
                        void* stream);
+/* Several mm_reduce_partials in one launch (the backward pass defers a layer's reductions and runs them together). */
+typedef struct mm_reduce_job {
+  const float* part;
+  float* out;
+  int64_t stride, n;
+  int32_t n_partials, accumulate;
+} mm_reduce_job;
+int mm_reduce_partials_many(const mm_reduce_job* jobs, int32_t count, void* stream);
 int mm_layernorm_bwd_blocks(void);
 int mm_layernorm_bwd(const float* x, const float* gamma, const float* dy, int64_t rows, int32_t dim, float eps,
                      const float* resid, float* dx, float* partials, void* dx_op, int32_t dtype, void* stream);

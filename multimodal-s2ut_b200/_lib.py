@@ -92,6 +92,13 @@ class GemmArgs(C.Structure):
     ]
 
 
+class ReduceJob(C.Structure):
+    """``mm_reduce_job`` (include/mms2ut_b200.h)."""
+
+    _fields_ = [("part", C.c_void_p), ("out", C.c_void_p), ("stride", C.c_int64), ("n", C.c_int64),
+                ("n_partials", C.c_int32), ("accumulate", C.c_int32)]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "mm_abi_version": (C.c_int, []),
@@ -139,6 +146,7 @@ EXPORTS = {
                             C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "mm_rowsum": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "mm_reduce_partials": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mm_reduce_partials_many": (C.c_int, [C.POINTER(ReduceJob), C.c_int32, C.c_void_p]),
     "mm_layernorm_bwd_blocks": (C.c_int, []),
     "mm_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),

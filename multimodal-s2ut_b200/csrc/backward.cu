@@ -181,6 +181,27 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
   out[i] = accumulate ? out[i] + s : s;
 }
 
+// several reductions in one launch (blockIdx.y = job): the backward pass defers the ~10 partial reductions of a layer
+// (split-K wgrad partials, bias column sums, LayerNorm parameter partials) and runs them together
+struct ReduceJobs {
+  const float* part[16];
+  float* out[16];
+  long long stride[16], n[16];
+  int S[16], accumulate[16];
+};
+__global__ void __launch_bounds__(256) reduce_many_kernel(ReduceJobs t) {
+  const int j = blockIdx.y;
+  const float* __restrict__ part = t.part[j];
+  float* __restrict__ out = t.out[j];
+  const long long n = t.n[j], stride = t.stride[j];
+  const int S = t.S[j], acc = t.accumulate[j];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < S; ++k) s += part[(long long)k * stride + i];
+    out[i] = acc ? out[i] + s : s;
+  }
+}
+
 // column sums of a 16-bit [rows, cols] matrix (bias gradients): block = 64 columns x one chunk of rows; partials
 // [gridDim.y][cols], summed by reduce_partials.  Rows with (r % period) >= valid are skipped when period > 0.
 template <typename OpT>
@@ -788,6 +809,29 @@ extern "C" int mm_reduce_partials(const float* part, int32_t n_partials, int64_t
   reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       part, n_partials, stride, n, out, accumulate);
   MM_CHECK_LAUNCH("reduce_partials_kernel launch");
+  return 0;
+}
+
+extern "C" int mm_reduce_partials_many(const mm_reduce_job* jobs, int32_t count, void* stream) {
+  if (!jobs || count <= 0) return bad_arg("reduce_partials_many");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (int base = 0; base < count; base += 16) {
+    ReduceJobs t;
+    memset(&t, 0, sizeof(t));
+    const int m = count - base < 16 ? count - base : 16;
+    long long max_n = 0;
+    for (int i = 0; i < m; ++i) {
+      const mm_reduce_job& j = jobs[base + i];
+      if (!j.part || !j.out || j.n_partials <= 0 || j.n <= 0) return bad_arg("reduce_partials_many: job");
+      t.part[i] = j.part, t.out[i] = j.out, t.stride[i] = j.stride, t.n[i] = j.n, t.S[i] = j.n_partials;
+      t.accumulate[i] = j.accumulate;
+      if (j.n > max_n) max_n = j.n;
+    }
+    long long gx = (max_n + 255) / 256;
+    if (gx > 1024) gx = 1024;
+    reduce_many_kernel<<<dim3((unsigned)gx, (unsigned)m), 256, 0, s>>>(t);
+    MM_CHECK_LAUNCH("reduce_many_kernel launch");
+  }
   return 0;
 }
 

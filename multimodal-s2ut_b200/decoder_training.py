@@ -50,7 +50,11 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
     activation_dropout_p = 0.0
 
     # backward helpers shared with the encoder engine (they only use self.buf / block_n / op_dtype / _ln_blocks)
+    _ARENA = TrainEngine._ARENA
     _partials = TrainEngine._partials
+    _defer = TrainEngine._defer
+    _flush = TrainEngine._flush
+    _lnp = TrainEngine._lnp
     _wgrad_mn = TrainEngine._wgrad_mn
     _bias_grad = TrainEngine._bias_grad
     _linear_bwd = TrainEngine._linear_bwd
@@ -325,7 +329,6 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
         loss, nll = K.label_smoothed_nll(logits, self.vocab, target, self.padding_idx, epsilon)
         dlog = self.buf("dlogits", (M, Vp), op)
         K.label_smoothed_nll_bwd(logits, self.vocab, target, self.padding_idx, epsilon, dlog, grad_scale)
-        lnp = self.buf("ln_part", (self._ln_blocks * 2 * max(d, 1024),), torch.float32)
         dh = self.buf("b_dh", (M, d), torch.float32)
         g = self.buf("b_g", (M, d), torch.float32)
         g_op = self.buf("b_g_op", (M, d), op)
@@ -334,8 +337,10 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
             self._wgrad_mn(dlog, Vp, [(sv["h_out"], d, d)], M, Vp, self.g("embed_tokens.weight"), accumulate)
             K.gemm(a0=dlog, a0_ld=Vp, rows=M, w=self.emb_op, w_ld=d, w_mn=True, n=d, k=Vp, mode=K.EPI_F32, out0=dh,
                    out0_ld=d, block_n=bn)
+            lnp = self._lnp()
             K.layernorm_bwd(sv["x_final"], self.ln_out[0], dh, lnp, dx=g, dx_op=g_op)
             self._ln_param_grads(lnp, d, self.g("layer_norm.weight", "layer_norm.bias"), accumulate)
+            self._flush()
         denc = self.buf("denc_btc", (B * T, d), torch.float32)
         first_kv = True
         p_drop, p_attn, p_act, seed, seed_dev = sv["drop"]
@@ -363,6 +368,7 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                 self._linear_bwd(dF, ffn, s["h3"], M, ffn, d, self.g(p + "fc1.weight"), self.g(p + "fc1.bias"), accumulate)
                 K.gemm(a0=dF, a0_ld=ffn, rows=M, w=Lr["w1"], w_ld=d, w_mn=True, n=d, k=ffn, mode=K.EPI_F32, out0=dh,
                        out0_ld=d, block_n=bn)
+                lnp = self._lnp()
                 K.layernorm_bwd(s["x2"], Lr["ln3"][0], dh, lnp, dx=g, resid=g, dx_op=g_op)
                 self._ln_param_grads(lnp, d, self.g(p + "final_layer_norm.weight", p + "final_layer_norm.bias"), accumulate)
                 # ---- encoder attention
@@ -390,6 +396,7 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                 else:
                     K.gemm(a0=dkv2, a0_ld=2 * d, rows=B * T, w=Lr["wkv"], w_ld=d, w_mn=True, n=d, k=2 * d,
                            mode=K.EPI_RESID_F32, aux0=denc, aux_ld=d, out0=denc, out0_ld=d, block_n=bn)
+                lnp = self._lnp()
                 K.layernorm_bwd(s["x1"], Lr["ln2"][0], dh, lnp, dx=g, resid=g, dx_op=g_op)
                 self._ln_param_grads(lnp, d, self.g(p + "encoder_attn_layer_norm.weight", p + "encoder_attn_layer_norm.bias"),
                                      accumulate)
@@ -408,9 +415,11 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                                  self.g(sa + "q_proj.bias", sa + "k_proj.bias", sa + "v_proj.bias"), accumulate)
                 K.gemm(a0=dqkv, a0_ld=3 * d, rows=M, w=Lr["wqkv"], w_ld=d, w_mn=True, n=d, k=3 * d, mode=K.EPI_F32, out0=dh,
                        out0_ld=d, block_n=bn)
+                lnp = self._lnp()
                 K.layernorm_bwd(s["x0"], Lr["ln1"][0], dh, lnp, dx=g, resid=g, dx_op=g_op)
                 self._ln_param_grads(lnp, d, self.g(p + "self_attn_layer_norm.weight", p + "self_attn_layer_norm.bias"),
                                      accumulate)
+                self._flush()       # the layer's deferred reductions in one launch (per 16)
         # ---- embedding: x0 = dropout(sqrt(d) * E[tokens] + positions)
         if p_drop > 0:
             K.dropout(g, g, p_drop, seed, DSITE_EMBED, seed_dev=seed_dev)

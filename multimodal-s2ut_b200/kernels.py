@@ -350,6 +350,21 @@ def reduce_partials(part: torch.Tensor, n_partials: int, stride: int, n: int, ou
                                           int(accumulate), _stream()), "mm_reduce_partials")
 
 
+def reduce_partials_many(jobs) -> None:
+    """jobs: list of (part, n_partials, stride, n, out, accumulate): all reductions in one launch per 16 jobs."""
+    if not jobs:
+        return
+    arr = (_lib.ReduceJob * len(jobs))()
+    work = 0.0
+    for a, (part, S, stride, n, out, acc) in zip(arr, jobs):
+        assert part.dtype == torch.float32 and out.dtype == torch.float32 and out.numel() >= n
+        a.part, a.out, a.stride, a.n, a.n_partials, a.accumulate = _ptr(part), _ptr(out), stride, n, S, int(acc)
+        work += 4.0 * n * S
+    lib = _lib.load()
+    with _Launch("reduce_partials_many", work):
+        _lib.check(lib.mm_reduce_partials_many(arr, len(jobs), _stream()), "mm_reduce_partials_many")
+
+
 def layernorm_bwd_blocks() -> int:
     return _lib.load().mm_layernorm_bwd_blocks()
 

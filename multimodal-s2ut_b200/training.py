@@ -469,9 +469,38 @@ class TrainEngine(EncoderEngine):
     def _mp(self, M: int) -> int:
         return _round_up(M, 1024)
 
+    _ARENA = 64 * 1024 * 1024      # floats: partial sums of the reductions a layer defers (256 MB)
+
     def _partials(self, n: int) -> torch.Tensor:
-        part = self.buf("wgrad_part", (16 * 1024 * 1024,), torch.float32)
-        return part if n <= part.numel() else self.buf(f"wgrad_part_{n}", (n,), torch.float32)
+        """n floats of partial-sum workspace that stay untouched until the next ``_flush()`` (bump allocation)."""
+        if n > self._ARENA:
+            self._flush()
+            return self.buf(f"wgrad_part_{n}", (n,), torch.float32)
+        arena = self.buf("reduce_arena", (self._ARENA,), torch.float32)
+        off = getattr(self, "_arena_off", 0)
+        if off + n > self._ARENA:
+            self._flush()
+            off = 0
+        self._arena_off = off + _round_up(n, 64)
+        return arena[off:off + n]
+
+    def _defer(self, part: torch.Tensor, S: int, stride: int, n: int, out: torch.Tensor, accumulate: bool) -> None:
+        """Queue out[:n] (+)= sum_s part[s * stride : s * stride + n]; runs at the next ``_flush()``."""
+        if not hasattr(self, "_jobs"):
+            self._jobs = []
+        self._jobs.append((part, S, stride, n, out, accumulate))
+
+    def _flush(self) -> None:
+        """Run the queued reductions in one launch (per 16) and release the partial-sum workspace."""
+        jobs = getattr(self, "_jobs", None)
+        if jobs:
+            K.reduce_partials_many(jobs)
+            self._jobs = []
+        self._arena_off = 0
+
+    def _lnp(self) -> torch.Tensor:
+        """Per-block (dgamma, dbeta) partial workspace of one LayerNorm backward."""
+        return self._partials(self._ln_blocks * 2 * 1024)
 
     def _wgrad(self, dyt: torch.Tensor, xt: torch.Tensor, n: int, kin: int, mp: int, out: torch.Tensor,
                accumulate: bool) -> None:
@@ -499,13 +528,13 @@ class TrainEngine(EncoderEngine):
                    mode=K.EPI_F32, out0=part[col:], out0_ld=kin_all, out0_bs=n * kin_all, block_n=self.block_n,
                    a_mn=True, w_mn=True, a_kbatch=True, w_kbatch=True, a_k_total=M, w_k_total=M)
             col += kin
-        K.reduce_partials(part, S, n * kin_all, n * kin_all, gw, accumulate)
+        self._defer(part, S, n * kin_all, n * kin_all, gw, accumulate)
 
     def _bias_grad(self, dy_op: torch.Tensor, dy_ld: int, M: int, n: int, gb: torch.Tensor, accumulate: bool,
                    period: int = 0, valid: int = 0) -> None:
-        part = self.buf("colsum_part", (K.colsum_blocks(M) * n,), torch.float32)
+        part = self._partials(K.colsum_blocks(M) * n)
         nb = K.colsum(dy_op, dy_ld, M, n, part, period, valid)
-        K.reduce_partials(part, nb, n, n, gb, accumulate)
+        self._defer(part, nb, n, n, gb, accumulate)
 
     def _linear_bwd(self, dy_op: torch.Tensor, dy_ld: int, x_op: torch.Tensor, M: int, n: int, kin: int,
                     gw: torch.Tensor, gb: Optional[torch.Tensor], accumulate: bool) -> None:
@@ -515,7 +544,7 @@ class TrainEngine(EncoderEngine):
             self._bias_grad(dy_op, dy_ld, M, n, gb, accumulate)
 
     def _ln_param_grads(self, part: torch.Tensor, dim: int, gwb: torch.Tensor, accumulate: bool) -> None:
-        K.reduce_partials(part, self._ln_blocks, 2 * dim, 2 * dim, gwb, accumulate)
+        self._defer(part, self._ln_blocks, 2 * dim, 2 * dim, gwb, accumulate)
 
     # ------------------------------------------------------------------------------------------
     # backward
@@ -553,7 +582,6 @@ class TrainEngine(EncoderEngine):
         mod = self.enc.transformer_layers[i]
         a = mod.self_attn
         d, ffn, M, op, bn = self.d, self.ffn, B * T, self.op_dtype, self.block_n
-        lnp = self.buf("ln_part", (self._ln_blocks * 2 * max(d, 1024),), torch.float32)
         p_drop, p_act, seed, seed_dev = self._saved["drop"]
         gm = g_op
         if p_drop > 0:       # gradient entering fc2 = g o mask / (1 - p); the residual branch keeps g itself
@@ -572,6 +600,7 @@ class TrainEngine(EncoderEngine):
         dh = self.buf("b_dh", (M, d), torch.float32)
         K.gemm(a0=dF, a0_ld=ffn, rows=M, w=L["w1"], w_ld=d, w_mn=True, n=d, k=ffn, mode=K.EPI_F32, out0=dh, out0_ld=d,
                block_n=bn)
+        lnp = self._lnp()
         K.layernorm_bwd(s["x_mid"], L["ln2_g"], dh, lnp, dx=g, resid=g, dx_op=g_op)
         self._ln_param_grads(lnp, d, self.g(mod.final_layer_norm.weight, mod.final_layer_norm.bias), accumulate)
         # ---- attention: x_mid = x_in + dropout(out_proj(attn(LN1(x_in))))
@@ -590,8 +619,10 @@ class TrainEngine(EncoderEngine):
                          self.g(a.q_proj.bias, a.k_proj.bias, a.v_proj.bias), accumulate)
         K.gemm(a0=dqkv, a0_ld=3 * d, rows=M, w=L["wqkv"], w_ld=d, w_mn=True, n=d, k=3 * d, mode=K.EPI_F32, out0=dh,
                out0_ld=d, block_n=bn)
+        lnp = self._lnp()
         K.layernorm_bwd(s["x_in"], L["ln1_g"], dh, lnp, dx=g, resid=g, dx_op=g_op)
         self._ln_param_grads(lnp, d, self.g(mod.self_attn_layer_norm.weight, mod.self_attn_layer_norm.bias), accumulate)
+        self._flush()           # the layer's ten deferred reductions in one launch
 
     def _fusion_bwd(self, dres: torch.Tensor, gtext: torch.Tensor, B: int, T: int, accumulate: bool) -> None:
         """dres [T, B, d] -> gtext [M, d] = d loss / d text (the final LayerNorm output) + fusion parameter grads."""
@@ -667,7 +698,7 @@ class TrainEngine(EncoderEngine):
             part = self._partials(B * 2 * d * dk)
             K.gemm(a0=dkv, a0_ld=2 * d, a0_bs=Tk * 2 * d, a_mn=True, rows=2 * d, w=img_op, w_ld=dk, w_bs=Tk_img * dk,
                    w_mn=True, n=dk, k=Tk_img, mode=K.EPI_F32, out0=part, out0_ld=dk, out0_bs=2 * d * dk, **bt)
-            K.reduce_partials(part, B, 2 * d * dk, 2 * d * dk, self.g(*ps["wkv"]), accumulate)
+            self._defer(part, B, 2 * d * dk, 2 * d * dk, self.g(*ps["wkv"]), accumulate)
             self._bias_grad(dkv, 2 * d, B * Tk, 2 * d, gbkv, accumulate, period=Tk, valid=Tk_img)
             # learned bias_k | bias_v: key / value number Tk_img of every utterance
             self._bias_grad(dkv.view(-1)[Tk_img * 2 * d:], Tk * 2 * d, B, 2 * d, self.g(*ps["bias_kv"]), accumulate)
@@ -675,10 +706,10 @@ class TrainEngine(EncoderEngine):
             dimg = self.buf("f_dimg", (B * Tk_img, dk), torch.float32)
             K.gemm(a0=dkv, a0_ld=2 * d, a0_bs=Tk * 2 * d, rows=Tk_img, batches=B, w=F["wkv"], w_ld=dk, w_mn=True, n=dk,
                    k=2 * d, mode=K.EPI_F32, out0=dimg, out0_ld=dk, out0_bs=Tk_img * dk, block_n=bn)
-            lnp = self.buf("ln_part", (self._ln_blocks * 2 * max(d, 1024),), torch.float32)
             if self._saved["p_img"] > 0:     # SA_image_dropout sat between the pre-norm and the K|V projection
                 _, _, seed, seed_dev = self._saved["drop"]
                 K.dropout(dimg, dimg, self._saved["p_img"], seed, SITE_IMAGE, seed_dev=seed_dev)
+            lnp = self._lnp()
             K.layernorm_bwd(img.view(B * Tk_img, dk), self.img_ln[0], dimg, lnp)
             pn = enc.image_pre_norm_module
             self._ln_param_grads(lnp, dk, self.g(pn.weight, pn.bias), accumulate)
@@ -793,11 +824,12 @@ class TrainEngine(EncoderEngine):
                     K.dropout(gtext, gtext, sv["p_text"], sv["drop"][2], SITE_TEXT, seed_dev=sv["drop"][3])
         else:
             K.tbc_to_btc(grad_out, B, T, d, gtext)
-        lnp = self.buf("ln_part", (self._ln_blocks * 2 * max(d, 1024),), torch.float32)
         g = self.buf("b_g", (M, d), torch.float32)
         g_op = self.buf("b_g_op", (M, d), self.op_dtype)
+        lnp = self._lnp()
         K.layernorm_bwd(sv["x_final"], self.ln_g, gtext, lnp, dx=g, dx_op=g_op)
         self._ln_param_grads(lnp, d, self.g(self.enc.layer_norm.weight, self.enc.layer_norm.bias), accumulate)
+        self._flush()           # fusion + final LayerNorm reductions
         if overlap:
             self._reduce_async(*self.bucket_top)
         for i in reversed(range(self.n_layers)):
@@ -809,6 +841,7 @@ class TrainEngine(EncoderEngine):
             if sv["drop"][0] > 0:      # dropout after the scaled, position-added subsampler output
                 K.dropout(g, g, sv["drop"][0], sv["drop"][2], SITE_EMBED, seed_dev=sv["drop"][3])
             self._conv_bwd(g, B, T, accumulate)
+            self._flush()
         if overlap:
             self._reduce_async(*self.bucket_conv)
             self._reduce_join()

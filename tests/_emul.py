@@ -337,6 +337,11 @@ def reduce_partials(part, n_partials, stride, n, out, accumulate=False, part_off
     out.view(-1)[:n] = out.view(-1)[:n] + s if accumulate else s
 
 
+def reduce_partials_many(jobs):
+    for part, S, stride, n, out, acc in jobs:
+        reduce_partials(part, S, stride, n, out, acc)
+
+
 def layernorm_bwd_blocks():
     return 4
 
