@@ -78,6 +78,45 @@ def golden_fuse():
     print("fuse goldens written")
 
 
+def golden_fuse_grads():
+    """Gradients of the reference's own fuse.py modules under PyTorch autograd (what the reference's training step
+    computes for the fusion block): pins the oracle's differentiable path, which in turn is the yardstick of the CUDA
+    backward pass (tests/test_gpu_training.py)."""
+    fuse = import_reference_fuse()
+    torch.manual_seed(20251019)
+    d, dk, Tq, Tk, B = 128, 192, 17, 53, 2
+    q = torch.randn(Tq, B, d)
+    img = torch.randn(Tk, B, dk)
+    R = torch.randn(Tq, B, d)
+    sa = fuse.SelectiveAttention(qdim=d, kdim=dk, vdim=dk, attn_dim=d, intermediate_dim=d, output_dim=d, num_heads=1,
+                                 attn_drop=0.0).eval()
+    with torch.no_grad():
+        for p in sa.parameters():
+            if p.dim() == 1:
+                p.normal_(0, 0.1)
+    qg, ig = q.clone().requires_grad_(), img.clone().requires_grad_()
+    out, _ = sa(qg, ig, ig, key_padding_mask=None)
+    (out * R).sum().backward()
+    np.savez_compressed(OUT / "fuse_selective_attention_grads.npz", q=q.numpy(), img=img.numpy(), R=R.numpy(),
+                        dq=qg.grad.numpy(), dimg=ig.grad.numpy(),
+                        **{"sd." + k: v.detach().numpy() for k, v in sa.state_dict().items()},
+                        **{"grad." + k: v.grad.numpy() for k, v in sa.named_parameters()})
+    ma = fuse.MultimodalAttention(embed_dim=d, kdim=dk, vdim=dk, num_heads=1, dropout=0.0, add_bias_kv=True).eval()
+    with torch.no_grad():
+        ma.in_proj_bias.normal_(0, 0.1)
+        ma.out_proj.bias.normal_(0, 0.1)
+        ma.bias_k.normal_(0, 0.5)
+        ma.bias_v.normal_(0, 0.5)
+    qg, ig = q.clone().requires_grad_(), img.clone().requires_grad_()
+    o, _ = ma(text=qg, text_mask=torch.zeros(B, Tq, dtype=torch.bool), img=ig, img_mask=None, is_merge_text_img=False)
+    (o * R).sum().backward()
+    np.savez_compressed(OUT / "fuse_multimodal_attention_grads.npz", q=q.numpy(), img=img.numpy(), R=R.numpy(),
+                        dq=qg.grad.numpy(), dimg=ig.grad.numpy(),
+                        **{"sd." + k: v.detach().numpy() for k, v in ma.state_dict().items()},
+                        **{"grad." + k: v.grad.numpy() for k, v in ma.named_parameters()})
+    print("fuse gradient goldens written")
+
+
 def golden_fbank():
     from mm_s2ut_b200 import synth  # noqa: E402
     import torchaudio.compliance.kaldi as ta_kaldi
@@ -146,4 +185,5 @@ if __name__ == "__main__":
     OUT.mkdir(parents=True, exist_ok=True)
     golden_fbank()
     golden_fuse()
+    golden_fuse_grads()
     golden_hf_encoder()

@@ -79,3 +79,39 @@ def test_utterance_cmvn_semantics():
     assert abs(float(y.mean())) < 1e-4 and abs(float(y.std()) - 1.0) < 1e-2
     out, lens = ofb.collate_frames([y, y[:20]])
     assert out.shape == (2, 57, 80) and lens.tolist() == [57, 20] and np.all(out[1, 20:] == 0)
+
+
+def _grads_match(z, sd, grads_of, atol=3e-5, rtol=2e-4):
+    for k in z.files:
+        if k.startswith("grad."):
+            got = grads_of[k[5:]]
+            ref = torch.from_numpy(z[k])
+            assert torch.allclose(got, ref, atol=atol * max(1.0, ref.abs().max().item()), rtol=rtol), k
+
+
+def test_selective_attention_gradients_match_reference_fuse_py_autograd():
+    """The oracle's differentiable path against gradients computed by autograd through the reference's own fuse.py
+    (the yardstick of the CUDA backward pass is pinned by the reference itself)."""
+    from oracle import fusion
+
+    z = np.load(G / "fuse_selective_attention_grads.npz")
+    sd = {k: v.clone().requires_grad_() for k, v in _sd(z, "sa.").items()}
+    q, img = torch.from_numpy(z["q"]).requires_grad_(), torch.from_numpy(z["img"]).requires_grad_()
+    out, _ = fusion.selective_attention(sd, "sa.", q, img, img, None)
+    (out * torch.from_numpy(z["R"])).sum().backward()
+    _grads_match(z, sd, {k[3:]: v.grad for k, v in sd.items()})
+    assert torch.allclose(q.grad, torch.from_numpy(z["dq"]), atol=1e-5, rtol=1e-4)
+    assert torch.allclose(img.grad, torch.from_numpy(z["dimg"]), atol=1e-5, rtol=1e-4)
+
+
+def test_multimodal_attention_gradients_match_reference_fuse_py_autograd():
+    from oracle import fusion
+
+    z = np.load(G / "fuse_multimodal_attention_grads.npz")
+    sd = {k: v.clone().requires_grad_() for k, v in _sd(z, "ma.").items()}
+    q, img = torch.from_numpy(z["q"]).requires_grad_(), torch.from_numpy(z["img"]).requires_grad_()
+    out = fusion.multimodal_attention(sd, "ma.", q, img, None)
+    (out * torch.from_numpy(z["R"])).sum().backward()
+    _grads_match(z, sd, {k[3:]: v.grad for k, v in sd.items()})
+    assert torch.allclose(q.grad, torch.from_numpy(z["dq"]), atol=1e-5, rtol=1e-4)
+    assert torch.allclose(img.grad, torch.from_numpy(z["dimg"]), atol=1e-5, rtol=1e-4)
