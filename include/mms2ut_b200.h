@@ -208,6 +208,20 @@ int mm_attention(const void* q, int64_t q_ld, int32_t q_col0, int32_t q_len, con
                  const void* v, int64_t v_ld, int32_t v_col0, int32_t kv_len, const int32_t* kv_lens, int32_t batch,
                  int32_t heads, int32_t causal, void* out, int64_t out_ld, int32_t dtype, void* stream);
 
+/* Fused (flash-style) speech -> image attention: out = softmax(q k^T + key mask) v for ONE head of width d_model
+ * (SelectiveAttention.forward, mm_s2ut/models/fuse.py:80-113, built with num_heads = 1 at
+ * mm_s2s_transformer.py:132-137; MultimodalAttention, fuse.py:145-167, with the learned bias_k / bias_v stored as the
+ * last key / value row).  Scores and probabilities stay in TMEM: nothing but q, k, v is read and only out (and the
+ * optional per-row log-sum-exp) is written.  q [batch * q_len, q_ld] 16-bit, pre-scaled by d_model^-0.5; k / v
+ * [batch][kv_len][ld] 16-bit with the d_model-wide blocks at *_col0 (they may be the two halves of one K|V projection
+ * output; kv_batch_stride elements between utterances, 0 = kv_len * ld); key_mask optional [batch][mask_ld] uint8,
+ * non-zero = key masked out (the reference's masked_fill(-inf), fuse.py:88-91); out [batch * q_len, out_ld] 16-bit;
+ * lse optional [batch * q_len] fp32.  d_model must be a multiple of 256. */
+int mm_cross_attention(const void* q, int64_t q_ld, int32_t q_len, const void* k, int64_t k_ld, int32_t k_col0,
+                       const void* v, int64_t v_ld, int32_t v_col0, int32_t kv_len, int64_t kv_batch_stride,
+                       const uint8_t* key_mask, int64_t mask_ld, int32_t batch, int32_t d_model, void* out,
+                       int64_t out_ld, float* lse, int32_t dtype, void* stream);
+
 /* Row softmax for the speech->image attention (fuse.py:88-111): scores fp32 [rows, ld_in] -> probabilities
  * 16-bit [rows, ld_out]; columns [n_keys, ld_out) written as 0.  key_mask: optional [n_seqs, n_keys] uint8
  * (1 = padded key -> -inf); rows_per_seq maps a row to its sequence. */

@@ -63,6 +63,8 @@ class EncoderEngine:
             raise NotImplementedError("self-attention kernel is built for head_dim 64 and d_model % 128 == 0")
         self.embed_scale = float(enc.embed_scale)
         self.fused_ln = self.d == 512 and getattr(enc, "fuse_layernorm", True)   # mm_gemm_resid_ln needs n == 512
+        # flash-style speech -> image attention (mm_cross_attention) needs 256-column blocks of the output
+        self.fused_xattn = self.d % 256 == 0 and getattr(enc, "fuse_cross_attention", True)
         self.enc = enc
         self._buf: Dict[Tuple, torch.Tensor] = {}
         self._pos: Optional[torch.Tensor] = None
@@ -270,10 +272,13 @@ class EncoderEngine:
 
     def fuse(self, j: int, text_f32: torch.Tensor, text_op: torch.Tensor, img: torch.Tensor,
              img_mask: Optional[torch.Tensor], B: int, T: int, out_tbc: torch.Tensor, img_dropout=None,
-             attn_dropout=None) -> None:
+             attn_dropout=None, keep_scores: bool = False, tag: str = "") -> None:
         """fuse_img_feat for image type j; writes the fused states into out_tbc [T, B, d] fp32.
         img_dropout / attn_dropout = (p, seed, seed_dev, site): SA_image_dropout on the pre-normed image (:596) and
-        SA_attention_dropout on the attention probabilities (fuse.py:111), training only."""
+        SA_attention_dropout on the attention probabilities (fuse.py:111), training only.
+        keep_scores: the training forward keeps S / P / K / V^T for the backward pass, i.e. runs the attention as
+        scores GEMM -> softmax -> P V GEMM; otherwise (d % 256 == 0) the fused flash-style kernel runs and the scores
+        never leave the SM.  tag: suffix of the per-call workspaces (several image types in one training step)."""
         enc, F, d, op, bn = self.enc, self.fusion[j], self.d, self.op_dtype, self.block_n
         M = B * T
         Tk_img, dk = img.shape[1], img.shape[2]
@@ -296,9 +301,49 @@ class EncoderEngine:
                 K.convert(img.view(B * Tk_img, dk), img_op)
         if img_dropout is not None and img_dropout[0] > 0:
             K.dropout(img_op, img_op, img_dropout[0], img_dropout[1], img_dropout[3], seed_dev=img_dropout[2])
+        mask = None
+        if img_mask is not None:
+            mask = img_mask.to(self.device).to(torch.uint8)
+            if extra:
+                mask = torch.nn.functional.pad(mask, (0, 1))
+            mask = mask.contiguous()
+        fused = self.fused_xattn and not keep_scores and not (attn_dropout is not None and attn_dropout[0] > 0)
+        if fused:
+            self._fuse_attention_fused(j, F, text_op, img_op, mask, B, T, Tk_img, Tk, dk)
+            o = self.buf("o_img", (M, d), op)
+        else:
+            o = self._fuse_attention_unfused(j, F, text_op, img_op, mask, B, T, Tk_img, Tk, Tkp, dk, attn_dropout)
+        self._fuse_output(F, o, text_f32, text_op, B, T, out_tbc)
+
+    def _fuse_attention_fused(self, j, F, text_op, img_op, mask, B, T, Tk_img, Tk, dk) -> None:
+        """K|V projection into ONE [B, Tk, 2d] tensor, q projection, then mm_cross_attention -> o_img."""
+        d, op, bn, M = self.d, self.op_dtype, self.block_n, B * T
+        extra = Tk - Tk_img
+        new_kv = (f"kv{j}", (B, Tk, 2 * d), op) not in self._buf
+        kv = self.buf(f"kv{j}", (B, Tk, 2 * d), op)
+        if extra == 0:
+            K.gemm(a0=img_op, a0_ld=dk, rows=B * Tk_img, w=F["wkv"], n=2 * d, k=dk, mode=K.EPI_OP, bias=F["bkv"],
+                   out0=kv, out0_ld=2 * d, block_n=bn)
+        else:
+            K.gemm(a0=img_op, a0_ld=dk, a0_bs=Tk_img * dk, rows=Tk_img, batches=B, w=F["wkv"], n=2 * d, k=dk,
+                   mode=K.EPI_OP, bias=F["bkv"], out0=kv, out0_ld=2 * d, out0_bs=Tk * 2 * d, block_n=bn)
+            if new_kv:   # learned bias_k | bias_v = key / value row Tk_img; the GEMM never writes it (see below)
+                kv[:, Tk_img, :d] = F["bias_kv"][0]
+                kv[:, Tk_img, d:] = F["bias_kv"][1]
+        q = self.buf("q_img", (M, d), op)
+        K.gemm(a0=text_op, a0_ld=d, rows=M, w=F["wq"], n=d, k=d, mode=K.EPI_OP, bias=F["bq"], scale=d ** -0.5,
+               scale_cols=d, out0=q, out0_ld=d, block_n=bn)
+        o = self.buf("o_img", (M, d), op)
+        kv2 = kv.view(B * Tk, 2 * d)
+        K.cross_attention(q, T, kv2, 0, kv2, d, Tk, B, d, o, key_mask=mask)
+
+    def _fuse_attention_unfused(self, j, F, text_op, img_op, mask, B, T, Tk_img, Tk, Tkp, dk, attn_dropout):
+        """scores GEMM -> softmax (+ attention dropout) -> P V GEMM with S, P, K and V^T kept in HBM (training)."""
+        d, op, bn, M = self.d, self.op_dtype, self.block_n, B * T
+        extra = Tk - Tk_img
         new_kv = (f"k{j}", (B, Tk, d), op) not in self._buf
         kbuf = self.buf(f"k{j}", (B, Tk, d), op)
-        vt = self.buf(f"vt_img{j}", (B, d, Tkp), op, zero=True)
+        vt = self.buf(f"vt_img{j}_{Tk}", (B, d, Tkp), op, zero=True)
         if extra == 0:   # keys are contiguous over the batch: one flat GEMM over all B * Tk image tokens
             K.gemm(a0=img_op, a0_ld=dk, rows=B * Tk_img, w=F["wkv"], n=2 * d, k=dk, mode=K.EPI_OP, bias=F["bkv"],
                    out0=kbuf, out0_ld=d, rows_per_seq=Tk_img, vt=vt, vt_col0=d, vt_rows=d, vt_ld=Tkp, block_n=bn)
@@ -319,12 +364,6 @@ class EncoderEngine:
         K.gemm(a0=q, a0_ld=d, a0_bs=T * d, rows=T, batches=B, w=kbuf, w_ld=d, w_bs=Tk * d, w_batched=True, n=Tk, k=d,
                mode=K.EPI_F32, out0=S, out0_ld=Tkp, out0_bs=T * Tkp, block_n=bn)
         P = self.buf(f"P{j}", (B, T, Tkp), op)
-        mask = None
-        if img_mask is not None:
-            mask = img_mask.to(self.device).to(torch.uint8)
-            if extra:
-                mask = torch.nn.functional.pad(mask, (0, 1))
-            mask = mask.contiguous()
         if attn_dropout is not None and attn_dropout[0] > 0:
             if mask is not None:
                 raise NotImplementedError("SA_attention_dropout with an image key mask")
@@ -335,6 +374,11 @@ class EncoderEngine:
         o = self.buf("o_img", (M, d), op)
         K.gemm(a0=P, a0_ld=Tkp, a0_bs=T * Tkp, rows=T, batches=B, w=vt, w_ld=Tkp, w_bs=d * Tkp, w_batched=True, n=d,
                k=Tkp, mode=K.EPI_OP, out0=o, out0_ld=d, out0_bs=T * d, block_n=bn)
+        return o
+
+    def _fuse_output(self, F, o, text_f32, text_op, B, T, out_tbc) -> None:
+        """out_proj of the attention, then the selective gate (or the plain residual) -> out_tbc [T, B, d]."""
+        enc, d, op, bn, M = self.enc, self.d, self.op_dtype, self.block_n, B * T
         if enc.use_selective_gate:
             a_f32 = self.buf("attn_f32", (M, d), torch.float32)
             a_op = self.buf("attn_op", (M, d), op)

@@ -293,6 +293,28 @@ def attention(q: torch.Tensor, q_col0: int, q_len: int, k: torch.Tensor, k_col0:
                                     out.stride(0), dtype_code(q.dtype), _stream()), "mm_attention")
 
 
+def cross_attention(q: torch.Tensor, q_len: int, k: torch.Tensor, k_col0: int, v: torch.Tensor, v_col0: int, kv_len: int,
+                    batch: int, d_model: int, out: torch.Tensor, key_mask: Optional[torch.Tensor] = None,
+                    lse: Optional[torch.Tensor] = None, kv_batch_stride: int = 0) -> None:
+    """Fused speech -> image attention for one head of width d_model (see ``mm_cross_attention``): q [batch*q_len, ld]
+    (pre-scaled), k / v rows [batch][kv_len][ld] with their d_model-wide blocks at *_col0, key_mask [batch, >= kv_len]
+    uint8 (non-zero = masked out); out [batch*q_len, d_model]; lse [batch*q_len] fp32 (optional)."""
+    assert q.dtype == k.dtype == v.dtype == out.dtype and q.dtype in _DT
+    assert all(t.dim() == 2 and t.stride(1) == 1 for t in (q, k, v, out))
+    assert q.shape[0] == batch * q_len and out.shape[0] == batch * q_len
+    if key_mask is not None:
+        assert key_mask.dtype == torch.uint8 and key_mask.dim() == 2 and key_mask.stride(1) == 1
+        assert key_mask.shape[0] == batch and key_mask.shape[1] >= kv_len
+    if lse is not None:
+        assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == batch * q_len
+    lib = _lib.load()
+    with _Launch("cross_attention", 4.0 * batch * q_len * kv_len * d_model):
+        _lib.check(lib.mm_cross_attention(_ptr(q), q.stride(0), q_len, _ptr(k), k.stride(0), k_col0, _ptr(v), v.stride(0),
+                                          v_col0, kv_len, kv_batch_stride, _ptr(key_mask),
+                                          key_mask.stride(0) if key_mask is not None else 0, batch, d_model, _ptr(out),
+                                          out.stride(0), _ptr(lse), dtype_code(q.dtype), _stream()), "mm_cross_attention")
+
+
 def softmax_rows(scores: torch.Tensor, ld_in: int, rows: int, n_keys: int, probs: torch.Tensor, ld_out: int,
                  key_mask: Optional[torch.Tensor] = None, rows_per_seq: int = 0) -> None:
     assert scores.dtype == torch.float32

@@ -312,13 +312,15 @@ class TrainEngine(EncoderEngine):
         for j, F in enumerate(self.fusion):     # learned extra key / value rows live in the cached K / V^T workspaces
             if F["bias_kv"] is None:
                 continue
+            d = self.d
             for (name, shape, _), t in self._buf.items():
-                if name == f"k{j}":
+                if name == f"k{j}":                       # [B, Tk, d]
                     t[:, shape[1] - 1, :] = F["bias_kv"][0]
-                elif name == f"vt_img{j}":
-                    for (n2, s2, _2) in self._buf:
-                        if n2 == f"k{j}" and s2[0] == shape[0]:
-                            t[:, :, s2[1] - 1] = F["bias_kv"][1]
+                elif name.startswith(f"vt_img{j}_"):      # [B, d, Tkp], one per key count Tk (in the name)
+                    t[:, :, int(name.rsplit("_", 1)[1]) - 1] = F["bias_kv"][1]
+                elif name == f"kv{j}":                    # [B, Tk, 2d] of the fused attention path
+                    t[:, shape[1] - 1, :d] = F["bias_kv"][0]
+                    t[:, shape[1] - 1, d:] = F["bias_kv"][1]
 
     def grads_attached(self) -> bool:
         """True when every ``param.grad`` still is this engine's view of ``flat_g`` (an optimizer's
@@ -455,7 +457,7 @@ class TrainEngine(EncoderEngine):
                 saved["p_text"] = p_text
             self.fuse(0, text_f32, text_op, img, None, B, T, out,
                       img_dropout=(p_img, self._drop[2], dropout_seed_dev, SITE_IMAGE),
-                      attn_dropout=(p_sa, self._drop[2], dropout_seed_dev, SITE_SA_ATTN))
+                      attn_dropout=(p_sa, self._drop[2], dropout_seed_dev, SITE_SA_ATTN), keep_scores=True)
             saved.update(fused=True, img=img)
         else:
             out = text_f32.view(B, T, d).transpose(0, 1).contiguous()
@@ -638,7 +640,7 @@ class TrainEngine(EncoderEngine):
         o = self.buf("o_img", (M, d), op)
         q = self.buf("q_img", (M, d), op)
         kbuf = self.buf("k0", (B, Tk, d), op)
-        vt = self.buf("vt_img0", (B, d, Tkp), op)
+        vt = self.buf(f"vt_img0_{Tk}", (B, d, Tkp), op)
         S = self.buf("S0", (B, T, Tkp), torch.float32)
         P = self.buf("P0", (B, T, Tkp), op)
         img_op = self.buf("img_op0", (B * Tk_img, dk), op)

@@ -109,20 +109,29 @@ def mm_encoder_forward(sd, mm_cfg, src_tokens: Tensor, src_lengths: Tensor, imgs
     out = s2t_encoder_forward(sd, src_tokens, src_lengths, num_heads, prefix, return_all_hiddens, rnd=rnd, drop=drop)
     if mm_cfg is None or not mm_cfg.is_fusion_top or not imgs_list:
         return out
+    out["encoder_out"][0] = fusion_top(sd, prefix, mm_cfg, out["encoder_out"][0], imgs_list, img_masks_list, training,
+                                       draws, rnd, drop)
+    return out
+
+
+def fusion_top(sd, prefix: str, mm_cfg, text: Tensor, imgs_list: List[Tensor], img_masks_list: List[Optional[Tensor]],
+               training: bool = False, draws: Optional[tuple] = None, rnd: Callable = _id,
+               drop: Callable = lambda site, x: x) -> Tensor:
+    """The fusion-at-top statements of the reference's forward (mm_s2s_transformer.py:496-560): modality dropout,
+    ``fuse_img_feat`` per image type, sum over the types.  text [T,B,d]; imgs_list entries [B,Tk,Dk].  Pinned by
+    tests/golden/fuse_img_feat_*.npz (``glue_*`` keys: the reference's own statements, ast-extracted)."""
     imgs_list = list(imgs_list)
     if training and draws is not None:
         p_mod, p_aud = draws
         if p_mod < mm_cfg.modality_dropout:
             if p_aud < mm_cfg.audio_dropout:
-                out["encoder_out"][0] = torch.zeros_like(out["encoder_out"][0])
+                text = torch.zeros_like(text)
             else:
                 imgs_list = [torch.zeros_like(i) for i in imgs_list]
     xs = []
     for idx, (img, img_mask) in enumerate(zip(imgs_list, img_masks_list)):
-        xs.append(fuse_img_feat(sd, prefix, mm_cfg, out["encoder_out"][0], idx, img.transpose(0, 1), img_mask, rnd,
-                                drop))
+        xs.append(fuse_img_feat(sd, prefix, mm_cfg, text, idx, img.transpose(0, 1), img_mask, rnd, drop))
     res = xs[0]
     for x in xs[1:]:
         res = res + x
-    out["encoder_out"][0] = res
-    return out
+    return res

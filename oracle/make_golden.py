@@ -1,9 +1,11 @@
 """Generate the committed golden vectors under tests/golden/ (run in the BUILD container only).
 
-Three sources pin the oracle (the reference ships no tests of its own):
+Four sources pin the oracle (the reference ships no tests of its own):
   1. the reference's OWN fusion code: /root/reference/mm_s2ut/models/fuse.py is imported through a two-symbol
      fairseq stub (its only fairseq imports are FairseqDataclass and with_incremental_state, fuse.py:13-14) and
-     SelectiveAttention / MultimodalAttention are run on seeded inputs;
+     SelectiveAttention / MultimodalAttention are run on seeded inputs; the reference's fuse_img_feat method and the
+     fusion-at-top statements of its forward() (modality dropout, per-image-type loop, sum) are cut out of
+     mm_s2s_transformer.py with `ast` (the module itself needs fairseq / omegaconf / timm) and run bound to them;
   2. the real torchaudio.compliance.kaldi.fbank (what fairseq's _get_torchaudio_fbank executes) on seeded waveforms;
   3. HF transformers' Speech2TextEncoder -- an independent port of the same fairseq S2T encoder -- with copied weights.
 /root/reference does not exist on the GPU box: only the .npz files produced here travel.
@@ -117,6 +119,135 @@ def golden_fuse_grads():
     print("fuse gradient goldens written")
 
 
+def _reference_encoder_methods():
+    """``fuse_img_feat`` and ``f`` of the reference's MM_S2STransformerEncoder, plus the fusion-at-top statements of
+    its ``forward`` (modality dropout :496-512, the per-image-type loop :513-556 and the sum :557-560), cut out of
+    /root/reference/mm_s2ut/models/mm_s2s_transformer.py with ``ast`` -- the module itself cannot be imported here
+    (fairseq, omegaconf, timm are absent) but these statements only need torch and numpy."""
+    import ast
+
+    src = (REF / "mm_s2ut" / "models" / "mm_s2s_transformer.py").read_text()
+    tree = ast.parse(src)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "MM_S2STransformerEncoder")
+    fns = {n.name: n for n in cls.body if isinstance(n, ast.FunctionDef)}
+    ns = {"torch": torch, "np": np}
+    mod = ast.Module(body=[fns["fuse_img_feat"], fns["f"]], type_ignores=[])
+    exec(compile(mod, "ref:mm_s2s_transformer.py", "exec"), ns)
+
+    # the glue statements inside forward(): find `if self.training and not self.only_img:` and what follows it
+    def walk(body):
+        for i, st in enumerate(body):
+            if isinstance(st, ast.If) and ast.unparse(st.test) == "self.training and (not self.only_img)":
+                return body[i:]
+            for sub in ("body", "orelse"):
+                r = walk(getattr(st, sub, []) or []) if isinstance(getattr(st, sub, None), list) else None
+                if r:
+                    return r
+        return None
+
+    glue = walk(fns["forward"].body)
+    assert glue is not None and isinstance(glue[1], ast.For) and isinstance(glue[2], ast.If), "reference layout changed"
+    glue_code = compile(ast.Module(body=glue[:3], type_ignores=[]), "ref:mm_s2s_transformer.py:forward", "exec")
+    return ns["fuse_img_feat"], ns["f"], glue_code
+
+
+def golden_fuse_img_feat():
+    """Pins oracle.fusion.fuse_img_feat and the modality-dropout / per-type-sum glue of mm_encoder_forward on the
+    reference's OWN statements (ast-extracted, see above) bound to the reference's own fuse.py modules."""
+    import types as _t
+
+    fuse = import_reference_fuse()
+    ref_fuse_img_feat, ref_f, glue_code = _reference_encoder_methods()
+    torch.manual_seed(20251020)
+    d, T, B = 64, 13, 3
+    cases = {}
+
+    def build(kind, dims, gate, pre_norm):
+        me = _t.SimpleNamespace()
+        me.multimodal_attention_type = kind
+        me.use_selective_gate = gate
+        me.is_merge_text_img = False
+        me.only_img = False
+        me.image_dropout_module = torch.nn.Dropout(0.3).eval()        # FairseqDropout in eval mode = identity
+        me.text_dropout_module = torch.nn.Dropout(0.3).eval()
+        me.image_pre_norm_module = torch.nn.LayerNorm(dims, 1e-5, True) if pre_norm else torch.nn.Identity()
+        if kind == "selective_attention":
+            me.selective_attns = torch.nn.ModuleList(
+                fuse.SelectiveAttention(qdim=d, kdim=i, vdim=i, attn_dim=d, intermediate_dim=d, output_dim=d, num_heads=1,
+                                        attn_drop=0.1) for i in dims).eval()
+            mods = me.selective_attns
+        else:
+            me.multimodal_attns = torch.nn.ModuleList(
+                fuse.MultimodalAttention(embed_dim=d, kdim=i, vdim=i, num_heads=1, dropout=0.1, add_bias_kv=True)
+                for i in dims).eval()
+            mods = me.multimodal_attns
+        me.gate_denses = torch.nn.ModuleList(torch.nn.Linear(2 * d, d) for _ in dims).eval()
+        with torch.no_grad():
+            for m in list(mods.parameters()) + list(me.gate_denses.parameters()) + list(me.image_pre_norm_module.parameters()):
+                if m.dim() == 1 or m.shape[0] == 1:
+                    m.normal_(0, 0.3)
+            if pre_norm:
+                me.image_pre_norm_module.weight.add_(1.0)
+        me.fuse_img_feat = _t.MethodType(ref_fuse_img_feat, me)
+        me.f = _t.MethodType(ref_f, me)
+        sd = {}
+        name = "selective_attns" if kind == "selective_attention" else "multimodal_attns"
+        for k, v in mods.state_dict().items():
+            sd[f"{name}.{k}"] = v
+        for k, v in me.gate_denses.state_dict().items():
+            sd[f"gate_denses.{k}"] = v
+        for k, v in me.image_pre_norm_module.state_dict().items():
+            sd[f"image_pre_norm_module.{k}"] = v
+        return me, sd
+
+    for name, kind, dims, tks, gate, pre_norm in [
+            ("sa_gate_prenorm", "selective_attention", [96], [37], True, True),
+            ("sa_nogate", "selective_attention", [96], [37], False, False),
+            ("ma_gate_prenorm", "multimodal_attention", [96], [37], True, True),
+            ("sa_two_types", "selective_attention", [96, 48], [37, 21], True, False)]:
+        me, sd = build(kind, dims, gate, pre_norm)
+        text = torch.randn(T, B, d)
+        imgs = [torch.randn(B, tk, dk) for tk, dk in zip(tks, dims)]
+        masks = []
+        for tk in tks:
+            m = torch.zeros(B, tk, dtype=torch.bool)
+            m[2, tk // 2:] = True
+            masks.append(m)
+        tmask = torch.zeros(B, T, dtype=torch.bool)
+        tmask[1, 9:] = True
+        rec = {"text": text.numpy(), "text_mask": tmask.numpy(), "n_types": np.array(len(dims)),
+               "gate": np.array(gate), "pre_norm": np.array(pre_norm), "kind": np.array(kind)}
+        for j, (im, mk) in enumerate(zip(imgs, masks)):
+            rec[f"img{j}"], rec[f"mask{j}"] = im.numpy(), mk.numpy()
+        with torch.no_grad():
+            # (1) the method alone, first image type, without and with the image key mask
+            r0, _ = me.fuse_img_feat(text, 0, imgs[0].transpose(0, 1), None, text_mask=tmask)
+            r1, _ = me.fuse_img_feat(text, 0, imgs[0].transpose(0, 1), masks[0], text_mask=tmask)
+            rec["res"], rec["res_masked"] = r0.numpy(), r1.numpy()
+            # (2) the glue of forward(): eval; training without a drop; training with the image-drop branch
+            for tag, training, draws in [("eval", False, None), ("keep", True, (0.9, 0.9)), ("drop_image", True, (0.1, 0.9))]:
+                me.training = training
+                me.modality_dropout, me.audio_dropout = 0.5, -0.5
+                seq = list(draws or ())
+
+                class _NP:   # the two per-batch np.random.random() draws of :497, replayed
+                    class random:   # noqa: N801
+                        @staticmethod
+                        def random():
+                            return seq.pop(0)
+
+                out = {"encoder_out": [text.clone()], "encoder_padding_mask": [tmask.clone()], "encoder_states": []}
+                env = {"self": me, "out": out, "imgs_list": [i.clone() for i in imgs], "img_masks_list": list(masks),
+                       "xs": [], "idx": 0, "torch": torch, "np": _NP, "img_feat_list": None}
+                exec(glue_code, env)
+                rec[f"glue_{tag}"] = out["encoder_out"][0].numpy()
+        rec.update({"sd." + k: v.numpy() for k, v in sd.items()})
+        cases[name] = rec
+    for name, rec in cases.items():
+        np.savez_compressed(OUT / f"fuse_img_feat_{name}.npz", **rec)
+    print("fuse_img_feat / glue goldens written:", ", ".join(cases))
+
+
 def golden_fbank():
     from mm_s2ut_b200 import synth  # noqa: E402
     import torchaudio.compliance.kaldi as ta_kaldi
@@ -186,4 +317,5 @@ if __name__ == "__main__":
     golden_fbank()
     golden_fuse()
     golden_fuse_grads()
+    golden_fuse_img_feat()
     golden_hf_encoder()

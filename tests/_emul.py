@@ -227,9 +227,24 @@ def self_attention(qkv, seq_lens_, batch, seq, heads, out):
     out.copy_(o.to(out.dtype))
 
 
+def cross_attention(q, q_len, k, k_col0, v, v_col0, kv_len, batch, d_model, out, key_mask=None, lse=None,
+                    kv_batch_stride=0):
+    Q = q[:, :d_model].float().view(batch, q_len, d_model)
+    Kx = _v(k, (batch, kv_len, d_model), (kv_batch_stride or kv_len * k.stride(0), k.stride(0), 1), k_col0).float()
+    V = _v(v, (batch, kv_len, d_model), (kv_batch_stride or kv_len * v.stride(0), v.stride(0), 1), v_col0).float()
+    s = Q @ Kx.transpose(-1, -2)
+    if key_mask is not None:
+        s = s.masked_fill(key_mask[:, None, :kv_len].bool(), float("-inf"))
+    if lse is not None:
+        lse.copy_(torch.logsumexp(s, -1).reshape(-1))
+    p = s.softmax(-1).to(q.dtype).float()
+    out.copy_((p @ V).reshape(batch * q_len, d_model).to(out.dtype))
+
+
 def softmax_rows(scores, ld_in, rows, n_keys, probs, ld_out, key_mask=None, rows_per_seq=0):
-    assert key_mask is None
     s = _v(scores, (rows, n_keys), (ld_in, 1))
+    if key_mask is not None:
+        s = s.masked_fill(key_mask.bool().repeat_interleave(rows_per_seq, 0)[:, :n_keys], float("-inf"))
     P = _v(probs, (rows, ld_out), (ld_out, 1))
     P.zero_()
     P[:, :n_keys] = s.softmax(-1).to(probs.dtype)

@@ -3,6 +3,7 @@ from the reference's own fuse.py, real torchaudio and HF's port of the fairseq S
 from pathlib import Path
 
 import numpy as np
+import pytest
 import torch
 
 from _util import fbank_errors
@@ -39,6 +40,36 @@ def test_multimodal_attention_matches_reference_fuse_py():
     assert torch.allclose(out, torch.from_numpy(z["out"]), atol=2e-6, rtol=1e-5)
     out = fusion.multimodal_attention(sd, "ma.", q, img, mask)
     assert torch.allclose(out, torch.from_numpy(z["out_masked"]), atol=2e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("case", ["sa_gate_prenorm", "sa_nogate", "ma_gate_prenorm", "sa_two_types"])
+def test_fuse_img_feat_and_glue_match_reference_statements(case):
+    """oracle.fusion.fuse_img_feat / fusion_top against the reference's OWN fuse_img_feat method and the
+    fusion-at-top statements of its forward() (mm_s2s_transformer.py:594-622, :496-560), which
+    oracle/make_golden.py cut out with ``ast`` and ran bound to the reference's fuse.py modules."""
+    from types import SimpleNamespace
+
+    from oracle import fusion
+
+    z = np.load(G / f"fuse_img_feat_{case}.npz")
+    sd = _sd(z)
+    n = int(z["n_types"])
+    cfg = SimpleNamespace(image_pre_norm=bool(z["pre_norm"]), multimodal_attention_type=str(z["kind"]),
+                          use_selective_gate=bool(z["gate"]), modality_dropout=0.5, audio_dropout=-0.5,
+                          is_fusion_top=True)
+    text = torch.from_numpy(z["text"])
+    imgs = [torch.from_numpy(z[f"img{j}"]) for j in range(n)]
+    masks = [torch.from_numpy(z[f"mask{j}"]) for j in range(n)]
+    tol = dict(atol=3e-6, rtol=1e-5)
+    res = fusion.fuse_img_feat(sd, "", cfg, text, 0, imgs[0].transpose(0, 1), None)
+    assert torch.allclose(res, torch.from_numpy(z["res"]), **tol)
+    res = fusion.fuse_img_feat(sd, "", cfg, text, 0, imgs[0].transpose(0, 1), masks[0])
+    assert torch.allclose(res, torch.from_numpy(z["res_masked"]), **tol)
+    for tag, training, draws in [("eval", False, None), ("keep", True, (0.9, 0.9)), ("drop_image", True, (0.1, 0.9))]:
+        got = fusion.fusion_top(sd, "", cfg, text, imgs, masks, training, draws)
+        assert torch.allclose(got, torch.from_numpy(z[f"glue_{tag}"]), **tol), tag
+    assert not np.allclose(z["glue_keep"], z["glue_drop_image"])      # the image-drop branch did something
+    assert np.array_equal(z["glue_keep"], z["glue_eval"])
 
 
 def test_fbank_restatement_matches_torchaudio_golden():
