@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const float* __restrict__ l
   const float* x = logits + row * ld;
   OpT* o = dlogits + row * ld_out;
   const long long t = target[row];
-  if (t == padding_idx) {
+  if (t == padding_idx || t < 0 || t >= vocab) {   // the same rows mm_label_smoothed_nll ignores
     for (int j = lane; j < ld_out; j += 32) o[j] = OpTraits<OpT>::cvt(0.f);
     return;
   }

@@ -293,6 +293,10 @@ class EncoderEngine:
                 raise NotImplementedError("ImageFeatureStore batches need image_pre_norm: True (the gather is fused "
                                           "into the pre-norm kernel)")
             K.layernorm_gather(img.store.data, img.index, Tk_img, self.img_ln[0], self.img_ln[1], img_op)
+        elif img.dtype in (torch.float16, torch.bfloat16) and self.img_ln is not None:
+            # features shipped (or kept) in 16 bit: the pre-norm kernel reads them as they are, rows in order
+            img = img.to(self.device, non_blocking=True).contiguous()
+            K.layernorm_gather(img, None, Tk_img, self.img_ln[0], self.img_ln[1], img_op)
         else:
             img = img.to(self.device, non_blocking=True).float().contiguous()
             if self.img_ln is not None:
@@ -403,8 +407,9 @@ class EncoderEngine:
         if training and max(enc.dropout_p, getattr(enc, "SA_image_dropout", 0.0), getattr(enc, "SA_text_dropout", 0.0),
                             getattr(enc, "SA_attention_dropout", 0.0)) > 0:
             raise NotImplementedError(
-                "training-mode element dropout / backward kernels are not built yet (forward + modality dropout "
-                "only); call .eval() or set the dropout probabilities to 0")
+                "EncoderEngine.forward is the inference forward (no dropout masks, no saved activations): a training-mode "
+                "forward under torch.no_grad() with non-zero dropout is not defined here; the training step runs through "
+                "TrainEngine.forward_train (enc.train() with gradients enabled), or call .eval()")
         x1, m, seq_lens, _ = self.frontend(src_tokens, src_lengths)
         B = x1.shape[0]
         x, T = self.subsample(x1, m, seq_lens)

@@ -53,6 +53,8 @@ class ImageFeatureStore:
     def batch(self, indices, out: Optional[torch.Tensor] = None) -> StoredImages:
         """indices: int sequence / tensor of dataset positions (the sample ids the reference's collater gathers)."""
         idx = torch.as_tensor(indices, dtype=torch.int64)
+        if idx.device.type == "cpu" and idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= len(self)):
+            raise IndexError(f"image index out of range for a store of {len(self)} samples")   # the gather trusts them
         if out is not None:
             out.copy_(idx, non_blocking=True)
             idx = out

@@ -18,9 +18,11 @@ from .feature_store import StoredImages
 
 class GraphedEncoder:
     def __init__(self, enc, batch: int, n_samples: int, img_shapes: List[tuple], warmup: int = 2,
-                 wav_dtype: torch.dtype = torch.float32, stores: Optional[list] = None):
+                 wav_dtype: torch.dtype = torch.float32, stores: Optional[list] = None,
+                 img_dtype: torch.dtype = torch.float32):
         """stores: optional list (one entry per image type) of ImageFeatureStore or None.  For a store the static
-        input is a [batch] int64 index vector instead of a [batch, Tk, Dk] fp32 feature tensor."""
+        input is a [batch] int64 index vector instead of a [batch, Tk, Dk] feature tensor.  img_dtype: float32 (the
+        reference's collater output) or float16 / bfloat16 (features shipped in 16 bit: half the H2D bytes)."""
         if enc.training:
             raise RuntimeError("graph capture is for eval-mode forwards (modality dropout draws are per batch)")
         self.enc = enc
@@ -29,7 +31,7 @@ class GraphedEncoder:
         self.wav = torch.zeros(batch, n_samples, dtype=wav_dtype, device=dev)   # float32 (x 2**15) or int16 PCM
         self.lens = torch.full((batch,), n_samples, dtype=torch.int64, device=dev)
         self.stores = list(stores) if stores is not None else [None for _ in img_shapes]
-        self.imgs = [torch.zeros(batch, *s, dtype=torch.float32, device=dev) if st is None else
+        self.imgs = [torch.zeros(batch, *s, dtype=img_dtype, device=dev) if st is None else
                      StoredImages(st, torch.zeros(batch, dtype=torch.int64, device=dev))
                      for s, st in zip(img_shapes, self.stores)]
         self.masks: List[Optional[torch.Tensor]] = [None for _ in img_shapes]

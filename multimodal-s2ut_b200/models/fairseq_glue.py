@@ -17,8 +17,11 @@ def register(encoder_cls, arch_fn):
 
     class _Encoder(encoder_cls, FairseqEncoder):  # FairseqEncoder supplies the generator-facing helpers
         def __init__(self, args):
-            FairseqEncoder.__init__(self, None)
+            # encoder_cls initialises nn.Module itself (explicitly, see S2TTransformerEncoderParams.__init__), so the
+            # MRO never routes an argument-less __init__ into FairseqEncoder.__init__(dictionary); what that
+            # constructor would have done for a speech encoder is one attribute:
             encoder_cls.__init__(self, args)
+            self.dictionary = None
 
     @register_model("mm_s2ut_transformer")
     class MM_S2UTTransformerModel(S2UTTransformerModel):

@@ -50,7 +50,10 @@ class S2TTransformerEncoderParams(nn.Module):
     """Parameters of fairseq ``S2TTransformerEncoder`` (the base class the reference subclasses, :87)."""
 
     def __init__(self, args):
-        super().__init__()
+        # nn.Module.__init__ explicitly, not super(): when fairseq is present the registered encoder class also
+        # inherits FairseqEncoder (models/fairseq_glue.py), whose __init__ takes a dictionary -- a cooperative
+        # super().__init__() here would land there without one
+        nn.Module.__init__(self)
         s2ut_architecture_base(args)
         self.args = args
         d = args.encoder_embed_dim
@@ -180,6 +183,12 @@ class MM_S2STransformerEncoder(S2TTransformerEncoderParams):
     def set_num_updates(self, num_updates):
         self.num_updates = num_updates
 
+    def _frozen(self) -> bool:
+        """fairseq ``S2TTransformerEncoder.forward``: the encoder runs under ``torch.no_grad()`` while
+        ``num_updates < encoder_freezing_updates``."""
+        n = int(getattr(self.args, "encoder_freezing_updates", 0) or 0)
+        return n > 0 and self.num_updates is not None and self.num_updates < n
+
     def max_positions(self):
         return self.args.max_source_positions
 
@@ -196,7 +205,8 @@ class MM_S2STransformerEncoder(S2TTransformerEncoderParams):
                     drop_audio = True        # reference: NameError at :500; intent = zero the speech states
                 else:
                     drop_image = True        # (:504-505) every image tensor zeroed
-        if self.training and torch.is_grad_enabled():
+        frozen = self.training and self._frozen()
+        if self.training and (torch.is_grad_enabled() or frozen):
             # training step: autograd reaches the path through one Function on the fused states
             from ..training import EncoderOutGrad
 
@@ -216,9 +226,17 @@ class MM_S2STransformerEncoder(S2TTransformerEncoderParams):
                 specaug = (torch.from_numpy(sa.draw_batch(frames, 80, self.modality_rng)), sa.freq_mask_n,
                            sa.time_mask_n, sa.mask_value)
             out = eng.forward_train(src_tokens, src_lengths, imgs_list if fuse else [], img_masks_list if fuse else [],
-                                    drop_audio=drop_audio, drop_image=drop_image, specaug=specaug)
-            out["encoder_out"] = [EncoderOutGrad.apply(out["encoder_out"][0], eng, *eng.params)]
+                                    drop_audio=drop_audio, drop_image=drop_image, specaug=specaug,
+                                    return_all_hiddens=return_all_hiddens)
+            if not frozen:      # inside fairseq's encoder_freezing_updates window the states carry no gradient
+                out["encoder_out"] = [EncoderOutGrad.apply(out["encoder_out"][0], eng, eng.generation, *eng.params)]
             return out
+        from ..training import TrainEngine
+
+        if isinstance(eng, TrainEngine) and getattr(self, "_external_optimizer", True):
+            # validation / generation after training with a torch or fairseq optimizer: that optimizer stepped the fp32
+            # parameters, the 16-bit operand copies (and the re-laid-out conv weights) are one step old
+            eng.refresh_operands()
         return eng.forward(src_tokens, src_lengths, imgs_list if fuse else [], img_masks_list if fuse else [],
                            return_all_hiddens=return_all_hiddens, drop_audio=drop_audio, drop_image=drop_image,
                            training=self.training)

@@ -110,20 +110,27 @@ class EncoderOutGrad(torch.autograd.Function):
     mode, gradient hooks and DistributedDataParallel's reducer all behave as for any other module."""
 
     @staticmethod
-    def forward(ctx, out, eng, *params):
-        ctx.eng = eng
+    def forward(ctx, out, eng, generation, *params):
+        ctx.eng, ctx.generation = eng, generation
         return out.view_as(out)
 
     @staticmethod
     def backward(ctx, grad):
         eng = ctx.eng
+        if eng.generation != ctx.generation or eng._saved is None:
+            # the engine keeps ONE set of saved activations (fixed workspaces): a second training forward before this
+            # backward has overwritten them, and running on would give silently wrong gradients
+            raise RuntimeError(
+                "mm_s2ut_transformer (B200 build): backward of a training forward whose saved activations were "
+                "overwritten by a later training forward of the same encoder; run forward -> backward per batch "
+                "(gradient accumulation over micro-batches works: backward each micro-batch before the next forward)")
         eng.backward(grad, accumulate=False)
         g = eng.flat_g.clone()          # one 4-byte-per-parameter copy: autograd owns what it is given
         grads = []
         for p in eng.params:
             o, n = eng._slices[id(p)]
             grads.append(g[o:o + n].view(p.shape))
-        return (None, None, *grads)
+        return (None, None, None, *grads)
 
 
 class TrainEngine(EncoderEngine):
@@ -134,6 +141,7 @@ class TrainEngine(EncoderEngine):
         # training forward: fused GEMM + residual + LayerNorm with a separate output buffer (needs n == 512)
         self.train_fused_ln = self.d == 512 and getattr(enc, "fuse_layernorm", True)
         self._saved = None
+        self.generation = 0            # advanced by every forward_train: ties an autograd node to ITS saved activations
         self.step_count = 0
         n = self.flat_p.numel()
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=self.device)
@@ -400,10 +408,15 @@ class TrainEngine(EncoderEngine):
     @torch.no_grad()
     def forward_train(self, src_tokens, src_lengths, imgs_list: List[torch.Tensor], img_masks_list: List,
                       drop_audio: bool = False, drop_image: bool = False, specaug=None,
-                      dropout_seed: Optional[int] = None, dropout_seed_dev: Optional[torch.Tensor] = None):
+                      dropout_seed: Optional[int] = None, dropout_seed_dev: Optional[torch.Tensor] = None,
+                      return_all_hiddens: bool = False):
         """dropout_seed (+ the int64 device scalar dropout_seed_dev, for CUDA-graph replay) seeds the element-wise
-        dropout masks of this step; default: a counter advanced per call on top of torch.initial_seed()."""
+        dropout masks of this step; default: a counter advanced per call on top of torch.initial_seed().
+        return_all_hiddens: ``encoder_states`` = every layer's output [T, B, C] (the criterion of the reference always
+        asks for them, criterions/speech_to_speech_criterion.py:64); they are copies outside the autograd boundary --
+        gradients reach the path only through ``encoder_out``."""
         enc = self.enc
+        self.generation += 1
         p_text = float(getattr(enc, "SA_text_dropout", 0.0) or 0.0)
         self._p_attn = float(getattr(enc, "attention_dropout_p", 0.0) or 0.0)
         p_sa = float(getattr(enc, "SA_attention_dropout", 0.0) or 0.0)
@@ -425,6 +438,7 @@ class TrainEngine(EncoderEngine):
         M, d = B * T, self.d
         if p_drop > 0:      # S2TTransformerEncoder: x = dropout_module(embed_scale * x + positions)
             K.dropout(x, x, p_drop, self._drop[2], SITE_EMBED, seed_dev=dropout_seed_dev)
+        states: List[torch.Tensor] = []
         saved = dict(B=B, T=T, m=m, x1=x1, seq_lens=seq_lens, layers=[], fused=False, drop=self._drop, p_img=p_img,
                      p_attn=self._p_attn, p_sa=p_sa, p_text=0.0)
         text_f32 = self.buf("text_f32", (M, d), torch.float32)
@@ -438,6 +452,8 @@ class TrainEngine(EncoderEngine):
             s = self._layer_train(i, x, B, T, seq_lens, h_next=h_next, h_next_f32=text_f32 if last else None)
             saved["layers"].append(s)
             x = s["x_out"]
+            if return_all_hiddens:
+                states.append(x.view(B, T, d).transpose(0, 1).contiguous())
         if not fused_fwd:
             K.layernorm(x, self.ln_g, self.ln_b, out_op=text_op, out_f32=text_f32)
         saved["x_final"] = x
@@ -462,7 +478,7 @@ class TrainEngine(EncoderEngine):
         else:
             out = text_f32.view(B, T, d).transpose(0, 1).contiguous()
         self._saved = saved
-        return {"encoder_out": [out], "encoder_padding_mask": [mask], "encoder_embedding": [], "encoder_states": [],
+        return {"encoder_out": [out], "encoder_padding_mask": [mask], "encoder_embedding": [], "encoder_states": states,
                 "src_tokens": [], "src_lengths": []}
 
     # ------------------------------------------------------------------------------------------

@@ -14,9 +14,10 @@ def record(name: str, value, bound=None) -> None:
 
 def fbank_errors(got: np.ndarray, ref: np.ndarray):
     """(err_main, err_all): max |got-ref| / max(|ref|, 1) over bins within 14 nats (~61 dB) of the frame maximum, and
-    over all bins.  Bins more than 60 dB below the frame's strongest bin sit on the fp32 rounding floor of the
-    reference's OWN rfft (two faithful fp32 implementations differ there by ~1e-3), so the north-star 1e-4
-    tolerance is asserted on the former and a loose sanity bound on the latter."""
+    over ALL bins.  The north-star tolerance (1e-4 relative) is asserted on the former; bins more than 60 dB below the
+    frame's strongest bin sit on the fp32 rounding floor of the reference's OWN rfft, where two faithful fp32
+    implementations differ by a few 1e-4, so the all-bin figure gets the bound that is actually measured: 2e-4 for the
+    CUDA kernel (worst of six utterances 1.0e-4, profiles/r01/parity.txt), 5e-4 for the numpy restatement."""
     got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
     rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)
     main = ref >= ref.max(axis=1, keepdims=True) - 14.0

@@ -126,3 +126,53 @@ def test_full_size_config1_properties(cuda):
         # final two positions legitimately depend on the batch; everything before them must agree
         n = int((~o4["encoder_padding_mask"][0][j]).sum()) - 2
         assert (o1[:n, i] - o4["encoder_out"][0][:n, j]).abs().max().item() < 1e-2, (i, T4)
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_timed_configuration_graphs_vs_oracle(cuda, ragged):
+    """The objects bench.py times -- ``GraphedEncoder`` replays at BASELINE configs[1]'s full size (base model,
+    B = 64 x 10 s, 577 x 768 image features) with fp32-waveform, int16-PCM, fp16-image and feature-store inputs --
+    against the fp32 CPU oracle on the same inputs (north-star tolerance: 2e-2 max-abs over valid positions).
+    ragged=False is exactly the bench shape (every utterance 160 000 samples, no padding)."""
+    from mm_s2ut_b200 import synth
+    from mm_s2ut_b200.feature_store import ImageFeatureStore
+    from mm_s2ut_b200.graph import GraphedEncoder
+
+    B, n_max = 64, 160000
+    enc, args, cfg = _build("base")
+    wavs, _ = synth.synth_batch(1, B, 10.0, ragged=ragged, zero_utt=5 if ragged else None)
+    wavs = [w.round().clip(-32768, 32767) for w in wavs]          # 16-bit PCM values: the fp32 and int16 inputs agree
+    imgs = synth.synth_images(1, B)
+    ref = _oracle(enc, args, cfg, wavs, imgs)
+    wav, lens = synth.pad_waveforms(wavs)
+    if wav.shape[1] < n_max:
+        wav = torch.nn.functional.pad(wav, (0, n_max - wav.shape[1]))
+    enc.cuda()
+    wav, lens, imgs = wav.cuda(), lens.cuda(), imgs.cuda()
+    Tref = ref["encoder_out"][0].shape[0]
+
+    def check(name, ge, inputs, tol=TOL):
+        ge.load_inputs(*inputs)
+        ge.capture()
+        for _ in range(2):                  # the replay, not the capture pass, is what the bench times
+            ge.load_inputs(*inputs)
+            out = ge.replay()
+        torch.cuda.synchronize()
+        got = {"encoder_out": [out["encoder_out"][0][:Tref]], "encoder_padding_mask": [out["encoder_padding_mask"][0][:, :Tref]]}
+        if out["encoder_out"][0].shape[0] > Tref:      # static batch shape is 10 s: positions past the longest utterance are padding
+            assert bool(out["encoder_padding_mask"][0][:, Tref:].all())
+        err = _compare(got, ref)
+        record(f"configs[1] FULL SIZE base B=64x10s {'ragged' if ragged else 'bench shape'}, GraphedEncoder {name}: "
+               f"fused states max-abs err", err, tol)
+        assert err < tol, (name, err)
+
+    shapes = [(577, 768)]
+    check("fp32 waveform", GraphedEncoder(enc, B, n_max, shapes), (wav, lens, [imgs]))
+    check("int16 PCM", GraphedEncoder(enc, B, n_max, shapes, wav_dtype=torch.int16), (wav.to(torch.int16), lens, [imgs]))
+    check("int16 PCM + fp16 image features", GraphedEncoder(enc, B, n_max, shapes, wav_dtype=torch.int16,
+                                                            img_dtype=torch.float16),
+          (wav.to(torch.int16), lens, [imgs.half()]))
+    store = ImageFeatureStore(torch.cat([imgs.flip(0), imgs], 0), cuda)
+    idx = torch.arange(B, 2 * B, dtype=torch.int64, device=cuda)
+    check("int16 PCM + device feature store", GraphedEncoder(enc, B, n_max, shapes, wav_dtype=torch.int16, stores=[store]),
+          (wav.to(torch.int16), lens, [idx]))

@@ -381,3 +381,47 @@ def test_decoder_backward_d512_fused_forward(monkeypatch):
     setup = _decoder_setup(B=2, L=7, T=9, d=512, heads=8, ffn=256, layers=2, vocab=29)
     eng = dt.UnitDecoderTrainEngine(setup[0], setup[5], "cpu")
     _check_decoder(eng, setup, REL, ZERO, _rel)
+
+
+def test_eval_after_external_optimizer_step_uses_the_updated_weights(monkeypatch):
+    """training forward + backward -> torch optimizer step -> eval() forward: the 16-bit operand copies (and the
+    re-laid-out conv weights) must be re-derived from the stepped fp32 parameters, not be one step old."""
+    from oracle import fbank as ofb, fusion as ofu
+    from test_gpu_training import _train_setup
+
+    _emulated(monkeypatch)
+    enc, wav, lens, imgs, R, ref_grads, out_ref, mask = _train_setup("selective_attention", True, B=2, dur=1.0)
+    enc.train()
+    out = enc(wav, lens, None, None, None, imgs_list=[imgs], img_masks_list=[None])
+    (out["encoder_out"][0] * R).sum().backward()
+    torch.optim.SGD(enc.parameters(), lr=0.005).step()                 # moves the output by O(5): stale operands would show
+    enc.eval()
+    with torch.no_grad():
+        got = enc(wav, lens, None, None, None, imgs_list=[imgs], img_masks_list=[None], return_all_hiddens=True)
+    sd = {k: v.detach().clone().float() for k, v in enc.state_dict().items()}
+    feats, flens = ofb.features_from_waveforms([w[:int(n)].numpy() for w, n in zip(wav, lens)])
+    ref = ofu.mm_encoder_forward(sd, enc.mm_config, torch.from_numpy(feats), torch.from_numpy(flens), [imgs], [None],
+                                 enc.num_heads)
+    valid = (~ref["encoder_padding_mask"][0]).t().unsqueeze(-1)
+    err = ((got["encoder_out"][0] - ref["encoder_out"][0]).abs() * valid).max().item()
+    stale = ((out_ref - ref["encoder_out"][0]).abs() * valid).max().item()
+    assert stale > 0.1, stale          # the step really moved the output ...
+    assert err < 2e-2, err             # ... and the eval forward follows it
+    assert len(got["encoder_states"]) == enc.num_layers
+
+
+def test_second_training_forward_before_backward_raises(monkeypatch):
+    """One set of saved activations per engine: backward of an OLDER forward must fail loudly, not return the
+    gradients of the newer one.  Also: return_all_hiddens is honoured in training mode."""
+    from test_gpu_training import _train_setup
+
+    _emulated(monkeypatch)
+    enc, wav, lens, imgs, R, *_ = _train_setup("selective_attention", True, B=2, dur=1.0)
+    enc.train()
+    o1 = enc(wav, lens, None, None, None, imgs_list=[imgs], img_masks_list=[None], return_all_hiddens=True)
+    assert len(o1["encoder_states"]) == enc.num_layers
+    assert o1["encoder_states"][0].shape == o1["encoder_out"][0].shape
+    o2 = enc(wav, lens, None, None, None, imgs_list=[imgs], img_masks_list=[None])
+    with pytest.raises(RuntimeError, match="overwritten by a later training forward"):
+        (o1["encoder_out"][0] * R).sum().backward()
+    (o2["encoder_out"][0] * R).sum().backward()         # the latest forward is fine

@@ -81,7 +81,7 @@ def test_fbank_restatement_matches_torchaudio_golden():
         ref = z[f"fbank{u}"]
         assert got.shape == ref.shape
         e_main, e_all = fbank_errors(got, ref)
-        assert e_main < 1e-4 and e_all < 5e-3, (e_main, e_all)
+        assert e_main < 1e-4 and e_all < 5e-4, (e_main, e_all)   # measured: 3e-6 .. 5e-6 / 8e-6 .. 3.1e-4
         live = ofb.kaldi_fbank_ta(z[f"wav{u}"])         # the installed torchaudio still agrees with the fixture
         assert np.max(np.abs(live - ref)) < 1e-4
     assert np.array_equal(ofb.kaldi_fbank_np(z["wav_zero"]), z["fbank_zero"])   # silence: the log(eps) floor
