@@ -208,6 +208,12 @@ int mm_attention(const void* q, int64_t q_ld, int32_t q_col0, int32_t q_len, con
                  const void* v, int64_t v_ld, int32_t v_col0, int32_t kv_len, const int32_t* kv_lens, int32_t batch,
                  int32_t heads, int32_t causal, void* out, int64_t out_ld, int32_t dtype, void* stream);
 
+/* scores[r, k] = -inf where key_mask[r / rows_per_seq][k] != 0, in place (the reference's key-padding masked_fill,
+ * fuse.py:88-91), for the training forward: the backward pass recomputes the probabilities from the kept scores, so
+ * the mask has to live in them.  scores fp32 [rows, ld]; key_mask uint8 [rows / rows_per_seq][mask_ld]. */
+int mm_mask_scores(float* scores, int64_t ld, int64_t rows, int32_t n_keys, const uint8_t* key_mask, int64_t mask_ld,
+                   int32_t rows_per_seq, void* stream);
+
 /* Fused (flash-style) speech -> image attention: out = softmax(q k^T + key mask) v for ONE head of width d_model
  * (SelectiveAttention.forward, mm_s2ut/models/fuse.py:80-113, built with num_heads = 1 at
  * mm_s2s_transformer.py:132-137; MultimodalAttention, fuse.py:145-167, with the learned bias_k / bias_v stored as the

@@ -142,6 +142,7 @@ EXPORTS = {
                                     C.c_int64, C.c_int32, C.c_void_p]),
     "mm_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                   C.c_int64, C.c_int32, C.c_void_p]),
+    "mm_mask_scores": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "mm_convert_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     # training-step variant (csrc/backward.cu)
     "mm_pack_t": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,

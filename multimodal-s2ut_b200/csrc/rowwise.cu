@@ -583,6 +583,33 @@ extern "C" int mm_softmax_rows(const float* scores, int64_t ld_in, int64_t rows,
   return 0;
 }
 
+// scores[r, k] = -inf where key_mask[r / rows_per_seq][k] != 0: one warp per row, writes only the masked cells
+namespace mm {
+__global__ void __launch_bounds__(256) mask_scores_kernel(float* __restrict__ scores, long long ld, long long rows, int n_keys,
+                                                          const uint8_t* __restrict__ key_mask, long long mask_ld,
+                                                          int rows_per_seq) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const uint8_t* mk = key_mask + (row / rows_per_seq) * mask_ld;
+  float* srow = scores + row * ld;
+  for (int k = threadIdx.x & 31; k < n_keys; k += 32)
+    if (mk[k]) srow[k] = -INFINITY;
+}
+}  // namespace mm
+
+extern "C" int mm_mask_scores(float* scores, int64_t ld, int64_t rows, int32_t n_keys, const uint8_t* key_mask,
+                              int64_t mask_ld, int32_t rows_per_seq, void* stream) {
+  if (!scores || !key_mask) return bad_arg("mask_scores: null pointer");
+  if (n_keys <= 0 || ld < n_keys || mask_ld < n_keys || rows_per_seq <= 0) return bad_arg("mask_scores: extents");
+  if (rows <= 0) return 0;
+  launch_pdl(mm::mask_scores_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+             scores, (long long)ld, (long long)rows, n_keys, key_mask, (long long)mask_ld, rows_per_seq);
+  MM_CHECK_LAUNCH("mask_scores_kernel launch");
+  return 0;
+}
+
 extern "C" int mm_convert_f32(const float* x, void* out, int64_t n, int32_t dtype, void* stream) {
   if (!x || !out) return bad_arg("convert: null pointer");
   if (n <= 0) return 0;

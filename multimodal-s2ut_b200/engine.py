@@ -316,8 +316,8 @@ class EncoderEngine:
             self._fuse_attention_fused(j, F, text_op, img_op, mask, B, T, Tk_img, Tk, dk)
             o = self.buf("o_img", (M, d), op)
         else:
-            o = self._fuse_attention_unfused(j, F, text_op, img_op, mask, B, T, Tk_img, Tk, Tkp, dk, attn_dropout)
-        self._fuse_output(F, o, text_f32, text_op, B, T, out_tbc)
+            o = self._fuse_attention_unfused(j, F, text_op, img_op, mask, B, T, Tk_img, Tk, Tkp, dk, attn_dropout, tag)
+        self._fuse_output(F, o, text_f32, text_op, B, T, out_tbc, tag)
 
     def _fuse_attention_fused(self, j, F, text_op, img_op, mask, B, T, Tk_img, Tk, dk) -> None:
         """K|V projection into ONE [B, Tk, 2d] tensor, q projection, then mm_cross_attention -> o_img."""
@@ -341,8 +341,10 @@ class EncoderEngine:
         kv2 = kv.view(B * Tk, 2 * d)
         K.cross_attention(q, T, kv2, 0, kv2, d, Tk, B, d, o, key_mask=mask)
 
-    def _fuse_attention_unfused(self, j, F, text_op, img_op, mask, B, T, Tk_img, Tk, Tkp, dk, attn_dropout):
-        """scores GEMM -> softmax (+ attention dropout) -> P V GEMM with S, P, K and V^T kept in HBM (training)."""
+    def _fuse_attention_unfused(self, j, F, text_op, img_op, mask, B, T, Tk_img, Tk, Tkp, dk, attn_dropout, tag=""):
+        """scores GEMM -> softmax (+ attention dropout) -> P V GEMM with S, P, K and V^T kept in HBM (training).
+        A key mask is burnt into S as -inf (``mm_mask_scores``), so the backward pass, which recomputes the
+        probabilities from S, sees the same masked softmax."""
         d, op, bn, M = self.d, self.op_dtype, self.block_n, B * T
         extra = Tk - Tk_img
         new_kv = (f"k{j}", (B, Tk, d), op) not in self._buf
@@ -361,31 +363,31 @@ class EncoderEngine:
             # key / value is written ONCE, when the workspace is created, not per forward.
             kbuf[:, Tk_img, :] = F["bias_kv"][0]
             vt[:, :, Tk_img] = F["bias_kv"][1]
-        q = self.buf("q_img", (M, d), op)
+        q = self.buf("q_img" + tag, (M, d), op)
         K.gemm(a0=text_op, a0_ld=d, rows=M, w=F["wq"], n=d, k=d, mode=K.EPI_OP, bias=F["bq"], scale=d ** -0.5,
                scale_cols=d, out0=q, out0_ld=d, block_n=bn)
         S = self.buf(f"S{j}", (B, T, Tkp), torch.float32)
         K.gemm(a0=q, a0_ld=d, a0_bs=T * d, rows=T, batches=B, w=kbuf, w_ld=d, w_bs=Tk * d, w_batched=True, n=Tk, k=d,
                mode=K.EPI_F32, out0=S, out0_ld=Tkp, out0_bs=T * Tkp, block_n=bn)
         P = self.buf(f"P{j}", (B, T, Tkp), op)
+        if mask is not None:
+            K.mask_scores(S, Tkp, M, Tk, mask, T)
         if attn_dropout is not None and attn_dropout[0] > 0:
-            if mask is not None:
-                raise NotImplementedError("SA_attention_dropout with an image key mask")
             K.softmax_bwd(S, None, Tkp, M, T, Tk, None, Tkp, probs=P, drop_p=attn_dropout[0], seed=attn_dropout[1],
                           seed_dev=attn_dropout[2], site=attn_dropout[3])
         else:
-            K.softmax_rows(S, Tkp, M, Tk, P, Tkp, key_mask=mask, rows_per_seq=T)
-        o = self.buf("o_img", (M, d), op)
+            K.softmax_rows(S, Tkp, M, Tk, P, Tkp)
+        o = self.buf("o_img" + tag, (M, d), op)
         K.gemm(a0=P, a0_ld=Tkp, a0_bs=T * Tkp, rows=T, batches=B, w=vt, w_ld=Tkp, w_bs=d * Tkp, w_batched=True, n=d,
                k=Tkp, mode=K.EPI_OP, out0=o, out0_ld=d, out0_bs=T * d, block_n=bn)
         return o
 
-    def _fuse_output(self, F, o, text_f32, text_op, B, T, out_tbc) -> None:
+    def _fuse_output(self, F, o, text_f32, text_op, B, T, out_tbc, tag="") -> None:
         """out_proj of the attention, then the selective gate (or the plain residual) -> out_tbc [T, B, d]."""
         enc, d, op, bn, M = self.enc, self.d, self.op_dtype, self.block_n, B * T
         if enc.use_selective_gate:
-            a_f32 = self.buf("attn_f32", (M, d), torch.float32)
-            a_op = self.buf("attn_op", (M, d), op)
+            a_f32 = self.buf("attn_f32" + tag, (M, d), torch.float32)
+            a_op = self.buf("attn_op" + tag, (M, d), op)
             K.gemm(a0=o, a0_ld=d, rows=M, w=F["wp"], n=d, k=d, mode=K.EPI_F32_OP, bias=F["bp"], out0=a_f32, out0_ld=d,
                    out1=a_op, out1_ld=d, block_n=bn)
             # rows batched per utterance so that a tile never straddles two utterances of the T x B x C output

@@ -326,6 +326,16 @@ def softmax_rows(scores: torch.Tensor, ld_in: int, rows: int, n_keys: int, probs
                                        ld_out, dtype_code(probs.dtype), _stream()), "mm_softmax_rows")
 
 
+def mask_scores(scores: torch.Tensor, ld: int, rows: int, n_keys: int, key_mask: torch.Tensor, rows_per_seq: int) -> None:
+    """scores[r, k] = -inf where key_mask[r // rows_per_seq, k] != 0 (the reference's masked_fill, fuse.py:88-91), in place."""
+    assert scores.dtype == torch.float32 and key_mask.dtype == torch.uint8 and key_mask.dim() == 2
+    assert key_mask.stride(1) == 1 and key_mask.shape[1] >= n_keys and key_mask.shape[0] * rows_per_seq == rows
+    lib = _lib.load()
+    with _Launch("mask_scores", 1.0 * rows * n_keys):
+        _lib.check(lib.mm_mask_scores(_ptr(scores), ld, rows, n_keys, _ptr(key_mask), key_mask.stride(0), rows_per_seq,
+                                      _stream()), "mm_mask_scores")
+
+
 def convert(x: torch.Tensor, out: torch.Tensor) -> None:
     assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous() and out.numel() == x.numel()
     lib = _lib.load()

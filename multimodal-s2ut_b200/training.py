@@ -28,8 +28,9 @@ are contiguous slices.  ``all_reduce_grads`` runs NCCL (or gloo) over ``flat_g``
 Element-wise dropout (embedding, residual and activation sites, SA_image_dropout, SA_text_dropout) uses counter-based
 masks that the backward pass regenerates (``mm_dropout``); attention dropout (encoder self-attention,
 SA_attention_dropout) runs the un-fused score / softmax+dropout / P V path in the training forward; modality dropout
-(per-batch image zeroing) works.  Not built (raises): image key masks, several image-feature types, and the device
-feature store in the backward pass.
+(per-batch image zeroing) works; so do image key masks (burnt into the kept scores as -inf), several image-feature
+types (one attention + gate each, summed) and batches that live in the device feature store.  Not built (raises): the
+audio-drop branch, which is broken in the reference (:500).
 """
 from __future__ import annotations
 
@@ -426,10 +427,6 @@ class TrainEngine(EncoderEngine):
             self._drop_calls = getattr(self, "_drop_calls", 0) + 1
             dropout_seed = (torch.initial_seed() + 0x51ED270B * self._drop_calls) & 0x7FFFFFFFFFFFFFFF
         self._drop = (p_drop, p_act, int(dropout_seed), dropout_seed_dev)
-        if len(imgs_list) > 1:
-            raise NotImplementedError("the backward pass handles one image-feature type")
-        if any(m is not None for m in img_masks_list):
-            raise NotImplementedError("image key masks are not supported in the backward pass")
         if drop_audio:
             raise NotImplementedError("audio-drop branch (broken in the reference, :500) has no backward here")
         x1, m, seq_lens, _ = self.frontend(src_tokens, src_lengths, specaug=specaug)
@@ -460,21 +457,32 @@ class TrainEngine(EncoderEngine):
         mask = torch.empty(B, T, dtype=torch.bool, device=self.device)
         K.padding_mask(seq_lens, T, mask)
         if imgs_list and self.fusion:
-            img = imgs_list[0]
-            if isinstance(img, StoredImages):
-                raise NotImplementedError("ImageFeatureStore batches are forward-only")
-            if drop_image:
-                img = torch.zeros(tuple(img.shape), dtype=torch.float32, device=self.device)
-            img = img.to(self.device, non_blocking=True).float().contiguous()
+            if len(imgs_list) > len(self.fusion) or len(img_masks_list) != len(imgs_list):
+                raise ValueError("imgs_list / img_masks_list do not match image_feat_dim")
             out = torch.empty(T, B, d, dtype=torch.float32, device=self.device)
             if p_text > 0:      # SA_text_dropout (:597): the dropped states feed the query, the gate and the mix
                 K.dropout(text_f32, text_f32, p_text, self._drop[2], SITE_TEXT, seed_dev=dropout_seed_dev)
                 K.convert(text_f32, text_op)
                 saved["p_text"] = p_text
-            self.fuse(0, text_f32, text_op, img, None, B, T, out,
-                      img_dropout=(p_img, self._drop[2], dropout_seed_dev, SITE_IMAGE),
-                      attn_dropout=(p_sa, self._drop[2], dropout_seed_dev, SITE_SA_ATTN), keep_scores=True)
-            saved.update(fused=True, img=img)
+            imgs = []
+            # one attention + gate per image-feature type, fused states = sum over the types (reference :513-530, :557-560)
+            for j, (img, img_mask) in enumerate(zip(imgs_list, img_masks_list)):
+                if isinstance(img, StoredImages):
+                    # a batch that lives in the device feature store: the backward pass (image pre-norm parameter
+                    # gradients) needs the rows as a tensor -> gather them once (layout glue, like the reference's collater)
+                    img = img.store.data.index_select(0, img.index.to(self.device))
+                if drop_image:      # modality dropout: every image tensor zeroed (:504-505)
+                    img = torch.zeros(tuple(img.shape), dtype=torch.float32, device=self.device)
+                img = img.to(self.device, non_blocking=True).float().contiguous()
+                res = out if j == 0 else self.buf(f"res_tbc{j}", (T, B, d), torch.float32)
+                self.fuse(j, text_f32, text_op, img, img_mask, B, T, res,
+                          img_dropout=(p_img, self._drop[2], dropout_seed_dev, SITE_IMAGE + 32 * j),
+                          attn_dropout=(p_sa, self._drop[2], dropout_seed_dev, SITE_SA_ATTN + 32 * j), keep_scores=True,
+                          tag=str(j))
+                if j > 0:
+                    K.dropout(res, out, 0.0, 0, 0, resid=out)      # out += res (p = 0: the plain fp32 accumulate)
+                imgs.append(img)
+            saved.update(fused=True, imgs=imgs)
         else:
             out = text_f32.view(B, T, d).transpose(0, 1).contiguous()
         self._saved = saved
@@ -642,27 +650,31 @@ class TrainEngine(EncoderEngine):
         self._ln_param_grads(lnp, d, self.g(mod.self_attn_layer_norm.weight, mod.self_attn_layer_norm.bias), accumulate)
         self._flush()           # the layer's ten deferred reductions in one launch
 
-    def _fusion_bwd(self, dres: torch.Tensor, gtext: torch.Tensor, B: int, T: int, accumulate: bool) -> None:
-        """dres [T, B, d] -> gtext [M, d] = d loss / d text (the final LayerNorm output) + fusion parameter grads."""
-        enc, F, Fb = self.enc, self.fusion[0], self.fusion_bwd[0]
+    def _fusion_bwd(self, j: int, dres: torch.Tensor, gtext: torch.Tensor, B: int, T: int, accumulate: bool,
+                    ln_accumulate: bool) -> None:
+        """Image type j: dres [T, B, d] -> gtext [M, d] = d loss / d text (the final LayerNorm output) through this
+        type's attention + gate, and the type's parameter gradients.  ln_accumulate: the shared image pre-norm's
+        gradient already holds an earlier type's contribution."""
+        enc, F, Fb = self.enc, self.fusion[j], self.fusion_bwd[j]
         ps = Fb["p"]
         d, M, op, bn, dk = self.d, B * T, self.op_dtype, self.block_n, F["dk"]
-        img = self._saved["img"]
+        img = self._saved["imgs"][j]
+        tag = str(j)
         Tk_img = img.shape[1]
         extra = 1 if F["bias_kv"] is not None else 0
         Tk = Tk_img + extra
         Tkp = _round_up(Tk, 8)
         text_f32, text_op = self.buf("text_f32", (M, d), torch.float32), self.buf("text_op", (M, d), op)
-        o = self.buf("o_img", (M, d), op)
-        q = self.buf("q_img", (M, d), op)
-        kbuf = self.buf("k0", (B, Tk, d), op)
-        vt = self.buf(f"vt_img0_{Tk}", (B, d, Tkp), op)
-        S = self.buf("S0", (B, T, Tkp), torch.float32)
-        P = self.buf("P0", (B, T, Tkp), op)
-        img_op = self.buf("img_op0", (B * Tk_img, dk), op)
+        o = self.buf("o_img" + tag, (M, d), op)
+        q = self.buf("q_img" + tag, (M, d), op)
+        kbuf = self.buf(f"k{j}", (B, Tk, d), op)
+        vt = self.buf(f"vt_img{j}_{Tk}", (B, d, Tkp), op)
+        S = self.buf(f"S{j}", (B, T, Tkp), torch.float32)
+        P = self.buf(f"P{j}", (B, T, Tkp), op)
+        img_op = self.buf(f"img_op{j}", (B * Tk_img, dk), op)
         da_op = self.buf("f_da_op", (M, d), op)
         if enc.use_selective_gate:
-            a_f32, a_op = self.buf("attn_f32", (M, d), torch.float32), self.buf("attn_op", (M, d), op)
+            a_f32, a_op = self.buf("attn_f32" + tag, (M, d), torch.float32), self.buf("attn_op" + tag, (M, d), op)
             z = self.buf("f_z", (M, d), torch.float32)
             K.gemm(a0=a_op, a0_ld=d, a1=text_op, a1_ld=d, k_split=d, rows=M, w=F["wg"], n=d, k=2 * d, mode=K.EPI_F32,
                    bias=F["bg"], out0=z, out0_ld=d, block_n=bn)
@@ -692,7 +704,7 @@ class TrainEngine(EncoderEngine):
                out0=dP, out0_ld=Tkp, out0_bs=T * Tkp, **bt)                                        # dP = dO V^T
         dS = self.buf("f_dS", (B, T, Tkp), op)
         K.softmax_bwd(S, dP, Tkp, M, T, Tk, dS, Tkp, drop_p=self._saved["p_sa"], seed=self._saved["drop"][2],
-                      seed_dev=self._saved["drop"][3], site=SITE_SA_ATTN)
+                      seed_dev=self._saved["drop"][3], site=SITE_SA_ATTN + 32 * j)      # (a key mask lives in S as -inf)
         dkv = self.buf("f_dkv", (B, Tk, 2 * d), op)
         kvg = dict(rows=Tk, a0_ld=Tkp, a0_bs=T * Tkp, a_mn=True, w_ld=d, w_bs=T * d, w_mn=True, n=d, k=T, mode=K.EPI_OP,
                    out0_ld=2 * d, out0_bs=Tk * 2 * d, **bt)
@@ -726,11 +738,11 @@ class TrainEngine(EncoderEngine):
                    k=2 * d, mode=K.EPI_F32, out0=dimg, out0_ld=dk, out0_bs=Tk_img * dk, block_n=bn)
             if self._saved["p_img"] > 0:     # SA_image_dropout sat between the pre-norm and the K|V projection
                 _, _, seed, seed_dev = self._saved["drop"]
-                K.dropout(dimg, dimg, self._saved["p_img"], seed, SITE_IMAGE, seed_dev=seed_dev)
+                K.dropout(dimg, dimg, self._saved["p_img"], seed, SITE_IMAGE + 32 * j, seed_dev=seed_dev)
             lnp = self._lnp()
             K.layernorm_bwd(img.view(B * Tk_img, dk), self.img_ln[0], dimg, lnp)
             pn = enc.image_pre_norm_module
-            self._ln_param_grads(lnp, dk, self.g(pn.weight, pn.bias), accumulate)
+            self._ln_param_grads(lnp, dk, self.g(pn.weight, pn.bias), accumulate or ln_accumulate)
 
     def _conv_bwd(self, g: torch.Tensor, B: int, T: int, accumulate: bool) -> None:
         """g = d loss / d x0 [B*T, d] (x0 = glu(conv2) * sqrt(d) + positions) -> conv parameter gradients."""
@@ -837,7 +849,16 @@ class TrainEngine(EncoderEngine):
             self.flat_g[self.bucket_top[0]:].zero_()
         if sv["fused"]:
             with _scope("fusion"):
-                self._fusion_bwd(grad_out, gtext, B, T, accumulate)
+                n_types = len(sv["imgs"])
+                if not accumulate and n_types < len(self.fusion):
+                    # image types absent from this batch compute no gradients: theirs must read 0
+                    self.flat_g[self.bucket_top[0]:].zero_()
+                for j in range(n_types):
+                    # every type sees the same d loss / d res (the fused states are their sum); d loss / d text adds up
+                    gt = gtext if j == 0 else self.buf("b_gtext_j", (M, d), torch.float32)
+                    self._fusion_bwd(j, grad_out, gt, B, T, accumulate, ln_accumulate=j > 0)
+                    if j > 0:
+                        K.dropout(gt, gtext, 0.0, 0, 0, resid=gtext)       # gtext += gt
                 if sv["p_text"] > 0:
                     K.dropout(gtext, gtext, sv["p_text"], sv["drop"][2], SITE_TEXT, seed_dev=sv["drop"][3])
         else:

@@ -241,6 +241,11 @@ def cross_attention(q, q_len, k, k_col0, v, v_col0, kv_len, batch, d_model, out,
     out.copy_((p @ V).reshape(batch * q_len, d_model).to(out.dtype))
 
 
+def mask_scores(scores, ld, rows, n_keys, key_mask, rows_per_seq):
+    s = _v(scores, (rows, n_keys), (ld, 1))
+    s.masked_fill_(key_mask.bool().repeat_interleave(rows_per_seq, 0)[:, :n_keys], float("-inf"))
+
+
 def softmax_rows(scores, ld_in, rows, n_keys, probs, ld_out, key_mask=None, rows_per_seq=0):
     s = _v(scores, (rows, n_keys), (ld_in, 1))
     if key_mask is not None:

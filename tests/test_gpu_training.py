@@ -542,3 +542,39 @@ def test_graphed_train_step_with_specaugment(cuda):
         if t:
             assert (feats[t0:t0 + t] == 0).all()
         assert (feats[: 50] != 0).any()
+
+
+@pytest.mark.parametrize("kind", ["mask", "two_types", "store"])
+def test_backward_key_mask_several_image_types_store_batches(cuda, kind):
+    """What the reference's training loop can feed (mm_s2s_transformer.py:513-530: one attention + gate per image
+    type, summed; ``img_masks_list`` key masks; fuse.py:88-91) and the device feature store: forward + backward on
+    the CUDA kernels against autograd over the fp32 oracle."""
+    from test_host_training import _multi_setup
+
+    enc, wav, lens, imgs, masks, R, ref_grads, out_ref, pmask = _multi_setup(kind)
+    enc.cuda().train()
+    eng = enc.train_engine()
+    feed = [i.cuda() for i in imgs]
+    if kind == "store":
+        from mm_s2ut_b200.feature_store import ImageFeatureStore
+
+        store = ImageFeatureStore(torch.cat([imgs[0].flip(0), imgs[0]], 0), cuda)
+        feed = [store.batch([2, 3])]
+    out = eng.forward_train(wav.cuda(), lens.cuda(), feed, [None if m is None else m.cuda() for m in masks])
+    valid = (~pmask).t().unsqueeze(-1)
+    ferr = ((out["encoder_out"][0].cpu() - out_ref).abs() * valid).max().item()
+    assert ferr < 3e-2, ferr
+    eng.backward(R.cuda())
+    torch.cuda.synchronize()
+    names = dict(enc.named_parameters())
+    worst, checked = 0.0, 0
+    for k, gref in ref_grads.items():
+        if k not in names or gref.norm() < ZERO:
+            continue
+        rel = _rel(names[k].grad, gref)
+        worst = max(worst, rel)
+        assert rel < REL, (kind, k, rel)
+        checked += 1
+    record(f"configs[2] backward, {kind} (image key mask / two image-feature types / device feature store batch): worst "
+           f"parameter-gradient relative L2 error ({checked} tensors)", worst, REL)
+    assert checked >= 2 * 15 + 2 + 9

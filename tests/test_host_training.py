@@ -425,3 +425,79 @@ def test_second_training_forward_before_backward_raises(monkeypatch):
     with pytest.raises(RuntimeError, match="overwritten by a later training forward"):
         (o1["encoder_out"][0] * R).sum().backward()
     (o2["encoder_out"][0] * R).sum().backward()         # the latest forward is fine
+
+
+def _multi_setup(kind):
+    """Encoder + oracle gradients for the cases the backward pass used to refuse: 'mask' = image key mask,
+    'two_types' = image_feat_dim [96, 64] (one attention + gate each, summed; image_pre_norm off as in the
+    reference, whose single shared LayerNorm cannot serve two dims), 'store' = the batch lives in the feature store."""
+    from mm_s2ut_b200 import synth
+    from mm_s2ut_b200.config import DEFAULT_YAML, load_mm_config, make_args
+    from mm_s2ut_b200.models.mm_s2s_transformer import MM_S2STransformerEncoder
+    from oracle import fbank as ofb, fusion as ofu
+
+    cfg = dict(load_mm_config(DEFAULT_YAML))
+    dims = [96, 64] if kind == "two_types" else [96]
+    cfg.update(image_feat_dim=dims, image_pre_norm=kind != "two_types",
+               multimodal_attention_type="multimodal_attention" if kind == "mask" else "selective_attention")
+    torch.manual_seed(3)
+    args = make_args("small", multimodal_translation_config_yaml=cfg, encoder_layers=2)
+    enc = MM_S2STransformerEncoder(args, build_unused_projections=False)
+    enc.dropout_p = enc.activation_dropout_p = enc.attention_dropout_p = 0.0
+    enc.SA_image_dropout = enc.SA_attention_dropout = enc.SA_text_dropout = 0.0
+    B = 2
+    wavs, _ = synth.synth_batch(4, B, 1.0, ragged=True)
+    g = torch.Generator().manual_seed(9)
+    imgs = [torch.randn(B, tk, dk, generator=g) for tk, dk in zip([37, 21], dims)]
+    masks = [None for _ in dims]
+    if kind == "mask":
+        m = torch.zeros(B, 37, dtype=torch.bool)
+        m[1, 20:] = True
+        m[0, ::5] = True
+        masks = [m]
+    if kind == "store":
+        imgs = [imgs[0].half().float()]          # what a 16-bit store holds
+    sd = {k: v.detach().clone().float().requires_grad_(v.is_floating_point()) for k, v in enc.state_dict().items()}
+    feats, flens = ofb.features_from_waveforms(wavs)
+    ref = ofu.mm_encoder_forward(sd, load_mm_config(cfg), torch.from_numpy(feats), torch.from_numpy(flens), imgs, masks,
+                                 args.encoder_attention_heads)
+    out_ref, pmask = ref["encoder_out"][0], ref["encoder_padding_mask"][0]
+    R = torch.randn(out_ref.shape, generator=torch.Generator().manual_seed(11)) * (~pmask).t().unsqueeze(-1)
+    (out_ref * R).sum().backward()
+    ref_grads = {k: v.grad for k, v in sd.items() if v.requires_grad and v.grad is not None}
+    wav, lens = synth.pad_waveforms(wavs)
+    return enc, wav, lens, imgs, masks, R, ref_grads, out_ref.detach(), pmask
+
+
+@pytest.mark.parametrize("kind", ["mask", "two_types", "store"])
+def test_backward_with_key_mask_several_image_types_and_store_batches(monkeypatch, kind):
+    from test_gpu_training import REL, ZERO, _rel
+
+    _emulated(monkeypatch)
+    enc, wav, lens, imgs, masks, R, ref_grads, out_ref, pmask = _multi_setup(kind)
+    enc.train()
+    eng = enc.train_engine()
+    feed = imgs
+    if kind == "store":
+        from mm_s2ut_b200.feature_store import ImageFeatureStore, StoredImages
+
+        monkeypatch.setattr(ImageFeatureStore, "__init__", lambda self, feats, device, dtype=torch.float16, chunk=1024:
+                            self.__dict__.update(device=torch.device("cpu"), tokens=feats.shape[1], dim=feats.shape[2],
+                                                 data=feats.to(dtype)))
+        store = ImageFeatureStore(torch.cat([imgs[0].flip(0), imgs[0]], 0), "cpu")
+        feed = [StoredImages(store, torch.tensor([2, 3]))]
+    out = eng.forward_train(wav, lens, feed, masks)
+    valid = (~pmask).t().unsqueeze(-1)
+    assert ((out["encoder_out"][0] - out_ref).abs() * valid).max().item() < 3e-2
+    eng.backward(R)
+    names = dict(enc.named_parameters())
+    checked = 0
+    for k, gref in ref_grads.items():
+        if k not in names or gref.norm() < ZERO:
+            continue
+        rel = _rel(names[k].grad, gref)
+        assert rel < REL, (kind, k, rel)
+        checked += 1
+    want = {"mask": 10, "two_types": 2 * 9, "store": 11}[kind]          # fusion tensors with a non-zero gradient (k bias: 0)
+    assert sum(1 for k in ref_grads if ("attns" in k or "gate" in k or "pre_norm" in k) and ref_grads[k].norm() >= ZERO) >= want
+    assert checked >= 2 * 15 + 2 + want
