@@ -551,7 +551,7 @@ def test_backward_key_mask_several_image_types_store_batches(cuda, kind):
     the CUDA kernels against autograd over the fp32 oracle."""
     from test_host_training import _multi_setup
 
-    enc, wav, lens, imgs, masks, R, ref_grads, out_ref, pmask = _multi_setup(kind)
+    enc, wav, lens, imgs, masks, R, ref_grads, out_ref, pmask = _multi_setup(kind, dim0=512)   # LayerNorm kernel dims: 256/512/768/1024; != d, else nn.MultiheadAttention packs in_proj_weight
     enc.cuda().train()
     eng = enc.train_engine()
     feed = [i.cuda() for i in imgs]

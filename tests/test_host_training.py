@@ -427,7 +427,7 @@ def test_second_training_forward_before_backward_raises(monkeypatch):
     (o2["encoder_out"][0] * R).sum().backward()         # the latest forward is fine
 
 
-def _multi_setup(kind):
+def _multi_setup(kind, dim0=96):
     """Encoder + oracle gradients for the cases the backward pass used to refuse: 'mask' = image key mask,
     'two_types' = image_feat_dim [96, 64] (one attention + gate each, summed; image_pre_norm off as in the
     reference, whose single shared LayerNorm cannot serve two dims), 'store' = the batch lives in the feature store."""
@@ -437,7 +437,7 @@ def _multi_setup(kind):
     from oracle import fbank as ofb, fusion as ofu
 
     cfg = dict(load_mm_config(DEFAULT_YAML))
-    dims = [96, 64] if kind == "two_types" else [96]
+    dims = [dim0, 64] if kind == "two_types" else [dim0]
     cfg.update(image_feat_dim=dims, image_pre_norm=kind != "two_types",
                multimodal_attention_type="multimodal_attention" if kind == "mask" else "selective_attention")
     torch.manual_seed(3)
