@@ -69,6 +69,9 @@ int mm_cmvn_apply_specaug(const float* feats, const float* mean_std, const int64
  * frames = 1 + (n - 400) / 160 when lengths_are_samples.  (fairseq Conv1dSubsampler.get_out_seq_lens_tensor) */
 int mm_seq_lens(const int64_t* n_samples_or_frames, int32_t lengths_are_samples, int32_t batch, int32_t n_layers,
                 int32_t* out_lens, void* stream);
+/* mm_seq_lens and mm_padding_mask (below) in one launch: out_lens [batch] and mask [batch, T]. */
+int mm_seq_lens_mask(const int64_t* n_samples_or_frames, int32_t lengths_are_samples, int32_t batch, int32_t n_layers,
+                     int32_t T, int32_t* out_lens, uint8_t* mask, void* stream);
 /* mask[b, t] = (t >= seq_lens[b]) as bytes (PyTorch bool layout): fairseq lengths_to_padding_mask applied to the
  * subsampled lengths, i.e. the encoder_padding_mask of the encoder-out dict (mm_s2s_transformer.py:378-562). */
 int mm_padding_mask(const int32_t* seq_lens, int32_t batch, int32_t T, uint8_t* mask, void* stream);
@@ -227,6 +230,28 @@ int mm_cross_attention(const void* q, int64_t q_ld, int32_t q_len, const void* k
                        const void* v, int64_t v_ld, int32_t v_col0, int32_t kv_len, int64_t kv_batch_stride,
                        const uint8_t* key_mask, int64_t mask_ld, int32_t batch, int32_t d_model, void* out,
                        int64_t out_ld, float* lse, int32_t dtype, void* stream);
+
+/* The same two kernels with one more output for the training step: lse [batch][heads][queries] fp32 = natural-log
+ * sum-exp of every query row's (masked) scores, from which the backward pass rebuilds the probabilities without the
+ * scores ever having been stored (mm_attention_bwd_scores).  lse == NULL: identical to the calls above. */
+int mm_self_attention_lse(const void* qkv, int64_t qkv_ld, const int32_t* seq_lens, int32_t batch, int32_t seq,
+                          int32_t heads, void* out, int64_t out_ld, float* lse, int32_t dtype, void* stream);
+int mm_attention_lse(const void* q, int64_t q_ld, int32_t q_col0, int32_t q_len, const void* k, int64_t k_ld,
+                     int32_t k_col0, const void* v, int64_t v_ld, int32_t v_col0, int32_t kv_len, const int32_t* kv_lens,
+                     int32_t batch, int32_t heads, int32_t causal, void* out, int64_t out_ld, float* lse, int32_t dtype,
+                     void* stream);
+
+/* Attention backward, score side (what PyTorch autograd does for fairseq's MultiheadAttention in the reference's
+ * training step): P = exp(q k^T - lse) with the key-length / causal masks, dS = P o (dO v^T - rowsum(dO o O)), written
+ * as 16-bit [batch * heads][..][..] matrices with row stride pd_ld and matrix stride pd_bs (elements), for the
+ * dV = P^T dO, dK = dS^T q, dQ = dS k contractions that follow (mm_gemm).  Arguments as mm_attention; dout / out are
+ * the gradient and the forward result of the attention output [batch * q_len, heads * 64]; lse as written by
+ * mm_self_attention_lse / mm_attention_lse.  Scores, dP and the softmax backward stay in TMEM / registers. */
+int mm_attention_bwd_scores(const void* q, int64_t q_ld, int32_t q_col0, int32_t q_len, const void* k, int64_t k_ld,
+                            int32_t k_col0, const void* v, int64_t v_ld, int32_t v_col0, int32_t kv_len,
+                            const int32_t* kv_lens, int32_t batch, int32_t heads, int32_t causal, const void* dout,
+                            int64_t do_ld, const void* out, int64_t o_ld, const float* lse, void* probs, void* dscores,
+                            int64_t pd_ld, int64_t pd_bs, int32_t dtype, void* stream);
 
 /* Row softmax for the speech->image attention (fuse.py:88-111): scores fp32 [rows, ld_in] -> probabilities
  * 16-bit [rows, ld_out]; columns [n_keys, ld_out) written as 0.  key_mask: optional [n_seqs, n_keys] uint8

@@ -17,7 +17,7 @@ _PKG = Path(__file__).resolve().parent
 CSRC = _PKG / "csrc"
 INCLUDE = _PKG.parent / "include"
 LIB_PATH = _PKG / "libmms2ut_b200.so"
-SOURCES = ["abi.cu", "gemm.cu", "gemm_ln.cu", "rowwise.cu", "fbank.cu", "attention.cu", "cross_attention.cu", "backward.cu"]
+SOURCES = ["abi.cu", "gemm.cu", "gemm_ln.cu", "rowwise.cu", "fbank.cu", "attention.cu", "cross_attention.cu", "attention_bwd.cu", "backward.cu"]
 ABI_VERSION = 3
 
 NVCC_FLAGS = [
@@ -116,6 +116,7 @@ EXPORTS = {
                                         C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                         C.c_float, C.c_void_p]),
     "mm_seq_lens": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mm_seq_lens_mask": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mm_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "mm_padding_mask": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "mm_label_smoothed_nll": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
@@ -125,6 +126,15 @@ EXPORTS = {
     "mm_attention": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                C.c_int64, C.c_int32, C.c_void_p]),
+    "mm_self_attention_lse": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                        C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mm_attention_lse": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                   C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                   C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mm_attention_bwd_scores": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
+                                          C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                          C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]),
     "mm_cross_attention": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                      C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
                                      C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),

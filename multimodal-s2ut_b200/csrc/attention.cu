@@ -98,7 +98,8 @@ __device__ long long g_att_trace[148 * 2 * 8 * 6];
 template <typename OpT>
 __global__ void __launch_bounds__(PA_THREADS, 1)
 self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant__ CUtensorMap mapOut,
-                           const int* __restrict__ seq_lens, int T, int d_model, int H, int nqt, int n_items) {
+                           const int* __restrict__ seq_lens, int T, int d_model, int H, int nqt, int n_items,
+                           float* __restrict__ lse) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sOut = smem + 2 * PA_STAGE_BYTES;
@@ -319,7 +320,11 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
         const bool elected = (warp & 7) == 0 && lane == 0;
         if (elected) bulk_wait_read<0>();           // the previous item's store has finished reading the tile
         group_sync();                               // ... and both halves of the row sum are visible
-        const float inv = 1.0f / (l + x_sum[(hf ^ 1) * AT_BM + row]);
+        const float lt = l + x_sum[(hf ^ 1) * AT_BM + row];
+        const float inv = 1.0f / lt;
+        // log-sum-exp of the row's scores (natural log), [batch][head][query]: what a backward pass needs to rebuild P
+        if (lse != nullptr && hf == 0 && qt * AT_BM + row < T)
+          lse[((long long)b * H + h) * T + qt * AT_BM + row] = m + __logf(lt);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -355,7 +360,7 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
 
 template <typename OpT>
 static int launch_attn_t256(const CUtensorMap& mqk, const CUtensorMap& mout, const int* lens, int B, int T, int H,
-                            int d, cudaStream_t s) {
+                            int d, float* lse, cudaStream_t s) {
   auto kern = self_attention_t256_kernel<OpT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -377,7 +382,7 @@ static int launch_attn_t256(const CUtensorMap& mqk, const CUtensorMap& mout, con
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mqk, mout, lens, T, d, H, nqt, n_items);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mqk, mout, lens, T, d, H, nqt, n_items, lse);
   if (e != cudaSuccess) return fail(e, "self_attention_t256_kernel launch");
   return 0;
 }
@@ -408,7 +413,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1)
 self_attention_long_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                            const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapOut,
                            const int* __restrict__ seq_lens, int T, int q_col0, int k_col0, int v_col0, int causal,
-                           int H, int nqt, int n_items) {
+                           int H, int nqt, int n_items, int q_len, float* __restrict__ lse) {
   // Q, K, V may be three different tensors (decoder cross-attention: queries from the decoder states, keys / values
   // from the projected encoder states) or column blocks of one (self-attention: q | k | v of the QKV GEMM).  T is
   // the key extent, seq_lens[b] (NULL: T) the number of valid keys of utterance b; the number of query rows only
@@ -648,7 +653,10 @@ self_attention_long_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
         const bool elected = (warp & 7) == 0 && lane == 0;
         if (elected) bulk_wait_read<0>();
         group_sync();
-        const float inv = 1.0f / (l + x_sum[(hf ^ 1) * AT_BM + row]);
+        const float lt = l + x_sum[(hf ^ 1) * AT_BM + row];
+        const float inv = 1.0f / lt;
+        if (lse != nullptr && hf == 0 && qt * AT_BM + row < q_len)      // [batch][head][query], natural log
+          lse[((long long)b * H + h) * q_len + qt * AT_BM + row] = m + __logf(lt);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -684,7 +692,7 @@ self_attention_long_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
 template <typename OpT>
 static int launch_attn_long(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mout,
                             const int* lens, int B, int Tq, int Tk, int q_col0, int k_col0, int v_col0, int causal,
-                            int H, cudaStream_t s) {
+                            int H, float* lse, cudaStream_t s) {
   auto kern = self_attention_long_kernel<OpT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -707,7 +715,7 @@ static int launch_attn_long(const CUtensorMap& mq, const CUtensorMap& mk, const 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mq, mk, mv, mout, lens, Tk, q_col0, k_col0, v_col0, causal, H, nqt,
-                                     n_items);
+                                     n_items, Tq, lse);
   if (e != cudaSuccess) return fail(e, "self_attention_long_kernel launch");
   return 0;
 }
@@ -724,6 +732,11 @@ extern "C" int mm_debug_att_trace(long long* host) {
 
 extern "C" int mm_self_attention(const void* qkv, int64_t qkv_ld, const int32_t* seq_lens, int32_t batch, int32_t seq,
                                  int32_t heads, void* out, int64_t out_ld, int32_t dtype, void* stream) {
+  return mm_self_attention_lse(qkv, qkv_ld, seq_lens, batch, seq, heads, out, out_ld, nullptr, dtype, stream);
+}
+
+extern "C" int mm_self_attention_lse(const void* qkv, int64_t qkv_ld, const int32_t* seq_lens, int32_t batch, int32_t seq,
+                                     int32_t heads, void* out, int64_t out_ld, float* lse, int32_t dtype, void* stream) {
   if (!qkv || !seq_lens || !out) return bad_arg("self_attention: null pointer");
   if (batch <= 0 || seq <= 0 || heads <= 0) return bad_arg("self_attention: extents");
   const int d = heads * AT_HD;
@@ -742,22 +755,30 @@ extern "C" int mm_self_attention(const void* qkv, int64_t qkv_ld, const int32_t*
     rc = make_tmap_3d(&mout, out, f16, (uint64_t)d, (uint64_t)seq, (uint64_t)batch, (uint64_t)out_ld,
                       (uint64_t)seq * out_ld, 128);
     if (rc) return rc;
-    return f16 ? launch_attn_t256<__half>(mqk, mout, seq_lens, batch, seq, heads, d, s)
-               : launch_attn_t256<__nv_bfloat16>(mqk, mout, seq_lens, batch, seq, heads, d, s);
+    return f16 ? launch_attn_t256<__half>(mqk, mout, seq_lens, batch, seq, heads, d, lse, s)
+               : launch_attn_t256<__nv_bfloat16>(mqk, mout, seq_lens, batch, seq, heads, d, lse, s);
   }
   // T > 256: persistent online-softmax kernel, 128-key chunks; mqk (box 64 x 128) serves Q, K and V chunks alike
   CUtensorMap mout;
   rc = make_tmap_3d(&mout, out, f16, (uint64_t)d, (uint64_t)seq, (uint64_t)batch, (uint64_t)out_ld,
                     (uint64_t)seq * out_ld, 128);
   if (rc) return rc;
-  return f16 ? launch_attn_long<__half>(mqk, mqk, mqk, mout, seq_lens, batch, seq, seq, 0, d, 2 * d, 0, heads, s)
-             : launch_attn_long<__nv_bfloat16>(mqk, mqk, mqk, mout, seq_lens, batch, seq, seq, 0, d, 2 * d, 0, heads, s);
+  return f16 ? launch_attn_long<__half>(mqk, mqk, mqk, mout, seq_lens, batch, seq, seq, 0, d, 2 * d, 0, heads, lse, s)
+             : launch_attn_long<__nv_bfloat16>(mqk, mqk, mqk, mout, seq_lens, batch, seq, seq, 0, d, 2 * d, 0, heads, lse, s);
 }
 
 extern "C" int mm_attention(const void* q, int64_t q_ld, int32_t q_col0, int32_t q_len, const void* k, int64_t k_ld,
                             int32_t k_col0, const void* v, int64_t v_ld, int32_t v_col0, int32_t kv_len,
                             const int32_t* kv_lens, int32_t batch, int32_t heads, int32_t causal, void* out,
                             int64_t out_ld, int32_t dtype, void* stream) {
+  return mm_attention_lse(q, q_ld, q_col0, q_len, k, k_ld, k_col0, v, v_ld, v_col0, kv_len, kv_lens, batch, heads, causal,
+                          out, out_ld, nullptr, dtype, stream);
+}
+
+extern "C" int mm_attention_lse(const void* q, int64_t q_ld, int32_t q_col0, int32_t q_len, const void* k, int64_t k_ld,
+                                int32_t k_col0, const void* v, int64_t v_ld, int32_t v_col0, int32_t kv_len,
+                                const int32_t* kv_lens, int32_t batch, int32_t heads, int32_t causal, void* out,
+                                int64_t out_ld, float* lse, int32_t dtype, void* stream) {
   if (!q || !k || !v || !out) return bad_arg("attention: null pointer");
   if (batch <= 0 || q_len <= 0 || kv_len <= 0 || heads <= 0) return bad_arg("attention: extents");
   const int d = heads * AT_HD;
@@ -781,7 +802,7 @@ extern "C" int mm_attention(const void* q, int64_t q_ld, int32_t q_col0, int32_t
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return f16 ? launch_attn_long<__half>(mq, mk, mv, mout, kv_lens, batch, q_len, kv_len, q_col0, k_col0, v_col0,
-                                         causal != 0, heads, s)
+                                         causal != 0, heads, lse, s)
              : launch_attn_long<__nv_bfloat16>(mq, mk, mv, mout, kv_lens, batch, q_len, kv_len, q_col0, k_col0,
-                                                 v_col0, causal != 0, heads, s);
+                                                 v_col0, causal != 0, heads, lse, s);
 }

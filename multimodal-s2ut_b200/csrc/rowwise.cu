@@ -683,6 +683,31 @@ extern "C" int mm_padding_mask(const int32_t* seq_lens, int32_t batch, int32_t T
   return 0;
 }
 
+// seq_lens + padding mask in one launch: block b computes its utterance's subsampled length and writes mask row b
+namespace mm {
+__global__ void __launch_bounds__(128) seq_lens_mask_kernel(const long long* __restrict__ lens, int lengths_are_samples,
+                                                            int n_layers, int T, int* __restrict__ out,
+                                                            uint8_t* __restrict__ mask) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x;
+  int n = frames_of(lens[b], lengths_are_samples);
+  for (int i = 0; i < n_layers; ++i) n = n <= 0 ? 0 : (n - 1) / 2 + 1;
+  if (threadIdx.x == 0) out[b] = n;
+  for (int t = threadIdx.x; t < T; t += 128) mask[(long long)b * T + t] = t >= n;
+}
+}  // namespace mm
+
+extern "C" int mm_seq_lens_mask(const int64_t* lens, int32_t lengths_are_samples, int32_t batch, int32_t n_layers, int32_t T,
+                                int32_t* out_lens, uint8_t* mask, void* stream) {
+  if (!lens || !out_lens || !mask) return bad_arg("seq_lens_mask: null pointer");
+  if (batch <= 0 || T <= 0) return 0;
+  mm::launch_pdl(mm::seq_lens_mask_kernel, dim3(batch), dim3(128), 0, static_cast<cudaStream_t>(stream),
+                 reinterpret_cast<const long long*>(lens), lengths_are_samples, n_layers, T, out_lens, mask);
+  MM_CHECK_LAUNCH("seq_lens_mask_kernel launch");
+  return 0;
+}
+
 extern "C" int mm_seq_lens(const int64_t* lens, int32_t lengths_are_samples, int32_t batch, int32_t n_layers,
                            int32_t* out_lens, void* stream) {
   if (!lens || !out_lens) return bad_arg("seq_lens: null pointer");

@@ -73,6 +73,7 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
         self.vocab_pad = _round_up(self.vocab, 8)
         self.embed_scale = math.sqrt(self.d)
         self.fused_ln = False
+        self.fused_attn_bwd = True     # attention backward: scores / dP / softmax backward in one kernel
         self._buf: Dict[Tuple, torch.Tensor] = {}
         self._pos = None
         self.n_layers = 0
@@ -257,7 +258,8 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                 self._attn_fwd(s["qkv"], 3 * d, L * 3 * d, s["qkv"][:, d:], s["qkv"][:, 2 * d:], 3 * d, L * 3 * d, s["att"],
                                B, L, L, None, True, dsite_layer(i, 1))
             else:
-                K.attention(s["qkv"], 0, L, s["qkv"], d, s["qkv"], 2 * d, L, None, B, H, s["att"], causal=True)
+                s["lse1"] = self.buf(f"lse1_{i}", (B, H, L), torch.float32)      # kept for mm_attention_bwd_scores
+                K.attention(s["qkv"], 0, L, s["qkv"], d, s["qkv"], 2 * d, L, None, B, H, s["att"], causal=True, lse=s["lse1"])
             self._resid(s["att"], d, Lr["wo"], Lr["bo"], d, s["x0"], s["x1"], M, dsite_layer(i, 0), Lr["ln2"], s["h2"])
             K.gemm(a0=s["h2"], a0_ld=d, rows=M, w=Lr["wq"], n=d, k=d, mode=K.EPI_OP, bias=Lr["bq"], scale=scale,
                    scale_cols=d, out0=s["q2"], out0_ld=d, block_n=bn)
@@ -267,7 +269,8 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                 self._attn_fwd(s["q2"], d, L * d, s["kv2"], s["kv2"][:, d:], 2 * d, T * 2 * d, s["att2"], B, L, T, enc_lens,
                                False, dsite_layer(i, 3))
             else:
-                K.attention(s["q2"], 0, L, s["kv2"], 0, s["kv2"], d, T, enc_lens, B, H, s["att2"])
+                s["lse2"] = self.buf(f"lse2_{i}", (B, H, L), torch.float32)
+                K.attention(s["q2"], 0, L, s["kv2"], 0, s["kv2"], d, T, enc_lens, B, H, s["att2"], lse=s["lse2"])
             self._resid(s["att2"], d, Lr["wo2"], Lr["bo2"], d, s["x1"], s["x2"], M, dsite_layer(i, 2), Lr["ln3"], s["h3"])
             K.gemm(a0=s["h3"], a0_ld=d, rows=M, w=Lr["w1"], n=self.ffn, k=d, mode=K.EPI_RELU_OP, bias=Lr["b1"],
                    out0=s["f"], out0_ld=self.ffn, block_n=bn)
@@ -291,23 +294,28 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
     # backward
     # ------------------------------------------------------------------------------------------
     def _attn_bwd(self, q, q_ld, q_bs, k, v, kv_ld, kv_bs, dO, dq, dk, dv, dkv_ld, dkv_bs, B, Lq, Tk, kv_lens, causal,
-                  site=0):
+                  site=0, out=None, lse=None):
         """Attention backward per (sequence, head): q [B][Lq][..] pre-scaled, k / v [B][Tk][..] (column blocks of the
-        given tensors), dO [B*Lq, d] -> dq (x head_dim^-0.5), dk, dv written at their heads' column blocks."""
+        given tensors), dO [B*Lq, d] -> dq (x head_dim^-0.5), dk, dv written at their heads' column blocks.
+        out / lse: the forward attention output and its per-row log-sum-exp -- with them (no attention dropout) the
+        scores, dP and the softmax backward are one kernel (mm_attention_bwd_scores)."""
         d, H, op, bn = self.d, self.heads, self.op_dtype, self.block_n
         BH = B * H
         Lp, Tp = _round_up(Lq, 64), _round_up(Tk, 64)
         hd = dict(heads=H, head_stride=64, batches=BH, w_batched=True, block_n=bn)
-        S = self.buf("a_S", (BH, Lp, Tp), torch.float32)
-        dP = self.buf("a_dP16", (BH, Lp, Tp), op)      # 16-bit gradient; the scores stay fp32
-        sc = dict(rows=Lq, n=Tk, k=64, out0_ld=Tp, out0_bs=Lp * Tp, a_hm=True, w_hm=True, **hd)
-        K.gemm(a0=q, a0_ld=q_ld, a0_bs=q_bs, w=k, w_ld=kv_ld, w_bs=kv_bs, out0=S, mode=K.EPI_F32, **sc)
-        K.gemm(a0=dO, a0_ld=d, a0_bs=Lq * d, w=v, w_ld=kv_ld, w_bs=kv_bs, out0=dP, mode=K.EPI_OP, **sc)
         P = self.buf("a_P", (BH, Lp, Tp), op)
         dS = self.buf("a_dS", (BH, Lp, Tp), op)
         _, p_attn, _, seed, seed_dev = self._saved["drop"]
-        K.softmax_bwd(S, dP, Tp, BH * Lp, Lp, Tk, dS, Tp, probs=P, kv_lens=kv_lens, heads=H, valid_rows=Lq, causal=causal,
-                      drop_p=p_attn, seed=seed, seed_dev=seed_dev, site=site)
+        if lse is not None and p_attn == 0 and self.fused_attn_bwd:
+            K.attention_bwd_scores(q, 0, Lq, k, 0, v, 0, Tk, kv_lens, B, H, dO, out, lse, P, dS, causal=causal)
+        else:
+            S = self.buf("a_S", (BH, Lp, Tp), torch.float32)
+            dP = self.buf("a_dP16", (BH, Lp, Tp), op)      # 16-bit gradient; the scores stay fp32
+            sc = dict(rows=Lq, n=Tk, k=64, out0_ld=Tp, out0_bs=Lp * Tp, a_hm=True, w_hm=True, **hd)
+            K.gemm(a0=q, a0_ld=q_ld, a0_bs=q_bs, w=k, w_ld=kv_ld, w_bs=kv_bs, out0=S, mode=K.EPI_F32, **sc)
+            K.gemm(a0=dO, a0_ld=d, a0_bs=Lq * d, w=v, w_ld=kv_ld, w_bs=kv_bs, out0=dP, mode=K.EPI_OP, **sc)
+            K.softmax_bwd(S, dP, Tp, BH * Lp, Lp, Tk, dS, Tp, probs=P, kv_lens=kv_lens, heads=H, valid_rows=Lq,
+                          causal=causal, drop_p=p_attn, seed=seed, seed_dev=seed_dev, site=site)
         og = dict(n=64, mode=K.EPI_OP, out_hm=True, w_mn=True, w_hm=True, a0_ld=Tp, a0_bs=Lp * Tp, **hd)
         K.gemm(a0=P, a_mn=True, rows=Tk, k=Lq, w=dO, w_ld=d, w_bs=Lq * d, out0=dv, out0_ld=dkv_ld, out0_bs=dkv_bs, **og)
         K.gemm(a0=dS, a_mn=True, rows=Tk, k=Lq, w=q, w_ld=q_ld, w_bs=q_bs, out0=dk, out0_ld=dkv_ld, out0_bs=dkv_bs, **og)
@@ -382,7 +390,8 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                 dkv2 = self.buf("b_dkv2", (B * T, 2 * d), op)
                 kv2 = s["kv2"]
                 self._attn_bwd(s["q2"], d, L * d, kv2, kv2[:, d:], 2 * d, T * 2 * d, datt, dq2, dkv2, dkv2[:, d:], 2 * d,
-                               T * 2 * d, B, L, T, sv["enc_lens"], False, dsite_layer(i, 3))
+                               T * 2 * d, B, L, T, sv["enc_lens"], False, dsite_layer(i, 3), out=s["att2"],
+                               lse=s.get("lse2"))
                 self._linear_bwd(dq2, d, s["h2"], M, d, d, self.g(ea + "q_proj.weight"), self.g(ea + "q_proj.bias"),
                                  accumulate)
                 K.gemm(a0=dq2, a0_ld=d, rows=M, w=Lr["wq"], w_ld=d, w_mn=True, n=d, k=d, mode=K.EPI_F32, out0=dh,
@@ -409,7 +418,8 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                 dqkv = self.buf("b_dqkv", (M, 3 * d), op)
                 qkv = s["qkv"]
                 self._attn_bwd(qkv, 3 * d, L * 3 * d, qkv[:, d:], qkv[:, 2 * d:], 3 * d, L * 3 * d, datt, dqkv, dqkv[:, d:],
-                               dqkv[:, 2 * d:], 3 * d, L * 3 * d, B, L, L, None, True, dsite_layer(i, 1))
+                               dqkv[:, 2 * d:], 3 * d, L * 3 * d, B, L, L, None, True, dsite_layer(i, 1), out=s["att"],
+                               lse=s.get("lse1"))
                 self._linear_bwd(dqkv, 3 * d, s["h1"], M, 3 * d, d,
                                  self.g(sa + "q_proj.weight", sa + "k_proj.weight", sa + "v_proj.weight"),
                                  self.g(sa + "q_proj.bias", sa + "k_proj.bias", sa + "v_proj.bias"), accumulate)

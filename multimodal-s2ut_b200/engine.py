@@ -216,7 +216,9 @@ class EncoderEngine:
         else:
             K.cmvn_apply(raw, stats, lens, is_samples, feats_norm, x1, op_row_offset=2)
         seq_lens = self.buf("seq_lens", (B,), torch.int32)
-        K.seq_lens(lens, is_samples, 2, seq_lens)
+        # subsampled lengths and the encoder padding mask [B, T] (fairseq lengths_to_padding_mask) in one launch
+        self.pad_mask = torch.empty(B, sub_len(sub_len(m)), dtype=torch.bool, device=dev)
+        K.seq_lens_mask(lens, is_samples, 2, seq_lens, self.pad_mask)
         return x1, m, seq_lens, feats_norm
 
     def subsample(self, x1: torch.Tensor, m: int, seq_lens: torch.Tensor) -> Tuple[torch.Tensor, int]:
@@ -430,8 +432,7 @@ class EncoderEngine:
                 states.append(x.view(B, T, self.d).transpose(0, 1).contiguous())
         if not self.fused_ln:
             K.layernorm(x, self.ln_g, self.ln_b, out_op=text_op, out_f32=text_f32)
-        mask = torch.empty(B, T, dtype=torch.bool, device=self.device)
-        K.padding_mask(seq_lens, T, mask)
+        mask = self.pad_mask            # written by frontend()
         if imgs_list and self.fusion:
             if drop_audio:
                 text_f32.zero_()

@@ -132,6 +132,16 @@ def seq_lens(lens: torch.Tensor, lengths_are_samples: bool, n_layers: int, out: 
                                    _stream()), "mm_seq_lens")
 
 
+def seq_lens_mask(lens: torch.Tensor, lengths_are_samples: bool, n_layers: int, out: torch.Tensor, mask: torch.Tensor) -> None:
+    """out [B] int32 = subsampled lengths, mask [B, T] bool = t >= out[b]: ``seq_lens`` + ``padding_mask`` in one launch."""
+    assert lens.dtype == torch.int64 and out.dtype == torch.int32 and mask.dtype == torch.bool and mask.is_contiguous()
+    assert mask.shape[0] == lens.numel() == out.numel()
+    lib = _lib.load()
+    with _Launch("seq_lens_mask"):
+        _lib.check(lib.mm_seq_lens_mask(_ptr(lens), int(lengths_are_samples), lens.numel(), n_layers, mask.shape[1],
+                                        _ptr(out), _ptr(mask), _stream()), "mm_seq_lens_mask")
+
+
 def padding_mask(seq_lens: torch.Tensor, T: int, out: torch.Tensor) -> None:
     """out [B, T] bool = t >= seq_lens[b]."""
     assert seq_lens.dtype == torch.int32 and out.dtype == torch.bool and out.is_contiguous()
@@ -235,13 +245,16 @@ def layernorm_gather(store: torch.Tensor, index: Optional[torch.Tensor], rows_pe
 
 
 def self_attention(qkv: torch.Tensor, seq_lens_: torch.Tensor, batch: int, seq: int, heads: int,
-                   out: torch.Tensor) -> None:
-    """qkv [B*T, 3d] (q pre-scaled | k | v) -> out [B*T, d]; head_dim 64."""
+                   out: torch.Tensor, lse: Optional[torch.Tensor] = None) -> None:
+    """qkv [B*T, 3d] (q pre-scaled | k | v) -> out [B*T, d]; head_dim 64.  lse (optional): [B, heads, T] fp32
+    log-sum-exp of every query row's scores (kept by the training forward for ``attention_bwd_scores``)."""
     assert qkv.dtype == out.dtype and seq_lens_.dtype == torch.int32 and qkv.stride(-1) == 1
+    assert lse is None or (lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == batch * heads * seq)
     lib = _lib.load()
     with _Launch("self_attention", 4.0 * batch * seq * seq * heads * 64):
-        _lib.check(lib.mm_self_attention(_ptr(qkv), qkv.stride(-2), _ptr(seq_lens_), batch, seq, heads, _ptr(out),
-                                         out.stride(-2), dtype_code(qkv.dtype), _stream()), "mm_self_attention")
+        _lib.check(lib.mm_self_attention_lse(_ptr(qkv), qkv.stride(-2), _ptr(seq_lens_), batch, seq, heads, _ptr(out),
+                                             out.stride(-2), _ptr(lse), dtype_code(qkv.dtype), _stream()),
+                   "mm_self_attention")
 
 
 def label_smoothed_nll(logits: torch.Tensor, vocab: int, target: torch.Tensor, padding_idx: int, epsilon: float):
@@ -278,7 +291,7 @@ def embed_tokens(tokens: torch.Tensor, padding_idx: int, table: torch.Tensor, sc
 
 def attention(q: torch.Tensor, q_col0: int, q_len: int, k: torch.Tensor, k_col0: int, v: torch.Tensor, v_col0: int,
               kv_len: int, kv_lens: Optional[torch.Tensor], batch: int, heads: int, out: torch.Tensor,
-              causal: bool = False) -> None:
+              causal: bool = False, lse: Optional[torch.Tensor] = None) -> None:
     """General attention core (see ``mm_attention``): q [batch*q_len, ld] (pre-scaled), k / v [batch*kv_len, ld],
     head h in columns [col0 + 64 h, col0 + 64 h + 64); out [batch*q_len, heads*64]."""
     assert q.dtype == k.dtype == v.dtype == out.dtype and q.dtype in _DT
@@ -288,9 +301,32 @@ def attention(q: torch.Tensor, q_col0: int, q_len: int, k: torch.Tensor, k_col0:
         assert kv_lens.dtype == torch.int32 and kv_lens.numel() == batch
     lib = _lib.load()
     with _Launch("attention", 4.0 * batch * heads * q_len * kv_len * 64 * (0.5 if causal else 1.0)):
-        _lib.check(lib.mm_attention(_ptr(q), q.stride(0), q_col0, q_len, _ptr(k), k.stride(0), k_col0, _ptr(v),
-                                    v.stride(0), v_col0, kv_len, _ptr(kv_lens), batch, heads, int(causal), _ptr(out),
-                                    out.stride(0), dtype_code(q.dtype), _stream()), "mm_attention")
+        assert lse is None or (lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == batch * heads * q_len)
+        _lib.check(lib.mm_attention_lse(_ptr(q), q.stride(0), q_col0, q_len, _ptr(k), k.stride(0), k_col0, _ptr(v),
+                                        v.stride(0), v_col0, kv_len, _ptr(kv_lens), batch, heads, int(causal), _ptr(out),
+                                        out.stride(0), _ptr(lse), dtype_code(q.dtype), _stream()), "mm_attention")
+
+
+def attention_bwd_scores(q: torch.Tensor, q_col0: int, q_len: int, k: torch.Tensor, k_col0: int, v: torch.Tensor,
+                         v_col0: int, kv_len: int, kv_lens: Optional[torch.Tensor], batch: int, heads: int, dout: torch.Tensor,
+                         out: torch.Tensor, lse: torch.Tensor, probs: torch.Tensor, dscores: torch.Tensor,
+                         causal: bool = False) -> None:
+    """P = exp(q k^T - lse) (masked), dS = P o (dO v^T - rowsum(dO o O)) -> probs / dscores [batch*heads, Lp, Tp] 16-bit
+    (see ``mm_attention_bwd_scores``); q / k / v as in ``attention``; dout / out [batch*q_len, heads*64]."""
+    assert q.dtype == k.dtype == v.dtype == dout.dtype == out.dtype == probs.dtype == dscores.dtype and q.dtype in _DT
+    assert all(t.dim() == 2 and t.stride(1) == 1 for t in (q, k, v, dout, out))
+    assert probs.dim() == 3 and probs.is_contiguous() and dscores.shape == probs.shape and dscores.is_contiguous()
+    assert probs.shape[0] == batch * heads and probs.shape[1] >= q_len and probs.shape[2] >= kv_len
+    assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == batch * heads * q_len
+    if kv_lens is not None:
+        assert kv_lens.dtype == torch.int32 and kv_lens.numel() == batch
+    lib = _lib.load()
+    with _Launch("attention_bwd_scores", 4.0 * batch * heads * q_len * kv_len * 64 * (0.5 if causal else 1.0)):
+        _lib.check(lib.mm_attention_bwd_scores(_ptr(q), q.stride(0), q_col0, q_len, _ptr(k), k.stride(0), k_col0, _ptr(v),
+                                               v.stride(0), v_col0, kv_len, _ptr(kv_lens), batch, heads, int(causal),
+                                               _ptr(dout), dout.stride(0), _ptr(out), out.stride(0), _ptr(lse),
+                                               _ptr(probs), _ptr(dscores), probs.stride(1), probs.stride(0),
+                                               dtype_code(q.dtype), _stream()), "mm_attention_bwd_scores")
 
 
 def cross_attention(q: torch.Tensor, q_len: int, k: torch.Tensor, k_col0: int, v: torch.Tensor, v_col0: int, kv_len: int,

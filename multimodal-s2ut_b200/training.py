@@ -141,6 +141,8 @@ class TrainEngine(EncoderEngine):
         # (the inference forward of this engine keeps the base class's fused GEMM+LN path)
         # training forward: fused GEMM + residual + LayerNorm with a separate output buffer (needs n == 512)
         self.train_fused_ln = self.d == 512 and getattr(enc, "fuse_layernorm", True)
+        # attention backward: scores, dP and the softmax backward in one kernel (mm_attention_bwd_scores)
+        self.fused_attn_bwd = getattr(enc, "fuse_attention_backward", True)
         self._saved = None
         self.generation = 0            # advanced by every forward_train: ties an autograd node to ITS saved activations
         self.step_count = 0
@@ -375,7 +377,9 @@ class TrainEngine(EncoderEngine):
             K.gemm(a0=P, a0_ld=Tp, a0_bs=Tp * Tp, rows=T, k=T, w=s["qkv"][:, 2 * d:], w_ld=3 * d, w_bs=T * 3 * d,
                    w_mn=True, w_hm=True, n=64, mode=K.EPI_OP, out0=s["att"], out0_ld=d, out0_bs=T * d, out_hm=True, **hd)
         else:
-            K.self_attention(s["qkv"], seq_lens, B, T, self.heads, s["att"])
+            # the log-sum-exp of every score row is all the backward pass needs to rebuild the probabilities
+            s["lse"] = self.buf(f"t_lse_{i}", (B, self.heads, T), torch.float32)
+            K.self_attention(s["qkv"], seq_lens, B, T, self.heads, s["att"], lse=s["lse"])
         if fused:
             K.gemm_resid_ln(s["att"], L["wo"], L["bo"], x_in, L["ln2_g"], L["ln2_b"], s["h2"], x_out=s["x_mid"])
         elif p_drop > 0:     # x_mid = x_in + dropout(out_proj(att))
@@ -454,8 +458,7 @@ class TrainEngine(EncoderEngine):
         if not fused_fwd:
             K.layernorm(x, self.ln_g, self.ln_b, out_op=text_op, out_f32=text_f32)
         saved["x_final"] = x
-        mask = torch.empty(B, T, dtype=torch.bool, device=self.device)
-        K.padding_mask(seq_lens, T, mask)
+        mask = self.pad_mask            # written by frontend()
         if imgs_list and self.fusion:
             if len(imgs_list) > len(self.fusion) or len(img_masks_list) != len(imgs_list):
                 raise ValueError("imgs_list / img_masks_list do not match image_feat_dim")
@@ -584,16 +587,20 @@ class TrainEngine(EncoderEngine):
         BH = B * H
         qkv = s["qkv"]
         hd = dict(heads=H, head_stride=64, batches=BH, w_batched=True, block_n=bn)
-        S = self.buf("a_S", (BH, Tp, Tp), torch.float32)
-        dP = self.buf("a_dP16", (BH, Tp, Tp), op)      # 16-bit: it is a gradient (dS is 16-bit anyway); S stays fp32
-        sc = dict(rows=T, n=T, k=64, out0_ld=Tp, out0_bs=Tp * Tp, a_hm=True, w_hm=True, **hd)
-        K.gemm(a0=qkv, a0_ld=3 * d, a0_bs=T * 3 * d, w=qkv[:, d:], w_ld=3 * d, w_bs=T * 3 * d, out0=S, mode=K.EPI_F32, **sc)
-        K.gemm(a0=datt, a0_ld=d, a0_bs=T * d, w=qkv[:, 2 * d:], w_ld=3 * d, w_bs=T * 3 * d, out0=dP, mode=K.EPI_OP, **sc)
         P = self.buf("a_P", (BH, Tp, Tp), op)
         dS = self.buf("a_dS", (BH, Tp, Tp), op)
-        _, _, seed, seed_dev = self._saved["drop"]
-        K.softmax_bwd(S, dP, Tp, BH * Tp, Tp, T, dS, Tp, probs=P, kv_lens=seq_lens, heads=H, valid_rows=T,
-                      drop_p=self._saved["p_attn"], seed=seed, seed_dev=seed_dev, site=site_layer(layer_index, 3))
+        if "lse" in s and self.fused_attn_bwd:
+            # one kernel: S = q k^T and dP = dO v^T in TMEM, P = exp(S - lse), dS = P o (dP - rowsum(dO o O))
+            K.attention_bwd_scores(qkv, 0, T, qkv, d, qkv, 2 * d, T, seq_lens, B, H, datt, s["att"], s["lse"], P, dS)
+        else:   # attention dropout (the mask is regenerated by the row kernel): scores and dP through HBM
+            S = self.buf("a_S", (BH, Tp, Tp), torch.float32)
+            dP = self.buf("a_dP16", (BH, Tp, Tp), op)      # 16-bit: it is a gradient (dS is 16-bit anyway); S stays fp32
+            sc = dict(rows=T, n=T, k=64, out0_ld=Tp, out0_bs=Tp * Tp, a_hm=True, w_hm=True, **hd)
+            K.gemm(a0=qkv, a0_ld=3 * d, a0_bs=T * 3 * d, w=qkv[:, d:], w_ld=3 * d, w_bs=T * 3 * d, out0=S, mode=K.EPI_F32, **sc)
+            K.gemm(a0=datt, a0_ld=d, a0_bs=T * d, w=qkv[:, 2 * d:], w_ld=3 * d, w_bs=T * 3 * d, out0=dP, mode=K.EPI_OP, **sc)
+            _, _, seed, seed_dev = self._saved["drop"]
+            K.softmax_bwd(S, dP, Tp, BH * Tp, Tp, T, dS, Tp, probs=P, kv_lens=seq_lens, heads=H, valid_rows=T,
+                          drop_p=self._saved["p_attn"], seed=seed, seed_dev=seed_dev, site=site_layer(layer_index, 3))
         og = dict(rows=T, n=64, k=T, mode=K.EPI_OP, out0_ld=3 * d, out0_bs=T * 3 * d, out_hm=True, w_mn=True, w_hm=True,
                   a0_ld=Tp, a0_bs=Tp * Tp, **hd)
         K.gemm(a0=P, a_mn=True, w=datt, w_ld=d, w_bs=T * d, out0=dqkv[:, 2 * d:], **og)          # dV = P^T dO

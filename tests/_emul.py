@@ -88,6 +88,11 @@ def seq_lens(lens, lengths_are_samples, n_layers, out):
         out[b] = m
 
 
+def seq_lens_mask(lens, lengths_are_samples, n_layers, out, mask):
+    seq_lens(lens, lengths_are_samples, n_layers, out)
+    padding_mask(out, mask.shape[1], mask)
+
+
 def padding_mask(seq_lens_, T, out):
     out.copy_(torch.arange(T)[None, :] >= seq_lens_[:, None])
 
@@ -215,13 +220,15 @@ def layernorm(x, gamma, beta, out_op=None, out_f32=None, eps=1e-5):
         out_f32.view(-1, dim).copy_(y)
 
 
-def self_attention(qkv, seq_lens_, batch, seq, heads, out):
+def self_attention(qkv, seq_lens_, batch, seq, heads, out, lse=None):
     d = heads * 64
     x = qkv.float().view(batch, seq, 3, heads, 64)
     q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))
     s = q @ k.transpose(-1, -2)
     mask = torch.arange(seq)[None, :] >= seq_lens_[:, None]
     s = s.masked_fill(mask[:, None, None, :], float("-inf"))
+    if lse is not None:
+        lse.copy_(torch.logsumexp(s, -1).reshape(lse.shape))
     p = s.softmax(-1).to(qkv.dtype).float()
     o = (p @ v).permute(0, 2, 1, 3).reshape(batch * seq, d)
     out.copy_(o.to(out.dtype))
@@ -255,7 +262,33 @@ def softmax_rows(scores, ld_in, rows, n_keys, probs, ld_out, key_mask=None, rows
     P[:, :n_keys] = s.softmax(-1).to(probs.dtype)
 
 
-def attention(q, q_col0, q_len, k, k_col0, v, v_col0, kv_len, kv_lens, batch, heads, out, causal=False):
+def _qkv_heads(q, q_col0, q_len, k, k_col0, v, v_col0, kv_len, batch, heads):
+    d = heads * 64
+    Q = q[:, q_col0:q_col0 + d].float().view(batch, q_len, heads, 64).permute(0, 2, 1, 3)
+    Kx = k[:, k_col0:k_col0 + d].float().view(batch, kv_len, heads, 64).permute(0, 2, 1, 3)
+    V = v[:, v_col0:v_col0 + d].float().view(batch, kv_len, heads, 64).permute(0, 2, 1, 3)
+    return Q, Kx, V
+
+
+def attention_bwd_scores(q, q_col0, q_len, k, k_col0, v, v_col0, kv_len, kv_lens, batch, heads, dout, out, lse, probs,
+                         dscores, causal=False):
+    Q, Kx, V = _qkv_heads(q, q_col0, q_len, k, k_col0, v, v_col0, kv_len, batch, heads)
+    s = Q @ Kx.transpose(-1, -2)
+    dead = torch.zeros(batch, 1, q_len, kv_len, dtype=torch.bool)
+    if kv_lens is not None:
+        dead = dead | (torch.arange(kv_len)[None, :] >= kv_lens[:, None])[:, None, None, :]
+    if causal:
+        dead = dead | (torch.arange(kv_len)[None, :] > torch.arange(q_len)[:, None])[None, None]
+    P = torch.exp(s - lse.view(batch, heads, q_len, 1)).masked_fill(dead, 0.0)
+    dO = dout[:, :heads * 64].float().view(batch, q_len, heads, 64).permute(0, 2, 1, 3)
+    O = out[:, :heads * 64].float().view(batch, q_len, heads, 64).permute(0, 2, 1, 3)
+    delta = (dO * O).sum(-1, keepdim=True)
+    dS = P * (dO @ V.transpose(-1, -2) - delta)
+    probs.view(batch, heads, probs.shape[1], probs.shape[2])[:, :, :q_len, :kv_len] = P.to(probs.dtype)
+    dscores.view(batch, heads, probs.shape[1], probs.shape[2])[:, :, :q_len, :kv_len] = dS.to(dscores.dtype)
+
+
+def attention(q, q_col0, q_len, k, k_col0, v, v_col0, kv_len, kv_lens, batch, heads, out, causal=False, lse=None):
     d = heads * 64
     Q = q[:, q_col0:q_col0 + d].float().view(batch, q_len, heads, 64).permute(0, 2, 1, 3)
     Kx = k[:, k_col0:k_col0 + d].float().view(batch, kv_len, heads, 64).permute(0, 2, 1, 3)
@@ -265,6 +298,8 @@ def attention(q, q_col0, q_len, k, k_col0, v, v_col0, kv_len, kv_lens, batch, he
         s = s.masked_fill((torch.arange(kv_len)[None, :] >= kv_lens[:, None])[:, None, None, :], float("-inf"))
     if causal:
         s = s.masked_fill(torch.arange(kv_len)[None, :] > torch.arange(q_len)[:, None], float("-inf"))
+    if lse is not None:
+        lse.copy_(torch.logsumexp(s, -1).reshape(lse.shape))
     p = s.softmax(-1).to(q.dtype).float()
     out.copy_((p @ V).permute(0, 2, 1, 3).reshape(batch * q_len, d).to(out.dtype))
 
