@@ -92,6 +92,9 @@ int mm_padding_mask(const int32_t* seq_lens, int32_t batch, int32_t T, uint8_t* 
  *   MM_EPI_GATE      selective gate, mm_s2s_transformer.py:612-618: g = sigmoid(acc + b),
  *                    out = (1-g)*text + g*attn, stored as T x B x C
  *   MM_EPI_F32       plain fp32 store (attention scores q k^T, fuse.py:87)
+ *   MM_EPI_MASK_OP   backward of fc1's ReLU (+ activation dropout) fused into the fc2 dgrad (autograd of fairseq
+ *                    TransformerEncoderLayer): out = aux0 > 0 ? (acc + bias) * scale : 0, 16-bit, aux0 = the kept
+ *                    16-bit activation [rows, n]
  * --------------------------------------------------------------------------------------------- */
 enum {
   MM_EPI_OP = 0,
@@ -101,7 +104,8 @@ enum {
   MM_EPI_GLU_POS_F32 = 4,
   MM_EPI_F32_OP = 5,
   MM_EPI_GATE = 6,
-  MM_EPI_F32 = 7
+  MM_EPI_F32 = 7,
+  MM_EPI_MASK_OP = 8
 };
 
 typedef struct mm_gemm_args {
@@ -120,7 +124,7 @@ typedef struct mm_gemm_args {
   int64_t out0_ld, out0_bs;
   void* out1;          /* secondary output (MM_EPI_F32_OP: the 16-bit copy) */
   int64_t out1_ld, out1_bs;
-  const float* aux0;   /* RESID: residual ; GATE: text (fp32) */
+  const void* aux0;    /* RESID: residual ; GATE: text (fp32) ; MASK_OP: kept activation (16-bit, row stride aux_ld) */
   const float* aux1;   /* GATE: attention output (fp32) */
   int64_t aux_ld;
   int32_t rows_per_seq; /* >0: batches==1 and row r is (b, t) = divmod(r, rows_per_seq) */

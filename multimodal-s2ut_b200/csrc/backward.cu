@@ -182,55 +182,178 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 }
 
 // several reductions in one launch (blockIdx.y = job): the backward pass defers the ~10 partial reductions of a layer
-// (split-K wgrad partials, bias column sums, LayerNorm parameter partials) and runs them together
+// (split-K wgrad partials, bias column sums, LayerNorm parameter partials) and runs them together.  A block covers
+// 256 / slices float4 columns and cuts the S partials of a job into `slices` interleaved slices (slice s sums partials
+// s, s + slices, ... with four 128-bit loads in flight), so a job with few outputs and many partials (a bias gradient:
+// 512 outputs x 125 partials) is as parallel as one with many outputs and few partials (a weight gradient).  The slices
+// are combined through shared memory in a fixed order: the result depends only on (S, slices), never on the launch.
 struct ReduceJobs {
   const float* part[16];
   float* out[16];
   long long stride[16], n[16];
-  int S[16], accumulate[16];
+  int S[16], accumulate[16], slices[16];
 };
 __global__ void __launch_bounds__(256) reduce_many_kernel(ReduceJobs t) {
+  __shared__ float4 red[2][256];
   const int j = blockIdx.y;
   const float* __restrict__ part = t.part[j];
   float* __restrict__ out = t.out[j];
   const long long n = t.n[j], stride = t.stride[j];
-  const int S = t.S[j], acc = t.accumulate[j];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < S; ++k) s += part[(long long)k * stride + i];
-    out[i] = acc ? out[i] + s : s;
+  const int S = t.S[j], acc = t.accumulate[j], sl = t.slices[j];
+  const int cols4 = 256 / sl;                       // float4 columns per half tile
+  const int c4 = threadIdx.x % cols4, slice = threadIdx.x / cols4;
+  const bool vec = ((stride & 3) == 0) && ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(part) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const long long n4 = (n + 3) >> 2;                // float4 columns (the last one may be partial when !vec)
+  const long long tiles = (n4 + 2 * cols4 - 1) / (2 * cols4);     // a tile = two half tiles: 8 loads per thread in flight
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    long long i4[2];
+    float4 s[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) i4[u] = (2 * tile + u) * cols4 + c4, s[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec) {
+      const long long s4 = stride >> 2;
+      const float4* p4 = reinterpret_cast<const float4*>(part);
+      int k = slice;
+      for (; k + 3 * sl < S; k += 4 * sl) {
+        float4 v[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            v[u][q] = i4[u] < n4 ? __ldcs(p4 + (long long)(k + q * sl) * s4 + i4[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) s[u].x += v[u][q].x, s[u].y += v[u][q].y, s[u].z += v[u][q].z, s[u].w += v[u][q].w;
+      }
+      for (; k < S; k += sl) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (i4[u] < n4) {
+            const float4 a = __ldcs(p4 + (long long)k * s4 + i4[u]);
+            s[u].x += a.x, s[u].y += a.y, s[u].z += a.z, s[u].w += a.w;
+          }
+      }
+    } else {
+      for (int u = 0; u < 2; ++u) {
+        float* sv = reinterpret_cast<float*>(&s[u]);
+        for (int e = 0; e < 4; ++e) {
+          const long long i = 4 * i4[u] + e;
+          if (i >= n) break;
+          for (int k = slice; k < S; k += sl) sv[e] += part[(long long)k * stride + i];
+        }
+      }
+    }
+    if (sl > 1) {
+      __syncthreads();                              // the previous tile's combine has read `red`
+      red[0][threadIdx.x] = s[0], red[1][threadIdx.x] = s[1];
+      __syncthreads();
+    }
+    if (slice == 0) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (i4[u] >= n4) continue;
+        float4 r = s[u];
+        for (int q = 1; q < sl; ++q) {
+          const float4 o = red[u][q * cols4 + c4];
+          r.x += o.x, r.y += o.y, r.z += o.z, r.w += o.w;
+        }
+        if (vec) {
+          float4* o4 = reinterpret_cast<float4*>(out) + i4[u];
+          if (acc) {
+            const float4 o = *o4;
+            r.x += o.x, r.y += o.y, r.z += o.z, r.w += o.w;
+          }
+          *o4 = r;
+        } else {
+          const float* sv = reinterpret_cast<const float*>(&r);
+          for (int e = 0; e < 4; ++e) {
+            const long long i = 4 * i4[u] + e;
+            if (i < n) out[i] = acc ? out[i] + sv[e] : sv[e];
+          }
+        }
+      }
+    }
   }
 }
 
-// column sums of a 16-bit [rows, cols] matrix (bias gradients): block = 64 columns x one chunk of rows; partials
-// [gridDim.y][cols], summed by reduce_partials.  Rows with (r % period) >= valid are skipped when period > 0.
-template <typename OpT>
+// column sums of a 16-bit [rows, cols] matrix (bias gradients): a block owns 256 columns x COLSUM_ROWS rows.  A lane
+// owns 8 consecutive columns (one 128-bit word per row) and the 8 warps take the block's rows round robin.  The words
+// travel global -> shared memory by cp.async, 16 per lane issued back to back (ptxas interleaved plain 128-bit loads
+// with their consumption and kept only ~5 in flight: 2 TB/s instead of 5), and each lane then sums the words it
+// fetched itself.  Partials [gridDim.y][cols] are summed by reduce_partials.  Rows with (r % period) >= valid are
+// skipped when period > 0.
+constexpr int COLSUM_ROWS = 128;
+constexpr int COLSUM_SMEM = COLSUM_ROWS * 32 * 16;     // 64 KB
+template <typename OpT, bool PERIODIC>
 __global__ void __launch_bounds__(256) colsum_kernel(const OpT* __restrict__ in, long long ld, int rows, int cols,
-                                                      int rows_per_block, int period, int valid,
-                                                      float* __restrict__ partials) {
-  __shared__ float red[8][64];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 64 + 2 * tx;
-  const int r_begin = blockIdx.y * rows_per_block;
-  const int r_end = min(rows, r_begin + rows_per_block);
-  float s0 = 0.f, s1 = 0.f;
-  if (c < cols) {
-    for (int r = r_begin + ty; r < r_end; r += 8) {
-      if (period > 0 && (r % period) >= valid) continue;
-      const uint32_t q = *reinterpret_cast<const uint32_t*>(in + (long long)r * ld + c);
-      const OpT* e = reinterpret_cast<const OpT*>(&q);
-      s0 += OpTraits<OpT>::to_float(e[0]);
-      s1 += OpTraits<OpT>::to_float(e[1]);
+                                                      int period, int valid, float* __restrict__ partials) {
+  extern __shared__ __align__(16) uint4 cs_tile[];     // [COLSUM_ROWS][32 lanes]
+  __shared__ float red[8][256 + 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + 8 * lane;
+  const int r_begin = blockIdx.y * COLSUM_ROWS;
+  const int r_end = min(rows, r_begin + COLSUM_ROWS);
+  const bool vec = ((ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && (c + 8 <= cols);
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  if (vec) {
+    const OpT* p0 = in + (long long)(r_begin + warp) * ld + c;
+    const uint32_t d0 = smem_u32(cs_tile + warp * 32 + lane);
+#pragma unroll
+    for (int j = 0; j < COLSUM_ROWS / 8; ++j)
+      if (r_begin + warp + 8 * j < r_end)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + j * 8 * 32 * 16), "l"(p0 + (long long)j * 8 * ld)
+                     : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < COLSUM_ROWS / 8; ++j) {
+      const int r = r_begin + warp + 8 * j;
+      bool ok = r < r_end;
+      if (PERIODIC) ok = ok && (r % period) < valid;
+      if (ok) {
+        const uint4 q = cs_tile[(warp + 8 * j) * 32 + lane];
+        const OpT* e = reinterpret_cast<const OpT*>(&q);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] += OpTraits<OpT>::to_float(e[i]);
+      }
+    }
+  } else if (c < cols) {
+    for (int r = r_begin + warp; r < r_end; r += 8) {
+      if (PERIODIC && (r % period) >= valid) continue;
+      for (int i = 0; i < 8 && c + i < cols; ++i) s[i] += OpTraits<OpT>::to_float(in[(long long)r * ld + c + i]);
     }
   }
-  red[ty][2 * tx] = s0, red[ty][2 * tx + 1] = s1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[warp][8 * lane + i] = s[i];
   __syncthreads();
-  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < cols) {
+  const int cc = blockIdx.x * 256 + threadIdx.x;
+  if (cc < cols) {
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
-    partials[(long long)blockIdx.y * cols + blockIdx.x * 64 + threadIdx.x] = t;
+    partials[(long long)blockIdx.y * cols + cc] = t;
   }
+}
+
+template <typename OpT, bool PERIODIC>
+static int launch_colsum(const void* in, long long ld, int rows, int cols, int period, int valid, float* partials,
+                         cudaStream_t s) {
+  auto kern = colsum_kernel<OpT, PERIODIC>;
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, COLSUM_SMEM);
+    if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute(colsum)");
+    attr_set = true;
+  }
+  dim3 grid((cols + 255) / 256, (rows + COLSUM_ROWS - 1) / COLSUM_ROWS);
+  if (grid.y > 65535) return bad_arg("colsum: too many rows");
+  kern<<<grid, 256, COLSUM_SMEM, s>>>(reinterpret_cast<const OpT*>(in), ld, rows, cols, period, valid, partials);
+  MM_CHECK_LAUNCH("colsum_kernel launch");
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -253,14 +376,18 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   for (long long row = (long long)blockIdx.x * 8 + warp; row < rows; row += (long long)gridDim.x * 8) {
     const float4* xr = reinterpret_cast<const float4*>(x + row * DIM);
     const float4* dr = reinterpret_cast<const float4*>(dy + row * DIM);
-    float4 v[V], d[V];
+    float4 v[V], d[V], rs[V];
     float s = 0.f;
+    // every load of the row (x, dy and the residual gradient) is issued before the first reduction: one memory round
+    // trip per row instead of two
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       v[i] = xr[lane + 32 * i];
-      d[i] = dr[lane + 32 * i];
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      d[i] = __ldcs(dr + lane + 32 * i);
+      if (dx_out && resid) rs[i] = reinterpret_cast<const float4*>(resid + row * DIM)[lane + 32 * i];
     }
+#pragma unroll
+    for (int i = 0; i < V; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     const float mean = warp_sum(s) * (1.0f / DIM);
     float q = 0.f;
 #pragma unroll
@@ -290,10 +417,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         o.y = rstd * (d[i].y - c1 - v[i].y * c2);
         o.z = rstd * (d[i].z - c1 - v[i].z * c2);
         o.w = rstd * (d[i].w - c1 - v[i].w * c2);
-        if (resid) {
-          const float4 r = reinterpret_cast<const float4*>(resid + row * DIM)[lane + 32 * i];
-          o.x += r.x, o.y += r.y, o.z += r.z, o.w += r.w;
-        }
+        if (resid) o.x += rs[i].x, o.y += rs[i].y, o.z += rs[i].z, o.w += rs[i].w;
         reinterpret_cast<float4*>(dx_out + row * DIM)[lane + 32 * i] = o;
         if (dx_op) {   // 16-bit copy of the gradient: the A operand of the next dgrad / wgrad GEMMs
           uint2 pk;
@@ -786,21 +910,19 @@ extern "C" int mm_rowsum(const void* in, int64_t ld, int32_t rows, int32_t cols,
   return 0;
 }
 
-extern "C" int mm_colsum_blocks(int32_t rows) { return (rows + 511) / 512; }
+extern "C" int mm_colsum_blocks(int32_t rows) { return (rows + mm::COLSUM_ROWS - 1) / mm::COLSUM_ROWS; }
 
 extern "C" int mm_colsum(const void* in, int64_t ld, int32_t rows, int32_t cols, int32_t period, int32_t valid,
                          float* partials, int32_t dtype, void* stream) {
   if (!in || !partials || rows <= 0 || cols <= 0 || (cols & 1) || (ld & 1)) return bad_arg("colsum");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  dim3 grid((cols + 63) / 64, (rows + 511) / 512);
+  const bool per = period > 0;
+  if (per && valid <= 0) return bad_arg("colsum: period needs valid > 0");
   if (dtype == MM_DTYPE_F16)
-    colsum_kernel<__half><<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(in), ld, rows, cols, 512, period, valid,
-                                               partials);
-  else
-    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(in), ld, rows, cols, 512,
-                                                       period, valid, partials);
-  MM_CHECK_LAUNCH("colsum_kernel launch");
-  return 0;
+    return per ? launch_colsum<__half, true>(in, ld, rows, cols, period, valid, partials, s)
+               : launch_colsum<__half, false>(in, ld, rows, cols, period, valid, partials, s);
+  return per ? launch_colsum<__nv_bfloat16, true>(in, ld, rows, cols, period, valid, partials, s)
+             : launch_colsum<__nv_bfloat16, false>(in, ld, rows, cols, period, valid, partials, s);
 }
 
 extern "C" int mm_reduce_partials(const float* part, int32_t n_partials, int64_t stride, int64_t n, float* out,
@@ -819,16 +941,19 @@ extern "C" int mm_reduce_partials_many(const mm_reduce_job* jobs, int32_t count,
     ReduceJobs t;
     memset(&t, 0, sizeof(t));
     const int m = count - base < 16 ? count - base : 16;
-    long long max_n = 0;
+    long long gx = 1;
     for (int i = 0; i < m; ++i) {
       const mm_reduce_job& j = jobs[base + i];
       if (!j.part || !j.out || j.n_partials <= 0 || j.n <= 0) return bad_arg("reduce_partials_many: job");
       t.part[i] = j.part, t.out[i] = j.out, t.stride[i] = j.stride, t.n[i] = j.n, t.S[i] = j.n_partials;
       t.accumulate[i] = j.accumulate;
-      if (j.n > max_n) max_n = j.n;
+      int sl = 1;                                   // at least two partials per slice, at most 16 slices
+      while (sl < 16 && 4 * sl <= j.n_partials) sl *= 2;
+      t.slices[i] = sl;
+      const long long tiles = ((j.n + 3) / 4 + 512 / sl - 1) / (512 / sl);
+      if (tiles > gx) gx = tiles;
     }
-    long long gx = (max_n + 255) / 256;
-    if (gx > 1024) gx = 1024;
+    if (gx > 592) gx = 592;                         // 4 blocks per SM per job; a block walks its tiles
     reduce_many_kernel<<<dim3((unsigned)gx, (unsigned)m), 256, 0, s>>>(t);
     MM_CHECK_LAUNCH("reduce_many_kernel launch");
   }

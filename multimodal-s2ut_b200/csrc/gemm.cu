@@ -238,7 +238,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
     uint32_t as = 0, aphase = 0;
     uint32_t slab_ctr = 0;                   // running slab counter -> staging buffer ring
     uint32_t aux_phase = 0;                  // bit b = parity of auxfull[b]
-    constexpr bool kAux = (MODE == MM_EPI_RESID_F32 || MODE == MM_EPI_GATE);
+    constexpr bool kAux = (MODE == MM_EPI_RESID_F32 || MODE == MM_EPI_GATE || MODE == MM_EPI_MASK_OP);
+    constexpr int kAuxCols = (MODE == MM_EPI_MASK_OP) ? 64 : 32;   // columns per aux slab (128 B rows)
 
     for (int tile = pid; tile < p.num_tiles; tile += npairs) {
       const int n_tile = tile % p.n_tiles;
@@ -262,9 +263,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
             const uint32_t b = (slab_ctr + s) % NB;
-            if (col_tile + s * 32 < p.n) {
+            if (col_tile + s * kAuxCols < p.n) {
               mbar_expect_tx(&auxfull[b], Cfg::SLAB_BYTES);
-              tma_load_3d(sSlab + b * Cfg::SLAB_BYTES, &mapAux0, &auxfull[b], col_tile + s * 32, row0, bi);
+              tma_load_3d(sSlab + b * Cfg::SLAB_BYTES, &mapAux0, &auxfull[b], col_tile + s * kAuxCols, row0, bi);
             }
           }
         }
@@ -337,6 +338,61 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
             ++slab_ctr;
           }
           __syncwarp();
+        }
+      } else if constexpr (MODE == MM_EPI_MASK_OP) {
+        // dgrad through an activation: out = mask > 0 ? (acc + bias) * scale : 0, where `mask` is the 16-bit activation
+        // the forward pass kept (ReLU output, already activation-dropped).  Its 128 x 64 slabs arrive by TMA two slabs
+        // ahead and are overwritten in place with the masked gradient, which leaves by TMA store.
+        uint32_t ra0[32], ra1[32];
+        tmem_ld32(taddr, ra0);
+        tmem_ld32(taddr + 32, ra1);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+          const int col = col_tile + c0;
+          if (col >= p.n) break;                                          // uniform
+          const uint32_t b = slab_ctr % NB;
+          uint8_t* slab = sSlab + b * Cfg::SLAB_BYTES;
+          if (et == 0 && col + 128 < p.n && c0 + 128 < BN) {              // prefetch the mask slab two ahead
+            bulk_wait_read<1>();
+            const uint32_t b2 = (slab_ctr + 2) % NB;
+            mbar_expect_tx(&auxfull[b2], Cfg::SLAB_BYTES);
+            tma_load_3d(sSlab + b2 * Cfg::SLAB_BYTES, &mapAux0, &auxfull[b2], col + 128, row0, bi);
+          }
+          tmem_ld_wait();
+          float v[64];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v[i] = (__uint_as_float(ra0[i]) + sBias[c0 + i]) * p.scale;
+            v[32 + i] = (__uint_as_float(ra1[i]) + sBias[c0 + 32 + i]) * p.scale;
+          }
+          if (c0 + 64 < BN && col + 64 < p.n) {
+            tmem_ld32(taddr + c0 + 64, ra0);
+            tmem_ld32(taddr + c0 + 96, ra1);
+          }
+          mbar_wait(&auxfull[b], (aux_phase >> b) & 1);
+          aux_phase ^= (1u << b);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint4* ch = slab_chunk(slab, lrow, i);
+            const uint4 m = *ch;
+            const OpT* e = reinterpret_cast<const OpT*>(&m);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (!(OpTraits<OpT>::to_float(e[j]) > 0.f)) v[8 * i + j] = 0.f;
+            uint4 q;
+            q.x = OpTraits<OpT>::pack2(v[8 * i + 0], v[8 * i + 1]);
+            q.y = OpTraits<OpT>::pack2(v[8 * i + 2], v[8 * i + 3]);
+            q.z = OpTraits<OpT>::pack2(v[8 * i + 4], v[8 * i + 5]);
+            q.w = OpTraits<OpT>::pack2(v[8 * i + 6], v[8 * i + 7]);
+            *ch = q;
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) {
+            tma_store_3d(&mapOut0, slab, col, row0, bi);
+            bulk_commit();
+          }
+          ++slab_ctr;
         }
       } else if constexpr (MODE == MM_EPI_GLU_OP) {
         constexpr int HALF = BN / 2;
@@ -655,6 +711,7 @@ static int dispatch_mode(int mode, const GemmMaps& m, const GemmDev& p, cudaStre
     case MM_EPI_F32_OP: return launch_gemm<MM_EPI_F32_OP, OpT>(m, p, s);
     case MM_EPI_GATE: return launch_gemm<MM_EPI_GATE, OpT>(m, p, s);
     case MM_EPI_F32: return launch_gemm<MM_EPI_F32, OpT>(m, p, s);
+    case MM_EPI_MASK_OP: return launch_gemm<MM_EPI_MASK_OP, OpT>(m, p, s);
   }
   return bad_arg("unknown epilogue mode");
 }
@@ -682,6 +739,7 @@ extern "C" int mm_gemm(const mm_gemm_args* a, void* stream) {
   if (mode == MM_EPI_RESID_F32 && !a->aux0) return bad_arg("RESID needs aux0");
   if (mode == MM_EPI_GATE && (!a->aux0 || !a->aux1)) return bad_arg("GATE needs aux0 and aux1");
   if (mode == MM_EPI_F32_OP && !a->out1) return bad_arg("F32_OP needs out1");
+  if (mode == MM_EPI_MASK_OP && (!a->aux0 || a->out_tbc || a->vt)) return bad_arg("MASK_OP needs aux0 (16-bit), no tbc / vt");
   if (mode == MM_EPI_GLU_POS_F32 && !a->pos) return bad_arg("GLU_POS needs pos");
   if (a->out_tbc && (a->n_seqs <= 0 || a->batches != a->n_seqs))
     return bad_arg("out_tbc needs batched rows (batches == n_seqs)");
@@ -744,7 +802,7 @@ extern "C" int mm_gemm(const mm_gemm_args* a, void* stream) {
   if (rc) return rc;
 
   // outputs: 3-D maps (columns, rows, batch); T x B x C stores are just another stride pair
-  const bool out_op = mode == MM_EPI_OP || mode == MM_EPI_RELU_OP || mode == MM_EPI_GLU_OP;
+  const bool out_op = mode == MM_EPI_OP || mode == MM_EPI_RELU_OP || mode == MM_EPI_GLU_OP || mode == MM_EPI_MASK_OP;
   uint64_t n_out = glu ? (uint64_t)a->n / 2 : (uint64_t)a->n;
   if (mode == MM_EPI_OP && a->vt) n_out = (uint64_t)a->vt_col0;
   const uint64_t out_rows = rows + (uint64_t)a->out_row_offset;
@@ -767,6 +825,10 @@ extern "C" int mm_gemm(const mm_gemm_args* a, void* stream) {
   if (mode == MM_EPI_RESID_F32 || mode == MM_EPI_GATE) {
     rc = make_tmap_3d_ex(&m.aux0, a->aux0, 2, (uint64_t)a->n, rows, nb, (uint64_t)a->aux_ld,
                          (uint64_t)a->rows * a->aux_ld, 32, 128);
+    if (rc) return rc;
+  } else if (mode == MM_EPI_MASK_OP) {
+    rc = make_tmap_3d_ex(&m.aux0, a->aux0, f16 ? 1 : 0, (uint64_t)a->n, rows, nb, (uint64_t)a->aux_ld,
+                         (uint64_t)a->rows * a->aux_ld, 64, 128);
     if (rc) return rc;
   } else {
     m.aux0 = m.out0;

@@ -369,10 +369,10 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                 gm = masked(dsite_layer(i, 5))
                 self._linear_bwd(gm, d, s["f"], M, d, ffn, self.g(p + "fc2.weight"), self.g(p + "fc2.bias"), accumulate)
                 dF = self.buf("b_dF", (M, ffn), op)
-                K.gemm(a0=gm, a0_ld=d, rows=M, w=Lr["w2"], w_ld=ffn, w_mn=True, n=ffn, k=d, mode=K.EPI_OP, out0=dF,
-                       out0_ld=ffn, block_n=bn)
-                K.pack_t(dF, rows=M, cols=ffn, in_ld=ffn, out_n=dF, n_ld=ffn, mask=s["f"], mask_ld=ffn,
-                         scale=1.0 / (1.0 - p_act))
+                # ReLU (and activation-dropout) mask in the dgrad's epilogue: the kept activation is > 0 exactly where ReLU passed
+                # and the dropout kept it; the surviving gradient is scaled by 1 / (1 - p_act)
+                K.gemm(a0=gm, a0_ld=d, rows=M, w=Lr["w2"], w_ld=ffn, w_mn=True, n=ffn, k=d, mode=K.EPI_MASK_OP, out0=dF,
+                       out0_ld=ffn, aux0=s["f"], aux_ld=ffn, scale=1.0 / (1.0 - p_act), block_n=bn)
                 self._linear_bwd(dF, ffn, s["h3"], M, ffn, d, self.g(p + "fc1.weight"), self.g(p + "fc1.bias"), accumulate)
                 K.gemm(a0=dF, a0_ld=ffn, rows=M, w=Lr["w1"], w_ld=d, w_mn=True, n=d, k=ffn, mode=K.EPI_F32, out0=dh,
                        out0_ld=d, block_n=bn)

@@ -12,8 +12,8 @@ import torch
 
 from . import _lib
 
-EPI_OP, EPI_RELU_OP, EPI_RESID_F32, EPI_GLU_OP, EPI_GLU_POS_F32, EPI_F32_OP, EPI_GATE, EPI_F32 = range(8)
-EPI_NAMES = ["op", "relu_op", "resid_f32", "glu_op", "glu_pos_f32", "f32_op", "gate", "f32"]
+EPI_OP, EPI_RELU_OP, EPI_RESID_F32, EPI_GLU_OP, EPI_GLU_POS_F32, EPI_F32_OP, EPI_GATE, EPI_F32, EPI_MASK_OP = range(9)
+EPI_NAMES = ["op", "relu_op", "resid_f32", "glu_op", "glu_pos_f32", "f32_op", "gate", "f32", "mask_op"]
 _DT = {torch.bfloat16: 0, torch.float16: 1}
 
 # Launch counter: bench.py reports how many of OUR kernels ran inside the timed region.
@@ -166,9 +166,11 @@ def gemm(*, a0: torch.Tensor, w: torch.Tensor, rows: int, n: int, k: int, mode: 
     """acc = A @ W^T with a fused epilogue; see ``mm_gemm_args`` in include/mms2ut_b200.h."""
     if a0.dtype != w.dtype or (a1 is not None and a1.dtype != w.dtype):
         raise TypeError("A and W must share the 16-bit operand dtype")
-    for t in (bias, aux0, aux1, pos):
+    for t in (bias, aux0 if mode != EPI_MASK_OP else None, aux1, pos):
         if t is not None and t.dtype != torch.float32:
             raise TypeError("bias/aux/pos must be float32")
+    if mode == EPI_MASK_OP and (aux0 is None or aux0.dtype != w.dtype):
+        raise TypeError("MASK_OP: aux0 is the kept 16-bit activation")
     if seq_lens is not None and seq_lens.dtype != torch.int32:
         raise TypeError("seq_lens must be int32")
     g = _lib.GemmArgs()
@@ -438,7 +440,7 @@ def layernorm_bwd_blocks() -> int:
 
 
 def colsum_blocks(rows: int) -> int:
-    return (rows + 511) // 512
+    return (rows + 127) // 128
 
 
 def colsum(x: torch.Tensor, ld: int, rows: int, cols: int, partials: torch.Tensor, period: int = 0,

@@ -623,12 +623,10 @@ class TrainEngine(EncoderEngine):
         # ---- FFN: x_out = x_mid + dropout(fc2(dropout(relu(fc1(LN2(x_mid))))))
         self._linear_bwd(gm, d, s["f"], M, d, ffn, self.g(mod.fc2.weight), self.g(mod.fc2.bias), accumulate)
         dF = self.buf("b_dF", (M, ffn), op)
-        K.gemm(a0=gm, a0_ld=d, rows=M, w=L["w2"], w_ld=ffn, w_mn=True, n=ffn, k=d, mode=K.EPI_OP, out0=dF,
-               out0_ld=ffn, block_n=bn)
-        # ReLU (and activation-dropout) mask in place: the kept activation is > 0 exactly where ReLU passed and the
-        # dropout kept it; the surviving gradient is scaled by 1 / (1 - p_act)
-        K.pack_t(dF, rows=M, cols=ffn, in_ld=ffn, out_n=dF, n_ld=ffn, mask=s["f"], mask_ld=ffn,
-                 scale=1.0 / (1.0 - p_act))
+        # ReLU (and activation-dropout) mask in the dgrad's epilogue: the kept activation is > 0 exactly where ReLU passed
+        # and the dropout kept it; the surviving gradient is scaled by 1 / (1 - p_act)
+        K.gemm(a0=gm, a0_ld=d, rows=M, w=L["w2"], w_ld=ffn, w_mn=True, n=ffn, k=d, mode=K.EPI_MASK_OP, out0=dF,
+               out0_ld=ffn, aux0=s["f"], aux_ld=ffn, scale=1.0 / (1.0 - p_act), block_n=bn)
         self._linear_bwd(dF, ffn, s["h2"], M, ffn, d, self.g(mod.fc1.weight), self.g(mod.fc1.bias), accumulate)
         dh = self.buf("b_dh", (M, d), torch.float32)
         K.gemm(a0=dF, a0_ld=ffn, rows=M, w=L["w1"], w_ld=d, w_mn=True, n=d, k=ffn, mode=K.EPI_F32, out0=dh, out0_ld=d,

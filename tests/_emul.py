@@ -13,7 +13,7 @@ import math
 import numpy as np
 import torch
 
-EPI_OP, EPI_RELU_OP, EPI_RESID_F32, EPI_GLU_OP, EPI_GLU_POS_F32, EPI_F32_OP, EPI_GATE, EPI_F32 = range(8)
+EPI_OP, EPI_RELU_OP, EPI_RESID_F32, EPI_GLU_OP, EPI_GLU_POS_F32, EPI_F32_OP, EPI_GATE, EPI_F32, EPI_MASK_OP = range(9)
 launch_count = 0
 timing = None
 scope = ""
@@ -185,6 +185,9 @@ def gemm(*, a0, w, rows, n, k, mode, out0, a0_ld, out0_ld, batches=1, a0_bs=0, a
         o = _v(aux1, (batches, rows, n), (rows * aux_ld, aux_ld, 1))
         g = torch.sigmoid(acc)
         out_view(out0, n, out0_ld, out0_bs).copy_((1 - g) * x + g * o)
+    elif mode == EPI_MASK_OP:
+        m = _v(aux0, (batches, rows, n), (rows * aux_ld, aux_ld, 1)).float() > 0
+        out_view(out0, n, out0_ld, out0_bs).copy_(torch.where(m, acc * scale, torch.zeros_like(acc)).to(op))
     else:
         raise ValueError(mode)
 
@@ -373,7 +376,7 @@ def rowsum(x, ld, rows, cols, out, accumulate=False):
 
 
 def colsum_blocks(rows):
-    return (rows + 511) // 512
+    return (rows + 127) // 128
 
 
 def colsum(x, ld, rows, cols, partials, period=0, valid=0):

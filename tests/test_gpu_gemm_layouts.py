@@ -80,3 +80,46 @@ def test_attention_backward_gemms_head_mode(cuda):
     _close(dqkv[:, 2 * d:], back(Pf.transpose(-1, -2) @ do), 3e-2)
     _close(dqkv[:, d:2 * d], back(Pf.transpose(-1, -2) @ q), 3e-2)
     _close(dqkv[:, :d], back(Pf @ k) * 0.125, 3e-2)
+
+
+@pytest.mark.parametrize("M,N,Kc,scale", [(300, 2048, 256, 1.0), (1000, 320, 512, 1.25), (77, 64, 64, 1.0),
+                                          (16000, 2048, 512, 1.0)])
+def test_dgrad_relu_mask_epilogue(cuda, M, N, Kc, scale):
+    """MM_EPI_MASK_OP: the fc2 dgrad with the backward of fc1's ReLU (+ activation dropout) in its epilogue:
+    out = kept > 0 ? (A W) * scale : 0, `kept` = the 16-bit activation the forward pass saved (autograd of fairseq's
+    TransformerEncoderLayer: relu -> activation_dropout -> fc2)."""
+    from mm_s2ut_b200 import kernels as K
+
+    A, W = _rnd(M, Kc, seed=11), _rnd(Kc, N, seed=12)
+    kept = (_rnd(M, N, seed=13).float().relu() * (torch.rand(M, N, device=cuda) > 0.1)).bfloat16()
+    out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=cuda)
+    K.gemm(a0=A, a0_ld=Kc, rows=M, w=W, w_ld=N, n=N, k=Kc, mode=K.EPI_MASK_OP, out0=out, out0_ld=N, w_mn=True,
+           aux0=kept, aux_ld=N, scale=scale)
+    ref = torch.where(kept.float() > 0, (A.float() @ W.float()) * scale, torch.zeros((), device=cuda))
+    _close(out, ref, 3e-2)
+    assert torch.equal(out == 0, ~(kept.float() > 0) | (ref.bfloat16() == 0))     # the mask is exact
+    assert torch.equal(kept, kept.clone())
+
+
+@pytest.mark.parametrize("M,N", [(16000, 512), (16000, 2048), (1000, 1536), (130, 64), (577 * 3, 1024)])
+def test_colsum_and_batched_reduction(cuda, M, N):
+    """Bias gradients: per-chunk column sums of a 16-bit [M, N] matrix + the deterministic partial reduction."""
+    from mm_s2ut_b200 import kernels as K
+
+    x = _rnd(M, N, seed=21)
+    nb = K.colsum_blocks(M)
+    part = torch.full((nb * N,), float("nan"), device=cuda)
+    assert K.colsum(x, N, M, N, part) == nb
+    out = torch.full((N,), 3.0, device=cuda)
+    acc = torch.full((N,), 3.0, device=cuda)
+    K.reduce_partials_many([(part, nb, N, N, out, False), (part, nb, N, N, acc, True)])
+    ref = x.float().sum(0)
+    tol = 1e-3 * max(1.0, ref.abs().max().item())
+    assert (out - ref).abs().max().item() <= tol
+    assert (acc - 3.0 - ref).abs().max().item() <= tol
+    # rows with (r % period) >= valid are skipped
+    period, valid = 577, 500
+    K.colsum(x, N, M, N, part, period, valid)
+    K.reduce_partials_many([(part, nb, N, N, out, False)])
+    keep = (torch.arange(M, device=cuda) % period) < valid
+    assert (out - (x.float() * keep[:, None]).sum(0)).abs().max().item() <= tol
