@@ -311,6 +311,24 @@ int mm_rowsum(const void* in, int64_t ld, int32_t rows, int32_t cols, float* out
 int mm_reduce_partials(const float* part, int32_t n_partials, int64_t stride, int64_t n, float* out, int32_t accumulate,
                        void* stream);
 /* Several mm_reduce_partials in one launch (the backward pass defers a layer's reductions and runs them together). */
+/* Grouped weight gradient (autograd of nn.Linear inside fairseq's TransformerEncoderLayer / MultiheadAttention under
+ * `loss.backward()`, scripts/textless/1_train.sh): for every group g
+ *     out_g[n, k] (+)= sum_t dy_g[t, n] * x_g[t, k]        t = 0 .. tokens-1, fp32 accumulation, fp32 output
+ * in ONE launch: the 256 x 256 output tiles of all groups share the persistent grid, so no token split (and no
+ * partial sums) is needed to fill the GPU.  dy_g [tokens, n_out] and x_g [tokens, k_in] are the 16-bit tensors the
+ * backward pass already holds (row strides dy_ld / x_ld, elements); out_g is the fp32 gradient [n_out, k_in] with row
+ * stride out_ld.  accumulate != 0 adds to out (gradient accumulation over micro-batches). */
+#define MM_WGRAD_MAX_GROUPS 64
+typedef struct mm_wgrad_group {
+  const void* dy;
+  const void* x;
+  float* out;
+  int64_t dy_ld, x_ld, out_ld;
+  int32_t n_out, k_in;
+} mm_wgrad_group;
+int mm_wgrad_grouped(const mm_wgrad_group* groups, int32_t count, int64_t tokens, int32_t accumulate, int32_t dtype,
+                     void* stream);
+
 typedef struct mm_reduce_job {
   const float* part;
   float* out;

@@ -17,7 +17,7 @@ _PKG = Path(__file__).resolve().parent
 CSRC = _PKG / "csrc"
 INCLUDE = _PKG.parent / "include"
 LIB_PATH = _PKG / "libmms2ut_b200.so"
-SOURCES = ["abi.cu", "gemm.cu", "gemm_ln.cu", "rowwise.cu", "fbank.cu", "attention.cu", "cross_attention.cu", "attention_bwd.cu", "backward.cu"]
+SOURCES = ["abi.cu", "gemm.cu", "gemm_ln.cu", "rowwise.cu", "fbank.cu", "attention.cu", "cross_attention.cu", "attention_bwd.cu", "backward.cu", "wgrad.cu"]
 ABI_VERSION = 3
 
 NVCC_FLAGS = [
@@ -99,6 +99,15 @@ class ReduceJob(C.Structure):
                 ("n_partials", C.c_int32), ("accumulate", C.c_int32)]
 
 
+class WgradGroup(C.Structure):
+    """``mm_wgrad_group`` (include/mms2ut_b200.h)."""
+
+    _fields_ = [("dy", C.c_void_p), ("x", C.c_void_p), ("out", C.c_void_p), ("dy_ld", C.c_int64), ("x_ld", C.c_int64),
+                ("out_ld", C.c_int64), ("n_out", C.c_int32), ("k_in", C.c_int32)]
+
+
+WGRAD_MAX_GROUPS = 64
+
 EXPORTS = {
     # name: (restype, argtypes)
     "mm_abi_version": (C.c_int, []),
@@ -161,6 +170,7 @@ EXPORTS = {
     "mm_rowsum": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "mm_reduce_partials": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "mm_reduce_partials_many": (C.c_int, [C.POINTER(ReduceJob), C.c_int32, C.c_void_p]),
+    "mm_wgrad_grouped": (C.c_int, [C.POINTER(WgradGroup), C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "mm_layernorm_bwd_blocks": (C.c_int, []),
     "mm_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),

@@ -1,0 +1,315 @@
+// Grouped weight-gradient GEMM of the training step (BASELINE configs[2]):
+//
+//   out_g[n, k] (+)= sum_t dY_g[t, n] * X_g[t, k]        g = 0 .. count-1, t over ALL tokens, fp32 accumulation in TMEM
+//
+// One launch runs the weight gradients of several Linear layers (q|k|v, out_proj, fc1, fc2 of up to three encoder
+// layers).  A single wgrad has only 4-16 output tiles of 256 x 256, far fewer than the 74 CTA pairs of a B200, which is
+// why gemm.cu's wgrad had to split the token contraction 6-18 ways and write fp32 partials (108 MB per encoder layer,
+// reduced by another kernel).  Pooled, the tiles of 12 gradients fill two whole waves with the FULL contraction per
+// tile: no partials, no reduction, one long main loop per tile (16000 tokens = 250 k-blocks) instead of a short one
+// with an exposed fp32 epilogue.  Both operands are read as stored (MN-major: memory is [token][feature]).
+//
+// Structure = gemm.cu (persistent, warp-specialised, cta_group::2, 256 x 256 tile per CTA pair, 2 x 256 TMEM columns):
+//   warp 0 TMA producer, warp 1 MMA issuer (leader), warp 2 TMEM allocator, warps 4-7 epilogue (fp32 slabs -> TMA store;
+//   ACC: the current gradient is TMA-loaded into the slab two slabs ahead and updated in place).
+#include "common.cuh"
+#include "host.cuh"
+#include "../../include/mms2ut_b200.h"
+
+namespace mm {
+
+constexpr int WG_MAX = MM_WGRAD_MAX_GROUPS;
+
+struct WgMaps {
+  CUtensorMap a[WG_MAX], w[WG_MAX], out[WG_MAX];
+};
+struct WgDev {
+  int count, num_tiles, num_kb, tail_steps;
+  int tile_start[WG_MAX + 1];
+  int n_tiles[WG_MAX];   // column tiles of group g
+  int n[WG_MAX];         // output columns (k_in) of group g
+};
+
+struct WgCfg {
+  static constexpr int BM = 128, BN = 256, BK = 64, STAGES = 5, NB = 4;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int SLAB_BYTES = BM * 128;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + NB * SLAB_BYTES + BAR_BYTES + 1024;
+};
+
+__device__ __forceinline__ uint4* wg_slab_chunk(uint8_t* slab, int row, int c) {
+  return reinterpret_cast<uint4*>(slab + row * 128 + ((c ^ (row & 7)) << 4));
+}
+
+__device__ __forceinline__ int wg_group_of(const WgDev& p, int tile) {
+  int g = 0;
+  while (g + 1 < p.count && tile >= p.tile_start[g + 1]) ++g;
+  return g;
+}
+
+template <bool ACC, typename OpT>
+__global__ void __launch_bounds__(256, 1)
+wgrad_grouped_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgDev p) {
+  using Cfg = WgCfg;
+  constexpr int STAGES = Cfg::STAGES, NB = Cfg::NB, BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + STAGES * Cfg::A_BYTES;
+  uint8_t* sSlab = sB + STAGES * Cfg::B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sSlab + NB * Cfg::SLAB_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* auxfull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(auxfull + NB);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pid = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);
+    }
+    for (int i = 0; i < NB; ++i) mbar_init(&auxfull[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = pid; tile < p.num_tiles; tile += npairs) {
+        const int g = wg_group_of(p, tile);
+        const int local = tile - p.tile_start[g];
+        const int n_tile = local % p.n_tiles[g], mp = local / p.n_tiles[g];
+        const int row0 = mp * (2 * Cfg::BM) + rank * Cfg::BM;
+        const int wrow0 = n_tile * BN + rank * (BN / 2);
+        const CUtensorMap* mA = &maps.a[g];
+        const CUtensorMap* mW = &maps.w[g];
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+          uint8_t* dA = sA + stage * Cfg::A_BYTES;
+          uint8_t* dB = sB + stage * Cfg::B_BYTES;
+          const int kc = kb * Cfg::BK;
+          // MN-major operands: two 64 (features) x 64 (tokens) boxes each; tokens / features past the end are zero-filled
+          tma_load_3d_2sm(dA, mA, &full[stage], row0, kc, 0);
+          tma_load_3d_2sm(dA + Cfg::A_BYTES / 2, mA, &full[stage], row0 + 64, kc, 0);
+          tma_load_3d_2sm(dB, mW, &full[stage], wrow0, kc, 0);
+          tma_load_3d_2sm(dB + Cfg::B_BYTES / 2, mW, &full[stage], wrow0 + 64, kc, 0);
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = umma_idesc(2 * Cfg::BM, BN, OpTraits<OpT>::fmt) | (1u << 15) | (1u << 16);   // A, B MN-major
+      uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+      for (int tile = pid; tile < p.num_tiles; tile += npairs) {
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128_mn(smem_u32(sA + stage * Cfg::A_BYTES), Cfg::A_BYTES / 2);
+          const uint64_t bdesc = umma_desc_sw128_mn(smem_u32(sB + stage * Cfg::B_BYTES), Cfg::B_BYTES / 2);
+          const int steps = (kb == p.num_kb - 1) ? p.tail_steps : 4;
+          for (int kk = 0; kk < steps; ++kk)
+            umma_f16_2sm(tmem_d, adesc + 128ull * kk, bdesc + 128ull * kk, idesc, (kb | kk) != 0);
+          umma_commit_2sm(&empty[stage], 3);
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+        umma_commit_2sm(&tfull[as], 3);
+        if (++as == 2) as = 0, aphase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs) =====================
+    const int ew = warp - 4, et = threadIdx.x - 128, lrow = ew * 32 + lane;
+    const uint32_t tempty_leader = mapa_u32(&tempty[0], 0);
+    uint32_t as = 0, aphase = 0, slab_ctr = 0, aux_phase = 0;
+    for (int tile = pid; tile < p.num_tiles; tile += npairs) {
+      const int g = wg_group_of(p, tile);
+      const int local = tile - p.tile_start[g];
+      const int n_tile = local % p.n_tiles[g], mp = local / p.n_tiles[g];
+      const int row0 = mp * (2 * Cfg::BM) + rank * Cfg::BM;
+      const int col_tile = n_tile * BN, ncols = p.n[g];
+      const CUtensorMap* mO = &maps.out[g];
+      if constexpr (ACC) {
+        if (et == 0) {   // gradient slabs 0 and 1 of this tile: buffers last used 4 and 3 slabs ago
+          bulk_wait_read<2>();
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const uint32_t b = (slab_ctr + s) % NB;
+            if (col_tile + s * 32 < ncols) {
+              mbar_expect_tx(&auxfull[b], Cfg::SLAB_BYTES);
+              tma_load_3d(sSlab + b * Cfg::SLAB_BYTES, mO, &auxfull[b], col_tile + s * 32, row0, 0);
+            }
+          }
+        }
+      }
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(ew * 32) << 16);
+      uint32_t ra[32], rb[32];
+      tmem_ld32(taddr, ra);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 64) {      // two 32-column slabs per step, the next TMEM load always in flight
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int col = col_tile + c0 + 32 * h;
+          if (col >= ncols) break;                                          // uniform
+          const uint32_t b = slab_ctr % NB;
+          uint8_t* slab = sSlab + b * Cfg::SLAB_BYTES;
+          uint32_t(&r)[32] = h == 0 ? ra : rb;
+          if constexpr (ACC) {
+            if (et == 0 && col + 64 < ncols && c0 + 32 * h + 64 < BN) {     // prefetch the gradient slab two ahead
+              bulk_wait_read<1>();
+              const uint32_t b2 = (slab_ctr + 2) % NB;
+              mbar_expect_tx(&auxfull[b2], Cfg::SLAB_BYTES);
+              tma_load_3d(sSlab + b2 * Cfg::SLAB_BYTES, mO, &auxfull[b2], col + 64, row0, 0);
+            }
+          } else {
+            if (et == 0) bulk_wait_read<NB - 1>();
+            asm volatile("bar.sync 1, 128;" ::: "memory");                  // slab free
+          }
+          tmem_ld_wait();
+          if (col + 32 < ncols && c0 + 32 * h + 32 < BN) tmem_ld32(taddr + c0 + 32 * h + 32, h == 0 ? rb : ra);
+          if constexpr (ACC) {
+            mbar_wait(&auxfull[b], (aux_phase >> b) & 1);
+            aux_phase ^= (1u << b);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              uint4* ch = wg_slab_chunk(slab, lrow, i);
+              uint4 q = *ch;
+              q.x = __float_as_uint(__uint_as_float(q.x) + __uint_as_float(r[4 * i]));
+              q.y = __float_as_uint(__uint_as_float(q.y) + __uint_as_float(r[4 * i + 1]));
+              q.z = __float_as_uint(__uint_as_float(q.z) + __uint_as_float(r[4 * i + 2]));
+              q.w = __float_as_uint(__uint_as_float(q.w) + __uint_as_float(r[4 * i + 3]));
+              *ch = q;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              *wg_slab_chunk(slab, lrow, i) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) {
+            tma_store_3d(mO, slab, col, row0, 0);
+            bulk_commit();
+          }
+          ++slab_ctr;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0)
+          mbar_arrive(&tempty[as]);
+        else
+          mbar_arrive_cluster(tempty_leader + as * 8);
+      }
+      if (++as == 2) as = 0, aphase ^= 1;
+    }
+    if (et == 0) bulk_wait<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <bool ACC, typename OpT>
+static int launch_wgrad(const WgMaps& m, const WgDev& p, cudaStream_t s) {
+  auto kern = wgrad_grouped_kernel<ACC, OpT>;
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg::SMEM_BYTES);
+    if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute(wgrad_grouped)");
+    attr_set = true;
+  }
+  const int max_pairs = kNumSMs / 2;
+  const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = WgCfg::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, m, p);
+  if (e != cudaSuccess) return fail(e, "wgrad_grouped_kernel launch");
+  return 0;
+}
+
+}  // namespace mm
+
+extern "C" int mm_wgrad_grouped(const mm_wgrad_group* groups, int32_t count, int64_t tokens, int32_t accumulate,
+                                int32_t dtype, void* stream) {
+  using namespace mm;
+  if (!groups || count <= 0 || count > WG_MAX) return bad_arg("wgrad_grouped: 1 .. MM_WGRAD_MAX_GROUPS groups");
+  if (tokens <= 0) return bad_arg("wgrad_grouped: tokens");
+  if (dtype != MM_DTYPE_BF16 && dtype != MM_DTYPE_F16) return bad_arg("wgrad_grouped: dtype");
+  const int kind = dtype == MM_DTYPE_F16 ? 1 : 0;
+  static thread_local WgMaps m;
+  WgDev p;
+  memset(&p, 0, sizeof(p));
+  p.count = count;
+  p.num_kb = (int)((tokens + 63) / 64);
+  p.tail_steps = (int)((tokens - (int64_t)(p.num_kb - 1) * 64 + 15) >> 4);
+  int tiles = 0;
+  for (int g = 0; g < count; ++g) {
+    const mm_wgrad_group& q = groups[g];
+    if (!q.dy || !q.x || !q.out || q.n_out <= 0 || q.k_in <= 0) return bad_arg("wgrad_grouped: group");
+    if (q.k_in % 4) return bad_arg("wgrad_grouped: k_in must be a multiple of 4");
+    int rc = make_tmap_3d_ex(&m.a[g], q.dy, kind, (uint64_t)q.n_out, (uint64_t)tokens, 1, (uint64_t)q.dy_ld, 0, 64, 64);
+    if (rc) return rc;
+    rc = make_tmap_3d_ex(&m.w[g], q.x, kind, (uint64_t)q.k_in, (uint64_t)tokens, 1, (uint64_t)q.x_ld, 0, 64, 64);
+    if (rc) return rc;
+    rc = make_tmap_3d_ex(&m.out[g], q.out, 2, (uint64_t)q.k_in, (uint64_t)q.n_out, 1, (uint64_t)q.out_ld, 0, 32, 128);
+    if (rc) return rc;
+    p.tile_start[g] = tiles;
+    p.n_tiles[g] = (q.k_in + 255) / 256;
+    p.n[g] = q.k_in;
+    tiles += ((q.n_out + 255) / 256) * p.n_tiles[g];
+  }
+  for (int g = count; g <= WG_MAX; ++g) p.tile_start[g] = tiles;
+  for (int g = count; g < WG_MAX; ++g) m.a[g] = m.a[0], m.w[g] = m.w[0], m.out[g] = m.out[0];
+  p.num_tiles = tiles;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (accumulate)
+    return kind ? launch_wgrad<true, __half>(m, p, s) : launch_wgrad<true, __nv_bfloat16>(m, p, s);
+  return kind ? launch_wgrad<false, __half>(m, p, s) : launch_wgrad<false, __nv_bfloat16>(m, p, s);
+}

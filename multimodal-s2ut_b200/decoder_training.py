@@ -22,6 +22,8 @@ fairseq's sites.  No CPU fallback.
 """
 from __future__ import annotations
 
+import os
+
 import math
 from typing import Dict, List, Optional, Tuple
 
@@ -56,6 +58,8 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
     _flush = TrainEngine._flush
     _lnp = TrainEngine._lnp
     _wgrad_mn = TrainEngine._wgrad_mn
+    _wgrad_flush = TrainEngine._wgrad_flush
+    grouped_wgrad = os.environ.get("MM_GROUPED_WGRAD", "1") != "0"     # see TrainEngine.grouped_wgrad
     _bias_grad = TrainEngine._bias_grad
     _linear_bwd = TrainEngine._linear_bwd
     _ln_param_grads = TrainEngine._ln_param_grads
@@ -353,10 +357,12 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
         first_kv = True
         p_drop, p_attn, p_act, seed, seed_dev = sv["drop"]
 
+        grouped = self.grouped_wgrad     # queued weight gradients: every layer keeps its own gradient buffers
+
         def masked(site):       # gradient entering a dropped branch = g o mask / (1 - p); the residual keeps g itself
             if p_drop == 0:
                 return g_op
-            gm = self.buf("b_gm_op", (M, d), op)
+            gm = self.buf(f"b_gm_op@{site}" if grouped else "b_gm_op", (M, d), op)
             K.dropout(g_op, gm, p_drop, seed, site, seed_dev=seed_dev)
             return gm
 
@@ -364,11 +370,12 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
             s, Lr = sv["layers"][i], self.layers[i]
             p = Lr["prefix"]
             sa, ea = p + "self_attn.", p + "encoder_attn."
+            tag = f"@{i}" if grouped else ""
             with _scope("dec_layer"):
                 # ---- FFN
                 gm = masked(dsite_layer(i, 5))
                 self._linear_bwd(gm, d, s["f"], M, d, ffn, self.g(p + "fc2.weight"), self.g(p + "fc2.bias"), accumulate)
-                dF = self.buf("b_dF", (M, ffn), op)
+                dF = self.buf("b_dF" + tag, (M, ffn), op)
                 # ReLU (and activation-dropout) mask in the dgrad's epilogue: the kept activation is > 0 exactly where ReLU passed
                 # and the dropout kept it; the surviving gradient is scaled by 1 / (1 - p_act)
                 K.gemm(a0=gm, a0_ld=d, rows=M, w=Lr["w2"], w_ld=ffn, w_mn=True, n=ffn, k=d, mode=K.EPI_MASK_OP, out0=dF,
@@ -377,6 +384,8 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                 K.gemm(a0=dF, a0_ld=ffn, rows=M, w=Lr["w1"], w_ld=d, w_mn=True, n=d, k=ffn, mode=K.EPI_F32, out0=dh,
                        out0_ld=d, block_n=bn)
                 lnp = self._lnp()
+                if grouped:
+                    g_op = self.buf("b_g_op2" + tag, (M, d), op)
                 K.layernorm_bwd(s["x2"], Lr["ln3"][0], dh, lnp, dx=g, resid=g, dx_op=g_op)
                 self._ln_param_grads(lnp, d, self.g(p + "final_layer_norm.weight", p + "final_layer_norm.bias"), accumulate)
                 # ---- encoder attention
@@ -386,8 +395,8 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                 datt = self.buf("b_datt", (M, d), op)
                 K.gemm(a0=gm, a0_ld=d, rows=M, w=Lr["wo2"], w_ld=d, w_mn=True, n=d, k=d, mode=K.EPI_OP, out0=datt,
                        out0_ld=d, block_n=bn)
-                dq2 = self.buf("b_dq2", (M, d), op)
-                dkv2 = self.buf("b_dkv2", (B * T, 2 * d), op)
+                dq2 = self.buf("b_dq2" + tag, (M, d), op)
+                dkv2 = self.buf("b_dkv2" + tag, (B * T, 2 * d), op)
                 kv2 = s["kv2"]
                 self._attn_bwd(s["q2"], d, L * d, kv2, kv2[:, d:], 2 * d, T * 2 * d, datt, dq2, dkv2, dkv2[:, d:], 2 * d,
                                T * 2 * d, B, L, T, sv["enc_lens"], False, dsite_layer(i, 3), out=s["att2"],
@@ -406,6 +415,8 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                     K.gemm(a0=dkv2, a0_ld=2 * d, rows=B * T, w=Lr["wkv"], w_ld=d, w_mn=True, n=d, k=2 * d,
                            mode=K.EPI_RESID_F32, aux0=denc, aux_ld=d, out0=denc, out0_ld=d, block_n=bn)
                 lnp = self._lnp()
+                if grouped:
+                    g_op = self.buf("b_g_op1" + tag, (M, d), op)
                 K.layernorm_bwd(s["x1"], Lr["ln2"][0], dh, lnp, dx=g, resid=g, dx_op=g_op)
                 self._ln_param_grads(lnp, d, self.g(p + "encoder_attn_layer_norm.weight", p + "encoder_attn_layer_norm.bias"),
                                      accumulate)
@@ -415,7 +426,7 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                                  accumulate)
                 K.gemm(a0=gm, a0_ld=d, rows=M, w=Lr["wo"], w_ld=d, w_mn=True, n=d, k=d, mode=K.EPI_OP, out0=datt,
                        out0_ld=d, block_n=bn)
-                dqkv = self.buf("b_dqkv", (M, 3 * d), op)
+                dqkv = self.buf("b_dqkv" + tag, (M, 3 * d), op)
                 qkv = s["qkv"]
                 self._attn_bwd(qkv, 3 * d, L * 3 * d, qkv[:, d:], qkv[:, 2 * d:], 3 * d, L * 3 * d, datt, dqkv, dqkv[:, d:],
                                dqkv[:, 2 * d:], 3 * d, L * 3 * d, B, L, L, None, True, dsite_layer(i, 1), out=s["att"],
@@ -426,10 +437,14 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                 K.gemm(a0=dqkv, a0_ld=3 * d, rows=M, w=Lr["wqkv"], w_ld=d, w_mn=True, n=d, k=3 * d, mode=K.EPI_F32, out0=dh,
                        out0_ld=d, block_n=bn)
                 lnp = self._lnp()
+                if grouped:
+                    g_op = self.buf("b_g_op0" + tag, (M, d), op)
                 K.layernorm_bwd(s["x0"], Lr["ln1"][0], dh, lnp, dx=g, resid=g, dx_op=g_op)
                 self._ln_param_grads(lnp, d, self.g(p + "self_attn_layer_norm.weight", p + "self_attn_layer_norm.bias"),
                                      accumulate)
                 self._flush()       # the layer's deferred reductions in one launch (per 16)
+        with _scope("dec_layer"):
+            self._wgrad_flush()     # every queued weight gradient (the embedding's wgrad must precede its scatter-add below)
         # ---- embedding: x0 = dropout(sqrt(d) * E[tokens] + positions)
         if p_drop > 0:
             K.dropout(g, g, p_drop, seed, DSITE_EMBED, seed_dev=seed_dev)

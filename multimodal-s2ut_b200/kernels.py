@@ -435,6 +435,28 @@ def reduce_partials_many(jobs) -> None:
         _lib.check(lib.mm_reduce_partials_many(arr, len(jobs), _stream()), "mm_reduce_partials_many")
 
 
+def wgrad_grouped(groups, tokens: int, accumulate: bool = False) -> None:
+    """groups: list of (dy [tokens, n_out] 16-bit, dy_ld, x [tokens, k_in] 16-bit, x_ld, out fp32, out_ld, n_out, k_in):
+    out[n, k] (+)= sum_t dy[t, n] x[t, k] for every group in one launch (``mm_wgrad_grouped``: the groups' output tiles
+    share the persistent grid, full token contraction per tile, no partials); out_ld = row stride of out (a column
+    block of a wider gradient is out = wide.view(-1)[col:], out_ld = wide row length)."""
+    lib = _lib.load()
+    for base in range(0, len(groups), _lib.WGRAD_MAX_GROUPS):
+        chunk = groups[base:base + _lib.WGRAD_MAX_GROUPS]
+        arr = (_lib.WgradGroup * len(chunk))()
+        work = 0.0
+        for a, (dy, dy_ld, x, x_ld, out, out_ld, n_out, k_in) in zip(arr, chunk):
+            if dy.dtype != x.dtype or out.dtype != torch.float32:
+                raise TypeError("wgrad_grouped: dy / x share the 16-bit operand dtype, out is float32")
+            assert out.numel() >= (n_out - 1) * out_ld + k_in
+            a.dy, a.x, a.out = _ptr(dy), _ptr(x), _ptr(out)
+            a.dy_ld, a.x_ld, a.out_ld, a.n_out, a.k_in = dy_ld, x_ld, out_ld, n_out, k_in
+            work += 2.0 * tokens * n_out * k_in
+        with _Launch("wgrad_grouped", work):
+            _lib.check(lib.mm_wgrad_grouped(arr, len(chunk), tokens, int(accumulate), dtype_code(chunk[0][0].dtype),
+                                            _stream()), "mm_wgrad_grouped")
+
+
 def layernorm_bwd_blocks() -> int:
     return _lib.load().mm_layernorm_bwd_blocks()
 

@@ -35,6 +35,7 @@ audio-drop branch, which is broken in the reference (:500).
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -143,6 +144,12 @@ class TrainEngine(EncoderEngine):
         self.train_fused_ln = self.d == 512 and getattr(enc, "fuse_layernorm", True)
         # attention backward: scores, dP and the softmax backward in one kernel (mm_attention_bwd_scores)
         self.fused_attn_bwd = getattr(enc, "fuse_attention_backward", True)
+        # weight gradients of the Linear layers are queued and run pooled in one grouped launch at the end of the
+        # backward pass (``mm_wgrad_grouped``: full token contraction per tile, no split-K partials); off: one split-K
+        # GEMM per gradient + deferred partial reduction.  wgrad_flush_layers > 0 flushes every that many layers instead
+        # (bucketed gradient all-reduce overlapping the backward pass needs complete layers early).
+        self.grouped_wgrad = os.environ.get("MM_GROUPED_WGRAD", "1") != "0"
+        self.wgrad_flush_layers = 0
         self._saved = None
         self.generation = 0            # advanced by every forward_train: ties an autograd node to ITS saved activations
         self.step_count = 0
@@ -547,6 +554,15 @@ class TrainEngine(EncoderEngine):
         """gw [n, sum kin] (+)= dy^T [x_0 | x_1 | ...]: both operands read as stored (MN-major), the token contraction
         split into S batches; x_ops = [(tensor [M, kin], ld, kin), ...] fill consecutive column blocks of gw."""
         kin_all = sum(x[2] for x in x_ops)
+        if getattr(self, "grouped_wgrad", False):
+            # queued: the operands must stay untouched until _wgrad_flush() (the backward pass gives every layer its own
+            # gradient buffers in this mode)
+            q = self.__dict__.setdefault("_wq", {}).setdefault((M, bool(accumulate)), [])
+            col = 0
+            for x, x_ld, kin in x_ops:
+                q.append((dy_op, dy_ld, x, x_ld, gw.view(-1)[col:], kin_all, n, kin))
+                col += kin
+            return
         tiles = ((n + 255) // 256) * sum((x[2] + 255) // 256 for x in x_ops)
         S = _best_split(tiles, M)
         chunk = _round_up((M + S - 1) // S, 64)
@@ -558,6 +574,13 @@ class TrainEngine(EncoderEngine):
                    a_mn=True, w_mn=True, a_kbatch=True, w_kbatch=True, a_k_total=M, w_k_total=M)
             col += kin
         self._defer(part, S, n * kin_all, n * kin_all, gw, accumulate)
+
+    def _wgrad_flush(self) -> None:
+        """Run the queued weight gradients: one grouped launch per (token count, accumulate) pool."""
+        for (M, acc), q in self.__dict__.get("_wq", {}).items():
+            if q:
+                K.wgrad_grouped(q, M, acc)
+                q.clear()
 
     def _bias_grad(self, dy_op: torch.Tensor, dy_ld: int, M: int, n: int, gb: torch.Tensor, accumulate: bool,
                    period: int = 0, valid: int = 0) -> None:
@@ -609,8 +632,11 @@ class TrainEngine(EncoderEngine):
                scale_cols=64, **og)
 
     def _layer_bwd(self, i: int, g: torch.Tensor, g_op: torch.Tensor, B: int, T: int, seq_lens: torch.Tensor,
-                   accumulate: bool) -> None:
-        """g = d loss / d x_out [M, d] fp32 with its 16-bit copy g_op; both are overwritten with d loss / d x_in."""
+                   accumulate: bool) -> torch.Tensor:
+        """g = d loss / d x_out [M, d] fp32 with its 16-bit copy g_op; g is overwritten with d loss / d x_in, whose 16-bit
+        copy is returned (g_op itself unless the weight gradients are queued: their operands -- g_op, dF, dqkv of every
+        layer -- then live in per-layer buffers until the grouped launch)."""
+        tag = f"@{i}" if self.grouped_wgrad else ""
         s, L = self._saved["layers"][i], self.layers[i]
         mod = self.enc.transformer_layers[i]
         a = mod.self_attn
@@ -618,11 +644,11 @@ class TrainEngine(EncoderEngine):
         p_drop, p_act, seed, seed_dev = self._saved["drop"]
         gm = g_op
         if p_drop > 0:       # gradient entering fc2 = g o mask / (1 - p); the residual branch keeps g itself
-            gm = self.buf("b_gm_op", (M, d), op)
+            gm = self.buf("b_gm_op" + tag, (M, d), op)
             K.dropout(g_op, gm, p_drop, seed, site_layer(i, 2), seed_dev=seed_dev)
         # ---- FFN: x_out = x_mid + dropout(fc2(dropout(relu(fc1(LN2(x_mid))))))
         self._linear_bwd(gm, d, s["f"], M, d, ffn, self.g(mod.fc2.weight), self.g(mod.fc2.bias), accumulate)
-        dF = self.buf("b_dF", (M, ffn), op)
+        dF = self.buf("b_dF" + tag, (M, ffn), op)
         # ReLU (and activation-dropout) mask in the dgrad's epilogue: the kept activation is > 0 exactly where ReLU passed
         # and the dropout kept it; the surviving gradient is scaled by 1 / (1 - p_act)
         K.gemm(a0=gm, a0_ld=d, rows=M, w=L["w2"], w_ld=ffn, w_mn=True, n=ffn, k=d, mode=K.EPI_MASK_OP, out0=dF,
@@ -632,18 +658,20 @@ class TrainEngine(EncoderEngine):
         K.gemm(a0=dF, a0_ld=ffn, rows=M, w=L["w1"], w_ld=d, w_mn=True, n=d, k=ffn, mode=K.EPI_F32, out0=dh, out0_ld=d,
                block_n=bn)
         lnp = self._lnp()
+        if tag:
+            g_op = self.buf("b_g_op_mid" + tag, (M, d), op)
         K.layernorm_bwd(s["x_mid"], L["ln2_g"], dh, lnp, dx=g, resid=g, dx_op=g_op)
         self._ln_param_grads(lnp, d, self.g(mod.final_layer_norm.weight, mod.final_layer_norm.bias), accumulate)
         # ---- attention: x_mid = x_in + dropout(out_proj(attn(LN1(x_in))))
         gm = g_op
         if p_drop > 0:
-            gm = self.buf("b_gm_op", (M, d), op)
+            gm = self.buf("b_gm_op_mid" + tag, (M, d), op)
             K.dropout(g_op, gm, p_drop, seed, site_layer(i, 0), seed_dev=seed_dev)
         self._linear_bwd(gm, d, s["att"], M, d, d, self.g(a.out_proj.weight), self.g(a.out_proj.bias), accumulate)
         datt = self.buf("b_datt", (M, d), op)
         K.gemm(a0=gm, a0_ld=d, rows=M, w=L["wo"], w_ld=d, w_mn=True, n=d, k=d, mode=K.EPI_OP, out0=datt, out0_ld=d,
                block_n=bn)
-        dqkv = self.buf("b_dqkv", (M, 3 * d), op)
+        dqkv = self.buf("b_dqkv" + tag, (M, 3 * d), op)
         with _scope("attn"):
             self._attention_bwd(s, datt, dqkv, B, T, seq_lens, i)
         self._linear_bwd(dqkv, 3 * d, s["h1"], M, 3 * d, d, self.g(a.q_proj.weight, a.k_proj.weight, a.v_proj.weight),
@@ -651,9 +679,12 @@ class TrainEngine(EncoderEngine):
         K.gemm(a0=dqkv, a0_ld=3 * d, rows=M, w=L["wqkv"], w_ld=d, w_mn=True, n=d, k=3 * d, mode=K.EPI_F32, out0=dh,
                out0_ld=d, block_n=bn)
         lnp = self._lnp()
+        if tag:
+            g_op = self.buf("b_g_op_in" + tag, (M, d), op)
         K.layernorm_bwd(s["x_in"], L["ln1_g"], dh, lnp, dx=g, resid=g, dx_op=g_op)
         self._ln_param_grads(lnp, d, self.g(mod.self_attn_layer_norm.weight, mod.self_attn_layer_norm.bias), accumulate)
-        self._flush()           # the layer's ten deferred reductions in one launch
+        self._flush()           # the layer's deferred reductions (bias / LayerNorm partials, split-K partials) in one launch
+        return g_op
 
     def _fusion_bwd(self, j: int, dres: torch.Tensor, gtext: torch.Tensor, B: int, T: int, accumulate: bool,
                     ln_accumulate: bool) -> None:
@@ -677,14 +708,14 @@ class TrainEngine(EncoderEngine):
         S = self.buf(f"S{j}", (B, T, Tkp), torch.float32)
         P = self.buf(f"P{j}", (B, T, Tkp), op)
         img_op = self.buf(f"img_op{j}", (B * Tk_img, dk), op)
-        da_op = self.buf("f_da_op", (M, d), op)
+        da_op = self.buf("f_da_op" + tag, (M, d), op)
         if enc.use_selective_gate:
             a_f32, a_op = self.buf("attn_f32" + tag, (M, d), torch.float32), self.buf("attn_op" + tag, (M, d), op)
             z = self.buf("f_z", (M, d), torch.float32)
             K.gemm(a0=a_op, a0_ld=d, a1=text_op, a1_ld=d, k_split=d, rows=M, w=F["wg"], n=d, k=2 * d, mode=K.EPI_F32,
                    bias=F["bg"], out0=z, out0_ld=d, block_n=bn)
-            dz = self.buf("f_dz", (M, d), op)
-            dcat = self.buf("f_dcat", (M, 2 * d), torch.float32)
+            dz = self.buf("f_dz" + tag, (M, d), op)
+            dcat = self.buf("f_dcat" + tag, (M, 2 * d), torch.float32)
             K.gate_bwd(z, dres, text_f32, a_f32, B, T, d, dz, dcat)
             # gate Linear(2d -> d) on [attn | text]: the two operand halves fill the two column blocks of dWg
             self._wgrad_mn(dz, d, [(a_op, d, d), (text_op, d, d)], M, d, self.g(*ps["wg"]), accumulate)
@@ -693,7 +724,7 @@ class TrainEngine(EncoderEngine):
                    aux0=dcat, aux_ld=2 * d, out0=dcat, out0_ld=2 * d, block_n=bn)
             da, da_ld, dtext_part, dtext_ld = dcat, 2 * d, dcat[:, d:], 2 * d
         else:   # res = text + attn
-            dflat = self.buf("f_dflat", (M, d), torch.float32)
+            dflat = self.buf("f_dflat" + tag, (M, d), torch.float32)
             K.tbc_to_btc(dres, B, T, d, dflat)
             da, da_ld, dtext_part, dtext_ld = dflat, d, dflat, d
         # ---- proj: attn = o Wp^T + bp
@@ -710,12 +741,12 @@ class TrainEngine(EncoderEngine):
         dS = self.buf("f_dS", (B, T, Tkp), op)
         K.softmax_bwd(S, dP, Tkp, M, T, Tk, dS, Tkp, drop_p=self._saved["p_sa"], seed=self._saved["drop"][2],
                       seed_dev=self._saved["drop"][3], site=SITE_SA_ATTN + 32 * j)      # (a key mask lives in S as -inf)
-        dkv = self.buf("f_dkv", (B, Tk, 2 * d), op)
+        dkv = self.buf("f_dkv" + tag, (B, Tk, 2 * d), op)
         kvg = dict(rows=Tk, a0_ld=Tkp, a0_bs=T * Tkp, a_mn=True, w_ld=d, w_bs=T * d, w_mn=True, n=d, k=T, mode=K.EPI_OP,
                    out0_ld=2 * d, out0_bs=Tk * 2 * d, **bt)
         K.gemm(a0=dS, w=q, out0=dkv, **kvg)                                                       # dK = dS^T q
         K.gemm(a0=P, w=do, out0=dkv.view(-1)[d:], **kvg)                                          # dV = P^T dO
-        dq = self.buf("f_dq", (M, d), op)
+        dq = self.buf("f_dq" + tag, (M, d), op)
         K.gemm(a0=dS, a0_ld=Tkp, a0_bs=T * Tkp, rows=T, w=kbuf, w_ld=d, w_bs=Tk * d, w_mn=True, n=d, k=Tk, mode=K.EPI_OP,
                scale=d ** -0.5, scale_cols=d, out0=dq, out0_ld=d, out0_bs=T * d, **bt)            # dq = dS k
         # ---- q projection: parameter grads + text gradient
@@ -874,13 +905,22 @@ class TrainEngine(EncoderEngine):
         K.layernorm_bwd(sv["x_final"], self.ln_g, gtext, lnp, dx=g, dx_op=g_op)
         self._ln_param_grads(lnp, d, self.g(self.enc.layer_norm.weight, self.enc.layer_norm.bias), accumulate)
         self._flush()           # fusion + final LayerNorm reductions
+        flush_every = self.wgrad_flush_layers or (3 if overlap else 0)
         if overlap:
+            self._wgrad_flush()
             self._reduce_async(*self.bucket_top)
+        pending = []
         for i in reversed(range(self.n_layers)):
             with _scope("layer"):
-                self._layer_bwd(i, g, g_op, B, T, sv["seq_lens"], accumulate)
-            if overlap:
-                self._reduce_async(*self.bucket_layers[i])
+                g_op = self._layer_bwd(i, g, g_op, B, T, sv["seq_lens"], accumulate)
+            pending.append(i)
+            if not self.grouped_wgrad or (flush_every and len(pending) >= flush_every) or i == 0:
+                with _scope("layer"):
+                    self._wgrad_flush()
+                if overlap:
+                    for j in pending:
+                        self._reduce_async(*self.bucket_layers[j])
+                pending = []
         with _scope("conv"):
             if sv["drop"][0] > 0:      # dropout after the scaled, position-added subsampler output
                 K.dropout(g, g, sv["drop"][0], sv["drop"][2], SITE_EMBED, seed_dev=sv["drop"][3])

@@ -390,6 +390,15 @@ def colsum(x, ld, rows, cols, partials, period=0, valid=0):
     return nb
 
 
+def wgrad_grouped(groups, tokens, accumulate=False):
+    global launch_count
+    launch_count += 1
+    for dy, dy_ld, x, x_ld, out, out_ld, n_out, k_in in groups:
+        g = _v(dy, (tokens, n_out), (dy_ld, 1)).float().t() @ _v(x, (tokens, k_in), (x_ld, 1)).float()
+        o = _v(out, (n_out, k_in), (out_ld, 1))
+        o.copy_(o + g if accumulate else g)
+
+
 def reduce_partials(part, n_partials, stride, n, out, accumulate=False, part_offset=0):
     s = _v(part, (n_partials, n), (stride, 1), part_offset).sum(0)
     out.view(-1)[:n] = out.view(-1)[:n] + s if accumulate else s
