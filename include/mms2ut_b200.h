@@ -325,6 +325,7 @@ typedef struct mm_wgrad_group {
   float* out;
   int64_t dy_ld, x_ld, out_ld;
   int32_t n_out, k_in;
+  float* bias;          /* optional: bias[n] (+)= sum_t dy[t, n]; k_in == 0 (x, out NULL) computes only this */
 } mm_wgrad_group;
 int mm_wgrad_grouped(const mm_wgrad_group* groups, int32_t count, int64_t tokens, int32_t accumulate, int32_t dtype,
                      void* stream);

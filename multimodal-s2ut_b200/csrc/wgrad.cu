@@ -9,6 +9,11 @@
 // tile: no partials, no reduction, one long main loop per tile (16000 tokens = 250 k-blocks) instead of a short one
 // with an exposed fp32 epilogue.  Both operands are read as stored (MN-major: memory is [token][feature]).
 //
+// Bias gradients ride along: db_g[n] = sum_t dY_g[t, n] is the same contraction against a vector of ones, so a group
+// with a bias gets one extra "bias tile" per 256 output features whose B operand is a constant 16 x 64 tile of ones in
+// shared memory (N = 16 UMMA: 1/16 of the tensor work, no W loads); the epilogue writes column 0.  These short tiles
+// are scheduled after all regular tiles.  This replaces a column-sum kernel + partial reduction per Linear layer.
+//
 // Structure = gemm.cu (persistent, warp-specialised, cta_group::2, 256 x 256 tile per CTA pair, 2 x 256 TMEM columns):
 //   warp 0 TMA producer, warp 1 MMA issuer (leader), warp 2 TMEM allocator, warps 4-7 epilogue (fp32 slabs -> TMA store;
 //   ACC: the current gradient is TMA-loaded into the slab two slabs ahead and updated in place).
@@ -24,10 +29,13 @@ struct WgMaps {
   CUtensorMap a[WG_MAX], w[WG_MAX], out[WG_MAX];
 };
 struct WgDev {
-  int count, num_tiles, num_kb, tail_steps;
-  int tile_start[WG_MAX + 1];
-  int n_tiles[WG_MAX];   // column tiles of group g
-  int n[WG_MAX];         // output columns (k_in) of group g
+  int count, num_tiles, num_reg_tiles, num_kb, tail_steps, accumulate;
+  int tile_start[WG_MAX + 1];   // regular tiles: prefix sum over groups
+  int bias_start[WG_MAX + 1];   // bias tiles (one per 256 output features of a group with a bias): prefix sum
+  int n_tiles[WG_MAX];          // column tiles of group g (0: bias only)
+  int n[WG_MAX];                // output columns (k_in) of group g
+  int n_out[WG_MAX];            // output rows (features) of group g
+  float* bias[WG_MAX];          // bias gradient [n_out] or null
 };
 
 struct WgCfg {
@@ -36,18 +44,35 @@ struct WgCfg {
   static constexpr int B_BYTES = (BN / 2) * BK * 2;
   static constexpr int SLAB_BYTES = BM * 128;
   static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int ONES_BYTES = 1024;    // 8 rows x 128 B of 16-bit ones: this CTA's half of the N = 16 bias operand
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + NB * SLAB_BYTES + BAR_BYTES + 1024;
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + NB * SLAB_BYTES + ONES_BYTES + BAR_BYTES + 1024;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
 };
 
 __device__ __forceinline__ uint4* wg_slab_chunk(uint8_t* slab, int row, int c) {
   return reinterpret_cast<uint4*>(slab + row * 128 + ((c ^ (row & 7)) << 4));
 }
 
-__device__ __forceinline__ int wg_group_of(const WgDev& p, int tile) {
+struct WgTile {
+  int g, mp, n_tile;
+  bool bias;
+};
+__device__ __forceinline__ WgTile wg_decode(const WgDev& p, int tile) {
+  WgTile t;
+  t.bias = tile >= p.num_reg_tiles;
+  const int* start = t.bias ? p.bias_start : p.tile_start;
+  const int tt = t.bias ? tile - p.num_reg_tiles : tile;
   int g = 0;
-  while (g + 1 < p.count && tile >= p.tile_start[g + 1]) ++g;
-  return g;
+  while (g + 1 < p.count && tt >= start[g + 1]) ++g;
+  t.g = g;
+  const int local = tt - start[g];
+  if (t.bias) {
+    t.mp = local, t.n_tile = 0;
+  } else {
+    t.n_tile = local % p.n_tiles[g], t.mp = local / p.n_tiles[g];
+  }
+  return t;
 }
 
 template <bool ACC, typename OpT>
@@ -60,7 +85,8 @@ wgrad_grouped_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
   uint8_t* sA = smem;
   uint8_t* sB = sA + STAGES * Cfg::A_BYTES;
   uint8_t* sSlab = sB + STAGES * Cfg::B_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sSlab + NB * Cfg::SLAB_BYTES);
+  uint8_t* sOnes = sSlab + NB * Cfg::SLAB_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + Cfg::ONES_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
@@ -85,6 +111,11 @@ wgrad_grouped_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 3) {   // the ones operand of the bias tiles (every element 1.0: any operand layout reads the same)
+    const uint32_t one2 = OpTraits<OpT>::pack2(1.0f, 1.0f);
+    for (int i = lane; i < Cfg::ONES_BYTES / 4; i += 32) reinterpret_cast<uint32_t*>(sOnes)[i] = one2;
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -97,24 +128,24 @@ wgrad_grouped_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int tile = pid; tile < p.num_tiles; tile += npairs) {
-        const int g = wg_group_of(p, tile);
-        const int local = tile - p.tile_start[g];
-        const int n_tile = local % p.n_tiles[g], mp = local / p.n_tiles[g];
-        const int row0 = mp * (2 * Cfg::BM) + rank * Cfg::BM;
-        const int wrow0 = n_tile * BN + rank * (BN / 2);
-        const CUtensorMap* mA = &maps.a[g];
-        const CUtensorMap* mW = &maps.w[g];
+        const WgTile t = wg_decode(p, tile);
+        const int row0 = t.mp * (2 * Cfg::BM) + rank * Cfg::BM;
+        const int wrow0 = t.n_tile * BN + rank * (BN / 2);
+        const CUtensorMap* mA = &maps.a[t.g];
+        const CUtensorMap* mW = &maps.w[t.g];
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          if (rank == 0) mbar_expect_tx(&full[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * (Cfg::A_BYTES + (t.bias ? 0 : Cfg::B_BYTES)));
           uint8_t* dA = sA + stage * Cfg::A_BYTES;
           uint8_t* dB = sB + stage * Cfg::B_BYTES;
           const int kc = kb * Cfg::BK;
           // MN-major operands: two 64 (features) x 64 (tokens) boxes each; tokens / features past the end are zero-filled
           tma_load_3d_2sm(dA, mA, &full[stage], row0, kc, 0);
           tma_load_3d_2sm(dA + Cfg::A_BYTES / 2, mA, &full[stage], row0 + 64, kc, 0);
-          tma_load_3d_2sm(dB, mW, &full[stage], wrow0, kc, 0);
-          tma_load_3d_2sm(dB + Cfg::B_BYTES / 2, mW, &full[stage], wrow0 + 64, kc, 0);
+          if (!t.bias) {
+            tma_load_3d_2sm(dB, mW, &full[stage], wrow0, kc, 0);
+            tma_load_3d_2sm(dB + Cfg::B_BYTES / 2, mW, &full[stage], wrow0 + 64, kc, 0);
+          }
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
       }
@@ -123,8 +154,11 @@ wgrad_grouped_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
     // ===================== MMA issuer (leader CTA only) =====================
     if (rank == 0 && lane == 0) {
       const uint32_t idesc = umma_idesc(2 * Cfg::BM, BN, OpTraits<OpT>::fmt) | (1u << 15) | (1u << 16);   // A, B MN-major
+      const uint32_t idesc_bias = umma_idesc(2 * Cfg::BM, 16, OpTraits<OpT>::fmt) | (1u << 15);           // B = ones, N = 16
+      const uint64_t ones_desc = umma_desc_sw128(smem_u32(sOnes));
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       for (int tile = pid; tile < p.num_tiles; tile += npairs) {
+        const bool bias = tile >= p.num_reg_tiles;
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
@@ -134,8 +168,13 @@ wgrad_grouped_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
           const uint64_t adesc = umma_desc_sw128_mn(smem_u32(sA + stage * Cfg::A_BYTES), Cfg::A_BYTES / 2);
           const uint64_t bdesc = umma_desc_sw128_mn(smem_u32(sB + stage * Cfg::B_BYTES), Cfg::B_BYTES / 2);
           const int steps = (kb == p.num_kb - 1) ? p.tail_steps : 4;
-          for (int kk = 0; kk < steps; ++kk)
-            umma_f16_2sm(tmem_d, adesc + 128ull * kk, bdesc + 128ull * kk, idesc, (kb | kk) != 0);
+          if (bias) {
+            for (int kk = 0; kk < steps; ++kk)
+              umma_f16_2sm(tmem_d, adesc + 128ull * kk, ones_desc + 2ull * kk, idesc_bias, (kb | kk) != 0);
+          } else {
+            for (int kk = 0; kk < steps; ++kk)
+              umma_f16_2sm(tmem_d, adesc + 128ull * kk, bdesc + 128ull * kk, idesc, (kb | kk) != 0);
+          }
           umma_commit_2sm(&empty[stage], 3);
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
@@ -149,12 +188,35 @@ wgrad_grouped_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
     const uint32_t tempty_leader = mapa_u32(&tempty[0], 0);
     uint32_t as = 0, aphase = 0, slab_ctr = 0, aux_phase = 0;
     for (int tile = pid; tile < p.num_tiles; tile += npairs) {
-      const int g = wg_group_of(p, tile);
-      const int local = tile - p.tile_start[g];
-      const int n_tile = local % p.n_tiles[g], mp = local / p.n_tiles[g];
-      const int row0 = mp * (2 * Cfg::BM) + rank * Cfg::BM;
-      const int col_tile = n_tile * BN, ncols = p.n[g];
+      const WgTile t = wg_decode(p, tile);
+      const int g = t.g;
+      const int row0 = t.mp * (2 * Cfg::BM) + rank * Cfg::BM;
+      const int col_tile = t.n_tile * BN, ncols = p.n[g];
       const CUtensorMap* mO = &maps.out[g];
+      if (t.bias) {
+        // column 0 of the N = 16 accumulator = sum over tokens of this thread's output feature
+        mbar_wait(&tfull[as], aphase);
+        tc_fence_after();
+        uint32_t rz[32];
+        tmem_ld32(tmem_base + as * BN + (static_cast<uint32_t>(ew * 32) << 16), rz);
+        tmem_ld_wait();
+        const int r = row0 + lrow;
+        if (r < p.n_out[g]) {
+          float* dst = p.bias[g] + r;
+          const float v = __uint_as_float(rz[0]);
+          *dst = ACC ? *dst + v : v;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0)
+            mbar_arrive(&tempty[as]);
+          else
+            mbar_arrive_cluster(tempty_leader + as * 8);
+        }
+        if (++as == 2) as = 0, aphase ^= 1;
+        continue;
+      }
       if constexpr (ACC) {
         if (et == 0) {   // gradient slabs 0 and 1 of this tile: buffers last used 4 and 3 slabs ago
           bulk_wait_read<2>();
@@ -287,27 +349,40 @@ extern "C" int mm_wgrad_grouped(const mm_wgrad_group* groups, int32_t count, int
   WgDev p;
   memset(&p, 0, sizeof(p));
   p.count = count;
+  p.accumulate = accumulate != 0;
   p.num_kb = (int)((tokens + 63) / 64);
   p.tail_steps = (int)((tokens - (int64_t)(p.num_kb - 1) * 64 + 15) >> 4);
-  int tiles = 0;
+  int tiles = 0, btiles = 0;
   for (int g = 0; g < count; ++g) {
     const mm_wgrad_group& q = groups[g];
-    if (!q.dy || !q.x || !q.out || q.n_out <= 0 || q.k_in <= 0) return bad_arg("wgrad_grouped: group");
+    if (!q.dy || q.n_out <= 0 || q.k_in < 0) return bad_arg("wgrad_grouped: group");
+    if (q.k_in > 0 && (!q.x || !q.out)) return bad_arg("wgrad_grouped: group with k_in > 0 needs x and out");
+    if (q.k_in == 0 && !q.bias) return bad_arg("wgrad_grouped: group computes nothing");
     if (q.k_in % 4) return bad_arg("wgrad_grouped: k_in must be a multiple of 4");
     int rc = make_tmap_3d_ex(&m.a[g], q.dy, kind, (uint64_t)q.n_out, (uint64_t)tokens, 1, (uint64_t)q.dy_ld, 0, 64, 64);
     if (rc) return rc;
-    rc = make_tmap_3d_ex(&m.w[g], q.x, kind, (uint64_t)q.k_in, (uint64_t)tokens, 1, (uint64_t)q.x_ld, 0, 64, 64);
-    if (rc) return rc;
-    rc = make_tmap_3d_ex(&m.out[g], q.out, 2, (uint64_t)q.k_in, (uint64_t)q.n_out, 1, (uint64_t)q.out_ld, 0, 32, 128);
-    if (rc) return rc;
+    if (q.k_in > 0) {
+      rc = make_tmap_3d_ex(&m.w[g], q.x, kind, (uint64_t)q.k_in, (uint64_t)tokens, 1, (uint64_t)q.x_ld, 0, 64, 64);
+      if (rc) return rc;
+      rc = make_tmap_3d_ex(&m.out[g], q.out, 2, (uint64_t)q.k_in, (uint64_t)q.n_out, 1, (uint64_t)q.out_ld, 0, 32, 128);
+      if (rc) return rc;
+    } else {
+      m.w[g] = m.a[g], m.out[g] = m.a[g];   // never used
+    }
+    const int m_pairs = (q.n_out + 255) / 256;
     p.tile_start[g] = tiles;
+    p.bias_start[g] = btiles;
     p.n_tiles[g] = (q.k_in + 255) / 256;
     p.n[g] = q.k_in;
-    tiles += ((q.n_out + 255) / 256) * p.n_tiles[g];
+    p.n_out[g] = q.n_out;
+    p.bias[g] = q.bias;
+    tiles += m_pairs * p.n_tiles[g];
+    if (q.bias) btiles += m_pairs;
   }
-  for (int g = count; g <= WG_MAX; ++g) p.tile_start[g] = tiles;
+  for (int g = count; g <= WG_MAX; ++g) p.tile_start[g] = tiles, p.bias_start[g] = btiles;
   for (int g = count; g < WG_MAX; ++g) m.a[g] = m.a[0], m.w[g] = m.w[0], m.out[g] = m.out[0];
-  p.num_tiles = tiles;
+  p.num_reg_tiles = tiles;
+  p.num_tiles = tiles + btiles;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (accumulate)
     return kind ? launch_wgrad<true, __half>(m, p, s) : launch_wgrad<true, __nv_bfloat16>(m, p, s);

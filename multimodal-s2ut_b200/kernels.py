@@ -436,8 +436,9 @@ def reduce_partials_many(jobs) -> None:
 
 
 def wgrad_grouped(groups, tokens: int, accumulate: bool = False) -> None:
-    """groups: list of (dy [tokens, n_out] 16-bit, dy_ld, x [tokens, k_in] 16-bit, x_ld, out fp32, out_ld, n_out, k_in):
-    out[n, k] (+)= sum_t dy[t, n] x[t, k] for every group in one launch (``mm_wgrad_grouped``: the groups' output tiles
+    """groups: list of (dy [tokens, n_out] 16-bit, dy_ld, x [tokens, k_in] 16-bit, x_ld, out fp32, out_ld, n_out, k_in,
+    bias fp32 [n_out] or None): out[n, k] (+)= sum_t dy[t, n] x[t, k] and bias[n] (+)= sum_t dy[t, n] (x = out = None,
+    k_in = 0: the bias only) for every group in one launch (``mm_wgrad_grouped``: the groups' output tiles
     share the persistent grid, full token contraction per tile, no partials); out_ld = row stride of out (a column
     block of a wider gradient is out = wide.view(-1)[col:], out_ld = wide row length)."""
     lib = _lib.load()
@@ -445,11 +446,14 @@ def wgrad_grouped(groups, tokens: int, accumulate: bool = False) -> None:
         chunk = groups[base:base + _lib.WGRAD_MAX_GROUPS]
         arr = (_lib.WgradGroup * len(chunk))()
         work = 0.0
-        for a, (dy, dy_ld, x, x_ld, out, out_ld, n_out, k_in) in zip(arr, chunk):
-            if dy.dtype != x.dtype or out.dtype != torch.float32:
-                raise TypeError("wgrad_grouped: dy / x share the 16-bit operand dtype, out is float32")
-            assert out.numel() >= (n_out - 1) * out_ld + k_in
-            a.dy, a.x, a.out = _ptr(dy), _ptr(x), _ptr(out)
+        for a, (dy, dy_ld, x, x_ld, out, out_ld, n_out, k_in, bias) in zip(arr, chunk):
+            if k_in > 0:
+                if dy.dtype != x.dtype or out.dtype != torch.float32:
+                    raise TypeError("wgrad_grouped: dy / x share the 16-bit operand dtype, out is float32")
+                assert out.numel() >= (n_out - 1) * out_ld + k_in
+            if bias is not None:
+                assert bias.dtype == torch.float32 and bias.numel() >= n_out
+            a.dy, a.x, a.out, a.bias = _ptr(dy), _ptr(x), _ptr(out), _ptr(bias)
             a.dy_ld, a.x_ld, a.out_ld, a.n_out, a.k_in = dy_ld, x_ld, out_ld, n_out, k_in
             work += 2.0 * tokens * n_out * k_in
         with _Launch("wgrad_grouped", work):

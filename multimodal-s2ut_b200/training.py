@@ -550,7 +550,8 @@ class TrainEngine(EncoderEngine):
                block_n=self.block_n)
         K.reduce_partials(part, S, n * kin, n * kin, out, accumulate)
 
-    def _wgrad_mn(self, dy_op: torch.Tensor, dy_ld: int, x_ops, M: int, n: int, gw: torch.Tensor, accumulate: bool) -> None:
+    def _wgrad_mn(self, dy_op: torch.Tensor, dy_ld: int, x_ops, M: int, n: int, gw: torch.Tensor, accumulate: bool,
+                  gb: Optional[torch.Tensor] = None) -> None:
         """gw [n, sum kin] (+)= dy^T [x_0 | x_1 | ...]: both operands read as stored (MN-major), the token contraction
         split into S batches; x_ops = [(tensor [M, kin], ld, kin), ...] fill consecutive column blocks of gw."""
         kin_all = sum(x[2] for x in x_ops)
@@ -559,10 +560,11 @@ class TrainEngine(EncoderEngine):
             # gradient buffers in this mode)
             q = self.__dict__.setdefault("_wq", {}).setdefault((M, bool(accumulate)), [])
             col = 0
-            for x, x_ld, kin in x_ops:
-                q.append((dy_op, dy_ld, x, x_ld, gw.view(-1)[col:], kin_all, n, kin))
+            for x, x_ld, kin in x_ops:     # gb: the bias gradient (column sums of dy) rides along with the first operand
+                q.append((dy_op, dy_ld, x, x_ld, gw.view(-1)[col:], kin_all, n, kin, gb if col == 0 else None))
                 col += kin
             return
+        assert gb is None
         tiles = ((n + 255) // 256) * sum((x[2] + 255) // 256 for x in x_ops)
         S = _best_split(tiles, M)
         chunk = _round_up((M + S - 1) // S, 64)
@@ -584,6 +586,10 @@ class TrainEngine(EncoderEngine):
 
     def _bias_grad(self, dy_op: torch.Tensor, dy_ld: int, M: int, n: int, gb: torch.Tensor, accumulate: bool,
                    period: int = 0, valid: int = 0) -> None:
+        if getattr(self, "grouped_wgrad", False) and period == 0:
+            q = self.__dict__.setdefault("_wq", {}).setdefault((M, bool(accumulate)), [])
+            q.append((dy_op, dy_ld, None, 0, None, 0, n, 0, gb))
+            return
         part = self._partials(K.colsum_blocks(M) * n)
         nb = K.colsum(dy_op, dy_ld, M, n, part, period, valid)
         self._defer(part, nb, n, n, gb, accumulate)
@@ -591,6 +597,9 @@ class TrainEngine(EncoderEngine):
     def _linear_bwd(self, dy_op: torch.Tensor, dy_ld: int, x_op: torch.Tensor, M: int, n: int, kin: int,
                     gw: torch.Tensor, gb: Optional[torch.Tensor], accumulate: bool) -> None:
         """Parameter gradients of y = x W^T + b from the 16-bit dy [M, n] and x [M, kin]."""
+        if getattr(self, "grouped_wgrad", False):
+            self._wgrad_mn(dy_op, dy_ld, [(x_op, x_op.stride(0), kin)], M, n, gw, accumulate, gb)
+            return
         self._wgrad_mn(dy_op, dy_ld, [(x_op, x_op.stride(0), kin)], M, n, gw, accumulate)
         if gb is not None:
             self._bias_grad(dy_op, dy_ld, M, n, gb, accumulate)

@@ -393,10 +393,15 @@ def colsum(x, ld, rows, cols, partials, period=0, valid=0):
 def wgrad_grouped(groups, tokens, accumulate=False):
     global launch_count
     launch_count += 1
-    for dy, dy_ld, x, x_ld, out, out_ld, n_out, k_in in groups:
-        g = _v(dy, (tokens, n_out), (dy_ld, 1)).float().t() @ _v(x, (tokens, k_in), (x_ld, 1)).float()
-        o = _v(out, (n_out, k_in), (out_ld, 1))
-        o.copy_(o + g if accumulate else g)
+    for dy, dy_ld, x, x_ld, out, out_ld, n_out, k_in, bias in groups:
+        dyf = _v(dy, (tokens, n_out), (dy_ld, 1)).float()
+        if k_in > 0:
+            g = dyf.t() @ _v(x, (tokens, k_in), (x_ld, 1)).float()
+            o = _v(out, (n_out, k_in), (out_ld, 1))
+            o.copy_(o + g if accumulate else g)
+        if bias is not None:
+            b = bias.view(-1)[:n_out]
+            b.copy_(b + dyf.sum(0) if accumulate else dyf.sum(0))
 
 
 def reduce_partials(part, n_partials, stride, n, out, accumulate=False, part_offset=0):

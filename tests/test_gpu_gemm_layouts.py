@@ -133,24 +133,35 @@ def test_grouped_weight_gradients(cuda, tokens, accumulate):
     + ragged extents."""
     from mm_s2ut_b200 import kernels as K
 
-    shapes = [(1536, 512), (512, 512), (2048, 512), (512, 2048), (304, 72), (512, 768)]
+    shapes = [(1536, 512), (512, 512), (2048, 512), (512, 2048), (304, 72), (512, 768), (1000, 0)]
     gen = torch.Generator().manual_seed(5)
     groups, refs, outs = [], [], []
     for gi, (n_out, k_in) in enumerate(shapes):
         ld_dy = n_out + (8 if gi == 4 else 0)                 # a strided gradient (column block of a wider tensor)
         dy = (torch.randn(tokens, ld_dy, generator=gen) * 0.5).bfloat16().cuda()
+        bias = torch.full((n_out,), 0.25, device=cuda) if gi != 1 else None
+        if k_in == 0:                                          # a bias-only group
+            groups.append((dy, ld_dy, None, 0, None, 0, n_out, 0, bias))
+            refs.append(None)
+            outs.append((None, 0, 0, bias, dy[:, :n_out].float().sum(0)))
+            continue
         x = torch.randn(tokens, k_in, generator=gen).bfloat16().cuda()
         wide = 2 * k_in if gi == 1 else k_in                   # group 1 fills the second column block of a [n, 2k] gradient
         out = torch.full((n_out, wide), 0.25, device=cuda)
         col = k_in if gi == 1 else 0
-        groups.append((dy, ld_dy, x, k_in, out.view(-1)[col:], wide, n_out, k_in))
+        groups.append((dy, ld_dy, x, k_in, out.view(-1)[col:], wide, n_out, k_in, bias))
         refs.append(dy[:, :n_out].float().t() @ x.float())
-        outs.append((out, col, k_in))
+        outs.append((out, col, k_in, bias, dy[:, :n_out].float().sum(0)))
     K.wgrad_grouped(groups, tokens, accumulate)
     torch.cuda.synchronize()
-    for (out, col, k_in), ref in zip(outs, refs):
-        got = out[:, col:col + k_in] - (0.25 if accumulate else 0.0)
-        err = (got - ref).abs().max().item()
-        assert err <= 2e-3 * max(1.0, ref.abs().max().item()) + (1e-3 if accumulate else 0), err
-        if col:                                                # the other column block is untouched
-            assert torch.equal(out[:, :col], torch.full_like(out[:, :col], 0.25))
+    base = 0.25 if accumulate else 0.0
+    for (out, col, k_in, bias, bref), ref in zip(outs, refs):
+        if out is not None:
+            got = out[:, col:col + k_in] - base
+            err = (got - ref).abs().max().item()
+            assert err <= 2e-3 * max(1.0, ref.abs().max().item()) + (1e-3 if accumulate else 0), err
+            if col:                                            # the other column block is untouched
+                assert torch.equal(out[:, :col], torch.full_like(out[:, :col], 0.25))
+        if bias is not None:
+            err = (bias - base - bref).abs().max().item()
+            assert err <= 2e-3 * max(1.0, bref.abs().max().item()), err
