@@ -320,7 +320,7 @@ def train_step_probe(ctx, wav, img, steps=20, warmup=3, model_step=True):
     e1.record()
     torch.cuda.synchronize()
     ms = ctx.max_over_ranks(e0.elapsed_time(e1) / steps)
-    # the exchange alone: the same bucketed all-reduce of the flat gradient, timed by itself
+    # the exchange alone: the same all-reduce of the flat gradient, timed by itself
     ar_ms = None
     if world > 1:
         ctx.barrier()
@@ -338,8 +338,8 @@ def train_step_probe(ctx, wav, img, steps=20, warmup=3, model_step=True):
            "launches_per_step_approx": launches // 2, "params": int(gs.eng.flat_p.numel()), "grad_norm_last": norm,
            "allreduce_ms": ar_ms, "allreduce_bytes": gbytes if world > 1 else 0,
            "allreduce_busbw_gbs": (2 * (world - 1) / world * gbytes / (ar_ms * 1e-3) / 1e9) if ar_ms else None,
-           "collective": ("NCCL all-reduce of the flat fp32 gradient (%d MB) in 32 MB buckets between the backward and "
-                          "the optimizer graphs" % (gbytes >> 20)) if world > 1 else "none (1 GPU)",
+           "collective": ("one NCCL all-reduce of the flat fp32 gradient (%d MB) between the backward and the "
+                          "optimizer graphs" % (gbytes >> 20)) if world > 1 else "none (1 GPU)",
            "what": "BASELINE configs[2]: forward (activations kept) + backward of every encoder/fusion/conv parameter + "
                    "gradient all-reduce + fairseq Adam with clip-norm, batch 64 x 10 s per GPU, modality dropout 0.5 "
                    "(image-drop branch), synthetic d loss/d encoder_out; element-wise dropout off"}

@@ -311,6 +311,17 @@ int mm_rowsum(const void* in, int64_t ld, int32_t rows, int32_t cols, float* out
 int mm_reduce_partials(const float* part, int32_t n_partials, int64_t stride, int64_t n, float* out, int32_t accumulate,
                        void* stream);
 /* Several mm_reduce_partials in one launch (the backward pass defers a layer's reductions and runs them together). */
+/* Attention backward, output side (autograd of fairseq's MultiheadAttention: dV = P^T dO, dK = dS^T q, dQ = dS k): per
+ * sequence b and head h (head_dim 64)
+ *     out[b][r][out_col0 + 64 h + c] = scale * sum_j A_bh[r, j] * w[b][j][w_col0 + 64 h + c]      r < rows, j < k
+ * a holds the [rows, k] matrices of all (b, h) as mm_attention_bwd_scores wrote them: a_transposed == 0: element
+ * (r, j) at a[bh * a_bs + r * a_ld + j]; != 0: at a[bh * a_bs + j * a_ld + r] (P^T, dS^T without a transposed copy).
+ * w [batch][k tokens][w_ld] and out [batch][rows][out_ld] are token-major tensors with the heads' 64-wide column blocks
+ * starting at *_col0 (q | k | v and their gradient), *_bs elements between sequences.  16-bit in and out. */
+int mm_heads_gemm(const void* a, int64_t a_ld, int64_t a_bs, int32_t a_transposed, const void* w, int64_t w_ld,
+                  int64_t w_bs, int32_t w_col0, void* out, int64_t out_ld, int64_t out_bs, int32_t out_col0,
+                  int32_t rows, int32_t k, int32_t batch, int32_t heads, float scale, int32_t dtype, void* stream);
+
 /* Grouped weight gradient (autograd of nn.Linear inside fairseq's TransformerEncoderLayer / MultiheadAttention under
  * `loss.backward()`, scripts/textless/1_train.sh): for every group g
  *     out_g[n, k] (+)= sum_t dy_g[t, n] * x_g[t, k]        t = 0 .. tokens-1, fp32 accumulation, fp32 output

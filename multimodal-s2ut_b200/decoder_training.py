@@ -60,6 +60,7 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
     _wgrad_mn = TrainEngine._wgrad_mn
     _wgrad_flush = TrainEngine._wgrad_flush
     grouped_wgrad = os.environ.get("MM_GROUPED_WGRAD", "1") != "0"     # see TrainEngine.grouped_wgrad
+    heads_gemm = os.environ.get("MM_HEADS_GEMM", "1") != "0"
     _bias_grad = TrainEngine._bias_grad
     _linear_bwd = TrainEngine._linear_bwd
     _ln_param_grads = TrainEngine._ln_param_grads
@@ -320,6 +321,15 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
             K.gemm(a0=dO, a0_ld=d, a0_bs=Lq * d, w=v, w_ld=kv_ld, w_bs=kv_bs, out0=dP, mode=K.EPI_OP, **sc)
             K.softmax_bwd(S, dP, Tp, BH * Lp, Lp, Tk, dS, Tp, probs=P, kv_lens=kv_lens, heads=H, valid_rows=Lq,
                           causal=causal, drop_p=p_attn, seed=seed, seed_dev=seed_dev, site=site)
+        if self.heads_gemm:     # 128 x 64 tiles per (sequence, head): no wasted columns (see TrainEngine.heads_gemm)
+            hg = dict(a_ld=Tp, a_bs=Lp * Tp, batch=B, heads=H)
+            K.heads_gemm(P, transposed=True, w=dO, w_ld=d, w_bs=Lq * d, out=dv, out_ld=dkv_ld, out_bs=dkv_bs, rows=Tk,
+                         k=Lq, **hg)
+            K.heads_gemm(dS, transposed=True, w=q, w_ld=q_ld, w_bs=q_bs, out=dk, out_ld=dkv_ld, out_bs=dkv_bs, rows=Tk,
+                         k=Lq, **hg)
+            K.heads_gemm(dS, transposed=False, w=k, w_ld=kv_ld, w_bs=kv_bs, out=dq, out_ld=q_ld, out_bs=q_bs, rows=Lq,
+                         k=Tk, scale=64 ** -0.5, **hg)
+            return
         og = dict(n=64, mode=K.EPI_OP, out_hm=True, w_mn=True, w_hm=True, a0_ld=Tp, a0_bs=Lp * Tp, **hd)
         K.gemm(a0=P, a_mn=True, rows=Tk, k=Lq, w=dO, w_ld=d, w_bs=Lq * d, out0=dv, out0_ld=dkv_ld, out0_bs=dkv_bs, **og)
         K.gemm(a0=dS, a_mn=True, rows=Tk, k=Lq, w=q, w_ld=q_ld, w_bs=q_bs, out0=dk, out0_ld=dkv_ld, out0_bs=dkv_bs, **og)

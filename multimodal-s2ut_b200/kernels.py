@@ -435,6 +435,21 @@ def reduce_partials_many(jobs) -> None:
         _lib.check(lib.mm_reduce_partials_many(arr, len(jobs), _stream()), "mm_reduce_partials_many")
 
 
+def heads_gemm(a: torch.Tensor, a_ld: int, a_bs: int, transposed: bool, w: torch.Tensor, w_ld: int, w_bs: int,
+               out: torch.Tensor, out_ld: int, out_bs: int, rows: int, k: int, batch: int, heads: int,
+               scale: float = 1.0) -> None:
+    """Per (sequence, head), head_dim 64: out[b][r][64 h + c] = scale * sum_j A_bh[r, j] w[b][j][64 h + c] with A_bh the
+    [rows, k] matrix number b * heads + h of ``a`` (read transposed when ``transposed``); w / out are (views of)
+    token-major tensors whose first column is head 0's (``mm_heads_gemm``: dV = P^T dO, dK = dS^T q, dQ = dS k)."""
+    if not (a.dtype == w.dtype == out.dtype):
+        raise TypeError("heads_gemm: a, w and out share the 16-bit operand dtype")
+    lib = _lib.load()
+    with _Launch("heads_gemm", 2.0 * batch * heads * rows * k * 64):
+        _lib.check(lib.mm_heads_gemm(_ptr(a), a_ld, a_bs, int(transposed), _ptr(w), w_ld, w_bs, 0, _ptr(out), out_ld,
+                                     out_bs, 0, rows, k, batch, heads, scale, dtype_code(w.dtype), _stream()),
+                   "mm_heads_gemm")
+
+
 def wgrad_grouped(groups, tokens: int, accumulate: bool = False) -> None:
     """groups: list of (dy [tokens, n_out] 16-bit, dy_ld, x [tokens, k_in] 16-bit, x_ld, out fp32, out_ld, n_out, k_in,
     bias fp32 [n_out] or None): out[n, k] (+)= sum_t dy[t, n] x[t, k] and bias[n] (+)= sum_t dy[t, n] (x = out = None,

@@ -92,12 +92,16 @@ class _scope:
         return False
 
 
-def all_reduce_flat(flat: torch.Tensor, bucket_elems: int = 8 * 1024 * 1024) -> int:
-    """Bucketed asynchronous SUM all-reduce of a flat gradient buffer over the default process group."""
+def all_reduce_flat(flat: torch.Tensor, bucket_elems: int = 0) -> int:
+    """SUM all-reduce of a flat gradient buffer over the default process group: ONE collective by default (nothing
+    overlaps it here, and on NVLink one 162 MB NCCL call takes 0.35 ms where five 32 MB buckets take 0.45:
+    profiles/r02/allreduce_probe_n2.txt); bucket_elems > 0 issues asynchronous buckets of that many elements."""
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return 1
+    if bucket_elems <= 0:
+        bucket_elems = max(1, flat.numel())
     works = [dist.all_reduce(flat[o:o + bucket_elems], op=dist.ReduceOp.SUM, async_op=True)
              for o in range(0, flat.numel(), bucket_elems)]
     for wk in works:
@@ -149,6 +153,8 @@ class TrainEngine(EncoderEngine):
         # GEMM per gradient + deferred partial reduction.  wgrad_flush_layers > 0 flushes every that many layers instead
         # (bucketed gradient all-reduce overlapping the backward pass needs complete layers early).
         self.grouped_wgrad = os.environ.get("MM_GROUPED_WGRAD", "1") != "0"
+        # dV / dK / dQ of attention backward on the 128 x 64-tile kernel (mm_heads_gemm); off: mm_gemm's 256-wide tiles
+        self.heads_gemm = os.environ.get("MM_HEADS_GEMM", "1") != "0"
         self.wgrad_flush_layers = 0
         self._saved = None
         self.generation = 0            # advanced by every forward_train: ties an autograd node to ITS saved activations
@@ -616,8 +622,8 @@ class TrainEngine(EncoderEngine):
         contractions read q|k|v / datt and write dqkv in place of their (sequence, head) column blocks."""
         d, H, op, bn = self.d, self.heads, self.op_dtype, self.block_n
         Tp = _round_up(T, 64)
-        BH = B * H
         qkv = s["qkv"]
+        BH = B * H
         hd = dict(heads=H, head_stride=64, batches=BH, w_batched=True, block_n=bn)
         P = self.buf("a_P", (BH, Tp, Tp), op)
         dS = self.buf("a_dS", (BH, Tp, Tp), op)
@@ -633,6 +639,13 @@ class TrainEngine(EncoderEngine):
             _, _, seed, seed_dev = self._saved["drop"]
             K.softmax_bwd(S, dP, Tp, BH * Tp, Tp, T, dS, Tp, probs=P, kv_lens=seq_lens, heads=H, valid_rows=T,
                           drop_p=self._saved["p_attn"], seed=seed, seed_dev=seed_dev, site=site_layer(layer_index, 3))
+        if self.heads_gemm:     # 128 x 64 tiles per (sequence, head): no wasted columns
+            hg = dict(a_ld=Tp, a_bs=Tp * Tp, out_ld=3 * d, out_bs=T * 3 * d, rows=T, k=T, batch=B, heads=H)
+            K.heads_gemm(P, transposed=True, w=datt, w_ld=d, w_bs=T * d, out=dqkv[:, 2 * d:], **hg)             # dV = P^T dO
+            K.heads_gemm(dS, transposed=True, w=qkv, w_ld=3 * d, w_bs=T * 3 * d, out=dqkv[:, d:], **hg)         # dK = dS^T q
+            K.heads_gemm(dS, transposed=False, w=qkv[:, d:], w_ld=3 * d, w_bs=T * 3 * d, out=dqkv,               # dQ = dS k
+                         scale=64 ** -0.5, **hg)
+            return
         og = dict(rows=T, n=64, k=T, mode=K.EPI_OP, out0_ld=3 * d, out0_bs=T * 3 * d, out_hm=True, w_mn=True, w_hm=True,
                   a0_ld=Tp, a0_bs=Tp * Tp, **hd)
         K.gemm(a0=P, a_mn=True, w=datt, w_ld=d, w_bs=T * d, out0=dqkv[:, 2 * d:], **og)          # dV = P^T dO
@@ -942,8 +955,8 @@ class TrainEngine(EncoderEngine):
     # ------------------------------------------------------------------------------------------
     # gradient exchange + optimizer
     # ------------------------------------------------------------------------------------------
-    def all_reduce_grads(self, bucket_elems: int = 8 * 1024 * 1024) -> int:
-        """Sum ``flat_g`` over the ranks of the default process group, in buckets (async, then waited); returns the
+    def all_reduce_grads(self, bucket_elems: int = 0) -> int:
+        """Sum ``flat_g`` over the ranks of the default process group (one collective; buckets on request); returns the
         world size (fairseq then multiplies the gradients by world_size / sample_size: pass that as ``grad_scale`` to
         ``adam_step``).  The only collective of the path: NCCL over NVLink on the GPU box, gloo in
         the CPU tests (``all_reduce_flat``).  A no-op when ``backward(overlap_reduce=True)`` already reduced them."""

@@ -390,6 +390,16 @@ def colsum(x, ld, rows, cols, partials, period=0, valid=0):
     return nb
 
 
+def heads_gemm(a, a_ld, a_bs, transposed, w, w_ld, w_bs, out, out_ld, out_bs, rows, k, batch, heads, scale=1.0):
+    global launch_count
+    launch_count += 1
+    BH = batch * heads
+    A = (_v(a, (BH, k, rows), (a_bs, a_ld, 1)).transpose(1, 2) if transposed else _v(a, (BH, rows, k), (a_bs, a_ld, 1)))
+    W = _v(w, (batch, heads, k, 64), (w_bs, 64, w_ld, 1)).float().reshape(BH, k, 64)
+    o = (A.float() @ W * scale).view(batch, heads, rows, 64)
+    _v(out, (batch, heads, rows, 64), (out_bs, 64, out_ld, 1)).copy_(o.to(out.dtype))
+
+
 def wgrad_grouped(groups, tokens, accumulate=False):
     global launch_count
     launch_count += 1

@@ -165,3 +165,37 @@ def test_grouped_weight_gradients(cuda, tokens, accumulate):
         if bias is not None:
             err = (bias - base - bref).abs().max().item()
             assert err <= 2e-3 * max(1.0, bref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("B,H,Lq,Tk", [(3, 4, 50, 50), (2, 8, 250, 250), (2, 2, 500, 250), (1, 4, 130, 577)])
+def test_heads_gemm_attention_backward_outputs(cuda, B, H, Lq, Tk):
+    """mm_heads_gemm: dV = P^T dO, dK = dS^T q, dQ = dS k * 1/8 per (sequence, head) straight from / into the token-major
+    q | k | v layouts, on 128 x 64 tiles (autograd of fairseq MultiheadAttention; same contractions as
+    test_attention_backward_gemms_head_mode runs on mm_gemm)."""
+    from mm_s2ut_b200 import kernels as K
+
+    d = 64 * H
+    Lp, Tp = (Lq + 63) // 64 * 64, (Tk + 63) // 64 * 64
+    q = _rnd(B * Lq, d, seed=31)
+    kv = _rnd(B * Tk, 2 * d, seed=32)
+    dO = _rnd(B * Lq, d, seed=33)
+    P = torch.full((B * H, Lp, Tp), float("nan"), dtype=torch.bfloat16, device=cuda)      # padding is never read
+    dS = torch.full((B * H, Lp, Tp), float("nan"), dtype=torch.bfloat16, device=cuda)
+    P[:, :Lq, :Tk] = _rnd(B * H, Lq, Tk, seed=34) * 0.1
+    dS[:, :Lq, :Tk] = _rnd(B * H, Lq, Tk, seed=35) * 0.1
+    dq = torch.full((B * Lq, d), float("nan"), dtype=torch.bfloat16, device=cuda)
+    dkv = torch.full((B * Tk, 2 * d), float("nan"), dtype=torch.bfloat16, device=cuda)
+    hg = dict(a_ld=Tp, a_bs=Lp * Tp, batch=B, heads=H)
+    K.heads_gemm(P, transposed=True, w=dO, w_ld=d, w_bs=Lq * d, out=dkv[:, d:], out_ld=2 * d, out_bs=Tk * 2 * d, rows=Tk,
+                 k=Lq, **hg)
+    K.heads_gemm(dS, transposed=True, w=q, w_ld=d, w_bs=Lq * d, out=dkv, out_ld=2 * d, out_bs=Tk * 2 * d, rows=Tk, k=Lq,
+                 **hg)
+    K.heads_gemm(dS, transposed=False, w=kv, w_ld=2 * d, w_bs=Tk * 2 * d, out=dq, out_ld=d, out_bs=Lq * d, rows=Lq, k=Tk,
+                 scale=0.125, **hg)
+    heads = lambda x, L: x.float().view(B, L, H, 64).permute(0, 2, 1, 3)            # [B, H, L, 64]
+    back = lambda x, L: x.permute(0, 2, 1, 3).reshape(B * L, d)
+    Pf = P[:, :Lq, :Tk].float().view(B, H, Lq, Tk)
+    dSf = dS[:, :Lq, :Tk].float().view(B, H, Lq, Tk)
+    _close(dkv[:, d:], back(Pf.transpose(-1, -2) @ heads(dO, Lq), Tk), 2e-2)
+    _close(dkv[:, :d], back(dSf.transpose(-1, -2) @ heads(q, Lq), Tk), 2e-2)
+    _close(dq, back(dSf @ heads(kv[:, :d], Tk), Lq) * 0.125, 2e-2)
