@@ -311,6 +311,18 @@ int mm_rowsum(const void* in, int64_t ld, int32_t rows, int32_t cols, float* out
 int mm_reduce_partials(const float* part, int32_t n_partials, int64_t stride, int64_t n, float* out, int32_t accumulate,
                        void* stream);
 /* Several mm_reduce_partials in one launch (the backward pass defers a layer's reductions and runs them together). */
+/* Attention backward in one kernel for self-attention over sequences of up to 256 positions (the encoder at 10 s
+ * utterances): dq | dk | dv from q | k | v, dO, O and lse with S, dP, P and dS never leaving the SM (TMEM / shared
+ * memory).  qkv [batch * seq_len, qkv_ld] and dqkv [batch * seq_len, dqkv_ld] hold the heads' 64-wide column blocks of
+ * q, k, v (and their gradients) at q_col0 / k_col0 / v_col0; q pre-scaled by head_dim^-0.5 and dq scaled likewise, as
+ * in mm_attention_bwd_scores + mm_heads_gemm, which this replaces when seq_len <= 256.  kv_lens: valid keys per
+ * sequence or NULL; dout / out: gradient and forward result of the attention output [batch * seq_len, heads * 64]; lse
+ * [batch][heads][seq_len] from mm_self_attention_lse. */
+int mm_attention_bwd_fused(const void* qkv, int64_t qkv_ld, int32_t q_col0, int32_t k_col0, int32_t v_col0,
+                           int32_t seq_len, const int32_t* kv_lens, int32_t batch, int32_t heads, const void* dout,
+                           int64_t do_ld, const void* out, int64_t o_ld, const float* lse, void* dqkv, int64_t dqkv_ld,
+                           int32_t dtype, void* stream);
+
 /* Attention backward, output side (autograd of fairseq's MultiheadAttention: dV = P^T dO, dK = dS^T q, dQ = dS k): per
  * sequence b and head h (head_dim 64)
  *     out[b][r][out_col0 + 64 h + c] = scale * sum_j A_bh[r, j] * w[b][j][w_col0 + 64 h + c]      r < rows, j < k

@@ -435,6 +435,25 @@ def reduce_partials_many(jobs) -> None:
         _lib.check(lib.mm_reduce_partials_many(arr, len(jobs), _stream()), "mm_reduce_partials_many")
 
 
+def attention_bwd_fused(qkv: torch.Tensor, seq_len: int, kv_lens: Optional[torch.Tensor], batch: int, heads: int,
+                        dout: torch.Tensor, out: torch.Tensor, lse: torch.Tensor, dqkv: torch.Tensor) -> None:
+    """dq | dk | dv [batch*seq_len, 3 * heads*64] from q | k | v (same layout), dout, out and lse in one kernel; seq_len
+    <= 256 (``mm_attention_bwd_fused``)."""
+    d = heads * 64
+    assert qkv.dtype == dout.dtype == out.dtype == dqkv.dtype and qkv.dtype in _DT
+    assert all(t.dim() == 2 and t.stride(1) == 1 for t in (qkv, dout, out, dqkv))
+    assert qkv.shape[1] >= 3 * d and dqkv.shape[1] >= 3 * d and seq_len <= 256
+    assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == batch * heads * seq_len
+    if kv_lens is not None:
+        assert kv_lens.dtype == torch.int32 and kv_lens.numel() == batch
+    lib = _lib.load()
+    with _Launch("attention_bwd_fused", 10.0 * batch * heads * seq_len * seq_len * 64):
+        _lib.check(lib.mm_attention_bwd_fused(_ptr(qkv), qkv.stride(0), 0, d, 2 * d, seq_len, _ptr(kv_lens), batch, heads,
+                                              _ptr(dout), dout.stride(0), _ptr(out), out.stride(0), _ptr(lse), _ptr(dqkv),
+                                              dqkv.stride(0), dtype_code(qkv.dtype), _stream()),
+                   "mm_attention_bwd_fused")
+
+
 def heads_gemm(a: torch.Tensor, a_ld: int, a_bs: int, transposed: bool, w: torch.Tensor, w_ld: int, w_bs: int,
                out: torch.Tensor, out_ld: int, out_bs: int, rows: int, k: int, batch: int, heads: int,
                scale: float = 1.0) -> None:

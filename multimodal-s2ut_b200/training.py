@@ -155,6 +155,8 @@ class TrainEngine(EncoderEngine):
         self.grouped_wgrad = os.environ.get("MM_GROUPED_WGRAD", "1") != "0"
         # dV / dK / dQ of attention backward on the 128 x 64-tile kernel (mm_heads_gemm); off: mm_gemm's 256-wide tiles
         self.heads_gemm = os.environ.get("MM_HEADS_GEMM", "1") != "0"
+        # sequences of up to 256 positions: the whole attention backward in one kernel (mm_attention_bwd_fused)
+        self.fused_attn_bwd_onchip = os.environ.get("MM_ATTN_BWD_ONCHIP", "1") != "0"
         self.wgrad_flush_layers = 0
         self._saved = None
         self.generation = 0            # advanced by every forward_train: ties an autograd node to ITS saved activations
@@ -623,6 +625,10 @@ class TrainEngine(EncoderEngine):
         d, H, op, bn = self.d, self.heads, self.op_dtype, self.block_n
         Tp = _round_up(T, 64)
         qkv = s["qkv"]
+        if "lse" in s and self.fused_attn_bwd and self.fused_attn_bwd_onchip and T <= 256:
+            # one kernel: S, dP, P, dS never leave the SM; dq | dk | dv accumulate in TMEM
+            K.attention_bwd_fused(qkv, T, seq_lens, B, H, datt, s["att"], s["lse"], dqkv)
+            return
         BH = B * H
         hd = dict(heads=H, head_stride=64, batches=BH, w_batched=True, block_n=bn)
         P = self.buf("a_P", (BH, Tp, Tp), op)

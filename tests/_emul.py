@@ -291,6 +291,26 @@ def attention_bwd_scores(q, q_col0, q_len, k, k_col0, v, v_col0, kv_len, kv_lens
     dscores.view(batch, heads, probs.shape[1], probs.shape[2])[:, :, :q_len, :kv_len] = dS.to(dscores.dtype)
 
 
+def attention_bwd_fused(qkv, seq_len, kv_lens, batch, heads, dout, out, lse, dqkv):
+    global launch_count
+    launch_count += 1
+    d = heads * 64
+    Q, Kx, V = _qkv_heads(qkv, 0, seq_len, qkv, d, qkv, 2 * d, seq_len, batch, heads)
+    s = Q @ Kx.transpose(-1, -2)
+    dead = torch.zeros(batch, 1, seq_len, seq_len, dtype=torch.bool)
+    if kv_lens is not None:
+        dead = dead | (torch.arange(seq_len)[None, :] >= kv_lens[:, None])[:, None, None, :]
+    P = torch.exp(s - lse.view(batch, heads, seq_len, 1)).masked_fill(dead, 0.0)
+    dO = dout[:, :d].float().view(batch, seq_len, heads, 64).permute(0, 2, 1, 3)
+    O = out[:, :d].float().view(batch, seq_len, heads, 64).permute(0, 2, 1, 3)
+    dS = P * (dO @ V.transpose(-1, -2) - (dO * O).sum(-1, keepdim=True))
+    P, dS = P.to(qkv.dtype).float(), dS.to(qkv.dtype).float()
+    back = lambda x: x.permute(0, 2, 1, 3).reshape(batch * seq_len, d).to(dqkv.dtype)
+    dqkv[:, :d] = back(dS @ Kx * 0.125)
+    dqkv[:, d:2 * d] = back(dS.transpose(-1, -2) @ Q)
+    dqkv[:, 2 * d:3 * d] = back(P.transpose(-1, -2) @ dO)
+
+
 def attention(q, q_col0, q_len, k, k_col0, v, v_col0, kv_len, kv_lens, batch, heads, out, causal=False, lse=None):
     d = heads * 64
     Q = q[:, q_col0:q_col0 + d].float().view(batch, q_len, heads, 64).permute(0, 2, 1, 3)

@@ -80,3 +80,55 @@ def test_scores_backward_matches_autograd(cuda, B, Lq, Tk, H, lens, causal, dt):
     assert (dSg - ds_ref).abs().max().item() < 6e-2 * max(1.0, ds_ref.abs().max().item())
     dead = p_ref == 0
     assert (Pg[dead] == 0).all() and (dSg[dead] == 0).all()      # masked cells are exact zeros
+
+
+@pytest.mark.parametrize("B,H,T,ragged", [(2, 4, 250, True), (3, 8, 256, False), (2, 2, 100, True), (1, 4, 128, False),
+                                           (2, 4, 130, True), (64, 8, 250, True)])
+def test_fused_attention_backward_on_chip(cuda, B, H, T, ragged):
+    """mm_attention_bwd_fused (S, dP, P, dS on chip; dq | dk | dv accumulated in TMEM) against autograd over the same
+    16-bit q | k | v in fp32, and against the two-kernel path it replaces (mm_attention_bwd_scores + mm_heads_gemm)."""
+    from mm_s2ut_b200 import kernels as K
+
+    d = 64 * H
+    g = torch.Generator().manual_seed(T * 7 + B)
+    qkv = (torch.randn(B * T, 3 * d, generator=g) * 0.5).bfloat16().cuda()
+    qkv[:, :d] *= 0.125                                           # q arrives pre-scaled by head_dim^-0.5
+    dO = (torch.randn(B * T, d, generator=g) * 0.1).bfloat16().cuda()
+    lens = torch.tensor([T - (7 * b) % (T // 2) if ragged else T for b in range(B)], dtype=torch.int32, device=cuda)
+    out = torch.empty(B * T, d, dtype=torch.bfloat16, device=cuda)
+    lse = torch.empty(B, H, T, device=cuda)
+    K.self_attention(qkv, lens, B, T, H, out, lse=lse)
+    dqkv = torch.full((B * T, 3 * d), float("nan"), dtype=torch.bfloat16, device=cuda)
+    K.attention_bwd_fused(qkv, T, lens, B, H, dO, out, lse, dqkv)
+    torch.cuda.synchronize()
+    assert torch.isfinite(dqkv.float()).all()
+    # ---- the two-kernel path
+    Tp = (T + 63) // 64 * 64
+    P = torch.zeros(B * H, Tp, Tp, dtype=torch.bfloat16, device=cuda)
+    dS = torch.zeros_like(P)
+    ref2 = torch.zeros_like(dqkv)
+    K.attention_bwd_scores(qkv, 0, T, qkv, d, qkv, 2 * d, T, lens, B, H, dO, out, lse, P, dS)
+    hg = dict(a_ld=Tp, a_bs=Tp * Tp, out_ld=3 * d, out_bs=T * 3 * d, rows=T, k=T, batch=B, heads=H)
+    K.heads_gemm(P, transposed=True, w=dO, w_ld=d, w_bs=T * d, out=ref2[:, 2 * d:], **hg)
+    K.heads_gemm(dS, transposed=True, w=qkv, w_ld=3 * d, w_bs=T * 3 * d, out=ref2[:, d:], **hg)
+    K.heads_gemm(dS, transposed=False, w=qkv[:, d:], w_ld=3 * d, w_bs=T * 3 * d, out=ref2, scale=0.125, **hg)
+    err2 = (dqkv.float() - ref2.float()).abs().max().item()
+    assert err2 <= 2e-2 * max(1.0, ref2.float().abs().max().item()), err2
+    if B > 8:
+        return
+    # ---- autograd in fp32 over the same operands (q un-scaled for autograd, scale applied inside)
+    x = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4).clone()           # [3, B, H, T, 64]
+    q, k, v = (x[i].detach().requires_grad_(True) for i in range(3))
+    s = q @ k.transpose(-1, -2)                                                     # q already scaled
+    mask = torch.arange(T, device=cuda)[None, :] >= lens[:, None]
+    p = s.masked_fill(mask[:, None, None, :], float("-inf")).softmax(-1)
+    o = p @ v
+    do = dO.float().view(B, T, H, 64).permute(0, 2, 1, 3)
+    (o * do).sum().backward()
+    back = lambda t: t.permute(0, 2, 1, 3).reshape(B * T, d)
+    ref = torch.cat([back(q.grad), back(k.grad), back(v.grad)], 1)                 # d/d(scaled q) == dS k; ours is * 1/8
+    ref[:, :d] *= 0.125
+    for name, c0 in (("dq", 0), ("dk", d), ("dv", 2 * d)):
+        got, want = dqkv[:, c0:c0 + d].float(), ref[:, c0:c0 + d]
+        rel = ((got - want).norm() / want.norm().clamp_min(1e-9)).item()
+        assert rel < 2e-2, (name, rel)
