@@ -334,6 +334,19 @@ int mm_heads_gemm(const void* a, int64_t a_ld, int64_t a_bs, int32_t a_transpose
                   int64_t w_bs, int32_t w_col0, void* out, int64_t out_ld, int64_t out_bs, int32_t out_col0,
                   int32_t rows, int32_t k, int32_t batch, int32_t heads, float scale, int32_t dtype, void* stream);
 
+/* Gradient exchange over NVLink peer memory (the reference's data-parallel training, scripts/textless/1_train.sh:105-125,
+ * exchanges gradients through fairseq's DDP all-reduce).  One process per GPU:
+ *   mm_ipc_get_handle    CUDA IPC handle of the allocation holding `ptr` + ptr's byte offset inside it
+ *   mm_ipc_open_handle   map another process's allocation (peer access enabled lazily); mm_ipc_close_handle unmaps it
+ *   mm_p2p_allreduce_f32 bufs[p] = rank p's n-element fp32 buffer as mapped here (bufs[rank] = the local one): rank r
+ *                        sums slice r of all buffers (rank order) and stores the result into slice r of all buffers.
+ *                        The caller brackets the launch with stream-ordered barriers over the ranks. */
+#define MM_P2P_MAX_RANKS 8
+int mm_ipc_get_handle(const void* ptr, uint8_t* handle64, int64_t* offset);
+int mm_ipc_open_handle(const uint8_t* handle64, void** mapped_base);
+int mm_ipc_close_handle(void* mapped_base);
+int mm_p2p_allreduce_f32(float* const* bufs, int32_t world, int32_t rank, int64_t n, void* stream);
+
 /* Grouped weight gradient (autograd of nn.Linear inside fairseq's TransformerEncoderLayer / MultiheadAttention under
  * `loss.backward()`, scripts/textless/1_train.sh): for every group g
  *     out_g[n, k] (+)= sum_t dy_g[t, n] * x_g[t, k]        t = 0 .. tokens-1, fp32 accumulation, fp32 output

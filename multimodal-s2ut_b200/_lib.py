@@ -17,7 +17,7 @@ _PKG = Path(__file__).resolve().parent
 CSRC = _PKG / "csrc"
 INCLUDE = _PKG.parent / "include"
 LIB_PATH = _PKG / "libmms2ut_b200.so"
-SOURCES = ["abi.cu", "gemm.cu", "gemm_ln.cu", "rowwise.cu", "fbank.cu", "attention.cu", "cross_attention.cu", "attention_bwd.cu", "backward.cu", "wgrad.cu", "heads_gemm.cu", "attention_bwd_fused.cu"]
+SOURCES = ["abi.cu", "gemm.cu", "gemm_ln.cu", "rowwise.cu", "fbank.cu", "attention.cu", "cross_attention.cu", "attention_bwd.cu", "backward.cu", "wgrad.cu", "heads_gemm.cu", "attention_bwd_fused.cu", "p2p.cu"]
 ABI_VERSION = 3
 
 NVCC_FLAGS = [
@@ -173,6 +173,10 @@ EXPORTS = {
     "mm_attention_bwd_fused": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                          C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                          C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "mm_ipc_get_handle": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mm_ipc_open_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mm_ipc_close_handle": (C.c_int, [C.c_void_p]),
+    "mm_p2p_allreduce_f32": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
     "mm_heads_gemm": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
                                 C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_float, C.c_int32, C.c_void_p]),

@@ -1,0 +1,146 @@
+// Gradient exchange of the training step over NVLink peer memory (BASELINE configs[2]: the path's one collective).
+//
+// One process per GPU; every rank maps the other ranks' flat gradient buffers (CUDA IPC) once.  The exchange is one
+// kernel per rank, two-shot and in place:
+//     rank r owns slice r of the buffer: it LOADS that slice from every rank over NVLink (its own from HBM), adds the
+//     world's values in rank order (so the sum is bit-identical on every rank and from run to run), and STORES the
+//     result into slice r of every rank's buffer.
+// Slice r of any buffer is read and written by rank r alone, so the kernel needs no flags and no in-kernel waiting:
+// two stream-ordered host-side barriers (tiny NCCL all-reduces issued by the caller) bracket it -- "every rank's
+// backward pass is complete" before, "every rank's stores have landed" after.  Inbound loads and outbound stores use
+// the two directions of the links at the same time: (N-1)/N of the buffer each way per GPU, the same bytes as a ring
+// all-reduce, without its 2 (N-1) dependent steps.
+#include "common.cuh"
+#include "host.cuh"
+#include "../../include/mms2ut_b200.h"
+
+namespace mm {
+
+constexpr int P2P_MAX_RANKS = MM_P2P_MAX_RANKS;
+
+struct P2PArgs {
+  float* buf[P2P_MAX_RANKS];   // buf[p] = rank p's buffer as mapped into THIS process (buf[rank] = the local one)
+  int world, rank;
+  long long lo, hi;            // this rank's slice [lo, hi), multiples of 4 elements except hi == n
+};
+
+template <int WORLD>
+__global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
+  constexpr int U = 16 / WORLD;       // float4 positions per thread per round: 16 loads (256 B) in flight per thread
+  const long long n4 = (a.hi - a.lo) >> 2;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += step * U) {
+    float4 v[U][WORLD];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * step;
+      if (i < n4) {
+#pragma unroll
+        for (int p = 0; p < WORLD; ++p) v[u][p] = __ldcg(reinterpret_cast<const float4*>(a.buf[p] + a.lo + 4 * i));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * step;
+      if (i < n4) {
+        float4 s = v[u][0];
+#pragma unroll
+        for (int p = 1; p < WORLD; ++p) s.x += v[u][p].x, s.y += v[u][p].y, s.z += v[u][p].z, s.w += v[u][p].w;
+#pragma unroll
+        for (int p = 0; p < WORLD; ++p) __stcg(reinterpret_cast<float4*>(a.buf[p] + a.lo + 4 * i), s);
+      }
+    }
+  }
+  // tail (slice length not a multiple of 4: only the last rank's)
+  const long long t0 = a.lo + 4 * n4;
+  for (long long e = t0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; e < a.hi; e += step) {
+    float s = 0.f;
+#pragma unroll
+    for (int p = 0; p < WORLD; ++p) s += __ldcg(a.buf[p] + e);
+#pragma unroll
+    for (int p = 0; p < WORLD; ++p) __stcg(a.buf[p] + e, s);
+  }
+}
+
+typedef CUresult (*MemGetAddressRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+
+static MemGetAddressRangeFn get_address_range_fn() {
+  static MemGetAddressRangeFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<MemGetAddressRangeFn>(p);
+  return fn;
+}
+
+}  // namespace mm
+
+using namespace mm;
+
+extern "C" int mm_ipc_get_handle(const void* ptr, uint8_t* handle64, int64_t* offset) {
+  if (!ptr || !handle64 || !offset) return bad_arg("ipc_get_handle: null pointer");
+  MemGetAddressRangeFn range = get_address_range_fn();
+  if (!range) return bad_arg("cuMemGetAddressRange entry point not available");
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (range(&base, &size, reinterpret_cast<CUdeviceptr>(ptr)) != CUDA_SUCCESS) return bad_arg("ipc_get_handle: not a device allocation");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base));
+  if (e != cudaSuccess) return fail(e, "cudaIpcGetMemHandle");
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  *offset = (int64_t)(reinterpret_cast<CUdeviceptr>(ptr) - base);
+  return 0;
+}
+
+extern "C" int mm_ipc_open_handle(const uint8_t* handle64, void** mapped_base) {
+  if (!handle64 || !mapped_base) return bad_arg("ipc_open_handle: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(mapped_base, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return fail(e, "cudaIpcOpenMemHandle");
+  return 0;
+}
+
+extern "C" int mm_ipc_close_handle(void* mapped_base) {
+  if (!mapped_base) return 0;
+  cudaError_t e = cudaIpcCloseMemHandle(mapped_base);
+  if (e != cudaSuccess) return fail(e, "cudaIpcCloseMemHandle");
+  return 0;
+}
+
+extern "C" int mm_p2p_allreduce_f32(float* const* bufs, int32_t world, int32_t rank, int64_t n, void* stream) {
+  if (!bufs || world < 2 || world > P2P_MAX_RANKS || rank < 0 || rank >= world || n <= 0)
+    return bad_arg("p2p_allreduce: 2 .. MM_P2P_MAX_RANKS ranks");
+  P2PArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int p = 0; p < world; ++p) {
+    if (!bufs[p] || (reinterpret_cast<uintptr_t>(bufs[p]) & 15)) return bad_arg("p2p_allreduce: buffers must be 16-byte aligned");
+    a.buf[p] = bufs[p];
+  }
+  a.world = world, a.rank = rank;
+  const long long per = (((n + world - 1) / world) + 3) & ~3LL;     // slice length, a multiple of 4 elements
+  a.lo = per * rank < n ? per * rank : n;
+  a.hi = per * (rank + 1) < n ? per * (rank + 1) : n;
+  if (a.hi <= a.lo) return 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long n4 = (a.hi - a.lo + 3) >> 2;
+  long long blocks = (n4 + 511) / 512;
+  if (blocks > 4LL * kNumSMs) blocks = 4LL * kNumSMs;
+  const dim3 grid((unsigned)blocks), block(512);
+  switch (world) {
+    case 2: p2p_allreduce_kernel<2><<<grid, block, 0, s>>>(a); break;
+    case 3: p2p_allreduce_kernel<3><<<grid, block, 0, s>>>(a); break;
+    case 4: p2p_allreduce_kernel<4><<<grid, block, 0, s>>>(a); break;
+    case 5: p2p_allreduce_kernel<5><<<grid, block, 0, s>>>(a); break;
+    case 6: p2p_allreduce_kernel<6><<<grid, block, 0, s>>>(a); break;
+    case 7: p2p_allreduce_kernel<7><<<grid, block, 0, s>>>(a); break;
+    case 8: p2p_allreduce_kernel<8><<<grid, block, 0, s>>>(a); break;
+    default: return bad_arg("p2p_allreduce: world size");
+  }
+  MM_CHECK_LAUNCH("p2p_allreduce_kernel launch");
+  return 0;
+}

@@ -263,7 +263,9 @@ class GraphedModelTrainStep(GraphedTrainStep):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             ws = dist.get_world_size()
             if not self.overlap_reduce:
+                from .training import all_reduce_flat
+
                 self.eng.all_reduce_grads()
-                dist.all_reduce(self.dec.flat_g, op=dist.ReduceOp.SUM)
+                all_reduce_flat(self.dec.flat_g)
         self.optimizer_step(lr, weight_decay, clip_norm, grad_scale=1.0 / ws)
         return out, self.loss[bool(drop_image)]

@@ -92,7 +92,7 @@ class _scope:
         return False
 
 
-def all_reduce_flat(flat: torch.Tensor, bucket_elems: int = 0) -> int:
+def all_reduce_flat(flat: torch.Tensor, bucket_elems: int = 0, peer_memory: bool = True) -> int:
     """SUM all-reduce of a flat gradient buffer over the default process group: ONE collective by default (nothing
     overlaps it here, and on NVLink one 162 MB NCCL call takes 0.35 ms where five 32 MB buckets take 0.45:
     profiles/r02/allreduce_probe_n2.txt); bucket_elems > 0 issues asynchronous buckets of that many elements."""
@@ -101,6 +101,12 @@ def all_reduce_flat(flat: torch.Tensor, bucket_elems: int = 0) -> int:
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return 1
     if bucket_elems <= 0:
+        if peer_memory and flat.dtype == torch.float32 and os.environ.get("MM_P2P_ALLREDUCE", "1") != "0":
+            from .peer import peer_all_reduce       # two-shot in-place kernel over NVLink peer memory (csrc/p2p.cu)
+
+            ws = peer_all_reduce(flat)
+            if ws is not None:
+                return ws
         bucket_elems = max(1, flat.numel())
     works = [dist.all_reduce(flat[o:o + bucket_elems], op=dist.ReduceOp.SUM, async_op=True)
              for o in range(0, flat.numel(), bucket_elems)]

@@ -47,4 +47,34 @@ for name, buf in (("fp32", flat), ("bf16", half)):
 ms = timed(lambda: (half.copy_(flat), dist.all_reduce(half), flat.copy_(half)))
 if rank == 0:
     print(f"fp32 -> bf16 convert + all-reduce + back: {ms:.3f} ms")
+# ---- the peer-memory kernel (csrc/p2p.cu) against NCCL: same sums, device time incl. its two barriers
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
+import mm_s2ut_b200  # noqa: E402,F401
+from mm_s2ut_b200.peer import PeerGroup  # noqa: E402
+
+torch.manual_seed(rank)
+a = torch.randn(n, device="cuda")
+b = a.clone()
+dist.all_reduce(b)
+grp = PeerGroup(a)
+grp.all_reduce()
+torch.cuda.synchronize()
+err = (a - b).abs().max().item()
+same = torch.tensor([float(a.double().sum().item())], device="cuda", dtype=torch.float64)
+lo, hi = same.clone(), same.clone()
+dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+ms = timed(grp.all_reduce)
+if rank == 0:
+    nbytes = n * 4
+    print(f"peer-memory all-reduce (barrier + kernel + barrier): {ms:.3f} ms  busbw "
+          f"{2 * (world - 1) / world * nbytes / ms / 1e6:.0f} GB/s   max |p2p - nccl| = {err:.3e}   "
+          f"identical on every rank: {lo.item() == hi.item()}", flush=True)
+ms_b = timed(grp.barrier)
+if rank == 0:
+    print(f"one barrier (4-byte NCCL all-reduce): {ms_b:.3f} ms")
+grp.close()
 dist.destroy_process_group()
