@@ -340,12 +340,18 @@ int mm_heads_gemm(const void* a, int64_t a_ld, int64_t a_bs, int32_t a_transpose
  *   mm_ipc_open_handle   map another process's allocation (peer access enabled lazily); mm_ipc_close_handle unmaps it
  *   mm_p2p_allreduce_f32 bufs[p] = rank p's n-element fp32 buffer as mapped here (bufs[rank] = the local one): rank r
  *                        sums slice r of all buffers (rank order) and stores the result into slice r of all buffers.
- *                        The caller brackets the launch with stream-ordered barriers over the ranks. */
+ *                        The caller brackets the launch with barriers over the ranks (mm_p2p_barrier); bufs may point
+ *                        at any common offset inside the mapped buffers (a gradient bucket). */
 #define MM_P2P_MAX_RANKS 8
 int mm_ipc_get_handle(const void* ptr, uint8_t* handle64, int64_t* offset);
 int mm_ipc_open_handle(const uint8_t* handle64, void** mapped_base);
 int mm_ipc_close_handle(void* mapped_base);
 int mm_p2p_allreduce_f32(float* const* bufs, int32_t world, int32_t rank, int64_t n, void* stream);
+/* Barrier over the ranks as a kernel (graph-capturable, no shared memory): flags[p] = rank p's array of
+ * MM_P2P_MAX_RANKS uint32 (zero-initialised once) as mapped here, epoch = a local uint32 counter.  Work enqueued before
+ * the barrier on any rank is visible to work enqueued after it on every rank.  Every rank must issue the same sequence
+ * of barriers. */
+int mm_p2p_barrier(unsigned int* const* flags, unsigned int* epoch, int32_t world, int32_t rank, void* stream);
 
 /* Grouped weight gradient (autograd of nn.Linear inside fairseq's TransformerEncoderLayer / MultiheadAttention under
  * `loss.backward()`, scripts/textless/1_train.sh): for every group g

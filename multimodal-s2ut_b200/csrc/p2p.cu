@@ -5,9 +5,13 @@
 //     rank r owns slice r of the buffer: it LOADS that slice from every rank over NVLink (its own from HBM), adds the
 //     world's values in rank order (so the sum is bit-identical on every rank and from run to run), and STORES the
 //     result into slice r of every rank's buffer.
-// Slice r of any buffer is read and written by rank r alone, so the kernel needs no flags and no in-kernel waiting:
-// two stream-ordered host-side barriers (tiny NCCL all-reduces issued by the caller) bracket it -- "every rank's
-// backward pass is complete" before, "every rank's stores have landed" after.  Inbound loads and outbound stores use
+// Slice r of any buffer is read and written by rank r alone, so the exchange kernel itself needs no flags; it is
+// bracketed by two barriers over the ranks -- "every rank's gradients are complete" before, "every rank's stores have
+// landed" after.  The barrier is a kernel too (mm_p2p_barrier: one warp; rank r stores a growing epoch number into slot r
+// of every rank's flag array and spins until every slot of its own array has reached it), so the whole exchange is
+// plain kernel launches: it is captured into the backward pass's CUDA graph on a side stream and overlaps the rest of
+// the backward pass (an NCCL kernel cannot run beside the persistent GEMMs, which leave it no shared memory; these
+// kernels use none).  Inbound loads and outbound stores use
 // the two directions of the links at the same time: (N-1)/N of the buffer each way per GPU, the same bytes as a ring
 // all-reduce, without its 2 (N-1) dependent steps.
 #include "common.cuh"
@@ -17,6 +21,36 @@
 namespace mm {
 
 constexpr int P2P_MAX_RANKS = MM_P2P_MAX_RANKS;
+constexpr int P2P_THREADS = 128;      // 128 threads x <= 64 registers and no shared memory: a CTA (8 K registers) fits beside
+                                      // a persistent GEMM CTA (256 threads x 199 registers) on the same SM
+
+struct BarrierArgs {
+  unsigned int* flags[P2P_MAX_RANKS];  // flags[p] = rank p's flag array [P2P_MAX_RANKS] as mapped here
+  unsigned int* epoch;                 // local counter (device memory), bumped once per barrier
+  int world, rank;
+};
+
+// One warp.  Lane p < world: store the new epoch into slot `rank` of rank p's array, then wait until slot p of the local
+// array has reached it.  Everything earlier in this stream (on every rank) is visible to everything later (on every rank).
+__global__ void __launch_bounds__(32) p2p_barrier_kernel(const BarrierArgs a) {
+  unsigned int e = 0;
+  if (threadIdx.x == 0) {
+    e = *a.epoch + 1u;
+    *a.epoch = e;
+  }
+  e = __shfl_sync(0xffffffffu, e, 0);
+  __threadfence_system();
+  const int p = threadIdx.x;
+  if (p < a.world) {
+    volatile unsigned int* remote = a.flags[p] + a.rank;
+    *remote = e;
+    volatile unsigned int* mine = a.flags[a.rank] + p;
+    while ((int)(*mine - e) < 0) {
+    }
+  }
+  __syncwarp();
+  __threadfence_system();
+}
 
 struct P2PArgs {
   float* buf[P2P_MAX_RANKS];   // buf[p] = rank p's buffer as mapped into THIS process (buf[rank] = the local one)
@@ -25,8 +59,8 @@ struct P2PArgs {
 };
 
 template <int WORLD>
-__global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
-  constexpr int U = 16 / WORLD;       // float4 positions per thread per round: 16 loads (256 B) in flight per thread
+__global__ void __launch_bounds__(P2P_THREADS, 8) p2p_allreduce_kernel(const P2PArgs a) {
+  constexpr int U = 8 / WORLD > 0 ? 8 / WORLD : 1;   // float4 positions per thread per round: 8 loads (128 B) in flight per thread
   const long long n4 = (a.hi - a.lo) >> 2;
   const long long step = (long long)gridDim.x * blockDim.x;
   for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += step * U) {
@@ -125,12 +159,13 @@ extern "C" int mm_p2p_allreduce_f32(float* const* bufs, int32_t world, int32_t r
   const long long per = (((n + world - 1) / world) + 3) & ~3LL;     // slice length, a multiple of 4 elements
   a.lo = per * rank < n ? per * rank : n;
   a.hi = per * (rank + 1) < n ? per * (rank + 1) : n;
-  if (a.hi <= a.lo) return 0;
+  if (a.hi <= a.lo) a.hi = a.lo;       // an empty slice still launches (graph capture keeps the same node set on every rank)
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const long long n4 = (a.hi - a.lo + 3) >> 2;
-  long long blocks = (n4 + 511) / 512;
-  if (blocks > 4LL * kNumSMs) blocks = 4LL * kNumSMs;
-  const dim3 grid((unsigned)blocks), block(512);
+  long long blocks = (n4 + P2P_THREADS - 1) / P2P_THREADS;
+  if (blocks > 8LL * kNumSMs) blocks = 8LL * kNumSMs;
+  if (blocks < 1) blocks = 1;
+  const dim3 grid((unsigned)blocks), block(P2P_THREADS);
   switch (world) {
     case 2: p2p_allreduce_kernel<2><<<grid, block, 0, s>>>(a); break;
     case 3: p2p_allreduce_kernel<3><<<grid, block, 0, s>>>(a); break;
@@ -142,5 +177,19 @@ extern "C" int mm_p2p_allreduce_f32(float* const* bufs, int32_t world, int32_t r
     default: return bad_arg("p2p_allreduce: world size");
   }
   MM_CHECK_LAUNCH("p2p_allreduce_kernel launch");
+  return 0;
+}
+
+extern "C" int mm_p2p_barrier(unsigned int* const* flags, unsigned int* epoch, int32_t world, int32_t rank, void* stream) {
+  if (!flags || !epoch || world < 2 || world > P2P_MAX_RANKS || rank < 0 || rank >= world) return bad_arg("p2p_barrier");
+  BarrierArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int p = 0; p < world; ++p) {
+    if (!flags[p]) return bad_arg("p2p_barrier: null flag array");
+    a.flags[p] = flags[p];
+  }
+  a.epoch = epoch, a.world = world, a.rank = rank;
+  p2p_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  MM_CHECK_LAUNCH("p2p_barrier_kernel launch");
   return 0;
 }

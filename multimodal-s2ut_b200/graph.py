@@ -235,9 +235,15 @@ class GraphedModelTrainStep(GraphedTrainStep):
             ev.record()
             if self.eng._comm_stream is None:
                 self.eng._comm_stream = torch.cuda.Stream(device=self.device)
+            from .peer import peer_group
+
+            grp = peer_group(self.dec.flat_g)
             with torch.cuda.stream(self.eng._comm_stream):
                 self.eng._comm_stream.wait_event(ev)
-                self.eng._reduce_works.append(dist.all_reduce(self.dec.flat_g, op=dist.ReduceOp.SUM, async_op=True))
+                if grp is not None:
+                    grp.all_reduce()
+                else:
+                    self.eng._reduce_works.append(dist.all_reduce(self.dec.flat_g, op=dist.ReduceOp.SUM, async_op=True))
         self.eng.backward(d_enc, overlap_reduce=self.overlap_reduce)
         self.loss[bool(drop_image)] = (loss, nll)
         return out

@@ -1,5 +1,7 @@
-"""Peer-memory gradient exchange (``csrc/p2p.cu``): every rank maps the other ranks' flat gradient buffers through
-CUDA IPC once; ``all_reduce`` then runs the two-shot in-place kernel between two stream-ordered barriers.
+"""Peer-memory gradient exchange (``csrc/p2p.cu``): every rank maps the other ranks' flat gradient buffers (and a small
+flag array) through CUDA IPC once; ``all_reduce`` is then three plain kernel launches -- barrier, two-shot in-place
+exchange, barrier -- on the current stream, so it can be captured into a CUDA graph and run on a side stream beside the
+backward pass.
 
 The reference trains data-parallel through fairseq's DDP wrapper (scripts/textless/1_train.sh:105-125,
 ``--distributed-world-size``), i.e. an NCCL all-reduce of the gradients.  This is the same exchange for this path's flat
@@ -15,6 +17,32 @@ import torch
 from . import _lib
 
 
+def _exchange_handles(t: torch.Tensor):
+    """CUDA IPC handle + offset of ``t`` gathered over the ranks -> this rank's view of every rank's tensor (pointers)."""
+    import torch.distributed as dist
+
+    lib = _lib.load()
+    handle = (C.c_uint8 * 64)()
+    off = C.c_int64(0)
+    _lib.check(lib.mm_ipc_get_handle(t.data_ptr(), handle, C.byref(off)), "mm_ipc_get_handle")
+    world, rank = dist.get_world_size(), dist.get_rank()
+    everyone: List = [None] * world
+    dist.all_gather_object(everyone, (bytes(handle), int(off.value), int(t.numel())))
+    ptrs, mapped = [], []
+    for r, (h, o, n) in enumerate(everyone):
+        if n != t.numel():
+            raise ValueError(f"peer mapping: rank {r} holds {n} elements, this rank {t.numel()}")
+        if r == rank:
+            ptrs.append(t.data_ptr())
+            continue
+        base = C.c_void_p()
+        buf = (C.c_uint8 * 64).from_buffer_copy(h)
+        _lib.check(lib.mm_ipc_open_handle(buf, C.byref(base)), "mm_ipc_open_handle")
+        mapped.append(base.value)
+        ptrs.append(base.value + o)
+    return ptrs, mapped
+
+
 class PeerGroup:
     """Maps ``tensor`` (same shape on every rank of the default process group) into every rank's address space."""
 
@@ -22,47 +50,42 @@ class PeerGroup:
         import torch.distributed as dist
 
         assert tensor.is_cuda and tensor.dtype == torch.float32 and tensor.is_contiguous()
-        self.dist = dist
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
         if not 2 <= self.world <= 8:
             raise ValueError("PeerGroup: 2 .. 8 ranks of one node")
         self.tensor = tensor
-        lib = _lib.load()
-        handle = (C.c_uint8 * 64)()
-        off = C.c_int64(0)
-        _lib.check(lib.mm_ipc_get_handle(tensor.data_ptr(), handle, C.byref(off)), "mm_ipc_get_handle")
-        mine = (bytes(handle), int(off.value), int(tensor.numel()), torch.cuda.current_device())
-        everyone: List = [None] * self.world
-        dist.all_gather_object(everyone, mine)
-        self._mapped: List[int] = []
-        ptrs = []
-        for r, (h, o, n, _dev) in enumerate(everyone):
-            if n != tensor.numel():
-                raise ValueError(f"PeerGroup: rank {r} holds {n} elements, this rank {tensor.numel()}")
-            if r == self.rank:
-                ptrs.append(tensor.data_ptr())
-                continue
-            base = C.c_void_p()
-            buf = (C.c_uint8 * 64).from_buffer_copy(h)
-            _lib.check(lib.mm_ipc_open_handle(buf, C.byref(base)), "mm_ipc_open_handle")
-            self._mapped.append(base.value)
-            ptrs.append(base.value + o)
-        self._ptrs = (C.c_void_p * self.world)(*ptrs)
-        self._flag = torch.zeros(1, device=tensor.device)
+        # flag array (slot p written by rank p) + the local epoch counter: one dedicated allocation per rank
+        self._sync = torch.zeros(64, dtype=torch.int32, device=tensor.device)
+        torch.cuda.synchronize(tensor.device)
+        self._ptrs, m1 = _exchange_handles(tensor)
+        flag_ptrs, m2 = _exchange_handles(self._sync)
+        self._mapped = m1 + m2
+        self._flags = (C.c_void_p * self.world)(*flag_ptrs)
+        self._epoch = self._sync.data_ptr() + 32 * 4          # elements 32.. of the local array: never written by peers
+        dist.barrier()          # every rank has zeroed and mapped its flags before the first device-side barrier
 
     def barrier(self) -> None:
-        """Stream-ordered: later work of this stream starts after every rank's earlier work (a 4-byte NCCL all-reduce)."""
-        self.dist.all_reduce(self._flag)
-
-    def all_reduce(self) -> None:
-        """tensor <- sum over ranks, in place on every rank (fixed summation order: bit-identical everywhere)."""
+        """Device-side barrier kernel on the current stream (capturable): see ``mm_p2p_barrier``."""
         from . import kernels as K
 
         lib = _lib.load()
-        self.barrier()              # every rank's gradients are complete
-        with K._Launch("p2p_allreduce", 8.0 * self.tensor.numel() * (self.world - 1) / self.world):
-            _lib.check(lib.mm_p2p_allreduce_f32(self._ptrs, self.world, self.rank, self.tensor.numel(), K._stream()),
-                       "mm_p2p_allreduce_f32")
+        with K._Launch("p2p_barrier"):
+            _lib.check(lib.mm_p2p_barrier(self._flags, self._epoch, self.world, self.rank, K._stream()), "mm_p2p_barrier")
+
+    def all_reduce(self, lo: int = 0, hi: Optional[int] = None) -> None:
+        """tensor[lo:hi] <- sum over ranks, in place on every rank (fixed summation order: bit-identical everywhere).
+        lo and hi must be multiples of 4 elements (16-byte vector accesses) unless hi is the end of the tensor."""
+        from . import kernels as K
+
+        hi = self.tensor.numel() if hi is None else hi
+        if hi <= lo:
+            return
+        assert lo % 4 == 0 and (hi % 4 == 0 or hi == self.tensor.numel()), (lo, hi)
+        lib = _lib.load()
+        ptrs = (C.c_void_p * self.world)(*[p + 4 * lo for p in self._ptrs])
+        self.barrier()              # every rank's gradients in [lo, hi) are complete
+        with K._Launch("p2p_allreduce", 8.0 * (hi - lo) * (self.world - 1) / self.world):
+            _lib.check(lib.mm_p2p_allreduce_f32(ptrs, self.world, self.rank, hi - lo, K._stream()), "mm_p2p_allreduce_f32")
         self.barrier()              # every rank's stores into this rank's buffer have landed
 
     def close(self) -> None:
@@ -75,19 +98,29 @@ class PeerGroup:
 _groups: Dict[int, PeerGroup] = {}
 
 
-def peer_all_reduce(flat: torch.Tensor) -> Optional[int]:
-    """All-reduce ``flat`` over peer memory if this process group can (NCCL backend, CUDA tensor, <= 8 ranks); returns
-    the world size, or None when the caller should use the library collective instead."""
+def peer_group(flat: torch.Tensor) -> Optional[PeerGroup]:
+    """The PeerGroup of ``flat`` (created on first use: a collective call -- every rank must get here), or None when
+    this process group cannot use peer memory (not NCCL / not CUDA / more than 8 ranks / MM_P2P_ALLREDUCE=0)."""
+    import os
+
     import torch.distributed as dist
 
-    if not (flat.is_cuda and dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl"):
+    if os.environ.get("MM_P2P_ALLREDUCE", "1") == "0":
         return None
-    world = dist.get_world_size()
-    if not 2 <= world <= 8:
+    if not (flat.is_cuda and flat.dtype == torch.float32 and dist.is_available() and dist.is_initialized()
+            and dist.get_backend() == "nccl" and 2 <= dist.get_world_size() <= 8):
         return None
-    key = flat.data_ptr()
-    g = _groups.get(key)
+    g = _groups.get(flat.data_ptr())
     if g is None or g.tensor.numel() != flat.numel():
-        g = _groups[key] = PeerGroup(flat)
+        g = _groups[flat.data_ptr()] = PeerGroup(flat)
+    return g
+
+
+def peer_all_reduce(flat: torch.Tensor) -> Optional[int]:
+    """All-reduce ``flat`` over peer memory if this process group can; returns the world size, or None when the caller
+    should use the library collective instead."""
+    g = peer_group(flat)
+    if g is None:
+        return None
     g.all_reduce()
-    return world
+    return g.world

@@ -101,7 +101,7 @@ def all_reduce_flat(flat: torch.Tensor, bucket_elems: int = 0, peer_memory: bool
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return 1
     if bucket_elems <= 0:
-        if peer_memory and flat.dtype == torch.float32 and os.environ.get("MM_P2P_ALLREDUCE", "1") != "0":
+        if peer_memory:
             from .peer import peer_all_reduce       # two-shot in-place kernel over NVLink peer memory (csrc/p2p.cu)
 
             ws = peer_all_reduce(flat)
@@ -163,7 +163,7 @@ class TrainEngine(EncoderEngine):
         self.heads_gemm = os.environ.get("MM_HEADS_GEMM", "1") != "0"
         # sequences of up to 256 positions: the whole attention backward in one kernel (mm_attention_bwd_fused)
         self.fused_attn_bwd_onchip = os.environ.get("MM_ATTN_BWD_ONCHIP", "1") != "0"
-        self.wgrad_flush_layers = 0
+        self.wgrad_flush_layers = int(os.environ.get("MM_WGRAD_FLUSH_LAYERS", "0"))
         self._saved = None
         self.generation = 0            # advanced by every forward_train: ties an autograd node to ITS saved activations
         self.step_count = 0
@@ -881,11 +881,17 @@ class TrainEngine(EncoderEngine):
             return
         if self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream(device=self.device)
+        from .peer import peer_group
+
+        grp = peer_group(self.flat_g)      # created on first use (outside graph capture: the eager warm-up pass)
         ev = torch.cuda.Event()
         ev.record()
         with torch.cuda.stream(self._comm_stream):
             self._comm_stream.wait_event(ev)
-            self._reduce_works.append(dist.all_reduce(bucket, op=dist.ReduceOp.SUM, async_op=True))
+            if grp is not None and lo % 4 == 0 and (hi % 4 == 0 or hi == self.flat_g.numel()):
+                grp.all_reduce(lo, hi)      # barrier + exchange + barrier kernels: captured with the backward pass
+            else:
+                self._reduce_works.append(dist.all_reduce(bucket, op=dist.ReduceOp.SUM, async_op=True))
 
     def _reduce_join(self) -> None:
         for wk in self._reduce_works:
@@ -951,9 +957,9 @@ class TrainEngine(EncoderEngine):
             if not self.grouped_wgrad or (flush_every and len(pending) >= flush_every) or i == 0:
                 with _scope("layer"):
                     self._wgrad_flush()
-                if overlap:
-                    for j in pending:
-                        self._reduce_async(*self.bucket_layers[j])
+                if overlap:     # the pending layers' buckets are adjacent in flat_g: one exchange
+                    self._reduce_async(min(self.bucket_layers[j][0] for j in pending),
+                                       max(self.bucket_layers[j][1] for j in pending))
                 pending = []
         with _scope("conv"):
             if sv["drop"][0] > 0:      # dropout after the scaled, position-added subsampler output
