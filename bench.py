@@ -40,6 +40,14 @@ METRIC = "audio-sec encoded/sec (fbank->fused enc)"
 REF_SAMPLE = int(os.environ.get("MM_BENCH_REF_SAMPLE", "8"))    # utterances per step of the reference (CPU) arm
 
 
+def _peer_exchange_active() -> bool:
+    try:
+        from mm_s2ut_b200 import peer
+        return bool(peer._groups)
+    except Exception:
+        return False
+
+
 def _peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -338,8 +346,10 @@ def train_step_probe(ctx, wav, img, steps=20, warmup=3, model_step=True):
            "launches_per_step_approx": launches // 2, "params": int(gs.eng.flat_p.numel()), "grad_norm_last": norm,
            "allreduce_ms": ar_ms, "allreduce_bytes": gbytes if world > 1 else 0,
            "allreduce_busbw_gbs": (2 * (world - 1) / world * gbytes / (ar_ms * 1e-3) / 1e9) if ar_ms else None,
-           "collective": ("one NCCL all-reduce of the flat fp32 gradient (%d MB) between the backward and the "
-                          "optimizer graphs" % (gbytes >> 20)) if world > 1 else "none (1 GPU)",
+           "collective": (("two-shot in-place exchange kernel over NVLink peer memory (csrc/p2p.cu: device-side barrier, rank r "
+                           "sums slice r of every rank's buffer and stores it back to all, barrier) "
+                           if _peer_exchange_active() else "one NCCL all-reduce ") +
+                          "of the flat fp32 gradient (%d MB) between the backward and the optimizer graphs" % (gbytes >> 20)) if world > 1 else "none (1 GPU)",
            "what": "BASELINE configs[2]: forward (activations kept) + backward of every encoder/fusion/conv parameter + "
                    "gradient all-reduce + fairseq Adam with clip-norm, batch 64 x 10 s per GPU, modality dropout 0.5 "
                    "(image-drop branch), synthetic d loss/d encoder_out; element-wise dropout off"}
