@@ -323,6 +323,20 @@ int mm_attention_bwd_fused(const void* qkv, int64_t qkv_ld, int32_t q_col0, int3
                            int64_t do_ld, const void* out, int64_t o_ld, const float* lse, void* dqkv, int64_t dqkv_ld,
                            int32_t dtype, void* stream);
 
+/* The same for any query / key length, a causal mask and q / k|v (and dq / dk|dv) in different tensors: the unit
+ * decoder's causal self-attention and its encoder attention (fairseq TransformerDecoderLayer under autograd), the
+ * encoder beyond 256 positions.  Query tiles are processed in pairs; the dk / dv partial sums of the earlier pairs wait
+ * in `scratch` (fp32, mm_attention_bwd_general_scratch_floats(kv_len) elements, caller-owned).  Arguments as
+ * mm_attention_bwd_scores; dq [batch * q_len, dq_ld], dk / dv [batch * kv_len, ld] with the heads' column blocks at
+ * *_col0. */
+int64_t mm_attention_bwd_general_scratch_floats(int32_t kv_len);
+int mm_attention_bwd_general(const void* q, int64_t q_ld, int32_t q_col0, int32_t q_len, const void* k, int64_t k_ld,
+                             int32_t k_col0, const void* v, int64_t v_ld, int32_t v_col0, int32_t kv_len,
+                             const int32_t* kv_lens, int32_t batch, int32_t heads, int32_t causal, const void* dout,
+                             int64_t do_ld, const void* out, int64_t o_ld, const float* lse, void* dq, int64_t dq_ld,
+                             int32_t dq_col0, void* dk, int64_t dk_ld, int32_t dk_col0, void* dv, int64_t dv_ld,
+                             int32_t dv_col0, float* scratch, int32_t dtype, void* stream);
+
 /* Attention backward, output side (autograd of fairseq's MultiheadAttention: dV = P^T dO, dK = dS^T q, dQ = dS k): per
  * sequence b and head h (head_dim 64)
  *     out[b][r][out_col0 + 64 h + c] = scale * sum_j A_bh[r, j] * w[b][j][w_col0 + 64 h + c]      r < rows, j < k

@@ -338,6 +338,397 @@ attention_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
   }
 }
 
+// =====================================================================================================================
+// General variant: any query / key length, causal mask, q and k|v in different tensors (the decoder's causal
+// self-attention and its encoder attention; the encoder beyond 256 positions).  Same steps and the same TMEM plan, but
+//   * query tiles are taken in PAIRS (dQ of two tiles is what fits TMEM): for pair: for key chunk: for tile in pair
+//   * dV_c / dK_c are complete only after the last pair: pairs before the last leave their fp32 partial in a scratch
+//     buffer of the CTA (L2-resident, 64 KB per chunk), later pairs add it back -- the same CTA in a fixed order, so the
+//     result stays deterministic
+//   * q / dO / O tiles are loaded per pair, (k_c | v_c) through a 2-stage ring per (pair, chunk)
+//   * causal: steps whose chunk lies entirely above the tile's diagonal are skipped by all three roles alike.
+// =====================================================================================================================
+struct AgDev {
+  int q_len, kv_len, H, nq, nc, npairs, n_items, causal;
+  int q_col0, k_col0, v_col0, dq_col0, dk_col0, dv_col0;
+  const int* kv_lens;        // [batch] valid keys, or NULL
+  const float* lse;          // [batch][H][q_len]
+  float* scratch;            // [gridDim.x][nc][2][128 * 64] fp32
+  float scale;
+};
+
+template <typename OpT>
+__global__ void __launch_bounds__(AF_THREADS, 1)
+attention_bwd_general_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                             const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapDO,
+                             const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapDQ,
+                             const __grid_constant__ CUtensorMap mapDK, const __grid_constant__ CUtensorMap mapDV,
+                             const AgDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                       // [2 tiles of the pair]
+  uint8_t* sDO = sQ + 2 * AF_TILE;          // [2]
+  uint8_t* sKV = sDO + 2 * AF_TILE;         // [2 stages] (k_c 16 KB | v_c 16 KB)
+  uint8_t* sStage = sKV + 4 * AF_TILE;      // P slab 0, 1, dS slab 0, 1 (O tiles of the pair before its first step)
+  uint8_t* sOut = sStage + 4 * AF_TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + AF_TILE);
+  uint64_t* pair_full = bars;         // TMA (q, dO, O of a pair) -> MMA + consumers
+  uint64_t* pair_empty = bars + 1;    // last MMAs of the pair done -> TMA
+  uint64_t* sdp_full = bars + 2;
+  uint64_t* sdp_empty = bars + 3;
+  uint64_t* slab_full = bars + 4;
+  uint64_t* slab_empty = bars + 5;
+  uint64_t* acc_full = bars + 6;
+  uint64_t* acc_empty = bars + 7;
+  uint64_t* dq_full = bars + 8;
+  uint64_t* dq_empty = bars + 9;
+  uint64_t* kv_full = bars + 10;      // [2]
+  uint64_t* kv_empty = bars + 12;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  float* x_delta = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_local = (int)blockIdx.x < p.n_items ? (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  constexpr float L2E = 1.4426950408889634f;
+  constexpr uint32_t C_S = 0, C_DP = 128, C_DV = 256, C_DK = 320, C_DQ = 384;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    tma_prefetch_desc(&mapDO);
+    tma_prefetch_desc(&mapO);
+    mbar_init(pair_full, 1);
+    mbar_init(pair_empty, 1);
+    mbar_init(sdp_full, 1);
+    mbar_init(sdp_empty, 8);
+    mbar_init(slab_full, 8);
+    mbar_init(slab_empty, 1);
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 8);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 8);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  // step (chunk c, query tile qt) carries at least one visible (query, key) pair
+  auto step_live = [&](int c, int qt) {
+    if (qt >= p.nq) return false;
+    return !(p.causal && c * AF_KC > min(qt * AF_BM + AF_BM, p.q_len) - 1);
+  };
+  auto chunk_live = [&](int pr, int c) { return step_live(c, 2 * pr) || step_live(c, 2 * pr + 1); };
+  auto last_tile = [&](int pr, int c) { return step_live(c, 2 * pr + 1) ? 1 : 0; };     // last live tile of (pair, chunk)
+  auto first_tile = [&](int pr, int c) { return step_live(c, 2 * pr) ? 0 : 1; };
+
+  if (warp == 8) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      uint32_t pn = 0, kvn = 0;
+      for (int i = 0; i < n_local; ++i) {
+        const int item = blockIdx.x + i * gridDim.x;
+        const int h = item % p.H, b = item / p.H;
+        for (int pr = 0; pr < p.npairs; ++pr, ++pn) {
+          const int nt = min(2, p.nq - 2 * pr);
+          mbar_wait(pair_empty, (pn & 1) ^ 1);
+          mbar_expect_tx(pair_full, 3 * nt * AF_TILE);
+          for (int t = 0; t < nt; ++t) {
+            const int qt = 2 * pr + t;
+            tma_load_3d(sQ + t * AF_TILE, &mapQ, pair_full, p.q_col0 + h * AF_HD, qt * AF_BM, b);
+            tma_load_3d(sDO + t * AF_TILE, &mapDO, pair_full, h * AF_HD, qt * AF_BM, b);
+            tma_load_3d(sStage + t * AF_TILE, &mapO, pair_full, h * AF_HD, qt * AF_BM, b);
+          }
+          for (int c = 0; c < p.nc; ++c) {
+            if (!chunk_live(pr, c)) continue;
+            const uint32_t st = kvn & 1;
+            mbar_wait(&kv_empty[st], ((kvn >> 1) & 1) ^ 1);
+            mbar_expect_tx(&kv_full[st], 2 * AF_TILE);
+            tma_load_3d(sKV + st * 2 * AF_TILE, &mapK, &kv_full[st], p.k_col0 + h * AF_HD, c * AF_KC, b);
+            tma_load_3d(sKV + st * 2 * AF_TILE + AF_TILE, &mapV, &kv_full[st], p.v_col0 + h * AF_HD, c * AF_KC, b);
+            ++kvn;
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc(AF_BM, AF_KC, OpTraits<OpT>::fmt);
+      constexpr uint32_t idesc_kv = umma_idesc(AF_BM, AF_HD, OpTraits<OpT>::fmt) | (1u << 15) | (1u << 16);
+      constexpr uint32_t idesc_q = umma_idesc(AF_BM, AF_HD, OpTraits<OpT>::fmt) | (1u << 16);
+      uint32_t steps = 0, accs = 0, pn = 0, kvn = 0;
+      for (int i = 0; i < n_local; ++i) {
+        for (int pr = 0; pr < p.npairs; ++pr, ++pn) {
+          mbar_wait(pair_full, pn & 1);
+          mbar_wait(dq_empty, (pn & 1) ^ 1);         // the previous pair's dQ has been drained
+          tc_fence_after();
+          bool dq_started[2] = {false, false};
+          int pc = -1, pt = 0, pfirst = 0, plast = 0;
+          uint32_t pstep = 0, pst = 0;
+          auto outputs = [&](int t, bool first, bool last, uint32_t step, uint32_t st) {
+            mbar_wait(slab_full, step & 1);
+            if (first) mbar_wait(acc_empty, (accs & 1) ^ 1);
+            tc_fence_after();
+            const uint64_t p_mn = umma_desc_sw128_mn(smem_u32(sStage), AF_TILE);
+            const uint64_t ds_mn = umma_desc_sw128_mn(smem_u32(sStage + 2 * AF_TILE), AF_TILE);
+            const uint64_t do_b = umma_desc_sw128_mn(smem_u32(sDO + t * AF_TILE), AF_TILE);
+            const uint64_t q_b = umma_desc_sw128_mn(smem_u32(sQ + t * AF_TILE), AF_TILE);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_f16(tmem_base + C_DV, p_mn + 128ull * kk, do_b + 128ull * kk, idesc_kv, (!first) || kk != 0);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_f16(tmem_base + C_DK, ds_mn + 128ull * kk, q_b + 128ull * kk, idesc_kv, (!first) || kk != 0);
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+              const uint64_t ds_k = umma_desc_sw128(smem_u32(sStage + (2 + s2) * AF_TILE));
+              const uint64_t k_b = umma_desc_sw128_mn(smem_u32(sKV + st * 2 * AF_TILE + s2 * 64 * 128), AF_TILE);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_f16(tmem_base + C_DQ + t * AF_HD, ds_k + 2ull * kk, k_b + 128ull * kk, idesc_q,
+                         dq_started[t] || (s2 | kk) != 0);
+            }
+            dq_started[t] = true;
+            umma_commit(slab_empty);
+            if (last) {
+              umma_commit(acc_full);
+              ++accs;
+              umma_commit(&kv_empty[st]);        // the chunk's k / v tiles are no longer read
+            }
+          };
+          for (int c = 0; c < p.nc; ++c) {
+            if (!chunk_live(pr, c)) continue;
+            const uint32_t st = kvn & 1;
+            mbar_wait(&kv_full[st], (kvn >> 1) & 1);
+            ++kvn;
+            const int ft = first_tile(pr, c), lt = last_tile(pr, c);
+            for (int t = ft; t <= lt; ++t) {
+              mbar_wait(sdp_empty, (steps & 1) ^ 1);
+              tc_fence_after();
+              const uint64_t qd = umma_desc_sw128(smem_u32(sQ + t * AF_TILE));
+              const uint64_t dod = umma_desc_sw128(smem_u32(sDO + t * AF_TILE));
+              const uint64_t kd = umma_desc_sw128(smem_u32(sKV + st * 2 * AF_TILE));
+              const uint64_t vd = umma_desc_sw128(smem_u32(sKV + st * 2 * AF_TILE + AF_TILE));
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) umma_f16(tmem_base + C_S, qd + 2 * kk, kd + 2 * kk, idesc_s, kk != 0);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) umma_f16(tmem_base + C_DP, dod + 2 * kk, vd + 2 * kk, idesc_s, kk != 0);
+              umma_commit(sdp_full);
+              if (pc >= 0) outputs(pt, pfirst != 0, plast != 0, pstep, pst);
+              pc = c, pt = t, pfirst = (t == ft), plast = (t == lt), pstep = steps, pst = st;
+              ++steps;
+            }
+          }
+          if (pc >= 0) outputs(pt, pfirst != 0, plast != 0, pstep, pst);
+          umma_commit(dq_full);
+          umma_commit(pair_empty);
+        }
+      }
+    }
+  } else {
+    // ---------------- consumers ----------------
+    const int hf = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t t_lane = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    auto group_sync = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    const bool elected = tid == 0;
+    uint32_t steps = 0, accs = 0, pn = 0;
+    float* my_scratch = p.scratch + (size_t)blockIdx.x * p.nc * 2 * (AF_BM * AF_HD);
+    // 32 of the 64 columns of this thread's accumulator row (+ the scratch partial) -> scratch (fp32) or 16-bit store
+    auto drain_tile = [&](uint32_t tcol, float scale, float* part, bool add_part, bool to_scratch, const CUtensorMap* m,
+                          int col, int row0, int b, uint64_t* drained) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + tcol + t_lane + 32 * hf, r);
+      if (!to_scratch && elected) bulk_wait_read<0>();
+      tmem_ld_wait();
+      if (drained != nullptr) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(drained);
+      }
+      float v[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+      float4* pp = reinterpret_cast<float4*>(part + row * AF_HD + 32 * hf);
+      if (add_part) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 q = __ldcg(pp + k);
+          v[4 * k] += q.x, v[4 * k + 1] += q.y, v[4 * k + 2] += q.z, v[4 * k + 3] += q.w;
+        }
+      }
+      if (to_scratch) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) __stcg(pp + k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+        return;
+      }
+      group_sync();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint4 q;
+        q.x = OpTraits<OpT>::pack2(v[8 * k + 0] * scale, v[8 * k + 1] * scale);
+        q.y = OpTraits<OpT>::pack2(v[8 * k + 2] * scale, v[8 * k + 3] * scale);
+        q.z = OpTraits<OpT>::pack2(v[8 * k + 4] * scale, v[8 * k + 5] * scale);
+        q.w = OpTraits<OpT>::pack2(v[8 * k + 6] * scale, v[8 * k + 7] * scale);
+        *reinterpret_cast<uint4*>(sOut + row * 128 + (((4 * hf + k) ^ (row & 7)) << 4)) = q;
+      }
+      fence_proxy_async_smem();
+      group_sync();
+      if (elected) {
+        tma_store_3d(m, sOut, col, row0, b);
+        bulk_commit();
+      }
+    };
+    for (int i = 0; i < n_local; ++i) {
+      const int item = blockIdx.x + i * gridDim.x;
+      const int h = item % p.H, b = item / p.H;
+      const int len = p.kv_lens ? max(0, min(p.kv_lens[b], p.kv_len)) : p.kv_len;
+      for (int pr = 0; pr < p.npairs; ++pr, ++pn) {
+        const int nt = min(2, p.nq - 2 * pr);
+        mbar_wait(pair_full, pn & 1);
+        float delta[2] = {0.f, 0.f}, lb[2] = {0.f, 0.f};
+        for (int t = 0; t < nt; ++t) {
+          float dsum = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int chunk = ((4 * hf + k) ^ (row & 7)) << 4;
+            const uint4 a = *reinterpret_cast<const uint4*>(sDO + t * AF_TILE + row * 128 + chunk);
+            const uint4 o = *reinterpret_cast<const uint4*>(sStage + t * AF_TILE + row * 128 + chunk);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const OpT* ap = reinterpret_cast<const OpT*>(&aw[j]);
+              const OpT* op = reinterpret_cast<const OpT*>(&ow[j]);
+              dsum = fmaf(OpTraits<OpT>::to_float(ap[0]), OpTraits<OpT>::to_float(op[0]), dsum);
+              dsum = fmaf(OpTraits<OpT>::to_float(ap[1]), OpTraits<OpT>::to_float(op[1]), dsum);
+            }
+          }
+          x_delta[hf * AF_BM + row] = dsum;
+          group_sync();
+          delta[t] = dsum + x_delta[(hf ^ 1) * AF_BM + row];
+          group_sync();
+          const int qrow = (2 * pr + t) * AF_BM + row;
+          lb[t] = (qrow < p.q_len ? __ldg(p.lse + ((long long)b * p.H + h) * p.q_len + qrow) : 0.f) * L2E;
+        }
+        for (int c = 0; c < p.nc; ++c) {
+          if (!chunk_live(pr, c)) continue;
+          const int ft = first_tile(pr, c), lt = last_tile(pr, c);
+          for (int t = ft; t <= lt; ++t) {
+            const int qrow = (2 * pr + t) * AF_BM + row;
+            const int k0 = c * AF_KC + 64 * hf;
+            int nv = qrow < p.q_len ? min(64, max(0, len - k0)) : 0;
+            if (p.causal) nv = min(nv, max(0, qrow + 1 - k0));
+            const float dl = delta[t], lbq = lb[t];
+            uint8_t* sP = sStage + hf * AF_TILE;
+            uint8_t* sD = sStage + 2 * AF_TILE + hf * AF_TILE;
+            mbar_wait(sdp_full, steps & 1);
+            mbar_wait(slab_empty, (steps & 1) ^ 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+              uint32_t pk[16], dk[16];
+              uint32_t rs[32], rd[32];
+              const uint32_t t_s = tmem_base + C_S + t_lane + 64 * hf + 32 * half;
+              tmem_ld32(t_s, rs);
+              tmem_ld32(t_s + (C_DP - C_S), rd);
+              tmem_ld_wait();
+              if (half == 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sdp_empty);
+              }
+              const int nvh = nv - 32 * half;
+#pragma unroll
+              for (int k = 0; k < 32; k += 2) {
+                float p0 = af_ex2(fmaf(__uint_as_float(rs[k]), L2E, -lbq));
+                float p1 = af_ex2(fmaf(__uint_as_float(rs[k + 1]), L2E, -lbq));
+                p0 = k < nvh ? p0 : 0.f;
+                p1 = k + 1 < nvh ? p1 : 0.f;
+                const float d0 = p0 * (__uint_as_float(rd[k]) - dl);
+                const float d1 = p1 * (__uint_as_float(rd[k + 1]) - dl);
+                pk[k >> 1] = OpTraits<OpT>::pack2(p0, p1);
+                dk[k >> 1] = OpTraits<OpT>::pack2(d0, d1);
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int chunk = ((4 * half + k) ^ (row & 7)) << 4;
+                *reinterpret_cast<uint4*>(sP + row * 128 + chunk) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+                *reinterpret_cast<uint4*>(sD + row * 128 + chunk) = make_uint4(dk[4 * k], dk[4 * k + 1], dk[4 * k + 2], dk[4 * k + 3]);
+              }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(slab_full);
+            ++steps;
+            if (t == lt) {
+              // ---- dV_c, dK_c of this pair: add the earlier pairs' partial, store (last pair) or keep as the partial ----
+              int first_pr = 0;
+              while (!chunk_live(first_pr, c)) ++first_pr;
+              const bool add_part = pr > first_pr, to_scratch = pr < p.npairs - 1;
+              float* part = my_scratch + (size_t)c * 2 * (AF_BM * AF_HD);
+              mbar_wait(acc_full, accs & 1);
+              tc_fence_after();
+              drain_tile(C_DV, 1.0f, part, add_part, to_scratch, &mapDV, p.dv_col0 + h * AF_HD, c * AF_KC, b, nullptr);
+              drain_tile(C_DK, 1.0f, part + AF_BM * AF_HD, add_part, to_scratch, &mapDK, p.dk_col0 + h * AF_HD, c * AF_KC, b,
+                         acc_empty);
+              ++accs;
+            }
+          }
+        }
+        // ---- dQ of the pair's tiles ----
+        mbar_wait(dq_full, pn & 1);
+        tc_fence_after();
+        for (int t = 0; t < nt; ++t)
+          drain_tile(C_DQ + t * AF_HD, p.scale, nullptr, false, false, &mapDQ, p.dq_col0 + h * AF_HD, (2 * pr + t) * AF_BM, b,
+                     t == nt - 1 ? dq_empty : nullptr);
+      }
+    }
+    if (elected) bulk_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <typename OpT>
+static int launch_attention_bwd_general(const CUtensorMap (&m)[8], const AgDev& p, int grid, cudaStream_t s) {
+  auto kern = attention_bwd_general_kernel<OpT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute(attention_bwd_general)");
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(AF_THREADS);
+  cfg.dynamicSmemBytes = AF_SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], p);
+  if (e != cudaSuccess) return fail(e, "attention_bwd_general_kernel launch");
+  return 0;
+}
+
 template <typename OpT>
 static int launch_attention_bwd_fused(const CUtensorMap (&m)[8], const AfDev& p, cudaStream_t s) {
   auto kern = attention_bwd_fused_kernel<OpT>;
@@ -403,4 +794,59 @@ extern "C" int mm_attention_bwd_fused(const void* qkv, int64_t qkv_ld, int32_t q
   p.scale = 0.125f;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return f16 ? launch_attention_bwd_fused<__half>(m, p, s) : launch_attention_bwd_fused<__nv_bfloat16>(m, p, s);
+}
+
+extern "C" int64_t mm_attention_bwd_general_scratch_floats(int32_t kv_len) {
+  const int nc = (kv_len + AF_KC - 1) / AF_KC;
+  return (int64_t)kNumSMs * nc * 2 * (AF_BM * AF_HD);
+}
+
+extern "C" int mm_attention_bwd_general(const void* q, int64_t q_ld, int32_t q_col0, int32_t q_len, const void* k,
+                                        int64_t k_ld, int32_t k_col0, const void* v, int64_t v_ld, int32_t v_col0,
+                                        int32_t kv_len, const int32_t* kv_lens, int32_t batch, int32_t heads,
+                                        int32_t causal, const void* dout, int64_t do_ld, const void* out, int64_t o_ld,
+                                        const float* lse, void* dq, int64_t dq_ld, int32_t dq_col0, void* dk,
+                                        int64_t dk_ld, int32_t dk_col0, void* dv, int64_t dv_ld, int32_t dv_col0,
+                                        float* scratch, int32_t dtype, void* stream) {
+  if (!q || !k || !v || !dout || !out || !lse || !dq || !dk || !dv || !scratch) return bad_arg("attention_bwd_general: null pointer");
+  if (batch <= 0 || q_len <= 0 || kv_len <= 0 || heads <= 0) return bad_arg("attention_bwd_general: extents");
+  if (causal && q_len != kv_len) return bad_arg("attention_bwd_general: a causal mask needs q_len == kv_len");
+  const int d = heads * AF_HD;
+  if ((q_ld % 8) || (k_ld % 8) || (v_ld % 8) || (do_ld % 8) || (o_ld % 8) || (dq_ld % 8) || (dk_ld % 8) || (dv_ld % 8) ||
+      q_ld < q_col0 + d || k_ld < k_col0 + d || v_ld < v_col0 + d || do_ld < d || o_ld < d || dq_ld < dq_col0 + d ||
+      dk_ld < dk_col0 + d || dv_ld < dv_col0 + d || (q_col0 % 8) || (k_col0 % 8) || (v_col0 % 8) || (dq_col0 % 8) ||
+      (dk_col0 % 8) || (dv_col0 % 8))
+    return bad_arg("attention_bwd_general: leading dims / column offsets (head_dim must be 64)");
+  const int f16 = dtype == MM_DTYPE_F16;
+  CUtensorMap m[8];
+  const uint64_t Lq = (uint64_t)q_len, Tk = (uint64_t)kv_len, B = (uint64_t)batch;
+  int rc = make_tmap_3d(&m[0], q, f16, (uint64_t)q_ld, Lq, B, (uint64_t)q_ld, Lq * q_ld, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&m[1], k, f16, (uint64_t)k_ld, Tk, B, (uint64_t)k_ld, Tk * k_ld, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&m[2], v, f16, (uint64_t)v_ld, Tk, B, (uint64_t)v_ld, Tk * v_ld, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&m[3], dout, f16, (uint64_t)d, Lq, B, (uint64_t)do_ld, Lq * do_ld, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&m[4], out, f16, (uint64_t)d, Lq, B, (uint64_t)o_ld, Lq * o_ld, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&m[5], dq, f16, (uint64_t)dq_ld, Lq, B, (uint64_t)dq_ld, Lq * dq_ld, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&m[6], dk, f16, (uint64_t)dk_ld, Tk, B, (uint64_t)dk_ld, Tk * dk_ld, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&m[7], dv, f16, (uint64_t)dv_ld, Tk, B, (uint64_t)dv_ld, Tk * dv_ld, 128);
+  if (rc) return rc;
+  AgDev p;
+  memset(&p, 0, sizeof(p));
+  p.q_len = q_len, p.kv_len = kv_len, p.H = heads, p.causal = causal != 0;
+  p.nq = (q_len + AF_BM - 1) / AF_BM;
+  p.nc = (kv_len + AF_KC - 1) / AF_KC;
+  p.npairs = (p.nq + 1) / 2;
+  p.n_items = batch * heads;
+  p.q_col0 = q_col0, p.k_col0 = k_col0, p.v_col0 = v_col0, p.dq_col0 = dq_col0, p.dk_col0 = dk_col0, p.dv_col0 = dv_col0;
+  p.kv_lens = kv_lens, p.lse = lse, p.scratch = scratch;
+  p.scale = 0.125f;
+  const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return f16 ? launch_attention_bwd_general<__half>(m, p, grid, s) : launch_attention_bwd_general<__nv_bfloat16>(m, p, grid, s);
 }

@@ -61,6 +61,7 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
     _wgrad_flush = TrainEngine._wgrad_flush
     grouped_wgrad = os.environ.get("MM_GROUPED_WGRAD", "1") != "0"     # see TrainEngine.grouped_wgrad
     heads_gemm = os.environ.get("MM_HEADS_GEMM", "1") != "0"
+    fused_attn_bwd_onchip = os.environ.get("MM_ATTN_BWD_ONCHIP", "1") != "0"
     _bias_grad = TrainEngine._bias_grad
     _linear_bwd = TrainEngine._linear_bwd
     _ln_param_grads = TrainEngine._ln_param_grads
@@ -308,9 +309,14 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
         BH = B * H
         Lp, Tp = _round_up(Lq, 64), _round_up(Tk, 64)
         hd = dict(heads=H, head_stride=64, batches=BH, w_batched=True, block_n=bn)
+        _, p_attn, _, seed, seed_dev = self._saved["drop"]
+        if lse is not None and p_attn == 0 and self.fused_attn_bwd and self.fused_attn_bwd_onchip:
+            # one kernel: S, dP, P, dS never leave the SM (mm_attention_bwd_general: query-tile pairs, fp32 dk / dv partials)
+            scratch = self.buf("a_bwd_scratch", (K.attention_bwd_general_scratch_floats(Tk),), torch.float32)
+            K.attention_bwd_general(q, Lq, k, v, Tk, kv_lens, B, H, dO, out, lse, dq, dk, dv, scratch, causal=causal)
+            return
         P = self.buf("a_P", (BH, Lp, Tp), op)
         dS = self.buf("a_dS", (BH, Lp, Tp), op)
-        _, p_attn, _, seed, seed_dev = self._saved["drop"]
         if lse is not None and p_attn == 0 and self.fused_attn_bwd:
             K.attention_bwd_scores(q, 0, Lq, k, 0, v, 0, Tk, kv_lens, B, H, dO, out, lse, P, dS, causal=causal)
         else:

@@ -454,6 +454,33 @@ def attention_bwd_fused(qkv: torch.Tensor, seq_len: int, kv_lens: Optional[torch
                    "mm_attention_bwd_fused")
 
 
+def attention_bwd_general_scratch_floats(kv_len: int) -> int:
+    return int(_lib.load().mm_attention_bwd_general_scratch_floats(kv_len))
+
+
+def attention_bwd_general(q: torch.Tensor, q_len: int, k: torch.Tensor, v: torch.Tensor, kv_len: int,
+                          kv_lens: Optional[torch.Tensor], batch: int, heads: int, dout: torch.Tensor, out: torch.Tensor,
+                          lse: torch.Tensor, dq: torch.Tensor, dk: torch.Tensor, dv: torch.Tensor, scratch: torch.Tensor,
+                          causal: bool = False) -> None:
+    """dq / dk / dv from q / k / v (2-D token-major views whose first column is head 0's), dout, out and lse in one kernel
+    for any lengths, causal or not (``mm_attention_bwd_general``); scratch: fp32, attention_bwd_general_scratch_floats."""
+    ts = (q, k, v, dout, out, dq, dk, dv)
+    assert all(t.dtype == q.dtype for t in ts) and q.dtype in _DT
+    assert all(t.dim() == 2 and t.stride(1) == 1 for t in ts)
+    assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == batch * heads * q_len
+    assert scratch.dtype == torch.float32 and scratch.numel() >= attention_bwd_general_scratch_floats(kv_len)
+    if kv_lens is not None:
+        assert kv_lens.dtype == torch.int32 and kv_lens.numel() == batch
+    lib = _lib.load()
+    with _Launch("attention_bwd_general", 10.0 * batch * heads * q_len * kv_len * 64 * (0.5 if causal else 1.0)):
+        _lib.check(lib.mm_attention_bwd_general(_ptr(q), q.stride(0), 0, q_len, _ptr(k), k.stride(0), 0, _ptr(v), v.stride(0),
+                                                0, kv_len, _ptr(kv_lens), batch, heads, int(causal), _ptr(dout),
+                                                dout.stride(0), _ptr(out), out.stride(0), _ptr(lse), _ptr(dq),
+                                                dq.stride(0), 0, _ptr(dk), dk.stride(0), 0, _ptr(dv), dv.stride(0), 0,
+                                                _ptr(scratch), dtype_code(q.dtype), _stream()),
+                   "mm_attention_bwd_general")
+
+
 def heads_gemm(a: torch.Tensor, a_ld: int, a_bs: int, transposed: bool, w: torch.Tensor, w_ld: int, w_bs: int,
                out: torch.Tensor, out_ld: int, out_bs: int, rows: int, k: int, batch: int, heads: int,
                scale: float = 1.0) -> None:

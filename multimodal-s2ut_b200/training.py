@@ -635,6 +635,12 @@ class TrainEngine(EncoderEngine):
             # one kernel: S, dP, P, dS never leave the SM; dq | dk | dv accumulate in TMEM
             K.attention_bwd_fused(qkv, T, seq_lens, B, H, datt, s["att"], s["lse"], dqkv)
             return
+        if "lse" in s and self.fused_attn_bwd and self.fused_attn_bwd_onchip:
+            # longer sequences: the same on chip with query tiles taken in pairs (mm_attention_bwd_general)
+            scratch = self.buf("a_bwd_scratch", (K.attention_bwd_general_scratch_floats(T),), torch.float32)
+            K.attention_bwd_general(qkv, T, qkv[:, d:], qkv[:, 2 * d:], T, seq_lens, B, H, datt, s["att"], s["lse"], dqkv,
+                                    dqkv[:, d:], dqkv[:, 2 * d:], scratch)
+            return
         BH = B * H
         hd = dict(heads=H, head_stride=64, batches=BH, w_batched=True, block_n=bn)
         P = self.buf("a_P", (BH, Tp, Tp), op)

@@ -291,6 +291,32 @@ def attention_bwd_scores(q, q_col0, q_len, k, k_col0, v, v_col0, kv_len, kv_lens
     dscores.view(batch, heads, probs.shape[1], probs.shape[2])[:, :, :q_len, :kv_len] = dS.to(dscores.dtype)
 
 
+def attention_bwd_general_scratch_floats(kv_len):
+    return 1
+
+
+def attention_bwd_general(q, q_len, k, v, kv_len, kv_lens, batch, heads, dout, out, lse, dq, dk, dv, scratch, causal=False):
+    global launch_count
+    launch_count += 1
+    d = heads * 64
+    Q, Kx, V = _qkv_heads(q, 0, q_len, k, 0, v, 0, kv_len, batch, heads)
+    s = Q @ Kx.transpose(-1, -2)
+    dead = torch.zeros(batch, 1, q_len, kv_len, dtype=torch.bool)
+    if kv_lens is not None:
+        dead = dead | (torch.arange(kv_len)[None, :] >= kv_lens[:, None])[:, None, None, :]
+    if causal:
+        dead = dead | (torch.arange(kv_len)[None, :] > torch.arange(q_len)[:, None])[None, None]
+    P = torch.exp(s - lse.view(batch, heads, q_len, 1)).masked_fill(dead, 0.0)
+    dO = dout[:, :d].float().view(batch, q_len, heads, 64).permute(0, 2, 1, 3)
+    O = out[:, :d].float().view(batch, q_len, heads, 64).permute(0, 2, 1, 3)
+    dS = P * (dO @ V.transpose(-1, -2) - (dO * O).sum(-1, keepdim=True))
+    P, dS = P.to(q.dtype).float(), dS.to(q.dtype).float()
+    back = lambda x, L: x.permute(0, 2, 1, 3).reshape(batch * L, d)
+    dq[:, :d] = back(dS @ Kx * 0.125, q_len).to(dq.dtype)
+    dk[:, :d] = back(dS.transpose(-1, -2) @ Q, kv_len).to(dk.dtype)
+    dv[:, :d] = back(P.transpose(-1, -2) @ dO, kv_len).to(dv.dtype)
+
+
 def attention_bwd_fused(qkv, seq_len, kv_lens, batch, heads, dout, out, lse, dqkv):
     global launch_count
     launch_count += 1

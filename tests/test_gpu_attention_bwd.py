@@ -132,3 +132,52 @@ def test_fused_attention_backward_on_chip(cuda, B, H, T, ragged):
         got, want = dqkv[:, c0:c0 + d].float(), ref[:, c0:c0 + d]
         rel = ((got - want).norm() / want.norm().clamp_min(1e-9)).item()
         assert rel < 2e-2, (name, rel)
+
+
+@pytest.mark.parametrize("B,H,Lq,Tk,causal,ragged", [(2, 4, 500, 500, True, False), (2, 4, 500, 250, False, True),
+                                                      (3, 2, 130, 130, True, False), (2, 4, 750, 750, False, True),
+                                                      (1, 8, 300, 64, False, False), (2, 2, 257, 257, True, False),
+                                                      (16, 8, 500, 500, True, False)])
+def test_general_attention_backward_on_chip(cuda, B, H, Lq, Tk, causal, ragged):
+    """mm_attention_bwd_general (query-tile pairs, fp32 dk / dv partials of the earlier pairs in scratch, causal steps
+    skipped) against autograd in fp32 over the same 16-bit operands: the decoder's causal self-attention (L = 500), its
+    encoder attention (500 x 250 with encoder lengths), the encoder at 30 s (T = 750)."""
+    from mm_s2ut_b200 import kernels as K
+
+    d = 64 * H
+    g = torch.Generator().manual_seed(Lq * 3 + Tk + B)
+    q = (torch.randn(B * Lq, d, generator=g) * 0.5 * 0.125).bfloat16().cuda()         # pre-scaled by head_dim^-0.5
+    kv = (torch.randn(B * Tk, 2 * d, generator=g) * 0.5).bfloat16().cuda()
+    dO = (torch.randn(B * Lq, d, generator=g) * 0.1).bfloat16().cuda()
+    lens = None
+    if ragged:
+        lens = torch.tensor([Tk - (11 * b) % (Tk // 2) for b in range(B)], dtype=torch.int32, device=cuda)
+    out = torch.empty(B * Lq, d, dtype=torch.bfloat16, device=cuda)
+    lse = torch.empty(B, H, Lq, device=cuda)
+    K.attention(q, 0, Lq, kv, 0, kv, d, Tk, lens, B, H, out, causal=causal, lse=lse)
+    dq = torch.full((B * Lq, d), float("nan"), dtype=torch.bfloat16, device=cuda)
+    dkv = torch.full((B * Tk, 2 * d), float("nan"), dtype=torch.bfloat16, device=cuda)
+    scratch = torch.empty(K.attention_bwd_general_scratch_floats(Tk), device=cuda)
+    K.attention_bwd_general(q, Lq, kv, kv[:, d:], Tk, lens, B, H, dO, out, lse, dq, dkv, dkv[:, d:], scratch, causal=causal)
+    torch.cuda.synchronize()
+    assert torch.isfinite(dq.float()).all() and torch.isfinite(dkv.float()).all()
+    if B > 8:
+        # twice: the scratch partials of the first run must not leak into the second
+        dq2, dkv2 = torch.empty_like(dq), torch.empty_like(dkv)
+        K.attention_bwd_general(q, Lq, kv, kv[:, d:], Tk, lens, B, H, dO, out, lse, dq2, dkv2, dkv2[:, d:], scratch, causal=causal)
+        assert torch.equal(dq, dq2) and torch.equal(dkv, dkv2)
+        return
+    heads = lambda x, L: x.float().view(B, L, H, 64).permute(0, 2, 1, 3).clone()
+    qf, kf, vf = heads(q, Lq).requires_grad_(), heads(kv[:, :d], Tk).requires_grad_(), heads(kv[:, d:], Tk).requires_grad_()
+    s = qf @ kf.transpose(-1, -2)
+    if lens is not None:
+        s = s.masked_fill((torch.arange(Tk, device=cuda)[None, :] >= lens[:, None])[:, None, None, :], float("-inf"))
+    if causal:
+        s = s.masked_fill(torch.arange(Tk, device=cuda)[None, :] > torch.arange(Lq, device=cuda)[:, None], float("-inf"))
+    o = s.softmax(-1) @ vf
+    (o * heads(dO, Lq)).sum().backward()
+    back = lambda t, L: t.permute(0, 2, 1, 3).reshape(B * L, d)
+    for name, got, want in (("dq", dq, back(qf.grad, Lq) * 0.125), ("dk", dkv[:, :d], back(kf.grad, Tk)),
+                            ("dv", dkv[:, d:], back(vf.grad, Tk))):
+        rel = ((got.float() - want).norm() / want.norm().clamp_min(1e-9)).item()
+        assert rel < 2e-2, (name, rel)
