@@ -37,9 +37,6 @@ struct LnDev {
   float eps;
   int want_f32;
   int l2_hints;   // bit 0: residual stream evict_last, bit 1: A operand evict_first
-  int fold;       // 1: no LayerNorm here -- write bf16(x_new) and the row statistics (mean, rstd); the consumer GEMM
-                  // applies the normalisation in its epilogue (MM "LN fold", see mm_gemm_resid_fold)
-  float* stats;   // fold: [rows][2] fp32
 };
 
 __device__ __forceinline__ uint4* ln_slab_chunk(uint8_t* slab, int row, int c) {
@@ -169,92 +166,6 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     mbar_wait(tfull, it & 1);     // accumulator complete => every MMA has finished reading the operand ring
     tc_fence_after();
     LN_TRACE(1);
-    if (p.fold) {
-      // ---- fold epilogue: one sweep.  Per 64 columns: x slabs (2 x 32 fp32 columns) arrive by TMA one step ahead,
-      //      v = acc + bias + x goes back into them (new residual) and as 16-bit into a third slab; three TMA stores.
-      //      Buffers of this half: set s = {3 s, 3 s + 1 (fp32), 3 s + 2 (16-bit)}, s = step & 1. ----
-      float sum = 0.f, sumsq = 0.f;
-      auto prefetch = [&](int step) {
-        const int sb = 3 * (step & 1);
-#pragma unroll 1
-        for (int q = 0; q < 2; ++q) {
-          mbar_expect_tx(&aux[sb + q], Cfg::SLAB_BYTES);
-          tma_load_3d_hint(slab_ptr(sb + q), &mapX, &aux[sb + q], 256 * h + 64 * step + 32 * q, row0, 0, pol_x);
-        }
-      };
-      if (ht == 0) prefetch(0);
-      uint32_t ra[32], rb[32];
-      tmem_ld32(taddr, ra);
-      tmem_ld32(taddr + 32, rb);
-#pragma unroll 1
-      for (int step = 0; step < 4; ++step) {
-        const int sb = 3 * (step & 1);
-        if (ht == 0 && step + 1 < 4) {
-          bulk_wait_read<1>();           // the stores of step - 1 have finished reading the other buffer set
-          prefetch(step + 1);
-        }
-        uint8_t* hs = slab_ptr(sb + 2);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          uint32_t (&r)[32] = q == 0 ? ra : rb;
-          uint8_t* slab = slab_ptr(sb + q);
-          const float4* b4 = reinterpret_cast<const float4*>(s_bias + 256 * h + 64 * step + 32 * q);
-          mbar_wait(&aux[sb + q], (aux_phase >> (sb + q)) & 1);
-          aux_phase ^= (1u << (sb + q));
-          float v[32];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 bq = b4[c];
-            const uint4 xq = *ln_slab_chunk(slab, lrow, c);
-            v[4 * c + 0] = __uint_as_float(r[4 * c + 0]) + bq.x + __uint_as_float(xq.x);
-            v[4 * c + 1] = __uint_as_float(r[4 * c + 1]) + bq.y + __uint_as_float(xq.y);
-            v[4 * c + 2] = __uint_as_float(r[4 * c + 2]) + bq.z + __uint_as_float(xq.z);
-            v[4 * c + 3] = __uint_as_float(r[4 * c + 3]) + bq.w + __uint_as_float(xq.w);
-            sum += (v[4 * c] + v[4 * c + 1]) + (v[4 * c + 2] + v[4 * c + 3]);
-            sumsq += (v[4 * c] * v[4 * c] + v[4 * c + 1] * v[4 * c + 1]) + (v[4 * c + 2] * v[4 * c + 2] + v[4 * c + 3] * v[4 * c + 3]);
-            *ln_slab_chunk(slab, lrow, c) = make_uint4(__float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]),
-                                                       __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3]));
-          }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint4 o;
-            o.x = OpTraits<OpT>::pack2(v[8 * c + 0], v[8 * c + 1]);
-            o.y = OpTraits<OpT>::pack2(v[8 * c + 2], v[8 * c + 3]);
-            o.z = OpTraits<OpT>::pack2(v[8 * c + 4], v[8 * c + 5]);
-            o.w = OpTraits<OpT>::pack2(v[8 * c + 6], v[8 * c + 7]);
-            *ln_slab_chunk(hs, lrow, 4 * q + c) = o;
-          }
-        }
-        if (step + 1 < 4) {
-          tmem_ld32(taddr + 64 * (step + 1), ra);
-          tmem_ld32(taddr + 64 * (step + 1) + 32, rb);
-        }
-        fence_proxy_async_smem();
-        if (h == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (ht == 0) {
-          tma_store_3d_hint(&mapXo, slab_ptr(sb), 256 * h + 64 * step, row0, 0, pol_x);
-          tma_store_3d_hint(&mapXo, slab_ptr(sb + 1), 256 * h + 64 * step + 32, row0, 0, pol_x);
-          tma_store_3d(&mapH, hs, 256 * h + 64 * step, row0, 0);
-          bulk_commit();
-        }
-      }
-      // row statistics for the consumer: (mean, rstd) of the complete 512-wide row
-      stat[h * 128 + lrow] = sum;
-      stat[256 + h * 128 + lrow] = sumsq;
-      asm volatile("bar.sync 3, 256;" ::: "memory");
-      if (h == 0 && row0 + lrow < p.rows) {
-        const float mean = (sum + stat[128 + lrow]) * (1.0f / Cfg::N);
-        const float ex2 = (sumsq + stat[256 + 128 + lrow]) * (1.0f / Cfg::N);
-        const float rstd = rsqrtf(fmaxf(ex2 - mean * mean, 0.f) + p.eps);
-        reinterpret_cast<float2*>(p.stats)[row0 + lrow] = make_float2(mean, rstd);
-      }
-      if (ht == 0) bulk_wait_read<0>();
-      tc_fence_before();
-      cluster_sync_all();
-      tc_fence_after();
-      continue;
-    }
     if (ht == 0) {                // this half's residual slabs 0..5 (slabs 6, 7 recycle buffers 0, 1)
 #pragma unroll 1
       for (int j = 0; j < 6; ++j) {
@@ -465,32 +376,10 @@ extern "C" int mm_gemm_resid_ln(const void* a, int64_t a_ld, const void* w, int6
   return mm_gemm_resid_ln_out(a, a_ld, w, w_ld, rows, k, n, bias, x, x, gamma, beta, eps, h_op, h_f32, dtype, stream);
 }
 
-static int gemm_resid_ln_impl(const void* a, int64_t a_ld, const void* w, int64_t w_ld, int32_t rows, int32_t k,
-                              int32_t n, const float* bias, const float* x, float* x_out, const float* gamma,
-                              const float* beta, float eps, void* h_op, float* h_f32, float* fold_stats, int32_t dtype,
-                              void* stream);
-
 extern "C" int mm_gemm_resid_ln_out(const void* a, int64_t a_ld, const void* w, int64_t w_ld, int32_t rows, int32_t k,
                                     int32_t n, const float* bias, const float* x, float* x_out, const float* gamma,
                                     const float* beta, float eps, void* h_op, float* h_f32, int32_t dtype,
                                     void* stream) {
-  if (!gamma || !beta) return mm::bad_arg("gemm_resid_ln: null pointer");
-  return gemm_resid_ln_impl(a, a_ld, w, w_ld, rows, k, n, bias, x, x_out, gamma, beta, eps, h_op, h_f32, nullptr, dtype,
-                            stream);
-}
-
-extern "C" int mm_gemm_resid_fold(const void* a, int64_t a_ld, const void* w, int64_t w_ld, int32_t rows, int32_t k,
-                                  int32_t n, const float* bias, const float* x, float* x_out, float eps, void* x_op,
-                                  float* stats, int32_t dtype, void* stream) {
-  if (!stats) return mm::bad_arg("gemm_resid_fold: null stats");
-  return gemm_resid_ln_impl(a, a_ld, w, w_ld, rows, k, n, bias, x, x_out, bias, bias, eps, x_op, nullptr, stats, dtype,
-                            stream);
-}
-
-static int gemm_resid_ln_impl(const void* a, int64_t a_ld, const void* w, int64_t w_ld, int32_t rows, int32_t k,
-                              int32_t n, const float* bias, const float* x, float* x_out, const float* gamma,
-                              const float* beta, float eps, void* h_op, float* h_f32, float* fold_stats, int32_t dtype,
-                              void* stream) {
   using namespace mm;
   if (!x_out) return bad_arg("gemm_resid_ln: null x_out");
   if (!a || !w || !bias || !x || !gamma || !beta || !h_op) return bad_arg("gemm_resid_ln: null pointer");
@@ -518,7 +407,6 @@ static int gemm_resid_ln_impl(const void* a, int64_t a_ld, const void* w, int64_
   memset(&p, 0, sizeof(p));
   p.rows = rows, p.k = k, p.num_kb = (k + 63) / 64, p.num_tiles = (rows + 255) / 256;
   p.bias = bias, p.gamma = gamma, p.beta = beta, p.eps = eps, p.want_f32 = h_f32 != nullptr;
-  p.fold = fold_stats != nullptr, p.stats = fold_stats;
   static const int l2_hints = getenv("MM_LN_L2_HINTS") ? atoi(getenv("MM_LN_L2_HINTS")) : 3;
   p.l2_hints = l2_hints;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
