@@ -96,6 +96,12 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
     n = all_reduce_flat(flat, bucket_elems=256)
+    # default path: the peer-memory exchange applies to NCCL / CUDA only; under gloo it must fall back to one collective
+    from mm_s2ut_b200.peer import peer_group
+
+    assert peer_group(flat) is None
+    one = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    assert all_reduce_flat(one) == world and torch.equal(one, flat)
     q.put((rank, n, flat.sum().item()))
     dist.destroy_process_group()
 
