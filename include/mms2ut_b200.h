@@ -147,6 +147,14 @@ typedef struct mm_gemm_args {
    *                   (attention backward straight from / into the q|k|v layout).  out_hm: MM_EPI_OP, n % 64 == 0. */
   int32_t a_mn, w_mn, a_kbatch, w_kbatch, a_hm, w_hm, out_hm, heads, head_stride;
   int64_t a_k_total, w_k_total;
+  /* MM_EPI_RELU_OP, training forward: activation dropout on relu(acc + bias) (fairseq --activation-dropout /
+   * --relu-dropout, scripts/textless/1_train.sh:112): kept values are scaled by 1 / (1 - drop_p); the mask of element
+   * (row, column) is the counter-based one of mm_dropout at index row * n + column, site drop_site, seed drop_seed +
+   * *drop_seed_dev (drop_seed_dev optional).  drop_p == 0: off. */
+  float drop_p;
+  uint32_t drop_site;
+  uint64_t drop_seed;
+  const uint64_t* drop_seed_dev;
 } mm_gemm_args;
 
 int mm_gemm(const mm_gemm_args* args, void* stream);
@@ -159,6 +167,14 @@ int mm_gemm(const mm_gemm_args* args, void* stream);
 int mm_gemm_resid_ln(const void* a, int64_t a_ld, const void* w, int64_t w_ld, int32_t rows, int32_t k, int32_t n,
                      const float* bias, float* x, const float* gamma, const float* beta, float eps, void* h_op,
                      float* h_f32, int32_t dtype, void* stream);
+
+/* The same with dropout on the sub-layer output before the residual add (training forward: fairseq
+ * TransformerEncoderLayer's dropout_module after out_proj / fc2): x_out <- x + dropout(a W^T + bias); mask as
+ * mm_dropout at element index row * n + column. */
+int mm_gemm_resid_ln_drop(const void* a, int64_t a_ld, const void* w, int64_t w_ld, int32_t rows, int32_t k, int32_t n,
+                          const float* bias, const float* x, float* x_out, const float* gamma, const float* beta,
+                          float eps, void* h_op, float* h_f32, float drop_p, uint64_t seed, const uint64_t* seed_dev,
+                          uint32_t site, int32_t dtype, void* stream);
 
 /* Same with the updated residual stream written to x_out instead of over x (x_out == x: in place): the training-step
  * forward keeps every sub-layer's input for the backward pass. */
@@ -396,6 +412,12 @@ int mm_reduce_partials_many(const mm_reduce_job* jobs, int32_t count, void* stre
 int mm_layernorm_bwd_blocks(void);
 int mm_layernorm_bwd(const float* x, const float* gamma, const float* dy, int64_t rows, int32_t dim, float eps,
                      const float* resid, float* dx, float* partials, void* dx_op, int32_t dtype, void* stream);
+/* The same with the dropout mask of the sub-layer branch the gradient enters next burnt into its 16-bit copy:
+ * dx_op = (dx o keep) / (1 - drop_p) (mask as mm_dropout, element index row * dim + column); dx itself (the residual
+ * path) stays unmasked. */
+int mm_layernorm_bwd_drop(const float* x, const float* gamma, const float* dy, int64_t rows, int32_t dim, float eps,
+                          const float* resid, float* dx, float* partials, void* dx_op, float drop_p, uint64_t seed,
+                          const uint64_t* seed_dev, uint32_t site, int32_t dtype, void* stream);
 int mm_softmax_bwd(const float* scores, const void* dprobs, int32_t dprobs_is_op, int64_t ld_dprobs, int64_t ld_in,
                    int64_t rows, int32_t rows_per_batch,
                    int32_t n_keys, const int32_t* kv_lens, int32_t heads, void* probs, void* dscores, int64_t ld_out,

@@ -18,7 +18,7 @@ CSRC = _PKG / "csrc"
 INCLUDE = _PKG.parent / "include"
 LIB_PATH = _PKG / "libmms2ut_b200.so"
 SOURCES = ["abi.cu", "gemm.cu", "gemm_ln.cu", "rowwise.cu", "fbank.cu", "attention.cu", "cross_attention.cu", "attention_bwd.cu", "backward.cu", "wgrad.cu", "heads_gemm.cu", "attention_bwd_fused.cu", "p2p.cu"]
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -89,6 +89,7 @@ class GemmArgs(C.Structure):
         ("a_mn", C.c_int32), ("w_mn", C.c_int32), ("a_kbatch", C.c_int32), ("w_kbatch", C.c_int32),
         ("a_hm", C.c_int32), ("w_hm", C.c_int32), ("out_hm", C.c_int32), ("heads", C.c_int32),
         ("head_stride", C.c_int32), ("a_k_total", C.c_int64), ("w_k_total", C.c_int64),
+        ("drop_p", C.c_float), ("drop_site", C.c_uint32), ("drop_seed", C.c_uint64), ("drop_seed_dev", C.c_void_p),
     ]
 
 
@@ -152,6 +153,9 @@ EXPORTS = {
     "mm_gemm_resid_ln": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
                                    C.c_int32, C.c_void_p]),
+    "mm_gemm_resid_ln_drop": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
+                                        C.c_void_p, C.c_float, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p]),
     "mm_gemm_resid_ln_out": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
                                        C.c_void_p, C.c_int32, C.c_void_p]),
@@ -191,6 +195,9 @@ EXPORTS = {
     "mm_layernorm_bwd_blocks": (C.c_int, []),
     "mm_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mm_layernorm_bwd_drop": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_uint64, C.c_void_p, C.c_uint32,
+                                        C.c_int32, C.c_void_p]),
     "mm_softmax_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                  C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "mm_softmax_dropout_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32,

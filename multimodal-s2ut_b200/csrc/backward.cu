@@ -361,12 +361,19 @@ static int launch_colsum(const void* in, long long ld, int rows, int cols, int p
 //   xhat = (x - mean) * rstd ; dyg = dy * gamma ; dx = rstd * (dyg - mean(dyg) - xhat * mean(dyg * xhat))
 //   dx_out = (resid ? resid : 0) + dx ; partials[block] = (sum_r dy * xhat, sum_r dy)
 // ---------------------------------------------------------------------------------------------------
-template <int DIM, typename OpT>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+template <int DIM, typename OpT, bool DROP>
+__global__ void __launch_bounds__(256, DIM <= 512 ? 2 : 1) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                              const float* __restrict__ dy, long long rows, float eps,
                                                              const float* resid, float* dx_out,
-                                                             float* __restrict__ partials, OpT* __restrict__ dx_op) {
+                                                             float* __restrict__ partials, OpT* __restrict__ dx_op,
+                                                             float drop_p, unsigned long long seed,
+                                                             const unsigned long long* seed_dev, unsigned site) {
   constexpr int V = DIM / 128;
+  // drop_p > 0: the 16-bit copy carries the dropout mask of the sub-layer branch it feeds (gradient entering
+  // out_proj / fc2 = g o mask / (1 - p)); the fp32 gradient (the residual path) stays unmasked
+  if (DROP && seed_dev) seed += *seed_dev;
+  const unsigned thr = dropout_threshold(drop_p);
+  const float dinv = 1.0f / (1.0f - drop_p);
   __shared__ float red[8][DIM];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 ag[V], ab[V];
@@ -420,6 +427,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         if (resid) o.x += rs[i].x, o.y += rs[i].y, o.z += rs[i].z, o.w += rs[i].w;
         reinterpret_cast<float4*>(dx_out + row * DIM)[lane + 32 * i] = o;
         if (dx_op) {   // 16-bit copy of the gradient: the A operand of the next dgrad / wgrad GEMMs
+          if constexpr (DROP)
+            dropout_apply4(dropout_bits4(seed, site, (unsigned long long)(row * (DIM / 4) + lane + 32 * i)), thr, dinv, o.x,
+                           o.y, o.z, o.w);
           uint2 pk;
           pk.x = OpTraits<OpT>::pack2(o.x, o.y);
           pk.y = OpTraits<OpT>::pack2(o.z, o.w);
@@ -451,15 +461,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 //   P = softmax(S[:, :valid]) ; D = sum_k P dP ; dS = P (dP - D)   (keys >= valid: P = dS = 0 up to ld_out)
 // rows are laid out [batch][rows_per_batch]; valid keys of a batch = kv_lens[batch / heads] (or n_keys).
 // ---------------------------------------------------------------------------------------------------
-// counter-based dropout mask: see the dropout kernel below
-__device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned site, unsigned long long i, float p) {
-  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(site + 1) + i * 0xD1342543DE82EF95ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (float)(z >> 40) * (1.0f / 16777216.0f) >= p;      // 24 uniform bits
-}
-
+// (counter-based dropout mask: dropout_keep in common.cuh)
 
 // NPL = keys per lane held in registers (n_keys <= 32 * NPL): scores and dP are read once.
 // With drop_p > 0 the probabilities carry attention dropout: m = keep(seed, site, row * ld_out + k) / (1 - p);
@@ -964,31 +966,51 @@ extern "C" int mm_layernorm_bwd_blocks(void) { return 2 * kNumSMs; }
 
 template <typename OpT>
 static int launch_ln_bwd(const float* x, const float* gamma, const float* dy, long long rows, int dim, float eps,
-                         const float* resid, float* dx, float* partials, void* dx_op, cudaStream_t s) {
+                         const float* resid, float* dx, float* partials, void* dx_op, float drop_p,
+                         unsigned long long seed, const unsigned long long* seed_dev, unsigned site, cudaStream_t s) {
   const unsigned grid = 2 * kNumSMs;
   OpT* o = reinterpret_cast<OpT*>(dx_op);
+#define MM_LNB(D)                                                                                                        \
+  do {                                                                                                                   \
+    if (drop_p > 0.f)                                                                                                    \
+      layernorm_bwd_kernel<D, OpT, true><<<grid, 256, 0, s>>>(x, gamma, dy, rows, eps, resid, dx, partials, o, drop_p,  \
+                                                              seed, seed_dev, site);                                     \
+    else                                                                                                                 \
+      layernorm_bwd_kernel<D, OpT, false><<<grid, 256, 0, s>>>(x, gamma, dy, rows, eps, resid, dx, partials, o, drop_p, \
+                                                               seed, seed_dev, site);                                    \
+  } while (0)
   switch (dim) {
-    case 256: layernorm_bwd_kernel<256, OpT><<<grid, 256, 0, s>>>(x, gamma, dy, rows, eps, resid, dx, partials, o); break;
-    case 512: layernorm_bwd_kernel<512, OpT><<<grid, 256, 0, s>>>(x, gamma, dy, rows, eps, resid, dx, partials, o); break;
-    case 768: layernorm_bwd_kernel<768, OpT><<<grid, 256, 0, s>>>(x, gamma, dy, rows, eps, resid, dx, partials, o); break;
-    case 1024: layernorm_bwd_kernel<1024, OpT><<<grid, 256, 0, s>>>(x, gamma, dy, rows, eps, resid, dx, partials, o); break;
+    case 256: MM_LNB(256); break;
+    case 512: MM_LNB(512); break;
+    case 768: MM_LNB(768); break;
+    case 1024: MM_LNB(1024); break;
     default: return bad_arg("layernorm_bwd dim must be 256, 512, 768 or 1024");
   }
+#undef MM_LNB
+  return 0;
+}
+
+extern "C" int mm_layernorm_bwd_drop(const float* x, const float* gamma, const float* dy, int64_t rows, int32_t dim,
+                                     float eps, const float* resid, float* dx, float* partials, void* dx_op,
+                                     float drop_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site,
+                                     int32_t dtype, void* stream) {
+  if (!x || !gamma || !dy || !partials || rows <= 0) return bad_arg("layernorm_bwd");
+  if (dx_op && !dx) return bad_arg("layernorm_bwd: dx_op needs dx");
+  if (drop_p < 0.f || drop_p >= 1.f || (drop_p > 0.f && !dx_op)) return bad_arg("layernorm_bwd: dropout needs dx_op and p in [0, 1)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned long long* sd = reinterpret_cast<const unsigned long long*>(seed_dev);
+  int rc = dtype == MM_DTYPE_F16
+               ? launch_ln_bwd<__half>(x, gamma, dy, rows, dim, eps, resid, dx, partials, dx_op, drop_p, seed, sd, site, s)
+               : launch_ln_bwd<__nv_bfloat16>(x, gamma, dy, rows, dim, eps, resid, dx, partials, dx_op, drop_p, seed, sd, site, s);
+  if (rc) return rc;
+  MM_CHECK_LAUNCH("layernorm_bwd_kernel launch");
   return 0;
 }
 
 extern "C" int mm_layernorm_bwd(const float* x, const float* gamma, const float* dy, int64_t rows, int32_t dim, float eps,
                                 const float* resid, float* dx, float* partials, void* dx_op, int32_t dtype,
                                 void* stream) {
-  if (!x || !gamma || !dy || !partials || rows <= 0) return bad_arg("layernorm_bwd");
-  if (dx_op && !dx) return bad_arg("layernorm_bwd: dx_op needs dx");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int rc = dtype == MM_DTYPE_F16 ? launch_ln_bwd<__half>(x, gamma, dy, rows, dim, eps, resid, dx, partials, dx_op, s)
-                                       : launch_ln_bwd<__nv_bfloat16>(x, gamma, dy, rows, dim, eps, resid, dx, partials,
-                                                                      dx_op, s);
-  if (rc) return rc;
-  MM_CHECK_LAUNCH("layernorm_bwd_kernel launch");
-  return 0;
+  return mm_layernorm_bwd_drop(x, gamma, dy, rows, dim, eps, resid, dx, partials, dx_op, 0.f, 0, nullptr, 0, dtype, stream);
 }
 
 extern "C" int mm_softmax_bwd(const float* scores, const void* dprobs, int32_t dprobs_is_op, int64_t ld_dprobs,

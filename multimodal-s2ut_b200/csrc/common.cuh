@@ -355,6 +355,32 @@ struct OpTraits<__half> {
   __device__ static __forceinline__ float to_float(__half a) { return __half2float(a); }
 };
 
+// ---------------------------------------------------------------------------------------------
+// counter-based dropout masks (training step): element i of dropout site `site` is kept iff its 16 uniform bits are
+// >= round(p * 65536).  One splitmix64 finaliser yields the bits of FOUR consecutive elements (i >> 2 is hashed, i & 3
+// selects the 16-bit field), so a fused epilogue that owns 4 consecutive columns pays one hash for them.  Nothing is
+// stored: the backward pass regenerates the mask from (seed, site, i).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long dropout_bits4(unsigned long long seed, unsigned site, unsigned long long i4) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(site + 1) + i4 * 0xD1342543DE82EF95ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ unsigned dropout_threshold(float p) { return (unsigned)(p * 65536.0f + 0.5f); }
+__device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned site, unsigned long long i, float p) {
+  const unsigned long long z = dropout_bits4(seed, site, i >> 2);
+  return (unsigned)((z >> (16 * (unsigned)(i & 3))) & 0xFFFFu) >= dropout_threshold(p);
+}
+// the four keep flags of elements 4 i4 .. 4 i4 + 3 applied to (a, b, c, d): kept values are scaled by inv = 1 / (1 - p)
+__device__ __forceinline__ void dropout_apply4(unsigned long long z, unsigned thr, float inv, float& a, float& b, float& c,
+                                               float& d) {
+  a = (unsigned)(z & 0xFFFFu) >= thr ? a * inv : 0.f;
+  b = (unsigned)((z >> 16) & 0xFFFFu) >= thr ? b * inv : 0.f;
+  c = (unsigned)((z >> 32) & 0xFFFFu) >= thr ? c * inv : 0.f;
+  d = (unsigned)(z >> 48) >= thr ? d * inv : 0.f;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

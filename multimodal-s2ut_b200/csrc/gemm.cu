@@ -41,6 +41,12 @@ struct GemmDev {
   // operand layout extensions (backward pass): MN-major operands (memory is [contraction][rows]), split-K batches that
   // advance the contraction coordinate, and (batch, head) decomposition of the batch index with per-head column offsets
   int a_mn, w_mn, a_kbatch, w_kbatch, a_hm, w_hm, out_hm, heads, head_stride;
+  // MM_EPI_RELU_OP in the training forward: activation dropout on relu(acc + bias) (fairseq --activation-dropout /
+  // --relu-dropout); element index = row * n + column, mask = dropout_keep(seed, site, index)
+  float drop_p;
+  unsigned long long drop_seed;
+  const unsigned long long* drop_seed_dev;
+  unsigned drop_site;
 };
 
 struct GemmCfg {
@@ -312,6 +318,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ C
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v0[i] = fmaxf(v0[i], 0.f), v1[i] = fmaxf(v1[i], 0.f);
+            if (p.drop_p > 0.f) {     // n % 4 == 0 (checked on the host): a group of four columns shares one hash
+              const unsigned thr = dropout_threshold(p.drop_p);
+              const float inv = 1.0f / (1.0f - p.drop_p);
+              const unsigned long long seed = p.drop_seed + (p.drop_seed_dev ? *p.drop_seed_dev : 0ull);
+              const unsigned long long i4 = ((unsigned long long)((long long)bi * p.rows + r) * (unsigned)p.n + (unsigned)col) >> 2;
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                dropout_apply4(dropout_bits4(seed, p.drop_site, i4 + g), thr, inv, v0[4 * g], v0[4 * g + 1], v0[4 * g + 2],
+                               v0[4 * g + 3]);
+                dropout_apply4(dropout_bits4(seed, p.drop_site, i4 + 8 + g), thr, inv, v1[4 * g], v1[4 * g + 1],
+                               v1[4 * g + 2], v1[4 * g + 3]);
+              }
+            }
           }
           if (to_vt) {
             // transposed store: lanes hold consecutive t -> coalesced 2-byte stores per column
@@ -850,6 +869,12 @@ extern "C" int mm_gemm(const mm_gemm_args* a, void* stream) {
   p.pos = a->pos, p.seq_lens = a->seq_lens;
   p.a_mn = a->a_mn, p.w_mn = a->w_mn, p.a_kbatch = a->a_kbatch, p.w_kbatch = a->w_kbatch;
   p.a_hm = a->a_hm, p.w_hm = a->w_hm, p.out_hm = a->out_hm, p.heads = a->heads, p.head_stride = a->head_stride;
+  if (a->drop_p != 0.f) {
+    if (mode != MM_EPI_RELU_OP || a->drop_p < 0.f || a->drop_p >= 1.f || (a->n % 4))
+      return bad_arg("drop_p needs MM_EPI_RELU_OP, p in [0, 1) and n % 4 == 0");
+    p.drop_p = a->drop_p, p.drop_seed = a->drop_seed, p.drop_site = a->drop_site;
+    p.drop_seed_dev = reinterpret_cast<const unsigned long long*>(a->drop_seed_dev);
+  }
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return f16 ? dispatch_mode<__half>(mode, m, p, s) : dispatch_mode<__nv_bfloat16>(mode, m, p, s);

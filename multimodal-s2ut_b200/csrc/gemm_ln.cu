@@ -37,6 +37,12 @@ struct LnDev {
   float eps;
   int want_f32;
   int l2_hints;   // bit 0: residual stream evict_last, bit 1: A operand evict_first
+  // training: dropout on the sub-layer output before the residual add, x <- x + dropout(a W^T + b) (fairseq
+  // TransformerEncoderLayer dropout_module); element index = row * 512 + column, mask = dropout_keep(seed, site, index)
+  float drop_p;
+  unsigned long long seed;
+  const unsigned long long* seed_dev;
+  unsigned site;
 };
 
 __device__ __forceinline__ uint4* ln_slab_chunk(uint8_t* slab, int row, int c) {
@@ -176,6 +182,11 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     // ---- sweep 1: v = acc + bias + x ; new residual out ; row sum ----
     float sum = 0.f, sumsq = 0.f;
     uint32_t ra[32], rb[32];
+    const bool drop = p.drop_p > 0.f;
+    const unsigned drop_thr = dropout_threshold(p.drop_p);
+    const float drop_inv = 1.0f / (1.0f - p.drop_p);
+    const unsigned long long drop_seed = p.seed + ((drop && p.seed_dev) ? *p.seed_dev : 0ull);
+    const unsigned long long drop_row4 = (unsigned long long)(row0 + lrow) * (Cfg::N / 4);
     auto sweep1 = [&](int j, uint32_t (&r)[32]) {
       const int b = j < 6 ? j : j - 6;
       uint8_t* slab = slab_ptr(b);
@@ -191,10 +202,15 @@ gemm_resid_ln_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       uint32_t lo[16], hi[16];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        const float v0 = __uint_as_float(r[4 * c + 0]) + bq[c].x + __uint_as_float(xq[c].x);
-        const float v1 = __uint_as_float(r[4 * c + 1]) + bq[c].y + __uint_as_float(xq[c].y);
-        const float v2 = __uint_as_float(r[4 * c + 2]) + bq[c].z + __uint_as_float(xq[c].z);
-        const float v3 = __uint_as_float(r[4 * c + 3]) + bq[c].w + __uint_as_float(xq[c].w);
+        float a0 = __uint_as_float(r[4 * c + 0]) + bq[c].x, a1 = __uint_as_float(r[4 * c + 1]) + bq[c].y;
+        float a2 = __uint_as_float(r[4 * c + 2]) + bq[c].z, a3 = __uint_as_float(r[4 * c + 3]) + bq[c].w;
+        if (drop)
+          dropout_apply4(dropout_bits4(drop_seed, p.site, drop_row4 + (unsigned)(64 * h + 8 * j + c)), drop_thr, drop_inv, a0,
+                         a1, a2, a3);
+        const float v0 = a0 + __uint_as_float(xq[c].x);
+        const float v1 = a1 + __uint_as_float(xq[c].y);
+        const float v2 = a2 + __uint_as_float(xq[c].z);
+        const float v3 = a3 + __uint_as_float(xq[c].w);
         sum += (v0 + v1) + (v2 + v3);
         sumsq += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
         uint32_t* dst = c < 4 ? &lo[4 * c] : &hi[4 * (c - 4)];
@@ -380,7 +396,16 @@ extern "C" int mm_gemm_resid_ln_out(const void* a, int64_t a_ld, const void* w, 
                                     int32_t n, const float* bias, const float* x, float* x_out, const float* gamma,
                                     const float* beta, float eps, void* h_op, float* h_f32, int32_t dtype,
                                     void* stream) {
+  return mm_gemm_resid_ln_drop(a, a_ld, w, w_ld, rows, k, n, bias, x, x_out, gamma, beta, eps, h_op, h_f32, 0.f, 0, nullptr,
+                               0, dtype, stream);
+}
+
+extern "C" int mm_gemm_resid_ln_drop(const void* a, int64_t a_ld, const void* w, int64_t w_ld, int32_t rows, int32_t k,
+                                     int32_t n, const float* bias, const float* x, float* x_out, const float* gamma,
+                                     const float* beta, float eps, void* h_op, float* h_f32, float drop_p, uint64_t seed,
+                                     const uint64_t* seed_dev, uint32_t site, int32_t dtype, void* stream) {
   using namespace mm;
+  if (drop_p < 0.f || drop_p >= 1.f) return bad_arg("gemm_resid_ln: dropout p in [0, 1)");
   if (!x_out) return bad_arg("gemm_resid_ln: null x_out");
   if (!a || !w || !bias || !x || !gamma || !beta || !h_op) return bad_arg("gemm_resid_ln: null pointer");
   if (n != LnCfg::N) return bad_arg("gemm_resid_ln: n must be 512 (full rows in one accumulator)");
@@ -407,6 +432,7 @@ extern "C" int mm_gemm_resid_ln_out(const void* a, int64_t a_ld, const void* w, 
   memset(&p, 0, sizeof(p));
   p.rows = rows, p.k = k, p.num_kb = (k + 63) / 64, p.num_tiles = (rows + 255) / 256;
   p.bias = bias, p.gamma = gamma, p.beta = beta, p.eps = eps, p.want_f32 = h_f32 != nullptr;
+  p.drop_p = drop_p, p.seed = seed, p.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev), p.site = site;
   static const int l2_hints = getenv("MM_LN_L2_HINTS") ? atoi(getenv("MM_LN_L2_HINTS")) : 3;
   p.l2_hints = l2_hints;
   cudaStream_t s = static_cast<cudaStream_t>(stream);

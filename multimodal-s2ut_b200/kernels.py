@@ -162,7 +162,7 @@ def gemm(*, a0: torch.Tensor, w: torch.Tensor, rows: int, n: int, k: int, mode: 
          pos: Optional[torch.Tensor] = None, seq_lens: Optional[torch.Tensor] = None, block_n: int = 0,
          a_mn: bool = False, w_mn: bool = False, a_kbatch: bool = False, w_kbatch: bool = False, a_hm: bool = False,
          w_hm: bool = False, out_hm: bool = False, heads: int = 0, head_stride: int = 0, a_k_total: int = 0,
-         w_k_total: int = 0) -> None:
+         w_k_total: int = 0, drop=None) -> None:
     """acc = A @ W^T with a fused epilogue; see ``mm_gemm_args`` in include/mms2ut_b200.h."""
     if a0.dtype != w.dtype or (a1 is not None and a1.dtype != w.dtype):
         raise TypeError("A and W must share the 16-bit operand dtype")
@@ -189,6 +189,8 @@ def gemm(*, a0: torch.Tensor, w: torch.Tensor, rows: int, n: int, k: int, mode: 
     g.a_mn, g.w_mn, g.a_kbatch, g.w_kbatch = int(a_mn), int(w_mn), int(a_kbatch), int(w_kbatch)
     g.a_hm, g.w_hm, g.out_hm, g.heads, g.head_stride = int(a_hm), int(w_hm), int(out_hm), heads, head_stride
     g.a_k_total, g.w_k_total = a_k_total, w_k_total
+    if drop is not None and drop[0] > 0:      # RELU_OP: activation dropout in the epilogue, drop = (p, seed, seed_dev, site)
+        g.drop_p, g.drop_seed, g.drop_seed_dev, g.drop_site = drop[0], drop[1] & 0xFFFFFFFFFFFFFFFF, _ptr(drop[2]), drop[3]
     lib = _lib.load()
     with _Launch(f"gemm[{EPI_NAMES[mode]}]", 2.0 * rows * batches * n * k):          # algorithmic FLOPs
         _lib.check(lib.mm_gemm(C.byref(g), _stream()), "mm_gemm")
@@ -196,9 +198,10 @@ def gemm(*, a0: torch.Tensor, w: torch.Tensor, rows: int, n: int, k: int, mode: 
 
 def gemm_resid_ln(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor,
                   beta: torch.Tensor, h_op: torch.Tensor, h_f32: Optional[torch.Tensor] = None,
-                  eps: float = 1e-5, x_out: Optional[torch.Tensor] = None) -> None:
-    """x_out (default: x, in place) = x + a @ w.T + bias (fp32); h_op (and h_f32) = LayerNorm(x_out) * gamma + beta.
-    n = 512 only."""
+                  eps: float = 1e-5, x_out: Optional[torch.Tensor] = None, drop=None) -> None:
+    """x_out (default: x, in place) = x + dropout(a @ w.T + bias) (fp32); h_op (and h_f32) = LayerNorm(x_out) * gamma +
+    beta.  n = 512 only.  drop = (p, seed, seed_dev, site) or None: the counter-based mask of ``dropout`` over the
+    [rows, n] sub-layer output."""
     if x_out is None:
         x_out = x
     assert x_out.dtype == torch.float32 and x_out.is_contiguous() and x_out.shape == x.shape
@@ -208,10 +211,12 @@ def gemm_resid_ln(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, x: torch
     assert x.dtype == torch.float32 and x.is_contiguous() and x.shape == (rows, n) and h_op.shape == (rows, n)
     assert all(t.dtype == torch.float32 and t.numel() == n for t in (bias, gamma, beta))
     lib = _lib.load()
+    p_, seed, seed_dev, site = drop if drop is not None else (0.0, 0, None, 0)
     with _Launch("gemm_resid_ln", 2.0 * rows * n * k):
-        _lib.check(lib.mm_gemm_resid_ln_out(_ptr(a), k, _ptr(w), k, rows, k, n, _ptr(bias), _ptr(x), _ptr(x_out),
-                                            _ptr(gamma), _ptr(beta), eps, _ptr(h_op), _ptr(h_f32), dtype_code(w.dtype),
-                                            _stream()), "mm_gemm_resid_ln")
+        _lib.check(lib.mm_gemm_resid_ln_drop(_ptr(a), k, _ptr(w), k, rows, k, n, _ptr(bias), _ptr(x), _ptr(x_out),
+                                             _ptr(gamma), _ptr(beta), eps, _ptr(h_op), _ptr(h_f32), float(p_),
+                                             seed & 0xFFFFFFFFFFFFFFFF, _ptr(seed_dev), site, dtype_code(w.dtype),
+                                             _stream()), "mm_gemm_resid_ln")
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_op: Optional[torch.Tensor] = None,
@@ -545,8 +550,10 @@ def colsum(x: torch.Tensor, ld: int, rows: int, cols: int, partials: torch.Tenso
 
 def layernorm_bwd(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, partials: torch.Tensor,
                   dx: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None, eps: float = 1e-5,
-                  dx_op: Optional[torch.Tensor] = None) -> None:
-    """dx = resid + LayerNorm'(dy) (dx_op: its 16-bit copy); partials [blocks, 2, dim] per-block (dgamma, dbeta) sums."""
+                  dx_op: Optional[torch.Tensor] = None, drop=None) -> None:
+    """dx = resid + LayerNorm'(dy) (dx_op: its 16-bit copy); partials [blocks, 2, dim] per-block (dgamma, dbeta) sums.
+    drop = (p, seed, seed_dev, site): dx_op = dx o keep / (1 - p), the gradient entering the dropped sub-layer branch
+    that consumes it (dx, the residual path, stays unmasked)."""
     assert dx_op is None or (dx_op.is_contiguous() and dx_op.numel() == x.numel())
     dim = x.shape[-1]
     rows = x.numel() // dim
@@ -555,9 +562,11 @@ def layernorm_bwd(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, partia
     assert dy.numel() == x.numel() and partials.numel() >= layernorm_bwd_blocks() * 2 * dim
     lib = _lib.load()
     with _Launch("layernorm_bwd", 4.0 * x.numel() * (2 + (dx is not None) + (resid is not None))):
-        _lib.check(lib.mm_layernorm_bwd(_ptr(x), _ptr(gamma), _ptr(dy), rows, dim, eps, _ptr(resid), _ptr(dx),
-                                        _ptr(partials), _ptr(dx_op),
-                                        dtype_code(dx_op.dtype) if dx_op is not None else 0, _stream()),
+        p_, seed, seed_dev, site = drop if (drop is not None and drop[0] > 0) else (0.0, 0, None, 0)
+        _lib.check(lib.mm_layernorm_bwd_drop(_ptr(x), _ptr(gamma), _ptr(dy), rows, dim, eps, _ptr(resid), _ptr(dx),
+                                             _ptr(partials), _ptr(dx_op), float(p_), seed & 0xFFFFFFFFFFFFFFFF,
+                                             _ptr(seed_dev), site,
+                                             dtype_code(dx_op.dtype) if dx_op is not None else 0, _stream()),
                    "mm_layernorm_bwd")
 
 

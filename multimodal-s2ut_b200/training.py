@@ -379,7 +379,8 @@ class TrainEngine(EncoderEngine):
                  h2=self.buf(f"t_h2_{i}", (M, d), op), f=self.buf(f"t_f_{i}", (M, self.ffn), op),
                  x_out=self.buf(f"t_xout_{i}", (M, d), torch.float32))
         p_drop, p_act, seed, seed_dev = self._drop
-        fused = self.train_fused_ln and p_drop == 0
+        fused = self.train_fused_ln      # residual-site dropout runs inside the fused GEMM + residual + LayerNorm epilogue
+        dr = lambda p_, k_: (p_, seed, seed_dev, site_layer(i, k_)) if p_ > 0 else None
         if not fused:
             K.layernorm(x_in, L["ln1_g"], L["ln1_b"], out_op=s["h1"])
         K.gemm(a0=s["h1"], a0_ld=d, rows=M, w=L["wqkv"], n=3 * d, k=d, mode=K.EPI_OP, bias=L["bqkv"], scale=64 ** -0.5,
@@ -402,7 +403,8 @@ class TrainEngine(EncoderEngine):
             s["lse"] = self.buf(f"t_lse_{i}", (B, self.heads, T), torch.float32)
             K.self_attention(s["qkv"], seq_lens, B, T, self.heads, s["att"], lse=s["lse"])
         if fused:
-            K.gemm_resid_ln(s["att"], L["wo"], L["bo"], x_in, L["ln2_g"], L["ln2_b"], s["h2"], x_out=s["x_mid"])
+            K.gemm_resid_ln(s["att"], L["wo"], L["bo"], x_in, L["ln2_g"], L["ln2_b"], s["h2"], x_out=s["x_mid"],
+                            drop=dr(p_drop, 0))
         elif p_drop > 0:     # x_mid = x_in + dropout(out_proj(att))
             y = self.buf("t_y", (M, d), torch.float32)
             K.gemm(a0=s["att"], a0_ld=d, rows=M, w=L["wo"], n=d, k=d, mode=K.EPI_F32, bias=L["bo"], out0=y, out0_ld=d,
@@ -413,14 +415,14 @@ class TrainEngine(EncoderEngine):
             K.gemm(a0=s["att"], a0_ld=d, rows=M, w=L["wo"], n=d, k=d, mode=K.EPI_RESID_F32, bias=L["bo"], aux0=x_in,
                    aux_ld=d, out0=s["x_mid"], out0_ld=d, block_n=bn)
             K.layernorm(s["x_mid"], L["ln2_g"], L["ln2_b"], out_op=s["h2"])
+        # fc1 + ReLU + activation dropout in one epilogue
         K.gemm(a0=s["h2"], a0_ld=d, rows=M, w=L["w1"], n=self.ffn, k=d, mode=K.EPI_RELU_OP, bias=L["b1"], out0=s["f"],
-               out0_ld=self.ffn, block_n=bn)
-        if p_act > 0:
-            K.dropout(s["f"], s["f"], p_act, seed, site_layer(i, 1), seed_dev=seed_dev)
+               out0_ld=self.ffn, block_n=bn, drop=dr(p_act, 1))
         if fused:
             last = i + 1 == self.n_layers
             ng, nb_ = (self.ln_g, self.ln_b) if last else (self.layers[i + 1]["ln1_g"], self.layers[i + 1]["ln1_b"])
-            K.gemm_resid_ln(s["f"], L["w2"], L["b2"], s["x_mid"], ng, nb_, h_next, h_next_f32, x_out=s["x_out"])
+            K.gemm_resid_ln(s["f"], L["w2"], L["b2"], s["x_mid"], ng, nb_, h_next, h_next_f32, x_out=s["x_out"],
+                            drop=dr(p_drop, 2))
         elif p_drop > 0:     # x_out = x_mid + dropout(fc2(f))
             y = self.buf("t_y", (M, d), torch.float32)
             K.gemm(a0=s["f"], a0_ld=self.ffn, rows=M, w=L["w2"], n=d, k=self.ffn, mode=K.EPI_F32, bias=L["b2"], out0=y,
@@ -465,7 +467,7 @@ class TrainEngine(EncoderEngine):
                      p_attn=self._p_attn, p_sa=p_sa, p_text=0.0)
         text_f32 = self.buf("text_f32", (M, d), torch.float32)
         text_op = self.buf("text_op", (M, d), self.op_dtype)
-        fused_fwd = self.train_fused_ln and p_drop == 0
+        fused_fwd = self.train_fused_ln
         if fused_fwd:              # LN1 of layer 0 is the only stand-alone LayerNorm
             K.layernorm(x, self.layers[0]["ln1_g"], self.layers[0]["ln1_b"], out_op=self.buf("t_h1_0", (M, d), self.op_dtype))
         for i in range(self.n_layers):
@@ -682,10 +684,11 @@ class TrainEngine(EncoderEngine):
         a = mod.self_attn
         d, ffn, M, op, bn = self.d, self.ffn, B * T, self.op_dtype, self.block_n
         p_drop, p_act, seed, seed_dev = self._saved["drop"]
+        # with dropout the 16-bit gradient copy arrives ALREADY masked for this layer's fc2 branch (gradient entering fc2 =
+        # g o mask / (1 - p); the residual branch keeps the fp32 g): the LayerNorm backward that produced it burnt the
+        # mask of site (i, 2) in, and the one below burns in the mask of site (i, 0) for the attention branch
         gm = g_op
-        if p_drop > 0:       # gradient entering fc2 = g o mask / (1 - p); the residual branch keeps g itself
-            gm = self.buf("b_gm_op" + tag, (M, d), op)
-            K.dropout(g_op, gm, p_drop, seed, site_layer(i, 2), seed_dev=seed_dev)
+        drb = lambda k_, li=i: (p_drop, seed, seed_dev, site_layer(li, k_)) if p_drop > 0 else None
         # ---- FFN: x_out = x_mid + dropout(fc2(dropout(relu(fc1(LN2(x_mid))))))
         self._linear_bwd(gm, d, s["f"], M, d, ffn, self.g(mod.fc2.weight), self.g(mod.fc2.bias), accumulate)
         dF = self.buf("b_dF" + tag, (M, ffn), op)
@@ -700,13 +703,10 @@ class TrainEngine(EncoderEngine):
         lnp = self._lnp()
         if tag:
             g_op = self.buf("b_g_op_mid" + tag, (M, d), op)
-        K.layernorm_bwd(s["x_mid"], L["ln2_g"], dh, lnp, dx=g, resid=g, dx_op=g_op)
+        K.layernorm_bwd(s["x_mid"], L["ln2_g"], dh, lnp, dx=g, resid=g, dx_op=g_op, drop=drb(0))
         self._ln_param_grads(lnp, d, self.g(mod.final_layer_norm.weight, mod.final_layer_norm.bias), accumulate)
         # ---- attention: x_mid = x_in + dropout(out_proj(attn(LN1(x_in))))
         gm = g_op
-        if p_drop > 0:
-            gm = self.buf("b_gm_op_mid" + tag, (M, d), op)
-            K.dropout(g_op, gm, p_drop, seed, site_layer(i, 0), seed_dev=seed_dev)
         self._linear_bwd(gm, d, s["att"], M, d, d, self.g(a.out_proj.weight), self.g(a.out_proj.bias), accumulate)
         datt = self.buf("b_datt", (M, d), op)
         K.gemm(a0=gm, a0_ld=d, rows=M, w=L["wo"], w_ld=d, w_mn=True, n=d, k=d, mode=K.EPI_OP, out0=datt, out0_ld=d,
@@ -721,7 +721,8 @@ class TrainEngine(EncoderEngine):
         lnp = self._lnp()
         if tag:
             g_op = self.buf("b_g_op_in" + tag, (M, d), op)
-        K.layernorm_bwd(s["x_in"], L["ln1_g"], dh, lnp, dx=g, resid=g, dx_op=g_op)
+        # the copy that leaves this layer enters the fc2 branch of layer i - 1 (nothing below layer 0 reads it)
+        K.layernorm_bwd(s["x_in"], L["ln1_g"], dh, lnp, dx=g, resid=g, dx_op=g_op, drop=drb(2, i - 1) if i > 0 else None)
         self._ln_param_grads(lnp, d, self.g(mod.self_attn_layer_norm.weight, mod.self_attn_layer_norm.bias), accumulate)
         self._flush()           # the layer's deferred reductions (bias / LayerNorm partials, split-K partials) in one launch
         return g_op
@@ -948,7 +949,8 @@ class TrainEngine(EncoderEngine):
         g = self.buf("b_g", (M, d), torch.float32)
         g_op = self.buf("b_g_op", (M, d), self.op_dtype)
         lnp = self._lnp()
-        K.layernorm_bwd(sv["x_final"], self.ln_g, gtext, lnp, dx=g, dx_op=g_op)
+        top_drop = (sv["drop"][0], sv["drop"][2], sv["drop"][3], site_layer(self.n_layers - 1, 2)) if sv["drop"][0] > 0 else None
+        K.layernorm_bwd(sv["x_final"], self.ln_g, gtext, lnp, dx=g, dx_op=g_op, drop=top_drop)
         self._ln_param_grads(lnp, d, self.g(self.enc.layer_norm.weight, self.enc.layer_norm.bias), accumulate)
         self._flush()           # fusion + final LayerNorm reductions
         flush_every = self.wgrad_flush_layers or (3 if overlap else 0)

@@ -120,7 +120,8 @@ def gemm(*, a0, w, rows, n, k, mode, out0, a0_ld, out0_ld, batches=1, a0_bs=0, a
          w_ld=None, w_bs=0, w_batched=False, bias=None, scale=1.0, scale_cols=0, out0_bs=0, out1=None, out1_ld=0,
          out1_bs=0, aux0=None, aux1=None, aux_ld=0, rows_per_seq=0, out_tbc=False, n_seqs=0, out_row_offset=0, vt=None,
          vt_col0=0, vt_rows=0, vt_ld=0, pos=None, seq_lens=None, block_n=0, a_mn=False, w_mn=False, a_kbatch=False,
-         w_kbatch=False, a_hm=False, w_hm=False, out_hm=False, heads=0, head_stride=0, a_k_total=0, w_k_total=0):
+         w_kbatch=False, a_hm=False, w_hm=False, out_hm=False, heads=0, head_stride=0, a_k_total=0, w_k_total=0,
+         drop=None):
     global launch_count
     launch_count += 1
     w_ld = k if w_ld is None else w_ld
@@ -152,6 +153,8 @@ def gemm(*, a0, w, rows, n, k, mode, out0, a0_ld, out0_ld, batches=1, a0_bs=0, a
             acc[..., :scale_cols] *= scale
         if mode == EPI_RELU_OP:
             acc = acc.relu()
+            if drop is not None and drop[0] > 0:
+                acc = acc * _keep_scale(acc.numel(), drop[0], drop[1], drop[3], drop[2]).view(acc.shape)
         n_out = vt_col0 if (mode == EPI_OP and vt is not None) else n
         if n_out > 0:
             out_view(out0, n_out, out0_ld, out0_bs, roff=out_row_offset).copy_(acc[..., :n_out].to(op))
@@ -203,11 +206,14 @@ class _HeadView:
         self.v.copy_(src.reshape(self.shape))
 
 
-def gemm_resid_ln(a, w, bias, x, gamma, beta, h_op, h_f32=None, eps=1e-5, x_out=None):
+def gemm_resid_ln(a, w, bias, x, gamma, beta, h_op, h_f32=None, eps=1e-5, x_out=None, drop=None):
     global launch_count
     launch_count += 1
     x_out = x if x_out is None else x_out
-    x_out.copy_(x + a.float() @ w.float().t() + bias)
+    y = a.float() @ w.float().t() + bias
+    if drop is not None and drop[0] > 0:
+        y = y * _keep_scale(y.numel(), drop[0], drop[1], drop[3], drop[2]).view(y.shape)
+    x_out.copy_(x + y)
     y = torch.nn.functional.layer_norm(x_out, (x_out.shape[-1],), gamma, beta, eps)
     h_op.copy_(y.to(h_op.dtype))
     if h_f32 is not None:
@@ -474,7 +480,7 @@ def layernorm_bwd_blocks():
     return 4
 
 
-def layernorm_bwd(x, gamma, dy, partials, dx=None, resid=None, eps=1e-5, dx_op=None):
+def layernorm_bwd(x, gamma, dy, partials, dx=None, resid=None, eps=1e-5, dx_op=None, drop=None):
     dim = x.shape[-1]
     xr = x.reshape(-1, dim)
     dyr = dy.reshape(-1, dim)
@@ -486,7 +492,10 @@ def layernorm_bwd(x, gamma, dy, partials, dx=None, resid=None, eps=1e-5, dx_op=N
     if dx is not None:
         dx.view(-1, dim).copy_(d + (resid.reshape(-1, dim) if resid is not None else 0))
         if dx_op is not None:
-            dx_op.view(-1, dim).copy_(dx.view(-1, dim).to(dx_op.dtype))
+            g16 = dx.view(-1, dim)
+            if drop is not None and drop[0] > 0:
+                g16 = g16 * _keep_scale(g16.numel(), drop[0], drop[1], drop[3], drop[2]).view(g16.shape)
+            dx_op.view(-1, dim).copy_(g16.to(dx_op.dtype))
     p = partials[: layernorm_bwd_blocks() * 2 * dim].view(layernorm_bwd_blocks(), 2, dim)
     p.zero_()
     p[0, 0] = (dyr * xhat).sum(0)
@@ -595,6 +604,14 @@ class _FakeLib:
 
 
 _lib = _FakeLib
+
+
+def _keep_scale(numel, p, seed, site, seed_dev=None):
+    """The emulated counter-based mask of a site over `numel` elements (row-major), scaled by 1 / (1 - p)."""
+    if seed_dev is not None:
+        seed = int(seed) + int(seed_dev.view(-1)[0])
+    g = torch.Generator().manual_seed((int(seed) * 1000003 + int(site)) % (2 ** 63 - 1))
+    return (torch.rand(numel, generator=g) >= p).float() / (1.0 - p)
 
 
 def dropout(x, out, p, seed, site, resid=None, seed_dev=None):

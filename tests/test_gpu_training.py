@@ -399,7 +399,7 @@ def test_encoder_backward_other_shapes(cuda, name, preset, overrides, img, B, du
 # element-wise dropout in the training step
 # ---------------------------------------------------------------------------------------------------------
 def _dropout_parity(K, device, p_drop=0.1, p_act=0.15, p_img=0.2, p_attn=0.1, p_sa=0.1, p_text=0.1, seed=1234,
-                    emulated=False):
+                    emulated=False, preset="small", overrides=None, min_checked=6 * 15 + 2 + 4):
     """Forward + backward with dropout on, against autograd over the oracle run with THE SAME masks: the oracle's
     ``drop(site, x)`` hook multiplies by the mask the kernel produces for that site (dumped by running the dropout kernel
     on a tensor of ones), re-laid-out from token-major to the oracle's [T, B, C]."""
@@ -408,7 +408,24 @@ def _dropout_parity(K, device, p_drop=0.1, p_act=0.15, p_img=0.2, p_attn=0.1, p_
     from oracle import fbank as ofb, fusion as ofu
     from test_gpu_encoder import _build
 
-    enc, args, cfg = _build("small", "selective_attention", True)
+    if overrides:       # e.g. base width (d = 512: dropout inside the fused GEMM + residual + LayerNorm epilogue), fewer layers
+        from mm_s2ut_b200.config import DEFAULT_YAML, load_mm_config, make_args
+        from mm_s2ut_b200.models.mm_s2s_transformer import MM_S2STransformerEncoder
+
+        cfg = dict(load_mm_config(DEFAULT_YAML))
+        torch.manual_seed(0)
+        args = make_args(preset, multimodal_translation_config_yaml=cfg, **overrides)
+        enc = MM_S2STransformerEncoder(args, build_unused_projections=False).eval()
+        g0 = torch.Generator().manual_seed(1)
+        with torch.no_grad():
+            for n_, p_ in enc.named_parameters():
+                if "layer_norm" in n_ or "pre_norm" in n_:
+                    p_.add_(0.1 * torch.randn(p_.shape, generator=g0))
+                elif n_.endswith(".bias"):
+                    p_.add_(0.05 * torch.randn(p_.shape, generator=g0))
+        cfg = load_mm_config(cfg)
+    else:
+        enc, args, cfg = _build(preset, "selective_attention", True)
     enc.dropout_p, enc.activation_dropout_p, enc.attention_dropout_p = p_drop, p_act, p_attn
     enc.SA_image_dropout, enc.SA_attention_dropout, enc.SA_text_dropout = p_img, p_sa, p_text
     B = 2
@@ -472,7 +489,7 @@ def _dropout_parity(K, device, p_drop=0.1, p_act=0.15, p_img=0.2, p_attn=0.1, p_
         worst = max(worst, rel)
         assert rel < REL, (k, rel)
         checked += 1
-    assert checked >= 6 * 15 + 2 + 4
+    assert checked >= min_checked
     # a different seed gives a different output; the same seed reproduces it bit for bit
     o1 = eng.forward_train(wav.to(device), lens.to(device), [imgs.to(device)], [None], dropout_seed=seed)["encoder_out"][0].clone()
     o2 = eng.forward_train(wav.to(device), lens.to(device), [imgs.to(device)], [None], dropout_seed=seed + 1)["encoder_out"][0]
@@ -515,6 +532,19 @@ def test_training_step_with_dropout_matches_oracle_with_same_masks(cuda):
     worst, ferr = _dropout_parity(K, cuda)
     record("configs[2] backward with dropout 0.1 / activation-dropout 0.15 / attention-dropout 0.1 / SA_image_dropout 0.2 "
            "/ SA_attention_dropout 0.1 (same masks in the oracle): worst parameter-gradient relative L2 error", worst, REL)
+
+
+def test_training_step_with_dropout_in_fused_epilogues_d512(cuda):
+    """Base width (d = 512): the residual-site dropout runs inside the fused GEMM + residual + LayerNorm epilogue, the
+    activation dropout inside the fc1 epilogue, and the LayerNorm backward burns the masks into the 16-bit gradient
+    copies -- all against the oracle run with the same masks (the reference recipe: --dropout 0.1 --relu-dropout 0.1,
+    scripts/textless/1_train.sh:112)."""
+    from mm_s2ut_b200 import kernels as K
+
+    worst, ferr = _dropout_parity(K, cuda, p_drop=0.1, p_act=0.1, p_attn=0.1, preset="base",
+                                  overrides=dict(encoder_layers=3), min_checked=3 * 15 + 2 + 4)
+    record("configs[2] backward, base width d=512, dropout 0.1 / relu-dropout 0.1 / attention-dropout 0.1 in the fused "
+           "epilogues (same masks in the oracle): worst parameter-gradient relative L2 error", worst, REL)
 
 
 def test_graphed_train_step_draws_fresh_dropout_masks(cuda):
