@@ -338,6 +338,19 @@ int mm_attention_bwd_fused(const void* qkv, int64_t qkv_ld, int32_t q_col0, int3
                            int32_t seq_len, const int32_t* kv_lens, int32_t batch, int32_t heads, const void* dout,
                            int64_t do_ld, const void* out, int64_t o_ld, const float* lse, void* dqkv, int64_t dqkv_ld,
                            int32_t dtype, void* stream);
+/* The two with attention dropout (fairseq MultiheadAttention dropout_module on the probabilities, --attention-dropout
+ * 0.1 in scripts/textless/1_train.sh:112) generated INSIDE the kernels: the forward multiplies P by keep / (1 - p)
+ * before the P V product (the softmax denominator and lse stay un-dropped), the backward regenerates the same mask
+ * (counter-based, as mm_dropout, element index ((b heads + h) Tp + q) Tp + k with Tp = seq rounded up to 64).
+ * mm_self_attention_drop: 129 .. 256 positions (the single-chunk kernel). */
+int mm_self_attention_drop(const void* qkv, int64_t qkv_ld, const int32_t* seq_lens, int32_t batch, int32_t seq,
+                           int32_t heads, void* out, int64_t out_ld, float* lse, float drop_p, uint64_t seed,
+                           const uint64_t* seed_dev, uint32_t site, int32_t dtype, void* stream);
+int mm_attention_bwd_fused_drop(const void* qkv, int64_t qkv_ld, int32_t q_col0, int32_t k_col0, int32_t v_col0,
+                                int32_t seq_len, const int32_t* kv_lens, int32_t batch, int32_t heads, const void* dout,
+                                int64_t do_ld, const void* out, int64_t o_ld, const float* lse, void* dqkv,
+                                int64_t dqkv_ld, float drop_p, uint64_t seed, const uint64_t* seed_dev, uint32_t site,
+                                int32_t dtype, void* stream);
 
 /* The same for any query / key length, a causal mask and q / k|v (and dq / dk|dv) in different tensors: the unit
  * decoder's causal self-attention and its encoder attention (fairseq TransformerDecoderLayer under autograd), the

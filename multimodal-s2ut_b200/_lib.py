@@ -188,6 +188,13 @@ EXPORTS = {
                                            C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                            C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
                                            C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mm_self_attention_drop": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                         C.c_int64, C.c_void_p, C.c_float, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int32,
+                                         C.c_void_p]),
+    "mm_attention_bwd_fused_drop": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                              C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                              C.c_void_p, C.c_int64, C.c_float, C.c_uint64, C.c_void_p, C.c_uint32,
+                                              C.c_int32, C.c_void_p]),
     "mm_heads_gemm": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
                                 C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_float, C.c_int32, C.c_void_p]),

@@ -70,6 +70,41 @@ __device__ __forceinline__ float softmax_chunk(const uint32_t (&r)[32], uint32_t
   }
   return l0 + l1;
 }
+// The same with attention dropout (training forward; fairseq MultiheadAttention dropout_module on the probabilities):
+// the row sum (the softmax denominator) is taken over the UN-dropped probabilities, the packed operand of the P V product
+// carries keep / (1 - p).  i4 = (element index of the chunk's first key in the [batch*heads][Tp][Tp] mask) / 4.
+struct AttnDrop {
+  float p;
+  unsigned site;
+  unsigned long long seed;
+  const unsigned long long* seed_dev;
+  int tp;       // row length of the mask index space: round_up(T, 64)
+};
+template <typename OpT>
+__device__ __forceinline__ float softmax_chunk_drop(const uint32_t (&r)[32], uint32_t (&pk)[16], float mb, int valid,
+                                                    unsigned long long seed, unsigned site, unsigned long long i4,
+                                                    unsigned thr, float inv) {
+  constexpr float L2E = 1.4426950408889634f;
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const int k = 4 * g;
+    float p0 = ex2_approx(fmaf(__uint_as_float(r[k]), L2E, -mb));
+    float p1 = ex2_approx(fmaf(__uint_as_float(r[k + 1]), L2E, -mb));
+    float p2 = ex2_approx(fmaf(__uint_as_float(r[k + 2]), L2E, -mb));
+    float p3 = ex2_approx(fmaf(__uint_as_float(r[k + 3]), L2E, -mb));
+    p0 = k < valid ? p0 : 0.f;
+    p1 = k + 1 < valid ? p1 : 0.f;
+    p2 = k + 2 < valid ? p2 : 0.f;
+    p3 = k + 3 < valid ? p3 : 0.f;
+    l0 += p0 + p2;
+    l1 += p1 + p3;
+    dropout_apply4(dropout_bits4(seed, site, i4 + g), thr, inv, p0, p1, p2, p3);
+    pk[2 * g] = OpTraits<OpT>::pack2(p0, p1);
+    pk[2 * g + 1] = OpTraits<OpT>::pack2(p2, p3);
+  }
+  return l0 + l1;
+}
 template <bool MASKED>
 __device__ __forceinline__ float max_chunk(const uint32_t (&r)[32], int valid) {
   float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
@@ -95,11 +130,11 @@ __device__ long long g_att_trace[148 * 2 * 8 * 6];
 #define ATT_TRACE(slot)
 #endif
 
-template <typename OpT>
+template <typename OpT, bool DROP>
 __global__ void __launch_bounds__(PA_THREADS, 1)
 self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant__ CUtensorMap mapOut,
                            const int* __restrict__ seq_lens, int T, int d_model, int H, int nqt, int n_items,
-                           float* __restrict__ lse) {
+                           float* __restrict__ lse, const AttnDrop dr) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sOut = smem + 2 * PA_STAGE_BYTES;
@@ -246,10 +281,23 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
     auto group_sync = [&]() {
       if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 2, 256;" ::: "memory");
     };
+    const unsigned long long drop_seed = DROP ? dr.seed + (dr.seed_dev ? *dr.seed_dev : 0ull) : 0ull;
+    const unsigned drop_thr = dropout_threshold(dr.p);
+    const float drop_inv = 1.0f / (1.0f - dr.p);
     for (int i = g; i < n_local; i += 2) {
       const int item = blockIdx.x + i * gridDim.x;
       const int qt = item % nqt, h = (item / nqt) % H, b = item / (nqt * H);
       const int u = i >> 1;
+      // mask index of (this thread's query row, key 0): ((b H + h) Tp + q) Tp, in units of four elements
+      const unsigned long long i4row =
+          DROP ? ((unsigned long long)((long long)(b * H + h) * dr.tp + qt * AT_BM + row) * (unsigned)dr.tp) >> 2 : 0ull;
+      auto chunk = [&](const uint32_t (&r)[32], uint32_t (&pk)[16], float mb_, int cc, int nfull_, int rem_) -> float {
+        if constexpr (DROP)
+          return softmax_chunk_drop<OpT>(r, pk, mb_, cc < nfull_ ? 32 : rem_, drop_seed, dr.site, i4row + 8 * cc, drop_thr,
+                                         drop_inv);
+        else
+          return cc < nfull_ ? softmax_chunk<OpT, false>(r, pk, mb_, 32) : softmax_chunk<OpT, true>(r, pk, mb_, rem_);
+      };
       const int len = max(1, min(b < PA_MAX_LENS ? s_lens[b] : seq_lens[b], T));
       const int nch = (len + 31) >> 5;        // chunks holding at least one valid key
       const int nfull = len >> 5;             // chunks that need no masking
@@ -287,7 +335,7 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
         uint32_t pk[16];
         if (cc + 1 < nch) tmem_ld32(t_row + (cc + 1) * 32, rb);
         if (cc < nch) {
-          l += cc < nfull ? softmax_chunk<OpT, false>(ra, pk, mb, 32) : softmax_chunk<OpT, true>(ra, pk, mb, rem);
+          l += chunk(ra, pk, mb, cc, nfull, rem);
         } else {
 #pragma unroll
           for (int k = 0; k < 16; ++k) pk[k] = 0u;
@@ -296,7 +344,7 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
         tmem_st16(p_col + 16 * (cc - c0), pk);    // P over S columns that have already been consumed
         if (cc + 2 < c0 + 4 && cc + 2 < nch) tmem_ld32(t_row + (cc + 2) * 32, ra);
         if (cc + 1 < nch) {
-          l += cc + 1 < nfull ? softmax_chunk<OpT, false>(rb, pk, mb, 32) : softmax_chunk<OpT, true>(rb, pk, mb, rem);
+          l += chunk(rb, pk, mb, cc + 1, nfull, rem);
         } else {
 #pragma unroll
           for (int k = 0; k < 16; ++k) pk[k] = 0u;
@@ -358,10 +406,10 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
   }
 }
 
-template <typename OpT>
+template <typename OpT, bool DROP = false>
 static int launch_attn_t256(const CUtensorMap& mqk, const CUtensorMap& mout, const int* lens, int B, int T, int H,
-                            int d, float* lse, cudaStream_t s) {
-  auto kern = self_attention_t256_kernel<OpT>;
+                            int d, float* lse, cudaStream_t s, AttnDrop dr = AttnDrop{0.f, 0u, 0ull, nullptr, 0}) {
+  auto kern = self_attention_t256_kernel<OpT, DROP>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PA_SMEM_BYTES);
@@ -382,7 +430,7 @@ static int launch_attn_t256(const CUtensorMap& mqk, const CUtensorMap& mout, con
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mqk, mout, lens, T, d, H, nqt, n_items, lse);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mqk, mout, lens, T, d, H, nqt, n_items, lse, dr);
   if (e != cudaSuccess) return fail(e, "self_attention_t256_kernel launch");
   return 0;
 }
@@ -765,6 +813,29 @@ extern "C" int mm_self_attention_lse(const void* qkv, int64_t qkv_ld, const int3
   if (rc) return rc;
   return f16 ? launch_attn_long<__half>(mqk, mqk, mqk, mout, seq_lens, batch, seq, seq, 0, d, 2 * d, 0, heads, lse, s)
              : launch_attn_long<__nv_bfloat16>(mqk, mqk, mqk, mout, seq_lens, batch, seq, seq, 0, d, 2 * d, 0, heads, lse, s);
+}
+
+extern "C" int mm_self_attention_drop(const void* qkv, int64_t qkv_ld, const int32_t* seq_lens, int32_t batch, int32_t seq,
+                                      int32_t heads, void* out, int64_t out_ld, float* lse, float drop_p, uint64_t seed,
+                                      const uint64_t* seed_dev, uint32_t site, int32_t dtype, void* stream) {
+  if (!qkv || !seq_lens || !out) return bad_arg("self_attention_drop: null pointer");
+  if (batch <= 0 || heads <= 0) return bad_arg("self_attention_drop: extents");
+  if (!(seq > PL_KC && seq <= AT_KC)) return bad_arg("self_attention_drop: 129 .. 256 positions (the single-chunk kernel)");
+  if (!(drop_p > 0.f && drop_p < 1.f)) return bad_arg("self_attention_drop: p in (0, 1)");
+  const int d = heads * AT_HD;
+  if (qkv_ld < 3 * d || (qkv_ld % 8) || (out_ld % 8) || out_ld < d)
+    return bad_arg("self_attention_drop: leading dims (head_dim must be 64)");
+  const int f16 = dtype == MM_DTYPE_F16;
+  CUtensorMap mqk, mout;
+  int rc = make_tmap_3d(&mqk, qkv, f16, (uint64_t)(3 * d), (uint64_t)seq, (uint64_t)batch, (uint64_t)qkv_ld,
+                        (uint64_t)seq * qkv_ld, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&mout, out, f16, (uint64_t)d, (uint64_t)seq, (uint64_t)batch, (uint64_t)out_ld, (uint64_t)seq * out_ld, 128);
+  if (rc) return rc;
+  AttnDrop dr{drop_p, site, seed, reinterpret_cast<const unsigned long long*>(seed_dev), (seq + 63) / 64 * 64};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return f16 ? launch_attn_t256<__half, true>(mqk, mout, seq_lens, batch, seq, heads, d, lse, s, dr)
+             : launch_attn_t256<__nv_bfloat16, true>(mqk, mout, seq_lens, batch, seq, heads, d, lse, s, dr);
 }
 
 extern "C" int mm_attention(const void* q, int64_t q_ld, int32_t q_col0, int32_t q_len, const void* k, int64_t k_ld,

@@ -42,6 +42,13 @@ struct AfDev {
   const int* kv_lens;        // [batch] valid keys, or NULL
   const float* lse;          // [batch][H][len]
   float scale;               // head_dim^-0.5 on dQ
+  // attention dropout (training): the forward pass multiplied P by keep / (1 - p) (mm_self_attention_drop); the same
+  // mask is regenerated here: dV takes the dropped P, dS = P o (dP o keep / (1 - p) - delta)
+  float drop_p;
+  unsigned drop_site;
+  unsigned long long drop_seed;
+  const unsigned long long* drop_seed_dev;
+  int drop_tp;               // row length of the mask index space: round_up(len, 64)
 };
 
 __device__ __forceinline__ float af_ex2(float x) {
@@ -50,7 +57,7 @@ __device__ __forceinline__ float af_ex2(float x) {
   return y;
 }
 
-template <typename OpT>
+template <typename OpT, bool DROP>
 __global__ void __launch_bounds__(AF_THREADS, 1)
 attention_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                            const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapDO,
@@ -203,6 +210,9 @@ attention_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
     auto group_sync = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     const bool elected = tid == 0;
     uint32_t steps = 0, accs = 0;
+    const unsigned long long drop_seed = DROP ? p.drop_seed + (p.drop_seed_dev ? *p.drop_seed_dev : 0ull) : 0ull;
+    const unsigned drop_thr = dropout_threshold(p.drop_p);
+    const float drop_inv = 1.0f / (1.0f - p.drop_p);
     // 64 columns of a 128-row fp32 accumulator -> 16-bit -> staging slab -> TMA store at (col, row0, b)
     auto store_tile = [&](uint32_t tcol, float scale, const CUtensorMap* m, int col, int row0, int b, uint64_t* drained) {
       uint32_t r[32];
@@ -288,6 +298,29 @@ attention_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
               if (lane == 0) mbar_arrive(sdp_empty);
             }
             const int nvh = nv - 32 * half;
+            if constexpr (DROP) {
+              // mask index of (query row, first key of this half): ((b H + h) Tp + q) Tp + key, four elements per hash
+              const unsigned long long i4 =
+                  ((unsigned long long)((long long)(b * p.H + h) * p.drop_tp + qrow) * (unsigned)p.drop_tp + (unsigned)(k0 + 32 * half)) >> 2;
+#pragma unroll
+              for (int g4 = 0; g4 < 8; ++g4) {
+                const int k = 4 * g4;
+                float pr[4], m4[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  pr[e] = af_ex2(fmaf(__uint_as_float(rs[k + e]), L2E, -lbq));
+                  pr[e] = k + e < nvh ? pr[e] : 0.f;
+                }
+                dropout_apply4(dropout_bits4(drop_seed, p.drop_site, i4 + g4), drop_thr, drop_inv, m4[0], m4[1], m4[2], m4[3]);
+                float dd[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) dd[e] = pr[e] * (__uint_as_float(rd[k + e]) * m4[e] - dl);
+                pk[2 * g4] = OpTraits<OpT>::pack2(pr[0] * m4[0], pr[1] * m4[1]);
+                pk[2 * g4 + 1] = OpTraits<OpT>::pack2(pr[2] * m4[2], pr[3] * m4[3]);
+                dk[2 * g4] = OpTraits<OpT>::pack2(dd[0], dd[1]);
+                dk[2 * g4 + 1] = OpTraits<OpT>::pack2(dd[2], dd[3]);
+              }
+            } else {
 #pragma unroll
             for (int k = 0; k < 32; k += 2) {
               float p0 = af_ex2(fmaf(__uint_as_float(rs[k]), L2E, -lbq));
@@ -298,6 +331,7 @@ attention_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
               const float d1 = p1 * (__uint_as_float(rd[k + 1]) - dl);
               pk[k >> 1] = OpTraits<OpT>::pack2(p0, p1);
               dk[k >> 1] = OpTraits<OpT>::pack2(d0, d1);
+            }
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -729,9 +763,9 @@ static int launch_attention_bwd_general(const CUtensorMap (&m)[8], const AgDev& 
   return 0;
 }
 
-template <typename OpT>
+template <typename OpT, bool DROP>
 static int launch_attention_bwd_fused(const CUtensorMap (&m)[8], const AfDev& p, cudaStream_t s) {
-  auto kern = attention_bwd_fused_kernel<OpT>;
+  auto kern = attention_bwd_fused_kernel<OpT, DROP>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM_BYTES);
@@ -762,6 +796,16 @@ extern "C" int mm_attention_bwd_fused(const void* qkv, int64_t qkv_ld, int32_t q
                                       int32_t seq_len, const int32_t* kv_lens, int32_t batch, int32_t heads,
                                       const void* dout, int64_t do_ld, const void* out, int64_t o_ld, const float* lse,
                                       void* dqkv, int64_t dqkv_ld, int32_t dtype, void* stream) {
+  return mm_attention_bwd_fused_drop(qkv, qkv_ld, q_col0, k_col0, v_col0, seq_len, kv_lens, batch, heads, dout, do_ld, out,
+                                     o_ld, lse, dqkv, dqkv_ld, 0.f, 0, nullptr, 0, dtype, stream);
+}
+
+extern "C" int mm_attention_bwd_fused_drop(const void* qkv, int64_t qkv_ld, int32_t q_col0, int32_t k_col0,
+                                           int32_t v_col0, int32_t seq_len, const int32_t* kv_lens, int32_t batch,
+                                           int32_t heads, const void* dout, int64_t do_ld, const void* out, int64_t o_ld,
+                                           const float* lse, void* dqkv, int64_t dqkv_ld, float drop_p, uint64_t seed,
+                                           const uint64_t* seed_dev, uint32_t site, int32_t dtype, void* stream) {
+  if (drop_p < 0.f || drop_p >= 1.f) return bad_arg("attention_bwd_fused: dropout p in [0, 1)");
   if (!qkv || !dout || !out || !lse || !dqkv) return bad_arg("attention_bwd_fused: null pointer");
   if (batch <= 0 || seq_len <= 0 || heads <= 0) return bad_arg("attention_bwd_fused: extents");
   if (seq_len > 2 * AF_BM) return bad_arg("attention_bwd_fused: seq_len must be <= 256 (dQ of two query tiles in TMEM)");
@@ -792,8 +836,12 @@ extern "C" int mm_attention_bwd_fused(const void* qkv, int64_t qkv_ld, int32_t q
   p.q_col0 = q_col0, p.k_col0 = k_col0, p.v_col0 = v_col0;
   p.kv_lens = kv_lens, p.lse = lse;
   p.scale = 0.125f;
+  p.drop_p = drop_p, p.drop_site = site, p.drop_seed = seed;
+  p.drop_seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev), p.drop_tp = (seq_len + 63) / 64 * 64;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return f16 ? launch_attention_bwd_fused<__half>(m, p, s) : launch_attention_bwd_fused<__nv_bfloat16>(m, p, s);
+  if (drop_p > 0.f)
+    return f16 ? launch_attention_bwd_fused<__half, true>(m, p, s) : launch_attention_bwd_fused<__nv_bfloat16, true>(m, p, s);
+  return f16 ? launch_attention_bwd_fused<__half, false>(m, p, s) : launch_attention_bwd_fused<__nv_bfloat16, false>(m, p, s);
 }
 
 extern "C" int64_t mm_attention_bwd_general_scratch_floats(int32_t kv_len) {

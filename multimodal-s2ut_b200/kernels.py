@@ -251,13 +251,27 @@ def layernorm_gather(store: torch.Tensor, index: Optional[torch.Tensor], rows_pe
                                            eps, _stream()), "mm_layernorm_gather")
 
 
+def self_attention_drop_supported(seq: int) -> bool:
+    """Attention dropout inside the forward kernel: the single-chunk kernel only (129 .. 256 positions)."""
+    return 128 < seq <= 256
+
+
 def self_attention(qkv: torch.Tensor, seq_lens_: torch.Tensor, batch: int, seq: int, heads: int,
-                   out: torch.Tensor, lse: Optional[torch.Tensor] = None) -> None:
+                   out: torch.Tensor, lse: Optional[torch.Tensor] = None, drop=None) -> None:
     """qkv [B*T, 3d] (q pre-scaled | k | v) -> out [B*T, d]; head_dim 64.  lse (optional): [B, heads, T] fp32
-    log-sum-exp of every query row's scores (kept by the training forward for ``attention_bwd_scores``)."""
+    log-sum-exp of every query row's scores (kept by the training forward for ``attention_bwd_scores``).
+    drop = (p, seed, seed_dev, site): attention dropout on the probabilities inside the kernel (training forward;
+    ``self_attention_drop_supported(seq)`` must hold)."""
     assert qkv.dtype == out.dtype and seq_lens_.dtype == torch.int32 and qkv.stride(-1) == 1
     assert lse is None or (lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == batch * heads * seq)
     lib = _lib.load()
+    if drop is not None and drop[0] > 0:
+        with _Launch("self_attention", 4.0 * batch * seq * seq * heads * 64):
+            _lib.check(lib.mm_self_attention_drop(_ptr(qkv), qkv.stride(-2), _ptr(seq_lens_), batch, seq, heads, _ptr(out),
+                                                  out.stride(-2), _ptr(lse), float(drop[0]),
+                                                  drop[1] & 0xFFFFFFFFFFFFFFFF, _ptr(drop[2]), drop[3],
+                                                  dtype_code(qkv.dtype), _stream()), "mm_self_attention_drop")
+        return
     with _Launch("self_attention", 4.0 * batch * seq * seq * heads * 64):
         _lib.check(lib.mm_self_attention_lse(_ptr(qkv), qkv.stride(-2), _ptr(seq_lens_), batch, seq, heads, _ptr(out),
                                              out.stride(-2), _ptr(lse), dtype_code(qkv.dtype), _stream()),
@@ -441,9 +455,10 @@ def reduce_partials_many(jobs) -> None:
 
 
 def attention_bwd_fused(qkv: torch.Tensor, seq_len: int, kv_lens: Optional[torch.Tensor], batch: int, heads: int,
-                        dout: torch.Tensor, out: torch.Tensor, lse: torch.Tensor, dqkv: torch.Tensor) -> None:
+                        dout: torch.Tensor, out: torch.Tensor, lse: torch.Tensor, dqkv: torch.Tensor, drop=None) -> None:
     """dq | dk | dv [batch*seq_len, 3 * heads*64] from q | k | v (same layout), dout, out and lse in one kernel; seq_len
-    <= 256 (``mm_attention_bwd_fused``)."""
+    <= 256 (``mm_attention_bwd_fused``).  drop = (p, seed, seed_dev, site): the attention-dropout mask the forward
+    kernel applied (``self_attention(..., drop=)``) is regenerated."""
     d = heads * 64
     assert qkv.dtype == dout.dtype == out.dtype == dqkv.dtype and qkv.dtype in _DT
     assert all(t.dim() == 2 and t.stride(1) == 1 for t in (qkv, dout, out, dqkv))
@@ -452,10 +467,12 @@ def attention_bwd_fused(qkv: torch.Tensor, seq_len: int, kv_lens: Optional[torch
     if kv_lens is not None:
         assert kv_lens.dtype == torch.int32 and kv_lens.numel() == batch
     lib = _lib.load()
+    p_, seed, seed_dev, site = drop if (drop is not None and drop[0] > 0) else (0.0, 0, None, 0)
     with _Launch("attention_bwd_fused", 10.0 * batch * heads * seq_len * seq_len * 64):
-        _lib.check(lib.mm_attention_bwd_fused(_ptr(qkv), qkv.stride(0), 0, d, 2 * d, seq_len, _ptr(kv_lens), batch, heads,
-                                              _ptr(dout), dout.stride(0), _ptr(out), out.stride(0), _ptr(lse), _ptr(dqkv),
-                                              dqkv.stride(0), dtype_code(qkv.dtype), _stream()),
+        _lib.check(lib.mm_attention_bwd_fused_drop(_ptr(qkv), qkv.stride(0), 0, d, 2 * d, seq_len, _ptr(kv_lens), batch,
+                                                   heads, _ptr(dout), dout.stride(0), _ptr(out), out.stride(0), _ptr(lse),
+                                                   _ptr(dqkv), dqkv.stride(0), float(p_), seed & 0xFFFFFFFFFFFFFFFF,
+                                                   _ptr(seed_dev), site, dtype_code(qkv.dtype), _stream()),
                    "mm_attention_bwd_fused")
 
 

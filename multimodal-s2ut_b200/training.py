@@ -385,8 +385,14 @@ class TrainEngine(EncoderEngine):
             K.layernorm(x_in, L["ln1_g"], L["ln1_b"], out_op=s["h1"])
         K.gemm(a0=s["h1"], a0_ld=d, rows=M, w=L["wqkv"], n=3 * d, k=d, mode=K.EPI_OP, bias=L["bqkv"], scale=64 ** -0.5,
                scale_cols=d, out0=s["qkv"], out0_ld=3 * d, block_n=bn)
-        if self._p_attn > 0:
-            # attention dropout: un-fused S = q k^T -> softmax + dropout -> P V on the head-mode GEMMs (the fused
+        if self._p_attn > 0 and K.self_attention_drop_supported(T) and self.fused_attn_bwd_onchip:
+            # attention dropout generated inside the fused kernels (129 .. 256 positions): the forward keeps lse, the
+            # on-chip backward regenerates the mask
+            s["lse"] = self.buf(f"t_lse_{i}", (B, self.heads, T), torch.float32)
+            s["attn_drop"] = (self._p_attn, seed, seed_dev, site_layer(i, 3))
+            K.self_attention(s["qkv"], seq_lens, B, T, self.heads, s["att"], lse=s["lse"], drop=s["attn_drop"])
+        elif self._p_attn > 0:
+            # attention dropout: un-fused S = q k^T -> softmax + dropout -> P V on the head-mode GEMMs (the chunked
             # attention kernel has no mask generator); the backward pass regenerates the same mask
             H, Tp = self.heads, _round_up(T, 64)
             hd = dict(heads=H, head_stride=64, batches=B * H, w_batched=True, block_n=bn)
@@ -635,7 +641,7 @@ class TrainEngine(EncoderEngine):
         qkv = s["qkv"]
         if "lse" in s and self.fused_attn_bwd and self.fused_attn_bwd_onchip and T <= 256:
             # one kernel: S, dP, P, dS never leave the SM; dq | dk | dv accumulate in TMEM
-            K.attention_bwd_fused(qkv, T, seq_lens, B, H, datt, s["att"], s["lse"], dqkv)
+            K.attention_bwd_fused(qkv, T, seq_lens, B, H, datt, s["att"], s["lse"], dqkv, drop=s.get("attn_drop"))
             return
         if "lse" in s and self.fused_attn_bwd and self.fused_attn_bwd_onchip:
             # longer sequences: the same on chip with query tiles taken in pairs (mm_attention_bwd_general)

@@ -229,7 +229,18 @@ def layernorm(x, gamma, beta, out_op=None, out_f32=None, eps=1e-5):
         out_f32.view(-1, dim).copy_(y)
 
 
-def self_attention(qkv, seq_lens_, batch, seq, heads, out, lse=None):
+def self_attention_drop_supported(seq):
+    return 128 < seq <= 256
+
+
+def _attn_keep(batch, heads, seq, drop):
+    """keep / (1 - p) over [batch*heads][Tp][Tp] (Tp = seq rounded up to 64), cut to [batch, heads, seq, seq]."""
+    Tp = (seq + 63) // 64 * 64
+    m = _keep_scale(batch * heads * Tp * Tp, drop[0], drop[1], drop[3], drop[2]).view(batch, heads, Tp, Tp)
+    return m[:, :, :seq, :seq]
+
+
+def self_attention(qkv, seq_lens_, batch, seq, heads, out, lse=None, drop=None):
     d = heads * 64
     x = qkv.float().view(batch, seq, 3, heads, 64)
     q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))
@@ -238,7 +249,10 @@ def self_attention(qkv, seq_lens_, batch, seq, heads, out, lse=None):
     s = s.masked_fill(mask[:, None, None, :], float("-inf"))
     if lse is not None:
         lse.copy_(torch.logsumexp(s, -1).reshape(lse.shape))
-    p = s.softmax(-1).to(qkv.dtype).float()
+    p = s.softmax(-1)
+    if drop is not None and drop[0] > 0:
+        p = p * _attn_keep(batch, heads, seq, drop)
+    p = p.to(qkv.dtype).float()
     o = (p @ v).permute(0, 2, 1, 3).reshape(batch * seq, d)
     out.copy_(o.to(out.dtype))
 
@@ -323,7 +337,7 @@ def attention_bwd_general(q, q_len, k, v, kv_len, kv_lens, batch, heads, dout, o
     dv[:, :d] = back(P.transpose(-1, -2) @ dO, kv_len).to(dv.dtype)
 
 
-def attention_bwd_fused(qkv, seq_len, kv_lens, batch, heads, dout, out, lse, dqkv):
+def attention_bwd_fused(qkv, seq_len, kv_lens, batch, heads, dout, out, lse, dqkv, drop=None):
     global launch_count
     launch_count += 1
     d = heads * 64
@@ -335,7 +349,9 @@ def attention_bwd_fused(qkv, seq_len, kv_lens, batch, heads, dout, out, lse, dqk
     P = torch.exp(s - lse.view(batch, heads, seq_len, 1)).masked_fill(dead, 0.0)
     dO = dout[:, :d].float().view(batch, seq_len, heads, 64).permute(0, 2, 1, 3)
     O = out[:, :d].float().view(batch, seq_len, heads, 64).permute(0, 2, 1, 3)
-    dS = P * (dO @ V.transpose(-1, -2) - (dO * O).sum(-1, keepdim=True))
+    mk = _attn_keep(batch, heads, seq_len, drop) if (drop is not None and drop[0] > 0) else 1.0
+    dS = P * ((dO @ V.transpose(-1, -2)) * mk - (dO * O).sum(-1, keepdim=True))
+    P = P * mk
     P, dS = P.to(qkv.dtype).float(), dS.to(qkv.dtype).float()
     back = lambda x: x.permute(0, 2, 1, 3).reshape(batch * seq_len, d).to(dqkv.dtype)
     dqkv[:, :d] = back(dS @ Kx * 0.125)

@@ -399,7 +399,7 @@ def test_encoder_backward_other_shapes(cuda, name, preset, overrides, img, B, du
 # element-wise dropout in the training step
 # ---------------------------------------------------------------------------------------------------------
 def _dropout_parity(K, device, p_drop=0.1, p_act=0.15, p_img=0.2, p_attn=0.1, p_sa=0.1, p_text=0.1, seed=1234,
-                    emulated=False, preset="small", overrides=None, min_checked=6 * 15 + 2 + 4):
+                    emulated=False, preset="small", overrides=None, min_checked=6 * 15 + 2 + 4, dur=None):
     """Forward + backward with dropout on, against autograd over the oracle run with THE SAME masks: the oracle's
     ``drop(site, x)`` hook multiplies by the mask the kernel produces for that site (dumped by running the dropout kernel
     on a tensor of ones), re-laid-out from token-major to the oracle's [T, B, C]."""
@@ -429,7 +429,7 @@ def _dropout_parity(K, device, p_drop=0.1, p_act=0.15, p_img=0.2, p_attn=0.1, p_
     enc.dropout_p, enc.activation_dropout_p, enc.attention_dropout_p = p_drop, p_act, p_attn
     enc.SA_image_dropout, enc.SA_attention_dropout, enc.SA_text_dropout = p_img, p_sa, p_text
     B = 2
-    wavs, _ = synth.synth_batch(7, B, 1.0 if emulated else 2.0, ragged=True)
+    wavs, _ = synth.synth_batch(7, B, dur if dur is not None else (1.0 if emulated else 2.0), ragged=True)
     imgs = synth.synth_images(7, B, 50 if emulated else 577, 768)
     feats, flens = ofb.features_from_waveforms(wavs)
     sd = {k: v.detach().clone().float().requires_grad_(v.is_floating_point()) for k, v in enc.state_dict().items()}
@@ -545,6 +545,20 @@ def test_training_step_with_dropout_in_fused_epilogues_d512(cuda):
                                   overrides=dict(encoder_layers=3), min_checked=3 * 15 + 2 + 4)
     record("configs[2] backward, base width d=512, dropout 0.1 / relu-dropout 0.1 / attention-dropout 0.1 in the fused "
            "epilogues (same masks in the oracle): worst parameter-gradient relative L2 error", worst, REL)
+
+
+def test_training_step_with_attention_dropout_inside_the_attention_kernels(cuda):
+    """6 s utterances (T = 150: the single-chunk attention kernel): attention dropout is generated inside the forward
+    attention kernel (mm_self_attention_drop) and regenerated inside the on-chip backward (mm_attention_bwd_fused_drop);
+    small and base width, against the oracle run with the same masks."""
+    from mm_s2ut_b200 import kernels as K
+
+    w1, _ = _dropout_parity(K, cuda, p_drop=0.1, p_act=0.1, p_attn=0.1, overrides=dict(encoder_layers=2),
+                            min_checked=2 * 15 + 2 + 4, dur=6.0)
+    w2, _ = _dropout_parity(K, cuda, p_drop=0.1, p_act=0.1, p_attn=0.1, preset="base", overrides=dict(encoder_layers=2),
+                            min_checked=2 * 15 + 2 + 4, dur=6.0)
+    record("configs[2] backward, T = 150, attention dropout 0.1 inside the fused attention forward / backward kernels "
+           "(same masks in the oracle), small / base width: worst parameter-gradient relative L2 error", max(w1, w2), REL)
 
 
 def test_graphed_train_step_draws_fresh_dropout_masks(cuda):
