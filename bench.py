@@ -355,6 +355,37 @@ def train_step_probe(ctx, wav, img, steps=20, warmup=3, model_step=True):
                    "(image-drop branch), synthetic d loss/d encoder_out; element-wise dropout off"}
     del gs
     torch.cuda.empty_cache()
+    # ---- the same step with the dropout of the reference's own recipe (scripts/textless/1_train.sh:112 --dropout 0.1
+    # --attention-dropout 0.1 --relu-dropout 0.1; shipped YAML: SA_image_dropout 0.1, SA_attention_dropout 0.1), masks
+    # generated inside the fused kernels
+    try:
+        enc_d, _ = make_encoder(ctx, cfg_over=dict(modality_dropout=0.5, audio_dropout=-0.5, SA_image_dropout=0.1,
+                                                   SA_attention_dropout=0.1), train=True)
+        enc_d.dropout_p = enc_d.activation_dropout_p = enc_d.attention_dropout_p = 0.1
+        enc_d.SA_image_dropout = enc_d.SA_attention_dropout = 0.1
+        gd = GraphedTrainStep(enc_d, wav.shape[0], wav.shape[1], tuple(img.shape[1:]), overlap_reduce=False)
+        gd.wav.copy_(wav)
+        gd.img.copy_(img)
+        gd.grad_out = torch.randn(T, wav.shape[0], enc_d.embed_dim, device=dev, generator=g) * 1e-3
+        gd.capture()
+        for _ in range(warmup):
+            gd.step(5e-4, drop_image=rng.random() < 0.5, clip_norm=10.0)
+        ctx.barrier()
+        e0.record()
+        for _ in range(steps):
+            gd.step(5e-4, drop_image=rng.random() < 0.5, clip_norm=10.0)
+        e1.record()
+        torch.cuda.synchronize()
+        dms = ctx.max_over_ranks(e0.elapsed_time(e1) / steps)
+        out["recipe_dropout"] = {
+            "value": audio_s / (dms * 1e-3), "unit": "audio-s/s trained", "ms_per_step": dms, "steps": steps,
+            "what": "the same step with the reference recipe's dropout on: --dropout 0.1 --attention-dropout 0.1 "
+                    "--relu-dropout 0.1, SA_image_dropout 0.1, SA_attention_dropout 0.1 (counter-based masks generated "
+                    "inside the fused GEMM / attention kernels and regenerated in the backward pass)"}
+        del gd, enc_d
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out["recipe_dropout"] = {"error": f"{type(e).__name__}: {e}"}
     if not model_step:
         return out
     # ---- the complete model step: + 6-layer unit decoder (V = 1004, 500 target units per 10 s) + label-smoothed CE

@@ -5,7 +5,7 @@ behind a device spin so host latency is not timed); per-kernel-family breakdown 
     python profiles/tools/train_step.py [--steps 10] [--batch 64] [--seconds 10]
     torchrun --nproc-per-node N ... profiles/tools/train_step.py          (adds the NCCL gradient all-reduce)
 
-Element-wise dropout masks are not built (dropout probabilities are set to 0); modality dropout is on at 0.5
+Element-wise dropout is off by default (--dropout P switches every site on, masks generated in the fused kernels); modality dropout is on at 0.5
 (image-drop branch, per-batch numpy draw like the reference).
 """
 import argparse
@@ -82,7 +82,7 @@ def model_step(a, enc, eng, wav, lens, imgs, dev, world, rank, rng):
                     tgt_units_per_utt=a.tgt_len, encoder_params=int(eng.flat_p.numel()), decoder_params=int(dec.flat_p.numel()),
                     loss_per_unit_first=losses[0] / ntok, loss_per_unit_last=losses[-1] / ntok,
                     overlap_reduce=bool(world > 1 and not a.no_overlap),
-                    note="element-wise dropout off (masks not built); modality dropout 0.5; random target units")
+                    note="element-wise dropout off; modality dropout 0.5; random target units")
         print(json.dumps(line), flush=True)
     if world > 1:
         del gs
