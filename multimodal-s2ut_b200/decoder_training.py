@@ -185,12 +185,12 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
     # forward (activations kept)
     # ------------------------------------------------------------------------------------------
     def _resid(self, a, a_ld, w, b, k, x_in, x_out, M, site, ln=None, h=None):
-        """x_out = x_in + dropout(a w^T + b), then h = LayerNorm_ln(x_out): the fused GEMM + residual + LayerNorm kernel
-        with a separate output (d_model 512, no dropout), else GEMM (-> mm_dropout(+resid)) -> LayerNorm."""
+        """x_out = x_in + dropout(a w^T + b), then h = LayerNorm_ln(x_out): the fused GEMM + dropout + residual +
+        LayerNorm kernel with a separate output (d_model 512), else GEMM (-> mm_dropout(+resid)) -> LayerNorm."""
         d, bn = self.d, self.block_n
         p, _, _, seed, seed_dev = self._drop
-        if p == 0 and d == 512 and ln is not None:
-            K.gemm_resid_ln(a, w, b, x_in, ln[0], ln[1], h, x_out=x_out)
+        if d == 512 and ln is not None and a_ld == k:
+            K.gemm_resid_ln(a, w, b, x_in, ln[0], ln[1], h, x_out=x_out, drop=(p, seed, seed_dev, site) if p > 0 else None)
             return
         if p > 0:
             y = self.buf("t_y", (M, d), torch.float32)
@@ -279,9 +279,8 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                 K.attention(s["q2"], 0, L, s["kv2"], 0, s["kv2"], d, T, enc_lens, B, H, s["att2"], lse=s["lse2"])
             self._resid(s["att2"], d, Lr["wo2"], Lr["bo2"], d, s["x1"], s["x2"], M, dsite_layer(i, 2), Lr["ln3"], s["h3"])
             K.gemm(a0=s["h3"], a0_ld=d, rows=M, w=Lr["w1"], n=self.ffn, k=d, mode=K.EPI_RELU_OP, bias=Lr["b1"],
-                   out0=s["f"], out0_ld=self.ffn, block_n=bn)
-            if p_act > 0:
-                K.dropout(s["f"], s["f"], p_act, seed, dsite_layer(i, 4), seed_dev=seed_dev)
+                   out0=s["f"], out0_ld=self.ffn, block_n=bn,
+                   drop=(p_act, seed, seed_dev, dsite_layer(i, 4)) if p_act > 0 else None)     # activation dropout in the epilogue
             last = i + 1 == self.n_layers
             nxt_ln = self.ln_out if last else self.layers[i + 1]["ln1"]
             nxt_h = h_out if last else self.buf(f"h1_{i + 1}", (M, d), op)
@@ -360,27 +359,23 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
         dh = self.buf("b_dh", (M, d), torch.float32)
         g = self.buf("b_g", (M, d), torch.float32)
         g_op = self.buf("b_g_op", (M, d), op)
+        p_drop, p_attn, p_act, seed, seed_dev = sv["drop"]
+
+        def drb(site):      # the gradient entering a dropped branch is g o mask / (1 - p) (the residual path keeps g itself):
+            return (p_drop, seed, seed_dev, site) if p_drop > 0 else None      # the LayerNorm backward before it emits that 16-bit copy
         # ---- tied output projection: logits = h E^T
         with _scope("out_proj"):
             self._wgrad_mn(dlog, Vp, [(sv["h_out"], d, d)], M, Vp, self.g("embed_tokens.weight"), accumulate)
             K.gemm(a0=dlog, a0_ld=Vp, rows=M, w=self.emb_op, w_ld=d, w_mn=True, n=d, k=Vp, mode=K.EPI_F32, out0=dh,
                    out0_ld=d, block_n=bn)
             lnp = self._lnp()
-            K.layernorm_bwd(sv["x_final"], self.ln_out[0], dh, lnp, dx=g, dx_op=g_op)
+            K.layernorm_bwd(sv["x_final"], self.ln_out[0], dh, lnp, dx=g, dx_op=g_op, drop=drb(dsite_layer(self.n_layers - 1, 5)))
             self._ln_param_grads(lnp, d, self.g("layer_norm.weight", "layer_norm.bias"), accumulate)
             self._flush()
         denc = self.buf("denc_btc", (B * T, d), torch.float32)
         first_kv = True
-        p_drop, p_attn, p_act, seed, seed_dev = sv["drop"]
 
         grouped = self.grouped_wgrad     # queued weight gradients: every layer keeps its own gradient buffers
-
-        def masked(site):       # gradient entering a dropped branch = g o mask / (1 - p); the residual keeps g itself
-            if p_drop == 0:
-                return g_op
-            gm = self.buf(f"b_gm_op@{site}" if grouped else "b_gm_op", (M, d), op)
-            K.dropout(g_op, gm, p_drop, seed, site, seed_dev=seed_dev)
-            return gm
 
         for i in reversed(range(self.n_layers)):
             s, Lr = sv["layers"][i], self.layers[i]
@@ -389,7 +384,7 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
             tag = f"@{i}" if grouped else ""
             with _scope("dec_layer"):
                 # ---- FFN
-                gm = masked(dsite_layer(i, 5))
+                gm = g_op           # already masked for this branch's site by the LayerNorm backward that produced it
                 self._linear_bwd(gm, d, s["f"], M, d, ffn, self.g(p + "fc2.weight"), self.g(p + "fc2.bias"), accumulate)
                 dF = self.buf("b_dF" + tag, (M, ffn), op)
                 # ReLU (and activation-dropout) mask in the dgrad's epilogue: the kept activation is > 0 exactly where ReLU passed
@@ -402,10 +397,10 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                 lnp = self._lnp()
                 if grouped:
                     g_op = self.buf("b_g_op2" + tag, (M, d), op)
-                K.layernorm_bwd(s["x2"], Lr["ln3"][0], dh, lnp, dx=g, resid=g, dx_op=g_op)
+                K.layernorm_bwd(s["x2"], Lr["ln3"][0], dh, lnp, dx=g, resid=g, dx_op=g_op, drop=drb(dsite_layer(i, 2)))
                 self._ln_param_grads(lnp, d, self.g(p + "final_layer_norm.weight", p + "final_layer_norm.bias"), accumulate)
                 # ---- encoder attention
-                gm = masked(dsite_layer(i, 2))
+                gm = g_op
                 self._linear_bwd(gm, d, s["att2"], M, d, d, self.g(ea + "out_proj.weight"), self.g(ea + "out_proj.bias"),
                                  accumulate)
                 datt = self.buf("b_datt", (M, d), op)
@@ -433,11 +428,11 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                 lnp = self._lnp()
                 if grouped:
                     g_op = self.buf("b_g_op1" + tag, (M, d), op)
-                K.layernorm_bwd(s["x1"], Lr["ln2"][0], dh, lnp, dx=g, resid=g, dx_op=g_op)
+                K.layernorm_bwd(s["x1"], Lr["ln2"][0], dh, lnp, dx=g, resid=g, dx_op=g_op, drop=drb(dsite_layer(i, 0)))
                 self._ln_param_grads(lnp, d, self.g(p + "encoder_attn_layer_norm.weight", p + "encoder_attn_layer_norm.bias"),
                                      accumulate)
                 # ---- causal self-attention
-                gm = masked(dsite_layer(i, 0))
+                gm = g_op
                 self._linear_bwd(gm, d, s["att"], M, d, d, self.g(sa + "out_proj.weight"), self.g(sa + "out_proj.bias"),
                                  accumulate)
                 K.gemm(a0=gm, a0_ld=d, rows=M, w=Lr["wo"], w_ld=d, w_mn=True, n=d, k=d, mode=K.EPI_OP, out0=datt,
@@ -455,7 +450,8 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                 lnp = self._lnp()
                 if grouped:
                     g_op = self.buf("b_g_op0" + tag, (M, d), op)
-                K.layernorm_bwd(s["x0"], Lr["ln1"][0], dh, lnp, dx=g, resid=g, dx_op=g_op)
+                K.layernorm_bwd(s["x0"], Lr["ln1"][0], dh, lnp, dx=g, resid=g, dx_op=g_op,
+                                drop=drb(dsite_layer(i - 1, 5)) if i > 0 else None)
                 self._ln_param_grads(lnp, d, self.g(p + "self_attn_layer_norm.weight", p + "self_attn_layer_norm.bias"),
                                      accumulate)
                 self._flush()       # the layer's deferred reductions in one launch (per 16)

@@ -34,6 +34,8 @@ def model_step(a, enc, eng, wav, lens, imgs, dev, world, rank, rng):
     B, n = wav.shape
     d, ffn = enc.embed_dim, enc.ffn_dim
     dec = UnitDecoderTrainEngine(init_decoder(d, ffn, 6, 1004, seed=1), enc.num_heads, dev)
+    dec.dropout_p = dec.activation_dropout_p = a.dropout
+    dec.attention_dropout_p = a.dropout if not a.no_decoder_attention_dropout else 0.0
     gs = GraphedModelTrainStep(enc, dec, B, n, (577, 768), a.tgt_len, overlap_reduce=(world > 1 and not a.no_overlap))
     g = torch.Generator(device=dev).manual_seed(3 + rank)
     gs.wav.copy_(wav)
@@ -100,6 +102,8 @@ def main():
     ap.add_argument("--preset", default="base")
     ap.add_argument("--no-graph", action="store_true", help="eager launches only (for an ncu launch list)")
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce after the backward graph instead of inside it")
+    ap.add_argument("--no-decoder-attention-dropout", action="store_true",
+                    help="--model: keep the decoder's attention dropout off (its other dropout sites follow --dropout)")
     ap.add_argument("--dropout", type=float, default=0.0, help="value of --dropout / --activation-dropout / "
                     "--attention-dropout / SA_image_dropout / SA_attention_dropout")
     ap.add_argument("--model", action="store_true", help="complete model step: + 6-layer unit decoder + label-smoothed CE")

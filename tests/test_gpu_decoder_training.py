@@ -218,3 +218,15 @@ def test_decoder_training_step_with_dropout_matches_oracle_with_same_masks(cuda)
     worst = _decoder_dropout_parity(K, cuda, dt, B=3, L=40, T=50, d=256, heads=4, ffn=512, layers=2, vocab=104, seed=1)
     record("configs[2] decoder backward with dropout 0.1 / attention-dropout 0.1 / activation-dropout 0.15 (same masks in "
            "the oracle): worst parameter-gradient relative L2 error", worst, REL)
+
+
+def test_decoder_training_step_with_dropout_in_fused_kernels_d512(cuda):
+    """d_model 512: the residual-site masks are applied inside mm_gemm_resid_ln_drop, the activation mask in the fc1
+    epilogue, and every LayerNorm backward emits the masked 16-bit gradient of the next branch."""
+    import mm_s2ut_b200.decoder_training as dt
+    from mm_s2ut_b200 import kernels as K
+    from test_host_training import _decoder_dropout_parity
+
+    worst = _decoder_dropout_parity(K, cuda, dt, B=2, L=70, T=90, d=512, heads=8, ffn=1024, layers=2, vocab=104, seed=2)
+    record("configs[2] decoder backward, d_model 512, dropout inside the fused GEMM + LayerNorm / fc1 / LayerNorm-backward "
+           "kernels (same masks in the oracle): worst parameter-gradient relative L2 error", worst, REL)
