@@ -342,7 +342,8 @@ int mm_attention_bwd_fused(const void* qkv, int64_t qkv_ld, int32_t q_col0, int3
  * 0.1 in scripts/textless/1_train.sh:112) generated INSIDE the kernels: the forward multiplies P by keep / (1 - p)
  * before the P V product (the softmax denominator and lse stay un-dropped), the backward regenerates the same mask
  * (counter-based, as mm_dropout, element index ((b heads + h) Tp + q) Tp + k with Tp = seq rounded up to 64).
- * mm_self_attention_drop: 129 .. 256 positions (the single-chunk kernel). */
+ * mm_self_attention_drop: any length (the single-chunk kernel for 129 .. 256 positions, else the chunked one);
+ * mm_attention_bwd_fused_drop: up to 256 positions (beyond: mm_attention_bwd_general_drop). */
 int mm_self_attention_drop(const void* qkv, int64_t qkv_ld, const int32_t* seq_lens, int32_t batch, int32_t seq,
                            int32_t heads, void* out, int64_t out_ld, float* lse, float drop_p, uint64_t seed,
                            const uint64_t* seed_dev, uint32_t site, int32_t dtype, void* stream);
@@ -365,6 +366,22 @@ int mm_attention_bwd_general(const void* q, int64_t q_ld, int32_t q_col0, int32_
                              int64_t do_ld, const void* out, int64_t o_ld, const float* lse, void* dq, int64_t dq_ld,
                              int32_t dq_col0, void* dk, int64_t dk_ld, int32_t dk_col0, void* dv, int64_t dv_ld,
                              int32_t dv_col0, float* scratch, int32_t dtype, void* stream);
+/* Attention dropout inside the general kernels (the unit decoder's two attentions under --attention-dropout,
+ * scripts/textless/1_train.sh:112; the encoder beyond 256 positions): mm_attention_drop is mm_attention_lse with
+ * P o keep / (1 - p) entering the P V product, mm_attention_bwd_general_drop regenerates the mask.  Element index of
+ * (b, h, query q, key k) in the counter-based mask: ((b heads + h) Lp + q) Tp + k, Lp / Tp = q_len / kv_len rounded up
+ * to 64 (the layout mm_softmax_dropout_bwd uses on stored [batch * heads][Lp][Tp] scores). */
+int mm_attention_drop(const void* q, int64_t q_ld, int32_t q_col0, int32_t q_len, const void* k, int64_t k_ld,
+                      int32_t k_col0, const void* v, int64_t v_ld, int32_t v_col0, int32_t kv_len, const int32_t* kv_lens,
+                      int32_t batch, int32_t heads, int32_t causal, void* out, int64_t out_ld, float* lse, float drop_p,
+                      uint64_t seed, const uint64_t* seed_dev, uint32_t site, int32_t dtype, void* stream);
+int mm_attention_bwd_general_drop(const void* q, int64_t q_ld, int32_t q_col0, int32_t q_len, const void* k, int64_t k_ld,
+                                  int32_t k_col0, const void* v, int64_t v_ld, int32_t v_col0, int32_t kv_len,
+                                  const int32_t* kv_lens, int32_t batch, int32_t heads, int32_t causal, const void* dout,
+                                  int64_t do_ld, const void* out, int64_t o_ld, const float* lse, void* dq, int64_t dq_ld,
+                                  int32_t dq_col0, void* dk, int64_t dk_ld, int32_t dk_col0, void* dv, int64_t dv_ld,
+                                  int32_t dv_col0, float* scratch, float drop_p, uint64_t seed, const uint64_t* seed_dev,
+                                  uint32_t site, int32_t dtype, void* stream);
 
 /* Attention backward, output side (autograd of fairseq's MultiheadAttention: dV = P^T dO, dK = dS^T q, dQ = dS k): per
  * sequence b and head h (head_dim 64)

@@ -18,7 +18,7 @@ CSRC = _PKG / "csrc"
 INCLUDE = _PKG.parent / "include"
 LIB_PATH = _PKG / "libmms2ut_b200.so"
 SOURCES = ["abi.cu", "gemm.cu", "gemm_ln.cu", "rowwise.cu", "fbank.cu", "attention.cu", "cross_attention.cu", "attention_bwd.cu", "backward.cu", "wgrad.cu", "heads_gemm.cu", "attention_bwd_fused.cu", "p2p.cu"]
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -188,6 +188,16 @@ EXPORTS = {
                                            C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                            C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
                                            C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mm_attention_drop": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                    C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                    C.c_int64, C.c_void_p, C.c_float, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int32,
+                                    C.c_void_p]),
+    "mm_attention_bwd_general_drop": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
+                                                C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                                C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                                C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
+                                                C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_float, C.c_uint64,
+                                                C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p]),
     "mm_self_attention_drop": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_float, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int32,
                                          C.c_void_p]),

@@ -456,12 +456,12 @@ constexpr int PL_SMEM_BYTES = 2 * AT_Q_BYTES + 2 * 2 * PL_KV_BYTES + 2 * PA_OUT_
                               PA_XCH_BYTES + 1024;
 static_assert(PL_SMEM_BYTES <= 232448, "shared memory budget");
 
-template <typename OpT>
+template <typename OpT, bool DROP>
 __global__ void __launch_bounds__(PA_THREADS, 1)
 self_attention_long_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                            const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapOut,
                            const int* __restrict__ seq_lens, int T, int q_col0, int k_col0, int v_col0, int causal,
-                           int H, int nqt, int n_items, int q_len, float* __restrict__ lse) {
+                           int H, int nqt, int n_items, int q_len, float* __restrict__ lse, const AttnDrop dr) {
   // Q, K, V may be three different tensors (decoder cross-attention: queries from the decoder states, keys / values
   // from the projected encoder states) or column blocks of one (self-attention: q | k | v of the QKV GEMM).  T is
   // the key extent, seq_lens[b] (NULL: T) the number of valid keys of utterance b; the number of query rows only
@@ -633,6 +633,10 @@ self_attention_long_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
       if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 2, 256;" ::: "memory");
     };
     uint32_t s_n = 0, o_n = 0;                 // S chunks / P V chunks seen by this group (-> parities)
+    const unsigned long long drop_seed = DROP ? dr.seed + (dr.seed_dev ? *dr.seed_dev : 0ull) : 0ull;
+    const unsigned drop_thr = dropout_threshold(dr.p);
+    const float drop_inv = 1.0f / (1.0f - dr.p);
+    const int drop_lp = (q_len + 63) / 64 * 64;
     for (int i = g; i < n_local; i += 2) {
       int qt, h, b;
       item_coords(i, qt, h, b);
@@ -659,12 +663,23 @@ self_attention_long_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
         const float mb = m * L2E;
         uint32_t pk[16];
         float lc;
+        if constexpr (DROP) {
+          // mask index of (query row, first of my 64 keys): ((b H + h) Lp + q) Tp + key, four elements per hash
+          const unsigned long long i4 =
+              ((unsigned long long)((long long)(b * H + h) * drop_lp + qt * AT_BM + row) * (unsigned)dr.tp +
+               (unsigned)(c * PL_KC + 64 * hf)) >> 2;
+          lc = softmax_chunk_drop<OpT>(ra, pk, mb, min(valid, 32), drop_seed, dr.site, i4, drop_thr, drop_inv);
+          tmem_st16(t_row + 32 * hf, pk);
+          lc += softmax_chunk_drop<OpT>(rb, pk, mb, max(valid - 32, 0), drop_seed, dr.site, i4 + 8, drop_thr, drop_inv);
+          tmem_st16(t_row + 32 * hf + 16, pk);
+        } else {
         if (valid >= 32) lc = softmax_chunk<OpT, false>(ra, pk, mb, 32);
         else lc = softmax_chunk<OpT, true>(ra, pk, mb, valid);
         tmem_st16(t_row + 32 * hf, pk);
         if (valid >= 64) lc += softmax_chunk<OpT, false>(rb, pk, mb, 32);
         else lc += softmax_chunk<OpT, true>(rb, pk, mb, max(valid - 32, 0));
         tmem_st16(t_row + 32 * hf + 16, pk);
+        }
         l = l * alpha + lc;
         // O <- alpha O, only in warps where some row's maximum moved; P V of the previous chunk must have landed
         if (c > 0) {
@@ -737,11 +752,11 @@ self_attention_long_kernel(const __grid_constant__ CUtensorMap mapQ, const __gri
   }
 }
 
-template <typename OpT>
+template <typename OpT, bool DROP = false>
 static int launch_attn_long(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mout,
                             const int* lens, int B, int Tq, int Tk, int q_col0, int k_col0, int v_col0, int causal,
-                            int H, float* lse, cudaStream_t s) {
-  auto kern = self_attention_long_kernel<OpT>;
+                            int H, float* lse, cudaStream_t s, AttnDrop dr = AttnDrop{0.f, 0u, 0ull, nullptr, 0}) {
+  auto kern = self_attention_long_kernel<OpT, DROP>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PL_SMEM_BYTES);
@@ -763,7 +778,7 @@ static int launch_attn_long(const CUtensorMap& mq, const CUtensorMap& mk, const 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mq, mk, mv, mout, lens, Tk, q_col0, k_col0, v_col0, causal, H, nqt,
-                                     n_items, Tq, lse);
+                                     n_items, Tq, lse, dr);
   if (e != cudaSuccess) return fail(e, "self_attention_long_kernel launch");
   return 0;
 }
@@ -820,7 +835,6 @@ extern "C" int mm_self_attention_drop(const void* qkv, int64_t qkv_ld, const int
                                       const uint64_t* seed_dev, uint32_t site, int32_t dtype, void* stream) {
   if (!qkv || !seq_lens || !out) return bad_arg("self_attention_drop: null pointer");
   if (batch <= 0 || heads <= 0) return bad_arg("self_attention_drop: extents");
-  if (!(seq > PL_KC && seq <= AT_KC)) return bad_arg("self_attention_drop: 129 .. 256 positions (the single-chunk kernel)");
   if (!(drop_p > 0.f && drop_p < 1.f)) return bad_arg("self_attention_drop: p in (0, 1)");
   const int d = heads * AT_HD;
   if (qkv_ld < 3 * d || (qkv_ld % 8) || (out_ld % 8) || out_ld < d)
@@ -834,6 +848,10 @@ extern "C" int mm_self_attention_drop(const void* qkv, int64_t qkv_ld, const int
   if (rc) return rc;
   AttnDrop dr{drop_p, site, seed, reinterpret_cast<const unsigned long long*>(seed_dev), (seq + 63) / 64 * 64};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!(seq > PL_KC && seq <= AT_KC))     // the chunked kernel (same choice as mm_self_attention_lse)
+    return f16 ? launch_attn_long<__half, true>(mqk, mqk, mqk, mout, seq_lens, batch, seq, seq, 0, d, 2 * d, 0, heads, lse, s, dr)
+               : launch_attn_long<__nv_bfloat16, true>(mqk, mqk, mqk, mout, seq_lens, batch, seq, seq, 0, d, 2 * d, 0, heads,
+                                                         lse, s, dr);
   return f16 ? launch_attn_t256<__half, true>(mqk, mout, seq_lens, batch, seq, heads, d, lse, s, dr)
              : launch_attn_t256<__nv_bfloat16, true>(mqk, mout, seq_lens, batch, seq, heads, d, lse, s, dr);
 }
@@ -850,7 +868,17 @@ extern "C" int mm_attention_lse(const void* q, int64_t q_ld, int32_t q_col0, int
                                 int32_t k_col0, const void* v, int64_t v_ld, int32_t v_col0, int32_t kv_len,
                                 const int32_t* kv_lens, int32_t batch, int32_t heads, int32_t causal, void* out,
                                 int64_t out_ld, float* lse, int32_t dtype, void* stream) {
+  return mm_attention_drop(q, q_ld, q_col0, q_len, k, k_ld, k_col0, v, v_ld, v_col0, kv_len, kv_lens, batch, heads, causal,
+                           out, out_ld, lse, 0.f, 0, nullptr, 0, dtype, stream);
+}
+
+extern "C" int mm_attention_drop(const void* q, int64_t q_ld, int32_t q_col0, int32_t q_len, const void* k, int64_t k_ld,
+                                 int32_t k_col0, const void* v, int64_t v_ld, int32_t v_col0, int32_t kv_len,
+                                 const int32_t* kv_lens, int32_t batch, int32_t heads, int32_t causal, void* out,
+                                 int64_t out_ld, float* lse, float drop_p, uint64_t seed, const uint64_t* seed_dev,
+                                 uint32_t site, int32_t dtype, void* stream) {
   if (!q || !k || !v || !out) return bad_arg("attention: null pointer");
+  if (drop_p < 0.f || drop_p >= 1.f) return bad_arg("attention: dropout p in [0, 1)");
   if (batch <= 0 || q_len <= 0 || kv_len <= 0 || heads <= 0) return bad_arg("attention: extents");
   const int d = heads * AT_HD;
   if ((q_ld % 8) || (k_ld % 8) || (v_ld % 8) || (out_ld % 8) || out_ld < d || q_ld < q_col0 + d || k_ld < k_col0 + d ||
@@ -872,6 +900,13 @@ extern "C" int mm_attention_lse(const void* q, int64_t q_ld, int32_t q_col0, int
                     (uint64_t)q_len * out_ld, 128);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (drop_p > 0.f) {
+    AttnDrop dr{drop_p, site, seed, reinterpret_cast<const unsigned long long*>(seed_dev), (kv_len + 63) / 64 * 64};
+    return f16 ? launch_attn_long<__half, true>(mq, mk, mv, mout, kv_lens, batch, q_len, kv_len, q_col0, k_col0, v_col0,
+                                                 causal != 0, heads, lse, s, dr)
+               : launch_attn_long<__nv_bfloat16, true>(mq, mk, mv, mout, kv_lens, batch, q_len, kv_len, q_col0, k_col0,
+                                                         v_col0, causal != 0, heads, lse, s, dr);
+  }
   return f16 ? launch_attn_long<__half>(mq, mk, mv, mout, kv_lens, batch, q_len, kv_len, q_col0, k_col0, v_col0,
                                          causal != 0, heads, lse, s)
              : launch_attn_long<__nv_bfloat16>(mq, mk, mv, mout, kv_lens, batch, q_len, kv_len, q_col0, k_col0,

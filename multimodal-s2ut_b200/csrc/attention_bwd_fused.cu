@@ -389,9 +389,15 @@ struct AgDev {
   const float* lse;          // [batch][H][q_len]
   float* scratch;            // [gridDim.x][nc][2][128 * 64] fp32
   float scale;
+  // attention dropout (mm_attention_drop wrote O with the mask): index ((b H + h) drop_lp + q) drop_tp + key
+  float drop_p;
+  unsigned drop_site;
+  unsigned long long drop_seed;
+  const unsigned long long* drop_seed_dev;
+  int drop_lp, drop_tp;      // round_up(q_len, 64), round_up(kv_len, 64)
 };
 
-template <typename OpT>
+template <typename OpT, bool DROP>
 __global__ void __launch_bounds__(AF_THREADS, 1)
 attention_bwd_general_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                              const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapDO,
@@ -577,6 +583,9 @@ attention_bwd_general_kernel(const __grid_constant__ CUtensorMap mapQ, const __g
     auto group_sync = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     const bool elected = tid == 0;
     uint32_t steps = 0, accs = 0, pn = 0;
+    const unsigned long long drop_seed = DROP ? p.drop_seed + (p.drop_seed_dev ? *p.drop_seed_dev : 0ull) : 0ull;
+    const unsigned drop_thr = dropout_threshold(p.drop_p);
+    const float drop_inv = 1.0f / (1.0f - p.drop_p);
     float* my_scratch = p.scratch + (size_t)blockIdx.x * p.nc * 2 * (AF_BM * AF_HD);
     // 32 of the 64 columns of this thread's accumulator row (+ the scratch partial) -> scratch (fp32) or 16-bit store
     auto drain_tile = [&](uint32_t tcol, float scale, float* part, bool add_part, bool to_scratch, const CUtensorMap* m,
@@ -682,6 +691,29 @@ attention_bwd_general_kernel(const __grid_constant__ CUtensorMap mapQ, const __g
                 if (lane == 0) mbar_arrive(sdp_empty);
               }
               const int nvh = nv - 32 * half;
+              if constexpr (DROP) {
+                const unsigned long long i4 =
+                    ((unsigned long long)((long long)(b * p.H + h) * p.drop_lp + qrow) * (unsigned)p.drop_tp +
+                     (unsigned)(k0 + 32 * half)) >> 2;
+#pragma unroll
+                for (int g4 = 0; g4 < 8; ++g4) {
+                  const int k = 4 * g4;
+                  float pr4[4], m4[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    pr4[e] = af_ex2(fmaf(__uint_as_float(rs[k + e]), L2E, -lbq));
+                    pr4[e] = k + e < nvh ? pr4[e] : 0.f;
+                  }
+                  dropout_apply4(dropout_bits4(drop_seed, p.drop_site, i4 + g4), drop_thr, drop_inv, m4[0], m4[1], m4[2], m4[3]);
+                  float dd[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) dd[e] = pr4[e] * (__uint_as_float(rd[k + e]) * m4[e] - dl);
+                  pk[2 * g4] = OpTraits<OpT>::pack2(pr4[0] * m4[0], pr4[1] * m4[1]);
+                  pk[2 * g4 + 1] = OpTraits<OpT>::pack2(pr4[2] * m4[2], pr4[3] * m4[3]);
+                  dk[2 * g4] = OpTraits<OpT>::pack2(dd[0], dd[1]);
+                  dk[2 * g4 + 1] = OpTraits<OpT>::pack2(dd[2], dd[3]);
+                }
+              } else {
 #pragma unroll
               for (int k = 0; k < 32; k += 2) {
                 float p0 = af_ex2(fmaf(__uint_as_float(rs[k]), L2E, -lbq));
@@ -692,6 +724,7 @@ attention_bwd_general_kernel(const __grid_constant__ CUtensorMap mapQ, const __g
                 const float d1 = p1 * (__uint_as_float(rd[k + 1]) - dl);
                 pk[k >> 1] = OpTraits<OpT>::pack2(p0, p1);
                 dk[k >> 1] = OpTraits<OpT>::pack2(d0, d1);
+              }
               }
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -738,9 +771,9 @@ attention_bwd_general_kernel(const __grid_constant__ CUtensorMap mapQ, const __g
   }
 }
 
-template <typename OpT>
+template <typename OpT, bool DROP>
 static int launch_attention_bwd_general(const CUtensorMap (&m)[8], const AgDev& p, int grid, cudaStream_t s) {
-  auto kern = attention_bwd_general_kernel<OpT>;
+  auto kern = attention_bwd_general_kernel<OpT, DROP>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM_BYTES);
@@ -856,7 +889,21 @@ extern "C" int mm_attention_bwd_general(const void* q, int64_t q_ld, int32_t q_c
                                         const float* lse, void* dq, int64_t dq_ld, int32_t dq_col0, void* dk,
                                         int64_t dk_ld, int32_t dk_col0, void* dv, int64_t dv_ld, int32_t dv_col0,
                                         float* scratch, int32_t dtype, void* stream) {
+  return mm_attention_bwd_general_drop(q, q_ld, q_col0, q_len, k, k_ld, k_col0, v, v_ld, v_col0, kv_len, kv_lens, batch, heads,
+                                       causal, dout, do_ld, out, o_ld, lse, dq, dq_ld, dq_col0, dk, dk_ld, dk_col0, dv, dv_ld,
+                                       dv_col0, scratch, 0.f, 0, nullptr, 0, dtype, stream);
+}
+
+extern "C" int mm_attention_bwd_general_drop(const void* q, int64_t q_ld, int32_t q_col0, int32_t q_len, const void* k,
+                                             int64_t k_ld, int32_t k_col0, const void* v, int64_t v_ld, int32_t v_col0,
+                                             int32_t kv_len, const int32_t* kv_lens, int32_t batch, int32_t heads,
+                                             int32_t causal, const void* dout, int64_t do_ld, const void* out, int64_t o_ld,
+                                             const float* lse, void* dq, int64_t dq_ld, int32_t dq_col0, void* dk,
+                                             int64_t dk_ld, int32_t dk_col0, void* dv, int64_t dv_ld, int32_t dv_col0,
+                                             float* scratch, float drop_p, uint64_t seed, const uint64_t* seed_dev,
+                                             uint32_t site, int32_t dtype, void* stream) {
   if (!q || !k || !v || !dout || !out || !lse || !dq || !dk || !dv || !scratch) return bad_arg("attention_bwd_general: null pointer");
+  if (drop_p < 0.f || drop_p >= 1.f) return bad_arg("attention_bwd_general: dropout p in [0, 1)");
   if (batch <= 0 || q_len <= 0 || kv_len <= 0 || heads <= 0) return bad_arg("attention_bwd_general: extents");
   if (causal && q_len != kv_len) return bad_arg("attention_bwd_general: a causal mask needs q_len == kv_len");
   const int d = heads * AF_HD;
@@ -894,7 +941,14 @@ extern "C" int mm_attention_bwd_general(const void* q, int64_t q_ld, int32_t q_c
   p.q_col0 = q_col0, p.k_col0 = k_col0, p.v_col0 = v_col0, p.dq_col0 = dq_col0, p.dk_col0 = dk_col0, p.dv_col0 = dv_col0;
   p.kv_lens = kv_lens, p.lse = lse, p.scratch = scratch;
   p.scale = 0.125f;
+  p.drop_p = drop_p, p.drop_site = site, p.drop_seed = seed;
+  p.drop_seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
+  p.drop_lp = (q_len + 63) / 64 * 64, p.drop_tp = (kv_len + 63) / 64 * 64;
   const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return f16 ? launch_attention_bwd_general<__half>(m, p, grid, s) : launch_attention_bwd_general<__nv_bfloat16>(m, p, grid, s);
+  if (drop_p > 0.f)
+    return f16 ? launch_attention_bwd_general<__half, true>(m, p, grid, s)
+               : launch_attention_bwd_general<__nv_bfloat16, true>(m, p, grid, s);
+  return f16 ? launch_attention_bwd_general<__half, false>(m, p, grid, s)
+             : launch_attention_bwd_general<__nv_bfloat16, false>(m, p, grid, s);
 }

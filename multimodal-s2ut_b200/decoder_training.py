@@ -260,23 +260,26 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                 K.layernorm(s["x0"], Lr["ln1"][0], Lr["ln1"][1], out_op=s["h1"])
             K.gemm(a0=s["h1"], a0_ld=d, rows=M, w=Lr["wqkv"], n=3 * d, k=d, mode=K.EPI_OP, bias=Lr["bqkv"], scale=scale,
                    scale_cols=d, out0=s["qkv"], out0_ld=3 * d, block_n=bn)
-            if p_attn > 0:
+            onchip = self.fused_attn_bwd and self.fused_attn_bwd_onchip    # attention dropout inside the attention kernels
+            adr = lambda k_: (p_attn, seed, seed_dev, dsite_layer(i, k_)) if p_attn > 0 else None
+            if p_attn > 0 and not onchip:
                 self._attn_fwd(s["qkv"], 3 * d, L * 3 * d, s["qkv"][:, d:], s["qkv"][:, 2 * d:], 3 * d, L * 3 * d, s["att"],
                                B, L, L, None, True, dsite_layer(i, 1))
             else:
-                s["lse1"] = self.buf(f"lse1_{i}", (B, H, L), torch.float32)      # kept for mm_attention_bwd_scores
-                K.attention(s["qkv"], 0, L, s["qkv"], d, s["qkv"], 2 * d, L, None, B, H, s["att"], causal=True, lse=s["lse1"])
+                s["lse1"] = self.buf(f"lse1_{i}", (B, H, L), torch.float32)      # kept for the attention backward
+                K.attention(s["qkv"], 0, L, s["qkv"], d, s["qkv"], 2 * d, L, None, B, H, s["att"], causal=True, lse=s["lse1"],
+                            drop=adr(1))
             self._resid(s["att"], d, Lr["wo"], Lr["bo"], d, s["x0"], s["x1"], M, dsite_layer(i, 0), Lr["ln2"], s["h2"])
             K.gemm(a0=s["h2"], a0_ld=d, rows=M, w=Lr["wq"], n=d, k=d, mode=K.EPI_OP, bias=Lr["bq"], scale=scale,
                    scale_cols=d, out0=s["q2"], out0_ld=d, block_n=bn)
             K.gemm(a0=enc_btc, a0_ld=d, rows=B * T, w=Lr["wkv"], n=2 * d, k=d, mode=K.EPI_OP, bias=Lr["bkv"],
                    out0=s["kv2"], out0_ld=2 * d, block_n=bn)
-            if p_attn > 0:
+            if p_attn > 0 and not onchip:
                 self._attn_fwd(s["q2"], d, L * d, s["kv2"], s["kv2"][:, d:], 2 * d, T * 2 * d, s["att2"], B, L, T, enc_lens,
                                False, dsite_layer(i, 3))
             else:
                 s["lse2"] = self.buf(f"lse2_{i}", (B, H, L), torch.float32)
-                K.attention(s["q2"], 0, L, s["kv2"], 0, s["kv2"], d, T, enc_lens, B, H, s["att2"], lse=s["lse2"])
+                K.attention(s["q2"], 0, L, s["kv2"], 0, s["kv2"], d, T, enc_lens, B, H, s["att2"], lse=s["lse2"], drop=adr(3))
             self._resid(s["att2"], d, Lr["wo2"], Lr["bo2"], d, s["x1"], s["x2"], M, dsite_layer(i, 2), Lr["ln3"], s["h3"])
             K.gemm(a0=s["h3"], a0_ld=d, rows=M, w=Lr["w1"], n=self.ffn, k=d, mode=K.EPI_RELU_OP, bias=Lr["b1"],
                    out0=s["f"], out0_ld=self.ffn, block_n=bn,
@@ -309,10 +312,12 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
         Lp, Tp = _round_up(Lq, 64), _round_up(Tk, 64)
         hd = dict(heads=H, head_stride=64, batches=BH, w_batched=True, block_n=bn)
         _, p_attn, _, seed, seed_dev = self._saved["drop"]
-        if lse is not None and p_attn == 0 and self.fused_attn_bwd and self.fused_attn_bwd_onchip:
-            # one kernel: S, dP, P, dS never leave the SM (mm_attention_bwd_general: query-tile pairs, fp32 dk / dv partials)
+        if lse is not None and self.fused_attn_bwd and self.fused_attn_bwd_onchip:
+            # one kernel: S, dP, P, dS never leave the SM (mm_attention_bwd_general: query-tile pairs, fp32 dk / dv partials);
+            # the attention-dropout mask of the forward kernel is regenerated from the same site
             scratch = self.buf("a_bwd_scratch", (K.attention_bwd_general_scratch_floats(Tk),), torch.float32)
-            K.attention_bwd_general(q, Lq, k, v, Tk, kv_lens, B, H, dO, out, lse, dq, dk, dv, scratch, causal=causal)
+            K.attention_bwd_general(q, Lq, k, v, Tk, kv_lens, B, H, dO, out, lse, dq, dk, dv, scratch, causal=causal,
+                                    drop=(p_attn, seed, seed_dev, site) if p_attn > 0 else None)
             return
         P = self.buf("a_P", (BH, Lp, Tp), op)
         dS = self.buf("a_dS", (BH, Lp, Tp), op)

@@ -252,16 +252,15 @@ def layernorm_gather(store: torch.Tensor, index: Optional[torch.Tensor], rows_pe
 
 
 def self_attention_drop_supported(seq: int) -> bool:
-    """Attention dropout inside the forward kernel: the single-chunk kernel only (129 .. 256 positions)."""
-    return 128 < seq <= 256
+    """Attention dropout inside the forward kernel: every length (single-chunk and chunked kernels alike)."""
+    return seq > 0
 
 
 def self_attention(qkv: torch.Tensor, seq_lens_: torch.Tensor, batch: int, seq: int, heads: int,
                    out: torch.Tensor, lse: Optional[torch.Tensor] = None, drop=None) -> None:
     """qkv [B*T, 3d] (q pre-scaled | k | v) -> out [B*T, d]; head_dim 64.  lse (optional): [B, heads, T] fp32
     log-sum-exp of every query row's scores (kept by the training forward for ``attention_bwd_scores``).
-    drop = (p, seed, seed_dev, site): attention dropout on the probabilities inside the kernel (training forward;
-    ``self_attention_drop_supported(seq)`` must hold)."""
+    drop = (p, seed, seed_dev, site): attention dropout on the probabilities inside the kernel (training forward)."""
     assert qkv.dtype == out.dtype and seq_lens_.dtype == torch.int32 and qkv.stride(-1) == 1
     assert lse is None or (lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == batch * heads * seq)
     lib = _lib.load()
@@ -312,9 +311,10 @@ def embed_tokens(tokens: torch.Tensor, padding_idx: int, table: torch.Tensor, sc
 
 def attention(q: torch.Tensor, q_col0: int, q_len: int, k: torch.Tensor, k_col0: int, v: torch.Tensor, v_col0: int,
               kv_len: int, kv_lens: Optional[torch.Tensor], batch: int, heads: int, out: torch.Tensor,
-              causal: bool = False, lse: Optional[torch.Tensor] = None) -> None:
+              causal: bool = False, lse: Optional[torch.Tensor] = None, drop=None) -> None:
     """General attention core (see ``mm_attention``): q [batch*q_len, ld] (pre-scaled), k / v [batch*kv_len, ld],
-    head h in columns [col0 + 64 h, col0 + 64 h + 64); out [batch*q_len, heads*64]."""
+    head h in columns [col0 + 64 h, col0 + 64 h + 64); out [batch*q_len, heads*64].  drop = (p, seed, seed_dev, site):
+    attention dropout inside the kernel (``mm_attention_drop``; mask index ((b H + h) Lp + q) Tp + k)."""
     assert q.dtype == k.dtype == v.dtype == out.dtype and q.dtype in _DT
     assert all(t.dim() == 2 and t.stride(1) == 1 for t in (q, k, v, out))
     assert q.shape[0] == batch * q_len and k.shape[0] == batch * kv_len and v.shape[0] == batch * kv_len
@@ -323,9 +323,11 @@ def attention(q: torch.Tensor, q_col0: int, q_len: int, k: torch.Tensor, k_col0:
     lib = _lib.load()
     with _Launch("attention", 4.0 * batch * heads * q_len * kv_len * 64 * (0.5 if causal else 1.0)):
         assert lse is None or (lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == batch * heads * q_len)
-        _lib.check(lib.mm_attention_lse(_ptr(q), q.stride(0), q_col0, q_len, _ptr(k), k.stride(0), k_col0, _ptr(v),
-                                        v.stride(0), v_col0, kv_len, _ptr(kv_lens), batch, heads, int(causal), _ptr(out),
-                                        out.stride(0), _ptr(lse), dtype_code(q.dtype), _stream()), "mm_attention")
+        p_, seed, seed_dev, site = drop if (drop is not None and drop[0] > 0) else (0.0, 0, None, 0)
+        _lib.check(lib.mm_attention_drop(_ptr(q), q.stride(0), q_col0, q_len, _ptr(k), k.stride(0), k_col0, _ptr(v),
+                                         v.stride(0), v_col0, kv_len, _ptr(kv_lens), batch, heads, int(causal), _ptr(out),
+                                         out.stride(0), _ptr(lse), float(p_), seed & 0xFFFFFFFFFFFFFFFF, _ptr(seed_dev),
+                                         site, dtype_code(q.dtype), _stream()), "mm_attention")
 
 
 def attention_bwd_scores(q: torch.Tensor, q_col0: int, q_len: int, k: torch.Tensor, k_col0: int, v: torch.Tensor,
@@ -483,9 +485,10 @@ def attention_bwd_general_scratch_floats(kv_len: int) -> int:
 def attention_bwd_general(q: torch.Tensor, q_len: int, k: torch.Tensor, v: torch.Tensor, kv_len: int,
                           kv_lens: Optional[torch.Tensor], batch: int, heads: int, dout: torch.Tensor, out: torch.Tensor,
                           lse: torch.Tensor, dq: torch.Tensor, dk: torch.Tensor, dv: torch.Tensor, scratch: torch.Tensor,
-                          causal: bool = False) -> None:
+                          causal: bool = False, drop=None) -> None:
     """dq / dk / dv from q / k / v (2-D token-major views whose first column is head 0's), dout, out and lse in one kernel
-    for any lengths, causal or not (``mm_attention_bwd_general``); scratch: fp32, attention_bwd_general_scratch_floats."""
+    for any lengths, causal or not (``mm_attention_bwd_general``); scratch: fp32, attention_bwd_general_scratch_floats.
+    drop = (p, seed, seed_dev, site): the attention-dropout mask of the forward kernel is regenerated."""
     ts = (q, k, v, dout, out, dq, dk, dv)
     assert all(t.dtype == q.dtype for t in ts) and q.dtype in _DT
     assert all(t.dim() == 2 and t.stride(1) == 1 for t in ts)
@@ -495,12 +498,14 @@ def attention_bwd_general(q: torch.Tensor, q_len: int, k: torch.Tensor, v: torch
         assert kv_lens.dtype == torch.int32 and kv_lens.numel() == batch
     lib = _lib.load()
     with _Launch("attention_bwd_general", 10.0 * batch * heads * q_len * kv_len * 64 * (0.5 if causal else 1.0)):
-        _lib.check(lib.mm_attention_bwd_general(_ptr(q), q.stride(0), 0, q_len, _ptr(k), k.stride(0), 0, _ptr(v), v.stride(0),
-                                                0, kv_len, _ptr(kv_lens), batch, heads, int(causal), _ptr(dout),
-                                                dout.stride(0), _ptr(out), out.stride(0), _ptr(lse), _ptr(dq),
-                                                dq.stride(0), 0, _ptr(dk), dk.stride(0), 0, _ptr(dv), dv.stride(0), 0,
-                                                _ptr(scratch), dtype_code(q.dtype), _stream()),
-                   "mm_attention_bwd_general")
+        p_, seed, seed_dev, site = drop if (drop is not None and drop[0] > 0) else (0.0, 0, None, 0)
+        _lib.check(lib.mm_attention_bwd_general_drop(_ptr(q), q.stride(0), 0, q_len, _ptr(k), k.stride(0), 0, _ptr(v),
+                                                     v.stride(0), 0, kv_len, _ptr(kv_lens), batch, heads, int(causal),
+                                                     _ptr(dout), dout.stride(0), _ptr(out), out.stride(0), _ptr(lse),
+                                                     _ptr(dq), dq.stride(0), 0, _ptr(dk), dk.stride(0), 0, _ptr(dv),
+                                                     dv.stride(0), 0, _ptr(scratch), float(p_),
+                                                     seed & 0xFFFFFFFFFFFFFFFF, _ptr(seed_dev), site,
+                                                     dtype_code(q.dtype), _stream()), "mm_attention_bwd_general")
 
 
 def heads_gemm(a: torch.Tensor, a_ld: int, a_bs: int, transposed: bool, w: torch.Tensor, w_ld: int, w_bs: int,

@@ -386,8 +386,8 @@ class TrainEngine(EncoderEngine):
         K.gemm(a0=s["h1"], a0_ld=d, rows=M, w=L["wqkv"], n=3 * d, k=d, mode=K.EPI_OP, bias=L["bqkv"], scale=64 ** -0.5,
                scale_cols=d, out0=s["qkv"], out0_ld=3 * d, block_n=bn)
         if self._p_attn > 0 and K.self_attention_drop_supported(T) and self.fused_attn_bwd_onchip:
-            # attention dropout generated inside the fused kernels (129 .. 256 positions): the forward keeps lse, the
-            # on-chip backward regenerates the mask
+            # attention dropout generated inside the fused kernels: the forward keeps lse, the on-chip backward
+            # regenerates the mask
             s["lse"] = self.buf(f"t_lse_{i}", (B, self.heads, T), torch.float32)
             s["attn_drop"] = (self._p_attn, seed, seed_dev, site_layer(i, 3))
             K.self_attention(s["qkv"], seq_lens, B, T, self.heads, s["att"], lse=s["lse"], drop=s["attn_drop"])
@@ -647,7 +647,7 @@ class TrainEngine(EncoderEngine):
             # longer sequences: the same on chip with query tiles taken in pairs (mm_attention_bwd_general)
             scratch = self.buf("a_bwd_scratch", (K.attention_bwd_general_scratch_floats(T),), torch.float32)
             K.attention_bwd_general(qkv, T, qkv[:, d:], qkv[:, 2 * d:], T, seq_lens, B, H, datt, s["att"], s["lse"], dqkv,
-                                    dqkv[:, d:], dqkv[:, 2 * d:], scratch)
+                                    dqkv[:, d:], dqkv[:, 2 * d:], scratch, drop=s.get("attn_drop"))
             return
         BH = B * H
         hd = dict(heads=H, head_stride=64, batches=BH, w_batched=True, block_n=bn)

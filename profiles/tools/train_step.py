@@ -84,7 +84,10 @@ def model_step(a, enc, eng, wav, lens, imgs, dev, world, rank, rng):
                     tgt_units_per_utt=a.tgt_len, encoder_params=int(eng.flat_p.numel()), decoder_params=int(dec.flat_p.numel()),
                     loss_per_unit_first=losses[0] / ntok, loss_per_unit_last=losses[-1] / ntok,
                     overlap_reduce=bool(world > 1 and not a.no_overlap),
-                    note="element-wise dropout off; modality dropout 0.5; random target units")
+                    dropout=a.dropout,
+                    note=("element-wise dropout off" if a.dropout == 0 else
+                          f"dropout / activation-dropout / attention-dropout {a.dropout} in encoder and decoder, masks "
+                          "generated inside the fused kernels") + "; modality dropout 0.5; random target units")
         print(json.dumps(line), flush=True)
     if world > 1:
         del gs

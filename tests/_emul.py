@@ -233,11 +233,12 @@ def self_attention_drop_supported(seq):
     return 128 < seq <= 256
 
 
-def _attn_keep(batch, heads, seq, drop):
-    """keep / (1 - p) over [batch*heads][Tp][Tp] (Tp = seq rounded up to 64), cut to [batch, heads, seq, seq]."""
-    Tp = (seq + 63) // 64 * 64
-    m = _keep_scale(batch * heads * Tp * Tp, drop[0], drop[1], drop[3], drop[2]).view(batch, heads, Tp, Tp)
-    return m[:, :, :seq, :seq]
+def _attn_keep(batch, heads, seq, drop, kv=None):
+    """keep / (1 - p) over [batch*heads][Lp][Tp] (Lp / Tp = seq / kv rounded up to 64), cut to [batch, heads, seq, kv]."""
+    kv = seq if kv is None else kv
+    Lp, Tp = (seq + 63) // 64 * 64, (kv + 63) // 64 * 64
+    m = _keep_scale(batch * heads * Lp * Tp, drop[0], drop[1], drop[3], drop[2]).view(batch, heads, Lp, Tp)
+    return m[:, :, :seq, :kv]
 
 
 def self_attention(qkv, seq_lens_, batch, seq, heads, out, lse=None, drop=None):
@@ -315,7 +316,8 @@ def attention_bwd_general_scratch_floats(kv_len):
     return 1
 
 
-def attention_bwd_general(q, q_len, k, v, kv_len, kv_lens, batch, heads, dout, out, lse, dq, dk, dv, scratch, causal=False):
+def attention_bwd_general(q, q_len, k, v, kv_len, kv_lens, batch, heads, dout, out, lse, dq, dk, dv, scratch, causal=False,
+                          drop=None):
     global launch_count
     launch_count += 1
     d = heads * 64
@@ -329,7 +331,9 @@ def attention_bwd_general(q, q_len, k, v, kv_len, kv_lens, batch, heads, dout, o
     P = torch.exp(s - lse.view(batch, heads, q_len, 1)).masked_fill(dead, 0.0)
     dO = dout[:, :d].float().view(batch, q_len, heads, 64).permute(0, 2, 1, 3)
     O = out[:, :d].float().view(batch, q_len, heads, 64).permute(0, 2, 1, 3)
-    dS = P * (dO @ V.transpose(-1, -2) - (dO * O).sum(-1, keepdim=True))
+    mk = _attn_keep(batch, heads, q_len, drop, kv_len) if (drop is not None and drop[0] > 0) else 1.0
+    dS = P * ((dO @ V.transpose(-1, -2)) * mk - (dO * O).sum(-1, keepdim=True))
+    P = P * mk
     P, dS = P.to(q.dtype).float(), dS.to(q.dtype).float()
     back = lambda x, L: x.permute(0, 2, 1, 3).reshape(batch * L, d)
     dq[:, :d] = back(dS @ Kx * 0.125, q_len).to(dq.dtype)
@@ -359,7 +363,8 @@ def attention_bwd_fused(qkv, seq_len, kv_lens, batch, heads, dout, out, lse, dqk
     dqkv[:, 2 * d:3 * d] = back(P.transpose(-1, -2) @ dO)
 
 
-def attention(q, q_col0, q_len, k, k_col0, v, v_col0, kv_len, kv_lens, batch, heads, out, causal=False, lse=None):
+def attention(q, q_col0, q_len, k, k_col0, v, v_col0, kv_len, kv_lens, batch, heads, out, causal=False, lse=None,
+              drop=None):
     d = heads * 64
     Q = q[:, q_col0:q_col0 + d].float().view(batch, q_len, heads, 64).permute(0, 2, 1, 3)
     Kx = k[:, k_col0:k_col0 + d].float().view(batch, kv_len, heads, 64).permute(0, 2, 1, 3)
@@ -371,7 +376,10 @@ def attention(q, q_col0, q_len, k, k_col0, v, v_col0, kv_len, kv_lens, batch, he
         s = s.masked_fill(torch.arange(kv_len)[None, :] > torch.arange(q_len)[:, None], float("-inf"))
     if lse is not None:
         lse.copy_(torch.logsumexp(s, -1).reshape(lse.shape))
-    p = s.softmax(-1).to(q.dtype).float()
+    p = s.softmax(-1)
+    if drop is not None and drop[0] > 0:
+        p = p * _attn_keep(batch, heads, q_len, drop, kv_len)
+    p = p.to(q.dtype).float()
     out.copy_((p @ V).permute(0, 2, 1, 3).reshape(batch * q_len, d).to(out.dtype))
 
 

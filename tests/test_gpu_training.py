@@ -561,6 +561,17 @@ def test_training_step_with_attention_dropout_inside_the_attention_kernels(cuda)
            "(same masks in the oracle), small / base width: worst parameter-gradient relative L2 error", max(w1, w2), REL)
 
 
+def test_training_step_with_attention_dropout_in_the_chunked_kernels(cuda):
+    """12 s utterances (T = 300: beyond one 256-key chunk): attention dropout inside the chunked forward kernel
+    (mm_self_attention_drop -> online softmax over 128-key chunks) and inside mm_attention_bwd_general_drop."""
+    from mm_s2ut_b200 import kernels as K
+
+    w, _ = _dropout_parity(K, cuda, p_drop=0.1, p_act=0.1, p_attn=0.1, overrides=dict(encoder_layers=2),
+                           min_checked=2 * 15 + 2 + 4, dur=12.0)
+    record("configs[2] backward, T = 300, attention dropout 0.1 inside the chunked attention forward / general backward "
+           "kernels (same masks in the oracle): worst parameter-gradient relative L2 error", w, REL)
+
+
 def test_graphed_train_step_draws_fresh_dropout_masks(cuda):
     """Under CUDA-graph replay the dropout masks follow a device-resident per-step seed: two replays differ, and the
     backward pass of a replay uses the masks of its own forward (gradient of a fixed functional stays finite and the
