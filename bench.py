@@ -48,6 +48,14 @@ def _peer_exchange_active() -> bool:
         return False
 
 
+def _peer_exchange_dtype() -> str:
+    try:
+        from mm_s2ut_b200 import peer
+        return next(iter(peer._groups.values())).exchange_dtype
+    except Exception:
+        return "fp32"
+
+
 def _peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -347,9 +355,14 @@ def train_step_probe(ctx, wav, img, steps=20, warmup=3, model_step=True):
            "allreduce_ms": ar_ms, "allreduce_bytes": gbytes if world > 1 else 0,
            "allreduce_busbw_gbs": (2 * (world - 1) / world * gbytes / (ar_ms * 1e-3) / 1e9) if ar_ms else None,
            "collective": (("two-shot in-place exchange kernel over NVLink peer memory (csrc/p2p.cu: device-side barrier, rank r "
-                           "sums slice r of every rank's buffer and stores it back to all, barrier) "
+                           "sums slice r of every rank's buffer and stores it back to all, barrier)"
+                           + (", on a bf16 staging copy of the gradients (the recipe trains with --fp16: fairseq exchanges "
+                              "16-bit gradients; fp32 accumulation in rank order, pack / unpack kernels inside the timed "
+                              "exchange; MM_P2P_GRAD_DTYPE=fp32 exchanges the fp32 buffer) "
+                              if _peer_exchange_dtype() == "bf16" else " ")
                            if _peer_exchange_active() else "one NCCL all-reduce ") +
                           "of the flat fp32 gradient (%d MB) between the backward and the optimizer graphs" % (gbytes >> 20)) if world > 1 else "none (1 GPU)",
+           "allreduce_wire_dtype": (_peer_exchange_dtype() if _peer_exchange_active() else "fp32") if world > 1 else None,
            "what": "BASELINE configs[2]: forward (activations kept) + backward of every encoder/fusion/conv parameter + "
                    "gradient all-reduce + fairseq Adam with clip-norm, batch 64 x 10 s per GPU, modality dropout 0.5 "
                    "(image-drop branch), synthetic d loss/d encoder_out; element-wise dropout off"}

@@ -412,6 +412,14 @@ int mm_p2p_allreduce_f32(float* const* bufs, int32_t world, int32_t rank, int64_
  * the barrier on any rank is visible to work enqueued after it on every rank.  Every rank must issue the same sequence
  * of barriers. */
 int mm_p2p_barrier(unsigned int* const* flags, unsigned int* epoch, int32_t world, int32_t rank, void* stream);
+/* The same exchange on 16-bit gradients (the reference recipe trains with --fp16, scripts/textless/1_train.sh:125, so
+ * fairseq's all-reduce moves 16-bit gradients): mm_p2p_pack_bf16 rounds the fp32 gradients into a bf16 staging buffer
+ * of n_pad >= n elements (a multiple of 8; the tail is zeroed), mm_p2p_allreduce_bf16 runs the two-shot exchange on the
+ * ranks' staging buffers (fp32 accumulation in rank order, one rounding of the sum; n a multiple of 8), and
+ * mm_p2p_unpack_bf16 widens the result -- identical on every rank -- back into the fp32 buffer.  Half the NVLink bytes. */
+int mm_p2p_pack_bf16(const float* src, void* stage, int64_t n, int64_t n_pad, void* stream);
+int mm_p2p_allreduce_bf16(void* const* bufs, int32_t world, int32_t rank, int64_t n, void* stream);
+int mm_p2p_unpack_bf16(const void* stage, float* dst, int64_t n, void* stream);
 
 /* Grouped weight gradient (autograd of nn.Linear inside fairseq's TransformerEncoderLayer / MultiheadAttention under
  * `loss.backward()`, scripts/textless/1_train.sh): for every group g

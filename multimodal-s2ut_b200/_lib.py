@@ -182,6 +182,9 @@ EXPORTS = {
     "mm_ipc_close_handle": (C.c_int, [C.c_void_p]),
     "mm_p2p_barrier": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "mm_p2p_allreduce_f32": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
+    "mm_p2p_pack_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "mm_p2p_allreduce_bf16": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
+    "mm_p2p_unpack_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "mm_attention_bwd_general_scratch_floats": (C.c_int64, [C.c_int32]),
     "mm_attention_bwd_general": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
                                            C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,

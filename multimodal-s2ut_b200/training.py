@@ -901,7 +901,7 @@ class TrainEngine(EncoderEngine):
         ev.record()
         with torch.cuda.stream(self._comm_stream):
             self._comm_stream.wait_event(ev)
-            if grp is not None and lo % 4 == 0 and (hi % 4 == 0 or hi == self.flat_g.numel()):
+            if grp is not None and lo % grp.align == 0 and (hi % grp.align == 0 or hi == self.flat_g.numel()):
                 grp.all_reduce(lo, hi)      # barrier + exchange + barrier kernels: captured with the backward pass
             else:
                 self._reduce_works.append(dist.all_reduce(bucket, op=dist.ReduceOp.SUM, async_op=True))

@@ -55,26 +55,29 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 import mm_s2ut_b200  # noqa: E402,F401
 from mm_s2ut_b200.peer import PeerGroup  # noqa: E402
 
-torch.manual_seed(rank)
-a = torch.randn(n, device="cuda")
-b = a.clone()
-dist.all_reduce(b)
-grp = PeerGroup(a)
-grp.all_reduce()
-torch.cuda.synchronize()
-err = (a - b).abs().max().item()
-same = torch.tensor([float(a.double().sum().item())], device="cuda", dtype=torch.float64)
-lo, hi = same.clone(), same.clone()
-dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-ms = timed(grp.all_reduce)
-if rank == 0:
-    nbytes = n * 4
-    print(f"peer-memory all-reduce (barrier + kernel + barrier): {ms:.3f} ms  busbw "
-          f"{2 * (world - 1) / world * nbytes / ms / 1e6:.0f} GB/s   max |p2p - nccl| = {err:.3e}   "
-          f"identical on every rank: {lo.item() == hi.item()}", flush=True)
-ms_b = timed(grp.barrier)
-if rank == 0:
-    print(f"one barrier (4-byte NCCL all-reduce): {ms_b:.3f} ms")
-grp.close()
+for wire in ("fp32", "bf16"):
+    torch.manual_seed(rank)
+    a = torch.randn(n, device="cuda")
+    b = a.clone()
+    dist.all_reduce(b)
+    grp = PeerGroup(a, exchange_dtype=wire)
+    grp.all_reduce()
+    torch.cuda.synchronize()
+    err = (a - b).abs().max().item()
+    rel = ((a - b).norm() / b.norm()).item()
+    same = torch.tensor([float(a.double().sum().item())], device="cuda", dtype=torch.float64)
+    lo, hi = same.clone(), same.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    ms = timed(grp.all_reduce)
+    if rank == 0:
+        nbytes = n * 4
+        what = "barrier + kernel + barrier" if wire == "fp32" else "pack + barrier + kernel + barrier + unpack"
+        print(f"peer-memory all-reduce, {wire} on the wire ({what}): {ms:.3f} ms  busbw(fp32-equivalent) "
+              f"{2 * (world - 1) / world * nbytes / ms / 1e6:.0f} GB/s   max |p2p - nccl| = {err:.3e}  rel L2 {rel:.2e}   "
+              f"identical on every rank: {lo.item() == hi.item()}", flush=True)
+    ms_b = timed(grp.barrier)
+    if rank == 0 and wire == "fp32":
+        print(f"one barrier kernel: {ms_b:.3f} ms")
+    grp.close()
 dist.destroy_process_group()
