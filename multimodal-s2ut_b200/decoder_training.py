@@ -459,9 +459,11 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                                 drop=drb(dsite_layer(i - 1, 5)) if i > 0 else None)
                 self._ln_param_grads(lnp, d, self.g(p + "self_attn_layer_norm.weight", p + "self_attn_layer_norm.bias"),
                                      accumulate)
-                self._flush()       # the layer's deferred reductions in one launch (per 16)
+                if not grouped:
+                    self._flush()   # the layer's deferred reductions in one launch (per 16)
         with _scope("dec_layer"):
             self._wgrad_flush()     # every queued weight gradient (the embedding's wgrad must precede its scatter-add below)
+            self._flush()           # pooled weight gradients: only the LayerNorm-parameter partials are left, all layers at once
         # ---- embedding: x0 = dropout(sqrt(d) * E[tokens] + positions)
         if p_drop > 0:
             K.dropout(g, g, p_drop, seed, DSITE_EMBED, seed_dev=seed_dev)

@@ -730,7 +730,8 @@ class TrainEngine(EncoderEngine):
         # the copy that leaves this layer enters the fc2 branch of layer i - 1 (nothing below layer 0 reads it)
         K.layernorm_bwd(s["x_in"], L["ln1_g"], dh, lnp, dx=g, resid=g, dx_op=g_op, drop=drb(2, i - 1) if i > 0 else None)
         self._ln_param_grads(lnp, d, self.g(mod.self_attn_layer_norm.weight, mod.self_attn_layer_norm.bias), accumulate)
-        self._flush()           # the layer's deferred reductions (bias / LayerNorm partials, split-K partials) in one launch
+        if not self.grouped_wgrad:      # split-K partials fill the arena: reduce per layer.  Pooled weight gradients leave
+            self._flush()               # only the LayerNorm partials (4.8 MB per layer): reduced with the pool's flush
         return g_op
 
     def _fusion_bwd(self, j: int, dres: torch.Tensor, gtext: torch.Tensor, B: int, T: int, accumulate: bool,
@@ -971,6 +972,7 @@ class TrainEngine(EncoderEngine):
             if not self.grouped_wgrad or (flush_every and len(pending) >= flush_every) or i == 0:
                 with _scope("layer"):
                     self._wgrad_flush()
+                    self._flush()       # the pending layers' LayerNorm-parameter partials: one launch per 16 reductions
                 if overlap:     # the pending layers' buckets are adjacent in flat_g: one exchange
                     self._reduce_async(min(self.bucket_layers[j][0] for j in pending),
                                        max(self.bucket_layers[j][1] for j in pending))
