@@ -436,6 +436,9 @@ typedef struct mm_wgrad_group {
   int64_t dy_ld, x_ld, out_ld;
   int32_t n_out, k_in;
   float* bias;          /* optional: bias[n] (+)= sum_t dy[t, n]; k_in == 0 (x, out NULL) computes only this */
+  int64_t tokens;       /* this group's token count; 0: the call's `tokens`.  Groups of different lengths (the encoder
+                         * layers' B*T tokens, the image-side K / V projections' B*577) share one launch: the host
+                         * orders the tiles by cost so that the CTA pairs finish together */
 } mm_wgrad_group;
 int mm_wgrad_grouped(const mm_wgrad_group* groups, int32_t count, int64_t tokens, int32_t accumulate, int32_t dtype,
                      void* stream);

@@ -104,7 +104,8 @@ class WgradGroup(C.Structure):
     """``mm_wgrad_group`` (include/mms2ut_b200.h)."""
 
     _fields_ = [("dy", C.c_void_p), ("x", C.c_void_p), ("out", C.c_void_p), ("dy_ld", C.c_int64), ("x_ld", C.c_int64),
-                ("out_ld", C.c_int64), ("n_out", C.c_int32), ("k_in", C.c_int32), ("bias", C.c_void_p)]
+                ("out_ld", C.c_int64), ("n_out", C.c_int32), ("k_in", C.c_int32), ("bias", C.c_void_p),
+                ("tokens", C.c_int64)]
 
 
 WGRAD_MAX_GROUPS = 64

@@ -20,6 +20,9 @@
 #include "common.cuh"
 #include "host.cuh"
 #include "../../include/mms2ut_b200.h"
+#include <algorithm>
+#include <utility>
+#include <vector>
 
 namespace mm {
 
@@ -28,8 +31,19 @@ constexpr int WG_MAX = MM_WGRAD_MAX_GROUPS;
 struct WgMaps {
   CUtensorMap a[WG_MAX], w[WG_MAX], out[WG_MAX];
 };
+constexpr int WG_ORDER_MAX = 1536;    // entries of the host-made tile schedule (rounds x CTA pairs)
+constexpr unsigned short WG_NO_TILE = 0xFFFF;
+
 struct WgDev {
-  int count, num_tiles, num_reg_tiles, num_kb, tail_steps, accumulate;
+  int count, num_tiles, num_reg_tiles, accumulate;
+  int num_kb[WG_MAX];           // 64-token blocks of group g's contraction (groups may differ in their token count)
+  int tail_steps[WG_MAX];       // K = 16 steps of the last block
+  // Tile schedule.  Pair q runs order[q], order[q + pairs], ... (WG_NO_TILE: nothing this round).  The host fills it by
+  // greedy list scheduling over the tiles' costs (long contractions first), so that groups with different token counts
+  // -- the encoder layers' 16 000 tokens and the image-side projections' 36 928 -- share ONE balanced launch.
+  // sched_len == 0: tile i runs in round-robin position i.
+  int sched_len;
+  unsigned short order[WG_ORDER_MAX];
   int tile_start[WG_MAX + 1];   // regular tiles: prefix sum over groups
   int bias_start[WG_MAX + 1];   // bias tiles (one per 256 output features of a group with a bias): prefix sum
   int n_tiles[WG_MAX];          // column tiles of group g (0: bias only)
@@ -75,6 +89,12 @@ __device__ __forceinline__ WgTile wg_decode(const WgDev& p, int tile) {
   return t;
 }
 
+__device__ __forceinline__ int wg_tile_at(const WgDev& p, int i) {
+  if (p.sched_len == 0) return i;
+  const unsigned short t = p.order[i];
+  return t == WG_NO_TILE ? -1 : (int)t;
+}
+
 template <bool ACC, typename OpT>
 __global__ void __launch_bounds__(256, 1)
 wgrad_grouped_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgDev p) {
@@ -97,6 +117,7 @@ wgrad_grouped_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pid = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int n_sched = p.sched_len ? p.sched_len : p.num_tiles;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -127,13 +148,16 @@ wgrad_grouped_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = pid; tile < p.num_tiles; tile += npairs) {
+      for (int i = pid; i < n_sched; i += npairs) {
+        const int tile = wg_tile_at(p, i);
+        if (tile < 0) continue;
         const WgTile t = wg_decode(p, tile);
         const int row0 = t.mp * (2 * Cfg::BM) + rank * Cfg::BM;
         const int wrow0 = t.n_tile * BN + rank * (BN / 2);
         const CUtensorMap* mA = &maps.a[t.g];
         const CUtensorMap* mW = &maps.w[t.g];
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int num_kb = p.num_kb[t.g];
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           if (rank == 0) mbar_expect_tx(&full[stage], 2 * (Cfg::A_BYTES + (t.bias ? 0 : Cfg::B_BYTES)));
           uint8_t* dA = sA + stage * Cfg::A_BYTES;
@@ -157,17 +181,21 @@ wgrad_grouped_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
       const uint32_t idesc_bias = umma_idesc(2 * Cfg::BM, 16, OpTraits<OpT>::fmt) | (1u << 15);           // B = ones, N = 16
       const uint64_t ones_desc = umma_desc_sw128(smem_u32(sOnes));
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-      for (int tile = pid; tile < p.num_tiles; tile += npairs) {
+      for (int i = pid; i < n_sched; i += npairs) {
+        const int tile = wg_tile_at(p, i);
+        if (tile < 0) continue;
         const bool bias = tile >= p.num_reg_tiles;
+        const int g = wg_decode(p, tile).g;
+        const int num_kb = p.num_kb[g], tail_steps = p.tail_steps[g];
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128_mn(smem_u32(sA + stage * Cfg::A_BYTES), Cfg::A_BYTES / 2);
           const uint64_t bdesc = umma_desc_sw128_mn(smem_u32(sB + stage * Cfg::B_BYTES), Cfg::B_BYTES / 2);
-          const int steps = (kb == p.num_kb - 1) ? p.tail_steps : 4;
+          const int steps = (kb == num_kb - 1) ? tail_steps : 4;
           if (bias) {
             for (int kk = 0; kk < steps; ++kk)
               umma_f16_2sm(tmem_d, adesc + 128ull * kk, ones_desc + 2ull * kk, idesc_bias, (kb | kk) != 0);
@@ -187,7 +215,9 @@ wgrad_grouped_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
     const int ew = warp - 4, et = threadIdx.x - 128, lrow = ew * 32 + lane;
     const uint32_t tempty_leader = mapa_u32(&tempty[0], 0);
     uint32_t as = 0, aphase = 0, slab_ctr = 0, aux_phase = 0;
-    for (int tile = pid; tile < p.num_tiles; tile += npairs) {
+    for (int i = pid; i < n_sched; i += npairs) {
+      const int tile = wg_tile_at(p, i);
+      if (tile < 0) continue;
       const WgTile t = wg_decode(p, tile);
       const int g = t.g;
       const int row0 = t.mp * (2 * Cfg::BM) + rank * Cfg::BM;
@@ -305,6 +335,44 @@ wgrad_grouped_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
   }
 }
 
+// Greedy list scheduling on the host (groups with different token counts only; a uniform launch keeps the plain
+// round-robin walk, whose neighbouring tiles share operand columns in L2).  Tiles in descending cost order -- cost = the
+// tile's 64-token blocks + a fixed hand-off / epilogue share; a bias tile loads half the bytes -- each to the pair with
+// the least work so far (ties: the lowest pair, i.e. round-robin among equals, so neighbours still run together).
+static void wg_schedule(WgDev& p) {
+  const int max_pairs = kNumSMs / 2;
+  const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
+  if (p.num_tiles >= WG_NO_TILE) return;
+  std::vector<std::pair<float, int>> tiles(p.num_tiles);
+  for (int t = 0; t < p.num_tiles; ++t) {
+    const bool bias = t >= p.num_reg_tiles;
+    const int* start = bias ? p.bias_start : p.tile_start;
+    const int tt = bias ? t - p.num_reg_tiles : t;
+    int g = 0;
+    while (g + 1 < p.count && tt >= start[g + 1]) ++g;
+    tiles[t] = {bias ? 0.5f * p.num_kb[g] + 6.f : (float)p.num_kb[g] + 14.f, t};
+  }
+  std::stable_sort(tiles.begin(), tiles.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) {
+    return a.first > b.first;
+  });
+  std::vector<float> load(pairs, 0.f);
+  std::vector<std::vector<int>> lists(pairs);
+  for (const auto& tc : tiles) {
+    int best = 0;
+    for (int q = 1; q < pairs; ++q)
+      if (load[q] < load[best]) best = q;
+    load[best] += tc.first;
+    lists[best].push_back(tc.second);
+  }
+  size_t rounds = 0;
+  for (const auto& l : lists) rounds = l.size() > rounds ? l.size() : rounds;
+  if (rounds * pairs > (size_t)WG_ORDER_MAX) return;      // too many tiles for the table: round-robin
+  for (size_t r = 0; r < rounds; ++r)
+    for (int q = 0; q < pairs; ++q)
+      p.order[r * pairs + q] = r < lists[q].size() ? (unsigned short)lists[q][r] : WG_NO_TILE;
+  p.sched_len = (int)(rounds * pairs);
+}
+
 template <bool ACC, typename OpT>
 static int launch_wgrad(const WgMaps& m, const WgDev& p, cudaStream_t s) {
   auto kern = wgrad_grouped_kernel<ACC, OpT>;
@@ -338,23 +406,26 @@ static int launch_wgrad(const WgMaps& m, const WgDev& p, cudaStream_t s) {
 
 }  // namespace mm
 
-extern "C" int mm_wgrad_grouped(const mm_wgrad_group* groups, int32_t count, int64_t tokens, int32_t accumulate,
+extern "C" int mm_wgrad_grouped(const mm_wgrad_group* groups, int32_t count, int64_t tokens_all, int32_t accumulate,
                                 int32_t dtype, void* stream) {
   using namespace mm;
   if (!groups || count <= 0 || count > WG_MAX) return bad_arg("wgrad_grouped: 1 .. MM_WGRAD_MAX_GROUPS groups");
-  if (tokens <= 0) return bad_arg("wgrad_grouped: tokens");
   if (dtype != MM_DTYPE_BF16 && dtype != MM_DTYPE_F16) return bad_arg("wgrad_grouped: dtype");
   const int kind = dtype == MM_DTYPE_F16 ? 1 : 0;
   static thread_local WgMaps m;
-  WgDev p;
+  static thread_local WgDev p;
   memset(&p, 0, sizeof(p));
   p.count = count;
   p.accumulate = accumulate != 0;
-  p.num_kb = (int)((tokens + 63) / 64);
-  p.tail_steps = (int)((tokens - (int64_t)(p.num_kb - 1) * 64 + 15) >> 4);
   int tiles = 0, btiles = 0;
+  bool uniform = true;
   for (int g = 0; g < count; ++g) {
     const mm_wgrad_group& q = groups[g];
+    const int64_t tokens = q.tokens > 0 ? q.tokens : tokens_all;
+    if (tokens <= 0) return bad_arg("wgrad_grouped: tokens");
+    p.num_kb[g] = (int)((tokens + 63) / 64);
+    p.tail_steps[g] = (int)((tokens - (int64_t)(p.num_kb[g] - 1) * 64 + 15) >> 4);
+    uniform = uniform && p.num_kb[g] == p.num_kb[0];
     if (!q.dy || q.n_out <= 0 || q.k_in < 0) return bad_arg("wgrad_grouped: group");
     if (q.k_in > 0 && (!q.x || !q.out)) return bad_arg("wgrad_grouped: group with k_in > 0 needs x and out");
     if (q.k_in == 0 && !q.bias) return bad_arg("wgrad_grouped: group computes nothing");
@@ -383,6 +454,7 @@ extern "C" int mm_wgrad_grouped(const mm_wgrad_group* groups, int32_t count, int
   for (int g = count; g < WG_MAX; ++g) m.a[g] = m.a[0], m.w[g] = m.w[0], m.out[g] = m.out[0];
   p.num_reg_tiles = tiles;
   p.num_tiles = tiles + btiles;
+  if (!uniform) wg_schedule(p);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (accumulate)
     return kind ? launch_wgrad<true, __half>(m, p, s) : launch_wgrad<true, __nv_bfloat16>(m, p, s);

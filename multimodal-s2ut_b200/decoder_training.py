@@ -59,6 +59,7 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
     _lnp = TrainEngine._lnp
     _wgrad_mn = TrainEngine._wgrad_mn
     _wgrad_flush = TrainEngine._wgrad_flush
+    _wq_key = staticmethod(TrainEngine._wq_key)
     grouped_wgrad = os.environ.get("MM_GROUPED_WGRAD", "1") != "0"     # see TrainEngine.grouped_wgrad
     heads_gemm = os.environ.get("MM_HEADS_GEMM", "1") != "0"
     fused_attn_bwd_onchip = os.environ.get("MM_ATTN_BWD_ONCHIP", "1") != "0"

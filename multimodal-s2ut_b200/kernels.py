@@ -528,13 +528,17 @@ def wgrad_grouped(groups, tokens: int, accumulate: bool = False) -> None:
     bias fp32 [n_out] or None): out[n, k] (+)= sum_t dy[t, n] x[t, k] and bias[n] (+)= sum_t dy[t, n] (x = out = None,
     k_in = 0: the bias only) for every group in one launch (``mm_wgrad_grouped``: the groups' output tiles
     share the persistent grid, full token contraction per tile, no partials); out_ld = row stride of out (a column
-    block of a wider gradient is out = wide.view(-1)[col:], out_ld = wide row length)."""
+    block of a wider gradient is out = wide.view(-1)[col:], out_ld = wide row length).  A group may carry a 10th
+    element, its own token count (groups of different lengths share the launch; the library balances the tile order)."""
     lib = _lib.load()
     for base in range(0, len(groups), _lib.WGRAD_MAX_GROUPS):
         chunk = groups[base:base + _lib.WGRAD_MAX_GROUPS]
         arr = (_lib.WgradGroup * len(chunk))()
         work = 0.0
-        for a, (dy, dy_ld, x, x_ld, out, out_ld, n_out, k_in, bias) in zip(arr, chunk):
+        for a, grp in zip(arr, chunk):
+            dy, dy_ld, x, x_ld, out, out_ld, n_out, k_in, bias = grp[:9]
+            a.tokens = int(grp[9]) if len(grp) > 9 else 0
+            tokens_g = a.tokens or tokens
             if k_in > 0:
                 if dy.dtype != x.dtype or out.dtype != torch.float32:
                     raise TypeError("wgrad_grouped: dy / x share the 16-bit operand dtype, out is float32")
@@ -543,7 +547,7 @@ def wgrad_grouped(groups, tokens: int, accumulate: bool = False) -> None:
                 assert bias.dtype == torch.float32 and bias.numel() >= n_out
             a.dy, a.x, a.out, a.bias = _ptr(dy), _ptr(x), _ptr(out), _ptr(bias)
             a.dy_ld, a.x_ld, a.out_ld, a.n_out, a.k_in = dy_ld, x_ld, out_ld, n_out, k_in
-            work += 2.0 * tokens * n_out * k_in
+            work += 2.0 * tokens_g * n_out * k_in
         with _Launch("wgrad_grouped", work):
             _lib.check(lib.mm_wgrad_grouped(arr, len(chunk), tokens, int(accumulate), dtype_code(chunk[0][0].dtype),
                                             _stream()), "mm_wgrad_grouped")

@@ -580,10 +580,10 @@ class TrainEngine(EncoderEngine):
         if getattr(self, "grouped_wgrad", False):
             # queued: the operands must stay untouched until _wgrad_flush() (the backward pass gives every layer its own
             # gradient buffers in this mode)
-            q = self.__dict__.setdefault("_wq", {}).setdefault((M, bool(accumulate)), [])
+            q = self.__dict__.setdefault("_wq", {}).setdefault(self._wq_key(M, accumulate), [])
             col = 0
             for x, x_ld, kin in x_ops:     # gb: the bias gradient (column sums of dy) rides along with the first operand
-                q.append((dy_op, dy_ld, x, x_ld, gw.view(-1)[col:], kin_all, n, kin, gb if col == 0 else None))
+                q.append((dy_op, dy_ld, x, x_ld, gw.view(-1)[col:], kin_all, n, kin, gb if col == 0 else None, M))
                 col += kin
             return
         assert gb is None
@@ -599,18 +599,24 @@ class TrainEngine(EncoderEngine):
             col += kin
         self._defer(part, S, n * kin_all, n * kin_all, gw, accumulate)
 
+    @staticmethod
+    def _wq_key(M: int, accumulate: bool):
+        """Pool of a queued weight gradient: one pool for all token counts (the library orders the tiles of unequal groups
+        by cost); MM_WGRAD_MERGE_TOKENS=0 keeps one pool -- one launch -- per token count."""
+        return (0 if os.environ.get("MM_WGRAD_MERGE_TOKENS", "1") != "0" else M, bool(accumulate))
+
     def _wgrad_flush(self) -> None:
-        """Run the queued weight gradients: one grouped launch per (token count, accumulate) pool."""
-        for (M, acc), q in self.__dict__.get("_wq", {}).items():
+        """Run the queued weight gradients: one grouped launch per pool (every group carries its own token count)."""
+        for (_, acc), q in self.__dict__.get("_wq", {}).items():
             if q:
-                K.wgrad_grouped(q, M, acc)
+                K.wgrad_grouped(q, q[0][9], acc)
                 q.clear()
 
     def _bias_grad(self, dy_op: torch.Tensor, dy_ld: int, M: int, n: int, gb: torch.Tensor, accumulate: bool,
                    period: int = 0, valid: int = 0) -> None:
         if getattr(self, "grouped_wgrad", False) and period == 0:
-            q = self.__dict__.setdefault("_wq", {}).setdefault((M, bool(accumulate)), [])
-            q.append((dy_op, dy_ld, None, 0, None, 0, n, 0, gb))
+            q = self.__dict__.setdefault("_wq", {}).setdefault(self._wq_key(M, accumulate), [])
+            q.append((dy_op, dy_ld, None, 0, None, 0, n, 0, gb, M))
             return
         part = self._partials(K.colsum_blocks(M) * n)
         nb = K.colsum(dy_op, dy_ld, M, n, part, period, valid)

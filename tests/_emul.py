@@ -479,7 +479,10 @@ def heads_gemm(a, a_ld, a_bs, transposed, w, w_ld, w_bs, out, out_ld, out_bs, ro
 def wgrad_grouped(groups, tokens, accumulate=False):
     global launch_count
     launch_count += 1
-    for dy, dy_ld, x, x_ld, out, out_ld, n_out, k_in, bias in groups:
+    tokens_all = tokens
+    for grp in groups:
+        dy, dy_ld, x, x_ld, out, out_ld, n_out, k_in, bias = grp[:9]
+        tokens = (grp[9] if len(grp) > 9 and grp[9] else tokens_all)
         dyf = _v(dy, (tokens, n_out), (dy_ld, 1)).float()
         if k_in > 0:
             g = dyf.t() @ _v(x, (tokens, k_in), (x_ld, 1)).float()

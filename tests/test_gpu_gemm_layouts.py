@@ -167,6 +167,42 @@ def test_grouped_weight_gradients(cuda, tokens, accumulate):
             assert err <= 2e-3 * max(1.0, bref.abs().max().item()), err
 
 
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_grouped_weight_gradients_of_unequal_token_counts(cuda, accumulate):
+    """Groups with their own token counts in ONE launch (the encoder layers' B*T tokens next to the image-side K / V
+    projections' B*577): the library orders the tiles by cost (host-side greedy list schedule); more tiles than CTA
+    pairs, so the schedule has several rounds and unequal per-pair lists; bias tiles and a bias-only group included."""
+    from mm_s2ut_b200 import kernels as K
+
+    #          n_out, k_in, tokens
+    shapes = [(1536, 512, 700), (512, 768, 1810), (512, 768, 1810), (2048, 512, 700), (512, 2048, 700), (512, 512, 700),
+              (304, 72, 90), (1000, 0, 1810), (1536, 512, 333), (1024, 512, 1234)]
+    gen = torch.Generator().manual_seed(9)
+    groups, checks = [], []
+    for n_out, k_in, tokens in shapes:
+        dy = (torch.randn(tokens + 3, n_out, generator=gen) * 0.5).bfloat16().cuda()     # rows beyond `tokens` must not count
+        bias = torch.full((n_out,), 0.25, device=cuda)
+        bref = dy[:tokens].float().sum(0)
+        if k_in == 0:
+            groups.append((dy, n_out, None, 0, None, 0, n_out, 0, bias, tokens))
+            checks.append((None, None, bias, bref))
+            continue
+        x = torch.randn(tokens + 3, k_in, generator=gen).bfloat16().cuda()
+        out = torch.full((n_out, k_in), 0.25, device=cuda)
+        groups.append((dy, n_out, x, k_in, out, k_in, n_out, k_in, bias, tokens))
+        checks.append((out, dy[:tokens].float().t() @ x[:tokens].float(), bias, bref))
+    assert sum(((n + 255) // 256) * ((k + 255) // 256) for n, k, _ in shapes) > 74
+    K.wgrad_grouped(groups, shapes[0][2], accumulate)
+    torch.cuda.synchronize()
+    base = 0.25 if accumulate else 0.0
+    for out, ref, bias, bref in checks:
+        if out is not None:
+            err = (out - base - ref).abs().max().item()
+            assert err <= 2e-3 * max(1.0, ref.abs().max().item()) + (1e-3 if accumulate else 0), err
+        err = (bias - base - bref).abs().max().item()
+        assert err <= 2e-3 * max(1.0, bref.abs().max().item()), err
+
+
 @pytest.mark.parametrize("B,H,Lq,Tk", [(3, 4, 50, 50), (2, 8, 250, 250), (2, 2, 500, 250), (1, 4, 130, 577)])
 def test_heads_gemm_attention_backward_outputs(cuda, B, H, Lq, Tk):
     """mm_heads_gemm: dV = P^T dO, dK = dS^T q, dQ = dS k * 1/8 per (sequence, head) straight from / into the token-major
