@@ -27,6 +27,9 @@ Third-party code that carries the arithmetic and is absent from /root/reference:
 Pinning status: the reference has no tests or golden vectors ("parity unpinned" by the reference's
 own tests).  The oracle is pinned instead against (1) real torchaudio 2.11 fbank outputs, (2) outputs
 of the reference's own ``fuse.py`` imported in the build container (``oracle/make_golden.py`` ->
-``tests/golden/*.npz``), and (3) HF ``Speech2TextEncoder`` -- an independent port of the same fairseq
-encoder -- with copied weights.  The fairseq encoder itself could not be run (not installed, no network).
+``tests/golden/*.npz``: the attention modules, their gradients, and the ``fuse_img_feat`` glue method), and (3) HF
+``Speech2TextEncoder`` / ``Speech2TextDecoder`` -- independent ports of the same fairseq encoder and decoder -- with
+copied weights; ``adam.py`` additionally against ``torch.optim.Adam`` in the eps -> 0 limit (the two differ only in where
+eps enters).  fairseq itself could not be run (not installed, no network); the label-smoothed criterion, UtteranceCMVN
+and SpecAugment are restated from its published source and stay unpinned.
 """

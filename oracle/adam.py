@@ -3,7 +3,8 @@
 The reference trains with ``--optimizer adam --adam-betas '(0.9,0.98)' --clip-norm 10.0`` (scripts/textless/1_train.sh
 :111-113 region; fairseq's own ``fairseq/optim/adam.py`` ``Adam.step`` and ``fairseq/utils.py`` ``clip_grad_norm_`` --
 fairseq is un-vendored and absent here, so this restates its published algorithm: **parity unpinned** by reference
-tests).  fairseq's step differs from ``torch.optim.Adam`` only in where eps enters:
+tests; checked against ``torch.optim.Adam`` in the eps -> 0 limit, tests/test_oracle_golden.py).  fairseq's step
+differs from ``torch.optim.Adam`` only in where eps enters:
 
     exp_avg    = b1 * exp_avg    + (1 - b1) * g
     exp_avg_sq = b2 * exp_avg_sq + (1 - b2) * g * g

@@ -9,6 +9,11 @@ Structure per fairseq ``s2ut_architecture_base``: embed
 specials, padding_idx 1, scale sqrt(d)) + sinusoidal positions, 6 pre-LN layers (causal self-attention, encoder
 attention with key padding mask, ReLU FFN), final LayerNorm, output projection tied to the embedding,
 n_frames_per_step = 1.
+
+Pinning: ``unit_decoder_forward`` is checked against HF ``Speech2TextDecoder`` (the port of the same fairseq decoder) with
+copied weights, right-padded targets and an encoder padding mask (``make_golden.py: golden_hf_decoder`` ->
+``tests/golden/hf_speech2text_decoder.npz``, ``test_unit_decoder_restatement_matches_hf_port``: 1e-7).  The criterion
+below is restated from fairseq's source and unpinned.
 """
 from __future__ import annotations
 

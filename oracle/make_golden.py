@@ -312,6 +312,59 @@ def golden_hf_encoder():
     print("HF encoder golden written", tuple(out.shape))
 
 
+def golden_hf_decoder():
+    """HF Speech2TextDecoder (port of fairseq's TransformerDecoder as the S2T / S2UT models use it: scaled embedding +
+    fairseq sinusoidal positions, pre-LN layers with causal self-attention and encoder attention, final LayerNorm, output
+    projection tied to the embedding): copy weights into fairseq names, store tokens / encoder states / logits.  Pins
+    ``oracle/decoder.py: unit_decoder_forward`` (fairseq itself is not installed here)."""
+    from transformers import Speech2TextConfig
+    from transformers.models.speech_to_text.modeling_speech_to_text import Speech2TextDecoder
+
+    torch.manual_seed(11)
+    d, L, H, ffn, V = 64, 2, 2, 128, 57
+    cfg = Speech2TextConfig(vocab_size=V, d_model=d, decoder_layers=L, decoder_attention_heads=H, decoder_ffn_dim=ffn,
+                            max_target_positions=200, dropout=0.0, attention_dropout=0.0, activation_dropout=0.0,
+                            decoder_layerdrop=0.0, activation_function="relu", scale_embedding=True, pad_token_id=1,
+                            bos_token_id=0, eos_token_id=2, decoder_start_token_id=2)
+    dec = Speech2TextDecoder(cfg).eval()
+    with torch.no_grad():
+        for n, p in dec.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+        dec.embed_tokens.weight.mul_(8.0)      # HF initialises with std 0.02: make the token term comparable to the positions
+    B, Lt, T = 3, 23, 31
+    tokens = torch.randint(4, V, (B, Lt))
+    tokens[:, 0] = 2
+    tokens[1, 17:] = 1                    # trailing target padding (fairseq pads prev_output_tokens on the right)
+    tokens[2, 9:] = 1
+    enc_lens = torch.tensor([31, 22, 13])
+    enc = torch.randn(B, T, d)
+    enc_mask = (torch.arange(T)[None, :] < enc_lens[:, None]).long()
+    with torch.no_grad():
+        hid = dec(input_ids=tokens, attention_mask=tokens.ne(1).long(), encoder_hidden_states=enc,
+                  encoder_attention_mask=enc_mask).last_hidden_state           # [B, Lt, d]
+        logits = hid @ dec.embed_tokens.weight.t()                             # tied output projection
+    hs = dec.state_dict()
+    sd = {"embed_tokens.weight": hs["embed_tokens.weight"]}
+    for i in range(L):
+        a = f"layers.{i}."
+        for att in ("self_attn", "encoder_attn"):
+            for proj in ("q_proj", "k_proj", "v_proj", "out_proj"):
+                for t in ("weight", "bias"):
+                    sd[f"{a}{att}.{proj}.{t}"] = hs[f"{a}{att}.{proj}.{t}"]
+        for ln in ("self_attn_layer_norm", "encoder_attn_layer_norm", "final_layer_norm"):
+            for t in ("weight", "bias"):
+                sd[f"{a}{ln}.{t}"] = hs[f"{a}{ln}.{t}"]
+        for t in ("weight", "bias"):
+            sd[f"{a}fc1.{t}"] = hs[f"{a}fc1.{t}"]
+            sd[f"{a}fc2.{t}"] = hs[f"{a}fc2.{t}"]
+    sd["layer_norm.weight"], sd["layer_norm.bias"] = hs["layer_norm.weight"], hs["layer_norm.bias"]
+    np.savez_compressed(OUT / "hf_speech2text_decoder.npz", tokens=tokens.numpy(), enc=enc.numpy(),
+                        enc_lens=enc_lens.numpy(), logits=logits.numpy(), heads=np.array(H),
+                        **{"sd." + k: v.numpy() for k, v in sd.items()})
+    print("HF decoder golden written", tuple(logits.shape))
+
+
 if __name__ == "__main__":
     OUT.mkdir(parents=True, exist_ok=True)
     golden_fbank()
@@ -319,3 +372,4 @@ if __name__ == "__main__":
     golden_fuse_grads()
     golden_fuse_img_feat()
     golden_hf_encoder()
+    golden_hf_decoder()

@@ -101,6 +101,42 @@ def test_s2t_encoder_restatement_matches_hf_port():
     assert err < 1e-4, err
 
 
+def test_unit_decoder_restatement_matches_hf_port():
+    """oracle/decoder.py (fairseq TransformerDecoder as the S2UT unit decoder uses it) against HF's Speech2TextDecoder,
+    the port of the same fairseq module: scaled embedding, fairseq positions with right-padded targets, causal
+    self-attention, encoder attention under an encoder padding mask, tied output projection."""
+    from oracle import decoder as od
+
+    z = np.load(G / "hf_speech2text_decoder.npz")
+    sd = _sd(z)
+    tokens, enc, lens = torch.from_numpy(z["tokens"]), torch.from_numpy(z["enc"]), torch.from_numpy(z["enc_lens"])
+    mask = torch.arange(enc.shape[1])[None, :] >= lens[:, None]
+    out = od.unit_decoder_forward(sd, tokens, enc.transpose(0, 1).contiguous(), mask, int(z["heads"]))
+    ref = torch.from_numpy(z["logits"])
+    assert out.shape == ref.shape and ref.abs().max().item() > 1.0
+    err = ((out - ref).abs() * tokens.ne(1).unsqueeze(-1)).max().item()
+    assert err < 1e-4, err
+
+
+def test_adam_restatement_matches_torch_adam_in_the_eps_to_zero_limit():
+    """fairseq's Adam (oracle/adam.py) and torch.optim.Adam differ only in where eps enters (sqrt(v) + eps vs
+    sqrt(v / bias_correction2) + eps): with a vanishing eps the two must walk the same trajectory."""
+    from oracle import adam as oadam
+
+    rng = np.random.default_rng(3)
+    p0 = rng.standard_normal(257).astype(np.float32)
+    grads = [rng.standard_normal(257).astype(np.float32) * s for s in (1.0, 0.3, 2.0, 0.05, 1.0)]
+    t = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+    opt = torch.optim.Adam([t], lr=5e-4, betas=(0.9, 0.98), eps=1e-30)
+    p, m, v = p0.copy(), np.zeros_like(p0), np.zeros_like(p0)
+    for i, g in enumerate(grads):
+        t.grad = torch.from_numpy(g.copy())
+        opt.step()
+        p, m, v = oadam.adam_step(p, g, m, v, lr=5e-4, betas=(0.9, 0.98), eps=1e-30, step=i + 1)
+        assert np.max(np.abs(p - t.detach().numpy())) < 2e-7 * (i + 1)
+    assert np.max(np.abs(p - p0)) > 1e-3          # the parameters did move
+
+
 def test_utterance_cmvn_semantics():
     from oracle import fbank as ofb
 
