@@ -443,6 +443,18 @@ typedef struct mm_wgrad_group {
 int mm_wgrad_grouped(const mm_wgrad_group* groups, int32_t count, int64_t tokens, int32_t accumulate, int32_t dtype,
                      void* stream);
 
+/* Input gradient of a Linear that follows a LayerNorm, the LayerNorm backward and the residual add in ONE kernel (autograd
+ * of `x = residual + sublayer(layer_norm(x))` in fairseq's TransformerEncoderLayer / TransformerDecoderLayer, d_model 512):
+ *     dh = dy w                      dy [rows, k] 16-bit, w [k, 512] = the Linear's weight [out, in] as stored
+ *     g += LayerNorm'(dh; x, gamma)  x [rows, 512] fp32 = the LayerNorm's input, g [rows, 512] fp32 in place
+ *     g_op = 16-bit(g) (x keep / (1 - p) of dropout site `site` when drop_p > 0: the gradient entering the next branch)
+ *     partials [mm_gemm_ln_bwd_partial_rows(rows)][2][512] = (dgamma, dbeta) partial sums (sum the rows with
+ *     mm_reduce_partials_many).  dh stays in TMEM; replaces mm_gemm(MM_EPI_F32) + mm_layernorm_bwd_drop. */
+int mm_gemm_ln_bwd_partial_rows(int64_t rows);
+int mm_gemm_ln_bwd(const void* dy, int64_t dy_ld, const void* w, int64_t w_ld, int64_t rows, int32_t k, const float* x,
+                   const float* gamma, float eps, float* g, void* g_op, float* partials, float drop_p, uint64_t seed,
+                   const uint64_t* seed_dev, uint32_t site, int32_t dtype, void* stream);
+
 typedef struct mm_reduce_job {
   const float* part;
   float* out;

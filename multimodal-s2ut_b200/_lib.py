@@ -17,7 +17,7 @@ _PKG = Path(__file__).resolve().parent
 CSRC = _PKG / "csrc"
 INCLUDE = _PKG.parent / "include"
 LIB_PATH = _PKG / "libmms2ut_b200.so"
-SOURCES = ["abi.cu", "gemm.cu", "gemm_ln.cu", "rowwise.cu", "fbank.cu", "attention.cu", "cross_attention.cu", "attention_bwd.cu", "backward.cu", "wgrad.cu", "heads_gemm.cu", "attention_bwd_fused.cu", "p2p.cu"]
+SOURCES = ["abi.cu", "gemm.cu", "gemm_ln.cu", "rowwise.cu", "fbank.cu", "attention.cu", "cross_attention.cu", "attention_bwd.cu", "backward.cu", "wgrad.cu", "heads_gemm.cu", "attention_bwd_fused.cu", "p2p.cu", "gemm_ln_bwd.cu"]
 ABI_VERSION = 5
 
 NVCC_FLAGS = [
@@ -183,6 +183,10 @@ EXPORTS = {
     "mm_ipc_close_handle": (C.c_int, [C.c_void_p]),
     "mm_p2p_barrier": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "mm_p2p_allreduce_f32": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
+    "mm_gemm_ln_bwd_partial_rows": (C.c_int, [C.c_int64]),
+    "mm_gemm_ln_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                 C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_uint64, C.c_void_p,
+                                 C.c_uint32, C.c_int32, C.c_void_p]),
     "mm_p2p_pack_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "mm_p2p_allreduce_bf16": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
     "mm_p2p_unpack_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

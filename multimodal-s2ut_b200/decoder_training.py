@@ -60,6 +60,8 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
     _wgrad_mn = TrainEngine._wgrad_mn
     _wgrad_flush = TrainEngine._wgrad_flush
     _wq_key = staticmethod(TrainEngine._wq_key)
+    _dgrad_ln_bwd = TrainEngine._dgrad_ln_bwd
+    fused_ln_bwd = os.environ.get("MM_FUSED_LN_BWD", "0") != "0"      # see TrainEngine.fused_ln_bwd
     grouped_wgrad = os.environ.get("MM_GROUPED_WGRAD", "1") != "0"     # see TrainEngine.grouped_wgrad
     heads_gemm = os.environ.get("MM_HEADS_GEMM", "1") != "0"
     fused_attn_bwd_onchip = os.environ.get("MM_ATTN_BWD_ONCHIP", "1") != "0"
@@ -398,13 +400,11 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                 K.gemm(a0=gm, a0_ld=d, rows=M, w=Lr["w2"], w_ld=ffn, w_mn=True, n=ffn, k=d, mode=K.EPI_MASK_OP, out0=dF,
                        out0_ld=ffn, aux0=s["f"], aux_ld=ffn, scale=1.0 / (1.0 - p_act), block_n=bn)
                 self._linear_bwd(dF, ffn, s["h3"], M, ffn, d, self.g(p + "fc1.weight"), self.g(p + "fc1.bias"), accumulate)
-                K.gemm(a0=dF, a0_ld=ffn, rows=M, w=Lr["w1"], w_ld=d, w_mn=True, n=d, k=ffn, mode=K.EPI_F32, out0=dh,
-                       out0_ld=d, block_n=bn)
-                lnp = self._lnp()
                 if grouped:
                     g_op = self.buf("b_g_op2" + tag, (M, d), op)
-                K.layernorm_bwd(s["x2"], Lr["ln3"][0], dh, lnp, dx=g, resid=g, dx_op=g_op, drop=drb(dsite_layer(i, 2)))
-                self._ln_param_grads(lnp, d, self.g(p + "final_layer_norm.weight", p + "final_layer_norm.bias"), accumulate)
+                self._dgrad_ln_bwd(dF, Lr["w1"], s["x2"], Lr["ln3"][0], g, g_op,
+                                   self.g(p + "final_layer_norm.weight", p + "final_layer_norm.bias"), accumulate,
+                                   drb(dsite_layer(i, 2)))
                 # ---- encoder attention
                 gm = g_op
                 self._linear_bwd(gm, d, s["att2"], M, d, d, self.g(ea + "out_proj.weight"), self.g(ea + "out_proj.bias"),
@@ -420,8 +420,6 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                                lse=s.get("lse2"))
                 self._linear_bwd(dq2, d, s["h2"], M, d, d, self.g(ea + "q_proj.weight"), self.g(ea + "q_proj.bias"),
                                  accumulate)
-                K.gemm(a0=dq2, a0_ld=d, rows=M, w=Lr["wq"], w_ld=d, w_mn=True, n=d, k=d, mode=K.EPI_F32, out0=dh,
-                       out0_ld=d, block_n=bn)
                 self._linear_bwd(dkv2, 2 * d, sv["enc_btc"], B * T, 2 * d, d, self.g(ea + "k_proj.weight", ea + "v_proj.weight"),
                                  self.g(ea + "k_proj.bias", ea + "v_proj.bias"), accumulate)
                 if first_kv:   # gradient of the encoder states, summed over the layers
@@ -431,12 +429,11 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                 else:
                     K.gemm(a0=dkv2, a0_ld=2 * d, rows=B * T, w=Lr["wkv"], w_ld=d, w_mn=True, n=d, k=2 * d,
                            mode=K.EPI_RESID_F32, aux0=denc, aux_ld=d, out0=denc, out0_ld=d, block_n=bn)
-                lnp = self._lnp()
                 if grouped:
                     g_op = self.buf("b_g_op1" + tag, (M, d), op)
-                K.layernorm_bwd(s["x1"], Lr["ln2"][0], dh, lnp, dx=g, resid=g, dx_op=g_op, drop=drb(dsite_layer(i, 0)))
-                self._ln_param_grads(lnp, d, self.g(p + "encoder_attn_layer_norm.weight", p + "encoder_attn_layer_norm.bias"),
-                                     accumulate)
+                self._dgrad_ln_bwd(dq2, Lr["wq"], s["x1"], Lr["ln2"][0], g, g_op,
+                                   self.g(p + "encoder_attn_layer_norm.weight", p + "encoder_attn_layer_norm.bias"),
+                                   accumulate, drb(dsite_layer(i, 0)))
                 # ---- causal self-attention
                 gm = g_op
                 self._linear_bwd(gm, d, s["att"], M, d, d, self.g(sa + "out_proj.weight"), self.g(sa + "out_proj.bias"),
@@ -451,15 +448,11 @@ class UnitDecoderTrainEngine(UnitDecoderEngine):
                 self._linear_bwd(dqkv, 3 * d, s["h1"], M, 3 * d, d,
                                  self.g(sa + "q_proj.weight", sa + "k_proj.weight", sa + "v_proj.weight"),
                                  self.g(sa + "q_proj.bias", sa + "k_proj.bias", sa + "v_proj.bias"), accumulate)
-                K.gemm(a0=dqkv, a0_ld=3 * d, rows=M, w=Lr["wqkv"], w_ld=d, w_mn=True, n=d, k=3 * d, mode=K.EPI_F32, out0=dh,
-                       out0_ld=d, block_n=bn)
-                lnp = self._lnp()
                 if grouped:
                     g_op = self.buf("b_g_op0" + tag, (M, d), op)
-                K.layernorm_bwd(s["x0"], Lr["ln1"][0], dh, lnp, dx=g, resid=g, dx_op=g_op,
-                                drop=drb(dsite_layer(i - 1, 5)) if i > 0 else None)
-                self._ln_param_grads(lnp, d, self.g(p + "self_attn_layer_norm.weight", p + "self_attn_layer_norm.bias"),
-                                     accumulate)
+                self._dgrad_ln_bwd(dqkv, Lr["wqkv"], s["x0"], Lr["ln1"][0], g, g_op,
+                                   self.g(p + "self_attn_layer_norm.weight", p + "self_attn_layer_norm.bias"), accumulate,
+                                   drb(dsite_layer(i - 1, 5)) if i > 0 else None)
                 if not grouped:
                     self._flush()   # the layer's deferred reductions in one launch (per 16)
         with _scope("dec_layer"):

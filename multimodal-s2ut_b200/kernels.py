@@ -596,6 +596,34 @@ def layernorm_bwd(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, partia
                    "mm_layernorm_bwd")
 
 
+def gemm_ln_bwd_partial_rows(rows: int) -> int:
+    return int(_lib.load().mm_gemm_ln_bwd_partial_rows(rows))
+
+
+def gemm_ln_bwd(dy: torch.Tensor, w: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, g: torch.Tensor,
+                g_op: torch.Tensor, partials: torch.Tensor, eps: float = 1e-5, drop=None) -> int:
+    """g += LayerNorm'(dy @ w; x, gamma) in place, g_op = its 16-bit copy (x the dropout mask ``drop`` = (p, seed,
+    seed_dev, site) of the branch that consumes it), partials [rows_out, 2, 512] = (dgamma, dbeta) partial sums
+    (``mm_gemm_ln_bwd``: dgrad of a Linear after a LayerNorm + the LayerNorm backward + the residual add; d_model 512).
+    dy [rows, k] 16-bit (any row stride), w [k, 512] = the Linear's weight as stored.  Returns the number of partial
+    rows written."""
+    rows, k = dy.shape
+    assert dy.dtype == w.dtype == g_op.dtype and dy.dtype in _DT and dy.stride(1) == 1
+    assert w.shape == (k, 512) and w.stride(1) == 1
+    for t in (x, g):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == rows * 512
+    assert gamma.dtype == torch.float32 and gamma.numel() == 512 and g_op.is_contiguous() and g_op.numel() == rows * 512
+    nrows = gemm_ln_bwd_partial_rows(rows)
+    assert partials.dtype == torch.float32 and partials.numel() >= nrows * 1024
+    p_, seed, seed_dev, site = drop if (drop is not None and drop[0] > 0) else (0.0, 0, None, 0)
+    lib = _lib.load()
+    with _Launch("gemm_ln_bwd", 2.0 * rows * 512 * k):
+        _lib.check(lib.mm_gemm_ln_bwd(_ptr(dy), dy.stride(0), _ptr(w), w.stride(0), rows, k, _ptr(x), _ptr(gamma), eps,
+                                      _ptr(g), _ptr(g_op), _ptr(partials), float(p_), seed & 0xFFFFFFFFFFFFFFFF,
+                                      _ptr(seed_dev), site, dtype_code(dy.dtype), _stream()), "mm_gemm_ln_bwd")
+    return nrows
+
+
 def softmax_bwd(scores: torch.Tensor, dprobs: Optional[torch.Tensor], ld_in: int, rows: int, rows_per_batch: int,
                 n_keys: int, dscores: Optional[torch.Tensor], ld_out: int, probs: Optional[torch.Tensor] = None,
                 kv_lens: Optional[torch.Tensor] = None, heads: int = 1, valid_rows: int = 0,

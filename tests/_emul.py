@@ -529,6 +529,33 @@ def layernorm_bwd(x, gamma, dy, partials, dx=None, resid=None, eps=1e-5, dx_op=N
     p[0, 1] = dyr.sum(0)
 
 
+def gemm_ln_bwd_partial_rows(rows):
+    return 4
+
+
+def gemm_ln_bwd(dy, w, x, gamma, g, g_op, partials, eps=1e-5, drop=None):
+    global launch_count
+    launch_count += 1
+    rows = dy.shape[0]
+    dh = dy.float() @ w.float()
+    xr = x.view(rows, 512)
+    mean = xr.mean(1, keepdim=True)
+    rstd = torch.rsqrt(((xr - mean) ** 2).mean(1, keepdim=True) + eps)
+    xhat = (xr - mean) * rstd
+    dyg = dh * gamma
+    gv = g.view(rows, 512)
+    gv.add_(rstd * (dyg - dyg.mean(1, keepdim=True) - xhat * (dyg * xhat).mean(1, keepdim=True)))
+    g16 = gv
+    if drop is not None and drop[0] > 0:
+        g16 = gv * _keep_scale(gv.numel(), drop[0], drop[1], drop[3], drop[2]).view(gv.shape)
+    g_op.view(rows, 512).copy_(g16.to(g_op.dtype))
+    p = partials[: 4 * 1024].view(4, 2, 512)
+    p.zero_()
+    p[0, 0] = (dh * xhat).sum(0)
+    p[0, 1] = dh.sum(0)
+    return 4
+
+
 def softmax_bwd(scores, dprobs, ld_in, rows, rows_per_batch, n_keys, dscores, ld_out, probs=None, kv_lens=None, heads=1,
                 valid_rows=0, causal=False, ld_dprobs=None, drop_p=0.0, seed=0, seed_dev=None, site=0):
     S = _v(scores, (rows, n_keys), (ld_in, 1))

@@ -230,3 +230,15 @@ def test_decoder_training_step_with_dropout_in_fused_kernels_d512(cuda):
     worst = _decoder_dropout_parity(K, cuda, dt, B=2, L=70, T=90, d=512, heads=8, ffn=1024, layers=2, vocab=104, seed=2)
     record("configs[2] decoder backward, d_model 512, dropout inside the fused GEMM + LayerNorm / fc1 / LayerNorm-backward "
            "kernels (same masks in the oracle): worst parameter-gradient relative L2 error", worst, REL)
+
+
+def test_decoder_training_step_with_fused_dgrad_layernorm_backward(cuda, monkeypatch):
+    """The decoder's three LayerNorm backwards per layer through mm_gemm_ln_bwd (opt-in), d_model 512, dropout on."""
+    import mm_s2ut_b200.decoder_training as dt
+    from mm_s2ut_b200 import kernels as K
+    from test_host_training import _decoder_dropout_parity
+
+    monkeypatch.setattr(dt.UnitDecoderTrainEngine, "fused_ln_bwd", True)
+    worst = _decoder_dropout_parity(K, cuda, dt, B=2, L=70, T=90, d=512, heads=8, ffn=1024, layers=2, vocab=104, seed=3)
+    record("configs[2] decoder backward, d_model 512, fused dgrad + LayerNorm backward (opt-in), dropout on (same masks in "
+           "the oracle): worst parameter-gradient relative L2 error", worst, REL)

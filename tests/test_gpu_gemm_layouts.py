@@ -235,3 +235,41 @@ def test_heads_gemm_attention_backward_outputs(cuda, B, H, Lq, Tk):
     _close(dkv[:, d:], back(Pf.transpose(-1, -2) @ heads(dO, Lq), Tk), 2e-2)
     _close(dkv[:, :d], back(dSf.transpose(-1, -2) @ heads(q, Lq), Tk), 2e-2)
     _close(dq, back(dSf @ heads(kv[:, :d], Tk), Lq) * 0.125, 2e-2)
+
+
+@pytest.mark.parametrize("rows,k,p_drop", [(700, 1536, 0.0), (16000, 2048, 0.1), (333, 512, 0.25), (40000, 512, 0.0)])
+def test_dgrad_layernorm_backward_fused(cuda, rows, k, p_drop):
+    """mm_gemm_ln_bwd: dgrad of a Linear after a LayerNorm + the LayerNorm backward + the residual add in one kernel,
+    against the same steps in fp32 (autograd's formulas; the un-fused path is mm_gemm(EPI_F32) + mm_layernorm_bwd_drop)."""
+    from mm_s2ut_b200 import kernels as K
+
+    gen = torch.Generator().manual_seed(rows + k)
+    dy = (torch.randn(rows, k, generator=gen) * 0.05).bfloat16().cuda()
+    w = (torch.randn(k, 512, generator=gen) * 0.05).bfloat16().cuda()
+    x = (torch.randn(rows, 512, generator=gen) * 1.7 + 0.4).cuda()
+    gamma = (1.0 + 0.2 * torch.randn(512, generator=gen)).cuda()
+    g0 = (torch.randn(rows, 512, generator=gen) * 0.1).cuda()
+    g = g0.clone()
+    g_op = torch.full((rows, 512), float("nan"), dtype=torch.bfloat16, device=cuda)
+    nrows = K.gemm_ln_bwd_partial_rows(rows)
+    part = torch.full((nrows * 1024,), float("nan"), device=cuda)
+    drop = (p_drop, 77, None, 5) if p_drop > 0 else None
+    assert K.gemm_ln_bwd(dy, w, x, gamma, g, g_op, part, drop=drop) == nrows
+    torch.cuda.synchronize()
+    dh = dy.float() @ w.float()
+    mean = x.mean(1, keepdim=True)
+    rstd = torch.rsqrt(((x - mean) ** 2).mean(1, keepdim=True) + 1e-5)
+    xhat = (x - mean) * rstd
+    v = dh * gamma
+    ref = g0 + rstd * (v - v.mean(1, keepdim=True) - xhat * (v * xhat).mean(1, keepdim=True))
+    scale = ref.abs().max().item()
+    assert (g - ref).abs().max().item() <= 4e-3 * scale            # (dh, xhat) pass through bf16 between the two sweeps
+    rel = ((g - ref).norm() / (ref - g0).norm()).item()
+    assert rel < 6e-3, rel
+    keep = torch.ones_like(g)
+    if p_drop > 0:
+        K.dropout(keep, keep, p_drop, 77, 5)
+    assert torch.equal(g_op, (g * keep).bfloat16())
+    sums = part.view(nrows, 2, 512).sum(0)
+    for got, want in ((sums[0], (dh * xhat).sum(0)), (sums[1], dh.sum(0))):
+        assert (got - want).abs().max().item() <= 2e-3 * max(1.0, want.abs().max().item())

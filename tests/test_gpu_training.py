@@ -572,6 +572,21 @@ def test_training_step_with_attention_dropout_in_the_chunked_kernels(cuda):
            "kernels (same masks in the oracle): worst parameter-gradient relative L2 error", w, REL)
 
 
+def test_training_step_with_fused_dgrad_layernorm_backward(cuda, monkeypatch):
+    """MM_FUSED_LN_BWD=1: the QKV / fc1 input gradients, the LayerNorm backward and the residual add run as one kernel
+    (mm_gemm_ln_bwd) with the next branch's dropout mask in its 16-bit output; base width, dropout on, same masks in the
+    oracle.  Same bound as the un-fused path."""
+    from mm_s2ut_b200 import kernels as K
+
+    monkeypatch.setenv("MM_FUSED_LN_BWD", "1")
+    n0 = K.launch_count
+    worst, _ = _dropout_parity(K, cuda, p_drop=0.1, p_act=0.1, p_attn=0.1, preset="base",
+                               overrides=dict(encoder_layers=3), min_checked=3 * 15 + 2 + 4)
+    assert K.launch_count > n0
+    record("configs[2] backward, base width, fused dgrad + LayerNorm backward (mm_gemm_ln_bwd, opt-in), dropout 0.1 (same "
+           "masks in the oracle): worst parameter-gradient relative L2 error", worst, REL)
+
+
 def test_graphed_train_step_draws_fresh_dropout_masks(cuda):
     """Under CUDA-graph replay the dropout masks follow a device-resident per-step seed: two replays differ, and the
     backward pass of a replay uses the masks of its own forward (gradient of a fixed functional stays finite and the
