@@ -20,7 +20,18 @@ namespace mm {
 constexpr int FB_WIN = 400, FB_SHIFT = 160, FB_NFFT = 512, FB_BINS = 80;
 constexpr int FB_FRAMES_PER_CTA = 24;   // frames per work item: 3 rounds of 8 half-warps; the sample tile is 16 KB
 constexpr int FB_WAVE = FB_WIN + (FB_FRAMES_PER_CTA - 1) * FB_SHIFT;  // 4080 samples
-constexpr int FB_MAX_NNZ = 1536;   // mel weights, every filter zero-padded to its 16-filter group's longest
+// Mel weights: filters are taken in five groups of 16 (one per lane of a half-warp), every filter zero-padded to its
+// group's longest (rounded up to even).  For the 80-bin 20 Hz .. Nyquist bank at 512 points these lengths are fixed
+// numbers (mm_fbank_build_tables checks them), so the projection loop unrolls completely.  Weight i of lane l of group g
+// lives at FB_GOFF(g) + 16 i + l: a half-warp reads 16 consecutive floats per step (no bank conflicts; both half-warps
+// of a warp read the same address).  The per-filter layout this replaces had lane strides of 4 / 4 / 6 / 10 / 16
+// floats = up to 8-way conflicts: 160 shared-memory wavefronts per frame instead of 40.
+__host__ __device__ constexpr int FB_GMAX(int g) { return g == 0 ? 4 : g == 1 ? 4 : g == 2 ? 6 : g == 3 ? 10 : 16; }
+// (closed form on purpose: a recursive constexpr function called with an unrolled loop's index is emitted as a run-time call)
+__host__ __device__ constexpr int FB_GOFF(int g) { return 16 * (g == 0 ? 0 : g == 1 ? 4 : g == 2 ? 8 : g == 3 ? 14 : g == 4 ? 24 : 40); }
+static_assert(FB_GOFF(1) == 16 * FB_GMAX(0) && FB_GOFF(2) == FB_GOFF(1) + 16 * FB_GMAX(1) && FB_GOFF(3) == FB_GOFF(2) + 16 * FB_GMAX(2) &&
+              FB_GOFF(4) == FB_GOFF(3) + 16 * FB_GMAX(3) && FB_GOFF(5) == FB_GOFF(4) + 16 * FB_GMAX(4), "group offsets");
+constexpr int FB_MAX_NNZ = FB_GOFF(5);   // 640
 // table layout (floats)
 constexpr int TB_WIN = 0;                         // [400]
 constexpr int TB_TW256 = TB_WIN + 400;            // [256][2]  exp(-2 pi i m / 256)
@@ -75,7 +86,12 @@ __device__ __forceinline__ void dft16(float2 (&a)[16]) {
 
 constexpr int FB_THREADS = 128;
 constexpr int FB_HW = FB_THREADS / 16;                 // 8 half-warps: 4 frames each per 32-frame item
-constexpr int FB_XBUF = 16 * 17 * 2;                   // floats per half-warp: padded 16x17 complex transpose / spectrum
+// floats per half-warp: padded 16x17 complex transpose / spectrum (544) + 16, so that the two half-warps of a warp sit
+// 16 banks apart: their 16-float power-spectrum stores share one wavefront and the mel gather's reads collide half as often
+#ifndef MM_FB_XPAD
+#define MM_FB_XPAD 16
+#endif
+constexpr int FB_XBUF = 16 * 17 * 2 + MM_FB_XPAD;
 constexpr int FB_CTAS_PER_SM = 5;
 // shared memory (floats): sample tile | per-half-warp transpose / spectrum | povey window | mel weights | mel meta
 constexpr int FS_WAVE = 0;
@@ -85,8 +101,8 @@ constexpr int FS_MELW = FS_WIN + FB_WIN;
 constexpr int FS_META = FS_MELW + FB_MAX_NNZ;          // k0[80] | cnt[80] | off[80] | group max[8] (ints)
 constexpr int FS_TW1 = FS_META + 248;                    // [16 k2][16 lanes] float2: W256^(l k2), lane-contiguous
 constexpr int FB_SMEM_FLOATS = FS_TW1 + 512;
-constexpr int FB_SMEM_BYTES = FB_SMEM_FLOATS * 4;      // 44.5 KB -> 5 CTAs per SM
-static_assert(FB_SMEM_BYTES * FB_CTAS_PER_SM <= 227 * 1024, "shared memory per SM");
+constexpr int FB_SMEM_BYTES = FB_SMEM_FLOATS * 4;      // 40.5 KB -> 5 CTAs per SM
+static_assert((FB_SMEM_BYTES + 1024) * FB_CTAS_PER_SM <= 228 * 1024, "shared memory per SM");
 
 // W32^k = exp(-2 pi i k / 32), k = 0..15: the bin-block part of the real-FFT split twiddle W512^(16 k1 + l)
 __device__ __forceinline__ float2 w32(int k) {
@@ -121,8 +137,6 @@ __global__ void __launch_bounds__(FB_THREADS, FB_CTAS_PER_SM) fbank_kernel(const
   float2* s_win2 = reinterpret_cast<float2*>(fsm + FS_WIN);
   float* s_melw = fsm + FS_MELW;
   int* s_k0 = reinterpret_cast<int*>(fsm + FS_META);
-  int* s_cnt = s_k0 + 80;
-  int* s_off = s_cnt + 80;
 
   // ---- constants (tables are host-written once: nothing here depends on the previous kernel) ----
   // (window | mel weights + meta: two contiguous table regions copied as 128-bit words, all loads in flight at once)
@@ -302,20 +316,34 @@ __global__ void __launch_bounds__(FB_THREADS, FB_CTAS_PER_SM) fbank_kernel(const
       __syncwarp();
       // ---- sparse mel projection + log ----
       float* orow = feats + ((long long)b * max_frames + (f0 + fl)) * FB_BINS;
+      // filters 16 j .. 16 j + 15 have similar widths: every lane runs the group's longest filter (weights are
+      // zero-padded to it in the table): compile-time trip counts, and the 80 loads of the five groups are independent
+      // of each other (the logs and stores come after the last group, so nothing serialises the groups)
+      int kk[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) kk[j] = s_k0[l + 16 * j];
+      float e[5];
 #pragma unroll
       for (int j = 0; j < 5; ++j) {
-        // filters 16 j .. 16 j + 15 have similar widths: every lane runs the group's longest filter (weights are
-        // zero-padded to it in the table), so the trip count is uniform and the loads of a round are independent
-        const int m = l + 16 * j;
-        const float* wgt = s_melw + s_off[m];
-        const float* pw = xbuf + s_k0[m];
-        const int cnt = s_off[80 + j];          // group maximum (even): the ints right behind off[80]
+        const float* wgt = s_melw + FB_GOFF(j) + l;
+        const float* pw = xbuf + kk[j];
         float e0 = 0.f, e1 = 0.f;
-        for (int i = 0; i < cnt; i += 2) {
-          e0 = fmaf(wgt[i], pw[i], e0);
-          e1 = fmaf(wgt[i + 1], pw[i + 1], e1);
+#ifdef MM_FB_MEL_DYN
+        const int cnt_ = reinterpret_cast<const int*>(fsm + FS_META)[240 + j];
+#pragma unroll 1
+        for (int i = 0; i < cnt_; i += 2) {
+#else
+#pragma unroll
+        for (int i = 0; i < FB_GMAX(j); i += 2) {
+#endif
+          e0 = fmaf(wgt[16 * i], pw[i], e0);
+          e1 = fmaf(wgt[16 * i + 16], pw[i + 1], e1);
         }
-        if (live) orow[m] = logf(fmaxf(e0 + e1, 1.1920928955078125e-07f));
+        e[j] = logf(fmaxf(e0 + e1, 1.1920928955078125e-07f));
+      }
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) orow[l + 16 * j] = e[j];
       }
       __syncwarp();
     }
@@ -451,19 +479,18 @@ extern "C" int mm_fbank_build_tables(float* out) {
     k0[m] = first < 0 ? 0 : first;
     cnt[m] = first < 0 ? 0 : last - first + 1;
   }
-  int nnz = 0;
   for (int g = 0; g < FB_BINS / 16; ++g) {
     int mx = 0;
     for (int m = 16 * g; m < 16 * g + 16; ++m) mx = cnt[m] > mx ? cnt[m] : mx;
     mx = (mx + 1) & ~1;
     gmax[g] = mx;
+    if (mx != FB_GMAX(g)) return bad_arg("fbank tables: mel bank group widths differ from the compiled-in ones");
     for (int m = 16 * g; m < 16 * g + 16; ++m) {
-      off[m] = nnz;
-      if (nnz + mx > FB_MAX_NNZ) return bad_arg("fbank tables: mel bank too dense");
+      off[m] = FB_GOFF(g) + (m - 16 * g);
       // zero padding up to the group's longest filter; k0 + i may run past bin 255 for the top filters: the spectrum
-      // buffer is 544 floats long and the weight there is 0
-      for (int i = 0; i < mx; ++i) out[TB_MELW + nnz + i] = (i < cnt[m] && k0[m] + i < 256) ? wall[m][k0[m] + i] : 0.0f;
-      nnz += mx;
+      // buffer is 560 floats long and the weight there is 0
+      for (int i = 0; i < mx; ++i)
+        out[TB_MELW + off[m] + 16 * i] = (i < cnt[m] && k0[m] + i < 256) ? wall[m][k0[m] + i] : 0.0f;
     }
   }
   return 0;
