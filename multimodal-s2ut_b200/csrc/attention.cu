@@ -325,6 +325,15 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
       group_sync();
       m = fmaxf(m, x_max[(hf ^ 1) * AT_BM + row]);
       const float mb = m * L2E;
+#ifndef MM_ATT_NO_TURNS
+      // The exponentials of the two groups take turns in item order (0, 1, 2, ...: named barriers 3 / 4, 256 waiting +
+      // 256 arriving threads).  Left alone the groups drift into phase: both sit in sweep 2 at once, each at half the
+      // MUFU rate, and then both leave the MUFU pipe idle while they wait for O and store.  With turns a group has the
+      // pipe to itself and the other group's loads / maximum / P V wait / store run beside it.
+      if (i > 0) {
+        if (g == 0) asm volatile("bar.sync 3, 512;" ::: "memory"); else asm volatile("bar.sync 4, 512;" ::: "memory");
+      }
+#endif
       ATT_TRACE(2);
       // ---- sweep 2: probabilities of my 128 keys (next chunk prefetched while the current one goes through MUFU) ----
       float l = 0.f;
@@ -352,6 +361,11 @@ self_attention_t256_kernel(const __grid_constant__ CUtensorMap mapQK, const __gr
         tmem_ld_wait();
         tmem_st16(p_col + 16 * (cc + 1 - c0), pk);
       }
+#ifndef MM_ATT_NO_TURNS
+      if (i + 1 < n_local) {   // item i + 1 (the other group's) may exponentiate
+        if (g == 0) asm volatile("bar.arrive 4, 512;" ::: "memory"); else asm volatile("bar.arrive 3, 512;" ::: "memory");
+      }
+#endif
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
