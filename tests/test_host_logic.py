@@ -41,16 +41,24 @@ def test_mel_table_matches_torchaudio_bank():
     lib = _lib.load()
     t = np.zeros(lib.mm_fbank_table_floats(), dtype=np.float32)
     lib.mm_fbank_build_tables(t.ctypes.data)
-    o, nw = 400 + 512 + 512, 1536        # table layout of csrc/fbank.cu: window | W256 | W512 | mel weights | meta
+    # table layout of csrc/fbank.cu: window | W256 | W512 | mel weights | meta.  The weights are interleaved per group of
+    # 16 filters: weight i of filter 16 g + l sits at group_offset(g) + 16 i + l (a half-warp reads 16 consecutive floats)
+    gmax_expected = [4, 4, 6, 10, 16]                  # FB_GMAX: the longest filter of each group, rounded up to even
+    o, nw = 400 + 512 + 512, 16 * sum(gmax_expected)   # 640
     k0, cnt, off = (t[o + nw + 80 * i: o + nw + 80 + 80 * i].view(np.int32) for i in range(3))
     gmax = t[o + nw + 240: o + nw + 245].view(np.int32)
+    assert list(gmax) == gmax_expected
     mine = np.zeros((80, 256), dtype=np.float32)
-    for m in range(80):
-        mine[m, k0[m]: k0[m] + cnt[m]] = t[o + off[m]: o + off[m] + cnt[m]]
-        # every filter is zero-padded to the longest filter of its 16-filter group (uniform trip count in the kernel)
-        assert cnt[m] <= gmax[m // 16] and gmax[m // 16] % 2 == 0
-        assert not t[o + off[m] + cnt[m]: o + off[m] + gmax[m // 16]].any()
-        assert m == 79 or off[m + 1] == off[m] + gmax[m // 16]
+    goff = 0
+    for g in range(5):
+        for l in range(16):
+            m = 16 * g + l
+            assert off[m] == goff + l and cnt[m] <= gmax[g]
+            w = t[o + off[m]: o + off[m] + 16 * gmax[g]: 16]          # the filter's gmax[g] slots, stride 16
+            mine[m, k0[m]: k0[m] + cnt[m]] = w[: cnt[m]]
+            assert not w[cnt[m]:].any()                               # zero padding up to the group's longest filter
+        goff += 16 * gmax[g]
+    assert goff == nw
     bank, _ = K.get_mel_banks(80, 512, 16000.0, 20.0, 0.0, 100.0, -500.0, 1.0)
     assert int(cnt.sum()) == int((bank > 0).sum()) == 501
     assert np.abs(mine - bank.numpy()).max() < 2e-6
