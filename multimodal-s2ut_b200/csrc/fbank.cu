@@ -1,14 +1,14 @@
 // 80-bin Kaldi-compatible log-mel filterbank (torchaudio.compliance.kaldi.fbank defaults: 25 ms povey
 // window, 10 ms shift, snip_edges, DC removal, pre-emphasis 0.97, 512-point FFT, 20 Hz .. Nyquist mel bank,
-// log floor eps) + per-chunk CMVN statistics, fp32 throughout.
+// log floor eps) and the utterance CMVN statistics, fp32 throughout.
 //
 // One work item = 24 consecutive frames of one utterance.  The 4080 samples they span are staged once into shared
 // memory with 128-bit coalesced loads (frames overlap 2.5x, HBM sees each sample ~once).  Each HALF-warp
 // owns a frame: the 512-point real FFT runs as a 256-point complex FFT (16 x 16 Cooley-Tukey, one
 // 16-point DFT per lane entirely in registers, a single padded shared-memory transpose between the two
 // passes), followed by the real-FFT split, |X|^2, the sparse triangular mel projection (<= 2 filters per
-// FFT bin) and log.  Per-(utterance, chunk) sums / sums of squares for utterance CMVN are reduced in
-// registers -> shared memory -> one deterministic store (no atomics).
+// FFT bin) and log.  The utterance CMVN statistics are a separate kernel (cmvn_stats_kernel below): they replay
+// numpy's frame-sequential fp32 accumulation bit for bit, which a per-chunk partial sum would not.
 #include <math.h>
 
 #include "common.cuh"
