@@ -83,6 +83,66 @@ def test_fbank_vs_torchaudio(cuda):
     assert torch.equal(feats[5, : 1 + (len(wavs[5]) - 400) // 160].cpu(), torch.from_numpy(ofb.kaldi_fbank_ta(wavs[5])))
 
 
+def test_fbank_edge_lengths_and_unaligned_rows(cuda):
+    """Lengths the chunking has to get right -- shorter than one window (no frame, nothing written), exactly one window,
+    one short of / one past a 24-frame work item, one past an 8-frame round -- and a row stride that leaves every
+    utterance but the first off the 16-byte grid (the scalar staging path), fp32 and int16 alike: each utterance's
+    frames are the same bits as when it is run alone from an aligned buffer, and rows past the last frame stay untouched."""
+    from mm_s2ut_b200 import kernels as K
+
+    g = torch.Generator().manual_seed(11)
+    n_list = [399, 400, 559, 560, 400 + 160 * 22, 400 + 160 * 23, 400 + 160 * 24, 400 + 160 * 8, 400 + 160 * 47 + 159]
+    stride = max(n_list) + 3                                    # odd stride: rows 1.. start off the 16-byte grid
+    wav = torch.zeros(len(n_list), stride)
+    for i, n in enumerate(n_list):
+        wav[i, :n] = (torch.randn(n, generator=g) * 4000).round().clamp(-32768, 32767)
+    lens = torch.tensor(n_list, dtype=torch.int64)
+    m = 1 + (max(n_list) - 400) // 160
+    tables = K.fbank_tables(cuda)
+    for dt in (torch.float32, torch.int16):
+        feats = torch.full((len(n_list), m, 80), 7.0, device=cuda)
+        K.fbank(wav.to(dt).to(cuda), lens.to(cuda), feats, tables)
+        torch.cuda.synchronize()
+        for i, n in enumerate(n_list):
+            nf = 0 if n < 400 else 1 + (n - 400) // 160
+            assert (feats[i, nf:] == 7.0).all(), (dt, n)        # nothing written past the utterance's frames
+            if nf == 0:
+                continue
+            alone = torch.full((1, nf, 80), 7.0, device=cuda)
+            K.fbank(wav[i: i + 1, : n + (-n) % 8].contiguous().to(dt).to(cuda), lens[i: i + 1].to(cuda), alone, tables)
+            torch.cuda.synchronize()
+            assert torch.isfinite(alone).all()
+            assert torch.equal(feats[i, :nf], alone[0]), (dt, n)
+
+
+def test_fbank_full_size_shift_property(cuda):
+    """BASELINE size (64 x 10 s): a size-independent property instead of the CPU oracle.  Frame f of an utterance depends
+    on samples [160 f, 160 f + 400) only, so the features of the waveform advanced by 160 k samples are rows k.. of the
+    original's, bit for bit (same samples, same arithmetic, whichever work item, half-warp and round they land in); and
+    an utterance's features do not depend on its position in the batch."""
+    from mm_s2ut_b200 import kernels as K
+
+    g = torch.Generator().manual_seed(12)
+    B, n, k = 64, 160000, 37
+    wav = (torch.randn(B, n, generator=g) * 3000).round().to(cuda)
+    lens = torch.full((B,), n, dtype=torch.int64, device=cuda)
+    m = 1 + (n - 400) // 160
+    tables = K.fbank_tables(cuda)
+    feats = torch.zeros(B, m, 80, device=cuda)
+    K.fbank(wav, lens, feats, tables)
+    shifted = wav[:, 160 * k:].contiguous()
+    lens_s = torch.full((B,), n - 160 * k, dtype=torch.int64, device=cuda)
+    feats_s = torch.zeros(B, m - k, 80, device=cuda)
+    K.fbank(shifted, lens_s, feats_s, tables)
+    perm = torch.randperm(B, generator=g).to(cuda)
+    feats_p = torch.zeros(B, m, 80, device=cuda)
+    K.fbank(wav[perm].contiguous(), lens, feats_p, tables)
+    torch.cuda.synchronize()
+    assert torch.isfinite(feats).all()
+    assert torch.equal(feats[:, k:], feats_s)
+    assert torch.equal(feats[perm], feats_p)
+
+
 def test_cmvn_matches_reference_arithmetic(cuda):
     """CMVN statistics replay numpy's sequential fp32 accumulation: given the SAME fbank values the normalised
     features are bit-identical to fairseq UtteranceCMVN (incl. the all-zero utterance's floor behaviour)."""
