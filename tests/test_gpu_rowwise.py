@@ -219,6 +219,36 @@ def test_self_attention(cuda, T, lens):
     assert (out.float() - ref).abs().max().item() < 3e-2
 
 
+def test_self_attention_many_items_per_cta(cuda):
+    """BASELINE shape of the attention core: 64 utterances x 8 heads x 2 query tiles = 1024 items for 148 persistent CTAs
+    (six or seven items each, so both softmax groups of a CTA are busy and hand the exponential sweep to each other in
+    item order), ragged lengths, against plain fp32 PyTorch on the same 16-bit operands."""
+    from mm_s2ut_b200 import kernels as K
+
+    dt, B, T, H, hd = torch.bfloat16, 64, 250, 8, 64
+    d = H * hd
+    g = torch.Generator().manual_seed(64)
+    lens = torch.randint(1, T + 1, (B,), generator=g)
+    lens[0], lens[1] = T, 1
+    qkv = torch.randn(B * T, 3 * d, generator=g)
+    qkv[:, :d] *= 0.8
+    qkv = qkv.to(cuda).to(dt).contiguous()
+    sl = lens.to(torch.int32).to(cuda)
+    out = torch.zeros(B * T, d, dtype=dt, device=cuda)
+    for _ in range(3):      # the same bits every launch, whatever order the groups' turns were taken in
+        prev = out.clone()
+        K.self_attention(qkv, sl, B, T, H, out)
+        torch.cuda.synchronize()
+        assert _ == 0 or torch.equal(prev, out)
+    qf, kf, vf = (qkv[:, i * d: (i + 1) * d].float().view(B, T, H, hd).permute(0, 2, 1, 3) for i in range(3))
+    s = qf @ kf.transpose(-1, -2)
+    mask = torch.arange(T, device=cuda)[None, :] >= sl[:, None]
+    s = s.masked_fill(mask[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ vf).permute(0, 2, 1, 3).reshape(B * T, d)
+    assert torch.isfinite(out).all()
+    assert (out.float() - ref).abs().max().item() < 3e-2
+
+
 def test_specaugment_fused_into_cmvn_matches_oracle(cuda):
     """CMVN + SpecAugment in one pass == oracle CMVN followed by the oracle (fairseq) SpecAugment, same draws."""
     import numpy as np
