@@ -328,14 +328,8 @@ __global__ void __launch_bounds__(FB_THREADS, FB_CTAS_PER_SM) fbank_kernel(const
         const float* wgt = s_melw + FB_GOFF(j) + l;
         const float* pw = xbuf + kk[j];
         float e0 = 0.f, e1 = 0.f;
-#ifdef MM_FB_MEL_DYN
-        const int cnt_ = reinterpret_cast<const int*>(fsm + FS_META)[240 + j];
-#pragma unroll 1
-        for (int i = 0; i < cnt_; i += 2) {
-#else
 #pragma unroll
         for (int i = 0; i < FB_GMAX(j); i += 2) {
-#endif
           e0 = fmaf(wgt[16 * i], pw[i], e0);
           e1 = fmaf(wgt[16 * i + 16], pw[i + 1], e1);
         }
