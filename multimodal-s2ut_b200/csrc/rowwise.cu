@@ -309,8 +309,11 @@ __device__ __forceinline__ float4 cmvn4(const float4 v, const float* s_mean, con
   return y;
 }
 
-template <typename OpT>
-__global__ void __launch_bounds__(256) cmvn_apply_kernel(const float* __restrict__ feats,
+// F32 / OP: which of the two outputs exist (compile-time, so the variant the encoder runs -- 16-bit conv operand only --
+// does not carry the registers of the fp32 path: 4 blocks per SM instead of 3, i.e. two waves of blocks at the bench
+// shape instead of three, each wave one memory round trip deep)
+template <typename OpT, bool F32, bool OP>
+__global__ void __launch_bounds__(256, (F32 && OP) ? 3 : 4) cmvn_apply_kernel(const float* __restrict__ feats,
                                                           const float* __restrict__ mean_std,
                                                           const long long* __restrict__ lens, int lengths_are_samples,
                                                           int max_frames, float* __restrict__ out_f32,
@@ -360,10 +363,10 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const float* __restrict
       vf[u] = vo[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (rowi[u] < 0) continue;
       // fp32 output row `row` <-> utterance frame `row`; operand row `row` <-> frame `row - op_row_offset`
-      if (out_f32 != nullptr && row < nfr)
+      if (F32 && row < nfr)
         vf[u] = __ldg(reinterpret_cast<const float4*>(feats + ((long long)b * max_frames + row) * 80) + c4);
       const int fr = row - op_row_offset;
-      if (out_op != nullptr && fr >= 0 && fr < nfr)
+      if (OP && fr >= 0 && fr < nfr)
         vo[u] = __ldg(reinterpret_cast<const float4*>(feats + ((long long)b * max_frames + fr) * 80) + c4);
     }
     if (!stats_ready) {   // uniform: first trip only
@@ -379,12 +382,12 @@ __global__ void __launch_bounds__(256) cmvn_apply_kernel(const float* __restrict
       if (rowi[u] < 0) continue;
       const int idx = base + u * blockDim.x;
       const int row = rowi[u], c4 = idx % 20;
-      if (out_f32 != nullptr && row < max_frames) {
+      if (F32 && row < max_frames) {
         float4 y = (row < nfr && !ident) ? cmvn4(vf[u], s_mean, s_std, c4) : vf[u];
         if (sp && row < nfr) y = specaug(y, row, c4);
         reinterpret_cast<float4*>(out_f32 + ((long long)b * max_frames + row) * 80)[c4] = y;
       }
-      if (out_op != nullptr && row < op_frames) {
+      if (OP && row < op_frames) {
         const int fr = row - op_row_offset;
         float4 y = (fr >= 0 && fr < nfr && !ident) ? cmvn4(vo[u], s_mean, s_std, c4) : vo[u];
         if (sp && fr >= 0 && fr < nfr) y = specaug(y, fr, c4);
@@ -648,15 +651,22 @@ extern "C" int mm_cmvn_apply_specaug(const float* feats, const float* mean_std, 
   const int total_rows = op_frames > max_frames ? op_frames : max_frames;
   dim3 grid((total_rows + rows_per_block - 1) / rows_per_block, batch);
   const long long* l = reinterpret_cast<const long long*>(lens);
-  if (dtype == MM_DTYPE_F16)
-    launch_pdl(cmvn_apply_kernel<__half>, dim3(grid), dim3(256), 0, s, feats, mean_std, l, lengths_are_samples, max_frames, out_f32,
-                                                   reinterpret_cast<__half*>(out_op), op_frames, op_row_offset,
-                                                   rows_per_block, spec_masks, n_fmask, n_tmask, mask_value);
-  else
-    launch_pdl(cmvn_apply_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, feats, mean_std, l, lengths_are_samples, max_frames,
-                                                          out_f32, reinterpret_cast<__nv_bfloat16*>(out_op),
-                                                          op_frames, op_row_offset, rows_per_block, spec_masks, n_fmask,
-                                                          n_tmask, mask_value);
+  auto go = [&](auto kern, auto* op) {
+    launch_pdl(kern, dim3(grid), dim3(256), 0, s, feats, mean_std, l, lengths_are_samples, max_frames, out_f32, op, op_frames,
+               op_row_offset, rows_per_block, spec_masks, n_fmask, n_tmask, mask_value);
+  };
+  const bool f32 = out_f32 != nullptr, op = out_op != nullptr;
+  if (dtype == MM_DTYPE_F16) {
+    __half* o = reinterpret_cast<__half*>(out_op);
+    if (f32 && op) go(cmvn_apply_kernel<__half, true, true>, o);
+    else if (op) go(cmvn_apply_kernel<__half, false, true>, o);
+    else go(cmvn_apply_kernel<__half, true, false>, o);
+  } else {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_op);
+    if (f32 && op) go(cmvn_apply_kernel<__nv_bfloat16, true, true>, o);
+    else if (op) go(cmvn_apply_kernel<__nv_bfloat16, false, true>, o);
+    else go(cmvn_apply_kernel<__nv_bfloat16, true, false>, o);
+  }
   MM_CHECK_LAUNCH("cmvn_apply_kernel launch");
   return 0;
 }
